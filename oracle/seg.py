@@ -1,0 +1,211 @@
+"""ctypes front-end of liboracle.so (oracle/trex_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Restates, on the CPU, what the reference does in
+  RawProcessing::generate_binary   Application/src/commons/common/processing/RawProcessing.cpp:263-600
+  Source::extract_lines            .../processing/Source.cpp:156-255
+  merge_lines / run_fast           .../processing/CPULabeling.cpp:44-343
+  BackgroundSubtraction::apply     Application/src/tracker/python/BackgroundSubtraction.cpp:209-313
+  image::calculate_diff_image      Application/src/tracker/tracking/FilterCache.cpp:158-235
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ORDER_CANONICAL, ORDER_REF_LAZY, ORDER_REF_ABSORB = 0, 1, 2
+DIFF_NONE, DIFF_ABSOLUTE, DIFF_SIGN = 0, 1, 2
+
+LINE_DTYPE = np.dtype([("x0", "<u2"), ("x1", "<u2"), ("y", "<u2"), ("pad", "<u2")])
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("detect_threshold", C.c_int32), ("threshold_maximum", C.c_int32),
+        ("enable_difference", C.c_int32), ("detect_threshold_is_absolute", C.c_int32),
+        ("image_invert", C.c_int32), ("use_closing", C.c_int32), ("closing_size", C.c_int32),
+        ("dilation_size", C.c_int32), ("cm_per_pixel", C.c_float), ("n_size_ranges", C.c_int32),
+        ("size_lo", C.c_double * 4), ("size_hi", C.c_double * 4),
+    ]
+
+
+@dataclass
+class Params:
+    """The settings keys the path reads, with the reference defaults."""
+    detect_threshold: int = 15
+    threshold_maximum: int = 255
+    enable_difference: bool = True
+    detect_threshold_is_absolute: bool = True
+    image_invert: bool = False
+    use_closing: bool = False
+    closing_size: int = 3
+    dilation_size: int = 0
+    cm_per_pixel: float = 1.0
+    detect_size_filter: list = field(default_factory=lambda: [(10.0, 100000.0)])
+
+    def c(self) -> _Params:
+        p = _Params()
+        p.detect_threshold = self.detect_threshold
+        p.threshold_maximum = self.threshold_maximum
+        p.enable_difference = int(self.enable_difference)
+        p.detect_threshold_is_absolute = int(self.detect_threshold_is_absolute)
+        p.image_invert = int(self.image_invert)
+        p.use_closing = int(self.use_closing)
+        p.closing_size = self.closing_size
+        p.dilation_size = self.dilation_size
+        p.cm_per_pixel = self.cm_per_pixel
+        p.n_size_ranges = len(self.detect_size_filter)
+        for i, (lo, hi) in enumerate(self.detect_size_filter):
+            p.size_lo[i], p.size_hi[i] = lo, hi
+        return p
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so (and oracle/_ref when /root/reference exists) with the Makefile."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "trex_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        u8p, i64p, i32p, vp = C.POINTER(C.c_uint8), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p
+        L.to_generate_binary.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(_Params), vp]
+        L.to_generate_binary.restype = C.c_int
+        L.to_extract_lines.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]
+        L.to_extract_lines.restype = C.c_int64
+        L.to_label_runs.argtypes = [vp, C.c_int64, C.c_int, vp]
+        L.to_label_runs.restype = C.c_int64
+        L.to_segment_frame.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(_Params), C.c_int,
+                                       vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp]
+        L.to_segment_frame.restype = C.c_int64
+        L.to_blob_id.argtypes = [vp, C.c_int64]
+        L.to_blob_id.restype = C.c_uint32
+        L.to_image_from_lines.argtypes = [vp, C.c_int64, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.to_image_from_lines.restype = C.c_int64
+        L.to_crop_blob.argtypes = [vp, C.c_int64, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.to_crop_blob.restype = None
+        L.to_segment_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(_Params), C.c_int,
+                                       C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]
+        L.to_segment_batch.restype = C.c_int64
+        L.to_num_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def generate_binary(frame: np.ndarray, bg: np.ndarray, params: Params) -> np.ndarray:
+    frame = np.ascontiguousarray(frame, np.uint8); bg = np.ascontiguousarray(bg, np.uint8)
+    h, w = frame.shape
+    out = np.empty_like(frame)
+    pc = params.c()
+    if lib().to_generate_binary(_p(frame), _p(bg), w, h, C.byref(pc), _p(out)) != 0:
+        raise MemoryError
+    return out
+
+
+@dataclass
+class Blobs:
+    """SoA blob list of one frame (same content as the reference's blobs_t / blob::Pair list)."""
+    lines: np.ndarray      # LINE_DTYPE [L]
+    pixels: np.ndarray     # u8 [P]
+    line_off: np.ndarray   # i64 [K+1]
+    px_off: np.ndarray     # i64 [K+1]
+
+    def __len__(self):
+        return len(self.line_off) - 1
+
+    def blob(self, k):
+        return (self.lines[self.line_off[k]:self.line_off[k + 1]],
+                self.pixels[self.px_off[k]:self.px_off[k + 1]])
+
+    def as_set(self):
+        """Order-independent identity: {(lines bytes, pixel bytes)} (set equality)."""
+        return {(self.lines[self.line_off[k]:self.line_off[k + 1]].tobytes(),
+                 self.pixels[self.px_off[k]:self.px_off[k + 1]].tobytes()) for k in range(len(self))}
+
+    def as_list(self):
+        return [(self.lines[self.line_off[k]:self.line_off[k + 1]].tobytes(),
+                 self.pixels[self.px_off[k]:self.px_off[k + 1]].tobytes()) for k in range(len(self))]
+
+
+def segment_frame(frame, bg, params: Params, order=ORDER_CANONICAL, want_binary=False):
+    frame = np.ascontiguousarray(frame, np.uint8); bg = np.ascontiguousarray(bg, np.uint8)
+    h, w = frame.shape
+    capL, capP, capB = 1 << 16, max(1 << 16, w * h // 8), 1 << 14
+    binary = np.empty_like(frame) if want_binary else None
+    pc = params.c()
+    while True:
+        lines = np.zeros(capL, LINE_DTYPE); px = np.zeros(capP, np.uint8)
+        lo = np.zeros(capB + 1, np.int64); po = np.zeros(capB + 1, np.int64)
+        k = lib().to_segment_frame(_p(frame), _p(bg), w, h, C.byref(pc), order, _p(lines), capL,
+                                   _p(px), capP, _p(lo), _p(po), capB, _p(binary))
+        if k >= 0:
+            break
+        if k == -1:
+            raise MemoryError
+        need = -k
+        capL = max(capL, need); capP = max(capP, need); capB = max(capB, need)
+    b = Blobs(lines[:lo[k]].copy(), px[:po[k]].copy(), lo[:k + 1].copy(), po[:k + 1].copy())
+    return (b, binary) if want_binary else b
+
+
+def label_image(img, order=ORDER_CANONICAL):
+    """CPULabeling::run on a binary/grey image: no threshold, no size filter."""
+    p = Params(detect_threshold=0, enable_difference=False, detect_size_filter=[])
+    return segment_frame(img, img, p, order)
+
+
+def blob_id(lines: np.ndarray) -> int:
+    lines = np.ascontiguousarray(lines)
+    return int(lib().to_blob_id(_p(lines), len(lines)))
+
+
+def image_from_lines(lines, pixels, bg, method=DIFF_NONE, base_threshold=0):
+    lines = np.ascontiguousarray(lines); pixels = np.ascontiguousarray(pixels, np.uint8)
+    bg = np.ascontiguousarray(bg, np.uint8)
+    w = int(lines["x1"].max()) - int(lines["x0"].min()) + 1
+    h = int(lines["y"].max()) - int(lines["y"].min()) + 1
+    rect = np.zeros(4, np.int32)
+    mask = np.zeros((h, w), np.uint8); grey = np.zeros((h, w), np.uint8); diff = np.zeros((h, w), np.uint8)
+    n = lib().to_image_from_lines(_p(lines), len(lines), _p(pixels), _p(bg), bg.shape[1], method,
+                                  base_threshold, _p(rect), _p(mask), _p(grey), _p(diff))
+    return rect, int(n), mask, grey, diff
+
+
+def crop_blob(lines, pixels, bg, method=DIFF_ABSOLUTE, out_w=80, out_h=80):
+    lines = np.ascontiguousarray(lines); pixels = np.ascontiguousarray(pixels, np.uint8)
+    bg = np.ascontiguousarray(bg, np.uint8)
+    out = np.zeros((out_h, out_w), np.uint8)
+    lib().to_crop_blob(_p(lines), len(lines), _p(pixels), _p(bg), bg.shape[1], method, out_w, out_h, _p(out))
+    return out
+
+
+def segment_batch(frames, bg, params: Params, crop_method=DIFF_ABSOLUTE, out_w=80, out_h=80,
+                  max_crops=0, threads=0):
+    """CPU baseline driver: frames over pthreads.  Returns (n_blobs[n], crops or None)."""
+    frames = np.ascontiguousarray(frames, np.uint8); bg = np.ascontiguousarray(bg, np.uint8)
+    n, h, w = frames.shape
+    nb = np.zeros(n, np.int32)
+    crops = np.zeros((n, max_crops, out_h, out_w), np.uint8) if max_crops > 0 else None
+    pc = params.c()
+    lib().to_segment_batch(_p(frames), n, _p(bg), w, h, C.byref(pc), crop_method, out_w, out_h,
+                           max_crops, _p(crops), _p(nb), threads)
+    return nb, crops
+
+
+def num_threads() -> int:
+    return int(lib().to_num_threads())

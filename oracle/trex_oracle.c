@@ -1,0 +1,542 @@
+/*
+ * trex_oracle.c -- CPU restatement of the TRex segmentation / crop hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA path
+ * in trex_b200/csrc.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load it.  The product
+ * path never links or calls anything in oracle/.
+ *
+ * Parity status: PINNED for segmentation + labeling (reproduces every blob of
+ * the reference's own videos/test.pv fixture bit-exactly, see
+ * tests/golden/make_golden.py and tests/test_oracle_golden.py) and for
+ * imageFromLines (known-answer vector of Application/Tests/test_pixels.cpp:
+ * 1381-1466).  The pad/crop-to-80x80 geometry has no golden vector in the
+ * reference ("parity unpinned" for that sub-step; restated line by line).
+ *
+ * Every function cites the reference file:line it follows.  Paths are relative
+ * to the reference checkout:
+ *   C/ = Application/src/commons/common/    T/ = Application/src/tracker/
+ *
+ * Written from the reference's behaviour, not copied from its source: plain C,
+ * flat arrays, union-find bookkeeping instead of the reference's
+ * Brototype/DLList object graph.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include <pthread.h>
+#include <unistd.h>
+
+/* Same memory layout as HorizontalLine, C/misc/detail.h:73-76. */
+typedef struct { uint16_t x0, x1, y, pad; } to_line_t;
+
+/* Settings read by RawProcessing::generate_binary (C/processing/RawProcessing.cpp:266-327)
+ * and BackgroundSubtraction::apply (T/python/BackgroundSubtraction.cpp:137-139). */
+typedef struct {
+    int32_t detect_threshold;         /* grabber default_config.cpp:98  (15)   */
+    int32_t threshold_maximum;        /* :99 (255)                              */
+    int32_t enable_difference;        /* :126 (true)                            */
+    int32_t detect_threshold_is_absolute; /* T/core/default_config.cpp:1168 (true) */
+    int32_t image_invert;             /* :1159 (false)                          */
+    int32_t use_closing;              /* :1164 (false)                          */
+    int32_t closing_size;             /* :1165 (3)                              */
+    int32_t dilation_size;            /* :1163 (0)                              */
+    float   cm_per_pixel;             /* BackgroundSubtraction.cpp:137          */
+    int32_t n_size_ranges;            /* detect_size_filter: up to 4 half-open ranges */
+    double  size_lo[4], size_hi[4];
+} to_params_t;
+
+/* Blob emission order (SURVEY.md s7 "Blob order"):
+ *  0 canonical: by (y,x0) of the blob's first run (what the CUDA path emits)
+ *  1 reference, current source: survivor chosen by OWN run count, children attached lazily
+ *    (C/processing/CPULabeling.cpp:121-136, Brototype.cpp:84-137)
+ *  2 reference, older immediate-merge build that wrote videos/test.pv: survivor absorbs the
+ *    loser's runs (the commented-out variant CPULabeling.cpp:132-140) */
+enum { TO_ORDER_CANONICAL = 0, TO_ORDER_REF_LAZY = 1, TO_ORDER_REF_ABSORB = 2 };
+
+/* ------------------------------------------------------------------------------------------
+ * Morphology helpers: cv::dilate / cv::erode with a binary structuring element, anchor at the
+ * centre (k/2), one iteration, default border = pixels outside the image are ignored
+ * (RawProcessing.cpp:504-518,541-550; element shapes :419,:442).
+ * ------------------------------------------------------------------------------------------ */
+static void morph(const uint8_t *src, uint8_t *dst, int w, int h,
+                  const uint8_t *el, int kw, int kh, int ax, int ay, int is_dilate)
+{
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int v = is_dilate ? 0 : 255;
+            for (int j = 0; j < kh; ++j) {
+                int yy = y + j - ay;
+                if (yy < 0 || yy >= h) continue;
+                for (int i = 0; i < kw; ++i) {
+                    if (!el[j * kw + i]) continue;
+                    int xx = x + i - ax;
+                    if (xx < 0 || xx >= w) continue;
+                    int s = src[(size_t)yy * w + xx];
+                    if (is_dilate) { if (s > v) v = s; } else { if (s < v) v = s; }
+                }
+            }
+            dst[(size_t)y * w + x] = (uint8_t)v;
+        }
+}
+
+/* cv::getStructuringElement(MORPH_ELLIPSE, (2k+1,2k+1)) as OpenCV computes it (imgproc/morph:
+ * row i spans |dx| <= round(k * sqrt(1 - (dy/k)^2))).  Used at RawProcessing.cpp:442. */
+static void ellipse_element(uint8_t *el, int k)
+{
+    int n = 2 * k + 1;
+    double inv_r2 = k ? 1.0 / ((double)k * k) : 0.0;
+    for (int i = 0; i < n; ++i) {
+        int dy = i - k, j1 = 0, j2 = 0;
+        if (abs(dy) <= k) {
+            int dx = (int)lrint(k * sqrt((k * k - dy * dy) * inv_r2));
+            j1 = k - dx; if (j1 < 0) j1 = 0;
+            j2 = k + dx + 1; if (j2 > n) j2 = n;
+        }
+        for (int j = 0; j < n; ++j) el[i * n + j] = (j >= j1 && j < j2) ? 1 : 0;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * generate_binary, gray (1-channel) input.  C/processing/RawProcessing.cpp:263-600:
+ *   :364-369 image_invert (INPUT = 255 - input) | plain copy
+ *   :390-399 enable_difference: absdiff(INPUT, avg)  |  saturating subtract(avg, INPUT)
+ *   :529-534 threshold_maximum<255 ? inRange(d, T, Tmax) : threshold(d, |T|, 255, BINARY)  (strict >)
+ *   :537-539 detect_threshold<0 -> mask = 255 - mask
+ *   :504-505 use_closing: dilate, erode with the ellipse element
+ *   :541-550 dilation_size>0: dilate ones(n,n);  <0: erode, then re-threshold diff under the mask
+ *   :597-599 output = mask & input  (ORIGINAL input, grey values under the mask)
+ * Not restated: blur_difference, adaptive threshold, tags, 3-channel input (all default-off /
+ * out of scope).
+ * ------------------------------------------------------------------------------------------ */
+int to_generate_binary(const uint8_t *frame, const uint8_t *bg, int w, int h,
+                       const to_params_t *p, uint8_t *out)
+{
+    const size_t n = (size_t)w * h;
+    const int T = p->detect_threshold, aT = abs(T);
+    const int need_morph = p->use_closing || p->dilation_size != 0;
+    uint8_t *mask = (uint8_t *)malloc(n), *diff = NULL, *tmp = NULL;
+    if (!mask) return -1;
+    if (need_morph) {
+        diff = (uint8_t *)malloc(n); tmp = (uint8_t *)malloc(n);
+        if (!diff || !tmp) { free(mask); free(diff); free(tmp); return -1; }
+    }
+    for (size_t i = 0; i < n; ++i) {
+        int in = p->image_invert ? 255 - frame[i] : frame[i];
+        int d = in;
+        if (p->enable_difference) {
+            if (p->detect_threshold_is_absolute) d = abs(in - (int)bg[i]);
+            else { d = (int)bg[i] - in; if (d < 0) d = 0; }
+        }
+        if (diff) diff[i] = (uint8_t)d;
+        int m;
+        if (p->threshold_maximum < 255) m = (d >= T && d <= p->threshold_maximum);
+        else m = d > aT;
+        if (T < 0) m = !m;
+        mask[i] = m ? 255 : 0;
+    }
+    if (p->use_closing) {
+        int k = p->closing_size, kn = 2 * k + 1;
+        uint8_t *el = (uint8_t *)malloc((size_t)kn * kn);
+        ellipse_element(el, k);
+        morph(mask, tmp, w, h, el, kn, kn, k, k, 1);
+        morph(tmp, mask, w, h, el, kn, kn, k, k, 0);
+        free(el);
+    }
+    if (p->dilation_size != 0) {
+        int k = abs(p->dilation_size);
+        uint8_t *el = (uint8_t *)malloc((size_t)k * k);
+        memset(el, 1, (size_t)k * k);
+        if (p->dilation_size > 0) {
+            morph(mask, tmp, w, h, el, k, k, k / 2, k / 2, 1);
+            memcpy(mask, tmp, n);
+        } else {
+            /* erode; diff.copyTo(OUTPUT, mask) into a buffer that still holds older
+             * contents is order-dependent in the reference (CALLCV ping-pong); we restate
+             * the intended semantics: keep diff under the eroded mask, threshold again. */
+            morph(mask, tmp, w, h, el, k, k, k / 2, k / 2, 0);
+            for (size_t i = 0; i < n; ++i) mask[i] = (tmp[i] && diff[i] > aT) ? 255 : 0;
+            if (p->use_closing) {
+                int c = p->closing_size, kn = 2 * c + 1;
+                uint8_t *ce = (uint8_t *)malloc((size_t)kn * kn);
+                ellipse_element(ce, c);
+                morph(mask, tmp, w, h, ce, kn, kn, c, c, 1);
+                morph(tmp, mask, w, h, ce, kn, kn, c, c, 0);
+                free(ce);
+            }
+        }
+        free(el);
+    }
+    for (size_t i = 0; i < n; ++i) out[i] = mask[i] & frame[i];
+    free(mask); free(diff); free(tmp);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Source::extract_lines, C/processing/Source.cpp:156-255: per row, maximal runs of pixels
+ * with any channel non-zero.  Returns the number of runs (written up to cap).
+ * ------------------------------------------------------------------------------------------ */
+int64_t to_extract_lines(const uint8_t *img, int w, int h, int c, to_line_t *runs, int64_t cap)
+{
+    int64_t n = 0;
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *row = img + (size_t)y * w * c;
+        int prev = 0, x0 = 0;
+        for (int x = 0; x < w; ++x) {
+            int set = 0;
+            for (int k = 0; k < c; ++k) if (row[(size_t)x * c + k]) { set = 1; break; }
+            if (set && !prev) { x0 = x; prev = 1; }
+            else if (!set && prev) {
+                if (n < cap) { runs[n].x0 = (uint16_t)x0; runs[n].x1 = (uint16_t)(x - 1); runs[n].y = (uint16_t)y; runs[n].pad = 0; }
+                ++n; prev = 0;
+            }
+        }
+        if (prev) {
+            if (n < cap) { runs[n].x0 = (uint16_t)x0; runs[n].x1 = (uint16_t)(w - 1); runs[n].y = (uint16_t)y; runs[n].pad = 0; }
+            ++n;
+        }
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Labeling.  merge_lines two-pointer sweep, C/processing/CPULabeling.cpp:44-187, over the runs
+ * of the last non-empty row and the current one; 8-connectivity test HLine.h:90-92 /
+ * CPULabeling.cpp:60-62,91.  The reference's Brototype parent/child graph is replaced by a
+ * union-find whose representative is the reference's *survivor*, so the DLList emission order
+ * (creation order of surviving roots, CPULabeling.cpp:256-323) can be reproduced.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t parent;      /* union-find over blob ids                                      */
+    int64_t size;        /* run count used by the survivor rule (own / absorbed)          */
+    int32_t min_run;     /* smallest run index of the component (canonical order key)     */
+} blob_t;
+
+static int32_t bfind(blob_t *b, int32_t i)
+{
+    while (b[i].parent != i) { b[i].parent = b[b[i].parent].parent; i = b[i].parent; }
+    return i;
+}
+
+/* In: runs sorted (y,x0).  Out: label[i] = dense blob index in the requested emission order.
+ * Returns number of blobs, <0 on allocation failure. */
+int64_t to_label_runs(const to_line_t *runs, int64_t n, int order, int32_t *label)
+{
+    if (n == 0) return 0;
+    blob_t *bl = (blob_t *)malloc(sizeof(blob_t) * (size_t)n);
+    int32_t *node = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    if (!bl || !node) { free(bl); free(node); return -1; }
+    int32_t nb = 0;
+    for (int64_t i = 0; i < n; ++i) node[i] = -1;
+
+#define NEW_BLOB(i) do { bl[nb].parent = nb; bl[nb].size = 1; bl[nb].min_run = (int32_t)(i); node[i] = nb; ++nb; } while (0)
+
+    /* first non-empty row: one blob per run (CPULabeling.cpp:213-226) */
+    int64_t ps = 0, pe = 0;
+    while (pe < n && runs[pe].y == runs[0].y) { NEW_BLOB(pe); ++pe; }
+    int64_t cs = pe;
+    while (cs < n) {
+        int64_t ce = cs;
+        while (ce < n && runs[ce].y == runs[cs].y) ++ce;
+        int64_t cur = cs, prev = ps;
+        while (cur < ce) {
+            const to_line_t *c = &runs[cur];
+            const to_line_t *q = prev < pe ? &runs[prev] : NULL;
+            if (!q || (int)c->y > (int)q->y + 1 || (int)c->x1 + 1 < (int)q->x0) {
+                if (node[cur] < 0) NEW_BLOB(cur);            /* :60-86 */
+                ++cur;
+            } else if ((int)c->x0 > (int)q->x1 + 1) {
+                ++prev;                                       /* :91-95 */
+            } else {
+                int32_t pb = bfind(bl, node[prev]);
+                if (node[cur] < 0) {                          /* :103-107 */
+                    node[cur] = pb; bl[pb].size += 1;
+                    if ((int32_t)cur < bl[pb].min_run) bl[pb].min_run = (int32_t)cur;
+                } else {
+                    int32_t cb = bfind(bl, node[cur]);
+                    if (cb != pb) {                           /* :109-136 */
+                        int32_t win = pb, lose = cb;
+                        if (bl[pb].size <= bl[cb].size) { win = cb; lose = pb; }   /* :121-123 */
+                        bl[lose].parent = win;
+                        if (bl[lose].min_run < bl[win].min_run) bl[win].min_run = bl[lose].min_run;
+                        if (order == TO_ORDER_REF_ABSORB) bl[win].size += bl[lose].size;
+                    }
+                }
+                if (c->x1 <= q->x1) ++cur; else ++prev;        /* :181-184 */
+            }
+        }
+        ps = cs; pe = ce; cs = ce;
+    }
+#undef NEW_BLOB
+
+    /* dense numbering of surviving roots */
+    int32_t *dense = (int32_t *)malloc(sizeof(int32_t) * (size_t)nb);
+    if (!dense) { free(bl); free(node); return -1; }
+    int64_t k = 0;
+    if (order == TO_ORDER_CANONICAL) {
+        /* roots ordered by their smallest run index == (y,x0) of the first run */
+        for (int32_t b = 0; b < nb; ++b) dense[b] = -1;
+        for (int64_t i = 0; i < n; ++i) {
+            int32_t r = bfind(bl, node[i]);
+            if (bl[r].min_run == (int32_t)i) dense[r] = (int32_t)k++;
+        }
+    } else {
+        /* creation order of the survivors (DLList order) */
+        for (int32_t b = 0; b < nb; ++b) dense[b] = (bl[b].parent == b) ? (int32_t)k++ : -1;
+    }
+    for (int64_t i = 0; i < n; ++i) label[i] = dense[bfind(bl, node[i])];
+    free(dense); free(bl); free(node);
+    return k;
+}
+
+/* size filter: T/python/BackgroundSubtraction.cpp:259 -> SizeFilters::in_range_of_one
+ * (T/core/SizeFilters.cpp:36-53), Range<double>::contains half-open (C/misc/ranges.h:162-168);
+ * num_pixels * SQR(cm_per_pixel) is evaluated in float (Float2_t, C/misc/vec2.h:6). */
+static int size_ok(const to_params_t *p, uint64_t npx)
+{
+    if (p->n_size_ranges <= 0) return 1;
+    float sq = p->cm_per_pixel * p->cm_per_pixel;
+    float v = (float)npx * sq;
+    for (int i = 0; i < p->n_size_ranges; ++i)
+        if ((double)v >= p->size_lo[i] && (double)v < p->size_hi[i]) return 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One frame through BackgroundSubtraction::apply's per-image body
+ * (T/python/BackgroundSubtraction.cpp:209-313): generate_binary -> CPULabeling::run ->
+ * materialise (CPULabeling.cpp:256-323: lines in (y,x0) order, pixel bytes concatenated) ->
+ * size filter -> drop blobs with >= 65535 lines (:306).
+ * Output is SoA:  line_off[k]..line_off[k+1] / px_off[k]..px_off[k+1] index lines[] / pixels[].
+ * Returns number of kept blobs, or -(needed) if a capacity is too small (-1 on alloc failure).
+ * ------------------------------------------------------------------------------------------ */
+int64_t to_segment_frame(const uint8_t *frame, const uint8_t *bg, int w, int h,
+                         const to_params_t *p, int order,
+                         to_line_t *lines, int64_t cap_lines,
+                         uint8_t *pixels, int64_t cap_px,
+                         int64_t *line_off, int64_t *px_off, int64_t cap_blobs,
+                         uint8_t *binary_out /* optional w*h, may be NULL */)
+{
+    const size_t n = (size_t)w * h;
+    uint8_t *bin = binary_out ? binary_out : (uint8_t *)malloc(n);
+    if (!bin) return -1;
+    int64_t ret = -1;
+    to_line_t *runs = NULL; int32_t *label = NULL;
+    int64_t *cnt_l = NULL, *cnt_p = NULL, *cur_l = NULL, *cur_p = NULL; int32_t *remap = NULL;
+    if (to_generate_binary(frame, bg, w, h, p, bin)) goto done;
+
+    int64_t nr = to_extract_lines(bin, w, h, 1, NULL, 0);
+    runs = (to_line_t *)malloc(sizeof(to_line_t) * (size_t)(nr + 1));
+    label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nr + 1));
+    if (!runs || !label) goto done;
+    to_extract_lines(bin, w, h, 1, runs, nr);
+    int64_t nb = to_label_runs(runs, nr, order, label);
+    if (nb < 0) goto done;
+
+    cnt_l = (int64_t *)calloc((size_t)nb + 1, sizeof(int64_t));
+    cnt_p = (int64_t *)calloc((size_t)nb + 1, sizeof(int64_t));
+    cur_l = (int64_t *)calloc((size_t)nb + 1, sizeof(int64_t));
+    cur_p = (int64_t *)calloc((size_t)nb + 1, sizeof(int64_t));
+    remap = (int32_t *)malloc(sizeof(int32_t) * ((size_t)nb + 1));
+    if (!cnt_l || !cnt_p || !cur_l || !cur_p || !remap) goto done;
+    for (int64_t i = 0; i < nr; ++i) {
+        cnt_l[label[i]] += 1;
+        cnt_p[label[i]] += (int64_t)runs[i].x1 - runs[i].x0 + 1;
+    }
+    int64_t kept = 0, tl = 0, tp = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+        if (size_ok(p, (uint64_t)cnt_p[b]) && cnt_l[b] < 65535) {
+            remap[b] = (int32_t)kept;
+            if (kept < cap_blobs) { line_off[kept] = tl; px_off[kept] = tp; }
+            cur_l[b] = tl; cur_p[b] = tp;
+            tl += cnt_l[b]; tp += cnt_p[b]; ++kept;
+        } else remap[b] = -1;
+    }
+    if (kept > cap_blobs || tl > cap_lines || tp > cap_px) {
+        int64_t need = kept > tl ? kept : tl; if (tp > need) need = tp;
+        ret = -(need + 2); goto done;
+    }
+    line_off[kept] = tl; px_off[kept] = tp;
+    for (int64_t i = 0; i < nr; ++i) {            /* runs are visited in (y,x0) order */
+        int32_t b = label[i];
+        if (remap[b] < 0) continue;
+        lines[cur_l[b]++] = runs[i];
+        int64_t len = (int64_t)runs[i].x1 - runs[i].x0 + 1;
+        memcpy(pixels + cur_p[b], bin + (size_t)runs[i].y * w + runs[i].x0, (size_t)len);  /* :307 */
+        cur_p[b] += len;
+    }
+    ret = kept;
+done:
+    if (!binary_out) free(bin);
+    free(runs); free(label); free(cnt_l); free(cnt_p); free(cur_l); free(cur_p); free(remap);
+    return ret;
+}
+
+/* CPULabeling::run on an already-binary image (C/processing/CPULabeling.cpp:358-371), no
+ * size filter: used for the render -> relabel idempotence property of
+ * Application/Tests/test_matching.cpp:1556-1602. */
+int64_t to_label_image(const uint8_t *img, int w, int h, int order,
+                       to_line_t *lines, int64_t cap_lines, uint8_t *pixels, int64_t cap_px,
+                       int64_t *line_off, int64_t *px_off, int64_t cap_blobs)
+{
+    to_params_t p; memset(&p, 0, sizeof p);
+    p.detect_threshold = 0; p.threshold_maximum = 255; p.enable_difference = 0;
+    p.cm_per_pixel = 1.f; p.n_size_ranges = 0;
+    /* with enable_difference off and T=0, mask = (img > 0) and out = img: identity */
+    return to_segment_frame(img, img, w, h, &p, order, lines, cap_lines, pixels, cap_px,
+                            line_off, px_off, cap_blobs, NULL);
+}
+
+/* pv::bid::from_data, C/misc/bid.h:87-94 via blob_bid, C/processing/BlobIdentity.cpp:7-16 */
+uint32_t to_blob_id(const to_line_t *first, int64_t n_lines)
+{
+    return ((uint32_t)(((uint32_t)first->x0 + first->x1 + 1) / 2) << 19)
+         | (((uint32_t)first->y & 0x1FFFu) << 6)
+         | ((uint32_t)((uint8_t)n_lines) % 64u);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * imageFromLines, gray input, C/processing/Background.cpp:113-299, restricted to what the
+ * crop stage and the reference test use: mask + grey + difference images of bbox size,
+ * threshold >= (Background.h:415-427), difference method per Background.h:231-294:
+ *   method 0 none: value   1 absolute: |bg - v|   2 sign: max(0, bg - v)
+ * bbox = lines_dimensions (C/misc/detail.cpp:440-460).  Outputs may be NULL.
+ * Returns recount (pixels set); bbox in rect[4] = x,y,w,h.
+ * ------------------------------------------------------------------------------------------ */
+int64_t to_image_from_lines(const to_line_t *lines, int64_t n_lines, const uint8_t *px,
+                            const uint8_t *bg, int bg_w, int method, int base_threshold,
+                            int32_t rect[4], uint8_t *mask, uint8_t *grey, uint8_t *diffimg)
+{
+    int mx = 1 << 30, my = 1 << 30, Mx = -1, My = -1;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        if (lines[i].x0 < mx) mx = lines[i].x0;
+        if (lines[i].y < my) my = lines[i].y;
+        if (lines[i].x1 > Mx) Mx = lines[i].x1;
+        if (lines[i].y > My) My = lines[i].y;
+    }
+    int bw = Mx - mx + 1, bh = My - my + 1;
+    rect[0] = mx; rect[1] = my; rect[2] = bw; rect[3] = bh;
+    size_t n = (size_t)bw * bh;
+    if (mask) memset(mask, 0, n);
+    if (grey) memset(grey, 0, n);
+    if (diffimg) memset(diffimg, 0, n);
+    int64_t recount = 0;
+    for (int64_t i = 0; i < n_lines; ++i)
+        for (int x = lines[i].x0; x <= lines[i].x1; ++x, ++px) {
+            int v = *px, d = v;
+            if (method == 1) d = abs((int)bg[(size_t)lines[i].y * bg_w + x] - v);
+            else if (method == 2) { d = (int)bg[(size_t)lines[i].y * bg_w + x] - v; if (d < 0) d = 0; }
+            int set = base_threshold == 0 || d >= base_threshold;
+            if (!set) continue;
+            size_t o = (size_t)(lines[i].y - my) * bw + (x - mx);
+            if (mask) mask[o] = 255;
+            if (grey) grey[o] = (uint8_t)v;
+            if (diffimg) diffimg[o] = (uint8_t)d;
+            ++recount;
+        }
+    return recount;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * image::calculate_diff_image, T/tracking/FilterCache.cpp:158-235 ("none" normalisation,
+ * individual_image_scale == 1): render the blob (difference image when
+ * track_background_subtraction, else grey; :165-174), copy under its mask (:176), then centre
+ * pad (left = d - d/2, :187-190) or centre crop (start = d - d/2, :211-227) to out_w x out_h.
+ * method as in to_image_from_lines.  out is out_w*out_h bytes, zero filled.
+ * ------------------------------------------------------------------------------------------ */
+void to_crop_blob(const to_line_t *lines, int64_t n_lines, const uint8_t *px,
+                  const uint8_t *bg, int bg_w, int method, int out_w, int out_h, uint8_t *out)
+{
+    int32_t r[4];
+    int mx = 1 << 30, my = 1 << 30, Mx = -1, My = -1;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        if (lines[i].x0 < mx) mx = lines[i].x0;
+        if (lines[i].y < my) my = lines[i].y;
+        if (lines[i].x1 > Mx) Mx = lines[i].x1;
+        if (lines[i].y > My) My = lines[i].y;
+    }
+    int bw = Mx - mx + 1, bh = My - my + 1;
+    uint8_t *img = (uint8_t *)malloc((size_t)bw * bh), *mask = (uint8_t *)malloc((size_t)bw * bh);
+    if (method == 0) to_image_from_lines(lines, n_lines, px, bg, bg_w, 0, 0, r, mask, img, NULL);
+    else             to_image_from_lines(lines, n_lines, px, bg, bg_w, method, 0, r, mask, NULL, img);
+    /* offsets of the bbox image inside the output canvas (negative = cropped away) */
+    int offx, offy;
+    if (bw < out_w) { int d = out_w - bw; offx = d - d / 2; } else { int d = bw - out_w; offx = -(d - d / 2); }
+    if (bh < out_h) { int d = out_h - bh; offy = d - d / 2; } else { int d = bh - out_h; offy = -(d - d / 2); }
+    memset(out, 0, (size_t)out_w * out_h);
+    for (int y = 0; y < bh; ++y) {
+        int oy = y + offy; if (oy < 0 || oy >= out_h) continue;
+        for (int x = 0; x < bw; ++x) {
+            int ox = x + offx; if (ox < 0 || ox >= out_w) continue;
+            if (mask[(size_t)y * bw + x]) out[(size_t)oy * out_w + ox] = img[(size_t)y * bw + x];
+        }
+    }
+    free(img); free(mask);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Batch driver for the CPU baseline: n frames through to_segment_frame + to_crop_blob, frames
+ * handed to `threads` pthreads through a shared counter (frames are independent:
+ * BackgroundSubtraction::apply keeps no cross-frame state).  Returns total kept blobs; per-frame
+ * counts in n_blobs[].  crops (optional): n * max_crops * out_w*out_h bytes.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const uint8_t *frames, *bg; int n, w, h; const to_params_t *p;
+    int crop_method, out_w, out_h, max_crops; uint8_t *crops; int32_t *n_blobs;
+    int next; pthread_mutex_t mu; int64_t total;
+} batch_t;
+
+static void *batch_worker(void *arg)
+{
+    batch_t *b = (batch_t *)arg;
+    const int w = b->w, h = b->h;
+    const int64_t capL = 1 << 20, capP = (int64_t)w * h, capB = 1 << 18;
+    to_line_t *lines = (to_line_t *)malloc(sizeof(to_line_t) * (size_t)capL);
+    uint8_t *px = (uint8_t *)malloc((size_t)capP);
+    int64_t *lo = (int64_t *)malloc(sizeof(int64_t) * (size_t)(capB + 1));
+    int64_t *po = (int64_t *)malloc(sizeof(int64_t) * (size_t)(capB + 1));
+    int64_t local = 0;
+    for (;;) {
+        pthread_mutex_lock(&b->mu);
+        int f = b->next++;
+        pthread_mutex_unlock(&b->mu);
+        if (f >= b->n) break;
+        int64_t k = to_segment_frame(b->frames + (size_t)f * w * h, b->bg, w, h, b->p, TO_ORDER_CANONICAL,
+                                     lines, capL, px, capP, lo, po, capB, NULL);
+        if (k < 0) k = 0;
+        b->n_blobs[f] = (int32_t)k;
+        if (b->crops)
+            for (int64_t i = 0; i < k && i < b->max_crops; ++i)
+                to_crop_blob(lines + lo[i], lo[i + 1] - lo[i], px + po[i], b->bg, w, b->crop_method,
+                             b->out_w, b->out_h,
+                             b->crops + ((size_t)f * b->max_crops + (size_t)i) * b->out_w * b->out_h);
+        local += k;
+    }
+    pthread_mutex_lock(&b->mu); b->total += local; pthread_mutex_unlock(&b->mu);
+    free(lines); free(px); free(lo); free(po);
+    return NULL;
+}
+
+int to_num_threads(void)
+{
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+int64_t to_segment_batch(const uint8_t *frames, int n, const uint8_t *bg, int w, int h,
+                         const to_params_t *p, int crop_method, int out_w, int out_h,
+                         int max_crops, uint8_t *crops, int32_t *n_blobs, int threads)
+{
+    batch_t b = { frames, bg, n, w, h, p, crop_method, out_w, out_h, max_crops, crops, n_blobs,
+                  0, PTHREAD_MUTEX_INITIALIZER, 0 };
+    if (threads <= 0) threads = to_num_threads();
+    if (threads > n) threads = n > 0 ? n : 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    for (int i = 1; i < threads; ++i) pthread_create(&th[i], NULL, batch_worker, &b);
+    batch_worker(&b);
+    for (int i = 1; i < threads; ++i) pthread_join(th[i], NULL);
+    return b.total;
+}

@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures from the REFERENCE checkout (/root/reference).
+Run here (authoring container) only; the GPU box has no reference tree and just reads the .npz.
+
+  testpv_golden.npz  the reference's own segmentation output (videos/test.pv, written by TRex with
+                     videos/test.settings: detect_threshold=9, detect_size_filter=[[1,10000]], gray)
+                     for two full 2304x2304 frames and eight 512x640 windows, together with the
+                     decoded input frames (videos/test_frames/*.jpg) and the background stored in the pv.
+  vi_golden.npz      logits / probabilities of the reference's own V118_3 class
+                     (visual_identification_network_torch.py, imported from the reference tree)
+                     for the state_dict oracle.vi.init_state_dict(seed=0) generates.
+  pixels_golden.npz  known-answer vector transcribed from Application/Tests/test_pixels.cpp:1381-1466.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("TREX_REFERENCE", "/root/reference")
+
+
+def pack(blobs):
+    return dict(lines=blobs.lines, pixels=blobs.pixels, line_off=blobs.line_off, px_off=blobs.px_off)
+
+
+def make_testpv():
+    import cv2
+    from oracle import seg
+    from oracle.pv15 import PV15
+    pv = PV15(f"{REF}/videos/test.pv")
+    out = {"average": pv.average, "full_frames": np.array([0, 100])}
+    for i in (0, 100):
+        fr = cv2.imread(f"{REF}/videos/test_frames/frame_{i:03d}.jpg", cv2.IMREAD_UNCHANGED)
+        out[f"full{i}_frame"] = fr
+        for k, v in pack(pv.frame(i)).items():
+            out[f"full{i}_{k}"] = v
+    # windows centred on large blobs of other frames
+    WH, WW = 512, 640
+    wins = []
+    for i in (10, 30, 50, 70, 90, 120, 150, 180):
+        fr = cv2.imread(f"{REF}/videos/test_frames/frame_{i:03d}.jpg", cv2.IMREAD_UNCHANGED)
+        b = pv.frame(i)
+        sizes = np.diff(b.px_off)
+        k = int(np.argmax(sizes))
+        ln, _ = b.blob(k)
+        cy, cx = int(ln["y"].mean()), int(ln["x0"].mean())
+        y0 = min(max(cy - WH // 2, 0), pv.height - WH); x0 = min(max(cx - WW // 2, 0), pv.width - WW)
+        x0 -= x0 % 16
+        # expected: pv blobs strictly inside the window (1 px margin) -> window coordinates
+        lines, pixels, lo, po = [], [], [0], [0]
+        for j in range(len(b)):
+            l, p = b.blob(j)
+            if l["x0"].min() > x0 and l["x1"].max() < x0 + WW - 1 and l["y"].min() > y0 and l["y"].max() < y0 + WH - 1:
+                l = l.copy(); l["x0"] -= x0; l["x1"] -= x0; l["y"] -= y0
+                lines.append(l); pixels.append(p); lo.append(lo[-1] + len(l)); po.append(po[-1] + len(p))
+        wins.append((i, y0, x0))
+        out[f"win{i}_frame"] = fr[y0:y0 + WH, x0:x0 + WW].copy()
+        out[f"win{i}_lines"] = np.concatenate(lines); out[f"win{i}_pixels"] = np.concatenate(pixels)
+        out[f"win{i}_line_off"] = np.array(lo, np.int64); out[f"win{i}_px_off"] = np.array(po, np.int64)
+    out["windows"] = np.array(wins, np.int64)
+    np.savez_compressed(os.path.join(HERE, "testpv_golden.npz"), **out)
+    print("testpv_golden.npz", os.path.getsize(os.path.join(HERE, "testpv_golden.npz")) // 1024, "KiB")
+
+
+def make_vi():
+    import torch
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, f"{REF}/Application/src/tracker/python")
+    import visual_identification_network_torch as ref_net
+    from oracle import vi
+    out = {}
+    for tag, M in (("m100", 100), ("m8", 8)):
+        sd0 = vi.init_state_dict(M, 1, 80, 80, seed=0, perturb_norm=False)
+        torch.manual_seed(0)
+        ref = ref_net.ModelFetcher().get_model("v118_3", M, 1, 80, 80, device="cpu")
+        ref_sd = ref.state_dict()
+        # the oracle's init must consume the RNG exactly like the reference's constructor
+        for k, v in sd0.items():
+            assert torch.equal(ref_sd[k], v), k
+        sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=0, perturb_norm=True))
+        ref.load_state_dict(sd); ref.eval()
+        rng = np.random.default_rng(7)
+        crops = np.zeros((6, 80, 80, 1), np.uint8)
+        for n in range(6):     # blob-like: an ellipse of grey values on zero background
+            yy, xx = np.mgrid[0:80, 0:80]
+            a, b_, th = rng.uniform(12, 30), rng.uniform(4, 9), rng.uniform(0, np.pi)
+            u = (xx - 40) * np.cos(th) + (yy - 40) * np.sin(th); v = -(xx - 40) * np.sin(th) + (yy - 40) * np.cos(th)
+            m = (u / a) ** 2 + (v / b_) ** 2 <= 1
+            crops[n, ..., 0][m] = rng.integers(20, 200, m.sum())
+        with torch.no_grad():
+            logits = ref(torch.from_numpy(crops).to(torch.float32)).numpy()
+            probs = torch.softmax(torch.from_numpy(logits), 1).numpy()
+        out[f"{tag}_crops"] = crops; out[f"{tag}_logits"] = logits; out[f"{tag}_probs"] = probs
+        out[f"{tag}_checksum"] = np.array(vi.state_checksum(sd))
+        mine = vi.forward_logits(sd, crops)
+        print(tag, "oracle vs reference class max|dlogit| =", float(np.abs(mine - logits).max()),
+              "|logit|max =", float(np.abs(logits).max()))
+    np.savez_compressed(os.path.join(HERE, "vi_golden.npz"), **out)
+
+
+def make_pixels():
+    # Application/Tests/test_pixels.cpp:1381-1466 (gray leg): bg gray == the equal-channel BGR values,
+    # blob greys = cv::cvtColor of blob_values (only (10,200,10) is not grey: OpenCV fixed point -> 122).
+    bg = np.array([[30, 50, 70, 90], [40, 60, 80, 100]], np.uint8)
+    px = np.array([25, 110, 80, 122, 30, 95, 200, 100], np.uint8)
+    mask = np.array([[0, 255, 0, 255], [0, 255, 255, 0]], np.uint8)
+    np.savez(os.path.join(HERE, "pixels_golden.npz"), bg=bg, pixels=px, mask=mask, threshold=25, recount=4)
+
+
+if __name__ == "__main__":
+    make_testpv(); make_vi(); make_pixels()

@@ -1,0 +1,185 @@
+"""Pins the CPU oracle against the reference's own golden vectors (no GPU needed).
+
+ * videos/test.pv blobs (tests/golden/testpv_golden.npz, made by tests/golden/make_golden.py)
+ * Application/Tests/test_pixels.cpp:1381-1466 known-answer vector (pixels_golden.npz)
+ * the reference's V118_3 class outputs (vi_golden.npz)
+ * Application/Tests/test_matching.cpp:1556-1602 properties (one blob; render -> relabel idempotence)
+When /root/reference is present (authoring container) all 200 fixture frames are checked as well.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import seg, vi
+
+PV_PARAMS = seg.Params(detect_threshold=9, detect_size_filter=[(1, 10000)], cm_per_pixel=1.0)
+
+
+def _blobs(g, prefix):
+    return seg.Blobs(g[f"{prefix}_lines"], g[f"{prefix}_pixels"], g[f"{prefix}_line_off"], g[f"{prefix}_px_off"])
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "testpv_golden.npz"))
+
+
+@pytest.mark.parametrize("idx", [0, 100])
+def test_full_frames_match_test_pv(gold, idx):
+    ref = _blobs(gold, f"full{idx}")
+    got = seg.segment_frame(gold[f"full{idx}_frame"], gold["average"], PV_PARAMS, seg.ORDER_REF_ABSORB)
+    assert len(got) == len(ref)
+    assert got.as_list() == ref.as_list()          # exact file order with the absorb-size rule
+    canon = seg.segment_frame(gold[f"full{idx}_frame"], gold["average"], PV_PARAMS)
+    assert canon.as_set() == ref.as_set()
+    first = [tuple(canon.blob(k)[0][["y", "x0"]][0]) for k in range(len(canon))]
+    assert first == sorted(first)                  # canonical order = (y,x0) of first run
+
+
+def test_windows_match_test_pv(gold):
+    for (i, y0, x0) in gold["windows"]:
+        fr = gold[f"win{i}_frame"]
+        h, w = fr.shape
+        ref = _blobs(gold, f"win{i}")
+        got = seg.segment_frame(fr, gold["average"][y0:y0 + h, x0:x0 + w], PV_PARAMS)
+        inner = set()
+        for k in range(len(got)):
+            l, p = got.blob(k)
+            if l["x0"].min() > 0 and l["x1"].max() < w - 1 and l["y"].min() > 0 and l["y"].max() < h - 1:
+                inner.add((l.tobytes(), p.tobytes()))
+        assert inner == ref.as_set(), f"window of frame {i}"
+        assert len(ref) > 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/videos/test.pv"), reason="reference checkout absent")
+def test_all_200_frames_against_reference_checkout():
+    cv2 = pytest.importorskip("cv2")
+    from oracle.pv15 import PV15
+    pv = PV15("/root/reference/videos/test.pv")
+    total = 0
+    for i in range(0, 200):
+        fr = cv2.imread(f"/root/reference/videos/test_frames/frame_{i:03d}.jpg", cv2.IMREAD_UNCHANGED)
+        ref = pv.frame(i)
+        got = seg.segment_frame(fr, pv.average, PV_PARAMS, seg.ORDER_REF_ABSORB)
+        assert got.as_list() == ref.as_list(), i
+        total += len(ref)
+    assert total == 39908
+
+
+def test_image_from_lines_known_answer():
+    g = np.load(os.path.join(GOLDEN, "pixels_golden.npz"))
+    lines = np.zeros(2, seg.LINE_DTYPE)
+    lines["x0"] = 0; lines["x1"] = 3; lines["y"] = [0, 1]
+    rect, recount, mask, grey, diff = seg.image_from_lines(lines, g["pixels"], g["bg"], seg.DIFF_ABSOLUTE, int(g["threshold"]))
+    assert list(rect) == [0, 0, 4, 2]
+    assert recount == int(g["recount"])
+    assert np.array_equal(mask, g["mask"])
+    exp_diff = np.abs(g["bg"].astype(int) - g["pixels"].reshape(2, 4).astype(int)) * (g["mask"] > 0)
+    assert np.array_equal(diff, exp_diff)
+    assert np.array_equal(grey, g["pixels"].reshape(2, 4) * (g["mask"] > 0))
+
+
+def _circle_rect_image():
+    # test_matching.cpp:1556-1602: a filled circle overlapping a rectangle -> exactly one blob
+    img = np.zeros((240, 320), np.uint8)
+    yy, xx = np.mgrid[0:240, 0:320]
+    img[(yy - 100) ** 2 + (xx - 120) ** 2 <= 50 ** 2] = 255
+    img[90:160, 150:260] = 200
+    return img
+
+
+def test_ccl_single_blob_and_idempotence():
+    img = _circle_rect_image()
+    b = seg.label_image(img)
+    assert len(b) == 1
+    lines, px = b.blob(0)
+    render = np.zeros_like(img)
+    o = 0
+    for l in lines:
+        n = int(l["x1"]) - int(l["x0"]) + 1
+        render[l["y"], l["x0"]:l["x1"] + 1] = px[o:o + n]; o += n
+    assert np.array_equal(render, img)
+    b2 = seg.label_image(render)
+    assert b2.as_list() == b.as_list()
+
+
+def test_edge_cases():
+    P = seg.Params(detect_threshold=15, detect_size_filter=[])
+    bg = np.full((32, 48), 100, np.uint8)
+    fr = bg.copy()
+    assert len(seg.segment_frame(fr, bg, P)) == 0                       # empty frame
+    fr[31, 47] = 200; fr[0, 0] = 200                                     # corners, single pixels
+    fr[10, 10:20] = 50; fr[11, 20] = 50                                  # diagonal touch -> one blob
+    fr[20, 5:15] = 60; fr[20, 9] = 0                                     # grey 0 inside: splits (never foreground)
+    fr[25, 5] = 116; fr[25, 7] = 115                                     # strict >: 116 is fg, 115 is not
+    b = seg.segment_frame(fr, bg, P)
+    got = sorted((int(b.blob(k)[0]["y"][0]), int(b.blob(k)[0]["x0"][0]), len(b.blob(k)[1])) for k in range(len(b)))
+    assert got == [(0, 0, 1), (10, 10, 11), (20, 5, 4), (20, 10, 5), (25, 5, 1), (31, 47, 1)]
+    assert seg.blob_id(b.blob(0)[0]) == (((0 + 0 + 1) // 2) << 19) | (0 << 6) | 1
+
+
+def test_size_filter_half_open():
+    bg = np.full((16, 64), 100, np.uint8)
+    fr = bg.copy()
+    fr[2, 2:12] = 10       # 10 px
+    fr[6, 2:11] = 10       # 9 px
+    fr[10, 2:22] = 10      # 20 px
+    P = seg.Params(detect_threshold=15, detect_size_filter=[(10, 20)])
+    b = seg.segment_frame(fr, bg, P)
+    assert [len(b.blob(k)[1]) for k in range(len(b))] == [10]           # lo <= n < hi
+
+
+def test_morphology_matches_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    bg = np.full((96, 128), 120, np.uint8)
+    fr = bg.copy()
+    m = rng.random(fr.shape) < 0.08
+    fr[m] = 30
+    fr[40:60, 50:90] = 20; fr[48:52, 60:70] = 120
+    for closing, k, dil in ((True, 3, 0), (True, 2, 0), (False, 3, 3), (False, 3, 2), (True, 1, 2)):
+        P = seg.Params(detect_threshold=15, use_closing=closing, closing_size=k, dilation_size=dil)
+        got = seg.generate_binary(fr, bg, P)
+        d = cv2.absdiff(fr, bg)
+        _, mask = cv2.threshold(d, 15, 255, cv2.THRESH_BINARY)
+        if closing:
+            el = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2 * k + 1, 2 * k + 1), (k, k))
+            mask = cv2.erode(cv2.dilate(mask, el), el)
+        if dil > 0:
+            mask = cv2.dilate(mask, np.ones((dil, dil), np.uint8))
+        assert np.array_equal(got, cv2.bitwise_and(mask, fr)), (closing, k, dil)
+
+
+def test_crop_geometry():
+    bg = np.full((200, 300), 100, np.uint8)
+    # small blob: centre pad, left/top get the larger half (FilterCache.cpp:187-196)
+    lines = np.zeros(3, seg.LINE_DTYPE)
+    lines["y"] = [50, 51, 52]; lines["x0"] = [100, 99, 100]; lines["x1"] = [104, 105, 103]
+    px = np.arange(1, 1 + 5 + 7 + 4, dtype=np.uint8)
+    c = seg.crop_blob(lines, px, bg, seg.DIFF_NONE)
+    # bbox 7x3 at (99,50): left = 73 - 36 = 37, top = 77 - 38 = 39
+    assert c.sum() == px.sum()
+    assert np.array_equal(c[39, 38:43], px[0:5]) and np.array_equal(c[40, 37:44], px[5:12]) and np.array_equal(c[41, 38:42], px[12:16])
+    cd = seg.crop_blob(lines, px, bg, seg.DIFF_ABSOLUTE)
+    assert np.array_equal(cd[40, 37:44], 100 - px[5:12])
+    # large blob: centre crop, start = d - d/2 (FilterCache.cpp:211-227)
+    lines = np.zeros(1, seg.LINE_DTYPE); lines["y"] = 10; lines["x0"] = 20; lines["x1"] = 120   # 101 wide
+    px = np.arange(101, dtype=np.uint8) + 1
+    c = seg.crop_blob(lines, px, bg, seg.DIFF_NONE)
+    assert np.array_equal(c[40], px[11:91])        # d = 21 -> start 11
+
+
+def test_vi_oracle_matches_reference_class_outputs():
+    g = np.load(os.path.join(GOLDEN, "vi_golden.npz"))
+    for tag, M in (("m100", 100), ("m8", 8)):
+        sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=0))
+        assert vi.state_checksum(sd) == str(g[f"{tag}_checksum"])
+        lg = vi.forward_logits(sd, g[f"{tag}_crops"])
+        assert np.abs(lg - g[f"{tag}_logits"]).max() < 1e-5
+        pr = vi.predict(sd, g[f"{tag}_crops"])
+        assert np.abs(pr - g[f"{tag}_probs"]).max() < 1e-6
+    assert [vi.batch_size_for(m) for m in (0, 8, 64, 65, 100, 128, 256, 1024)] == [64, 64, 64, 128, 128, 128, 128, 128]
+    t = vi.transform_results(4, [0, 2, 3], {0: np.ones(3), 2: np.full(3, 2.0), 3: np.full(3, 3.0)}, 3)
+    assert np.array_equal(t[1], [-1, -1, -1]) and np.array_equal(t[2], [2, 2, 2])
