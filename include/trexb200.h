@@ -1,0 +1,195 @@
+/*
+ * trexb200.h -- C ABI of libtrexb200.so: TRex's per-frame segmentation + identification hot path
+ * on one NVIDIA B200 (sm_100a).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the TRex
+ * checkout; C/ = Application/src/commons/common/, T/ = Application/src/tracker/).
+ * INTEGRATION.md shows the reference-side shim that binds these.
+ *
+ * Conventions: every function returns TB_OK (0) or a negative tb_status; the message of the last
+ * failure on the calling thread is tb_last_error().  No exceptions cross the ABI.  A handle is
+ * single-producer (like the reference's `pipeline_async` thread, T/core/TaskPipeline.h:226-259).
+ * There is NO CPU fallback: without a CUDA device tb_*_create fails with TB_ERR_CUDA.
+ */
+#ifndef TREXB200_H
+#define TREXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TB_API __attribute__((visibility("default")))
+#else
+#define TB_API
+#endif
+
+typedef enum tb_status {
+    TB_OK = 0,
+    TB_ERR_INVALID = -1,      /* bad argument / unsupported configuration          */
+    TB_ERR_CUDA = -2,         /* CUDA runtime failure (no device, OOM, launch)     */
+    TB_ERR_STATE = -3,        /* call order (no background, no weights, no submit) */
+    TB_ERR_CAPACITY = -4      /* a per-frame capacity was exceeded (see tb_frame_info.status) */
+} tb_status;
+
+/* Same memory layout as cmn::HorizontalLine (C/misc/detail.h:73-76): 8 bytes. */
+typedef struct tb_line { uint16_t x0, x1, y, pad; } tb_line;
+
+/* The settings keys RawProcessing::generate_binary caches (C/processing/RawProcessing.cpp:266-327)
+ * plus those BackgroundSubtraction::apply reads (T/python/BackgroundSubtraction.cpp:137-139).
+ * Defaults (tb_seg_default_params) are the reference's. */
+typedef struct tb_seg_params {
+    int32_t detect_threshold;             /* 15;  <0 inverts the mask (RawProcessing.cpp:537)        */
+    int32_t threshold_maximum;            /* 255; <255 selects inRange[T,Tmax] (:529-531)            */
+    int32_t enable_difference;            /* 1                                                        */
+    int32_t detect_threshold_is_absolute; /* 1: |in-bg| ; 0: saturate(bg-in) (:393-399)              */
+    int32_t image_invert;                 /* 0                                                        */
+    int32_t use_closing;                  /* 0 (morphology: TB_ERR_INVALID in this release if != 0)   */
+    int32_t closing_size;                 /* 3                                                        */
+    int32_t dilation_size;                /* 0 (TB_ERR_INVALID in this release if != 0)               */
+    float   cm_per_pixel;                 /* 1                                                        */
+    int32_t n_size_ranges;                /* detect_size_filter: 0 = keep all; ranges are [lo,hi)    */
+    double  size_lo[4], size_hi[4];
+} tb_seg_params;
+
+typedef struct tb_seg_config {
+    int32_t device;               /* CUDA ordinal                                                    */
+    int32_t width, height;        /* frame size; channels fixed to 1 (meta_encoding gray)            */
+    int32_t max_batch;            /* frames per submit                                               */
+    int32_t max_runs_per_frame;   /* capacity of the run list of one frame (0 -> 32768)              */
+    int32_t max_pixels_per_frame; /* capacity of blob pixel bytes of one frame (0 -> width*height/4) */
+    int32_t max_crops_per_frame;  /* crops rendered per frame, first K blobs in canonical order (0 = no crops) */
+    int32_t crop_width, crop_height; /* individual_image_size, 80x80 (T/core/default_config.cpp:1091) */
+    int32_t crop_method;          /* 0 grey, 1 |bg-px|, 2 max(0,bg-px)  (Background.h:231-294)       */
+} tb_seg_config;
+
+/* Per-frame result header. status bit0: run capacity exceeded (frame dropped, n_blobs=0),
+ * bit1: pixel capacity exceeded, bit2: more blobs than max_crops_per_frame (crops truncated). */
+typedef struct tb_frame_info {
+    uint32_t blob_begin, n_blobs;     /* range in the batch's blob-record array   */
+    uint32_t line_begin, n_lines;     /* range in the batch's line arena           */
+    uint32_t px_begin, n_pixels;      /* range in the batch's pixel arena          */
+    uint32_t n_runs, status;
+} tb_frame_info;
+
+/* Per-blob record (32 bytes, fixed stride: also the unit of the multi-GPU metadata all-gather).
+ * Blobs of a frame are in canonical order: by (y,x0) of their first line.  bid is
+ * pv::bid::from_data (C/misc/bid.h:87-94). */
+typedef struct tb_blob_rec {
+    uint32_t line_off, px_off;        /* absolute offsets into the batch arenas    */
+    uint32_t n_lines, n_pixels;
+    uint16_t x0, y0, x1, y1;          /* inclusive bounding box                     */
+    uint32_t bid;
+    uint32_t frame;                   /* index of the frame inside the batch        */
+} tb_blob_rec;
+
+/* Host view of one frame's blobs: what CPULabeling::run returns as blobs_t
+ * (C/processing/CPULabeling.cpp:189-343) after the size filter of
+ * BackgroundSubtraction::apply (T/python/BackgroundSubtraction.cpp:259,306).
+ * Blob k owns lines[recs[k].line_off - line_base ...] etc.; pointers are valid until the next submit. */
+typedef struct tb_blob_view {
+    tb_frame_info info;
+    const tb_blob_rec *recs;          /* n_blobs records                                            */
+    const tb_line *lines;             /* frame's lines; blob k: lines + (recs[k].line_off - info.line_begin) */
+    const uint8_t *pixels;            /* frame's pixel bytes; blob k: pixels + (recs[k].px_off - info.px_begin) */
+} tb_blob_view;
+
+typedef struct tb_seg tb_seg;
+
+TB_API const char *tb_last_error(void);
+TB_API int tb_abi_version(void);
+TB_API int tb_device_count(void);
+
+TB_API void tb_seg_default_params(tb_seg_params *p);
+
+/* BackgroundSubtraction::BackgroundSubtraction / deinit (T/python/BackgroundSubtraction.cpp:50-84,118-120) */
+TB_API int tb_seg_create(const tb_seg_config *cfg, tb_seg **out);
+TB_API void tb_seg_destroy(tb_seg *h);
+
+/* settings callbacks of generate_binary (RawProcessing.cpp:283-327) */
+TB_API int tb_seg_set_params(tb_seg *h, const tb_seg_params *p);
+
+/* BackgroundSubtraction::set_background / Data::set (T/python/BackgroundSubtraction.cpp:86-101).
+ * stride in bytes between rows. */
+TB_API int tb_seg_set_background(tb_seg *h, const uint8_t *bg, int width, int height, int64_t stride);
+
+/* BackgroundSubtraction::apply(std::vector<TileImage>&&) (T/python/BackgroundSubtraction.cpp:126-347):
+ * n host frames (width*height bytes each, `stride` bytes between rows) are copied to the device,
+ * segmented, labelled and (optionally) cropped; results are copied back asynchronously.
+ * tb_seg_wait blocks until they are on the host.  With fetch=0 results stay on the device
+ * (only per-frame headers are fetched). */
+TB_API int tb_seg_submit(tb_seg *h, const uint8_t *const *frames, int n, int64_t stride, int fetch);
+
+/* Same for n packed frames already resident in device memory (n*width*height bytes).
+ * stream: a cudaStream_t (NULL = the handle's own stream); work is ordered on it. */
+TB_API int tb_seg_submit_device(tb_seg *h, const void *frames_dev, int n, void *stream, int fetch);
+
+TB_API int tb_seg_wait(tb_seg *h);
+
+/* blobs_t of frame i of the last batch (after tb_seg_wait, fetch=1). */
+TB_API int tb_seg_result(tb_seg *h, int i, tb_blob_view *out);
+
+/* Totals of the last batch (after tb_seg_wait): blobs, lines, pixel bytes, crops. */
+TB_API int tb_seg_totals(tb_seg *h, uint32_t out[4]);
+
+/* Device-side results of the last batch, for chaining without a host round trip:
+ *  crops  u8 [n_crops][crop_h][crop_w] (NHWC with C=1; image::calculate_diff_image,
+ *         T/tracking/FilterCache.cpp:158-235), n_crops_dev -> uint32 on the device,
+ *  recs   tb_blob_rec array, infos tb_frame_info[max_batch]. */
+TB_API int tb_seg_device_results(tb_seg *h, void **crops, void **n_crops_dev, void **crop_blob_index,
+                          void **recs, void **infos);
+
+/* Host copy of the crops of the last batch (after tb_seg_wait with fetch=1 and crops enabled). */
+TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_blob_index, uint32_t *n);
+
+/* Debug / parity: generate_binary's output image (mask & input) of one device- or host-resident
+ * frame, RawProcessing.cpp:597-600.  out is width*height host bytes. */
+TB_API int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t *out_host);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+TB_API uint64_t tb_seg_launch_count(tb_seg *h);
+
+/* ----------------------------------------------------------------------------------------------
+ * Visual identification: Python::VINetwork (T/ml/VisualIdentification.h:104-133) +
+ * predict_numpy (T/python/visual_recognition_torch.py:290-352) + V118_3
+ * (T/python/visual_identification_network_torch.py:184-258), inference only.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tb_vi tb_vi;
+
+typedef struct tb_vi_config {
+    int32_t device;
+    int32_t width, height, channels;   /* 80, 80, 1                                          */
+    int32_t num_classes;               /* track_max_individuals                              */
+    int32_t max_images;                /* capacity of one predict call                       */
+    int32_t precision;                 /* 0: fp32 CUDA cores (parity mode); 1: bf16x3 split on tcgen05 tensor cores */
+} tb_vi_config;
+
+TB_API int tb_vi_create(const tb_vi_config *cfg, tb_vi **out);
+TB_API void tb_vi_destroy(tb_vi *h);
+
+/* VINetwork::load_weights (T/ml/VisualIdentification.cpp:306-319): one call per state_dict entry,
+ * name exactly as in the reference's state_dict ("model.conv1.weight", "model.bn1.running_var",
+ * "model.bn4.bias", ...; torch layouts), then tb_vi_commit folds BatchNorm and uploads. */
+TB_API int tb_vi_set_tensor(tb_vi *h, const char *name, const float *data, int64_t count);
+TB_API int tb_vi_commit(tb_vi *h);
+
+/* VINetwork::probabilities (sync form, VisualIdentification.h:115-133): n images of
+ * height*width*channels u8 (NHWC) -> probs[n][num_classes] (softmax rows); logits optional (NULL). */
+TB_API int tb_vi_predict(tb_vi *h, const uint8_t *images, int n, float *probs, float *logits);
+
+/* Device-resident variant: images_dev u8 NHWC, n_dev optional device uint32 holding the actual
+ * count (<= n_max); outputs are device pointers ([n_max][num_classes]); stream NULL = own stream. */
+TB_API int tb_vi_predict_device(tb_vi *h, const void *images_dev, int n_max, const void *n_dev,
+                         void *probs_dev, void *logits_dev, void *stream);
+TB_API int tb_vi_wait(tb_vi *h);
+TB_API uint64_t tb_vi_launch_count(tb_vi *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREXB200_H */

@@ -1,0 +1,54 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
+header declares; creating a handle without a GPU fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from trex_b200 import _capi
+    return _capi
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "trexb200.h")).read()
+    declared = set(re.findall(r"\b(tb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(built.SYMBOLS), declared ^ set(built.SYMBOLS)
+    L = built.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.tb_abi_version() == 1
+
+
+def test_struct_sizes_match_header(built):
+    assert C.sizeof(built.BlobRec) == 32 and C.sizeof(built.FrameInfo) == 32
+    assert C.sizeof(built.SegParams) == 8 * 4 + 4 + 4 + 64
+    assert C.sizeof(built.SegConfig) == 40 and C.sizeof(built.ViConfig) == 28
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg = built.SegConfig(device=0, width=64, height=48, max_batch=1)
+    h = C.c_void_p()
+    rc = built.lib().tb_seg_create(C.byref(cfg), C.byref(h))
+    assert rc == built.TB_ERR_CUDA
+    assert b"no CUDA device" in built.lib().tb_last_error()
+    vcfg = built.ViConfig(device=0, width=80, height=80, channels=1, num_classes=10, max_images=4, precision=0)
+    assert built.lib().tb_vi_create(C.byref(vcfg), C.byref(h)) == built.TB_ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "trex_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU oracle", ""), f"{f} references oracle/"

@@ -1,0 +1,218 @@
+"""GPU parity tests of the segmentation path: CUDA (through the C ABI) vs the CPU oracle and the
+committed golden vectors of the reference (videos/test.pv).  Bit-exact: integer work."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+PV = dict(detect_threshold=9, detect_size_filter=[(1, 10000)], cm_per_pixel=1.0)
+
+
+def _mk(bg, max_batch=4, max_individuals=0, dense=False, **kw):
+    import trex_b200
+    s = trex_b200.DetectSettings(**kw)
+    h, w = bg.shape
+    cap = dict(max_runs_per_frame=h * w // 2 + 16, max_pixels_per_frame=h * w) if dense else {}
+    return trex_b200.BackgroundSubtraction(bg, settings=s, max_batch=max_batch, max_individuals=max_individuals, **cap)
+
+
+def _as_list(blobs):
+    return [(b.lines.tobytes(), b.pixels.tobytes()) for b in blobs]
+
+
+def _oracle(frame, bg, **kw):
+    from oracle import seg
+    keys = {k: v for k, v in kw.items() if k in seg.Params.__dataclass_fields__}
+    return seg.segment_frame(frame, bg, seg.Params(**keys))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "testpv_golden.npz"))
+
+
+def test_reference_fixture_full_frames(gold):
+    """The reference's own output for videos/test_frames 0 and 100 (2304x2304), as a set and via bid."""
+    from oracle import seg
+    bs = _mk(gold["average"], max_batch=2, **PV)
+    frames = [gold["full0_frame"], gold["full100_frame"]]
+    got = bs.apply(frames)
+    for idx, g in zip((0, 100), got):
+        ref = seg.Blobs(gold[f"full{idx}_lines"], gold[f"full{idx}_pixels"], gold[f"full{idx}_line_off"], gold[f"full{idx}_px_off"])
+        assert len(g) == len(ref)
+        assert set(_as_list(g)) == ref.as_set()
+        canon = seg.segment_frame(gold[f"full{idx}_frame"], gold["average"], seg.Params(**PV))
+        assert _as_list(g) == canon.as_list()            # canonical order too
+        for b in g:
+            assert b.bid == seg.blob_id(b.lines)
+            assert b.bounds == (int(b.lines["x0"].min()), int(b.lines["y"].min()), int(b.lines["x1"].max()), int(b.lines["y"].max()))
+
+
+def test_reference_fixture_windows(gold):
+    from oracle import seg
+    for (i, y0, x0) in gold["windows"]:
+        fr = gold[f"win{i}_frame"]
+        h, w = fr.shape
+        bs = _mk(gold["average"][y0:y0 + h, x0:x0 + w], max_batch=1, **PV)
+        (g,) = bs.apply([fr])
+        ref = seg.Blobs(gold[f"win{i}_lines"], gold[f"win{i}_pixels"], gold[f"win{i}_line_off"], gold[f"win{i}_px_off"])
+        inner = {(b.lines.tobytes(), b.pixels.tobytes()) for b in g
+                 if b.bounds[0] > 0 and b.bounds[1] > 0 and b.bounds[2] < w - 1 and b.bounds[3] < h - 1}
+        assert inner == ref.as_set()
+        bs.deinit()
+
+
+def test_synthetic_1080p_vs_oracle():
+    """BASELINE config 2: synthetic 1920x1080, 100 moving blobs, bit-exact masks/lines/pixels."""
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(n_blobs=100, seed=1234)
+    frames = world.frames(6)
+    kw = dict(detect_threshold=15, detect_size_filter=[(10, 100000)])
+    bs = _mk(world.bg, max_batch=4, **kw)
+    got = bs.apply(frames)       # two submits (4 + 2)
+    assert len(got) == 6
+    for f in range(6):
+        ref = _oracle(frames[f], world.bg, **kw)
+        assert _as_list(got[f]) == ref.as_list(), f
+        assert len(ref) >= 90
+    from oracle import seg
+    assert np.array_equal(bs.debug_binary(frames[0]), seg.generate_binary(frames[0], world.bg, seg.Params(**kw)))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(detect_threshold=15),
+    dict(detect_threshold=15, detect_threshold_is_absolute=False),
+    dict(detect_threshold=-15),
+    dict(detect_threshold=10, threshold_maximum=60),
+    dict(detect_threshold=40, enable_difference=False),
+    dict(detect_threshold=15, image_invert=True),
+    dict(detect_threshold=0),
+    dict(detect_threshold=255),
+])
+def test_threshold_variants(kw):
+    """The generate_binary branch family (RawProcessing.cpp:364-399,529-539) on a noisy frame."""
+    rng = np.random.default_rng(11)
+    bg = rng.integers(90, 160, (120, 208)).astype(np.uint8)
+    fr = np.clip(bg.astype(int) + rng.integers(-40, 41, bg.shape), 0, 255).astype(np.uint8)
+    fr[30:60, 50:120] = 10
+    fr[40:45, 70:80] = 0
+    kw = dict(kw, detect_size_filter=[])
+    bs = _mk(bg, max_batch=1, dense=True, **kw)
+    (g,) = bs.apply([fr])
+    ref = _oracle(fr, bg, **kw)
+    assert _as_list(g) == ref.as_list()
+    from oracle import seg
+    keys = {k: v for k, v in kw.items() if k in seg.Params.__dataclass_fields__}
+    assert np.array_equal(bs.debug_binary(fr), seg.generate_binary(fr, bg, seg.Params(**keys)))
+
+
+def test_adversarial_geometry():
+    """SURVEY s8d config 2 adversarial cases + generic widths (not a multiple of 16)."""
+    for (h, w) in ((64, 96), (37, 53), (200, 1000), (5, 16), (1, 1), (300, 17)):
+        rng = np.random.default_rng(h * 1000 + w)
+        bg = np.full((h, w), 100, np.uint8)
+        fr = bg.copy()
+        m = rng.random((h, w)) < 0.35                      # dense noise: many merges, diagonal contacts
+        fr[m] = 200
+        fr[rng.random((h, w)) < 0.02] = 0                  # grey 0 is never foreground
+        fr[h - 1, w - 1] = 200; fr[0, 0] = 200; fr[h - 1, 0] = 200; fr[0, w - 1] = 200
+        kw = dict(detect_threshold=15, detect_size_filter=[])
+        bs = _mk(bg, max_batch=1, dense=True, **kw)
+        (g,) = bs.apply([fr])
+        ref = _oracle(fr, bg, **kw)
+        assert _as_list(g) == ref.as_list(), (h, w)
+        bs.deinit()
+    # empty frame, full frame, spiral (one blob with many merges), checkerboard (8-conn: one blob)
+    h, w = 96, 160
+    bg = np.full((h, w), 100, np.uint8)
+    cases = {"empty": bg.copy(), "full": np.full((h, w), 200, np.uint8)}
+    cb = bg.copy(); yy, xx = np.mgrid[0:h, 0:w]; cb[(yy + xx) % 2 == 0] = 200; cases["checker"] = cb
+    sp = bg.copy()
+    for k in range(0, 40, 4):
+        sp[k, k:w - k] = 200; sp[h - 1 - k, k:w - k] = 200; sp[k:h - k, w - 1 - k] = 200; sp[k + 4:h - k, k] = 200
+    cases["spiral"] = sp
+    comb = bg.copy(); comb[10, :] = 200; comb[10:80, ::2] = 200; cases["comb"] = comb
+    bs = _mk(bg, max_batch=8, dense=True, detect_threshold=15, detect_size_filter=[])
+    got = bs.apply(list(cases.values()))
+    for (name, fr), g in zip(cases.items(), got):
+        ref = _oracle(fr, bg, detect_threshold=15, detect_size_filter=[])
+        assert _as_list(g) == ref.as_list(), name
+    assert len(got[0]) == 0 and len(got[1]) == 1 and len(got[2]) == 1
+
+
+def test_size_filter_and_cm_per_pixel():
+    bg = np.full((64, 256), 100, np.uint8)
+    fr = bg.copy()
+    for i, n in enumerate((9, 10, 11, 40, 41)):
+        fr[4 + 8 * i, 8:8 + n] = 30
+    for kw in (dict(detect_size_filter=[(10, 41)]), dict(detect_size_filter=[(2.5, 10.0)], cm_per_pixel=0.5),
+               dict(detect_size_filter=[(9, 10), (40, 41)]), dict(detect_size_filter=[])):
+        bs = _mk(bg, max_batch=1, detect_threshold=15, **kw)
+        (g,) = bs.apply([fr])
+        ref = _oracle(fr, bg, detect_threshold=15, **kw)
+        assert _as_list(g) == ref.as_list(), kw
+        bs.deinit()
+
+
+def test_crops_vs_oracle():
+    from oracle import seg
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(h=540, w=960, n_blobs=40, seed=3, semi=(22, 6))
+    frames = world.frames(3)
+    big = world.bg.copy(); big[100:300, 200:420] = 20          # a blob larger than the crop: centre crop
+    frames = np.concatenate([frames, big[None]])
+    for method, kw in ((seg.DIFF_ABSOLUTE, {}), (seg.DIFF_NONE, dict(track_background_subtraction=False)),
+                       (seg.DIFF_SIGN, dict(track_threshold_is_absolute=False))):
+        bs = _mk(world.bg, max_batch=4, max_individuals=64, detect_threshold=15, detect_size_filter=[(10, 100000)], **kw)
+        got = bs.apply(frames)
+        crops, idx = bs.crops()
+        n = 0
+        for f in range(len(frames)):
+            ref = _oracle(frames[f], world.bg, detect_threshold=15, detect_size_filter=[(10, 100000)])
+            assert _as_list(got[f]) == ref.as_list()
+            for k in range(min(len(ref), 64)):
+                assert np.array_equal(crops[n], seg.crop_blob(*ref.blob(k), world.bg, method)), (method, f, k)
+                n += 1
+        assert n == len(crops)
+        bs.deinit()
+
+
+def test_idempotence_render_relabel():
+    """test_matching.cpp:1556-1602 property on the GPU path: render blobs -> relabel -> same lines."""
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(h=272, w=480, n_blobs=15, seed=9, margin=30)
+    fr = world.frame()
+    kw = dict(detect_threshold=15, detect_size_filter=[])
+    bs = _mk(world.bg, max_batch=1, **kw)
+    (g,) = bs.apply([fr])
+    render = np.zeros_like(fr)
+    for b in g:
+        o = 0
+        for l in b.lines:
+            n = int(l["x1"]) - int(l["x0"]) + 1
+            render[l["y"], l["x0"]:l["x1"] + 1] = b.pixels[o:o + n]; o += n
+    bs2 = _mk(np.zeros_like(fr), max_batch=1, detect_threshold=0, enable_difference=False, detect_size_filter=[])
+    (g2,) = bs2.apply([render])
+    assert _as_list(g2) == _as_list(g)
+
+
+def test_capacity_and_state_errors():
+    import trex_b200
+    bg = np.full((64, 64), 100, np.uint8)
+    bs = trex_b200.BackgroundSubtraction(width=64, height=64, max_batch=1)
+    with pytest.raises(trex_b200.TrexB200Error) as e:
+        bs.apply([bg])                       # no background yet: the reference's pipeline stays paused
+    assert e.value.code == -3
+    bs.set_background(bg)
+    with pytest.raises(trex_b200.TrexB200Error):
+        bs.update_settings(trex_b200.DetectSettings(use_closing=True))
+    bs2 = trex_b200.BackgroundSubtraction(bg, max_batch=1, max_runs_per_frame=16,
+                                          settings=trex_b200.DetectSettings(detect_size_filter=[]))
+    fr = bg.copy(); fr[::2, ::2] = 200       # 1024 runs > capacity
+    with pytest.raises(trex_b200.TrexB200Error) as e:
+        bs2.apply([fr])
+    assert e.value.code == -4

@@ -1,0 +1,60 @@
+"""GPU parity tests of the identification path: CUDA V118_3 vs the fp32 oracle and the outputs of the
+reference's own class (tests/golden/vi_golden.npz).  Tolerance: 1e-3 on logits and probabilities
+(BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.mark.parametrize("tag,M", [("m100", 100), ("m8", 8)])
+def test_reference_class_golden(tag, M):
+    import trex_b200
+    from oracle import vi
+    g = np.load(os.path.join(GOLDEN, "vi_golden.npz"))
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=0))
+    assert vi.state_checksum(sd) == str(g[f"{tag}_checksum"])
+    net = trex_b200.VINetwork(M, max_images=16)
+    net.load_weights(sd)
+    probs, logits = net.probabilities(g[f"{tag}_crops"], return_logits=True)
+    assert np.abs(logits - g[f"{tag}_logits"]).max() < TOL
+    assert np.abs(probs - g[f"{tag}_probs"]).max() < TOL
+    assert np.allclose(probs.sum(1), 1, atol=1e-5)
+
+
+def test_batch_vs_oracle_and_chunking():
+    import trex_b200
+    from oracle import vi
+    M = 100
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=0))
+    rng = np.random.default_rng(5)
+    crops = np.zeros((70, 80, 80, 1), np.uint8)
+    for n in range(70):
+        h, w = rng.integers(8, 70), rng.integers(8, 70)
+        y, x = rng.integers(0, 80 - h), rng.integers(0, 80 - w)
+        crops[n, y:y + h, x:x + w, 0] = rng.integers(0, 256, (h, w))
+    crops[0] = 0; crops[1] = 255
+    net = trex_b200.VINetwork(M, max_images=32)       # forces 3 chunks through the C ABI
+    net.load_weights(sd)
+    probs, logits = net.probabilities(crops, return_logits=True)
+    ref = vi.forward_logits(sd, crops)
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(logits - ref).max() < TOL * scale
+    assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
+    assert (probs.argmax(1) == ref.argmax(1)).mean() > 0.98
+
+
+def test_errors():
+    import trex_b200
+    net = trex_b200.VINetwork(10, max_images=4)
+    with pytest.raises(trex_b200.TrexB200Error) as e:
+        net.probabilities(np.zeros((1, 80, 80, 1), np.uint8))
+    assert e.value.code == -3                            # no weights: reference throws SoftException
+    assert net.probabilities(np.zeros((0, 80, 80, 1), np.uint8)).shape == (0, 10)
+    with pytest.raises(trex_b200.TrexB200Error):
+        trex_b200.VINetwork(10, width=64, height=64)

@@ -1,0 +1,12 @@
+"""trex_b200: TRex's segmentation + identification hot path on NVIDIA B200 (sm_100a).
+
+Host-side mirror of the reference interfaces for this path, over the C ABI of include/trexb200.h:
+    BackgroundSubtraction   Application/src/tracker/python/BackgroundSubtraction.{h,cpp}
+    VINetwork               Application/src/tracker/ml/VisualIdentification.{h,cpp}
+The CUDA library is mandatory; nothing here computes on the CPU.
+"""
+from ._capi import LIB_PATH, TrexB200Error, lib  # noqa: F401
+from .background_subtraction import BackgroundSubtraction, Blob, DetectSettings  # noqa: F401
+from .visual_identification import VINetwork  # noqa: F401
+
+__all__ = ["BackgroundSubtraction", "Blob", "DetectSettings", "VINetwork", "TrexB200Error", "lib", "LIB_PATH"]

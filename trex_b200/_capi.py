@@ -1,0 +1,106 @@
+"""ctypes binding of libtrexb200.so (include/trexb200.h).  The library is required: importing the
+product without the built CUDA extension fails loudly -- there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtrexb200.so")
+
+TB_OK, TB_ERR_INVALID, TB_ERR_CUDA, TB_ERR_STATE, TB_ERR_CAPACITY = 0, -1, -2, -3, -4
+
+
+class TrexB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[tb_status {code}] {msg}")
+        self.code = code
+
+
+class SegParams(C.Structure):
+    _fields_ = [("detect_threshold", C.c_int32), ("threshold_maximum", C.c_int32),
+                ("enable_difference", C.c_int32), ("detect_threshold_is_absolute", C.c_int32),
+                ("image_invert", C.c_int32), ("use_closing", C.c_int32), ("closing_size", C.c_int32),
+                ("dilation_size", C.c_int32), ("cm_per_pixel", C.c_float), ("n_size_ranges", C.c_int32),
+                ("size_lo", C.c_double * 4), ("size_hi", C.c_double * 4)]
+
+
+class SegConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("max_batch", C.c_int32),
+                ("max_runs_per_frame", C.c_int32), ("max_pixels_per_frame", C.c_int32),
+                ("max_crops_per_frame", C.c_int32), ("crop_width", C.c_int32), ("crop_height", C.c_int32),
+                ("crop_method", C.c_int32)]
+
+
+class FrameInfo(C.Structure):
+    _fields_ = [("blob_begin", C.c_uint32), ("n_blobs", C.c_uint32), ("line_begin", C.c_uint32),
+                ("n_lines", C.c_uint32), ("px_begin", C.c_uint32), ("n_pixels", C.c_uint32),
+                ("n_runs", C.c_uint32), ("status", C.c_uint32)]
+
+
+class BlobRec(C.Structure):
+    _fields_ = [("line_off", C.c_uint32), ("px_off", C.c_uint32), ("n_lines", C.c_uint32), ("n_pixels", C.c_uint32),
+                ("x0", C.c_uint16), ("y0", C.c_uint16), ("x1", C.c_uint16), ("y1", C.c_uint16),
+                ("bid", C.c_uint32), ("frame", C.c_uint32)]
+
+
+class BlobView(C.Structure):
+    _fields_ = [("info", FrameInfo), ("recs", C.POINTER(BlobRec)), ("lines", C.c_void_p), ("pixels", C.c_void_p)]
+
+
+class ViConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
+                ("num_classes", C.c_int32), ("max_images", C.c_int32), ("precision", C.c_int32)]
+
+
+# every symbol include/trexb200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "tb_last_error", "tb_abi_version", "tb_device_count", "tb_seg_default_params", "tb_seg_create",
+    "tb_seg_destroy", "tb_seg_set_params", "tb_seg_set_background", "tb_seg_submit", "tb_seg_submit_device",
+    "tb_seg_wait", "tb_seg_result", "tb_seg_totals", "tb_seg_device_results", "tb_seg_crops",
+    "tb_seg_debug_binary", "tb_seg_launch_count", "tb_vi_create", "tb_vi_destroy", "tb_vi_set_tensor",
+    "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(trex_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+    L.tb_last_error.restype = C.c_char_p
+    L.tb_seg_default_params.argtypes = [C.POINTER(SegParams)]
+    L.tb_seg_create.argtypes = [C.POINTER(SegConfig), vpp]
+    L.tb_seg_destroy.argtypes = [vp]; L.tb_seg_destroy.restype = None
+    L.tb_seg_set_params.argtypes = [vp, C.POINTER(SegParams)]
+    L.tb_seg_set_background.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int64]
+    L.tb_seg_submit.argtypes = [vp, C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int]
+    L.tb_seg_submit_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.tb_seg_wait.argtypes = [vp]
+    L.tb_seg_result.argtypes = [vp, C.c_int, C.POINTER(BlobView)]
+    L.tb_seg_totals.argtypes = [vp, C.POINTER(C.c_uint32 * 4)]
+    L.tb_seg_device_results.argtypes = [vp, vpp, vpp, vpp, vpp, vpp]
+    L.tb_seg_crops.argtypes = [vp, vpp, vpp, C.POINTER(C.c_uint32)]
+    L.tb_seg_debug_binary.argtypes = [vp, vp, vp]
+    L.tb_seg_launch_count.argtypes = [vp]; L.tb_seg_launch_count.restype = C.c_uint64
+    L.tb_vi_create.argtypes = [C.POINTER(ViConfig), vpp]
+    L.tb_vi_destroy.argtypes = [vp]; L.tb_vi_destroy.restype = None
+    L.tb_vi_set_tensor.argtypes = [vp, C.c_char_p, vp, C.c_int64]
+    L.tb_vi_commit.argtypes = [vp]
+    L.tb_vi_predict.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.tb_vi_predict_device.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+    L.tb_vi_wait.argtypes = [vp]
+    L.tb_vi_launch_count.argtypes = [vp]; L.tb_vi_launch_count.restype = C.c_uint64
+    _lib = L
+    return L
+
+
+def check(code: int):
+    if code != TB_OK:
+        raise TrexB200Error(code, lib().tb_last_error().decode(errors="replace"))

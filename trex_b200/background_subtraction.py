@@ -1,0 +1,210 @@
+"""Host mirror of `track::BackgroundSubtraction` (Application/src/tracker/python/BackgroundSubtraction.h:10-27)
+on top of the tb_seg_* C ABI.  Same call shape as the reference class:
+
+    BackgroundSubtraction(average)          ctor with optional background      (.cpp:50-84)
+    set_background(average)                 un-pauses the pipeline             (.cpp:86-90)
+    apply(frames) -> list[list[Blob]]       one blob list per frame            (.cpp:126-347)
+    fps()                                   mean of batch / elapsed            (.cpp:21-35,345)
+    deinit()
+
+Settings are the reference's keys (DetectSettings), read where the reference reads them
+(RawProcessing.cpp:266-327, BackgroundSubtraction.cpp:137-139).  Errors: the reference fails the
+tile's promise with the exception; here the exception propagates to the caller of apply().
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+from ._capi import BlobView, SegConfig, SegParams, check, lib
+
+LINE_DTYPE = np.dtype([("x0", "<u2"), ("x1", "<u2"), ("y", "<u2"), ("pad", "<u2")])
+REC_DTYPE = np.dtype([("line_off", "<u4"), ("px_off", "<u4"), ("n_lines", "<u4"), ("n_pixels", "<u4"),
+                      ("x0", "<u2"), ("y0", "<u2"), ("x1", "<u2"), ("y1", "<u2"), ("bid", "<u4"), ("frame", "<u4")])
+INFO_DTYPE = np.dtype([("blob_begin", "<u4"), ("n_blobs", "<u4"), ("line_begin", "<u4"), ("n_lines", "<u4"),
+                       ("px_begin", "<u4"), ("n_pixels", "<u4"), ("n_runs", "<u4"), ("status", "<u4")])
+
+
+@dataclass
+class DetectSettings:
+    """GlobalSettings keys of the path with the reference defaults."""
+    detect_threshold: int = 15
+    threshold_maximum: int = 255
+    enable_difference: bool = True
+    detect_threshold_is_absolute: bool = True
+    image_invert: bool = False
+    use_closing: bool = False
+    closing_size: int = 3
+    dilation_size: int = 0
+    cm_per_pixel: float = 1.0
+    detect_size_filter: list = field(default_factory=lambda: [(10.0, 100000.0)])
+    individual_image_size: tuple = (80, 80)
+    # crop content: track_background_subtraction + track_threshold_is_absolute (FilterCache.cpp:165-174)
+    track_background_subtraction: bool = True
+    track_threshold_is_absolute: bool = True
+
+    def c_params(self) -> SegParams:
+        p = SegParams()
+        lib().tb_seg_default_params(C.byref(p))
+        p.detect_threshold = int(self.detect_threshold); p.threshold_maximum = int(self.threshold_maximum)
+        p.enable_difference = int(self.enable_difference)
+        p.detect_threshold_is_absolute = int(self.detect_threshold_is_absolute)
+        p.image_invert = int(self.image_invert); p.use_closing = int(self.use_closing)
+        p.closing_size = int(self.closing_size); p.dilation_size = int(self.dilation_size)
+        p.cm_per_pixel = float(self.cm_per_pixel)
+        p.n_size_ranges = len(self.detect_size_filter)
+        for i, (lo, hi) in enumerate(self.detect_size_filter[:4]):
+            p.size_lo[i], p.size_hi[i] = float(lo), float(hi)
+        return p
+
+    @property
+    def crop_method(self) -> int:
+        if not self.track_background_subtraction:
+            return 0
+        return 1 if self.track_threshold_is_absolute else 2
+
+
+@dataclass
+class Blob:
+    """blob::Pair (C/misc/types.h:591-604) + the geometric id pv::bid (C/misc/bid.h:87-94)."""
+    lines: np.ndarray      # LINE_DTYPE
+    pixels: np.ndarray     # uint8
+    bid: int
+    bounds: tuple          # x0, y0, x1, y1 inclusive
+
+
+class BackgroundSubtraction:
+    def __init__(self, average: np.ndarray | None = None, *, width=None, height=None, settings: DetectSettings | None = None,
+                 max_batch=16, max_individuals=0, device=0, max_runs_per_frame=0, max_pixels_per_frame=0):
+        if average is not None:
+            height, width = average.shape[:2]
+        if width is None or height is None:
+            raise ValueError("BackgroundSubtraction needs an average image or width/height")
+        self.settings = settings or DetectSettings()
+        self.width, self.height, self.max_batch = int(width), int(height), int(max_batch)
+        cfg = SegConfig(device=device, width=self.width, height=self.height, max_batch=self.max_batch,
+                        max_runs_per_frame=max_runs_per_frame, max_pixels_per_frame=max_pixels_per_frame,
+                        max_crops_per_frame=int(max_individuals),
+                        crop_width=self.settings.individual_image_size[0],
+                        crop_height=self.settings.individual_image_size[1],
+                        crop_method=self.settings.crop_method)
+        self.max_individuals = int(max_individuals)
+        self._h = C.c_void_p()
+        check(lib().tb_seg_create(C.byref(cfg), C.byref(self._h)))
+        self.update_settings(self.settings)
+        self._time = 0.0
+        self._samples = 0.0
+        self._has_background = False
+        if average is not None:
+            self.set_background(average)
+
+    # -- reference interface -------------------------------------------------------------------
+    def set_background(self, average: np.ndarray):
+        a = np.ascontiguousarray(average, np.uint8)
+        if a.ndim == 3 and a.shape[2] == 1:
+            a = a[..., 0]
+        if a.ndim != 2:
+            raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, "only meta_encoding=gray (1 channel) is built")
+        check(lib().tb_seg_set_background(self._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], a.strides[0]))
+        self._has_background = True
+
+    def update_settings(self, settings: DetectSettings):
+        self.settings = settings
+        p = settings.c_params()
+        check(lib().tb_seg_set_params(self._h, C.byref(p)))
+
+    def apply(self, frames, fetch=True):
+        """frames: sequence of HxW uint8 arrays (or one (n,H,W) array).  Returns one list of Blob per frame."""
+        t0 = time.perf_counter()
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        out = []
+        for i in range(0, len(frames), self.max_batch):
+            chunk = frames[i:i + self.max_batch]
+            ptrs = (C.c_void_p * len(chunk))(*[f.ctypes.data_as(C.c_void_p) for f in chunk])
+            for f in chunk:
+                if f.shape != (self.height, self.width):
+                    raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, f"frame shape {f.shape} != {(self.height, self.width)}")
+            check(lib().tb_seg_submit(self._h, ptrs, len(chunk), self.width, int(fetch)))
+            check(lib().tb_seg_wait(self._h))
+            if fetch:
+                out.extend(self.result(j) for j in range(len(chunk)))
+        dt = time.perf_counter() - t0
+        if frames:
+            self._time += len(frames) / max(dt, 1e-12)
+            self._samples += 1
+        return out
+
+    def apply_device(self, frames_ptr: int, n: int, stream: int = 0, fetch=False):
+        """Frames already resident in HBM (n packed HxW u8); work is ordered on `stream`."""
+        check(lib().tb_seg_submit_device(self._h, C.c_void_p(frames_ptr), n, C.c_void_p(stream), int(fetch)))
+
+    def wait(self):
+        check(lib().tb_seg_wait(self._h))
+
+    def fps(self) -> float:
+        return self._time / self._samples if self._samples else 0.0
+
+    def deinit(self):
+        if self._h:
+            lib().tb_seg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = deinit
+
+    # -- results -------------------------------------------------------------------------------
+    def raw_result(self, i):
+        """(info, recs, lines, pixels) numpy views of frame i (valid until the next apply)."""
+        v = BlobView()
+        check(lib().tb_seg_result(self._h, i, C.byref(v)))
+        nb, nl, npx = v.info.n_blobs, v.info.n_lines, v.info.n_pixels
+        recs = np.ctypeslib.as_array(C.cast(v.recs, C.POINTER(C.c_uint8)), (nb * 32,)).view(REC_DTYPE) if nb else np.zeros(0, REC_DTYPE)
+        lines = np.ctypeslib.as_array(C.cast(v.lines, C.POINTER(C.c_uint8)), (nl * 8,)).view(LINE_DTYPE) if nl else np.zeros(0, LINE_DTYPE)
+        px = np.ctypeslib.as_array(C.cast(v.pixels, C.POINTER(C.c_uint8)), (npx,)) if npx else np.zeros(0, np.uint8)
+        return v.info, recs, lines, px
+
+    def result(self, i):
+        info, recs, lines, px = self.raw_result(i)
+        blobs = []
+        for r in recs:
+            lo, po = int(r["line_off"]) - info.line_begin, int(r["px_off"]) - info.px_begin
+            blobs.append(Blob(lines[lo:lo + int(r["n_lines"])].copy(), px[po:po + int(r["n_pixels"])].copy(), int(r["bid"]),
+                              (int(r["x0"]), int(r["y0"]), int(r["x1"]), int(r["y1"]))))
+        return blobs
+
+    def frame_info(self, i):
+        return self.raw_result(i)[0]
+
+    def totals(self):
+        t = (C.c_uint32 * 4)()
+        check(lib().tb_seg_totals(self._h, C.byref(t)))
+        return tuple(int(x) for x in t)
+
+    def crops(self):
+        """(crops[n,h,w] u8, blob_index[n]) of the last fetched batch."""
+        cp, ip, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        check(lib().tb_seg_crops(self._h, C.byref(cp), C.byref(ip), C.byref(n)))
+        w, h = self.settings.individual_image_size
+        if n.value == 0:
+            return np.zeros((0, h, w), np.uint8), np.zeros(0, np.uint32)
+        crops = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint8)), (n.value, h, w)).copy()
+        idx = np.ctypeslib.as_array(C.cast(ip, C.POINTER(C.c_uint32)), (n.value,)).copy()
+        return crops, idx
+
+    def device_results(self):
+        """Device pointers (ints): crops, n_crops, crop_blob_index, recs, infos."""
+        ps = [C.c_void_p() for _ in range(5)]
+        check(lib().tb_seg_device_results(self._h, *[C.byref(p) for p in ps]))
+        return tuple(p.value for p in ps)
+
+    def debug_binary(self, frame: np.ndarray) -> np.ndarray:
+        f = np.ascontiguousarray(frame, np.uint8)
+        out = np.empty_like(f)
+        check(lib().tb_seg_debug_binary(self._h, f.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def launch_count(self) -> int:
+        return int(lib().tb_seg_launch_count(self._h))

@@ -1,0 +1,88 @@
+// Shared helpers for libtrexb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/trexb200.h"
+
+namespace tb {
+
+void set_error(const std::string &msg);
+const char *get_error();
+
+#define TB_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            tb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+            return TB_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define TB_REQUIRE(cond, code, msg)                                                          \
+    do {                                                                                     \
+        if (!(cond)) { tb::set_error(msg); return (code); }                                  \
+    } while (0)
+
+template <typename T>
+static inline int dev_alloc(T **p, size_t n)
+{
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return TB_ERR_CUDA; }
+    return TB_OK;
+}
+template <typename T>
+static inline int host_alloc(T **p, size_t n)
+{
+    cudaError_t e = cudaMallocHost((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) { set_error(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); return TB_ERR_CUDA; }
+    return TB_OK;
+}
+
+#ifdef __CUDACC__
+// Exclusive scan of one value per thread across the CTA; `total` = sum over all threads.
+// ws: shared array of >= 33 uint32. All threads must call.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *ws, uint32_t &total)
+{
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = (blockDim.x + 31u) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += t;
+    }
+    __syncthreads();                      // protect ws from a previous use
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nw ? ws[lane] : 0u, winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= (unsigned)d) winc += t;
+        }
+        if (lane < nw) ws[lane] = winc - w;
+        if (lane == 31) ws[32] = winc;
+    }
+    __syncthreads();
+    total = ws[32];
+    return ws[warp] + inc - v;
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t &total)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+#endif
+
+}  // namespace tb

@@ -1,0 +1,793 @@
+// Segmentation hot path on sm_100a:  |frame - background| -> threshold -> (mask & frame) -> row RLE
+// -> 8-connected run labeling -> per-blob sorted line lists + pixel bytes -> size filter ->
+// individual crops.  Replaces, behind the C ABI of include/trexb200.h,
+//   RawProcessing::generate_binary   C/processing/RawProcessing.cpp:263-600 (default branch family)
+//   Source::extract_lines            C/processing/Source.cpp:156-255
+//   merge_lines / run_fast           C/processing/CPULabeling.cpp:44-343
+//   BackgroundSubtraction::apply     T/python/BackgroundSubtraction.cpp:126-347 (size filter :259, :306)
+//   image::calculate_diff_image      T/tracking/FilterCache.cpp:158-235
+// Not a translation of those: the reference walks pixels serially and merges blobs through an
+// object graph; here a frame batch is streamed once from HBM (K1), runs are labelled with a
+// lock-free union-find whose root is the raster-first run (K2), and blobs are materialised by
+// warps walking their bounding boxes (K3).  Data layout and rooflines: DESIGN.md.
+#include "common.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace tb {
+
+// ------------------------------------------------------------------------------------------------
+// device-side description of one seg handle
+// ------------------------------------------------------------------------------------------------
+struct SegK {                  // threshold configuration, bytes replicated x4
+    uint32_t flags;            // bit0 enable_difference, bit1 absolute, bit2 image_invert,
+                               // bit3 invert mask (T<0), bit4 inRange
+    uint32_t t4, lo4, hi4;
+};
+enum { F_DIFF = 1, F_ABS = 2, F_INV = 4, F_INVMASK = 8, F_RANGE = 16 };
+
+struct SegDev {
+    int W, H, B, cpr, rpt, n_bands, aligned;
+    uint32_t rcap;             // runs per frame (scratch)
+    uint32_t lines_cap, px_cap, blobs_cap, crops_cap;   // batch arenas
+    uint32_t px_frame_cap, max_crops;
+    int crop_w, crop_h, crop_method;
+    float sqcm; int n_ranges; double lo[4], hi[4];
+    const uint8_t *bg;
+    // K1 outputs
+    uint32_t *run_count;       // [B]
+    uint32_t *band_base, *band_cnt;   // [B][n_bands]
+    tb_line *runs_raw;         // [B][rcap]
+    // K2 scratch
+    tb_line *runs;             // [B][rcap] raster order
+    uint32_t *parent;          // [B][rcap] -> final label (root run index)
+    uint32_t *bidx;            // [B][rcap] blob index of a root run
+    uint32_t *row_start, *row_end;    // [B][H]
+    uint32_t *b_npx, *b_nl, *b_xmin, *b_xmax, *b_ymax, *b_root, *b_loff, *b_poff, *kept; // [B][rcap]
+    uint32_t *frame_tot;       // [B][4]: kept blobs, lines, pixels, status
+    // K3 outputs
+    tb_frame_info *infos;      // [B]
+    tb_blob_rec *recs;         // [blobs_cap]
+    tb_line *lines;            // [lines_cap]
+    uint32_t *line_px;         // [lines_cap] pixel offset of each line
+    uint8_t *pixels;           // [px_cap]
+    uint8_t *crops;            // [crops_cap][crop_h*crop_w]
+    uint32_t *crop_blob;       // [crops_cap]
+    uint32_t *totals;          // [4]: blobs, lines, pixels, crops
+};
+
+// ------------------------------------------------------------------------------------------------
+// K1: fused difference / threshold / mask / run-length extraction.  HBM-bound: every frame byte is
+// read exactly once with 16-byte loads; the background tile is loaded once per CTA and reused for
+// `fpc` frames.  A CTA owns a band of whole rows (<= 1024 16-pixel chunks); run starts and ends are
+// ranked with warp scans and written straight into the frame's run array (one atomicAdd per band).
+// ------------------------------------------------------------------------------------------------
+constexpr int K1_NT = 256, K1_KPT = 4, K1_CHUNKS = K1_NT * K1_KPT;
+
+__device__ __forceinline__ uint32_t fg4(uint32_t f, uint32_t b, const SegK &p)
+{
+    uint32_t in = (p.flags & F_INV) ? ~f : f;                       // 255 - x
+    uint32_t d = in;
+    if (p.flags & F_DIFF) d = (p.flags & F_ABS) ? __vabsdiffu4(in, b) : __vsubus4(b, in);
+    uint32_t m = (p.flags & F_RANGE) ? (__vcmpgeu4(d, p.lo4) & __vcmpleu4(d, p.hi4)) : __vcmpgtu4(d, p.t4);
+    if (p.flags & F_INVMASK) m = ~m;
+    return m & __vcmpne4(f, 0u);                                    // (mask & input) != 0
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t m)               // 4 byte masks -> 4 bits
+{
+    return ((m & 0x08040201u) * 0x01010101u) >> 24;
+}
+__device__ __forceinline__ uint32_t fg16(const uint4 &f, const uint4 &b, const SegK &p)
+{
+    return pack4(fg4(f.x, b.x, p)) | (pack4(fg4(f.y, b.y, p)) << 4) | (pack4(fg4(f.z, b.z, p)) << 8) |
+           (pack4(fg4(f.w, b.w, p)) << 12);
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+// 16 pixels starting at column col*16 of a row that may be shorter / unaligned (generic widths)
+__device__ __forceinline__ uint4 ld_edge(const uint8_t *row, int col, int W)
+{
+    uint32_t v[4] = {0, 0, 0, 0};
+    int x0 = col * 16, n = min(16, W - x0);
+    for (int i = 0; i < n; ++i) v[i >> 2] |= (uint32_t)row[x0 + i] << (8 * (i & 3));
+    return make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(K1_NT)
+seg_rle_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
+{
+    __shared__ uint16_t s_mask[K1_CHUNKS];
+    __shared__ uint32_t s_wtot[K1_NT / 32];
+    __shared__ uint32_t s_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int band = blockIdx.x;
+    const int row0 = band * d.rpt;
+    const int tile_rows = min(d.rpt, d.H - row0);
+    const int tile_chunks = tile_rows * d.cpr;
+    const size_t frame_bytes = (size_t)d.W * d.H;
+
+    int c[K1_KPT]; uint16_t crow[K1_KPT], ccol[K1_KPT]; uint4 bgc[K1_KPT];
+#pragma unroll
+    for (int k = 0; k < K1_KPT; ++k) {
+        c[k] = warp * (32 * K1_KPT) + k * 32 + lane;
+        const bool valid = c[k] < tile_chunks;
+        crow[k] = valid ? (uint16_t)(c[k] / d.cpr) : 0;
+        ccol[k] = valid ? (uint16_t)(c[k] % d.cpr) : 0;
+        bgc[k] = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            if (d.aligned) bgc[k] = *reinterpret_cast<const uint4 *>(d.bg + (size_t)row0 * d.W + (size_t)c[k] * 16);
+            else bgc[k] = ld_edge(d.bg + (size_t)(row0 + crow[k]) * d.W, ccol[k], d.W);
+        }
+    }
+    auto load_frame = [&](int f, uint4 *dst) {
+        const uint8_t *fb = frames + (size_t)f * frame_bytes;
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) {
+            dst[k] = make_uint4(0, 0, 0, 0);
+            if (c[k] < tile_chunks) {
+                if (d.aligned) dst[k] = ld_stream(reinterpret_cast<const uint4 *>(fb + (size_t)row0 * d.W) + c[k]);
+                else dst[k] = ld_edge(fb + (size_t)(row0 + crow[k]) * d.W, ccol[k], d.W);
+            }
+        }
+    };
+
+    const int f0 = blockIdx.y * fpc, f1 = min(d.B, f0 + fpc);
+    uint4 cur[K1_KPT], nxt[K1_KPT];
+    if (f0 < f1) load_frame(f0, cur);
+    for (int f = f0; f < f1; ++f) {
+        if (f + 1 < f1) load_frame(f + 1, nxt);          // keep the next frame's loads in flight
+
+        uint32_t m[K1_KPT];
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) {
+            m[k] = (c[k] < tile_chunks) ? fg16(cur[k], bgc[k], p) : 0u;
+            s_mask[c[k]] = (uint16_t)m[k];
+        }
+        __syncthreads();
+
+        uint32_t st[K1_KPT], en[K1_KPT], off[K1_KPT], run = 0;
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) {
+            st[k] = en[k] = 0;
+            if (c[k] < tile_chunks) {
+                uint32_t prev = (ccol[k] > 0) ? (uint32_t)(s_mask[c[k] - 1] >> 15) : 0u;
+                uint32_t next = (ccol[k] + 1 < d.cpr) ? (uint32_t)(s_mask[c[k] + 1] & 1u) : 0u;
+                st[k] = m[k] & ~((m[k] << 1) | prev) & 0xFFFFu;
+                en[k] = m[k] & ~((m[k] >> 1) | (next << 15)) & 0xFFFFu;
+            }
+            uint32_t tot, ex = warp_excl_scan((uint32_t)__popc(st[k]) | ((uint32_t)__popc(en[k]) << 16), tot);
+            off[k] = run + ex;
+            run += tot;
+        }
+        if (lane == 0) s_wtot[warp] = run;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < K1_NT / 32; ++w) {
+            uint32_t t = s_wtot[w];
+            if (w < warp) wbase += t;
+            total += t;
+        }
+        if (tid == 0) {
+            uint32_t ns = total & 0xFFFFu;
+            uint32_t base = ns ? atomicAdd(&d.run_count[f], ns) : 0u;
+            s_base = base;
+            d.band_base[(size_t)f * d.n_bands + band] = base;
+            d.band_cnt[(size_t)f * d.n_bands + band] = ns;
+        }
+        __syncthreads();
+        const uint32_t base = s_base;
+        uint16_t *out = reinterpret_cast<uint16_t *>(d.runs_raw + (size_t)f * d.rcap);
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) {
+            uint32_t os = base + ((wbase + off[k]) & 0xFFFFu), oe = base + ((wbase + off[k]) >> 16);
+            const uint32_t x = (uint32_t)ccol[k] * 16u, y = (uint32_t)(row0 + crow[k]);
+            uint32_t s = st[k], e = en[k];
+            while (s) {
+                int j = __ffs(s) - 1; s &= s - 1;
+                if (os < d.rcap) {
+                    out[(size_t)os * 4 + 0] = (uint16_t)(x + j);
+                    *reinterpret_cast<uint32_t *>(out + (size_t)os * 4 + 2) = y;   // y, pad = 0
+                }
+                ++os;
+            }
+            while (e) {
+                int j = __ffs(e) - 1; e &= e - 1;
+                if (oe < d.rcap) out[(size_t)oe * 4 + 1] = (uint16_t)(x + j);
+                ++oe;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) cur[k] = nxt[k];
+    }
+}
+
+// generate_binary's output image, for parity tests only (RawProcessing.cpp:597-600)
+__global__ void binary_image_kernel(const uint8_t *__restrict__ frame, const uint8_t *__restrict__ bg,
+                                    uint8_t *__restrict__ out, size_t n, SegK p)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t f = frame[i];
+        uint32_t m = fg4(f, bg[i], p) & 0xFFu;
+        out[i] = m ? (uint8_t)f : (uint8_t)0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: one CTA per frame.  Orders the band chunks into raster order, labels runs with a union-find
+// (8-connectivity between vertically adjacent rows, HLine.h:90-92 / CPULabeling.cpp:60-62,91; the
+// root of a set is its smallest run index = the blob's first line), gathers per-blob statistics and
+// applies the size filter.
+// ------------------------------------------------------------------------------------------------
+constexpr int K2_NT = 512;
+constexpr uint32_t K2_SMEM_RUNS = 8192;      // union-find lives in shared memory up to this many runs
+
+__device__ __forceinline__ uint32_t uf_find(uint32_t *par, uint32_t i)
+{
+    uint32_t q;
+    while ((q = *(volatile uint32_t *)(par + i)) != i) i = q;
+    return i;
+}
+__device__ __forceinline__ void uf_union(uint32_t *par, uint32_t a, uint32_t b)
+{
+    for (;;) {
+        a = uf_find(par, a); b = uf_find(par, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }        // a > b: hook the larger root under the smaller
+        uint32_t old = atomicMin(par + a, b);
+        if (old == a) return;
+        a = old;                                            // lost a race: keep merging old's set with b
+    }
+}
+
+__global__ void __launch_bounds__(K2_NT)
+ccl_label_kernel(SegDev d)
+{
+    __shared__ uint32_t ws[34];
+    __shared__ uint32_t s_par[K2_SMEM_RUNS];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t R = d.run_count[f];
+    uint32_t *tot = d.frame_tot + (size_t)f * 4;
+    if (R > d.rcap) {                                      // capacity exceeded: drop the frame, flag it
+        if (tid == 0) { tot[0] = 0; tot[1] = 0; tot[2] = 0; tot[3] = 1u; }
+        return;
+    }
+    tb_line *runs = d.runs + (size_t)f * d.rcap;
+    const tb_line *raw = d.runs_raw + (size_t)f * d.rcap;
+    uint32_t *gpar = d.parent + (size_t)f * d.rcap;
+    uint32_t *par = (R <= K2_SMEM_RUNS) ? s_par : gpar;
+    uint32_t *bidx = d.bidx + (size_t)f * d.rcap;
+    uint32_t *rs = d.row_start + (size_t)f * d.H, *re = d.row_end + (size_t)f * d.H;
+    const uint32_t *bbase = d.band_base + (size_t)f * d.n_bands, *bcnt = d.band_cnt + (size_t)f * d.n_bands;
+
+    // 1. raster order: exclusive scan of the band counts, then copy band chunks (a warp per band)
+    for (int y = tid; y < d.H; y += K2_NT) { rs[y] = 0; re[y] = 0; }
+    uint32_t carry = 0;
+    for (int b0 = 0; b0 < d.n_bands; b0 += K2_NT) {
+        int b = b0 + tid;
+        uint32_t cnt = b < d.n_bands ? bcnt[b] : 0u, total;
+        uint32_t ex = block_excl_scan(cnt, ws, total);
+        if (b < d.n_bands) bidx[b] = carry + ex;          // bidx reused as the band offset table (n_bands <= rcap)
+        carry += total;
+    }
+    __syncthreads();
+    for (int b = warp; b < d.n_bands; b += K2_NT / 32) {
+        const uint32_t src = bbase[b], dst = bidx[b], n = bcnt[b];
+        for (uint32_t i = lane; i < n; i += 32) runs[dst + i] = raw[src + i];
+    }
+    __syncthreads();
+    // 2. init union-find, row table
+    for (uint32_t i = tid; i < R; i += K2_NT) {
+        par[i] = i;
+        const uint32_t y = runs[i].y;
+        if (i == 0 || runs[i - 1].y != y) rs[y] = i;
+        if (i + 1 == R || runs[i + 1].y != y) re[y] = i + 1;
+    }
+    __syncthreads();
+    // 3. unions with the runs of row y-1
+    for (uint32_t i = tid; i < R; i += K2_NT) {
+        const tb_line r = runs[i];
+        if (r.y == 0) continue;
+        uint32_t s = rs[r.y - 1], e = re[r.y - 1];
+        if (s >= e) continue;
+        uint32_t lo = s, hi = e;                           // first j with x1[j] + 1 >= x0
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t)runs[mid].x1 + 1u < (uint32_t)r.x0) lo = mid + 1; else hi = mid;
+        }
+        for (uint32_t j = lo; j < e && (uint32_t)runs[j].x0 <= (uint32_t)r.x1 + 1u; ++j) uf_union(par, i, j);
+    }
+    __syncthreads();
+    // 4. flatten; roots get dense blob indices in raster order of their first run
+    uint32_t kbase = 0;
+    for (uint32_t i0 = 0; i0 < R; i0 += K2_NT) {
+        uint32_t i = i0 + tid, root = 0, isroot = 0;
+        if (i < R) { root = uf_find(par, i); isroot = root == i; }
+        uint32_t total, ex = block_excl_scan(isroot, ws, total);
+        if (i < R) {
+            gpar[i] = root;                                // final label, global for K3
+            if (isroot) { bidx[i] = kbase + ex; d.b_root[(size_t)f * d.rcap + kbase + ex] = i; }
+        }
+        kbase += total;
+    }
+    const uint32_t K = kbase;
+    uint32_t *npx = d.b_npx + (size_t)f * d.rcap, *nl = d.b_nl + (size_t)f * d.rcap;
+    uint32_t *xmin = d.b_xmin + (size_t)f * d.rcap, *xmax = d.b_xmax + (size_t)f * d.rcap;
+    uint32_t *ymax = d.b_ymax + (size_t)f * d.rcap;
+    for (uint32_t k = tid; k < K; k += K2_NT) { npx[k] = 0; nl[k] = 0; xmin[k] = 0xFFFFFFFFu; xmax[k] = 0; ymax[k] = 0; }
+    __syncthreads();
+    // 5. per-blob statistics
+    for (uint32_t i = tid; i < R; i += K2_NT) {
+        const tb_line r = runs[i];
+        const uint32_t k = bidx[gpar[i]];
+        atomicAdd(npx + k, (uint32_t)r.x1 - r.x0 + 1u);
+        atomicAdd(nl + k, 1u);
+        atomicMin(xmin + k, (uint32_t)r.x0);
+        atomicMax(xmax + k, (uint32_t)r.x1);
+        atomicMax(ymax + k, (uint32_t)r.y);
+    }
+    __syncthreads();
+    // 6. size filter (BackgroundSubtraction.cpp:259: lo <= npx*cm^2 < hi in float; :306 line limit),
+    //    offsets of the kept blobs inside the frame
+    uint32_t *loff = d.b_loff + (size_t)f * d.rcap, *poff = d.b_poff + (size_t)f * d.rcap;
+    uint32_t *kept = d.kept + (size_t)f * d.rcap;
+    uint32_t kk = 0, kl = 0, kp = 0;
+    for (uint32_t k0 = 0; k0 < K; k0 += K2_NT) {
+        uint32_t k = k0 + tid, keep = 0, l = 0, px = 0;
+        if (k < K) {
+            l = nl[k]; px = npx[k];
+            keep = d.n_ranges == 0;
+            const double v = (double)((float)px * d.sqcm);
+            for (int q = 0; q < d.n_ranges; ++q) keep |= (v >= d.lo[q] && v < d.hi[q]);
+            keep = keep && l < 65535u;
+        }
+        uint32_t t0, t1, t2;
+        uint32_t e0 = block_excl_scan(keep, ws, t0);
+        uint32_t e1 = block_excl_scan(keep ? l : 0u, ws, t1);
+        uint32_t e2 = block_excl_scan(keep ? px : 0u, ws, t2);
+        if (k < K && keep) { kept[kk + e0] = k; loff[k] = kl + e1; poff[k] = kp + e2; }
+        kk += t0; kl += t1; kp += t2;
+    }
+    if (tid == 0) {
+        uint32_t status = 0;
+        if (kp > d.px_frame_cap) { status |= 2u; kk = 0; kl = 0; kp = 0; }
+        tot[0] = kk; tot[1] = kl; tot[2] = kp; tot[3] = status;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: one CTA per frame, one warp per kept blob.  The warp walks the blob's bounding box, one lane
+// per row, collecting the blob's runs in (y,x0) order (CPULabeling.cpp:256-323), then copies pixel
+// bytes (:307) and renders the individual crop (FilterCache.cpp:158-235).  Arena offsets of the
+// frame are the prefix sums over the batch of the totals K2 wrote.
+// ------------------------------------------------------------------------------------------------
+constexpr int K3_NT = 256;
+
+__global__ void __launch_bounds__(K3_NT)
+blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
+{
+    __shared__ uint32_t s_red[4][K3_NT / 32];
+    __shared__ uint32_t s_base[4];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // prefix over frames < f of (blobs, lines, pixels, crops)
+    uint32_t acc[4] = {0, 0, 0, 0};
+    for (int g = tid; g < f; g += K3_NT) {
+        const uint32_t *t = d.frame_tot + (size_t)g * 4;
+        acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2]; acc[3] += min(t[0], d.max_crops);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) s_red[q][warp] = acc[q];
+    }
+    __syncthreads();
+    if (tid < 4) { uint32_t s = 0; for (int w = 0; w < K3_NT / 32; ++w) s += s_red[tid][w]; s_base[tid] = s; }
+    __syncthreads();
+    const uint32_t *tot = d.frame_tot + (size_t)f * 4;
+    uint32_t Kk = tot[0], Lk = tot[1], Pk = tot[2], status = tot[3];
+    const uint32_t Bb = s_base[0], Lb = s_base[1], Pb = s_base[2], Cb = s_base[3];
+    if (Bb + Kk > d.blobs_cap || Lb + Lk > d.lines_cap || Pb + Pk > d.px_cap) { status |= 8u; Kk = 0; Lk = 0; Pk = 0; }
+    const uint32_t ncrop = min(Kk, d.max_crops);
+    if (Kk > d.max_crops && d.max_crops) status |= 4u;
+    if (tid == 0) {
+        tb_frame_info fi;
+        fi.blob_begin = Bb; fi.n_blobs = Kk; fi.line_begin = Lb; fi.n_lines = Lk;
+        fi.px_begin = Pb; fi.n_pixels = Pk; fi.n_runs = d.run_count[f]; fi.status = status;
+        d.infos[f] = fi;
+        if (f == d.B - 1) { d.totals[0] = Bb + Kk; d.totals[1] = Lb + Lk; d.totals[2] = Pb + Pk; d.totals[3] = Cb + ncrop; }
+    }
+    if (Kk == 0) return;
+
+    const tb_line *runs = d.runs + (size_t)f * d.rcap;
+    const uint32_t *label = d.parent + (size_t)f * d.rcap;
+    const uint32_t *rs = d.row_start + (size_t)f * d.H, *re = d.row_end + (size_t)f * d.H;
+    const uint8_t *frame = frames + (size_t)f * d.W * d.H;
+    const size_t o = (size_t)f * d.rcap;
+    const int cw = d.crop_w, ch = d.crop_h;
+
+    for (uint32_t q = warp; q < Kk; q += K3_NT / 32) {
+        const uint32_t k = d.kept[o + q];
+        const uint32_t root = d.b_root[o + k];
+        const uint32_t bx0 = d.b_xmin[o + k], bx1 = d.b_xmax[o + k], by1 = d.b_ymax[o + k];
+        const uint32_t by0 = runs[root].y;
+        const uint32_t L0 = Lb + d.b_loff[o + k], P0 = Pb + d.b_poff[o + k];
+        const uint32_t bh = by1 - by0 + 1, bw = bx1 - bx0 + 1;
+        // phase A: lines in (y,x0) order
+        uint32_t cl = 0, cp = 0;
+        for (uint32_t rb = 0; rb < bh; rb += 32) {
+            const uint32_t y = by0 + rb + lane;
+            uint32_t j0 = 0, e = 0, nl = 0, np = 0;
+            if (rb + lane < bh) {
+                uint32_t s = rs[y]; e = re[y];
+                uint32_t lo = s, hi = e;                   // first run with x1 >= bx0
+                while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (runs[mid].x1 < bx0) lo = mid + 1; else hi = mid; }
+                j0 = lo;
+                for (uint32_t j = j0; j < e && runs[j].x0 <= bx1; ++j)
+                    if (label[j] == root) { ++nl; np += (uint32_t)runs[j].x1 - runs[j].x0 + 1u; }
+            }
+            uint32_t tl, tp, el = warp_excl_scan(nl, tl), ep = warp_excl_scan(np, tp);
+            if (nl) {
+                uint32_t wl = L0 + cl + el, wp = P0 + cp + ep;
+                for (uint32_t j = j0; j < e && runs[j].x0 <= bx1; ++j)
+                    if (label[j] == root) {
+                        d.lines[wl] = runs[j]; d.line_px[wl] = wp;
+                        ++wl; wp += (uint32_t)runs[j].x1 - runs[j].x0 + 1u;
+                    }
+            }
+            cl += tl; cp += tp;
+        }
+        const bool do_crop = q < ncrop;
+        uint8_t *crop = d.crops + (size_t)(Cb + q) * cw * ch;
+        int offx = 0, offy = 0;
+        if (do_crop) {
+            int dd;
+            if ((int)bw < cw) { dd = cw - (int)bw; offx = dd - dd / 2; } else { dd = (int)bw - cw; offx = -(dd - dd / 2); }
+            if ((int)bh < ch) { dd = ch - (int)bh; offy = dd - dd / 2; } else { dd = (int)bh - ch; offy = -(dd - dd / 2); }
+            if (((cw * ch) & 15) == 0) {
+                uint4 *c4 = reinterpret_cast<uint4 *>(crop);
+                for (int i = lane; i < (cw * ch) >> 4; i += 32) c4[i] = make_uint4(0, 0, 0, 0);
+            } else {
+                for (int i = lane; i < cw * ch; i += 32) crop[i] = 0;
+            }
+        }
+        if (lane == 0) {
+            tb_blob_rec rec;
+            rec.line_off = L0; rec.px_off = P0; rec.n_lines = cl; rec.n_pixels = cp;
+            rec.x0 = (uint16_t)bx0; rec.y0 = (uint16_t)by0; rec.x1 = (uint16_t)bx1; rec.y1 = (uint16_t)by1;
+            const tb_line fl = runs[root];
+            rec.bid = ((((uint32_t)fl.x0 + fl.x1 + 1u) / 2u) << 19) | (((uint32_t)fl.y & 0x1FFFu) << 6) | ((cl & 0xFFu) % 64u);
+            rec.frame = (uint32_t)f;
+            d.recs[Bb + q] = rec;
+            if (do_crop) d.crop_blob[Cb + q] = Bb + q;
+        }
+        __syncwarp();                                      // lines / line_px / zero fill visible to the warp
+        // phase B: pixel bytes + crop
+        for (uint32_t l = 0; l < cl; ++l) {
+            const tb_line ln = d.lines[L0 + l];
+            const uint32_t po = d.line_px[L0 + l];
+            for (uint32_t x = ln.x0 + lane; x <= ln.x1; x += 32) {
+                const uint8_t v = frame[(size_t)ln.y * d.W + x];
+                d.pixels[po + (x - ln.x0)] = v;
+                if (do_crop) {
+                    const int cx = (int)(x - bx0) + offx, cy = (int)(ln.y - by0) + offy;
+                    if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
+                        int val = v;
+                        if (d.crop_method) {
+                            const int b = d.bg[(size_t)ln.y * d.W + x];
+                            val = d.crop_method == 1 ? abs(b - val) : max(0, b - val);
+                        }
+                        crop[cy * cw + cx] = (uint8_t)val;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace tb
+
+// ================================================================================================
+// host side: the tb_seg handle
+// ================================================================================================
+using namespace tb;
+
+struct tb_seg {
+    tb_seg_config cfg{};
+    tb_seg_params params{};
+    SegDev d{};
+    SegK k{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_done = nullptr;
+    bool has_bg = false;
+    uint8_t *d_bg = nullptr, *d_frames = nullptr, *d_tmp = nullptr;
+    std::vector<void *> dev_allocs;
+    // pinned host mirrors
+    tb_frame_info *h_infos = nullptr; uint32_t *h_totals = nullptr;
+    tb_blob_rec *h_recs = nullptr; tb_line *h_lines = nullptr; uint8_t *h_pixels = nullptr;
+    uint8_t *h_crops = nullptr; uint32_t *h_crop_blob = nullptr;
+    int last_n = 0; bool last_fetch = false, pending = false, fetched_payload = false;
+    cudaStream_t last_stream = nullptr;
+    uint64_t launches = 0;
+};
+
+static int seg_make_k(const tb_seg_params &p, SegK &k, std::string &why)
+{
+    if (p.use_closing || p.dilation_size != 0) { why = "morphology (use_closing / dilation_size) is not built in this release"; return TB_ERR_INVALID; }
+    if (p.n_size_ranges < 0 || p.n_size_ranges > 4) { why = "n_size_ranges must be 0..4"; return TB_ERR_INVALID; }
+    auto rep = [](int v) { uint32_t b = (uint32_t)std::min(std::max(v, 0), 255); return b * 0x01010101u; };
+    k.flags = (p.enable_difference ? F_DIFF : 0) | (p.detect_threshold_is_absolute ? F_ABS : 0) |
+              (p.image_invert ? F_INV : 0) | (p.detect_threshold < 0 ? F_INVMASK : 0) |
+              (p.threshold_maximum < 255 ? F_RANGE : 0);
+    const int T = p.detect_threshold, aT = T < 0 ? -T : T;
+    k.t4 = rep(aT);                       // d > |T|; |T| >= 255 can never be exceeded by a byte
+    k.lo4 = rep(T); k.hi4 = rep(p.threshold_maximum);
+    if (T > 255 || p.threshold_maximum < 0) { k.lo4 = rep(255); k.hi4 = rep(0); }   // empty range
+    return TB_OK;
+}
+
+extern "C" void tb_seg_default_params(tb_seg_params *p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->detect_threshold = 15; p->threshold_maximum = 255; p->enable_difference = 1;
+    p->detect_threshold_is_absolute = 1; p->closing_size = 3; p->cm_per_pixel = 1.f;
+    p->n_size_ranges = 0;
+}
+
+template <typename T>
+static int seg_dev(tb_seg *h, T **p, size_t n)
+{
+    int r = dev_alloc(p, std::max<size_t>(n, 1));
+    if (r == TB_OK) h->dev_allocs.push_back((void *)*p);
+    return r;
+}
+
+extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
+{
+    TB_REQUIRE(cfg && out, TB_ERR_INVALID, "tb_seg_create: null argument");
+    TB_REQUIRE(cfg->width > 0 && cfg->height > 0 && cfg->width <= 16384 && cfg->height < 65535, TB_ERR_INVALID,
+               "tb_seg_create: frame size must be 1..16384 x 1..65534");
+    TB_REQUIRE(cfg->max_batch > 0 && cfg->max_batch <= 4096, TB_ERR_INVALID, "tb_seg_create: max_batch must be 1..4096");
+    TB_REQUIRE(cfg->crop_method >= 0 && cfg->crop_method <= 2, TB_ERR_INVALID, "tb_seg_create: crop_method must be 0..2");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("tb_seg_create: no CUDA device (there is no CPU fallback)");
+        return TB_ERR_CUDA;
+    }
+    TB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, TB_ERR_INVALID, "tb_seg_create: bad device ordinal");
+    TB_CUDA(cudaSetDevice(cfg->device));
+    tb_seg *h = new tb_seg();
+    h->cfg = *cfg;
+    tb_seg_default_params(&h->params);
+    std::string why;
+    seg_make_k(h->params, h->k, why);
+    SegDev &d = h->d;
+    d.W = cfg->width; d.H = cfg->height; d.B = cfg->max_batch;
+    d.cpr = (d.W + 15) / 16;
+    d.aligned = (d.W % 16) == 0;
+    d.rpt = std::max(1, K1_CHUNKS / d.cpr);
+    d.n_bands = (d.H + d.rpt - 1) / d.rpt;
+    d.rcap = cfg->max_runs_per_frame > 0 ? (uint32_t)cfg->max_runs_per_frame : 32768u;
+    d.rcap = std::max<uint32_t>(d.rcap, (uint32_t)d.n_bands);
+    d.px_frame_cap = cfg->max_pixels_per_frame > 0 ? (uint32_t)cfg->max_pixels_per_frame
+                                                   : (uint32_t)std::max<int64_t>((int64_t)d.W * d.H / 8, std::min<int64_t>((int64_t)d.W * d.H, 1 << 18));
+    d.max_crops = cfg->max_crops_per_frame > 0 ? (uint32_t)cfg->max_crops_per_frame : 0u;
+    d.crop_w = cfg->crop_width > 0 ? cfg->crop_width : 80;
+    d.crop_h = cfg->crop_height > 0 ? cfg->crop_height : 80;
+    d.crop_method = cfg->crop_method;
+    const size_t B = d.B;
+    // batch arenas: an average budget per frame, but never less than one worst-case frame
+    d.lines_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)B * std::min<uint32_t>(d.rcap, 8192u), d.rcap), 0x7FFFFFFFu);
+    d.blobs_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)B * std::min<uint32_t>(d.rcap, 2048u), d.rcap), 0x7FFFFFFFu);
+    d.px_cap = (uint32_t)std::min<uint64_t>((uint64_t)B * d.px_frame_cap, 0x7FFFFFFFu);
+    d.crops_cap = (uint32_t)(B * d.max_crops);
+    d.sqcm = 1.f; d.n_ranges = 0;
+
+    int r = TB_OK;
+#define A(p, n) if (r == TB_OK) r = seg_dev(h, &(p), (n))
+    A(h->d_bg, (size_t)d.W * d.H + 16);
+    A(h->d_frames, B * d.W * d.H + 16);
+    A(h->d_tmp, (size_t)d.W * d.H);
+    A(d.run_count, B); A(d.band_base, B * d.n_bands); A(d.band_cnt, B * d.n_bands);
+    A(d.runs_raw, B * d.rcap); A(d.runs, B * d.rcap); A(d.parent, B * d.rcap); A(d.bidx, B * d.rcap);
+    A(d.row_start, B * d.H); A(d.row_end, B * d.H);
+    A(d.b_npx, B * d.rcap); A(d.b_nl, B * d.rcap); A(d.b_xmin, B * d.rcap); A(d.b_xmax, B * d.rcap);
+    A(d.b_ymax, B * d.rcap); A(d.b_root, B * d.rcap); A(d.b_loff, B * d.rcap); A(d.b_poff, B * d.rcap);
+    A(d.kept, B * d.rcap); A(d.frame_tot, B * 4);
+    A(d.infos, B); A(d.recs, d.blobs_cap); A(d.lines, d.lines_cap); A(d.line_px, d.lines_cap);
+    A(d.pixels, (size_t)d.px_cap + 16); A(d.crops, (size_t)d.crops_cap * d.crop_w * d.crop_h + 16);
+    A(d.crop_blob, d.crops_cap); A(d.totals, 4);
+#undef A
+    if (r == TB_OK) r = host_alloc(&h->h_infos, B);
+    if (r == TB_OK) r = host_alloc(&h->h_totals, 4);
+    if (r == TB_OK) r = host_alloc(&h->h_recs, d.blobs_cap);
+    if (r == TB_OK) r = host_alloc(&h->h_lines, d.lines_cap);
+    if (r == TB_OK) r = host_alloc(&h->h_pixels, (size_t)d.px_cap + 16);
+    if (r == TB_OK) r = host_alloc(&h->h_crops, (size_t)d.crops_cap * d.crop_w * d.crop_h + 16);
+    if (r == TB_OK) r = host_alloc(&h->h_crop_blob, std::max<size_t>(d.crops_cap, 1));
+    if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
+    if (r == TB_OK && cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); r = TB_ERR_CUDA; }
+    if (r != TB_OK) { tb_seg_destroy(h); return r; }
+    d.bg = h->d_bg;
+    std::memset(h->h_totals, 0, 16);
+    *out = h;
+    return TB_OK;
+}
+
+extern "C" void tb_seg_destroy(tb_seg *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->dev_allocs) cudaFree(p);
+    void *hp[] = {h->h_infos, h->h_totals, h->h_recs, h->h_lines, h->h_pixels, h->h_crops, h->h_crop_blob};
+    for (void *p : hp) if (p) cudaFreeHost(p);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
+{
+    TB_REQUIRE(h && p, TB_ERR_INVALID, "tb_seg_set_params: null argument");
+    SegK k; std::string why;
+    if (seg_make_k(*p, k, why) != TB_OK) { set_error("tb_seg_set_params: " + why); return TB_ERR_INVALID; }
+    h->params = *p; h->k = k;
+    h->d.sqcm = p->cm_per_pixel * p->cm_per_pixel;        // SQR(cm_per_pixel) in float, BackgroundSubtraction.cpp:139
+    h->d.n_ranges = p->n_size_ranges;
+    for (int i = 0; i < 4; ++i) { h->d.lo[i] = p->size_lo[i]; h->d.hi[i] = p->size_hi[i]; }
+    return TB_OK;
+}
+
+extern "C" int tb_seg_set_background(tb_seg *h, const uint8_t *bg, int width, int height, int64_t stride)
+{
+    TB_REQUIRE(h && bg, TB_ERR_INVALID, "tb_seg_set_background: null argument");
+    TB_REQUIRE(width == h->d.W && height == h->d.H, TB_ERR_INVALID, "tb_seg_set_background: size differs from the handle's frame size");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    if (stride <= 0) stride = width;
+    TB_CUDA(cudaMemcpy2DAsync(h->d_bg, (size_t)width, bg, (size_t)stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    TB_CUDA(cudaStreamSynchronize(h->stream));
+    h->has_bg = true;
+    return TB_OK;
+}
+
+static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s, int fetch)
+{
+    SegDev d = h->d;
+    d.B = n;
+    TB_CUDA(cudaMemsetAsync(d.run_count, 0, sizeof(uint32_t) * (size_t)n, s));
+    const int fpc = n >= 64 ? 4 : 1;
+    dim3 g1((unsigned)d.n_bands, (unsigned)((n + fpc - 1) / fpc));
+    seg_rle_kernel<<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
+    ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
+    blob_emit_kernel<<<n, K3_NT, 0, s>>>(frames_dev, d);
+    h->launches += 3;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpyAsync(h->h_totals, d.totals, 16, cudaMemcpyDeviceToHost, s));
+    TB_CUDA(cudaMemcpyAsync(h->h_infos, d.infos, sizeof(tb_frame_info) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    h->last_n = n; h->last_fetch = fetch != 0; h->pending = true; h->fetched_payload = false; h->last_stream = s;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_submit_device(tb_seg *h, const void *frames_dev, int n, void *stream, int fetch)
+{
+    TB_REQUIRE(h && frames_dev, TB_ERR_INVALID, "tb_seg_submit_device: null argument");
+    TB_REQUIRE(n > 0 && n <= h->cfg.max_batch, TB_ERR_INVALID, "tb_seg_submit_device: n must be 1..max_batch");
+    TB_REQUIRE(h->has_bg, TB_ERR_STATE, "tb_seg_submit_device: no background set (pipeline is paused until set_background)");
+    TB_REQUIRE(((uintptr_t)frames_dev & 15) == 0 || !h->d.aligned, TB_ERR_INVALID, "tb_seg_submit_device: frames must be 16-byte aligned");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    return seg_launch(h, (const uint8_t *)frames_dev, n, stream ? (cudaStream_t)stream : h->stream, fetch);
+}
+
+extern "C" int tb_seg_submit(tb_seg *h, const uint8_t *const *frames, int n, int64_t stride, int fetch)
+{
+    TB_REQUIRE(h && frames, TB_ERR_INVALID, "tb_seg_submit: null argument");
+    TB_REQUIRE(n > 0 && n <= h->cfg.max_batch, TB_ERR_INVALID, "tb_seg_submit: n must be 1..max_batch");
+    TB_REQUIRE(h->has_bg, TB_ERR_STATE, "tb_seg_submit: no background set (pipeline is paused until set_background)");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t W = h->d.W, H = h->d.H;
+    if (stride <= 0) stride = (int64_t)W;
+    for (int i = 0; i < n; ++i) {
+        TB_REQUIRE(frames[i], TB_ERR_INVALID, "tb_seg_submit: null frame pointer");
+        TB_CUDA(cudaMemcpy2DAsync(h->d_frames + (size_t)i * W * H, W, frames[i], (size_t)stride, W, H, cudaMemcpyHostToDevice, h->stream));
+    }
+    return seg_launch(h, h->d_frames, n, h->stream, fetch);
+}
+
+extern "C" int tb_seg_wait(tb_seg *h)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_wait: null handle");
+    TB_REQUIRE(h->pending || h->last_n > 0, TB_ERR_STATE, "tb_seg_wait: nothing submitted");
+    if (!h->pending) return TB_OK;
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->last_stream;
+    TB_CUDA(cudaStreamSynchronize(s));
+    if (h->last_fetch) {
+        const uint32_t *t = h->h_totals;
+        const SegDev &d = h->d;
+        if (t[0]) TB_CUDA(cudaMemcpyAsync(h->h_recs, d.recs, sizeof(tb_blob_rec) * (size_t)t[0], cudaMemcpyDeviceToHost, s));
+        if (t[1]) TB_CUDA(cudaMemcpyAsync(h->h_lines, d.lines, sizeof(tb_line) * (size_t)t[1], cudaMemcpyDeviceToHost, s));
+        if (t[2]) TB_CUDA(cudaMemcpyAsync(h->h_pixels, d.pixels, (size_t)t[2], cudaMemcpyDeviceToHost, s));
+        if (t[3]) {
+            TB_CUDA(cudaMemcpyAsync(h->h_crops, d.crops, (size_t)t[3] * d.crop_w * d.crop_h, cudaMemcpyDeviceToHost, s));
+            TB_CUDA(cudaMemcpyAsync(h->h_crop_blob, d.crop_blob, sizeof(uint32_t) * (size_t)t[3], cudaMemcpyDeviceToHost, s));
+        }
+        TB_CUDA(cudaStreamSynchronize(s));
+        h->fetched_payload = true;
+    }
+    h->pending = false;
+    for (int i = 0; i < h->last_n; ++i)
+        if (h->h_infos[i].status & ~4u) {
+            set_error("tb_seg_wait: capacity exceeded for at least one frame (see tb_frame_info.status)");
+            return TB_ERR_CAPACITY;
+        }
+    return TB_OK;
+}
+
+extern "C" int tb_seg_result(tb_seg *h, int i, tb_blob_view *out)
+{
+    TB_REQUIRE(h && out, TB_ERR_INVALID, "tb_seg_result: null argument");
+    TB_REQUIRE(!h->pending && h->last_n > 0, TB_ERR_STATE, "tb_seg_result: call tb_seg_wait first");
+    TB_REQUIRE(i >= 0 && i < h->last_n, TB_ERR_INVALID, "tb_seg_result: frame index out of range");
+    TB_REQUIRE(h->fetched_payload, TB_ERR_STATE, "tb_seg_result: batch was submitted with fetch=0");
+    const tb_frame_info &fi = h->h_infos[i];
+    out->info = fi;
+    out->recs = h->h_recs + fi.blob_begin;
+    out->lines = h->h_lines + fi.line_begin;
+    out->pixels = h->h_pixels + fi.px_begin;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_totals(tb_seg *h, uint32_t out[4])
+{
+    TB_REQUIRE(h && out, TB_ERR_INVALID, "tb_seg_totals: null argument");
+    TB_REQUIRE(!h->pending && h->last_n > 0, TB_ERR_STATE, "tb_seg_totals: call tb_seg_wait first");
+    std::memcpy(out, h->h_totals, 16);
+    return TB_OK;
+}
+
+extern "C" int tb_seg_device_results(tb_seg *h, void **crops, void **n_crops_dev, void **crop_blob_index, void **recs, void **infos)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_device_results: null handle");
+    if (crops) *crops = h->d.crops;
+    if (n_crops_dev) *n_crops_dev = h->d.totals + 3;
+    if (crop_blob_index) *crop_blob_index = h->d.crop_blob;
+    if (recs) *recs = h->d.recs;
+    if (infos) *infos = h->d.infos;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_blob_index, uint32_t *n)
+{
+    TB_REQUIRE(h && n, TB_ERR_INVALID, "tb_seg_crops: null argument");
+    TB_REQUIRE(!h->pending && h->fetched_payload, TB_ERR_STATE, "tb_seg_crops: call tb_seg_wait after a fetch=1 submit first");
+    if (crops) *crops = h->h_crops;
+    if (crop_blob_index) *crop_blob_index = h->h_crop_blob;
+    *n = h->h_totals[3];
+    return TB_OK;
+}
+
+extern "C" int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t *out_host)
+{
+    TB_REQUIRE(h && frame_host && out_host, TB_ERR_INVALID, "tb_seg_debug_binary: null argument");
+    TB_REQUIRE(h->has_bg, TB_ERR_STATE, "tb_seg_debug_binary: no background set");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->d.W * h->d.H;
+    TB_CUDA(cudaMemcpyAsync(h->d_frames, frame_host, n, cudaMemcpyHostToDevice, h->stream));
+    binary_image_kernel<<<592, 256, 0, h->stream>>>(h->d_frames, h->d_bg, h->d_tmp, n, h->k);
+    h->launches += 1;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpyAsync(out_host, h->d_tmp, n, cudaMemcpyDeviceToHost, h->stream));
+    TB_CUDA(cudaStreamSynchronize(h->stream));
+    return TB_OK;
+}
+
+extern "C" uint64_t tb_seg_launch_count(tb_seg *h) { return h ? h->launches : 0; }

@@ -1,0 +1,516 @@
+// Visual identification inference (V118_3) on sm_100a behind the tb_vi_* C ABI.
+// Replaces Python::VINetwork::probabilities (T/ml/VisualIdentification.h:104-133, .cpp:440-494)
+// -> predict_numpy (T/python/visual_recognition_torch.py:290-352) -> V118_3.forward
+// (T/python/visual_identification_network_torch.py:216-258), eval mode:
+//   conv5x5(C->16)+BN+ReLU+pool2 -> conv5x5(16->64)+BN+ReLU+pool2 -> conv5x5(64->128)+BN+ReLU+pool2
+//   -> flatten (NCHW order) -> fc 12800->100 -> LayerNorm(100) -> ReLU -> fc 100->M -> softmax.
+// Inputs are raw u8 crops cast to float (no /255, visual_recognition_torch.py:337).
+// precision 0: fp32 CUDA-core kernels below (parity mode).  Activations are NHWC fp32.
+#include "common.h"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace tb {
+
+constexpr float BN_EPS = 1e-5f, LN_EPS = 1e-5f;
+
+// ------------------------------------------------------------------------------------------------
+// conv1: u8 crop [H][W] (C=1) -> pooled [H/2][W/2][16] fp32.  One CTA per image; each thread owns
+// pooled pixels (a 2x2 window of conv outputs) x 16 output channels.  ~2 % of the network's FLOPs.
+// ------------------------------------------------------------------------------------------------
+constexpr int C1_NT = 256;
+
+__global__ void __launch_bounds__(C1_NT)
+conv1_kernel(const uint8_t *__restrict__ img, int H, int W, int n_max, const uint32_t *__restrict__ n_dev, int base,
+             const float *__restrict__ w /*[25][16]*/, const float *__restrict__ sc, const float *__restrict__ sh,
+             float *__restrict__ out)
+{
+    extern __shared__ float sm[];
+    const int n = blockIdx.x;
+    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+    if (n >= n_act) return;
+    const int PW = W + 4, PH = H + 4;
+    float *patch = sm;                       // [PH][PW], zero halo
+    float *sw = sm + PH * PW;                // [25][16]
+    float *ssc = sw + 400, *ssh = ssc + 16;
+    const uint8_t *src = img + (size_t)n * H * W;
+    for (int i = threadIdx.x; i < PH * PW; i += C1_NT) {
+        int y = i / PW - 2, x = i % PW - 2;
+        patch[i] = (y >= 0 && y < H && x >= 0 && x < W) ? (float)src[y * W + x] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 400; i += C1_NT) sw[i] = w[i];
+    if (threadIdx.x < 16) { ssc[threadIdx.x] = sc[threadIdx.x]; ssh[threadIdx.x] = sh[threadIdx.x]; }
+    __syncthreads();
+    const int OW = W / 2, OH = H / 2;
+    float *dst = out + (size_t)n * OH * OW * 16;
+    for (int q = threadIdx.x; q < OH * OW; q += C1_NT) {
+        const int py = q / OW, px = q % OW;
+        float acc[4][16];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[a][c] = 0.f;
+        for (int dy = 0; dy < 5; ++dy) {
+            float r0[6], r1[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                r0[i] = patch[(2 * py + dy) * PW + 2 * px + i];
+                r1[i] = patch[(2 * py + dy + 1) * PW + 2 * px + i];
+            }
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+                const float4 *wp = reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 16);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 wv = wp[c4];
+                    const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[0][c4 * 4 + j] = fmaf(r0[dx], ww[j], acc[0][c4 * 4 + j]);
+                        acc[1][c4 * 4 + j] = fmaf(r0[dx + 1], ww[j], acc[1][c4 * 4 + j]);
+                        acc[2][c4 * 4 + j] = fmaf(r1[dx], ww[j], acc[2][c4 * 4 + j]);
+                        acc[3][c4 * 4 + j] = fmaf(r1[dx + 1], ww[j], acc[3][c4 * 4 + j]);
+                    }
+                }
+            }
+        }
+        float o[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float m = fmaxf(fmaxf(fmaf(acc[0][c], ssc[c], ssh[c]), fmaf(acc[1][c], ssc[c], ssh[c])),
+                            fmaxf(fmaf(acc[2][c], ssc[c], ssh[c]), fmaf(acc[3][c], ssc[c], ssh[c])));
+            o[c] = fmaxf(m, 0.f);
+        }
+        float4 *d4 = reinterpret_cast<float4 *>(dst + (size_t)q * 16);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) d4[c4] = make_float4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv2 / conv3: NHWC fp32 [HW][HW][CIN] -> pooled [HW/2][HW/2][COUT].  A CTA computes a TWP x THP
+// tile of pooled pixels (<= 64 windows of 2x2 conv outputs) x 64 output channels of one image;
+// thread = (window, 16 couts).  Input patch (zero halo) and weights are staged through shared
+// memory in chunks of 8 input channels.
+// ------------------------------------------------------------------------------------------------
+constexpr int CV_NT = 256, CV_CK = 8;
+
+template <int TWP, int THP>
+struct ConvTile {
+    static constexpr int PR = 2 * THP + 4, PC = 2 * TWP + 4, PITCH = PC + 1;
+    static constexpr int SMEM = (CV_CK * PR * PITCH + 25 * CV_CK * 64) * 4;
+};
+
+template <int CIN, int COUT, int HW, int TWP, int THP>
+__global__ void __launch_bounds__(CV_NT)
+conv_kernel(const float *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
+            const float *__restrict__ w /*[25][CIN][COUT]*/, const float *__restrict__ sc, const float *__restrict__ sh,
+            float *__restrict__ out)
+{
+    using T = ConvTile<TWP, THP>;
+    static_assert(TWP * THP <= 64, "tile has at most 64 windows");
+    extern __shared__ float sm[];
+    float *patch = sm;                                  // [CV_CK][PR][PITCH]
+    float *sw = sm + CV_CK * T::PR * T::PITCH;          // [25][CV_CK][64]
+    constexpr int OHW = HW / 2;
+    constexpr int TX = (OHW + TWP - 1) / TWP, TY = (OHW + THP - 1) / THP;
+    const int n = blockIdx.x / (TX * TY);
+    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+    if (n >= n_act) return;
+    const int tile = blockIdx.x % (TX * TY);
+    const int ty = tile / TX, tx = tile % TX;
+    const int co0 = blockIdx.y * 64;
+    const int tid = threadIdx.x, win = tid & 63, cg = tid >> 6;
+    const bool active = win < TWP * THP;
+    const int wy = active ? win / TWP : 0, wx = active ? win % TWP : 0;
+    const int y0 = ty * THP * 2 - 2, x0 = tx * TWP * 2 - 2;   // patch origin in the image
+    const float *src = in + (size_t)n * HW * HW * CIN;
+
+    float acc[4][16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[a][c] = 0.f;
+
+    for (int c0 = 0; c0 < CIN; c0 += CV_CK) {
+        __syncthreads();
+        for (int i = tid; i < T::PR * T::PC * CV_CK; i += CV_NT) {
+            const int c = i % CV_CK, p = i / CV_CK, px = p % T::PC, py = p / T::PC;
+            const int y = y0 + py, x = x0 + px;
+            float v = 0.f;
+            if (y >= 0 && y < HW && x >= 0 && x < HW) v = src[((size_t)y * HW + x) * CIN + c0 + c];
+            patch[(c * T::PR + py) * T::PITCH + px] = v;
+        }
+        for (int i = tid; i < 25 * CV_CK * 64; i += CV_NT) {
+            const int co = i & 63, c = (i >> 6) % CV_CK, t = i / (64 * CV_CK);
+            sw[i] = w[((size_t)t * CIN + c0 + c) * COUT + co0 + co];
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int c = 0; c < CV_CK; ++c) {
+            const float *pc = patch + (c * T::PR + 2 * wy) * T::PITCH + 2 * wx;
+#pragma unroll 1
+            for (int dy = 0; dy < 5; ++dy) {
+                float r0[6], r1[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { r0[i] = pc[dy * T::PITCH + i]; r1[i] = pc[(dy + 1) * T::PITCH + i]; }
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx) {
+                    const float4 *wp = reinterpret_cast<const float4 *>(sw + ((dy * 5 + dx) * CV_CK + c) * 64 + cg * 16);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 wv = wp[c4];
+                        const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            acc[0][c4 * 4 + j] = fmaf(r0[dx], ww[j], acc[0][c4 * 4 + j]);
+                            acc[1][c4 * 4 + j] = fmaf(r0[dx + 1], ww[j], acc[1][c4 * 4 + j]);
+                            acc[2][c4 * 4 + j] = fmaf(r1[dx], ww[j], acc[2][c4 * 4 + j]);
+                            acc[3][c4 * 4 + j] = fmaf(r1[dx + 1], ww[j], acc[3][c4 * 4 + j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const int py = ty * THP + wy, px = tx * TWP + wx;
+    if (active && py < OHW && px < OHW) {
+        float o[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float s = sc[co0 + cg * 16 + c], t = sh[co0 + cg * 16 + c];
+            float m = fmaxf(fmaxf(fmaf(acc[0][c], s, t), fmaf(acc[1][c], s, t)), fmaxf(fmaf(acc[2][c], s, t), fmaf(acc[3][c], s, t)));
+            o[c] = fmaxf(m, 0.f);
+        }
+        float4 *d4 = reinterpret_cast<float4 *>(out + (((size_t)n * OHW + py) * OHW + px) * COUT + co0 + cg * 16);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) d4[c4] = make_float4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fc1: [n][K] x Wt[K][100] + b -> [n][100].  CTA = 32 images x 104 outputs, K staged in chunks of 32.
+// ------------------------------------------------------------------------------------------------
+constexpr int FC_NT = 256, FC_IMG = 32, FC_KC = 32, FC_OUT = 100, FC_OPAD = 104;
+
+__global__ void __launch_bounds__(FC_NT)
+fc1_kernel(const float *__restrict__ x, int K, int n_max, const uint32_t *__restrict__ n_dev, int base,
+           const float *__restrict__ wt /*[K][100]*/, const float *__restrict__ b, float *__restrict__ out)
+{
+    __shared__ float sx[FC_IMG][FC_KC + 1];
+    __shared__ float swt[FC_KC][FC_OPAD];
+    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+    const int i0 = blockIdx.x * FC_IMG;
+    if (i0 >= n_act) return;
+    const int tid = threadIdx.x, img = tid >> 3, og = tid & 7;
+    float acc[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) acc[j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += FC_KC) {
+        __syncthreads();
+        for (int i = tid; i < FC_IMG * FC_KC; i += FC_NT) {
+            const int r = i / FC_KC, c = i % FC_KC;
+            sx[r][c] = (i0 + r < n_act) ? x[(size_t)(i0 + r) * K + k0 + c] : 0.f;
+        }
+        for (int i = tid; i < FC_KC * FC_OPAD; i += FC_NT) {
+            const int r = i / FC_OPAD, c = i % FC_OPAD;
+            swt[r][c] = c < FC_OUT ? wt[(size_t)(k0 + r) * FC_OUT + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < FC_KC; ++k) {
+            const float xv = sx[img][k];
+#pragma unroll
+            for (int j = 0; j < 13; ++j) acc[j] = fmaf(xv, swt[k][og + 8 * j], acc[j]);
+        }
+    }
+    if (i0 + img < n_act)
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            const int o = og + 8 * j;
+            if (o < FC_OUT) out[(size_t)(i0 + img) * FC_OUT + o] = acc[j] + b[o];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: LayerNorm(100) -> ReLU -> fc2 (100 -> M) -> softmax.  One warp per image.
+// ------------------------------------------------------------------------------------------------
+constexpr int HD_WARPS = 4;
+
+__global__ void __launch_bounds__(HD_WARPS * 32)
+head_kernel(const float *__restrict__ h1, int M, int n_max, const uint32_t *__restrict__ n_dev, int base,
+            const float *__restrict__ g, const float *__restrict__ be, const float *__restrict__ w2t /*[100][M]*/,
+            const float *__restrict__ b2, float *__restrict__ probs, float *__restrict__ logits)
+{
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+    const int n = blockIdx.x * HD_WARPS + warp;
+    if (n >= n_act) return;
+    float *sh = sm + warp * (100 + M), *sl = sh + 100;
+    float v[4], s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int i = lane + 32 * j; v[j] = i < 100 ? h1[(size_t)n * 100 + i] : 0.f; s += v[j]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / 100.f;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int i = lane + 32 * j; const float dlt = i < 100 ? v[j] - mean : 0.f; q += dlt * dlt; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / 100.f + LN_EPS);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = lane + 32 * j;
+        if (i < 100) sh[i] = fmaxf((v[j] - mean) * rstd * g[i] + be[i], 0.f);
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int o = lane; o < M; o += 32) {
+        float a = b2[o];
+        for (int k = 0; k < 100; ++k) a = fmaf(sh[k], w2t[(size_t)k * M + o], a);
+        sl[o] = a;
+        if (logits) logits[(size_t)n * M + o] = a;
+        mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int o = lane; o < M; o += 32) { const float e = expf(sl[o] - mx); sl[o] = e; sum += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int o = lane; o < M; o += 32) probs[(size_t)n * M + o] = sl[o] * inv;
+}
+
+}  // namespace tb
+
+// ================================================================================================
+// host side: the tb_vi handle
+// ================================================================================================
+using namespace tb;
+
+struct tb_vi {
+    tb_vi_config cfg{};
+    std::map<std::string, std::vector<float>> sd;
+    bool committed = false;
+    cudaStream_t stream = nullptr;
+    int chunk = 0;
+    std::vector<void *> dev_allocs;
+    // fp32 parameters
+    float *w1 = nullptr, *s1 = nullptr, *t1 = nullptr, *w2 = nullptr, *s2 = nullptr, *t2 = nullptr;
+    float *w3 = nullptr, *s3 = nullptr, *t3 = nullptr, *wf1 = nullptr, *bf1 = nullptr, *lng = nullptr, *lnb = nullptr;
+    float *wf2 = nullptr, *bf2 = nullptr;
+    // activations (one chunk)
+    float *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *h1 = nullptr;
+    uint8_t *d_img = nullptr; float *d_probs = nullptr, *d_logits = nullptr;
+    uint64_t launches = 0;
+    cudaStream_t last_stream = nullptr;
+};
+
+template <typename T>
+static int vi_dev(tb_vi *h, T **p, size_t n)
+{
+    int r = dev_alloc(p, std::max<size_t>(n, 1));
+    if (r == TB_OK) h->dev_allocs.push_back((void *)*p);
+    return r;
+}
+
+extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
+{
+    TB_REQUIRE(cfg && out, TB_ERR_INVALID, "tb_vi_create: null argument");
+    TB_REQUIRE(cfg->width == 80 && cfg->height == 80 && cfg->channels == 1, TB_ERR_INVALID,
+               "tb_vi_create: this release builds V118_3 for 80x80x1 crops (individual_image_size default, meta_encoding gray)");
+    TB_REQUIRE(cfg->num_classes > 0 && cfg->num_classes <= 1024, TB_ERR_INVALID, "tb_vi_create: num_classes must be 1..1024");
+    TB_REQUIRE(cfg->max_images > 0, TB_ERR_INVALID, "tb_vi_create: max_images must be > 0");
+    TB_REQUIRE(cfg->precision == 0, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32) in this build");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("tb_vi_create: no CUDA device (there is no CPU fallback)"); return TB_ERR_CUDA; }
+    TB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, TB_ERR_INVALID, "tb_vi_create: bad device ordinal");
+    TB_CUDA(cudaSetDevice(cfg->device));
+    tb_vi *h = new tb_vi();
+    h->cfg = *cfg;
+    h->chunk = std::min(cfg->max_images, 4096);
+    const size_t CH = h->chunk, M = cfg->num_classes, N = cfg->max_images;
+    int r = TB_OK;
+#define A(p, n) if (r == TB_OK) r = vi_dev(h, &(p), (n))
+    A(h->w1, 400); A(h->s1, 16); A(h->t1, 16);
+    A(h->w2, 25 * 16 * 64); A(h->s2, 64); A(h->t2, 64);
+    A(h->w3, 25 * 64 * 128); A(h->s3, 128); A(h->t3, 128);
+    A(h->wf1, 12800 * 100); A(h->bf1, 100); A(h->lng, 100); A(h->lnb, 100);
+    A(h->wf2, 100 * M); A(h->bf2, M);
+    A(h->a1, CH * 40 * 40 * 16); A(h->a2, CH * 20 * 20 * 64); A(h->a3, CH * 10 * 10 * 128); A(h->h1, CH * 100);
+    A(h->d_img, N * 6400 + 16); A(h->d_probs, N * M); A(h->d_logits, N * M);
+#undef A
+    if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
+    if (r != TB_OK) { tb_vi_destroy(h); return r; }
+    *out = h;
+    return TB_OK;
+}
+
+extern "C" void tb_vi_destroy(tb_vi *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->dev_allocs) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int tb_vi_set_tensor(tb_vi *h, const char *name, const float *data, int64_t count)
+{
+    TB_REQUIRE(h && name && data && count > 0, TB_ERR_INVALID, "tb_vi_set_tensor: null/empty argument");
+    h->sd[name].assign(data, data + count);
+    h->committed = false;
+    return TB_OK;
+}
+
+static int vi_need(tb_vi *h, const char *name, size_t count, const std::vector<float> **out)
+{
+    auto it = h->sd.find(name);
+    if (it == h->sd.end()) { set_error(std::string("tb_vi_commit: missing tensor ") + name); return TB_ERR_STATE; }
+    if (it->second.size() != count) {
+        set_error(std::string("tb_vi_commit: tensor ") + name + " has " + std::to_string(it->second.size()) + " elements, expected " + std::to_string(count));
+        return TB_ERR_INVALID;
+    }
+    *out = &it->second;
+    return TB_OK;
+}
+
+static int vi_upload(float *dst, const std::vector<float> &v)
+{
+    TB_CUDA(cudaMemcpy(dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return TB_OK;
+}
+
+// conv weight torch [Cout][Cin][5][5] -> [tap][Cin][Cout]; BN(eval) folded with the conv bias into
+// y = conv * s + t,  s = gamma / sqrt(var + eps),  t = (bias - mean) * s + beta
+static int vi_conv(tb_vi *h, int idx, int cin, int cout, float *dw, float *ds, float *dt)
+{
+    const std::string c = "model.conv" + std::to_string(idx), b = "model.bn" + std::to_string(idx);
+    const std::vector<float> *w, *bias, *g, *be, *mu, *var;
+    int r;
+    if ((r = vi_need(h, (c + ".weight").c_str(), (size_t)cout * cin * 25, &w))) return r;
+    if ((r = vi_need(h, (c + ".bias").c_str(), cout, &bias))) return r;
+    if ((r = vi_need(h, (b + ".weight").c_str(), cout, &g))) return r;
+    if ((r = vi_need(h, (b + ".bias").c_str(), cout, &be))) return r;
+    if ((r = vi_need(h, (b + ".running_mean").c_str(), cout, &mu))) return r;
+    if ((r = vi_need(h, (b + ".running_var").c_str(), cout, &var))) return r;
+    std::vector<float> wt((size_t)25 * cin * cout), s(cout), t(cout);
+    for (int co = 0; co < cout; ++co) {
+        for (int ci = 0; ci < cin; ++ci)
+            for (int tap = 0; tap < 25; ++tap) wt[((size_t)tap * cin + ci) * cout + co] = (*w)[((size_t)co * cin + ci) * 25 + tap];
+        s[co] = (*g)[co] / std::sqrt((*var)[co] + BN_EPS);
+        t[co] = ((*bias)[co] - (*mu)[co]) * s[co] + (*be)[co];
+    }
+    if ((r = vi_upload(dw, wt))) return r;
+    if ((r = vi_upload(ds, s))) return r;
+    return vi_upload(dt, t);
+}
+
+extern "C" int tb_vi_commit(tb_vi *h)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_vi_commit: null handle");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    int r;
+    if ((r = vi_conv(h, 1, 1, 16, h->w1, h->s1, h->t1))) return r;
+    if ((r = vi_conv(h, 2, 16, 64, h->w2, h->s2, h->t2))) return r;
+    if ((r = vi_conv(h, 3, 64, 128, h->w3, h->s3, h->t3))) return r;
+    const int M = h->cfg.num_classes;
+    const std::vector<float> *w, *b, *g, *be, *w2, *b2;
+    if ((r = vi_need(h, "model.fc1.weight", (size_t)100 * 12800, &w))) return r;
+    if ((r = vi_need(h, "model.fc1.bias", 100, &b))) return r;
+    if ((r = vi_need(h, "model.bn4.weight", 100, &g))) return r;
+    if ((r = vi_need(h, "model.bn4.bias", 100, &be))) return r;
+    if ((r = vi_need(h, "model.fc2.weight", (size_t)M * 100, &w2))) return r;
+    if ((r = vi_need(h, "model.fc2.bias", M, &b2))) return r;
+    // fc1: torch flattens NCHW (k = c*100 + y*10 + x); activations here are NHWC (k' = (y*10+x)*128 + c)
+    std::vector<float> wt((size_t)12800 * 100);
+    for (int o = 0; o < 100; ++o)
+        for (int c = 0; c < 128; ++c)
+            for (int p = 0; p < 100; ++p) wt[((size_t)p * 128 + c) * 100 + o] = (*w)[(size_t)o * 12800 + c * 100 + p];
+    if ((r = vi_upload(h->wf1, wt))) return r;
+    if ((r = vi_upload(h->bf1, *b))) return r;
+    if ((r = vi_upload(h->lng, *g))) return r;
+    if ((r = vi_upload(h->lnb, *be))) return r;
+    std::vector<float> w2t((size_t)100 * M);
+    for (int o = 0; o < M; ++o)
+        for (int k = 0; k < 100; ++k) w2t[(size_t)k * M + o] = (*w2)[(size_t)o * 100 + k];
+    if ((r = vi_upload(h->wf2, w2t))) return r;
+    if ((r = vi_upload(h->bf2, *b2))) return r;
+    h->committed = true;
+    return TB_OK;
+}
+
+static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n_dev, float *probs, float *logits, cudaStream_t s)
+{
+    const int M = h->cfg.num_classes;
+    static bool attr_done = false;
+    auto k2 = conv_kernel<16, 64, 40, 20, 3>;           // pooled 20x20: 7 tiles of 20x3
+    auto k3 = conv_kernel<64, 128, 20, 10, 6>;          // pooled 10x10: 2 tiles of 10x6
+    constexpr int SM2 = ConvTile<20, 3>::SMEM, SM3 = ConvTile<10, 6>::SMEM;
+    if (!attr_done) {
+        TB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, SM2));
+        TB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
+        attr_done = true;
+    }
+    for (int base = 0; base < n_max; base += h->chunk) {
+        const int n = std::min(h->chunk, n_max - base);
+        const int c1_smem = (84 * 84 + 400 + 32) * 4;
+        conv1_kernel<<<n, C1_NT, c1_smem, s>>>(img + (size_t)base * 6400, 80, 80, n, n_dev, base, h->w1, h->s1, h->t1, h->a1);
+        k2<<<dim3(n * 7, 1), CV_NT, SM2, s>>>(h->a1, n, n_dev, base, h->w2, h->s2, h->t2, h->a2);
+        k3<<<dim3(n * 2, 2), CV_NT, SM3, s>>>(h->a2, n, n_dev, base, h->w3, h->s3, h->t3, h->a3);
+        fc1_kernel<<<(n + FC_IMG - 1) / FC_IMG, FC_NT, 0, s>>>(h->a3, 12800, n, n_dev, base, h->wf1, h->bf1, h->h1);
+        head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, HD_WARPS * (100 + M) * 4, s>>>(
+            h->h1, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2, probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr);
+        h->launches += 5;
+    }
+    TB_CUDA(cudaGetLastError());
+    h->last_stream = s;
+    return TB_OK;
+}
+
+extern "C" int tb_vi_predict_device(tb_vi *h, const void *images_dev, int n_max, const void *n_dev, void *probs_dev, void *logits_dev, void *stream)
+{
+    TB_REQUIRE(h && images_dev && probs_dev, TB_ERR_INVALID, "tb_vi_predict_device: null argument");
+    TB_REQUIRE(h->committed, TB_ERR_STATE, "tb_vi_predict_device: no weights loaded (tb_vi_set_tensor + tb_vi_commit)");
+    TB_REQUIRE(n_max > 0, TB_ERR_INVALID, "tb_vi_predict_device: n_max must be > 0");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    return vi_forward(h, (const uint8_t *)images_dev, n_max, (const uint32_t *)n_dev, (float *)probs_dev, (float *)logits_dev,
+                      stream ? (cudaStream_t)stream : h->stream);
+}
+
+extern "C" int tb_vi_predict(tb_vi *h, const uint8_t *images, int n, float *probs, float *logits)
+{
+    TB_REQUIRE(h && images && probs, TB_ERR_INVALID, "tb_vi_predict: null argument");
+    TB_REQUIRE(h->committed, TB_ERR_STATE, "tb_vi_predict: no weights loaded (the reference throws SoftException here)");
+    TB_REQUIRE(n > 0, TB_ERR_INVALID, "tb_vi_predict: n must be > 0");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    const int M = h->cfg.num_classes;
+    for (int base = 0; base < n; base += h->cfg.max_images) {
+        const int m = std::min(h->cfg.max_images, n - base);
+        TB_CUDA(cudaMemcpyAsync(h->d_img, images + (size_t)base * 6400, (size_t)m * 6400, cudaMemcpyHostToDevice, h->stream));
+        int r = vi_forward(h, h->d_img, m, nullptr, h->d_probs, logits ? h->d_logits : nullptr, h->stream);
+        if (r) return r;
+        TB_CUDA(cudaMemcpyAsync(probs + (size_t)base * M, h->d_probs, (size_t)m * M * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (logits) TB_CUDA(cudaMemcpyAsync(logits + (size_t)base * M, h->d_logits, (size_t)m * M * 4, cudaMemcpyDeviceToHost, h->stream));
+        TB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return TB_OK;
+}
+
+extern "C" int tb_vi_wait(tb_vi *h)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_vi_wait: null handle");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    TB_CUDA(cudaStreamSynchronize(h->last_stream ? h->last_stream : h->stream));
+    return TB_OK;
+}
+
+extern "C" uint64_t tb_vi_launch_count(tb_vi *h) { return h ? h->launches : 0; }

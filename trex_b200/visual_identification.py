@@ -1,0 +1,85 @@
+"""Host mirror of `Python::VINetwork` (Application/src/tracker/ml/VisualIdentification.h:104-189) on top
+of the tb_vi_* C ABI: inference only (training stays in the reference).
+
+    VINetwork(num_classes, ...)                       setup(): classes = 0..N-1            (.cpp:98-125)
+    load_weights(state_dict)                           load_weights(VIWeights&&)            (.cpp:306-319)
+    probabilities(images) -> ndarray (N, M)            probabilities() + transform_results  (.h:115-133, .cpp:809-830)
+
+`state_dict` uses the reference's key names (model.conv1.weight ... model.fc2.bias, torch layouts), i.e.
+what `torch.load(..._weights_dict.pth)['state_dict']` holds (T/python/trex_utils.py:65-133).
+Calling probabilities() before weights are loaded raises (the reference throws SoftException).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._capi import ViConfig, check, lib
+
+STATE_KEYS = [f"model.conv{i}.{p}" for i in (1, 2, 3) for p in ("weight", "bias")] + \
+             [f"model.bn{i}.{p}" for i in (1, 2, 3) for p in ("weight", "bias", "running_mean", "running_var")] + \
+             ["model.fc1.weight", "model.fc1.bias", "model.bn4.weight", "model.bn4.bias", "model.fc2.weight", "model.fc2.bias"]
+
+
+def batch_size_for(num_classes: int) -> int:
+    """VisualIdentification.cpp:105-118 (kept for API parity; results do not depend on it in eval mode)."""
+    b = max(int(num_classes) if num_classes else 1, 64)
+    if b < 128:
+        p = 1
+        while p < b:
+            p <<= 1
+        return p
+    return 128
+
+
+class VINetwork:
+    def __init__(self, num_classes: int, width=80, height=80, channels=1, max_images=4096, device=0, precision="fp32"):
+        self.num_classes, self.width, self.height, self.channels = int(num_classes), width, height, channels
+        self.max_images = int(max_images)
+        cfg = ViConfig(device=device, width=width, height=height, channels=channels, num_classes=self.num_classes,
+                       max_images=self.max_images, precision={"fp32": 0, "bf16x3": 1}[precision])
+        self._h = C.c_void_p()
+        check(lib().tb_vi_create(C.byref(cfg), C.byref(self._h)))
+        self.batch_size = batch_size_for(num_classes)
+
+    def load_weights(self, state_dict):
+        for k in STATE_KEYS:
+            if k not in state_dict:
+                raise KeyError(f"state_dict lacks {k}")
+            v = state_dict[k]
+            a = np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, np.float32)
+            check(lib().tb_vi_set_tensor(self._h, k.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+        check(lib().tb_vi_commit(self._h))
+
+    def probabilities(self, images, return_logits=False):
+        """images: (N,H,W,C) or (N,H,W) uint8 (Image::Ptr list in the reference). Returns softmax rows."""
+        x = np.ascontiguousarray(images, np.uint8)
+        n = x.shape[0]
+        if n == 0:
+            z = np.zeros((0, self.num_classes), np.float32)
+            return (z, z.copy()) if return_logits else z
+        assert x.size == n * self.height * self.width * self.channels, x.shape
+        probs = np.empty((n, self.num_classes), np.float32)
+        logits = np.empty((n, self.num_classes), np.float32) if return_logits else None
+        check(lib().tb_vi_predict(self._h, x.ctypes.data_as(C.c_void_p), n, probs.ctypes.data_as(C.c_void_p),
+                                  logits.ctypes.data_as(C.c_void_p) if return_logits else None))
+        return (probs, logits) if return_logits else probs
+
+    def predict_device(self, images_ptr: int, n_max: int, n_dev_ptr: int, probs_ptr: int, logits_ptr: int = 0, stream: int = 0):
+        check(lib().tb_vi_predict_device(self._h, C.c_void_p(images_ptr), n_max, C.c_void_p(n_dev_ptr) if n_dev_ptr else None,
+                                         C.c_void_p(probs_ptr), C.c_void_p(logits_ptr) if logits_ptr else None,
+                                         C.c_void_p(stream)))
+
+    def wait(self):
+        check(lib().tb_vi_wait(self._h))
+
+    def launch_count(self) -> int:
+        return int(lib().tb_vi_launch_count(self._h))
+
+    def deinit(self):
+        if self._h:
+            lib().tb_vi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = deinit
