@@ -121,8 +121,8 @@ TB_API int tb_seg_set_background(tb_seg *h, const uint8_t *bg, int width, int he
 /* BackgroundSubtraction::apply(std::vector<TileImage>&&) (T/python/BackgroundSubtraction.cpp:126-347):
  * n host frames (width*height bytes each, `stride` bytes between rows) are copied to the device,
  * segmented, labelled and (optionally) cropped; results are copied back asynchronously.
- * tb_seg_wait blocks until they are on the host.  With fetch=0 results stay on the device
- * (only per-frame headers are fetched). */
+ * tb_seg_wait blocks until they are on the host.  fetch: 0 = results stay on the device (only
+ * per-frame headers and totals are fetched), 1 = blob records + lines + pixels, 2 = also the crops. */
 TB_API int tb_seg_submit(tb_seg *h, const uint8_t *const *frames, int n, int64_t stride, int fetch);
 
 /* Same for n packed frames already resident in device memory (n*width*height bytes).
@@ -144,7 +144,7 @@ TB_API int tb_seg_totals(tb_seg *h, uint32_t out[4]);
 TB_API int tb_seg_device_results(tb_seg *h, void **crops, void **n_crops_dev, void **crop_blob_index,
                           void **recs, void **infos);
 
-/* Host copy of the crops of the last batch (after tb_seg_wait with fetch=1 and crops enabled). */
+/* Host copy of the crops of the last batch (after tb_seg_wait with fetch=2 and crops enabled). */
 TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_blob_index, uint32_t *n);
 
 /* Debug / parity: generate_binary's output image (mask & input) of one device- or host-resident
@@ -153,6 +153,13 @@ TB_API int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t *ou
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 TB_API uint64_t tb_seg_launch_count(tb_seg *h);
+
+/* Measurement hooks (no reference counterpart; BackgroundSubtraction::fps() only averages wall time,
+ * T/python/BackgroundSubtraction.cpp:21-35).  With profiling enabled every kernel launch is bracketed
+ * by CUDA events on the launching stream; tb_seg_kernel_ms synchronises, then returns the summed
+ * durations (ms) of {seg_rle, ccl_label, blob_emit} and the number of batches they cover, and resets. */
+TB_API int tb_seg_profile(tb_seg *h, int enable);
+TB_API int tb_seg_kernel_ms(tb_seg *h, double out_ms[3], uint64_t *n_batches);
 
 /* ----------------------------------------------------------------------------------------------
  * Visual identification: Python::VINetwork (T/ml/VisualIdentification.h:104-133) +
@@ -188,6 +195,9 @@ TB_API int tb_vi_predict_device(tb_vi *h, const void *images_dev, int n_max, con
                          void *probs_dev, void *logits_dev, void *stream);
 TB_API int tb_vi_wait(tb_vi *h);
 TB_API uint64_t tb_vi_launch_count(tb_vi *h);
+/* As tb_seg_profile / tb_seg_kernel_ms for {conv1, conv2, conv3, fc1, head}; n = chunks covered. */
+TB_API int tb_vi_profile(tb_vi *h, int enable);
+TB_API int tb_vi_kernel_ms(tb_vi *h, double out_ms[5], uint64_t *n_chunks);
 
 #ifdef __cplusplus
 }

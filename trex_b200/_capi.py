@@ -60,6 +60,7 @@ SYMBOLS = [
     "tb_seg_wait", "tb_seg_result", "tb_seg_totals", "tb_seg_device_results", "tb_seg_crops",
     "tb_seg_debug_binary", "tb_seg_launch_count", "tb_vi_create", "tb_vi_destroy", "tb_vi_set_tensor",
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
+    "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms",
 ]
 
 _lib = None
@@ -97,6 +98,10 @@ def lib() -> C.CDLL:
     L.tb_vi_predict_device.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     L.tb_vi_wait.argtypes = [vp]
     L.tb_vi_launch_count.argtypes = [vp]; L.tb_vi_launch_count.restype = C.c_uint64
+    L.tb_seg_profile.argtypes = [vp, C.c_int]
+    L.tb_seg_kernel_ms.argtypes = [vp, C.POINTER(C.c_double * 3), C.POINTER(C.c_uint64)]
+    L.tb_vi_profile.argtypes = [vp, C.c_int]
+    L.tb_vi_kernel_ms.argtypes = [vp, C.POINTER(C.c_double * 5), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 

@@ -117,8 +117,12 @@ class BackgroundSubtraction:
         p = settings.c_params()
         check(lib().tb_seg_set_params(self._h, C.byref(p)))
 
-    def apply(self, frames, fetch=True):
-        """frames: sequence of HxW uint8 arrays (or one (n,H,W) array).  Returns one list of Blob per frame."""
+    def apply(self, frames, fetch=True, fetch_crops=None, materialize=True):
+        """frames: sequence of HxW uint8 arrays (or one (n,H,W) array).  Returns one list of Blob per frame
+        (materialize=False: results stay in the pinned result buffers, see raw_result / totals)."""
+        if fetch_crops is None:
+            fetch_crops = self.max_individuals > 0
+        level = 0 if not fetch else (2 if fetch_crops else 1)
         t0 = time.perf_counter()
         frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
         out = []
@@ -128,9 +132,9 @@ class BackgroundSubtraction:
             for f in chunk:
                 if f.shape != (self.height, self.width):
                     raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, f"frame shape {f.shape} != {(self.height, self.width)}")
-            check(lib().tb_seg_submit(self._h, ptrs, len(chunk), self.width, int(fetch)))
+            check(lib().tb_seg_submit(self._h, ptrs, len(chunk), self.width, level))
             check(lib().tb_seg_wait(self._h))
-            if fetch:
+            if fetch and materialize:
                 out.extend(self.result(j) for j in range(len(chunk)))
         dt = time.perf_counter() - t0
         if frames:
@@ -208,3 +212,12 @@ class BackgroundSubtraction:
 
     def launch_count(self) -> int:
         return int(lib().tb_seg_launch_count(self._h))
+
+    def profile(self, enable=True):
+        check(lib().tb_seg_profile(self._h, int(enable)))
+
+    def kernel_ms(self):
+        """({kernel: summed ms}, n_batches) since the last call (synchronises)."""
+        ms, n = (C.c_double * 3)(), C.c_uint64()
+        check(lib().tb_seg_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return dict(zip(("seg_rle", "ccl_label", "blob_emit"), ms)), int(n.value)

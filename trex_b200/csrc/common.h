@@ -41,6 +41,57 @@ static inline int host_alloc(T **p, size_t n)
     return TB_OK;
 }
 
+// Ring of CUDA-event brackets around the NK kernels of one launch sequence (measurement hook).
+template <int NK>
+struct EventRing {
+    static constexpr int SLOTS = 32;
+    cudaEvent_t ev[SLOTS][NK + 1] = {};
+    cudaStream_t stream[SLOTS] = {};
+    int used = 0;
+    bool enabled = false, created = false;
+    double acc[NK] = {};
+    uint64_t n = 0;
+    int enable(bool on)
+    {
+        if (on && !created) {
+            for (auto &row : ev)
+                for (auto &e : row)
+                    if (cudaEventCreate(&e) != cudaSuccess) return TB_ERR_CUDA;
+            created = true;
+        }
+        enabled = on;
+        return TB_OK;
+    }
+    int flush()
+    {
+        for (int s = 0; s < used; ++s) {
+            if (cudaEventSynchronize(ev[s][NK]) != cudaSuccess) return TB_ERR_CUDA;
+            for (int k = 0; k < NK; ++k) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, ev[s][k], ev[s][k + 1]) != cudaSuccess) return TB_ERR_CUDA;
+                acc[k] += ms;
+            }
+            ++n;
+        }
+        used = 0;
+        return TB_OK;
+    }
+    // returns the slot to record into, or -1 when profiling is off
+    int begin(cudaStream_t st)
+    {
+        if (!enabled) return -1;
+        if (used == SLOTS) flush();
+        stream[used] = st;
+        return used++;
+    }
+    void mark(int slot, int k) { if (slot >= 0) cudaEventRecord(ev[slot][k], stream[slot]); }
+    void destroy()
+    {
+        if (created) for (auto &row : ev) for (auto &e : row) cudaEventDestroy(e);
+        created = false;
+    }
+};
+
 #ifdef __CUDACC__
 // Exclusive scan of one value per thread across the CTA; `total` = sum over all threads.
 // ws: shared array of >= 33 uint32. All threads must call.

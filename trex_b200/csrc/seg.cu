@@ -514,9 +514,10 @@ struct tb_seg {
     tb_frame_info *h_infos = nullptr; uint32_t *h_totals = nullptr;
     tb_blob_rec *h_recs = nullptr; tb_line *h_lines = nullptr; uint8_t *h_pixels = nullptr;
     uint8_t *h_crops = nullptr; uint32_t *h_crop_blob = nullptr;
-    int last_n = 0; bool last_fetch = false, pending = false, fetched_payload = false;
+    int last_n = 0, last_fetch = 0; bool pending = false, fetched_payload = false, fetched_crops = false;
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;
+    EventRing<3> prof;
 };
 
 static int seg_make_k(const tb_seg_params &p, SegK &k, std::string &why)
@@ -630,6 +631,7 @@ extern "C" void tb_seg_destroy(tb_seg *h)
     for (void *p : h->dev_allocs) cudaFree(p);
     void *hp[] = {h->h_infos, h->h_totals, h->h_recs, h->h_lines, h->h_pixels, h->h_crops, h->h_crop_blob};
     for (void *p : hp) if (p) cudaFreeHost(p);
+    h->prof.destroy();
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -666,14 +668,19 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     TB_CUDA(cudaMemsetAsync(d.run_count, 0, sizeof(uint32_t) * (size_t)n, s));
     const int fpc = n >= 64 ? 4 : 1;
     dim3 g1((unsigned)d.n_bands, (unsigned)((n + fpc - 1) / fpc));
+    const int slot = h->prof.begin(s);
+    h->prof.mark(slot, 0);
     seg_rle_kernel<<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
+    h->prof.mark(slot, 1);
     ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
+    h->prof.mark(slot, 2);
     blob_emit_kernel<<<n, K3_NT, 0, s>>>(frames_dev, d);
+    h->prof.mark(slot, 3);
     h->launches += 3;
     TB_CUDA(cudaGetLastError());
     TB_CUDA(cudaMemcpyAsync(h->h_totals, d.totals, 16, cudaMemcpyDeviceToHost, s));
     TB_CUDA(cudaMemcpyAsync(h->h_infos, d.infos, sizeof(tb_frame_info) * (size_t)n, cudaMemcpyDeviceToHost, s));
-    h->last_n = n; h->last_fetch = fetch != 0; h->pending = true; h->fetched_payload = false; h->last_stream = s;
+    h->last_n = n; h->last_fetch = fetch; h->pending = true; h->fetched_payload = false; h->fetched_crops = false; h->last_stream = s;
     return TB_OK;
 }
 
@@ -716,12 +723,13 @@ extern "C" int tb_seg_wait(tb_seg *h)
         if (t[0]) TB_CUDA(cudaMemcpyAsync(h->h_recs, d.recs, sizeof(tb_blob_rec) * (size_t)t[0], cudaMemcpyDeviceToHost, s));
         if (t[1]) TB_CUDA(cudaMemcpyAsync(h->h_lines, d.lines, sizeof(tb_line) * (size_t)t[1], cudaMemcpyDeviceToHost, s));
         if (t[2]) TB_CUDA(cudaMemcpyAsync(h->h_pixels, d.pixels, (size_t)t[2], cudaMemcpyDeviceToHost, s));
-        if (t[3]) {
+        if (t[3] && h->last_fetch >= 2) {
             TB_CUDA(cudaMemcpyAsync(h->h_crops, d.crops, (size_t)t[3] * d.crop_w * d.crop_h, cudaMemcpyDeviceToHost, s));
             TB_CUDA(cudaMemcpyAsync(h->h_crop_blob, d.crop_blob, sizeof(uint32_t) * (size_t)t[3], cudaMemcpyDeviceToHost, s));
         }
         TB_CUDA(cudaStreamSynchronize(s));
         h->fetched_payload = true;
+        h->fetched_crops = h->last_fetch >= 2;
     }
     h->pending = false;
     for (int i = 0; i < h->last_n; ++i)
@@ -768,7 +776,7 @@ extern "C" int tb_seg_device_results(tb_seg *h, void **crops, void **n_crops_dev
 extern "C" int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_blob_index, uint32_t *n)
 {
     TB_REQUIRE(h && n, TB_ERR_INVALID, "tb_seg_crops: null argument");
-    TB_REQUIRE(!h->pending && h->fetched_payload, TB_ERR_STATE, "tb_seg_crops: call tb_seg_wait after a fetch=1 submit first");
+    TB_REQUIRE(!h->pending && h->fetched_crops, TB_ERR_STATE, "tb_seg_crops: call tb_seg_wait after a fetch=2 submit first");
     if (crops) *crops = h->h_crops;
     if (crop_blob_index) *crop_blob_index = h->h_crop_blob;
     *n = h->h_totals[3];
@@ -791,3 +799,21 @@ extern "C" int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t
 }
 
 extern "C" uint64_t tb_seg_launch_count(tb_seg *h) { return h ? h->launches : 0; }
+
+extern "C" int tb_seg_profile(tb_seg *h, int enable)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_profile: null handle");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->prof.enable(enable != 0) != TB_OK) { set_error("tb_seg_profile: cudaEventCreate failed"); return TB_ERR_CUDA; }
+    return TB_OK;
+}
+
+extern "C" int tb_seg_kernel_ms(tb_seg *h, double out_ms[3], uint64_t *n_batches)
+{
+    TB_REQUIRE(h && out_ms && n_batches, TB_ERR_INVALID, "tb_seg_kernel_ms: null argument");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->prof.flush() != TB_OK) { set_error("tb_seg_kernel_ms: event query failed"); return TB_ERR_CUDA; }
+    for (int k = 0; k < 3; ++k) { out_ms[k] = h->prof.acc[k]; h->prof.acc[k] = 0; }
+    *n_batches = h->prof.n; h->prof.n = 0;
+    return TB_OK;
+}

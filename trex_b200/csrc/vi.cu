@@ -311,6 +311,7 @@ struct tb_vi {
     uint8_t *d_img = nullptr; float *d_probs = nullptr, *d_logits = nullptr;
     uint64_t launches = 0;
     cudaStream_t last_stream = nullptr;
+    EventRing<5> prof;
 };
 
 template <typename T>
@@ -359,6 +360,7 @@ extern "C" void tb_vi_destroy(tb_vi *h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *p : h->dev_allocs) cudaFree(p);
+    h->prof.destroy();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -463,12 +465,19 @@ static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n
     for (int base = 0; base < n_max; base += h->chunk) {
         const int n = std::min(h->chunk, n_max - base);
         const int c1_smem = (84 * 84 + 400 + 32) * 4;
+        const int slot = h->prof.begin(s);
+        h->prof.mark(slot, 0);
         conv1_kernel<<<n, C1_NT, c1_smem, s>>>(img + (size_t)base * 6400, 80, 80, n, n_dev, base, h->w1, h->s1, h->t1, h->a1);
+        h->prof.mark(slot, 1);
         k2<<<dim3(n * 7, 1), CV_NT, SM2, s>>>(h->a1, n, n_dev, base, h->w2, h->s2, h->t2, h->a2);
+        h->prof.mark(slot, 2);
         k3<<<dim3(n * 2, 2), CV_NT, SM3, s>>>(h->a2, n, n_dev, base, h->w3, h->s3, h->t3, h->a3);
+        h->prof.mark(slot, 3);
         fc1_kernel<<<(n + FC_IMG - 1) / FC_IMG, FC_NT, 0, s>>>(h->a3, 12800, n, n_dev, base, h->wf1, h->bf1, h->h1);
+        h->prof.mark(slot, 4);
         head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, HD_WARPS * (100 + M) * 4, s>>>(
             h->h1, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2, probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr);
+        h->prof.mark(slot, 5);
         h->launches += 5;
     }
     TB_CUDA(cudaGetLastError());
@@ -514,3 +523,21 @@ extern "C" int tb_vi_wait(tb_vi *h)
 }
 
 extern "C" uint64_t tb_vi_launch_count(tb_vi *h) { return h ? h->launches : 0; }
+
+extern "C" int tb_vi_profile(tb_vi *h, int enable)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_vi_profile: null handle");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->prof.enable(enable != 0) != TB_OK) { set_error("tb_vi_profile: cudaEventCreate failed"); return TB_ERR_CUDA; }
+    return TB_OK;
+}
+
+extern "C" int tb_vi_kernel_ms(tb_vi *h, double out_ms[5], uint64_t *n_chunks)
+{
+    TB_REQUIRE(h && out_ms && n_chunks, TB_ERR_INVALID, "tb_vi_kernel_ms: null argument");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->prof.flush() != TB_OK) { set_error("tb_vi_kernel_ms: event query failed"); return TB_ERR_CUDA; }
+    for (int k = 0; k < 5; ++k) { out_ms[k] = h->prof.acc[k]; h->prof.acc[k] = 0; }
+    *n_chunks = h->prof.n; h->prof.n = 0;
+    return TB_OK;
+}

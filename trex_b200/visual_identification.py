@@ -77,6 +77,14 @@ class VINetwork:
     def launch_count(self) -> int:
         return int(lib().tb_vi_launch_count(self._h))
 
+    def profile(self, enable=True):
+        check(lib().tb_vi_profile(self._h, int(enable)))
+
+    def kernel_ms(self):
+        ms, n = (C.c_double * 5)(), C.c_uint64()
+        check(lib().tb_vi_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return dict(zip(("conv1", "conv2", "conv3", "fc1", "head"), ms)), int(n.value)
+
     def deinit(self):
         if self._h:
             lib().tb_vi_destroy(self._h)
