@@ -185,7 +185,9 @@ def run_ours(args):
         return torch.as_tensor(_CudaBuf(ptr, nbytes), device=dev)
 
     meta_local = as_tensor(recs_p, meta_bytes)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream carries seg, CNN, copies and the collective; its handle goes to the C ABI
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
 
     def step_device(i):
         fr = dev_batches[i % pool]

@@ -60,14 +60,20 @@ struct SegDev {
 
 // ------------------------------------------------------------------------------------------------
 // K1: fused difference / threshold / mask / run-length extraction.  HBM-bound: every frame byte is
-// read exactly once with 16-byte loads; the background tile is loaded once per CTA and reused for
-// `fpc` frames.  A CTA owns a band of whole rows (<= 1024 16-pixel chunks); run starts and ends are
-// ranked with warp scans and written straight into the frame's run array (one atomicAdd per band).
+// read exactly once with coalesced 16-byte loads; the background tile is loaded once per CTA and
+// reused for `fpc` frames.  A CTA owns a band of whole rows (<= 1024 16-pixel chunks).  Each thread
+// turns 4 chunks into 16-bit foreground masks (striped, for coalescing), the masks are transposed
+// through shared memory so that every thread then owns 64 consecutive pixels as one 64-bit word, in
+// which run starts / ends are single-bit events.  They are ranked with one warp scan + one block scan
+// and written straight into the frame's run array (one atomicAdd per band and frame).
 // ------------------------------------------------------------------------------------------------
 constexpr int K1_NT = 256, K1_KPT = 4, K1_CHUNKS = K1_NT * K1_KPT;
 
+template <bool GENERIC>
 __device__ __forceinline__ uint32_t fg4(uint32_t f, uint32_t b, const SegK &p)
 {
+    if (!GENERIC)                                                   // default settings: |f-b| > T, grey != 0
+        return __vcmpgtu4(__vabsdiffu4(f, b), p.t4) & __vcmpne4(f, 0u);
     uint32_t in = (p.flags & F_INV) ? ~f : f;                       // 255 - x
     uint32_t d = in;
     if (p.flags & F_DIFF) d = (p.flags & F_ABS) ? __vabsdiffu4(in, b) : __vsubus4(b, in);
@@ -79,10 +85,11 @@ __device__ __forceinline__ uint32_t pack4(uint32_t m)               // 4 byte ma
 {
     return ((m & 0x08040201u) * 0x01010101u) >> 24;
 }
+template <bool GENERIC>
 __device__ __forceinline__ uint32_t fg16(const uint4 &f, const uint4 &b, const SegK &p)
 {
-    return pack4(fg4(f.x, b.x, p)) | (pack4(fg4(f.y, b.y, p)) << 4) | (pack4(fg4(f.z, b.z, p)) << 8) |
-           (pack4(fg4(f.w, b.w, p)) << 12);
+    return pack4(fg4<GENERIC>(f.x, b.x, p)) | (pack4(fg4<GENERIC>(f.y, b.y, p)) << 4) |
+           (pack4(fg4<GENERIC>(f.z, b.z, p)) << 8) | (pack4(fg4<GENERIC>(f.w, b.w, p)) << 12);
 }
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 {
@@ -100,10 +107,11 @@ __device__ __forceinline__ uint4 ld_edge(const uint8_t *row, int col, int W)
     return make_uint4(v[0], v[1], v[2], v[3]);
 }
 
-__global__ void __launch_bounds__(K1_NT)
+template <bool GENERIC>
+__global__ void __launch_bounds__(K1_NT, 4)
 seg_rle_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
 {
-    __shared__ uint16_t s_mask[K1_CHUNKS];
+    __shared__ __align__(16) uint16_t s_mask[K1_CHUNKS + 8];
     __shared__ uint32_t s_wtot[K1_NT / 32];
     __shared__ uint32_t s_base;
 
@@ -114,59 +122,54 @@ seg_rle_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
     const int tile_chunks = tile_rows * d.cpr;
     const size_t frame_bytes = (size_t)d.W * d.H;
 
-    int c[K1_KPT]; uint16_t crow[K1_KPT], ccol[K1_KPT]; uint4 bgc[K1_KPT];
+    // load role: chunks warp*128 + k*32 + lane
+    uint4 bgc[K1_KPT];
 #pragma unroll
     for (int k = 0; k < K1_KPT; ++k) {
-        c[k] = warp * (32 * K1_KPT) + k * 32 + lane;
-        const bool valid = c[k] < tile_chunks;
-        crow[k] = valid ? (uint16_t)(c[k] / d.cpr) : 0;
-        ccol[k] = valid ? (uint16_t)(c[k] % d.cpr) : 0;
+        const int c = warp * (32 * K1_KPT) + k * 32 + lane;
         bgc[k] = make_uint4(0, 0, 0, 0);
-        if (valid) {
-            if (d.aligned) bgc[k] = *reinterpret_cast<const uint4 *>(d.bg + (size_t)row0 * d.W + (size_t)c[k] * 16);
-            else bgc[k] = ld_edge(d.bg + (size_t)(row0 + crow[k]) * d.W, ccol[k], d.W);
+        if (c < tile_chunks) {
+            if (d.aligned) bgc[k] = *reinterpret_cast<const uint4 *>(d.bg + (size_t)row0 * d.W + (size_t)c * 16);
+            else bgc[k] = ld_edge(d.bg + (size_t)(row0 + c / d.cpr) * d.W, c % d.cpr, d.W);
         }
     }
-    auto load_frame = [&](int f, uint4 *dst) {
-        const uint8_t *fb = frames + (size_t)f * frame_bytes;
+    // run role: chunks 4*tid .. 4*tid+3 = 64 consecutive pixels; row boundaries inside the word
+    const int g0 = 4 * tid;
+    const int gr0 = g0 / d.cpr, gc0 = g0 % d.cpr;
+    uint64_t RS = 0, RE = 0;
 #pragma unroll
-        for (int k = 0; k < K1_KPT; ++k) {
-            dst[k] = make_uint4(0, 0, 0, 0);
-            if (c[k] < tile_chunks) {
-                if (d.aligned) dst[k] = ld_stream(reinterpret_cast<const uint4 *>(fb + (size_t)row0 * d.W) + c[k]);
-                else dst[k] = ld_edge(fb + (size_t)(row0 + crow[k]) * d.W, ccol[k], d.W);
-            }
-        }
-    };
+    for (int i = 0; i < 4; ++i) {
+        const int col = (g0 + i) % d.cpr;
+        if (col == 0) RS |= 1ull << (16 * i);
+        if (col == d.cpr - 1) RE |= 1ull << (16 * i + 15);
+    }
+    if (tid == 0) for (int i = 0; i < 8; ++i) s_mask[K1_CHUNKS + i] = 0;
 
     const int f0 = blockIdx.y * fpc, f1 = min(d.B, f0 + fpc);
-    uint4 cur[K1_KPT], nxt[K1_KPT];
-    if (f0 < f1) load_frame(f0, cur);
     for (int f = f0; f < f1; ++f) {
-        if (f + 1 < f1) load_frame(f + 1, nxt);          // keep the next frame's loads in flight
-
-        uint32_t m[K1_KPT];
+        const uint8_t *fb = frames + (size_t)f * frame_bytes;
+        uint4 cur[K1_KPT];
 #pragma unroll
         for (int k = 0; k < K1_KPT; ++k) {
-            m[k] = (c[k] < tile_chunks) ? fg16(cur[k], bgc[k], p) : 0u;
-            s_mask[c[k]] = (uint16_t)m[k];
+            const int c = warp * (32 * K1_KPT) + k * 32 + lane;
+            cur[k] = make_uint4(0, 0, 0, 0);
+            if (c < tile_chunks) {
+                if (d.aligned) cur[k] = ld_stream(reinterpret_cast<const uint4 *>(fb + (size_t)row0 * d.W) + c);
+                else cur[k] = ld_edge(fb + (size_t)(row0 + c / d.cpr) * d.W, c % d.cpr, d.W);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) {
+            const int c = warp * (32 * K1_KPT) + k * 32 + lane;
+            s_mask[c] = (c < tile_chunks) ? (uint16_t)fg16<GENERIC>(cur[k], bgc[k], p) : (uint16_t)0;
         }
         __syncthreads();
-
-        uint32_t st[K1_KPT], en[K1_KPT], off[K1_KPT], run = 0;
-#pragma unroll
-        for (int k = 0; k < K1_KPT; ++k) {
-            st[k] = en[k] = 0;
-            if (c[k] < tile_chunks) {
-                uint32_t prev = (ccol[k] > 0) ? (uint32_t)(s_mask[c[k] - 1] >> 15) : 0u;
-                uint32_t next = (ccol[k] + 1 < d.cpr) ? (uint32_t)(s_mask[c[k] + 1] & 1u) : 0u;
-                st[k] = m[k] & ~((m[k] << 1) | prev) & 0xFFFFu;
-                en[k] = m[k] & ~((m[k] >> 1) | (next << 15)) & 0xFFFFu;
-            }
-            uint32_t tot, ex = warp_excl_scan((uint32_t)__popc(st[k]) | ((uint32_t)__popc(en[k]) << 16), tot);
-            off[k] = run + ex;
-            run += tot;
-        }
+        const uint64_t M = *reinterpret_cast<const uint64_t *>(s_mask + g0);
+        const uint64_t prev = g0 > 0 ? (uint64_t)(s_mask[g0 - 1] >> 15) : 0ull;
+        const uint64_t next = (uint64_t)(s_mask[g0 + 4] & 1u);
+        uint64_t st = M & ~(((M << 1) | prev) & ~RS);
+        uint64_t en = M & ~(((M >> 1) | (next << 63)) & ~RE);
+        uint32_t run, ex = warp_excl_scan((uint32_t)__popcll(st) | ((uint32_t)__popcll(en) << 16), run);
         if (lane == 0) s_wtot[warp] = run;
         __syncthreads();
         uint32_t wbase = 0, total = 0;
@@ -184,29 +187,27 @@ seg_rle_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
             d.band_cnt[(size_t)f * d.n_bands + band] = ns;
         }
         __syncthreads();
-        const uint32_t base = s_base;
-        uint16_t *out = reinterpret_cast<uint16_t *>(d.runs_raw + (size_t)f * d.rcap);
-#pragma unroll
-        for (int k = 0; k < K1_KPT; ++k) {
-            uint32_t os = base + ((wbase + off[k]) & 0xFFFFu), oe = base + ((wbase + off[k]) >> 16);
-            const uint32_t x = (uint32_t)ccol[k] * 16u, y = (uint32_t)(row0 + crow[k]);
-            uint32_t s = st[k], e = en[k];
-            while (s) {
-                int j = __ffs(s) - 1; s &= s - 1;
+        if (st | en) {
+            uint16_t *out = reinterpret_cast<uint16_t *>(d.runs_raw + (size_t)f * d.rcap);
+            uint32_t os = s_base + ((wbase + ex) & 0xFFFFu), oe = s_base + ((wbase + ex) >> 16);
+            while (st) {
+                const int b = __ffsll((long long)st) - 1; st &= st - 1;
+                int col = gc0 + (b >> 4), row = gr0;
+                while (col >= d.cpr) { col -= d.cpr; ++row; }
                 if (os < d.rcap) {
-                    out[(size_t)os * 4 + 0] = (uint16_t)(x + j);
-                    *reinterpret_cast<uint32_t *>(out + (size_t)os * 4 + 2) = y;   // y, pad = 0
+                    out[(size_t)os * 4 + 0] = (uint16_t)(col * 16 + (b & 15));
+                    *reinterpret_cast<uint32_t *>(out + (size_t)os * 4 + 2) = (uint32_t)(row0 + row);   // y, pad = 0
                 }
                 ++os;
             }
-            while (e) {
-                int j = __ffs(e) - 1; e &= e - 1;
-                if (oe < d.rcap) out[(size_t)oe * 4 + 1] = (uint16_t)(x + j);
+            while (en) {
+                const int b = __ffsll((long long)en) - 1; en &= en - 1;
+                int col = gc0 + (b >> 4);
+                while (col >= d.cpr) col -= d.cpr;
+                if (oe < d.rcap) out[(size_t)oe * 4 + 1] = (uint16_t)(col * 16 + (b & 15));
                 ++oe;
             }
         }
-#pragma unroll
-        for (int k = 0; k < K1_KPT; ++k) cur[k] = nxt[k];
     }
 }
 
@@ -216,7 +217,7 @@ __global__ void binary_image_kernel(const uint8_t *__restrict__ frame, const uin
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t f = frame[i];
-        uint32_t m = fg4(f, bg[i], p) & 0xFFu;
+        uint32_t m = fg4<true>(f, bg[i], p) & 0xFFu;
         out[i] = m ? (uint8_t)f : (uint8_t)0;
     }
 }
@@ -470,22 +471,30 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
             if (do_crop) d.crop_blob[Cb + q] = Bb + q;
         }
         __syncwarp();                                      // lines / line_px / zero fill visible to the warp
-        // phase B: pixel bytes + crop
-        for (uint32_t l = 0; l < cl; ++l) {
-            const tb_line ln = d.lines[L0 + l];
-            const uint32_t po = d.line_px[L0 + l];
-            for (uint32_t x = ln.x0 + lane; x <= ln.x1; x += 32) {
-                const uint8_t v = frame[(size_t)ln.y * d.W + x];
-                d.pixels[po + (x - ln.x0)] = v;
-                if (do_crop) {
-                    const int cx = (int)(x - bx0) + offx, cy = (int)(ln.y - by0) + offy;
-                    if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
-                        int val = v;
-                        if (d.crop_method) {
-                            const int b = d.bg[(size_t)ln.y * d.W + x];
-                            val = d.crop_method == 1 ? abs(b - val) : max(0, b - val);
+        // phase B: pixel bytes + crop.  32 lines are fetched at once (one per lane) and broadcast.
+        for (uint32_t lb = 0; lb < cl; lb += 32) {
+            tb_line mine = {0, 0, 0, 0}; uint32_t mypo = 0;
+            if (lb + lane < cl) { mine = d.lines[L0 + lb + lane]; mypo = d.line_px[L0 + lb + lane]; }
+            const uint32_t packed = (uint32_t)mine.x0 | ((uint32_t)mine.x1 << 16);
+            const uint32_t cnt = min(32u, cl - lb);
+            for (uint32_t l = 0; l < cnt; ++l) {
+                const uint32_t xx = __shfl_sync(0xffffffffu, packed, l);
+                const uint32_t ly = __shfl_sync(0xffffffffu, (uint32_t)mine.y, l);
+                const uint32_t po = __shfl_sync(0xffffffffu, mypo, l);
+                const uint32_t lx0 = xx & 0xFFFFu, lx1 = xx >> 16;
+                for (uint32_t x = lx0 + lane; x <= lx1; x += 32) {
+                    const uint8_t v = frame[(size_t)ly * d.W + x];
+                    d.pixels[po + (x - lx0)] = v;
+                    if (do_crop) {
+                        const int cx = (int)(x - bx0) + offx, cy = (int)(ly - by0) + offy;
+                        if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
+                            int val = v;
+                            if (d.crop_method) {
+                                const int b = d.bg[(size_t)ly * d.W + x];
+                                val = d.crop_method == 1 ? abs(b - val) : max(0, b - val);
+                            }
+                            crop[cy * cw + cx] = (uint8_t)val;
                         }
-                        crop[cy * cw + cx] = (uint8_t)val;
                     }
                 }
             }
@@ -670,7 +679,8 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     dim3 g1((unsigned)d.n_bands, (unsigned)((n + fpc - 1) / fpc));
     const int slot = h->prof.begin(s);
     h->prof.mark(slot, 0);
-    seg_rle_kernel<<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
+    if (h->k.flags == (F_DIFF | F_ABS)) seg_rle_kernel<false><<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
+    else seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
     h->prof.mark(slot, 1);
     ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
     h->prof.mark(slot, 2);
