@@ -1,0 +1,136 @@
+// trexb200.hpp -- header-only C++ host layer above the C ABI (include/trexb200.h), mirroring the
+// reference's C++ interfaces for this path so TRex code can call it with its own vocabulary:
+//   trexb200::HorizontalLine        == cmn::HorizontalLine        (C/misc/detail.h:71-131)
+//   trexb200::Pair                  ~  cmn::blob::Pair             (C/misc/types.h:591-604)
+//   trexb200::BackgroundSubtraction ~  track::BackgroundSubtraction (T/python/BackgroundSubtraction.h:10-27)
+//   trexb200::labeling_run          ~  cmn::CPULabeling::run       (C/processing/CPULabeling.h:16)
+//   trexb200::VINetwork             ~  Python::VINetwork           (T/ml/VisualIdentification.h:104-133)
+// Errors surface as std::runtime_error carrying tb_last_error(), which is what the reference's
+// callers already handle (promise->set_exception, BackgroundSubtraction.cpp:322-326; SoftException).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "trexb200.h"
+
+namespace trexb200 {
+
+using HorizontalLine = tb_line;                        // {u16 x0, x1, y, padding}
+static_assert(sizeof(HorizontalLine) == 8, "layout of cmn::HorizontalLine");
+
+struct Pair {                                          // blob::Pair: lines + pixels + flags
+    std::unique_ptr<std::vector<HorizontalLine>> lines;
+    std::unique_ptr<std::vector<uint8_t>> pixels;
+    uint8_t extra_flags = 0;
+    uint32_t bid = 0;                                  // pv::bid::from_data of the first line
+};
+using blobs_t = std::vector<Pair>;
+
+inline void check(int rc, const char *what)
+{
+    if (rc != TB_OK) throw std::runtime_error(std::string(what) + ": " + tb_last_error());
+}
+
+class BackgroundSubtraction {
+public:
+    BackgroundSubtraction(int width, int height, int max_batch = 1, int max_individuals = 0, int device = 0)
+    {
+        tb_seg_config cfg{};
+        cfg.device = device; cfg.width = width; cfg.height = height; cfg.max_batch = max_batch;
+        cfg.max_crops_per_frame = max_individuals; cfg.crop_width = 80; cfg.crop_height = 80; cfg.crop_method = 1;
+        check(tb_seg_create(&cfg, &_h), "tb_seg_create");
+        tb_seg_default_params(&_p);
+        _w = width; _hgt = height;
+    }
+    ~BackgroundSubtraction() { tb_seg_destroy(_h); }
+    BackgroundSubtraction(const BackgroundSubtraction &) = delete;
+    BackgroundSubtraction &operator=(const BackgroundSubtraction &) = delete;
+
+    tb_seg_params &settings() { return _p; }           // detect_threshold, detect_size_filter, cm_per_pixel ...
+    void update_settings() { check(tb_seg_set_params(_h, &_p), "tb_seg_set_params"); }
+
+    // set_background(Image::Ptr&&): un-pauses the pipeline (BackgroundSubtraction.cpp:86-90)
+    void set_background(const uint8_t *average, int64_t stride = 0)
+    {
+        check(tb_seg_set_background(_h, average, _w, _hgt, stride), "tb_seg_set_background");
+    }
+
+    // apply(std::vector<TileImage>&&): one blobs_t per image (BackgroundSubtraction.cpp:126-347)
+    std::vector<blobs_t> apply(const std::vector<const uint8_t *> &images, int64_t stride = 0)
+    {
+        check(tb_seg_submit(_h, images.data(), (int)images.size(), stride, 1), "tb_seg_submit");
+        check(tb_seg_wait(_h), "tb_seg_wait");
+        std::vector<blobs_t> out(images.size());
+        for (size_t i = 0; i < images.size(); ++i) {
+            tb_blob_view v;
+            check(tb_seg_result(_h, (int)i, &v), "tb_seg_result");
+            out[i].reserve(v.info.n_blobs);
+            for (uint32_t k = 0; k < v.info.n_blobs; ++k) {
+                const tb_blob_rec &r = v.recs[k];
+                Pair p;
+                const tb_line *l = v.lines + (r.line_off - v.info.line_begin);
+                const uint8_t *px = v.pixels + (r.px_off - v.info.px_begin);
+                p.lines = std::make_unique<std::vector<HorizontalLine>>(l, l + r.n_lines);
+                p.pixels = std::make_unique<std::vector<uint8_t>>(px, px + r.n_pixels);
+                p.bid = r.bid;
+                out[i].emplace_back(std::move(p));
+            }
+        }
+        return out;
+    }
+    tb_seg *handle() { return _h; }
+
+private:
+    tb_seg *_h = nullptr;
+    tb_seg_params _p{};
+    int _w = 0, _hgt = 0;
+};
+
+// CPULabeling::run(const cv::Mat&, ...): label an already-binary image (any non-zero pixel is foreground)
+inline blobs_t labeling_run(const uint8_t *image, int width, int height)
+{
+    BackgroundSubtraction bs(width, height, 1, 0);
+    bs.settings().detect_threshold = 0; bs.settings().enable_difference = 0; bs.settings().n_size_ranges = 0;
+    bs.update_settings();
+    std::vector<uint8_t> zero((size_t)width * height, 0);
+    bs.set_background(zero.data());
+    return std::move(bs.apply({image})[0]);
+}
+
+class VINetwork {
+public:
+    VINetwork(int num_classes, int max_images = 4096, int device = 0) : _m(num_classes)
+    {
+        tb_vi_config cfg{};
+        cfg.device = device; cfg.width = 80; cfg.height = 80; cfg.channels = 1;
+        cfg.num_classes = num_classes; cfg.max_images = max_images; cfg.precision = 0;
+        check(tb_vi_create(&cfg, &_h), "tb_vi_create");
+    }
+    ~VINetwork() { tb_vi_destroy(_h); }
+    VINetwork(const VINetwork &) = delete;
+    VINetwork &operator=(const VINetwork &) = delete;
+
+    // load_weights(VIWeights&&): tensors under their state_dict names, then commit
+    void set_tensor(const std::string &name, const std::vector<float> &v) { check(tb_vi_set_tensor(_h, name.c_str(), v.data(), (int64_t)v.size()), "tb_vi_set_tensor"); }
+    void commit() { check(tb_vi_commit(_h), "tb_vi_commit"); }
+
+    // probabilities(std::vector<Image::Ptr>&&) (sync form): N x M softmax rows, flat
+    std::vector<float> probabilities(const std::vector<const uint8_t *> &images)
+    {
+        std::vector<uint8_t> packed(images.size() * 6400);
+        for (size_t i = 0; i < images.size(); ++i) std::memcpy(packed.data() + i * 6400, images[i], 6400);
+        std::vector<float> probs(images.size() * (size_t)_m);
+        if (!images.empty()) check(tb_vi_predict(_h, packed.data(), (int)images.size(), probs.data(), nullptr), "tb_vi_predict");
+        return probs;
+    }
+
+private:
+    tb_vi *_h = nullptr;
+    int _m;
+};
+
+}  // namespace trexb200

@@ -1,0 +1,46 @@
+// Drives the C++ host layer (include/trexb200.hpp) the way TRex's test_matching.cpp:1556-1602 drives
+// CPULabeling::run: circle + rectangle -> exactly one blob; render -> relabel -> identical lines.
+// Prints "OK <n_lines> <n_pixels>" on success. Built and run by tests/test_gpu_cpp_shim.py.
+#include <cstdio>
+#include <vector>
+
+#include "trexb200.hpp"
+
+int main()
+{
+    const int W = 320, H = 240;
+    std::vector<uint8_t> img((size_t)W * H, 0);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            if ((y - 100) * (y - 100) + (x - 120) * (x - 120) <= 50 * 50) img[(size_t)y * W + x] = 255;
+            if (y >= 90 && y < 160 && x >= 150 && x < 260) img[(size_t)y * W + x] = 200;
+        }
+    try {
+        auto blobs = trexb200::labeling_run(img.data(), W, H);
+        if (blobs.size() != 1) { std::printf("FAIL blobs=%zu\n", blobs.size()); return 1; }
+        std::vector<uint8_t> render((size_t)W * H, 0);
+        size_t o = 0;
+        for (auto &l : *blobs[0].lines)
+            for (int x = l.x0; x <= l.x1; ++x) render[(size_t)l.y * W + x] = (*blobs[0].pixels)[o++];
+        if (render != img) { std::printf("FAIL render differs\n"); return 1; }
+        auto again = trexb200::labeling_run(render.data(), W, H);
+        if (again.size() != 1 || again[0].lines->size() != blobs[0].lines->size() || *again[0].pixels != *blobs[0].pixels) {
+            std::printf("FAIL not idempotent\n"); return 1;
+        }
+        // threshold path with a background + size filter, as BackgroundSubtraction::apply
+        trexb200::BackgroundSubtraction bs(W, H, 2);
+        std::vector<uint8_t> bg((size_t)W * H, 100), fr(bg);
+        for (int x = 10; x < 30; ++x) fr[(size_t)5 * W + x] = 20;      // 20 px blob
+        fr[(size_t)50 * W + 50] = 20;                                  // 1 px blob: filtered
+        bs.settings().n_size_ranges = 1; bs.settings().size_lo[0] = 10; bs.settings().size_hi[0] = 100000;
+        bs.update_settings();
+        bs.set_background(bg.data());
+        auto res = bs.apply({fr.data(), bg.data()});
+        if (res[0].size() != 1 || res[1].size() != 0 || res[0][0].pixels->size() != 20) { std::printf("FAIL apply\n"); return 1; }
+        std::printf("OK %zu %zu\n", blobs[0].lines->size(), blobs[0].pixels->size());
+    } catch (const std::exception &e) {
+        std::printf("EXC %s\n", e.what());
+        return 2;
+    }
+    return 0;
+}
