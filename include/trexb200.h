@@ -199,6 +199,11 @@ TB_API uint64_t tb_vi_launch_count(tb_vi *h);
 TB_API int tb_vi_profile(tb_vi *h, int enable);
 TB_API int tb_vi_kernel_ms(tb_vi *h, double out_ms[5], uint64_t *n_chunks);
 
+/* Debug / bring-up: one tcgen05 "shifted GEMM" D[128][N] = A[shift+m][:] . B[n][:]^T on bf16 operands in the
+ * channel-group-planar layout the convolution kernels use (a: [n_cg][n_pos][8] bf16, b: [n_cg][N][8] bf16,
+ * d: [128][N] f32; all host pointers).  Exercised by tests/test_gpu_umma.py. */
+TB_API int tb_debug_umma_shifted_gemm(const void *a, int n_pos, int n_cg, int shift, const void *b, int N, float *d);
+
 #ifdef __cplusplus
 }
 #endif

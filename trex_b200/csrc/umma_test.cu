@@ -1,0 +1,76 @@
+// Debug entry point: one tcgen05 "shifted GEMM", the building block of the implicit-GEMM convolutions.
+//   D[128][N] = sum_k A[shift + m][k] * B[n][k]
+// A is stored as channel-group planes [n_cg][n_pos][8] bf16 (16 bytes per position and group), i.e. the
+// SWIZZLE_NONE K-major canonical layout with SBO = 128 B and LBO = plane size; a tap of the convolution
+// is just a different start address.  B is [n_cg][N][8].  Used by tests/test_gpu_umma.py.
+#include "common.h"
+#include "umma.cuh"
+
+namespace tb {
+
+__global__ void __launch_bounds__(128)
+umma_shifted_gemm_kernel(const uint4 *__restrict__ a, int n_pos, int n_cg, int shift,
+                         const uint4 *__restrict__ b, int N, float *__restrict__ dout)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    uint4 *sa = reinterpret_cast<uint4 *>(smem);                     // [n_cg][n_pos]
+    uint4 *sb = sa + (size_t)n_cg * n_pos;                           // [n_cg][N]
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t ncols = 32; while ((int)ncols < N) ncols <<= 1;
+    if (warp == 0) umma::tmem_alloc(&tmem_base, ncols);
+    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::fence_mbar_init(); }
+    for (int i = tid; i < n_cg * n_pos; i += 128) sa[i] = a[i];
+    for (int i = tid; i < n_cg * N; i += 128) sb[i] = b[i];
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tm = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = umma::idesc_bf16_f32(128, N);
+        for (int ks = 0; ks < n_cg / 2; ++ks) {                      // one MMA = K 16 = two channel groups
+            const uint64_t ad = umma::smem_desc(umma::smem_u32(sa + (size_t)(2 * ks) * n_pos + shift), (uint32_t)n_pos * 16u, 128u);
+            const uint64_t bd = umma::smem_desc(umma::smem_u32(sb + (size_t)(2 * ks) * N), (uint32_t)N * 16u, 128u);
+            umma::mma_bf16(tm, ad, bd, idesc, ks > 0);
+        }
+        umma::commit(&mbar);
+    }
+    umma::mbar_wait(&mbar, 0);
+    umma::fence_after_sync();
+    const int row = tid;                                             // TMEM lane = D row
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        umma::tmem_ld8(tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dout[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tm, ncols);
+}
+
+}  // namespace tb
+
+extern "C" int tb_debug_umma_shifted_gemm(const void *a_host, int n_pos, int n_cg, int shift, const void *b_host, int N, float *d_host)
+{
+    using namespace tb;
+    TB_REQUIRE(a_host && b_host && d_host, TB_ERR_INVALID, "tb_debug_umma_shifted_gemm: null argument");
+    TB_REQUIRE(n_cg >= 2 && n_cg % 2 == 0 && N >= 16 && N <= 256 && N % 16 == 0 && shift >= 0 && shift + 128 <= n_pos,
+               TB_ERR_INVALID, "tb_debug_umma_shifted_gemm: bad shape");
+    const size_t abytes = (size_t)n_cg * n_pos * 16, bbytes = (size_t)n_cg * N * 16;
+    TB_REQUIRE(abytes + bbytes <= 200 * 1024, TB_ERR_INVALID, "tb_debug_umma_shifted_gemm: operands exceed shared memory");
+    void *da = nullptr, *db = nullptr; float *dd = nullptr;
+    TB_CUDA(cudaMalloc(&da, abytes)); TB_CUDA(cudaMalloc(&db, bbytes)); TB_CUDA(cudaMalloc((void **)&dd, (size_t)128 * N * 4));
+    TB_CUDA(cudaMemcpy(da, a_host, abytes, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMemcpy(db, b_host, bbytes, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaFuncSetAttribute(umma_shifted_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(abytes + bbytes)));
+    umma_shifted_gemm_kernel<<<1, 128, abytes + bbytes>>>((const uint4 *)da, n_pos, n_cg, shift, (const uint4 *)db, N, dd);
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaDeviceSynchronize());
+    TB_CUDA(cudaMemcpy(d_host, dd, (size_t)128 * N * 4, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    return TB_OK;
+}
