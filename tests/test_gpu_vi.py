@@ -12,14 +12,18 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
+PRECISIONS = ["fp32", "bf16x3"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("tag,M", [("m100", 100), ("m8", 8)])
-def test_reference_class_golden(tag, M):
+def test_reference_class_golden(tag, M, precision):
     import trex_b200
     from oracle import vi
     g = np.load(os.path.join(GOLDEN, "vi_golden.npz"))
     sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=0))
     assert vi.state_checksum(sd) == str(g[f"{tag}_checksum"])
-    net = trex_b200.VINetwork(M, max_images=16)
+    net = trex_b200.VINetwork(M, max_images=16, precision=precision)
     net.load_weights(sd)
     probs, logits = net.probabilities(g[f"{tag}_crops"], return_logits=True)
     assert np.abs(logits - g[f"{tag}_logits"]).max() < TOL
@@ -27,7 +31,8 @@ def test_reference_class_golden(tag, M):
     assert np.allclose(probs.sum(1), 1, atol=1e-5)
 
 
-def test_batch_vs_oracle_and_chunking():
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_batch_vs_oracle_and_chunking(precision):
     import trex_b200
     from oracle import vi
     M = 100
@@ -39,7 +44,7 @@ def test_batch_vs_oracle_and_chunking():
         y, x = rng.integers(0, 80 - h), rng.integers(0, 80 - w)
         crops[n, y:y + h, x:x + w, 0] = rng.integers(0, 256, (h, w))
     crops[0] = 0; crops[1] = 255
-    net = trex_b200.VINetwork(M, max_images=32)       # forces 3 chunks through the C ABI
+    net = trex_b200.VINetwork(M, max_images=32, precision=precision)       # forces 3 chunks through the C ABI
     net.load_weights(sd)
     probs, logits = net.probabilities(crops, return_logits=True)
     ref = vi.forward_logits(sd, crops)
@@ -58,3 +63,26 @@ def test_errors():
     assert net.probabilities(np.zeros((0, 80, 80, 1), np.uint8)).shape == (0, 10)
     with pytest.raises(trex_b200.TrexB200Error):
         trex_b200.VINetwork(10, width=64, height=64)
+
+
+def test_tensor_path_many_images_persistent_ctas():
+    """More images than SMs: persistent CTAs loop, weight/accumulator barriers wrap their phases."""
+    import trex_b200
+    from oracle import vi
+    M = 100
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=0))
+    rng = np.random.default_rng(17)
+    n = 333
+    crops = np.zeros((n, 80, 80, 1), np.uint8)
+    for i in range(n):
+        h, w = rng.integers(10, 60), rng.integers(10, 60)
+        y, x = rng.integers(0, 80 - h), rng.integers(0, 80 - w)
+        crops[i, y:y + h, x:x + w, 0] = rng.integers(1, 256, (h, w))
+    net = trex_b200.VINetwork(M, max_images=512, precision="bf16x3")
+    net.load_weights(sd)
+    probs, logits = net.probabilities(crops, return_logits=True)
+    ref = vi.forward_logits(sd, crops)
+    assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
+    probs2 = net.probabilities(crops[:100])          # handle reuse, different n
+    assert np.abs(probs2 - probs[:100]).max() < 1e-6

@@ -5,8 +5,10 @@
 //   conv5x5(C->16)+BN+ReLU+pool2 -> conv5x5(16->64)+BN+ReLU+pool2 -> conv5x5(64->128)+BN+ReLU+pool2
 //   -> flatten (NCHW order) -> fc 12800->100 -> LayerNorm(100) -> ReLU -> fc 100->M -> softmax.
 // Inputs are raw u8 crops cast to float (no /255, visual_recognition_torch.py:337).
-// precision 0: fp32 CUDA-core kernels below (parity mode).  Activations are NHWC fp32.
+// precision 0: fp32 CUDA-core kernels below.  precision 1: tcgen05 tensor-core kernels of vi_tc.cuh
+// (bf16 hi/lo split, three MMAs per k-step, fp32 accumulation in TMEM) for conv2, conv3 and fc1.
 #include "common.h"
+#include "vi_tc.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -309,6 +311,9 @@ struct tb_vi {
     // activations (one chunk)
     float *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *h1 = nullptr;
     uint8_t *d_img = nullptr; float *d_probs = nullptr, *d_logits = nullptr;
+    // tensor-core path (precision 1)
+    uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w2t = nullptr, *w3t = nullptr, *wfc = nullptr;
+    int fc_groups = 0, n_sms = 148;
     uint64_t launches = 0;
     cudaStream_t last_stream = nullptr;
     EventRing<5> prof;
@@ -329,7 +334,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
                "tb_vi_create: this release builds V118_3 for 80x80x1 crops (individual_image_size default, meta_encoding gray)");
     TB_REQUIRE(cfg->num_classes > 0 && cfg->num_classes <= 1024, TB_ERR_INVALID, "tb_vi_create: num_classes must be 1..1024");
     TB_REQUIRE(cfg->max_images > 0, TB_ERR_INVALID, "tb_vi_create: max_images must be > 0");
-    TB_REQUIRE(cfg->precision == 0, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32) in this build");
+    TB_REQUIRE(cfg->precision == 0 || cfg->precision == 1, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32) or 1 (bf16x3 tensor cores)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("tb_vi_create: no CUDA device (there is no CPU fallback)"); return TB_ERR_CUDA; }
     TB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, TB_ERR_INVALID, "tb_vi_create: bad device ordinal");
@@ -345,7 +350,21 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     A(h->w3, 25 * 64 * 128); A(h->s3, 128); A(h->t3, 128);
     A(h->wf1, 12800 * 100); A(h->bf1, 100); A(h->lng, 100); A(h->lnb, 100);
     A(h->wf2, 100 * M); A(h->bf2, M);
-    A(h->a1, CH * 40 * 40 * 16); A(h->a2, CH * 20 * 20 * 64); A(h->a3, CH * 10 * 10 * 128); A(h->h1, CH * 100);
+    if (cfg->precision == 0) { A(h->a1, CH * 40 * 40 * 16); A(h->a2, CH * 20 * 20 * 64); A(h->a3, CH * 10 * 10 * 128); }
+    A(h->h1, CH * 100);
+    if (cfg->precision == 1) {
+        h->fc_groups = (int)((CH + 127) / 128 * 16);
+        A(h->in2, CH * tc::Conv2Cfg::IMG_BYTES + 256); A(h->in3, CH * tc::Conv3Cfg::IMG_BYTES + 256);
+        A(h->fca, (size_t)2 * h->fc_groups * tc::FC_KC * 128);
+        A(h->w2t, (size_t)25 * tc::Conv2Cfg::WTAP_BYTES); A(h->w3t, (size_t)25 * tc::Conv3Cfg::WTAP_BYTES);
+        A(h->wfc, (size_t)2 * tc::FC_KC * tc::FC_N * 16);
+        if (r == TB_OK) {   // halo positions are never written by the kernels: zero once
+            if (cudaMemset(h->in2, 0, CH * tc::Conv2Cfg::IMG_BYTES + 256) != cudaSuccess || cudaMemset(h->in3, 0, CH * tc::Conv3Cfg::IMG_BYTES + 256) != cudaSuccess ||
+                cudaMemset(h->fca, 0, (size_t)2 * h->fc_groups * tc::FC_KC * 128) != cudaSuccess) { set_error("cudaMemset failed"); r = TB_ERR_CUDA; }
+        }
+        int dev_sms = 0;
+        if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && dev_sms > 0) h->n_sms = dev_sms;
+    }
     A(h->d_img, N * 6400 + 16); A(h->d_probs, N * M); A(h->d_logits, N * M);
 #undef A
     if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
@@ -388,6 +407,37 @@ static int vi_need(tb_vi *h, const char *name, size_t count, const std::vector<f
 static int vi_upload(float *dst, const std::vector<float> &v)
 {
     TB_CUDA(cudaMemcpy(dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return TB_OK;
+}
+
+static inline uint16_t f2bf_host(float f)
+{
+    uint32_t u; std::memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline void split_bf16_host(float x, uint16_t &hi, uint16_t &lo)
+{
+    hi = f2bf_host(x);
+    uint32_t u = (uint32_t)hi << 16; float fh; std::memcpy(&fh, &u, 4);
+    lo = f2bf_host(x - fh);
+}
+// tensor path: conv weight torch [Cout][Cin][25] -> B operand [tap][hi|lo][cin group][Cout][8] bf16
+static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, int NOUT)
+{
+    const int cin = G * 8;
+    std::vector<uint16_t> b((size_t)25 * 2 * G * NOUT * 8);
+    for (int tap = 0; tap < 25; ++tap)
+        for (int g = 0; g < G; ++g)
+            for (int co = 0; co < NOUT; ++co)
+                for (int e = 0; e < 8; ++e) {
+                    uint16_t hi, lo;
+                    split_bf16_host(w[((size_t)co * cin + g * 8 + e) * 25 + tap], hi, lo);
+                    b[((((size_t)tap * 2 + 0) * G + g) * NOUT + co) * 8 + e] = hi;
+                    b[((((size_t)tap * 2 + 1) * G + g) * NOUT + co) * 8 + e] = lo;
+                }
+    TB_CUDA(cudaMemcpy(dst, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
     return TB_OK;
 }
 
@@ -446,12 +496,67 @@ extern "C" int tb_vi_commit(tb_vi *h)
         for (int k = 0; k < 100; ++k) w2t[(size_t)k * M + o] = (*w2)[(size_t)o * 100 + k];
     if ((r = vi_upload(h->wf2, w2t))) return r;
     if ((r = vi_upload(h->bf2, *b2))) return r;
+    if (h->cfg.precision == 1) {
+        const std::vector<float> *c2, *c3;
+        if ((r = vi_need(h, "model.conv2.weight", (size_t)64 * 16 * 25, &c2))) return r;
+        if ((r = vi_need(h, "model.conv3.weight", (size_t)128 * 64 * 25, &c3))) return r;
+        if ((r = vi_upload_tc_conv(h->w2t, *c2, 2, 64))) return r;
+        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128))) return r;
+        // fc1 B operand [hi|lo][kc = c8*100 + pp][112][8]; torch column = (c8*8+e)*100 + pp
+        std::vector<uint16_t> wb((size_t)2 * tc::FC_KC * tc::FC_N * 8, 0);
+        for (int kc = 0; kc < tc::FC_KC; ++kc)
+            for (int n = 0; n < tc::FC_NREAL; ++n)
+                for (int e = 0; e < 8; ++e) {
+                    const int c8 = kc / 100, pp = kc % 100;
+                    uint16_t hi, lo;
+                    split_bf16_host((*w)[(size_t)n * 12800 + (c8 * 8 + e) * 100 + pp], hi, lo);
+                    wb[(((size_t)0 * tc::FC_KC + kc) * tc::FC_N + n) * 8 + e] = hi;
+                    wb[(((size_t)1 * tc::FC_KC + kc) * tc::FC_N + n) * 8 + e] = lo;
+                }
+        TB_CUDA(cudaMemcpy(h->wfc, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+    }
     h->committed = true;
+    return TB_OK;
+}
+
+static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n_dev, float *probs, float *logits, cudaStream_t s)
+{
+    using namespace tb::tc;
+    const int M = h->cfg.num_classes;
+    static bool attr_done = false;
+    auto k2 = conv_tc_kernel<Conv2Cfg, OUT_PLANES>;
+    auto k3 = conv_tc_kernel<Conv3Cfg, OUT_FC>;
+    if (!attr_done) {
+        TB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3Cfg::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+        attr_done = true;
+    }
+    for (int base = 0; base < n_max; base += h->chunk) {
+        const int n = std::min(h->chunk, n_max - base);
+        const int slot = h->prof.begin(s);
+        h->prof.mark(slot, 0);
+        conv1_planes_kernel<<<n, 256, 0, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1, h->s1, h->t1, h->in2);
+        h->prof.mark(slot, 1);
+        k2<<<std::min(n * Conv2Cfg::PASSES, h->n_sms), NT, Conv2Cfg::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3, 0);
+        h->prof.mark(slot, 2);
+        k3<<<std::min(n, h->n_sms), NT, Conv3Cfg::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+        h->prof.mark(slot, 3);
+        fc1_tc_kernel<<<(n + 127) / 128, NT, FC_SMEM, s>>>(h->fca, h->fc_groups, n, n_dev, base, h->wfc, h->bf1, h->h1);
+        h->prof.mark(slot, 4);
+        head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, HD_WARPS * (100 + M) * 4, s>>>(
+            h->h1, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2, probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr);
+        h->prof.mark(slot, 5);
+        h->launches += 5;
+    }
+    TB_CUDA(cudaGetLastError());
+    h->last_stream = s;
     return TB_OK;
 }
 
 static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n_dev, float *probs, float *logits, cudaStream_t s)
 {
+    if (h->cfg.precision == 1) return vi_forward_tc(h, img, n_max, n_dev, probs, logits, s);
     const int M = h->cfg.num_classes;
     static bool attr_done = false;
     auto k2 = conv_kernel<16, 64, 40, 20, 3>;           // pooled 20x20: 7 tiles of 20x3
