@@ -131,6 +131,11 @@ TB_API int tb_seg_submit_device(tb_seg *h, const void *frames_dev, int n, void *
 
 TB_API int tb_seg_wait(tb_seg *h);
 
+/* Stream (cudaStream_t) on which tb_seg_submit / tb_seg_set_background enqueue their copies and kernels
+ * (default: a private stream).  Lets a caller chain the identification network behind the segmentation
+ * of the same batch and overlap the H2D copy of the next batch on a second handle. */
+TB_API int tb_seg_set_stream(tb_seg *h, void *stream);
+
 /* blobs_t of frame i of the last batch (after tb_seg_wait, fetch=1). */
 TB_API int tb_seg_result(tb_seg *h, int i, tb_blob_view *out);
 

@@ -60,7 +60,7 @@ SYMBOLS = [
     "tb_seg_wait", "tb_seg_result", "tb_seg_totals", "tb_seg_device_results", "tb_seg_crops",
     "tb_seg_debug_binary", "tb_seg_launch_count", "tb_vi_create", "tb_vi_destroy", "tb_vi_set_tensor",
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
-    "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_debug_umma_shifted_gemm",
+    "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_debug_umma_shifted_gemm", "tb_seg_set_stream",
 ]
 
 _lib = None
@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
     L.tb_seg_kernel_ms.argtypes = [vp, C.POINTER(C.c_double * 3), C.POINTER(C.c_uint64)]
     L.tb_vi_profile.argtypes = [vp, C.c_int]
     L.tb_vi_kernel_ms.argtypes = [vp, C.POINTER(C.c_double * 5), C.POINTER(C.c_uint64)]
+    L.tb_seg_set_stream.argtypes = [vp, vp]
     L.tb_debug_umma_shifted_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     _lib = L
     return L

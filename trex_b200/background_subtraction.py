@@ -142,6 +142,18 @@ class BackgroundSubtraction:
             self._samples += 1
         return out
 
+    def set_stream(self, stream: int):
+        """cudaStream_t handle used by submit()/apply() (0 = the handle's private stream)."""
+        check(lib().tb_seg_set_stream(self._h, C.c_void_p(stream)))
+
+    def submit(self, frames, fetch=1):
+        """Asynchronous half of apply(): enqueue H2D + kernels for up to max_batch frames ((n,H,W) u8 array,
+        ideally pinned).  fetch: 0 headers only, 1 blobs, 2 blobs + crops.  Pair with wait()."""
+        n = len(frames)
+        base, stride = frames.ctypes.data, frames.strides[0]
+        ptrs = (C.c_void_p * n)(*[base + i * stride for i in range(n)])
+        check(lib().tb_seg_submit(self._h, ptrs, n, frames.strides[1], int(fetch)))
+
     def apply_device(self, frames_ptr: int, n: int, stream: int = 0, fetch=False):
         """Frames already resident in HBM (n packed HxW u8); work is ordered on `stream`."""
         check(lib().tb_seg_submit_device(self._h, C.c_void_p(frames_ptr), n, C.c_void_p(stream), int(fetch)))

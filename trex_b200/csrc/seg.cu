@@ -514,7 +514,7 @@ struct tb_seg {
     tb_seg_params params{};
     SegDev d{};
     SegK k{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev_done = nullptr;
     bool has_bg = false;
     uint8_t *d_bg = nullptr, *d_frames = nullptr, *d_tmp = nullptr;
@@ -624,6 +624,7 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     if (r == TB_OK) r = host_alloc(&h->h_crops, (size_t)d.crops_cap * d.crop_w * d.crop_h + 16);
     if (r == TB_OK) r = host_alloc(&h->h_crop_blob, std::max<size_t>(d.crops_cap, 1));
     if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
+    h->own_stream = h->stream;
     if (r == TB_OK && cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); r = TB_ERR_CUDA; }
     if (r != TB_OK) { tb_seg_destroy(h); return r; }
     d.bg = h->d_bg;
@@ -636,14 +637,22 @@ extern "C" void tb_seg_destroy(tb_seg *h)
 {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();
     for (void *p : h->dev_allocs) cudaFree(p);
     void *hp[] = {h->h_infos, h->h_totals, h->h_recs, h->h_lines, h->h_pixels, h->h_crops, h->h_crop_blob};
     for (void *p : hp) if (p) cudaFreeHost(p);
     h->prof.destroy();
     if (h->ev_done) cudaEventDestroy(h->ev_done);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+}
+
+extern "C" int tb_seg_set_stream(tb_seg *h, void *stream)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_set_stream: null handle");
+    TB_REQUIRE(!h->pending, TB_ERR_STATE, "tb_seg_set_stream: a batch is pending (call tb_seg_wait first)");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return TB_OK;
 }
 
 extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
