@@ -11,6 +11,7 @@
 #include "vi_tc.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -314,6 +315,8 @@ struct tb_vi {
     // tensor-core path (precision 1)
     uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w2t = nullptr, *w3t = nullptr, *wfc = nullptr;
     int fc_groups = 0, n_sms = 148;
+    bool conv2_flat = getenv("TB_CONV2_FLAT") != nullptr;
+    bool conv3_flat = getenv("TB_CONV3_FLAT") != nullptr;   // bring-up switch: position-major conv3 kernel
     uint64_t launches = 0;
     cudaStream_t last_stream = nullptr;
     EventRing<5> prof;
@@ -529,6 +532,8 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
     if (!attr_done) {
         TB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::SMEM));
         TB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3Cfg::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
         attr_done = true;
     }
@@ -538,9 +543,11 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         h->prof.mark(slot, 0);
         conv1_planes_kernel<<<n, 256, 0, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1, h->s1, h->t1, h->in2);
         h->prof.mark(slot, 1);
-        k2<<<std::min(n * Conv2Cfg::PASSES, h->n_sms), NT, Conv2Cfg::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3, 0);
+        if (h->conv2_flat) k2<<<std::min(n * Conv2Cfg::PASSES, h->n_sms), NT, Conv2Cfg::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3, 0);
+        else conv2_2d_kernel<<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
         h->prof.mark(slot, 2);
-        k3<<<std::min(n, h->n_sms), NT, Conv3Cfg::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+        if (h->conv3_flat) k3<<<std::min(n, h->n_sms), NT, Conv3Cfg::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+        else conv3_t_kernel<<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
         h->prof.mark(slot, 3);
         fc1_tc_kernel<<<(n + 127) / 128, NT, FC_SMEM, s>>>(h->fca, h->fc_groups, n, n_dev, base, h->wfc, h->bf1, h->h1);
         h->prof.mark(slot, 4);

@@ -228,6 +228,307 @@ conv_tc_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv3, channel-major orientation:  D[128 cout][positions] = W[128][K] * X[positions][K]^T.
+// The weights are the A operand (M = 128 output channels), a run of flat positions of the activation
+// planes is the B operand (N = 240 = 10 image rows x pitch 24), shifted per tap exactly as above.
+// Each TMEM lane then holds ONE output channel and the columns are positions, so BN + ReLU + the 2x2
+// max-pool are thread-local (columns q, q+1, q+24, q+25): no shuffles, no staging, no block barriers.
+// 8 epilogue warps (2 per TMEM lane quarter, one per row half); the next image's planes are fetched
+// while the epilogue drains TMEM.
+// ------------------------------------------------------------------------------------------------
+struct Conv3T {
+    static constexpr int G = 8, NOUT = 128, H = 20, W = 20, WP = 24;
+    static constexpr int NT_ROWS = 10, N = NT_ROWS * WP, TILES = H / NT_ROWS;      // 2 tiles of 240 positions
+    static constexpr int PIN = ((TILES - 1) * N + N + 4 * WP + 4 + 7) / 8 * 8;     // 584 positions staged
+    static constexpr int PL = Conv3Cfg::PL;                                        // plane pitch in global memory
+    static constexpr int IN_BYTES = 2 * G * PIN * 16;
+    static constexpr int WTAP_BYTES = 2 * G * NOUT * 16;
+    static constexpr int SMEM = (IN_BYTES + 127) / 128 * 128 + 2 * WTAP_BYTES + 128;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int THREADS = 64 + 256;
+    static_assert(PIN <= PL, "staged positions exceed the plane");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(Conv3T::THREADS, 1)
+conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
+               const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
+               uint8_t *__restrict__ out, int out_groups)
+{
+    using C = Conv3T;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_in_full, bar_in_empty, bar_acc_full, bar_acc_empty, bar_w_full[2], bar_w_empty[2];
+    __shared__ uint32_t s_tmem;
+    uint8_t *s_in = smem;
+    uint8_t *s_w = smem + (C::IN_BYTES + 127) / 128 * 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+
+    if (tid == 0) {
+        umma::mbar_init(&bar_in_full, 1); umma::mbar_init(&bar_in_empty, 1);
+        umma::mbar_init(&bar_acc_full, 1); umma::mbar_init(&bar_acc_empty, 1);
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_w_full[i], 1); umma::mbar_init(&bar_w_empty[i], 1); }
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(&s_tmem, C::TMEM_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tm = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, tapc = 0;
+            for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
+                umma::mbar_wait(&bar_in_empty, (it & 1) ^ 1);
+                umma::mbar_expect_tx(&bar_in_full, C::IN_BYTES);
+                const uint8_t *src = in + (size_t)img * Conv3Cfg::IMG_BYTES;
+                for (int p = 0; p < 2 * C::G; ++p)
+                    umma::bulk_g2s(s_in + (size_t)p * C::PIN * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full);
+                for (int tap = 0; tap < 25; ++tap, ++tapc) {
+                    const uint32_t s = tapc & 1;
+                    umma::mbar_wait(&bar_w_empty[s], ((tapc >> 1) & 1) ^ 1);
+                    umma::mbar_expect_tx(&bar_w_full[s], C::WTAP_BYTES);
+                    umma::bulk_g2s(s_w + s * C::WTAP_BYTES, wgt + (size_t)tap * C::WTAP_BYTES, C::WTAP_BYTES, &bar_w_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_bf16_f32(128, C::N);
+            const uint64_t x_base = umma::smem_desc(umma::smem_u32(s_in), C::PIN * 16, 128);
+            const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
+            uint32_t it = 0, tapc = 0;
+            for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
+                umma::mbar_wait(&bar_in_full, it & 1);
+                umma::mbar_wait(&bar_acc_empty, (it & 1) ^ 1);
+                umma::fence_after_sync();
+                for (int tap = 0; tap < 25; ++tap, ++tapc) {
+                    const uint32_t s = tapc & 1;
+                    umma::mbar_wait(&bar_w_full[s], (tapc >> 1) & 1);
+                    umma::fence_after_sync();
+                    const uint32_t wofs = (s * C::WTAP_BYTES) >> 4;
+                    const uint32_t shift = (uint32_t)((tap / 5) * C::WP + (tap % 5));
+#pragma unroll
+                    for (int t = 0; t < C::TILES; ++t) {
+#pragma unroll
+                        for (int ks = 0; ks < C::G / 2; ++ks) {
+                            const uint32_t x_hi = (0 * C::G + 2 * ks) * C::PIN + t * C::N + shift;
+                            const uint32_t x_lo = (1 * C::G + 2 * ks) * C::PIN + t * C::N + shift;
+                            const uint32_t w_hi = wofs + (0 * C::G + 2 * ks) * C::NOUT;
+                            const uint32_t w_lo = wofs + (1 * C::G + 2 * ks) * C::NOUT;
+                            const uint32_t d = tm + (uint32_t)(t * C::N);
+                            umma::mma_bf16(d, w_base + w_hi, x_base + x_hi, idesc, (tap | ks) != 0);
+                            umma::mma_bf16(d, w_base + w_hi, x_base + x_lo, idesc, 1);
+                            umma::mma_bf16(d, w_base + w_lo, x_base + x_hi, idesc, 1);
+                        }
+                    }
+                    umma::commit(&bar_w_empty[s]);
+                }
+                umma::commit(&bar_in_empty);              // planes consumed: the producer may fetch the next image
+                umma::commit(&bar_acc_full);
+            }
+        }
+    } else {
+        // epilogue: 8 warps; warp handles TMEM lane quarter (warp & 3) of tile (ew >> 2)
+        const int ew = warp - 2, quarter = warp & 3, t = ew >> 2;
+        const int c = quarter * 32 + lane;                    // output channel of this thread
+        const float s = sc[c], b = sh[c];
+        const int c8 = c >> 3, e = c & 7;
+        uint32_t it = 0;
+        for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
+            umma::mbar_wait(&bar_acc_full, it & 1);
+            umma::fence_after_sync();
+            uint8_t *o_hi = out + ((((size_t)0 * out_groups + (img >> 3)) * FC_KC + c8 * 100) * 8 + (img & 7)) * 16 + e * 2;
+            uint8_t *o_lo = out + ((((size_t)1 * out_groups + (img >> 3)) * FC_KC + c8 * 100) * 8 + (img & 7)) * 16 + e * 2;
+#pragma unroll 1
+            for (int pr = 0; pr < C::NT_ROWS / 2; ++pr) {         // pairs of image rows: 48 consecutive columns
+                uint32_t v[48];
+                const uint32_t col = (uint32_t)(t * C::N + pr * 2 * C::WP);
+                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + col;
+                umma::tmem_ld16(ta, *reinterpret_cast<uint32_t (*)[16]>(&v[0]));
+                umma::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t (*)[16]>(&v[16]));
+                umma::tmem_ld16(ta + 32, *reinterpret_cast<uint32_t (*)[16]>(&v[32]));
+                umma::tmem_ld_wait();
+                const int py = t * (C::NT_ROWS / 2) + pr;
+#pragma unroll
+                for (int px = 0; px < C::W / 2; ++px) {
+                    const float a0 = fmaf(__uint_as_float(v[2 * px]), s, b), a1 = fmaf(__uint_as_float(v[2 * px + 1]), s, b);
+                    const float a2 = fmaf(__uint_as_float(v[C::WP + 2 * px]), s, b), a3 = fmaf(__uint_as_float(v[C::WP + 2 * px + 1]), s, b);
+                    const float m = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), 0.f);
+                    __nv_bfloat16 h, l;
+                    umma::split_bf16(m, h, l);
+                    const size_t o = (size_t)(py * (C::W / 2) + px) * 128;        // kc advances by one: 8 rows x 16 B
+                    *reinterpret_cast<__nv_bfloat16 *>(o_hi + o) = h;
+                    *reinterpret_cast<__nv_bfloat16 *>(o_lo + o) = l;
+                }
+            }
+            umma::fence_before_sync();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ew == 0 && lane == 0) umma::mbar_arrive(&bar_acc_empty);
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tm, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv2, position-major with 2-D tiles: an MMA tile is 8 pixels wide x 16 rows (SBO = row pitch), so the
+// 2x2 pool partners of TMEM lane r are lanes r^1 and r^8 of the same warp: two shuffles, no staging.
+// Work item = a band of 16 output rows of one image (5 tiles); input bands are double buffered, all
+// 25 taps of weights stay resident, accumulators rotate through a ring of 8 TMEM buffers (64 columns
+// each) so the 8 epilogue warps drain tile i while the tensor core works on tiles i+1..i+7.
+// ------------------------------------------------------------------------------------------------
+struct Conv2D {
+    static constexpr int G = 2, NOUT = 64, H = 40, W = 40, WP = 44;
+    static constexpr int BAND_ROWS = 16, IN_ROWS = BAND_ROWS + 4, BAND_POS = IN_ROWS * WP;     // 880 positions
+    static constexpr int BANDS = 3, TILES = W / 8;                                              // y0 = 0, 16, 24
+    static constexpr int IN_BYTES = 2 * G * BAND_POS * 16;
+    static constexpr int WTAP_BYTES = 2 * G * NOUT * 16, W_BYTES = 25 * WTAP_BYTES;
+    static constexpr int NACC = 8;
+    static constexpr int SMEM = 2 * IN_BYTES + W_BYTES + NOUT * 8 + 128;
+    static constexpr int THREADS = 64 + 256;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(Conv2D::THREADS, 1)
+conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
+                const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
+                uint8_t *__restrict__ out)
+{
+    using C = Conv2D;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_in_full[2], bar_in_empty[2], bar_acc_full[C::NACC], bar_acc_empty[C::NACC], bar_w_full;
+    __shared__ uint32_t s_tmem;
+    uint8_t *s_in = smem;                                            // [2][IN_BYTES]
+    uint8_t *s_w = smem + 2 * C::IN_BYTES;
+    float *s_sc = reinterpret_cast<float *>(s_w + C::W_BYTES), *s_sh = s_sc + C::NOUT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+    const int n_items = max(n_act, 0) * C::BANDS;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_in_full[i], 1); umma::mbar_init(&bar_in_empty[i], 1); }
+        for (int i = 0; i < C::NACC; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 8); }
+        umma::mbar_init(&bar_w_full, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(&s_tmem, 512);
+    for (int i = tid; i < C::NOUT; i += C::THREADS) { s_sc[i] = sc[i]; s_sh[i] = sh[i]; }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tm = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            umma::mbar_expect_tx(&bar_w_full, C::W_BYTES);
+            for (int o = 0; o < C::W_BYTES; o += C::WTAP_BYTES) umma::bulk_g2s(s_w + o, wgt + o, C::WTAP_BYTES, &bar_w_full);
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int img = item / C::BANDS, band = item % C::BANDS;
+                const int y0 = band == 2 ? 24 : band * 16;
+                const uint32_t b = it & 1;
+                umma::mbar_wait(&bar_in_empty[b], ((it >> 1) & 1) ^ 1);
+                umma::mbar_expect_tx(&bar_in_full[b], C::IN_BYTES);
+                const uint8_t *src = in + (size_t)img * Conv2Cfg::IMG_BYTES + (size_t)y0 * C::WP * 16;
+                for (int p = 0; p < 2 * C::G; ++p)
+                    umma::bulk_g2s(s_in + (size_t)b * C::IN_BYTES + (size_t)p * C::BAND_POS * 16, src + (size_t)p * Conv2Cfg::PL * 16,
+                                   C::BAND_POS * 16, &bar_in_full[b]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_bf16_f32(128, C::NOUT);
+            const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
+            umma::mbar_wait(&bar_w_full, 0);
+            uint32_t it = 0, ai = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t b = it & 1;
+                const uint64_t a_base = umma::smem_desc(umma::smem_u32(s_in + (size_t)b * C::IN_BYTES), C::BAND_POS * 16, C::WP * 16);
+                umma::mbar_wait(&bar_in_full[b], (it >> 1) & 1);
+                umma::fence_after_sync();
+#pragma unroll 1
+                for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
+                    const uint32_t buf = ai % C::NACC;
+                    umma::mbar_wait(&bar_acc_empty[buf], ((ai / C::NACC) & 1) ^ 1);
+                    umma::fence_after_sync();
+                    const uint32_t d = tm + buf * C::NOUT;
+#pragma unroll 5
+                    for (int tap = 0; tap < 25; ++tap) {
+                        const uint32_t pos = (uint32_t)((tap / 5) * C::WP + (tap % 5) + tx * 8);
+                        const uint32_t a_hi = 0 * C::G * C::BAND_POS + pos, a_lo = 1 * C::G * C::BAND_POS + pos;
+                        const uint32_t w_hi = (uint32_t)(tap * C::WTAP_BYTES >> 4), w_lo = w_hi + C::G * C::NOUT;
+                        umma::mma_bf16(d, a_base + a_hi, w_base + w_hi, idesc, tap != 0);
+                        umma::mma_bf16(d, a_base + a_lo, w_base + w_hi, idesc, 1);
+                        umma::mma_bf16(d, a_base + a_hi, w_base + w_lo, idesc, 1);
+                    }
+                    umma::commit(&bar_acc_full[buf]);
+                }
+                umma::commit(&bar_in_empty[b]);
+            }
+        }
+    } else {
+        const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;     // half: which 32 of the 64 output channels
+        const int r = quarter * 32 + lane, ty = r >> 3, tx8 = r & 7;
+        uint32_t ai = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int img = item / C::BANDS, band = item % C::BANDS;
+            const int y0 = band == 2 ? 24 : band * 16, ymin = band == 2 ? 32 : y0;
+            const int y = y0 + ty;
+            const bool row_ok = !(ty & 1) && !(tx8 & 1) && y >= ymin && y < C::H;
+#pragma unroll 1
+            for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
+                const uint32_t buf = ai % C::NACC;
+                umma::mbar_wait(&bar_acc_full[buf], (ai / C::NACC) & 1);
+                umma::fence_after_sync();
+                uint32_t v[32];
+                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::NOUT + half * 32;
+                umma::tmem_ld16(ta, *reinterpret_cast<uint32_t (*)[16]>(&v[0]));
+                umma::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t (*)[16]>(&v[16]));
+                umma::tmem_ld_wait();
+                umma::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);     // values are in registers: buffer reusable
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float a[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int ch = half * 32 + j + u;
+                        float q = fmaxf(fmaf(__uint_as_float(v[j + u]), s_sc[ch], s_sh[ch]), 0.f);
+                        q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 1));
+                        q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
+                        a[u] = q;
+                    }
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    umma::split_bf16(a[0], h0, l0); umma::split_bf16(a[1], h1, l1);
+                    hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo[j >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                if (row_ok) {
+                    constexpr int WPN = Conv3Cfg::WP, PLN = Conv3Cfg::PL, GN = Conv3Cfg::G;
+                    const int pos = ((y >> 1) + 2) * WPN + ((tx * 8 + tx8) >> 1) + 2;
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        const int g = half * 4 + g4;
+                        *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 0) * GN + g) * PLN + pos) * 16) =
+                            make_uint4(hi[4 * g4], hi[4 * g4 + 1], hi[4 * g4 + 2], hi[4 * g4 + 3]);
+                        *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 1) * GN + g) * PLN + pos) * 16) =
+                            make_uint4(lo[4 * g4], lo[4 * g4 + 1], lo[4 * g4 + 2], lo[4 * g4 + 3]);
+                    }
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tm, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // fc1 on tensor cores: h1[128 images][112] = A[128][12800] * B[112][12800]^T (+ bias), bf16x3.
 // One CTA per 128 images, 3-stage bulk-copy pipeline over K (4 k-steps of 16 per stage).
 // ------------------------------------------------------------------------------------------------
