@@ -370,7 +370,7 @@ ccl_label_kernel(SegDev d)
 // bytes (:307) and renders the individual crop (FilterCache.cpp:158-235).  Arena offsets of the
 // frame are the prefix sums over the batch of the totals K2 wrote.
 // ------------------------------------------------------------------------------------------------
-constexpr int K3_NT = 256;
+constexpr int K3_NT = 256, K3_SPLIT = 4;     // CTAs per frame: blobs are dealt round-robin to K3_SPLIT * 8 warps
 
 __global__ void __launch_bounds__(K3_NT)
 blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
@@ -378,6 +378,7 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
     __shared__ uint32_t s_red[4][K3_NT / 32];
     __shared__ uint32_t s_base[4];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int part = blockIdx.y, nparts = gridDim.y;
     // prefix over frames < f of (blobs, lines, pixels, crops)
     uint32_t acc[4] = {0, 0, 0, 0};
     for (int g = tid; g < f; g += K3_NT) {
@@ -399,7 +400,7 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
     if (Bb + Kk > d.blobs_cap || Lb + Lk > d.lines_cap || Pb + Pk > d.px_cap) { status |= 8u; Kk = 0; Lk = 0; Pk = 0; }
     const uint32_t ncrop = min(Kk, d.max_crops);
     if (Kk > d.max_crops && d.max_crops) status |= 4u;
-    if (tid == 0) {
+    if (tid == 0 && part == 0) {
         tb_frame_info fi;
         fi.blob_begin = Bb; fi.n_blobs = Kk; fi.line_begin = Lb; fi.n_lines = Lk;
         fi.px_begin = Pb; fi.n_pixels = Pk; fi.n_runs = d.run_count[f]; fi.status = status;
@@ -415,7 +416,7 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
     const size_t o = (size_t)f * d.rcap;
     const int cw = d.crop_w, ch = d.crop_h;
 
-    for (uint32_t q = warp; q < Kk; q += K3_NT / 32) {
+    for (uint32_t q = part * (K3_NT / 32) + warp; q < Kk; q += nparts * (K3_NT / 32)) {
         const uint32_t k = d.kept[o + q];
         const uint32_t root = d.b_root[o + k];
         const uint32_t bx0 = d.b_xmin[o + k], bx1 = d.b_xmax[o + k], by1 = d.b_ymax[o + k];
@@ -693,7 +694,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     h->prof.mark(slot, 1);
     ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
     h->prof.mark(slot, 2);
-    blob_emit_kernel<<<n, K3_NT, 0, s>>>(frames_dev, d);
+    blob_emit_kernel<<<dim3((unsigned)n, K3_SPLIT), K3_NT, 0, s>>>(frames_dev, d);
     h->prof.mark(slot, 3);
     h->launches += 3;
     TB_CUDA(cudaGetLastError());

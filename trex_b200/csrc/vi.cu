@@ -240,24 +240,41 @@ fc1_kernel(const float *__restrict__ x, int K, int n_max, const uint32_t *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// head: LayerNorm(100) -> ReLU -> fc2 (100 -> M) -> softmax.  One warp per image.
+// head: (sum of fc1 partials + bias) -> LayerNorm(100) -> ReLU -> fc2 (100 -> M) -> softmax.
+// One warp per image, 8 warps per CTA; fc2 weights staged in shared memory when they fit.
 // ------------------------------------------------------------------------------------------------
-constexpr int HD_WARPS = 4;
+constexpr int HD_WARPS = 8;
 
 __global__ void __launch_bounds__(HD_WARPS * 32)
-head_kernel(const float *__restrict__ h1, int M, int n_max, const uint32_t *__restrict__ n_dev, int base,
+head_kernel(const float *__restrict__ h1, int nsplit, size_t split_stride, const float *__restrict__ b1,
+            int M, int n_max, const uint32_t *__restrict__ n_dev, int base,
             const float *__restrict__ g, const float *__restrict__ be, const float *__restrict__ w2t /*[100][M]*/,
-            const float *__restrict__ b2, float *__restrict__ probs, float *__restrict__ logits)
+            const float *__restrict__ b2, float *__restrict__ probs, float *__restrict__ logits, int w_in_smem)
 {
     extern __shared__ float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+    if ((int)(blockIdx.x * HD_WARPS) >= n_act) return;
+    float *sw = sm + HD_WARPS * (100 + M);
+    if (w_in_smem) {
+        for (int i = threadIdx.x; i < 100 * M; i += HD_WARPS * 32) sw[i] = w2t[i];
+        __syncthreads();
+    }
+    const float *W = w_in_smem ? sw : w2t;
     const int n = blockIdx.x * HD_WARPS + warp;
     if (n >= n_act) return;
     float *sh = sm + warp * (100 + M), *sl = sh + 100;
     float v[4], s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const int i = lane + 32 * j; v[j] = i < 100 ? h1[(size_t)n * 100 + i] : 0.f; s += v[j]; }
+    for (int j = 0; j < 4; ++j) {
+        const int i = lane + 32 * j;
+        float a = 0.f;
+        if (i < 100) {
+            a = b1 ? b1[i] : 0.f;
+            for (int q = 0; q < nsplit; ++q) a += h1[(size_t)q * split_stride + (size_t)n * 100 + i];
+        }
+        v[j] = a; s += a;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / 100.f;
@@ -276,7 +293,8 @@ head_kernel(const float *__restrict__ h1, int M, int n_max, const uint32_t *__re
     float mx = -INFINITY;
     for (int o = lane; o < M; o += 32) {
         float a = b2[o];
-        for (int k = 0; k < 100; ++k) a = fmaf(sh[k], w2t[(size_t)k * M + o], a);
+#pragma unroll 4
+        for (int k = 0; k < 100; ++k) a = fmaf(sh[k], W[(size_t)k * M + o], a);
         sl[o] = a;
         if (logits) logits[(size_t)n * M + o] = a;
         mx = fmaxf(mx, a);
@@ -314,13 +332,15 @@ struct tb_vi {
     uint8_t *d_img = nullptr; float *d_probs = nullptr, *d_logits = nullptr;
     // tensor-core path (precision 1)
     uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w2t = nullptr, *w3t = nullptr, *wfc = nullptr;
-    int fc_groups = 0, n_sms = 148;
+    int fc_groups = 0, n_sms = 148, head_w_smem = 0;
     bool conv2_flat = getenv("TB_CONV2_FLAT") != nullptr;
     bool conv3_flat = getenv("TB_CONV3_FLAT") != nullptr;   // bring-up switch: position-major conv3 kernel
     uint64_t launches = 0;
     cudaStream_t last_stream = nullptr;
     EventRing<5> prof;
 };
+
+static int head_smem(const tb_vi *h, int M) { return (HD_WARPS * (100 + M) + (h->head_w_smem ? 100 * M : 0)) * 4; }
 
 template <typename T>
 static int vi_dev(tb_vi *h, T **p, size_t n)
@@ -354,7 +374,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     A(h->wf1, 12800 * 100); A(h->bf1, 100); A(h->lng, 100); A(h->lnb, 100);
     A(h->wf2, 100 * M); A(h->bf2, M);
     if (cfg->precision == 0) { A(h->a1, CH * 40 * 40 * 16); A(h->a2, CH * 20 * 20 * 64); A(h->a3, CH * 10 * 10 * 128); }
-    A(h->h1, CH * 100);
+    A(h->h1, CH * 100 * (cfg->precision == 1 ? tc::FC_SPLIT : 1));
     if (cfg->precision == 1) {
         h->fc_groups = (int)((CH + 127) / 128 * 16);
         A(h->in2, CH * tc::Conv2Cfg::IMG_BYTES + 256); A(h->in3, CH * tc::Conv3Cfg::IMG_BYTES + 256);
@@ -371,6 +391,11 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     A(h->d_img, N * 6400 + 16); A(h->d_probs, N * M); A(h->d_logits, N * M);
 #undef A
     if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
+    if (r == TB_OK) {
+        const int with_w = (HD_WARPS * (100 + (int)M) + 100 * (int)M) * 4;
+        h->head_w_smem = with_w <= 200 * 1024;
+        if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(head_smem(h, (int)M), 48 * 1024)) != cudaSuccess) { set_error("head_kernel smem attribute failed"); r = TB_ERR_CUDA; }
+    }
     if (r != TB_OK) { tb_vi_destroy(h); return r; }
     *out = h;
     return TB_OK;
@@ -427,7 +452,8 @@ static inline void split_bf16_host(float x, uint16_t &hi, uint16_t &lo)
     lo = f2bf_host(x - fh);
 }
 // tensor path: conv weight torch [Cout][Cin][25] -> B operand [tap][hi|lo][cin group][Cout][8] bf16
-static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, int NOUT)
+// scale: BatchNorm scale per output channel, folded into the weights (y = conv(x, w*s) + t), or nullptr
+static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale)
 {
     const int cin = G * 8;
     std::vector<uint16_t> b((size_t)25 * 2 * G * NOUT * 8);
@@ -436,7 +462,7 @@ static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, i
             for (int co = 0; co < NOUT; ++co)
                 for (int e = 0; e < 8; ++e) {
                     uint16_t hi, lo;
-                    split_bf16_host(w[((size_t)co * cin + g * 8 + e) * 25 + tap], hi, lo);
+                    split_bf16_host(w[((size_t)co * cin + g * 8 + e) * 25 + tap] * (scale ? scale[co] : 1.f), hi, lo);
                     b[((((size_t)tap * 2 + 0) * G + g) * NOUT + co) * 8 + e] = hi;
                     b[((((size_t)tap * 2 + 1) * G + g) * NOUT + co) * 8 + e] = lo;
                 }
@@ -503,8 +529,12 @@ extern "C" int tb_vi_commit(tb_vi *h)
         const std::vector<float> *c2, *c3;
         if ((r = vi_need(h, "model.conv2.weight", (size_t)64 * 16 * 25, &c2))) return r;
         if ((r = vi_need(h, "model.conv3.weight", (size_t)128 * 64 * 25, &c3))) return r;
-        if ((r = vi_upload_tc_conv(h->w2t, *c2, 2, 64))) return r;
-        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128))) return r;
+        // the 2-D conv2 and channel-major conv3 kernels expect the BN scale inside the weights
+        std::vector<float> sc2(64), sc3(128);
+        TB_CUDA(cudaMemcpy(sc2.data(), h->s2, 64 * 4, cudaMemcpyDeviceToHost));
+        TB_CUDA(cudaMemcpy(sc3.data(), h->s3, 128 * 4, cudaMemcpyDeviceToHost));
+        if ((r = vi_upload_tc_conv(h->w2t, *c2, 2, 64, h->conv2_flat ? nullptr : sc2.data()))) return r;
+        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, h->conv3_flat ? nullptr : sc3.data()))) return r;
         // fc1 B operand [hi|lo][kc = c8*100 + pp][112][8]; torch column = (c8*8+e)*100 + pp
         std::vector<uint16_t> wb((size_t)2 * tc::FC_KC * tc::FC_N * 8, 0);
         for (int kc = 0; kc < tc::FC_KC; ++kc)
@@ -549,10 +579,11 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         if (h->conv3_flat) k3<<<std::min(n, h->n_sms), NT, Conv3Cfg::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
         else conv3_t_kernel<<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
         h->prof.mark(slot, 3);
-        fc1_tc_kernel<<<(n + 127) / 128, NT, FC_SMEM, s>>>(h->fca, h->fc_groups, n, n_dev, base, h->wfc, h->bf1, h->h1);
+        fc1_tc_kernel<<<dim3((n + 127) / 128, FC_SPLIT), NT, FC_SMEM, s>>>(h->fca, h->fc_groups, n, n_dev, base, h->wfc, h->h1, h->chunk);
         h->prof.mark(slot, 4);
-        head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, HD_WARPS * (100 + M) * 4, s>>>(
-            h->h1, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2, probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr);
+        head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, head_smem(h, M), s>>>(
+            h->h1, FC_SPLIT, (size_t)h->chunk * 100, h->bf1, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2,
+            probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr, h->head_w_smem);
         h->prof.mark(slot, 5);
         h->launches += 5;
     }
@@ -587,8 +618,9 @@ static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n
         h->prof.mark(slot, 3);
         fc1_kernel<<<(n + FC_IMG - 1) / FC_IMG, FC_NT, 0, s>>>(h->a3, 12800, n, n_dev, base, h->wf1, h->bf1, h->h1);
         h->prof.mark(slot, 4);
-        head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, HD_WARPS * (100 + M) * 4, s>>>(
-            h->h1, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2, probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr);
+        head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, head_smem(h, M), s>>>(
+            h->h1, 1, 0, nullptr, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2,
+            probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr, h->head_w_smem);
         h->prof.mark(slot, 5);
         h->launches += 5;
     }

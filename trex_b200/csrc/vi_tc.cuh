@@ -53,8 +53,13 @@ using Conv3Cfg = ConvCfg<8, 128, 20, 20, 20, false>;   // 64 -> 128, 20x20, weig
 
 enum { OUT_PLANES = 0, OUT_FC = 1 };
 
-// fc1 A operand: [hi|lo][group of 8 images][kc][8 images][8] bf16 with kc = c8 * 100 + pooled pixel
-constexpr int FC_K = 12800, FC_KC = FC_K / 8, FC_N = 112, FC_NREAL = 100;
+// fc1 A operand: [hi|lo][kc block of 8][group of 8 images][kc in block][8 images][8] bf16, kc = c8 * 100 + pooled pixel.
+// One (hi|lo, kc block) slab of 16 consecutive image groups is 16 KB contiguous: one bulk copy per pipeline stage.
+constexpr int FC_K = 12800, FC_KC = FC_K / 8, FC_KB = FC_KC / 8, FC_N = 112, FC_NREAL = 100, FC_SPLIT = 4;
+__host__ __device__ inline size_t fc_a_offset(int hl, int n_groups, int img, int kc)
+{
+    return (((((size_t)hl * FC_KB + (kc >> 3)) * n_groups + (img >> 3)) * 8 + (kc & 7)) * 8 + (img & 7)) * 16;
+}
 
 template <class C, int OUTMODE>
 __global__ void __launch_bounds__(NT, 1)
@@ -211,8 +216,8 @@ conv_tc_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                     o_lo = ((((size_t)img * 2 + 1) * C8 + c8) * PLN + pos) * 16;
                 } else {
                     const int kc = c8 * PP + pp;
-                    o_hi = ((((size_t)0 * out_groups + (img >> 3)) * FC_KC + kc) * 8 + (img & 7)) * 16;
-                    o_lo = ((((size_t)1 * out_groups + (img >> 3)) * FC_KC + kc) * 8 + (img & 7)) * 16;
+                    o_hi = fc_a_offset(0, out_groups, img, kc);
+                    o_lo = fc_a_offset(1, out_groups, img, kc);
                 }
                 *reinterpret_cast<uint4 *>(out + o_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(out + o_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -333,14 +338,13 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
         // epilogue: 8 warps; warp handles TMEM lane quarter (warp & 3) of tile (ew >> 2)
         const int ew = warp - 2, quarter = warp & 3, t = ew >> 2;
         const int c = quarter * 32 + lane;                    // output channel of this thread
-        const float s = sc[c], b = sh[c];
+        const float b = sh[c];
         const int c8 = c >> 3, e = c & 7;
         uint32_t it = 0;
         for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
             umma::mbar_wait(&bar_acc_full, it & 1);
             umma::fence_after_sync();
-            uint8_t *o_hi = out + ((((size_t)0 * out_groups + (img >> 3)) * FC_KC + c8 * 100) * 8 + (img & 7)) * 16 + e * 2;
-            uint8_t *o_lo = out + ((((size_t)1 * out_groups + (img >> 3)) * FC_KC + c8 * 100) * 8 + (img & 7)) * 16 + e * 2;
+            const size_t lo_ofs = fc_a_offset(1, out_groups, 0, 0);
 #pragma unroll 1
             for (int pr = 0; pr < C::NT_ROWS / 2; ++pr) {         // pairs of image rows: 48 consecutive columns
                 uint32_t v[48];
@@ -353,14 +357,14 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                 const int py = t * (C::NT_ROWS / 2) + pr;
 #pragma unroll
                 for (int px = 0; px < C::W / 2; ++px) {
-                    const float a0 = fmaf(__uint_as_float(v[2 * px]), s, b), a1 = fmaf(__uint_as_float(v[2 * px + 1]), s, b);
-                    const float a2 = fmaf(__uint_as_float(v[C::WP + 2 * px]), s, b), a3 = fmaf(__uint_as_float(v[C::WP + 2 * px + 1]), s, b);
-                    const float m = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), 0.f);
+                    const float a0 = __uint_as_float(v[2 * px]), a1 = __uint_as_float(v[2 * px + 1]);
+                    const float a2 = __uint_as_float(v[C::WP + 2 * px]), a3 = __uint_as_float(v[C::WP + 2 * px + 1]);
+                    const float m = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) + b, 0.f);      // BN scale folded into the weights
                     __nv_bfloat16 h, l;
                     umma::split_bf16(m, h, l);
-                    const size_t o = (size_t)(py * (C::W / 2) + px) * 128;        // kc advances by one: 8 rows x 16 B
-                    *reinterpret_cast<__nv_bfloat16 *>(o_hi + o) = h;
-                    *reinterpret_cast<__nv_bfloat16 *>(o_lo + o) = l;
+                    uint8_t *o = out + fc_a_offset(0, out_groups, img, c8 * 100 + py * (C::W / 2) + px) + e * 2;
+                    *reinterpret_cast<__nv_bfloat16 *>(o) = h;
+                    *reinterpret_cast<__nv_bfloat16 *>(o + lo_ofs) = l;
                 }
             }
             umma::fence_before_sync();
@@ -472,12 +476,14 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
     } else {
         const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;     // half: which 32 of the 64 output channels
         const int r = quarter * 32 + lane, ty = r >> 3, tx8 = r & 7;
+        const bool p1 = tx8 & 1, p2 = ty & 1;
+        const int g = half * 4 + (p1 ? 2 : 0) + (p2 ? 1 : 0);           // channel group this lane ends up owning
         uint32_t ai = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int img = item / C::BANDS, band = item % C::BANDS;
             const int y0 = band == 2 ? 24 : band * 16, ymin = band == 2 ? 32 : y0;
             const int y = y0 + ty;
-            const bool row_ok = !(ty & 1) && !(tx8 & 1) && y >= ymin && y < C::H;
+            const bool blk_ok = (y & ~1) >= ymin && (y & ~1) < C::H;      // the 2x2 block of this lane quad is stored
 #pragma unroll 1
             for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
                 const uint32_t buf = ai % C::NACC;
@@ -491,34 +497,37 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                 umma::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);     // values are in registers: buffer reusable
-                uint32_t hi[16], lo[16];
+                // 2x2 max-pool as a butterfly over the lane quad (r, r^1, r^8, r^9): after the exchange with
+                // lane^1 a lane keeps 16 of its 32 channels, after lane^8 it keeps 8 = one channel group.
+                // BN scale is folded into the weights, so pooling runs on raw accumulators (+shift is monotone).
+                float m1[16], m2[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float a[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int ch = half * 32 + j + u;
-                        float q = fmaxf(fmaf(__uint_as_float(v[j + u]), s_sc[ch], s_sh[ch]), 0.f);
-                        q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 1));
-                        q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
-                        a[u] = q;
-                    }
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    umma::split_bf16(a[0], h0, l0); umma::split_bf16(a[1], h1, l1);
-                    hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[j >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                for (int j = 0; j < 16; ++j) {
+                    const float lo_v = __uint_as_float(v[j]), hi_v = __uint_as_float(v[j + 16]);
+                    const float keep = p1 ? hi_v : lo_v, send = p1 ? lo_v : hi_v;
+                    m1[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
                 }
-                if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float keep = p2 ? m1[j + 8] : m1[j], send = p2 ? m1[j] : m1[j + 8];
+                    m2[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                }
+                if (blk_ok) {
+                    const float4 t0 = *reinterpret_cast<const float4 *>(s_sh + g * 8), t1 = *reinterpret_cast<const float4 *>(s_sh + g * 8 + 4);
+                    const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        umma::split_bf16(fmaxf(m2[j] + tt[j], 0.f), h0, l0);
+                        umma::split_bf16(fmaxf(m2[j + 1] + tt[j + 1], 0.f), h1, l1);
+                        hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[j >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
                     constexpr int WPN = Conv3Cfg::WP, PLN = Conv3Cfg::PL, GN = Conv3Cfg::G;
                     const int pos = ((y >> 1) + 2) * WPN + ((tx * 8 + tx8) >> 1) + 2;
-#pragma unroll
-                    for (int g4 = 0; g4 < 4; ++g4) {
-                        const int g = half * 4 + g4;
-                        *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 0) * GN + g) * PLN + pos) * 16) =
-                            make_uint4(hi[4 * g4], hi[4 * g4 + 1], hi[4 * g4 + 2], hi[4 * g4 + 3]);
-                        *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 1) * GN + g) * PLN + pos) * 16) =
-                            make_uint4(lo[4 * g4], lo[4 * g4 + 1], lo[4 * g4 + 2], lo[4 * g4 + 3]);
-                    }
+                    *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 0) * GN + g) * PLN + pos) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 1) * GN + g) * PLN + pos) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
         }
@@ -539,14 +548,14 @@ constexpr int FC_SMEM = FC_STAGES * (FC_A_STAGE + FC_B_STAGE) + 128;
 
 __global__ void __launch_bounds__(NT, 1)
 fc1_tc_kernel(const uint8_t *__restrict__ a, int n_groups, int n_max, const uint32_t *__restrict__ n_dev, int base,
-              const uint8_t *__restrict__ b, const float *__restrict__ bias, float *__restrict__ h1)
+              const uint8_t *__restrict__ b, float *__restrict__ h1p /*[FC_SPLIT][n_alloc][100] partial sums*/, int n_alloc)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_full[FC_STAGES], bar_empty[FC_STAGES], bar_acc;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
-    const int i0 = blockIdx.x * 128;
+    const int i0 = blockIdx.x * 128, split = blockIdx.y;
     if (i0 >= n_act) return;
     if (tid == 0) {
         for (int i = 0; i < FC_STAGES; ++i) { umma::mbar_init(&bar_full[i], 1); umma::mbar_init(&bar_empty[i], 1); }
@@ -558,7 +567,9 @@ fc1_tc_kernel(const uint8_t *__restrict__ a, int n_groups, int n_max, const uint
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tm = s_tmem;
-    constexpr int NSTEP = FC_KC / (2 * FC_KS);                            // 200 stages of 8 kc
+    constexpr int NSTEP = FC_KB / FC_SPLIT;                               // kc blocks handled by this CTA
+    static_assert(FC_KB % FC_SPLIT == 0 && 2 * FC_KS == 8, "stage = one kc block");
+    const int kb0 = split * NSTEP;
     if (warp == 0) {
         if (lane == 0) {
             for (int st = 0; st < NSTEP; ++st) {
@@ -566,12 +577,10 @@ fc1_tc_kernel(const uint8_t *__restrict__ a, int n_groups, int n_max, const uint
                 umma::mbar_wait(&bar_empty[s], ((st / FC_STAGES) & 1) ^ 1);
                 umma::mbar_expect_tx(&bar_full[s], FC_A_STAGE + FC_B_STAGE);
                 uint8_t *sa = smem + (size_t)s * (FC_A_STAGE + FC_B_STAGE), *sb = sa + FC_A_STAGE;
-                const int kc0 = st * 2 * FC_KS;
+                const int kb = kb0 + st;
                 for (int hl = 0; hl < 2; ++hl) {
-                    for (int g = 0; g < 16; ++g)
-                        umma::bulk_g2s(sa + ((size_t)(hl * 16 + g) * (2 * FC_KS)) * 128,
-                                       a + ((((size_t)hl * n_groups + blockIdx.x * 16 + g) * FC_KC + kc0) * 128), 2 * FC_KS * 128, &bar_full[s]);
-                    umma::bulk_g2s(sb + (size_t)hl * (2 * FC_KS) * FC_N * 16, b + (((size_t)hl * FC_KC + kc0) * FC_N * 16), 2 * FC_KS * FC_N * 16, &bar_full[s]);
+                    umma::bulk_g2s(sa + (size_t)hl * (FC_A_STAGE / 2), a + (((size_t)hl * FC_KB + kb) * n_groups + blockIdx.x * 16) * 1024, FC_A_STAGE / 2, &bar_full[s]);
+                    umma::bulk_g2s(sb + (size_t)hl * (FC_B_STAGE / 2), b + (((size_t)hl * FC_KC + kb * 8) * FC_N * 16), FC_B_STAGE / 2, &bar_full[s]);
                 }
             }
         }
@@ -584,9 +593,9 @@ fc1_tc_kernel(const uint8_t *__restrict__ a, int n_groups, int n_max, const uint
                 umma::fence_after_sync();
                 const uint8_t *sa = smem + (size_t)s * (FC_A_STAGE + FC_B_STAGE), *sb = sa + FC_A_STAGE;
                 const uint64_t a_hi = umma::smem_desc(umma::smem_u32(sa), 128, 2 * FC_KS * 128);
-                const uint64_t a_lo = umma::smem_desc(umma::smem_u32(sa + 16 * (2 * FC_KS) * 128), 128, 2 * FC_KS * 128);
+                const uint64_t a_lo = umma::smem_desc(umma::smem_u32(sa + FC_A_STAGE / 2), 128, 2 * FC_KS * 128);
                 const uint64_t b_hi = umma::smem_desc(umma::smem_u32(sb), FC_N * 16, 128);
-                const uint64_t b_lo = umma::smem_desc(umma::smem_u32(sb + (2 * FC_KS) * FC_N * 16), FC_N * 16, 128);
+                const uint64_t b_lo = umma::smem_desc(umma::smem_u32(sb + FC_B_STAGE / 2), FC_N * 16, 128);
 #pragma unroll
                 for (int j = 0; j < FC_KS; ++j) {
                     const uint32_t ao = (uint32_t)(2 * j * 128) >> 4, bo = (uint32_t)(2 * j * FC_N * 16) >> 4;
@@ -603,6 +612,7 @@ fc1_tc_kernel(const uint8_t *__restrict__ a, int n_groups, int n_max, const uint
         umma::mbar_wait(&bar_acc, 0);
         umma::fence_after_sync();
         const int img = i0 + row;
+        float *dst = h1p + ((size_t)split * n_alloc + img) * FC_NREAL;
 #pragma unroll 1
         for (int c0 = 0; c0 < FC_N; c0 += 16) {
             uint32_t v[16];
@@ -611,7 +621,7 @@ fc1_tc_kernel(const uint8_t *__restrict__ a, int n_groups, int n_max, const uint
             if (img < n_act)
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c0 + j < FC_NREAL) h1[(size_t)img * FC_NREAL + c0 + j] = __uint_as_float(v[j]) + bias[c0 + j];
+                    if (c0 + j < FC_NREAL) dst[c0 + j] = __uint_as_float(v[j]);
         }
     }
     umma::fence_before_sync();
