@@ -174,7 +174,8 @@ def run_ours(args):
     probs = torch.empty((B * MAX_CROPS, M_CLASSES), dtype=torch.float32, device=dev)
     probs_host = torch.empty((B * MAX_CROPS, M_CLASSES), dtype=torch.float32, pin_memory=True)
     # fixed-stride metadata for the all-gather: the first B*MAX_CROPS blob records (32 B each) + headers
-    meta_bytes = B * MAX_CROPS * 32
+    from trex_b200 import sharding
+    meta_bytes = sharding.meta_bytes(B, MAX_CROPS)
     meta_all = torch.empty((world_size, meta_bytes), dtype=torch.uint8, device=dev) if world_size > 1 else None
 
     class _CudaBuf:      # zero-copy torch view of a device buffer owned by the C library
@@ -184,7 +185,6 @@ def run_ours(args):
     def as_tensor(ptr, nbytes):
         return torch.as_tensor(_CudaBuf(ptr, nbytes), device=dev)
 
-    meta_local = as_tensor(recs_p, meta_bytes)
     # one explicit (non-default) stream carries seg, CNN, copies and the collective; its handle goes to the C ABI
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
@@ -193,8 +193,8 @@ def run_ours(args):
         fr = dev_batches[i % pool]
         bs.apply_device(fr.data_ptr(), B, stream.cuda_stream, fetch=False)
         net.predict_device(crops_p, B * MAX_CROPS, ncrops_p, probs.data_ptr(), 0, stream.cuda_stream)
-        if world_size > 1:
-            dist.all_gather_into_tensor(meta_all.view(-1), meta_local)
+        if world_size > 1:    # one collective per step: fixed-stride headers + blob records of every rank's frames
+            sharding.all_gather_metadata(sharding.pack_metadata(as_tensor(infos_p, B * 32), as_tensor(recs_p, B * MAX_CROPS * 32), B, MAX_CROPS), out=meta_all)
 
     # e2e: two slots (seg handle + CNN handle + stream each) so the H2D copy of batch i+1 overlaps the
     # kernels of batch i; every step still moves its frames host->device and its results device->host.
@@ -220,7 +220,7 @@ def run_ours(args):
             # identity probabilities back to the host (upper bound of rows: crops of this batch are not known yet)
             sl["probs_host"][:B * N_INDIV].copy_(sl["probs"][:B * N_INDIV], non_blocking=True)
             if world_size > 1:
-                dist.all_gather_into_tensor(meta_all.view(-1), as_tensor(sl["res"][3], meta_bytes))
+                sharding.all_gather_metadata(sharding.pack_metadata(as_tensor(sl["res"][4], B * 32), as_tensor(sl["res"][3], B * MAX_CROPS * 32), B, MAX_CROPS), out=meta_all)
         sl["pending"] = True
 
     def e2e_wait(i):

@@ -1,0 +1,80 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes shard frames, all-gather the fixed-stride blob
+metadata and every rank reassembles all frames in order."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from trex_b200 import sharding
+from trex_b200.background_subtraction import INFO_DTYPE, REC_DTYPE
+
+B, KMAX, ROUNDS = 4, 8, 3
+
+
+def _fake_meta(rank, world, rnd):
+    """Deterministic metadata a rank would produce for its frames of a round."""
+    lo, hi = sharding.frame_range(rnd, rank, world, B)
+    infos = np.zeros(B, INFO_DTYPE)
+    recs = np.zeros(B * KMAX, REC_DTYPE)
+    k = 0
+    for i, f in enumerate(range(lo, hi)):
+        n = (f * 7 + 3) % (KMAX + 1)
+        infos[i]["blob_begin"], infos[i]["n_blobs"] = k, n
+        for j in range(n):
+            recs[k]["bid"] = f * 1000 + j
+            recs[k]["frame"] = i
+            recs[k]["n_pixels"] = 10 + j
+            k += 1
+    return infos, recs
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for rnd in range(ROUNDS):
+            infos, recs = _fake_meta(rank, world, rnd)
+            local = sharding.pack_metadata(torch.from_numpy(infos.view(np.uint8).copy()), torch.from_numpy(recs.view(np.uint8).copy()), B, KMAX)
+            assert local.numel() == sharding.meta_bytes(B, KMAX)
+            gathered = sharding.all_gather_metadata(local)
+            frames = sharding.unpack_round(gathered, rnd, B, KMAX)
+            exp_frames = list(range(rnd * world * B, (rnd + 1) * world * B))
+            ok &= list(frames) == exp_frames
+            for f, (info, r, trunc) in frames.items():
+                n = (f * 7 + 3) % (KMAX + 1)
+                ok &= int(info["n_blobs"]) == n and not trunc
+                ok &= [int(x) for x in r["bid"]] == [f * 1000 + j for j in range(n)]
+                rr, rk, idx = sharding.owner_of(f, world, B)
+                ok &= rr == rnd and sharding.frame_range(rr, rk, world, B)[0] + idx == f
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_metadata_allgather():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_frame_partition_covers_everything_once():
+    world, batch = 8, 64
+    seen = []
+    for rnd in range(3):
+        for rank in range(world):
+            lo, hi = sharding.frame_range(rnd, rank, world, batch)
+            seen.extend(range(lo, hi))
+    assert seen == list(range(3 * world * batch))

@@ -722,9 +722,16 @@ extern "C" int tb_seg_submit(tb_seg *h, const uint8_t *const *frames, int n, int
     TB_CUDA(cudaSetDevice(h->cfg.device));
     const size_t W = h->d.W, H = h->d.H;
     if (stride <= 0) stride = (int64_t)W;
+    bool contiguous = (size_t)stride == W;
     for (int i = 0; i < n; ++i) {
         TB_REQUIRE(frames[i], TB_ERR_INVALID, "tb_seg_submit: null frame pointer");
-        TB_CUDA(cudaMemcpy2DAsync(h->d_frames + (size_t)i * W * H, W, frames[i], (size_t)stride, W, H, cudaMemcpyHostToDevice, h->stream));
+        if (i && frames[i] != frames[i - 1] + W * H) contiguous = false;
+    }
+    if (contiguous) {          // packed batch: one copy instead of n
+        TB_CUDA(cudaMemcpyAsync(h->d_frames, frames[0], (size_t)n * W * H, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            TB_CUDA(cudaMemcpy2DAsync(h->d_frames + (size_t)i * W * H, W, frames[i], (size_t)stride, W, H, cudaMemcpyHostToDevice, h->stream));
     }
     return seg_launch(h, h->d_frames, n, h->stream, fetch);
 }
