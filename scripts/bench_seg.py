@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the segmentation kernels alone (K1 seg_rle, K2 ccl_label, K3 blob_emit) on resident
+synthetic 1080p batches; prints per-kernel ms and the HBM roofline fraction of K1.
+Knobs (env): TB_SEG_FPC (frames per CTA), TB_SEG_NO_TMA=1 (register-streaming K1)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import trex_b200  # noqa: E402
+from trex_b200.synthetic import BlobWorld  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+world = BlobWorld(n_blobs=100, seed=1234)
+src = world.frames(16)
+dev = torch.device("cuda", 0)
+pool = [torch.from_numpy(src[np.random.default_rng(i).permutation(np.arange(B) % 16)]).to(dev) for i in range(4)]
+bs = trex_b200.BackgroundSubtraction(world.bg, max_batch=B, max_individuals=128)
+stream = torch.cuda.Stream(dev)
+for i in range(3):
+    bs.apply_device(pool[i % 4].data_ptr(), B, stream.cuda_stream)
+bs.wait()
+bs.profile(True)
+for i in range(reps):
+    bs.apply_device(pool[i % 4].data_ptr(), B, stream.cuda_stream)
+bs.wait()
+ms, n = bs.kernel_ms()
+tot = bs.totals()
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+k1 = ms["seg_rle"] / n
+alg = B * 1920 * 1080 + 8 * tot[1]
+print(json.dumps({"B": B, "fpc": os.environ.get("TB_SEG_FPC"), "no_tma": os.environ.get("TB_SEG_NO_TMA"),
+                  "seg_rle_ms": k1, "GBps": alg / k1 / 1e6, "frac": alg / k1 / 1e6 / peak,
+                  "ccl_ms": ms["ccl_label"] / n, "emit_ms": ms["blob_emit"] / n, "blobs": tot[0]}))

@@ -169,7 +169,11 @@ class BackgroundSubtraction:
             lib().tb_seg_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = deinit
+    def __del__(self):
+        try:
+            self.deinit()
+        except Exception:      # interpreter shutdown
+            pass
 
     # -- results -------------------------------------------------------------------------------
     def raw_result(self, i):

@@ -11,8 +11,10 @@
 // lock-free union-find whose root is the raster-first run (K2), and blobs are materialised by
 // warps walking their bounding boxes (K3).  Data layout and rooflines: DESIGN.md.
 #include "common.h"
+#include "umma.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -90,6 +92,23 @@ __device__ __forceinline__ uint32_t fg16(const uint4 &f, const uint4 &b, const S
 {
     return pack4(fg4<GENERIC>(f.x, b.x, p)) | (pack4(fg4<GENERIC>(f.y, b.y, p)) << 4) |
            (pack4(fg4<GENERIC>(f.z, b.z, p)) << 8) | (pack4(fg4<GENERIC>(f.w, b.w, p)) << 12);
+}
+// Fast path (default settings and |T| <= 127): per-byte flags in bit 7 by SWAR arithmetic, then the 16
+// flags are gathered with four dp4a (bytes 0x80 times weights 1,2,4,8 / 16,32,64,128).
+__device__ __forceinline__ uint32_t fgflag_fast(uint32_t f, uint32_t b, uint32_t kadd)
+{
+    const uint32_t d = __vabsdiffu4(f, b);
+    const uint32_t t = (d & 0x7f7f7f7fu) + kadd;               // bit 7: (d & 127) > T
+    const uint32_t u = (f & 0x7f7f7f7fu) + 0x7f7f7f7fu;        // bit 7: (f & 127) != 0
+    return (t | d) & (u | f) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t fg16_fast(const uint4 &f, const uint4 &b, uint32_t kadd)
+{
+    uint32_t lo = __dp4a(fgflag_fast(f.x, b.x, kadd), 0x08040201u, 0u);
+    lo = __dp4a(fgflag_fast(f.y, b.y, kadd), 0x80402010u, lo);
+    uint32_t hi = __dp4a(fgflag_fast(f.z, b.z, kadd), 0x08040201u, 0u);
+    hi = __dp4a(fgflag_fast(f.w, b.w, kadd), 0x80402010u, hi);
+    return (lo >> 7) | ((hi >> 7) << 8);
 }
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 {
@@ -205,6 +224,143 @@ seg_rle_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
                 int col = gc0 + (b >> 4);
                 while (col >= d.cpr) col -= d.cpr;
                 if (oe < d.rcap) out[(size_t)oe * 4 + 1] = (uint16_t)(col * 16 + (b & 15));
+                ++oe;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, bulk-copy variant (frame widths that are multiples of 16): the band's tile of every frame is a
+// contiguous <= 16 KB range, so a producer warp streams it into a 3-stage shared-memory ring with
+// cp.async.bulk (TMA engine, mbarrier completion) while 8 consumer warps pull their chunks out of the
+// ring into registers, release the stage at once and run the same mask / 64-bit run-word / ranking code.
+// The memory pipeline depth no longer depends on registers or occupancy.
+// ------------------------------------------------------------------------------------------------
+constexpr int K1T_STAGES = 3, K1T_NT = K1_NT + 32, K1T_SMEM = K1T_STAGES * K1_CHUNKS * 16;
+
+template <bool GENERIC>
+__global__ void __launch_bounds__(K1T_NT, 4)
+seg_rle_tma_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
+{
+    extern __shared__ __align__(128) uint8_t k1t_dsm[];
+    uint4 (*s_tile)[K1_CHUNKS] = reinterpret_cast<uint4 (*)[K1_CHUNKS]>(k1t_dsm);
+    __shared__ __align__(16) uint16_t s_mask[K1_CHUNKS + 8];
+    __shared__ uint32_t s_wtot[K1_NT / 32];
+    __shared__ uint32_t s_base;
+    __shared__ uint64_t bar_full[K1T_STAGES], bar_empty[K1T_STAGES];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int band = blockIdx.x;
+    const int row0 = band * d.rpt;
+    const int tile_rows = min(d.rpt, d.H - row0);
+    const int tile_chunks = tile_rows * d.cpr;
+    const size_t frame_bytes = (size_t)d.W * d.H;
+    const int f0 = blockIdx.y * fpc, f1 = min(d.B, f0 + fpc);
+
+    if (tid == 0) {
+        for (int i = 0; i < K1T_STAGES; ++i) { umma::mbar_init(&bar_full[i], 1); umma::mbar_init(&bar_empty[i], K1_NT / 32); }
+        umma::fence_mbar_init();
+        for (int i = 0; i < 8; ++i) s_mask[K1_CHUNKS + i] = 0;
+    }
+    __syncthreads();
+
+    if (warp == K1_NT / 32) {                      // producer warp
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)tile_chunks * 16u;
+            for (int f = f0, it = 0; f < f1; ++f, ++it) {
+                const int s = it % K1T_STAGES;
+                umma::mbar_wait(&bar_empty[s], ((it / K1T_STAGES) & 1) ^ 1);
+                umma::mbar_expect_tx(&bar_full[s], bytes);
+                umma::bulk_g2s(&s_tile[s][0], frames + (size_t)f * frame_bytes + (size_t)row0 * d.W, bytes, &bar_full[s]);
+            }
+        }
+        return;
+    }
+
+    uint4 bgc[K1_KPT];
+#pragma unroll
+    for (int k = 0; k < K1_KPT; ++k) {
+        const int c = warp * (32 * K1_KPT) + k * 32 + lane;
+        bgc[k] = make_uint4(0, 0, 0, 0);
+        if (c < tile_chunks) bgc[k] = *reinterpret_cast<const uint4 *>(d.bg + (size_t)row0 * d.W + (size_t)c * 16);
+    }
+    const int g0 = 4 * tid;
+    const int gr0 = g0 / d.cpr, gc0 = g0 % d.cpr;
+    uint64_t RS = 0, RE = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int col = (g0 + i) % d.cpr;
+        if (col == 0) RS |= 1ull << (16 * i);
+        if (col == d.cpr - 1) RE |= 1ull << (16 * i + 15);
+    }
+
+    // pixel coordinates of the 64-pixel word: at most one row break when a row holds >= 4 chunks
+    const bool single_break = d.cpr >= 4;
+    const int x_first = gc0 * 16, y_first = row0 + gr0;
+    const int brk = min(64, (d.cpr - gc0) * 16);                 // bit index at which the next row starts
+    for (int f = f0, it = 0; f < f1; ++f, ++it) {
+        const int s = it % K1T_STAGES;
+        umma::mbar_wait(&bar_full[s], (it / K1T_STAGES) & 1);
+        uint4 cur[K1_KPT];
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) {
+            const int c = warp * (32 * K1_KPT) + k * 32 + lane;
+            cur[k] = (c < tile_chunks) ? s_tile[s][c] : make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bar_empty[s]);          // stage is in registers: refill it
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) {
+            const int c = warp * (32 * K1_KPT) + k * 32 + lane;
+            uint32_t m16 = 0;
+            if (c < tile_chunks) m16 = GENERIC ? fg16<true>(cur[k], bgc[k], p) : fg16_fast(cur[k], bgc[k], p.lo4);
+            s_mask[c] = (uint16_t)m16;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint64_t M = *reinterpret_cast<const uint64_t *>(s_mask + g0);
+        const uint64_t prev = g0 > 0 ? (uint64_t)(s_mask[g0 - 1] >> 15) : 0ull;
+        const uint64_t next = (uint64_t)(s_mask[g0 + 4] & 1u);
+        uint64_t st = M & ~(((M << 1) | prev) & ~RS);
+        uint64_t en = M & ~(((M >> 1) | (next << 63)) & ~RE);
+        uint32_t run, ex = warp_excl_scan((uint32_t)__popcll(st) | ((uint32_t)__popcll(en) << 16), run);
+        if (lane == 0) s_wtot[warp] = run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < K1_NT / 32; ++w) {
+            uint32_t t = s_wtot[w];
+            if (w < warp) wbase += t;
+            total += t;
+        }
+        if (tid == 0) {
+            uint32_t ns = total & 0xFFFFu;
+            uint32_t base = ns ? atomicAdd(&d.run_count[f], ns) : 0u;
+            s_base = base;
+            d.band_base[(size_t)f * d.n_bands + band] = base;
+            d.band_cnt[(size_t)f * d.n_bands + band] = ns;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (st | en) {
+            uint16_t *out = reinterpret_cast<uint16_t *>(d.runs_raw + (size_t)f * d.rcap);
+            uint32_t os = s_base + ((wbase + ex) & 0xFFFFu), oe = s_base + ((wbase + ex) >> 16);
+            while (st) {
+                const int b = __ffsll((long long)st) - 1; st &= st - 1;
+                int x, y;
+                if (single_break) { const bool nx = b >= brk; x = nx ? b - brk : x_first + b; y = y_first + (nx ? 1 : 0); }
+                else { int col = gc0 + (b >> 4), row = gr0; while (col >= d.cpr) { col -= d.cpr; ++row; } x = col * 16 + (b & 15); y = row0 + row; }
+                if (os < d.rcap) {
+                    out[(size_t)os * 4 + 0] = (uint16_t)x;
+                    *reinterpret_cast<uint32_t *>(out + (size_t)os * 4 + 2) = (uint32_t)y;
+                }
+                ++os;
+            }
+            while (en) {
+                const int b = __ffsll((long long)en) - 1; en &= en - 1;
+                int x;
+                if (single_break) x = b >= brk ? b - brk : x_first + b;
+                else { int col = gc0 + (b >> 4); while (col >= d.cpr) col -= d.cpr; x = col * 16 + (b & 15); }
+                if (oe < d.rcap) out[(size_t)oe * 4 + 1] = (uint16_t)x;
                 ++oe;
             }
         }
@@ -685,12 +841,28 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     SegDev d = h->d;
     d.B = n;
     TB_CUDA(cudaMemsetAsync(d.run_count, 0, sizeof(uint32_t) * (size_t)n, s));
-    const int fpc = n >= 64 ? 4 : 1;
+    static const int fpc_env = getenv("TB_SEG_FPC") ? atoi(getenv("TB_SEG_FPC")) : 0;
+    const int fpc = fpc_env > 0 ? fpc_env : (n >= 64 ? 8 : (n >= 8 ? 2 : 1));
     dim3 g1((unsigned)d.n_bands, (unsigned)((n + fpc - 1) / fpc));
     const int slot = h->prof.begin(s);
     h->prof.mark(slot, 0);
-    if (h->k.flags == (F_DIFF | F_ABS)) seg_rle_kernel<false><<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
-    else seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
+    static const bool no_tma = getenv("TB_SEG_NO_TMA") != nullptr;      // bring-up switch
+    const bool plain = h->k.flags == (F_DIFF | F_ABS) && (h->k.t4 & 0xFFu) <= 127u;
+    SegK kk = h->k;
+    if (plain) kk.lo4 = (127u - (kk.t4 & 0xFFu)) * 0x01010101u;      // SWAR addend of the fast path
+    if (d.aligned && !no_tma) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            TB_CUDA(cudaFuncSetAttribute(seg_rle_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM));
+            TB_CUDA(cudaFuncSetAttribute(seg_rle_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM));
+            attr_done = true;
+        }
+        if (plain) seg_rle_tma_kernel<false><<<g1, K1T_NT, K1T_SMEM, s>>>(frames_dev, d, kk, fpc);
+        else seg_rle_tma_kernel<true><<<g1, K1T_NT, K1T_SMEM, s>>>(frames_dev, d, h->k, fpc);
+    } else {
+        if (plain) seg_rle_kernel<false><<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
+        else seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
+    }
     h->prof.mark(slot, 1);
     ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
     h->prof.mark(slot, 2);

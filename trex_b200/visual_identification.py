@@ -90,4 +90,8 @@ class VINetwork:
             lib().tb_vi_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = deinit
+    def __del__(self):
+        try:
+            self.deinit()
+        except Exception:      # interpreter shutdown
+            pass
