@@ -331,8 +331,9 @@ struct tb_vi {
     float *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *h1 = nullptr;
     uint8_t *d_img = nullptr; float *d_probs = nullptr, *d_logits = nullptr;
     // tensor-core path (precision 1)
-    uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w2t = nullptr, *w3t = nullptr, *wfc = nullptr;
+    uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w1t = nullptr, *w2t = nullptr, *w3t = nullptr, *wfc = nullptr;
     int fc_groups = 0, n_sms = 148, head_w_smem = 0;
+    bool conv1_cuda = getenv("TB_CONV1_CUDA") != nullptr;  // bring-up switch: CUDA-core conv1 on the tensor path
     bool conv2_flat = getenv("TB_CONV2_FLAT") != nullptr;
     bool conv3_flat = getenv("TB_CONV3_FLAT") != nullptr;   // bring-up switch: position-major conv3 kernel
     uint64_t launches = 0;
@@ -379,6 +380,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
         h->fc_groups = (int)((CH + 127) / 128 * 16);
         A(h->in2, CH * tc::Conv2Cfg::IMG_BYTES + 256); A(h->in3, CH * tc::Conv3Cfg::IMG_BYTES + 256);
         A(h->fca, (size_t)2 * h->fc_groups * tc::FC_KC * 128);
+        A(h->w1t, (size_t)tc::Conv1T::W_BYTES);
         A(h->w2t, (size_t)25 * tc::Conv2Cfg::WTAP_BYTES); A(h->w3t, (size_t)25 * tc::Conv3Cfg::WTAP_BYTES);
         A(h->wfc, (size_t)2 * tc::FC_KC * tc::FC_N * 16);
         if (r == TB_OK) {   // halo positions are never written by the kernels: zero once
@@ -529,6 +531,25 @@ extern "C" int tb_vi_commit(tb_vi *h)
         const std::vector<float> *c2, *c3;
         if ((r = vi_need(h, "model.conv2.weight", (size_t)64 * 16 * 25, &c2))) return r;
         if ((r = vi_need(h, "model.conv3.weight", (size_t)128 * 64 * 25, &c3))) return r;
+        {   // conv1 B operand: [j = filter row pair][k-chunk][16 cout hi + 16 cout lo][8]; chunk c of pair j holds filter row 2j+c, taps 0..4
+            const std::vector<float> *c1;
+            if ((r = vi_need(h, "model.conv1.weight", (size_t)16 * 25, &c1))) return r;
+            std::vector<float> sc1(16);
+            TB_CUDA(cudaMemcpy(sc1.data(), h->s1, 16 * 4, cudaMemcpyDeviceToHost));
+            std::vector<uint16_t> wb(tc::Conv1T::W_BYTES / 2, 0);
+            for (int j = 0; j < 3; ++j)
+                for (int c = 0; c < 2; ++c)
+                    for (int co = 0; co < 16; ++co)
+                        for (int e = 0; e < 5; ++e) {
+                            const int dy = 2 * j + c;
+                            if (dy >= 5) continue;
+                            uint16_t hi, lo;
+                            split_bf16_host((*c1)[(size_t)co * 25 + dy * 5 + e] * sc1[co], hi, lo);
+                            wb[(((size_t)j * 2 + c) * 32 + co) * 8 + e] = hi;
+                            wb[(((size_t)j * 2 + c) * 32 + 16 + co) * 8 + e] = lo;
+                        }
+            TB_CUDA(cudaMemcpy(h->w1t, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+        }
         // the 2-D conv2 and channel-major conv3 kernels expect the BN scale inside the weights
         std::vector<float> sc2(64), sc3(128);
         TB_CUDA(cudaMemcpy(sc2.data(), h->s2, 64 * 4, cudaMemcpyDeviceToHost));
@@ -562,6 +583,7 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
     if (!attr_done) {
         TB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::SMEM));
         TB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3Cfg::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
@@ -571,7 +593,8 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         const int n = std::min(h->chunk, n_max - base);
         const int slot = h->prof.begin(s);
         h->prof.mark(slot, 0);
-        conv1_planes_kernel<<<n, 256, 0, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1, h->s1, h->t1, h->in2);
+        if (h->conv1_cuda) conv1_planes_kernel<<<n, 256, 0, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1, h->s1, h->t1, h->in2);
+        else conv1_tc_kernel<<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::SMEM, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
         h->prof.mark(slot, 1);
         if (h->conv2_flat) k2<<<std::min(n * Conv2Cfg::PASSES, h->n_sms), NT, Conv2Cfg::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3, 0);
         else conv2_2d_kernel<<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
