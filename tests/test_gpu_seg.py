@@ -216,3 +216,27 @@ def test_capacity_and_state_errors():
     with pytest.raises(trex_b200.TrexB200Error) as e:
         bs2.apply([fr])
     assert e.value.code == -4
+
+
+def test_config4_256_individuals_and_config5_4k():
+    """BASELINE configs[3] / [4] geometry: 256 blobs at 1080p and 100 blobs at 3840x2160, bit-exact vs oracle."""
+    from trex_b200.synthetic import BlobWorld
+    kw = dict(detect_threshold=15, detect_size_filter=[(10, 100000)])
+    for (h, w, n, frames) in ((1080, 1920, 256, 2), (2160, 3840, 100, 2)):
+        world = BlobWorld(h=h, w=w, n_blobs=n, seed=77)
+        fr = world.frames(frames)
+        bs = _mk(world.bg, max_batch=frames, max_individuals=256, **kw)
+        got = bs.apply(fr)
+        crops, idx = bs.crops()
+        from oracle import seg
+        k = 0
+        for f in range(frames):
+            ref = _oracle(fr[f], world.bg, **kw)
+            assert _as_list(got[f]) == ref.as_list(), (h, w, f)
+            assert len(ref) >= int(0.85 * n)
+            for j in range(min(len(ref), 256)):
+                if j % 37 == 0:
+                    assert np.array_equal(crops[k + j], seg.crop_blob(*ref.blob(j), world.bg, seg.DIFF_ABSOLUTE))
+            k += min(len(ref), 256)
+        assert k == len(crops)
+        bs.deinit()

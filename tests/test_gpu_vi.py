@@ -86,3 +86,22 @@ def test_tensor_path_many_images_persistent_ctas():
     assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
     probs2 = net.probabilities(crops[:100])          # handle reuse, different n
     assert np.abs(probs2 - probs[:100]).max() < 1e-6
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_256_classes(precision):
+    """BASELINE configs[3]: 256 individuals -> M = 256 classes."""
+    import trex_b200
+    from oracle import vi
+    M = 256
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=3))
+    rng = np.random.default_rng(2)
+    crops = np.zeros((40, 80, 80, 1), np.uint8)
+    for i in range(40):
+        crops[i, 20:60, 10 + i % 20:50 + i % 20, 0] = rng.integers(1, 200, (40, 40))
+    net = trex_b200.VINetwork(M, max_images=64, precision=precision)
+    net.load_weights(sd)
+    probs, logits = net.probabilities(crops, return_logits=True)
+    ref = vi.forward_logits(sd, crops)
+    assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
