@@ -472,6 +472,24 @@ static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, i
     return TB_OK;
 }
 
+// conv2 (2-D tile kernel): B operand [tap][cin group][Cout rows of W_hi, then Cout rows of W_lo][8] bf16
+static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale)
+{
+    const int cin = G * 8;
+    std::vector<uint16_t> b((size_t)25 * G * 2 * NOUT * 8);
+    for (int tap = 0; tap < 25; ++tap)
+        for (int g = 0; g < G; ++g)
+            for (int co = 0; co < NOUT; ++co)
+                for (int e = 0; e < 8; ++e) {
+                    uint16_t hi, lo;
+                    split_bf16_host(w[((size_t)co * cin + g * 8 + e) * 25 + tap] * (scale ? scale[co] : 1.f), hi, lo);
+                    b[((((size_t)tap * G + g) * 2 + 0) * NOUT + co) * 8 + e] = hi;
+                    b[((((size_t)tap * G + g) * 2 + 1) * NOUT + co) * 8 + e] = lo;
+                }
+    TB_CUDA(cudaMemcpy(dst, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+    return TB_OK;
+}
+
 // conv weight torch [Cout][Cin][5][5] -> [tap][Cin][Cout]; BN(eval) folded with the conv bias into
 // y = conv * s + t,  s = gamma / sqrt(var + eps),  t = (bias - mean) * s + beta
 static int vi_conv(tb_vi *h, int idx, int cin, int cout, float *dw, float *ds, float *dt)
@@ -554,7 +572,8 @@ extern "C" int tb_vi_commit(tb_vi *h)
         std::vector<float> sc2(64), sc3(128);
         TB_CUDA(cudaMemcpy(sc2.data(), h->s2, 64 * 4, cudaMemcpyDeviceToHost));
         TB_CUDA(cudaMemcpy(sc3.data(), h->s3, 128 * 4, cudaMemcpyDeviceToHost));
-        if ((r = vi_upload_tc_conv(h->w2t, *c2, 2, 64, h->conv2_flat ? nullptr : sc2.data()))) return r;
+        if (h->conv2_flat) { if ((r = vi_upload_tc_conv(h->w2t, *c2, 2, 64, nullptr))) return r; }
+        else if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data()))) return r;
         if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, h->conv3_flat ? nullptr : sc3.data()))) return r;
         // fc1 B operand [hi|lo][kc = c8*100 + pp][112][8]; torch column = (c8*8+e)*100 + pp
         std::vector<uint16_t> wb((size_t)2 * tc::FC_KC * tc::FC_N * 8, 0);

@@ -390,7 +390,7 @@ struct Conv2D {
     static constexpr int BANDS = 3, TILES = W / 8;                                              // y0 = 0, 16, 24
     static constexpr int IN_BYTES = 2 * G * BAND_POS * 16;
     static constexpr int WTAP_BYTES = 2 * G * NOUT * 16, W_BYTES = 25 * WTAP_BYTES;
-    static constexpr int NACC = 8;
+    static constexpr int NACC = 4, ACC_COLS = 2 * NOUT;    // [A_hi*W_hi + A_lo*W_hi | A_hi*W_lo], summed in the epilogue
     static constexpr int SMEM = 2 * IN_BYTES + W_BYTES + NOUT * 8 + 128;
     static constexpr int THREADS = 64 + 256;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -444,8 +444,10 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma::idesc_bf16_f32(128, C::NOUT);
-            const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
+            // weights per tap: [group][64 rows W_hi + 64 rows W_lo][8]; one N = 128 MMA gives A_hi*(W_hi | W_lo),
+            // one N = 64 MMA adds A_lo*W_hi: 14 KB of operand reads per tap instead of 18 KB for three N = 64 MMAs
+            const uint32_t idesc128 = umma::idesc_bf16_f32(128, 2 * C::NOUT), idesc64 = umma::idesc_bf16_f32(128, C::NOUT);
+            const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), 2 * C::NOUT * 16, 128);
             umma::mbar_wait(&bar_w_full, 0);
             uint32_t it = 0, ai = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -458,15 +460,14 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                     const uint32_t buf = ai % C::NACC;
                     umma::mbar_wait(&bar_acc_empty[buf], ((ai / C::NACC) & 1) ^ 1);
                     umma::fence_after_sync();
-                    const uint32_t d = tm + buf * C::NOUT;
+                    const uint32_t d = tm + buf * C::ACC_COLS;
 #pragma unroll 5
                     for (int tap = 0; tap < 25; ++tap) {
                         const uint32_t pos = (uint32_t)((tap / 5) * C::WP + (tap % 5) + tx * 8);
                         const uint32_t a_hi = 0 * C::G * C::BAND_POS + pos, a_lo = 1 * C::G * C::BAND_POS + pos;
-                        const uint32_t w_hi = (uint32_t)(tap * C::WTAP_BYTES >> 4), w_lo = w_hi + C::G * C::NOUT;
-                        umma::mma_bf16(d, a_base + a_hi, w_base + w_hi, idesc, tap != 0);
-                        umma::mma_bf16(d, a_base + a_lo, w_base + w_hi, idesc, 1);
-                        umma::mma_bf16(d, a_base + a_hi, w_base + w_lo, idesc, 1);
+                        const uint32_t w = (uint32_t)(tap * C::WTAP_BYTES >> 4);
+                        umma::mma_bf16(d, a_base + a_hi, w_base + w, idesc128, tap != 0);
+                        umma::mma_bf16(d, a_base + a_lo, w_base + w, idesc64, 1);
                     }
                     umma::commit(&bar_acc_full[buf]);
                 }
@@ -489,14 +490,18 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                 const uint32_t buf = ai % C::NACC;
                 umma::mbar_wait(&bar_acc_full[buf], (ai / C::NACC) & 1);
                 umma::fence_after_sync();
-                uint32_t v[32];
-                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::NOUT + half * 32;
+                uint32_t v[32], vb[32];
+                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::ACC_COLS + half * 32;
                 umma::tmem_ld16(ta, *reinterpret_cast<uint32_t (*)[16]>(&v[0]));
                 umma::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t (*)[16]>(&v[16]));
+                umma::tmem_ld16(ta + C::NOUT, *reinterpret_cast<uint32_t (*)[16]>(&vb[0]));
+                umma::tmem_ld16(ta + C::NOUT + 16, *reinterpret_cast<uint32_t (*)[16]>(&vb[16]));
                 umma::tmem_ld_wait();
                 umma::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);     // values are in registers: buffer reusable
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vb[j]));
                 // 2x2 max-pool as a butterfly over the lane quad (r, r^1, r^8, r^9): after the exchange with
                 // lane^1 a lane keeps 16 of its 32 channels, after lane^8 it keeps 8 = one channel group.
                 // BN scale is folded into the weights, so pooling runs on raw accumulators (+shift is monotone).
