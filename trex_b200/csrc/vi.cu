@@ -549,7 +549,8 @@ extern "C" int tb_vi_commit(tb_vi *h)
         const std::vector<float> *c2, *c3;
         if ((r = vi_need(h, "model.conv2.weight", (size_t)64 * 16 * 25, &c2))) return r;
         if ((r = vi_need(h, "model.conv3.weight", (size_t)128 * 64 * 25, &c3))) return r;
-        {   // conv1 B operand: [j = filter row pair][k-chunk][16 cout hi + 16 cout lo][8]; chunk c of pair j holds filter row 2j+c, taps 0..4
+        {   // conv1 B operand [hi|lo][k-step j][k-chunk c][row = wp*16 + cout][8]: window row u = 2j+c, window col e;
+            // row (wp = 2i+jj, cout) holds the 5x5 filter shifted by (i, jj) inside the 6x8 window, BN scale folded
             const std::vector<float> *c1;
             if ((r = vi_need(h, "model.conv1.weight", (size_t)16 * 25, &c1))) return r;
             std::vector<float> sc1(16);
@@ -557,15 +558,17 @@ extern "C" int tb_vi_commit(tb_vi *h)
             std::vector<uint16_t> wb(tc::Conv1T::W_BYTES / 2, 0);
             for (int j = 0; j < 3; ++j)
                 for (int c = 0; c < 2; ++c)
-                    for (int co = 0; co < 16; ++co)
-                        for (int e = 0; e < 5; ++e) {
-                            const int dy = 2 * j + c;
-                            if (dy >= 5) continue;
-                            uint16_t hi, lo;
-                            split_bf16_host((*c1)[(size_t)co * 25 + dy * 5 + e] * sc1[co], hi, lo);
-                            wb[(((size_t)j * 2 + c) * 32 + co) * 8 + e] = hi;
-                            wb[(((size_t)j * 2 + c) * 32 + 16 + co) * 8 + e] = lo;
-                        }
+                    for (int wp = 0; wp < 4; ++wp)
+                        for (int co = 0; co < 16; ++co)
+                            for (int e = 0; e < 8; ++e) {
+                                const int u = 2 * j + c, dy = u - (wp >> 1), dx = e - (wp & 1);
+                                if (dy < 0 || dy > 4 || dx < 0 || dx > 4) continue;
+                                uint16_t hi, lo;
+                                split_bf16_host((*c1)[(size_t)co * 25 + dy * 5 + dx] * sc1[co], hi, lo);
+                                const size_t idx = ((((size_t)j * 2 + c) * tc::Conv1T::N) + wp * 16 + co) * 8 + e;
+                                wb[idx] = hi;
+                                wb[(size_t)3 * 2 * tc::Conv1T::N * 8 + idx] = lo;
+                            }
             TB_CUDA(cudaMemcpy(h->w1t, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
         }
         // the 2-D conv2 and channel-major conv3 kernels expect the BN scale inside the weights

@@ -635,25 +635,27 @@ fc1_tc_kernel(const uint8_t *__restrict__ a, int n_groups, int n_max, const uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv1 on tensor cores.  C_in = 1, so the "channel group" of a position is made of the pixel and its 7
-// right neighbours:  P[yy*80 + x][e] = padded_crop[yy][x + e]  (bf16; u8 values are exact).  One filter
-// row dy is then a K = 8 dot product with the weights (w[dy][0..4], 0, 0, 0), and one K = 16 MMA covers the
-// two filter rows dy, dy+1 by using LBO = one image row (the second k-chunk is the same plane one row
-// down).  3 MMAs x (W_hi, W_lo) per 8 px x 16 row tile, N = 16 output channels; the pooling is the same
-// lane butterfly as conv2.  The whole crop's plane (85 rows) is built in shared memory by all warps.
+// conv1 on tensor cores, pooled-window formulation.  One GEMM row = one POOLED pixel (py,px); its K = 48
+// operand is the 6x6 input window that feeds the 2x2 block of conv outputs (6 window rows x 8 columns, the
+// last two columns meet zero weights); the N = 64 columns are (position inside the 2x2 block) x 16 output
+// channels, each with the 5x5 filter shifted inside the window.  The max-pool is then a thread-local max
+// over 4 column groups: no shuffles.  C_in = 1, so the "channel group" of a position is the pixel and its
+// right neighbours, decimated by two:  P2[yy][px][e] = padded_crop[yy][2*px + e]  (bf16, exact for u8).
+// A k-step (K = 16) covers window rows u, u+1 via LBO = one P2 row; consecutive pooled rows are two P2
+// rows apart (SBO).  Tiles are 8 pooled px x 16 pooled rows; W_hi and W_lo accumulate into the same columns.
 // ------------------------------------------------------------------------------------------------
 struct Conv1T {
-    static constexpr int H = 80, W = 80, WP = 80, PROWS = 85, IMG_PITCH = 96;
-    static constexpr int P_BYTES = PROWS * WP * 16, IMG_BYTES = PROWS * IMG_PITCH, W_BYTES = 3 * 2 * 32 * 16;   // [j][k-chunk][16 hi + 16 lo rows][8]
-    static constexpr int NACC = 8, TILES_X = 10, TILES_Y = 5, TILES = TILES_X * TILES_Y;
+    static constexpr int H = 80, W = 80, PW = 40, PROWS = 84, IMG_PITCH = 96;
+    static constexpr int P_BYTES = PROWS * PW * 16, IMG_BYTES = PROWS * IMG_PITCH;
+    static constexpr int N = 64, W_BYTES = 2 * 3 * 2 * N * 16;       // [hi|lo][k-step][k-chunk][64 rows][8]
+    static constexpr int NACC = 8, TILES_X = 5, TILES_Y = 3, TILES = TILES_X * TILES_Y;   // y0 = 0, 16, 24
     static constexpr int SMEM = P_BYTES + IMG_BYTES + W_BYTES + 64 + 128;
     static constexpr int THREADS = 64 + 256;
 };
 
 __global__ void __launch_bounds__(Conv1T::THREADS, 1)
 conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__restrict__ n_dev, int base,
-                const uint8_t *__restrict__ wgt /* [3][2 kchunks][32 = 16 cout hi + 16 cout lo][8] bf16, BN scale folded */,
-                const float *__restrict__ sh, uint8_t *__restrict__ out)
+                const uint8_t *__restrict__ wgt, const float *__restrict__ sh, uint8_t *__restrict__ out)
 {
     using C = Conv1T;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -670,7 +672,7 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
         for (int i = 0; i < C::NACC; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 4); }
         umma::fence_mbar_init();
     }
-    if (warp == 1) umma::tmem_alloc(&s_tmem, 256);
+    if (warp == 1) umma::tmem_alloc(&s_tmem, 512);
     for (int i = tid; i < C::W_BYTES / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(s_w)[i] = reinterpret_cast<const uint32_t *>(wgt)[i];
     if (tid < 16) s_sh[tid] = sh[tid];
     for (int i = tid; i < C::IMG_BYTES / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(s_img)[i] = 0u;   // zero halo, kept
@@ -681,37 +683,30 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
     uint32_t ai = 0;                                                   // running tile counter (ring phase)
 
     for (int n = blockIdx.x; n < n_act; n += gridDim.x) {
-        // ---- stage the crop: interior of the zero-padded u8 image, then the bf16 plane ----
+        // ---- stage the crop: interior of the zero-padded u8 image, then the decimated bf16 plane ----
         const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)n * C::H * C::W);
         for (int i = tid; i < C::H * C::W / 4; i += C::THREADS) {
             const int y = i / (C::W / 4), x4 = i % (C::W / 4);
             const uint32_t v = src[i];
-            uint8_t *d8 = s_img + (y + 2) * C::IMG_PITCH + 2 + x4 * 4;     // 2-byte aligned only
-            d8[0] = (uint8_t)v; d8[1] = (uint8_t)(v >> 8); d8[2] = (uint8_t)(v >> 16); d8[3] = (uint8_t)(v >> 24);
+            uint16_t *d16 = reinterpret_cast<uint16_t *>(s_img + (y + 2) * C::IMG_PITCH + 2 + x4 * 4);   // 2-byte aligned
+            d16[0] = (uint16_t)v; d16[1] = (uint16_t)(v >> 16);
         }
         __syncthreads();
-        // four positions per step: 11 source bytes -> bf16 once, then the 4 sliding windows are byte permutes
-        for (int i = tid; i < C::PROWS * (C::WP / 4); i += C::THREADS) {
-            const int yy = i / (C::WP / 4), x4 = i % (C::WP / 4);
-            const uint32_t *pw = reinterpret_cast<const uint32_t *>(s_img + yy * C::IMG_PITCH + x4 * 4);
-            const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
-            uint32_t fb[11];                                   // fp32 bit patterns; bf16 = their high halves (exact for < 256)
+        // four pooled positions per step: 14 source bytes -> bf16 once; position j uses bytes 2j .. 2j+7
+        for (int i = tid; i < C::PROWS * (C::PW / 4); i += C::THREADS) {
+            const int yy = i / (C::PW / 4), p4 = i % (C::PW / 4);
+            const uint2 wa = *reinterpret_cast<const uint2 *>(s_img + yy * C::IMG_PITCH + p4 * 8);
+            const uint2 wb2 = *reinterpret_cast<const uint2 *>(s_img + yy * C::IMG_PITCH + p4 * 8 + 8);
+            const uint32_t ws[4] = {wa.x, wa.y, wb2.x, wb2.y};
+            uint32_t ev[7];
 #pragma unroll
-            for (int k = 0; k < 11; ++k) {
-                const uint32_t wsel = k < 4 ? w0 : (k < 8 ? w1 : w2);
-                fb[k] = __float_as_uint((float)((wsel >> (8 * (k & 3))) & 0xFFu));
+            for (int k = 0; k < 7; ++k) {                      // bf16 pair (byte 2k, byte 2k+1): high halves of the fp32 patterns
+                const uint32_t b0 = (ws[(2 * k) >> 2] >> (8 * ((2 * k) & 3))) & 0xFFu, b1 = (ws[(2 * k + 1) >> 2] >> (8 * ((2 * k + 1) & 3))) & 0xFFu;
+                ev[k] = __byte_perm(__float_as_uint((float)b0), __float_as_uint((float)b1), 0x7632);
             }
-            uint32_t ev[5], od[5];                             // packed pairs (k,k+1) for even / odd k
+            uint4 *dst = s_p + yy * C::PW + p4 * 4;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                ev[k] = __byte_perm(fb[2 * k], fb[2 * k + 1], 0x7632);
-                od[k] = __byte_perm(fb[2 * k + 1], fb[2 * k + 2], 0x7632);
-            }
-            uint4 *dst = s_p + yy * C::WP + x4 * 4;
-            dst[0] = make_uint4(ev[0], ev[1], ev[2], ev[3]);
-            dst[1] = make_uint4(od[0], od[1], od[2], od[3]);
-            dst[2] = make_uint4(ev[1], ev[2], ev[3], ev[4]);
-            dst[3] = make_uint4(od[1], od[2], od[3], od[4]);
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3]);
         }
         umma::fence_async_smem();
         __syncthreads();
@@ -719,21 +714,22 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
 
         if (warp == 1) {
             if (lane == 0) {
-                // one MMA per filter-row pair: N = 32 columns = W_hi (16 couts) | W_lo (16 couts), summed in the epilogue
-                const uint32_t idesc = umma::idesc_bf16_f32(128, 32);
-                const uint64_t a_base = umma::smem_desc(umma::smem_u32(s_p), C::WP * 16, C::WP * 16);
-                const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), 32 * 16, 128);
+                const uint32_t idesc = umma::idesc_bf16_f32(128, C::N);
+                const uint64_t a_base = umma::smem_desc(umma::smem_u32(s_p), C::PW * 16, 2 * C::PW * 16);
+                const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::N * 16, 128);
                 uint32_t a2 = ai;
                 for (int t = 0; t < C::TILES; ++t, ++a2) {
                     const int ty = t / C::TILES_X, tx = t % C::TILES_X;
+                    const int y0 = ty == 2 ? 24 : ty * 16;
                     const uint32_t buf = a2 % C::NACC;
                     umma::mbar_wait(&bar_acc_empty[buf], ((a2 / C::NACC) & 1) ^ 1);
                     umma::fence_after_sync();
-                    const uint32_t d = tm + buf * 32;
+                    const uint32_t d = tm + buf * C::N;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        const uint32_t pos = (uint32_t)((ty * 16 + 2 * j) * C::WP + tx * 8);
-                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)((j * 1024) >> 4), idesc, j != 0);
+                        const uint32_t pos = (uint32_t)((2 * y0 + 2 * j) * C::PW + tx * 8);
+                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)((j * 2 * C::N * 16) >> 4), idesc, j != 0);
+                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)(((3 + j) * 2 * C::N * 16) >> 4), idesc, 1);
                     }
                     umma::commit(&bar_acc_full[buf]);
                 }
@@ -741,48 +737,43 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
         } else if (warp >= 2) {
             const int es = (warp - 2) >> 2, quarter = warp & 3;
             const int r = quarter * 32 + lane, trow = r >> 3, tx8 = r & 7;
-            const bool p1 = tx8 & 1, p2 = trow & 1;
             for (int t = es; t < C::TILES; t += 2) {
                 const uint32_t a2 = ai + t, buf = a2 % C::NACC;
                 const int ty = t / C::TILES_X, tx = t % C::TILES_X;
+                const int y0 = ty == 2 ? 24 : ty * 16, ymin = ty == 2 ? 32 : y0;
                 umma::mbar_wait(&bar_acc_full[buf], (a2 / C::NACC) & 1);
                 umma::fence_after_sync();
-                uint32_t v[16], vl[16];
-                umma::tmem_ld16(tm + ((uint32_t)(quarter * 32) << 16) + buf * 32, v);
-                umma::tmem_ld16(tm + ((uint32_t)(quarter * 32) << 16) + buf * 32 + 16, vl);
+                uint32_t v[4][16];
+                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::N;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) umma::tmem_ld16(ta + 16 * q, v[q]);
                 umma::tmem_ld_wait();
                 umma::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);
+                const int y = y0 + trow, px = tx * 8 + tx8;
+                if (y >= ymin && y < C::PW) {
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vl[j]));
-                float m1[8], m2[4];
+                    for (int c = 0; c < 16; c += 2) {
+                        float m[2];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float lo_v = __uint_as_float(v[j]), hi_v = __uint_as_float(v[j + 8]);
-                    const float keep = p1 ? hi_v : lo_v, send = p1 ? lo_v : hi_v;
-                    m1[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                        for (int u = 0; u < 2; ++u)
+                            m[u] = fmaxf(fmaxf(fmaxf(__uint_as_float(v[0][c + u]), __uint_as_float(v[1][c + u])),
+                                               fmaxf(__uint_as_float(v[2][c + u]), __uint_as_float(v[3][c + u]))) + s_sh[c + u], 0.f);
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        umma::split_bf16(m[0], h0, l0); umma::split_bf16(m[1], h1, l1);
+                        hi[c >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[c >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
+                    const int pos = (y + 2) * Conv2Cfg::WP + px + 2;
+                    uint8_t *o = out + (size_t)n * Conv2Cfg::IMG_BYTES + (size_t)pos * 16;
+                    constexpr size_t PLB = (size_t)Conv2Cfg::PL * 16;
+                    *reinterpret_cast<uint4 *>(o + 0 * PLB) = make_uint4(hi[0], hi[1], hi[2], hi[3]);      // hi, channels 0-7
+                    *reinterpret_cast<uint4 *>(o + 1 * PLB) = make_uint4(hi[4], hi[5], hi[6], hi[7]);      // hi, channels 8-15
+                    *reinterpret_cast<uint4 *>(o + 2 * PLB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4 *>(o + 3 * PLB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float keep = p2 ? m1[j + 4] : m1[j], send = p2 ? m1[j] : m1[j + 4];
-                    m2[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-                }
-                const int ch0 = (p1 ? 8 : 0) + (p2 ? 4 : 0);              // this lane now owns channels ch0..ch0+3
-                uint32_t hi[2], lo[2];
-#pragma unroll
-                for (int j = 0; j < 4; j += 2) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    umma::split_bf16(fmaxf(m2[j] + s_sh[ch0 + j], 0.f), h0, l0);
-                    umma::split_bf16(fmaxf(m2[j + 1] + s_sh[ch0 + j + 1], 0.f), h1, l1);
-                    hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[j >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-                const int y = ty * 16 + trow, x = tx * 8 + tx8;
-                const int pos = ((y >> 1) + 2) * Conv2Cfg::WP + (x >> 1) + 2;
-                uint8_t *o = out + (size_t)n * Conv2Cfg::IMG_BYTES + (((size_t)(p1 ? 1 : 0)) * Conv2Cfg::PL + pos) * 16 + (p2 ? 8 : 0);
-                *reinterpret_cast<uint2 *>(o) = make_uint2(hi[0], hi[1]);
-                *reinterpret_cast<uint2 *>(o + (size_t)2 * Conv2Cfg::PL * 16) = make_uint2(lo[0], lo[1]);
             }
         }
         ai += C::TILES;
@@ -792,7 +783,7 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tm, 256);
+    if (warp == 1) umma::tmem_dealloc(tm, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
