@@ -49,9 +49,9 @@ typedef struct tb_seg_params {
     int32_t enable_difference;            /* 1                                                        */
     int32_t detect_threshold_is_absolute; /* 1: |in-bg| ; 0: saturate(bg-in) (:393-399)              */
     int32_t image_invert;                 /* 0                                                        */
-    int32_t use_closing;                  /* 0 (morphology: TB_ERR_INVALID in this release if != 0)   */
-    int32_t closing_size;                 /* 3                                                        */
-    int32_t dilation_size;                /* 0 (TB_ERR_INVALID in this release if != 0)               */
+    int32_t use_closing;                  /* 0; dilate+erode with the elliptical (2k+1)^2 element (:438-448,504-505) */
+    int32_t closing_size;                 /* 3 (1..7)                                                 */
+    int32_t dilation_size;                /* 0; >0 dilate ones(n,n), <0 erode + re-threshold (:541-550); |n| <= 15 */
     float   cm_per_pixel;                 /* 1                                                        */
     int32_t n_size_ranges;                /* detect_size_filter: 0 = keep all; ranges are [lo,hi)    */
     double  size_lo[4], size_hi[4];

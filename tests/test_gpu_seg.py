@@ -209,7 +209,7 @@ def test_capacity_and_state_errors():
     assert e.value.code == -3
     bs.set_background(bg)
     with pytest.raises(trex_b200.TrexB200Error):
-        bs.update_settings(trex_b200.DetectSettings(use_closing=True))
+        bs.update_settings(trex_b200.DetectSettings(use_closing=True, closing_size=9))     # element larger than 15x15
     bs2 = trex_b200.BackgroundSubtraction(bg, max_batch=1, max_runs_per_frame=16,
                                           settings=trex_b200.DetectSettings(detect_size_filter=[]))
     fr = bg.copy(); fr[::2, ::2] = 200       # 1024 runs > capacity
@@ -240,3 +240,32 @@ def test_config4_256_individuals_and_config5_4k():
             k += min(len(ref), 256)
         assert k == len(crops)
         bs.deinit()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(use_closing=True, closing_size=3),
+    dict(use_closing=True, closing_size=2),
+    dict(dilation_size=3),
+    dict(dilation_size=2),
+    dict(use_closing=True, closing_size=1, dilation_size=2),
+    dict(dilation_size=-3),
+    dict(use_closing=True, closing_size=2, dilation_size=-2),
+])
+def test_morphology_vs_oracle(kw):
+    """Optional closing / dilation of generate_binary (RawProcessing.cpp:438-550); the oracle's closing and
+    positive dilation are themselves checked against OpenCV in tests/test_oracle_golden.py."""
+    from oracle import seg
+    rng = np.random.default_rng(21)
+    bg = np.full((144, 208), 120, np.uint8)
+    fr = bg.copy()
+    fr[rng.random(fr.shape) < 0.06] = 30
+    fr[40:70, 50:120] = 20; fr[50:55, 70:90] = 120; fr[100:103, 10:200:3] = 200
+    fr[rng.random(fr.shape) < 0.01] = 0
+    kw = dict(kw, detect_threshold=15, detect_size_filter=[])
+    bs = _mk(bg, max_batch=2, dense=True, **kw)
+    got = bs.apply([fr, bg])
+    ref = _oracle(fr, bg, **kw)
+    assert _as_list(got[0]) == ref.as_list()
+    assert _as_list(got[1]) == _oracle(bg, bg, **kw).as_list()
+    keys = {k: v for k, v in kw.items() if k in seg.Params.__dataclass_fields__}
+    assert np.array_equal(bs.debug_binary(fr), seg.generate_binary(fr, bg, seg.Params(**keys)))

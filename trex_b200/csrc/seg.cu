@@ -14,6 +14,7 @@
 #include "umma.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -28,7 +29,7 @@ struct SegK {                  // threshold configuration, bytes replicated x4
                                // bit3 invert mask (T<0), bit4 inRange
     uint32_t t4, lo4, hi4;
 };
-enum { F_DIFF = 1, F_ABS = 2, F_INV = 4, F_INVMASK = 8, F_RANGE = 16 };
+enum { F_DIFF = 1, F_ABS = 2, F_INV = 4, F_INVMASK = 8, F_RANGE = 16, F_PREMASK = 32 };
 
 struct SegDev {
     int W, H, B, cpr, rpt, n_bands, aligned;
@@ -38,6 +39,7 @@ struct SegDev {
     int crop_w, crop_h, crop_method;
     float sqcm; int n_ranges; double lo[4], hi[4];
     const uint8_t *bg;
+    size_t bg_stride;          // 0: one background for all frames; else `bg` holds one mask image per frame (morphology path)
     // K1 outputs
     uint32_t *run_count;       // [B]
     uint32_t *band_base, *band_cnt;   // [B][n_bands]
@@ -76,6 +78,7 @@ __device__ __forceinline__ uint32_t fg4(uint32_t f, uint32_t b, const SegK &p)
 {
     if (!GENERIC)                                                   // default settings: |f-b| > T, grey != 0
         return __vcmpgtu4(__vabsdiffu4(f, b), p.t4) & __vcmpne4(f, 0u);
+    if (p.flags & F_PREMASK) return b & __vcmpne4(f, 0u);           // b = mask bytes after morphology
     uint32_t in = (p.flags & F_INV) ? ~f : f;                       // 255 - x
     uint32_t d = in;
     if (p.flags & F_DIFF) d = (p.flags & F_ABS) ? __vabsdiffu4(in, b) : __vsubus4(b, in);
@@ -167,6 +170,17 @@ seg_rle_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
     const int f0 = blockIdx.y * fpc, f1 = min(d.B, f0 + fpc);
     for (int f = f0; f < f1; ++f) {
         const uint8_t *fb = frames + (size_t)f * frame_bytes;
+        if (d.bg_stride) {                                      // per-frame mask image instead of the background
+            const uint8_t *mb = d.bg + (size_t)f * d.bg_stride;
+#pragma unroll
+            for (int k = 0; k < K1_KPT; ++k) {
+                const int c = warp * (32 * K1_KPT) + k * 32 + lane;
+                if (c < tile_chunks) {
+                    if (d.aligned) bgc[k] = *reinterpret_cast<const uint4 *>(mb + (size_t)row0 * d.W + (size_t)c * 16);
+                    else bgc[k] = ld_edge(mb + (size_t)(row0 + c / d.cpr) * d.W, c % d.cpr, d.W);
+                }
+            }
+        }
         uint4 cur[K1_KPT];
 #pragma unroll
         for (int k = 0; k < K1_KPT; ++k) {
@@ -376,6 +390,67 @@ __global__ void binary_image_kernel(const uint8_t *__restrict__ frame, const uin
         uint32_t m = fg4<true>(f, bg[i], p) & 0xFFu;
         out[i] = m ? (uint8_t)f : (uint8_t)0;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Optional morphology of generate_binary (default off in the reference): threshold mask ->
+// closing (dilate, erode with the elliptical (2k+1)^2 element, RawProcessing.cpp:438-448,504-505) ->
+// dilation_size > 0: dilate ones(n,n); < 0: erode, keep pixels whose difference still exceeds |T|,
+// closing again (:541-550).  Pixels outside the image are ignored (OpenCV's default morphology border).
+// These are plain per-pixel kernels over a mask image; K1 then runs on (mask, frame) with F_PREMASK.
+// ------------------------------------------------------------------------------------------------
+struct MorphEl { uint32_t rows[15]; int kw, kh, ax, ay; };
+
+__global__ void thresh_mask_kernel(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ bg, uint8_t *__restrict__ mask,
+                                   uint8_t *__restrict__ diff, size_t frame_px, size_t total, SegK p)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t f = frames[i], b = bg[i % frame_px];
+        const uint32_t in = (p.flags & F_INV) ? 255u - f : f;
+        uint32_t d = in;
+        if (p.flags & F_DIFF) d = (p.flags & F_ABS) ? (in > b ? in - b : b - in) : (b > in ? b - in : 0u);
+        const uint32_t t = p.t4 & 0xFFu, lo = p.lo4 & 0xFFu, hi = p.hi4 & 0xFFu;
+        bool m = (p.flags & F_RANGE) ? (d >= lo && d <= hi) : (d > t);
+        if (p.flags & F_INVMASK) m = !m;
+        mask[i] = m ? 255 : 0;
+        if (diff) diff[i] = (uint8_t)d;
+    }
+}
+
+__global__ void morph_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int W, int H, size_t total, MorphEl el, int dilate)
+{
+    const size_t frame_px = (size_t)W * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t fo = i / frame_px * frame_px;
+        const int y = (int)((i - fo) / W), x = (int)((i - fo) % W);
+        int v = dilate ? 0 : 255;
+        for (int j = 0; j < el.kh; ++j) {
+            const int yy = y + j - el.ay;
+            if (yy < 0 || yy >= H) continue;
+            const uint32_t bits = el.rows[j];
+            for (int k = 0; k < el.kw; ++k) {
+                if (!((bits >> k) & 1u)) continue;
+                const int xx = x + k - el.ax;
+                if (xx < 0 || xx >= W) continue;
+                const int sv = src[fo + (size_t)yy * W + xx];
+                v = dilate ? max(v, sv) : min(v, sv);
+            }
+        }
+        dst[i] = (uint8_t)v;
+    }
+}
+
+// dilation_size < 0: keep the eroded mask where the difference still exceeds |T|
+__global__ void remask_kernel(const uint8_t *__restrict__ eroded, const uint8_t *__restrict__ diff, uint8_t *__restrict__ mask, size_t total, uint32_t t)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        mask[i] = (eroded[i] && diff[i] > t) ? 255 : 0;
+}
+
+__global__ void mask_and_kernel(const uint8_t *__restrict__ mask, const uint8_t *__restrict__ frame, uint8_t *__restrict__ out, size_t total)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = mask[i] & frame[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -684,11 +759,16 @@ struct tb_seg {
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;
     EventRing<3> prof;
+    // optional morphology (use_closing / dilation_size): mask images of one batch, allocated on first use
+    bool morph = false;
+    uint8_t *m_a = nullptr, *m_b = nullptr, *m_diff = nullptr;
+    MorphEl el_close{}, el_dil{};
 };
 
 static int seg_make_k(const tb_seg_params &p, SegK &k, std::string &why)
 {
-    if (p.use_closing || p.dilation_size != 0) { why = "morphology (use_closing / dilation_size) is not built in this release"; return TB_ERR_INVALID; }
+    if (p.use_closing && (p.closing_size < 1 || p.closing_size > 7)) { why = "closing_size must be 1..7 (element up to 15x15)"; return TB_ERR_INVALID; }
+    if (p.dilation_size < -15 || p.dilation_size > 15) { why = "dilation_size must be -15..15"; return TB_ERR_INVALID; }
     if (p.n_size_ranges < 0 || p.n_size_ranges > 4) { why = "n_size_ranges must be 0..4"; return TB_ERR_INVALID; }
     auto rep = [](int v) { uint32_t b = (uint32_t)std::min(std::max(v, 0), 255); return b * 0x01010101u; };
     k.flags = (p.enable_difference ? F_DIFF : 0) | (p.detect_threshold_is_absolute ? F_ABS : 0) |
@@ -699,6 +779,30 @@ static int seg_make_k(const tb_seg_params &p, SegK &k, std::string &why)
     k.lo4 = rep(T); k.hi4 = rep(p.threshold_maximum);
     if (T > 255 || p.threshold_maximum < 0) { k.lo4 = rep(255); k.hi4 = rep(0); }   // empty range
     return TB_OK;
+}
+
+// cv::getStructuringElement(MORPH_ELLIPSE, (2k+1, 2k+1)) as OpenCV computes it: row i spans
+// |dx| <= round(k * sqrt(1 - (dy/k)^2))  (used at RawProcessing.cpp:442)
+static MorphEl ellipse_element(int k)
+{
+    MorphEl e{};
+    const int n = 2 * k + 1;
+    e.kw = e.kh = n; e.ax = e.ay = k;
+    const double inv_r2 = k ? 1.0 / ((double)k * k) : 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int dy = i - k;
+        const int dx = (int)std::lrint(k * std::sqrt((k * k - dy * dy) * inv_r2));
+        const int j1 = std::max(k - dx, 0), j2 = std::min(k + dx + 1, n);
+        for (int j = j1; j < j2; ++j) e.rows[i] |= 1u << j;
+    }
+    return e;
+}
+static MorphEl ones_element(int n)          // cv::Mat::ones(n, n), anchor at the centre (n / 2)
+{
+    MorphEl e{};
+    e.kw = e.kh = n; e.ax = e.ay = n / 2;
+    for (int i = 0; i < n; ++i) e.rows[i] = (1u << n) - 1u;
+    return e;
 }
 
 extern "C" void tb_seg_default_params(tb_seg_params *p)
@@ -818,6 +922,19 @@ extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
     SegK k; std::string why;
     if (seg_make_k(*p, k, why) != TB_OK) { set_error("tb_seg_set_params: " + why); return TB_ERR_INVALID; }
     h->params = *p; h->k = k;
+    h->morph = p->use_closing || p->dilation_size != 0;
+    if (h->morph) {
+        TB_CUDA(cudaSetDevice(h->cfg.device));
+        const size_t bytes = (size_t)h->cfg.max_batch * h->d.W * h->d.H;
+        if (!h->m_a) {
+            int r = seg_dev(h, &h->m_a, bytes + 16);
+            if (r == TB_OK) r = seg_dev(h, &h->m_b, bytes + 16);
+            if (r == TB_OK) r = seg_dev(h, &h->m_diff, bytes + 16);
+            if (r != TB_OK) return r;
+        }
+        if (p->use_closing) h->el_close = ellipse_element(p->closing_size);
+        if (p->dilation_size) h->el_dil = ones_element(std::abs(p->dilation_size));
+    }
     h->d.sqcm = p->cm_per_pixel * p->cm_per_pixel;        // SQR(cm_per_pixel) in float, BackgroundSubtraction.cpp:139
     h->d.n_ranges = p->n_size_ranges;
     for (int i = 0; i < 4; ++i) { h->d.lo[i] = p->size_lo[i]; h->d.hi[i] = p->size_hi[i]; }
@@ -836,10 +953,41 @@ extern "C" int tb_seg_set_background(tb_seg *h, const uint8_t *bg, int width, in
     return TB_OK;
 }
 
+// threshold mask -> closing -> dilation / erosion for n frames; returns the buffer holding the final mask
+static int seg_morph(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s, const uint8_t **mask_out)
+{
+    const tb_seg_params &p = h->params;
+    const size_t px = (size_t)h->d.W * h->d.H, total = px * (size_t)n;
+    const int grid = 148 * 8, nt = 256;
+    uint8_t *cur = h->m_a, *tmp = h->m_b;
+    thresh_mask_kernel<<<grid, nt, 0, s>>>(frames_dev, h->d_bg, cur, p.dilation_size < 0 ? h->m_diff : nullptr, px, total, h->k);
+    h->launches += 1;
+    auto closing = [&]() {
+        morph_kernel<<<grid, nt, 0, s>>>(cur, tmp, h->d.W, h->d.H, total, h->el_close, 1);
+        morph_kernel<<<grid, nt, 0, s>>>(tmp, cur, h->d.W, h->d.H, total, h->el_close, 0);
+        h->launches += 2;
+    };
+    if (p.use_closing) closing();
+    if (p.dilation_size > 0) {
+        morph_kernel<<<grid, nt, 0, s>>>(cur, tmp, h->d.W, h->d.H, total, h->el_dil, 1);
+        std::swap(cur, tmp);
+        h->launches += 1;
+    } else if (p.dilation_size < 0) {
+        morph_kernel<<<grid, nt, 0, s>>>(cur, tmp, h->d.W, h->d.H, total, h->el_dil, 0);
+        remask_kernel<<<grid, nt, 0, s>>>(tmp, h->m_diff, cur, total, h->k.t4 & 0xFFu);
+        h->launches += 2;
+        if (p.use_closing) closing();
+    }
+    TB_CUDA(cudaGetLastError());
+    *mask_out = cur;
+    return TB_OK;
+}
+
 static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s, int fetch)
 {
     SegDev d = h->d;
     d.B = n;
+    d.bg_stride = 0;
     TB_CUDA(cudaMemsetAsync(d.run_count, 0, sizeof(uint32_t) * (size_t)n, s));
     static const int fpc_env = getenv("TB_SEG_FPC") ? atoi(getenv("TB_SEG_FPC")) : 0;
     const int fpc = fpc_env > 0 ? fpc_env : (n >= 64 ? 8 : (n >= 8 ? 2 : 1));
@@ -847,10 +995,17 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     const int slot = h->prof.begin(s);
     h->prof.mark(slot, 0);
     static const bool no_tma = getenv("TB_SEG_NO_TMA") != nullptr;      // bring-up switch
-    const bool plain = h->k.flags == (F_DIFF | F_ABS) && (h->k.t4 & 0xFFu) <= 127u;
+    const bool plain = !h->morph && h->k.flags == (F_DIFF | F_ABS) && (h->k.t4 & 0xFFu) <= 127u;
     SegK kk = h->k;
     if (plain) kk.lo4 = (127u - (kk.t4 & 0xFFu)) * 0x01010101u;      // SWAR addend of the fast path
-    if (d.aligned && !no_tma) {
+    if (h->morph) {
+        const uint8_t *mask = nullptr;
+        int r = seg_morph(h, frames_dev, n, s, &mask);
+        if (r != TB_OK) return r;
+        d.bg = mask; d.bg_stride = (size_t)d.W * d.H;
+        kk.flags = F_PREMASK;
+        seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, kk, fpc);
+    } else if (d.aligned && !no_tma) {
         static bool attr_done = false;
         if (!attr_done) {
             TB_CUDA(cudaFuncSetAttribute(seg_rle_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM));
@@ -866,6 +1021,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     h->prof.mark(slot, 1);
     ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
     h->prof.mark(slot, 2);
+    d.bg = h->d_bg; d.bg_stride = 0;                               // crops difference against the real background
     blob_emit_kernel<<<dim3((unsigned)n, K3_SPLIT), K3_NT, 0, s>>>(frames_dev, d);
     h->prof.mark(slot, 3);
     h->launches += 3;
@@ -989,7 +1145,12 @@ extern "C" int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t
     TB_CUDA(cudaSetDevice(h->cfg.device));
     const size_t n = (size_t)h->d.W * h->d.H;
     TB_CUDA(cudaMemcpyAsync(h->d_frames, frame_host, n, cudaMemcpyHostToDevice, h->stream));
-    binary_image_kernel<<<592, 256, 0, h->stream>>>(h->d_frames, h->d_bg, h->d_tmp, n, h->k);
+    if (h->morph) {
+        const uint8_t *mask = nullptr;
+        int r = seg_morph(h, h->d_frames, 1, h->stream, &mask);
+        if (r != TB_OK) return r;
+        mask_and_kernel<<<592, 256, 0, h->stream>>>(mask, h->d_frames, h->d_tmp, n);
+    } else binary_image_kernel<<<592, 256, 0, h->stream>>>(h->d_frames, h->d_bg, h->d_tmp, n, h->k);
     h->launches += 1;
     TB_CUDA(cudaGetLastError());
     TB_CUDA(cudaMemcpyAsync(out_host, h->d_tmp, n, cudaMemcpyDeviceToHost, h->stream));
