@@ -204,6 +204,19 @@ TB_API uint64_t tb_vi_launch_count(tb_vi *h);
 TB_API int tb_vi_profile(tb_vi *h, int enable);
 TB_API int tb_vi_kernel_ms(tb_vi *h, double out_ms[5], uint64_t *n_chunks);
 
+/* ----------------------------------------------------------------------------------------------
+ * Background image generation ("next" row N2b): cmn::AveragingAccumulator
+ * (C/video/AveragingAccumulator.{h,cpp}); method = averaging_method_t: 0 mean, 1 mode, 2 max, 3 min.
+ * add() takes n packed width*height u8 frames; finalize() writes the width*height background that
+ * tb_seg_set_background consumes (VideoSource::generate_average, C/video/VideoSource.cpp:940-1030).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tb_avg tb_avg;
+TB_API int tb_avg_create(int device, int width, int height, int method, tb_avg **out);
+TB_API void tb_avg_destroy(tb_avg *h);
+TB_API int tb_avg_add(tb_avg *h, const uint8_t *frames, int n);
+TB_API int tb_avg_add_device(tb_avg *h, const void *frames_dev, int n, void *stream);
+TB_API int tb_avg_finalize(tb_avg *h, uint8_t *out);
+
 /* Debug / bring-up: one tcgen05 "shifted GEMM" D[128][N] = A[shift+m][:] . B[n][:]^T on bf16 operands in the
  * channel-group-planar layout the convolution kernels use (a: [n_cg][n_pos][8] bf16, b: [n_cg][N][8] bf16,
  * d: [128][N] f32; all host pointers).  Exercised by tests/test_gpu_umma.py. */

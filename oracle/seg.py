@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
                                        C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]
         L.to_segment_batch.restype = C.c_int64
         L.to_num_threads.restype = C.c_int
+        L.to_average.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.to_average.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -209,3 +211,12 @@ def segment_batch(frames, bg, params: Params, crop_method=DIFF_ABSOLUTE, out_w=8
 
 def num_threads() -> int:
     return int(lib().to_num_threads())
+
+
+def average(frames, method="mean"):
+    """AveragingAccumulator restated: frames (n,H,W) u8 -> background (H,W) u8."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    out = np.empty((h, w), np.uint8)
+    lib().to_average(_p(frames), n, w, h, {"mean": 0, "mode": 1, "max": 2, "min": 3}[method], _p(out))
+    return out

@@ -477,6 +477,36 @@ void to_crop_blob(const to_line_t *lines, int64_t n_lines, const uint8_t *px,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * AveragingAccumulator, C/video/AveragingAccumulator.cpp:23-196 (gray): method 0 mean (float sum,
+ * cv::divide = true float division, convertTo = round half to even + saturate), 1 mode (per-pixel
+ * histogram, first maximum = smallest value among ties, :168-171), 2 max, 3 min.
+ * ------------------------------------------------------------------------------------------ */
+int to_average(const uint8_t *frames, int n, int w, int h, int method, uint8_t *out)
+{
+    const size_t px = (size_t)w * h;
+    for (size_t i = 0; i < px; ++i) {
+        if (method == 0) {
+            float s = 0.f;
+            for (int f = 0; f < n; ++f) s += (float)frames[(size_t)f * px + i];
+            float q = s / (float)n;
+            long r = lrintf(q);
+            out[i] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+        } else if (method == 1) {
+            uint32_t hist[256]; memset(hist, 0, sizeof hist);
+            for (int f = 0; f < n; ++f) hist[frames[(size_t)f * px + i]]++;
+            int best = 0;
+            for (int b = 1; b < 256; ++b) if (hist[b] > hist[best]) best = b;
+            out[i] = (uint8_t)best;
+        } else {
+            int v = method == 3 ? 255 : 0;
+            for (int f = 0; f < n; ++f) { int q = frames[(size_t)f * px + i]; v = method == 2 ? (q > v ? q : v) : (q < v ? q : v); }
+            out[i] = (uint8_t)v;
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Batch driver for the CPU baseline: n frames through to_segment_frame + to_crop_blob, frames
  * handed to `threads` pthreads through a shared counter (frames are independent:
  * BackgroundSubtraction::apply keeps no cross-frame state).  Returns total kept blobs; per-frame

@@ -183,3 +183,22 @@ def test_vi_oracle_matches_reference_class_outputs():
     assert [vi.batch_size_for(m) for m in (0, 8, 64, 65, 100, 128, 256, 1024)] == [64, 64, 64, 128, 128, 128, 128, 128]
     t = vi.transform_results(4, [0, 2, 3], {0: np.ones(3), 2: np.full(3, 2.0), 3: np.full(3, 3.0)}, 3)
     assert np.array_equal(t[1], [-1, -1, -1]) and np.array_equal(t[2], [2, 2, 2])
+
+
+def test_averaging_matches_opencv():
+    """oracle.average vs the OpenCV calls AveragingAccumulator makes (add in CV_32F, divide, convertTo; max; min)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    for n in (3, 10, 37):
+        fr = rng.integers(0, 256, (n, 48, 64)).astype(np.uint8)
+        acc = np.zeros((48, 64), np.float32)
+        for f in fr:
+            acc = cv2.add(acc, f.astype(np.float32))
+        mean = np.clip(np.rint(cv2.divide(acc, float(n))), 0, 255).astype(np.uint8)     # convertTo(CV_8U) = cvRound + saturate
+        assert np.array_equal(seg.average(fr, "mean"), mean)
+        assert np.array_equal(seg.average(fr, "max"), fr.max(0)) and np.array_equal(seg.average(fr, "min"), fr.min(0))
+    fr = rng.integers(100, 104, (25, 16, 16)).astype(np.uint8)
+    mode = seg.average(fr, "mode")
+    for y, x in ((0, 0), (5, 7), (15, 15)):
+        c = np.bincount(fr[:, y, x], minlength=256)
+        assert mode[y, x] == int(np.argmax(c))           # first maximum
