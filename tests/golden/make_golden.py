@@ -110,5 +110,21 @@ def make_pixels():
     np.savez(os.path.join(HERE, "pixels_golden.npz"), bg=bg, pixels=px, mask=mask, threshold=25, recount=4)
 
 
+def make_average():
+    """The background stored in videos/test.pv was generated by TRex itself (averaging_method=mode,
+    average_samples=100, see the pv's metadata) from videos/test_frames: a 96x128 window of the 100 sampled
+    frames (VideoSource.cpp:1040-1060) and of that background pins AveragingAccumulator's mode path."""
+    import cv2
+    from oracle.pv15 import PV15
+    from trex_b200.averaging import sample_indices
+    pv = PV15(f"{REF}/videos/test.pv")
+    idx = sample_indices(200, 100)
+    y0, x0, hh, ww = 1400, 2000, 96, 128
+    frames = np.stack([cv2.imread(f"{REF}/videos/test_frames/frame_{i:03d}.jpg", cv2.IMREAD_UNCHANGED)[y0:y0 + hh, x0:x0 + ww] for i in idx])
+    np.savez_compressed(os.path.join(HERE, "avg_golden.npz"), frames=frames, expected=pv.average[y0:y0 + hh, x0:x0 + ww],
+                        indices=np.array(idx), window=np.array([y0, x0, hh, ww]))
+    print("avg_golden.npz", os.path.getsize(os.path.join(HERE, "avg_golden.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    make_testpv(); make_vi(); make_pixels()
+    make_testpv(); make_vi(); make_pixels(); make_average()

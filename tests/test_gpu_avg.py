@@ -38,3 +38,15 @@ def test_average_feeds_segmentation():
         assert [(b.lines.tobytes(), b.pixels.tobytes()) for b in got[f]] == seg.segment_frame(frames[f], bg, P).as_list()
     with pytest.raises(trex_b200.TrexB200Error):
         trex_b200.AveragingAccumulator(480, 272, "mean").finalize()      # no samples
+
+
+def test_average_golden_from_test_pv():
+    """GPU mode-averaging reproduces the background TRex stored in videos/test.pv (committed window)."""
+    import os
+    import trex_b200
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "avg_golden.npz"))
+    fr = g["frames"]
+    acc = trex_b200.AveragingAccumulator(fr.shape[2], fr.shape[1], "mode")
+    acc.add(fr)
+    assert np.array_equal(acc.finalize(), g["expected"])

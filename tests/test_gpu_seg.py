@@ -269,3 +269,24 @@ def test_morphology_vs_oracle(kw):
     assert _as_list(got[1]) == _oracle(bg, bg, **kw).as_list()
     keys = {k: v for k, v in kw.items() if k in seg.Params.__dataclass_fields__}
     assert np.array_equal(bs.debug_binary(fr), seg.generate_binary(fr, bg, seg.Params(**keys)))
+
+
+def test_pv_file_from_gpu_results(tmp_path, gold):
+    """GPU blobs -> PV15 file (trex_b200.pv_writer) -> oracle reader: same blobs as the reference's file."""
+    import trex_b200
+    from oracle import seg
+    from trex_b200.pv_writer import PVWriter
+    bs = _mk(gold["average"], max_batch=2, **PV)
+    bs.apply([gold["full0_frame"], gold["full100_frame"]], materialize=False)
+    path = str(tmp_path / "gpu.pv")
+    with PVWriter(path, 2304, 2304, gold["average"], name="gpu") as w:
+        for i, idx in enumerate((0, 100)):
+            w.add_result(bs, i, timestamp_us=idx * 40000, source_index=idx)
+    try:
+        from oracle.pv15 import PV15
+        pv = PV15(path)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libminilzo.so not available")
+    for i, idx in enumerate((0, 100)):
+        ref = seg.Blobs(gold[f"full{idx}_lines"], gold[f"full{idx}_pixels"], gold[f"full{idx}_line_off"], gold[f"full{idx}_px_off"])
+        assert pv.frame(i).as_set() == ref.as_set()

@@ -202,3 +202,19 @@ def test_averaging_matches_opencv():
     for y, x in ((0, 0), (5, 7), (15, 15)):
         c = np.bincount(fr[:, y, x], minlength=256)
         assert mode[y, x] == int(np.argmax(c))           # first maximum
+
+
+def test_average_golden_from_test_pv():
+    """The background image inside videos/test.pv (written by TRex, averaging_method=mode over 100 samples)
+    is reproduced bit-exactly from the sampled test frames (committed window; all pixels when the reference is present)."""
+    from trex_b200.averaging import sample_indices
+    g = np.load(os.path.join(GOLDEN, "avg_golden.npz"))
+    assert list(g["indices"]) == sample_indices(200, 100)
+    assert np.array_equal(seg.average(g["frames"], "mode"), g["expected"])
+    if os.path.exists("/root/reference/videos/test.pv"):
+        cv2 = pytest.importorskip("cv2")
+        from oracle.pv15 import PV15
+        pv = PV15("/root/reference/videos/test.pv")
+        rows = slice(1000, 1200)          # a 200-row band of the full 2304-wide frames keeps the test quick
+        fr = np.stack([cv2.imread(f"/root/reference/videos/test_frames/frame_{i:03d}.jpg", cv2.IMREAD_UNCHANGED)[rows] for i in sample_indices(200, 100)])
+        assert np.array_equal(seg.average(fr, "mode"), pv.average[rows])

@@ -9,5 +9,6 @@ from ._capi import LIB_PATH, TrexB200Error, lib  # noqa: F401
 from .background_subtraction import BackgroundSubtraction, Blob, DetectSettings  # noqa: F401
 from .visual_identification import VINetwork  # noqa: F401
 from .averaging import AveragingAccumulator  # noqa: F401
+from .pv_writer import PVWriter  # noqa: F401
 
-__all__ = ["AveragingAccumulator", "BackgroundSubtraction", "Blob", "DetectSettings", "VINetwork", "TrexB200Error", "lib", "LIB_PATH"]
+__all__ = ["AveragingAccumulator", "PVWriter", "BackgroundSubtraction", "Blob", "DetectSettings", "VINetwork", "TrexB200Error", "lib", "LIB_PATH"]

@@ -12,6 +12,20 @@ from ._capi import check, lib
 METHODS = {"mean": 0, "mode": 1, "max": 2, "min": 3}      # averaging_method_t (AveragingAccumulator.h:6)
 
 
+def sample_indices(num_frames: int, samples: int, start: int = 0):
+    """Frames VideoSource::generate_average feeds to the accumulator (C/video/VideoSource.cpp:1040-1060):
+    `samples` indices spread over [start, start+num_frames), offset_i = round(i * max(1, (num_frames-1)/samples))."""
+    if samples <= 1:
+        return [start]
+    samples = min(samples, num_frames)
+    step = max(1.0, (num_frames - 1) / float(samples))
+    out = []
+    for i in range(samples):
+        off = int(i * step + 0.5)                       # std::round for non-negative values
+        out.append(start + min(off, num_frames - 1))
+    return out
+
+
 class AveragingAccumulator:
     def __init__(self, width: int, height: int, mode: str = "mean", device: int = 0):
         self.width, self.height, self.mode = int(width), int(height), mode
