@@ -29,6 +29,9 @@ import numpy as np  # noqa: E402
 H, W, N_INDIV, M_CLASSES = 1080, 1920, 100, 100
 MAX_CROPS = 128
 WORKLOAD = "synthetic 1920x1080 u8 gray, 100 individuals, bg-sub+threshold+CCL+80x80 crops+V118_3 CNN (random-init weights)"
+# DRAM traffic per unit (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture divided by the
+# units of that launch; profiles/r1_final_ncu_summary.txt and profiles/r1_seg_rle_v1_ncu_details.csv)
+NCU_TRAFFIC = {"seg_rle": (134.87e6 + 3.59e6) / 64, "conv2": (507.7e6 + 385.1e6) / 4096, "conv3": (614.06e6 + 184.99e6) / 4096}
 MACS = {"conv1": 2.56e6, "conv2": 40.96e6, "conv3": 81.92e6, "fc1": 1.28e6, "head": 100.0 * M_CLASSES}
 
 
@@ -321,8 +324,12 @@ def run_ours(args):
             if "achieved" in v:
                 v["frac"] = v["achieved"] / v["peak"]
         dom = max(("seg_rle", "conv1", "conv2", "conv3", "fc1"), key=lambda k: per[k])
+        units = {"seg_rle": B, "conv2": n_crops, "conv3": n_crops}
+        for k, per_unit in NCU_TRAFFIC.items():
+            kern[k]["traffic"] = per_unit * units[k]              # bytes per step, from the committed ncu capture
         roof = {"kernel": dom, "bound": kern[dom]["bound"], "achieved": kern[dom]["achieved"], "peak": kern[dom]["peak"],
-                "unit": kern[dom]["unit"], "frac": kern[dom]["frac"], "traffic": None, "peak_source": pk["src"]}
+                "unit": kern[dom]["unit"], "frac": kern[dom]["frac"], "traffic": kern[dom].get("traffic"), "peak_source": pk["src"],
+                "note": "algorithmic FLOPs (2*MAC per crop); the bf16x3 split issues 3 MMAs per k-step on top of that"}
         # cpu baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None
         if world_size == 1 and not args.no_cpu:
@@ -359,7 +366,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="frames per step per GPU")
     ap.add_argument("--pool", type=int, default=4, help="distinct resident batches rotated through (defeats L2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU arm / cpu_baseline sample")
