@@ -152,6 +152,14 @@ TB_API int tb_seg_device_results(tb_seg *h, void **crops, void **n_crops_dev, vo
 /* Host copy of the crops of the last batch (after tb_seg_wait with fetch=2 and crops enabled). */
 TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_blob_index, uint32_t *n);
 
+/* Tracker-side re-threshold ("next" row N3a): pixel::threshold_blob (C/processing/PixelTree.cpp:186-291) applied to
+ * every blob of det's last batch, on the device.  trk is a second handle of the same frame size whose params carry
+ * the tracker settings: detect_threshold = track_threshold (comparison >=, Background.h:415-427),
+ * enable_difference = track_background_subtraction, detect_threshold_is_absolute = track_threshold_is_absolute,
+ * size ranges = track_size_filter (or none).  Afterwards tb_seg_wait / tb_seg_result / tb_seg_crops /
+ * tb_seg_device_results on trk return the tracker-side blobs (and their crops: what the reference feeds the CNN). */
+TB_API int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch);
+
 /* Debug / parity: generate_binary's output image (mask & input) of one device- or host-resident
  * frame, RawProcessing.cpp:597-600.  out is width*height host bytes. */
 TB_API int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t *out_host);

@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
                                        C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]
         L.to_segment_batch.restype = C.c_int64
         L.to_num_threads.restype = C.c_int
+        L.to_rethreshold_frame.argtypes = [vp, vp, vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64]
+        L.to_rethreshold_frame.restype = C.c_int64
         L.to_average.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.to_average.restype = C.c_int
         _LIB = L
@@ -220,3 +222,17 @@ def average(frames, method="mean"):
     out = np.empty((h, w), np.uint8)
     lib().to_average(_p(frames), n, w, h, {"mean": 0, "mode": 1, "max": 2, "min": 3}[method], _p(out))
     return out
+
+
+def rethreshold(blobs: "Blobs", bg, threshold: int, method=DIFF_ABSOLUTE) -> "Blobs":
+    """pixel::threshold_blob on every blob of a frame (tracker-side re-threshold, comparison >=)."""
+    bg = np.ascontiguousarray(bg, np.uint8)
+    lines = np.ascontiguousarray(blobs.lines); px = np.ascontiguousarray(blobs.pixels, np.uint8)
+    lo = np.ascontiguousarray(blobs.line_off, np.int64); po = np.ascontiguousarray(blobs.px_off, np.int64)
+    capL = capB = max(16, len(px) + 1); capP = max(16, len(px))
+    ol = np.zeros(capL, LINE_DTYPE); op = np.zeros(capP, np.uint8)
+    olo = np.zeros(capB + 1, np.int64); opo = np.zeros(capB + 1, np.int64)
+    k = lib().to_rethreshold_frame(_p(lines), _p(lo), _p(px), _p(po), len(blobs), _p(bg), bg.shape[1], method, int(threshold),
+                                   _p(ol), capL, _p(op), capP, _p(olo), _p(opo), capB)
+    assert k >= 0, k
+    return Blobs(ol[:olo[k]].copy(), op[:opo[k]].copy(), olo[:k + 1].copy(), opo[:k + 1].copy())

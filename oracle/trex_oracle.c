@@ -477,6 +477,70 @@ void to_crop_blob(const to_line_t *lines, int64_t n_lines, const uint8_t *px,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Tracker-side re-threshold of one frame's blobs ("next" row N3a): pixel::threshold_blob
+ * (C/processing/PixelTree.cpp:186-291) applied to every blob: line_without_grid keeps the pixels whose
+ * difference to the background is >= threshold (Background::is_value_different, Background.h:415-427;
+ * method 0 none: value, 1 absolute: |bg - v|, 2 sign: max(0, bg - v), Background.h:231-294), cutting each
+ * line into sub-lines, then CPULabeling::run(lines, pixels) (CPULabeling.cpp:378-414) relabels them.
+ * Input / output are SoA blob lists; sub-blobs of parent k come out consecutively (canonical order inside
+ * a parent).  Returns the number of sub-blobs, or -(needed) if a capacity is too small.
+ * ------------------------------------------------------------------------------------------ */
+int64_t to_rethreshold_frame(const to_line_t *lines, const int64_t *line_off, const uint8_t *px, const int64_t *px_off,
+                             int64_t n_blobs, const uint8_t *bg, int bg_w, int method, int threshold,
+                             to_line_t *olines, int64_t cap_lines, uint8_t *opx, int64_t cap_px,
+                             int64_t *oline_off, int64_t *opx_off, int64_t cap_blobs)
+{
+    int64_t kept = 0, tl = 0, tp = 0;
+    for (int64_t k = 0; k < n_blobs; ++k) {
+        const int64_t nl = line_off[k + 1] - line_off[k], np_ = px_off[k + 1] - px_off[k];
+        to_line_t *sub = (to_line_t *)malloc(sizeof(to_line_t) * (size_t)(np_ + 1));
+        int64_t *src = (int64_t *)malloc(sizeof(int64_t) * (size_t)(np_ + 1));      /* pixel offset of each sub-line */
+        int32_t *label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(np_ + 1));
+        int64_t ns = 0;
+        const uint8_t *p = px + px_off[k];
+        int64_t o = 0;
+        for (int64_t i = 0; i < nl; ++i) {                      /* PixelTree.cpp:108-166 */
+            const to_line_t *l = &lines[line_off[k] + i];
+            int start = -1;
+            for (int x = l->x0; x <= l->x1; ++x, ++o) {
+                int v = p[o], d = v;
+                if (method == 1) d = abs((int)bg[(size_t)l->y * bg_w + x] - v);
+                else if (method == 2) { d = (int)bg[(size_t)l->y * bg_w + x] - v; if (d < 0) d = 0; }
+                if (d >= threshold) { if (start < 0) start = x; }
+                else if (start >= 0) {
+                    sub[ns].x0 = (uint16_t)start; sub[ns].x1 = (uint16_t)(x - 1); sub[ns].y = l->y; sub[ns].pad = 0;
+                    src[ns++] = o - (x - start); start = -1;
+                }
+            }
+            if (start >= 0) {
+                sub[ns].x0 = (uint16_t)start; sub[ns].x1 = l->x1; sub[ns].y = l->y; sub[ns].pad = 0;
+                src[ns++] = o - (l->x1 + 1 - start);
+            }
+        }
+        int64_t nb = to_label_runs(sub, ns, TO_ORDER_CANONICAL, label);
+        if (nb < 0) { free(sub); free(src); free(label); return -1; }
+        for (int64_t b = 0; b < nb; ++b) {
+            if (kept < cap_blobs) { oline_off[kept] = tl; opx_off[kept] = tp; }
+            for (int64_t i = 0; i < ns; ++i) {
+                if (label[i] != b) continue;
+                const int64_t len = (int64_t)sub[i].x1 - sub[i].x0 + 1;
+                if (tl < cap_lines) olines[tl] = sub[i];
+                if (tp + len <= cap_px) memcpy(opx + tp, p + src[i], (size_t)len);
+                ++tl; tp += len;
+            }
+            ++kept;
+        }
+        free(sub); free(src); free(label);
+    }
+    if (kept > cap_blobs || tl > cap_lines || tp > cap_px) {
+        int64_t need = kept > tl ? kept : tl; if (tp > need) need = tp;
+        return -(need + 2);
+    }
+    oline_off[kept] = tl; opx_off[kept] = tp;
+    return kept;
+}
+
+/* ------------------------------------------------------------------------------------------
  * AveragingAccumulator, C/video/AveragingAccumulator.cpp:23-196 (gray): method 0 mean (float sum,
  * cv::divide = true float division, convertTo = round half to even + saturate), 1 mode (per-pixel
  * histogram, first maximum = smallest value among ties, :168-171), 2 max, 3 min.

@@ -290,3 +290,39 @@ def test_pv_file_from_gpu_results(tmp_path, gold):
     for i, idx in enumerate((0, 100)):
         ref = seg.Blobs(gold[f"full{idx}_lines"], gold[f"full{idx}_pixels"], gold[f"full{idx}_line_off"], gold[f"full{idx}_px_off"])
         assert pv.frame(i).as_set() == ref.as_set()
+
+
+@pytest.mark.parametrize("trk_kw,method", [
+    (dict(detect_threshold=40), 1),                                                  # absolute, >=
+    (dict(detect_threshold=40, detect_threshold_is_absolute=False), 2),              # sign
+    (dict(detect_threshold=60, enable_difference=False), 0),                         # none: grey value >= T
+    (dict(detect_threshold=15), 1),                                                  # T2 == T1: >= vs > differs only outside blobs
+])
+def test_tracker_side_rethreshold(trk_kw, method):
+    """pixel::threshold_blob on every detection blob (N3a): GPU vs oracle, bit-exact, incl. crops of tracker-side blobs."""
+    from oracle import seg
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(h=540, w=960, n_blobs=40, seed=12, semi=(26, 9))
+    frames = world.frames(3).copy()
+    rng = np.random.default_rng(5)
+    for f in frames:                                   # texture inside the blobs so that a higher threshold splits them
+        m = np.abs(f.astype(int) - world.bg.astype(int)) > 15
+        f[m] = np.clip(f[m].astype(int) + rng.integers(0, 70, int(m.sum())), 1, 255).astype(np.uint8)
+    det_kw = dict(detect_threshold=15, detect_size_filter=[(10, 100000)])
+    det = _mk(world.bg, max_batch=4, **det_kw)
+    trk = _mk(world.bg, max_batch=4, max_individuals=64, detect_size_filter=[], **trk_kw)
+    det.apply(frames, materialize=False)
+    got = det.rethreshold(trk, fetch=2)
+    crops, _ = trk.crops()
+    c = 0
+    for f in range(3):
+        parents = _oracle(frames[f], world.bg, **det_kw)
+        ref = seg.rethreshold(parents, world.bg, trk_kw["detect_threshold"], method)
+        exp = sorted(ref.as_list(), key=lambda lp: tuple(np.frombuffer(lp[0], seg.LINE_DTYPE)[["y", "x0"]][0]))
+        assert _as_list(got[f]) == exp, f
+        assert len(ref) >= len(parents) or method != 1
+        for k in range(min(len(got[f]), 64)):
+            b = got[f][k]
+            want = seg.crop_blob(b.lines, b.pixels, world.bg, seg.DIFF_ABSOLUTE)
+            assert np.array_equal(crops[c + k], want)
+        c += min(len(got[f]), 64)

@@ -218,3 +218,24 @@ def test_average_golden_from_test_pv():
         rows = slice(1000, 1200)          # a 200-row band of the full 2304-wide frames keeps the test quick
         fr = np.stack([cv2.imread(f"/root/reference/videos/test_frames/frame_{i:03d}.jpg", cv2.IMREAD_UNCHANGED)[rows] for i in sample_indices(200, 100)])
         assert np.array_equal(seg.average(fr, "mode"), pv.average[rows])
+
+
+def test_rethreshold_known_answers():
+    """line_without_grid vectors of Application/Tests/test_pixels.cpp:981-1071 (gray): bg = 100, two lines of
+    pixels 0,10,...,190, threshold 50, comparison >=, methods absolute / sign / none."""
+    bg = np.full((10, 10), 100, np.uint8)
+    lines = np.zeros(2, seg.LINE_DTYPE); lines["x0"] = 0; lines["x1"] = 9; lines["y"] = [0, 1]
+    px = (np.arange(20) * 10).astype(np.uint8)
+    parent = seg.Blobs(lines, px, np.array([0, 2], np.int64), np.array([0, 20], np.int64))
+
+    def flat(b):
+        return [(int(l["y"]), int(l["x0"]), int(l["x1"])) for l in b.lines], list(map(int, b.pixels))
+
+    l, p = flat(seg.rethreshold(parent, bg, 50, seg.DIFF_ABSOLUTE))
+    assert l == [(0, 0, 5), (1, 5, 9)] and p == [0, 10, 20, 30, 40, 50, 150, 160, 170, 180, 190]
+    l, p = flat(seg.rethreshold(parent, bg, 50, seg.DIFF_SIGN))
+    assert l == [(0, 0, 5)] and p == [0, 10, 20, 30, 40, 50]
+    l, p = flat(seg.rethreshold(parent, bg, 50, seg.DIFF_NONE))
+    assert l == [(0, 5, 9), (1, 0, 9)] and p == [50, 60, 70, 80, 90, 100, 110, 120, 130, 140, 150, 160, 170, 180, 190]
+    # the absolute case splits into two blobs? rows 0 and 1 touch diagonally at x 5 -> one blob (8-connectivity)
+    assert len(seg.rethreshold(parent, bg, 50, seg.DIFF_ABSOLUTE)) == 1

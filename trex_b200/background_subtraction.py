@@ -99,6 +99,7 @@ class BackgroundSubtraction:
         self._time = 0.0
         self._samples = 0.0
         self._has_background = False
+        self._last_n = 0
         if average is not None:
             self.set_background(average)
 
@@ -133,6 +134,7 @@ class BackgroundSubtraction:
                 if f.shape != (self.height, self.width):
                     raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, f"frame shape {f.shape} != {(self.height, self.width)}")
             check(lib().tb_seg_submit(self._h, ptrs, len(chunk), self.width, level))
+            self._last_n = len(chunk)
             check(lib().tb_seg_wait(self._h))
             if fetch and materialize:
                 out.extend(self.result(j) for j in range(len(chunk)))
@@ -153,10 +155,23 @@ class BackgroundSubtraction:
         base, stride = frames.ctypes.data, frames.strides[0]
         ptrs = (C.c_void_p * n)(*[base + i * stride for i in range(n)])
         check(lib().tb_seg_submit(self._h, ptrs, n, frames.strides[1], int(fetch)))
+        self._last_n = n
 
     def apply_device(self, frames_ptr: int, n: int, stream: int = 0, fetch=False):
         """Frames already resident in HBM (n packed HxW u8); work is ordered on `stream`."""
         check(lib().tb_seg_submit_device(self._h, C.c_void_p(frames_ptr), n, C.c_void_p(stream), int(fetch)))
+        self._last_n = n
+
+    def rethreshold(self, tracker: "BackgroundSubtraction", fetch=1, materialize=True):
+        """pixel::threshold_blob on every blob of this handle's last batch (PixelTree.cpp:186-291).  `tracker` is a
+        second BackgroundSubtraction of the same size whose settings hold the tracker keys (detect_threshold :=
+        track_threshold with comparison >=, enable_difference := track_background_subtraction, ...).  Returns one
+        list of Blob per frame (tracker-side blobs) when fetch and materialize are set."""
+        check(lib().tb_seg_rethreshold(self._h, tracker._h, int(fetch)))
+        check(lib().tb_seg_wait(tracker._h))
+        if fetch and materialize:
+            return [tracker.result(i) for i in range(self._last_n)]
+        return None
 
     def wait(self):
         check(lib().tb_seg_wait(self._h))

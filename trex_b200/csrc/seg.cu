@@ -29,7 +29,7 @@ struct SegK {                  // threshold configuration, bytes replicated x4
                                // bit3 invert mask (T<0), bit4 inRange
     uint32_t t4, lo4, hi4;
 };
-enum { F_DIFF = 1, F_ABS = 2, F_INV = 4, F_INVMASK = 8, F_RANGE = 16, F_PREMASK = 32 };
+enum { F_DIFF = 1, F_ABS = 2, F_INV = 4, F_INVMASK = 8, F_RANGE = 16, F_PREMASK = 32, F_GE = 64 };
 
 struct SegDev {
     int W, H, B, cpr, rpt, n_bands, aligned;
@@ -40,6 +40,7 @@ struct SegDev {
     float sqcm; int n_ranges; double lo[4], hi[4];
     const uint8_t *bg;
     size_t bg_stride;          // 0: one background for all frames; else `bg` holds one mask image per frame (morphology path)
+    const uint8_t *keep_mask;  // optional [B][H][W] 0xFF/0 image ANDed with the foreground (tracker-side re-threshold), or null
     // K1 outputs
     uint32_t *run_count;       // [B]
     uint32_t *band_base, *band_cnt;   // [B][n_bands]
@@ -82,7 +83,8 @@ __device__ __forceinline__ uint32_t fg4(uint32_t f, uint32_t b, const SegK &p)
     uint32_t in = (p.flags & F_INV) ? ~f : f;                       // 255 - x
     uint32_t d = in;
     if (p.flags & F_DIFF) d = (p.flags & F_ABS) ? __vabsdiffu4(in, b) : __vsubus4(b, in);
-    uint32_t m = (p.flags & F_RANGE) ? (__vcmpgeu4(d, p.lo4) & __vcmpleu4(d, p.hi4)) : __vcmpgtu4(d, p.t4);
+    uint32_t m = (p.flags & F_RANGE) ? (__vcmpgeu4(d, p.lo4) & __vcmpleu4(d, p.hi4))
+               : (p.flags & F_GE) ? __vcmpgeu4(d, p.t4) : __vcmpgtu4(d, p.t4);     // F_GE: tracker-side comparison >=
     if (p.flags & F_INVMASK) m = ~m;
     return m & __vcmpne4(f, 0u);                                    // (mask & input) != 0
 }
@@ -194,7 +196,14 @@ seg_rle_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
 #pragma unroll
         for (int k = 0; k < K1_KPT; ++k) {
             const int c = warp * (32 * K1_KPT) + k * 32 + lane;
-            s_mask[c] = (c < tile_chunks) ? (uint16_t)fg16<GENERIC>(cur[k], bgc[k], p) : (uint16_t)0;
+            uint32_t m16 = (c < tile_chunks) ? fg16<GENERIC>(cur[k], bgc[k], p) : 0u;
+            if (d.keep_mask && c < tile_chunks) {               // pixels outside the kept detection blobs are never foreground
+                const uint8_t *kb = d.keep_mask + (size_t)f * frame_bytes;
+                const uint4 mk = d.aligned ? *reinterpret_cast<const uint4 *>(kb + (size_t)row0 * d.W + (size_t)c * 16)
+                                           : ld_edge(kb + (size_t)(row0 + c / d.cpr) * d.W, c % d.cpr, d.W);
+                m16 &= pack4(mk.x) | (pack4(mk.y) << 4) | (pack4(mk.z) << 8) | (pack4(mk.w) << 12);
+            }
+            s_mask[c] = (uint16_t)m16;
         }
         __syncthreads();
         const uint64_t M = *reinterpret_cast<const uint64_t *>(s_mask + g0);
@@ -451,6 +460,25 @@ __global__ void mask_and_kernel(const uint8_t *__restrict__ mask, const uint8_t 
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
         out[i] = mask[i] & frame[i];
+}
+
+// Tracker-side re-threshold ("next" row N3a, pixel::threshold_blob, C/processing/PixelTree.cpp:186-291):
+// the pixels of the kept detection blobs of a batch are painted into a per-frame mask; K1 then runs with the
+// tracker's comparison (difference >= track_threshold) ANDed with that mask, and K2/K3 relabel.  Blobs of one
+// frame are never 8-adjacent, so relabelling the frame equals relabelling every blob on its own.
+__global__ void paint_blobs_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__restrict__ totals, const tb_line *__restrict__ lines,
+                                   uint8_t *__restrict__ mask, int W, int H)
+{
+    const uint32_t nb = totals[0];
+    const int lane = threadIdx.x & 31;
+    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nb; b += gridDim.x * (blockDim.x >> 5)) {
+        const tb_blob_rec r = recs[b];
+        uint8_t *m = mask + (size_t)r.frame * W * H;
+        for (uint32_t l = 0; l < r.n_lines; ++l) {
+            const tb_line ln = lines[r.line_off + l];
+            for (uint32_t x = ln.x0 + lane; x <= ln.x1; x += 32) m[(size_t)ln.y * W + x] = 0xFF;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -762,6 +790,8 @@ struct tb_seg {
     // optional morphology (use_closing / dilation_size): mask images of one batch, allocated on first use
     bool morph = false;
     uint8_t *m_a = nullptr, *m_b = nullptr, *m_diff = nullptr;
+    const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
+    uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
     MorphEl el_close{}, el_dil{};
 };
 
@@ -983,11 +1013,13 @@ static int seg_morph(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s
     return TB_OK;
 }
 
-static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s, int fetch)
+static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s, int fetch, const uint8_t *keep_mask = nullptr)
 {
     SegDev d = h->d;
     d.B = n;
     d.bg_stride = 0;
+    d.keep_mask = nullptr;
+    h->last_frames_dev = frames_dev;
     TB_CUDA(cudaMemsetAsync(d.run_count, 0, sizeof(uint32_t) * (size_t)n, s));
     static const int fpc_env = getenv("TB_SEG_FPC") ? atoi(getenv("TB_SEG_FPC")) : 0;
     const int fpc = fpc_env > 0 ? fpc_env : (n >= 64 ? 8 : (n >= 8 ? 2 : 1));
@@ -998,7 +1030,12 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     const bool plain = !h->morph && h->k.flags == (F_DIFF | F_ABS) && (h->k.t4 & 0xFFu) <= 127u;
     SegK kk = h->k;
     if (plain) kk.lo4 = (127u - (kk.t4 & 0xFFu)) * 0x01010101u;      // SWAR addend of the fast path
-    if (h->morph) {
+    if (keep_mask) {                 // tracker-side re-threshold: comparison >=, restricted to the painted detection blobs
+        TB_REQUIRE(!h->morph, TB_ERR_INVALID, "tb_seg_rethreshold: the tracker-side handle must not enable morphology");
+        d.keep_mask = keep_mask;
+        kk = h->k; kk.flags |= F_GE;
+        seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, kk, fpc);
+    } else if (h->morph) {
         const uint8_t *mask = nullptr;
         int r = seg_morph(h, frames_dev, n, s, &mask);
         if (r != TB_OK) return r;
@@ -1021,7 +1058,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     h->prof.mark(slot, 1);
     ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
     h->prof.mark(slot, 2);
-    d.bg = h->d_bg; d.bg_stride = 0;                               // crops difference against the real background
+    d.bg = h->d_bg; d.bg_stride = 0; d.keep_mask = nullptr;        // crops difference against the real background
     blob_emit_kernel<<<dim3((unsigned)n, K3_SPLIT), K3_NT, 0, s>>>(frames_dev, d);
     h->prof.mark(slot, 3);
     h->launches += 3;
@@ -1176,4 +1213,32 @@ extern "C" int tb_seg_kernel_ms(tb_seg *h, double out_ms[3], uint64_t *n_batches
     for (int k = 0; k < 3; ++k) { out_ms[k] = h->prof.acc[k]; h->prof.acc[k] = 0; }
     *n_batches = h->prof.n; h->prof.n = 0;
     return TB_OK;
+}
+
+// pixel::threshold_blob for every blob of the detection handle's last batch, on the device: `trk` is a second
+// handle of the same geometry whose params carry the TRACKER settings (detect_threshold = track_threshold,
+// enable_difference = track_background_subtraction, detect_threshold_is_absolute = track_threshold_is_absolute,
+// size ranges = track_size_filter or none).  Results are read from `trk` like after a submit.
+extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch)
+{
+    TB_REQUIRE(det && trk && det != trk, TB_ERR_INVALID, "tb_seg_rethreshold: need two distinct handles");
+    TB_REQUIRE(det->last_n > 0 && det->last_frames_dev, TB_ERR_STATE, "tb_seg_rethreshold: the detection handle has no batch");
+    TB_REQUIRE(trk->d.W == det->d.W && trk->d.H == det->d.H && trk->cfg.device == det->cfg.device, TB_ERR_INVALID,
+               "tb_seg_rethreshold: handles differ in frame size or device");
+    TB_REQUIRE(det->last_n <= trk->cfg.max_batch, TB_ERR_INVALID, "tb_seg_rethreshold: tracker-side max_batch too small");
+    TB_REQUIRE(trk->has_bg, TB_ERR_STATE, "tb_seg_rethreshold: the tracker-side handle has no background");
+    TB_REQUIRE(!trk->pending, TB_ERR_STATE, "tb_seg_rethreshold: the tracker-side handle has a pending batch");
+    TB_CUDA(cudaSetDevice(det->cfg.device));
+    const size_t px = (size_t)det->d.W * det->d.H;
+    if (!trk->keep_mask) {
+        int r = seg_dev(trk, &trk->keep_mask, (size_t)trk->cfg.max_batch * px + 16);
+        if (r != TB_OK) return r;
+    }
+    cudaStream_t s = det->last_stream ? det->last_stream : det->stream;
+    const int n = det->last_n;
+    TB_CUDA(cudaMemsetAsync(trk->keep_mask, 0, (size_t)n * px, s));
+    paint_blobs_kernel<<<148 * 4, 256, 0, s>>>(det->d.recs, det->d.totals, det->d.lines, trk->keep_mask, det->d.W, det->d.H);
+    trk->launches += 1;
+    TB_CUDA(cudaGetLastError());
+    return seg_launch(trk, det->last_frames_dev, n, s, fetch, trk->keep_mask);
 }
