@@ -333,9 +333,6 @@ struct tb_vi {
     // tensor-core path (precision 1)
     uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w1t = nullptr, *w2t = nullptr, *w3t = nullptr, *wfc = nullptr;
     int fc_groups = 0, n_sms = 148, head_w_smem = 0;
-    bool conv1_cuda = getenv("TB_CONV1_CUDA") != nullptr;  // bring-up switch: CUDA-core conv1 on the tensor path
-    bool conv2_flat = getenv("TB_CONV2_FLAT") != nullptr;
-    bool conv3_flat = getenv("TB_CONV3_FLAT") != nullptr;   // bring-up switch: position-major conv3 kernel
     uint64_t launches = 0;
     cudaStream_t last_stream = nullptr;
     EventRing<5> prof;
@@ -381,7 +378,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
         A(h->in2, CH * tc::Conv2Cfg::IMG_BYTES + 256); A(h->in3, CH * tc::Conv3Cfg::IMG_BYTES + 256);
         A(h->fca, (size_t)2 * h->fc_groups * tc::FC_KC * 128);
         A(h->w1t, (size_t)tc::Conv1T::W_BYTES);
-        A(h->w2t, (size_t)25 * tc::Conv2Cfg::WTAP_BYTES); A(h->w3t, (size_t)25 * tc::Conv3Cfg::WTAP_BYTES);
+        A(h->w2t, (size_t)tc::Conv2D::W_BYTES); A(h->w3t, (size_t)25 * tc::Conv3Cfg::WTAP_BYTES);
         A(h->wfc, (size_t)2 * tc::FC_KC * tc::FC_N * 16);
         if (r == TB_OK) {   // halo positions are never written by the kernels: zero once
             if (cudaMemset(h->in2, 0, CH * tc::Conv2Cfg::IMG_BYTES + 256) != cudaSuccess || cudaMemset(h->in3, 0, CH * tc::Conv3Cfg::IMG_BYTES + 256) != cudaSuccess ||
@@ -575,9 +572,8 @@ extern "C" int tb_vi_commit(tb_vi *h)
         std::vector<float> sc2(64), sc3(128);
         TB_CUDA(cudaMemcpy(sc2.data(), h->s2, 64 * 4, cudaMemcpyDeviceToHost));
         TB_CUDA(cudaMemcpy(sc3.data(), h->s3, 128 * 4, cudaMemcpyDeviceToHost));
-        if (h->conv2_flat) { if ((r = vi_upload_tc_conv(h->w2t, *c2, 2, 64, nullptr))) return r; }
-        else if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data()))) return r;
-        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, h->conv3_flat ? nullptr : sc3.data()))) return r;
+        if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data()))) return r;
+        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, sc3.data()))) return r;
         // fc1 B operand [hi|lo][kc = c8*100 + pp][112][8]; torch column = (c8*8+e)*100 + pp
         std::vector<uint16_t> wb((size_t)2 * tc::FC_KC * tc::FC_N * 8, 0);
         for (int kc = 0; kc < tc::FC_KC; ++kc)
@@ -600,11 +596,7 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
     using namespace tb::tc;
     const int M = h->cfg.num_classes;
     static bool attr_done = false;
-    auto k2 = conv_tc_kernel<Conv2Cfg, OUT_PLANES>;
-    auto k3 = conv_tc_kernel<Conv3Cfg, OUT_FC>;
     if (!attr_done) {
-        TB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3Cfg::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
@@ -615,14 +607,11 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         const int n = std::min(h->chunk, n_max - base);
         const int slot = h->prof.begin(s);
         h->prof.mark(slot, 0);
-        if (h->conv1_cuda) conv1_planes_kernel<<<n, 256, 0, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1, h->s1, h->t1, h->in2);
-        else conv1_tc_kernel<<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::SMEM, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
+        conv1_tc_kernel<<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::SMEM, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
         h->prof.mark(slot, 1);
-        if (h->conv2_flat) k2<<<std::min(n * Conv2Cfg::PASSES, h->n_sms), NT, Conv2Cfg::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3, 0);
-        else conv2_2d_kernel<<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
+        conv2_2d_kernel<<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
         h->prof.mark(slot, 2);
-        if (h->conv3_flat) k3<<<std::min(n, h->n_sms), NT, Conv3Cfg::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
-        else conv3_t_kernel<<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+        conv3_t_kernel<<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
         h->prof.mark(slot, 3);
         fc1_tc_kernel<<<dim3((n + 127) / 128, FC_SPLIT), NT, FC_SMEM, s>>>(h->fca, h->fc_groups, n, n_dev, base, h->wfc, h->h1, h->chunk);
         h->prof.mark(slot, 4);

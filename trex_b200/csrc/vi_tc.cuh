@@ -11,9 +11,9 @@
 // fp32 parity (1e-3 on logits, BASELINE.json north_star) is kept with a 2-term bf16 split of both
 // operands and three MMAs per k-step: A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (fp32 accumulation in TMEM).
 //
-// Warp roles per CTA (192 threads): warp 0 = bulk-copy (TMA engine) producer, warp 1 = MMA issuer and
-// TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> BN scale/shift -> ReLU -> 2x2 max-pool ->
-// bf16 hi/lo planes for the next layer).  mbarrier pipelines connect them; CTAs are persistent.
+// Warp roles per CTA: warp 0 = bulk-copy (TMA engine) producer, warp 1 = MMA issuer and TMEM owner,
+// warps 2.. = epilogue (TMEM -> registers -> max-pool -> BN shift -> ReLU -> bf16 hi/lo planes for the
+// next layer).  mbarrier pipelines connect them; CTAs are persistent.
 #pragma once
 #include "umma.cuh"
 
@@ -24,34 +24,19 @@ constexpr int NT = 192;
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-template <int G_, int NOUT_, int H_, int W_, int ROWS_, bool WRES_>
-struct ConvCfg {
-    static constexpr int G = G_, NOUT = NOUT_, H = H_, W = W_, ROWS = ROWS_;
-    static constexpr bool WRES = WRES_;                       // all 25 taps of weights resident in smem
-    static constexpr int WP = W + 4;
-    static constexpr int Q = (ROWS - 1) * WP + W;             // flat output positions per pass
-    static constexpr int T = (Q + 127) / 128;                 // 128-row MMA tiles per pass
-    static constexpr int PIN = ((T * 128 + 4 * WP + 4) + 7) / 8 * 8;   // input positions staged per pass
-    static constexpr int PASSES = H / ROWS;
-    static constexpr int PL = (PASSES - 1) * ROWS * WP + PIN; // plane size in global memory (positions)
-    static constexpr int IN_BYTES = 2 * G * PIN * 16;
-    static constexpr int WTAP_BYTES = 2 * G * NOUT * 16;
-    static constexpr int W_BYTES = WRES ? 25 * WTAP_BYTES : 2 * WTAP_BYTES;
-    static constexpr int SP = ROWS * (W / 2) + 1;             // staging pitch per channel (floats)
-    static constexpr int STAGE_BYTES = NOUT * SP * 4;
-    static constexpr int REGION0 = (cmax(IN_BYTES, STAGE_BYTES) + 127) / 128 * 128;
-    static constexpr int SMEM = REGION0 + W_BYTES + NOUT * 8 + 128;
-    static constexpr int TMEM_COLS = pow2_cols(T * NOUT);
-    static constexpr size_t IMG_BYTES = (size_t)2 * G * PL * 16;      // one image's input planes
-    static_assert(T * NOUT <= 512, "accumulators exceed TMEM");
-    static_assert(PL >= (H + 4) * WP, "plane too small");
-    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+// Geometry of the activation planes in global memory.
+// conv2 input (conv1 output, 16 ch, 40x40): 2 groups, row pitch 44 (2-pixel zero halo on each side), 1960 positions.
+struct Conv2Cfg {
+    static constexpr int G = 2, WP = 44, PL = 1960;
+    static constexpr size_t IMG_BYTES = (size_t)2 * G * PL * 16;
 };
-
-using Conv2Cfg = ConvCfg<2, 64, 40, 40, 20, true>;     // 16 -> 64, 40x40, half an image per pass
-using Conv3Cfg = ConvCfg<8, 128, 20, 20, 20, false>;   // 64 -> 128, 20x20, weights streamed per tap
-
-enum { OUT_PLANES = 0, OUT_FC = 1 };
+// conv3 input (conv2 output, 64 ch, 20x20): 8 groups, row pitch 22: the two zero columns between image rows
+// serve as right halo of one row and left halo of the next, so a run of flat positions wastes only 2 of 22.
+struct Conv3Cfg {
+    static constexpr int G = 8, WP = 22, ROWS = 24, PL = 536;
+    static constexpr size_t IMG_BYTES = (size_t)2 * G * PL * 16;
+    static constexpr int WTAP_BYTES = 2 * G * 128 * 16;
+};
 
 // fc1 A operand: [hi|lo][kc block of 8][group of 8 images][kc in block][8 images][8] bf16, kc = c8 * 100 + pooled pixel.
 // One (hi|lo, kc block) slab of 16 consecutive image groups is 16 KB contiguous: one bulk copy per pipeline stage.
@@ -61,191 +46,20 @@ __host__ __device__ inline size_t fc_a_offset(int hl, int n_groups, int img, int
     return (((((size_t)hl * FC_KB + (kc >> 3)) * n_groups + (img >> 3)) * 8 + (kc & 7)) * 8 + (img & 7)) * 16;
 }
 
-template <class C, int OUTMODE>
-__global__ void __launch_bounds__(NT, 1)
-conv_tc_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
-               const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
-               uint8_t *__restrict__ out, int out_groups /* OUT_FC: 8-image groups allocated */)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar_in_full, bar_in_empty, bar_acc_full, bar_acc_empty, bar_w_full[2], bar_w_empty[2];
-    __shared__ uint32_t s_tmem;
-    uint8_t *s_in = smem;                                     // input planes, later the pooling staging
-    float *s_stage = reinterpret_cast<float *>(smem);
-    uint8_t *s_w = smem + C::REGION0;
-    float *s_sc = reinterpret_cast<float *>(s_w + C::W_BYTES), *s_sh = s_sc + C::NOUT;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
-    const int n_items = max(n_act, 0) * C::PASSES;
-
-    if (tid == 0) {
-        umma::mbar_init(&bar_in_full, 1); umma::mbar_init(&bar_in_empty, 1);
-        umma::mbar_init(&bar_acc_full, 1); umma::mbar_init(&bar_acc_empty, 1);
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_w_full[i], 1); umma::mbar_init(&bar_w_empty[i], 1); }
-        umma::fence_mbar_init();
-    }
-    if (warp == 1) umma::tmem_alloc(&s_tmem, C::TMEM_COLS);
-    for (int i = tid; i < C::NOUT; i += NT) { s_sc[i] = sc[i]; s_sh[i] = sh[i]; }
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tm = s_tmem;
-
-    if (warp == 0) {
-        // ================================ producer ================================
-        if (lane == 0) {
-            if (C::WRES) {
-                umma::mbar_expect_tx(&bar_w_full[0], C::W_BYTES);
-                for (int o = 0; o < C::W_BYTES; o += C::WTAP_BYTES) umma::bulk_g2s(s_w + o, wgt + o, C::WTAP_BYTES, &bar_w_full[0]);
-            }
-            uint32_t it = 0, tapc = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int img = item / C::PASSES, pass = item % C::PASSES;
-                umma::mbar_wait(&bar_in_empty, (it & 1) ^ 1);
-                umma::mbar_expect_tx(&bar_in_full, C::IN_BYTES);
-                const uint8_t *src = in + (size_t)img * C::IMG_BYTES + (size_t)pass * C::ROWS * C::WP * 16;
-                for (int p = 0; p < 2 * C::G; ++p)
-                    umma::bulk_g2s(s_in + (size_t)p * C::PIN * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full);
-                if (!C::WRES) {
-                    for (int tap = 0; tap < 25; ++tap, ++tapc) {
-                        const uint32_t s = tapc & 1;
-                        umma::mbar_wait(&bar_w_empty[s], ((tapc >> 1) & 1) ^ 1);
-                        umma::mbar_expect_tx(&bar_w_full[s], C::WTAP_BYTES);
-                        umma::bulk_g2s(s_w + s * C::WTAP_BYTES, wgt + (size_t)tap * C::WTAP_BYTES, C::WTAP_BYTES, &bar_w_full[s]);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            const uint32_t idesc = umma::idesc_bf16_f32(128, C::NOUT);
-            const uint64_t a_base = umma::smem_desc(umma::smem_u32(s_in), C::PIN * 16, 128);
-            const uint64_t b_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
-            if (C::WRES) { umma::mbar_wait(&bar_w_full[0], 0); }
-            uint32_t it = 0, tapc = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                umma::mbar_wait(&bar_in_full, it & 1);
-                umma::mbar_wait(&bar_acc_empty, (it & 1) ^ 1);
-                umma::fence_after_sync();
-                for (int tap = 0; tap < 25; ++tap) {
-                    uint32_t wofs;                                        // byte offset of this tap's weights in s_w
-                    uint32_t s = 0;
-                    if (C::WRES) wofs = tap * C::WTAP_BYTES;
-                    else {
-                        s = tapc & 1;
-                        umma::mbar_wait(&bar_w_full[s], (tapc >> 1) & 1);
-                        umma::fence_after_sync();
-                        wofs = s * C::WTAP_BYTES;
-                    }
-                    const uint32_t shift = (uint32_t)((tap / 5) * C::WP + (tap % 5));
-#pragma unroll 1
-                    for (int t = 0; t < C::T; ++t) {
-#pragma unroll
-                        for (int ks = 0; ks < C::G / 2; ++ks) {
-                            const uint32_t a_hi = ((0 * C::G + 2 * ks) * C::PIN + t * 128 + shift);           // in 16-byte units
-                            const uint32_t a_lo = ((1 * C::G + 2 * ks) * C::PIN + t * 128 + shift);
-                            const uint32_t b_hi = (wofs >> 4) + (0 * C::G + 2 * ks) * C::NOUT;
-                            const uint32_t b_lo = (wofs >> 4) + (1 * C::G + 2 * ks) * C::NOUT;
-                            const uint32_t d = tm + (uint32_t)(t * C::NOUT);
-                            umma::mma_bf16(d, a_base + a_hi, b_base + b_hi, idesc, (tap | ks) != 0);
-                            umma::mma_bf16(d, a_base + a_lo, b_base + b_hi, idesc, 1);
-                            umma::mma_bf16(d, a_base + a_hi, b_base + b_lo, idesc, 1);
-                        }
-                    }
-                    if (!C::WRES) { umma::commit(&bar_w_empty[s]); ++tapc; }
-                }
-                umma::commit(&bar_acc_full);
-            }
-        }
-    } else {
-        // ================================ epilogue (warps 2..5) ================================
-        const int etid = tid - 64;                                        // 0..127
-        const int quarter = warp & 3;                                     // TMEM lanes this warp may read
-        const int row = quarter * 32 + lane;
-        uint32_t it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int img = item / C::PASSES, pass = item % C::PASSES;
-            umma::mbar_wait(&bar_acc_full, it & 1);
-            umma::fence_after_sync();
-            // phase 1: BN + ReLU, horizontal max with the x^1 neighbour (adjacent TMEM lane), to staging
-#pragma unroll 1
-            for (int t = 0; t < C::T; ++t) {
-                const int q = t * 128 + row, y = q / C::WP, x = q % C::WP;
-                const bool keep = (y < C::ROWS) && (x < C::W) && !(x & 1);
-                float *dst = s_stage + y * (C::W / 2) + (x >> 1);
-#pragma unroll 1
-                for (int c0 = 0; c0 < C::NOUT; c0 += 16) {
-                    uint32_t v[16];
-                    umma::tmem_ld16(tm + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * C::NOUT + c0), v);
-                    umma::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float a = fmaxf(fmaf(__uint_as_float(v[j]), s_sc[c0 + j], s_sh[c0 + j]), 0.f);
-                        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
-                        if (keep) dst[(c0 + j) * C::SP] = a;
-                    }
-                }
-            }
-            umma::fence_before_sync();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (etid == 0) umma::mbar_arrive(&bar_acc_empty);            // TMEM drained: next pass may accumulate
-            // phase 2: vertical max, split to bf16 hi/lo, write the next layer's operand layout
-            constexpr int PW = C::W / 2, PH = C::ROWS / 2, PP = PW * PH, C8 = C::NOUT / 8;
-            for (int idx = etid; idx < PP * C8; idx += 128) {
-                const int pp = idx % PP, c8 = idx / PP, py = pp / PW, px = pp % PW;
-                const float *s0 = s_stage + (2 * py) * PW + px;
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    const int c = c8 * 8 + e;
-                    const float m0 = fmaxf(s0[c * C::SP], s0[c * C::SP + PW]);
-                    const float m1 = fmaxf(s0[(c + 1) * C::SP], s0[(c + 1) * C::SP + PW]);
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    umma::split_bf16(m0, h0, l0); umma::split_bf16(m1, h1, l1);
-                    hi[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[e >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-                size_t o_hi, o_lo;
-                if (OUTMODE == OUT_PLANES) {
-                    constexpr int WPN = PW + 4;                            // next layer: W/2 wide, pitch W/2 + 4
-                    constexpr int PLN = Conv3Cfg::PL;
-                    const int pos = (pass * PH + py + 2) * WPN + px + 2;
-                    o_hi = ((((size_t)img * 2 + 0) * C8 + c8) * PLN + pos) * 16;
-                    o_lo = ((((size_t)img * 2 + 1) * C8 + c8) * PLN + pos) * 16;
-                } else {
-                    const int kc = c8 * PP + pp;
-                    o_hi = fc_a_offset(0, out_groups, img, kc);
-                    o_lo = fc_a_offset(1, out_groups, img, kc);
-                }
-                *reinterpret_cast<uint4 *>(out + o_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(out + o_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            umma::fence_async_smem();                                     // staging (generic proxy) before the next bulk copy
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (etid == 0) umma::mbar_arrive(&bar_in_empty);
-        }
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tm, C::TMEM_COLS);
-}
-
 // ------------------------------------------------------------------------------------------------
 // conv3, channel-major orientation:  D[128 cout][positions] = W[128][K] * X[positions][K]^T.
 // The weights are the A operand (M = 128 output channels), a run of flat positions of the activation
-// planes is the B operand (N = 240 = 10 image rows x pitch 24), shifted per tap exactly as above.
+// planes is the B operand (N = 224 covering 10 image rows x pitch 22), shifted per tap exactly as above.
 // Each TMEM lane then holds ONE output channel and the columns are positions, so BN + ReLU + the 2x2
-// max-pool are thread-local (columns q, q+1, q+24, q+25): no shuffles, no staging, no block barriers.
+// max-pool are thread-local (columns q, q+1, q+22, q+23): no shuffles, no staging, no block barriers.
 // 8 epilogue warps (2 per TMEM lane quarter, one per row half); the next image's planes are fetched
 // while the epilogue drains TMEM.
 // ------------------------------------------------------------------------------------------------
 struct Conv3T {
-    static constexpr int G = 8, NOUT = 128, H = 20, W = 20, WP = 24;
-    static constexpr int NT_ROWS = 10, N = NT_ROWS * WP, TILES = H / NT_ROWS;      // 2 tiles of 240 positions
-    static constexpr int PIN = ((TILES - 1) * N + N + 4 * WP + 4 + 7) / 8 * 8;     // 584 positions staged
-    static constexpr int PL = Conv3Cfg::PL;                                        // plane pitch in global memory
+    static constexpr int G = 8, NOUT = 128, H = 20, W = 20, WP = Conv3Cfg::WP;
+    static constexpr int NT_ROWS = 10, TSTEP = NT_ROWS * WP, N = (TSTEP + 15) / 16 * 16, TILES = H / NT_ROWS;   // 2 tiles: 220 positions each, N = 224
+    static constexpr int PIN = ((TILES - 1) * TSTEP + N + 4 * WP + 4 + 7) / 8 * 8;  // 536 positions staged
+    static constexpr int PL = Conv3Cfg::PL;                                        // plane size in global memory (positions)
     static constexpr int IN_BYTES = 2 * G * PIN * 16;
     static constexpr int WTAP_BYTES = 2 * G * NOUT * 16;
     static constexpr int SMEM = (IN_BYTES + 127) / 128 * 128 + 2 * WTAP_BYTES + 128;
@@ -318,8 +132,8 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                     for (int t = 0; t < C::TILES; ++t) {
 #pragma unroll
                         for (int ks = 0; ks < C::G / 2; ++ks) {
-                            const uint32_t x_hi = (0 * C::G + 2 * ks) * C::PIN + t * C::N + shift;
-                            const uint32_t x_lo = (1 * C::G + 2 * ks) * C::PIN + t * C::N + shift;
+                            const uint32_t x_hi = (0 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
+                            const uint32_t x_lo = (1 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
                             const uint32_t w_hi = wofs + (0 * C::G + 2 * ks) * C::NOUT;
                             const uint32_t w_lo = wofs + (1 * C::G + 2 * ks) * C::NOUT;
                             const uint32_t d = tm + (uint32_t)(t * C::N);
@@ -784,87 +598,6 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 1) umma::tmem_dealloc(tm, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
-// conv1 for the tensor path: u8 crop -> pooled 40x40x16, written as conv2's input planes (bf16 hi/lo).
-// CUDA cores (C_in = 1, K = 25: not a tensor-core shape; ~2 % of the FLOPs).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-conv1_planes_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__restrict__ n_dev, int base,
-                    const float *__restrict__ w /*[25][16]*/, const float *__restrict__ sc, const float *__restrict__ sh,
-                    uint8_t *__restrict__ out)
-{
-    constexpr int H = 80, W = 80, PW = W + 4, PH = H + 4, OW = 40, OH = 40;
-    __shared__ float patch[PH * PW];
-    __shared__ __align__(16) float sw[400];
-    __shared__ float ssc[16], ssh[16];
-    const int n = blockIdx.x;
-    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
-    if (n >= n_act) return;
-    const uint8_t *src = img + (size_t)n * H * W;
-    for (int i = threadIdx.x; i < PH * PW; i += 256) {
-        const int y = i / PW - 2, x = i % PW - 2;
-        patch[i] = (y >= 0 && y < H && x >= 0 && x < W) ? (float)src[y * W + x] : 0.f;
-    }
-    for (int i = threadIdx.x; i < 400; i += 256) sw[i] = w[i];
-    if (threadIdx.x < 16) { ssc[threadIdx.x] = sc[threadIdx.x]; ssh[threadIdx.x] = sh[threadIdx.x]; }
-    __syncthreads();
-    constexpr int WP2 = Conv2Cfg::WP, PL2 = Conv2Cfg::PL;
-    uint8_t *dst = out + (size_t)n * Conv2Cfg::IMG_BYTES;
-    for (int q = threadIdx.x; q < OH * OW; q += 256) {
-        const int py = q / OW, px = q % OW;
-        float acc[4][16];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 16; ++c) acc[a][c] = 0.f;
-        for (int dy = 0; dy < 5; ++dy) {
-            float r0[6], r1[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                r0[i] = patch[(2 * py + dy) * PW + 2 * px + i];
-                r1[i] = patch[(2 * py + dy + 1) * PW + 2 * px + i];
-            }
-#pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-                const float4 *wp = reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 16);
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 wv = wp[c4];
-                    const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        acc[0][c4 * 4 + j] = fmaf(r0[dx], ww[j], acc[0][c4 * 4 + j]);
-                        acc[1][c4 * 4 + j] = fmaf(r0[dx + 1], ww[j], acc[1][c4 * 4 + j]);
-                        acc[2][c4 * 4 + j] = fmaf(r1[dx], ww[j], acc[2][c4 * 4 + j]);
-                        acc[3][c4 * 4 + j] = fmaf(r1[dx + 1], ww[j], acc[3][c4 * 4 + j]);
-                    }
-                }
-            }
-        }
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-            float o[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float s = ssc[c + u], t = ssh[c + u];
-                o[u] = fmaxf(fmaxf(fmaxf(fmaf(acc[0][c + u], s, t), fmaf(acc[1][c + u], s, t)),
-                                   fmaxf(fmaf(acc[2][c + u], s, t), fmaf(acc[3][c + u], s, t))), 0.f);
-            }
-            __nv_bfloat16 h0, l0, h1, l1;
-            umma::split_bf16(o[0], h0, l0); umma::split_bf16(o[1], h1, l1);
-            hi[c >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[c >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        const int pos = (py + 2) * WP2 + px + 2;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            *reinterpret_cast<uint4 *>(dst + (((size_t)0 * 2 + g) * PL2 + pos) * 16) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-            *reinterpret_cast<uint4 *>(dst + (((size_t)1 * 2 + g) * PL2 + pos) * 16) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
-        }
-    }
 }
 
 }}  // namespace tb::tc
