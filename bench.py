@@ -180,7 +180,10 @@ def run_ours(args):
     probs_host = torch.empty((B * MAX_CROPS, M_CLASSES), dtype=torch.float32, pin_memory=True)
     # fixed-stride metadata for the all-gather: the first B*MAX_CROPS blob records (32 B each) + headers
     from trex_b200 import sharding
-    meta_bytes = sharding.meta_bytes(B, MAX_CROPS)
+    meta_bytes = sharding.meta_bytes(B, MAX_CROPS, with_identity=True)
+    top_id = torch.zeros(B * MAX_CROPS, dtype=torch.int32, device=dev)
+    top_p = torch.zeros(B * MAX_CROPS, dtype=torch.float32, device=dev)
+    net.set_top1(top_id.data_ptr(), top_p.data_ptr())
     meta_all = torch.empty((world_size, meta_bytes), dtype=torch.uint8, device=dev) if world_size > 1 else None
 
     class _CudaBuf:      # zero-copy torch view of a device buffer owned by the C library
@@ -199,7 +202,7 @@ def run_ours(args):
         bs.apply_device(fr.data_ptr(), B, stream.cuda_stream, fetch=False)
         net.predict_device(crops_p, B * MAX_CROPS, ncrops_p, probs.data_ptr(), 0, stream.cuda_stream)
         if world_size > 1:    # one collective per step: fixed-stride headers + blob records of every rank's frames
-            sharding.all_gather_metadata(sharding.pack_metadata(as_tensor(infos_p, B * 32), as_tensor(recs_p, B * MAX_CROPS * 32), B, MAX_CROPS), out=meta_all)
+            sharding.all_gather_metadata(sharding.pack_metadata(as_tensor(infos_p, B * 32), as_tensor(recs_p, B * MAX_CROPS * 32), B, MAX_CROPS, top_id, top_p), out=meta_all)
 
     # e2e: two slots (seg handle + CNN handle + stream each) so the H2D copy of batch i+1 overlaps the
     # kernels of batch i; every step still moves its frames host->device and its results device->host.
@@ -212,12 +215,15 @@ def run_ours(args):
             sbs = trex_b200.BackgroundSubtraction(bg, settings=settings, max_batch=B, max_individuals=MAX_CROPS, device=local_rank)
             snet = trex_b200.VINetwork(M_CLASSES, max_images=B * MAX_CROPS, device=local_rank, precision=args.precision)
             snet.load_weights(weights())
-        slots.append(dict(bs=sbs, net=snet, stream=st, res=sbs.device_results(), pending=False,
+        s_id = torch.zeros(B * MAX_CROPS, dtype=torch.int32, device=dev)
+        s_p = torch.zeros(B * MAX_CROPS, dtype=torch.float32, device=dev)
+        slots.append(dict(bs=sbs, net=snet, stream=st, res=sbs.device_results(), pending=False, top_id=s_id, top_p=s_p,
                           probs=torch.empty((B * MAX_CROPS, M_CLASSES), dtype=torch.float32, device=dev),
                           probs_host=torch.empty((B * MAX_CROPS, M_CLASSES), dtype=torch.float32, pin_memory=True)))
 
     def e2e_submit(i):
         sl = slots[i % 2]
+        sl["net"].set_top1(sl["top_id"].data_ptr(), sl["top_p"].data_ptr())
         sl["bs"].submit(host_batches[i % pool].numpy(), fetch=1)            # tb_seg_submit: H2D frames + kernels
         crops_q, ncrops_q = sl["res"][0], sl["res"][1]
         sl["net"].predict_device(crops_q, B * MAX_CROPS, ncrops_q, sl["probs"].data_ptr(), 0, sl["stream"].cuda_stream)
@@ -225,7 +231,7 @@ def run_ours(args):
             # identity probabilities back to the host (upper bound of rows: crops of this batch are not known yet)
             sl["probs_host"][:B * N_INDIV].copy_(sl["probs"][:B * N_INDIV], non_blocking=True)
             if world_size > 1:
-                sharding.all_gather_metadata(sharding.pack_metadata(as_tensor(sl["res"][4], B * 32), as_tensor(sl["res"][3], B * MAX_CROPS * 32), B, MAX_CROPS), out=meta_all)
+                sharding.all_gather_metadata(sharding.pack_metadata(as_tensor(sl["res"][4], B * 32), as_tensor(sl["res"][3], B * MAX_CROPS * 32), B, MAX_CROPS, sl["top_id"], sl["top_p"]), out=meta_all)
         sl["pending"] = True
 
     def e2e_wait(i):

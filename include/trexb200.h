@@ -207,6 +207,10 @@ TB_API int tb_vi_predict(tb_vi *h, const uint8_t *images, int n, float *probs, f
 TB_API int tb_vi_predict_device(tb_vi *h, const void *images_dev, int n_max, const void *n_dev,
                          void *probs_dev, void *logits_dev, void *stream);
 TB_API int tb_vi_wait(tb_vi *h);
+/* Optional device outputs of the following predict calls: arg-max class (uint32) and its probability (float) per image,
+ * i.e. the identity the tracker assigns (Tracker::predicted, T/tracking/Tracker.cpp:237-246); part of the per-blob
+ * metadata gathered across GPUs.  NULL, NULL disables. */
+TB_API int tb_vi_set_top1(tb_vi *h, void *ids_dev, void *probs_dev);
 TB_API uint64_t tb_vi_launch_count(tb_vi *h);
 /* As tb_seg_profile / tb_seg_kernel_ms for {conv1, conv2, conv3, fc1, head}; n = chunks covered. */
 TB_API int tb_vi_profile(tb_vi *h, int enable);

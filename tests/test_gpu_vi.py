@@ -105,3 +105,30 @@ def test_256_classes(precision):
     ref = vi.forward_logits(sd, crops)
     assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max()))
     assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
+
+
+def test_top1_device_outputs():
+    """Arg-max identity + its probability written on the device (metadata for Tracker::predicted / the all-gather)."""
+    import torch
+    import trex_b200
+    from oracle import vi
+    M = 100
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=0))
+    rng = np.random.default_rng(9)
+    crops = np.zeros((50, 80, 80, 1), np.uint8)
+    for i in range(50):
+        crops[i, 10:70, 20:60, 0] = rng.integers(1, 255, (60, 40))
+    dev = torch.device("cuda", 0)
+    x = torch.from_numpy(crops).to(dev)
+    probs = torch.empty((50, M), dtype=torch.float32, device=dev)
+    ids = torch.zeros(50, dtype=torch.int32, device=dev); p = torch.zeros(50, dtype=torch.float32, device=dev)
+    net = trex_b200.VINetwork(M, max_images=64, precision="bf16x3")
+    net.load_weights(sd)
+    net.set_top1(ids.data_ptr(), p.data_ptr())
+    s = torch.cuda.Stream(dev)
+    net.predict_device(x.data_ptr(), 50, 0, probs.data_ptr(), 0, s.cuda_stream)
+    net.wait()
+    pr = probs.cpu().numpy()
+    assert np.array_equal(ids.cpu().numpy(), pr.argmax(1))
+    assert np.allclose(p.cpu().numpy(), pr.max(1), rtol=1e-6, atol=1e-7)
+    assert np.abs(pr - vi.predict(sd, crops)).max() < TOL

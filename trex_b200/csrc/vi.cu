@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(HD_WARPS * 32)
 head_kernel(const float *__restrict__ h1, int nsplit, size_t split_stride, const float *__restrict__ b1,
             int M, int n_max, const uint32_t *__restrict__ n_dev, int base,
             const float *__restrict__ g, const float *__restrict__ be, const float *__restrict__ w2t /*[100][M]*/,
-            const float *__restrict__ b2, float *__restrict__ probs, float *__restrict__ logits, int w_in_smem)
+            const float *__restrict__ b2, float *__restrict__ probs, float *__restrict__ logits, int w_in_smem,
+            uint32_t *__restrict__ top_id, float *__restrict__ top_p)
 {
     extern __shared__ float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -290,23 +291,28 @@ head_kernel(const float *__restrict__ h1, int nsplit, size_t split_stride, const
         if (i < 100) sh[i] = fmaxf((v[j] - mean) * rstd * g[i] + be[i], 0.f);
     }
     __syncwarp();
-    float mx = -INFINITY;
+    float mx = -INFINITY; int arg = 0;
     for (int o = lane; o < M; o += 32) {
         float a = b2[o];
 #pragma unroll 4
         for (int k = 0; k < 100; ++k) a = fmaf(sh[k], W[(size_t)k * M + o], a);
         sl[o] = a;
         if (logits) logits[(size_t)n * M + o] = a;
-        mx = fmaxf(mx, a);
+        if (a > mx) { mx = a; arg = o; }                    // first maximum per lane (o ascending)
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o > 0; o >>= 1) {                       // warp arg-max, ties -> smallest class index
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
     float sum = 0.f;
     for (int o = lane; o < M; o += 32) { const float e = expf(sl[o] - mx); sl[o] = e; sum += e; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.f / sum;
     for (int o = lane; o < M; o += 32) probs[(size_t)n * M + o] = sl[o] * inv;
+    if (top_id && lane == 0) { top_id[n] = (uint32_t)arg; top_p[n] = inv; }     // exp(max - max) = 1
 }
 
 }  // namespace tb
@@ -333,6 +339,7 @@ struct tb_vi {
     // tensor-core path (precision 1)
     uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w1t = nullptr, *w2t = nullptr, *w3t = nullptr, *wfc = nullptr;
     int fc_groups = 0, n_sms = 148, head_w_smem = 0;
+    uint32_t *top_id = nullptr; float *top_p = nullptr;     // optional device outputs: arg-max class and its probability per image
     uint64_t launches = 0;
     cudaStream_t last_stream = nullptr;
     EventRing<5> prof;
@@ -617,7 +624,8 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         h->prof.mark(slot, 4);
         head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, head_smem(h, M), s>>>(
             h->h1, FC_SPLIT, (size_t)h->chunk * 100, h->bf1, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2,
-            probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr, h->head_w_smem);
+            probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr, h->head_w_smem,
+            h->top_id ? h->top_id + base : nullptr, h->top_p ? h->top_p + base : nullptr);
         h->prof.mark(slot, 5);
         h->launches += 5;
     }
@@ -654,7 +662,8 @@ static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n
         h->prof.mark(slot, 4);
         head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, head_smem(h, M), s>>>(
             h->h1, 1, 0, nullptr, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2,
-            probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr, h->head_w_smem);
+            probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr, h->head_w_smem,
+            h->top_id ? h->top_id + base : nullptr, h->top_p ? h->top_p + base : nullptr);
         h->prof.mark(slot, 5);
         h->launches += 5;
     }
@@ -717,5 +726,13 @@ extern "C" int tb_vi_kernel_ms(tb_vi *h, double out_ms[5], uint64_t *n_chunks)
     if (h->prof.flush() != TB_OK) { set_error("tb_vi_kernel_ms: event query failed"); return TB_ERR_CUDA; }
     for (int k = 0; k < 5; ++k) { out_ms[k] = h->prof.acc[k]; h->prof.acc[k] = 0; }
     *n_chunks = h->prof.n; h->prof.n = 0;
+    return TB_OK;
+}
+
+extern "C" int tb_vi_set_top1(tb_vi *h, void *ids_dev, void *probs_dev)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_vi_set_top1: null handle");
+    TB_REQUIRE((ids_dev == nullptr) == (probs_dev == nullptr), TB_ERR_INVALID, "tb_vi_set_top1: give both outputs or none");
+    h->top_id = (uint32_t *)ids_dev; h->top_p = (float *)probs_dev;
     return TB_OK;
 }

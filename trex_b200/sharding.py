@@ -27,13 +27,18 @@ def owner_of(frame: int, world: int, batch: int):
     return chunk // world, chunk % world, frame % batch
 
 
-def meta_bytes(batch: int, kmax: int) -> int:
-    return batch * INFO_DTYPE.itemsize + batch * kmax * REC_DTYPE.itemsize
+def meta_bytes(batch: int, kmax: int, with_identity: bool = False) -> int:
+    return batch * INFO_DTYPE.itemsize + batch * kmax * (REC_DTYPE.itemsize + (8 if with_identity else 0))
 
 
-def pack_metadata(infos: torch.Tensor, recs: torch.Tensor, batch: int, kmax: int) -> torch.Tensor:
-    """Concatenate the per-frame headers and the first batch*kmax blob records (uint8 tensors on any device)."""
-    return torch.cat([infos.view(torch.uint8)[: batch * 32], recs.view(torch.uint8)[: batch * kmax * 32]])
+def pack_metadata(infos: torch.Tensor, recs: torch.Tensor, batch: int, kmax: int,
+                  top_id: torch.Tensor | None = None, top_p: torch.Tensor | None = None) -> torch.Tensor:
+    """Concatenate the per-frame headers, the first batch*kmax blob records and (optionally) the identity the CNN
+    assigned to each of them (arg-max class uint32 + probability float32); uint8 tensors on any device."""
+    parts = [infos.view(torch.uint8)[: batch * 32], recs.view(torch.uint8)[: batch * kmax * 32]]
+    if top_id is not None:
+        parts += [top_id.view(torch.uint8)[: batch * kmax * 4], top_p.view(torch.uint8)[: batch * kmax * 4]]
+    return torch.cat(parts)
 
 
 def all_gather_metadata(local: torch.Tensor, out: torch.Tensor | None = None, group=None) -> torch.Tensor:
@@ -53,7 +58,7 @@ def unpack_round(gathered: torch.Tensor, round_idx: int, batch: int, kmax: int):
     out = {}
     for rank in range(world):
         infos = g[rank, : batch * 32].view(INFO_DTYPE)
-        recs = g[rank, batch * 32:].view(REC_DTYPE)
+        recs = g[rank, batch * 32: batch * 32 + batch * kmax * 32].view(REC_DTYPE)
         lo, _ = frame_range(round_idx, rank, world, batch)
         for i in range(batch):
             b0, n = int(infos[i]["blob_begin"]), int(infos[i]["n_blobs"])

@@ -71,6 +71,10 @@ class VINetwork:
                                          C.c_void_p(probs_ptr), C.c_void_p(logits_ptr) if logits_ptr else None,
                                          C.c_void_p(stream)))
 
+    def set_top1(self, ids_ptr: int, probs_ptr: int):
+        """Device buffers (uint32[n], float32[n]) that predict_device fills with the arg-max identity and its probability."""
+        check(lib().tb_vi_set_top1(self._h, C.c_void_p(ids_ptr) if ids_ptr else None, C.c_void_p(probs_ptr) if probs_ptr else None))
+
     def wait(self):
         check(lib().tb_vi_wait(self._h))
 
