@@ -33,6 +33,7 @@ enum { F_DIFF = 1, F_ABS = 2, F_INV = 4, F_INVMASK = 8, F_RANGE = 16, F_PREMASK 
 
 struct SegDev {
     int W, H, B, cpr, rpt, n_bands, aligned;
+    int wpr;                   // 64-bit words per row of K1's row-padded bit image (ceil(cpr / 4) + 1 zero word)
     uint32_t rcap;             // runs per frame (scratch)
     uint32_t lines_cap, px_cap, blobs_cap, crops_cap;   // batch arenas
     uint32_t px_frame_cap, max_crops;
@@ -387,6 +388,238 @@ seg_rle_tma_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc
                 ++oe;
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, warp-specialised persistent variant (the default for widths that are multiples of 16).
+// The batch is cut into units (band of rows, frame) in band-major order.  A grid of (SMs x resident CTAs)
+// persistent CTAs first works through a static contiguous share of the units (so the background tile,
+// kept in registers, changes only a few times per CTA) and then takes the remaining units one at a time
+// from a global counter, which absorbs the speed differences between SMs.  Roles inside a CTA:
+//   * 1 producer warp: picks the units and streams their tiles into a shared-memory ring with
+//     cp.async.bulk (TMA engine); the unit's (band, frame) travels with the stage;
+//   * 8 mask warps: 16 pixels -> 16 foreground bits (SWAR + dp4a), written into a row-padded bit image
+//     (every image row starts on a 64-bit word and is followed by at least one zero word, so a run never
+//     crosses a word boundary between rows and no row-break masks are needed);
+//   * EW extraction warps, taking units round-robin: each lane owns 8 consecutive 64-bit words of the
+//     bit image (512 pixels), counts run starts with 8 popcounts, ranks them with one warp scan, reserves
+//     space in the frame's run array with one atomicAdd per unit and writes x0,y / x1.
+// Mask warps never wait for the extraction of the same unit (ring of EW bit images), all waits are
+// hardware-suspended mbarrier waits, and per byte the kernel issues about half the instructions of the
+// variant above, where every thread ranks its own word behind three block barriers.
+// ------------------------------------------------------------------------------------------------
+constexpr int K1W_MW = 8, K1W_STAGES = 3;
+constexpr int K1W_STAGE_BYTES = K1_CHUNKS * 16;
+constexpr int K1W_WORDS = 256;                              // 64-bit words of the padded bit image (32 lanes x 8)
+constexpr int K1W_MASK_BYTES = (K1W_WORDS / 8 + 1) * 80 + 128;   // per lane 64 B (8 words) + 16 B pad (bank spread); 1 spare zero block; 128 B dump area
+constexpr uint32_t K1W_DONE = 0xFFFFFFFFu;
+constexpr int k1w_smem(int ew) { return K1W_STAGES * K1W_STAGE_BYTES + ew * K1W_MASK_BYTES; }
+
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) { uint64_t r; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r) : "r"(a)); return r; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory"); }
+
+template <bool GENERIC, int EW>
+__global__ void __launch_bounds__((K1W_MW + EW + 1) * 32, 3)
+seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t static_units)
+{
+    constexpr int NT = (K1W_MW + EW + 1) * 32;
+    extern __shared__ __align__(128) uint8_t k1w_dsm[];
+    __shared__ uint64_t s_bar[2 * K1W_STAGES + 2 * EW];
+    __shared__ uint32_t s_meta[K1W_STAGES + EW];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile_a = umma::smem_u32(k1w_dsm), mask_a = tile_a + K1W_STAGES * K1W_STAGE_BYTES;
+    const uint32_t full_a = umma::smem_u32(s_bar), empty_a = full_a + 8 * K1W_STAGES;
+    const uint32_t mkf_a = empty_a + 8 * K1W_STAGES, mke_a = mkf_a + 8 * EW;
+    const uint32_t meta_a = umma::smem_u32(s_meta), mmeta_a = meta_a + 4 * K1W_STAGES;
+
+    if (tid == 0) {
+        for (int i = 0; i < K1W_STAGES; ++i) { umma::mbar_init(&s_bar[i], 1); umma::mbar_init(&s_bar[K1W_STAGES + i], K1W_MW); }
+        for (int i = 0; i < EW; ++i) { umma::mbar_init(&s_bar[2 * K1W_STAGES + i], K1W_MW); umma::mbar_init(&s_bar[2 * K1W_STAGES + EW + i], 1); }
+        umma::fence_mbar_init();
+    }
+    for (int i = tid; i < EW * K1W_MASK_BYTES / 4; i += NT) sts_u32(mask_a + 4 * i, 0u);
+    __syncthreads();
+
+    if (warp == K1W_MW + EW) {                     // ---- producer warp ----
+        if (lane != 0) return;
+        const uint32_t B = (uint32_t)d.B, U = (uint32_t)d.n_bands * B;
+        const size_t frame_bytes = (size_t)d.W * d.H;
+        uint32_t s = 0, ph = 0;
+        auto issue = [&](uint32_t band, uint32_t f) {
+            const int row0 = (int)band * d.rpt;
+            const uint32_t bytes = (uint32_t)min(d.rpt, d.H - row0) * (uint32_t)d.W;
+            umma::mbar_wait_suspend_a(empty_a + 8 * s, ph ^ 1);
+            sts_u32(meta_a + 4 * s, (band << 16) | f);
+            umma::mbar_expect_tx_a(full_a + 8 * s, bytes);
+            umma::bulk_g2s_a(tile_a + s * K1W_STAGE_BYTES, frames + (size_t)f * frame_bytes + (size_t)row0 * d.W, bytes, full_a + 8 * s);
+            if (++s == K1W_STAGES) { s = 0; ph ^= 1; }
+        };
+        {                                          // static share: units [i * static_units, (i + 1) * static_units)
+            const uint32_t u0 = blockIdx.x * static_units;
+            uint32_t band = u0 / B, f = u0 % B;
+            for (uint32_t i = 0; i < static_units; ++i) {
+                issue(band, f);
+                if (++f == B) { f = 0; ++band; }
+            }
+        }
+        uint32_t *counter = d.run_count + d.B;     // zeroed with run_count before every launch
+        const uint32_t dyn0 = gridDim.x * static_units;
+        uint32_t u = dyn0 + atomicAdd(counter, 1u);
+        while (u < U) {
+            const uint32_t un = dyn0 + atomicAdd(counter, 1u);     // in flight while this unit is issued
+            issue(u / B, u % B);
+            u = un;
+        }
+        umma::mbar_wait_suspend_a(empty_a + 8 * s, ph ^ 1);
+        sts_u32(meta_a + 4 * s, K1W_DONE);
+        umma::mbar_arrive_a(full_a + 8 * s);
+        return;
+    }
+
+    if (warp < K1W_MW) {                           // ---- mask warps ----
+        const int full_chunks = d.rpt * d.cpr;
+        const int cb = warp * (32 * K1_KPT) + lane;                   // chunks cb + 32 k
+        uint32_t mpos[K1_KPT];                                        // byte offset of the chunk's 16 flags inside a bit image
+#pragma unroll
+        for (int k = 0; k < K1_KPT; ++k) {
+            const int c = cb + 32 * k;
+            mpos[k] = (uint32_t)(K1W_MASK_BYTES - 128 + 2 * lane);    // chunks beyond the band: dump area
+            if (c < full_chunks) {
+                const int q = (c / d.cpr) * d.wpr * 4 + c % d.cpr;    // chunk position in the row-padded bit image
+                mpos[k] = (uint32_t)((q >> 5) * 80 + (q & 31) * 2);
+            }
+        }
+        const uint32_t my_tile = tile_a + (uint32_t)cb * 16u;
+        uint4 bgc[K1_KPT];
+        uint32_t cur_band = 0xFFFFFFFFu, s = 0, ph = 0, b = 0, bph = 0;
+        int tile_chunks = 0;
+        for (;;) {
+            umma::mbar_wait_suspend_a(full_a + 8 * s, ph);
+            const uint32_t meta = lds_u32(meta_a + 4 * s);
+            if (meta == K1W_DONE) break;
+            const uint32_t band = meta >> 16;
+            if (band != cur_band) {                                   // new band: background tile into registers (L2-resident)
+                cur_band = band;
+                const int row0 = (int)band * d.rpt;
+                tile_chunks = min(d.rpt, d.H - row0) * d.cpr;
+                const uint4 *bgp = reinterpret_cast<const uint4 *>(d.bg + (size_t)row0 * d.W) + cb;
+#pragma unroll
+                for (int k = 0; k < K1_KPT; ++k) bgc[k] = (cb + 32 * k < tile_chunks) ? bgp[32 * k] : make_uint4(0, 0, 0, 0);
+            }
+            uint4 cur[K1_KPT];
+#pragma unroll
+            for (int k = 0; k < K1_KPT; ++k) cur[k] = lds_v4(my_tile + s * K1W_STAGE_BYTES + k * 512);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive_a(empty_a + 8 * s);      // stage is in registers: refill it
+            uint32_t m16[K1_KPT];
+#pragma unroll
+            for (int k = 0; k < K1_KPT; ++k) {
+                const uint32_t m = GENERIC ? fg16<true>(cur[k], bgc[k], p) : fg16_fast(cur[k], bgc[k], p.lo4);
+                m16[k] = (cb + 32 * k < tile_chunks) ? m : 0u;        // rows below the image (last band) are stale shared memory
+            }
+            umma::mbar_wait_suspend_a(mke_a + 8 * b, bph ^ 1);
+            const uint32_t mb = mask_a + b * K1W_MASK_BYTES;
+#pragma unroll
+            for (int k = 0; k < K1_KPT; ++k) sts_u16(mb + mpos[k], m16[k]);
+            if (tid == 0) sts_u32(mmeta_a + 4 * b, meta);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive_a(mkf_a + 8 * b);
+            if (++s == K1W_STAGES) { s = 0; ph ^= 1; }
+            if (++b == EW) { b = 0; bph ^= 1; }
+        }
+        for (int i = 0; i < EW; ++i) {                                // tell every extraction warp that the CTA is done
+            umma::mbar_wait_suspend_a(mke_a + 8 * b, bph ^ 1);
+            if (tid == 0) sts_u32(mmeta_a + 4 * b, K1W_DONE);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive_a(mkf_a + 8 * b);
+            if (++b == EW) { b = 0; bph ^= 1; }
+        }
+        return;
+    }
+
+    // ---- extraction warps ----
+    const int e = warp - K1W_MW;
+    const uint32_t mb = mask_a + e * K1W_MASK_BYTES;
+    const uint32_t wpr = (uint32_t)d.wpr;
+    const uint32_t r0 = (uint32_t)(lane * 8) / wpr, c0 = (uint32_t)(lane * 8) % wpr;
+    for (uint32_t ph = 0;; ph ^= 1) {
+        umma::mbar_wait_suspend_a(mkf_a + 8 * e, ph);
+        const uint32_t meta = lds_u32(mmeta_a + 4 * e);
+        if (meta == K1W_DONE) break;
+        const uint32_t band = meta >> 16, f = meta & 0xFFFFu;
+        uint64_t M[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 q = lds_v4(mb + lane * 80 + j * 16);
+            M[2 * j] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+            M[2 * j + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+        }
+        // starts / ends inside this lane's 512 pixels
+        uint32_t up = __shfl_up_sync(0xffffffffu, (uint32_t)(M[7] >> 63), 1);
+        uint32_t dn = __shfl_down_sync(0xffffffffu, (uint32_t)M[0] & 1u, 1);
+        if (lane == 0) up = 0;
+        if (lane == 31) dn = 0;
+        uint32_t cs = 0, nz = 0;
+        uint64_t prev = up;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            cs += (uint32_t)__popcll(M[j] & ~((M[j] << 1) | prev));
+            prev = M[j] >> 63;
+            nz |= (M[j] != 0ull ? 1u : 0u) << j;
+        }
+        const uint32_t ce = cs + (up & (uint32_t)M[0] & 1u) - ((uint32_t)(M[7] >> 63) & dn);
+        uint32_t total;
+        const uint32_t ex = warp_excl_scan(cs | (ce << 16), total);
+        const uint32_t ns = total & 0xFFFFu;
+        uint32_t base = 0;
+        if (lane == 0) {
+            if (ns) base = atomicAdd(&d.run_count[f], ns);
+            d.band_base[(size_t)f * d.n_bands + band] = base;
+            d.band_cnt[(size_t)f * d.n_bands + band] = ns;
+        }
+        if (ns) {
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t os = base + (ex & 0xFFFFu), oe = base + (ex >> 16);
+            uint16_t *out = reinterpret_cast<uint16_t *>(d.runs_raw + (size_t)f * d.rcap);
+            const uint32_t y0 = band * (uint32_t)d.rpt;
+            while (nz) {
+                const uint32_t j = (uint32_t)__ffs((int)nz) - 1u; nz &= nz - 1u;
+                const uint32_t w = (uint32_t)lane * 8u + j;
+                const uint64_t Mw = lds_u64(mb + lane * 80 + j * 8);
+                const uint64_t pw = w ? lds_u64(mb + ((w - 1) >> 3) * 80 + ((w - 1) & 7) * 8) : 0ull;
+                const uint64_t nw = lds_u64(mb + ((w + 1) >> 3) * 80 + ((w + 1) & 7) * 8);
+                uint64_t st = Mw & ~((Mw << 1) | (pw >> 63));
+                uint64_t en = Mw & ~((Mw >> 1) | (nw << 63));
+                uint32_t c = c0 + j, r = r0;
+                while (c >= wpr) { c -= wpr; ++r; }
+                const uint32_t xb = c * 64u, y = y0 + r;
+                while (st) {
+                    const uint32_t bit = (uint32_t)__ffsll((long long)st) - 1u; st &= st - 1;
+                    if (os < d.rcap) {
+                        out[(size_t)os * 4 + 0] = (uint16_t)(xb + bit);
+                        *reinterpret_cast<uint32_t *>(out + (size_t)os * 4 + 2) = y;                 // y, pad = 0
+                    }
+                    ++os;
+                }
+                while (en) {
+                    const uint32_t bit = (uint32_t)__ffsll((long long)en) - 1u; en &= en - 1;
+                    if (oe < d.rcap) out[(size_t)oe * 4 + 1] = (uint16_t)(xb + bit);
+                    ++oe;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive_a(mke_a + 8 * e);
     }
 }
 
@@ -874,7 +1107,8 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     d.W = cfg->width; d.H = cfg->height; d.B = cfg->max_batch;
     d.cpr = (d.W + 15) / 16;
     d.aligned = (d.W % 16) == 0;
-    d.rpt = std::max(1, K1_CHUNKS / d.cpr);
+    d.wpr = (d.cpr + 3) / 4 + 1;
+    d.rpt = std::max(1, std::min(K1_CHUNKS / d.cpr, K1W_WORDS / d.wpr));        // rows per band: fits the chunk tile and the padded bit image
     d.n_bands = (d.H + d.rpt - 1) / d.rpt;
     d.rcap = cfg->max_runs_per_frame > 0 ? (uint32_t)cfg->max_runs_per_frame : 32768u;
     d.rcap = std::max<uint32_t>(d.rcap, (uint32_t)d.n_bands);
@@ -897,7 +1131,7 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     A(h->d_bg, (size_t)d.W * d.H + 16);
     A(h->d_frames, B * d.W * d.H + 16);
     A(h->d_tmp, (size_t)d.W * d.H);
-    A(d.run_count, B); A(d.band_base, B * d.n_bands); A(d.band_cnt, B * d.n_bands);
+    A(d.run_count, B + 1); A(d.band_base, B * d.n_bands); A(d.band_cnt, B * d.n_bands);
     A(d.runs_raw, B * d.rcap); A(d.runs, B * d.rcap); A(d.parent, B * d.rcap); A(d.bidx, B * d.rcap);
     A(d.row_start, B * d.H); A(d.row_end, B * d.H);
     A(d.b_npx, B * d.rcap); A(d.b_nl, B * d.rcap); A(d.b_xmin, B * d.rcap); A(d.b_xmax, B * d.rcap);
@@ -1020,13 +1254,14 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     d.bg_stride = 0;
     d.keep_mask = nullptr;
     h->last_frames_dev = frames_dev;
-    TB_CUDA(cudaMemsetAsync(d.run_count, 0, sizeof(uint32_t) * (size_t)n, s));
+    TB_CUDA(cudaMemsetAsync(d.run_count, 0, sizeof(uint32_t) * ((size_t)n + 1), s));      // + the unit counter of the persistent K1
     static const int fpc_env = getenv("TB_SEG_FPC") ? atoi(getenv("TB_SEG_FPC")) : 0;
     const int fpc = fpc_env > 0 ? fpc_env : (n >= 64 ? 8 : (n >= 8 ? 2 : 1));
     dim3 g1((unsigned)d.n_bands, (unsigned)((n + fpc - 1) / fpc));
     const int slot = h->prof.begin(s);
     h->prof.mark(slot, 0);
-    static const bool no_tma = getenv("TB_SEG_NO_TMA") != nullptr;      // bring-up switch
+    static const bool no_tma = getenv("TB_SEG_NO_TMA") != nullptr;      // bring-up switches
+    static const bool no_ws = getenv("TB_SEG_NO_WS") != nullptr;
     const bool plain = !h->morph && h->k.flags == (F_DIFF | F_ABS) && (h->k.t4 & 0xFFu) <= 127u;
     SegK kk = h->k;
     if (plain) kk.lo4 = (127u - (kk.t4 & 0xFFu)) * 0x01010101u;      // SWAR addend of the fast path
@@ -1042,6 +1277,27 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
         d.bg = mask; d.bg_stride = (size_t)d.W * d.H;
         kk.flags = F_PREMASK;
         seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, kk, fpc);
+    } else if (d.aligned && d.wpr <= K1W_WORDS && n <= 65536 && d.n_bands < 65535 && !no_tma && !no_ws) {
+        static const int ew = getenv("TB_SEG_EW") ? atoi(getenv("TB_SEG_EW")) : 3;                   // tuning knobs
+        static const double static_frac = getenv("TB_SEG_STATIC") ? atof(getenv("TB_SEG_STATIC")) : 0.85;
+        static int ws_ctas = 0;
+        const int nt = (K1W_MW + (ew == 4 ? 4 : 3) + 1) * 32, smem = k1w_smem(ew == 4 ? 4 : 3);
+        if (!ws_ctas) {
+            TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(3)));
+            TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(3)));
+            TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(4)));
+            int per_sm = 0, sms = 0;
+            if (ew == 4) TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 4>, nt, smem));
+            else TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3>, nt, smem));
+            TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+            ws_ctas = std::max(1, per_sm) * std::max(1, sms);
+        }
+        const unsigned units = (unsigned)d.n_bands * (unsigned)n;
+        const unsigned grid = std::min<unsigned>(units, (unsigned)ws_ctas);
+        const uint32_t static_units = (uint32_t)((double)(units / grid) * static_frac);
+        if (plain && ew == 4) seg_rle_ws_kernel<false, 4><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units);
+        else if (plain) seg_rle_ws_kernel<false, 3><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units);
+        else seg_rle_ws_kernel<true, 3><<<grid, (K1W_MW + 3 + 1) * 32, k1w_smem(3), s>>>(frames_dev, d, h->k, static_units);
     } else if (d.aligned && !no_tma) {
         static bool attr_done = false;
         if (!attr_done) {

@@ -70,6 +70,33 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *mbar, uint32_t parit
     return ok;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) { while (!mbar_try_wait(mbar, parity)) { } }
+// same, but the thread is suspended by the hardware until the phase completes (or the time hint expires) instead of
+// polling: waiting warps do not take issue slots from the warps they wait for
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t *mbar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(smem_u32(mbar)), "r"(parity), "r"(0x989680u) : "memory");
+}
+// variants taking 32-bit shared-window addresses (no generic -> shared conversion in inner loops)
+__device__ __forceinline__ void mbar_wait_suspend_a(uint32_t a, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(a), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t a, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *mbar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(mbar)) : "memory");
