@@ -67,7 +67,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.005)
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 

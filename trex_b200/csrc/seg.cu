@@ -429,7 +429,7 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("
 
 template <bool GENERIC, int EW>
 __global__ void __launch_bounds__((K1W_MW + EW + 1) * 32, 3)
-seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t static_units)
+seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t static_units, unsigned long long *dbg)
 {
     constexpr int NT = (K1W_MW + EW + 1) * 32;
     extern __shared__ __align__(128) uint8_t k1w_dsm[];
@@ -452,6 +452,7 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
 
     if (warp == K1W_MW + EW) {                     // ---- producer warp ----
         if (lane != 0) return;
+        if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 4 + 0] = t; }
         const uint32_t B = (uint32_t)d.B, U = (uint32_t)d.n_bands * B;
         const size_t frame_bytes = (size_t)d.W * d.H;
         uint32_t s = 0, ph = 0;
@@ -474,15 +475,16 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
         }
         uint32_t *counter = d.run_count + d.B;     // zeroed with run_count before every launch
         const uint32_t dyn0 = gridDim.x * static_units;
-        uint32_t u = dyn0 + atomicAdd(counter, 1u);
-        while (u < U) {
-            const uint32_t un = dyn0 + atomicAdd(counter, 1u);     // in flight while this unit is issued
+        for (;;) {                                 // a unit is taken only once a stage is free for it, so that no CTA sits on
+            umma::mbar_wait_suspend_a(empty_a + 8 * s, ph ^ 1);      // queued work while others run dry at the end
+            const uint32_t u = dyn0 + atomicAdd(counter, 1u);
+            if (u >= U) break;
             issue(u / B, u % B);
-            u = un;
         }
         umma::mbar_wait_suspend_a(empty_a + 8 * s, ph ^ 1);
         sts_u32(meta_a + 4 * s, K1W_DONE);
         umma::mbar_arrive_a(full_a + 8 * s);
+        if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 4 + 1] = t; }
         return;
     }
 
@@ -621,6 +623,7 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
         __syncwarp();
         if (lane == 0) umma::mbar_arrive_a(mke_a + 8 * e);
     }
+    if (dbg && e == 0 && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 4 + 2] = t; }
 }
 
 // generate_binary's output image, for parity tests only (RawProcessing.cpp:597-600)
@@ -1279,7 +1282,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
         seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, kk, fpc);
     } else if (d.aligned && d.wpr <= K1W_WORDS && n <= 65536 && d.n_bands < 65535 && !no_tma && !no_ws) {
         static const int ew = getenv("TB_SEG_EW") ? atoi(getenv("TB_SEG_EW")) : 3;                   // tuning knobs
-        static const double static_frac = getenv("TB_SEG_STATIC") ? atof(getenv("TB_SEG_STATIC")) : 0.85;
+        static const double static_frac = getenv("TB_SEG_STATIC") ? atof(getenv("TB_SEG_STATIC")) : 0.5;
         static int ws_ctas = 0;
         const int nt = (K1W_MW + (ew == 4 ? 4 : 3) + 1) * 32, smem = k1w_smem(ew == 4 ? 4 : 3);
         if (!ws_ctas) {
@@ -1295,9 +1298,25 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
         const unsigned units = (unsigned)d.n_bands * (unsigned)n;
         const unsigned grid = std::min<unsigned>(units, (unsigned)ws_ctas);
         const uint32_t static_units = (uint32_t)((double)(units / grid) * static_frac);
-        if (plain && ew == 4) seg_rle_ws_kernel<false, 4><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units);
-        else if (plain) seg_rle_ws_kernel<false, 3><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units);
-        else seg_rle_ws_kernel<true, 3><<<grid, (K1W_MW + 3 + 1) * 32, k1w_smem(3), s>>>(frames_dev, d, h->k, static_units);
+        static const bool timeline = getenv("TB_SEG_TIMELINE") != nullptr;                            // debug: per-CTA start / end times
+        static unsigned long long *dbg = nullptr;
+        if (timeline && !dbg) TB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 4 * ws_ctas));
+        if (plain && ew == 4) seg_rle_ws_kernel<false, 4><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, dbg);
+        else if (plain) seg_rle_ws_kernel<false, 3><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, dbg);
+        else seg_rle_ws_kernel<true, 3><<<grid, (K1W_MW + 3 + 1) * 32, k1w_smem(3), s>>>(frames_dev, d, h->k, static_units, dbg);
+        if (timeline) {
+            std::vector<unsigned long long> t(4 * grid);
+            TB_CUDA(cudaStreamSynchronize(s));
+            TB_CUDA(cudaMemcpy(t.data(), dbg, sizeof(unsigned long long) * 4 * grid, cudaMemcpyDeviceToHost));
+            unsigned long long s0 = ~0ull, s1 = 0, p0 = ~0ull, p1 = 0, e0 = ~0ull, e1 = 0;
+            for (unsigned i = 0; i < grid; ++i) {
+                s0 = std::min(s0, t[4 * i]); s1 = std::max(s1, t[4 * i]);
+                p0 = std::min(p0, t[4 * i + 1]); p1 = std::max(p1, t[4 * i + 1]);
+                e0 = std::min(e0, t[4 * i + 2]); e1 = std::max(e1, t[4 * i + 2]);
+            }
+            fprintf(stderr, "[K1 timeline] grid %u static %u: CTA start spread %.2f us; producer done %.2f..%.2f us; extraction done %.2f..%.2f us after first start\n",
+                    grid, static_units, (s1 - s0) * 1e-3, (p0 - s0) * 1e-3, (p1 - s0) * 1e-3, (e0 - s0) * 1e-3, (e1 - s0) * 1e-3);
+        }
     } else if (d.aligned && !no_tma) {
         static bool attr_done = false;
         if (!attr_done) {
