@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TB_ABI_VERSION 1
+#define TB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TB_API __attribute__((visibility("default")))
@@ -55,21 +55,30 @@ typedef struct tb_seg_params {
     float   cm_per_pixel;                 /* 1                                                        */
     int32_t n_size_ranges;                /* detect_size_filter: 0 = keep all; ranges are [lo,hi)    */
     double  size_lo[4], size_hi[4];
+    int32_t color_channel;                /* -1 (none); 0..3: with gray encoding take this plane of a colour frame
+                                             instead of cvtColor (T/python/BackgroundSubtraction.cpp:161-173)      */
+    int32_t reserved0;
 } tb_seg_params;
 
 typedef struct tb_seg_config {
     int32_t device;               /* CUDA ordinal                                                    */
-    int32_t width, height;        /* frame size; channels fixed to 1 (meta_encoding gray)            */
+    int32_t width, height;        /* frame size                                                      */
     int32_t max_batch;            /* frames per submit                                               */
     int32_t max_runs_per_frame;   /* capacity of the run list of one frame (0 -> 32768)              */
     int32_t max_pixels_per_frame; /* capacity of blob pixel bytes of one frame (0 -> width*height/4) */
     int32_t max_crops_per_frame;  /* crops rendered per frame, first K blobs in canonical order (0 = no crops) */
     int32_t crop_width, crop_height; /* individual_image_size, 80x80 (T/core/default_config.cpp:1091) */
     int32_t crop_method;          /* 0 grey, 1 |bg-px|, 2 max(0,bg-px)  (Background.h:231-294)       */
+    int32_t channels;             /* bytes per pixel of the submitted frames: 0/1 gray, 3 BGR, 4 BGRA (interleaved;
+                                     TileImage.images[0], T/python/BackgroundSubtraction.cpp:151-188)               */
+    int32_t encoding;             /* meta_encoding: 0 gray (colour frames -> cv::cvtColor(BGR[A]2GRAY) or color_channel;
+                                     1 byte per blob pixel), 1 rgb8 (mask from the grey images, B,G,R per blob pixel,
+                                     blob flag is_rgb; RawProcessing.cpp:355-358,557-593; needs channels 3 or 4)    */
 } tb_seg_config;
 
 /* Per-frame result header. status bit0: run capacity exceeded (frame dropped, n_blobs=0),
- * bit1: pixel capacity exceeded, bit2: more blobs than max_crops_per_frame (crops truncated). */
+ * bit1: pixel capacity exceeded, bit2: more blobs than max_crops_per_frame (crops truncated).
+ * px_begin / n_pixels count BYTES of the pixel arena (= pixels for gray, 3 per pixel for rgb8). */
 typedef struct tb_frame_info {
     uint32_t blob_begin, n_blobs;     /* range in the batch's blob-record array   */
     uint32_t line_begin, n_lines;     /* range in the batch's line arena           */
@@ -81,8 +90,8 @@ typedef struct tb_frame_info {
  * Blobs of a frame are in canonical order: by (y,x0) of their first line.  bid is
  * pv::bid::from_data (C/misc/bid.h:87-94). */
 typedef struct tb_blob_rec {
-    uint32_t line_off, px_off;        /* absolute offsets into the batch arenas    */
-    uint32_t n_lines, n_pixels;
+    uint32_t line_off, px_off;        /* absolute offsets into the batch arenas (px_off in bytes) */
+    uint32_t n_lines, n_pixels;       /* n_pixels counts pixels (payload = n_pixels * bytes per pixel) */
     uint16_t x0, y0, x1, y1;          /* inclusive bounding box                     */
     uint32_t bid;
     uint32_t frame;                   /* index of the frame inside the batch        */
@@ -115,17 +124,20 @@ TB_API void tb_seg_destroy(tb_seg *h);
 TB_API int tb_seg_set_params(tb_seg *h, const tb_seg_params *p);
 
 /* BackgroundSubtraction::set_background / Data::set (T/python/BackgroundSubtraction.cpp:86-101).
- * stride in bytes between rows. */
+ * stride in bytes between rows.  1-channel image (gray encoding). */
 TB_API int tb_seg_set_background(tb_seg *h, const uint8_t *bg, int width, int height, int64_t stride);
+/* The same with an explicit channel count: 1 for gray encoding, 3 (B,G,R interleaved) for rgb8, where the grey
+ * background the threshold runs against is derived once on the device (_grey_average, RawProcessing.cpp:356-357). */
+TB_API int tb_seg_set_background_c(tb_seg *h, const uint8_t *bg, int width, int height, int channels, int64_t stride);
 
 /* BackgroundSubtraction::apply(std::vector<TileImage>&&) (T/python/BackgroundSubtraction.cpp:126-347):
- * n host frames (width*height bytes each, `stride` bytes between rows) are copied to the device,
+ * n host frames (width*height*channels bytes each, `stride` bytes between rows) are copied to the device,
  * segmented, labelled and (optionally) cropped; results are copied back asynchronously.
  * tb_seg_wait blocks until they are on the host.  fetch: 0 = results stay on the device (only
  * per-frame headers and totals are fetched), 1 = blob records + lines + pixels, 2 = also the crops. */
 TB_API int tb_seg_submit(tb_seg *h, const uint8_t *const *frames, int n, int64_t stride, int fetch);
 
-/* Same for n packed frames already resident in device memory (n*width*height bytes).
+/* Same for n packed frames already resident in device memory (n*width*height*channels bytes).
  * stream: a cudaStream_t (NULL = the handle's own stream); work is ordered on it. */
 TB_API int tb_seg_submit_device(tb_seg *h, const void *frames_dev, int n, void *stream, int fetch);
 
@@ -143,7 +155,7 @@ TB_API int tb_seg_result(tb_seg *h, int i, tb_blob_view *out);
 TB_API int tb_seg_totals(tb_seg *h, uint32_t out[4]);
 
 /* Device-side results of the last batch, for chaining without a host round trip:
- *  crops  u8 [n_crops][crop_h][crop_w] (NHWC with C=1; image::calculate_diff_image,
+ *  crops  u8 [n_crops][crop_h][crop_w][C] (NHWC, C = 1 gray / 3 rgb8; image::calculate_diff_image,
  *         T/tracking/FilterCache.cpp:158-235), n_crops_dev -> uint32 on the device,
  *  recs   tb_blob_rec array, infos tb_frame_info[max_batch]. */
 TB_API int tb_seg_device_results(tb_seg *h, void **crops, void **n_crops_dev, void **crop_blob_index,
@@ -161,7 +173,7 @@ TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_
 TB_API int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch);
 
 /* Debug / parity: generate_binary's output image (mask & input) of one device- or host-resident
- * frame, RawProcessing.cpp:597-600.  out is width*height host bytes. */
+ * frame, RawProcessing.cpp:597-600.  out is width*height (gray) or width*height*3 (rgb8) host bytes. */
 TB_API int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t *out_host);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */

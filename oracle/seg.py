@@ -103,6 +103,19 @@ def lib() -> C.CDLL:
         L.to_rethreshold_frame.restype = C.c_int64
         L.to_average.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.to_average.restype = C.c_int
+        L.to_bgr2gray.argtypes = [vp, C.c_int64, C.c_int, vp]
+        L.to_bgr2gray.restype = None
+        L.to_bgr2gray_tracker.argtypes = [vp, C.c_int64, vp]
+        L.to_bgr2gray_tracker.restype = None
+        L.to_generate_binary_color.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.POINTER(_Params), vp, vp]
+        L.to_generate_binary_color.restype = C.c_int
+        L.to_segment_frame_color.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.POINTER(_Params), C.c_int,
+                                             vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp]
+        L.to_segment_frame_color.restype = C.c_int64
+        L.to_image_from_lines_rgb.argtypes = [vp, C.c_int64, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.to_image_from_lines_rgb.restype = C.c_int64
+        L.to_crop_blob_rgb.argtypes = [vp, C.c_int64, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.to_crop_blob_rgb.restype = None
         _LIB = L
     return _LIB
 
@@ -195,6 +208,77 @@ def crop_blob(lines, pixels, bg, method=DIFF_ABSOLUTE, out_w=80, out_h=80):
     bg = np.ascontiguousarray(bg, np.uint8)
     out = np.zeros((out_h, out_w), np.uint8)
     lib().to_crop_blob(_p(lines), len(lines), _p(pixels), _p(bg), bg.shape[1], method, out_w, out_h, _p(out))
+    return out
+
+
+ENC_GRAY, ENC_RGB8 = 0, 1
+
+
+def bgr2gray(img: np.ndarray) -> np.ndarray:
+    """cv::cvtColor(BGR2GRAY / BGRA2GRAY) on u8 (H,W,3|4) -> (H,W)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape[:-1], np.uint8)
+    lib().to_bgr2gray(_p(img), out.size, img.shape[-1], _p(out))
+    return out
+
+
+def bgr2gray_tracker(img: np.ndarray) -> np.ndarray:
+    """cmn::bgr2gray (Background.h:76-81) on u8 (...,3)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape[:-1], np.uint8)
+    lib().to_bgr2gray_tracker(_p(img), out.size, _p(out))
+    return out
+
+
+def generate_binary_color(frame, bg, params: Params, encoding=ENC_GRAY, color_channel=-1):
+    """frame (H,W,C) u8, bg (H,W) for gray encoding / (H,W,3) for rgb8 -> (H,W) or (H,W,3), grey plane."""
+    frame = np.ascontiguousarray(frame, np.uint8); bg = np.ascontiguousarray(bg, np.uint8)
+    h, w, cn = frame.shape
+    out = np.empty((h, w, 3) if encoding else (h, w), np.uint8)
+    gray = np.empty((h, w), np.uint8)
+    pc = params.c()
+    if lib().to_generate_binary_color(_p(frame), cn, encoding, color_channel, _p(bg), w, h, C.byref(pc), _p(out), _p(gray)) != 0:
+        raise ValueError("generate_binary_color failed (channels / encoding)")
+    return out, gray
+
+
+def segment_frame_color(frame, bg, params: Params, encoding=ENC_GRAY, color_channel=-1, order=ORDER_CANONICAL):
+    """BackgroundSubtraction::apply's body for one colour frame; Blobs.pixels holds 1 (gray) or 3 (rgb8) bytes per pixel."""
+    frame = np.ascontiguousarray(frame, np.uint8); bg = np.ascontiguousarray(bg, np.uint8)
+    h, w, cn = frame.shape
+    capL, capP, capB = 1 << 16, max(1 << 16, w * h // 4), 1 << 14
+    pc = params.c()
+    while True:
+        lines = np.zeros(capL, LINE_DTYPE); px = np.zeros(capP, np.uint8)
+        lo = np.zeros(capB + 1, np.int64); po = np.zeros(capB + 1, np.int64)
+        k = lib().to_segment_frame_color(_p(frame), cn, encoding, color_channel, _p(bg), w, h, C.byref(pc), order,
+                                         _p(lines), capL, _p(px), capP, _p(lo), _p(po), capB, None)
+        if k >= 0:
+            break
+        if k == -1:
+            raise MemoryError
+        need = -k * 3
+        capL = max(capL, need); capP = max(capP, need); capB = max(capB, need)
+    return Blobs(lines[:lo[k]].copy(), px[:po[k]].copy(), lo[:k + 1].copy(), po[:k + 1].copy())
+
+
+def image_from_lines_rgb(lines, pixels, bg3, method=DIFF_NONE, base_threshold=0):
+    lines = np.ascontiguousarray(lines); pixels = np.ascontiguousarray(pixels, np.uint8)
+    bg3 = np.ascontiguousarray(bg3, np.uint8)
+    w = int(lines["x1"].max()) - int(lines["x0"].min()) + 1
+    h = int(lines["y"].max()) - int(lines["y"].min()) + 1
+    rect = np.zeros(4, np.int32)
+    mask = np.zeros((h, w), np.uint8); img = np.zeros((h, w, 3), np.uint8); diff = np.zeros((h, w, 3), np.uint8)
+    n = lib().to_image_from_lines_rgb(_p(lines), len(lines), _p(pixels), _p(bg3), bg3.shape[1], method,
+                                      base_threshold, _p(rect), _p(mask), _p(img), _p(diff))
+    return rect, int(n), mask, img, diff
+
+
+def crop_blob_rgb(lines, pixels, bg3, method=DIFF_ABSOLUTE, out_w=80, out_h=80):
+    lines = np.ascontiguousarray(lines); pixels = np.ascontiguousarray(pixels, np.uint8)
+    bg3 = np.ascontiguousarray(bg3, np.uint8)
+    out = np.zeros((out_h, out_w, 3), np.uint8)
+    lib().to_crop_blob_rgb(_p(lines), len(lines), _p(pixels), _p(bg3), bg3.shape[1], method, out_w, out_h, _p(out))
     return out
 
 

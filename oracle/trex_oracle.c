@@ -108,20 +108,19 @@ static void ellipse_element(uint8_t *el, int k)
  *   :504-505 use_closing: dilate, erode with the ellipse element
  *   :541-550 dilation_size>0: dilate ones(n,n);  <0: erode, then re-threshold diff under the mask
  *   :597-599 output = mask & input  (ORIGINAL input, grey values under the mask)
- * Not restated: blur_difference, adaptive threshold, tags, 3-channel input (all default-off /
+ * Not restated: blur_difference, adaptive threshold, tags (all default-off /
  * out of scope).
  * ------------------------------------------------------------------------------------------ */
-int to_generate_binary(const uint8_t *frame, const uint8_t *bg, int w, int h,
-                       const to_params_t *p, uint8_t *out)
+/* the threshold mask (255 / 0) of generate_binary, before it is ANDed with the input (:597-599) */
+static int gen_mask(const uint8_t *frame, const uint8_t *bg, int w, int h, const to_params_t *p, uint8_t *mask)
 {
     const size_t n = (size_t)w * h;
     const int T = p->detect_threshold, aT = abs(T);
     const int need_morph = p->use_closing || p->dilation_size != 0;
-    uint8_t *mask = (uint8_t *)malloc(n), *diff = NULL, *tmp = NULL;
-    if (!mask) return -1;
+    uint8_t *diff = NULL, *tmp = NULL;
     if (need_morph) {
         diff = (uint8_t *)malloc(n); tmp = (uint8_t *)malloc(n);
-        if (!diff || !tmp) { free(mask); free(diff); free(tmp); return -1; }
+        if (!diff || !tmp) { free(diff); free(tmp); return -1; }
     }
     for (size_t i = 0; i < n; ++i) {
         int in = p->image_invert ? 255 - frame[i] : frame[i];
@@ -169,9 +168,88 @@ int to_generate_binary(const uint8_t *frame, const uint8_t *bg, int w, int h,
         }
         free(el);
     }
-    for (size_t i = 0; i < n; ++i) out[i] = mask[i] & frame[i];
-    free(mask); free(diff); free(tmp);
+    free(diff); free(tmp);
     return 0;
+}
+
+int to_generate_binary(const uint8_t *frame, const uint8_t *bg, int w, int h,
+                       const to_params_t *p, uint8_t *out)
+{
+    const size_t n = (size_t)w * h;
+    uint8_t *mask = (uint8_t *)malloc(n);
+    if (!mask) return -1;
+    if (gen_mask(frame, bg, w, h, p, mask)) { free(mask); return -1; }
+    for (size_t i = 0; i < n; ++i) out[i] = mask[i] & frame[i];
+    free(mask);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Colour inputs.  The arithmetic of cv::cvtColor lives in OpenCV (third party, not vendored in the
+ * reference; conda/meta.yaml asks for opencv 4.x): COLOR_BGR2GRAY / COLOR_BGRA2GRAY on 8-bit data is
+ * the fixed-point  Y = (B*3735 + G*19235 + R*9798 + 16384) >> 15  (imgproc color_rgb: RGB2Gray<uchar>,
+ * BY15 / GY15 / RY15, shift 15); checked against cv2 4.13 in tests/test_oracle_color.py.
+ * Call sites: T/python/BackgroundSubtraction.cpp:165-169 (gray / binary encoding),
+ * C/processing/RawProcessing.cpp:355-358 (3-channel input of generate_binary).
+ * ------------------------------------------------------------------------------------------ */
+void to_bgr2gray(const uint8_t *src, int64_t npx, int cn, uint8_t *dst)
+{
+    for (int64_t i = 0; i < npx; ++i) {
+        const uint8_t *q = src + (size_t)i * cn;
+        dst[i] = (uint8_t)((q[0] * 3735 + q[1] * 19235 + q[2] * 9798 + 16384) >> 15);
+    }
+}
+
+/* The tracker-side grey value of a BGR triple, C/processing/Background.h:76-81:
+ * saturate(float(B)*0.114 + float(G)*0.587 + float(R)*0.299 + 0.5, 0, 255) in double, truncated. */
+static uint8_t bgr2gray_tracker(const uint8_t *q)
+{
+    double v = (double)(float)q[0] * 0.114 + (double)(float)q[1] * 0.587 + (double)(float)q[2] * 0.299 + 0.5;
+    if (v < 0) v = 0;
+    if (v > 255) v = 255;
+    return (uint8_t)v;
+}
+void to_bgr2gray_tracker(const uint8_t *src, int64_t npx, uint8_t *dst)
+{
+    for (int64_t i = 0; i < npx; ++i) dst[i] = bgr2gray_tracker(src + 3 * (size_t)i);
+}
+
+/* The detect-side colour handling of BackgroundSubtraction::apply (T/python/BackgroundSubtraction.cpp:151-188)
+ * followed by generate_binary (C/processing/RawProcessing.cpp:355-358,557-599):
+ *   encoding 0 gray: cn 3/4 -> cvtColor(BGR[A]2GRAY), or the plane `color_channel` (0..cn-1) when set (:171-173);
+ *                    then the 1-channel generate_binary against the 1-channel background.  out: w*h bytes.
+ *   encoding 1 rgb8: cn 4 -> BGRA2BGR (:177-178); mask from gray(input) vs gray(background) (bg3 is 3-channel,
+ *                    _grey_average :356-357); out = mask & each of B,G,R (:581-589).  out: w*h*3 bytes.
+ * gray_out (optional, w*h): the grey plane the threshold ran on. */
+int to_generate_binary_color(const uint8_t *frame, int cn, int encoding, int color_channel, const uint8_t *bg,
+                             int w, int h, const to_params_t *p, uint8_t *out, uint8_t *gray_out)
+{
+    const size_t n = (size_t)w * h;
+    uint8_t *g = (uint8_t *)malloc(n), *mask = (uint8_t *)malloc(n), *bgg = NULL;
+    int ret = -1;
+    if (!g || !mask) goto done;
+    if (cn == 1) memcpy(g, frame, n);
+    else if (encoding == 0 && color_channel >= 0 && color_channel < 4) {
+        if (color_channel >= cn) goto done;
+        for (size_t i = 0; i < n; ++i) g[i] = frame[i * cn + color_channel];
+    } else to_bgr2gray(frame, (int64_t)n, cn, g);
+    if (gray_out) memcpy(gray_out, g, n);
+    if (encoding == 0) {
+        if (gen_mask(g, bg, w, h, p, mask)) goto done;
+        for (size_t i = 0; i < n; ++i) out[i] = mask[i] & g[i];
+    } else {
+        if (cn < 3) goto done;
+        bgg = (uint8_t *)malloc(n);
+        if (!bgg) goto done;
+        to_bgr2gray(bg, (int64_t)n, 3, bgg);
+        if (gen_mask(g, bgg, w, h, p, mask)) goto done;
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) out[i * 3 + k] = mask[i] & frame[i * cn + k];
+    }
+    ret = 0;
+done:
+    free(g); free(mask); free(bgg);
+    return ret;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -312,26 +390,24 @@ static int size_ok(const to_params_t *p, uint64_t npx)
  * Output is SoA:  line_off[k]..line_off[k+1] / px_off[k]..px_off[k+1] index lines[] / pixels[].
  * Returns number of kept blobs, or -(needed) if a capacity is too small (-1 on alloc failure).
  * ------------------------------------------------------------------------------------------ */
-int64_t to_segment_frame(const uint8_t *frame, const uint8_t *bg, int w, int h,
-                         const to_params_t *p, int order,
-                         to_line_t *lines, int64_t cap_lines,
-                         uint8_t *pixels, int64_t cap_px,
-                         int64_t *line_off, int64_t *px_off, int64_t cap_blobs,
-                         uint8_t *binary_out /* optional w*h, may be NULL */)
+/* CPULabeling::run + materialisation + size filter on generate_binary's output image `bin` (w*h*c bytes,
+ * c = 1 or 3: a pixel is set when any channel is non-zero, Source.cpp:200-206,221-231; pixel payload is
+ * c bytes per pixel, CPULabeling.cpp:302-311).  px_off counts BYTES. */
+static int64_t segment_binary(const uint8_t *bin, int w, int h, int c,
+                              const to_params_t *p, int order,
+                              to_line_t *lines, int64_t cap_lines,
+                              uint8_t *pixels, int64_t cap_px,
+                              int64_t *line_off, int64_t *px_off, int64_t cap_blobs)
 {
-    const size_t n = (size_t)w * h;
-    uint8_t *bin = binary_out ? binary_out : (uint8_t *)malloc(n);
-    if (!bin) return -1;
     int64_t ret = -1;
     to_line_t *runs = NULL; int32_t *label = NULL;
     int64_t *cnt_l = NULL, *cnt_p = NULL, *cur_l = NULL, *cur_p = NULL; int32_t *remap = NULL;
-    if (to_generate_binary(frame, bg, w, h, p, bin)) goto done;
 
-    int64_t nr = to_extract_lines(bin, w, h, 1, NULL, 0);
+    int64_t nr = to_extract_lines(bin, w, h, c, NULL, 0);
     runs = (to_line_t *)malloc(sizeof(to_line_t) * (size_t)(nr + 1));
     label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nr + 1));
     if (!runs || !label) goto done;
-    to_extract_lines(bin, w, h, 1, runs, nr);
+    to_extract_lines(bin, w, h, c, runs, nr);
     int64_t nb = to_label_runs(runs, nr, order, label);
     if (nb < 0) goto done;
 
@@ -351,7 +427,7 @@ int64_t to_segment_frame(const uint8_t *frame, const uint8_t *bg, int w, int h,
             remap[b] = (int32_t)kept;
             if (kept < cap_blobs) { line_off[kept] = tl; px_off[kept] = tp; }
             cur_l[b] = tl; cur_p[b] = tp;
-            tl += cnt_l[b]; tp += cnt_p[b]; ++kept;
+            tl += cnt_l[b]; tp += cnt_p[b] * c; ++kept;
         } else remap[b] = -1;
     }
     if (kept > cap_blobs || tl > cap_lines || tp > cap_px) {
@@ -364,13 +440,48 @@ int64_t to_segment_frame(const uint8_t *frame, const uint8_t *bg, int w, int h,
         if (remap[b] < 0) continue;
         lines[cur_l[b]++] = runs[i];
         int64_t len = (int64_t)runs[i].x1 - runs[i].x0 + 1;
-        memcpy(pixels + cur_p[b], bin + (size_t)runs[i].y * w + runs[i].x0, (size_t)len);  /* :307 */
-        cur_p[b] += len;
+        memcpy(pixels + cur_p[b], bin + ((size_t)runs[i].y * w + runs[i].x0) * c, (size_t)len * c);  /* :307 */
+        cur_p[b] += len * c;
     }
     ret = kept;
 done:
-    if (!binary_out) free(bin);
     free(runs); free(label); free(cnt_l); free(cnt_p); free(cur_l); free(cur_p); free(remap);
+    return ret;
+}
+
+int64_t to_segment_frame(const uint8_t *frame, const uint8_t *bg, int w, int h,
+                         const to_params_t *p, int order,
+                         to_line_t *lines, int64_t cap_lines,
+                         uint8_t *pixels, int64_t cap_px,
+                         int64_t *line_off, int64_t *px_off, int64_t cap_blobs,
+                         uint8_t *binary_out /* optional w*h, may be NULL */)
+{
+    const size_t n = (size_t)w * h;
+    uint8_t *bin = binary_out ? binary_out : (uint8_t *)malloc(n);
+    if (!bin) return -1;
+    int64_t ret = -1;
+    if (!to_generate_binary(frame, bg, w, h, p, bin))
+        ret = segment_binary(bin, w, h, 1, p, order, lines, cap_lines, pixels, cap_px, line_off, px_off, cap_blobs);
+    if (!binary_out) free(bin);
+    return ret;
+}
+
+/* The same for colour frames (cn = 3 BGR / 4 BGRA interleaved; see to_generate_binary_color): encoding 0 gray
+ * yields 1 byte per pixel, encoding 1 rgb8 yields B,G,R per pixel (blob flag is_rgb, CPULabeling.cpp:193). */
+int64_t to_segment_frame_color(const uint8_t *frame, int cn, int encoding, int color_channel, const uint8_t *bg,
+                               int w, int h, const to_params_t *p, int order,
+                               to_line_t *lines, int64_t cap_lines, uint8_t *pixels, int64_t cap_px,
+                               int64_t *line_off, int64_t *px_off, int64_t cap_blobs,
+                               uint8_t *binary_out /* optional w*h*(encoding ? 3 : 1) */)
+{
+    const int c = encoding ? 3 : 1;
+    const size_t n = (size_t)w * h * c;
+    uint8_t *bin = binary_out ? binary_out : (uint8_t *)malloc(n);
+    if (!bin) return -1;
+    int64_t ret = -1;
+    if (!to_generate_binary_color(frame, cn, encoding, color_channel, bg, w, h, p, bin, NULL))
+        ret = segment_binary(bin, w, h, c, p, order, lines, cap_lines, pixels, cap_px, line_off, px_off, cap_blobs);
+    if (!binary_out) free(bin);
     return ret;
 }
 
@@ -471,6 +582,79 @@ void to_crop_blob(const to_line_t *lines, int64_t n_lines, const uint8_t *px,
         for (int x = 0; x < bw; ++x) {
             int ox = x + offx; if (ox < 0 || ox >= out_w) continue;
             if (mask[(size_t)y * bw + x]) out[(size_t)oy * out_w + ox] = img[(size_t)y * bw + x];
+        }
+    }
+    free(img); free(mask);
+}
+
+/* imageFromLines for rgb8 blobs (input 3 channels -> output 3 channels, Background.cpp:134-139,209-221):
+ * value = the B,G,R bytes, diff = per-channel difference against the 3-channel background
+ * (DifferenceImpl on RGBArray, Background.h:238-262), a pixel is set when base_threshold == 0 or
+ * bgr2gray(diff) >= base_threshold (is_value_different, Background.h:415-427, tracker grey formula :76-81).
+ * Pinned by Application/Tests/test_pixels.cpp:1381-1466.  Images are bbox-sized, 3 bytes per pixel. */
+int64_t to_image_from_lines_rgb(const to_line_t *lines, int64_t n_lines, const uint8_t *px,
+                                const uint8_t *bg3, int bg_w, int method, int base_threshold,
+                                int32_t rect[4], uint8_t *mask, uint8_t *image, uint8_t *diffimg)
+{
+    int mx = 1 << 30, my = 1 << 30, Mx = -1, My = -1;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        if (lines[i].x0 < mx) mx = lines[i].x0;
+        if (lines[i].y < my) my = lines[i].y;
+        if (lines[i].x1 > Mx) Mx = lines[i].x1;
+        if (lines[i].y > My) My = lines[i].y;
+    }
+    int bw = Mx - mx + 1, bh = My - my + 1;
+    rect[0] = mx; rect[1] = my; rect[2] = bw; rect[3] = bh;
+    size_t n = (size_t)bw * bh;
+    if (mask) memset(mask, 0, n);
+    if (image) memset(image, 0, n * 3);
+    if (diffimg) memset(diffimg, 0, n * 3);
+    int64_t recount = 0;
+    for (int64_t i = 0; i < n_lines; ++i)
+        for (int x = lines[i].x0; x <= lines[i].x1; ++x, px += 3) {
+            uint8_t d[3];
+            for (int k = 0; k < 3; ++k) {
+                int v = px[k], b = method ? bg3[((size_t)lines[i].y * bg_w + x) * 3 + k] : 0, q = v;
+                if (method == 1) q = abs(b - v);
+                else if (method == 2) { q = b - v; if (q < 0) q = 0; }
+                d[k] = (uint8_t)q;
+            }
+            int set = base_threshold == 0 || (int)bgr2gray_tracker(d) >= base_threshold;
+            if (!set) continue;
+            size_t o = (size_t)(lines[i].y - my) * bw + (x - mx);
+            if (mask) mask[o] = 255;
+            if (image) memcpy(image + o * 3, px, 3);
+            if (diffimg) memcpy(diffimg + o * 3, d, 3);
+            ++recount;
+        }
+    return recount;
+}
+
+/* calculate_diff_image for rgb8 blobs: as to_crop_blob with 3 bytes per pixel (out: out_w*out_h*3). */
+void to_crop_blob_rgb(const to_line_t *lines, int64_t n_lines, const uint8_t *px,
+                      const uint8_t *bg3, int bg_w, int method, int out_w, int out_h, uint8_t *out)
+{
+    int32_t r[4];
+    int mx = 1 << 30, my = 1 << 30, Mx = -1, My = -1;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        if (lines[i].x0 < mx) mx = lines[i].x0;
+        if (lines[i].y < my) my = lines[i].y;
+        if (lines[i].x1 > Mx) Mx = lines[i].x1;
+        if (lines[i].y > My) My = lines[i].y;
+    }
+    int bw = Mx - mx + 1, bh = My - my + 1;
+    uint8_t *img = (uint8_t *)malloc((size_t)bw * bh * 3), *mask = (uint8_t *)malloc((size_t)bw * bh);
+    if (method == 0) to_image_from_lines_rgb(lines, n_lines, px, bg3, bg_w, 0, 0, r, mask, img, NULL);
+    else             to_image_from_lines_rgb(lines, n_lines, px, bg3, bg_w, method, 0, r, mask, NULL, img);
+    int offx, offy;
+    if (bw < out_w) { int d = out_w - bw; offx = d - d / 2; } else { int d = bw - out_w; offx = -(d - d / 2); }
+    if (bh < out_h) { int d = out_h - bh; offy = d - d / 2; } else { int d = bh - out_h; offy = -(d - d / 2); }
+    memset(out, 0, (size_t)out_w * out_h * 3);
+    for (int y = 0; y < bh; ++y) {
+        int oy = y + offy; if (oy < 0 || oy >= out_h) continue;
+        for (int x = 0; x < bw; ++x) {
+            int ox = x + offx; if (ox < 0 || ox >= out_w) continue;
+            if (mask[(size_t)y * bw + x]) memcpy(out + ((size_t)oy * out_w + ox) * 3, img + ((size_t)y * bw + x) * 3, 3);
         }
     }
     free(img); free(mask);

@@ -1,0 +1,152 @@
+"""GPU parity tests of the colour path (BGR / BGRA frames; meta_encoding gray and rgb8): CUDA through the C ABI vs the
+CPU oracle, bit-exact.  Reference: T/python/BackgroundSubtraction.cpp:151-188, C/processing/RawProcessing.cpp:355-358,
+557-593, C/processing/Source.cpp:200-231, T/tracking/FilterCache.cpp:158-235."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _as_list(blobs):
+    return [(b.lines.tobytes(), b.pixels.tobytes()) for b in blobs]
+
+
+def _world(h, w, n, seed, channels):
+    from trex_b200.synthetic import BlobWorld, to_color
+    world = BlobWorld(h=h, w=w, n_blobs=n, seed=seed, margin=30)
+    gray = world.frames(3)
+    frames = to_color(gray, seed=seed, channels=channels)
+    bg3 = to_color(world.bg, seed=seed + 1, channels=3)
+    # adversarial pixels inside / outside blobs: grey value 0 with a non-zero channel, all-zero pixels, saturated pixels
+    rng = np.random.default_rng(seed)
+    for f in range(len(frames)):
+        for _ in range(200):
+            y, x = int(rng.integers(0, h)), int(rng.integers(0, w))
+            frames[f, y, x, :3] = [(4, 0, 0), (0, 0, 0), (255, 255, 255), (0, 1, 0)][int(rng.integers(0, 4))]
+    return frames, bg3
+
+
+def _mk(bg, channels, encoding, max_batch=4, max_individuals=0, **kw):
+    import trex_b200
+    s = trex_b200.DetectSettings(meta_encoding=encoding, **kw)
+    return trex_b200.BackgroundSubtraction(bg, settings=s, max_batch=max_batch, max_individuals=max_individuals, channels=channels)
+
+
+def _params(**kw):
+    from oracle import seg
+    keys = {k: v for k, v in kw.items() if k in seg.Params.__dataclass_fields__}
+    return seg.Params(**keys)
+
+
+@pytest.mark.parametrize("channels", [3, 4])
+@pytest.mark.parametrize("size", [(272, 480), (1080, 1920), (123, 250)])
+def test_gray_encoding_from_colour_frames(channels, size):
+    """cvtColor(BGR[A]2GRAY) fused into K1 (aligned widths) or through the grey plane (250 is not a multiple of 16)."""
+    from oracle import seg
+    h, w = size
+    frames, bg3 = _world(h, w, 30, 7, channels)
+    bg = seg.bgr2gray(bg3)
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 100000)])
+    bs = _mk(bg, channels, "gray", max_individuals=40, **kw)
+    got = bs.apply(frames)
+    crops, _ = bs.crops()
+    n = 0
+    for f in range(len(frames)):
+        ref = seg.segment_frame_color(frames[f], bg, _params(**kw), encoding=seg.ENC_GRAY)
+        assert _as_list(got[f]) == ref.as_list(), f
+        assert np.array_equal(bs.debug_binary(frames[f]), seg.generate_binary_color(frames[f], bg, _params(**kw))[0])
+        for k in range(min(len(ref), 40)):
+            assert np.array_equal(crops[n], seg.crop_blob(*ref.blob(k), bg, seg.DIFF_ABSOLUTE)), (f, k)
+            n += 1
+    assert n == len(crops) and n > 0
+
+
+@pytest.mark.parametrize("channels", [3, 4])
+@pytest.mark.parametrize("size", [(272, 480), (1080, 1920), (123, 250)])
+def test_rgb8_encoding(channels, size):
+    """3 bytes per blob pixel, foreground = grey difference > T and any of B,G,R != 0, 80x80x3 crops."""
+    from oracle import seg
+    h, w = size
+    frames, bg3 = _world(h, w, 30, 11, channels)
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 100000)])
+    bs = _mk(bg3, channels, "rgb8", max_individuals=40, **kw)
+    got = bs.apply(frames)
+    crops, _ = bs.crops()
+    assert crops.shape[1:] == (80, 80, 3)
+    n = 0
+    for f in range(len(frames)):
+        ref = seg.segment_frame_color(frames[f], bg3, _params(**kw), encoding=seg.ENC_RGB8)
+        assert len(ref) > 0
+        assert _as_list(got[f]) == ref.as_list(), f
+        assert np.array_equal(bs.debug_binary(frames[f]), seg.generate_binary_color(frames[f], bg3, _params(**kw), encoding=seg.ENC_RGB8)[0])
+        for k in range(min(len(ref), 40)):
+            assert np.array_equal(crops[n], seg.crop_blob_rgb(*ref.blob(k), bg3, seg.DIFF_ABSOLUTE)), (f, k)
+            n += 1
+    assert n == len(crops) and n > 0
+
+
+@pytest.mark.parametrize("encoding", ["gray", "rgb8"])
+@pytest.mark.parametrize("kw", [
+    dict(detect_threshold=200), dict(detect_threshold=-15), dict(detect_threshold=12, threshold_maximum=60),
+    dict(detect_threshold=15, detect_threshold_is_absolute=False), dict(detect_threshold=15, image_invert=True),
+    dict(detect_threshold=15, use_closing=True, closing_size=2), dict(detect_threshold=15, dilation_size=3),
+])
+def test_colour_non_default_settings(encoding, kw):
+    """Everything but the default settings runs on the grey plane (plus the non-zero plane for rgb8)."""
+    from oracle import seg
+    frames, bg3 = _world(144, 256, 12, 3, 3)
+    enc = seg.ENC_RGB8 if encoding == "rgb8" else seg.ENC_GRAY
+    bg = bg3 if enc else seg.bgr2gray(bg3)
+    kw = dict(kw, detect_size_filter=[(1, 1000000)])
+    cap = dict(max_runs_per_frame=144 * 256 // 2 + 16, max_pixels_per_frame=144 * 256 * 3)
+    import trex_b200
+    bs = trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding=encoding, **kw), max_batch=4, channels=3, **cap)
+    got = bs.apply(frames)
+    for f in range(len(frames)):
+        ref = seg.segment_frame_color(frames[f], bg, _params(**kw), encoding=enc)
+        assert _as_list(got[f]) == ref.as_list(), f
+        assert np.array_equal(bs.debug_binary(frames[f]), seg.generate_binary_color(frames[f], bg, _params(**kw), encoding=enc)[0])
+
+
+def test_color_channel_selects_a_plane():
+    """color_channel (BackgroundSubtraction.cpp:161-173): the plane replaces cvtColor under gray encoding."""
+    from oracle import seg
+    frames, bg3 = _world(144, 256, 12, 5, 3)
+    bg = bg3[..., 1].copy()
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 100000)])
+    bs = _mk(bg, 3, "gray", color_channel=1, **kw)
+    got = bs.apply(frames)
+    for f in range(len(frames)):
+        ref = seg.segment_frame(frames[f][..., 1].copy(), bg, _params(**kw))
+        assert _as_list(got[f]) == ref.as_list(), f
+
+
+def test_colour_errors():
+    import trex_b200
+    from trex_b200._capi import TrexB200Error
+    bg = np.full((64, 64), 100, np.uint8)
+    with pytest.raises(TrexB200Error):       # rgb8 needs colour frames (BackgroundSubtraction.cpp:177-181)
+        trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding="rgb8"), channels=1)
+    with pytest.raises(TrexB200Error):       # rgb8 needs a 3-channel background (RawProcessing.cpp:343)
+        trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding="rgb8"), channels=3)
+    with pytest.raises(TrexB200Error):
+        trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding="r3g3b2"), channels=3)
+    bs = trex_b200.BackgroundSubtraction(bg, channels=3)
+    with pytest.raises(TrexB200Error):       # wrong frame shape
+        bs.apply([np.zeros((64, 64), np.uint8)])
+
+
+def test_rethreshold_on_colour_frames_gray_encoding():
+    """Tracker-side re-threshold of blobs detected on BGR frames (gray encoding): equals the 1-channel path on cvtColor."""
+    import trex_b200
+    from oracle import seg
+    frames, bg3 = _world(272, 480, 20, 9, 3)
+    bg = seg.bgr2gray(bg3)
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 100000)])
+    det = _mk(bg, 3, "gray", **kw)
+    trk = trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(detect_threshold=40, detect_size_filter=[]), max_batch=4)
+    det.apply(frames)
+    got = det.rethreshold(trk)
+    for f in range(len(frames)):
+        ref = seg.rethreshold(seg.segment_frame_color(frames[f], bg, _params(**kw)), bg, 40, seg.DIFF_ABSOLUTE)
+        assert set(_as_list(got[f])) == ref.as_set(), f

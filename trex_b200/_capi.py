@@ -22,14 +22,15 @@ class SegParams(C.Structure):
                 ("enable_difference", C.c_int32), ("detect_threshold_is_absolute", C.c_int32),
                 ("image_invert", C.c_int32), ("use_closing", C.c_int32), ("closing_size", C.c_int32),
                 ("dilation_size", C.c_int32), ("cm_per_pixel", C.c_float), ("n_size_ranges", C.c_int32),
-                ("size_lo", C.c_double * 4), ("size_hi", C.c_double * 4)]
+                ("size_lo", C.c_double * 4), ("size_hi", C.c_double * 4),
+                ("color_channel", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class SegConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("max_batch", C.c_int32),
                 ("max_runs_per_frame", C.c_int32), ("max_pixels_per_frame", C.c_int32),
                 ("max_crops_per_frame", C.c_int32), ("crop_width", C.c_int32), ("crop_height", C.c_int32),
-                ("crop_method", C.c_int32)]
+                ("crop_method", C.c_int32), ("channels", C.c_int32), ("encoding", C.c_int32)]
 
 
 class FrameInfo(C.Structure):
@@ -56,7 +57,7 @@ class ViConfig(C.Structure):
 # every symbol include/trexb200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "tb_last_error", "tb_abi_version", "tb_device_count", "tb_seg_default_params", "tb_seg_create",
-    "tb_seg_destroy", "tb_seg_set_params", "tb_seg_set_background", "tb_seg_submit", "tb_seg_submit_device",
+    "tb_seg_destroy", "tb_seg_set_params", "tb_seg_set_background", "tb_seg_set_background_c", "tb_seg_submit", "tb_seg_submit_device",
     "tb_seg_wait", "tb_seg_result", "tb_seg_totals", "tb_seg_device_results", "tb_seg_crops",
     "tb_seg_debug_binary", "tb_seg_launch_count", "tb_vi_create", "tb_vi_destroy", "tb_vi_set_tensor",
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
@@ -82,6 +83,7 @@ def lib() -> C.CDLL:
     L.tb_seg_destroy.argtypes = [vp]; L.tb_seg_destroy.restype = None
     L.tb_seg_set_params.argtypes = [vp, C.POINTER(SegParams)]
     L.tb_seg_set_background.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int64]
+    L.tb_seg_set_background_c.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64]
     L.tb_seg_submit.argtypes = [vp, C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int]
     L.tb_seg_submit_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.tb_seg_wait.argtypes = [vp]

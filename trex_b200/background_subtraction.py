@@ -46,6 +46,9 @@ class DetectSettings:
     # crop content: track_background_subtraction + track_threshold_is_absolute (FilterCache.cpp:165-174)
     track_background_subtraction: bool = True
     track_threshold_is_absolute: bool = True
+    # colour handling of BackgroundSubtraction::apply (.cpp:151-188): meta_encoding "gray" | "rgb8", color_channel
+    meta_encoding: str = "gray"
+    color_channel: int | None = None
 
     def c_params(self) -> SegParams:
         p = SegParams()
@@ -59,6 +62,7 @@ class DetectSettings:
         p.n_size_ranges = len(self.detect_size_filter)
         for i, (lo, hi) in enumerate(self.detect_size_filter[:4]):
             p.size_lo[i], p.size_hi[i] = float(lo), float(hi)
+        p.color_channel = -1 if self.color_channel is None else int(self.color_channel)
         return p
 
     @property
@@ -79,19 +83,25 @@ class Blob:
 
 class BackgroundSubtraction:
     def __init__(self, average: np.ndarray | None = None, *, width=None, height=None, settings: DetectSettings | None = None,
-                 max_batch=16, max_individuals=0, device=0, max_runs_per_frame=0, max_pixels_per_frame=0):
+                 max_batch=16, max_individuals=0, device=0, max_runs_per_frame=0, max_pixels_per_frame=0, channels=1):
+        """channels: bytes per pixel of the frames apply() receives (1 gray, 3 BGR, 4 BGRA; TileImage.images[0])."""
         if average is not None:
             height, width = average.shape[:2]
         if width is None or height is None:
             raise ValueError("BackgroundSubtraction needs an average image or width/height")
         self.settings = settings or DetectSettings()
+        if self.settings.meta_encoding not in ("gray", "rgb8"):
+            raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, f"meta_encoding {self.settings.meta_encoding!r} is not built (gray, rgb8)")
         self.width, self.height, self.max_batch = int(width), int(height), int(max_batch)
+        self.channels = int(channels)
+        self.out_channels = 3 if self.settings.meta_encoding == "rgb8" else 1
         cfg = SegConfig(device=device, width=self.width, height=self.height, max_batch=self.max_batch,
                         max_runs_per_frame=max_runs_per_frame, max_pixels_per_frame=max_pixels_per_frame,
                         max_crops_per_frame=int(max_individuals),
                         crop_width=self.settings.individual_image_size[0],
                         crop_height=self.settings.individual_image_size[1],
-                        crop_method=self.settings.crop_method)
+                        crop_method=self.settings.crop_method, channels=self.channels,
+                        encoding=int(self.settings.meta_encoding == "rgb8"))
         self.max_individuals = int(max_individuals)
         self._h = C.c_void_p()
         check(lib().tb_seg_create(C.byref(cfg), C.byref(self._h)))
@@ -108,9 +118,8 @@ class BackgroundSubtraction:
         a = np.ascontiguousarray(average, np.uint8)
         if a.ndim == 3 and a.shape[2] == 1:
             a = a[..., 0]
-        if a.ndim != 2:
-            raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, "only meta_encoding=gray (1 channel) is built")
-        check(lib().tb_seg_set_background(self._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], a.strides[0]))
+        ch = 1 if a.ndim == 2 else a.shape[2]
+        check(lib().tb_seg_set_background_c(self._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], ch, a.strides[0]))
         self._has_background = True
 
     def update_settings(self, settings: DetectSettings):
@@ -130,10 +139,11 @@ class BackgroundSubtraction:
         for i in range(0, len(frames), self.max_batch):
             chunk = frames[i:i + self.max_batch]
             ptrs = (C.c_void_p * len(chunk))(*[f.ctypes.data_as(C.c_void_p) for f in chunk])
+            want = (self.height, self.width) if self.channels == 1 else (self.height, self.width, self.channels)
             for f in chunk:
-                if f.shape != (self.height, self.width):
-                    raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, f"frame shape {f.shape} != {(self.height, self.width)}")
-            check(lib().tb_seg_submit(self._h, ptrs, len(chunk), self.width, level))
+                if f.shape != want:
+                    raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, f"frame shape {f.shape} != {want}")
+            check(lib().tb_seg_submit(self._h, ptrs, len(chunk), self.width * self.channels, level))
             self._last_n = len(chunk)
             check(lib().tb_seg_wait(self._h))
             if fetch and materialize:
@@ -206,7 +216,7 @@ class BackgroundSubtraction:
         blobs = []
         for r in recs:
             lo, po = int(r["line_off"]) - info.line_begin, int(r["px_off"]) - info.px_begin
-            blobs.append(Blob(lines[lo:lo + int(r["n_lines"])].copy(), px[po:po + int(r["n_pixels"])].copy(), int(r["bid"]),
+            blobs.append(Blob(lines[lo:lo + int(r["n_lines"])].copy(), px[po:po + int(r["n_pixels"]) * self.out_channels].copy(), int(r["bid"]),
                               (int(r["x0"]), int(r["y0"]), int(r["x1"]), int(r["y1"]))))
         return blobs
 
@@ -223,9 +233,10 @@ class BackgroundSubtraction:
         cp, ip, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
         check(lib().tb_seg_crops(self._h, C.byref(cp), C.byref(ip), C.byref(n)))
         w, h = self.settings.individual_image_size
+        shape = (h, w) if self.out_channels == 1 else (h, w, 3)
         if n.value == 0:
-            return np.zeros((0, h, w), np.uint8), np.zeros(0, np.uint32)
-        crops = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint8)), (n.value, h, w)).copy()
+            return np.zeros((0,) + shape, np.uint8), np.zeros(0, np.uint32)
+        crops = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint8)), (n.value,) + shape).copy()
         idx = np.ctypeslib.as_array(C.cast(ip, C.POINTER(C.c_uint32)), (n.value,)).copy()
         return crops, idx
 
@@ -237,7 +248,7 @@ class BackgroundSubtraction:
 
     def debug_binary(self, frame: np.ndarray) -> np.ndarray:
         f = np.ascontiguousarray(frame, np.uint8)
-        out = np.empty_like(f)
+        out = np.empty((self.height, self.width) if self.out_channels == 1 else (self.height, self.width, 3), np.uint8)
         check(lib().tb_seg_debug_binary(self._h, f.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
         return out
 

@@ -42,6 +42,13 @@ struct SegDev {
     const uint8_t *bg;
     size_t bg_stride;          // 0: one background for all frames; else `bg` holds one mask image per frame (morphology path)
     const uint8_t *keep_mask;  // optional [B][H][W] 0xFF/0 image ANDed with the foreground (tracker-side re-threshold), or null
+    // colour inputs (T/python/BackgroundSubtraction.cpp:151-188): frames are [B][H][W][CN] interleaved B,G,R(,A)
+    int CN;                    // bytes per pixel of the submitted frames: 1, 3, 4
+    int enc;                   // 0 gray (1 byte per blob pixel), 1 rgb8 (B,G,R per blob pixel)
+    int cc;                    // color_channel (gray encoding): -1 = cvtColor, else the plane to take
+    int opx;                   // bytes per blob pixel / crop pixel: enc ? 3 : 1
+    const uint8_t *bg3;        // rgb8: the 3-channel background (crops difference against it); `bg` is its grey image
+    const uint8_t *nz_plane;   // rgb8 on the plane path: [B][H][W] "any of B,G,R != 0" bytes (0xFF / 0), or null
     // K1 outputs
     uint32_t *run_count;       // [B]
     uint32_t *band_base, *band_cnt;   // [B][n_bands]
@@ -75,19 +82,24 @@ struct SegDev {
 // ------------------------------------------------------------------------------------------------
 constexpr int K1_NT = 256, K1_KPT = 4, K1_CHUNKS = K1_NT * K1_KPT;
 
+// the threshold mask of 4 pixels (0xFF / 0 bytes), before it is ANDed with the input
 template <bool GENERIC>
-__device__ __forceinline__ uint32_t fg4(uint32_t f, uint32_t b, const SegK &p)
+__device__ __forceinline__ uint32_t mask4(uint32_t f, uint32_t b, const SegK &p)
 {
-    if (!GENERIC)                                                   // default settings: |f-b| > T, grey != 0
-        return __vcmpgtu4(__vabsdiffu4(f, b), p.t4) & __vcmpne4(f, 0u);
-    if (p.flags & F_PREMASK) return b & __vcmpne4(f, 0u);           // b = mask bytes after morphology
+    if (!GENERIC) return __vcmpgtu4(__vabsdiffu4(f, b), p.t4);      // default settings: |f-b| > T
+    if (p.flags & F_PREMASK) return b;                              // b = mask bytes after morphology
     uint32_t in = (p.flags & F_INV) ? ~f : f;                       // 255 - x
     uint32_t d = in;
     if (p.flags & F_DIFF) d = (p.flags & F_ABS) ? __vabsdiffu4(in, b) : __vsubus4(b, in);
     uint32_t m = (p.flags & F_RANGE) ? (__vcmpgeu4(d, p.lo4) & __vcmpleu4(d, p.hi4))
                : (p.flags & F_GE) ? __vcmpgeu4(d, p.t4) : __vcmpgtu4(d, p.t4);     // F_GE: tracker-side comparison >=
     if (p.flags & F_INVMASK) m = ~m;
-    return m & __vcmpne4(f, 0u);                                    // (mask & input) != 0
+    return m;
+}
+template <bool GENERIC>
+__device__ __forceinline__ uint32_t fg4(uint32_t f, uint32_t b, const SegK &p)
+{
+    return mask4<GENERIC>(f, b, p) & __vcmpne4(f, 0u);              // (mask & input) != 0
 }
 __device__ __forceinline__ uint32_t pack4(uint32_t m)               // 4 byte masks -> 4 bits
 {
@@ -98,6 +110,12 @@ __device__ __forceinline__ uint32_t fg16(const uint4 &f, const uint4 &b, const S
 {
     return pack4(fg4<GENERIC>(f.x, b.x, p)) | (pack4(fg4<GENERIC>(f.y, b.y, p)) << 4) |
            (pack4(fg4<GENERIC>(f.z, b.z, p)) << 8) | (pack4(fg4<GENERIC>(f.w, b.w, p)) << 12);
+}
+template <bool GENERIC>
+__device__ __forceinline__ uint32_t mask16(const uint4 &f, const uint4 &b, const SegK &p)
+{
+    return pack4(mask4<GENERIC>(f.x, b.x, p)) | (pack4(mask4<GENERIC>(f.y, b.y, p)) << 4) |
+           (pack4(mask4<GENERIC>(f.z, b.z, p)) << 8) | (pack4(mask4<GENERIC>(f.w, b.w, p)) << 12);
 }
 // Fast path (default settings and |T| <= 127): per-byte flags in bit 7 by SWAR arithmetic, then the 16
 // flags are gathered with four dp4a (bytes 0x80 times weights 1,2,4,8 / 16,32,64,128).
@@ -116,6 +134,20 @@ __device__ __forceinline__ uint32_t fg16_fast(const uint4 &f, const uint4 &b, ui
     hi = __dp4a(fgflag_fast(f.w, b.w, kadd), 0x80402010u, hi);
     return (lo >> 7) | ((hi >> 7) << 8);
 }
+// the same without the "grey != 0" test (rgb8: the non-zero test is on B|G|R)
+__device__ __forceinline__ uint32_t fgflag_fast_nonz(uint32_t f, uint32_t b, uint32_t kadd)
+{
+    const uint32_t d = __vabsdiffu4(f, b);
+    return (((d & 0x7f7f7f7fu) + kadd) | d) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t fg16_fast_nonz(const uint4 &f, const uint4 &b, uint32_t kadd)
+{
+    uint32_t lo = __dp4a(fgflag_fast_nonz(f.x, b.x, kadd), 0x08040201u, 0u);
+    lo = __dp4a(fgflag_fast_nonz(f.y, b.y, kadd), 0x80402010u, lo);
+    uint32_t hi = __dp4a(fgflag_fast_nonz(f.z, b.z, kadd), 0x08040201u, 0u);
+    hi = __dp4a(fgflag_fast_nonz(f.w, b.w, kadd), 0x80402010u, hi);
+    return (lo >> 7) | ((hi >> 7) << 8);
+}
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 {
     uint4 r;
@@ -130,6 +162,36 @@ __device__ __forceinline__ uint4 ld_edge(const uint8_t *row, int col, int W)
     int x0 = col * 16, n = min(16, W - x0);
     for (int i = 0; i < n; ++i) v[i >> 2] |= (uint32_t)row[x0 + i] << (8 * (i & 3));
     return make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+// cv::cvtColor(BGR[A]2GRAY) on 8-bit data (OpenCV's fixed point, T/python/BackgroundSubtraction.cpp:165-169,
+// C/processing/RawProcessing.cpp:358): Y = (3735 B + 19235 G + 9798 R + 16384) >> 15.  p = B | G << 8 | R << 16 | x << 24;
+// the 16-bit weights are split into byte halves so that two dp4a do the three multiplications (byte 3 has weight 0).
+__device__ __forceinline__ uint32_t gray_of(uint32_t p)
+{
+    const uint32_t t = __dp4a(p, 0x00462397u, 16384u);          // low bytes  151, 35, 70
+    const uint32_t s = __dp4a(p, 0x00264B0Eu, 0u);              // high bytes  14, 75, 38
+    return ((s << 8) + t) >> 15;
+}
+__device__ __forceinline__ uint32_t gray_px(const uint8_t *q, int CN, int cc)
+{
+    if (CN == 1) return q[0];
+    if (cc >= 0) return q[cc];
+    return gray_of((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16));
+}
+// 4 consecutive pixels of an interleaved colour row -> 4 grey bytes; a, b, c = the 12 (CN 3) or a, b, c, e = the 16
+// (CN 4) bytes.  nz4 (RGB only): bit i set when any of B,G,R of pixel i is non-zero (Source.cpp:200-206).
+template <int CN, bool RGB>
+__device__ __forceinline__ uint32_t gray4(uint32_t a, uint32_t b, uint32_t c, uint32_t e, uint32_t &nz4)
+{
+    uint32_t p0, p1, p2, p3;
+    if (CN == 3) { p0 = a; p1 = __byte_perm(a, b, 0x0543); p2 = __byte_perm(b, c, 0x0432); p3 = c >> 8; }
+    else { p0 = a; p1 = b; p2 = c; p3 = e; }
+    if (RGB) {
+        nz4 = (((p0 & 0xFFFFFFu) + 0xFFFFFFu) >> 24) | ((((p1 & 0xFFFFFFu) + 0xFFFFFFu) >> 24) << 1) |
+              ((((p2 & 0xFFFFFFu) + 0xFFFFFFu) >> 24) << 2) | ((((p3 & 0xFFFFFFu) + 0xFFFFFFu) >> 24) << 3);
+    }
+    return gray_of(p0) | (gray_of(p1) << 8) | (gray_of(p2) << 16) | (gray_of(p3) << 24);
 }
 
 template <bool GENERIC>
@@ -198,6 +260,12 @@ seg_rle_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, int fpc)
         for (int k = 0; k < K1_KPT; ++k) {
             const int c = warp * (32 * K1_KPT) + k * 32 + lane;
             uint32_t m16 = (c < tile_chunks) ? fg16<GENERIC>(cur[k], bgc[k], p) : 0u;
+            if (d.nz_plane && c < tile_chunks) {                // rgb8: the pixel is set when any of B,G,R is, not the grey value
+                const uint8_t *nb = d.nz_plane + (size_t)f * frame_bytes;
+                const uint4 nz = d.aligned ? *reinterpret_cast<const uint4 *>(nb + (size_t)row0 * d.W + (size_t)c * 16)
+                                           : ld_edge(nb + (size_t)(row0 + c / d.cpr) * d.W, c % d.cpr, d.W);
+                m16 = mask16<GENERIC>(cur[k], bgc[k], p) & (pack4(nz.x) | (pack4(nz.y) << 4) | (pack4(nz.z) << 8) | (pack4(nz.w) << 12));
+            }
             if (d.keep_mask && c < tile_chunks) {               // pixels outside the kept detection blobs are never foreground
                 const uint8_t *kb = d.keep_mask + (size_t)f * frame_bytes;
                 const uint4 mk = d.aligned ? *reinterpret_cast<const uint4 *>(kb + (size_t)row0 * d.W + (size_t)c * 16)
@@ -414,7 +482,7 @@ constexpr int K1W_STAGE_BYTES = K1_CHUNKS * 16;
 constexpr int K1W_WORDS = 256;                              // 64-bit words of the padded bit image (32 lanes x 8)
 constexpr int K1W_MASK_BYTES = (K1W_WORDS / 8 + 1) * 80 + 128;   // per lane 64 B (8 words) + 16 B pad (bank spread); 1 spare zero block; 128 B dump area
 constexpr uint32_t K1W_DONE = 0xFFFFFFFFu;
-constexpr int k1w_smem(int ew) { return K1W_STAGES * K1W_STAGE_BYTES + ew * K1W_MASK_BYTES; }
+constexpr int k1w_smem(int ew, int cn = 1) { return K1W_STAGES * (cn == 1 ? K1W_STAGE_BYTES : 512 * 16 * cn) + ew * K1W_MASK_BYTES; }
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 {
@@ -427,17 +495,24 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t r; asm volati
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory"); }
 
-template <bool GENERIC, int EW>
-__global__ void __launch_bounds__((K1W_MW + EW + 1) * 32, 3)
+// Colour frames (CN = 3 BGR / 4 BGRA, fused cvtColor): a unit holds half as many pixels (KPT = 2 chunks per mask
+// thread) so that three stages of CN x 8 KB still leave room for 2-3 CTAs per SM; the mask warps turn every 4 pixels
+// into 4 grey bytes with dp4a (gray4) and continue as for grey frames.  RGB (rgb8 encoding): a pixel is foreground
+// when the grey difference exceeds T and any of B,G,R is non-zero.
+template <bool GENERIC, int EW, int CN = 1, bool RGB = false>
+__global__ void __launch_bounds__((K1W_MW + EW + 1) * 32, CN == 1 ? 3 : 2)
 seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t static_units, unsigned long long *dbg)
 {
+    static_assert(CN == 1 || !GENERIC, "colour frames with non-default settings take the plane path");
     constexpr int NT = (K1W_MW + EW + 1) * 32;
+    constexpr int KPT = CN == 1 ? K1_KPT : 2;                       // chunks per mask thread and unit
+    constexpr int STAGE_BYTES = K1W_MW * 32 * KPT * 16 * CN;
     extern __shared__ __align__(128) uint8_t k1w_dsm[];
     __shared__ uint64_t s_bar[2 * K1W_STAGES + 2 * EW];
     __shared__ uint32_t s_meta[K1W_STAGES + EW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile_a = umma::smem_u32(k1w_dsm), mask_a = tile_a + K1W_STAGES * K1W_STAGE_BYTES;
+    const uint32_t tile_a = umma::smem_u32(k1w_dsm), mask_a = tile_a + K1W_STAGES * STAGE_BYTES;
     const uint32_t full_a = umma::smem_u32(s_bar), empty_a = full_a + 8 * K1W_STAGES;
     const uint32_t mkf_a = empty_a + 8 * K1W_STAGES, mke_a = mkf_a + 8 * EW;
     const uint32_t meta_a = umma::smem_u32(s_meta), mmeta_a = meta_a + 4 * K1W_STAGES;
@@ -454,15 +529,15 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
         if (lane != 0) return;
         if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 4 + 0] = t; }
         const uint32_t B = (uint32_t)d.B, U = (uint32_t)d.n_bands * B;
-        const size_t frame_bytes = (size_t)d.W * d.H;
+        const size_t frame_bytes = (size_t)d.W * d.H * CN;
         uint32_t s = 0, ph = 0;
         auto issue = [&](uint32_t band, uint32_t f) {
             const int row0 = (int)band * d.rpt;
-            const uint32_t bytes = (uint32_t)min(d.rpt, d.H - row0) * (uint32_t)d.W;
+            const uint32_t bytes = (uint32_t)min(d.rpt, d.H - row0) * (uint32_t)d.W * CN;
             umma::mbar_wait_suspend_a(empty_a + 8 * s, ph ^ 1);
             sts_u32(meta_a + 4 * s, (band << 16) | f);
             umma::mbar_expect_tx_a(full_a + 8 * s, bytes);
-            umma::bulk_g2s_a(tile_a + s * K1W_STAGE_BYTES, frames + (size_t)f * frame_bytes + (size_t)row0 * d.W, bytes, full_a + 8 * s);
+            umma::bulk_g2s_a(tile_a + s * STAGE_BYTES, frames + (size_t)f * frame_bytes + (size_t)row0 * d.W * CN, bytes, full_a + 8 * s);
             if (++s == K1W_STAGES) { s = 0; ph ^= 1; }
         };
         {                                          // static share: units [i * static_units, (i + 1) * static_units)
@@ -490,10 +565,10 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
 
     if (warp < K1W_MW) {                           // ---- mask warps ----
         const int full_chunks = d.rpt * d.cpr;
-        const int cb = warp * (32 * K1_KPT) + lane;                   // chunks cb + 32 k
-        uint32_t mpos[K1_KPT];                                        // byte offset of the chunk's 16 flags inside a bit image
+        const int cb = warp * (32 * KPT) + lane;                      // chunks cb + 32 k
+        uint32_t mpos[KPT];                                           // byte offset of the chunk's 16 flags inside a bit image
 #pragma unroll
-        for (int k = 0; k < K1_KPT; ++k) {
+        for (int k = 0; k < KPT; ++k) {
             const int c = cb + 32 * k;
             mpos[k] = (uint32_t)(K1W_MASK_BYTES - 128 + 2 * lane);    // chunks beyond the band: dump area
             if (c < full_chunks) {
@@ -501,8 +576,8 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
                 mpos[k] = (uint32_t)((q >> 5) * 80 + (q & 31) * 2);
             }
         }
-        const uint32_t my_tile = tile_a + (uint32_t)cb * 16u;
-        uint4 bgc[K1_KPT];
+        const uint32_t my_tile = tile_a + (uint32_t)cb * (16u * CN);
+        uint4 bgc[KPT];
         uint32_t cur_band = 0xFFFFFFFFu, s = 0, ph = 0, b = 0, bph = 0;
         int tile_chunks = 0;
         for (;;) {
@@ -516,23 +591,51 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
                 tile_chunks = min(d.rpt, d.H - row0) * d.cpr;
                 const uint4 *bgp = reinterpret_cast<const uint4 *>(d.bg + (size_t)row0 * d.W) + cb;
 #pragma unroll
-                for (int k = 0; k < K1_KPT; ++k) bgc[k] = (cb + 32 * k < tile_chunks) ? bgp[32 * k] : make_uint4(0, 0, 0, 0);
+                for (int k = 0; k < KPT; ++k) bgc[k] = (cb + 32 * k < tile_chunks) ? bgp[32 * k] : make_uint4(0, 0, 0, 0);
             }
-            uint4 cur[K1_KPT];
+            uint32_t m16[KPT];
+            if (CN == 1) {
+                uint4 cur[KPT];
 #pragma unroll
-            for (int k = 0; k < K1_KPT; ++k) cur[k] = lds_v4(my_tile + s * K1W_STAGE_BYTES + k * 512);
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive_a(empty_a + 8 * s);      // stage is in registers: refill it
-            uint32_t m16[K1_KPT];
+                for (int k = 0; k < KPT; ++k) cur[k] = lds_v4(my_tile + s * STAGE_BYTES + k * 512);
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive_a(empty_a + 8 * s);  // stage is in registers: refill it
 #pragma unroll
-            for (int k = 0; k < K1_KPT; ++k) {
-                const uint32_t m = GENERIC ? fg16<true>(cur[k], bgc[k], p) : fg16_fast(cur[k], bgc[k], p.lo4);
-                m16[k] = (cb + 32 * k < tile_chunks) ? m : 0u;        // rows below the image (last band) are stale shared memory
+                for (int k = 0; k < KPT; ++k) {
+                    const uint32_t m = GENERIC ? fg16<true>(cur[k], bgc[k], p) : fg16_fast(cur[k], bgc[k], p.lo4);
+                    m16[k] = (cb + 32 * k < tile_chunks) ? m : 0u;    // rows below the image (last band) are stale shared memory
+                }
+            } else {
+                uint4 cur[KPT][CN];
+#pragma unroll
+                for (int k = 0; k < KPT; ++k)
+#pragma unroll
+                    for (int j = 0; j < CN; ++j) cur[k][j] = lds_v4(my_tile + s * STAGE_BYTES + k * (512 * CN) + j * 16);
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive_a(empty_a + 8 * s);
+#pragma unroll
+                for (int k = 0; k < KPT; ++k) {
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(&cur[k][0]);
+                    uint4 g; uint32_t nz = 0, n4 = 0;
+                    if (CN == 3) {
+                        g.x = gray4<3, RGB>(w[0], w[1], w[2], 0u, n4);  nz |= n4;
+                        g.y = gray4<3, RGB>(w[3], w[4], w[5], 0u, n4);  nz |= n4 << 4;
+                        g.z = gray4<3, RGB>(w[6], w[7], w[8], 0u, n4);  nz |= n4 << 8;
+                        g.w = gray4<3, RGB>(w[9], w[10], w[11], 0u, n4); nz |= n4 << 12;
+                    } else {
+                        g.x = gray4<4, RGB>(w[0], w[1], w[2], w[3], n4);    nz |= n4;
+                        g.y = gray4<4, RGB>(w[4], w[5], w[6], w[7], n4);    nz |= n4 << 4;
+                        g.z = gray4<4, RGB>(w[8], w[9], w[10], w[11], n4);  nz |= n4 << 8;
+                        g.w = gray4<4, RGB>(w[12], w[13], w[14], w[15], n4); nz |= n4 << 12;
+                    }
+                    const uint32_t m = RGB ? (fg16_fast_nonz(g, bgc[k], p.lo4) & nz) : fg16_fast(g, bgc[k], p.lo4);
+                    m16[k] = (cb + 32 * k < tile_chunks) ? m : 0u;
+                }
             }
             umma::mbar_wait_suspend_a(mke_a + 8 * b, bph ^ 1);
             const uint32_t mb = mask_a + b * K1W_MASK_BYTES;
 #pragma unroll
-            for (int k = 0; k < K1_KPT; ++k) sts_u16(mb + mpos[k], m16[k]);
+            for (int k = 0; k < KPT; ++k) sts_u16(mb + mpos[k], m16[k]);
             if (tid == 0) sts_u32(mmeta_a + 4 * b, meta);
             __syncwarp();
             if (lane == 0) umma::mbar_arrive_a(mkf_a + 8 * b);
@@ -624,6 +727,42 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
         if (lane == 0) umma::mbar_arrive_a(mke_a + 8 * e);
     }
     if (dbg && e == 0 && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 4 + 2] = t; }
+}
+
+// Colour frames on the plane path (non-default settings, widths that are not multiples of 16, tracker-side
+// re-threshold): the grey plane the threshold runs on (cvtColor or color_channel) and, for rgb8, the plane of
+// "any of B,G,R != 0" bytes.  One thread per 4 pixels.
+__global__ void to_gray_kernel(const uint8_t *__restrict__ frames, uint8_t *__restrict__ gray, uint8_t *__restrict__ nz,
+                               size_t total, int CN, int cc)
+{
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (size_t)gridDim.x * blockDim.x * 4) {
+        uint32_t g = 0, z = 0;
+        const int n = (int)min((size_t)4, total - i);
+        for (int k = 0; k < n; ++k) {
+            const uint8_t *q = frames + (i + k) * CN;
+            g |= gray_px(q, CN, cc) << (8 * k);
+            if (nz) z |= ((q[0] | q[1] | q[2]) ? 0xFFu : 0u) << (8 * k);
+        }
+        if (n == 4 && (i & 3) == 0) {
+            *reinterpret_cast<uint32_t *>(gray + i) = g;
+            if (nz) *reinterpret_cast<uint32_t *>(nz + i) = z;
+        } else {
+            for (int k = 0; k < n; ++k) { gray[i + k] = (uint8_t)(g >> (8 * k)); if (nz) nz[i + k] = (uint8_t)(z >> (8 * k)); }
+        }
+    }
+}
+
+// generate_binary's output for a colour frame, parity tests only: mask & grey (gray encoding) or mask & each of
+// B,G,R (rgb8, RawProcessing.cpp:581-589).  mask: optional 0xFF/0 plane after morphology, else thresholded here.
+__global__ void binary_image_color_kernel(const uint8_t *__restrict__ frame, const uint8_t *__restrict__ gray, const uint8_t *__restrict__ bg,
+                                          const uint8_t *__restrict__ mask, uint8_t *__restrict__ out, size_t n, SegK p, int CN, int enc)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t g = gray[i];
+        const uint32_t m = mask ? mask[i] : (mask4<true>(g, bg[i], p) & 0xFFu);
+        if (!enc) out[i] = m ? (uint8_t)g : (uint8_t)0;
+        else for (int k = 0; k < 3; ++k) out[i * 3 + k] = m ? frame[i * CN + k] : (uint8_t)0;
+    }
 }
 
 // generate_binary's output image, for parity tests only (RawProcessing.cpp:597-600)
@@ -848,7 +987,7 @@ ccl_label_kernel(SegDev d)
         uint32_t t0, t1, t2;
         uint32_t e0 = block_excl_scan(keep, ws, t0);
         uint32_t e1 = block_excl_scan(keep ? l : 0u, ws, t1);
-        uint32_t e2 = block_excl_scan(keep ? px : 0u, ws, t2);
+        uint32_t e2 = block_excl_scan(keep ? px * (uint32_t)d.opx : 0u, ws, t2);     // pixel arena offsets count bytes
         if (k < K && keep) { kept[kk + e0] = k; loff[k] = kl + e1; poff[k] = kp + e2; }
         kk += t0; kl += t1; kp += t2;
     }
@@ -907,7 +1046,8 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
     const tb_line *runs = d.runs + (size_t)f * d.rcap;
     const uint32_t *label = d.parent + (size_t)f * d.rcap;
     const uint32_t *rs = d.row_start + (size_t)f * d.H, *re = d.row_end + (size_t)f * d.H;
-    const uint8_t *frame = frames + (size_t)f * d.W * d.H;
+    const int CN = d.CN, opx = d.opx;
+    const uint8_t *frame = frames + (size_t)f * d.W * d.H * CN;
     const size_t o = (size_t)f * d.rcap;
     const int cw = d.crop_w, ch = d.crop_h;
 
@@ -931,34 +1071,34 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
                 for (uint32_t j = j0; j < e && runs[j].x0 <= bx1; ++j)
                     if (label[j] == root) { ++nl; np += (uint32_t)runs[j].x1 - runs[j].x0 + 1u; }
             }
-            uint32_t tl, tp, el = warp_excl_scan(nl, tl), ep = warp_excl_scan(np, tp);
+            uint32_t tl, tp, el = warp_excl_scan(nl, tl), ep = warp_excl_scan(np * (uint32_t)opx, tp);
             if (nl) {
                 uint32_t wl = L0 + cl + el, wp = P0 + cp + ep;
                 for (uint32_t j = j0; j < e && runs[j].x0 <= bx1; ++j)
                     if (label[j] == root) {
                         d.lines[wl] = runs[j]; d.line_px[wl] = wp;
-                        ++wl; wp += (uint32_t)runs[j].x1 - runs[j].x0 + 1u;
+                        ++wl; wp += ((uint32_t)runs[j].x1 - runs[j].x0 + 1u) * (uint32_t)opx;
                     }
             }
             cl += tl; cp += tp;
         }
         const bool do_crop = q < ncrop;
-        uint8_t *crop = d.crops + (size_t)(Cb + q) * cw * ch;
+        uint8_t *crop = d.crops + (size_t)(Cb + q) * cw * ch * opx;
         int offx = 0, offy = 0;
         if (do_crop) {
             int dd;
             if ((int)bw < cw) { dd = cw - (int)bw; offx = dd - dd / 2; } else { dd = (int)bw - cw; offx = -(dd - dd / 2); }
             if ((int)bh < ch) { dd = ch - (int)bh; offy = dd - dd / 2; } else { dd = (int)bh - ch; offy = -(dd - dd / 2); }
-            if (((cw * ch) & 15) == 0) {
+            if (((cw * ch * opx) & 15) == 0) {
                 uint4 *c4 = reinterpret_cast<uint4 *>(crop);
-                for (int i = lane; i < (cw * ch) >> 4; i += 32) c4[i] = make_uint4(0, 0, 0, 0);
+                for (int i = lane; i < (cw * ch * opx) >> 4; i += 32) c4[i] = make_uint4(0, 0, 0, 0);
             } else {
-                for (int i = lane; i < cw * ch; i += 32) crop[i] = 0;
+                for (int i = lane; i < cw * ch * opx; i += 32) crop[i] = 0;
             }
         }
         if (lane == 0) {
             tb_blob_rec rec;
-            rec.line_off = L0; rec.px_off = P0; rec.n_lines = cl; rec.n_pixels = cp;
+            rec.line_off = L0; rec.px_off = P0; rec.n_lines = cl; rec.n_pixels = cp / (uint32_t)opx;
             rec.x0 = (uint16_t)bx0; rec.y0 = (uint16_t)by0; rec.x1 = (uint16_t)bx1; rec.y1 = (uint16_t)by1;
             const tb_line fl = runs[root];
             rec.bid = ((((uint32_t)fl.x0 + fl.x1 + 1u) / 2u) << 19) | (((uint32_t)fl.y & 0x1FFFu) << 6) | ((cl & 0xFFu) % 64u);
@@ -979,17 +1119,33 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
                 const uint32_t po = __shfl_sync(0xffffffffu, mypo, l);
                 const uint32_t lx0 = xx & 0xFFFFu, lx1 = xx >> 16;
                 for (uint32_t x = lx0 + lane; x <= lx1; x += 32) {
-                    const uint8_t v = frame[(size_t)ly * d.W + x];
-                    d.pixels[po + (x - lx0)] = v;
-                    if (do_crop) {
-                        const int cx = (int)(x - bx0) + offx, cy = (int)(ly - by0) + offy;
-                        if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
+                    const size_t pi = (size_t)ly * d.W + x;
+                    const int cx = (int)(x - bx0) + offx, cy = (int)(ly - by0) + offy;
+                    const bool in_crop = do_crop && cx >= 0 && cx < cw && cy >= 0 && cy < ch;
+                    if (opx == 1) {                            // gray encoding: the grey value (of a colour pixel: cvtColor / plane)
+                        const uint8_t v = (uint8_t)gray_px(frame + pi * CN, CN, d.cc);
+                        d.pixels[po + (x - lx0)] = v;
+                        if (in_crop) {
                             int val = v;
                             if (d.crop_method) {
-                                const int b = d.bg[(size_t)ly * d.W + x];
+                                const int b = d.bg[pi];
                                 val = d.crop_method == 1 ? abs(b - val) : max(0, b - val);
                             }
                             crop[cy * cw + cx] = (uint8_t)val;
+                        }
+                    } else {                                   // rgb8: B,G,R; crops difference per channel (Background.h:238-262)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const uint8_t v = frame[pi * CN + k];
+                            d.pixels[po + (x - lx0) * 3 + k] = v;
+                            if (in_crop) {
+                                int val = v;
+                                if (d.crop_method) {
+                                    const int b = d.bg3[pi * 3 + k];
+                                    val = d.crop_method == 1 ? abs(b - val) : max(0, b - val);
+                                }
+                                crop[(cy * cw + cx) * 3 + k] = (uint8_t)val;
+                            }
                         }
                     }
                 }
@@ -1014,6 +1170,9 @@ struct tb_seg {
     cudaEvent_t ev_done = nullptr;
     bool has_bg = false;
     uint8_t *d_bg = nullptr, *d_frames = nullptr, *d_tmp = nullptr;
+    uint8_t *d_bg3 = nullptr;                   // rgb8: the 3-channel background
+    uint8_t *d_gray = nullptr, *d_nz = nullptr; // colour frames on the plane path: grey plane / non-zero plane of a batch (allocated on first use)
+    bool gray_valid = false;                    // d_gray holds the grey plane of the last batch
     std::vector<void *> dev_allocs;
     // pinned host mirrors
     tb_frame_info *h_infos = nullptr; uint32_t *h_totals = nullptr;
@@ -1044,6 +1203,7 @@ static int seg_make_k(const tb_seg_params &p, SegK &k, std::string &why)
     k.t4 = rep(aT);                       // d > |T|; |T| >= 255 can never be exceeded by a byte
     k.lo4 = rep(T); k.hi4 = rep(p.threshold_maximum);
     if (T > 255 || p.threshold_maximum < 0) { k.lo4 = rep(255); k.hi4 = rep(0); }   // empty range
+    if (p.color_channel < -1) { why = "color_channel must be -1 (none) or a plane index"; return TB_ERR_INVALID; }
     return TB_OK;
 }
 
@@ -1076,7 +1236,7 @@ extern "C" void tb_seg_default_params(tb_seg_params *p)
     std::memset(p, 0, sizeof(*p));
     p->detect_threshold = 15; p->threshold_maximum = 255; p->enable_difference = 1;
     p->detect_threshold_is_absolute = 1; p->closing_size = 3; p->cm_per_pixel = 1.f;
-    p->n_size_ranges = 0;
+    p->n_size_ranges = 0; p->color_channel = -1;
 }
 
 template <typename T>
@@ -1094,6 +1254,11 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
                "tb_seg_create: frame size must be 1..16384 x 1..65534");
     TB_REQUIRE(cfg->max_batch > 0 && cfg->max_batch <= 4096, TB_ERR_INVALID, "tb_seg_create: max_batch must be 1..4096");
     TB_REQUIRE(cfg->crop_method >= 0 && cfg->crop_method <= 2, TB_ERR_INVALID, "tb_seg_create: crop_method must be 0..2");
+    TB_REQUIRE(cfg->channels == 0 || cfg->channels == 1 || cfg->channels == 3 || cfg->channels == 4, TB_ERR_INVALID,
+               "tb_seg_create: channels must be 1 (gray), 3 (BGR) or 4 (BGRA)");
+    TB_REQUIRE(cfg->encoding == 0 || cfg->encoding == 1, TB_ERR_INVALID, "tb_seg_create: encoding must be 0 (gray) or 1 (rgb8); r3g3b2 is not built");
+    TB_REQUIRE(cfg->encoding == 0 || cfg->channels >= 3, TB_ERR_INVALID,
+               "tb_seg_create: rgb8 encoding needs colour frames (Invalid number of channels, BackgroundSubtraction.cpp:177-181)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("tb_seg_create: no CUDA device (there is no CPU fallback)");
@@ -1108,15 +1273,17 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     seg_make_k(h->params, h->k, why);
     SegDev &d = h->d;
     d.W = cfg->width; d.H = cfg->height; d.B = cfg->max_batch;
+    d.CN = cfg->channels > 1 ? cfg->channels : 1; d.enc = cfg->encoding; d.cc = -1; d.opx = d.enc ? 3 : 1;
     d.cpr = (d.W + 15) / 16;
     d.aligned = (d.W % 16) == 0;
     d.wpr = (d.cpr + 3) / 4 + 1;
-    d.rpt = std::max(1, std::min(K1_CHUNKS / d.cpr, K1W_WORDS / d.wpr));        // rows per band: fits the chunk tile and the padded bit image
+    const int unit_chunks = d.CN == 1 ? K1_CHUNKS : 512;                         // colour units hold half the pixels (seg_rle_ws_kernel)
+    d.rpt = std::max(1, std::min((d.cpr <= unit_chunks ? unit_chunks : K1_CHUNKS) / d.cpr, K1W_WORDS / d.wpr));   // rows per band: fits the chunk tile and the padded bit image
     d.n_bands = (d.H + d.rpt - 1) / d.rpt;
     d.rcap = cfg->max_runs_per_frame > 0 ? (uint32_t)cfg->max_runs_per_frame : 32768u;
     d.rcap = std::max<uint32_t>(d.rcap, (uint32_t)d.n_bands);
     d.px_frame_cap = cfg->max_pixels_per_frame > 0 ? (uint32_t)cfg->max_pixels_per_frame
-                                                   : (uint32_t)std::max<int64_t>((int64_t)d.W * d.H / 8, std::min<int64_t>((int64_t)d.W * d.H, 1 << 18));
+                                                   : (uint32_t)std::max<int64_t>((int64_t)d.W * d.H / 8, std::min<int64_t>((int64_t)d.W * d.H, 1 << 18)) * (uint32_t)d.opx;
     d.max_crops = cfg->max_crops_per_frame > 0 ? (uint32_t)cfg->max_crops_per_frame : 0u;
     d.crop_w = cfg->crop_width > 0 ? cfg->crop_width : 80;
     d.crop_h = cfg->crop_height > 0 ? cfg->crop_height : 80;
@@ -1132,8 +1299,9 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     int r = TB_OK;
 #define A(p, n) if (r == TB_OK) r = seg_dev(h, &(p), (n))
     A(h->d_bg, (size_t)d.W * d.H + 16);
-    A(h->d_frames, B * d.W * d.H + 16);
-    A(h->d_tmp, (size_t)d.W * d.H);
+    A(h->d_frames, B * d.W * d.H * d.CN + 16);
+    A(h->d_tmp, (size_t)d.W * d.H * d.opx);
+    if (d.enc) A(h->d_bg3, (size_t)d.W * d.H * 3 + 16);
     A(d.run_count, B + 1); A(d.band_base, B * d.n_bands); A(d.band_cnt, B * d.n_bands);
     A(d.runs_raw, B * d.rcap); A(d.runs, B * d.rcap); A(d.parent, B * d.rcap); A(d.bidx, B * d.rcap);
     A(d.row_start, B * d.H); A(d.row_end, B * d.H);
@@ -1141,7 +1309,7 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     A(d.b_ymax, B * d.rcap); A(d.b_root, B * d.rcap); A(d.b_loff, B * d.rcap); A(d.b_poff, B * d.rcap);
     A(d.kept, B * d.rcap); A(d.frame_tot, B * 4);
     A(d.infos, B); A(d.recs, d.blobs_cap); A(d.lines, d.lines_cap); A(d.line_px, d.lines_cap);
-    A(d.pixels, (size_t)d.px_cap + 16); A(d.crops, (size_t)d.crops_cap * d.crop_w * d.crop_h + 16);
+    A(d.pixels, (size_t)d.px_cap + 16); A(d.crops, (size_t)d.crops_cap * d.crop_w * d.crop_h * d.opx + 16);
     A(d.crop_blob, d.crops_cap); A(d.totals, 4);
 #undef A
     if (r == TB_OK) r = host_alloc(&h->h_infos, B);
@@ -1149,13 +1317,13 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     if (r == TB_OK) r = host_alloc(&h->h_recs, d.blobs_cap);
     if (r == TB_OK) r = host_alloc(&h->h_lines, d.lines_cap);
     if (r == TB_OK) r = host_alloc(&h->h_pixels, (size_t)d.px_cap + 16);
-    if (r == TB_OK) r = host_alloc(&h->h_crops, (size_t)d.crops_cap * d.crop_w * d.crop_h + 16);
+    if (r == TB_OK) r = host_alloc(&h->h_crops, (size_t)d.crops_cap * d.crop_w * d.crop_h * d.opx + 16);
     if (r == TB_OK) r = host_alloc(&h->h_crop_blob, std::max<size_t>(d.crops_cap, 1));
     if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
     h->own_stream = h->stream;
     if (r == TB_OK && cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); r = TB_ERR_CUDA; }
     if (r != TB_OK) { tb_seg_destroy(h); return r; }
-    d.bg = h->d_bg;
+    d.bg = h->d_bg; d.bg3 = h->d_bg3;
     std::memset(h->h_totals, 0, 16);
     *out = h;
     return TB_OK;
@@ -1188,7 +1356,9 @@ extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
     TB_REQUIRE(h && p, TB_ERR_INVALID, "tb_seg_set_params: null argument");
     SegK k; std::string why;
     if (seg_make_k(*p, k, why) != TB_OK) { set_error("tb_seg_set_params: " + why); return TB_ERR_INVALID; }
+    TB_REQUIRE(h->d.CN == 1 || p->color_channel < h->d.CN || p->color_channel >= 4, TB_ERR_INVALID, "tb_seg_set_params: color_channel beyond the frame's channels");
     h->params = *p; h->k = k;
+    h->d.cc = (h->d.CN > 1 && h->d.enc == 0 && p->color_channel >= 0 && p->color_channel < 4) ? p->color_channel : -1;   // >= 4: cvtColor (BackgroundSubtraction.cpp:161-163)
     h->morph = p->use_closing || p->dilation_size != 0;
     if (h->morph) {
         TB_CUDA(cudaSetDevice(h->cfg.device));
@@ -1208,15 +1378,46 @@ extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
     return TB_OK;
 }
 
-extern "C" int tb_seg_set_background(tb_seg *h, const uint8_t *bg, int width, int height, int64_t stride)
+extern "C" int tb_seg_set_background_c(tb_seg *h, const uint8_t *bg, int width, int height, int channels, int64_t stride)
 {
     TB_REQUIRE(h && bg, TB_ERR_INVALID, "tb_seg_set_background: null argument");
     TB_REQUIRE(width == h->d.W && height == h->d.H, TB_ERR_INVALID, "tb_seg_set_background: size differs from the handle's frame size");
+    TB_REQUIRE(channels == (h->d.enc ? 3 : 1), TB_ERR_INVALID,
+               "tb_seg_set_background: the background must have 1 channel for gray and 3 for rgb8 encoding (RawProcessing.cpp:343)");
     TB_CUDA(cudaSetDevice(h->cfg.device));
-    if (stride <= 0) stride = width;
-    TB_CUDA(cudaMemcpy2DAsync(h->d_bg, (size_t)width, bg, (size_t)stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    const size_t row = (size_t)width * channels;
+    if (stride <= 0) stride = (int64_t)row;
+    if (channels == 1) {
+        TB_CUDA(cudaMemcpy2DAsync(h->d_bg, row, bg, (size_t)stride, row, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    } else {                  // _grey_average = cvtColor(average, BGR2GRAY), RawProcessing.cpp:356-357
+        TB_CUDA(cudaMemcpy2DAsync(h->d_bg3, row, bg, (size_t)stride, row, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+        to_gray_kernel<<<296, 256, 0, h->stream>>>(h->d_bg3, h->d_bg, nullptr, (size_t)width * height, 3, -1);
+        h->launches += 1;
+        TB_CUDA(cudaGetLastError());
+    }
     TB_CUDA(cudaStreamSynchronize(h->stream));
     h->has_bg = true;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_set_background(tb_seg *h, const uint8_t *bg, int width, int height, int64_t stride)
+{
+    return tb_seg_set_background_c(h, bg, width, height, 1, stride);
+}
+
+// grey plane (and, for rgb8, non-zero plane) of n colour frames into the handle's plane buffers
+static int seg_to_gray(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s)
+{
+    const size_t px = (size_t)h->d.W * h->d.H;
+    if (!h->d_gray) {
+        int r = seg_dev(h, &h->d_gray, (size_t)h->cfg.max_batch * px + 16);
+        if (r == TB_OK && h->d.enc) r = seg_dev(h, &h->d_nz, (size_t)h->cfg.max_batch * px + 16);
+        if (r != TB_OK) return r;
+    }
+    to_gray_kernel<<<148 * 8, 256, 0, s>>>(frames_dev, h->d_gray, h->d.enc ? h->d_nz : nullptr, px * (size_t)n, h->d.CN, h->d.cc);
+    h->launches += 1;
+    TB_CUDA(cudaGetLastError());
+    h->gray_valid = true;
     return TB_OK;
 }
 
@@ -1256,7 +1457,9 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     d.B = n;
     d.bg_stride = 0;
     d.keep_mask = nullptr;
+    d.nz_plane = nullptr;
     h->last_frames_dev = frames_dev;
+    h->gray_valid = false;
     TB_CUDA(cudaMemsetAsync(d.run_count, 0, sizeof(uint32_t) * ((size_t)n + 1), s));      // + the unit counter of the persistent K1
     static const int fpc_env = getenv("TB_SEG_FPC") ? atoi(getenv("TB_SEG_FPC")) : 0;
     const int fpc = fpc_env > 0 ? fpc_env : (n >= 64 ? 8 : (n >= 8 ? 2 : 1));
@@ -1268,19 +1471,56 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     const bool plain = !h->morph && h->k.flags == (F_DIFF | F_ABS) && (h->k.t4 & 0xFFu) <= 127u;
     SegK kk = h->k;
     if (plain) kk.lo4 = (127u - (kk.t4 & 0xFFu)) * 0x01010101u;      // SWAR addend of the fast path
-    if (keep_mask) {                 // tracker-side re-threshold: comparison >=, restricted to the painted detection blobs
+    const bool ws_ok = d.aligned && d.wpr <= K1W_WORDS && n <= 65536 && d.n_bands < 65535 && !no_tma && !no_ws;
+    // colour frames: fused cvtColor inside the persistent K1 for the default settings, else a grey plane first
+    const bool fused_colour = d.CN > 1 && plain && !keep_mask && d.cc < 0 && ws_ok && d.rpt * d.cpr <= 512;
+    const uint8_t *plane = frames_dev;          // what the 1-channel K1 variants read
+    if (d.CN > 1 && !fused_colour) {
+        int r = seg_to_gray(h, frames_dev, n, s);
+        if (r != TB_OK) return r;
+        plane = h->d_gray;
+        if (d.enc) d.nz_plane = h->d_nz;
+    }
+    if (fused_colour) {
+        static int ctas[2] = {0, 0};
+        const int ci = d.CN == 3 ? 0 : 1;
+        const int nt = (K1W_MW + 3 + 1) * 32, smem = k1w_smem(3, d.CN);
+        if (!ctas[ci]) {
+            int per_sm = 0, sms = 0;
+            if (d.CN == 3) {
+                TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3, 3, true>, nt, smem));
+            } else {
+                TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3, 4, true>, nt, smem));
+            }
+            TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+            ctas[ci] = std::max(1, per_sm) * std::max(1, sms);
+        }
+        const unsigned units = (unsigned)d.n_bands * (unsigned)n;
+        const unsigned grid = std::min<unsigned>(units, (unsigned)ctas[ci]);
+        const uint32_t static_units = (uint32_t)((double)(units / grid) * 0.5);
+        if (d.CN == 3 && !d.enc) seg_rle_ws_kernel<false, 3, 3, false><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, nullptr);
+        else if (d.CN == 3) seg_rle_ws_kernel<false, 3, 3, true><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, nullptr);
+        else if (!d.enc) seg_rle_ws_kernel<false, 3, 4, false><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, nullptr);
+        else seg_rle_ws_kernel<false, 3, 4, true><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, nullptr);
+    } else if (keep_mask) {                 // tracker-side re-threshold: comparison >=, restricted to the painted detection blobs
         TB_REQUIRE(!h->morph, TB_ERR_INVALID, "tb_seg_rethreshold: the tracker-side handle must not enable morphology");
         d.keep_mask = keep_mask;
         kk = h->k; kk.flags |= F_GE;
-        seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, kk, fpc);
+        seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(plane, d, kk, fpc);
     } else if (h->morph) {
         const uint8_t *mask = nullptr;
-        int r = seg_morph(h, frames_dev, n, s, &mask);
+        int r = seg_morph(h, plane, n, s, &mask);
         if (r != TB_OK) return r;
         d.bg = mask; d.bg_stride = (size_t)d.W * d.H;
         kk.flags = F_PREMASK;
-        seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, kk, fpc);
-    } else if (d.aligned && d.wpr <= K1W_WORDS && n <= 65536 && d.n_bands < 65535 && !no_tma && !no_ws) {
+        seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(plane, d, kk, fpc);
+    } else if (d.nz_plane) {          // rgb8 on the plane path: only the plain kernel reads the non-zero plane
+        seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(plane, d, h->k, fpc);
+    } else if (ws_ok && d.rpt * d.cpr <= K1_CHUNKS) {
         static const int ew = getenv("TB_SEG_EW") ? atoi(getenv("TB_SEG_EW")) : 3;                   // tuning knobs
         static const double static_frac = getenv("TB_SEG_STATIC") ? atof(getenv("TB_SEG_STATIC")) : 0.5;
         static int ws_ctas = 0;
@@ -1301,9 +1541,9 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
         static const bool timeline = getenv("TB_SEG_TIMELINE") != nullptr;                            // debug: per-CTA start / end times
         static unsigned long long *dbg = nullptr;
         if (timeline && !dbg) TB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 4 * ws_ctas));
-        if (plain && ew == 4) seg_rle_ws_kernel<false, 4><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, dbg);
-        else if (plain) seg_rle_ws_kernel<false, 3><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, dbg);
-        else seg_rle_ws_kernel<true, 3><<<grid, (K1W_MW + 3 + 1) * 32, k1w_smem(3), s>>>(frames_dev, d, h->k, static_units, dbg);
+        if (plain && ew == 4) seg_rle_ws_kernel<false, 4><<<grid, nt, smem, s>>>(plane, d, kk, static_units, dbg);
+        else if (plain) seg_rle_ws_kernel<false, 3><<<grid, nt, smem, s>>>(plane, d, kk, static_units, dbg);
+        else seg_rle_ws_kernel<true, 3><<<grid, (K1W_MW + 3 + 1) * 32, k1w_smem(3), s>>>(plane, d, h->k, static_units, dbg);
         if (timeline) {
             std::vector<unsigned long long> t(4 * grid);
             TB_CUDA(cudaStreamSynchronize(s));
@@ -1324,16 +1564,16 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
             TB_CUDA(cudaFuncSetAttribute(seg_rle_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM));
             attr_done = true;
         }
-        if (plain) seg_rle_tma_kernel<false><<<g1, K1T_NT, K1T_SMEM, s>>>(frames_dev, d, kk, fpc);
-        else seg_rle_tma_kernel<true><<<g1, K1T_NT, K1T_SMEM, s>>>(frames_dev, d, h->k, fpc);
+        if (plain) seg_rle_tma_kernel<false><<<g1, K1T_NT, K1T_SMEM, s>>>(plane, d, kk, fpc);
+        else seg_rle_tma_kernel<true><<<g1, K1T_NT, K1T_SMEM, s>>>(plane, d, h->k, fpc);
     } else {
-        if (plain) seg_rle_kernel<false><<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
-        else seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(frames_dev, d, h->k, fpc);
+        if (plain) seg_rle_kernel<false><<<g1, K1_NT, 0, s>>>(plane, d, h->k, fpc);
+        else seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(plane, d, h->k, fpc);
     }
     h->prof.mark(slot, 1);
     ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
     h->prof.mark(slot, 2);
-    d.bg = h->d_bg; d.bg_stride = 0; d.keep_mask = nullptr;        // crops difference against the real background
+    d.bg = h->d_bg; d.bg_stride = 0; d.keep_mask = nullptr; d.nz_plane = nullptr;   // crops difference against the real background
     blob_emit_kernel<<<dim3((unsigned)n, K3_SPLIT), K3_NT, 0, s>>>(frames_dev, d);
     h->prof.mark(slot, 3);
     h->launches += 3;
@@ -1360,7 +1600,7 @@ extern "C" int tb_seg_submit(tb_seg *h, const uint8_t *const *frames, int n, int
     TB_REQUIRE(n > 0 && n <= h->cfg.max_batch, TB_ERR_INVALID, "tb_seg_submit: n must be 1..max_batch");
     TB_REQUIRE(h->has_bg, TB_ERR_STATE, "tb_seg_submit: no background set (pipeline is paused until set_background)");
     TB_CUDA(cudaSetDevice(h->cfg.device));
-    const size_t W = h->d.W, H = h->d.H;
+    const size_t W = (size_t)h->d.W * h->d.CN, H = h->d.H;       // bytes per row
     if (stride <= 0) stride = (int64_t)W;
     bool contiguous = (size_t)stride == W;
     for (int i = 0; i < n; ++i) {
@@ -1391,7 +1631,7 @@ extern "C" int tb_seg_wait(tb_seg *h)
         if (t[1]) TB_CUDA(cudaMemcpyAsync(h->h_lines, d.lines, sizeof(tb_line) * (size_t)t[1], cudaMemcpyDeviceToHost, s));
         if (t[2]) TB_CUDA(cudaMemcpyAsync(h->h_pixels, d.pixels, (size_t)t[2], cudaMemcpyDeviceToHost, s));
         if (t[3] && h->last_fetch >= 2) {
-            TB_CUDA(cudaMemcpyAsync(h->h_crops, d.crops, (size_t)t[3] * d.crop_w * d.crop_h, cudaMemcpyDeviceToHost, s));
+            TB_CUDA(cudaMemcpyAsync(h->h_crops, d.crops, (size_t)t[3] * d.crop_w * d.crop_h * d.opx, cudaMemcpyDeviceToHost, s));
             TB_CUDA(cudaMemcpyAsync(h->h_crop_blob, d.crop_blob, sizeof(uint32_t) * (size_t)t[3], cudaMemcpyDeviceToHost, s));
         }
         TB_CUDA(cudaStreamSynchronize(s));
@@ -1456,6 +1696,20 @@ extern "C" int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t
     TB_REQUIRE(h->has_bg, TB_ERR_STATE, "tb_seg_debug_binary: no background set");
     TB_CUDA(cudaSetDevice(h->cfg.device));
     const size_t n = (size_t)h->d.W * h->d.H;
+    if (h->d.CN > 1) {
+        TB_CUDA(cudaMemcpyAsync(h->d_frames, frame_host, n * h->d.CN, cudaMemcpyHostToDevice, h->stream));
+        int r = seg_to_gray(h, h->d_frames, 1, h->stream);
+        if (r != TB_OK) return r;
+        h->gray_valid = false;
+        const uint8_t *mask = nullptr;
+        if (h->morph && (r = seg_morph(h, h->d_gray, 1, h->stream, &mask)) != TB_OK) return r;
+        binary_image_color_kernel<<<592, 256, 0, h->stream>>>(h->d_frames, h->d_gray, h->d_bg, mask, h->d_tmp, n, h->k, h->d.CN, h->d.enc);
+        h->launches += 1;
+        TB_CUDA(cudaGetLastError());
+        TB_CUDA(cudaMemcpyAsync(out_host, h->d_tmp, n * h->d.opx, cudaMemcpyDeviceToHost, h->stream));
+        TB_CUDA(cudaStreamSynchronize(h->stream));
+        return TB_OK;
+    }
     TB_CUDA(cudaMemcpyAsync(h->d_frames, frame_host, n, cudaMemcpyHostToDevice, h->stream));
     if (h->morph) {
         const uint8_t *mask = nullptr;
@@ -1502,6 +1756,8 @@ extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch)
                "tb_seg_rethreshold: handles differ in frame size or device");
     TB_REQUIRE(det->last_n <= trk->cfg.max_batch, TB_ERR_INVALID, "tb_seg_rethreshold: tracker-side max_batch too small");
     TB_REQUIRE(trk->has_bg, TB_ERR_STATE, "tb_seg_rethreshold: the tracker-side handle has no background");
+    TB_REQUIRE(det->d.enc == 0 && trk->d.CN == 1, TB_ERR_INVALID,
+               "tb_seg_rethreshold: built for gray encoding (the tracker-side handle takes the grey plane: channels = 1)");
     TB_REQUIRE(!trk->pending, TB_ERR_STATE, "tb_seg_rethreshold: the tracker-side handle has a pending batch");
     TB_CUDA(cudaSetDevice(det->cfg.device));
     const size_t px = (size_t)det->d.W * det->d.H;
@@ -1515,5 +1771,10 @@ extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch)
     paint_blobs_kernel<<<148 * 4, 256, 0, s>>>(det->d.recs, det->d.totals, det->d.lines, trk->keep_mask, det->d.W, det->d.H);
     trk->launches += 1;
     TB_CUDA(cudaGetLastError());
-    return seg_launch(trk, det->last_frames_dev, n, s, fetch, trk->keep_mask);
+    const uint8_t *plane = det->last_frames_dev;
+    if (det->d.CN > 1) {                       // colour frames, gray encoding: re-threshold the grey plane
+        if (!det->gray_valid) { int r = seg_to_gray(det, det->last_frames_dev, n, s); if (r != TB_OK) return r; }
+        plane = det->d_gray;
+    }
+    return seg_launch(trk, plane, n, s, fetch, trk->keep_mask);
 }

@@ -53,3 +53,16 @@ class BlobWorld:
 
     def frames(self, n):
         return np.stack([self.frame() for _ in range(n)])
+
+
+def to_color(gray: np.ndarray, seed=0, channels=3) -> np.ndarray:
+    """Grey frames / background (..., H, W) -> interleaved B,G,R(,A) images (..., H, W, channels): every channel is the
+    grey value times a fixed gain plus a small per-pixel offset, so that cvtColor of the result stays close to the
+    input (the colour variant of the same workload; video sources hand TRex BGR(A) frames)."""
+    rng = np.random.default_rng(seed)
+    g = gray.astype(np.int16)[..., None]
+    gains = np.array([0.9, 1.0, 1.1])
+    out = np.clip(np.rint(g * gains) + rng.integers(-1, 2, gray.shape + (3,)), 0, 255).astype(np.uint8)
+    if channels == 4:
+        out = np.concatenate([out, np.full(gray.shape + (1,), 255, np.uint8)], -1)
+    return out
