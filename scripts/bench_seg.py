@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Micro-benchmark of the segmentation kernels alone (K1 seg_rle, K2 ccl_label, K3 blob_emit) on resident
 synthetic 1080p batches; prints per-kernel ms and the HBM roofline fraction of K1.
-Knobs (env): TB_SEG_FPC (frames per CTA), TB_SEG_NO_TMA=1 (register-streaming K1)."""
+Knobs (env): TB_SEG_FPC (frames per CTA), TB_SEG_NO_TMA=1 (register-streaming K1).
+Usage: bench_seg.py [B] [reps] [channels] [gray|rgb8]   (channels 3/4: BGR/BGRA frames, cvtColor fused into K1)"""
 import json
 import os
 import sys
@@ -13,13 +14,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import trex_b200  # noqa: E402
 from trex_b200.synthetic import BlobWorld  # noqa: E402
 
+from trex_b200.synthetic import to_color  # noqa: E402
+
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+CN = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+ENC = sys.argv[4] if len(sys.argv) > 4 else "gray"
 world = BlobWorld(n_blobs=100, seed=1234)
 src = world.frames(16)
+bg = world.bg
+if CN > 1:
+    src = to_color(src, seed=1, channels=CN)
+    bg3 = to_color(world.bg, seed=2, channels=3)
+    bg = bg3 if ENC == "rgb8" else ((3735 * bg3[..., 0].astype(np.int64) + 19235 * bg3[..., 1].astype(np.int64) + 9798 * bg3[..., 2].astype(np.int64) + 16384) >> 15).astype(np.uint8)
 dev = torch.device("cuda", 0)
 pool = [torch.from_numpy(src[np.random.default_rng(i).permutation(np.arange(B) % 16)]).to(dev) for i in range(4)]
-bs = trex_b200.BackgroundSubtraction(world.bg, max_batch=B, max_individuals=128)
+bs = trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding=ENC), max_batch=B, max_individuals=128, channels=CN)
 stream = torch.cuda.Stream(dev)
 for i in range(3):
     bs.apply_device(pool[i % 4].data_ptr(), B, stream.cuda_stream)
@@ -32,7 +42,7 @@ ms, n = bs.kernel_ms()
 tot = bs.totals()
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
 k1 = ms["seg_rle"] / n
-alg = B * 1920 * 1080 + 8 * tot[1]
-print(json.dumps({"B": B, "fpc": os.environ.get("TB_SEG_FPC"), "no_tma": os.environ.get("TB_SEG_NO_TMA"),
+alg = B * 1920 * 1080 * CN + 8 * tot[1]
+print(json.dumps({"B": B, "channels": CN, "encoding": ENC, "fpc": os.environ.get("TB_SEG_FPC"), "no_tma": os.environ.get("TB_SEG_NO_TMA"),
                   "seg_rle_ms": k1, "GBps": alg / k1 / 1e6, "frac": alg / k1 / 1e6 / peak,
                   "ccl_ms": ms["ccl_label"] / n, "emit_ms": ms["blob_emit"] / n, "blobs": tot[0]}))

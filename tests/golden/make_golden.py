@@ -72,24 +72,25 @@ def make_vi():
     import visual_identification_network_torch as ref_net
     from oracle import vi
     out = {}
-    for tag, M in (("m100", 100), ("m8", 8)):
-        sd0 = vi.init_state_dict(M, 1, 80, 80, seed=0, perturb_norm=False)
+    for tag, M, CI in (("m100", 100, 1), ("m8", 8, 1), ("m16c3", 16, 3)):       # c3: rgb8 crops (meta_encoding rgb8)
+        sd0 = vi.init_state_dict(M, CI, 80, 80, seed=0, perturb_norm=False)
         torch.manual_seed(0)
-        ref = ref_net.ModelFetcher().get_model("v118_3", M, 1, 80, 80, device="cpu")
+        ref = ref_net.ModelFetcher().get_model("v118_3", M, CI, 80, 80, device="cpu")
         ref_sd = ref.state_dict()
         # the oracle's init must consume the RNG exactly like the reference's constructor
         for k, v in sd0.items():
             assert torch.equal(ref_sd[k], v), k
-        sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=0, perturb_norm=True))
+        sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, CI, 80, 80, seed=0, perturb_norm=True))
         ref.load_state_dict(sd); ref.eval()
         rng = np.random.default_rng(7)
-        crops = np.zeros((6, 80, 80, 1), np.uint8)
+        crops = np.zeros((6, 80, 80, CI), np.uint8)
         for n in range(6):     # blob-like: an ellipse of grey values on zero background
             yy, xx = np.mgrid[0:80, 0:80]
             a, b_, th = rng.uniform(12, 30), rng.uniform(4, 9), rng.uniform(0, np.pi)
             u = (xx - 40) * np.cos(th) + (yy - 40) * np.sin(th); v = -(xx - 40) * np.sin(th) + (yy - 40) * np.cos(th)
             m = (u / a) ** 2 + (v / b_) ** 2 <= 1
-            crops[n, ..., 0][m] = rng.integers(20, 200, m.sum())
+            for c in range(CI):
+                crops[n, ..., c][m] = rng.integers(20, 200, m.sum())
         with torch.no_grad():
             logits = ref(torch.from_numpy(crops).to(torch.float32)).numpy()
             probs = torch.softmax(torch.from_numpy(logits), 1).numpy()

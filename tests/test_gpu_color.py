@@ -150,3 +150,36 @@ def test_rethreshold_on_colour_frames_gray_encoding():
     for f in range(len(frames)):
         ref = seg.rethreshold(seg.segment_frame_color(frames[f], bg, _params(**kw)), bg, 40, seg.DIFF_ABSOLUTE)
         assert set(_as_list(got[f])) == ref.as_set(), f
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_rgb8_chain_frames_to_identities(precision):
+    """BGRA frames -> rgb8 blobs -> 80x80x3 crops -> V118_3(channels=3), chained on the device like bench.py does."""
+    import torch
+    import trex_b200
+    from oracle import seg, vi
+    frames, bg3 = _world(272, 480, 12, 21, 4)
+    kw = dict(detect_threshold=15, detect_size_filter=[(10, 100000)])
+    bs = _mk(bg3, 4, "rgb8", max_individuals=16, **kw)
+    M = 12
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 3, 80, 80, seed=0))
+    net = trex_b200.VINetwork(M, channels=3, max_images=64, precision=precision)
+    net.load_weights(sd)
+    bs.apply(frames)
+    crops, _ = bs.crops()
+    exp = []
+    for f in range(len(frames)):
+        ref = seg.segment_frame_color(frames[f], bg3, _params(**kw), encoding=seg.ENC_RGB8)
+        exp += [seg.crop_blob_rgb(*ref.blob(k), bg3, seg.DIFF_ABSOLUTE) for k in range(min(len(ref), 16))]
+    exp = np.stack(exp)
+    assert np.array_equal(crops, exp)
+    # device chain: crops never leave HBM
+    crops_p, ncrops_p, _, _, _ = bs.device_results()
+    dev = torch.device("cuda", 0)
+    probs = torch.zeros((64, M), dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream(dev)
+    bs.apply_device(torch.from_numpy(frames).to(dev).data_ptr(), len(frames), stream.cuda_stream)
+    net.predict_device(crops_p, 64, ncrops_p, probs.data_ptr(), 0, stream.cuda_stream)
+    net.wait()
+    got = probs.cpu().numpy()[:len(exp)]
+    assert np.abs(got - vi.predict(sd, exp)).max() < 1e-3

@@ -132,3 +132,31 @@ def test_top1_device_outputs():
     assert np.array_equal(ids.cpu().numpy(), pr.argmax(1))
     assert np.allclose(p.cpu().numpy(), pr.max(1), rtol=1e-6, atol=1e-7)
     assert np.abs(pr - vi.predict(sd, crops)).max() < TOL
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_rgb8_crops_three_input_channels(precision):
+    """meta_encoding rgb8: 80x80x3 crops (NHWC), conv1 3->16.  Golden = the reference's own V118_3(channels=3)."""
+    import trex_b200
+    from oracle import vi
+    g = np.load(os.path.join(GOLDEN, "vi_golden.npz"))
+    M = 16
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 3, 80, 80, seed=0))
+    assert vi.state_checksum(sd) == str(g["m16c3_checksum"])
+    net = trex_b200.VINetwork(M, channels=3, max_images=64, precision=precision)
+    net.load_weights(sd)
+    probs, logits = net.probabilities(g["m16c3_crops"], return_logits=True)
+    assert np.abs(logits - g["m16c3_logits"]).max() < TOL
+    assert np.abs(probs - g["m16c3_probs"]).max() < TOL
+    rng = np.random.default_rng(23)
+    n = 200                                              # more crops than SMs, 4 chunks
+    crops = np.zeros((n, 80, 80, 3), np.uint8)
+    for i in range(n):
+        h, w = rng.integers(8, 70), rng.integers(8, 70)
+        y, x = rng.integers(0, 80 - h), rng.integers(0, 80 - w)
+        crops[i, y:y + h, x:x + w] = rng.integers(0, 256, (h, w, 3))
+    crops[0] = 0; crops[1] = 255; crops[2, ..., 0] = 255; crops[3, ..., 2] = 255
+    probs, logits = net.probabilities(crops, return_logits=True)
+    ref = vi.forward_logits(sd, crops)
+    assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(probs - vi.predict(sd, crops)).max() < TOL

@@ -22,14 +22,14 @@ namespace tb {
 constexpr float BN_EPS = 1e-5f, LN_EPS = 1e-5f;
 
 // ------------------------------------------------------------------------------------------------
-// conv1: u8 crop [H][W] (C=1) -> pooled [H/2][W/2][16] fp32.  One CTA per image; each thread owns
-// pooled pixels (a 2x2 window of conv outputs) x 16 output channels.  ~2 % of the network's FLOPs.
+// conv1: u8 crop [H][W][C] (C = 1 gray, 3 rgb8: NHWC as the reference hands it over) -> pooled [H/2][W/2][16] fp32.
+// One CTA per image; each thread owns pooled pixels (a 2x2 window of conv outputs) x 16 output channels.
 // ------------------------------------------------------------------------------------------------
 constexpr int C1_NT = 256;
 
 __global__ void __launch_bounds__(C1_NT)
-conv1_kernel(const uint8_t *__restrict__ img, int H, int W, int n_max, const uint32_t *__restrict__ n_dev, int base,
-             const float *__restrict__ w /*[25][16]*/, const float *__restrict__ sc, const float *__restrict__ sh,
+conv1_kernel(const uint8_t *__restrict__ img, int H, int W, int C, int n_max, const uint32_t *__restrict__ n_dev, int base,
+             const float *__restrict__ w /*[25][C][16]*/, const float *__restrict__ sc, const float *__restrict__ sh,
              float *__restrict__ out)
 {
     extern __shared__ float sm[];
@@ -37,15 +37,15 @@ conv1_kernel(const uint8_t *__restrict__ img, int H, int W, int n_max, const uin
     const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
     if (n >= n_act) return;
     const int PW = W + 4, PH = H + 4;
-    float *patch = sm;                       // [PH][PW], zero halo
-    float *sw = sm + PH * PW;                // [25][16]
-    float *ssc = sw + 400, *ssh = ssc + 16;
-    const uint8_t *src = img + (size_t)n * H * W;
-    for (int i = threadIdx.x; i < PH * PW; i += C1_NT) {
-        int y = i / PW - 2, x = i % PW - 2;
-        patch[i] = (y >= 0 && y < H && x >= 0 && x < W) ? (float)src[y * W + x] : 0.f;
+    float *patch = sm;                       // [C][PH][PW], zero halo
+    float *sw = sm + C * PH * PW;            // [25][C][16]
+    float *ssc = sw + 400 * C, *ssh = ssc + 16;
+    const uint8_t *src = img + (size_t)n * H * W * C;
+    for (int i = threadIdx.x; i < C * PH * PW; i += C1_NT) {
+        int ci = i / (PH * PW), y = (i % (PH * PW)) / PW - 2, x = i % PW - 2;
+        patch[i] = (y >= 0 && y < H && x >= 0 && x < W) ? (float)src[(y * W + x) * C + ci] : 0.f;
     }
-    for (int i = threadIdx.x; i < 400; i += C1_NT) sw[i] = w[i];
+    for (int i = threadIdx.x; i < 400 * C; i += C1_NT) sw[i] = w[i];
     if (threadIdx.x < 16) { ssc[threadIdx.x] = sc[threadIdx.x]; ssh[threadIdx.x] = sh[threadIdx.x]; }
     __syncthreads();
     const int OW = W / 2, OH = H / 2;
@@ -57,16 +57,17 @@ conv1_kernel(const uint8_t *__restrict__ img, int H, int W, int n_max, const uin
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[a][c] = 0.f;
+        for (int ci = 0; ci < C; ++ci)
         for (int dy = 0; dy < 5; ++dy) {
             float r0[6], r1[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                r0[i] = patch[(2 * py + dy) * PW + 2 * px + i];
-                r1[i] = patch[(2 * py + dy + 1) * PW + 2 * px + i];
+                r0[i] = patch[(ci * PH + 2 * py + dy) * PW + 2 * px + i];
+                r1[i] = patch[(ci * PH + 2 * py + dy + 1) * PW + 2 * px + i];
             }
 #pragma unroll
             for (int dx = 0; dx < 5; ++dx) {
-                const float4 *wp = reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 16);
+                const float4 *wp = reinterpret_cast<const float4 *>(sw + ((dy * 5 + dx) * C + ci) * 16);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const float4 wv = wp[c4];
@@ -358,8 +359,8 @@ static int vi_dev(tb_vi *h, T **p, size_t n)
 extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
 {
     TB_REQUIRE(cfg && out, TB_ERR_INVALID, "tb_vi_create: null argument");
-    TB_REQUIRE(cfg->width == 80 && cfg->height == 80 && cfg->channels == 1, TB_ERR_INVALID,
-               "tb_vi_create: this release builds V118_3 for 80x80x1 crops (individual_image_size default, meta_encoding gray)");
+    TB_REQUIRE(cfg->width == 80 && cfg->height == 80 && (cfg->channels == 1 || cfg->channels == 3), TB_ERR_INVALID,
+               "tb_vi_create: this release builds V118_3 for 80x80 crops with 1 (meta_encoding gray) or 3 (rgb8) channels");
     TB_REQUIRE(cfg->num_classes > 0 && cfg->num_classes <= 1024, TB_ERR_INVALID, "tb_vi_create: num_classes must be 1..1024");
     TB_REQUIRE(cfg->max_images > 0, TB_ERR_INVALID, "tb_vi_create: max_images must be > 0");
     TB_REQUIRE(cfg->precision == 0 || cfg->precision == 1, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32) or 1 (bf16x3 tensor cores)");
@@ -370,10 +371,10 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     tb_vi *h = new tb_vi();
     h->cfg = *cfg;
     h->chunk = std::min(cfg->max_images, 4096);
-    const size_t CH = h->chunk, M = cfg->num_classes, N = cfg->max_images;
+    const size_t CH = h->chunk, M = cfg->num_classes, N = cfg->max_images, CI = cfg->channels;
     int r = TB_OK;
 #define A(p, n) if (r == TB_OK) r = vi_dev(h, &(p), (n))
-    A(h->w1, 400); A(h->s1, 16); A(h->t1, 16);
+    A(h->w1, 400 * CI); A(h->s1, 16); A(h->t1, 16);
     A(h->w2, 25 * 16 * 64); A(h->s2, 64); A(h->t2, 64);
     A(h->w3, 25 * 64 * 128); A(h->s3, 128); A(h->t3, 128);
     A(h->wf1, 12800 * 100); A(h->bf1, 100); A(h->lng, 100); A(h->lnb, 100);
@@ -384,7 +385,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
         h->fc_groups = (int)((CH + 127) / 128 * 16);
         A(h->in2, CH * tc::Conv2Cfg::IMG_BYTES + 256); A(h->in3, CH * tc::Conv3Cfg::IMG_BYTES + 256);
         A(h->fca, (size_t)2 * h->fc_groups * tc::FC_KC * 128);
-        A(h->w1t, (size_t)tc::Conv1T::W_BYTES);
+        A(h->w1t, (size_t)tc::Conv1T::W_BYTES * CI);
         A(h->w2t, (size_t)tc::Conv2D::W_BYTES); A(h->w3t, (size_t)25 * tc::Conv3Cfg::WTAP_BYTES);
         A(h->wfc, (size_t)2 * tc::FC_KC * tc::FC_N * 16);
         if (r == TB_OK) {   // halo positions are never written by the kernels: zero once
@@ -394,7 +395,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
         int dev_sms = 0;
         if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && dev_sms > 0) h->n_sms = dev_sms;
     }
-    A(h->d_img, N * 6400 + 16); A(h->d_probs, N * M); A(h->d_logits, N * M);
+    A(h->d_img, N * 6400 * CI + 16); A(h->d_probs, N * M); A(h->d_logits, N * M);
 #undef A
     if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
     if (r == TB_OK) {
@@ -524,7 +525,8 @@ extern "C" int tb_vi_commit(tb_vi *h)
     TB_REQUIRE(h, TB_ERR_INVALID, "tb_vi_commit: null handle");
     TB_CUDA(cudaSetDevice(h->cfg.device));
     int r;
-    if ((r = vi_conv(h, 1, 1, 16, h->w1, h->s1, h->t1))) return r;
+    const int CI = h->cfg.channels;
+    if ((r = vi_conv(h, 1, CI, 16, h->w1, h->s1, h->t1))) return r;
     if ((r = vi_conv(h, 2, 16, 64, h->w2, h->s2, h->t2))) return r;
     if ((r = vi_conv(h, 3, 64, 128, h->w3, h->s3, h->t3))) return r;
     const int M = h->cfg.num_classes;
@@ -553,13 +555,14 @@ extern "C" int tb_vi_commit(tb_vi *h)
         const std::vector<float> *c2, *c3;
         if ((r = vi_need(h, "model.conv2.weight", (size_t)64 * 16 * 25, &c2))) return r;
         if ((r = vi_need(h, "model.conv3.weight", (size_t)128 * 64 * 25, &c3))) return r;
-        {   // conv1 B operand [hi|lo][k-step j][k-chunk c][row = wp*16 + cout][8]: window row u = 2j+c, window col e;
+        {   // conv1 B operand [cin][hi|lo][k-step j][k-chunk c][row = wp*16 + cout][8]: window row u = 2j+c, window col e;
             // row (wp = 2i+jj, cout) holds the 5x5 filter shifted by (i, jj) inside the 6x8 window, BN scale folded
             const std::vector<float> *c1;
-            if ((r = vi_need(h, "model.conv1.weight", (size_t)16 * 25, &c1))) return r;
+            if ((r = vi_need(h, "model.conv1.weight", (size_t)16 * CI * 25, &c1))) return r;
             std::vector<float> sc1(16);
             TB_CUDA(cudaMemcpy(sc1.data(), h->s1, 16 * 4, cudaMemcpyDeviceToHost));
-            std::vector<uint16_t> wb(tc::Conv1T::W_BYTES / 2, 0);
+            std::vector<uint16_t> wb(tc::Conv1T::W_BYTES / 2 * CI, 0);
+            for (int ci = 0; ci < CI; ++ci)
             for (int j = 0; j < 3; ++j)
                 for (int c = 0; c < 2; ++c)
                     for (int wp = 0; wp < 4; ++wp)
@@ -568,8 +571,8 @@ extern "C" int tb_vi_commit(tb_vi *h)
                                 const int u = 2 * j + c, dy = u - (wp >> 1), dx = e - (wp & 1);
                                 if (dy < 0 || dy > 4 || dx < 0 || dx > 4) continue;
                                 uint16_t hi, lo;
-                                split_bf16_host((*c1)[(size_t)co * 25 + dy * 5 + dx] * sc1[co], hi, lo);
-                                const size_t idx = ((((size_t)j * 2 + c) * tc::Conv1T::N) + wp * 16 + co) * 8 + e;
+                                split_bf16_host((*c1)[((size_t)co * CI + ci) * 25 + dy * 5 + dx] * sc1[co], hi, lo);
+                                const size_t idx = (size_t)ci * (tc::Conv1T::W_BYTES / 2) + ((((size_t)j * 2 + c) * tc::Conv1T::N) + wp * 16 + co) * 8 + e;
                                 wb[idx] = hi;
                                 wb[(size_t)3 * 2 * tc::Conv1T::N * 8 + idx] = lo;
                             }
@@ -604,7 +607,8 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
     const int M = h->cfg.num_classes;
     static bool attr_done = false;
     if (!attr_done) {
-        TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(1)));
+        TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(3)));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
@@ -614,7 +618,8 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         const int n = std::min(h->chunk, n_max - base);
         const int slot = h->prof.begin(s);
         h->prof.mark(slot, 0);
-        conv1_tc_kernel<<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::SMEM, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
+        if (h->cfg.channels == 1) conv1_tc_kernel<1><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(1), s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
+        else conv1_tc_kernel<3><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(3), s>>>(img + (size_t)base * 6400 * 3, n, n_dev, base, h->w1t, h->t1, h->in2);
         h->prof.mark(slot, 1);
         conv2_2d_kernel<<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
         h->prof.mark(slot, 2);
@@ -649,10 +654,12 @@ static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n
     }
     for (int base = 0; base < n_max; base += h->chunk) {
         const int n = std::min(h->chunk, n_max - base);
-        const int c1_smem = (84 * 84 + 400 + 32) * 4;
+        const int CI = h->cfg.channels, c1_smem = (CI * 84 * 84 + 400 * CI + 32) * 4;
+        static bool c1_attr = false;
+        if (!c1_attr) { TB_CUDA(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * 84 * 84 + 1200 + 32) * 4)); c1_attr = true; }
         const int slot = h->prof.begin(s);
         h->prof.mark(slot, 0);
-        conv1_kernel<<<n, C1_NT, c1_smem, s>>>(img + (size_t)base * 6400, 80, 80, n, n_dev, base, h->w1, h->s1, h->t1, h->a1);
+        conv1_kernel<<<n, C1_NT, c1_smem, s>>>(img + (size_t)base * 6400 * CI, 80, 80, CI, n, n_dev, base, h->w1, h->s1, h->t1, h->a1);
         h->prof.mark(slot, 1);
         k2<<<dim3(n * 7, 1), CV_NT, SM2, s>>>(h->a1, n, n_dev, base, h->w2, h->s2, h->t2, h->a2);
         h->prof.mark(slot, 2);
@@ -691,7 +698,8 @@ extern "C" int tb_vi_predict(tb_vi *h, const uint8_t *images, int n, float *prob
     const int M = h->cfg.num_classes;
     for (int base = 0; base < n; base += h->cfg.max_images) {
         const int m = std::min(h->cfg.max_images, n - base);
-        TB_CUDA(cudaMemcpyAsync(h->d_img, images + (size_t)base * 6400, (size_t)m * 6400, cudaMemcpyHostToDevice, h->stream));
+        const size_t ib = (size_t)6400 * h->cfg.channels;
+        TB_CUDA(cudaMemcpyAsync(h->d_img, images + (size_t)base * ib, (size_t)m * ib, cudaMemcpyHostToDevice, h->stream));
         int r = vi_forward(h, h->d_img, m, nullptr, h->d_probs, logits ? h->d_logits : nullptr, h->stream);
         if (r) return r;
         TB_CUDA(cudaMemcpyAsync(probs + (size_t)base * M, h->d_probs, (size_t)m * M * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -463,10 +463,13 @@ struct Conv1T {
     static constexpr int P_BYTES = PROWS * PW * 16, IMG_BYTES = PROWS * IMG_PITCH;
     static constexpr int N = 64, W_BYTES = 2 * 3 * 2 * N * 16;       // [hi|lo][k-step][k-chunk][64 rows][8]
     static constexpr int NACC = 8, TILES_X = 5, TILES_Y = 3, TILES = TILES_X * TILES_Y;   // y0 = 0, 16, 24
-    static constexpr int SMEM = P_BYTES + IMG_BYTES + W_BYTES + 64 + 128;
+    static constexpr int smem(int cin) { return cin * (P_BYTES + IMG_BYTES + W_BYTES) + 64 + 128; }   // 3 channels: 217 KB
     static constexpr int THREADS = 64 + 256;
 };
 
+// CIN = 3 (rgb8 crops, NHWC u8): one decimated plane, one padded image and one weight block per input channel;
+// the three channels accumulate into the same TMEM columns (3 x 6 MMAs per tile).
+template <int CIN>
 __global__ void __launch_bounds__(Conv1T::THREADS, 1)
 conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__restrict__ n_dev, int base,
                 const uint8_t *__restrict__ wgt, const float *__restrict__ sh, uint8_t *__restrict__ out)
@@ -475,10 +478,10 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_acc_full[C::NACC], bar_acc_empty[C::NACC];
     __shared__ uint32_t s_tmem;
-    uint4 *s_p = reinterpret_cast<uint4 *>(smem);
-    uint8_t *s_img = smem + C::P_BYTES;
-    uint8_t *s_w = s_img + C::IMG_BYTES;
-    float *s_sh = reinterpret_cast<float *>(s_w + C::W_BYTES);
+    uint4 *s_p = reinterpret_cast<uint4 *>(smem);                      // [CIN] planes
+    uint8_t *s_img = smem + CIN * C::P_BYTES;                          // [CIN] padded images
+    uint8_t *s_w = s_img + CIN * C::IMG_BYTES;                         // [CIN] weight blocks
+    float *s_sh = reinterpret_cast<float *>(s_w + CIN * C::W_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
 
@@ -487,9 +490,9 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
         umma::fence_mbar_init();
     }
     if (warp == 1) umma::tmem_alloc(&s_tmem, 512);
-    for (int i = tid; i < C::W_BYTES / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(s_w)[i] = reinterpret_cast<const uint32_t *>(wgt)[i];
+    for (int i = tid; i < CIN * C::W_BYTES / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(s_w)[i] = reinterpret_cast<const uint32_t *>(wgt)[i];
     if (tid < 16) s_sh[tid] = sh[tid];
-    for (int i = tid; i < C::IMG_BYTES / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(s_img)[i] = 0u;   // zero halo, kept
+    for (int i = tid; i < CIN * C::IMG_BYTES / 4; i += C::THREADS) reinterpret_cast<uint32_t *>(s_img)[i] = 0u;   // zero halo, kept
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -498,19 +501,32 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
 
     for (int n = blockIdx.x; n < n_act; n += gridDim.x) {
         // ---- stage the crop: interior of the zero-padded u8 image, then the decimated bf16 plane ----
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)n * C::H * C::W);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)n * C::H * C::W * CIN);
         for (int i = tid; i < C::H * C::W / 4; i += C::THREADS) {
             const int y = i / (C::W / 4), x4 = i % (C::W / 4);
-            const uint32_t v = src[i];
-            uint16_t *d16 = reinterpret_cast<uint16_t *>(s_img + (y + 2) * C::IMG_PITCH + 2 + x4 * 4);   // 2-byte aligned
-            d16[0] = (uint16_t)v; d16[1] = (uint16_t)(v >> 16);
+            if (CIN == 1) {
+                const uint32_t v = src[i];
+                uint16_t *d16 = reinterpret_cast<uint16_t *>(s_img + (y + 2) * C::IMG_PITCH + 2 + x4 * 4);   // 2-byte aligned
+                d16[0] = (uint16_t)v; d16[1] = (uint16_t)(v >> 16);
+            } else {                                                   // 4 interleaved B,G,R pixels = 12 bytes -> 4 bytes per channel
+                const uint32_t w0 = src[3 * i], w1 = src[3 * i + 1], w2 = src[3 * i + 2];
+                const uint32_t ch[3] = {__byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210),    // bytes 0,3,6,9
+                                        __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210),    // bytes 1,4,7,10
+                                        __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410)};   // bytes 2,5,8,11
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    uint16_t *d16 = reinterpret_cast<uint16_t *>(s_img + ci * C::IMG_BYTES + (y + 2) * C::IMG_PITCH + 2 + x4 * 4);
+                    d16[0] = (uint16_t)ch[ci]; d16[1] = (uint16_t)(ch[ci] >> 16);
+                }
+            }
         }
         __syncthreads();
         // four pooled positions per step: 14 source bytes -> bf16 once; position j uses bytes 2j .. 2j+7
-        for (int i = tid; i < C::PROWS * (C::PW / 4); i += C::THREADS) {
-            const int yy = i / (C::PW / 4), p4 = i % (C::PW / 4);
-            const uint2 wa = *reinterpret_cast<const uint2 *>(s_img + yy * C::IMG_PITCH + p4 * 8);
-            const uint2 wb2 = *reinterpret_cast<const uint2 *>(s_img + yy * C::IMG_PITCH + p4 * 8 + 8);
+        for (int i = tid; i < CIN * C::PROWS * (C::PW / 4); i += C::THREADS) {
+            const int ci = i / (C::PROWS * (C::PW / 4)), ii = i % (C::PROWS * (C::PW / 4));
+            const int yy = ii / (C::PW / 4), p4 = ii % (C::PW / 4);
+            const uint2 wa = *reinterpret_cast<const uint2 *>(s_img + ci * C::IMG_BYTES + yy * C::IMG_PITCH + p4 * 8);
+            const uint2 wb2 = *reinterpret_cast<const uint2 *>(s_img + ci * C::IMG_BYTES + yy * C::IMG_PITCH + p4 * 8 + 8);
             const uint32_t ws[4] = {wa.x, wa.y, wb2.x, wb2.y};
             uint32_t ev[7];
 #pragma unroll
@@ -518,7 +534,7 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
                 const uint32_t b0 = (ws[(2 * k) >> 2] >> (8 * ((2 * k) & 3))) & 0xFFu, b1 = (ws[(2 * k + 1) >> 2] >> (8 * ((2 * k + 1) & 3))) & 0xFFu;
                 ev[k] = __byte_perm(__float_as_uint((float)b0), __float_as_uint((float)b1), 0x7632);
             }
-            uint4 *dst = s_p + yy * C::PW + p4 * 4;
+            uint4 *dst = s_p + ci * (C::P_BYTES / 16) + yy * C::PW + p4 * 4;
 #pragma unroll
             for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3]);
         }
@@ -540,11 +556,14 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
                     umma::fence_after_sync();
                     const uint32_t d = tm + buf * C::N;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const uint32_t pos = (uint32_t)((2 * y0 + 2 * j) * C::PW + tx * 8);
-                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)((j * 2 * C::N * 16) >> 4), idesc, j != 0);
-                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)(((3 + j) * 2 * C::N * 16) >> 4), idesc, 1);
-                    }
+                    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const uint32_t pos = (uint32_t)(ci * (C::P_BYTES / 16) + (2 * y0 + 2 * j) * C::PW + tx * 8);
+                            const uint32_t wo = (uint32_t)(ci * (C::W_BYTES / 16));
+                            umma::mma_bf16(d, a_base + pos, w_base + wo + (uint32_t)((j * 2 * C::N * 16) >> 4), idesc, (ci | j) != 0);
+                            umma::mma_bf16(d, a_base + pos, w_base + wo + (uint32_t)(((3 + j) * 2 * C::N * 16) >> 4), idesc, 1);
+                        }
                     umma::commit(&bar_acc_full[buf]);
                 }
             }
