@@ -883,11 +883,11 @@ __device__ __forceinline__ void uf_union(uint32_t *par, uint32_t a, uint32_t b)
     }
 }
 
-__global__ void __launch_bounds__(K2_NT)
-ccl_label_kernel(SegDev d)
+// General path: any run count up to rcap, any height; scratch in global memory (the union-find in shared memory up to
+// K2_SMEM_RUNS runs).  s_par: K2_SMEM_RUNS words of shared memory, ws: 34 words.
+__device__ void ccl_label_body(const SegDev &d, uint32_t *s_par, uint32_t *ws)
 {
-    __shared__ uint32_t ws[34];
-    __shared__ uint32_t s_par[K2_SMEM_RUNS];
+    const int K2_NT = (int)blockDim.x;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t R = d.run_count[f];
     uint32_t *tot = d.frame_tot + (size_t)f * 4;
@@ -998,13 +998,182 @@ ccl_label_kernel(SegDev d)
     }
 }
 
+
+// three exclusive block scans behind one set of barriers (ws: 3 x 34 words)
+__device__ __forceinline__ void block_excl_scan3(const uint32_t v[3], uint32_t *ws, uint32_t ex[3], uint32_t total[3])
+{
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = (blockDim.x + 31u) >> 5;
+    uint32_t inc[3] = {v[0], v[1], v[2]};
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc[q], d);
+            if (lane >= (unsigned)d) inc[q] += t;
+        }
+    __syncthreads();
+    if (lane == 31) { ws[warp] = inc[0]; ws[34 + warp] = inc[1]; ws[68 + warp] = inc[2]; }
+    __syncthreads();
+    if (warp < 3) {
+        uint32_t *w = ws + 34 * warp;
+        const uint32_t x = lane < nw ? w[lane] : 0u;
+        uint32_t winc = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= (unsigned)d) winc += t;
+        }
+        if (lane < nw) w[lane] = winc - x;
+        if (lane == 31) w[32] = winc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { total[q] = ws[34 * q + 32]; ex[q] = ws[34 * q + warp] + inc[q] - v[q]; }
+}
+
+// K2, fast path (the common case: <= 8192 runs per frame, <= 4352 rows): the raster-ordered runs (packed x0 | x1 << 16
+// and y), the union-find, the row table and the per-blob statistics all live in shared memory, every thread owns a
+// contiguous chunk of runs when roots are numbered (one block scan for the whole frame) and the three prefix sums
+// of the size filter share their barriers: ~16 barriers and no dependent global loads between them, instead of ~45
+// phases with global-memory binary searches.  Frames beyond the limits take ccl_label_body.
+constexpr int K2F_NT = 1024;
+constexpr uint32_t K2F_RUNS = K2_SMEM_RUNS, K2F_ROWS = 4352, K2F_BLOBS = 512;
+constexpr int K2F_SMEM = K2F_RUNS * 4 * 2 + K2F_RUNS * 2 + K2F_ROWS * 2 * 2 + K2F_BLOBS * 5 * 4;
+
+__global__ void __launch_bounds__(K2F_NT, 1)
+ccl_label_kernel(SegDev d)
+{
+    extern __shared__ __align__(16) uint8_t k2_dsm[];
+    __shared__ uint32_t ws[3 * 34];
+    uint32_t *s_par = reinterpret_cast<uint32_t *>(k2_dsm);
+    uint32_t *s_x = s_par + K2F_RUNS;
+    uint16_t *s_y = reinterpret_cast<uint16_t *>(s_x + K2F_RUNS);
+    uint16_t *s_rs = s_y + K2F_RUNS, *s_re = s_rs + K2F_ROWS;
+    uint32_t *s_st = reinterpret_cast<uint32_t *>(s_re + K2F_ROWS);          // [5][K2F_BLOBS]
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t R = d.run_count[f];
+    if (R > K2F_RUNS || R > d.rcap || (uint32_t)d.H > K2F_ROWS || (uint32_t)d.n_bands > K2F_RUNS) { ccl_label_body(d, s_par, ws); return; }
+    uint32_t *tot = d.frame_tot + (size_t)f * 4;
+    const size_t o = (size_t)f * d.rcap;
+    tb_line *runs = d.runs + o;
+    const tb_line *raw = d.runs_raw + o;
+    uint32_t *gpar = d.parent + o;
+    uint32_t *rs = d.row_start + (size_t)f * d.H, *re = d.row_end + (size_t)f * d.H;
+    const uint32_t *bbase = d.band_base + (size_t)f * d.n_bands, *bcnt = d.band_cnt + (size_t)f * d.n_bands;
+
+    // 1. raster order: exclusive scan of the band counts (offsets parked in s_par), then copy band chunks (a warp per band)
+    for (int y = tid; y < d.H; y += K2F_NT) { s_rs[y] = 0; s_re[y] = 0; }
+    uint32_t carry = 0;
+    for (int b0 = 0; b0 < d.n_bands; b0 += K2F_NT) {
+        const int b = b0 + tid;
+        uint32_t cnt = b < d.n_bands ? bcnt[b] : 0u, total;
+        const uint32_t ex = block_excl_scan(cnt, ws, total);
+        if (b < d.n_bands) s_par[b] = carry + ex;
+        carry += total;
+    }
+    __syncthreads();
+    for (int b = warp; b < d.n_bands; b += K2F_NT / 32) {
+        const uint32_t n = bcnt[b];
+        if (!n) continue;
+        const uint32_t src = bbase[b], dst = s_par[b];
+        for (uint32_t i = lane; i < n; i += 32) {
+            const tb_line r = raw[src + i];
+            runs[dst + i] = r;
+            s_x[dst + i] = (uint32_t)r.x0 | ((uint32_t)r.x1 << 16);
+            s_y[dst + i] = r.y;
+        }
+    }
+    __syncthreads();
+    // 2. union-find init, row table
+    for (uint32_t i = tid; i < R; i += K2F_NT) {
+        s_par[i] = i;
+        const uint32_t y = s_y[i];
+        if (i == 0 || s_y[i - 1] != y) s_rs[y] = (uint16_t)i;
+        if (i + 1 == R || s_y[i + 1] != y) s_re[y] = (uint16_t)(i + 1);
+    }
+    __syncthreads();
+    for (int y = tid; y < d.H; y += K2F_NT) { rs[y] = s_rs[y]; re[y] = s_re[y]; }      // K3 reads the global copy
+    // 3. unions with the runs of row y-1 (8-connectivity, HLine.h:90-92)
+    for (uint32_t i = tid; i < R; i += K2F_NT) {
+        const uint32_t y = s_y[i];
+        if (y == 0) continue;
+        const uint32_t s = s_rs[y - 1], e = s_re[y - 1];
+        if (s >= e) continue;
+        const uint32_t x = s_x[i], x0 = x & 0xFFFFu, x1 = x >> 16;
+        uint32_t lo = s, hi = e;                               // first j with x1[j] + 1 >= x0
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((s_x[mid] >> 16) + 1u < x0) lo = mid + 1; else hi = mid;
+        }
+        for (uint32_t j = lo; j < e && (s_x[j] & 0xFFFFu) <= x1 + 1u; ++j) uf_union(s_par, i, j);
+    }
+    __syncthreads();
+    // 4. flatten (label = root run index), then number the roots in raster order: every thread owns a chunk of runs
+    for (uint32_t i = tid; i < R; i += K2F_NT) {
+        const uint32_t root = uf_find(s_par, i);
+        gpar[i] = root;
+        if (root != i) s_par[i] = root;
+    }
+    __syncthreads();
+    const uint32_t per = (R + K2F_NT - 1) / K2F_NT, c0 = min(R, (uint32_t)tid * per), c1 = min(R, c0 + per);
+    uint32_t nroot = 0;
+    for (uint32_t i = c0; i < c1; ++i) nroot += s_par[i] == i;
+    uint32_t K;
+    uint32_t kx = block_excl_scan(nroot, ws, K);
+    for (uint32_t i = c0; i < c1; ++i)
+        if (s_par[i] == i) { s_par[i] = 0x80000000u | kx; d.b_root[o + kx] = i; ++kx; }     // a root's slot now holds its blob index
+    // 5. per-blob statistics (shared-memory atomics when the frame has <= K2F_BLOBS components)
+    const bool st_smem = K <= K2F_BLOBS;
+    uint32_t *npx = st_smem ? s_st : d.b_npx + o, *nl = st_smem ? s_st + K2F_BLOBS : d.b_nl + o;
+    uint32_t *xmin = st_smem ? s_st + 2 * K2F_BLOBS : d.b_xmin + o, *xmax = st_smem ? s_st + 3 * K2F_BLOBS : d.b_xmax + o;
+    uint32_t *ymax = st_smem ? s_st + 4 * K2F_BLOBS : d.b_ymax + o;
+    for (uint32_t k = tid; k < K; k += K2F_NT) { npx[k] = 0; nl[k] = 0; xmin[k] = 0xFFFFFFFFu; xmax[k] = 0; ymax[k] = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < R; i += K2F_NT) {
+        const uint32_t p = s_par[i];
+        const uint32_t k = ((p & 0x80000000u) ? p : s_par[p]) & 0x7FFFFFFFu;
+        const uint32_t x = s_x[i], x0 = x & 0xFFFFu, x1 = x >> 16;
+        atomicAdd(npx + k, x1 - x0 + 1u);
+        atomicAdd(nl + k, 1u);
+        atomicMin(xmin + k, x0);
+        atomicMax(xmax + k, x1);
+        atomicMax(ymax + k, (uint32_t)s_y[i]);
+    }
+    __syncthreads();
+    // 6. size filter (BackgroundSubtraction.cpp:259: lo <= npx*cm^2 < hi in float; :306 line limit), offsets of the kept blobs
+    uint32_t *loff = d.b_loff + o, *poff = d.b_poff + o, *kept = d.kept + o;
+    uint32_t kk = 0, kl = 0, kp = 0;
+    for (uint32_t k0 = 0; k0 < K; k0 += K2F_NT) {
+        const uint32_t k = k0 + tid;
+        uint32_t keep = 0, l = 0, px = 0;
+        if (k < K) {
+            l = nl[k]; px = npx[k];
+            keep = d.n_ranges == 0;
+            const double v = (double)((float)px * d.sqcm);
+            for (int q = 0; q < d.n_ranges; ++q) keep |= (v >= d.lo[q] && v < d.hi[q]);
+            keep = keep && l < 65535u;
+            if (st_smem) { d.b_xmin[o + k] = xmin[k]; d.b_xmax[o + k] = xmax[k]; d.b_ymax[o + k] = ymax[k]; }
+        }
+        const uint32_t v3[3] = {keep, keep ? l : 0u, keep ? px * (uint32_t)d.opx : 0u};      // pixel arena offsets count bytes
+        uint32_t e3[3], t3[3];
+        block_excl_scan3(v3, ws, e3, t3);
+        if (k < K && keep) { kept[kk + e3[0]] = k; loff[k] = kl + e3[1]; poff[k] = kp + e3[2]; }
+        kk += t3[0]; kl += t3[1]; kp += t3[2];
+    }
+    if (tid == 0) {
+        uint32_t status = 0;
+        if (kp > d.px_frame_cap) { status |= 2u; kk = 0; kl = 0; kp = 0; }
+        tot[0] = kk; tot[1] = kl; tot[2] = kp; tot[3] = status;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: one CTA per frame, one warp per kept blob.  The warp walks the blob's bounding box, one lane
 // per row, collecting the blob's runs in (y,x0) order (CPULabeling.cpp:256-323), then copies pixel
 // bytes (:307) and renders the individual crop (FilterCache.cpp:158-235).  Arena offsets of the
 // frame are the prefix sums over the batch of the totals K2 wrote.
 // ------------------------------------------------------------------------------------------------
-constexpr int K3_NT = 256, K3_SPLIT = 4;     // CTAs per frame: blobs are dealt round-robin to K3_SPLIT * 8 warps
+constexpr int K3_NT = 256, K3_SPLIT = 4;     // minimum CTAs per frame: blobs are dealt round-robin to split * 8 warps
 
 __global__ void __launch_bounds__(K3_NT)
 blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
@@ -1107,47 +1276,78 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
             if (do_crop) d.crop_blob[Cb + q] = Bb + q;
         }
         __syncwarp();                                      // lines / line_px / zero fill visible to the warp
-        // phase B: pixel bytes + crop.  32 lines are fetched at once (one per lane) and broadcast.
+        // phase B: pixel bytes + crop.  32 lines are fetched at once (one per lane); the warp then walks their pixels as
+        // one flat range, 64 pixels per step (two per lane): a pixel finds its line by a 5-step binary search over the
+        // lines' first-pixel indices (shuffles), so that short lines do not leave lanes idle and the loads of a step are
+        // all in flight before the first store.
         for (uint32_t lb = 0; lb < cl; lb += 32) {
-            tb_line mine = {0, 0, 0, 0}; uint32_t mypo = 0;
-            if (lb + lane < cl) { mine = d.lines[L0 + lb + lane]; mypo = d.line_px[L0 + lb + lane]; }
-            const uint32_t packed = (uint32_t)mine.x0 | ((uint32_t)mine.x1 << 16);
             const uint32_t cnt = min(32u, cl - lb);
-            for (uint32_t l = 0; l < cnt; ++l) {
-                const uint32_t xx = __shfl_sync(0xffffffffu, packed, l);
-                const uint32_t ly = __shfl_sync(0xffffffffu, (uint32_t)mine.y, l);
-                const uint32_t po = __shfl_sync(0xffffffffu, mypo, l);
-                const uint32_t lx0 = xx & 0xFFFFu, lx1 = xx >> 16;
-                for (uint32_t x = lx0 + lane; x <= lx1; x += 32) {
-                    const size_t pi = (size_t)ly * d.W + x;
-                    const int cx = (int)(x - bx0) + offx, cy = (int)(ly - by0) + offy;
-                    const bool in_crop = do_crop && cx >= 0 && cx < cw && cy >= 0 && cy < ch;
-                    if (opx == 1) {                            // gray encoding: the grey value (of a colour pixel: cvtColor / plane)
-                        const uint8_t v = (uint8_t)gray_px(frame + pi * CN, CN, d.cc);
-                        d.pixels[po + (x - lx0)] = v;
-                        if (in_crop) {
-                            int val = v;
-                            if (d.crop_method) {
-                                const int b = d.bg[pi];
-                                val = d.crop_method == 1 ? abs(b - val) : max(0, b - val);
-                            }
-                            crop[cy * cw + cx] = (uint8_t)val;
-                        }
-                    } else {                                   // rgb8: B,G,R; crops difference per channel (Background.h:238-262)
+            tb_line mine = {0, 0, 0, 0}; uint32_t mypo = 0, myq = 0xFFFFFFFFu;
+            if (lane < cnt) { mine = d.lines[L0 + lb + lane]; mypo = d.line_px[L0 + lb + lane]; myq = (mypo - P0) / (uint32_t)opx; }
+            const uint32_t packed = (uint32_t)mine.x0 | ((uint32_t)mine.x1 << 16);
+            const uint32_t qb = __shfl_sync(0xffffffffu, myq, 0);
+            const uint32_t qe = __shfl_sync(0xffffffffu, myq + (uint32_t)mine.x1 - mine.x0 + 1u, (int)cnt - 1);
+            for (uint32_t q0 = qb; q0 < qe; q0 += 64) {
+                uint32_t qq[2] = {q0 + lane, q0 + 32 + lane};
+                int li[2] = {0, 0};
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const uint8_t v = frame[pi * CN + k];
-                            d.pixels[po + (x - lx0) * 3 + k] = v;
-                            if (in_crop) {
-                                int val = v;
-                                if (d.crop_method) {
-                                    const int b = d.bg3[pi * 3 + k];
-                                    val = d.crop_method == 1 ? abs(b - val) : max(0, b - val);
-                                }
-                                crop[(cy * cw + cx) * 3 + k] = (uint8_t)val;
+                for (int step = 16; step > 0; step >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t v = __shfl_sync(0xffffffffu, myq, (li[u] + step) & 31);
+                        if (li[u] + step < (int)cnt && v <= qq[u]) li[u] += step;
+                    }
+                }
+                size_t pi[2]; uint32_t po[2]; int ci[2]; bool act[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t xx = __shfl_sync(0xffffffffu, packed, li[u]);
+                    const uint32_t ly = __shfl_sync(0xffffffffu, (uint32_t)mine.y, li[u]);
+                    const uint32_t lq = __shfl_sync(0xffffffffu, myq, li[u]);
+                    const uint32_t lp = __shfl_sync(0xffffffffu, mypo, li[u]);
+                    act[u] = qq[u] < qe;
+                    const uint32_t x = (xx & 0xFFFFu) + (qq[u] - lq);
+                    pi[u] = (size_t)ly * d.W + x;
+                    po[u] = lp + (qq[u] - lq) * (uint32_t)opx;
+                    const int cx = (int)(x - bx0) + offx, cy = (int)(ly - by0) + offy;
+                    ci[u] = (do_crop && cx >= 0 && cx < cw && cy >= 0 && cy < ch) ? cy * cw + cx : -1;
+                }
+                if (opx == 1) {                                // gray encoding: the grey value (of a colour pixel: cvtColor / plane)
+                    uint32_t v[2] = {0, 0}; int bgv[2] = {0, 0};
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (act[u]) {
+                            v[u] = gray_px(frame + pi[u] * CN, CN, d.cc);
+                            if (d.crop_method && ci[u] >= 0) bgv[u] = d.bg[pi[u]];
+                        }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (act[u]) {
+                            d.pixels[po[u]] = (uint8_t)v[u];
+                            if (ci[u] >= 0) {
+                                int val = (int)v[u];
+                                if (d.crop_method) val = d.crop_method == 1 ? abs(bgv[u] - val) : max(0, bgv[u] - val);
+                                crop[ci[u]] = (uint8_t)val;
                             }
                         }
-                    }
+                } else {                                       // rgb8: B,G,R; crops difference per channel (Background.h:238-262)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (act[u]) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const uint8_t v = frame[pi[u] * CN + k];
+                                d.pixels[po[u] + k] = v;
+                                if (ci[u] >= 0) {
+                                    int val = v;
+                                    if (d.crop_method) {
+                                        const int bb = d.bg3[pi[u] * 3 + k];
+                                        val = d.crop_method == 1 ? abs(bb - val) : max(0, bb - val);
+                                    }
+                                    crop[ci[u] * 3 + k] = (uint8_t)val;
+                                }
+                            }
+                        }
                 }
             }
         }
@@ -1571,10 +1771,15 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
         else seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(plane, d, h->k, fpc);
     }
     h->prof.mark(slot, 1);
-    ccl_label_kernel<<<n, K2_NT, 0, s>>>(d);
+    static bool k2_attr = false;
+    if (!k2_attr) { TB_CUDA(cudaFuncSetAttribute(ccl_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2F_SMEM)); k2_attr = true; }
+    ccl_label_kernel<<<n, K2F_NT, K2F_SMEM, s>>>(d);
     h->prof.mark(slot, 2);
     d.bg = h->d_bg; d.bg_stride = 0; d.keep_mask = nullptr; d.nz_plane = nullptr;   // crops difference against the real background
-    blob_emit_kernel<<<dim3((unsigned)n, K3_SPLIT), K3_NT, 0, s>>>(frames_dev, d);
+    // CTAs per frame: enough to fill the GPU's warp slots (6 resident CTAs per SM) at small batches
+    static const int k3_env = getenv("TB_SEG_K3_SPLIT") ? atoi(getenv("TB_SEG_K3_SPLIT")) : 0;
+    const int k3_split = k3_env > 0 ? k3_env : std::min(16, std::max(K3_SPLIT, (148 * 8 + n - 1) / n));
+    blob_emit_kernel<<<dim3((unsigned)n, (unsigned)k3_split), K3_NT, 0, s>>>(frames_dev, d);
     h->prof.mark(slot, 3);
     h->launches += 3;
     TB_CUDA(cudaGetLastError());
