@@ -609,6 +609,7 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
     if (!attr_done) {
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(1)));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(3)));
+        TB_CUDA(cudaFuncSetAttribute(conv1_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1P::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
@@ -618,7 +619,9 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         const int n = std::min(h->chunk, n_max - base);
         const int slot = h->prof.begin(s);
         h->prof.mark(slot, 0);
-        if (h->cfg.channels == 1) conv1_tc_kernel<1><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(1), s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
+        static const bool c1_nopipe = getenv("TB_VI_CONV1_NOPIPE") != nullptr;      // bring-up switch: the per-crop barrier variant
+        if (h->cfg.channels == 1 && !c1_nopipe) conv1_tc_pipe_kernel<<<std::min(n, h->n_sms), Conv1P::THREADS, Conv1P::SMEM, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
+        else if (h->cfg.channels == 1) conv1_tc_kernel<1><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(1), s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
         else conv1_tc_kernel<3><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(3), s>>>(img + (size_t)base * 6400 * 3, n, n_dev, base, h->w1t, h->t1, h->in2);
         h->prof.mark(slot, 1);
         conv2_2d_kernel<<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);

@@ -619,4 +619,171 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
     if (warp == 1) umma::tmem_dealloc(tm, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// conv1, C_in = 1, software-pipelined over crops (the default for grey crops).  Same GEMM formulation as above, but
+// the three stages of a crop run in different warps and overlap across crops:
+//   * 4 producer warps: crop n+1 from global memory -> padded u8 image -> decimated bf16 plane (double buffered),
+//   * 1 MMA warp: 15 tiles x 6 MMAs of crop n into a ring of 8 TMEM accumulators; a tcgen05.commit after the last
+//     tile of a crop frees its plane,
+//   * 8 epilogue warps: tiles of crop n-1 / n out of TMEM: max-pool (thread-local), shift, ReLU, hi/lo split, store.
+// No block-wide barrier inside the crop loop; everything is mbarrier hand-offs.
+// ------------------------------------------------------------------------------------------------
+struct Conv1P {
+    using C = Conv1T;
+    static constexpr int PRODUCERS = 128, THREADS = 64 + 256 + PRODUCERS;
+    static constexpr int SMEM = 2 * C::P_BYTES + C::IMG_BYTES + C::W_BYTES + 64 + 128;
+};
+
+__global__ void __launch_bounds__(Conv1P::THREADS, 1)
+conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__restrict__ n_dev, int base,
+                     const uint8_t *__restrict__ wgt, const float *__restrict__ sh, uint8_t *__restrict__ out)
+{
+    using C = Conv1T;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_acc_full[C::NACC], bar_acc_empty[C::NACC], bar_plane_full[2], bar_plane_empty[2];
+    __shared__ uint32_t s_tmem;
+    uint8_t *s_img = smem + 2 * C::P_BYTES;
+    uint8_t *s_w = s_img + C::IMG_BYTES;
+    float *s_sh = reinterpret_cast<float *>(s_w + C::W_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+
+    if (tid == 0) {
+        for (int i = 0; i < C::NACC; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_plane_full[i], 1); umma::mbar_init(&bar_plane_empty[i], 1); }
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(&s_tmem, 512);
+    for (int i = tid; i < C::W_BYTES / 4; i += Conv1P::THREADS) reinterpret_cast<uint32_t *>(s_w)[i] = reinterpret_cast<const uint32_t *>(wgt)[i];
+    if (tid < 16) s_sh[tid] = sh[tid];
+    for (int i = tid; i < C::IMG_BYTES / 4; i += Conv1P::THREADS) reinterpret_cast<uint32_t *>(s_img)[i] = 0u;   // zero halo, kept
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tm = s_tmem;
+
+    if (warp >= 10) {                                                  // ---- producers ----
+        const int pt = tid - 320;
+        int it = 0;
+        for (int n = blockIdx.x; n < n_act; n += gridDim.x, ++it) {
+            const int b = it & 1;
+            uint4 *s_p = reinterpret_cast<uint4 *>(smem + b * C::P_BYTES);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)n * C::H * C::W);
+            uint32_t v[(C::H * C::W / 4 + Conv1P::PRODUCERS - 1) / Conv1P::PRODUCERS];
+#pragma unroll
+            for (int k = 0; k < (C::H * C::W / 4 + Conv1P::PRODUCERS - 1) / Conv1P::PRODUCERS; ++k) {   // all loads of the crop in flight
+                const int i = pt + k * Conv1P::PRODUCERS;
+                v[k] = i < C::H * C::W / 4 ? src[i] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < (C::H * C::W / 4 + Conv1P::PRODUCERS - 1) / Conv1P::PRODUCERS; ++k) {
+                const int i = pt + k * Conv1P::PRODUCERS;
+                if (i < C::H * C::W / 4) {
+                    const int y = i / (C::W / 4), x4 = i % (C::W / 4);
+                    uint16_t *d16 = reinterpret_cast<uint16_t *>(s_img + (y + 2) * C::IMG_PITCH + 2 + x4 * 4);   // 2-byte aligned
+                    d16[0] = (uint16_t)v[k]; d16[1] = (uint16_t)(v[k] >> 16);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            umma::mbar_wait(&bar_plane_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);       // the MMAs that read this plane have retired
+            for (int i = pt; i < C::PROWS * (C::PW / 4); i += Conv1P::PRODUCERS) {
+                const int yy = i / (C::PW / 4), p4 = i % (C::PW / 4);
+                const uint2 wa = *reinterpret_cast<const uint2 *>(s_img + yy * C::IMG_PITCH + p4 * 8);
+                const uint2 wb2 = *reinterpret_cast<const uint2 *>(s_img + yy * C::IMG_PITCH + p4 * 8 + 8);
+                const uint32_t ws4[4] = {wa.x, wa.y, wb2.x, wb2.y};
+                uint32_t ev[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {                  // bf16 pair (byte 2k, byte 2k+1): high halves of the fp32 patterns
+                    const uint32_t b0 = (ws4[(2 * k) >> 2] >> (8 * ((2 * k) & 3))) & 0xFFu, b1 = (ws4[(2 * k + 1) >> 2] >> (8 * ((2 * k + 1) & 3))) & 0xFFu;
+                    ev[k] = __byte_perm(__float_as_uint((float)b0), __float_as_uint((float)b1), 0x7632);
+                }
+                uint4 *dst = s_p + yy * C::PW + p4 * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3]);
+            }
+            umma::fence_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");             // plane complete; s_img free for the next crop
+            if (pt == 0) umma::mbar_arrive(&bar_plane_full[b]);
+        }
+    } else if (warp == 1) {                                            // ---- MMA issue ----
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_bf16_f32(128, C::N);
+            const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::N * 16, 128);
+            uint32_t a2 = 0;
+            int it = 0;
+            for (int n = blockIdx.x; n < n_act; n += gridDim.x, ++it) {
+                const int b = it & 1;
+                const uint64_t a_base = umma::smem_desc(umma::smem_u32(smem + b * C::P_BYTES), C::PW * 16, 2 * C::PW * 16);
+                umma::mbar_wait(&bar_plane_full[b], ((uint32_t)it >> 1) & 1u);
+                umma::fence_after_sync();
+                for (int t = 0; t < C::TILES; ++t, ++a2) {
+                    const int ty = t / C::TILES_X, tx = t % C::TILES_X;
+                    const int y0 = ty == 2 ? 24 : ty * 16;
+                    const uint32_t buf = a2 % C::NACC;
+                    umma::mbar_wait(&bar_acc_empty[buf], ((a2 / C::NACC) & 1) ^ 1);
+                    umma::fence_after_sync();
+                    const uint32_t d = tm + buf * C::N;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint32_t pos = (uint32_t)((2 * y0 + 2 * j) * C::PW + tx * 8);
+                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)((j * 2 * C::N * 16) >> 4), idesc, j != 0);
+                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)(((3 + j) * 2 * C::N * 16) >> 4), idesc, 1);
+                    }
+                    umma::commit(&bar_acc_full[buf]);
+                }
+                umma::commit(&bar_plane_empty[b]);
+            }
+        }
+    } else if (warp >= 2) {                                            // ---- epilogue ----
+        const int es = (warp - 2) >> 2, quarter = warp & 3;
+        const int r = quarter * 32 + lane, trow = r >> 3, tx8 = r & 7;
+        uint32_t ai = 0;
+        for (int n = blockIdx.x; n < n_act; n += gridDim.x, ai += C::TILES) {
+            for (int t = es; t < C::TILES; t += 2) {
+                const uint32_t a2 = ai + t, buf = a2 % C::NACC;
+                const int ty = t / C::TILES_X, tx = t % C::TILES_X;
+                const int y0 = ty == 2 ? 24 : ty * 16, ymin = ty == 2 ? 32 : y0;
+                umma::mbar_wait(&bar_acc_full[buf], (a2 / C::NACC) & 1);
+                umma::fence_after_sync();
+                uint32_t v[4][16];
+                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::N;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) umma::tmem_ld16(ta + 16 * q, v[q]);
+                umma::tmem_ld_wait();
+                umma::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);
+                const int y = y0 + trow, px = tx * 8 + tx8;
+                if (y >= ymin && y < C::PW) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int c = 0; c < 16; c += 2) {
+                        float m[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+                            m[u] = fmaxf(fmaxf(fmaxf(__uint_as_float(v[0][c + u]), __uint_as_float(v[1][c + u])),
+                                               fmaxf(__uint_as_float(v[2][c + u]), __uint_as_float(v[3][c + u]))) + s_sh[c + u], 0.f);
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        umma::split_bf16(m[0], h0, l0); umma::split_bf16(m[1], h1, l1);
+                        hi[c >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[c >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
+                    const int pos = (y + 2) * Conv2Cfg::WP + px + 2;
+                    uint8_t *o = out + (size_t)n * Conv2Cfg::IMG_BYTES + (size_t)pos * 16;
+                    constexpr size_t PLB = (size_t)Conv2Cfg::PL * 16;
+                    *reinterpret_cast<uint4 *>(o + 0 * PLB) = make_uint4(hi[0], hi[1], hi[2], hi[3]);      // hi, channels 0-7
+                    *reinterpret_cast<uint4 *>(o + 1 * PLB) = make_uint4(hi[4], hi[5], hi[6], hi[7]);      // hi, channels 8-15
+                    *reinterpret_cast<uint4 *>(o + 2 * PLB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4 *>(o + 3 * PLB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tm, 512);
+}
+
 }}  // namespace tb::tc
