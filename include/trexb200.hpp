@@ -35,16 +35,24 @@ inline void check(int rc, const char *what)
     if (rc != TB_OK) throw std::runtime_error(std::string(what) + ": " + tb_last_error());
 }
 
+// meta_encoding_t (T/core/default_config.cpp:59): the encodings this library builds
+enum class meta_encoding_t { gray = 0, rgb8 = 1 };
+
 class BackgroundSubtraction {
 public:
-    BackgroundSubtraction(int width, int height, int max_batch = 1, int max_individuals = 0, int device = 0)
+    // channels = Image::dims of the frames apply() receives (TileImage.images[0]): 1 gray, 3 BGR, 4 BGRA.
+    // Like BackgroundSubtraction::apply (T/python/BackgroundSubtraction.cpp:177-181), rgb8 refuses gray frames
+    // ("Invalid number of channels"): here at construction instead of per image.
+    BackgroundSubtraction(int width, int height, int max_batch = 1, int max_individuals = 0, int device = 0,
+                          int channels = 1, meta_encoding_t encoding = meta_encoding_t::gray)
     {
         tb_seg_config cfg{};
         cfg.device = device; cfg.width = width; cfg.height = height; cfg.max_batch = max_batch;
         cfg.max_crops_per_frame = max_individuals; cfg.crop_width = 80; cfg.crop_height = 80; cfg.crop_method = 1;
+        cfg.channels = channels; cfg.encoding = (int)encoding;
         check(tb_seg_create(&cfg, &_h), "tb_seg_create");
         tb_seg_default_params(&_p);
-        _w = width; _hgt = height;
+        _w = width; _hgt = height; _opx = encoding == meta_encoding_t::rgb8 ? 3 : 1;
     }
     ~BackgroundSubtraction() { tb_seg_destroy(_h); }
     BackgroundSubtraction(const BackgroundSubtraction &) = delete;
@@ -54,9 +62,10 @@ public:
     void update_settings() { check(tb_seg_set_params(_h, &_p), "tb_seg_set_params"); }
 
     // set_background(Image::Ptr&&): un-pauses the pipeline (BackgroundSubtraction.cpp:86-90)
+    // the average image has 1 channel for gray and 3 (B,G,R) for rgb8 (RawProcessing.cpp:343)
     void set_background(const uint8_t *average, int64_t stride = 0)
     {
-        check(tb_seg_set_background(_h, average, _w, _hgt, stride), "tb_seg_set_background");
+        check(tb_seg_set_background_c(_h, average, _w, _hgt, _opx, stride), "tb_seg_set_background");
     }
 
     // apply(std::vector<TileImage>&&): one blobs_t per image (BackgroundSubtraction.cpp:126-347)
@@ -75,7 +84,8 @@ public:
                 const tb_line *l = v.lines + (r.line_off - v.info.line_begin);
                 const uint8_t *px = v.pixels + (r.px_off - v.info.px_begin);
                 p.lines = std::make_unique<std::vector<HorizontalLine>>(l, l + r.n_lines);
-                p.pixels = std::make_unique<std::vector<uint8_t>>(px, px + r.n_pixels);
+                p.pixels = std::make_unique<std::vector<uint8_t>>(px, px + (size_t)r.n_pixels * _opx);
+                p.extra_flags = _opx == 3 ? (1u << 5) : 0;     // pv::Blob::Flags::is_rgb = bit 5 (CPULabeling.cpp:193, PVBlob.h:138-169)
                 p.bid = r.bid;
                 out[i].emplace_back(std::move(p));
             }
@@ -87,7 +97,7 @@ public:
 private:
     tb_seg *_h = nullptr;
     tb_seg_params _p{};
-    int _w = 0, _hgt = 0;
+    int _w = 0, _hgt = 0, _opx = 1;
 };
 
 // CPULabeling::run(const cv::Mat&, ...): label an already-binary image (any non-zero pixel is foreground)
@@ -103,10 +113,10 @@ inline blobs_t labeling_run(const uint8_t *image, int width, int height)
 
 class VINetwork {
 public:
-    VINetwork(int num_classes, int max_images = 4096, int device = 0) : _m(num_classes)
+    VINetwork(int num_classes, int max_images = 4096, int device = 0, int channels = 1) : _m(num_classes), _c(channels)
     {
         tb_vi_config cfg{};
-        cfg.device = device; cfg.width = 80; cfg.height = 80; cfg.channels = 1;
+        cfg.device = device; cfg.width = 80; cfg.height = 80; cfg.channels = channels;
         cfg.num_classes = num_classes; cfg.max_images = max_images; cfg.precision = 0;
         check(tb_vi_create(&cfg, &_h), "tb_vi_create");
     }
@@ -121,8 +131,9 @@ public:
     // probabilities(std::vector<Image::Ptr>&&) (sync form): N x M softmax rows, flat
     std::vector<float> probabilities(const std::vector<const uint8_t *> &images)
     {
-        std::vector<uint8_t> packed(images.size() * 6400);
-        for (size_t i = 0; i < images.size(); ++i) std::memcpy(packed.data() + i * 6400, images[i], 6400);
+        const size_t ib = (size_t)6400 * _c;
+        std::vector<uint8_t> packed(images.size() * ib);
+        for (size_t i = 0; i < images.size(); ++i) std::memcpy(packed.data() + i * ib, images[i], ib);
         std::vector<float> probs(images.size() * (size_t)_m);
         if (!images.empty()) check(tb_vi_predict(_h, packed.data(), (int)images.size(), probs.data(), nullptr), "tb_vi_predict");
         return probs;
@@ -130,7 +141,7 @@ public:
 
 private:
     tb_vi *_h = nullptr;
-    int _m;
+    int _m, _c;
 };
 
 }  // namespace trexb200

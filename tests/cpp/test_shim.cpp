@@ -37,6 +37,21 @@ int main()
         bs.set_background(bg.data());
         auto res = bs.apply({fr.data(), bg.data()});
         if (res[0].size() != 1 || res[1].size() != 0 || res[0][0].pixels->size() != 20) { std::printf("FAIL apply\n"); return 1; }
+        // colour frames: BGRA input, meta_encoding rgb8 -> B,G,R per blob pixel; gray frames are refused for rgb8
+        {
+            trexb200::BackgroundSubtraction cs(W, H, 1, 0, 0, 4, trexb200::meta_encoding_t::rgb8);
+            std::vector<uint8_t> bg3((size_t)W * H * 3, 100), f4((size_t)W * H * 4, 100);
+            for (int x = 10; x < 30; ++x) { uint8_t *q = &f4[((size_t)5 * W + x) * 4]; q[0] = 10; q[1] = 20; q[2] = 30; }
+            cs.settings().n_size_ranges = 0;
+            cs.update_settings();
+            cs.set_background(bg3.data());
+            auto cr = cs.apply({f4.data()});
+            if (cr[0].size() != 1 || cr[0][0].pixels->size() != 60 || (*cr[0][0].pixels)[0] != 10 || (*cr[0][0].pixels)[2] != 30 ||
+                cr[0][0].extra_flags == 0) { std::printf("FAIL rgb8\n"); return 1; }
+            bool refused = false;
+            try { trexb200::BackgroundSubtraction bad(W, H, 1, 0, 0, 1, trexb200::meta_encoding_t::rgb8); } catch (const std::exception &) { refused = true; }
+            if (!refused) { std::printf("FAIL rgb8 accepted gray frames\n"); return 1; }
+        }
         std::printf("OK %zu %zu\n", blobs[0].lines->size(), blobs[0].pixels->size());
     } catch (const std::exception &e) {
         std::printf("EXC %s\n", e.what());
