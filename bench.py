@@ -175,21 +175,33 @@ def run_ours(args):
     # ---- inputs: `pool` distinct batches resident in HBM (> L2 so no step is served from cache) ----
     n_src = min(B, 32)
     bg, src = make_inputs(n_src, seed=1234 + rank)
+    CN, rgb8 = args.channels, args.encoding == "rgb8"
+    if CN > 1:      # the colour variant of the same workload (not the headline): BGR(A) frames, cvtColor fused into K1
+        from trex_b200.synthetic import to_color
+        src = to_color(src, seed=rank, channels=CN)
+        bg3 = to_color(bg, seed=99, channels=3)
+        bg = bg3 if rgb8 else ((3735 * bg3[..., 0].astype(np.int64) + 19235 * bg3[..., 1].astype(np.int64) + 9798 * bg3[..., 2].astype(np.int64) + 16384) >> 15).astype(np.uint8)
     rng = np.random.default_rng(rank)
     pool = max(2, args.pool)
     host_batches = []
     for _ in range(pool):
         idx = rng.permutation(np.arange(B) % n_src)
-        t = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
+        t = torch.empty((B, H, W) if CN == 1 else (B, H, W, CN), dtype=torch.uint8, pin_memory=True)
         t.numpy()[:] = src[idx]
         host_batches.append(t)
     dev_batches = [t.to(dev, non_blocking=True) for t in host_batches]
     torch.cuda.synchronize()
 
-    settings = trex_b200.DetectSettings()       # reference defaults: T=15, abs diff, size filter [10,100000)
-    bs = trex_b200.BackgroundSubtraction(bg, settings=settings, max_batch=B, max_individuals=MAX_CROPS, device=local_rank)
-    net = trex_b200.VINetwork(M_CLASSES, max_images=B * MAX_CROPS, device=local_rank, precision=args.precision)
-    net.load_weights(weights())
+    settings = trex_b200.DetectSettings(meta_encoding=args.encoding)       # reference defaults: T=15, abs diff, size filter [10,100000)
+    bs = trex_b200.BackgroundSubtraction(bg, settings=settings, max_batch=B, max_individuals=MAX_CROPS, device=local_rank, channels=CN)
+    CI = 3 if rgb8 else 1
+    if CI == 1:
+        sd = weights()
+    else:
+        from trex_b200.weights import random_v118_3_state_dict
+        sd = random_v118_3_state_dict(M_CLASSES, seed=0, channels=3)
+    net = trex_b200.VINetwork(M_CLASSES, channels=CI, max_images=B * MAX_CROPS, device=local_rank, precision=args.precision)
+    net.load_weights(sd)
     crops_p, ncrops_p, _, recs_p, infos_p = bs.device_results()
     probs = torch.empty((B * MAX_CROPS, M_CLASSES), dtype=torch.float32, device=dev)
     probs_host = torch.empty((B * MAX_CROPS, M_CLASSES), dtype=torch.float32, pin_memory=True)
@@ -227,9 +239,9 @@ def run_ours(args):
         if k == 0:
             sbs, snet = bs, net
         else:
-            sbs = trex_b200.BackgroundSubtraction(bg, settings=settings, max_batch=B, max_individuals=MAX_CROPS, device=local_rank)
-            snet = trex_b200.VINetwork(M_CLASSES, max_images=B * MAX_CROPS, device=local_rank, precision=args.precision)
-            snet.load_weights(weights())
+            sbs = trex_b200.BackgroundSubtraction(bg, settings=settings, max_batch=B, max_individuals=MAX_CROPS, device=local_rank, channels=CN)
+            snet = trex_b200.VINetwork(M_CLASSES, channels=CI, max_images=B * MAX_CROPS, device=local_rank, precision=args.precision)
+            snet.load_weights(sd)
         s_id = torch.zeros(B * MAX_CROPS, dtype=torch.int32, device=dev)
         s_p = torch.zeros(B * MAX_CROPS, dtype=torch.float32, device=dev)
         slots.append(dict(bs=sbs, net=snet, stream=st, res=sbs.device_results(), pending=False, top_id=s_id, top_p=s_p,
@@ -257,7 +269,7 @@ def run_ours(args):
         sl["stream"].synchronize()
         sl["pending"] = False
         nb, nl, npx, nc = sl["bs"].totals()
-        return B * H * W, B * 32 + 16 + nb * 32 + nl * 8 + npx + B * N_INDIV * M_CLASSES * 4
+        return B * H * W * CN, B * 32 + 16 + nb * 32 + nl * 8 + npx + B * N_INDIV * M_CLASSES * 4
 
     def barrier():
         torch.cuda.synchronize()
@@ -332,11 +344,11 @@ def run_ours(args):
             per[k] = v / max(args.steps, 1)          # vi events are per chunk; sum over the step
         total_k = sum(per.values())
         kern = {}
-        alg_seg = B * W * H + 8 * runs_per_batch    # frame read once + run records written
+        alg_seg = B * W * H * CN + 8 * runs_per_batch    # frame read once + run records written
         kern["seg_rle"] = {"ms": per["seg_rle"], "share": per["seg_rle"] / total_k, "bound": "hbm",
                            "achieved": alg_seg / (per["seg_rle"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
         for k in ("conv1", "conv2", "conv3", "fc1"):
-            fl = 2 * MACS[k] * n_crops
+            fl = 2 * MACS[k] * n_crops * (CI if k == "conv1" else 1)
             kern[k] = {"ms": per[k], "share": per[k] / total_k, "bound": "tensor",
                        "achieved": fl / (per[k] * 1e-3) / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s"}
         for k in ("ccl_label", "blob_emit", "head"):
@@ -347,13 +359,14 @@ def run_ours(args):
         dom = max(("seg_rle", "conv1", "conv2", "conv3", "fc1"), key=lambda k: per[k])
         units = {"seg_rle": B, "conv2": n_crops, "conv3": n_crops}
         for k, per_unit in NCU_TRAFFIC.items():
-            kern[k]["traffic"] = per_unit * units[k]              # bytes per step, from the committed ncu capture
+            if CN == 1 or k != "seg_rle":
+                kern[k]["traffic"] = per_unit * units[k]          # bytes per step, from the committed ncu capture
         roof = {"kernel": dom, "bound": kern[dom]["bound"], "achieved": kern[dom]["achieved"], "peak": kern[dom]["peak"],
                 "unit": kern[dom]["unit"], "frac": kern[dom]["frac"], "traffic": kern[dom].get("traffic"), "peak_source": pk["src"],
                 "note": "algorithmic FLOPs (2*MAC per crop); the bf16x3 split issues 3 MMAs per k-step on top of that"}
         # cpu baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None
-        if world_size == 1 and not args.no_cpu:
+        if world_size == 1 and not args.no_cpu and CN == 1:
             from oracle import seg as oseg, vi as ovi
             oseg.build()
             if all_cpus:
@@ -372,8 +385,9 @@ def run_ours(args):
             "metric": "frames/sec (1080p, 100 indiv, bg-sub->blobs->CNN ID)", "value": value, "unit": "frames/s",
             "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (seg) + " + ("bf16x3 split, f32 accumulate (CNN)" if args.precision == "bf16x3" else "f32 (CNN)"), "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "crops_per_step_per_gpu": n_crops,
-                       "blobs_per_step": tot[0], "l2": f"rotating pool of {pool} distinct batches ({pool * B * H * W / 1e6:.0f} MB) > 126 MB L2",
+            "config": {"workload": WORKLOAD if CN == 1 else WORKLOAD.replace("u8 gray", f"u8 x{CN} (BGR{'A' if CN == 4 else ''}), meta_encoding {args.encoding}"),
+                       "frames_per_step_per_gpu": B, "crops_per_step_per_gpu": n_crops,
+                       "blobs_per_step": tot[0], "l2": f"rotating pool of {pool} distinct batches ({pool * B * H * W * CN / 1e6:.0f} MB) > 126 MB L2",
                        "parallelism": f"frame-batch data parallel x{world_size}" + (", NCCL all-gather of blob metadata" if world_size > 1 else "")},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "timing": "wall clock bracketed by device syncs, max over ranks; 2 batches in flight (H2D of batch i+1 overlaps kernels of batch i)",
@@ -396,6 +410,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the CPUs of its GPU's NUMA node")
+    ap.add_argument("--channels", type=int, default=1, choices=[1, 3, 4], help="bytes per pixel of the frames (3 BGR, 4 BGRA: colour variant, not the headline)")
+    ap.add_argument("--encoding", default="gray", choices=["gray", "rgb8"], help="meta_encoding (rgb8 needs --channels 3|4; crops and conv1 then have 3 channels)")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3"], help="CNN arithmetic: fp32 CUDA cores or bf16x3 split on tcgen05")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -326,3 +326,41 @@ def test_tracker_side_rethreshold(trk_kw, method):
             want = seg.crop_blob(b.lines, b.pixels, world.bg, seg.DIFF_ABSOLUTE)
             assert np.array_equal(crops[c + k], want)
         c += min(len(got[f]), 64)
+
+
+@pytest.mark.parametrize("case", ["many_small_blobs", "runs_at_smem_limit", "runs_beyond_smem_limit", "tall_frame"])
+def test_labeling_kernel_paths(case):
+    """K2's shared-memory fast path (<= 8192 runs, <= 4352 rows; per-blob statistics in shared memory up to 512
+    components, global atomics beyond) and the general path must agree with the oracle on either side of the limits."""
+    rng = np.random.default_rng(42)
+    if case == "tall_frame":
+        h, w = 4400, 64                                   # more rows than the fast path's row table
+    else:
+        h, w = 512, 768
+    bg = np.full((h, w), 100, np.uint8)
+    fr = bg.copy()
+    if case == "many_small_blobs":                        # ~1500 components, ~1500 runs: statistics via global atomics
+        ys, xs = np.mgrid[2:h - 2:8, 2:w - 2:32]
+        fr[ys.ravel(), xs.ravel()] = 20
+        fr[4::16, 5:40] = 30                              # a few longer runs
+    elif case == "runs_at_smem_limit":                    # exactly 8192 runs
+        pts = [(y, x) for y in range(0, h, 2) for x in range(0, w, 3)][:8192]
+        for y, x in pts:
+            fr[y, x] = 20
+    elif case == "runs_beyond_smem_limit":                # 8193 + noise: general path
+        pts = [(y, x) for y in range(0, h, 2) for x in range(0, w, 3)][:8193]
+        for y, x in pts:
+            fr[y, x] = 20
+        fr[1::2, ::5] = 10                                # joins runs vertically / diagonally
+    else:
+        for _ in range(300):
+            y, x = int(rng.integers(0, h - 6)), int(rng.integers(0, w - 6))
+            fr[y:y + int(rng.integers(1, 6)), x:x + int(rng.integers(1, 6))] = int(rng.integers(1, 60))
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 1000000)])
+    bs = _mk(bg, max_batch=2, dense=True, **kw)
+    got = bs.apply([fr, bg])
+    ref = _oracle(fr, bg, **kw)
+    if case == "runs_at_smem_limit":
+        assert bs.frame_info(0).n_runs == 8192
+    assert len(ref) > 0 and _as_list(got[0]) == ref.as_list()
+    assert got[1] == []
