@@ -363,7 +363,7 @@ def run_ours(args):
                 kern[k]["traffic"] = per_unit * units[k]          # bytes per step, from the committed ncu capture
         roof = {"kernel": dom, "bound": kern[dom]["bound"], "achieved": kern[dom]["achieved"], "peak": kern[dom]["peak"],
                 "unit": kern[dom]["unit"], "frac": kern[dom]["frac"], "traffic": kern[dom].get("traffic"), "peak_source": pk["src"],
-                "note": "algorithmic FLOPs (2*MAC per crop); the bf16x3 split issues 3 MMAs per k-step on top of that"}
+                "note": "algorithmic FLOPs (2*MAC per crop)" + ("; the bf16x3 split issues 3 MMAs per k-step on top of that" if args.precision == "bf16x3" else "")}
         # cpu baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None
         if world_size == 1 and not args.no_cpu and CN == 1:
@@ -384,7 +384,7 @@ def run_ours(args):
         line = {
             "metric": "frames/sec (1080p, 100 indiv, bg-sub->blobs->CNN ID)", "value": value, "unit": "frames/s",
             "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (seg) + " + ("bf16x3 split, f32 accumulate (CNN)" if args.precision == "bf16x3" else "f32 (CNN)"), "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (seg) + " + {"bf16x3": "bf16x3 split, f32 accumulate (CNN)", "fp16": "f16 operands, f32 accumulate (CNN conv2/conv3; conv1, fc1 bf16x3)", "fp32": "f32 (CNN)"}[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD if CN == 1 else WORKLOAD.replace("u8 gray", f"u8 x{CN} (BGR{'A' if CN == 4 else ''}), meta_encoding {args.encoding}"),
                        "frames_per_step_per_gpu": B, "crops_per_step_per_gpu": n_crops,
                        "blobs_per_step": tot[0], "l2": f"rotating pool of {pool} distinct batches ({pool * B * H * W * CN / 1e6:.0f} MB) > 126 MB L2",
@@ -412,7 +412,8 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--channels", type=int, default=1, choices=[1, 3, 4], help="bytes per pixel of the frames (3 BGR, 4 BGRA: colour variant, not the headline)")
     ap.add_argument("--encoding", default="gray", choices=["gray", "rgb8"], help="meta_encoding (rgb8 needs --channels 3|4; crops and conv1 then have 3 channels)")
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3"], help="CNN arithmetic: fp32 CUDA cores or bf16x3 split on tcgen05")
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "fp16"],
+                    help="CNN arithmetic: fp32 CUDA cores, bf16x3 split (3 MMAs per k-step) or fp16 (1 MMA per k-step in conv2/conv3) on tcgen05")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

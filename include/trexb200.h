@@ -198,7 +198,8 @@ typedef struct tb_vi_config {
     int32_t width, height, channels;   /* 80, 80, 1                                          */
     int32_t num_classes;               /* track_max_individuals                              */
     int32_t max_images;                /* capacity of one predict call                       */
-    int32_t precision;                 /* 0: fp32 CUDA cores (parity mode); 1: bf16x3 split on tcgen05 tensor cores */
+    int32_t precision;                 /* 0: fp32 CUDA cores (parity mode); 1: bf16x3 split on tcgen05 tensor cores;
+                                          2: fp16 operands, one MMA per k-step in conv2/conv3 (max|dlogit| ~3e-4) */
 } tb_vi_config;
 
 TB_API int tb_vi_create(const tb_vi_config *cfg, tb_vi **out);

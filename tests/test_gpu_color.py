@@ -152,7 +152,7 @@ def test_rethreshold_on_colour_frames_gray_encoding():
         assert set(_as_list(got[f])) == ref.as_set(), f
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16"])
 def test_rgb8_chain_frames_to_identities(precision):
     """BGRA frames -> rgb8 blobs -> 80x80x3 crops -> V118_3(channels=3), chained on the device like bench.py does."""
     import torch

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-PRECISIONS = ["fp32", "bf16x3"]
+PRECISIONS = ["fp32", "bf16x3", "fp16"]
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -160,3 +160,33 @@ def test_rgb8_crops_three_input_channels(precision):
     ref = vi.forward_logits(sd, crops)
     assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max()))
     assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
+
+
+def test_precision_margins():
+    """Measured max|dlogit| of the two tensor-core precisions against the fp32 oracle on blob-like crops (tolerance 1e-3):
+    bf16x3 (three MMAs per k-step) ~1e-5, fp16 (one MMA per k-step in conv2 / conv3) a few 1e-4."""
+    import trex_b200
+    from oracle import vi
+    M = 100
+    rng = np.random.default_rng(99)
+    n = 256
+    crops = np.zeros((n, 80, 80, 1), np.uint8)
+    yy, xx = np.mgrid[0:80, 0:80]
+    for i in range(n):
+        a, b_, th = rng.uniform(12, 30), rng.uniform(4, 9), rng.uniform(0, np.pi)
+        u = (xx - 40) * np.cos(th) + (yy - 40) * np.sin(th); v = -(xx - 40) * np.sin(th) + (yy - 40) * np.cos(th)
+        m = (u / a) ** 2 + (v / b_) ** 2 <= 1
+        crops[i, ..., 0][m] = rng.integers(20, 200, int(m.sum()))
+    worst = {}
+    for seed in (0, 1, 2):
+        sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=seed))
+        ref = vi.forward_logits(sd, crops)
+        for precision in ("bf16x3", "fp16"):
+            net = trex_b200.VINetwork(M, max_images=256, precision=precision)
+            net.load_weights(sd)
+            _, logits = net.probabilities(crops, return_logits=True)
+            worst[precision] = max(worst.get(precision, 0.0), float(np.abs(logits - ref).max()))
+            net.deinit()
+    print("max|dlogit|", worst)
+    assert worst["bf16x3"] < 1e-4
+    assert worst["fp16"] < TOL

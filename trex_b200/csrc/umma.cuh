@@ -2,6 +2,7 @@
 // Descriptor encodings follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor".
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tb { namespace umma {
@@ -28,6 +29,12 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N)
     return (1u << 4)                    // D format F32
          | (1u << 7) | (1u << 10)       // A, B format BF16
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// The same with FP16 A/B (format code 0): 11-bit significands, used by the single-MMA "fp16" precision.
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N)
+{
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols)

@@ -363,7 +363,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
                "tb_vi_create: this release builds V118_3 for 80x80 crops with 1 (meta_encoding gray) or 3 (rgb8) channels");
     TB_REQUIRE(cfg->num_classes > 0 && cfg->num_classes <= 1024, TB_ERR_INVALID, "tb_vi_create: num_classes must be 1..1024");
     TB_REQUIRE(cfg->max_images > 0, TB_ERR_INVALID, "tb_vi_create: max_images must be > 0");
-    TB_REQUIRE(cfg->precision == 0 || cfg->precision == 1, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32) or 1 (bf16x3 tensor cores)");
+    TB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32), 1 (bf16x3 tensor cores) or 2 (fp16 tensor cores)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("tb_vi_create: no CUDA device (there is no CPU fallback)"); return TB_ERR_CUDA; }
     TB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, TB_ERR_INVALID, "tb_vi_create: bad device ordinal");
@@ -382,8 +382,8 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     A(h->wf1, 12800 * 100); A(h->bf1, 100); A(h->lng, 100); A(h->lnb, 100);
     A(h->wf2, 100 * M); A(h->bf2, M);
     if (cfg->precision == 0) { A(h->a1, CH * 40 * 40 * 16); A(h->a2, CH * 20 * 20 * 64); A(h->a3, CH * 10 * 10 * 128); }
-    A(h->h1, CH * 100 * (cfg->precision == 1 ? tc::FC_SPLIT : 1));
-    if (cfg->precision == 1) {
+    A(h->h1, CH * 100 * (cfg->precision >= 1 ? tc::FC_SPLIT : 1));
+    if (cfg->precision >= 1) {
         h->fc_groups = (int)((CH + 127) / 128 * 16);
         A(h->in2, CH * tc::Conv2Cfg::IMG_BYTES + 256); A(h->in3, CH * tc::Conv3Cfg::IMG_BYTES + 256);
         A(h->fca, (size_t)2 * h->fc_groups * tc::FC_KC * 128);
@@ -460,9 +460,15 @@ static inline void split_bf16_host(float x, uint16_t &hi, uint16_t &lo)
     uint32_t u = (uint32_t)hi << 16; float fh; std::memcpy(&fh, &u, 4);
     lo = f2bf_host(x - fh);
 }
+// operand encoding of the conv2 / conv3 weights: bf16 hi + lo ("bf16x3"), or one fp16 value in the hi slot ("fp16")
+static inline void split_operand_host(float x, bool f16, uint16_t &hi, uint16_t &lo)
+{
+    if (f16) { hi = __half_as_ushort(__float2half_rn(x)); lo = 0; }
+    else split_bf16_host(x, hi, lo);
+}
 // tensor path: conv weight torch [Cout][Cin][25] -> B operand [tap][hi|lo][cin group][Cout][8] bf16
 // scale: BatchNorm scale per output channel, folded into the weights (y = conv(x, w*s) + t), or nullptr
-static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale)
+static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale, bool f16)
 {
     const int cin = G * 8;
     std::vector<uint16_t> b((size_t)25 * 2 * G * NOUT * 8);
@@ -471,7 +477,7 @@ static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, i
             for (int co = 0; co < NOUT; ++co)
                 for (int e = 0; e < 8; ++e) {
                     uint16_t hi, lo;
-                    split_bf16_host(w[((size_t)co * cin + g * 8 + e) * 25 + tap] * (scale ? scale[co] : 1.f), hi, lo);
+                    split_operand_host(w[((size_t)co * cin + g * 8 + e) * 25 + tap] * (scale ? scale[co] : 1.f), f16, hi, lo);
                     b[((((size_t)tap * 2 + 0) * G + g) * NOUT + co) * 8 + e] = hi;
                     b[((((size_t)tap * 2 + 1) * G + g) * NOUT + co) * 8 + e] = lo;
                 }
@@ -480,7 +486,7 @@ static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, i
 }
 
 // conv2 (2-D tile kernel): B operand [tap][cin group][Cout rows of W_hi, then Cout rows of W_lo][8] bf16
-static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale)
+static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale, bool f16)
 {
     const int cin = G * 8;
     std::vector<uint16_t> b((size_t)25 * G * 2 * NOUT * 8);
@@ -489,7 +495,7 @@ static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int 
             for (int co = 0; co < NOUT; ++co)
                 for (int e = 0; e < 8; ++e) {
                     uint16_t hi, lo;
-                    split_bf16_host(w[((size_t)co * cin + g * 8 + e) * 25 + tap] * (scale ? scale[co] : 1.f), hi, lo);
+                    split_operand_host(w[((size_t)co * cin + g * 8 + e) * 25 + tap] * (scale ? scale[co] : 1.f), f16, hi, lo);
                     b[((((size_t)tap * G + g) * 2 + 0) * NOUT + co) * 8 + e] = hi;
                     b[((((size_t)tap * G + g) * 2 + 1) * NOUT + co) * 8 + e] = lo;
                 }
@@ -553,7 +559,7 @@ extern "C" int tb_vi_commit(tb_vi *h)
         for (int k = 0; k < 100; ++k) w2t[(size_t)k * M + o] = (*w2)[(size_t)o * 100 + k];
     if ((r = vi_upload(h->wf2, w2t))) return r;
     if ((r = vi_upload(h->bf2, *b2))) return r;
-    if (h->cfg.precision == 1) {
+    if (h->cfg.precision >= 1) {
         const std::vector<float> *c2, *c3;
         if ((r = vi_need(h, "model.conv2.weight", (size_t)64 * 16 * 25, &c2))) return r;
         if ((r = vi_need(h, "model.conv3.weight", (size_t)128 * 64 * 25, &c3))) return r;
@@ -584,8 +590,9 @@ extern "C" int tb_vi_commit(tb_vi *h)
         std::vector<float> sc2(64), sc3(128);
         TB_CUDA(cudaMemcpy(sc2.data(), h->s2, 64 * 4, cudaMemcpyDeviceToHost));
         TB_CUDA(cudaMemcpy(sc3.data(), h->s3, 128 * 4, cudaMemcpyDeviceToHost));
-        if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data()))) return r;
-        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, sc3.data()))) return r;
+        const bool f16 = h->cfg.precision == 2;
+        if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data(), f16))) return r;
+        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, sc3.data(), f16))) return r;
         // fc1 B operand [hi|lo][kc = c8*100 + pp][112][8]; torch column = (c8*8+e)*100 + pp
         std::vector<uint16_t> wb((size_t)2 * tc::FC_KC * tc::FC_N * 8, 0);
         for (int kc = 0; kc < tc::FC_KC; ++kc)
@@ -612,23 +619,28 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(1)));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(3)));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1P::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
         attr_done = true;
     }
+    const int f16 = h->cfg.precision == 2;
     for (int base = 0; base < n_max; base += h->chunk) {
         const int n = std::min(h->chunk, n_max - base);
         const int slot = h->prof.begin(s);
         h->prof.mark(slot, 0);
         static const bool c1_nopipe = getenv("TB_VI_CONV1_NOPIPE") != nullptr;      // bring-up switch: the per-crop barrier variant
-        if (h->cfg.channels == 1 && !c1_nopipe) conv1_tc_pipe_kernel<<<std::min(n, h->n_sms), Conv1P::THREADS, Conv1P::SMEM, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
-        else if (h->cfg.channels == 1) conv1_tc_kernel<1><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(1), s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2);
-        else conv1_tc_kernel<3><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(3), s>>>(img + (size_t)base * 6400 * 3, n, n_dev, base, h->w1t, h->t1, h->in2);
+        if (h->cfg.channels == 1 && !c1_nopipe) conv1_tc_pipe_kernel<<<std::min(n, h->n_sms), Conv1P::THREADS, Conv1P::SMEM, s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2, f16);
+        else if (h->cfg.channels == 1) conv1_tc_kernel<1><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(1), s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2, f16);
+        else conv1_tc_kernel<3><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(3), s>>>(img + (size_t)base * 6400 * 3, n, n_dev, base, h->w1t, h->t1, h->in2, f16);
         h->prof.mark(slot, 1);
-        conv2_2d_kernel<<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
+        if (f16) conv2_2d_kernel<true><<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
+        else conv2_2d_kernel<false><<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
         h->prof.mark(slot, 2);
-        conv3_t_kernel<<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+        if (f16) conv3_t_kernel<true><<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+        else conv3_t_kernel<false><<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
         h->prof.mark(slot, 3);
         fc1_tc_kernel<<<dim3((n + 127) / 128, FC_SPLIT), NT, FC_SMEM, s>>>(h->fca, h->fc_groups, n, n_dev, base, h->wfc, h->h1, h->chunk);
         h->prof.mark(slot, 4);
@@ -646,7 +658,7 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
 
 static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n_dev, float *probs, float *logits, cudaStream_t s)
 {
-    if (h->cfg.precision == 1) return vi_forward_tc(h, img, n_max, n_dev, probs, logits, s);
+    if (h->cfg.precision >= 1) return vi_forward_tc(h, img, n_max, n_dev, probs, logits, s);
     const int M = h->cfg.num_classes;
     static bool attr_done = false;
     auto k2 = conv_kernel<16, 64, 40, 20, 3>;           // pooled 20x20: 7 tiles of 20x3

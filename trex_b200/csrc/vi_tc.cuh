@@ -69,6 +69,9 @@ struct Conv3T {
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
+// F16 ("fp16" precision): activations and weights are single fp16 planes (the hi slots of the same buffers) and every
+// k-step is ONE MMA instead of three; max|dlogit| ~ 3e-4 against fp32 (tolerance 1e-3), see DESIGN.md.
+template <bool F16>
 __global__ void __launch_bounds__(Conv3T::THREADS, 1)
 conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
                const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
@@ -100,21 +103,22 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
             uint32_t it = 0, tapc = 0;
             for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
                 umma::mbar_wait(&bar_in_empty, (it & 1) ^ 1);
-                umma::mbar_expect_tx(&bar_in_full, C::IN_BYTES);
+                constexpr int NPL = F16 ? C::G : 2 * C::G, WB = F16 ? C::WTAP_BYTES / 2 : C::WTAP_BYTES;   // fp16: hi slots only
+                umma::mbar_expect_tx(&bar_in_full, NPL * C::PIN * 16);
                 const uint8_t *src = in + (size_t)img * Conv3Cfg::IMG_BYTES;
-                for (int p = 0; p < 2 * C::G; ++p)
+                for (int p = 0; p < NPL; ++p)
                     umma::bulk_g2s(s_in + (size_t)p * C::PIN * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full);
                 for (int tap = 0; tap < 25; ++tap, ++tapc) {
                     const uint32_t s = tapc & 1;
                     umma::mbar_wait(&bar_w_empty[s], ((tapc >> 1) & 1) ^ 1);
-                    umma::mbar_expect_tx(&bar_w_full[s], C::WTAP_BYTES);
-                    umma::bulk_g2s(s_w + s * C::WTAP_BYTES, wgt + (size_t)tap * C::WTAP_BYTES, C::WTAP_BYTES, &bar_w_full[s]);
+                    umma::mbar_expect_tx(&bar_w_full[s], WB);
+                    umma::bulk_g2s(s_w + s * C::WTAP_BYTES, wgt + (size_t)tap * C::WTAP_BYTES, WB, &bar_w_full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma::idesc_bf16_f32(128, C::N);
+            const uint32_t idesc = F16 ? umma::idesc_f16_f32(128, C::N) : umma::idesc_bf16_f32(128, C::N);
             const uint64_t x_base = umma::smem_desc(umma::smem_u32(s_in), C::PIN * 16, 128);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
             uint32_t it = 0, tapc = 0;
@@ -138,8 +142,10 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                             const uint32_t w_lo = wofs + (1 * C::G + 2 * ks) * C::NOUT;
                             const uint32_t d = tm + (uint32_t)(t * C::N);
                             umma::mma_bf16(d, w_base + w_hi, x_base + x_hi, idesc, (tap | ks) != 0);
-                            umma::mma_bf16(d, w_base + w_hi, x_base + x_lo, idesc, 1);
-                            umma::mma_bf16(d, w_base + w_lo, x_base + x_hi, idesc, 1);
+                            if (!F16) {
+                                umma::mma_bf16(d, w_base + w_hi, x_base + x_lo, idesc, 1);
+                                umma::mma_bf16(d, w_base + w_lo, x_base + x_hi, idesc, 1);
+                            }
                         }
                     }
                     umma::commit(&bar_w_empty[s]);
@@ -210,6 +216,7 @@ struct Conv2D {
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(Conv2D::THREADS, 1)
 conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
                 const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
@@ -249,9 +256,10 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                 const int y0 = band == 2 ? 24 : band * 16;
                 const uint32_t b = it & 1;
                 umma::mbar_wait(&bar_in_empty[b], ((it >> 1) & 1) ^ 1);
-                umma::mbar_expect_tx(&bar_in_full[b], C::IN_BYTES);
+                constexpr int NPL = F16 ? C::G : 2 * C::G;                 // fp16: hi planes only
+                umma::mbar_expect_tx(&bar_in_full[b], NPL * C::BAND_POS * 16);
                 const uint8_t *src = in + (size_t)img * Conv2Cfg::IMG_BYTES + (size_t)y0 * C::WP * 16;
-                for (int p = 0; p < 2 * C::G; ++p)
+                for (int p = 0; p < NPL; ++p)
                     umma::bulk_g2s(s_in + (size_t)b * C::IN_BYTES + (size_t)p * C::BAND_POS * 16, src + (size_t)p * Conv2Cfg::PL * 16,
                                    C::BAND_POS * 16, &bar_in_full[b]);
             }
@@ -260,7 +268,8 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
         if (lane == 0) {
             // weights per tap: [group][64 rows W_hi + 64 rows W_lo][8]; one N = 128 MMA gives A_hi*(W_hi | W_lo),
             // one N = 64 MMA adds A_lo*W_hi: 14 KB of operand reads per tap instead of 18 KB for three N = 64 MMAs
-            const uint32_t idesc128 = umma::idesc_bf16_f32(128, 2 * C::NOUT), idesc64 = umma::idesc_bf16_f32(128, C::NOUT);
+            const uint32_t idesc128 = umma::idesc_bf16_f32(128, 2 * C::NOUT);
+            const uint32_t idesc64 = F16 ? umma::idesc_f16_f32(128, C::NOUT) : umma::idesc_bf16_f32(128, C::NOUT);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), 2 * C::NOUT * 16, 128);
             umma::mbar_wait(&bar_w_full, 0);
             uint32_t it = 0, ai = 0;
@@ -280,8 +289,11 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                         const uint32_t pos = (uint32_t)((tap / 5) * C::WP + (tap % 5) + tx * 8);
                         const uint32_t a_hi = 0 * C::G * C::BAND_POS + pos, a_lo = 1 * C::G * C::BAND_POS + pos;
                         const uint32_t w = (uint32_t)(tap * C::WTAP_BYTES >> 4);
-                        umma::mma_bf16(d, a_base + a_hi, w_base + w, idesc128, tap != 0);
-                        umma::mma_bf16(d, a_base + a_lo, w_base + w, idesc64, 1);
+                        if (F16) umma::mma_bf16(d, a_base + a_hi, w_base + w, idesc64, tap != 0);      // fp16 x fp16, one MMA per tap
+                        else {
+                            umma::mma_bf16(d, a_base + a_hi, w_base + w, idesc128, tap != 0);
+                            umma::mma_bf16(d, a_base + a_lo, w_base + w, idesc64, 1);
+                        }
                     }
                     umma::commit(&bar_acc_full[buf]);
                 }
@@ -308,14 +320,18 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                 const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::ACC_COLS + half * 32;
                 umma::tmem_ld16(ta, *reinterpret_cast<uint32_t (*)[16]>(&v[0]));
                 umma::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t (*)[16]>(&v[16]));
-                umma::tmem_ld16(ta + C::NOUT, *reinterpret_cast<uint32_t (*)[16]>(&vb[0]));
-                umma::tmem_ld16(ta + C::NOUT + 16, *reinterpret_cast<uint32_t (*)[16]>(&vb[16]));
+                if (!F16) {
+                    umma::tmem_ld16(ta + C::NOUT, *reinterpret_cast<uint32_t (*)[16]>(&vb[0]));
+                    umma::tmem_ld16(ta + C::NOUT + 16, *reinterpret_cast<uint32_t (*)[16]>(&vb[16]));
+                }
                 umma::tmem_ld_wait();
                 umma::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);     // values are in registers: buffer reusable
+                if (!F16) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vb[j]));
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vb[j]));
+                }
                 // 2x2 max-pool as a butterfly over the lane quad (r, r^1, r^8, r^9): after the exchange with
                 // lane^1 a lane keeps 16 of its 32 channels, after lane^8 it keeps 8 = one channel group.
                 // BN scale is folded into the weights, so pooling runs on raw accumulators (+shift is monotone).
@@ -345,8 +361,14 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                     }
                     constexpr int WPN = Conv3Cfg::WP, PLN = Conv3Cfg::PL, GN = Conv3Cfg::G;
                     const int pos = ((y >> 1) + 2) * WPN + ((tx * 8 + tx8) >> 1) + 2;
+                    if (F16) {
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2)
+                            hi[j >> 1] = (uint32_t)__half_as_ushort(__float2half_rn(fmaxf(m2[j] + tt[j], 0.f))) |
+                                         ((uint32_t)__half_as_ushort(__float2half_rn(fmaxf(m2[j + 1] + tt[j + 1], 0.f))) << 16);
+                    }
                     *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 0) * GN + g) * PLN + pos) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 1) * GN + g) * PLN + pos) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    if (!F16) *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 1) * GN + g) * PLN + pos) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
         }
@@ -472,7 +494,7 @@ struct Conv1T {
 template <int CIN>
 __global__ void __launch_bounds__(Conv1T::THREADS, 1)
 conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__restrict__ n_dev, int base,
-                const uint8_t *__restrict__ wgt, const float *__restrict__ sh, uint8_t *__restrict__ out)
+                const uint8_t *__restrict__ wgt, const float *__restrict__ sh, uint8_t *__restrict__ out, int f16out)
 {
     using C = Conv1T;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -594,18 +616,25 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
                         for (int u = 0; u < 2; ++u)
                             m[u] = fmaxf(fmaxf(fmaxf(__uint_as_float(v[0][c + u]), __uint_as_float(v[1][c + u])),
                                                fmaxf(__uint_as_float(v[2][c + u]), __uint_as_float(v[3][c + u]))) + s_sh[c + u], 0.f);
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        umma::split_bf16(m[0], h0, l0); umma::split_bf16(m[1], h1, l1);
-                        hi[c >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        lo[c >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        if (f16out) {                          // "fp16" precision: conv2 reads one fp16 plane
+                            hi[c >> 1] = (uint32_t)__half_as_ushort(__float2half_rn(m[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(m[1])) << 16);
+                            lo[c >> 1] = 0u;
+                        } else {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            umma::split_bf16(m[0], h0, l0); umma::split_bf16(m[1], h1, l1);
+                            hi[c >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[c >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
                     }
                     const int pos = (y + 2) * Conv2Cfg::WP + px + 2;
                     uint8_t *o = out + (size_t)n * Conv2Cfg::IMG_BYTES + (size_t)pos * 16;
                     constexpr size_t PLB = (size_t)Conv2Cfg::PL * 16;
                     *reinterpret_cast<uint4 *>(o + 0 * PLB) = make_uint4(hi[0], hi[1], hi[2], hi[3]);      // hi, channels 0-7
                     *reinterpret_cast<uint4 *>(o + 1 * PLB) = make_uint4(hi[4], hi[5], hi[6], hi[7]);      // hi, channels 8-15
-                    *reinterpret_cast<uint4 *>(o + 2 * PLB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4 *>(o + 3 * PLB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    if (!f16out) {
+                        *reinterpret_cast<uint4 *>(o + 2 * PLB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4 *>(o + 3 * PLB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
                 }
             }
         }
@@ -637,7 +666,7 @@ struct Conv1P {
 
 __global__ void __launch_bounds__(Conv1P::THREADS, 1)
 conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__restrict__ n_dev, int base,
-                     const uint8_t *__restrict__ wgt, const float *__restrict__ sh, uint8_t *__restrict__ out)
+                     const uint8_t *__restrict__ wgt, const float *__restrict__ sh, uint8_t *__restrict__ out, int f16out)
 {
     using C = Conv1T;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -765,18 +794,25 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                         for (int u = 0; u < 2; ++u)
                             m[u] = fmaxf(fmaxf(fmaxf(__uint_as_float(v[0][c + u]), __uint_as_float(v[1][c + u])),
                                                fmaxf(__uint_as_float(v[2][c + u]), __uint_as_float(v[3][c + u]))) + s_sh[c + u], 0.f);
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        umma::split_bf16(m[0], h0, l0); umma::split_bf16(m[1], h1, l1);
-                        hi[c >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        lo[c >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        if (f16out) {                          // "fp16" precision: conv2 reads one fp16 plane
+                            hi[c >> 1] = (uint32_t)__half_as_ushort(__float2half_rn(m[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(m[1])) << 16);
+                            lo[c >> 1] = 0u;
+                        } else {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            umma::split_bf16(m[0], h0, l0); umma::split_bf16(m[1], h1, l1);
+                            hi[c >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[c >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
                     }
                     const int pos = (y + 2) * Conv2Cfg::WP + px + 2;
                     uint8_t *o = out + (size_t)n * Conv2Cfg::IMG_BYTES + (size_t)pos * 16;
                     constexpr size_t PLB = (size_t)Conv2Cfg::PL * 16;
                     *reinterpret_cast<uint4 *>(o + 0 * PLB) = make_uint4(hi[0], hi[1], hi[2], hi[3]);      // hi, channels 0-7
                     *reinterpret_cast<uint4 *>(o + 1 * PLB) = make_uint4(hi[4], hi[5], hi[6], hi[7]);      // hi, channels 8-15
-                    *reinterpret_cast<uint4 *>(o + 2 * PLB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4 *>(o + 3 * PLB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    if (!f16out) {
+                        *reinterpret_cast<uint4 *>(o + 2 * PLB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4 *>(o + 3 * PLB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
                 }
             }
         }

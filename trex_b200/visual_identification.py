@@ -38,7 +38,7 @@ class VINetwork:
         self.num_classes, self.width, self.height, self.channels = int(num_classes), width, height, channels
         self.max_images = int(max_images)
         cfg = ViConfig(device=device, width=width, height=height, channels=channels, num_classes=self.num_classes,
-                       max_images=self.max_images, precision={"fp32": 0, "bf16x3": 1}[precision])
+                       max_images=self.max_images, precision={"fp32": 0, "bf16x3": 1, "fp16": 2}[precision])
         self._h = C.c_void_p()
         check(lib().tb_vi_create(C.byref(cfg), C.byref(self._h)))
         self.batch_size = batch_size_for(num_classes)
