@@ -31,7 +31,8 @@ MAX_CROPS = 128
 WORKLOAD = "synthetic 1920x1080 u8 gray, 100 individuals, bg-sub+threshold+CCL+80x80 crops+V118_3 CNN (random-init weights)"
 # DRAM traffic per unit (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture divided by the
 # units of that launch; profiles/r1_final_ncu_summary.txt and profiles/r1_seg_rle_v1_ncu_details.csv)
-NCU_TRAFFIC = {"seg_rle": (134.87e6 + 3.59e6) / 64, "conv2": (507.7e6 + 385.1e6) / 4096, "conv3": (614.06e6 + 184.99e6) / 4096}
+NCU_TRAFFIC = {"bf16x3": {"seg_rle": (267.87e6 + 6.47e6) / 128, "conv2": (507.7e6 + 385.1e6) / 4096, "conv3": (614.06e6 + 184.99e6) / 4096},
+               "fp16": {"seg_rle": (267.87e6 + 6.47e6) / 128}, "fp32": {"seg_rle": (267.87e6 + 6.47e6) / 128}}
 MACS = {"conv1": 2.56e6, "conv2": 40.96e6, "conv3": 81.92e6, "fc1": 1.28e6, "head": 100.0 * M_CLASSES}
 
 
@@ -358,7 +359,7 @@ def run_ours(args):
                 v["frac"] = v["achieved"] / v["peak"]
         dom = max(("seg_rle", "conv1", "conv2", "conv3", "fc1"), key=lambda k: per[k])
         units = {"seg_rle": B, "conv2": n_crops, "conv3": n_crops}
-        for k, per_unit in NCU_TRAFFIC.items():
+        for k, per_unit in NCU_TRAFFIC[args.precision].items():
             if CN == 1 or k != "seg_rle":
                 kern[k]["traffic"] = per_unit * units[k]          # bytes per step, from the committed ncu capture
         roof = {"kernel": dom, "bound": kern[dom]["bound"], "achieved": kern[dom]["achieved"], "peak": kern[dom]["peak"],
@@ -412,7 +413,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--channels", type=int, default=1, choices=[1, 3, 4], help="bytes per pixel of the frames (3 BGR, 4 BGRA: colour variant, not the headline)")
     ap.add_argument("--encoding", default="gray", choices=["gray", "rgb8"], help="meta_encoding (rgb8 needs --channels 3|4; crops and conv1 then have 3 channels)")
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "fp16"],
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "bf16x3", "fp16"],
                     help="CNN arithmetic: fp32 CUDA cores, bf16x3 split (3 MMAs per k-step) or fp16 (1 MMA per k-step in conv2/conv3) on tcgen05")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -79,7 +79,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
 {
     using C = Conv3T;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar_in_full, bar_in_empty, bar_acc_full, bar_acc_empty, bar_w_full[2], bar_w_empty[2];
+    __shared__ uint64_t bar_in_full[2], bar_in_empty[2], bar_acc_full[Conv3T::TILES], bar_acc_empty[Conv3T::TILES], bar_w_full[4], bar_w_empty[4];
     __shared__ uint32_t s_tmem;
     uint8_t *s_in = smem;
     uint8_t *s_w = smem + (C::IN_BYTES + 127) / 128 * 128;
@@ -87,9 +87,9 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
     const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
 
     if (tid == 0) {
-        umma::mbar_init(&bar_in_full, 1); umma::mbar_init(&bar_in_empty, 1);
-        umma::mbar_init(&bar_acc_full, 1); umma::mbar_init(&bar_acc_empty, 1);
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_w_full[i], 1); umma::mbar_init(&bar_w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_in_full[i], 1); umma::mbar_init(&bar_in_empty[i], 1); }
+        for (int i = 0; i < C::TILES; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { umma::mbar_init(&bar_w_full[i], 1); umma::mbar_init(&bar_w_empty[i], 1); }
         umma::fence_mbar_init();
     }
     if (warp == 1) umma::tmem_alloc(&s_tmem, C::TMEM_COLS);
@@ -97,22 +97,32 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tm = s_tmem;
+    // fp16: the planes of one image are half the size, so the input is double buffered (stage = G planes) and the next
+    // image loads under the MMAs of the current one; bf16x3 keeps one stage of 2 G planes
+    constexpr int NBUF = F16 ? 2 : 1, STAGE_POS = C::G * C::PIN;
+    // weight ring: a tap is 32 KB (bf16 hi + lo: 2 stages, 1.4 us of MMAs per tap hide the L2 latency) or 16 KB (fp16:
+    // 4 stages, because 0.46 us of MMAs per tap do not).  bf16x3 runs tile-outer (the epilogue of a tile under the
+    // MMAs of the other one, taps streamed once per tile); fp16 runs tap-outer: twice the L2 weight stream measured slower.
+    constexpr int WB = F16 ? C::WTAP_BYTES / 2 : C::WTAP_BYTES, NWS = F16 ? 4 : 2;
+    constexpr bool TILE_OUTER = !F16;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0, tapc = 0;
             for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
-                umma::mbar_wait(&bar_in_empty, (it & 1) ^ 1);
-                constexpr int NPL = F16 ? C::G : 2 * C::G, WB = F16 ? C::WTAP_BYTES / 2 : C::WTAP_BYTES;   // fp16: hi slots only
-                umma::mbar_expect_tx(&bar_in_full, NPL * C::PIN * 16);
+                const uint32_t ib = it % NBUF, iph = (it / NBUF) & 1;
+                umma::mbar_wait(&bar_in_empty[ib], iph ^ 1);
+                constexpr int NPL = F16 ? C::G : 2 * C::G;                      // fp16: hi slots only
+                umma::mbar_expect_tx(&bar_in_full[ib], NPL * C::PIN * 16);
                 const uint8_t *src = in + (size_t)img * Conv3Cfg::IMG_BYTES;
                 for (int p = 0; p < NPL; ++p)
-                    umma::bulk_g2s(s_in + (size_t)p * C::PIN * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full);
-                for (int tap = 0; tap < 25; ++tap, ++tapc) {
-                    const uint32_t s = tapc & 1;
-                    umma::mbar_wait(&bar_w_empty[s], ((tapc >> 1) & 1) ^ 1);
+                    umma::bulk_g2s(s_in + ((size_t)ib * STAGE_POS + (size_t)p * C::PIN) * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full[ib]);
+                for (int tt = 0; tt < (TILE_OUTER ? 25 * C::TILES : 25); ++tt, ++tapc) {
+                    const int tap = tt % 25;
+                    const uint32_t s = tapc % NWS;
+                    umma::mbar_wait(&bar_w_empty[s], ((tapc / NWS) & 1) ^ 1);
                     umma::mbar_expect_tx(&bar_w_full[s], WB);
-                    umma::bulk_g2s(s_w + s * C::WTAP_BYTES, wgt + (size_t)tap * C::WTAP_BYTES, WB, &bar_w_full[s]);
+                    umma::bulk_g2s(s_w + s * WB, wgt + (size_t)tap * C::WTAP_BYTES, WB, &bar_w_full[s]);
                 }
             }
         }
@@ -123,35 +133,54 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
             uint32_t it = 0, tapc = 0;
             for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
-                umma::mbar_wait(&bar_in_full, it & 1);
-                umma::mbar_wait(&bar_acc_empty, (it & 1) ^ 1);
+                const uint32_t ib = it % NBUF, iph = (it / NBUF) & 1;
+                const uint32_t xofs = ib * STAGE_POS;
+                umma::mbar_wait(&bar_in_full[ib], iph);
                 umma::fence_after_sync();
-                for (int tap = 0; tap < 25; ++tap, ++tapc) {
-                    const uint32_t s = tapc & 1;
-                    umma::mbar_wait(&bar_w_full[s], (tapc >> 1) & 1);
-                    umma::fence_after_sync();
-                    const uint32_t wofs = (s * C::WTAP_BYTES) >> 4;
+                auto tap_mmas = [&](int t, int tap, uint32_t wofs) {
+                    const uint32_t d = tm + (uint32_t)(t * C::N);
                     const uint32_t shift = (uint32_t)((tap / 5) * C::WP + (tap % 5));
 #pragma unroll
-                    for (int t = 0; t < C::TILES; ++t) {
-#pragma unroll
-                        for (int ks = 0; ks < C::G / 2; ++ks) {
-                            const uint32_t x_hi = (0 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
-                            const uint32_t x_lo = (1 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
-                            const uint32_t w_hi = wofs + (0 * C::G + 2 * ks) * C::NOUT;
-                            const uint32_t w_lo = wofs + (1 * C::G + 2 * ks) * C::NOUT;
-                            const uint32_t d = tm + (uint32_t)(t * C::N);
-                            umma::mma_bf16(d, w_base + w_hi, x_base + x_hi, idesc, (tap | ks) != 0);
-                            if (!F16) {
-                                umma::mma_bf16(d, w_base + w_hi, x_base + x_lo, idesc, 1);
-                                umma::mma_bf16(d, w_base + w_lo, x_base + x_hi, idesc, 1);
-                            }
+                    for (int ks = 0; ks < C::G / 2; ++ks) {
+                        const uint32_t x_hi = xofs + (0 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
+                        const uint32_t x_lo = (1 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
+                        const uint32_t w_hi = wofs + (0 * C::G + 2 * ks) * C::NOUT;
+                        const uint32_t w_lo = wofs + (1 * C::G + 2 * ks) * C::NOUT;
+                        umma::mma_bf16(d, w_base + w_hi, x_base + x_hi, idesc, (tap | ks) != 0);
+                        if (!F16) {
+                            umma::mma_bf16(d, w_base + w_hi, x_base + x_lo, idesc, 1);
+                            umma::mma_bf16(d, w_base + w_lo, x_base + x_hi, idesc, 1);
                         }
                     }
-                    umma::commit(&bar_w_empty[s]);
+                };
+                if (TILE_OUTER) {
+#pragma unroll 1
+                    for (int t = 0; t < C::TILES; ++t) {
+                        umma::mbar_wait(&bar_acc_empty[t], (it & 1) ^ 1);
+                        umma::fence_after_sync();
+                        for (int tap = 0; tap < 25; ++tap, ++tapc) {
+                            const uint32_t s = tapc % NWS;
+                            umma::mbar_wait(&bar_w_full[s], (tapc / NWS) & 1);
+                            umma::fence_after_sync();
+                            tap_mmas(t, tap, (s * WB) >> 4);
+                            umma::commit(&bar_w_empty[s]);
+                        }
+                        umma::commit(&bar_acc_full[t]);
+                    }
+                } else {
+                    for (int t = 0; t < C::TILES; ++t) umma::mbar_wait(&bar_acc_empty[t], (it & 1) ^ 1);
+                    umma::fence_after_sync();
+                    for (int tap = 0; tap < 25; ++tap, ++tapc) {
+                        const uint32_t s = tapc % NWS;
+                        umma::mbar_wait(&bar_w_full[s], (tapc / NWS) & 1);
+                        umma::fence_after_sync();
+#pragma unroll
+                        for (int t = 0; t < C::TILES; ++t) tap_mmas(t, tap, (s * WB) >> 4);
+                        umma::commit(&bar_w_empty[s]);
+                    }
+                    for (int t = 0; t < C::TILES; ++t) umma::commit(&bar_acc_full[t]);
                 }
-                umma::commit(&bar_in_empty);              // planes consumed: the producer may fetch the next image
-                umma::commit(&bar_acc_full);
+                umma::commit(&bar_in_empty[ib]);          // planes consumed: the producer may refill this stage
             }
         }
     } else {
@@ -162,7 +191,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
         const int c8 = c >> 3, e = c & 7;
         uint32_t it = 0;
         for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
-            umma::mbar_wait(&bar_acc_full, it & 1);
+            umma::mbar_wait(&bar_acc_full[t], it & 1);
             umma::fence_after_sync();
             const size_t lo_ofs = fc_a_offset(1, out_groups, 0, 0);
 #pragma unroll 1
@@ -188,8 +217,8 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                 }
             }
             umma::fence_before_sync();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (ew == 0 && lane == 0) umma::mbar_arrive(&bar_acc_empty);
+            asm volatile("bar.sync %0, 128;" :: "r"(1 + t) : "memory");      // the 4 warps of this tile
+            if (quarter == 0 && lane == 0) umma::mbar_arrive(&bar_acc_empty[t]);
         }
     }
     umma::fence_before_sync();
@@ -210,9 +239,9 @@ struct Conv2D {
     static constexpr int BANDS = 3, TILES = W / 8;                                              // y0 = 0, 16, 24
     static constexpr int IN_BYTES = 2 * G * BAND_POS * 16;
     static constexpr int WTAP_BYTES = 2 * G * NOUT * 16, W_BYTES = 25 * WTAP_BYTES;
-    static constexpr int NACC = 4, ACC_COLS = 2 * NOUT;    // [A_hi*W_hi + A_lo*W_hi | A_hi*W_lo], summed in the epilogue
+    static constexpr int NACC = 4, ACC_COLS = 2 * NOUT;    // [A_hi*W_hi + A_lo*W_hi | A_hi*W_lo], summed in the epilogue (fp16: 8 x 64)
     static constexpr int SMEM = 2 * IN_BYTES + W_BYTES + NOUT * 8 + 128;
-    static constexpr int THREADS = 64 + 256;
+    static constexpr int EPI_SETS = 2, THREADS = 64 + EPI_SETS * 256;   // two sets of 8 epilogue warps take alternate tiles
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -224,7 +253,8 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
 {
     using C = Conv2D;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar_in_full[2], bar_in_empty[2], bar_acc_full[C::NACC], bar_acc_empty[C::NACC], bar_w_full;
+    constexpr int NACC = F16 ? 2 * C::NACC : C::NACC, ACC_COLS = F16 ? C::NOUT : C::ACC_COLS;
+    __shared__ uint64_t bar_in_full[2], bar_in_empty[2], bar_acc_full[2 * C::NACC], bar_acc_empty[2 * C::NACC], bar_w_full;
     __shared__ uint32_t s_tmem;
     uint8_t *s_in = smem;                                            // [2][IN_BYTES]
     uint8_t *s_w = smem + 2 * C::IN_BYTES;
@@ -235,7 +265,7 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_in_full[i], 1); umma::mbar_init(&bar_in_empty[i], 1); }
-        for (int i = 0; i < C::NACC; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 8); }
+        for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 8); }
         umma::mbar_init(&bar_w_full, 1);
         umma::fence_mbar_init();
     }
@@ -280,10 +310,10 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                 umma::fence_after_sync();
 #pragma unroll 1
                 for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
-                    const uint32_t buf = ai % C::NACC;
-                    umma::mbar_wait(&bar_acc_empty[buf], ((ai / C::NACC) & 1) ^ 1);
+                    const uint32_t buf = ai % NACC;
+                    umma::mbar_wait(&bar_acc_empty[buf], ((ai / NACC) & 1) ^ 1);
                     umma::fence_after_sync();
-                    const uint32_t d = tm + buf * C::ACC_COLS;
+                    const uint32_t d = tm + buf * ACC_COLS;
 #pragma unroll 5
                     for (int tap = 0; tap < 25; ++tap) {
                         const uint32_t pos = (uint32_t)((tap / 5) * C::WP + (tap % 5) + tx * 8);
@@ -301,7 +331,7 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
             }
         }
     } else {
-        const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;     // half: which 32 of the 64 output channels
+        const int ew = (warp - 2) & 7, set = (warp - 2) >> 3, quarter = warp & 3, half = ew >> 2;     // half: which 32 of the 64 output channels
         const int r = quarter * 32 + lane, ty = r >> 3, tx8 = r & 7;
         const bool p1 = tx8 & 1, p2 = ty & 1;
         const int g = half * 4 + (p1 ? 2 : 0) + (p2 ? 1 : 0);           // channel group this lane ends up owning
@@ -313,11 +343,12 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
             const bool blk_ok = (y & ~1) >= ymin && (y & ~1) < C::H;      // the 2x2 block of this lane quad is stored
 #pragma unroll 1
             for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
-                const uint32_t buf = ai % C::NACC;
-                umma::mbar_wait(&bar_acc_full[buf], (ai / C::NACC) & 1);
+                if ((int)(ai & (C::EPI_SETS - 1)) != set) continue;           // the other set's tile
+                const uint32_t buf = ai % NACC;
+                umma::mbar_wait(&bar_acc_full[buf], (ai / NACC) & 1);
                 umma::fence_after_sync();
                 uint32_t v[32], vb[32];
-                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::ACC_COLS + half * 32;
+                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + half * 32;
                 umma::tmem_ld16(ta, *reinterpret_cast<uint32_t (*)[16]>(&v[0]));
                 umma::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t (*)[16]>(&v[16]));
                 if (!F16) {
