@@ -23,6 +23,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;                                   // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
 
+// descriptor + offset (in 16-byte units) with ONE 32-bit add: the start-address field sits in bits 0-13 of the low
+// word and never carries out of it (shared memory < 256 KB), so the single MMA-issuing thread spends 1 instead of 2
+// dependent integer instructions per operand -- that thread's instruction latency bounds kernels of small MMAs
+__device__ __forceinline__ uint64_t desc_add(uint64_t base, uint32_t ofs16)
+{
+    return (base & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)base + ofs16);
+}
+
 // Instruction descriptor for kind::f16 with BF16 A/B (K-major both), FP32 accumulate.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N)
 {
@@ -50,6 +58,16 @@ __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand fetch, bulk copies)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One elected lane of a converged warp (elect.sync).  Unlike `lane == 0`, the compiler knows that exactly one lane
+// passes, so the tcgen05.mma / commit instructions (uniform datapath) inside the branch are emitted straight instead
+// of inside a per-lane election loop (~6 extra dependent instructions per MMA for the single issuing thread).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)

@@ -64,7 +64,7 @@ struct Conv3T {
     static constexpr int WTAP_BYTES = 2 * G * NOUT * 16;
     static constexpr int SMEM = (IN_BYTES + 127) / 128 * 128 + 2 * WTAP_BYTES + 128;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int THREADS = 64 + 256;
+    static constexpr int THREADS = 64 + 512;               // 16 epilogue warps: (TMEM lane quarter) x (tile) x (row-pair half)
     static_assert(PIN <= PL, "staged positions exceed the plane");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -127,7 +127,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (umma::elect_one()) {
             const uint32_t idesc = F16 ? umma::idesc_f16_f32(128, C::N) : umma::idesc_bf16_f32(128, C::N);
             const uint64_t x_base = umma::smem_desc(umma::smem_u32(s_in), C::PIN * 16, 128);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
@@ -184,8 +184,9 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
             }
         }
     } else {
-        // epilogue: 8 warps; warp handles TMEM lane quarter (warp & 3) of tile (ew >> 2)
-        const int ew = warp - 2, quarter = warp & 3, t = ew >> 2;
+        // epilogue: 16 warps; a warp handles TMEM lane quarter (warp & 3) of tile ((ew >> 2) & 1), row pairs 0-2 or 3-4
+        const int ew = warp - 2, quarter = warp & 3, t = (ew >> 2) & 1, sub = ew >> 3;
+        const int pr0 = sub ? 3 : 0, pr1 = sub ? C::NT_ROWS / 2 : 3;
         const int c = quarter * 32 + lane;                    // output channel of this thread
         const float b = sh[c];
         const int c8 = c >> 3, e = c & 7;
@@ -195,7 +196,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
             umma::fence_after_sync();
             const size_t lo_ofs = fc_a_offset(1, out_groups, 0, 0);
 #pragma unroll 1
-            for (int pr = 0; pr < C::NT_ROWS / 2; ++pr) {         // pairs of image rows: 48 consecutive columns
+            for (int pr = pr0; pr < pr1; ++pr) {                 // pairs of image rows: 48 consecutive columns
                 uint32_t v[48];
                 const uint32_t col = (uint32_t)(t * C::N + pr * 2 * C::WP);
                 const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + col;
@@ -217,8 +218,8 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                 }
             }
             umma::fence_before_sync();
-            asm volatile("bar.sync %0, 128;" :: "r"(1 + t) : "memory");      // the 4 warps of this tile
-            if (quarter == 0 && lane == 0) umma::mbar_arrive(&bar_acc_empty[t]);
+            asm volatile("bar.sync %0, 256;" :: "r"(1 + t) : "memory");      // the 8 warps of this tile
+            if (quarter == 0 && sub == 0 && lane == 0) umma::mbar_arrive(&bar_acc_empty[t]);
         }
     }
     umma::fence_before_sync();
@@ -295,7 +296,7 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (umma::elect_one()) {
             // weights per tap: [group][64 rows W_hi + 64 rows W_lo][8]; one N = 128 MMA gives A_hi*(W_hi | W_lo),
             // one N = 64 MMA adds A_lo*W_hi: 14 KB of operand reads per tap instead of 18 KB for three N = 64 MMAs
             const uint32_t idesc128 = umma::idesc_bf16_f32(128, 2 * C::NOUT);
@@ -314,15 +315,17 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                     umma::mbar_wait(&bar_acc_empty[buf], ((ai / NACC) & 1) ^ 1);
                     umma::fence_after_sync();
                     const uint32_t d = tm + buf * ACC_COLS;
-#pragma unroll 5
+                    // fully unrolled: per MMA the issuing thread executes two immediate adds and the MMA itself
+                    const uint64_t a_tile = umma::desc_add(a_base, (uint32_t)(tx * 8));
+#pragma unroll
                     for (int tap = 0; tap < 25; ++tap) {
-                        const uint32_t pos = (uint32_t)((tap / 5) * C::WP + (tap % 5) + tx * 8);
+                        const uint32_t pos = (uint32_t)((tap / 5) * C::WP + (tap % 5));
                         const uint32_t a_hi = 0 * C::G * C::BAND_POS + pos, a_lo = 1 * C::G * C::BAND_POS + pos;
                         const uint32_t w = (uint32_t)(tap * C::WTAP_BYTES >> 4);
-                        if (F16) umma::mma_bf16(d, a_base + a_hi, w_base + w, idesc64, tap != 0);      // fp16 x fp16, one MMA per tap
+                        if (F16) umma::mma_bf16(d, umma::desc_add(a_tile, a_hi), umma::desc_add(w_base, w), idesc64, tap != 0);   // fp16 x fp16, one MMA per tap
                         else {
-                            umma::mma_bf16(d, a_base + a_hi, w_base + w, idesc128, tap != 0);
-                            umma::mma_bf16(d, a_base + a_lo, w_base + w, idesc64, 1);
+                            umma::mma_bf16(d, umma::desc_add(a_tile, a_hi), umma::desc_add(w_base, w), idesc128, tap != 0);
+                            umma::mma_bf16(d, umma::desc_add(a_tile, a_lo), umma::desc_add(w_base, w), idesc64, 1);
                         }
                     }
                     umma::commit(&bar_acc_full[buf]);
@@ -457,7 +460,7 @@ fc1_tc_kernel(const uint8_t *__restrict__ a, int n_groups, int n_max, const uint
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (umma::elect_one()) {
             const uint32_t idesc = umma::idesc_bf16_f32(128, FC_N);
             for (int st = 0; st < NSTEP; ++st) {
                 const int s = st % FC_STAGES;
@@ -596,7 +599,7 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
         umma::fence_after_sync();
 
         if (warp == 1) {
-            if (lane == 0) {
+            if (umma::elect_one()) {
                 const uint32_t idesc = umma::idesc_bf16_f32(128, C::N);
                 const uint64_t a_base = umma::smem_desc(umma::smem_u32(s_p), C::PW * 16, 2 * C::PW * 16);
                 const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::N * 16, 128);
@@ -785,11 +788,12 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                     umma::mbar_wait(&bar_acc_empty[buf], ((a2 / C::NACC) & 1) ^ 1);
                     umma::fence_after_sync();
                     const uint32_t d = tm + buf * C::N;
+                    const uint64_t a_tile = umma::desc_add(a_base, (uint32_t)(2 * y0 * C::PW + tx * 8));
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        const uint32_t pos = (uint32_t)((2 * y0 + 2 * j) * C::PW + tx * 8);
-                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)((j * 2 * C::N * 16) >> 4), idesc, j != 0);
-                        umma::mma_bf16(d, a_base + pos, w_base + (uint32_t)(((3 + j) * 2 * C::N * 16) >> 4), idesc, 1);
+                        const uint64_t ad = umma::desc_add(a_tile, (uint32_t)(2 * j * C::PW));
+                        umma::mma_bf16(d, ad, umma::desc_add(w_base, (uint32_t)((j * 2 * C::N * 16) >> 4)), idesc, j != 0);
+                        umma::mma_bf16(d, ad, umma::desc_add(w_base, (uint32_t)(((3 + j) * 2 * C::N * 16) >> 4)), idesc, 1);
                     }
                     umma::commit(&bar_acc_full[buf]);
                 }
