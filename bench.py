@@ -167,8 +167,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     all_cpus, near_cpus = bind_near_gpu(local_rank) if not args.no_numa else (None, None)
     if world_size > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (a nccl.conf may ask for the version banner)
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     pk = peaks()
