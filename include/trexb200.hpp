@@ -117,7 +117,7 @@ public:
     {
         tb_vi_config cfg{};
         cfg.device = device; cfg.width = 80; cfg.height = 80; cfg.channels = channels;
-        cfg.num_classes = num_classes; cfg.max_images = max_images; cfg.precision = 0;
+        cfg.num_classes = num_classes; cfg.max_images = max_images; cfg.precision = 1;   // bf16x3 on tensor cores (~1e-5 of fp32)
         check(tb_vi_create(&cfg, &_h), "tb_vi_create");
     }
     ~VINetwork() { tb_vi_destroy(_h); }

@@ -34,7 +34,9 @@ def batch_size_for(num_classes: int) -> int:
 
 
 class VINetwork:
-    def __init__(self, num_classes: int, width=80, height=80, channels=1, max_images=4096, device=0, precision="fp32"):
+    def __init__(self, num_classes: int, width=80, height=80, channels=1, max_images=4096, device=0, precision="bf16x3"):
+        """precision: "bf16x3" (tensor cores, 3-MMA split, ~1e-5 of fp32; default), "fp16" (tensor cores, one MMA per k-step in
+        conv2/conv3, ~3e-4 on O(1) logits; what bench.py runs) or "fp32" (CUDA cores; an independent implementation for parity tests)."""
         self.num_classes, self.width, self.height, self.channels = int(num_classes), width, height, channels
         self.max_images = int(max_images)
         cfg = ViConfig(device=device, width=width, height=height, channels=channels, num_classes=self.num_classes,
