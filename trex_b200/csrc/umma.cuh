@@ -82,6 +82,31 @@ __device__ __forceinline__ void commit(uint64_t *mbar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
 }
 
+// the same on a shared::cluster address (e.g. a barrier of the peer CTA of a cluster, see mapa())
+__device__ __forceinline__ void commit_a(uint32_t cluster_addr)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(cluster_addr) : "memory");
+}
+// thread-block clusters: rank of this CTA, address of a shared-memory object in CTA `rank`, cluster-wide barrier
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 1-D bulk copy global -> the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier (same
+// offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *mbar, uint16_t cta_mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)), "h"(cta_mask) : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(count) : "memory");

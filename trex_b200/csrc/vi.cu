@@ -620,9 +620,10 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(3)));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1P::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
         attr_done = true;
     }
@@ -639,8 +640,23 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         if (f16) conv2_2d_kernel<true><<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
         else conv2_2d_kernel<false><<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
         h->prof.mark(slot, 2);
-        if (f16) conv3_t_kernel<true><<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
-        else conv3_t_kernel<false><<<std::min(n, h->n_sms), Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+        {
+            // full grids run as clusters of two CTAs sharing one multicast weight stream (TB_VI_CONV3_CLUSTER=0: off)
+            static const int cl_env = getenv("TB_VI_CONV3_CLUSTER") ? atoi(getenv("TB_VI_CONV3_CLUSTER")) : 1;
+            const int grid3 = std::min(n, h->n_sms);
+            const bool cluster = f16 && cl_env != 0 && grid3 == h->n_sms && (grid3 % 2) == 0;     // bf16x3: no gain measured (its taps hide the L2 latency)
+            if (cluster) {
+                cudaLaunchConfig_t lc{};
+                lc.gridDim = dim3((unsigned)grid3); lc.blockDim = dim3(Conv3T::THREADS); lc.dynamicSmemBytes = Conv3T::SMEM; lc.stream = s;
+                cudaLaunchAttribute at{};
+                at.id = cudaLaunchAttributeClusterDimension;
+                at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+                lc.attrs = &at; lc.numAttrs = 1;
+                const uint8_t *a_in = h->in3, *a_w = h->w3t; const float *a_s = h->s3, *a_t = h->t3; uint8_t *a_out = h->fca; int a_g = h->fc_groups;
+                TB_CUDA(cudaLaunchKernelEx(&lc, conv3_t_kernel<true, 2>, a_in, n, n_dev, base, a_w, a_s, a_t, a_out, a_g));
+            } else if (f16) conv3_t_kernel<true, 1><<<grid3, Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+            else conv3_t_kernel<false, 1><<<grid3, Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+        }
         h->prof.mark(slot, 3);
         fc1_tc_kernel<<<dim3((n + 127) / 128, FC_SPLIT), NT, FC_SMEM, s>>>(h->fca, h->fc_groups, n, n_dev, base, h->wfc, h->h1, h->chunk);
         h->prof.mark(slot, 4);

@@ -71,7 +71,13 @@ struct Conv3T {
 
 // F16 ("fp16" precision): activations and weights are single fp16 planes (the hi slots of the same buffers) and every
 // k-step is ONE MMA instead of three; max|dlogit| ~ 3e-4 against fp32 (tolerance 1e-3), see DESIGN.md.
-template <bool F16>
+// CL = 2: the kernel runs in clusters of two CTAs that share the weight stream.  The leader (rank 0) issues every
+// tap's weights once as a MULTICAST bulk copy into both CTAs' rings when both have released the stage (the peer
+// commits its MMAs onto the leader's "empty" barrier through the cluster address space); each CTA re-arms its own
+// "full" barrier.  Half the L2 weight reads per SM make the tile-outer order (epilogue of a tile under the MMAs of
+// the other tile) affordable for fp16 as well.  Both CTAs run the same number of image slots; a CTA without an
+// image in the last slot only takes part in the weight hand-shake.
+template <bool F16, int CL>
 __global__ void __launch_bounds__(Conv3T::THREADS, 1)
 conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
                const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
@@ -89,14 +95,21 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_in_full[i], 1); umma::mbar_init(&bar_in_empty[i], 1); }
         for (int i = 0; i < C::TILES; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { umma::mbar_init(&bar_w_full[i], 1); umma::mbar_init(&bar_w_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { umma::mbar_init(&bar_w_full[i], 1); umma::mbar_init(&bar_w_empty[i], CL); }
         umma::fence_mbar_init();
+        if (CL == 2) for (int i = 0; i < (F16 ? 4 : 2); ++i) umma::mbar_expect_tx(&bar_w_full[i], F16 ? C::WTAP_BYTES / 2 : C::WTAP_BYTES);   // armed for the first use
     }
     if (warp == 1) umma::tmem_alloc(&s_tmem, C::TMEM_COLS);
     umma::fence_before_sync();
     __syncthreads();
+    if (CL == 2) umma::cluster_sync();                    // the peer's barriers exist before anything is sent to them
     umma::fence_after_sync();
     const uint32_t tm = s_tmem;
+    const uint32_t crank = CL == 2 ? umma::cluster_ctarank() : 0u;
+    // image slots of this CTA: its own images, or (clusters) as many as the cluster's first CTA has
+    const int first = (int)blockIdx.x - (int)crank;
+    const int slots = CL == 2 ? (first < n_act ? (n_act - first + (int)gridDim.x - 1) / (int)gridDim.x : 0)
+                              : ((int)blockIdx.x < n_act ? (n_act - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
     // fp16: the planes of one image are half the size, so the input is double buffered (stage = G planes) and the next
     // image loads under the MMAs of the current one; bf16x3 keeps one stage of 2 G planes
     constexpr int NBUF = F16 ? 2 : 1, STAGE_POS = C::G * C::PIN;
@@ -104,25 +117,33 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
     // 4 stages, because 0.46 us of MMAs per tap do not).  bf16x3 runs tile-outer (the epilogue of a tile under the
     // MMAs of the other one, taps streamed once per tile); fp16 runs tap-outer: twice the L2 weight stream measured slower.
     constexpr int WB = F16 ? C::WTAP_BYTES / 2 : C::WTAP_BYTES, NWS = F16 ? 4 : 2;
-    constexpr bool TILE_OUTER = !F16;
+    constexpr bool TILE_OUTER = !F16 || CL == 2;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0, tapc = 0;
-            for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
-                const uint32_t ib = it % NBUF, iph = (it / NBUF) & 1;
-                umma::mbar_wait(&bar_in_empty[ib], iph ^ 1);
-                constexpr int NPL = F16 ? C::G : 2 * C::G;                      // fp16: hi slots only
-                umma::mbar_expect_tx(&bar_in_full[ib], NPL * C::PIN * 16);
-                const uint8_t *src = in + (size_t)img * Conv3Cfg::IMG_BYTES;
-                for (int p = 0; p < NPL; ++p)
-                    umma::bulk_g2s(s_in + ((size_t)ib * STAGE_POS + (size_t)p * C::PIN) * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full[ib]);
+            int img = blockIdx.x;
+            for (int k = 0; k < slots; ++k, img += gridDim.x) {
+                if (img < n_act) {
+                    const uint32_t ib = it % NBUF, iph = (it / NBUF) & 1;
+                    umma::mbar_wait(&bar_in_empty[ib], iph ^ 1);
+                    constexpr int NPL = F16 ? C::G : 2 * C::G;                  // fp16: hi slots only
+                    umma::mbar_expect_tx(&bar_in_full[ib], NPL * C::PIN * 16);
+                    const uint8_t *src = in + (size_t)img * Conv3Cfg::IMG_BYTES;
+                    for (int p = 0; p < NPL; ++p)
+                        umma::bulk_g2s(s_in + ((size_t)ib * STAGE_POS + (size_t)p * C::PIN) * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full[ib]);
+                    ++it;
+                }
+                if (CL == 2 && crank != 0) continue;                            // the leader streams the weights for both CTAs
                 for (int tt = 0; tt < (TILE_OUTER ? 25 * C::TILES : 25); ++tt, ++tapc) {
                     const int tap = tt % 25;
                     const uint32_t s = tapc % NWS;
-                    umma::mbar_wait(&bar_w_empty[s], ((tapc / NWS) & 1) ^ 1);
-                    umma::mbar_expect_tx(&bar_w_full[s], WB);
-                    umma::bulk_g2s(s_w + s * WB, wgt + (size_t)tap * C::WTAP_BYTES, WB, &bar_w_full[s]);
+                    umma::mbar_wait(&bar_w_empty[s], ((tapc / NWS) & 1) ^ 1);   // CL = 2: both CTAs have released the stage
+                    if (CL == 2) umma::bulk_g2s_multicast(s_w + s * WB, wgt + (size_t)tap * C::WTAP_BYTES, WB, &bar_w_full[s], (uint16_t)3);
+                    else {
+                        umma::mbar_expect_tx(&bar_w_full[s], WB);
+                        umma::bulk_g2s(s_w + s * WB, wgt + (size_t)tap * C::WTAP_BYTES, WB, &bar_w_full[s]);
+                    }
                 }
             }
         }
@@ -132,11 +153,18 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
             const uint64_t x_base = umma::smem_desc(umma::smem_u32(s_in), C::PIN * 16, 128);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
             uint32_t it = 0, tapc = 0;
-            for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
+            // "empty" barrier of a weight stage: this CTA's own, or (clusters) the leader's, through the cluster window
+            uint32_t w_empty_a[4];
+            for (int i = 0; i < 4; ++i) w_empty_a[i] = CL == 2 ? umma::mapa(umma::smem_u32(&bar_w_empty[i]), 0u) : umma::smem_u32(&bar_w_empty[i]);
+            int img = blockIdx.x;
+            for (int k = 0; k < slots; ++k, img += gridDim.x) {
+                const bool real = img < n_act;
                 const uint32_t ib = it % NBUF, iph = (it / NBUF) & 1;
                 const uint32_t xofs = ib * STAGE_POS;
-                umma::mbar_wait(&bar_in_full[ib], iph);
-                umma::fence_after_sync();
+                if (real) {
+                    umma::mbar_wait(&bar_in_full[ib], iph);
+                    umma::fence_after_sync();
+                }
                 auto tap_mmas = [&](int t, int tap, uint32_t wofs) {
                     const uint32_t d = tm + (uint32_t)(t * C::N);
                     const uint32_t shift = (uint32_t)((tap / 5) * C::WP + (tap % 5));
@@ -153,34 +181,42 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                         }
                     }
                 };
+                auto take_stage = [&](uint32_t s) {           // wait for the tap's weights; clusters: re-arm the barrier for its next use
+                    umma::mbar_wait(&bar_w_full[s], (tapc / NWS) & 1);
+                    if (CL == 2) umma::mbar_expect_tx(&bar_w_full[s], WB);
+                    umma::fence_after_sync();
+                };
                 if (TILE_OUTER) {
 #pragma unroll 1
                     for (int t = 0; t < C::TILES; ++t) {
-                        umma::mbar_wait(&bar_acc_empty[t], (it & 1) ^ 1);
-                        umma::fence_after_sync();
+                        if (real) {
+                            umma::mbar_wait(&bar_acc_empty[t], (it & 1) ^ 1);
+                            umma::fence_after_sync();
+                        }
                         for (int tap = 0; tap < 25; ++tap, ++tapc) {
                             const uint32_t s = tapc % NWS;
-                            umma::mbar_wait(&bar_w_full[s], (tapc / NWS) & 1);
-                            umma::fence_after_sync();
-                            tap_mmas(t, tap, (s * WB) >> 4);
-                            umma::commit(&bar_w_empty[s]);
+                            take_stage(s);
+                            if (real) tap_mmas(t, tap, (s * WB) >> 4);
+                            umma::commit_a(w_empty_a[s]);
                         }
-                        umma::commit(&bar_acc_full[t]);
+                        if (real) umma::commit(&bar_acc_full[t]);
                     }
                 } else {
                     for (int t = 0; t < C::TILES; ++t) umma::mbar_wait(&bar_acc_empty[t], (it & 1) ^ 1);
                     umma::fence_after_sync();
                     for (int tap = 0; tap < 25; ++tap, ++tapc) {
                         const uint32_t s = tapc % NWS;
-                        umma::mbar_wait(&bar_w_full[s], (tapc / NWS) & 1);
-                        umma::fence_after_sync();
+                        take_stage(s);
 #pragma unroll
                         for (int t = 0; t < C::TILES; ++t) tap_mmas(t, tap, (s * WB) >> 4);
-                        umma::commit(&bar_w_empty[s]);
+                        umma::commit_a(w_empty_a[s]);
                     }
                     for (int t = 0; t < C::TILES; ++t) umma::commit(&bar_acc_full[t]);
                 }
-                umma::commit(&bar_in_empty[ib]);          // planes consumed: the producer may refill this stage
+                if (real) {
+                    umma::commit(&bar_in_empty[ib]);          // planes consumed: the producer may refill this stage
+                    ++it;
+                }
             }
         }
     } else {
@@ -224,6 +260,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
     }
     umma::fence_before_sync();
     __syncthreads();
+    if (CL == 2) umma::cluster_sync();                    // no CTA leaves while its peer may still write to it
     if (warp == 1) umma::tmem_dealloc(tm, C::TMEM_COLS);
 }
 
