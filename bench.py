@@ -30,9 +30,10 @@ H, W, N_INDIV, M_CLASSES = 1080, 1920, 100, 100
 MAX_CROPS = 128
 WORKLOAD = "synthetic 1920x1080 u8 gray, 100 individuals, bg-sub+threshold+CCL+80x80 crops+V118_3 CNN (random-init weights)"
 # DRAM traffic per unit (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture divided by the
-# units of that launch; profiles/r1_final_ncu_summary.txt and profiles/r1_seg_rle_v1_ncu_details.csv)
+# units of that launch; profiles/r1_step_fp16_ncu_summary.txt and profiles/r1_step_bf16x3_ncu_summary.txt)
 NCU_TRAFFIC = {"bf16x3": {"seg_rle": (267.87e6 + 6.47e6) / 128, "conv2": (507.7e6 + 385.1e6) / 4096, "conv3": (614.06e6 + 184.99e6) / 4096},
-               "fp16": {"seg_rle": (267.87e6 + 6.47e6) / 128}, "fp32": {"seg_rle": (267.87e6 + 6.47e6) / 128}}
+               "fp16": {"seg_rle": (267.87e6 + 6.47e6) / 128, "conv2": (253.88e6 + 175.66e6) / 4096, "conv3": (282.11e6 + 166.10e6) / 4096},
+               "fp32": {"seg_rle": (267.87e6 + 6.47e6) / 128}}
 MACS = {"conv1": 2.56e6, "conv2": 40.96e6, "conv3": 81.92e6, "fc1": 1.28e6, "head": 100.0 * M_CLASSES}
 
 
@@ -40,8 +41,9 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured (MEASURED_PEAKS.json; tensor = sustained bf16)")
-    return dict(hbm=6650.0, tensor=1400.0, src="fallback (B200_PROFILING.md)")
+        return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), tensor_burst=d["bf16_tflops"],
+                    src="measured (MEASURED_PEAKS.json; tensor = sustained bf16)")
+    return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1400.0, src="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler(threading.Thread):
@@ -364,6 +366,7 @@ def run_ours(args):
                 kern[k]["traffic"] = per_unit * units[k]          # bytes per step, from the committed ncu capture
         roof = {"kernel": dom, "bound": kern[dom]["bound"], "achieved": kern[dom]["achieved"], "peak": kern[dom]["peak"],
                 "unit": kern[dom]["unit"], "frac": kern[dom]["frac"], "traffic": kern[dom].get("traffic"), "peak_source": pk["src"],
+                "frac_of_burst_peak": (kern[dom]["achieved"] / pk["tensor_burst"]) if kern[dom]["bound"] == "tensor" else None,
                 "note": "algorithmic FLOPs (2*MAC per crop)" + ("; the bf16x3 split issues 3 MMAs per k-step on top of that" if args.precision == "bf16x3" else "")}
         # cpu baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None

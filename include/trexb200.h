@@ -168,7 +168,9 @@ TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_
  * every blob of det's last batch, on the device.  trk is a second handle of the same frame size whose params carry
  * the tracker settings: detect_threshold = track_threshold (comparison >=, Background.h:415-427),
  * enable_difference = track_background_subtraction, detect_threshold_is_absolute = track_threshold_is_absolute,
- * size ranges = track_size_filter (or none).  Afterwards tb_seg_wait / tb_seg_result / tb_seg_crops /
+ * size ranges = track_size_filter (or none).  Gray encoding: trk is a channels = 1 handle (it runs on the grey plane);
+ * rgb8: trk has det's channels and encoding, pixels are compared through cmn::bgr2gray (Background.h:76-81) against
+ * the background's grey image and keep their B,G,R bytes (test_pixels.cpp:1073-1166).  Afterwards tb_seg_wait / tb_seg_result / tb_seg_crops /
  * tb_seg_device_results on trk return the tracker-side blobs (and their crops: what the reference feeds the CNN). */
 TB_API int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch);
 

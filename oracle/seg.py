@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.to_num_threads.restype = C.c_int
         L.to_rethreshold_frame.argtypes = [vp, vp, vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64]
         L.to_rethreshold_frame.restype = C.c_int64
+        L.to_rethreshold_frame_rgb.argtypes = L.to_rethreshold_frame.argtypes
+        L.to_rethreshold_frame_rgb.restype = C.c_int64
         L.to_average.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.to_average.restype = C.c_int
         L.to_bgr2gray.argtypes = [vp, C.c_int64, C.c_int, vp]
@@ -308,15 +310,17 @@ def average(frames, method="mean"):
     return out
 
 
-def rethreshold(blobs: "Blobs", bg, threshold: int, method=DIFF_ABSOLUTE) -> "Blobs":
-    """pixel::threshold_blob on every blob of a frame (tracker-side re-threshold, comparison >=)."""
+def rethreshold(blobs: "Blobs", bg, threshold: int, method=DIFF_ABSOLUTE, rgb=False) -> "Blobs":
+    """pixel::threshold_blob on every blob of a frame (tracker-side re-threshold, comparison >=).  rgb: the blobs carry
+    B,G,R per pixel and bg is the GREY image of the background (Background's cvtColor, Background.cpp:71-77)."""
     bg = np.ascontiguousarray(bg, np.uint8)
     lines = np.ascontiguousarray(blobs.lines); px = np.ascontiguousarray(blobs.pixels, np.uint8)
     lo = np.ascontiguousarray(blobs.line_off, np.int64); po = np.ascontiguousarray(blobs.px_off, np.int64)
     capL = capB = max(16, len(px) + 1); capP = max(16, len(px))
     ol = np.zeros(capL, LINE_DTYPE); op = np.zeros(capP, np.uint8)
     olo = np.zeros(capB + 1, np.int64); opo = np.zeros(capB + 1, np.int64)
-    k = lib().to_rethreshold_frame(_p(lines), _p(lo), _p(px), _p(po), len(blobs), _p(bg), bg.shape[1], method, int(threshold),
+    fn = lib().to_rethreshold_frame_rgb if rgb else lib().to_rethreshold_frame
+    k = fn(_p(lines), _p(lo), _p(px), _p(po), len(blobs), _p(bg), bg.shape[1], method, int(threshold),
                                    _p(ol), capL, _p(op), capP, _p(olo), _p(opo), capB)
     assert k >= 0, k
     return Blobs(ol[:olo[k]].copy(), op[:opo[k]].copy(), olo[:k + 1].copy(), opo[:k + 1].copy())

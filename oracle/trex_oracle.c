@@ -669,14 +669,41 @@ void to_crop_blob_rgb(const to_line_t *lines, int64_t n_lines, const uint8_t *px
  * Input / output are SoA blob lists; sub-blobs of parent k come out consecutively (canonical order inside
  * a parent).  Returns the number of sub-blobs, or -(needed) if a capacity is too small.
  * ------------------------------------------------------------------------------------------ */
+static int64_t rethreshold_frame_c(const to_line_t *lines, const int64_t *line_off, const uint8_t *px, const int64_t *px_off,
+                             int64_t n_blobs, const uint8_t *bg, int bg_w, int method, int threshold,
+                             to_line_t *olines, int64_t cap_lines, uint8_t *opx, int64_t cap_px,
+                             int64_t *oline_off, int64_t *opx_off, int64_t cap_blobs, int c);
+
 int64_t to_rethreshold_frame(const to_line_t *lines, const int64_t *line_off, const uint8_t *px, const int64_t *px_off,
                              int64_t n_blobs, const uint8_t *bg, int bg_w, int method, int threshold,
                              to_line_t *olines, int64_t cap_lines, uint8_t *opx, int64_t cap_px,
                              int64_t *oline_off, int64_t *opx_off, int64_t cap_blobs)
 {
+    return rethreshold_frame_c(lines, line_off, px, px_off, n_blobs, bg, bg_w, method, threshold,
+                               olines, cap_lines, opx, cap_px, oline_off, opx_off, cap_blobs, 1);
+}
+
+/* The same for rgb8 blobs (3 bytes per pixel; px_off counts bytes): line_without_grid<{3, rgb8}, {1, gray}> compares the
+ * pixel's tracker grey value (cmn::bgr2gray, Background.h:76-81, via diffable_pixel_value :84-160) with the background's
+ * grey image, which Background's constructor derives with cv::cvtColor(BGR2GRAY) (Background.cpp:71-77): bg here is that
+ * grey image.  Pinned by Application/Tests/test_pixels.cpp:1073-1166 and :1289-1379. */
+int64_t to_rethreshold_frame_rgb(const to_line_t *lines, const int64_t *line_off, const uint8_t *px, const int64_t *px_off,
+                                 int64_t n_blobs, const uint8_t *bg, int bg_w, int method, int threshold,
+                                 to_line_t *olines, int64_t cap_lines, uint8_t *opx, int64_t cap_px,
+                                 int64_t *oline_off, int64_t *opx_off, int64_t cap_blobs)
+{
+    return rethreshold_frame_c(lines, line_off, px, px_off, n_blobs, bg, bg_w, method, threshold,
+                               olines, cap_lines, opx, cap_px, oline_off, opx_off, cap_blobs, 3);
+}
+
+static int64_t rethreshold_frame_c(const to_line_t *lines, const int64_t *line_off, const uint8_t *px, const int64_t *px_off,
+                             int64_t n_blobs, const uint8_t *bg, int bg_w, int method, int threshold,
+                             to_line_t *olines, int64_t cap_lines, uint8_t *opx, int64_t cap_px,
+                             int64_t *oline_off, int64_t *opx_off, int64_t cap_blobs, int c)
+{
     int64_t kept = 0, tl = 0, tp = 0;
     for (int64_t k = 0; k < n_blobs; ++k) {
-        const int64_t nl = line_off[k + 1] - line_off[k], np_ = px_off[k + 1] - px_off[k];
+        const int64_t nl = line_off[k + 1] - line_off[k], np_ = (px_off[k + 1] - px_off[k]) / c;
         to_line_t *sub = (to_line_t *)malloc(sizeof(to_line_t) * (size_t)(np_ + 1));
         int64_t *src = (int64_t *)malloc(sizeof(int64_t) * (size_t)(np_ + 1));      /* pixel offset of each sub-line */
         int32_t *label = (int32_t *)malloc(sizeof(int32_t) * (size_t)(np_ + 1));
@@ -687,7 +714,7 @@ int64_t to_rethreshold_frame(const to_line_t *lines, const int64_t *line_off, co
             const to_line_t *l = &lines[line_off[k] + i];
             int start = -1;
             for (int x = l->x0; x <= l->x1; ++x, ++o) {
-                int v = p[o], d = v;
+                int v = c == 1 ? p[o] : (int)bgr2gray_tracker(p + 3 * o), d = v;
                 if (method == 1) d = abs((int)bg[(size_t)l->y * bg_w + x] - v);
                 else if (method == 2) { d = (int)bg[(size_t)l->y * bg_w + x] - v; if (d < 0) d = 0; }
                 if (d >= threshold) { if (start < 0) start = x; }
@@ -709,8 +736,8 @@ int64_t to_rethreshold_frame(const to_line_t *lines, const int64_t *line_off, co
                 if (label[i] != b) continue;
                 const int64_t len = (int64_t)sub[i].x1 - sub[i].x0 + 1;
                 if (tl < cap_lines) olines[tl] = sub[i];
-                if (tp + len <= cap_px) memcpy(opx + tp, p + src[i], (size_t)len);
-                ++tl; tp += len;
+                if (tp + len * c <= cap_px) memcpy(opx + tp, p + src[i] * c, (size_t)len * c);
+                ++tl; tp += len * c;
             }
             ++kept;
         }

@@ -183,3 +183,27 @@ def test_rgb8_chain_frames_to_identities(precision):
     net.wait()
     got = probs.cpu().numpy()[:len(exp)]
     assert np.abs(got - vi.predict(sd, exp)).max() < 1e-3
+
+
+@pytest.mark.parametrize("method", ["absolute", "sign"])
+def test_rethreshold_rgb8_blobs(method):
+    """Tracker-side re-threshold of rgb8 blobs: cmn::bgr2gray(pixel) vs the background's grey image, comparison >=,
+    B,G,R bytes kept (oracle pinned on test_pixels.cpp:1073-1166, 1289-1379)."""
+    import trex_b200
+    from oracle import seg
+    frames, bg3 = _world(272, 480, 20, 13, 3)
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 100000)])
+    det = _mk(bg3, 3, "rgb8", **kw)
+    trk_settings = trex_b200.DetectSettings(meta_encoding="rgb8", detect_threshold=35, detect_size_filter=[],
+                                            detect_threshold_is_absolute=(method == "absolute"))
+    trk = trex_b200.BackgroundSubtraction(bg3, settings=trk_settings, max_batch=4, channels=3)
+    det.apply(frames)
+    got = det.rethreshold(trk)
+    bg_gray = seg.bgr2gray(bg3)
+    m = seg.DIFF_ABSOLUTE if method == "absolute" else seg.DIFF_SIGN
+    total = 0
+    for f in range(len(frames)):
+        ref = seg.rethreshold(seg.segment_frame_color(frames[f], bg3, _params(**kw), encoding=seg.ENC_RGB8), bg_gray, 35, m, rgb=True)
+        assert set(_as_list(got[f])) == ref.as_set(), f
+        total += len(ref)
+    assert total > 0

@@ -97,3 +97,24 @@ def test_tracker_grey_formula():
     assert np.array_equal(a, exp)
     frac = float((a != seg.bgr2gray(t)).mean())
     assert 0 < frac < 0.01
+
+
+@pytest.mark.parametrize("last", [100, 90])
+def test_rethreshold_rgb8_known_answer(last):
+    """Application/Tests/test_pixels.cpp:1073-1166 (line_without_grid<rgb8 -> gray, absolute>) and :1289-1379
+    (Blob::threshold on an rgb8 blob): threshold 25 against the grey image of the rgb background."""
+    bg3, lines, vals = _vec()
+    vals = vals.copy(); vals[7] = last
+    bg_gray = cv2.cvtColor(bg3, cv2.COLOR_BGR2GRAY)                  # Background's _grey_image (Background.cpp:71-77)
+    assert np.array_equal(bg_gray, seg.bgr2gray(bg3))
+    blobs = seg.Blobs(lines, vals.reshape(-1).copy(), np.array([0, 2], np.int64), np.array([0, 24], np.int64))
+    out = seg.rethreshold(blobs, bg_gray, 25, seg.DIFF_ABSOLUTE, rgb=True)
+    assert len(out) == 1                                              # (0,1) (0,3) (1,1..2) are 8-connected
+    got = [(int(l["y"]), int(l["x0"]), int(l["x1"])) for l in out.lines]
+    assert got == [(0, 1, 1), (0, 3, 3), (1, 1, 2)]
+    assert out.pixels.tolist() == [110, 110, 110, 10, 200, 10, 95, 95, 95, 200, 200, 200]
+    # the grey twin of the same blob (pixels through cmn::bgr2gray) yields the same lines
+    grey = seg.Blobs(lines, seg.bgr2gray_tracker(vals[None])[0].copy(), np.array([0, 2], np.int64), np.array([0, 8], np.int64))
+    out_g = seg.rethreshold(grey, bg_gray, 25, seg.DIFF_ABSOLUTE)
+    assert np.array_equal(out_g.lines, out.lines)
+    assert np.array_equal(out_g.pixels, seg.bgr2gray_tracker(out.pixels.reshape(1, -1, 3))[0])

@@ -173,6 +173,17 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t p)
     const uint32_t s = __dp4a(p, 0x00264B0Eu, 0u);              // high bytes  14, 75, 38
     return ((s << 8) + t) >> 15;
 }
+// cmn::bgr2gray (C/processing/Background.h:76-81), the tracker side's grey value of a B,G,R triple:
+// saturate(float(B) * 0.114 + float(G) * 0.587 + float(R) * 0.299 + 0.5, 0, 255), evaluated in double without
+// contraction (explicit round-to-nearest multiplies and adds), truncated.  Differs from cvtColor on ~0.14 % of triples.
+__device__ __forceinline__ uint32_t gray_px_tracker(const uint8_t *q)
+{
+    double v = __dmul_rn((double)q[0], 0.114);
+    v = __dadd_rn(v, __dmul_rn((double)q[1], 0.587));
+    v = __dadd_rn(v, __dmul_rn((double)q[2], 0.299));
+    v = __dadd_rn(v, 0.5);
+    return (uint32_t)fmin(fmax(v, 0.0), 255.0);
+}
 __device__ __forceinline__ uint32_t gray_px(const uint8_t *q, int CN, int cc)
 {
     if (CN == 1) return q[0];
@@ -733,14 +744,14 @@ seg_rle_ws_kernel(const uint8_t *__restrict__ frames, SegDev d, SegK p, uint32_t
 // re-threshold): the grey plane the threshold runs on (cvtColor or color_channel) and, for rgb8, the plane of
 // "any of B,G,R != 0" bytes.  One thread per 4 pixels.
 __global__ void to_gray_kernel(const uint8_t *__restrict__ frames, uint8_t *__restrict__ gray, uint8_t *__restrict__ nz,
-                               size_t total, int CN, int cc)
+                               size_t total, int CN, int cc, int tracker_formula = 0)
 {
     for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (size_t)gridDim.x * blockDim.x * 4) {
         uint32_t g = 0, z = 0;
         const int n = (int)min((size_t)4, total - i);
         for (int k = 0; k < n; ++k) {
             const uint8_t *q = frames + (i + k) * CN;
-            g |= gray_px(q, CN, cc) << (8 * k);
+            g |= (tracker_formula ? gray_px_tracker(q) : gray_px(q, CN, cc)) << (8 * k);
             if (nz) z |= ((q[0] | q[1] | q[2]) ? 0xFFu : 0u) << (8 * k);
         }
         if (n == 4 && (i & 3) == 0) {
@@ -1606,7 +1617,7 @@ extern "C" int tb_seg_set_background(tb_seg *h, const uint8_t *bg, int width, in
 }
 
 // grey plane (and, for rgb8, non-zero plane) of n colour frames into the handle's plane buffers
-static int seg_to_gray(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s)
+static int seg_to_gray(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s, int tracker_formula = 0)
 {
     const size_t px = (size_t)h->d.W * h->d.H;
     if (!h->d_gray) {
@@ -1614,7 +1625,7 @@ static int seg_to_gray(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t
         if (r == TB_OK && h->d.enc) r = seg_dev(h, &h->d_nz, (size_t)h->cfg.max_batch * px + 16);
         if (r != TB_OK) return r;
     }
-    to_gray_kernel<<<148 * 8, 256, 0, s>>>(frames_dev, h->d_gray, h->d.enc ? h->d_nz : nullptr, px * (size_t)n, h->d.CN, h->d.cc);
+    to_gray_kernel<<<148 * 8, 256, 0, s>>>(frames_dev, h->d_gray, h->d.enc ? h->d_nz : nullptr, px * (size_t)n, h->d.CN, h->d.cc, tracker_formula);
     h->launches += 1;
     TB_CUDA(cudaGetLastError());
     h->gray_valid = true;
@@ -1676,7 +1687,8 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     const bool fused_colour = d.CN > 1 && plain && !keep_mask && d.cc < 0 && ws_ok && d.rpt * d.cpr <= 512;
     const uint8_t *plane = frames_dev;          // what the 1-channel K1 variants read
     if (d.CN > 1 && !fused_colour) {
-        int r = seg_to_gray(h, frames_dev, n, s);
+        // tracker-side re-threshold of rgb8 blobs compares cmn::bgr2gray of the pixel (not cvtColor) with the background's grey image
+        int r = seg_to_gray(h, frames_dev, n, s, keep_mask && d.enc ? 1 : 0);
         if (r != TB_OK) return r;
         plane = h->d_gray;
         if (d.enc) d.nz_plane = h->d_nz;
@@ -1961,8 +1973,9 @@ extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch)
                "tb_seg_rethreshold: handles differ in frame size or device");
     TB_REQUIRE(det->last_n <= trk->cfg.max_batch, TB_ERR_INVALID, "tb_seg_rethreshold: tracker-side max_batch too small");
     TB_REQUIRE(trk->has_bg, TB_ERR_STATE, "tb_seg_rethreshold: the tracker-side handle has no background");
-    TB_REQUIRE(det->d.enc == 0 && trk->d.CN == 1, TB_ERR_INVALID,
-               "tb_seg_rethreshold: built for gray encoding (the tracker-side handle takes the grey plane: channels = 1)");
+    TB_REQUIRE((det->d.enc == 0 && trk->d.CN == 1) || (det->d.enc == 1 && trk->d.enc == 1 && trk->d.CN == det->d.CN), TB_ERR_INVALID,
+               "tb_seg_rethreshold: the tracker-side handle takes the grey plane (channels = 1) for gray encoding, "
+               "or the same colour frames (same channels, rgb8) for rgb8");
     TB_REQUIRE(!trk->pending, TB_ERR_STATE, "tb_seg_rethreshold: the tracker-side handle has a pending batch");
     TB_CUDA(cudaSetDevice(det->cfg.device));
     const size_t px = (size_t)det->d.W * det->d.H;
@@ -1977,6 +1990,7 @@ extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch)
     trk->launches += 1;
     TB_CUDA(cudaGetLastError());
     const uint8_t *plane = det->last_frames_dev;
+    if (det->d.enc == 1) return seg_launch(trk, plane, n, s, fetch, trk->keep_mask);     // rgb8: trk converts with the tracker's grey formula
     if (det->d.CN > 1) {                       // colour frames, gray encoding: re-threshold the grey plane
         if (!det->gray_valid) { int r = seg_to_gray(det, det->last_frames_dev, n, s); if (r != TB_OK) return r; }
         plane = det->d_gray;
