@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TB_ABI_VERSION 2
+#define TB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define TB_API __attribute__((visibility("default")))
@@ -74,6 +74,10 @@ typedef struct tb_seg_config {
     int32_t encoding;             /* meta_encoding: 0 gray (colour frames -> cv::cvtColor(BGR[A]2GRAY) or color_channel;
                                      1 byte per blob pixel), 1 rgb8 (mask from the grey images, B,G,R per blob pixel,
                                      blob flag is_rgb; RawProcessing.cpp:355-358,557-593; needs channels 3 or 4)    */
+    int32_t crop_normalize;       /* individual_image_normalization (T/tracking/FilterCache.cpp:318-346): 0 none (centre pad /
+                                     crop, :158-235), 1 moments (rotation by the blob's second-moment orientation through
+                                     cv::warpAffine, :329-341 + :21-115; gray encoding); posture / legacy need the tracker's midline */
+    int32_t reserved0;
 } tb_seg_config;
 
 /* Per-frame result header. status bit0: run capacity exceeded (frame dropped, n_blobs=0),

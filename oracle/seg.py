@@ -101,6 +101,14 @@ def lib() -> C.CDLL:
         L.to_num_threads.restype = C.c_int
         L.to_rethreshold_frame.argtypes = [vp, vp, vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64]
         L.to_rethreshold_frame.restype = C.c_int64
+        L.to_blob_orientation.argtypes = [vp, C.c_int64, vp]
+        L.to_blob_orientation.restype = C.c_float
+        L.to_moments_matrix.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.to_moments_matrix.restype = None
+        L.to_warp_affine_u8.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int]
+        L.to_warp_affine_u8.restype = None
+        L.to_crop_blob_moments.argtypes = [vp, C.c_int64, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.to_crop_blob_moments.restype = None
         L.to_rethreshold_frame_rgb.argtypes = L.to_rethreshold_frame.argtypes
         L.to_rethreshold_frame_rgb.restype = C.c_int64
         L.to_average.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
@@ -281,6 +289,37 @@ def crop_blob_rgb(lines, pixels, bg3, method=DIFF_ABSOLUTE, out_w=80, out_h=80):
     bg3 = np.ascontiguousarray(bg3, np.uint8)
     out = np.zeros((out_h, out_w, 3), np.uint8)
     lib().to_crop_blob_rgb(_p(lines), len(lines), _p(pixels), _p(bg3), bg3.shape[1], method, out_w, out_h, _p(out))
+    return out
+
+
+def blob_orientation(lines):
+    """pv::Blob::calculate_moments -> (orientation, (cx, cy))."""
+    lines = np.ascontiguousarray(lines)
+    c = np.zeros(2, np.float32)
+    a = lib().to_blob_orientation(_p(lines), len(lines), _p(c))
+    return float(np.float32(a)), (float(c[0]), float(c[1]))
+
+
+def moments_matrix(orientation, bw, bh, out_w=80, out_h=80):
+    m = np.zeros(6, np.float64)
+    lib().to_moments_matrix(C.c_float(orientation), bw, bh, out_w, out_h, _p(m))
+    return m.reshape(2, 3)
+
+
+def warp_affine_u8(src, M, out_w=80, out_h=80):
+    """cv::warpAffine(src, M, (out_w, out_h), INTER_LINEAR, BORDER_CONSTANT) for 8-bit single-channel images."""
+    src = np.ascontiguousarray(src, np.uint8); M = np.ascontiguousarray(M, np.float64)
+    out = np.zeros((out_h, out_w), np.uint8)
+    lib().to_warp_affine_u8(_p(src), src.shape[1], src.shape[0], _p(M), _p(out), out_w, out_h)
+    return out
+
+
+def crop_blob_moments(lines, pixels, bg, method=DIFF_ABSOLUTE, out_w=80, out_h=80):
+    """individual_image_normalization = moments (FilterCache.cpp:329-341): rotated by the blob's orientation."""
+    lines = np.ascontiguousarray(lines); pixels = np.ascontiguousarray(pixels, np.uint8)
+    bg = np.ascontiguousarray(bg, np.uint8)
+    out = np.zeros((out_h, out_w), np.uint8)
+    lib().to_crop_blob_moments(_p(lines), len(lines), _p(pixels), _p(bg), bg.shape[1], method, out_w, out_h, _p(out))
     return out
 
 

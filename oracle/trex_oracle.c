@@ -661,6 +661,125 @@ void to_crop_blob_rgb(const to_line_t *lines, int64_t n_lines, const uint8_t *px
 }
 
 /* ------------------------------------------------------------------------------------------
+ * individual_image_normalization = moments ("next" row N3b): constraints::diff_image
+ * (T/tracking/FilterCache.cpp:329-341) -> calculate_normalized_diff_image (:133-154) -> normalize_image (:21-115).
+ *
+ * (1) pv::Blob::calculate_moments, C/processing/PVBlob.cpp:111-214, single-thread path (blobs with <= 1000 lines):
+ *     float accumulators, pixels visited line by line; centre = (m10/m00, m01/m00); central moments from INTEGER offsets
+ *     vx = int(x0 - centre.x) ..., products in float; angle = 0.5 * fast_atan2(2 mu'11, mu'20 - mu'02)
+ *     (C/misc/math.h:34-59: 3rd-order polynomial, no libm).
+ * ------------------------------------------------------------------------------------------ */
+static float fast_atan_f(float z) { const float n1 = 0.97239411f, n2 = -0.19194795f; return (n1 + n2 * z * z) * z; }
+static float fast_atan2_f(float y, float x)
+{
+    if (x == 0.0f) return copysignf((float)M_PI_2, y);
+    float abs_y = fabsf(y), r, angle;
+    if (abs_y < fabsf(x)) { r = abs_y / fabsf(x); angle = fast_atan_f(r); }
+    else { r = fabsf(x) / abs_y; angle = (float)(M_PI_2 - fast_atan_f(r)); }      /* M_PI_2 is a double constant */
+    if (x < 0.0f) angle = (float)(M_PI - angle);
+    if (y < 0.0f) angle = -angle;
+    return angle;
+}
+float to_blob_orientation(const to_line_t *lines, int64_t n_lines, float centre[2])
+{
+    float m00 = 0, m01 = 0, m10 = 0;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        const unsigned my = lines[i].y;
+        int mx = lines[i].x0;
+        for (int x = lines[i].x0; x <= lines[i].x1; ++x, ++mx) { m00 += 1; m01 += 1 * my; m10 += mx * 1; }
+    }
+    const float cx = m10 / m00, cy = m01 / m00;
+    if (centre) { centre[0] = cx; centre[1] = cy; }
+    float mu00 = 0, mu02 = 0, mu11 = 0, mu20 = 0;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        const int vy = (int)((lines[i].y) - cy);
+        const int vy2 = vy * vy;
+        int vx = (int)((lines[i].x0) - cx);
+        for (int x = lines[i].x0; x <= lines[i].x1; ++x, ++vx) {
+            const int vx2 = vx * vx;
+            mu00 += 1; mu02 += 1 * vy2; mu11 += (float)vx * (float)vy; mu20 += vx2 * 1;
+        }
+    }
+    const float inv = 1.0f / mu00;
+    const float n11 = mu11 * inv, n20 = mu20 * inv, n02 = mu02 * inv;
+    return (float)(0.5 * fast_atan2_f(2 * n11, n20 - n02));
+}
+
+/* (2) the affine map handed to cv::warpAffine: FilterCache.cpp:329-339 (rotate by DEGREE(-orientation + pi/4), translate by
+ *     -bounds.size()/2) combined behind normalize_image's translate(size/2) . scale(individual_image_scale = 1)
+ *     (:47-62); gui::Transform arithmetic in double (C/gui/Transform.cpp:118-176), toCV (Transform.h:65-78).
+ *     M = {m00, m01, m02, m10, m11, m12} row-major 2x3. */
+void to_moments_matrix(float orientation, int bw, int bh, int out_w, int out_h, double M[6])
+{
+    const float deg = (-orientation + (float)M_PI * 0.25f) * (1.0f / (float)M_PI * 180.0f);       /* DEGREE(), float */
+    const double rad = (double)deg * 3.141592654 / 180.0;
+    const double c = cos(rad), s = sin(rad);
+    const float txf = -((float)bw * 0.5f), tyf = -((float)bh * 0.5f);                               /* -bounds.size() * 0.5 (Vec2 of float) */
+    const double tx = txf, ty = tyf;
+    /* tr = rotation . translation */
+    const double r02 = c * tx + (-s) * ty + 0.0 * 1.0, r12 = s * tx + c * ty + 0.0 * 1.0;
+    /* normalize_image: translate(size * 0.5) . scale(1) . translate(0) . tr */
+    const double ox = (double)((float)out_w * 0.5f), oy = (double)((float)out_h * 0.5f);
+    M[0] = 1.0 * c + 0.0 * s + ox * 0.0;  M[1] = 1.0 * (-s) + 0.0 * c + ox * 0.0;  M[2] = 1.0 * r02 + 0.0 * r12 + ox * 1.0;
+    M[3] = 0.0 * c + 1.0 * s + oy * 0.0;  M[4] = 0.0 * (-s) + 1.0 * c + oy * 0.0;  M[5] = 0.0 * r02 + 1.0 * r12 + oy * 1.0;
+}
+
+/* (3) cv::warpAffine, 8-bit 1 channel, INTER_LINEAR, BORDER_CONSTANT(0), forward matrix M (OpenCV 4.x imgproc
+ *     imgwarp.cpp: the matrix is inverted in double, coordinates run in 10-bit fixed point with 5 fractional bits kept
+ *     (AB_BITS 10, INTER_BITS 5), the four taps are weighted with 15-bit coefficients (32-fx)(32-fy)*32 ... and the sum
+ *     is rounded with +2^14 >> 15).  OpenCV is third party (not vendored in the reference); checked bit-exactly against
+ *     cv2 4.13 in tests/test_oracle_moments.py. */
+void to_warp_affine_u8(const uint8_t *src, int sw, int sh, const double Min[6], uint8_t *dst, int dw, int dh)
+{
+    double M[6];
+    memcpy(M, Min, sizeof(M));
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+    const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1; M[5] = b2;
+    for (int y = 0; y < dh; ++y) {
+        const int X0 = (int)lrint((M[1] * y + M[2]) * 1024) + 16, Y0 = (int)lrint((M[4] * y + M[5]) * 1024) + 16;
+        for (int x = 0; x < dw; ++x) {
+            const int X = (X0 + (int)lrint(M[0] * x * 1024)) >> 5, Y = (Y0 + (int)lrint(M[3] * x * 1024)) >> 5;
+            const int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
+            int acc = 0;
+            for (int k = 0; k < 4; ++k) {
+                const int yy = sy + (k >> 1), xx = sx + (k & 1);
+                const int w = ((k & 1) ? fx : 32 - fx) * ((k >> 1) ? fy : 32 - fy) * 32;
+                if (yy >= 0 && yy < sh && xx >= 0 && xx < sw) acc += src[(size_t)yy * sw + xx] * w;
+            }
+            dst[(size_t)y * dw + x] = (uint8_t)((acc + (1 << 14)) >> 15);
+        }
+    }
+}
+
+/* (4) the crop: render the blob (difference image when track_background_subtraction, else grey; FilterCache.cpp:141-153),
+ *     warp it into the zero-filled out_w x out_h canvas (:39-73; no pad / crop step remains because the canvas already
+ *     has the output size).  method as in to_image_from_lines. */
+void to_crop_blob_moments(const to_line_t *lines, int64_t n_lines, const uint8_t *px,
+                          const uint8_t *bg, int bg_w, int method, int out_w, int out_h, uint8_t *out)
+{
+    int32_t r[4];
+    int mx = 1 << 30, my = 1 << 30, Mx = -1, My = -1;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        if (lines[i].x0 < mx) mx = lines[i].x0;
+        if (lines[i].y < my) my = lines[i].y;
+        if (lines[i].x1 > Mx) Mx = lines[i].x1;
+        if (lines[i].y > My) My = lines[i].y;
+    }
+    const int bw = Mx - mx + 1, bh = My - my + 1;
+    uint8_t *img = (uint8_t *)malloc((size_t)bw * bh);
+    if (method == 0) to_image_from_lines(lines, n_lines, px, bg, bg_w, 0, 0, r, NULL, img, NULL);
+    else             to_image_from_lines(lines, n_lines, px, bg, bg_w, method, 0, r, NULL, NULL, img);
+    double M[6];
+    to_moments_matrix(to_blob_orientation(lines, n_lines, NULL), bw, bh, out_w, out_h, M);
+    to_warp_affine_u8(img, bw, bh, M, out, out_w, out_h);
+    free(img);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Tracker-side re-threshold of one frame's blobs ("next" row N3a): pixel::threshold_blob
  * (C/processing/PixelTree.cpp:186-291) applied to every blob: line_without_grid keeps the pixels whose
  * difference to the background is >= threshold (Background::is_value_different, Background.h:415-427;

@@ -364,3 +364,35 @@ def test_labeling_kernel_paths(case):
         assert bs.frame_info(0).n_runs == 8192
     assert len(ref) > 0 and _as_list(got[0]) == ref.as_list()
     assert got[1] == []
+
+
+@pytest.mark.parametrize("method", ["absolute", "sign", "none"])
+def test_moments_normalised_crops(method):
+    """individual_image_normalization = moments (FilterCache.cpp:329-341): orientation from the blob's second moments,
+    cv::warpAffine into the 80x80 canvas.  Byte-equal to the oracle (itself equal to the cv2.warpAffine call)."""
+    import trex_b200
+    from oracle import seg
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(h=400, w=640, n_blobs=30, seed=31, margin=30)
+    frames = world.frames(3)
+    # adversarial blobs: a single pixel, a long thin line (wider than the canvas), a big square, a blob touching the border
+    frames[0][5, 7] = 10
+    frames[0][200, 100:330] = 20
+    frames[1][50:170, 300:420] = 30
+    frames[2][0:9, 0:30] = 25
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 1000000)])
+    tbs = dict(track_background_subtraction=method != "none", track_threshold_is_absolute=method != "sign")
+    s = trex_b200.DetectSettings(individual_image_normalization="moments", **kw, **tbs)
+    bs = trex_b200.BackgroundSubtraction(world.bg, settings=s, max_batch=4, max_individuals=64)
+    got = bs.apply(frames)
+    crops, idx = bs.crops()
+    m = {"absolute": seg.DIFF_ABSOLUTE, "sign": seg.DIFF_SIGN, "none": seg.DIFF_NONE}[method]
+    n = 0
+    for f in range(len(frames)):
+        ref = _oracle(frames[f], world.bg, **kw)
+        assert _as_list(got[f]) == ref.as_list()
+        for k in range(min(len(ref), 64)):
+            exp = seg.crop_blob_moments(*ref.blob(k), world.bg, m)
+            assert np.array_equal(crops[n], exp), (f, k, int(np.abs(crops[n].astype(int) - exp).max()))
+            n += 1
+    assert n == len(crops) and n > 60

@@ -49,6 +49,8 @@ class DetectSettings:
     # colour handling of BackgroundSubtraction::apply (.cpp:151-188): meta_encoding "gray" | "rgb8", color_channel
     meta_encoding: str = "gray"
     color_channel: int | None = None
+    # individual_image_normalization (FilterCache.cpp:318-346): "none" | "moments" (posture / legacy need the tracker's midline)
+    individual_image_normalization: str = "none"
 
     def c_params(self) -> SegParams:
         p = SegParams()
@@ -101,7 +103,8 @@ class BackgroundSubtraction:
                         crop_width=self.settings.individual_image_size[0],
                         crop_height=self.settings.individual_image_size[1],
                         crop_method=self.settings.crop_method, channels=self.channels,
-                        encoding=int(self.settings.meta_encoding == "rgb8"))
+                        encoding=int(self.settings.meta_encoding == "rgb8"),
+                        crop_normalize={"none": 0, "moments": 1}[self.settings.individual_image_normalization])
         self.max_individuals = int(max_individuals)
         self._h = C.c_void_p()
         check(lib().tb_seg_create(C.byref(cfg), C.byref(self._h)))

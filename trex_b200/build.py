@@ -9,7 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtrexb200.so")
-SOURCES = ["capi.cu", "seg.cu", "vi.cu", "avg.cu", "umma_test.cu"]
+SOURCES = ["capi.cu", "seg.cu", "vi.cu", "avg.cu", "umma_test.cu", "crop_norm.cu"]
+EXTRA_FLAGS = {"crop_norm.cu": ["-fmad=false"]}      # scalar float / double arithmetic that must round like the reference
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -41,7 +42,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             continue
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", path, "-o", obj]
+        cmd = [nvcc(), *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), "-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -92,6 +92,11 @@ struct EventRing {
     }
 };
 
+// crop_norm.cu: `moments` normalisation of the crops of a batch (moments + matrix per crop, then the warp); 2 launches
+int launch_crop_moments(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,
+                        const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
+                        int out_w, int out_h, uint8_t *crops, double *coef, int max_crops_total, cudaStream_t s);
+
 #ifdef __CUDACC__
 // Exclusive scan of one value per thread across the CTA; `total` = sum over all threads.
 // ws: shared array of >= 33 uint32. All threads must call.

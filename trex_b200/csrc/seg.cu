@@ -38,6 +38,7 @@ struct SegDev {
     uint32_t lines_cap, px_cap, blobs_cap, crops_cap;   // batch arenas
     uint32_t px_frame_cap, max_crops;
     int crop_w, crop_h, crop_method;
+    int crop_norm;             // 1: `moments` normalisation, rendered by crop_norm.cu after K3 (K3 only assigns the crop slots)
     float sqcm; int n_ranges; double lo[4], hi[4];
     const uint8_t *bg;
     size_t bg_stride;          // 0: one background for all frames; else `bg` holds one mask image per frame (morphology path)
@@ -1263,9 +1264,10 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
             cl += tl; cp += tp;
         }
         const bool do_crop = q < ncrop;
+        const bool render = do_crop && !d.crop_norm;       // normalised crops are rendered by the warp kernel
         uint8_t *crop = d.crops + (size_t)(Cb + q) * cw * ch * opx;
         int offx = 0, offy = 0;
-        if (do_crop) {
+        if (render) {
             int dd;
             if ((int)bw < cw) { dd = cw - (int)bw; offx = dd - dd / 2; } else { dd = (int)bw - cw; offx = -(dd - dd / 2); }
             if ((int)bh < ch) { dd = ch - (int)bh; offy = dd - dd / 2; } else { dd = (int)bh - ch; offy = -(dd - dd / 2); }
@@ -1321,7 +1323,7 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
                     pi[u] = (size_t)ly * d.W + x;
                     po[u] = lp + (qq[u] - lq) * (uint32_t)opx;
                     const int cx = (int)(x - bx0) + offx, cy = (int)(ly - by0) + offy;
-                    ci[u] = (do_crop && cx >= 0 && cx < cw && cy >= 0 && cy < ch) ? cy * cw + cx : -1;
+                    ci[u] = (render && cx >= 0 && cx < cw && cy >= 0 && cy < ch) ? cy * cw + cx : -1;
                 }
                 if (opx == 1) {                                // gray encoding: the grey value (of a colour pixel: cvtColor / plane)
                     uint32_t v[2] = {0, 0}; int bgv[2] = {0, 0};
@@ -1398,6 +1400,7 @@ struct tb_seg {
     uint8_t *m_a = nullptr, *m_b = nullptr, *m_diff = nullptr;
     const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
     uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
+    double *d_coef = nullptr;                   // `moments` normalisation: inverted warp matrix per crop
     MorphEl el_close{}, el_dil{};
 };
 
@@ -1468,6 +1471,8 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     TB_REQUIRE(cfg->channels == 0 || cfg->channels == 1 || cfg->channels == 3 || cfg->channels == 4, TB_ERR_INVALID,
                "tb_seg_create: channels must be 1 (gray), 3 (BGR) or 4 (BGRA)");
     TB_REQUIRE(cfg->encoding == 0 || cfg->encoding == 1, TB_ERR_INVALID, "tb_seg_create: encoding must be 0 (gray) or 1 (rgb8); r3g3b2 is not built");
+    TB_REQUIRE(cfg->crop_normalize == 0 || (cfg->crop_normalize == 1 && cfg->encoding == 0), TB_ERR_INVALID,
+               "tb_seg_create: crop_normalize must be 0 (none) or 1 (moments, gray encoding); posture / legacy need the tracker's midline");
     TB_REQUIRE(cfg->encoding == 0 || cfg->channels >= 3, TB_ERR_INVALID,
                "tb_seg_create: rgb8 encoding needs colour frames (Invalid number of channels, BackgroundSubtraction.cpp:177-181)");
     int ndev = 0;
@@ -1499,6 +1504,7 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     d.crop_w = cfg->crop_width > 0 ? cfg->crop_width : 80;
     d.crop_h = cfg->crop_height > 0 ? cfg->crop_height : 80;
     d.crop_method = cfg->crop_method;
+    d.crop_norm = cfg->crop_normalize;
     const size_t B = d.B;
     // batch arenas: an average budget per frame, but never less than one worst-case frame
     d.lines_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)B * std::min<uint32_t>(d.rcap, 8192u), d.rcap), 0x7FFFFFFFu);
@@ -1522,6 +1528,7 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     A(d.infos, B); A(d.recs, d.blobs_cap); A(d.lines, d.lines_cap); A(d.line_px, d.lines_cap);
     A(d.pixels, (size_t)d.px_cap + 16); A(d.crops, (size_t)d.crops_cap * d.crop_w * d.crop_h * d.opx + 16);
     A(d.crop_blob, d.crops_cap); A(d.totals, 4);
+    if (d.crop_norm) A(h->d_coef, (size_t)d.crops_cap * 6);
 #undef A
     if (r == TB_OK) r = host_alloc(&h->h_infos, B);
     if (r == TB_OK) r = host_alloc(&h->h_totals, 4);
@@ -1795,6 +1802,12 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     h->prof.mark(slot, 3);
     h->launches += 3;
     TB_CUDA(cudaGetLastError());
+    if (d.crop_norm && d.max_crops) {          // individual_image_normalization = moments: orientation + cv::warpAffine per crop
+        int r = launch_crop_moments(d.recs, d.totals, d.crop_blob, d.lines, d.line_px, d.pixels, h->d_bg, d.W, d.crop_method,
+                                    d.crop_w, d.crop_h, d.crops, h->d_coef, n * (int)d.max_crops, s);
+        if (r != TB_OK) return r;
+        h->launches += 2;
+    }
     TB_CUDA(cudaMemcpyAsync(h->h_totals, d.totals, 16, cudaMemcpyDeviceToHost, s));
     TB_CUDA(cudaMemcpyAsync(h->h_infos, d.infos, sizeof(tb_frame_info) * (size_t)n, cudaMemcpyDeviceToHost, s));
     h->last_n = n; h->last_fetch = fetch; h->pending = true; h->fetched_payload = false; h->fetched_crops = false; h->last_stream = s;
