@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TB_ABI_VERSION 3
+#define TB_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define TB_API __attribute__((visibility("default")))
@@ -195,7 +195,8 @@ TB_API int tb_seg_kernel_ms(tb_seg *h, double out_ms[3], uint64_t *n_batches);
 /* ----------------------------------------------------------------------------------------------
  * Visual identification: Python::VINetwork (T/ml/VisualIdentification.h:104-133) +
  * predict_numpy (T/python/visual_recognition_torch.py:290-352) + V118_3
- * (T/python/visual_identification_network_torch.py:184-258), inference only.
+ * (T/python/visual_identification_network_torch.py:184-258) or one of the other custom networks
+ * (tb_vi_config.arch), inference only.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct tb_vi tb_vi;
 
@@ -206,6 +207,9 @@ typedef struct tb_vi_config {
     int32_t max_images;                /* capacity of one predict call                       */
     int32_t precision;                 /* 0: fp32 CUDA cores (parity mode); 1: bf16x3 split on tcgen05 tensor cores;
                                           2: fp16 operands, one MMA per k-step in conv2/conv3 (max|dlogit| ~3e-4) */
+    int32_t arch;                      /* visual_identification_version (ModelFetcher, T/python/visual_identification_network_torch.py:537-567):
+                                          0 v118_3 (default, :184-258), 1 v100 (:328-386), 2 v110 (:262-325), 3 v119 (:106-181),
+                                          4 v200 (:30-103); 1..4 run on fp32 CUDA cores (precision must be 0)          */
 } tb_vi_config;
 
 TB_API int tb_vi_create(const tb_vi_config *cfg, tb_vi **out);

@@ -113,11 +113,14 @@ inline blobs_t labeling_run(const uint8_t *image, int width, int height)
 
 class VINetwork {
 public:
-    VINetwork(int num_classes, int max_images = 4096, int device = 0, int channels = 1) : _m(num_classes), _c(channels)
+    // version: visual_identification_version as tb_vi_config.arch (0 v118_3, 1 v100, 2 v110, 3 v119, 4 v200)
+    VINetwork(int num_classes, int max_images = 4096, int device = 0, int channels = 1, int version = 0) : _m(num_classes), _c(channels)
     {
         tb_vi_config cfg{};
         cfg.device = device; cfg.width = 80; cfg.height = 80; cfg.channels = channels;
-        cfg.num_classes = num_classes; cfg.max_images = max_images; cfg.precision = 1;   // bf16x3 on tensor cores (~1e-5 of fp32)
+        cfg.num_classes = num_classes; cfg.max_images = max_images;
+        cfg.arch = version;
+        cfg.precision = version == 0 ? 1 : 0;   // v118_3: bf16x3 on tensor cores (~1e-5 of fp32); the others: fp32
         check(tb_vi_create(&cfg, &_h), "tb_vi_create");
     }
     ~VINetwork() { tb_vi_destroy(_h); }

@@ -128,3 +128,93 @@ def transform_results(n, indexes, values, m):
         probs[idx] = values[idx]
         i += 1
     return probs
+
+
+# ------------------------------------------------------------------------------------------------
+# The other custom networks ModelFetcher offers (visual_identification_network_torch.py:537-567):
+#   V200 :30-103, V119 :106-181, V110 :262-325, V100 :328-386.  Same predict path (predict_numpy), eval mode
+# (Dropout / Dropout2d are identities).  Each entry lists the conv blocks in constructor order as
+# (cout, kernel, pool, batchnorm) -- `bn` "pre" = conv -> BN -> ReLU -> pool (V200 / V119 / V118_3),
+# "post" = conv -> pool -> BN -> ReLU (V110), None = conv -> ReLU -> pool (V100) -- then the head.
+# ------------------------------------------------------------------------------------------------
+ARCHS = {
+    "v100": dict(convs=[(16, 5, 2, None), (64, 5, 2, None), (100, 5, 2, None)], gap=False, fc1=100, fc_bn=None),
+    "v110": dict(convs=[(16, 5, 2, "post"), (64, 5, 2, "post"), (100, 5, 2, "post")], gap=False, fc1=100, fc_bn="bn4"),
+    "v119": dict(convs=[(256, 5, 2, "pre"), (128, 5, 2, "pre"), (32, 5, 2, "pre"), (128, 5, 2, "pre")], gap=False, fc1=1024, fc_bn="bn5"),
+    "v200": dict(convs=[(64, 3, 1, "pre"), (128, 3, 3, "pre"), (256, 3, 1, "pre"), (512, 3, 3, "pre"), (512, 3, 3, "pre")],
+                 gap=True, fc1=1024, fc_bn="bn6"),
+}
+
+
+def arch_fc1_in(arch, width=80, height=80):
+    a = ARCHS[arch]
+    w, h = width, height
+    for _, _, pool, _ in a["convs"]:
+        w, h = w // pool, h // pool
+    c = a["convs"][-1][0]
+    return c if a["gap"] else c * w * h
+
+
+def init_state_dict_arch(arch, num_classes=100, channels=1, width=80, height=80, seed=0, perturb_norm=True):
+    """Random-init state_dict of V100 / V110 / V119 / V200 with the RNG consumption order of the reference's constructors
+    (parameters are drawn layer by layer in __init__ order: the convs, fc1, fc2; norm layers draw nothing)."""
+    a = ARCHS[arch]
+    torch.manual_seed(seed)
+    sd, cin, mods = {}, channels, []
+    for i, (cout, ks, _, _) in enumerate(a["convs"], 1):
+        mods.append((f"conv{i}", torch.nn.Conv2d(cin, cout, ks, padding="same")))
+        cin = cout
+    mods.append(("fc1", torch.nn.Linear(arch_fc1_in(arch, width, height), a["fc1"])))
+    mods.append(("fc2", torch.nn.Linear(a["fc1"], num_classes)))
+    for name, m in mods:
+        sd[f"model.{name}.weight"] = m.weight.detach().clone()
+        sd[f"model.{name}.bias"] = m.bias.detach().clone()
+    g = torch.Generator().manual_seed(seed + 12345)
+    norms = [(f"bn{i}", cout) for i, (cout, _, _, bn) in enumerate(a["convs"], 1) if bn]
+    if a["fc_bn"]:
+        norms.append((a["fc_bn"], a["fc1"]))
+    for name, c in norms:
+        if perturb_norm:
+            sd[f"model.{name}.weight"] = 0.5 + torch.rand(c, generator=g)
+            sd[f"model.{name}.bias"] = 0.2 * torch.randn(c, generator=g)
+            sd[f"model.{name}.running_mean"] = 0.5 * torch.randn(c, generator=g)
+            sd[f"model.{name}.running_var"] = 0.5 + torch.rand(c, generator=g)
+        else:
+            sd[f"model.{name}.weight"] = torch.ones(c); sd[f"model.{name}.bias"] = torch.zeros(c)
+            sd[f"model.{name}.running_mean"] = torch.zeros(c); sd[f"model.{name}.running_var"] = torch.ones(c)
+        sd[f"model.{name}.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    return sd
+
+
+def forward_logits_arch(arch, sd, crops_nhwc_u8) -> np.ndarray:
+    """forward() of V100 / V110 / V119 / V200 behind PermuteAxesWrapper, eval mode: (N,H,W,C) uint8 -> logits (N,M)."""
+    a = ARCHS[arch]
+    x = torch.from_numpy(np.ascontiguousarray(crops_nhwc_u8)).to(torch.float32).permute(0, 3, 1, 2).contiguous()
+
+    def bn(x, name):
+        return F.batch_norm(x, sd[f"model.{name}.running_mean"], sd[f"model.{name}.running_var"],
+                            sd[f"model.{name}.weight"], sd[f"model.{name}.bias"], training=False, eps=BN_EPS)
+    with torch.no_grad():
+        for i, (_, ks, pool, mode) in enumerate(a["convs"], 1):
+            x = F.conv2d(x, sd[f"model.conv{i}.weight"], sd[f"model.conv{i}.bias"], padding=ks // 2)
+            if mode == "pre":
+                x = F.relu(bn(x, f"bn{i}"))
+                if pool > 1:
+                    x = F.max_pool2d(x, pool)
+            elif mode == "post":
+                x = F.relu(bn(F.max_pool2d(x, pool), f"bn{i}"))
+            else:
+                x = F.max_pool2d(F.relu(x), pool)
+        if a["gap"]:
+            x = F.adaptive_avg_pool2d(x, (1, 1))
+        x = x.reshape(x.size(0), -1)
+        x = F.linear(x, sd["model.fc1.weight"], sd["model.fc1.bias"])
+        if a["fc_bn"]:
+            x = bn(x, a["fc_bn"])
+        x = F.linear(F.relu(x), sd["model.fc2.weight"], sd["model.fc2.bias"])
+    return x.numpy()
+
+
+def predict_arch(arch, sd, crops_nhwc_u8) -> np.ndarray:
+    lg = torch.from_numpy(forward_logits_arch(arch, sd, crops_nhwc_u8))
+    return torch.softmax(lg, dim=1).numpy()

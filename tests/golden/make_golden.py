@@ -9,6 +9,7 @@ Run here (authoring container) only; the GPU box has no reference tree and just 
   vi_golden.npz      logits / probabilities of the reference's own V118_3 class
                      (visual_identification_network_torch.py, imported from the reference tree)
                      for the state_dict oracle.vi.init_state_dict(seed=0) generates.
+  vi_nets_golden.npz the same for the other custom networks (V100, V110, V119, V200).
   pixels_golden.npz  known-answer vector transcribed from Application/Tests/test_pixels.cpp:1381-1466.
 """
 import os
@@ -102,6 +103,47 @@ def make_vi():
     np.savez_compressed(os.path.join(HERE, "vi_golden.npz"), **out)
 
 
+def make_vi_nets():
+    """vi_nets_golden.npz: logits / probabilities of the reference's own V100 / V110 / V119 / V200 classes
+    (visual_identification_network_torch.py:30-181,262-386) for the state_dicts oracle.vi.init_state_dict_arch generates."""
+    import torch
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, f"{REF}/Application/src/tracker/python")
+    import visual_identification_network_torch as ref_net
+    from oracle import vi
+    out = {}
+    for arch in ("v100", "v110", "v119", "v200"):
+        for M, CI in ((12, 1), (9, 3)):
+            tag = f"{arch}_m{M}c{CI}"
+            sd0 = vi.init_state_dict_arch(arch, M, CI, 80, 80, seed=0, perturb_norm=False)
+            torch.manual_seed(0)
+            ref = ref_net.ModelFetcher().get_model(arch, M, CI, 80, 80, device="cpu")
+            ref_sd = ref.state_dict()
+            assert set(ref_sd) == set(sd0), (arch, set(ref_sd) ^ set(sd0))
+            for k, v in sd0.items():        # same RNG consumption as the reference's constructor
+                assert torch.equal(ref_sd[k], v), k
+            sd = vi.scale_for_u8_inputs(vi.init_state_dict_arch(arch, M, CI, 80, 80, seed=0))
+            ref.load_state_dict(sd); ref.eval()
+            rng = np.random.default_rng(11)
+            crops = np.zeros((4, 80, 80, CI), np.uint8)
+            for n in range(4):
+                yy, xx = np.mgrid[0:80, 0:80]
+                a, b_, th = rng.uniform(12, 34), rng.uniform(4, 12), rng.uniform(0, np.pi)
+                u = (xx - 40) * np.cos(th) + (yy - 40) * np.sin(th); v = -(xx - 40) * np.sin(th) + (yy - 40) * np.cos(th)
+                m = (u / a) ** 2 + (v / b_) ** 2 <= 1
+                for c in range(CI):
+                    crops[n, ..., c][m] = rng.integers(20, 256, m.sum())
+            with torch.no_grad():
+                logits = ref(torch.from_numpy(crops).to(torch.float32)).numpy()
+                probs = torch.softmax(torch.from_numpy(logits), 1).numpy()
+            out[f"{tag}_crops"] = crops; out[f"{tag}_logits"] = logits; out[f"{tag}_probs"] = probs
+            out[f"{tag}_checksum"] = np.array(vi.state_checksum(sd))
+            mine = vi.forward_logits_arch(arch, sd, crops)
+            print(tag, "oracle vs reference class max|dlogit| =", float(np.abs(mine - logits).max()), "|logit|max =", float(np.abs(logits).max()))
+    np.savez_compressed(os.path.join(HERE, "vi_nets_golden.npz"), **out)
+    print("vi_nets_golden.npz", os.path.getsize(os.path.join(HERE, "vi_nets_golden.npz")) // 1024, "KiB")
+
+
 def make_pixels():
     # Application/Tests/test_pixels.cpp:1381-1466 (gray leg): bg gray == the equal-channel BGR values,
     # blob greys = cv::cvtColor of blob_values (only (10,200,10) is not grey: OpenCV fixed point -> 122).
@@ -128,4 +170,4 @@ def make_average():
 
 
 if __name__ == "__main__":
-    make_testpv(); make_vi(); make_pixels(); make_average()
+    make_testpv(); make_vi(); make_vi_nets(); make_pixels(); make_average()

@@ -171,6 +171,20 @@ def test_crop_geometry():
     assert np.array_equal(c[40], px[11:91])        # d = 21 -> start 11
 
 
+def test_vi_nets_oracle_matches_reference_class_outputs():
+    """V100 / V110 / V119 / V200 restated in oracle.vi against the outputs of the reference's own classes."""
+    g = np.load(os.path.join(GOLDEN, "vi_nets_golden.npz"))
+    for arch in ("v100", "v110", "v119", "v200"):
+        for M, CI in ((12, 1), (9, 3)):
+            tag = f"{arch}_m{M}c{CI}"
+            sd = vi.scale_for_u8_inputs(vi.init_state_dict_arch(arch, M, CI, 80, 80, seed=0))
+            assert vi.state_checksum(sd) == str(g[f"{tag}_checksum"])
+            lg = vi.forward_logits_arch(arch, sd, g[f"{tag}_crops"])
+            assert np.abs(lg - g[f"{tag}_logits"]).max() < 1e-5
+            assert np.abs(vi.predict_arch(arch, sd, g[f"{tag}_crops"]) - g[f"{tag}_probs"]).max() < 1e-6
+    assert [vi.arch_fc1_in(a) for a in ("v100", "v110", "v119", "v200")] == [10000, 10000, 3200, 512]
+
+
 def test_vi_oracle_matches_reference_class_outputs():
     g = np.load(os.path.join(GOLDEN, "vi_golden.npz"))
     for tag, M in (("m100", 100), ("m8", 8)):

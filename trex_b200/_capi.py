@@ -52,7 +52,7 @@ class BlobView(C.Structure):
 
 class ViConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
-                ("num_classes", C.c_int32), ("max_images", C.c_int32), ("precision", C.c_int32)]
+                ("num_classes", C.c_int32), ("max_images", C.c_int32), ("precision", C.c_int32), ("arch", C.c_int32)]
 
 
 # every symbol include/trexb200.h declares (checked by tests/test_capi_symbols.py)

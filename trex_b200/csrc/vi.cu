@@ -9,6 +9,7 @@
 // (bf16 hi/lo split, three MMAs per k-step, fp32 accumulation in TMEM) for conv2, conv3 and fc1.
 #include "common.h"
 #include "vi_tc.cuh"
+#include "vi_nets.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -344,6 +345,7 @@ struct tb_vi {
     uint64_t launches = 0;
     cudaStream_t last_stream = nullptr;
     EventRing<5> prof;
+    ViNet *net = nullptr;                                    // arch != 0: V100 / V110 / V119 / V200 (vi_nets.cu)
 };
 
 static int head_smem(const tb_vi *h, int M) { return (HD_WARPS * (100 + M) + (h->head_w_smem ? 100 * M : 0)) * 4; }
@@ -364,6 +366,8 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     TB_REQUIRE(cfg->num_classes > 0 && cfg->num_classes <= 1024, TB_ERR_INVALID, "tb_vi_create: num_classes must be 1..1024");
     TB_REQUIRE(cfg->max_images > 0, TB_ERR_INVALID, "tb_vi_create: max_images must be > 0");
     TB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32), 1 (bf16x3 tensor cores) or 2 (fp16 tensor cores)");
+    TB_REQUIRE(cfg->arch >= 0 && cfg->arch <= 4, TB_ERR_INVALID, "tb_vi_create: arch must be 0 (v118_3), 1 (v100), 2 (v110), 3 (v119) or 4 (v200)");
+    TB_REQUIRE(cfg->arch == 0 || cfg->precision == 0, TB_ERR_INVALID, "tb_vi_create: v100 / v110 / v119 / v200 run in fp32 (precision 0); the tensor-core precisions are built for v118_3");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("tb_vi_create: no CUDA device (there is no CPU fallback)"); return TB_ERR_CUDA; }
     TB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, TB_ERR_INVALID, "tb_vi_create: bad device ordinal");
@@ -376,6 +380,14 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     const size_t CH = h->chunk, M = cfg->num_classes, N = cfg->max_images, CI = cfg->channels;
     int r = TB_OK;
 #define A(p, n) if (r == TB_OK) r = vi_dev(h, &(p), (n))
+    if (cfg->arch != 0) {
+        r = vinet_create(&h->net, cfg->arch, cfg->channels, cfg->num_classes, cfg->max_images, h->dev_allocs);
+        A(h->d_img, N * 6400 * CI + 16); A(h->d_probs, N * M); A(h->d_logits, N * M);
+        if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
+        if (r != TB_OK) { tb_vi_destroy(h); return r; }
+        *out = h;
+        return TB_OK;
+    }
     A(h->w1, 400 * CI); A(h->s1, 16); A(h->t1, 16);
     A(h->w2, 25 * 16 * 64); A(h->s2, 64); A(h->t2, 64);
     A(h->w3, 25 * 64 * 128); A(h->s3, 128); A(h->t3, 128);
@@ -418,6 +430,7 @@ extern "C" void tb_vi_destroy(tb_vi *h)
     for (void *p : h->dev_allocs) cudaFree(p);
     h->prof.destroy();
     if (h->stream) cudaStreamDestroy(h->stream);
+    vinet_destroy(h->net);
     delete h;
 }
 
@@ -533,6 +546,11 @@ extern "C" int tb_vi_commit(tb_vi *h)
     TB_REQUIRE(h, TB_ERR_INVALID, "tb_vi_commit: null handle");
     TB_CUDA(cudaSetDevice(h->cfg.device));
     int r;
+    if (h->net) {
+        if ((r = vinet_commit(h->net, h->sd))) return r;
+        h->committed = true;
+        return TB_OK;
+    }
     const int CI = h->cfg.channels;
     if ((r = vi_conv(h, 1, CI, 16, h->w1, h->s1, h->t1))) return r;
     if ((r = vi_conv(h, 2, 16, 64, h->w2, h->s2, h->t2))) return r;
@@ -674,6 +692,11 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
 
 static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n_dev, float *probs, float *logits, cudaStream_t s)
 {
+    if (h->net) {
+        int r = vinet_forward(h->net, img, n_max, n_dev, probs, logits, h->top_id, h->top_p, s, h->prof, h->launches);
+        h->last_stream = s;
+        return r;
+    }
     if (h->cfg.precision >= 1) return vi_forward_tc(h, img, n_max, n_dev, probs, logits, s);
     const int M = h->cfg.num_classes;
     static bool attr_done = false;

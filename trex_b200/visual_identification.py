@@ -21,6 +21,23 @@ STATE_KEYS = [f"model.conv{i}.{p}" for i in (1, 2, 3) for p in ("weight", "bias"
              [f"model.bn{i}.{p}" for i in (1, 2, 3) for p in ("weight", "bias", "running_mean", "running_var")] + \
              ["model.fc1.weight", "model.fc1.bias", "model.bn4.weight", "model.bn4.bias", "model.fc2.weight", "model.fc2.bias"]
 
+# visual_identification_version -> tb_vi_config.arch (ModelFetcher.add_custom_models, visual_identification_network_torch.py:537-567)
+VERSIONS = {"v118_3": 0, "v100": 1, "v110": 2, "v119": 3, "v200": 4}
+_BN = ("weight", "bias", "running_mean", "running_var")
+
+
+def state_keys(version: str):
+    """state_dict entries the library needs for a network version (num_batches_tracked is not used in eval mode)."""
+    if version == "v118_3":
+        return list(STATE_KEYS)
+    n_conv, conv_bn, fc_bn = {"v100": (3, False, None), "v110": (3, True, "bn4"), "v119": (4, True, "bn5"), "v200": (5, True, "bn6")}[version]
+    keys = [f"model.conv{i}.{p}" for i in range(1, n_conv + 1) for p in ("weight", "bias")]
+    if conv_bn:
+        keys += [f"model.bn{i}.{p}" for i in range(1, n_conv + 1) for p in _BN]
+    if fc_bn:
+        keys += [f"model.{fc_bn}.{p}" for p in _BN]
+    return keys + ["model.fc1.weight", "model.fc1.bias", "model.fc2.weight", "model.fc2.bias"]
+
 
 def batch_size_for(num_classes: int) -> int:
     """VisualIdentification.cpp:105-118 (kept for API parity; results do not depend on it in eval mode)."""
@@ -34,19 +51,25 @@ def batch_size_for(num_classes: int) -> int:
 
 
 class VINetwork:
-    def __init__(self, num_classes: int, width=80, height=80, channels=1, max_images=4096, device=0, precision="bf16x3"):
-        """precision: "bf16x3" (tensor cores, 3-MMA split, ~1e-5 of fp32; default), "fp16" (tensor cores, one MMA per k-step in
+    def __init__(self, num_classes: int, width=80, height=80, channels=1, max_images=4096, device=0, precision=None, version="v118_3"):
+        """version: visual_identification_version ("v118_3" default; "v100", "v110", "v119", "v200" run in fp32).
+        precision (v118_3; default "bf16x3"): "bf16x3" (tensor cores, 3-MMA split, ~1e-5 of fp32; default), "fp16" (tensor cores, one MMA per k-step in
         conv2/conv3, ~3e-4 on O(1) logits; what bench.py runs) or "fp32" (CUDA cores; an independent implementation for parity tests)."""
         self.num_classes, self.width, self.height, self.channels = int(num_classes), width, height, channels
         self.max_images = int(max_images)
+        if version not in VERSIONS:
+            raise ValueError(f"Model {version} not found. Available models are: {list(VERSIONS)}")      # ModelFetcher.get_model
+        self.version = version
+        if precision is None:
+            precision = "bf16x3" if version == "v118_3" else "fp32"
         cfg = ViConfig(device=device, width=width, height=height, channels=channels, num_classes=self.num_classes,
-                       max_images=self.max_images, precision={"fp32": 0, "bf16x3": 1, "fp16": 2}[precision])
+                       max_images=self.max_images, precision={"fp32": 0, "bf16x3": 1, "fp16": 2}[precision], arch=VERSIONS[version])
         self._h = C.c_void_p()
         check(lib().tb_vi_create(C.byref(cfg), C.byref(self._h)))
         self.batch_size = batch_size_for(num_classes)
 
     def load_weights(self, state_dict):
-        for k in STATE_KEYS:
+        for k in state_keys(self.version):
             if k not in state_dict:
                 raise KeyError(f"state_dict lacks {k}")
             v = state_dict[k]
