@@ -73,7 +73,11 @@ typedef struct tb_seg_config {
                                      TileImage.images[0], T/python/BackgroundSubtraction.cpp:151-188)               */
     int32_t encoding;             /* meta_encoding: 0 gray (colour frames -> cv::cvtColor(BGR[A]2GRAY) or color_channel;
                                      1 byte per blob pixel), 1 rgb8 (mask from the grey images, B,G,R per blob pixel,
-                                     blob flag is_rgb; RawProcessing.cpp:355-358,557-593; needs channels 3 or 4)    */
+                                     blob flag is_rgb; RawProcessing.cpp:355-358,557-593; needs channels 3 or 4),
+                                     2 r3g3b2 (frames become 1-byte codes, convert_to_r3g3b2, C/misc/detail.h:508-555 +
+                                     T/python/BackgroundSubtraction.cpp:151-158; the 1-channel path then runs on the codes against a
+                                     1-channel background of codes; 1 byte per blob pixel, blob flag is_r3g3b2; crops are rendered as
+                                     B,G,R like imageFromLines does for such blobs, C/processing/Background.cpp:134-139)          */
     int32_t crop_normalize;       /* individual_image_normalization (T/tracking/FilterCache.cpp:318-346): 0 none (centre pad /
                                      crop, :158-235), 1 moments (rotation by the blob's second-moment orientation through
                                      cv::warpAffine, :329-341 + :21-115; gray encoding); posture / legacy need the tracker's midline */

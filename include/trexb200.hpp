@@ -36,7 +36,7 @@ inline void check(int rc, const char *what)
 }
 
 // meta_encoding_t (T/core/default_config.cpp:59): the encodings this library builds
-enum class meta_encoding_t { gray = 0, rgb8 = 1 };
+enum class meta_encoding_t { gray = 0, rgb8 = 1, r3g3b2 = 2 };
 
 class BackgroundSubtraction {
 public:
@@ -52,7 +52,7 @@ public:
         cfg.channels = channels; cfg.encoding = (int)encoding;
         check(tb_seg_create(&cfg, &_h), "tb_seg_create");
         tb_seg_default_params(&_p);
-        _w = width; _hgt = height; _opx = encoding == meta_encoding_t::rgb8 ? 3 : 1;
+        _w = width; _hgt = height; _opx = encoding == meta_encoding_t::rgb8 ? 3 : 1; _r3 = encoding == meta_encoding_t::r3g3b2;
     }
     ~BackgroundSubtraction() { tb_seg_destroy(_h); }
     BackgroundSubtraction(const BackgroundSubtraction &) = delete;
@@ -85,7 +85,7 @@ public:
                 const uint8_t *px = v.pixels + (r.px_off - v.info.px_begin);
                 p.lines = std::make_unique<std::vector<HorizontalLine>>(l, l + r.n_lines);
                 p.pixels = std::make_unique<std::vector<uint8_t>>(px, px + (size_t)r.n_pixels * _opx);
-                p.extra_flags = _opx == 3 ? (1u << 5) : 0;     // pv::Blob::Flags::is_rgb = bit 5 (CPULabeling.cpp:193, PVBlob.h:138-169)
+                p.extra_flags = _opx == 3 ? (1u << 5) : (_r3 ? (1u << 6) : 0);     // pv::Blob::Flags::is_rgb = bit 5 (CPULabeling.cpp:193), is_r3g3b2 = bit 6 (BackgroundSubtraction.cpp:221; PVBlob.h:138-169)
                 p.bid = r.bid;
                 out[i].emplace_back(std::move(p));
             }
@@ -98,6 +98,7 @@ private:
     tb_seg *_h = nullptr;
     tb_seg_params _p{};
     int _w = 0, _hgt = 0, _opx = 1;
+    bool _r3 = false;
 };
 
 // CPULabeling::run(const cv::Mat&, ...): label an already-binary image (any non-zero pixel is foreground)

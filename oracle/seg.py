@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
         L.to_bgr2gray.argtypes = [vp, C.c_int64, C.c_int, vp]
         L.to_bgr2gray.restype = None
         L.to_bgr2gray_tracker.argtypes = [vp, C.c_int64, vp]
+        L.to_convert_to_r3g3b2.argtypes = [vp, C.c_int64, C.c_int, vp]; L.to_convert_to_r3g3b2.restype = None
+        L.to_convert_from_r3g3b2.argtypes = [vp, C.c_int64, vp]; L.to_convert_from_r3g3b2.restype = None
         L.to_bgr2gray_tracker.restype = None
         L.to_generate_binary_color.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.POINTER(_Params), vp, vp]
         L.to_generate_binary_color.restype = C.c_int
@@ -221,7 +223,7 @@ def crop_blob(lines, pixels, bg, method=DIFF_ABSOLUTE, out_w=80, out_h=80):
     return out
 
 
-ENC_GRAY, ENC_RGB8 = 0, 1
+ENC_GRAY, ENC_RGB8, ENC_R3G3B2 = 0, 1, 2
 
 
 def bgr2gray(img: np.ndarray) -> np.ndarray:
@@ -240,11 +242,35 @@ def bgr2gray_tracker(img: np.ndarray) -> np.ndarray:
     return out
 
 
+def convert_to_r3g3b2(img: np.ndarray) -> np.ndarray:
+    """convert_to_r3g3b2<3|4> (C/misc/detail.h:533-555): (H,W,3|4) B,G,R(,A) -> (H,W) codes."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape[:-1], np.uint8)
+    lib().to_convert_to_r3g3b2(_p(img), out.size, img.shape[-1], _p(out))
+    return out
+
+
+def convert_from_r3g3b2(codes: np.ndarray) -> np.ndarray:
+    """convert_from_r3g3b2<3> / r3g3b2_to_vec (C/misc/detail.h:515-531): codes (...) -> (...,3)."""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    out = np.empty(codes.shape + (3,), np.uint8)
+    lib().to_convert_from_r3g3b2(_p(codes), codes.size, _p(out))
+    return out
+
+
+def crop_blob_r3g3b2(lines, pixels, bg_codes, method=DIFF_ABSOLUTE, out_w=80, out_h=80):
+    """calculate_diff_image for an r3g3b2 blob: imageFromLines renders 3 channels (Background.cpp:134-139), each pixel code
+    expanded by r3g3b2_to_vec (Background.h:113-116) and differenced per channel against the tracker's background, which
+    Background's constructor expanded the same way (Background.cpp:65-69)."""
+    return crop_blob_rgb(lines, convert_from_r3g3b2(np.ascontiguousarray(pixels, np.uint8)).reshape(-1),
+                         convert_from_r3g3b2(bg_codes), method, out_w, out_h)
+
+
 def generate_binary_color(frame, bg, params: Params, encoding=ENC_GRAY, color_channel=-1):
-    """frame (H,W,C) u8, bg (H,W) for gray encoding / (H,W,3) for rgb8 -> (H,W) or (H,W,3), grey plane."""
+    """frame (H,W,C) u8, bg (H,W) for gray / r3g3b2 encoding, (H,W,3) for rgb8 -> (H,W) or (H,W,3), grey plane."""
     frame = np.ascontiguousarray(frame, np.uint8); bg = np.ascontiguousarray(bg, np.uint8)
     h, w, cn = frame.shape
-    out = np.empty((h, w, 3) if encoding else (h, w), np.uint8)
+    out = np.empty((h, w, 3) if encoding == ENC_RGB8 else (h, w), np.uint8)
     gray = np.empty((h, w), np.uint8)
     pc = params.c()
     if lib().to_generate_binary_color(_p(frame), cn, encoding, color_channel, _p(bg), w, h, C.byref(pc), _p(out), _p(gray)) != 0:

@@ -214,12 +214,34 @@ void to_bgr2gray_tracker(const uint8_t *src, int64_t npx, uint8_t *dst)
     for (int64_t i = 0; i < npx; ++i) dst[i] = bgr2gray_tracker(src + 3 * (size_t)i);
 }
 
+/* meta_encoding r3g3b2: vec_to_r3g3b2 / convert_to_r3g3b2 (C/misc/detail.h:508-555) and r3g3b2_to_vec /
+ * convert_from_r3g3b2 (:515-531,557-590).  Known answers: Application/Tests/test_pixels.cpp:629-795. */
+void to_convert_to_r3g3b2(const uint8_t *src, int64_t npx, int cn, uint8_t *dst)
+{
+    for (int64_t i = 0; i < npx; ++i) {
+        const uint8_t *q = src + (size_t)i * cn;
+        dst[i] = (uint8_t)(((uint8_t)(q[0] / 64) << 6) | ((uint8_t)(q[1] / 32) << 3) | ((uint8_t)(q[2] / 32) << 0));
+    }
+}
+void to_convert_from_r3g3b2(const uint8_t *src, int64_t npx, uint8_t *dst3)
+{
+    for (int64_t i = 0; i < npx; ++i) {
+        const uint8_t c = src[i];
+        dst3[3 * i + 0] = (uint8_t)(((c >> 6) & 3) * 64);
+        dst3[3 * i + 1] = (uint8_t)(((c >> 3) & 7) * 32);
+        dst3[3 * i + 2] = (uint8_t)((c & 7) * 32);
+    }
+}
+
 /* The detect-side colour handling of BackgroundSubtraction::apply (T/python/BackgroundSubtraction.cpp:151-188)
  * followed by generate_binary (C/processing/RawProcessing.cpp:355-358,557-599):
  *   encoding 0 gray: cn 3/4 -> cvtColor(BGR[A]2GRAY), or the plane `color_channel` (0..cn-1) when set (:171-173);
  *                    then the 1-channel generate_binary against the 1-channel background.  out: w*h bytes.
  *   encoding 1 rgb8: cn 4 -> BGRA2BGR (:177-178); mask from gray(input) vs gray(background) (bg3 is 3-channel,
  *                    _grey_average :356-357); out = mask & each of B,G,R (:581-589).  out: w*h*3 bytes.
+ *   encoding 2 r3g3b2: cn 3/4 -> convert_to_r3g3b2 (:151-158); the 1-channel generate_binary then runs on the CODES
+ *                    against the 1-channel background of codes (RawProcessing.cpp:344: average has input.channels()).
+ *                    out: w*h bytes (mask & code); blob flag is_r3g3b2 (BackgroundSubtraction.cpp:221).
  * gray_out (optional, w*h): the grey plane the threshold ran on. */
 int to_generate_binary_color(const uint8_t *frame, int cn, int encoding, int color_channel, const uint8_t *bg,
                              int w, int h, const to_params_t *p, uint8_t *out, uint8_t *gray_out)
@@ -229,12 +251,13 @@ int to_generate_binary_color(const uint8_t *frame, int cn, int encoding, int col
     int ret = -1;
     if (!g || !mask) goto done;
     if (cn == 1) memcpy(g, frame, n);
+    else if (encoding == 2) to_convert_to_r3g3b2(frame, (int64_t)n, cn, g);
     else if (encoding == 0 && color_channel >= 0 && color_channel < 4) {
         if (color_channel >= cn) goto done;
         for (size_t i = 0; i < n; ++i) g[i] = frame[i * cn + color_channel];
     } else to_bgr2gray(frame, (int64_t)n, cn, g);
     if (gray_out) memcpy(gray_out, g, n);
-    if (encoding == 0) {
+    if (encoding == 0 || encoding == 2) {
         if (gen_mask(g, bg, w, h, p, mask)) goto done;
         for (size_t i = 0; i < n; ++i) out[i] = mask[i] & g[i];
     } else {
@@ -474,7 +497,7 @@ int64_t to_segment_frame_color(const uint8_t *frame, int cn, int encoding, int c
                                int64_t *line_off, int64_t *px_off, int64_t cap_blobs,
                                uint8_t *binary_out /* optional w*h*(encoding ? 3 : 1) */)
 {
-    const int c = encoding ? 3 : 1;
+    const int c = encoding == 1 ? 3 : 1;
     const size_t n = (size_t)w * h * c;
     uint8_t *bin = binary_out ? binary_out : (uint8_t *)malloc(n);
     if (!bin) return -1;

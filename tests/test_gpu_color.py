@@ -26,10 +26,11 @@ def _world(h, w, n, seed, channels):
     return frames, bg3
 
 
-def _mk(bg, channels, encoding, max_batch=4, max_individuals=0, **kw):
+def _mk(bg, channels, encoding, max_batch=4, max_individuals=0, max_runs_per_frame=0, **kw):
     import trex_b200
     s = trex_b200.DetectSettings(meta_encoding=encoding, **kw)
-    return trex_b200.BackgroundSubtraction(bg, settings=s, max_batch=max_batch, max_individuals=max_individuals, channels=channels)
+    return trex_b200.BackgroundSubtraction(bg, settings=s, max_batch=max_batch, max_individuals=max_individuals, channels=channels,
+                                           max_runs_per_frame=max_runs_per_frame)
 
 
 def _params(**kw):
@@ -129,8 +130,10 @@ def test_colour_errors():
         trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding="rgb8"), channels=1)
     with pytest.raises(TrexB200Error):       # rgb8 needs a 3-channel background (RawProcessing.cpp:343)
         trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding="rgb8"), channels=3)
-    with pytest.raises(TrexB200Error):
-        trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding="r3g3b2"), channels=3)
+    with pytest.raises(TrexB200Error):       # r3g3b2 needs colour frames too (BackgroundSubtraction.cpp:151-158)
+        trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(meta_encoding="r3g3b2"), channels=1)
+    with pytest.raises(TrexB200Error):       # and a 1-channel background of codes
+        trex_b200.BackgroundSubtraction(np.zeros((64, 64, 3), np.uint8), settings=trex_b200.DetectSettings(meta_encoding="r3g3b2"), channels=3)
     bs = trex_b200.BackgroundSubtraction(bg, channels=3)
     with pytest.raises(TrexB200Error):       # wrong frame shape
         bs.apply([np.zeros((64, 64), np.uint8)])
@@ -207,3 +210,75 @@ def test_rethreshold_rgb8_blobs(method):
         assert set(_as_list(got[f])) == ref.as_set(), f
         total += len(ref)
     assert total > 0
+
+
+@pytest.mark.parametrize("channels", [3, 4])
+@pytest.mark.parametrize("size,crop_method", [((272, 480), "absolute"), ((1080, 1920), "absolute"), ((123, 250), "sign"), ((272, 480), "none")])
+def test_r3g3b2_encoding(channels, size, crop_method):
+    """meta_encoding r3g3b2: frames become 1-byte codes (convert_to_r3g3b2), the 1-channel path runs on the codes against a
+    background of codes; one code byte per blob pixel; crops are B,G,R renderings (r3g3b2_to_vec) differenced per channel."""
+    from oracle import seg
+    h, w = size
+    frames, bg3 = _world(h, w, 30, 13, channels)
+    bg = seg.convert_to_r3g3b2(bg3)
+    method = {"none": seg.DIFF_NONE, "absolute": seg.DIFF_ABSOLUTE, "sign": seg.DIFF_SIGN}[crop_method]
+    kw = dict(detect_threshold=20, detect_size_filter=[(1, 100000)],
+              track_background_subtraction=crop_method != "none", track_threshold_is_absolute=crop_method != "sign")
+    # the codes of a noisy frame flicker around the quantisation steps: ~20k small blobs per 1080p frame -> large run capacity
+    bs = _mk(bg, channels, "r3g3b2", max_individuals=40, max_runs_per_frame=1 << 17, **kw)
+    got = bs.apply(frames)
+    crops, _ = bs.crops()
+    assert crops.shape[1:] == (80, 80, 3)
+    n = 0
+    for f in range(len(frames)):
+        ref = seg.segment_frame_color(frames[f], bg, _params(**kw), encoding=seg.ENC_R3G3B2)
+        assert len(ref) > 0
+        assert _as_list(got[f]) == ref.as_list(), f
+        assert np.array_equal(bs.debug_binary(frames[f]), seg.generate_binary_color(frames[f], bg, _params(**kw), encoding=seg.ENC_R3G3B2)[0])
+        for k in range(min(len(ref), 40)):
+            assert np.array_equal(crops[n], seg.crop_blob_r3g3b2(*ref.blob(k), bg, method)), (f, k)
+            n += 1
+    assert n == len(crops) and n > 0
+
+
+def test_r3g3b2_chain_to_identities():
+    """r3g3b2 crops (80x80x3) feed the 3-channel V118_3 like rgb8 crops do."""
+    import trex_b200
+    from oracle import seg, vi
+    frames, bg3 = _world(272, 480, 12, 5, 3)
+    bg = seg.convert_to_r3g3b2(bg3)
+    kw = dict(detect_threshold=20, detect_size_filter=[(20, 100000)])
+    bs = _mk(bg, 3, "r3g3b2", max_individuals=16, **kw)
+    bs.apply(frames)
+    crops, _ = bs.crops()
+    assert len(crops) > 0
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(10, 3, 80, 80, seed=0))
+    net = trex_b200.VINetwork(10, channels=3, max_images=64)
+    net.load_weights(sd)
+    probs = net.probabilities(crops)
+    assert np.abs(probs - vi.predict(sd, crops)).max() < 1e-3
+
+
+def test_batch_arena_overflow_is_reported_not_corrupting():
+    """More blobs in a batch than the blob / line arenas hold: tb_seg_wait reports TB_ERR_CAPACITY, the frames before the
+    overflow keep their results and the batch totals stay inside the arenas."""
+    import trex_b200
+    from trex_b200._capi import TrexB200Error
+    from oracle import seg
+    rng = np.random.default_rng(2)
+    h, w = 256, 512
+    bg = np.full((h, w), 100, np.uint8)
+    frames = np.repeat(bg[None], 4, 0).copy()
+    frames[:, ::2, ::2] = 200                                   # 32768 single-pixel blobs per frame
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 100000)])
+    bs = trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(**kw), max_batch=4, max_runs_per_frame=40000)
+    with pytest.raises(TrexB200Error) as e:
+        bs.apply(frames)
+    assert e.value.code == -4
+    tb, tl, tp, _ = bs.totals()
+    assert tb == tl == tp == 32768                              # arenas hold max(4 * 2048, 40000) blobs: one frame fits
+    infos = [bs.frame_info(i) for i in range(4)]
+    assert infos[0].n_blobs == 32768 and infos[0].status == 0
+    assert all(i.n_blobs == 0 and (i.status & 8) for i in infos[1:])
+    ref = seg.segment_frame(frames[0], bg, _params(**kw))
+    assert _as_list(bs.result(0)) == ref.as_list()

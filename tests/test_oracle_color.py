@@ -118,3 +118,41 @@ def test_rethreshold_rgb8_known_answer(last):
     out_g = seg.rethreshold(grey, bg_gray, 25, seg.DIFF_ABSOLUTE)
     assert np.array_equal(out_g.lines, out.lines)
     assert np.array_equal(out_g.pixels, seg.bgr2gray_tracker(out.pixels.reshape(1, -1, 3))[0])
+
+
+def test_r3g3b2_known_answers():
+    """Application/Tests/test_pixels.cpp:629-795 (vec_to_r3g3b2, r3g3b2_to_vec, convert_to / convert_from)."""
+    to = lambda *bgr: int(seg.convert_to_r3g3b2(np.array([[bgr]], np.uint8))[0, 0])
+    assert to(255, 128, 64) == 0b11100010 and to(255, 128, 64, 255) == 0b11100010
+    assert [to(255, 0, 0), to(0, 255, 0), to(0, 0, 255), to(255, 255, 255), to(0, 0, 0)] == [0b11000000, 0b00111000, 0b00000111, 0xFF, 0]
+    back = seg.convert_from_r3g3b2(np.array([0b11100010, 0b11000000, 0b00111000, 0b00000111, 0xFF], np.uint8))
+    assert back.tolist() == [[192, 128, 64], [192, 0, 0], [0, 224, 0], [0, 0, 224], [192, 224, 224]]
+    img = np.array([[[255, 0, 0], [0, 255, 0]], [[0, 0, 255], [255, 255, 255]]], np.uint8)      # ImageConversionTest :745-767
+    assert seg.convert_from_r3g3b2(seg.convert_to_r3g3b2(img)).tolist() == [[[192, 0, 0], [0, 224, 0]], [[0, 0, 224], [192, 224, 224]]]
+
+
+def test_generate_binary_r3g3b2_matches_opencv_pipeline():
+    """r3g3b2: BackgroundSubtraction::apply converts the frame to codes (:151-158); generate_binary then runs its
+    1-channel path on the codes (absdiff / threshold / bitwise_and as for a grey image)."""
+    rng = np.random.default_rng(4)
+    bg3 = rng.integers(90, 170, (96, 128, 3), dtype=np.uint8)
+    fr = np.clip(bg3.astype(int) + rng.integers(-80, 80, bg3.shape), 0, 255).astype(np.uint8)
+    fr[3, 3] = (63, 31, 31)                                  # code 0: never foreground
+    fr4 = np.dstack([fr, np.full(fr.shape[:2], 255, np.uint8)])
+    bg = seg.convert_to_r3g3b2(bg3)
+    for T, absolute in ((15, True), (30, False)):
+        P = seg.Params(detect_threshold=T, detect_threshold_is_absolute=absolute, detect_size_filter=[(2, 100000)])
+        out, codes = seg.generate_binary_color(fr, bg, P, encoding=seg.ENC_R3G3B2)
+        exp_codes = ((fr[..., 0] // 64) << 6) | ((fr[..., 1] // 32) << 3) | (fr[..., 2] // 32)
+        assert np.array_equal(codes, exp_codes)
+        d = cv2.absdiff(codes, bg) if absolute else cv2.subtract(bg, codes)
+        _, m = cv2.threshold(d, T, 255, cv2.THRESH_BINARY)
+        assert np.array_equal(out, cv2.bitwise_and(m, codes))
+        out4, _ = seg.generate_binary_color(fr4, bg, P, encoding=seg.ENC_R3G3B2)
+        assert np.array_equal(out4, out)
+        b = seg.segment_frame_color(fr, bg, P, encoding=seg.ENC_R3G3B2)
+        b1 = seg.segment_frame(codes, bg, P)
+        assert b.as_list() == b1.as_list() and len(b) > 0
+        lines, px = b.blob(0)
+        crop = seg.crop_blob_r3g3b2(lines, px, bg, seg.DIFF_ABSOLUTE)
+        assert crop.shape == (80, 80, 3) and crop.any()

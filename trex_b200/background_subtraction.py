@@ -47,7 +47,7 @@ class DetectSettings:
     track_background_subtraction: bool = True
     track_threshold_is_absolute: bool = True
     # colour handling of BackgroundSubtraction::apply (.cpp:151-188): meta_encoding "gray" | "rgb8", color_channel
-    meta_encoding: str = "gray"
+    meta_encoding: str = "gray"        # "gray" | "rgb8" | "r3g3b2"
     color_channel: int | None = None
     # individual_image_normalization (FilterCache.cpp:318-346): "none" | "moments" (posture / legacy need the tracker's midline)
     individual_image_normalization: str = "none"
@@ -92,18 +92,19 @@ class BackgroundSubtraction:
         if width is None or height is None:
             raise ValueError("BackgroundSubtraction needs an average image or width/height")
         self.settings = settings or DetectSettings()
-        if self.settings.meta_encoding not in ("gray", "rgb8"):
-            raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, f"meta_encoding {self.settings.meta_encoding!r} is not built (gray, rgb8)")
+        if self.settings.meta_encoding not in ("gray", "rgb8", "r3g3b2"):
+            raise _capi.TrexB200Error(_capi.TB_ERR_INVALID, f"meta_encoding {self.settings.meta_encoding!r} is not built (gray, rgb8, r3g3b2)")
         self.width, self.height, self.max_batch = int(width), int(height), int(max_batch)
         self.channels = int(channels)
-        self.out_channels = 3 if self.settings.meta_encoding == "rgb8" else 1
+        self.out_channels = 3 if self.settings.meta_encoding == "rgb8" else 1           # bytes per blob pixel
+        self.crop_channels = 1 if self.settings.meta_encoding == "gray" else 3           # r3g3b2 blobs render as B,G,R (Background.cpp:134-139)
         cfg = SegConfig(device=device, width=self.width, height=self.height, max_batch=self.max_batch,
                         max_runs_per_frame=max_runs_per_frame, max_pixels_per_frame=max_pixels_per_frame,
                         max_crops_per_frame=int(max_individuals),
                         crop_width=self.settings.individual_image_size[0],
                         crop_height=self.settings.individual_image_size[1],
                         crop_method=self.settings.crop_method, channels=self.channels,
-                        encoding=int(self.settings.meta_encoding == "rgb8"),
+                        encoding={"gray": 0, "rgb8": 1, "r3g3b2": 2}[self.settings.meta_encoding],
                         crop_normalize={"none": 0, "moments": 1}[self.settings.individual_image_normalization])
         self.max_individuals = int(max_individuals)
         self._h = C.c_void_p()
@@ -236,7 +237,7 @@ class BackgroundSubtraction:
         cp, ip, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
         check(lib().tb_seg_crops(self._h, C.byref(cp), C.byref(ip), C.byref(n)))
         w, h = self.settings.individual_image_size
-        shape = (h, w) if self.out_channels == 1 else (h, w, 3)
+        shape = (h, w) if self.crop_channels == 1 else (h, w, 3)
         if n.value == 0:
             return np.zeros((0,) + shape, np.uint8), np.zeros(0, np.uint32)
         crops = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint8)), (n.value,) + shape).copy()

@@ -47,7 +47,9 @@ struct SegDev {
     int CN;                    // bytes per pixel of the submitted frames: 1, 3, 4
     int enc;                   // 0 gray (1 byte per blob pixel), 1 rgb8 (B,G,R per blob pixel)
     int cc;                    // color_channel (gray encoding): -1 = cvtColor, else the plane to take
-    int opx;                   // bytes per blob pixel / crop pixel: enc ? 3 : 1
+    int opx;                   // bytes per blob pixel: enc ? 3 : 1
+    int cpx;                   // bytes per crop pixel: 3 for rgb8 and r3g3b2 (imageFromLines renders r3g3b2 blobs as B,G,R), else 1
+    int r3;                    // meta_encoding r3g3b2: frames become 1-byte codes (convert_to_r3g3b2, cc = CC_R3G3B2); enc stays 0
     const uint8_t *bg3;        // rgb8: the 3-channel background (crops difference against it); `bg` is its grey image
     const uint8_t *nz_plane;   // rgb8 on the plane path: [B][H][W] "any of B,G,R != 0" bytes (0xFF / 0), or null
     // K1 outputs
@@ -185,9 +187,14 @@ __device__ __forceinline__ uint32_t gray_px_tracker(const uint8_t *q)
     v = __dadd_rn(v, 0.5);
     return (uint32_t)fmin(fmax(v, 0.0), 255.0);
 }
+constexpr int CC_R3G3B2 = 8;      // SegDev.cc value: the "plane" of a colour frame is its r3g3b2 code image
+// vec_to_r3g3b2 / r3g3b2_to_vec, C/misc/detail.h:508-531
+__device__ __forceinline__ uint32_t to_r3g3b2(uint32_t b, uint32_t g, uint32_t r) { return ((b >> 6) << 6) | ((g >> 5) << 3) | (r >> 5); }
+__device__ __forceinline__ int r3g3b2_channel(uint32_t code, int k) { return k == 0 ? (int)((code >> 6) & 3u) * 64 : (k == 1 ? (int)((code >> 3) & 7u) * 32 : (int)(code & 7u) * 32); }
 __device__ __forceinline__ uint32_t gray_px(const uint8_t *q, int CN, int cc)
 {
     if (CN == 1) return q[0];
+    if (cc == CC_R3G3B2) return to_r3g3b2(q[0], q[1], q[2]);
     if (cc >= 0) return q[cc];
     return gray_of((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16));
 }
@@ -1220,7 +1227,18 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
         fi.blob_begin = Bb; fi.n_blobs = Kk; fi.line_begin = Lb; fi.n_lines = Lk;
         fi.px_begin = Pb; fi.n_pixels = Pk; fi.n_runs = d.run_count[f]; fi.status = status;
         d.infos[f] = fi;
-        if (f == d.B - 1) { d.totals[0] = Bb + Kk; d.totals[1] = Lb + Lk; d.totals[2] = Pb + Pk; d.totals[3] = Cb + ncrop; }
+        if (f == d.B - 1) {
+            uint32_t tb = Bb + Kk, tl = Lb + Lk, tp = Pb + Pk, tc = Cb + ncrop;
+            if (status & 8u) {          // a batch arena overflowed at or before this frame (every later frame is dropped too):
+                tb = tl = tp = tc = 0;  // the totals cover the frames before the first overflow
+                for (int g = 0; g < d.B; ++g) {
+                    const uint32_t *t = d.frame_tot + (size_t)g * 4;
+                    if (tb + t[0] > d.blobs_cap || tl + t[1] > d.lines_cap || tp + t[2] > d.px_cap) break;
+                    tb += t[0]; tl += t[1]; tp += t[2]; tc += min(t[0], d.max_crops);
+                }
+            }
+            d.totals[0] = tb; d.totals[1] = tl; d.totals[2] = tp; d.totals[3] = tc;
+        }
     }
     if (Kk == 0) return;
 
@@ -1265,17 +1283,18 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
         }
         const bool do_crop = q < ncrop;
         const bool render = do_crop && !d.crop_norm;       // normalised crops are rendered by the warp kernel
-        uint8_t *crop = d.crops + (size_t)(Cb + q) * cw * ch * opx;
+        const int cpx = d.cpx;
+        uint8_t *crop = d.crops + (size_t)(Cb + q) * cw * ch * cpx;
         int offx = 0, offy = 0;
         if (render) {
             int dd;
             if ((int)bw < cw) { dd = cw - (int)bw; offx = dd - dd / 2; } else { dd = (int)bw - cw; offx = -(dd - dd / 2); }
             if ((int)bh < ch) { dd = ch - (int)bh; offy = dd - dd / 2; } else { dd = (int)bh - ch; offy = -(dd - dd / 2); }
-            if (((cw * ch * opx) & 15) == 0) {
+            if (((cw * ch * cpx) & 15) == 0) {
                 uint4 *c4 = reinterpret_cast<uint4 *>(crop);
-                for (int i = lane; i < (cw * ch * opx) >> 4; i += 32) c4[i] = make_uint4(0, 0, 0, 0);
+                for (int i = lane; i < (cw * ch * cpx) >> 4; i += 32) c4[i] = make_uint4(0, 0, 0, 0);
             } else {
-                for (int i = lane; i < cw * ch * opx; i += 32) crop[i] = 0;
+                for (int i = lane; i < cw * ch * cpx; i += 32) crop[i] = 0;
             }
         }
         if (lane == 0) {
@@ -1337,7 +1356,17 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
                     for (int u = 0; u < 2; ++u)
                         if (act[u]) {
                             d.pixels[po[u]] = (uint8_t)v[u];
-                            if (ci[u] >= 0) {
+                            if (ci[u] >= 0 && d.r3) {          // r3g3b2 blob: rendered as B,G,R = r3g3b2_to_vec(code), differences per channel
+#pragma unroll                                               // against the background's expanded codes (Background.cpp:65-69, Background.h:113-116)
+                                for (int k = 0; k < 3; ++k) {
+                                    int val = r3g3b2_channel(v[u], k);
+                                    if (d.crop_method) {
+                                        const int bb = r3g3b2_channel((uint32_t)bgv[u], k);
+                                        val = d.crop_method == 1 ? abs(bb - val) : max(0, bb - val);
+                                    }
+                                    crop[ci[u] * 3 + k] = (uint8_t)val;
+                                }
+                            } else if (ci[u] >= 0) {
                                 int val = (int)v[u];
                                 if (d.crop_method) val = d.crop_method == 1 ? abs(bgv[u] - val) : max(0, bgv[u] - val);
                                 crop[ci[u]] = (uint8_t)val;
@@ -1470,11 +1499,12 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     TB_REQUIRE(cfg->crop_method >= 0 && cfg->crop_method <= 2, TB_ERR_INVALID, "tb_seg_create: crop_method must be 0..2");
     TB_REQUIRE(cfg->channels == 0 || cfg->channels == 1 || cfg->channels == 3 || cfg->channels == 4, TB_ERR_INVALID,
                "tb_seg_create: channels must be 1 (gray), 3 (BGR) or 4 (BGRA)");
-    TB_REQUIRE(cfg->encoding == 0 || cfg->encoding == 1, TB_ERR_INVALID, "tb_seg_create: encoding must be 0 (gray) or 1 (rgb8); r3g3b2 is not built");
+    TB_REQUIRE(cfg->encoding >= 0 && cfg->encoding <= 2, TB_ERR_INVALID, "tb_seg_create: encoding must be 0 (gray), 1 (rgb8) or 2 (r3g3b2)");
     TB_REQUIRE(cfg->crop_normalize == 0 || (cfg->crop_normalize == 1 && cfg->encoding == 0), TB_ERR_INVALID,
                "tb_seg_create: crop_normalize must be 0 (none) or 1 (moments, gray encoding); posture / legacy need the tracker's midline");
     TB_REQUIRE(cfg->encoding == 0 || cfg->channels >= 3, TB_ERR_INVALID,
-               "tb_seg_create: rgb8 encoding needs colour frames (Invalid number of channels, BackgroundSubtraction.cpp:177-181)");
+               "tb_seg_create: rgb8 / r3g3b2 encoding needs colour frames (Invalid number of channels, BackgroundSubtraction.cpp:151-158,177-181)");
+    TB_REQUIRE(cfg->encoding != 2 || cfg->crop_normalize == 0, TB_ERR_INVALID, "tb_seg_create: crop_normalize = moments is built for the gray encoding");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("tb_seg_create: no CUDA device (there is no CPU fallback)");
@@ -1489,7 +1519,8 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     seg_make_k(h->params, h->k, why);
     SegDev &d = h->d;
     d.W = cfg->width; d.H = cfg->height; d.B = cfg->max_batch;
-    d.CN = cfg->channels > 1 ? cfg->channels : 1; d.enc = cfg->encoding; d.cc = -1; d.opx = d.enc ? 3 : 1;
+    d.CN = cfg->channels > 1 ? cfg->channels : 1; d.r3 = cfg->encoding == 2; d.enc = cfg->encoding == 1; d.opx = d.enc ? 3 : 1;
+    d.cc = d.r3 ? CC_R3G3B2 : -1; d.cpx = (d.enc || d.r3) ? 3 : 1;
     d.cpr = (d.W + 15) / 16;
     d.aligned = (d.W % 16) == 0;
     d.wpr = (d.cpr + 3) / 4 + 1;
@@ -1526,7 +1557,7 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     A(d.b_ymax, B * d.rcap); A(d.b_root, B * d.rcap); A(d.b_loff, B * d.rcap); A(d.b_poff, B * d.rcap);
     A(d.kept, B * d.rcap); A(d.frame_tot, B * 4);
     A(d.infos, B); A(d.recs, d.blobs_cap); A(d.lines, d.lines_cap); A(d.line_px, d.lines_cap);
-    A(d.pixels, (size_t)d.px_cap + 16); A(d.crops, (size_t)d.crops_cap * d.crop_w * d.crop_h * d.opx + 16);
+    A(d.pixels, (size_t)d.px_cap + 16); A(d.crops, (size_t)d.crops_cap * d.crop_w * d.crop_h * d.cpx + 16);
     A(d.crop_blob, d.crops_cap); A(d.totals, 4);
     if (d.crop_norm) A(h->d_coef, (size_t)d.crops_cap * 6);
 #undef A
@@ -1535,7 +1566,7 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     if (r == TB_OK) r = host_alloc(&h->h_recs, d.blobs_cap);
     if (r == TB_OK) r = host_alloc(&h->h_lines, d.lines_cap);
     if (r == TB_OK) r = host_alloc(&h->h_pixels, (size_t)d.px_cap + 16);
-    if (r == TB_OK) r = host_alloc(&h->h_crops, (size_t)d.crops_cap * d.crop_w * d.crop_h * d.opx + 16);
+    if (r == TB_OK) r = host_alloc(&h->h_crops, (size_t)d.crops_cap * d.crop_w * d.crop_h * d.cpx + 16);
     if (r == TB_OK) r = host_alloc(&h->h_crop_blob, std::max<size_t>(d.crops_cap, 1));
     if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
     h->own_stream = h->stream;
@@ -1576,7 +1607,8 @@ extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
     if (seg_make_k(*p, k, why) != TB_OK) { set_error("tb_seg_set_params: " + why); return TB_ERR_INVALID; }
     TB_REQUIRE(h->d.CN == 1 || p->color_channel < h->d.CN || p->color_channel >= 4, TB_ERR_INVALID, "tb_seg_set_params: color_channel beyond the frame's channels");
     h->params = *p; h->k = k;
-    h->d.cc = (h->d.CN > 1 && h->d.enc == 0 && p->color_channel >= 0 && p->color_channel < 4) ? p->color_channel : -1;   // >= 4: cvtColor (BackgroundSubtraction.cpp:161-163)
+    h->d.cc = h->d.r3 ? CC_R3G3B2       // r3g3b2 ignores color_channel (BackgroundSubtraction.cpp:151-158)
+              : ((h->d.CN > 1 && h->d.enc == 0 && p->color_channel >= 0 && p->color_channel < 4) ? p->color_channel : -1);   // >= 4: cvtColor (:161-163)
     h->morph = p->use_closing || p->dilation_size != 0;
     if (h->morph) {
         TB_CUDA(cudaSetDevice(h->cfg.device));
@@ -1861,7 +1893,7 @@ extern "C" int tb_seg_wait(tb_seg *h)
         if (t[1]) TB_CUDA(cudaMemcpyAsync(h->h_lines, d.lines, sizeof(tb_line) * (size_t)t[1], cudaMemcpyDeviceToHost, s));
         if (t[2]) TB_CUDA(cudaMemcpyAsync(h->h_pixels, d.pixels, (size_t)t[2], cudaMemcpyDeviceToHost, s));
         if (t[3] && h->last_fetch >= 2) {
-            TB_CUDA(cudaMemcpyAsync(h->h_crops, d.crops, (size_t)t[3] * d.crop_w * d.crop_h * d.opx, cudaMemcpyDeviceToHost, s));
+            TB_CUDA(cudaMemcpyAsync(h->h_crops, d.crops, (size_t)t[3] * d.crop_w * d.crop_h * d.cpx, cudaMemcpyDeviceToHost, s));
             TB_CUDA(cudaMemcpyAsync(h->h_crop_blob, d.crop_blob, sizeof(uint32_t) * (size_t)t[3], cudaMemcpyDeviceToHost, s));
         }
         TB_CUDA(cudaStreamSynchronize(s));
@@ -1986,6 +2018,7 @@ extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch)
                "tb_seg_rethreshold: handles differ in frame size or device");
     TB_REQUIRE(det->last_n <= trk->cfg.max_batch, TB_ERR_INVALID, "tb_seg_rethreshold: tracker-side max_batch too small");
     TB_REQUIRE(trk->has_bg, TB_ERR_STATE, "tb_seg_rethreshold: the tracker-side handle has no background");
+    TB_REQUIRE(!det->d.r3 && !trk->d.r3, TB_ERR_INVALID, "tb_seg_rethreshold: the tracker-side re-threshold is built for gray and rgb8 blobs");
     TB_REQUIRE((det->d.enc == 0 && trk->d.CN == 1) || (det->d.enc == 1 && trk->d.enc == 1 && trk->d.CN == det->d.CN), TB_ERR_INVALID,
                "tb_seg_rethreshold: the tracker-side handle takes the grey plane (channels = 1) for gray encoding, "
                "or the same colour frames (same channels, rgb8) for rgb8");
