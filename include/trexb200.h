@@ -57,7 +57,11 @@ typedef struct tb_seg_params {
     double  size_lo[4], size_hi[4];
     int32_t color_channel;                /* -1 (none); 0..3: with gray encoding take this plane of a colour frame
                                              instead of cvtColor (T/python/BackgroundSubtraction.cpp:161-173)      */
-    int32_t reserved0;
+    int32_t blur_difference;              /* 0; 1: difference -> zero values <= |T| -> cv::blur 25x25 -> > |T| (:371-387); replaces the
+                                             rest of the mask pipeline; 1-channel backgrounds only                     */
+    int32_t use_adaptive_threshold;       /* 0; 1: cv::adaptiveThreshold(MEAN_C, BINARY, n, -T) on the difference image instead of the
+                                             plain threshold (:487,526), n = int(width * adaptive_threshold_scale) made odd, >= 3 (:427-434) */
+    float   adaptive_threshold_scale;     /* 2 (T/core/default_config.cpp:1161)                        */
 } tb_seg_params;
 
 typedef struct tb_seg_config {

@@ -32,6 +32,7 @@ class _Params(C.Structure):
         ("image_invert", C.c_int32), ("use_closing", C.c_int32), ("closing_size", C.c_int32),
         ("dilation_size", C.c_int32), ("cm_per_pixel", C.c_float), ("n_size_ranges", C.c_int32),
         ("size_lo", C.c_double * 4), ("size_hi", C.c_double * 4),
+        ("blur_difference", C.c_int32), ("use_adaptive_threshold", C.c_int32), ("adaptive_threshold_scale", C.c_float), ("pad0", C.c_int32),
     ]
 
 
@@ -48,6 +49,9 @@ class Params:
     dilation_size: int = 0
     cm_per_pixel: float = 1.0
     detect_size_filter: list = field(default_factory=lambda: [(10.0, 100000.0)])
+    blur_difference: bool = False
+    use_adaptive_threshold: bool = False
+    adaptive_threshold_scale: float = 2.0
 
     def c(self) -> _Params:
         p = _Params()
@@ -60,6 +64,9 @@ class Params:
         p.closing_size = self.closing_size
         p.dilation_size = self.dilation_size
         p.cm_per_pixel = self.cm_per_pixel
+        p.blur_difference = int(self.blur_difference)
+        p.use_adaptive_threshold = int(self.use_adaptive_threshold)
+        p.adaptive_threshold_scale = self.adaptive_threshold_scale
         p.n_size_ranges = len(self.detect_size_filter)
         for i, (lo, hi) in enumerate(self.detect_size_filter):
             p.size_lo[i], p.size_hi[i] = lo, hi
@@ -113,6 +120,8 @@ def lib() -> C.CDLL:
         L.to_rethreshold_frame_rgb.restype = C.c_int64
         L.to_average.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.to_average.restype = C.c_int
+        L.to_box_mean.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]; L.to_box_mean.restype = C.c_int
+        L.to_adaptive_neighbourhood.argtypes = [C.c_int, C.c_float]; L.to_adaptive_neighbourhood.restype = C.c_int
         L.to_bgr2gray.argtypes = [vp, C.c_int64, C.c_int, vp]
         L.to_bgr2gray.restype = None
         L.to_bgr2gray_tracker.argtypes = [vp, C.c_int64, vp]
@@ -134,6 +143,19 @@ def lib() -> C.CDLL:
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def box_mean(img: np.ndarray, k: int, border: str = "replicate") -> np.ndarray:
+    """cv::boxFilter(normalize=true) / cv::blur of an 8-bit image; border "replicate" or "reflect101"."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    if lib().to_box_mean(_p(img), img.shape[1], img.shape[0], int(k), {"replicate": 0, "reflect101": 1}[border], _p(out)) != 0:
+        raise MemoryError
+    return out
+
+
+def adaptive_neighbourhood(cols: int, scale: float) -> int:
+    return int(lib().to_adaptive_neighbourhood(int(cols), C.c_float(scale)))
 
 
 def generate_binary(frame: np.ndarray, bg: np.ndarray, params: Params) -> np.ndarray:

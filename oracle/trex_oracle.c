@@ -46,6 +46,10 @@ typedef struct {
     float   cm_per_pixel;             /* BackgroundSubtraction.cpp:137          */
     int32_t n_size_ranges;            /* detect_size_filter: up to 4 half-open ranges */
     double  size_lo[4], size_hi[4];
+    int32_t blur_difference;          /* grabber default_config.cpp:125 (false) */
+    int32_t use_adaptive_threshold;   /* T/core/default_config.cpp:1162 (false) */
+    float   adaptive_threshold_scale; /* :1161 (2)                              */
+    int32_t pad0;
 } to_params_t;
 
 /* Blob emission order (SURVEY.md s7 "Blob order"):
@@ -108,9 +112,57 @@ static void ellipse_element(uint8_t *el, int k)
  *   :504-505 use_closing: dilate, erode with the ellipse element
  *   :541-550 dilation_size>0: dilate ones(n,n);  <0: erode, then re-threshold diff under the mask
  *   :597-599 output = mask & input  (ORIGINAL input, grey values under the mask)
- * Not restated: blur_difference, adaptive threshold, tags (all default-off /
- * out of scope).
+ *   :371-387 blur_difference: difference -> THRESH_TOZERO(|T|) -> cv::blur 25x25 -> THRESH_BINARY(|T|); nothing else applies
+ *   :427-434,487,526 use_adaptive_threshold: cv::adaptiveThreshold(MEAN_C, BINARY, n, -T) on the difference image replaces
+ *            the plain threshold, n = int(cols * adaptive_threshold_scale) made odd, at least 3
+ * Not restated: tags (out of scope).
  * ------------------------------------------------------------------------------------------ */
+
+/* Normalised box filter of an 8-bit image as cv::boxFilter / cv::blur compute it (OpenCV is a third-party dependency of
+ * the reference, not vendored): window k x k around the pixel, border 0 = BORDER_REPLICATE (what cv::adaptiveThreshold
+ * passes), 1 = BORDER_REFLECT_101 (cv::blur's default); result = the window sum divided by k*k, rounded to nearest
+ * (k odd: never a tie).  Checked against cv2 4.13 for k = 3 .. 3841 in tests/test_oracle_golden.py.  OpenCV accumulates in
+ * int32; a window whose sum reaches 2^31 (k*k*mean >= 2^31) would wrap there and does not here. */
+static int border_index(int i, int n, int border)
+{
+    if (border == 0) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) { if (i < 0) i = -i; if (i >= n) i = 2 * (n - 1) - i; }
+    return i;
+}
+int to_box_mean(const uint8_t *src, int w, int h, int k, int border, uint8_t *dst)
+{
+    const int p = k / 2;
+    int64_t *hs = (int64_t *)malloc(sizeof(int64_t) * (size_t)w * h);
+    if (!hs) return -1;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int64_t s = 0;                             /* direct sum for the first pixel of a row, sliding update afterwards */
+            if (x == 0) { for (int i = -p; i <= p; ++i) s += src[(size_t)y * w + border_index(i, w, border)]; }
+            else s = hs[(size_t)y * w + x - 1] - src[(size_t)y * w + border_index(x - 1 - p, w, border)]
+                                               + src[(size_t)y * w + border_index(x + p, w, border)];
+            hs[(size_t)y * w + x] = s;
+        }
+    const int64_t kk = (int64_t)k * k;
+    for (int x = 0; x < w; ++x) {
+        int64_t s = 0;
+        for (int i = -p; i <= p; ++i) s += hs[(size_t)border_index(i, h, border) * w + x];
+        for (int y = 0; y < h; ++y) {
+            if (y) s += hs[(size_t)border_index(y + p, h, border) * w + x] - hs[(size_t)border_index(y - 1 - p, h, border) * w + x];
+            dst[(size_t)y * w + x] = (uint8_t)((2 * s + kk) / (2 * kk));
+        }
+    }
+    free(hs);
+    return 0;
+}
+/* neighbourhood of cv::adaptiveThreshold as generate_binary derives it, RawProcessing.cpp:427-434 */
+int to_adaptive_neighbourhood(int cols, float scale)
+{
+    int n = (int)((float)cols * scale);
+    if (n % 2 == 0) n++;
+    if (n < 3) n = 3;
+    return n;
+}
 /* the threshold mask (255 / 0) of generate_binary, before it is ANDed with the input (:597-599) */
 static int gen_mask(const uint8_t *frame, const uint8_t *bg, int w, int h, const to_params_t *p, uint8_t *mask)
 {
@@ -118,7 +170,21 @@ static int gen_mask(const uint8_t *frame, const uint8_t *bg, int w, int h, const
     const int T = p->detect_threshold, aT = abs(T);
     const int need_morph = p->use_closing || p->dilation_size != 0;
     uint8_t *diff = NULL, *tmp = NULL;
-    if (need_morph) {
+    if (p->blur_difference) {          /* RawProcessing.cpp:371-387; the difference is taken regardless of enable_difference */
+        uint8_t *tz = (uint8_t *)malloc(n), *bl = (uint8_t *)malloc(n);
+        if (!tz || !bl) { free(tz); free(bl); return -1; }
+        for (size_t i = 0; i < n; ++i) {
+            int in = p->image_invert ? 255 - frame[i] : frame[i], d;
+            if (p->detect_threshold_is_absolute) d = abs(in - (int)bg[i]);
+            else { d = (int)bg[i] - in; if (d < 0) d = 0; }
+            tz[i] = d > aT ? (uint8_t)d : 0;                          /* THRESH_TOZERO */
+        }
+        if (to_box_mean(tz, w, h, 25, 1, bl)) { free(tz); free(bl); return -1; }
+        for (size_t i = 0; i < n; ++i) mask[i] = bl[i] > aT ? 255 : 0;
+        free(tz); free(bl);
+        return 0;
+    }
+    if (need_morph || p->use_adaptive_threshold) {
         diff = (uint8_t *)malloc(n); tmp = (uint8_t *)malloc(n);
         if (!diff || !tmp) { free(diff); free(tmp); return -1; }
     }
@@ -135,6 +201,14 @@ static int gen_mask(const uint8_t *frame, const uint8_t *bg, int w, int h, const
         else m = d > aT;
         if (T < 0) m = !m;
         mask[i] = m ? 255 : 0;
+    }
+    if (p->use_adaptive_threshold) {   /* dst = src > mean - C ? 255 : 0 with C = -T (:487,526), then the T < 0 inversion (:498,537) */
+        if (to_box_mean(diff, w, h, to_adaptive_neighbourhood(w, p->adaptive_threshold_scale), 0, tmp)) { free(diff); free(tmp); return -1; }
+        for (size_t i = 0; i < n; ++i) {
+            int m = (int)diff[i] - (int)tmp[i] > T;
+            if (T < 0) m = !m;
+            mask[i] = m ? 255 : 0;
+        }
     }
     if (p->use_closing) {
         int k = p->closing_size, kn = 2 * k + 1;

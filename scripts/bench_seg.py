@@ -2,7 +2,8 @@
 """Micro-benchmark of the segmentation kernels alone (K1 seg_rle, K2 ccl_label, K3 blob_emit) on resident
 synthetic 1080p batches; prints per-kernel ms and the HBM roofline fraction of K1.
 Knobs (env): TB_SEG_FPC (frames per CTA), TB_SEG_NO_TMA=1 (register-streaming K1).
-Usage: bench_seg.py [B] [reps] [channels] [gray|rgb8] [none|moments]   (channels 3/4: BGR/BGRA frames, cvtColor fused
+Usage: bench_seg.py [B] [reps] [channels] [gray|rgb8] [none|moments] [WxH]   (WxH: frame size, default 1920x1080; 3840x2160 is
+BASELINE config 5's segmentation part; channels 3/4: BGR/BGRA frames, cvtColor fused
 into K1; moments: the two extra kernels of the normalised crops are timed by the wall clock of the whole batch)"""
 import json
 import os
@@ -22,7 +23,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 CN = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 ENC = sys.argv[4] if len(sys.argv) > 4 else "gray"
 NORM = sys.argv[5] if len(sys.argv) > 5 else "none"
-world = BlobWorld(n_blobs=100, seed=1234)
+W, H = (int(v) for v in (sys.argv[6] if len(sys.argv) > 6 else "1920x1080").split("x"))
+world = BlobWorld(h=H, w=W, n_blobs=100, seed=1234)
 src = world.frames(16)
 bg = world.bg
 if CN > 1:
@@ -51,7 +53,7 @@ ms, n = bs.kernel_ms()
 tot = bs.totals()
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
 k1 = ms["seg_rle"] / n
-alg = B * 1920 * 1080 * CN + 8 * tot[1]
-print(json.dumps({"B": B, "channels": CN, "encoding": ENC, "normalization": NORM, "batch_ms_wall": batch_ms, "fpc": os.environ.get("TB_SEG_FPC"), "no_tma": os.environ.get("TB_SEG_NO_TMA"),
+alg = B * W * H * CN + 8 * tot[1]
+print(json.dumps({"B": B, "size": f"{W}x{H}", "channels": CN, "encoding": ENC, "normalization": NORM, "batch_ms_wall": batch_ms, "fpc": os.environ.get("TB_SEG_FPC"), "no_tma": os.environ.get("TB_SEG_NO_TMA"),
                   "seg_rle_ms": k1, "GBps": alg / k1 / 1e6, "frac": alg / k1 / 1e6 / peak,
                   "ccl_ms": ms["ccl_label"] / n, "emit_ms": ms["blob_emit"] / n, "blobs": tot[0]}))

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_struct_sizes_match_header(built):
     assert C.sizeof(built.BlobRec) == 32 and C.sizeof(built.FrameInfo) == 32
-    assert C.sizeof(built.SegParams) == 8 * 4 + 4 + 4 + 64 + 8
+    assert C.sizeof(built.SegParams) == 8 * 4 + 4 + 4 + 64 + 16
     assert C.sizeof(built.SegConfig) == 56 and C.sizeof(built.ViConfig) == 32
 
 

@@ -271,6 +271,54 @@ def test_morphology_vs_oracle(kw):
     assert np.array_equal(bs.debug_binary(fr), seg.generate_binary(fr, bg, seg.Params(**keys)))
 
 
+@pytest.mark.parametrize("kw,size", [
+    (dict(blur_difference=True), (144, 208)),
+    (dict(blur_difference=True, detect_threshold_is_absolute=False, image_invert=True), (97, 131)),
+    (dict(blur_difference=True), (540, 960)),
+    (dict(use_adaptive_threshold=True, adaptive_threshold_scale=0.1), (144, 208)),
+    (dict(use_adaptive_threshold=True), (144, 208)),                                     # default scale 2: neighbourhood 2 * cols + 1
+    (dict(use_adaptive_threshold=True, adaptive_threshold_scale=0.02, detect_threshold=-4), (97, 131)),
+    (dict(use_adaptive_threshold=True, adaptive_threshold_scale=0.05, use_closing=True, closing_size=2), (144, 208)),
+    (dict(use_adaptive_threshold=True, adaptive_threshold_scale=0.07, dilation_size=-3), (144, 208)),
+    (dict(use_adaptive_threshold=True, adaptive_threshold_scale=0.03, enable_difference=False, detect_threshold=30), (540, 960)),
+])
+def test_blur_difference_and_adaptive_threshold_vs_oracle(kw, size):
+    """generate_binary's blur_difference (RawProcessing.cpp:371-387) and use_adaptive_threshold (:427-434,487,526) stages; the
+    oracle's versions are checked against the OpenCV calls in tests/test_oracle_golden.py.  11 frames: the box filter works in
+    sub-batches of 8."""
+    from oracle import seg
+    h, w = size
+    rng = np.random.default_rng(h)
+    bg = rng.integers(110, 130, (h, w)).astype(np.uint8)
+    frames = []
+    for f in range(11):
+        fr = np.clip(bg.astype(int) + rng.integers(-7, 8, bg.shape), 1, 255).astype(np.uint8)
+        y, x = int(rng.integers(0, h - 40)), int(rng.integers(0, w - 60))
+        fr[y:y + 30, x:x + 50] = 20; fr[y + 10:y + 14, x + 10:x + 30] = 120
+        fr[0:9, w - 17:w] = 30; fr[h - 3:h, 0:40] = 250
+        fr[rng.random(fr.shape) < 0.003] = 0
+        frames.append(fr)
+    kw = dict(dict(detect_threshold=9, detect_size_filter=[]), **kw)
+    bs = _mk(bg, max_batch=11, dense=True, **kw)
+    got = bs.apply(frames)
+    keys = {k: v for k, v in kw.items() if k in seg.Params.__dataclass_fields__}
+    n_blobs = 0
+    for f in (0, 5, 8, 10):
+        ref = _oracle(frames[f], bg, **kw)
+        assert _as_list(got[f]) == ref.as_list(), f
+        n_blobs += len(ref)
+    assert n_blobs > 0
+    assert np.array_equal(bs.debug_binary(frames[3]), seg.generate_binary(frames[3], bg, seg.Params(**keys)))
+
+
+def test_blur_difference_errors():
+    import trex_b200
+    with pytest.raises(trex_b200.TrexB200Error):      # the 25x25 window does not fit
+        _mk(np.zeros((12, 64), np.uint8), blur_difference=True)
+    with pytest.raises(trex_b200.TrexB200Error):
+        _mk(np.zeros((64, 64), np.uint8), use_adaptive_threshold=True, adaptive_threshold_scale=-1.0)
+
+
 def test_pv_file_from_gpu_results(tmp_path, gold):
     """GPU blobs -> PV15 file (trex_b200.pv_writer) -> oracle reader: same blobs as the reference's file."""
     import trex_b200

@@ -253,3 +253,61 @@ def test_rethreshold_known_answers():
     assert l == [(0, 5, 9), (1, 0, 9)] and p == [50, 60, 70, 80, 90, 100, 110, 120, 130, 140, 150, 160, 170, 180, 190]
     # the absolute case splits into two blobs? rows 0 and 1 touch diagonally at x 5 -> one blob (8-connectivity)
     assert len(seg.rethreshold(parent, bg, 50, seg.DIFF_ABSOLUTE)) == 1
+
+
+def test_box_mean_matches_opencv():
+    """oracle.box_mean vs cv::boxFilter / cv::blur (the calls behind blur_difference and cv::adaptiveThreshold)."""
+    import cv2
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (150, 217), dtype=np.uint8)
+    img[50:90, 100:200] = 255; img[100:130] = 0
+    assert np.array_equal(seg.box_mean(img, 25, "reflect101"), cv2.blur(img, (25, 25)))
+    for k in (3, 7, 15, 17, 63, 255, 435, 1001):
+        got = cv2.boxFilter(img, -1, (k, k), normalize=True, borderType=cv2.BORDER_REPLICATE | cv2.BORDER_ISOLATED)
+        assert np.array_equal(seg.box_mean(img, k, "replicate"), got), k
+    assert [seg.adaptive_neighbourhood(c, s) for c, s in ((1920, 2.0), (1920, 0.01), (100, 0.01), (640, 0.05))] == [3841, 19, 3, 33]
+
+
+@pytest.mark.parametrize("absolute", [True, False])
+def test_generate_binary_blur_difference_matches_opencv(absolute):
+    """RawProcessing.cpp:371-387: difference -> THRESH_TOZERO -> blur 25x25 -> THRESH_BINARY -> mask & input."""
+    import cv2
+    rng = np.random.default_rng(5)
+    bg = rng.integers(120, 140, (140, 200), dtype=np.uint8)
+    fr = np.clip(bg.astype(int) + rng.integers(-12, 13, bg.shape), 1, 255).astype(np.uint8)
+    fr[40:70, 60:120] = 30; fr[100:104, 20:24] = 250; fr[0:20, 180:200] = 60
+    T = 9
+    P = seg.Params(detect_threshold=T, detect_threshold_is_absolute=absolute, blur_difference=True, enable_difference=False)
+    d = cv2.absdiff(fr, bg) if absolute else cv2.subtract(bg, fr)
+    _, tz = cv2.threshold(d, T, 255, cv2.THRESH_TOZERO)
+    _, m = cv2.threshold(cv2.blur(tz, (25, 25)), T, 255, cv2.THRESH_BINARY)
+    exp = cv2.bitwise_and(m, fr)
+    assert exp.any() and np.array_equal(seg.generate_binary(fr, bg, P), exp)
+
+
+@pytest.mark.parametrize("T,scale,closing,dilation", [(9, 0.1, False, 0), (15, 2.0, False, 0), (-5, 0.05, False, 0), (9, 0.1, True, 0), (9, 0.06, False, -3), (12, 0.2, True, 2)])
+def test_generate_binary_adaptive_threshold_matches_opencv(T, scale, closing, dilation):
+    """use_adaptive_threshold (RawProcessing.cpp:427-434,487,526) followed by the same closing / dilation / erosion stages."""
+    import cv2
+    rng = np.random.default_rng(T + 100)
+    bg = rng.integers(120, 140, (120, 170), dtype=np.uint8)
+    fr = np.clip(bg.astype(int) + rng.integers(-6, 7, bg.shape), 1, 255).astype(np.uint8)
+    fr[40:70, 60:120] = 30; fr[100:104, 20:24] = 250; fr[0:20, 150:170] = 60
+    P = seg.Params(detect_threshold=T, use_adaptive_threshold=True, adaptive_threshold_scale=scale, use_closing=closing, closing_size=2,
+                   dilation_size=dilation)
+    d = cv2.absdiff(fr, bg)
+    n = seg.adaptive_neighbourhood(fr.shape[1], scale)
+    m = cv2.adaptiveThreshold(d, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, n, -T)
+    if T < 0:
+        m = cv2.subtract(255, m)
+    el = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5), (2, 2))
+    if closing:
+        m = cv2.erode(cv2.dilate(m, el), el)
+    if dilation > 0:
+        m = cv2.dilate(m, np.ones((dilation, dilation), np.uint8))
+    elif dilation < 0:
+        e = cv2.erode(m, np.ones((-dilation, -dilation), np.uint8))
+        kept = np.where(e > 0, d, 0).astype(np.uint8)
+        _, m = cv2.threshold(kept, abs(T), 255, cv2.THRESH_BINARY)
+    exp = cv2.bitwise_and(m, fr)
+    assert exp.any() and np.array_equal(seg.generate_binary(fr, bg, P), exp)

@@ -23,7 +23,8 @@ class SegParams(C.Structure):
                 ("image_invert", C.c_int32), ("use_closing", C.c_int32), ("closing_size", C.c_int32),
                 ("dilation_size", C.c_int32), ("cm_per_pixel", C.c_float), ("n_size_ranges", C.c_int32),
                 ("size_lo", C.c_double * 4), ("size_hi", C.c_double * 4),
-                ("color_channel", C.c_int32), ("reserved0", C.c_int32)]
+                ("color_channel", C.c_int32), ("blur_difference", C.c_int32),
+                ("use_adaptive_threshold", C.c_int32), ("adaptive_threshold_scale", C.c_float)]
 
 
 class SegConfig(C.Structure):

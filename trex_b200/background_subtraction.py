@@ -40,6 +40,9 @@ class DetectSettings:
     use_closing: bool = False
     closing_size: int = 3
     dilation_size: int = 0
+    blur_difference: bool = False              # grabber default_config.cpp:125
+    use_adaptive_threshold: bool = False       # T/core/default_config.cpp:1162
+    adaptive_threshold_scale: float = 2.0      # :1161
     cm_per_pixel: float = 1.0
     detect_size_filter: list = field(default_factory=lambda: [(10.0, 100000.0)])
     individual_image_size: tuple = (80, 80)
@@ -65,6 +68,8 @@ class DetectSettings:
         for i, (lo, hi) in enumerate(self.detect_size_filter[:4]):
             p.size_lo[i], p.size_hi[i] = float(lo), float(hi)
         p.color_channel = -1 if self.color_channel is None else int(self.color_channel)
+        p.blur_difference = int(self.blur_difference); p.use_adaptive_threshold = int(self.use_adaptive_threshold)
+        p.adaptive_threshold_scale = float(self.adaptive_threshold_scale)
         return p
 
     @property

@@ -97,6 +97,10 @@ int launch_crop_moments(const tb_blob_rec *recs, const uint32_t *totals, const u
                         const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
                         int out_w, int out_h, uint8_t *crops, double *coef, int max_crops_total, cudaStream_t s);
 
+// box.cu: cv::boxFilter / cv::blur of n u8 planes (k x k mean, border 0 replicate / 1 reflect-101); hs = scratch of sub*W*H words;
+// 2 launches per sub-batch of `sub` frames
+int launch_box_mean(const uint8_t *src, uint8_t *dst, uint32_t *hs, int sub, int W, int H, int n, int k, int border, cudaStream_t s);
+
 #ifdef __CUDACC__
 // Exclusive scan of one value per thread across the CTA; `total` = sum over all threads.
 // ws: shared array of >= 33 uint32. All threads must call.

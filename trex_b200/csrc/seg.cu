@@ -820,6 +820,34 @@ __global__ void thresh_mask_kernel(const uint8_t *__restrict__ frames, const uin
     }
 }
 
+// blur_difference (RawProcessing.cpp:371-380): the difference (always taken, absolute or signed) with values <= |T| zeroed
+// (cv::threshold THRESH_TOZERO); the 25x25 blur and the second threshold follow
+__global__ void diff_tozero_kernel(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ bg, uint8_t *__restrict__ out,
+                                   size_t frame_px, size_t total, SegK p)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t f = frames[i], b = bg[i % frame_px];
+        const uint32_t in = (p.flags & F_INV) ? 255u - f : f;
+        const uint32_t d = (p.flags & F_ABS) ? (in > b ? in - b : b - in) : (b > in ? b - in : 0u);
+        out[i] = d > (p.t4 & 0xFFu) ? (uint8_t)d : (uint8_t)0;
+    }
+}
+__global__ void gt_mask_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ mask, size_t total, uint32_t t)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        mask[i] = src[i] > t ? 255 : 0;
+}
+// cv::adaptiveThreshold(MEAN_C, THRESH_BINARY, n, -T) on the difference image: 255 where diff - mean > T; inverted for T < 0
+// (RawProcessing.cpp:487,498 / :526,537)
+__global__ void adaptive_mask_kernel(const uint8_t *__restrict__ diff, const uint8_t *__restrict__ mean, uint8_t *__restrict__ mask, size_t total, int T)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        bool m = (int)diff[i] - (int)mean[i] > T;
+        if (T < 0) m = !m;
+        mask[i] = m ? 255 : 0;
+    }
+}
+
 __global__ void morph_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int W, int H, size_t total, MorphEl el, int dilate)
 {
     const size_t frame_px = (size_t)W * H;
@@ -1427,6 +1455,7 @@ struct tb_seg {
     // optional morphology (use_closing / dilation_size): mask images of one batch, allocated on first use
     bool morph = false;
     uint8_t *m_a = nullptr, *m_b = nullptr, *m_diff = nullptr;
+    uint32_t *box_hs = nullptr; int box_sub = 0;    // blur_difference / use_adaptive_threshold: row-sum scratch of box_sub frames
     const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
     uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
     double *d_coef = nullptr;                   // `moments` normalisation: inverted warp matrix per crop
@@ -1479,7 +1508,7 @@ extern "C" void tb_seg_default_params(tb_seg_params *p)
     std::memset(p, 0, sizeof(*p));
     p->detect_threshold = 15; p->threshold_maximum = 255; p->enable_difference = 1;
     p->detect_threshold_is_absolute = 1; p->closing_size = 3; p->cm_per_pixel = 1.f;
-    p->n_size_ranges = 0; p->color_channel = -1;
+    p->n_size_ranges = 0; p->color_channel = -1; p->adaptive_threshold_scale = 2.f;
 }
 
 template <typename T>
@@ -1609,7 +1638,11 @@ extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
     h->params = *p; h->k = k;
     h->d.cc = h->d.r3 ? CC_R3G3B2       // r3g3b2 ignores color_channel (BackgroundSubtraction.cpp:151-158)
               : ((h->d.CN > 1 && h->d.enc == 0 && p->color_channel >= 0 && p->color_channel < 4) ? p->color_channel : -1);   // >= 4: cvtColor (:161-163)
-    h->morph = p->use_closing || p->dilation_size != 0;
+    h->morph = p->use_closing || p->dilation_size != 0 || p->blur_difference || p->use_adaptive_threshold;
+    TB_REQUIRE(!p->blur_difference || !h->d.enc, TB_ERR_INVALID, "tb_seg_set_params: blur_difference takes a 1-channel background (gray / r3g3b2 encoding)");
+    TB_REQUIRE(!p->blur_difference || (h->d.W > 12 && h->d.H > 12), TB_ERR_INVALID, "tb_seg_set_params: blur_difference needs frames larger than its 25x25 window");
+    TB_REQUIRE(!p->use_adaptive_threshold || (p->adaptive_threshold_scale >= 0.f && p->adaptive_threshold_scale <= 8.f), TB_ERR_INVALID,
+               "tb_seg_set_params: adaptive_threshold_scale must be 0..8");
     if (h->morph) {
         TB_CUDA(cudaSetDevice(h->cfg.device));
         const size_t bytes = (size_t)h->cfg.max_batch * h->d.W * h->d.H;
@@ -1617,6 +1650,11 @@ extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
             int r = seg_dev(h, &h->m_a, bytes + 16);
             if (r == TB_OK) r = seg_dev(h, &h->m_b, bytes + 16);
             if (r == TB_OK) r = seg_dev(h, &h->m_diff, bytes + 16);
+            if (r != TB_OK) return r;
+        }
+        if ((p->blur_difference || p->use_adaptive_threshold) && !h->box_hs) {
+            h->box_sub = std::min(h->cfg.max_batch, 8);
+            int r = seg_dev(h, &h->box_hs, (size_t)h->box_sub * h->d.W * h->d.H);
             if (r != TB_OK) return r;
         }
         if (p->use_closing) h->el_close = ellipse_element(p->closing_size);
@@ -1678,8 +1716,27 @@ static int seg_morph(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s
     const size_t px = (size_t)h->d.W * h->d.H, total = px * (size_t)n;
     const int grid = 148 * 8, nt = 256;
     uint8_t *cur = h->m_a, *tmp = h->m_b;
-    thresh_mask_kernel<<<grid, nt, 0, s>>>(frames_dev, h->d_bg, cur, p.dilation_size < 0 ? h->m_diff : nullptr, px, total, h->k);
+    if (p.blur_difference) {               // RawProcessing.cpp:371-387: nothing else of the mask pipeline applies
+        diff_tozero_kernel<<<grid, nt, 0, s>>>(frames_dev, h->d_bg, cur, px, total, h->k);
+        int r = launch_box_mean(cur, tmp, h->box_hs, h->box_sub, h->d.W, h->d.H, n, 25, 1, s);
+        if (r != TB_OK) return r;
+        gt_mask_kernel<<<grid, nt, 0, s>>>(tmp, cur, total, h->k.t4 & 0xFFu);
+        h->launches += 2 + 2 * (uint64_t)((n + h->box_sub - 1) / h->box_sub);
+        TB_CUDA(cudaGetLastError());
+        *mask_out = cur;
+        return TB_OK;
+    }
+    thresh_mask_kernel<<<grid, nt, 0, s>>>(frames_dev, h->d_bg, cur, (p.dilation_size < 0 || p.use_adaptive_threshold) ? h->m_diff : nullptr, px, total, h->k);
     h->launches += 1;
+    if (p.use_adaptive_threshold) {        // neighbourhood = int(cols * adaptive_threshold_scale), odd, >= 3 (:427-434)
+        int nb = (int)((float)h->d.W * p.adaptive_threshold_scale);
+        if (nb % 2 == 0) nb++;
+        if (nb < 3) nb = 3;
+        int r = launch_box_mean(h->m_diff, tmp, h->box_hs, h->box_sub, h->d.W, h->d.H, n, nb, 0, s);
+        if (r != TB_OK) return r;
+        adaptive_mask_kernel<<<grid, nt, 0, s>>>(h->m_diff, tmp, cur, total, p.detect_threshold);
+        h->launches += 1 + 2 * (uint64_t)((n + h->box_sub - 1) / h->box_sub);
+    }
     auto closing = [&]() {
         morph_kernel<<<grid, nt, 0, s>>>(cur, tmp, h->d.W, h->d.H, total, h->el_close, 1);
         morph_kernel<<<grid, nt, 0, s>>>(tmp, cur, h->d.W, h->d.H, total, h->el_close, 0);
