@@ -186,6 +186,19 @@ TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_
  * tb_seg_device_results on trk return the tracker-side blobs (and their crops: what the reference feeds the CNN). */
 TB_API int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch);
 
+/* Outlines ("next" row N4, first stage): pixel::find_outer_points (C/processing/PixelTree.cpp:497-651) for every blob of the
+ * handle's last batch (after tb_seg_wait with fetch >= 1), the outline calculate_posture selects (the first of maximal
+ * size, T/tracking/Posture.cpp:341-348), and Outline::resample(outline_resample) of it (T/tracking/Outline.cpp:724-766;
+ * <= 0: no resampling).  Points are x,y float pairs relative to the blob's bounding-box origin (tb_blob_rec.x0, y0), pixel
+ * centres at +0.5 -- the frame of the blob after add_offset(-bounds.pos()), Posture.cpp:337.  Record k belongs to blob k of
+ * the batch (tb_blob_rec order).  The result pointers are valid until the next tb_seg_outlines call on the handle. */
+typedef struct tb_outline_rec {
+    uint32_t raw_off, n_raw;          /* range in raw_points (in points): the outline as find_outer_points returns it */
+    uint32_t res_off, n_res;          /* range in points: after Outline::resample                                     */
+} tb_outline_rec;
+TB_API int tb_seg_outlines(tb_seg *h, float outline_resample);
+TB_API int tb_seg_outline_result(tb_seg *h, const tb_outline_rec **recs, const float **raw_points, const float **points, uint32_t *n_blobs);
+
 /* Debug / parity: generate_binary's output image (mask & input) of one device- or host-resident
  * frame, RawProcessing.cpp:597-600.  out is width*height (gray) or width*height*3 (rgb8) host bytes. */
 TB_API int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t *out_host);

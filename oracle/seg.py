@@ -120,6 +120,8 @@ def lib() -> C.CDLL:
         L.to_rethreshold_frame_rgb.restype = C.c_int64
         L.to_average.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.to_average.restype = C.c_int
+        L.to_find_outer_points.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]; L.to_find_outer_points.restype = C.c_int64
+        L.to_outline_resample.argtypes = [vp, C.c_int64, C.c_float, vp, C.c_int64]; L.to_outline_resample.restype = C.c_int64
         L.to_box_mean.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]; L.to_box_mean.restype = C.c_int
         L.to_adaptive_neighbourhood.argtypes = [C.c_int, C.c_float]; L.to_adaptive_neighbourhood.restype = C.c_int
         L.to_bgr2gray.argtypes = [vp, C.c_int64, C.c_int, vp]
@@ -411,3 +413,36 @@ def rethreshold(blobs: "Blobs", bg, threshold: int, method=DIFF_ABSOLUTE, rgb=Fa
                                    _p(ol), capL, _p(op), capP, _p(olo), _p(opo), capB)
     assert k >= 0, k
     return Blobs(ol[:olo[k]].copy(), op[:opo[k]].copy(), olo[:k + 1].copy(), opo[:k + 1].copy())
+
+
+def find_outer_points(lines):
+    """pixel::find_outer_points (C/processing/PixelTree.cpp:497-651): every outline of a blob (list of (n,2) float32 arrays,
+    in the order Tree::generate_edges returns them), coordinates relative to the blob's bounding box origin."""
+    lines = np.ascontiguousarray(lines)
+    npx = int((lines["x1"].astype(np.int64) - lines["x0"] + 1).sum())
+    pts = np.zeros((4 * npx + 8, 2), np.float32); off = np.zeros(2 * npx + 8, np.int64)
+    k = lib().to_find_outer_points(_p(lines), len(lines), _p(pts), len(pts), _p(off), len(off) - 1)
+    if k < 0:
+        raise MemoryError
+    return [pts[off[i]:off[i + 1]].copy() for i in range(k)]
+
+
+def longest_outline(lines):
+    """The outline calculate_posture selects: the first one of maximal size (T/tracking/Posture.cpp:341-348)."""
+    best = None
+    for ol in find_outer_points(lines):
+        if best is None or len(ol) > len(best):
+            best = ol
+    return best if best is not None else np.zeros((0, 2), np.float32)
+
+
+def outline_resample(points, distance=1.0):
+    """Outline::resample (T/tracking/Outline.cpp:724-766)."""
+    points = np.ascontiguousarray(points, np.float32)
+    per = float(np.linalg.norm(np.roll(points, -1, 0) - points, axis=1).sum()) if len(points) else 0.0
+    cap = len(points) + 16 + (int(per / distance * 1.01) if distance > 0 else 0)
+    out = np.zeros((cap, 2), np.float32)
+    n = lib().to_outline_resample(_p(points), len(points), C.c_float(distance), _p(out), cap)
+    if n < 0:
+        raise MemoryError
+    return out[:n].copy()

@@ -1061,3 +1061,160 @@ int64_t to_segment_batch(const uint8_t *frames, int n, const uint8_t *bg, int w,
     for (int i = 1; i < threads; ++i) pthread_join(th[i], NULL);
     return b.total;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" row N4, first stage: the outline of a blob.
+ *   pixel::find_outer_points  C/processing/PixelTree.cpp:497-651  (+ finalize :393-495)
+ *   Tree::add / generate_edges / add_edge / walk   :783-1130, :657-781
+ *   Outline::resample         T/tracking/Outline.cpp:724-766
+ * Restated as a literal emulation of the reference's bookkeeping: border pixels become nodes sorted by
+ * leaf_index (x << 32 | y, PixelTree.h Node::leaf_index: column-major), every missing 4-neighbour side
+ * (order TOP, LEFT, RIGHT, BOTTOM = direction_from_bool) emits one edge from its side midpoint to the next side midpoint
+ * walking with the blob on the right hand (generate_edges :876-965), add_edge keeps the `non_full_nodes` / `_sides`
+ * vectors with the reference's linear search, and walk() is the reference's deque walk (push_front of edges[0], edges[1]).
+ * One deliberate simplification: the node set is "pixels with a missing 4-neighbour" -- what the streaming three-row scan
+ * (:543-633) is built to find; a node without missing sides emits no edge, so a superset is harmless.
+ * parity unpinned: the reference holds no test vectors for find_outer_points.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { float x, y; int32_t e[2]; int walked; uint64_t index; } subnode_t;
+
+static int px_set(const to_line_t *lines, int64_t n, int x, int y)
+{
+    if (x < 0 || y < 0) return 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (lines[i].y == y && lines[i].x0 <= x && x <= lines[i].x1) return 1;
+    return 0;
+}
+
+typedef struct { int x, y; uint8_t nb[8]; } onode_t;       /* nb[d]: pixel in Direction d set (TOP, TOPR, RIGHT, BOTTOMR, BOTTOM, BOTTOML, LEFT, TOPL) */
+static int onode_cmp(const void *a, const void *b)
+{
+    const onode_t *p = (const onode_t *)a, *q = (const onode_t *)b;
+    if (p->x != q->x) return p->x < q->x ? -1 : 1;
+    return p->y < q->y ? -1 : (p->y > q->y);
+}
+
+/* All outlines of a blob in the order Tree::generate_edges returns them.  Coordinates are relative to the blob's
+ * bounding box origin (the blob after add_offset(-bounds.pos()), Posture.cpp:337): pixel centres at +0.5.
+ * pts: x,y pairs; loop_off[k]..loop_off[k+1] = points of outline k.  Returns the number of outlines, or -1 when a
+ * capacity is too small. */
+int64_t to_find_outer_points(const to_line_t *lines_in, int64_t n_lines, float *pts, int64_t cap_pts, int64_t *loop_off, int64_t cap_loops)
+{
+    static const int VX[8] = {0, 1, 1, 1, 0, -1, -1, -1}, VY[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+    static const int FROM_BOOL[4] = {0, 6, 2, 4};            /* direction_from_bool: TOP, LEFT, RIGHT, BOTTOM */
+    if (n_lines <= 0) return 0;
+    int mx = 1 << 30, my = 1 << 30;
+    int64_t npx = 0;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        if (lines_in[i].x0 < mx) mx = lines_in[i].x0;
+        if (lines_in[i].y < my) my = lines_in[i].y;
+        npx += lines_in[i].x1 - lines_in[i].x0 + 1;
+    }
+    to_line_t *lines = (to_line_t *)malloc(sizeof(to_line_t) * (size_t)n_lines);
+    for (int64_t i = 0; i < n_lines; ++i) { lines[i] = lines_in[i]; lines[i].x0 -= mx; lines[i].x1 -= mx; lines[i].y -= my; }
+    onode_t *nodes = (onode_t *)malloc(sizeof(onode_t) * (size_t)npx);
+    int64_t nn = 0;
+    for (int64_t i = 0; i < n_lines; ++i)
+        for (int x = lines[i].x0; x <= lines[i].x1; ++x) {
+            onode_t nd; nd.x = x; nd.y = lines[i].y;
+            for (int d = 0; d < 8; ++d) nd.nb[d] = (uint8_t)px_set(lines, n_lines, x + VX[d], nd.y + VY[d]);
+            if (!nd.nb[0] || !nd.nb[6] || !nd.nb[2] || !nd.nb[4]) nodes[nn++] = nd;
+        }
+    qsort(nodes, (size_t)nn, sizeof(onode_t), onode_cmp);
+    const int64_t cap_sub = 4 * nn + 4;
+    subnode_t *sub = (subnode_t *)malloc(sizeof(subnode_t) * (size_t)cap_sub);
+    int32_t *non_full = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap_sub), *sides = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap_sub);
+    int64_t n_sub = 0, n_nf = 0, n_sides = 0;
+    for (int64_t k = 0; k < nn; ++k) {
+        const onode_t *nd = &nodes[k];
+        for (int bi = 0; bi < 4; ++bi) {
+            const int border = FROM_BOOL[bi];
+            if (nd->nb[border]) continue;                     /* node->border[i]: this 4-neighbour is missing */
+            const int left = (border + 7) & 7, left_left = (border + 6) & 7, opposite = (border + 2) & 7;
+            int bx, by, out_dir = border, in_dir;             /* Edge(out_direction, in_direction, A = node, B) */
+            if (nd->nb[left]) { bx = nd->x + VX[left]; by = nd->y + VY[left]; in_dir = opposite; }
+            else if (nd->nb[left_left]) { bx = nd->x + VX[left_left]; by = nd->y + VY[left_left]; in_dir = border; }
+            else { bx = nd->x; by = nd->y; in_dir = left_left; }
+            /* add_edge (:657-781) */
+            const float ox = ((float)nd->x + 0.5f) + (float)VX[out_dir] * 0.5f, oy = ((float)nd->y + 0.5f) + (float)VY[out_dir] * 0.5f;
+            const float ix = ((float)bx + 0.5f) + (float)VX[in_dir] * 0.5f, iy = ((float)by + 0.5f) + (float)VY[in_dir] * 0.5f;
+            const uint64_t out_idx = (((uint64_t)(int64_t)(ox * 10)) << 32) | ((uint64_t)(int32_t)(oy * 10) & 0xFFFFFFFFull);
+            const uint64_t in_idx = (((uint64_t)(int64_t)(ix * 10)) << 32) | ((uint64_t)(int32_t)(iy * 10) & 0xFFFFFFFFull);
+            int32_t in_node = -1, out_node = -1;
+            for (int64_t it = 0; it < n_nf;) {
+                if (sub[non_full[it]].index == in_idx) {
+                    in_node = non_full[it]; sides[n_sides++] = non_full[it];
+                    memmove(non_full + it, non_full + it + 1, sizeof(int32_t) * (size_t)(n_nf - it - 1)); --n_nf;
+                    if (in_node >= 0 && out_node >= 0) break;
+                } else if (sub[non_full[it]].index == out_idx) {
+                    out_node = non_full[it]; sides[n_sides++] = non_full[it];
+                    memmove(non_full + it, non_full + it + 1, sizeof(int32_t) * (size_t)(n_nf - it - 1)); --n_nf;
+                    if (in_node >= 0 && out_node >= 0) break;
+                } else ++it;
+            }
+            const int found_out = out_node >= 0;
+            if (out_node < 0) {
+                subnode_t s; s.x = ox; s.y = oy; s.e[0] = in_node; s.e[1] = -1; s.walked = 0; s.index = out_idx;
+                out_node = (int32_t)n_sub; sub[n_sub++] = s; non_full[n_nf++] = out_node;
+            }
+            if (in_node < 0) {
+                subnode_t s; s.x = ix; s.y = iy; s.e[0] = out_node; s.e[1] = -1; s.walked = 0; s.index = in_idx;
+                in_node = (int32_t)n_sub; sub[n_sub++] = s; non_full[n_nf++] = in_node;
+                sub[out_node].e[found_out ? 1 : 0] = in_node;
+            } else if (found_out) sub[out_node].e[1] = in_node;
+        }
+    }
+    for (int64_t i = 0; i < n_nf; ++i) sides[n_sides++] = non_full[i];
+    /* walk (:1034-1130): deque with push_front / pop_front */
+    int32_t *dq = (int32_t *)malloc(sizeof(int32_t) * (size_t)(cap_sub + 2));
+    int64_t n_loops = 0, n_pts = 0, ret = 0;
+    loop_off[0] = 0;
+    for (int64_t si = 0; si < n_sides && ret == 0; ++si) {
+        if (sub[sides[si]].walked) continue;
+        if (n_loops >= cap_loops) { ret = -1; break; }
+        int64_t top = 0;                                      /* dq[top-1] is the front */
+        dq[top++] = sides[si]; sub[sides[si]].walked = 1;
+        while (top > 0) {
+            const int32_t nd = dq[--top];
+            if (n_pts >= cap_pts) { ret = -1; break; }
+            pts[2 * n_pts] = sub[nd].x; pts[2 * n_pts + 1] = sub[nd].y; ++n_pts;
+            for (int e = 0; e < 2; ++e) {
+                const int32_t t = sub[nd].e[e];
+                if (t < 0 || sub[t].walked) continue;
+                sub[t].walked = 1;
+                dq[top++] = t;
+            }
+        }
+        loop_off[++n_loops] = n_pts;
+    }
+    free(lines); free(nodes); free(sub); free(non_full); free(sides); free(dq);
+    return ret ? ret : n_loops;
+}
+
+/* Outline::resample (T/tracking/Outline.cpp:724-766), float arithmetic as written there (Float2_t = float, the step
+ * fraction offset * 1.0 / percent in double, then narrowed by Vector2D::operator*).  Returns the number of points. */
+int64_t to_outline_resample(const float *pts, int64_t L, float rd, float *out, int64_t cap)
+{
+    if (rd <= 0 || L <= 1) { if (L > cap) return -1; memcpy(out, pts, sizeof(float) * 2 * (size_t)L); return L; }
+    float walked = 0.0f;
+    int64_t n = 0;
+    for (int64_t i = 0; i < L; ++i) {
+        const int64_t i1 = i + 1 >= L ? i + 1 - L : i + 1;
+        const float x0 = pts[2 * i], y0 = pts[2 * i + 1];
+        const float lx = pts[2 * i1] - x0, ly = pts[2 * i1 + 1] - y0;
+        const float len = sqrtf(lx * lx + ly * ly);
+        walked += len;
+        const float percent = len / rd;
+        float walked_percent = walked / rd;
+        int offset = 0;
+        while (walked_percent >= 1.0) {
+            const float f = (float)(offset * 1.0 / percent);
+            if (n >= cap) return -1;
+            out[2 * n] = x0 + lx * f; out[2 * n + 1] = y0 + ly * f; ++n;
+            offset++;
+            walked -= rd;
+            walked_percent = (float)(walked_percent - 1.0);
+        }
+    }
+    return n;
+}

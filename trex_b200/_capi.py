@@ -64,7 +64,7 @@ SYMBOLS = [
     "tb_seg_debug_binary", "tb_seg_launch_count", "tb_vi_create", "tb_vi_destroy", "tb_vi_set_tensor",
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
     "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_debug_umma_shifted_gemm", "tb_seg_set_stream",
-    "tb_seg_rethreshold", "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
+    "tb_seg_rethreshold", "tb_seg_outlines", "tb_seg_outline_result", "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
 ]
 
 _lib = None
@@ -109,6 +109,8 @@ def lib() -> C.CDLL:
     L.tb_vi_kernel_ms.argtypes = [vp, C.POINTER(C.c_double * 5), C.POINTER(C.c_uint64)]
     L.tb_seg_set_stream.argtypes = [vp, vp]
     L.tb_seg_rethreshold.argtypes = [vp, vp, C.c_int]
+    L.tb_seg_outlines.argtypes = [vp, C.c_float]
+    L.tb_seg_outline_result.argtypes = [vp, vpp, vpp, vpp, C.POINTER(C.c_uint32)]
     L.tb_vi_set_top1.argtypes = [vp, vp, vp]
     L.tb_avg_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vpp]
     L.tb_avg_destroy.argtypes = [vp]; L.tb_avg_destroy.restype = None

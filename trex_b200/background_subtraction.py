@@ -192,6 +192,21 @@ class BackgroundSubtraction:
             return [tracker.result(i) for i in range(self._last_n)]
         return None
 
+    def outlines(self, outline_resample=1.0):
+        """pixel::find_outer_points + the outline calculate_posture selects + Outline::resample for every blob of the last
+        batch (PixelTree.cpp:497-651, Posture.cpp:341-348, Outline.cpp:724-766).  Returns (raw, resampled): two lists with
+        one (n,2) float32 array per blob of the batch (blob order of the batch), coordinates relative to the blob's bounds."""
+        check(lib().tb_seg_outlines(self._h, C.c_float(outline_resample)))
+        rp, pp, qp, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        check(lib().tb_seg_outline_result(self._h, C.byref(rp), C.byref(pp), C.byref(qp), C.byref(n)))
+        if n.value == 0:
+            return [], []
+        recs = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_uint32)), (n.value, 4))
+        n_raw, n_res = int(recs[-1, 0] + recs[-1, 1]), int(recs[-1, 2] + recs[-1, 3])
+        raw = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), (max(n_raw, 1), 2))
+        res = np.ctypeslib.as_array(C.cast(qp, C.POINTER(C.c_float)), (max(n_res, 1), 2))
+        return ([raw[o:o + k].copy() for o, k in recs[:, :2]], [res[o:o + k].copy() for o, k in recs[:, 2:]])
+
     def wait(self):
         check(lib().tb_seg_wait(self._h))
 

@@ -1455,7 +1455,11 @@ struct tb_seg {
     // optional morphology (use_closing / dilation_size): mask images of one batch, allocated on first use
     bool morph = false;
     uint8_t *m_a = nullptr, *m_b = nullptr, *m_diff = nullptr;
-    uint32_t *box_hs = nullptr; int box_sub = 0;    // blur_difference / use_adaptive_threshold: row-sum scratch of box_sub frames
+    uint32_t *box_hs = nullptr; int box_sub = 0;
+    // outlines (tb_seg_outlines), allocated on first use
+    uint8_t *o_visited = nullptr; int4 *o_sel = nullptr; tb_outline_rec *o_recs = nullptr; uint32_t *o_totals = nullptr;
+    float *o_raw = nullptr, *o_res = nullptr; uint32_t o_cap = 0, o_n = 0;
+    tb_outline_rec *h_o_recs = nullptr; float *h_o_raw = nullptr, *h_o_res = nullptr; uint32_t *h_o_totals = nullptr;    // blur_difference / use_adaptive_threshold: row-sum scratch of box_sub frames
     const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
     uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
     double *d_coef = nullptr;                   // `moments` normalisation: inverted warp matrix per crop
@@ -1613,7 +1617,8 @@ extern "C" void tb_seg_destroy(tb_seg *h)
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     for (void *p : h->dev_allocs) cudaFree(p);
-    void *hp[] = {h->h_infos, h->h_totals, h->h_recs, h->h_lines, h->h_pixels, h->h_crops, h->h_crop_blob};
+    void *hp[] = {h->h_infos, h->h_totals, h->h_recs, h->h_lines, h->h_pixels, h->h_crops, h->h_crop_blob,
+                  h->h_o_recs, h->h_o_raw, h->h_o_res, h->h_o_totals};
     for (void *p : hp) if (p) cudaFreeHost(p);
     h->prof.destroy();
     if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -2006,6 +2011,53 @@ extern "C" int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **c
     if (crops) *crops = h->h_crops;
     if (crop_blob_index) *crop_blob_index = h->h_crop_blob;
     *n = h->h_totals[3];
+    return TB_OK;
+}
+
+extern "C" int tb_seg_outlines(tb_seg *h, float outline_resample)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_outlines: null handle");
+    TB_REQUIRE(!h->pending && h->last_n > 0, TB_ERR_STATE, "tb_seg_outlines: call tb_seg_wait on a submitted batch first");
+    TB_REQUIRE(outline_resample < 255.f, TB_ERR_INVALID, "tb_seg_outlines: outline_resample must be < 255 (T/core/default_config.cpp:898)");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    const SegDev &d = h->d;
+    if (!h->o_recs) {
+        h->o_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, (uint64_t)h->cfg.max_batch << 15), 1u << 26);
+        int r = seg_dev(h, &h->o_visited, (size_t)d.px_cap / d.opx + 16);
+        if (r == TB_OK) r = seg_dev(h, &h->o_sel, d.blobs_cap);
+        if (r == TB_OK) r = seg_dev(h, &h->o_recs, d.blobs_cap);
+        if (r == TB_OK) r = seg_dev(h, &h->o_totals, 2);
+        if (r == TB_OK) r = seg_dev(h, &h->o_raw, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = seg_dev(h, &h->o_res, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = host_alloc(&h->h_o_recs, d.blobs_cap);
+        if (r == TB_OK) r = host_alloc(&h->h_o_raw, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = host_alloc(&h->h_o_res, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = host_alloc(&h->h_o_totals, 2);
+        if (r != TB_OK) return r;
+    }
+    cudaStream_t s = h->last_stream ? h->last_stream : h->stream;
+    const uint32_t nb = h->h_totals[0];
+    h->o_n = 0;
+    int r = launch_outlines(d.recs, nb, d.lines, d.line_px, d.opx, h->o_visited, (size_t)d.px_cap / d.opx + 16, outline_resample,
+                            h->o_sel, h->o_recs, h->o_totals, h->o_raw, h->o_res, h->o_cap, s);
+    if (r != TB_OK) return r;
+    h->launches += nb ? 3 : 0;
+    TB_CUDA(cudaMemcpyAsync(h->h_o_totals, h->o_totals, 8, cudaMemcpyDeviceToHost, s));
+    if (nb) TB_CUDA(cudaMemcpyAsync(h->h_o_recs, h->o_recs, sizeof(tb_outline_rec) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    TB_CUDA(cudaStreamSynchronize(s));
+    TB_REQUIRE(h->h_o_totals[0] <= h->o_cap && h->h_o_totals[1] <= h->o_cap, TB_ERR_CAPACITY, "tb_seg_outlines: the outline point arenas are too small for this batch");
+    if (h->h_o_totals[0]) TB_CUDA(cudaMemcpyAsync(h->h_o_raw, h->o_raw, sizeof(float) * 2 * (size_t)h->h_o_totals[0], cudaMemcpyDeviceToHost, s));
+    if (h->h_o_totals[1]) TB_CUDA(cudaMemcpyAsync(h->h_o_res, h->o_res, sizeof(float) * 2 * (size_t)h->h_o_totals[1], cudaMemcpyDeviceToHost, s));
+    TB_CUDA(cudaStreamSynchronize(s));
+    h->o_n = nb;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_outline_result(tb_seg *h, const tb_outline_rec **recs, const float **raw_points, const float **points, uint32_t *n_blobs)
+{
+    TB_REQUIRE(h && recs && raw_points && points && n_blobs, TB_ERR_INVALID, "tb_seg_outline_result: null argument");
+    TB_REQUIRE(h->h_o_recs, TB_ERR_STATE, "tb_seg_outline_result: call tb_seg_outlines first");
+    *recs = h->h_o_recs; *raw_points = h->h_o_raw; *points = h->h_o_res; *n_blobs = h->o_n;
     return TB_OK;
 }
 
