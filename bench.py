@@ -418,7 +418,16 @@ def main():
     ap.add_argument("--encoding", default="gray", choices=["gray", "rgb8"], help="meta_encoding (rgb8 needs --channels 3|4; crops and conv1 then have 3 channels)")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "bf16x3", "fp16"],
                     help="CNN arithmetic: fp32 CUDA cores, bf16x3 split (3 MMAs per k-step) or fp16 (1 MMA per k-step in conv2/conv3) on tcgen05")
+    ap.add_argument("--individuals", type=int, default=100, help="blobs per frame = classes of the network (256: BASELINE config 4; not the headline)")
+    ap.add_argument("--size", default="1920x1080", help="frame size WxH (3840x2160: BASELINE config 5's frames; not the headline)")
     args = ap.parse_args()
+    global H, W, N_INDIV, M_CLASSES, MAX_CROPS, WORKLOAD
+    if args.individuals != 100 or args.size != "1920x1080":
+        W, H = (int(v) for v in args.size.split("x"))
+        N_INDIV = M_CLASSES = args.individuals
+        MAX_CROPS = (N_INDIV * 5 // 4 + 31) // 32 * 32
+        MACS["head"] = 100.0 * M_CLASSES
+        WORKLOAD = WORKLOAD.replace("1920x1080", f"{W}x{H}").replace("100 individuals", f"{N_INDIV} individuals")
     if args.impl == "reference":
         run_reference(args)
     else:

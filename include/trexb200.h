@@ -194,7 +194,8 @@ TB_API int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch);
  * the batch (tb_blob_rec order).  The result pointers are valid until the next tb_seg_outlines call on the handle. */
 typedef struct tb_outline_rec {
     uint32_t raw_off, n_raw;          /* range in raw_points (in points): the outline as find_outer_points returns it */
-    uint32_t res_off, n_res;          /* range in points: after Outline::resample                                     */
+    uint32_t res_off, n_res;          /* range in points: after Outline::resample (ranges of different blobs do not
+                                         overlap but need not be contiguous)                                          */
 } tb_outline_rec;
 TB_API int tb_seg_outlines(tb_seg *h, float outline_resample);
 TB_API int tb_seg_outline_result(tb_seg *h, const tb_outline_rec **recs, const float **raw_points, const float **points, uint32_t *n_blobs);

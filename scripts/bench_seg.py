@@ -2,7 +2,7 @@
 """Micro-benchmark of the segmentation kernels alone (K1 seg_rle, K2 ccl_label, K3 blob_emit) on resident
 synthetic 1080p batches; prints per-kernel ms and the HBM roofline fraction of K1.
 Knobs (env): TB_SEG_FPC (frames per CTA), TB_SEG_NO_TMA=1 (register-streaming K1).
-Usage: bench_seg.py [B] [reps] [channels] [gray|rgb8] [none|moments] [WxH]   (WxH: frame size, default 1920x1080; 3840x2160 is
+Usage: bench_seg.py [B] [reps] [channels] [gray|rgb8] [none|moments] [WxH] [outlines]   (WxH: frame size, default 1920x1080; 3840x2160 is
 BASELINE config 5's segmentation part; channels 3/4: BGR/BGRA frames, cvtColor fused
 into K1; moments: the two extra kernels of the normalised crops are timed by the wall clock of the whole batch)"""
 import json
@@ -51,9 +51,19 @@ bs.wait(); torch.cuda.synchronize()
 batch_ms = (time.perf_counter() - t0) / reps * 1e3
 ms, n = bs.kernel_ms()
 tot = bs.totals()
+outline_ms = None
+if len(sys.argv) > 7 and sys.argv[7] == "outlines":      # N4 first stage: find_outer_points + resample of every blob (incl. D2H of the points)
+    bs.apply_device(pool[0].data_ptr(), B, stream.cuda_stream, fetch=True); bs.wait()
+    lib, h = trex_b200._capi.lib(), bs._h
+    import ctypes as C
+    lib.tb_seg_outlines(h, C.c_float(1.0))
+    t0 = time.perf_counter()
+    for i in range(5):
+        lib.tb_seg_outlines(h, C.c_float(1.0))
+    outline_ms = (time.perf_counter() - t0) / 5 * 1e3
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
 k1 = ms["seg_rle"] / n
 alg = B * W * H * CN + 8 * tot[1]
 print(json.dumps({"B": B, "size": f"{W}x{H}", "channels": CN, "encoding": ENC, "normalization": NORM, "batch_ms_wall": batch_ms, "fpc": os.environ.get("TB_SEG_FPC"), "no_tma": os.environ.get("TB_SEG_NO_TMA"),
                   "seg_rle_ms": k1, "GBps": alg / k1 / 1e6, "frac": alg / k1 / 1e6 / peak,
-                  "ccl_ms": ms["ccl_label"] / n, "emit_ms": ms["blob_emit"] / n, "blobs": tot[0]}))
+                  "ccl_ms": ms["ccl_label"] / n, "emit_ms": ms["blob_emit"] / n, "blobs": tot[0], "outlines_ms_incl_d2h": outline_ms}))

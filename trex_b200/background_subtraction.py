@@ -202,7 +202,7 @@ class BackgroundSubtraction:
         if n.value == 0:
             return [], []
         recs = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_uint32)), (n.value, 4))
-        n_raw, n_res = int(recs[-1, 0] + recs[-1, 1]), int(recs[-1, 2] + recs[-1, 3])
+        n_raw, n_res = int((recs[:, 0] + recs[:, 1]).max()), int((recs[:, 2] + recs[:, 3]).max())
         raw = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), (max(n_raw, 1), 2))
         res = np.ctypeslib.as_array(C.cast(qp, C.POINTER(C.c_float)), (max(n_res, 1), 2))
         return ([raw[o:o + k].copy() for o, k in recs[:, :2]], [res[o:o + k].copy() for o, k in recs[:, 2:]])
