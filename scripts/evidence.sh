@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round evidence on a B200 box (run through gpurun from the repo root): GPU parity suite, both bench arms, ncu launch list.
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_head.log
+timeout 280 python bench.py > gpurun_out/bench_head.json 2>gpurun_out/bench_head.err; tail -c 300 gpurun_out/bench_head.err
+timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_head.json 2>/dev/null
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_head.csv python bench.py --steps 2 --warmup 1 --no-cpu > /dev/null 2>&1
+python - <<PY
+import json
+d = json.loads(open("gpurun_out/bench_head.json").read().strip().splitlines()[-1])
+print(round(d["value"]), round(d["e2e"]["value"]), d["roofline"]["frac"], d["cpu_baseline"]["value"], d["clocks"])
+r = json.loads(open("gpurun_out/bench_ref_head.json").read().strip().splitlines()[-1]); print(r["value"], r.get("cpu_baseline"))
+PY
+wc -l gpurun_out/launches_head.csv

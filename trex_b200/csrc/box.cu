@@ -85,8 +85,8 @@ int launch_box_mean(const uint8_t *src, uint8_t *dst, uint32_t *hs, int sub, int
     TB_REQUIRE(k >= 1 && (k & 1), TB_ERR_INVALID, "box filter: the neighbourhood must be odd");
     TB_REQUIRE(border == 0 || (p <= W - 1 && p <= H - 1), TB_ERR_INVALID, "box filter: the blur window exceeds the frame");
     const int smem = (W + 1 + 33) * 4;
-    static bool attr = false;
-    if (!attr) { TB_CUDA(cudaFuncSetAttribute(box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 1 + 33) * 4)); attr = true; }
+    static DeviceOnce attr;
+    if (attr.need()) { TB_CUDA(cudaFuncSetAttribute(box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 1 + 33) * 4)); attr.done(); }
     for (int f0 = 0; f0 < n; f0 += sub) {
         const int m = min(sub, n - f0);
         box_rows_kernel<<<(unsigned)(m * H), BX_NT, smem, s>>>(src + (size_t)f0 * W * H, hs, W, p, border);

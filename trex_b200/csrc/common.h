@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/trexb200.h"
@@ -40,6 +41,14 @@ static inline int host_alloc(T **p, size_t n)
     if (e != cudaSuccess) { set_error(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); return TB_ERR_CUDA; }
     return TB_OK;
 }
+
+// cudaFuncSetAttribute is per device: a call site keeps one of these (static) and repeats its setup on every device it meets
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+    bool need() const { return !((mask.load(std::memory_order_acquire) >> dev()) & 1ull); }
+    void done() { mask.fetch_or(1ull << dev(), std::memory_order_release); }
+};
 
 // Ring of CUDA-event brackets around the NK kernels of one launch sequence (measurement hook).
 template <int NK>

@@ -1796,9 +1796,10 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     }
     if (fused_colour) {
         static int ctas[2] = {0, 0};
+        static DeviceOnce ctas_once[2];
         const int ci = d.CN == 3 ? 0 : 1;
         const int nt = (K1W_MW + 3 + 1) * 32, smem = k1w_smem(3, d.CN);
-        if (!ctas[ci]) {
+        if (ctas_once[ci].need()) {
             int per_sm = 0, sms = 0;
             if (d.CN == 3) {
                 TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1811,6 +1812,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
             }
             TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
             ctas[ci] = std::max(1, per_sm) * std::max(1, sms);
+            ctas_once[ci].done();
         }
         const unsigned units = (unsigned)d.n_bands * (unsigned)n;
         const unsigned grid = std::min<unsigned>(units, (unsigned)ctas[ci]);
@@ -1837,8 +1839,9 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
         static const int ew = getenv("TB_SEG_EW") ? atoi(getenv("TB_SEG_EW")) : 3;                   // tuning knobs
         static const double static_frac = getenv("TB_SEG_STATIC") ? atof(getenv("TB_SEG_STATIC")) : 0.5;
         static int ws_ctas = 0;
+        static DeviceOnce ws_once;
         const int nt = (K1W_MW + (ew == 4 ? 4 : 3) + 1) * 32, smem = k1w_smem(ew == 4 ? 4 : 3);
-        if (!ws_ctas) {
+        if (ws_once.need()) {
             TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(3)));
             TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(3)));
             TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(4)));
@@ -1847,6 +1850,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
             else TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3>, nt, smem));
             TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
             ws_ctas = std::max(1, per_sm) * std::max(1, sms);
+            ws_once.done();
         }
         const unsigned units = (unsigned)d.n_bands * (unsigned)n;
         const unsigned grid = std::min<unsigned>(units, (unsigned)ws_ctas);
@@ -1871,11 +1875,11 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
                     grid, static_units, (s1 - s0) * 1e-3, (p0 - s0) * 1e-3, (p1 - s0) * 1e-3, (e0 - s0) * 1e-3, (e1 - s0) * 1e-3);
         }
     } else if (d.aligned && !no_tma) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DeviceOnce attr_done;
+        if (attr_done.need()) {
             TB_CUDA(cudaFuncSetAttribute(seg_rle_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM));
             TB_CUDA(cudaFuncSetAttribute(seg_rle_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM));
-            attr_done = true;
+            attr_done.done();
         }
         if (plain) seg_rle_tma_kernel<false><<<g1, K1T_NT, K1T_SMEM, s>>>(plane, d, kk, fpc);
         else seg_rle_tma_kernel<true><<<g1, K1T_NT, K1T_SMEM, s>>>(plane, d, h->k, fpc);
@@ -1884,8 +1888,8 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
         else seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(plane, d, h->k, fpc);
     }
     h->prof.mark(slot, 1);
-    static bool k2_attr = false;
-    if (!k2_attr) { TB_CUDA(cudaFuncSetAttribute(ccl_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2F_SMEM)); k2_attr = true; }
+    static DeviceOnce k2_attr;
+    if (k2_attr.need()) { TB_CUDA(cudaFuncSetAttribute(ccl_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2F_SMEM)); k2_attr.done(); }
     ccl_label_kernel<<<n, K2F_NT, K2F_SMEM, s>>>(d);
     h->prof.mark(slot, 2);
     d.bg = h->d_bg; d.bg_stride = 0; d.keep_mask = nullptr; d.nz_plane = nullptr;   // crops difference against the real background

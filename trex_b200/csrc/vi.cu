@@ -632,8 +632,8 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
 {
     using namespace tb::tc;
     const int M = h->cfg.num_classes;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (attr_done.need()) {
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(1)));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(3)));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1P::SMEM));
@@ -643,7 +643,7 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
-        attr_done = true;
+        attr_done.done();
     }
     const int f16 = h->cfg.precision == 2;
     for (int base = 0; base < n_max; base += h->chunk) {
@@ -699,20 +699,20 @@ static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n
     }
     if (h->cfg.precision >= 1) return vi_forward_tc(h, img, n_max, n_dev, probs, logits, s);
     const int M = h->cfg.num_classes;
-    static bool attr_done = false;
+    static DeviceOnce attr_done;
     auto k2 = conv_kernel<16, 64, 40, 20, 3>;           // pooled 20x20: 7 tiles of 20x3
     auto k3 = conv_kernel<64, 128, 20, 10, 6>;          // pooled 10x10: 2 tiles of 10x6
     constexpr int SM2 = ConvTile<20, 3>::SMEM, SM3 = ConvTile<10, 6>::SMEM;
-    if (!attr_done) {
+    if (attr_done.need()) {
         TB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, SM2));
         TB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
-        attr_done = true;
+        attr_done.done();
     }
     for (int base = 0; base < n_max; base += h->chunk) {
         const int n = std::min(h->chunk, n_max - base);
         const int CI = h->cfg.channels, c1_smem = (CI * 84 * 84 + 400 * CI + 32) * 4;
-        static bool c1_attr = false;
-        if (!c1_attr) { TB_CUDA(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * 84 * 84 + 1200 + 32) * 4)); c1_attr = true; }
+        static DeviceOnce c1_attr;
+        if (c1_attr.need()) { TB_CUDA(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * 84 * 84 + 1200 + 32) * 4)); c1_attr.done(); }
         const int slot = h->prof.begin(s);
         h->prof.mark(slot, 0);
         conv1_kernel<<<n, C1_NT, c1_smem, s>>>(img + (size_t)base * 6400 * CI, 80, 80, CI, n, n_dev, base, h->w1, h->s1, h->t1, h->a1);

@@ -253,7 +253,6 @@ struct ViNet {
     int fc1_in = 0, fc1_out = 0; const char *fc_bn = nullptr;
     float *wf1 = nullptr, *sf1 = nullptr, *tf1 = nullptr, *wf2 = nullptr, *sf2 = nullptr, *tf2 = nullptr;
     float *act[2] = {nullptr, nullptr}, *h1 = nullptr, *lg = nullptr;
-    bool attr_done = false;
 };
 
 template <typename T>
@@ -417,8 +416,8 @@ static int launch_gconv(ViNet *n, GConvArgs &a, int n_img, cudaStream_t s)
     const int smem = (a.IPB * GC_CK * PR * PITCH + KS * KS * GC_CK * 4 * CPT) * 4;
     // the largest configuration of this instantiation: 8x8 windows, one image
     constexpr int PRM = WIN * 8 + KS - 1, SMEM_MAX = (GC_CK * PRM * (PRM | 1) * 2 + KS * KS * GC_CK * 4 * CPT) * 4;
-    static bool attr = false;
-    if (!attr) { TB_CUDA(cudaFuncSetAttribute(gconv_kernel<KS, WIN, CPT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); attr = true; }
+    static DeviceOnce attr;
+    if (attr.need()) { TB_CUDA(cudaFuncSetAttribute(gconv_kernel<KS, WIN, CPT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); attr.done(); }
     TB_REQUIRE(smem <= SMEM_MAX, TB_ERR_INVALID, "vinet: conv tile does not fit the shared-memory budget");
     const unsigned gx = a.IPB > 1 ? (unsigned)((n_img + a.IPB - 1) / a.IPB) : (unsigned)(n_img * a.TX * a.TY);
     gconv_kernel<KS, WIN, CPT, POOL><<<dim3(gx, (unsigned)((a.COUT + 4 * CPT - 1) / (4 * CPT))), GC_NT, smem, s>>>(a);
