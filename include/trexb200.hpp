@@ -92,6 +92,18 @@ public:
         }
         return out;
     }
+    // Posture's first stage for every blob of the last apply(), in apply()'s order (frame by frame): the points
+    // pixel::find_outer_points + the longest-outline choice + Outline::resample(outline_resample) leave in
+    // posture::Result::outline before calculate_midline (T/tracking/Posture.cpp:326-352); x,y pairs relative to the blob's bounds.
+    std::vector<std::vector<float>> outlines(float outline_resample = 1.f)
+    {
+        check(tb_seg_outlines(_h, outline_resample), "tb_seg_outlines");
+        const tb_outline_rec *recs = nullptr; const float *raw = nullptr, *pts = nullptr; uint32_t n = 0;
+        check(tb_seg_outline_result(_h, &recs, &raw, &pts, &n), "tb_seg_outline_result");
+        std::vector<std::vector<float>> out(n);
+        for (uint32_t k = 0; k < n; ++k) out[k].assign(pts + 2 * (size_t)recs[k].res_off, pts + 2 * ((size_t)recs[k].res_off + recs[k].n_res));
+        return out;
+    }
     tb_seg *handle() { return _h; }
 
 private:

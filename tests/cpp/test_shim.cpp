@@ -37,6 +37,9 @@ int main()
         bs.set_background(bg.data());
         auto res = bs.apply({fr.data(), bg.data()});
         if (res[0].size() != 1 || res[1].size() != 0 || res[0][0].pixels->size() != 20) { std::printf("FAIL apply\n"); return 1; }
+        // outline of the 20 x 1 blob: 42 side midpoints, blob on the right hand, no resampling
+        auto ol = bs.outlines(0.f);
+        if (ol.size() != 1 || ol[0].size() != 2 * 42 || ol[0][0] != 0.0f || ol[0][1] != 0.5f) { std::printf("FAIL outlines %zu\n", ol.empty() ? (size_t)0 : ol[0].size()); return 1; }
         // colour frames: BGRA input, meta_encoding rgb8 -> B,G,R per blob pixel; gray frames are refused for rgb8
         {
             trexb200::BackgroundSubtraction cs(W, H, 1, 0, 0, 4, trexb200::meta_encoding_t::rgb8);
