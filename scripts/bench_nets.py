@@ -11,7 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import trex_b200  # noqa: E402
-from trex_b200.weights import random_v118_3_state_dict  # noqa: E402
+from trex_b200.weights import random_state_dict  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
@@ -27,11 +27,7 @@ MACS = {
 
 
 def state_dict(version):
-    if version == "v118_3":
-        return random_v118_3_state_dict(M, 1)
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-    from oracle import vi                      # weight generator only (measurement script, not the product path)
-    return vi.scale_for_u8_inputs(vi.init_state_dict_arch(version, M, 1, seed=0))
+    return random_state_dict(version, M, 1)
 
 
 dev = torch.device("cuda", 0)
