@@ -85,7 +85,8 @@ typedef struct tb_seg_config {
     int32_t crop_normalize;       /* individual_image_normalization (T/tracking/FilterCache.cpp:318-346): 0 none (centre pad /
                                      crop, :158-235), 1 moments (rotation by the blob's second-moment orientation through
                                      cv::warpAffine, :329-341 + :21-115; gray encoding); posture / legacy need the tracker's midline */
-    int32_t reserved0;
+    float   crop_scale;           /* individual_image_scale (T/tracking/FilterCache.cpp:178-180): the masked blob image is resized with
+                                     cv::resize(INTER_NEAREST) before the pad / crop; 0 or 1 = no scaling; gray encoding, crop_normalize 0 */
 } tb_seg_config;
 
 /* Per-frame result header. status bit0: run capacity exceeded (frame dropped, n_blobs=0),

@@ -250,6 +250,38 @@ def crop_blob(lines, pixels, bg, method=DIFF_ABSOLUTE, out_w=80, out_h=80):
 ENC_GRAY, ENC_RGB8, ENC_R3G3B2 = 0, 1, 2
 
 
+def resize_nearest(img: np.ndarray, factor: float) -> np.ndarray:
+    """cv::resize(src, dst, Size(), f, f, INTER_NEAREST) -- resize_image's default (C/misc/detail.h:465-469): dsize = cvRound(n * f),
+    source index = min(floor(d * (1 / f)), n - 1).  Checked against cv2 in tests/test_oracle_golden.py."""
+    f = float(np.float32(factor))                       # individual_image_scale is a float setting, widened to double
+    h, w = img.shape[:2]
+    dw, dh = int(np.rint(w * f)), int(np.rint(h * f))
+    ifx = 1.0 / f
+    xs = np.minimum(np.floor(np.arange(dw) * ifx).astype(np.int64), w - 1)
+    ys = np.minimum(np.floor(np.arange(dh) * ifx).astype(np.int64), h - 1)
+    return img[ys][:, xs]
+
+
+def crop_blob_scaled(lines, pixels, bg, method=DIFF_ABSOLUTE, scale=1.0, out_w=80, out_h=80):
+    """calculate_diff_image with individual_image_scale != 1 (T/tracking/FilterCache.cpp:176-228): the masked blob image is
+    resized (resize_image, INTER_NEAREST) before the centre pad / centre crop to the output size."""
+    _, _, mask, img, diff = image_from_lines(lines, pixels, bg, method, 0)
+    src = img if method == DIFF_NONE else diff          # image.copyTo(padded, mask): both are zero outside the mask
+    out = np.zeros((out_h, out_w), np.uint8)
+    if float(np.float32(scale)) != 1.0:
+        src = resize_nearest(src, scale)
+    h, w = src.shape
+    if h == 0 or w == 0:
+        return out
+    def place(n, m):        # (offset in the output, offset in the source, count) along one axis: pad left = d - d/2, crop start = d - d/2
+        if n < m:
+            d = m - n; return d - d // 2, 0, n
+        d = n - m; return 0, d - d // 2, m
+    ox, sx, cw = place(w, out_w); oy, sy, ch = place(h, out_h)
+    out[oy:oy + ch, ox:ox + cw] = src[sy:sy + ch, sx:sx + cw]
+    return out
+
+
 def bgr2gray(img: np.ndarray) -> np.ndarray:
     """cv::cvtColor(BGR2GRAY / BGRA2GRAY) on u8 (H,W,3|4) -> (H,W)."""
     img = np.ascontiguousarray(img, np.uint8)

@@ -181,6 +181,30 @@ def test_crops_vs_oracle():
         bs.deinit()
 
 
+@pytest.mark.parametrize("scale,method", [(0.5, "absolute"), (1.5, "absolute"), (2.5, "sign"), (0.75, "none"), (1.1, "absolute")])
+def test_scaled_crops_vs_oracle(scale, method):
+    """individual_image_scale != 1 (FilterCache.cpp:178-180): nearest-neighbour resize of the masked blob image, then the centre
+    pad / centre crop; scale 2.5 makes the benchmark's blobs larger than 80x80 (crop branch)."""
+    from oracle import seg
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(h=272, w=480, n_blobs=14, seed=9, margin=30)
+    frames = world.frames(3)
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 100000)], individual_image_scale=scale,
+              track_background_subtraction=method != "none", track_threshold_is_absolute=method != "sign")
+    bs = _mk(world.bg, max_batch=4, max_individuals=32, **kw)
+    got = bs.apply(frames)
+    crops, idx = bs.crops()
+    m = {"none": seg.DIFF_NONE, "absolute": seg.DIFF_ABSOLUTE, "sign": seg.DIFF_SIGN}[method]
+    n = 0
+    for f in range(3):
+        ref = _oracle(frames[f], world.bg, **kw)
+        assert _as_list(got[f]) == ref.as_list()
+        for k in range(min(len(ref), 32)):
+            assert np.array_equal(crops[n], seg.crop_blob_scaled(*ref.blob(k), world.bg, m, scale)), (f, k)
+            n += 1
+    assert n == len(crops) and n > 20 and crops.any()
+
+
 def test_idempotence_render_relabel():
     """test_matching.cpp:1556-1602 property on the GPU path: render blobs -> relabel -> same lines."""
     from trex_b200.synthetic import BlobWorld

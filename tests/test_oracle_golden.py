@@ -311,3 +311,17 @@ def test_generate_binary_adaptive_threshold_matches_opencv(T, scale, closing, di
         _, m = cv2.threshold(kept, abs(T), 255, cv2.THRESH_BINARY)
     exp = cv2.bitwise_and(m, fr)
     assert exp.any() and np.array_equal(seg.generate_binary(fr, bg, P), exp)
+
+
+def test_resize_nearest_matches_opencv():
+    """resize_image's default interpolation (C/misc/detail.h:465-469) as calculate_diff_image applies it for
+    individual_image_scale != 1: oracle.resize_nearest vs cv::resize(INTER_NEAREST)."""
+    import cv2
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        w, h = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        s = float(np.float32(rng.choice([0.5, 0.6, 0.75, 1.25, 1.5, 2.0, 0.33, 0.9, 1.1, 3.0])))
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        if int(np.rint(w * s)) == 0 or int(np.rint(h * s)) == 0:
+            continue
+        assert np.array_equal(seg.resize_nearest(img, s), cv2.resize(img, None, fx=s, fy=s, interpolation=cv2.INTER_NEAREST))

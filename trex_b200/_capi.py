@@ -32,7 +32,7 @@ class SegConfig(C.Structure):
                 ("max_runs_per_frame", C.c_int32), ("max_pixels_per_frame", C.c_int32),
                 ("max_crops_per_frame", C.c_int32), ("crop_width", C.c_int32), ("crop_height", C.c_int32),
                 ("crop_method", C.c_int32), ("channels", C.c_int32), ("encoding", C.c_int32),
-                ("crop_normalize", C.c_int32), ("reserved0", C.c_int32)]
+                ("crop_normalize", C.c_int32), ("crop_scale", C.c_float)]
 
 
 class FrameInfo(C.Structure):

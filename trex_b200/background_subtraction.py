@@ -54,6 +54,7 @@ class DetectSettings:
     color_channel: int | None = None
     # individual_image_normalization (FilterCache.cpp:318-346): "none" | "moments" (posture / legacy need the tracker's midline)
     individual_image_normalization: str = "none"
+    individual_image_scale: float = 1.0        # T/core/default_config.cpp; != 1: resize_image (INTER_NEAREST) before the pad / crop
 
     def c_params(self) -> SegParams:
         p = SegParams()
@@ -110,7 +111,8 @@ class BackgroundSubtraction:
                         crop_height=self.settings.individual_image_size[1],
                         crop_method=self.settings.crop_method, channels=self.channels,
                         encoding={"gray": 0, "rgb8": 1, "r3g3b2": 2}[self.settings.meta_encoding],
-                        crop_normalize={"none": 0, "moments": 1}[self.settings.individual_image_normalization])
+                        crop_normalize={"none": 0, "moments": 1}[self.settings.individual_image_normalization],
+                        crop_scale=float(self.settings.individual_image_scale))
         self.max_individuals = int(max_individuals)
         self._h = C.c_void_p()
         check(lib().tb_seg_create(C.byref(cfg), C.byref(self._h)))

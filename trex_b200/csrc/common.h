@@ -106,6 +106,11 @@ int launch_crop_moments(const tb_blob_rec *recs, const uint32_t *totals, const u
                         const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
                         int out_w, int out_h, uint8_t *crops, double *coef, int max_crops_total, cudaStream_t s);
 
+// crop_norm.cu: crops with individual_image_scale != 1 (nearest-neighbour resize before the centre pad / crop); 1 launch
+int launch_crop_scaled(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,
+                       const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
+                       int out_w, int out_h, float scale, uint8_t *crops, int max_crops_total, cudaStream_t s);
+
 // box.cu: cv::boxFilter / cv::blur of n u8 planes (k x k mean, border 0 replicate / 1 reflect-101); hs = scratch of sub*W*H words;
 // 2 launches per sub-batch of `sub` frames
 int launch_box_mean(const uint8_t *src, uint8_t *dst, uint32_t *hs, int sub, int W, int H, int n, int k, int border, cudaStream_t s);

@@ -150,6 +150,74 @@ crop_warp_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__restric
     }
 }
 
+// individual_image_scale != 1 (T/tracking/FilterCache.cpp:178-180): the masked blob image goes through
+// resize_image = cv::resize(INTER_NEAREST) (C/misc/detail.h:465-469: dsize = cvRound(n * f), source = min(floor(d / f), n - 1))
+// before the centre pad / centre crop (:184-228).  One CTA per crop gathers the output pixels; a pixel finds its value
+// through the blob's rows like crop_warp_kernel does.
+__global__ void __launch_bounds__(CW_NT)
+crop_scale_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__restrict__ totals, const uint32_t *__restrict__ crop_blob,
+                  const tb_line *__restrict__ lines, const uint32_t *__restrict__ line_px, const uint8_t *__restrict__ pixels,
+                  const uint8_t *__restrict__ bg, int W, int crop_method, int out_w, int out_h, float scale, uint8_t *__restrict__ crops)
+{
+    __shared__ uint16_t s_first[CW_ROWS];
+    const uint32_t q = blockIdx.x;
+    if (q >= totals[3]) return;
+    const tb_blob_rec r = recs[crop_blob[q]];
+    const tb_line *L = lines + r.line_off;
+    const uint32_t *LP = line_px + r.line_off;
+    const int bw = (int)r.x1 - (int)r.x0 + 1, bh = (int)r.y1 - (int)r.y0 + 1;
+    const bool indexed = bh <= CW_ROWS && r.n_lines < 65536u;
+    if (indexed) {
+        for (uint32_t i = threadIdx.x; i < r.n_lines; i += CW_NT)
+            if (i == 0 || L[i - 1].y != L[i].y) s_first[(int)L[i].y - (int)r.y0] = (uint16_t)i;      // a connected blob has no empty row
+        __syncthreads();
+    }
+    const double f = (double)scale, inv = 1.0 / f;
+    const int dw = __double2int_rn((double)bw * f), dh = __double2int_rn((double)bh * f);            // cvRound
+    int offx, offy;                                  // output = resized + offset (pad: >= 0, crop: < 0)
+    if (dw < out_w) { const int d = out_w - dw; offx = d - d / 2; } else { const int d = dw - out_w; offx = -(d - d / 2); }
+    if (dh < out_h) { const int d = out_h - dh; offy = d - d / 2; } else { const int d = dh - out_h; offy = -(d - d / 2); }
+    uint8_t *out = crops + (size_t)q * out_w * out_h;
+    for (int i = threadIdx.x; i < out_w * out_h; i += CW_NT) {
+        const int rx = i % out_w - offx, ry = i / out_w - offy;
+        int v = 0;
+        if (rx >= 0 && rx < dw && ry >= 0 && ry < dh) {
+            const int sx = min((int)floor((double)rx * inv), bw - 1), sy = min((int)floor((double)ry * inv), bh - 1);
+            const int ax = sx + (int)r.x0, ay = sy + (int)r.y0;
+            uint32_t j0;
+            if (indexed) j0 = s_first[sy];
+            else {
+                uint32_t lo = 0, hi = r.n_lines;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((int)L[mid].y < ay) lo = mid + 1; else hi = mid; }
+                j0 = lo;
+            }
+            for (uint32_t j = j0; j < r.n_lines; ++j) {
+                const tb_line l = L[j];
+                if ((int)l.y != ay || (int)l.x0 > ax) break;
+                if (ax <= (int)l.x1) {
+                    v = pixels[LP[j] + (uint32_t)(ax - (int)l.x0)];
+                    if (crop_method) {
+                        const int b = bg[(size_t)ay * W + ax];
+                        v = crop_method == 1 ? abs(b - v) : max(0, b - v);
+                    }
+                    break;
+                }
+            }
+        }
+        out[i] = (uint8_t)v;
+    }
+}
+
+int launch_crop_scaled(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,
+                       const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
+                       int out_w, int out_h, float scale, uint8_t *crops, int max_crops_total, cudaStream_t s)
+{
+    if (max_crops_total <= 0) return TB_OK;
+    crop_scale_kernel<<<max_crops_total, CW_NT, 0, s>>>(recs, totals, crop_blob, lines, line_px, pixels, bg, W, crop_method, out_w, out_h, scale, crops);
+    TB_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
 int launch_crop_moments(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,
                         const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
                         int out_w, int out_h, uint8_t *crops, double *coef, int max_crops_total, cudaStream_t s)

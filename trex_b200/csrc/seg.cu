@@ -38,6 +38,7 @@ struct SegDev {
     uint32_t lines_cap, px_cap, blobs_cap, crops_cap;   // batch arenas
     uint32_t px_frame_cap, max_crops;
     int crop_w, crop_h, crop_method;
+    float crop_scale;          // individual_image_scale; != 1: crops are rendered by crop_scale_kernel after K3 (K3 only assigns the crop slots)
     int crop_norm;             // 1: `moments` normalisation, rendered by crop_norm.cu after K3 (K3 only assigns the crop slots)
     float sqcm; int n_ranges; double lo[4], hi[4];
     const uint8_t *bg;
@@ -1310,7 +1311,7 @@ blob_emit_kernel(const uint8_t *__restrict__ frames, SegDev d)
             cl += tl; cp += tp;
         }
         const bool do_crop = q < ncrop;
-        const bool render = do_crop && !d.crop_norm;       // normalised crops are rendered by the warp kernel
+        const bool render = do_crop && !d.crop_norm && d.crop_scale == 1.f;       // normalised / scaled crops are rendered by their own kernels
         const int cpx = d.cpx;
         uint8_t *crop = d.crops + (size_t)(Cb + q) * cw * ch * cpx;
         int offx = 0, offy = 0;
@@ -1538,6 +1539,9 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     TB_REQUIRE(cfg->encoding == 0 || cfg->channels >= 3, TB_ERR_INVALID,
                "tb_seg_create: rgb8 / r3g3b2 encoding needs colour frames (Invalid number of channels, BackgroundSubtraction.cpp:151-158,177-181)");
     TB_REQUIRE(cfg->encoding != 2 || cfg->crop_normalize == 0, TB_ERR_INVALID, "tb_seg_create: crop_normalize = moments is built for the gray encoding");
+    TB_REQUIRE(cfg->crop_scale >= 0.f && cfg->crop_scale <= 16.f, TB_ERR_INVALID, "tb_seg_create: crop_scale (individual_image_scale) must be in (0, 16]; 0 = 1");
+    TB_REQUIRE(cfg->crop_scale == 0.f || cfg->crop_scale == 1.f || (cfg->encoding == 0 && cfg->crop_normalize == 0), TB_ERR_INVALID,
+               "tb_seg_create: crop_scale != 1 is built for the gray encoding without crop normalisation");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("tb_seg_create: no CUDA device (there is no CPU fallback)");
@@ -1569,6 +1573,7 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     d.crop_h = cfg->crop_height > 0 ? cfg->crop_height : 80;
     d.crop_method = cfg->crop_method;
     d.crop_norm = cfg->crop_normalize;
+    d.crop_scale = cfg->crop_scale > 0.f ? cfg->crop_scale : 1.f;
     const size_t B = d.B;
     // batch arenas: an average budget per frame, but never less than one worst-case frame
     d.lines_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)B * std::min<uint32_t>(d.rcap, 8192u), d.rcap), 0x7FFFFFFFu);
@@ -1905,6 +1910,12 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
                                     d.crop_w, d.crop_h, d.crops, h->d_coef, n * (int)d.max_crops, s);
         if (r != TB_OK) return r;
         h->launches += 2;
+    }
+    if (d.crop_scale != 1.f && d.max_crops) {   // individual_image_scale: nearest-neighbour resize of the blob image before the pad / crop
+        int r = launch_crop_scaled(d.recs, d.totals, d.crop_blob, d.lines, d.line_px, d.pixels, h->d_bg, d.W, d.crop_method,
+                                   d.crop_w, d.crop_h, d.crop_scale, d.crops, n * (int)d.max_crops, s);
+        if (r != TB_OK) return r;
+        h->launches += 1;
     }
     TB_CUDA(cudaMemcpyAsync(h->h_totals, d.totals, 16, cudaMemcpyDeviceToHost, s));
     TB_CUDA(cudaMemcpyAsync(h->h_infos, d.infos, sizeof(tb_frame_info) * (size_t)n, cudaMemcpyDeviceToHost, s));
