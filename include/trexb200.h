@@ -232,7 +232,10 @@ typedef struct tb_vi_config {
                                           2: fp16 operands, one MMA per k-step in conv2/conv3 (max|dlogit| ~3e-4) */
     int32_t arch;                      /* visual_identification_version (ModelFetcher, T/python/visual_identification_network_torch.py:537-567):
                                           0 v118_3 (default, :184-258), 1 v100 (:328-386), 2 v110 (:262-325), 3 v119 (:106-181),
-                                          4 v200 (:30-103); 1..4 run on fp32 CUDA cores (precision must be 0)          */
+                                          4 v200 (:30-103).  v119 / v200 run on fp32 CUDA cores (precision must be 0); v100 / v110 do
+                                          with precision 0 and share v118_3's tensor-core kernels with precision 1 / 2 (conv3 and
+                                          fc1 zero-padded to 128 channels; v110 then needs positive BatchNorm2d scales: its
+                                          BatchNorm follows the max-pool and is folded into the filters)                */
 } tb_vi_config;
 
 TB_API int tb_vi_create(const tb_vi_config *cfg, tb_vi **out);

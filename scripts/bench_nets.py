@@ -35,7 +35,7 @@ rng = np.random.default_rng(0)
 crops = torch.from_numpy(rng.integers(0, 256, (N, 80, 80, 1), dtype=np.uint8)).to(dev)
 probs = torch.empty((N, M), dtype=torch.float32, device=dev)
 stream = torch.cuda.Stream(dev)
-for version, precision in (("v118_3", "fp16"), ("v118_3", "bf16x3"), ("v100", "fp32"), ("v110", "fp32"), ("v119", "fp32"), ("v200", "fp32")):
+for version, precision in (("v118_3", "fp16"), ("v118_3", "bf16x3"), ("v100", "fp16"), ("v110", "fp16"), ("v110", "bf16x3"), ("v100", "fp32"), ("v110", "fp32"), ("v119", "fp32"), ("v200", "fp32")):
     net = trex_b200.VINetwork(M, max_images=N, version=version, precision=precision)
     net.load_weights(state_dict(version))
     with torch.cuda.stream(stream):

@@ -252,7 +252,7 @@ head_kernel(const float *__restrict__ h1, int nsplit, size_t split_stride, const
             int M, int n_max, const uint32_t *__restrict__ n_dev, int base,
             const float *__restrict__ g, const float *__restrict__ be, const float *__restrict__ w2t /*[100][M]*/,
             const float *__restrict__ b2, float *__restrict__ probs, float *__restrict__ logits, int w_in_smem,
-            uint32_t *__restrict__ top_id, float *__restrict__ top_p)
+            uint32_t *__restrict__ top_id, float *__restrict__ top_p, int norm_mode)
 {
     extern __shared__ float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,6 +278,13 @@ head_kernel(const float *__restrict__ h1, int nsplit, size_t split_stride, const
         }
         v[j] = a; s += a;
     }
+    if (norm_mode) {           // V100 / V110 on the tensor path: no LayerNorm; g, be = BatchNorm1d folded to scale / shift (or 1, 0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = lane + 32 * j;
+            if (i < 100) sh[i] = fmaxf(fmaf(v[j], g[i], be[i]), 0.f);
+        }
+    } else {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / 100.f;
@@ -291,6 +298,7 @@ head_kernel(const float *__restrict__ h1, int nsplit, size_t split_stride, const
     for (int j = 0; j < 4; ++j) {
         const int i = lane + 32 * j;
         if (i < 100) sh[i] = fmaxf((v[j] - mean) * rstd * g[i] + be[i], 0.f);
+    }
     }
     __syncwarp();
     float mx = -INFINITY; int arg = 0;
@@ -367,7 +375,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     TB_REQUIRE(cfg->max_images > 0, TB_ERR_INVALID, "tb_vi_create: max_images must be > 0");
     TB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32), 1 (bf16x3 tensor cores) or 2 (fp16 tensor cores)");
     TB_REQUIRE(cfg->arch >= 0 && cfg->arch <= 4, TB_ERR_INVALID, "tb_vi_create: arch must be 0 (v118_3), 1 (v100), 2 (v110), 3 (v119) or 4 (v200)");
-    TB_REQUIRE(cfg->arch == 0 || cfg->precision == 0, TB_ERR_INVALID, "tb_vi_create: v100 / v110 / v119 / v200 run in fp32 (precision 0); the tensor-core precisions are built for v118_3");
+    TB_REQUIRE(cfg->arch <= 2 || cfg->precision == 0, TB_ERR_INVALID, "tb_vi_create: v119 / v200 run in fp32 (precision 0); the tensor-core precisions are built for v118_3, v100 and v110");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("tb_vi_create: no CUDA device (there is no CPU fallback)"); return TB_ERR_CUDA; }
     TB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, TB_ERR_INVALID, "tb_vi_create: bad device ordinal");
@@ -380,7 +388,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
     const size_t CH = h->chunk, M = cfg->num_classes, N = cfg->max_images, CI = cfg->channels;
     int r = TB_OK;
 #define A(p, n) if (r == TB_OK) r = vi_dev(h, &(p), (n))
-    if (cfg->arch != 0) {
+    if (cfg->arch != 0 && cfg->precision == 0) {        // fp32 layer-list executor; v100 / v110 with a tensor precision share v118_3's kernels below
         r = vinet_create(&h->net, cfg->arch, cfg->channels, cfg->num_classes, cfg->max_images, h->dev_allocs);
         A(h->d_img, N * 6400 * CI + 16); A(h->d_probs, N * M); A(h->d_logits, N * M);
         if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
@@ -518,23 +526,42 @@ static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int 
 
 // conv weight torch [Cout][Cin][5][5] -> [tap][Cin][Cout]; BN(eval) folded with the conv bias into
 // y = conv * s + t,  s = gamma / sqrt(var + eps),  t = (bias - mean) * s + beta
-static int vi_conv(tb_vi *h, int idx, int cin, int cout, float *dw, float *ds, float *dt)
+// `cout` is the width the kernels are built for, `creal` the network's (V100 / V110: conv3 has 100 channels, padded with zero
+// filters).  arch 0 (V118_3): conv -> BN -> ReLU -> pool.  arch 1 (V100): conv -> ReLU -> pool, s = 1, t = bias.
+// arch 2 (V110): conv -> pool -> BN -> ReLU = relu(maxpool(conv * sB) + sB * bias + tB) for sB > 0 (checked).
+static int vi_conv(tb_vi *h, int idx, int cin, int cout, int creal, float *dw, float *ds, float *dt, std::vector<float> *w_padded = nullptr)
 {
     const std::string c = "model.conv" + std::to_string(idx), b = "model.bn" + std::to_string(idx);
-    const std::vector<float> *w, *bias, *g, *be, *mu, *var;
+    const std::vector<float> *w, *bias, *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
+    const int arch = h->cfg.arch;
     int r;
-    if ((r = vi_need(h, (c + ".weight").c_str(), (size_t)cout * cin * 25, &w))) return r;
-    if ((r = vi_need(h, (c + ".bias").c_str(), cout, &bias))) return r;
-    if ((r = vi_need(h, (b + ".weight").c_str(), cout, &g))) return r;
-    if ((r = vi_need(h, (b + ".bias").c_str(), cout, &be))) return r;
-    if ((r = vi_need(h, (b + ".running_mean").c_str(), cout, &mu))) return r;
-    if ((r = vi_need(h, (b + ".running_var").c_str(), cout, &var))) return r;
-    std::vector<float> wt((size_t)25 * cin * cout), s(cout), t(cout);
-    for (int co = 0; co < cout; ++co) {
+    if ((r = vi_need(h, (c + ".weight").c_str(), (size_t)creal * cin * 25, &w))) return r;
+    if ((r = vi_need(h, (c + ".bias").c_str(), creal, &bias))) return r;
+    if (arch != 1) {
+        if ((r = vi_need(h, (b + ".weight").c_str(), creal, &g))) return r;
+        if ((r = vi_need(h, (b + ".bias").c_str(), creal, &be))) return r;
+        if ((r = vi_need(h, (b + ".running_mean").c_str(), creal, &mu))) return r;
+        if ((r = vi_need(h, (b + ".running_var").c_str(), creal, &var))) return r;
+    }
+    std::vector<float> wt((size_t)25 * cin * cout, 0.f), s(cout, 1.f), t(cout, 0.f);
+    for (int co = 0; co < creal; ++co) {
         for (int ci = 0; ci < cin; ++ci)
             for (int tap = 0; tap < 25; ++tap) wt[((size_t)tap * cin + ci) * cout + co] = (*w)[((size_t)co * cin + ci) * 25 + tap];
+        if (arch == 1) { s[co] = 1.f; t[co] = (*bias)[co]; continue; }
         s[co] = (*g)[co] / std::sqrt((*var)[co] + BN_EPS);
-        t[co] = ((*bias)[co] - (*mu)[co]) * s[co] + (*be)[co];
+        if (arch == 0) t[co] = ((*bias)[co] - (*mu)[co]) * s[co] + (*be)[co];
+        else {
+            if (!(s[co] > 0.f)) {
+                set_error("tb_vi_commit: v110 on the tensor path folds BatchNorm (applied after the max-pool) into the filters, which needs "
+                          "positive BatchNorm scales; " + b + ".weight has a non-positive entry -- use precision fp32");
+                return TB_ERR_INVALID;
+            }
+            t[co] = s[co] * (*bias)[co] + ((*be)[co] - (*mu)[co] * s[co]);
+        }
+    }
+    if (w_padded) {           // torch layout [cout][cin][25] at the padded width, for the tensor-path operand builders
+        w_padded->assign((size_t)cout * cin * 25, 0.f);
+        std::copy(w->begin(), w->end(), w_padded->begin());
     }
     if ((r = vi_upload(dw, wt))) return r;
     if ((r = vi_upload(ds, s))) return r;
@@ -552,15 +579,36 @@ extern "C" int tb_vi_commit(tb_vi *h)
         return TB_OK;
     }
     const int CI = h->cfg.channels;
-    if ((r = vi_conv(h, 1, CI, 16, h->w1, h->s1, h->t1))) return r;
-    if ((r = vi_conv(h, 2, 16, 64, h->w2, h->s2, h->t2))) return r;
-    if ((r = vi_conv(h, 3, 64, 128, h->w3, h->s3, h->t3))) return r;
+    // V100 / V110 (arch 1 / 2) share V118_3's kernels: their conv3 has 100 channels (padded to 128 with zero filters, zero
+    // shift -> ReLU(0) = 0 feeds zero fc1 columns) and fc1 therefore 10000 inputs; the head has no LayerNorm
+    const int arch = h->cfg.arch, C3 = arch == 0 ? 128 : 100;
+    std::vector<float> c3_padded;
+    if ((r = vi_conv(h, 1, CI, 16, 16, h->w1, h->s1, h->t1))) return r;
+    if ((r = vi_conv(h, 2, 16, 64, 64, h->w2, h->s2, h->t2))) return r;
+    if ((r = vi_conv(h, 3, 64, 128, C3, h->w3, h->s3, h->t3, &c3_padded))) return r;
     const int M = h->cfg.num_classes;
     const std::vector<float> *w, *b, *g, *be, *w2, *b2;
-    if ((r = vi_need(h, "model.fc1.weight", (size_t)100 * 12800, &w))) return r;
+    std::vector<float> fc1_padded, ng, nb;
+    if ((r = vi_need(h, "model.fc1.weight", (size_t)100 * C3 * 100, &w))) return r;
     if ((r = vi_need(h, "model.fc1.bias", 100, &b))) return r;
-    if ((r = vi_need(h, "model.bn4.weight", 100, &g))) return r;
-    if ((r = vi_need(h, "model.bn4.bias", 100, &be))) return r;
+    if (arch == 0) {          // LayerNorm(100)
+        if ((r = vi_need(h, "model.bn4.weight", 100, &g))) return r;
+        if ((r = vi_need(h, "model.bn4.bias", 100, &be))) return r;
+    } else {                  // V110: BatchNorm1d(100) in eval mode as scale / shift; V100: nothing (1, 0)
+        ng.assign(100, 1.f); nb.assign(100, 0.f);
+        if (arch == 2) {
+            const std::vector<float> *bg, *bb, *bm, *bv;
+            if ((r = vi_need(h, "model.bn4.weight", 100, &bg))) return r;
+            if ((r = vi_need(h, "model.bn4.bias", 100, &bb))) return r;
+            if ((r = vi_need(h, "model.bn4.running_mean", 100, &bm))) return r;
+            if ((r = vi_need(h, "model.bn4.running_var", 100, &bv))) return r;
+            for (int i = 0; i < 100; ++i) { ng[i] = (*bg)[i] / std::sqrt((*bv)[i] + BN_EPS); nb[i] = (*bb)[i] - (*bm)[i] * ng[i]; }
+        }
+        g = &ng; be = &nb;
+        fc1_padded.assign((size_t)100 * 12800, 0.f);           // torch column k = c * 100 + p: the first C3 * 100 columns of each row
+        for (int o = 0; o < 100; ++o) std::copy(w->begin() + (size_t)o * C3 * 100, w->begin() + (size_t)(o + 1) * C3 * 100, fc1_padded.begin() + (size_t)o * 12800);
+        w = &fc1_padded;
+    }
     if ((r = vi_need(h, "model.fc2.weight", (size_t)M * 100, &w2))) return r;
     if ((r = vi_need(h, "model.fc2.bias", M, &b2))) return r;
     // fc1: torch flattens NCHW (k = c*100 + y*10 + x); activations here are NHWC (k' = (y*10+x)*128 + c)
@@ -580,7 +628,7 @@ extern "C" int tb_vi_commit(tb_vi *h)
     if (h->cfg.precision >= 1) {
         const std::vector<float> *c2, *c3;
         if ((r = vi_need(h, "model.conv2.weight", (size_t)64 * 16 * 25, &c2))) return r;
-        if ((r = vi_need(h, "model.conv3.weight", (size_t)128 * 64 * 25, &c3))) return r;
+        c3 = &c3_padded;
         {   // conv1 B operand [cin][hi|lo][k-step j][k-chunk c][row = wp*16 + cout][8]: window row u = 2j+c, window col e;
             // row (wp = 2i+jj, cout) holds the 5x5 filter shifted by (i, jj) inside the 6x8 window, BN scale folded
             const std::vector<float> *c1;
@@ -681,7 +729,7 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, head_smem(h, M), s>>>(
             h->h1, FC_SPLIT, (size_t)h->chunk * 100, h->bf1, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2,
             probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr, h->head_w_smem,
-            h->top_id ? h->top_id + base : nullptr, h->top_p ? h->top_p + base : nullptr);
+            h->top_id ? h->top_id + base : nullptr, h->top_p ? h->top_p + base : nullptr, h->cfg.arch != 0);
         h->prof.mark(slot, 5);
         h->launches += 5;
     }
@@ -726,7 +774,7 @@ static int vi_forward(tb_vi *h, const uint8_t *img, int n_max, const uint32_t *n
         head_kernel<<<(n + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, head_smem(h, M), s>>>(
             h->h1, 1, 0, nullptr, M, n, n_dev, base, h->lng, h->lnb, h->wf2, h->bf2,
             probs + (size_t)base * M, logits ? logits + (size_t)base * M : nullptr, h->head_w_smem,
-            h->top_id ? h->top_id + base : nullptr, h->top_p ? h->top_p + base : nullptr);
+            h->top_id ? h->top_id + base : nullptr, h->top_p ? h->top_p + base : nullptr, h->cfg.arch != 0);
         h->prof.mark(slot, 5);
         h->launches += 5;
     }
