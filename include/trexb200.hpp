@@ -133,7 +133,7 @@ public:
         cfg.device = device; cfg.width = 80; cfg.height = 80; cfg.channels = channels;
         cfg.num_classes = num_classes; cfg.max_images = max_images;
         cfg.arch = version;
-        cfg.precision = version == 0 ? 1 : 0;   // v118_3: bf16x3 on tensor cores (~1e-5 of fp32); the others: fp32
+        cfg.precision = version <= 1 ? 1 : 0;   // v118_3, v100: bf16x3 on tensor cores (~1e-5 of fp32); the others: fp32
         check(tb_vi_create(&cfg, &_h), "tb_vi_create");
     }
     ~VINetwork() { tb_vi_destroy(_h); }

@@ -22,7 +22,7 @@ def test_reference_class_golden(arch, M, CI):
     tag = f"{arch}_m{M}c{CI}"
     sd = vi.scale_for_u8_inputs(vi.init_state_dict_arch(arch, M, CI, 80, 80, seed=0))
     assert vi.state_checksum(sd) == str(g[f"{tag}_checksum"])
-    net = trex_b200.VINetwork(M, channels=CI, max_images=8, version=arch)
+    net = trex_b200.VINetwork(M, channels=CI, max_images=8, version=arch, precision="fp32")
     net.load_weights(sd)
     probs, logits = net.probabilities(g[f"{tag}_crops"], return_logits=True)
     assert np.abs(logits - g[f"{tag}_logits"]).max() < TOL
@@ -45,7 +45,7 @@ def test_batch_vs_oracle_and_chunking(arch):
         y, x = rng.integers(0, 80 - h), rng.integers(0, 80 - w)
         crops[i, y:y + h, x:x + w, 0] = rng.integers(0, 256, (h, w))
     crops[0] = 0; crops[1] = 255
-    net = trex_b200.VINetwork(M, max_images=20, version=arch)
+    net = trex_b200.VINetwork(M, max_images=20, version=arch, precision="fp32")
     net.load_weights(sd)
     probs, logits = net.probabilities(crops, return_logits=True)
     ref = vi.forward_logits_arch(arch, sd, crops)
