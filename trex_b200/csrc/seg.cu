@@ -910,7 +910,6 @@ __global__ void paint_blobs_kernel(const tb_blob_rec *__restrict__ recs, const u
 // root of a set is its smallest run index = the blob's first line), gathers per-blob statistics and
 // applies the size filter.
 // ------------------------------------------------------------------------------------------------
-constexpr int K2_NT = 512;
 constexpr uint32_t K2_SMEM_RUNS = 8192;      // union-find lives in shared memory up to this many runs
 
 __device__ __forceinline__ uint32_t uf_find(uint32_t *par, uint32_t i)
