@@ -50,6 +50,23 @@ def test_outlines_of_the_benchmark_workload():
     assert all(len(b) >= len(a) for a, b in zip(raw, res) if len(a) > 8)
 
 
+def test_outlines_of_large_blobs_row_table_path():
+    """Blobs whose bounding box does not fit a bit image (or the CTA's pool) are traced through the row table: a frame-wide
+    dense blob with holes, next to small ones that share its CTA."""
+    import trex_b200
+    rng = np.random.default_rng(12)
+    h, w = 400, 640
+    bg = np.zeros((h, w), np.uint8)
+    fr = np.zeros((h, w), np.uint8)
+    fr[20:380, 16:620] = np.where(rng.random((360, 604)) < 0.93, 180, 0)        # one huge blob full of holes
+    fr[2:10, 2:30] = 99; fr[390:398, 100:140:3] = 77
+    fr2 = np.where(rng.random((h, w)) < 0.35, 150, 0).astype(np.uint8)
+    s = trex_b200.DetectSettings(detect_threshold=15, detect_size_filter=[])
+    bs = trex_b200.BackgroundSubtraction(bg, settings=s, max_batch=2, max_runs_per_frame=h * w // 2 + 16, max_pixels_per_frame=h * w)
+    n = _check(bs, [fr, fr2], 1.0)
+    assert n > 1000
+
+
 def test_outlines_errors_and_empty_batch():
     import trex_b200
     bg = np.full((64, 64), 100, np.uint8)

@@ -115,8 +115,9 @@ int launch_crop_scaled(const tb_blob_rec *recs, const uint32_t *totals, const ui
 // 2 launches per sub-batch of `sub` frames
 int launch_box_mean(const uint8_t *src, uint8_t *dst, uint32_t *hs, int sub, int W, int H, int n, int k, int border, cudaStream_t s);
 
-// outline.cu: longest outline (pixel::find_outer_points) of nb blobs + Outline::resample; 3 launches
-int launch_outlines(const tb_blob_rec *recs, uint32_t nb, const tb_line *lines, float rd, uint32_t *row_first, int4 *sel,
+// outline.cu: longest outline (pixel::find_outer_points) of nb blobs + Outline::resample; 1 memset + 3 launches
+int launch_outlines(const tb_blob_rec *recs, uint32_t nb, const tb_line *lines, const uint32_t *line_px, int opx,
+                    uint8_t *visited, size_t visited_bytes, float rd, uint32_t *row_first, int4 *sel,
                     tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, cudaStream_t s);
 
 #ifdef __CUDACC__

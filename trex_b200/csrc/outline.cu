@@ -13,8 +13,8 @@
 //     call going to the sub-node created first, min(t(s), t(pred(s))),
 //   * walk() starts at the first sub-node of `_sides` that is not walked yet and, because edges[1] (or the only edge) of a
 //     sub-node always points to its successor, emits s, succ(s), succ(succ(s)), ... once around the loop.
-// One warp per blob: the warp rasterises the blob's bounding box into a bit image in shared memory (boxes that do not fit
-// fall back to a row table into the blob's line list) and its lanes trace the loops.
+// One thread per blob, 64 blobs per CTA: a thread rasterises its blob's bounding box into a bit image in a slice of the
+// CTA's shared-memory pool (boxes that do not fit fall back to a row table into the blob's line list) and traces its loops.
 // Compiled with -fmad=false: the resampling arithmetic must round like the reference's scalar float code.
 #include "common.h"
 
@@ -24,11 +24,14 @@ __constant__ int c_vx[8] = {0, 1, 1, 1, 0, -1, -1, -1};
 __constant__ int c_vy[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
 
 // "Is pixel (x, y) of the blob set": either a bit image of the bounding box (+ 1 pixel border) in shared memory, built by
-// the blob's warp, or -- for blobs whose box does not fit -- a row table into the blob's line list in global memory.
-constexpr int OL_WARPS = 8, OL_BM_WORDS = 512;           // 2 KB of bit image per warp: boxes up to ~ 126 x 126 / 94 x 168 ...
+// the blob's thread from a pool its CTA shares, or -- for blobs whose box does not fit -- a row table into the blob's line
+// list in global memory.
+constexpr int OL_NT = 64, OL_POOL_WORDS = 12032, OL_MAX_WORDS = 2048;    // 47 KB of bit images (blob + visited run ends) per CTA of 64 blobs
 
 struct Occupancy {
     const uint32_t *bm; int pw;                 // bit image (nullptr: use the lines), words per row
+    uint32_t *vis;                              // select pass: visited run ends, a second bit image (bm != nullptr) ...
+    uint8_t *gvis; const uint32_t *line_px; int opx;   // ... or one byte per blob pixel in global memory (row-table path)
     const tb_line *l; int n; const uint32_t *row_first;
     int bx0, by0, bx1, by1;
     __device__ __forceinline__ bool set(int x, int y) const
@@ -45,38 +48,64 @@ struct Occupancy {
         }
         return false;
     }
+    // run end (x, y) seen before?  marks it
+    __device__ __forceinline__ bool visit(int x, int y) const
+    {
+        if (bm) {
+            const int rx = x - bx0 + 1, ry = y - by0 + 1;
+            uint32_t &wd = vis[ry * pw + (rx >> 5)];
+            const uint32_t bit = 1u << (rx & 31);
+            const bool seen = wd & bit;
+            wd |= bit;
+            return seen;
+        }
+        for (int li = (int)row_first[y - by0]; li < n; ++li) {
+            const tb_line t = l[li];
+            if (x <= (int)t.x1) {
+                uint8_t &f = gvis[line_px[li] / (uint32_t)opx + (uint32_t)(x - (int)t.x0)];
+                const bool seen = f != 0;
+                f = 1;
+                return seen;
+            }
+        }
+        return true;
+    }
 };
 
-// the warp's view of blob r: builds the bit image (all lanes) or the row table (fallback); bm_store = this warp's 2 KB
-__device__ __forceinline__ Occupancy make_occupancy(const tb_blob_rec &r, const tb_line *bl, uint32_t *bm_store, uint32_t *rf, bool build_rf, int lane)
+// One thread per blob.  All threads of the CTA call this (it contains block barriers); `valid` = the thread has a blob.
+// The blob's thread rasterises its lines into its slice of the pool; blobs that do not get a slice build / use the row table.
+// with_vis (select pass): the slice also holds the visited image.
+__device__ __forceinline__ Occupancy make_occupancy(bool valid, const tb_blob_rec &r, const tb_line *bl, uint32_t *pool, uint32_t *ws,
+                                                    uint32_t *rf, bool build_rf, bool with_vis)
 {
     Occupancy O;
-    O.l = bl; O.n = (int)r.n_lines; O.row_first = rf;
+    O.vis = nullptr; O.gvis = nullptr; O.line_px = nullptr; O.opx = 1;
+    O.l = bl; O.n = valid ? (int)r.n_lines : 0; O.row_first = rf;
     O.bx0 = r.x0; O.by0 = r.y0; O.bx1 = r.x1; O.by1 = r.y1;
     const int w = O.bx1 - O.bx0 + 1, h = O.by1 - O.by0 + 1;
     O.pw = (w + 2 + 31) >> 5;
-    if (O.pw * (h + 2) <= OL_BM_WORDS) {
-        for (int i = lane; i < O.pw * (h + 2); i += 32) bm_store[i] = 0u;
-        __syncwarp();
-        for (int li = lane; li < O.n; li += 32) {
+    const uint32_t words = (valid && (long long)O.pw * (h + 2) <= OL_MAX_WORDS) ? (uint32_t)(O.pw * (h + 2)) : 0u;
+    const uint32_t need = with_vis ? 2u * words : words;
+    uint32_t total;
+    const uint32_t off = block_excl_scan(need, ws, total);
+    O.bm = nullptr;
+    if (need && off + need <= OL_POOL_WORDS) {
+        uint32_t *bm = pool + off;
+        for (uint32_t i = 0; i < need; ++i) bm[i] = 0u;
+        if (with_vis) O.vis = bm + words;
+        for (int li = 0; li < O.n; ++li) {
             const tb_line t = bl[li];
             const int a = (int)t.x0 - O.bx0 + 1, b = (int)t.x1 - O.bx0 + 1;
-            uint32_t *row = bm_store + ((int)t.y - O.by0 + 1) * O.pw;
+            uint32_t *row = bm + ((int)t.y - O.by0 + 1) * O.pw;
             for (int wd = a >> 5; wd <= (b >> 5); ++wd) {
                 const int lo = max(a, wd << 5) & 31, hi = min(b, (wd << 5) + 31) & 31;
-                atomicOr(row + wd, (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo));
+                row[wd] |= (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
             }
         }
-        __syncwarp();
-        O.bm = bm_store;
-    } else {
-        O.bm = nullptr;
-        if (build_rf) {
-            for (int li = lane; li < O.n; li += 32)
-                if (li == 0 || bl[li - 1].y != bl[li].y) rf[(int)bl[li].y - O.by0] = (uint32_t)li;
-            __syncwarp();
-            __threadfence_block();
-        }
+        O.bm = bm;
+    } else if (valid && build_rf) {
+        for (int li = 0; li < O.n; ++li)
+            if (li == 0 || bl[li - 1].y != bl[li].y) rf[(int)bl[li].y - O.by0] = (uint32_t)li;
     }
     return O;
 }
@@ -123,71 +152,86 @@ struct Resampler {
     }
 };
 
-// pass 1, one warp per blob: the outline to take -- the longest loop, the earliest in `_sides` among equals.
+// pass 1, one thread per blob: the outline to take -- the longest loop, the earliest in `_sides` among equals.
 // Every loop holds at least one maximal horizontal run of TOP sides (a closed curve has sides facing up) and such a run lies
 // in one loop (TOP(x) -> TOP(x - 1) while the left neighbour exists and has no pixel above it).  The left ends of the runs are
-// the start candidates; they are dealt to the lanes line by line, every lane traces the loops of its candidates, and a trace
-// stops as soon as it meets a run end that precedes its own start in (y, x) order -- so each loop is completed by exactly one
-// lane, the one that holds its first run end.  No visited flags, no atomics; the lanes' best loops are then reduced.
-__global__ void __launch_bounds__(OL_WARPS * 32)
-outline_select_kernel(const tb_blob_rec *__restrict__ recs, uint32_t nb, const tb_line *__restrict__ lines, float rd,
+// the start candidates; a trace flags the run ends it passes (a second bit image, or a byte per blob pixel on the row-table
+// path), so every loop is walked exactly once, from its first run end in (y, x) order.
+struct LoopPick {
+    uint32_t best_n = 0; unsigned long long best_c = ~0ull, best_cr = ~0ull; int bx, by, bb;
+    __device__ void trace(const Occupancy &O, int x, int y, uint32_t max_n)
+    {
+        const Side start{x, y, 0};
+        Side cur = start;
+        uint32_t n = 0;
+        unsigned long long prev_key = 0, first_key = 0, lc = ~0ull, lcr = ~0ull; Side ls = start;
+        do {
+            const Side nx = side_succ(O, cur);
+            if (n && cur.b == 0 && !(nx.b == 0 && nx.y == cur.y)) O.visit(cur.x, cur.y);       // a run end of this loop: not a start any more
+            const unsigned long long k = side_key(cur, O.bx0, O.by0);
+            if (n == 0) first_key = k;
+            else {
+                const unsigned long long c = max(k, prev_key), cr = min(k, prev_key);
+                if (c < lc || (c == lc && cr < lcr)) { lc = c; lcr = cr; ls = cur; }
+            }
+            prev_key = k;
+            cur = nx;
+            ++n;
+        } while (!(cur.x == start.x && cur.y == start.y && cur.b == start.b) && n < max_n);
+        {   // the start's predecessor is the last sub-node of the loop
+            const unsigned long long c = max(first_key, prev_key), cr = min(first_key, prev_key);
+            if (c < lc || (c == lc && cr < lcr)) { lc = c; lcr = cr; ls = start; }
+        }
+        if (n > best_n || (n == best_n && (lc < best_c || (lc == best_c && lcr < best_cr)))) { best_n = n; best_c = lc; best_cr = lcr; bx = ls.x; by = ls.y; bb = ls.b; }
+    }
+};
+
+__global__ void __launch_bounds__(OL_NT)
+outline_select_kernel(const tb_blob_rec *__restrict__ recs, uint32_t nb, const tb_line *__restrict__ lines,
+                      const uint32_t *__restrict__ line_px, int opx, uint8_t *__restrict__ visited, float rd,
                       uint32_t *__restrict__ row_first, int4 *__restrict__ sel, tb_outline_rec *__restrict__ orecs)
 {
-    __shared__ uint32_t s_bm[OL_WARPS][OL_BM_WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * OL_WARPS + warp;
-    if (q >= nb) return;
-    const tb_blob_rec r = recs[q];
+    __shared__ uint32_t s_pool[OL_POOL_WORDS];
+    __shared__ uint32_t s_ws[33];
+    const uint32_t q = blockIdx.x * OL_NT + threadIdx.x;
+    const bool valid = q < nb;
+    tb_blob_rec r{};
+    if (valid) r = recs[q];
     const tb_line *bl = lines + r.line_off;
-    const Occupancy O = make_occupancy(r, bl, s_bm[warp], row_first + r.line_off, true, lane);
-    const int bx0 = r.x0, by0 = r.y0;
+    Occupancy O = make_occupancy(valid, r, bl, s_pool, s_ws, row_first + r.line_off, true, true);
+    if (!valid) return;
+    O.gvis = visited; O.line_px = line_px + r.line_off; O.opx = opx;
     const uint32_t max_n = 4u * r.n_pixels + 4u;            // a loop cannot hold more sides than the blob has
-    uint32_t best_n = 0; unsigned long long best_c = ~0ull, best_cr = ~0ull; Side best{0, 0, 0};
-    for (int li = lane; li < O.n; li += 32) {
-        const tb_line ln = bl[li];
-        const int y = ln.y;
-        for (int x = ln.x0; x <= (int)ln.x1; ++x) {
-            if (O.set(x, y - 1) || !(x == (int)ln.x0 || O.set(x - 1, y - 1))) continue;       // not the left end of a run without pixels above
-            const Side start{x, y, 0};
-            Side cur = start;
-            uint32_t n = 0;
-            bool mine = true;
-            unsigned long long prev_key = 0, first_key = 0, lc = ~0ull, lcr = ~0ull; Side ls = start;
-            do {
-                const Side nx = side_succ(O, cur);
-                if (cur.b == 0 && !(nx.b == 0 && nx.y == cur.y) && (cur.y < start.y || (cur.y == start.y && cur.x < start.x))) { mine = false; break; }
-                const unsigned long long k = side_key(cur, bx0, by0);
-                if (n == 0) first_key = k;
-                else {
-                    const unsigned long long c = max(k, prev_key), cr = min(k, prev_key);
-                    if (c < lc || (c == lc && cr < lcr)) { lc = c; lcr = cr; ls = cur; }
+    LoopPick pick; pick.bx = pick.by = pick.bb = 0;
+    if (O.bm) {
+        // run ends from the bit image: pixels without a pixel above whose left neighbour is not one of them
+        const int h = O.by1 - O.by0 + 1;
+        for (int ry = 1; ry <= h; ++ry) {
+            uint32_t carry = 0;                              // "no pixel above" flag of the previous word's last pixel
+            for (int wd = 0; wd < O.pw; ++wd) {
+                const uint32_t tm = O.bm[ry * O.pw + wd] & ~O.bm[(ry - 1) * O.pw + wd];
+                uint32_t ends = tm & ~((tm << 1) | carry);
+                carry = tm >> 31;
+                while (ends) {
+                    const int bit = __ffs(ends) - 1;
+                    ends &= ends - 1;
+                    const int x = (wd << 5) + bit - 1 + O.bx0, y = ry - 1 + O.by0;
+                    if (!O.visit(x, y)) pick.trace(O, x, y, max_n);
                 }
-                prev_key = k;
-                cur = nx;
-                ++n;
-            } while (!(cur.x == start.x && cur.y == start.y && cur.b == start.b) && n < max_n);
-            if (!mine) continue;
-            {   // the start's predecessor is the last sub-node of the loop
-                const unsigned long long c = max(first_key, prev_key), cr = min(first_key, prev_key);
-                if (c < lc || (c == lc && cr < lcr)) { lc = c; lcr = cr; ls = start; }
             }
-            if (n > best_n || (n == best_n && (lc < best_c || (lc == best_c && lcr < best_cr)))) { best_n = n; best_c = lc; best_cr = lcr; best = ls; }
+        }
+    } else {
+        for (int li = 0; li < O.n; ++li) {
+            const tb_line ln = bl[li];
+            for (int x = ln.x0; x <= (int)ln.x1; ++x)
+                if (!O.set(x, (int)ln.y - 1) && (x == (int)ln.x0 || O.set(x - 1, (int)ln.y - 1)) && !O.visit(x, ln.y)) pick.trace(O, x, ln.y, max_n);
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {          // the warp's best: most sides, then the smallest (entry time, creation time)
-        const uint32_t on = __shfl_xor_sync(0xffffffffu, best_n, o);
-        const unsigned long long oc = __shfl_xor_sync(0xffffffffu, best_c, o), ocr = __shfl_xor_sync(0xffffffffu, best_cr, o);
-        const int ox = __shfl_xor_sync(0xffffffffu, best.x, o), oy = __shfl_xor_sync(0xffffffffu, best.y, o), ob = __shfl_xor_sync(0xffffffffu, best.b, o);
-        if (on > best_n || (on == best_n && (oc < best_c || (oc == best_c && ocr < best_cr)))) { best_n = on; best_c = oc; best_cr = ocr; best = Side{ox, oy, ob}; }
-    }
-    if (lane == 0) {
-        sel[q] = make_int4(best.x, best.y, best.b, 0);
-        tb_outline_rec o; o.raw_off = 0; o.n_raw = best_n; o.res_off = 0;
-        // room for the resampled outline: the perimeter is at most n_raw (steps of 1 or sqrt(1/2)), one point per outline_resample walked
-        o.n_res = (best_n > 1 && rd > 0.f) ? (uint32_t)fminf((float)best_n / rd + 2.f, 4.0e9f) : best_n;
-        orecs[q] = o;
-    }
+    sel[q] = make_int4(pick.bx, pick.by, pick.bb, 0);
+    tb_outline_rec o; o.raw_off = 0; o.n_raw = pick.best_n; o.res_off = 0;
+    // room for the resampled outline: the perimeter is at most n_raw (steps of 1 or sqrt(1/2)), one point per outline_resample walked
+    o.n_res = (pick.best_n > 1 && rd > 0.f) ? (uint32_t)fminf((float)pick.best_n / rd + 2.f, 4.0e9f) : pick.best_n;
+    orecs[q] = o;
 }
 
 // arena offsets: exclusive prefix sums of n_raw / the n_res bounds over the blobs (one CTA); totals[0..1] = sums
@@ -209,22 +253,22 @@ __global__ void outline_scan_kernel(tb_outline_rec *__restrict__ orecs, uint32_t
     if (threadIdx.x == 0) { totals[0] = (uint32_t)min(base_raw, 0xFFFFFFFFull); totals[1] = (uint32_t)min(base_res, 0xFFFFFFFFull); }
 }
 
-// pass 2, one warp per blob (the warp builds the bit image, lane 0 walks): the raw outline and its resampled version;
-// n_res becomes the number of resampled points
-__global__ void __launch_bounds__(OL_WARPS * 32)
+// pass 2, one thread per blob: the raw outline and its resampled version; n_res becomes the number of resampled points
+__global__ void __launch_bounds__(OL_NT)
 outline_emit_kernel(const tb_blob_rec *__restrict__ recs, uint32_t nb, const tb_line *__restrict__ lines,
                     uint32_t *__restrict__ row_first, const int4 *__restrict__ sel,
                     tb_outline_rec *__restrict__ orecs, float rd, float *__restrict__ raw, float *__restrict__ res, uint32_t cap_pts)
 {
-    __shared__ uint32_t s_bm[OL_WARPS][OL_BM_WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * OL_WARPS + warp;
-    if (q >= nb) return;
-    const tb_outline_rec o = orecs[q];
-    if (o.n_raw == 0 || (unsigned long long)o.raw_off + o.n_raw > cap_pts || (unsigned long long)o.res_off + o.n_res > cap_pts) return;
-    const tb_blob_rec r = recs[q];
-    const Occupancy O = make_occupancy(r, lines + r.line_off, s_bm[warp], row_first + r.line_off, false, lane);
-    if (lane != 0) return;
+    __shared__ uint32_t s_pool[OL_POOL_WORDS];
+    __shared__ uint32_t s_ws[33];
+    const uint32_t q = blockIdx.x * OL_NT + threadIdx.x;
+    tb_outline_rec o{};
+    if (q < nb) o = orecs[q];
+    const bool valid = q < nb && o.n_raw != 0 && (unsigned long long)o.raw_off + o.n_raw <= cap_pts && (unsigned long long)o.res_off + o.n_res <= cap_pts;
+    tb_blob_rec r{};
+    if (valid) r = recs[q];
+    const Occupancy O = make_occupancy(valid, r, lines + r.line_off, s_pool, s_ws, row_first + r.line_off, false, false);
+    if (!valid) return;
     const int bx0 = r.x0, by0 = r.y0;
     const int4 s4 = sel[q];
     Side cur{s4.x, s4.y, s4.z};
@@ -243,14 +287,16 @@ outline_emit_kernel(const tb_blob_rec *__restrict__ recs, uint32_t nb, const tb_
     if (resample) orecs[q].n_res = min(rs.n, o.n_res);
 }
 
-int launch_outlines(const tb_blob_rec *recs, uint32_t nb, const tb_line *lines, float rd, uint32_t *row_first, int4 *sel,
+int launch_outlines(const tb_blob_rec *recs, uint32_t nb, const tb_line *lines, const uint32_t *line_px, int opx,
+                    uint8_t *visited, size_t visited_bytes, float rd, uint32_t *row_first, int4 *sel,
                     tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, cudaStream_t s)
 {
     if (nb == 0) { TB_CUDA(cudaMemsetAsync(totals, 0, 8, s)); return TB_OK; }
-    const unsigned grid = (nb + OL_WARPS - 1) / OL_WARPS;
-    outline_select_kernel<<<grid, OL_WARPS * 32, 0, s>>>(recs, nb, lines, rd, row_first, sel, orecs);
+    TB_CUDA(cudaMemsetAsync(visited, 0, visited_bytes, s));
+    const unsigned grid = (nb + OL_NT - 1) / OL_NT;
+    outline_select_kernel<<<grid, OL_NT, 0, s>>>(recs, nb, lines, line_px, opx, visited, rd, row_first, sel, orecs);
     outline_scan_kernel<<<1, 1024, 0, s>>>(orecs, nb, totals);
-    outline_emit_kernel<<<grid, OL_WARPS * 32, 0, s>>>(recs, nb, lines, row_first, sel, orecs, rd, raw, res, cap_pts);
+    outline_emit_kernel<<<grid, OL_NT, 0, s>>>(recs, nb, lines, row_first, sel, orecs, rd, raw, res, cap_pts);
     TB_CUDA(cudaGetLastError());
     return TB_OK;
 }

@@ -1457,7 +1457,7 @@ struct tb_seg {
     uint8_t *m_a = nullptr, *m_b = nullptr, *m_diff = nullptr;
     uint32_t *box_hs = nullptr; int box_sub = 0;
     // outlines (tb_seg_outlines), allocated on first use
-    uint32_t *o_rowfirst = nullptr; int4 *o_sel = nullptr; tb_outline_rec *o_recs = nullptr; uint32_t *o_totals = nullptr;
+    uint8_t *o_visited = nullptr; uint32_t *o_rowfirst = nullptr; int4 *o_sel = nullptr; tb_outline_rec *o_recs = nullptr; uint32_t *o_totals = nullptr;
     float *o_raw = nullptr, *o_res = nullptr; uint32_t o_cap = 0, o_n = 0;
     tb_outline_rec *h_o_recs = nullptr; float *h_o_raw = nullptr, *h_o_res = nullptr; uint32_t *h_o_totals = nullptr;    // blur_difference / use_adaptive_threshold: row-sum scratch of box_sub frames
     const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
@@ -2037,7 +2037,8 @@ extern "C" int tb_seg_outlines(tb_seg *h, float outline_resample)
     const SegDev &d = h->d;
     if (!h->o_recs) {
         h->o_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, (uint64_t)h->cfg.max_batch << 15), 1u << 26);
-        int r = seg_dev(h, &h->o_rowfirst, d.lines_cap);
+        int r = seg_dev(h, &h->o_visited, (size_t)d.px_cap / d.opx + 16);
+        if (r == TB_OK) r = seg_dev(h, &h->o_rowfirst, d.lines_cap);
         if (r == TB_OK) r = seg_dev(h, &h->o_sel, d.blobs_cap);
         if (r == TB_OK) r = seg_dev(h, &h->o_recs, d.blobs_cap);
         if (r == TB_OK) r = seg_dev(h, &h->o_totals, 2);
@@ -2052,7 +2053,8 @@ extern "C" int tb_seg_outlines(tb_seg *h, float outline_resample)
     cudaStream_t s = h->last_stream ? h->last_stream : h->stream;
     const uint32_t nb = h->h_totals[0];
     h->o_n = 0;
-    int r = launch_outlines(d.recs, nb, d.lines, outline_resample, h->o_rowfirst, h->o_sel, h->o_recs, h->o_totals, h->o_raw, h->o_res, h->o_cap, s);
+    int r = launch_outlines(d.recs, nb, d.lines, d.line_px, d.opx, h->o_visited, (size_t)d.px_cap / d.opx + 16, outline_resample,
+                            h->o_rowfirst, h->o_sel, h->o_recs, h->o_totals, h->o_raw, h->o_res, h->o_cap, s);
     if (r != TB_OK) return r;
     h->launches += nb ? 3 : 0;
     TB_CUDA(cudaMemcpyAsync(h->h_o_totals, h->o_totals, 8, cudaMemcpyDeviceToHost, s));
