@@ -52,3 +52,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU oracle", ""), f"{f} references oracle/"
+
+
+def test_transform_results_mirror_matches_oracle():
+    """Host-side mirror of VINetwork::transform_results (VisualIdentification.cpp:808-828) against the oracle's restatement."""
+    import numpy as np
+    from oracle import vi
+    from trex_b200.visual_identification import VINetwork
+    rng = np.random.default_rng(0)
+    rows = {i: rng.random(5).astype(np.float32) for i in range(7)}
+    for idx in ([0, 1, 2, 3, 4, 5, 6], [0, 2, 3], [1, 4], [3], []):
+        a = VINetwork.transform_results(7, idx, rows, 5)
+        b = vi.transform_results(7, idx, rows, 5)
+        assert np.array_equal(a, b), idx
+    assert (VINetwork.transform_results(4, [2], rows, 5)[:2] == -1).all()

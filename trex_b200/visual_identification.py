@@ -92,6 +92,22 @@ class VINetwork:
                                   logits.ctypes.data_as(C.c_void_p) if return_logits else None))
         return (probs, logits) if return_logits else probs
 
+    @staticmethod
+    def transform_results(n: int, indexes, values, num_classes: int) -> np.ndarray:
+        """VINetwork::transform_results (T/ml/VisualIdentification.cpp:808-828): the flat N x M result of the synchronous
+        probabilities() form.  `indexes` lists the images the network returned rows for (ascending), `values[idx]` is the row
+        of image idx; images skipped before a listed index get -1 rows, rows after the last listed index stay 0 (as in the
+        reference).  With this library every image is classified, so indexes = range(n)."""
+        probs = np.zeros((n, num_classes), np.float32)
+        i = 0
+        for idx in (int(v) for v in indexes):
+            if i < idx:
+                probs[i:idx] = -1.0
+                i = idx
+            probs[idx] = np.asarray(values[idx], np.float32)
+            i += 1
+        return probs
+
     def predict_device(self, images_ptr: int, n_max: int, n_dev_ptr: int, probs_ptr: int, logits_ptr: int = 0, stream: int = 0):
         check(lib().tb_vi_predict_device(self._h, C.c_void_p(images_ptr), n_max, C.c_void_p(n_dev_ptr) if n_dev_ptr else None,
                                          C.c_void_p(probs_ptr), C.c_void_p(logits_ptr) if logits_ptr else None,
