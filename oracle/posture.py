@@ -1,0 +1,124 @@
+"""ORACLE ONLY (no CUDA counterpart yet): from a resampled outline to the raw midline -- TEST INFRASTRUCTURE.
+
+Python face of the restatement in trex_oracle.c of
+  Outline::smooth / offset_to_middle / calculate_midline   Application/src/tracker/tracking/Outline.cpp:330-452,454-718,768-868
+  periodic::curvature / differentiate / find_peaks / eft / ieft, fast::cos
+                                                            Application/src/commons/common/misc/CircularGraph.cpp:12-606
+parity unpinned: the reference has no test vectors for these functions; tests/test_oracle_posture.py checks each piece
+against an independent numpy formulation and the whole chain on shapes whose midline is known by construction."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .seg import _p, lib
+
+
+class PostureParams(C.Structure):
+    _fields_ = [("outline_smooth_samples", C.c_int32), ("outline_smooth_step", C.c_int32), ("outline_approximate", C.c_int32),
+                ("outline_curvature_range_ratio", C.c_float), ("midline_walk_offset", C.c_float), ("peak_mode", C.c_int32),
+                ("midline_start_with_head", C.c_int32), ("midline_invert", C.c_int32)]
+
+
+PEAK_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("width", "<f4"), ("integral", "<f4"), ("r0", "<f4"), ("r1", "<f4"),
+                       ("max_y_extrema", "<f4"), ("max_y", "<f4"), ("n_pts", "<i4")])
+
+
+def _lib():
+    L = lib()
+    if not getattr(L, "_posture_ready", False):
+        vp = C.c_void_p
+        L.to_posture_default_params.argtypes = [C.POINTER(PostureParams)]; L.to_posture_default_params.restype = None
+        L.to_fast_cos.argtypes = [C.c_float]; L.to_fast_cos.restype = C.c_float
+        L.to_outline_smooth.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp]; L.to_outline_smooth.restype = C.c_int
+        L.to_periodic_curvature.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp]; L.to_periodic_curvature.restype = None
+        L.to_orientation_sum.argtypes = [vp, C.c_int64]; L.to_orientation_sum.restype = C.c_float
+        L.to_eft.argtypes = [vp, C.c_int64, C.c_int, vp]; L.to_eft.restype = None
+        L.to_ieft.argtypes = [vp, C.c_int, C.c_int64, C.c_float, C.c_float, vp]; L.to_ieft.restype = None
+        L.to_find_peaks.argtypes = [vp, C.c_int64, C.c_int, vp, C.c_int64]; L.to_find_peaks.restype = C.c_int64
+        L.to_offset_to_middle.argtypes = [vp, C.c_int64, C.POINTER(PostureParams), C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]
+        L.to_offset_to_middle.restype = C.c_int
+        L.to_calculate_midline.argtypes = [vp, C.c_int64, C.POINTER(PostureParams), vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.to_calculate_midline.restype = C.c_int64
+        L._posture_ready = True
+    return L
+
+
+def default_params(**kw) -> PostureParams:
+    p = PostureParams()
+    _lib().to_posture_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def fast_cos(x: float) -> float:
+    return float(_lib().to_fast_cos(C.c_float(x)))
+
+
+def smooth(points, samples=4, step=1):
+    pts = np.ascontiguousarray(points, np.float32)
+    out = np.empty_like(pts)
+    return out if _lib().to_outline_smooth(_p(pts), len(pts), samples, step, _p(out)) else pts.copy()
+
+
+def curvature(points, r, absolute=False):
+    pts = np.ascontiguousarray(points, np.float32)
+    out = np.zeros(len(pts), np.float32)
+    _lib().to_periodic_curvature(_p(pts), len(pts), int(r), int(absolute), _p(out))
+    return out
+
+
+def orientation_sum(points) -> float:
+    pts = np.ascontiguousarray(points, np.float32)
+    return float(_lib().to_orientation_sum(_p(pts), len(pts)))
+
+
+def eft(points, order=3):
+    pts = np.ascontiguousarray(points, np.float32)
+    out = np.zeros((order, 4), np.float32)
+    _lib().to_eft(_p(pts), len(pts), order, _p(out))
+    return out
+
+
+def ieft(coeffs, n_points, offset=(0.0, 0.0)):
+    c = np.ascontiguousarray(coeffs, np.float32)
+    out = np.zeros((n_points, 2), np.float32)
+    _lib().to_ieft(_p(c), len(c), n_points, C.c_float(offset[0]), C.c_float(offset[1]), _p(out))
+    return out
+
+
+def find_peaks(values, broad=False):
+    v = np.ascontiguousarray(values, np.float32)
+    out = np.zeros(len(v) + 1, PEAK_DTYPE)
+    n = _lib().to_find_peaks(_p(v), len(v), int(broad), _p(out), len(out))
+    if n < 0:
+        raise MemoryError
+    return out[:n].copy()
+
+
+def offset_to_middle(points, params: PostureParams | None = None):
+    """Returns (points after reversal / approximation / rotation, tail index, head index, curvature)."""
+    pts = np.ascontiguousarray(points, np.float32).copy()
+    P = params or default_params()
+    t, h = C.c_int64(), C.c_int64()
+    curv = np.zeros(len(pts), np.float32)
+    rc = _lib().to_offset_to_middle(_p(pts), len(pts), C.byref(P), C.byref(t), C.byref(h), _p(curv))
+    if rc:
+        raise ValueError(f"offset_to_middle failed ({rc})")
+    return pts, int(t.value), int(h.value), curv
+
+
+def calculate_midline(points, params: PostureParams | None = None):
+    """Returns (segments (n,4): pos.x, pos.y, height, l_length; tail index; head index; the outline as the walk saw it),
+    or raises ValueError like the reference returns std::unexpected."""
+    pts = np.ascontiguousarray(points, np.float32).copy()
+    P = params or default_params()
+    seg = np.zeros((len(pts) + 4, 4), np.float32)
+    t, h = C.c_int64(), C.c_int64()
+    n = _lib().to_calculate_midline(_p(pts), len(pts), C.byref(P), _p(seg), len(seg), C.byref(t), C.byref(h))
+    if n < 0:
+        raise ValueError({-1: "Empty outline was given, cannot calculate midline.", -2: "Too few midline segments calculated.",
+                          -3: "peak_mode broad is not restated", -4: "capacity"}[int(n)])
+    return seg[:n].copy(), int(t.value), int(h.value), pts

@@ -1218,3 +1218,412 @@ int64_t to_outline_resample(const float *pts, int64_t L, float rd, float *out, i
     }
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" row N4, second stage (ORACLE ONLY so far -- no CUDA counterpart yet): from the resampled outline to
+ * the raw midline.
+ *   Outline::smooth / smooth_outline         T/tracking/Outline.cpp:330-452
+ *   Outline::offset_to_middle                T/tracking/Outline.cpp:454-718   (the non-"old" method)
+ *   periodic::differentiate(_and_test_clockwise), curvature, find_peaks, eft, ieft, fast::cos
+ *                                            C/misc/CircularGraph.cpp:12-30,49-113,115-407,409-482,484-606
+ *   Outline::calculate_midline               T/tracking/Outline.cpp:768-868
+ * Float2_t = scalar_t = float; every double literal / M_PI in the reference promotes exactly as written below.
+ * parity unpinned: the reference holds no test vectors for these functions.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t outline_smooth_samples;        /* 4   T/core/default_config.cpp:890 */
+    int32_t outline_smooth_step;           /* 1   :889 */
+    int32_t outline_approximate;           /* 3   :888 */
+    float   outline_curvature_range_ratio; /* 0.03 :891 */
+    float   midline_walk_offset;           /* 0.025 :892 */
+    int32_t peak_mode;                     /* 0 pointy (default, :902), 1 broad */
+    int32_t midline_start_with_head;       /* 0   :900 */
+    int32_t midline_invert;                /* 0   :901 */
+} to_posture_params_t;
+
+void to_posture_default_params(to_posture_params_t *p)
+{
+    p->outline_smooth_samples = 4; p->outline_smooth_step = 1; p->outline_approximate = 3;
+    p->outline_curvature_range_ratio = 0.03f; p->midline_walk_offset = 0.025f;
+    p->peak_mode = 0; p->midline_start_with_head = 0; p->midline_invert = 0;
+}
+
+/* fast::cos<float> / fast::sin<float>, CircularGraph.cpp:12-30 */
+static float fast_cosf(float x)
+{
+    const float tp = (float)(1. / (2. * 3.14159265358979323846264338327950288));
+    x *= tp;
+    x -= 0.25f + floorf(x + 0.25f);
+    x *= 16.f * (fabsf(x) - 0.5f);
+    x += 0.225f * x * (fabsf(x) - 1.f);
+    return x;
+}
+static float fast_sinf(float x) { return fast_cosf(x - (float)1.57079632679489661923132169163975144); }
+float to_fast_cos(float x) { return fast_cosf(x); }
+
+/* smooth_outline (:330-378) as Outline::smooth calls it (:380-389).  Returns 1 when the points were replaced. */
+int to_outline_smooth(const float *pts, int64_t L, int samples, int step_i, float *out)
+{
+    const float range = (float)samples;
+    if (!((float)L > range)) return 0;
+    const long step = step_i;
+    const float step_row = range * (float)step;
+    float *weights = (float *)malloc(sizeof(float) * (size_t)(2 * (int64_t)step_row + 4));
+    int nw = 0;
+    float sum = 0;
+    for (int i = (int)(-step_row); (float)i <= step_row; i += (int)step) {
+        const float val = (step_row - (float)abs(i)) / step_row;
+        sum += val;
+        weights[nw++] = val;
+    }
+    for (int i = 0; i < nw; ++i) weights[i] /= sum;
+    for (long i = 0; i < L; ++i) {
+        long samples_n = 0;
+        float px = 0, py = 0;
+        for (long j = (long)((float)i - step_row); (float)j <= (float)i + step_row; j += step) {
+            long idx = j;
+            while (idx < 0) idx += L;
+            while (idx >= L) idx -= L;
+            const float wgt = weights[samples_n++];
+            px += pts[2 * idx] * wgt; py += pts[2 * idx + 1] * wgt;
+        }
+        out[2 * i] = px; out[2 * i + 1] = py;
+    }
+    free(weights);
+    return 1;
+}
+
+/* periodic::curvature (CircularGraph.cpp:49-113); out must be zero-initialised by the caller (std::vector::resize). */
+void to_periodic_curvature(const float *p, int64_t N, int r, int absolute, float *out)
+{
+    for (int64_t i = 0; i < N; ++i) {
+        const int64_t i1 = ((i - r) % N + N) % N, i3 = (i + r) % N;
+        const float x1 = p[2 * i1], y1 = p[2 * i1 + 1], x2 = p[2 * i], y2 = p[2 * i + 1], x3 = p[2 * i3], y3 = p[2 * i3 + 1];
+        const int e12 = x1 == x2 && y1 == y2, e13 = x1 == x3 && y1 == y3, e23 = x2 == x3 && y2 == y3;
+        if (!e12 && !e13 && !e23) {
+            const float cross = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
+            const float d12 = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1), d23 = (x3 - x2) * (x3 - x2) + (y3 - y2) * (y3 - y2),
+                        d13 = (x3 - x1) * (x3 - x1) + (y3 - y1) * (y3 - y1);
+            out[i] = 2.f * (absolute ? fabsf(cross) : cross) / sqrtf(d12 * d23 * d13);
+        } else out[i] = 0.f;
+    }
+}
+
+/* _differentiate<true> on points (:409-463): dxy[n] = a[n+1] - a[n] (cyclic) and the orientation sum as the reference
+ * accumulates it (the wrap-around term enters with the operands swapped, :458-459). */
+static float differentiate_points(const float *p, int64_t N, float *dxy)
+{
+    float sum = 0;
+    for (int64_t i = 1; i < N; ++i) {
+        dxy[2 * (i - 1)] = p[2 * i] - p[2 * (i - 1)]; dxy[2 * (i - 1) + 1] = p[2 * i + 1] - p[2 * (i - 1) + 1];
+        sum += p[2 * (i - 1)] * p[2 * i + 1] - p[2 * i] * p[2 * (i - 1) + 1];
+    }
+    dxy[2 * (N - 1)] = p[0] - p[2 * (N - 1)]; dxy[2 * (N - 1) + 1] = p[1] - p[2 * (N - 1) + 1];
+    sum += p[0] * p[2 * (N - 1) + 1] - p[2 * (N - 1)] * p[1];
+    return sum;
+}
+float to_orientation_sum(const float *p, int64_t N)
+{
+    float *d = (float *)malloc(sizeof(float) * 2 * (size_t)N);
+    const float s = differentiate_points(p, N, d);
+    free(d);
+    return s;
+}
+
+/* periodic::eft (:484-561) with EFT::dt (:466-482); coeffs: order x {a, b, c, d}. */
+void to_eft(const float *p, int64_t N, int order, float *coeffs)
+{
+    float *dxy = (float *)malloc(sizeof(float) * 2 * (size_t)N);
+    differentiate_points(p, N, dxy);
+    const int64_t nd = N - 1;                               /* dt has dxy.size() - 1 entries */
+    float *dt = (float *)malloc(sizeof(float) * (size_t)(nd + 1)), *phi = (float *)calloc((size_t)(nd + 2), sizeof(float));
+    float *cx = (float *)malloc(sizeof(float) * (size_t)(nd + 1)), *cy = (float *)malloc(sizeof(float) * (size_t)(nd + 1));
+    float *cum = (float *)calloc((size_t)(nd + 2), sizeof(float));
+    float sum = 0;
+    for (int64_t i = 0; i < nd; ++i) {
+        const float x = dxy[2 * i], y = dxy[2 * i + 1];
+        dt[i] = (float)((double)sqrtf(x * x + y * y) + 1e-10);
+        sum += dt[i];
+        cum[i + 1] = sum;
+        phi[i + 1] = (float)(2 * 3.14159265358979323846 * (double)cum[i + 1]);
+        cx[i] = x / dt[i]; cy[i] = y / dt[i];
+    }
+    const float T = cum[nd];
+    const float norm_base = (float)((double)T / (2 * (3.14159265358979323846 * 3.14159265358979323846)));
+    const int64_t np = nd + 1;                              /* phi.size() */
+    float *cs = (float *)malloc(sizeof(float) * 2 * (size_t)np);
+    for (int n = 1; n < order + 1; ++n) {
+        const float norm = norm_base / (float)((size_t)n * (size_t)n);
+        float cnx = 0, cny = 0, snx = 0, sny = 0;
+        for (int64_t i = 0; i < np; ++i) {
+            const float phi_n = phi[i] * (float)n / T;
+            cs[2 * i] = fast_cosf(phi_n); cs[2 * i + 1] = fast_sinf(phi_n);
+        }
+        for (int64_t i = 0; i < np - 1; ++i) {
+            const float dc = cs[2 * (i + 1)] - cs[2 * i], ds = cs[2 * (i + 1) + 1] - cs[2 * i + 1];
+            cnx += cx[i] * dc; cny += cy[i] * dc;
+            snx += cx[i] * ds; sny += cy[i] * ds;
+        }
+        cnx *= norm; cny *= norm; snx *= norm; sny *= norm;
+        coeffs[4 * (n - 1) + 0] = cnx; coeffs[4 * (n - 1) + 1] = snx; coeffs[4 * (n - 1) + 2] = cny; coeffs[4 * (n - 1) + 3] = sny;
+    }
+    free(dxy); free(dt); free(phi); free(cx); free(cy); free(cum); free(cs);
+}
+
+/* periodic::ieft (:563-606), save_steps = false, scale = 1 */
+void to_ieft(const float *coeffs, int order, int64_t n_points, float offx, float offy, float *out)
+{
+    for (int64_t j = 0; j < n_points; ++j) { out[2 * j] = offx; out[2 * j + 1] = offy; }
+    for (int i = 0; i < order; ++i)
+        for (int64_t j = 0; j < n_points; ++j) {
+            const float t = (float)((double)j / (double)(n_points - 1) * 3.14159265358979323846 * 2.0);
+            const float ct = fast_cosf(t * (float)(i + 1)), st = fast_sinf(t * (float)(i + 1));
+            out[2 * j] += 1.f * (coeffs[4 * i] * ct + coeffs[4 * i + 1] * st);
+            out[2 * j + 1] += 1.f * (coeffs[4 * i + 2] * ct + coeffs[4 * i + 3] * st);
+        }
+}
+
+/* periodic::find_peaks (:115-407) for the call in offset_to_middle: diffs = {first difference, first difference}
+ * (differentiate(curv, 2) writes the same difference into both outputs, :441-444). */
+typedef struct { float x, y, width, integral, r0, r1, max_y_extrema, max_y; int n_pts; } to_peak_t;
+typedef struct { float i; int is_max; } extremum_t;
+
+int64_t to_find_peaks(const float *pt, int64_t N, int broad, to_peak_t *maxima, int64_t cap)
+{
+    if (N <= 0) return 0;
+    float *diff = (float *)malloc(sizeof(float) * (size_t)N);
+    for (int64_t i = 0; i + 1 < N; ++i) diff[i] = pt[i + 1] - pt[i];
+    diff[N - 1] = pt[0] - pt[N - 1];
+    const float *second = diff;
+    extremum_t *ext = (extremum_t *)malloc(sizeof(extremum_t) * (size_t)N);
+    int64_t n_ext = 0, n_max = 0;
+    int sign = diff[N - 1] < 0;
+    float minimum = 3.402823466e+38f;
+    for (int64_t i = 0; i < N; ++i) {
+        const int c = diff[i] < 0;
+        if (pt[i] < minimum) minimum = pt[i];
+        if (c != sign) {
+            if (second[i] != 0) {
+                if (!sign) {
+                    if (n_max >= cap) { free(diff); free(ext); return -1; }
+                    to_peak_t pk; memset(&pk, 0, sizeof pk);
+                    pk.x = (float)i; pk.y = pt[i]; pk.r0 = -1; pk.r1 = -1;
+                    maxima[n_max++] = pk;
+                }
+                ext[n_ext].i = (float)i; ext[n_ext].is_max = !sign; ++n_ext;        /* std::set ordered by i: inserted ascending */
+            }
+            sign = c;
+        }
+    }
+    const float min_y = minimum;
+    /* maxima in descending (y, index) order: std::set<tuple<y, idx>, greater<>> */
+    int64_t *order = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_max + 1));
+    for (int64_t i = 0; i < n_max; ++i) order[i] = i;
+    for (int64_t i = 1; i < n_max; ++i) {
+        const int64_t k = order[i]; int64_t j = i - 1;
+        while (j >= 0 && (maxima[order[j]].y < maxima[k].y || (maxima[order[j]].y == maxima[k].y && order[j] < k))) { order[j + 1] = order[j]; --j; }
+        order[j + 1] = k;
+    }
+    float *rng = (float *)malloc(sizeof(float) * 2 * (size_t)(n_max + 1));
+    int64_t n_rng = 0;
+    for (int64_t oi = 0; oi < n_max; ++oi) {
+        to_peak_t *peak = &maxima[order[oi]];
+        int64_t after = 0, prev = n_ext - 1;
+        for (; after != n_ext; ++after) {
+            if (ext[after].i == peak->x) { ++after; if (after == n_ext) after = 0; break; }
+            prev = after;
+        }
+        if (after == n_ext) after = 0;       /* cannot happen: the peak is in extrema */
+        float minimum_left = 3.402823466e+38f, index_left = ext[prev].i, minimum_right = 3.402823466e+38f, index_right = ext[after].i;
+        float left_border = 0, right_border = (float)N;
+        for (int64_t k = 0; k < n_rng; ++k) {
+            const float rs = rng[2 * k], re = rng[2 * k + 1];
+            if (re > left_border && re < peak->x) left_border = re;
+            if (rs < right_border && rs > peak->x) right_border = rs;
+        }
+        int64_t cl = prev;
+        float last_y = peak->y, offset = 0;
+        while (ext[cl].i + offset >= left_border) {
+            const float x = ext[cl].i, y = pt[(size_t)x];
+            if (ext[cl].is_max) { if ((double)y > (double)last_y * 1.05) break; last_y = y; }
+            if (y < minimum_left) { minimum_left = y; index_left = x; }
+            if (y > peak->max_y_extrema) peak->max_y_extrema = y;
+            if (cl == 0) { offset = -(float)N; cl = n_ext - 1; }
+            if (cl == after) break;
+            --cl;
+            if (cl < 0) break;                /* decrementing begin() is undefined in the reference; only reachable with one extremum */
+        }
+        offset = 0; cl = after; last_y = peak->y;
+        while (ext[cl].i + offset <= right_border) {
+            const float x = ext[cl].i, y = pt[(size_t)x];
+            if (ext[cl].is_max) { if ((double)y > (double)last_y * 1.05) break; last_y = y; }
+            if (y < minimum_right) { minimum_right = y; index_right = x; }
+            if (y > peak->max_y_extrema) peak->max_y_extrema = y;
+            if (++cl == n_ext) { offset = (float)N; cl = 0; }
+            if (cl == prev) break;
+        }
+        while (index_left > peak->x) index_left -= (float)N;
+        while (index_right < peak->x) index_right += (float)N;
+        peak->width = right_border - left_border;
+        peak->r0 = index_left; peak->r1 = index_right;
+        rng[2 * n_rng] = index_left; rng[2 * n_rng + 1] = index_right; ++n_rng;
+    }
+    /* points above half height inside the (periodically split) range, then the integral (:336-402) */
+    for (int64_t k = 0; k < n_max; ++k) {
+        to_peak_t *peak = &maxima[k];
+        float chk[3][2]; int nchk = 1;
+        chk[0][0] = peak->r0; chk[0][1] = peak->r1;
+        float x0 = peak->r0, x1 = peak->r1;
+        if (x0 < 0) { x0 += (float)N; chk[0][0] = 0; chk[nchk][0] = x0; chk[nchk][1] = (float)(N - 1); ++nchk; }
+        if (x1 >= (float)N) { x1 -= (float)N; chk[0][1] = (float)(N - 1); chk[nchk][0] = 0; chk[nchk][1] = x1; ++nchk; }
+        /* first pass: max_y and count; second pass: the integral needs max_y of ALL points first */
+        float max_y = 0; int n_pts = 0;
+        for (int c = 0; c < nchk; ++c) {
+            const float first = chk[c][0], last = chk[c][1];
+            if (!(last - first >= 0)) continue;
+            const size_t steps = (size_t)((last - first) / 1.f);
+            for (size_t s = 0; s < steps; ++s) {
+                const float i = first + (float)s * 1.f;
+                const float y = pt[(size_t)i] - min_y;
+                if ((double)(y / (peak->y - min_y)) >= 0.5) { ++n_pts; if (y > max_y) max_y = y; }
+            }
+        }
+        peak->max_y = max_y; peak->n_pts = n_pts;
+        const double median = (double)max_y * 0.5;
+        const float factor = broad ? 1.f : peak->y;
+        float integral = 0;
+        for (int c = 0; c < nchk; ++c) {
+            const float first = chk[c][0], last = chk[c][1];
+            if (!(last - first >= 0)) continue;
+            const size_t steps = (size_t)((last - first) / 1.f);
+            for (size_t s = 0; s < steps; ++s) {
+                const float i = first + (float)s * 1.f;
+                const float y = pt[(size_t)i] - min_y;
+                if ((double)(y / (peak->y - min_y)) >= 0.5) integral = (float)((double)integral + ((double)y - median) * (double)factor);
+            }
+        }
+        peak->integral = integral;
+    }
+    free(diff); free(ext); free(order); free(rng);
+    return n_max;
+}
+
+static void rotate_points(float *p, int64_t N, int64_t k)      /* std::rotate(begin, begin + k, end) */
+{
+    if (N <= 0 || k <= 0 || k >= N) return;
+    float *t = (float *)malloc(sizeof(float) * 2 * (size_t)N);
+    memcpy(t, p + 2 * k, sizeof(float) * 2 * (size_t)(N - k));
+    memcpy(t + 2 * (N - k), p, sizeof(float) * 2 * (size_t)k);
+    memcpy(p, t, sizeof(float) * 2 * (size_t)N);
+    free(t);
+}
+
+/* Outline::offset_to_middle (T/tracking/Outline.cpp:454-718), peak_mode pointy (the default; the broad branch :621-650 is not
+ * restated).  Works in place on the N points (they may be reversed, replaced by their elliptic-Fourier approximation and
+ * rotated); curv_out (optional, N floats) receives the curvature the peaks were searched in.
+ * Returns 0 and tail / head indices, or a negative code: -1 empty, -3 broad mode. */
+int to_offset_to_middle(float *p, int64_t N, const to_posture_params_t *P, int64_t *tail_out, int64_t *head_out, float *curv_out)
+{
+    if (N <= 0) return -1;
+    if (P->peak_mode != 0) return -3;
+    if (to_orientation_sum(p, N) < 0)                         /* make it clockwise (:496-498) */
+        for (int64_t i = 0, j = N - 1; i < j; ++i, --j) {
+            float tx = p[2 * i], ty = p[2 * i + 1];
+            p[2 * i] = p[2 * j]; p[2 * i + 1] = p[2 * j + 1]; p[2 * j] = tx; p[2 * j + 1] = ty;
+        }
+    if (P->outline_approximate > 0) {
+        float cx = 0, cy = 0;
+        for (int64_t i = 0; i < N; ++i) { cx += p[2 * i]; cy += p[2 * i + 1]; }
+        cx /= (float)(size_t)N; cy /= (float)(size_t)N;
+        float *coeffs = (float *)malloc(sizeof(float) * 4 * (size_t)P->outline_approximate);
+        to_eft(p, N, P->outline_approximate, coeffs);
+        to_ieft(coeffs, P->outline_approximate, N, cx, cy, p);
+        free(coeffs);
+    }
+    float rf = P->outline_curvature_range_ratio * (float)(size_t)N;          /* max(1, ratio * size) as int (:514) */
+    if (rf < 1.f) rf = 1.f;
+    const int r = (int)rf;
+    float *curv = (float *)calloc((size_t)N, sizeof(float));
+    to_periodic_curvature(p, N, r, P->outline_approximate > 0, curv);
+    if (curv_out) memcpy(curv_out, curv, sizeof(float) * (size_t)N);
+    to_peak_t *mx = (to_peak_t *)malloc(sizeof(to_peak_t) * (size_t)(N + 1));
+    const int64_t nm = to_find_peaks(curv, N, 0, mx, N + 1);
+    float max_y = -1, max_y_idx = 0;
+    for (int64_t k = 0; k < nm; ++k)
+        if (mx[k].y > max_y) { max_y = mx[k].y; max_y_idx = mx[k].x; }
+    const float idx = max_y_idx;                              /* FIND_POINTY (:617-619) */
+    int64_t tail = (int64_t)idx, head = -1;
+    float max_d = 0;
+    for (int64_t k = 0; k < nm; ++k) {
+        float d;
+        const float px = mx[k].x, sz = (float)(size_t)N;
+        if (px >= idx) { const float a = fabsf(px - idx), b = fabsf(px - idx - sz); d = a < b ? a : b; }
+        else { const float a = fabsf(idx - px), b = fabsf(idx - px - sz); d = a < b ? a : b; }
+        if (d > max_d) { max_d = d; head = (int64_t)px; }
+    }
+    if (P->midline_start_with_head && head != -1) {
+        if (tail != -1) { tail -= head; if (tail < 0) tail += N; }
+        rotate_points(p, N, head);
+        head = 0;
+    } else {
+        if (head != -1) { head -= tail; if (head < 0) head += N; }
+        rotate_points(p, N, tail);
+        tail = 0;
+    }
+    if (P->midline_invert) { const int64_t t = tail; tail = head; head = t; }
+    *tail_out = tail; *head_out = head;
+    free(curv); free(mx);
+    return 0;
+}
+
+/* Outline::calculate_midline (T/tracking/Outline.cpp:768-868) on a resampled outline: smooth -> offset_to_middle -> the pairing
+ * walk.  p (N points) is modified in place; segments: {pos.x, pos.y, height, l_length} per midline segment.
+ * Returns the number of segments (> 2), or a negative code: -1 empty, -2 too few segments, -3 broad mode, -4 capacity. */
+int64_t to_calculate_midline(float *p, int64_t N, const to_posture_params_t *P, float *segments, int64_t cap,
+                             int64_t *tail_out, int64_t *head_out)
+{
+    if (N <= 0) return -1;
+    if (P->outline_smooth_samples > 0) {
+        float *sm = (float *)malloc(sizeof(float) * 2 * (size_t)N);
+        if (to_outline_smooth(p, N, P->outline_smooth_samples, P->outline_smooth_step, sm)) memcpy(p, sm, sizeof(float) * 2 * (size_t)N);
+        free(sm);
+    }
+    int rc = to_offset_to_middle(p, N, P, tail_out, head_out, NULL);
+    if (rc) return rc;
+    if (N <= 1) return -1;
+    const long L = (long)N;
+    int idx_r = 1, idx_l = -1;
+    float mo = P->midline_walk_offset * (float)L;
+    if (mo < 3.f) mo = 3.f;
+    const int max_offset = (int)mo;
+    int64_t ns = 0;
+    while (idx_r < L + idx_l) {
+        float prx = 0, pry = 0, plx = p[2 * (L + idx_l)], ply = p[2 * (L + idx_l) + 1];
+        float min_d = 3.402823466e+38f; int min_idx = -1;
+        for (int i = 0; i < max_offset; ++i) {
+            if (idx_r + i >= L) break;
+            const float dx = p[2 * (idx_r + i)] - plx, dy = p[2 * (idx_r + i) + 1] - ply;
+            const float len = sqrtf(dx * dx + dy * dy);
+            if (len < min_d) { min_d = len; min_idx = idx_r + i; }
+        }
+        if (min_idx != -1) { prx = p[2 * min_idx]; pry = p[2 * min_idx + 1]; idx_r = min_idx; }
+        min_d = 3.402823466e+38f; min_idx = 1;
+        for (int i = 0; i < max_offset; ++i) {
+            if (idx_l - i <= -L) break;
+            const float dx = prx - p[2 * (L + idx_l - i)], dy = pry - p[2 * (L + idx_l - i) + 1];
+            const float len = sqrtf(dx * dx + dy * dy);
+            if (len < min_d) { min_d = len; min_idx = idx_l - i; }
+        }
+        if (min_idx != 1) { plx = p[2 * (L + min_idx)]; ply = p[2 * (L + min_idx) + 1]; idx_l = min_idx; }
+        const float lx = prx - plx, ly = pry - ply;
+        const float mx_ = plx + lx * 0.5f, my_ = ply + ly * 0.5f;
+        if (ns >= cap) return -4;
+        segments[4 * ns + 0] = mx_; segments[4 * ns + 1] = my_;
+        segments[4 * ns + 2] = sqrtf((prx - plx) * (prx - plx) + (pry - ply) * (pry - ply));
+        segments[4 * ns + 3] = sqrtf((plx - mx_) * (plx - mx_) + (ply - my_) * (ply - my_));
+        ++ns;
+        idx_r++; idx_l--;
+    }
+    if (ns <= 2) return -2;
+    return ns;
+}

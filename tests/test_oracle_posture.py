@@ -1,0 +1,116 @@
+"""CPU tests of the midline ORACLE (N4, second stage; no CUDA counterpart yet): every piece of oracle/posture.py against an
+independent numpy formulation of the same reference formula, and the whole chain on a shape whose midline is known by
+construction.  Reference: T/tracking/Outline.cpp:330-452,454-718,768-868, C/misc/CircularGraph.cpp:12-606.
+parity unpinned -- the reference has no test vectors for these functions."""
+import numpy as np
+import pytest
+
+from oracle import posture, seg
+
+
+def _fish():
+    yy, xx = np.mgrid[0:60, 0:120]
+    body = ((xx - 45) / 30.0) ** 2 + ((yy - 30) / 11.0) ** 2 <= 1
+    tail = (xx >= 70) & (xx <= 110) & (np.abs(yy - 30) <= (110 - xx) * 0.22)
+    img = ((body | tail) * 255).astype(np.uint8)
+    lines, _ = seg.label_image(img).blob(0)
+    return seg.outline_resample(seg.longest_outline(lines), 1.0)        # blob-relative: x0 = 15, y0 = 19
+
+
+def test_fast_cos_is_the_reference_polynomial():
+    xs = np.linspace(-20, 20, 4001, dtype=np.float32)
+    got = np.array([posture.fast_cos(float(x)) for x in xs])
+    assert np.abs(got - np.cos(xs.astype(np.float64))).max() < 1.2e-3          # the parabola approximation's error bound
+    assert posture.fast_cos(0.0) == pytest.approx(1.0, abs=1e-6)
+
+
+def test_smooth_is_a_circular_triangular_filter():
+    rng = np.random.default_rng(0)
+    pts = rng.random((50, 2)).astype(np.float32) * 40
+    w = np.array([(4 - abs(i)) / 4 for i in range(-4, 5)], np.float64); w /= w.sum()
+    exp = np.zeros((50, 2))
+    for i in range(50):
+        for k, j in enumerate(range(i - 4, i + 5)):
+            exp[i] += pts[j % 50] * w[k]
+    assert np.abs(posture.smooth(pts, 4, 1) - exp).max() < 1e-4
+    assert np.array_equal(posture.smooth(pts[:4], 4, 1), pts[:4])               # L <= samples: unchanged (:384)
+    w2 = np.array([(4 - abs(i)) / 4 for i in range(-4, 5, 2)], np.float64); w2 /= w2.sum()   # step 2: range 2, step_row 4
+    exp2 = np.zeros((50, 2))
+    for i in range(50):
+        for k, j in enumerate(range(i - 4, i + 5, 2)):
+            exp2[i] += pts[j % 50] * w2[k]
+    assert np.abs(posture.smooth(pts, 2, 2) - exp2).max() < 1e-4
+
+
+def test_curvature_formula():
+    t = np.linspace(0, 2 * np.pi, 200, endpoint=False)
+    pts = np.stack([30 + 20 * np.cos(t), 25 + 9 * np.sin(t)], 1).astype(np.float32)
+    r = 6
+    p1, p3 = np.roll(pts, r, 0).astype(np.float64), np.roll(pts, -r, 0).astype(np.float64)
+    p2 = pts.astype(np.float64)
+    cross = (p2[:, 0] - p1[:, 0]) * (p3[:, 1] - p2[:, 1]) - (p2[:, 1] - p1[:, 1]) * (p3[:, 0] - p2[:, 0])
+    sq = lambda a, b: ((a - b) ** 2).sum(1)
+    exp = 2 * cross / np.sqrt(sq(p1, p2) * sq(p2, p3) * sq(p1, p3))
+    assert np.abs(posture.curvature(pts, r) - exp).max() < 1e-4
+    assert np.abs(posture.curvature(pts, r, absolute=True) - np.abs(exp)).max() < 1e-4
+    # an ellipse bends most at the ends of its major axis
+    c = posture.curvature(pts, r, absolute=True)
+    assert int(np.argmax(c)) in (0, 100, 199, 99, 101, 1)
+    dup = pts.copy(); dup[5] = dup[5 + r]
+    assert posture.curvature(dup, r)[5] == 0                                    # coincident points: left at 0 (:87,107)
+
+
+def test_orientation_and_fourier_approximation():
+    ol = _fish()
+    s = posture.orientation_sum(ol)
+    assert posture.orientation_sum(ol[::-1].copy()) * s < 0
+    area2 = abs(np.sum(ol[:, 0] * np.roll(ol[:, 1], -1) - np.roll(ol[:, 0], -1) * ol[:, 1]))
+    assert abs(abs(s) - area2) / area2 < 0.05                                   # the wrap-around term enters with swapped operands
+    co = posture.eft(ol, 3)
+    # float64 restatement of eft with exact trigonometry
+    d = (np.roll(ol, -1, 0) - ol).astype(np.float64)[:-1]
+    dt = np.sqrt((d ** 2).sum(1)) + 1e-10
+    cum = np.concatenate([[0], np.cumsum(dt)]); T = cum[-1]; phi = 2 * np.pi * cum
+    exp = np.zeros((3, 4))
+    for n in (1, 2, 3):
+        c, s_ = np.cos(phi * n / T), np.sin(phi * n / T)
+        norm = T / (2 * np.pi ** 2) / n ** 2
+        cn = ((d / dt[:, None]) * np.diff(c)[:, None]).sum(0) * norm
+        sn = ((d / dt[:, None]) * np.diff(s_)[:, None]).sum(0) * norm
+        exp[n - 1] = [cn[0], sn[0], cn[1], sn[1]]
+    assert np.abs(co - exp).max() < 0.05                                        # fast::cos is accurate to ~1e-3
+    back = posture.ieft(co, len(ol), ol.mean(0))
+    # three harmonics keep the gross shape: every reconstructed point lies close to the outline
+    dist = np.sqrt(((back[:, None, :] - ol[None, :, :]) ** 2).sum(2)).min(1)
+    assert dist.max() < 8 and dist.mean() < 3
+
+
+def test_find_peaks_on_a_two_bump_signal():
+    x = np.arange(200)
+    v = (np.exp(-((x - 50) / 6.0) ** 2) * 2.0 + np.exp(-((x - 140) / 15.0) ** 2) * 1.0 + 0.05).astype(np.float32)
+    pk = posture.find_peaks(v)
+    assert sorted(int(p) for p in pk["x"]) == [50, 140]
+    hi, lo = pk[np.argmax(pk["y"])], pk[np.argmin(pk["y"])]
+    assert hi["x"] == 50 and hi["r0"] < 50 < hi["r1"] and lo["r0"] < 140 < lo["r1"]
+    assert hi["n_pts"] > 0 and lo["n_pts"] > hi["n_pts"]                        # the broad bump holds more points above half height
+    assert len(posture.find_peaks(np.full(50, 3.0, np.float32))) == 0           # flat: no sign change of the difference
+
+
+def test_midline_of_a_fish_shape():
+    ol = _fish()
+    segs, tail, head, pts = posture.calculate_midline(ol)
+    assert tail == 0 and 0 < head < len(pts)
+    # the pointy end (x ~ 95 in blob coordinates) is the tail, the blunt end (x ~ 0) the head; both on the axis y ~ 11.5
+    assert pts[tail][0] > 80 and pts[head][0] < 10
+    assert abs(pts[tail][1] - 11.5) < 1.5 and abs(pts[head][1] - 11.5) < 1.5
+    assert 60 < len(segs) < len(pts) // 2 + 2
+    assert np.abs(segs[:, 1] - 11.5).max() < 2.0                                # midline points stay on the symmetry axis
+    assert np.all(np.diff(segs[:, 0]) < 0.5)                                    # and run from the tail towards the head
+    assert segs[:, 2].max() < 24 and np.allclose(segs[:, 3], segs[:, 2] / 2, atol=1e-3)      # height <= body width, l_length = half
+    with pytest.raises(ValueError):
+        posture.calculate_midline(np.array([[0, 0], [1, 0], [1, 1]], np.float32))
+    with pytest.raises(ValueError):
+        posture.calculate_midline(ol, posture.default_params(peak_mode=1))
+    # midline_invert swaps the two indices (:712-713)
+    _, t2, h2, _ = posture.calculate_midline(ol, posture.default_params(midline_invert=1))
+    assert (t2, h2) == (head, tail)
