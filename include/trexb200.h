@@ -201,6 +201,29 @@ typedef struct tb_outline_rec {
 TB_API int tb_seg_outlines(tb_seg *h, float outline_resample);
 TB_API int tb_seg_outline_result(tb_seg *h, const tb_outline_rec **recs, const float **raw_points, const float **points, uint32_t *n_blobs);
 
+/* Midlines ("next" row N4, second stage), after tb_seg_outlines on the same batch: for every blob Outline::calculate_midline
+ * (T/tracking/Outline.cpp:768-868) on its resampled outline -- Outline::smooth (:330-452), offset_to_middle (:454-718: clockwise
+ * orientation, the elliptic-Fourier approximation periodic::eft / ieft with outline_approximate harmonics, curvature, find_peaks;
+ * tail = the highest curvature peak, head = the peak farthest from it; the outline is rotated to start at the tail) and the
+ * pairing walk.  peak_mode pointy only (the reference's default); Midline::post_process / normalize are not built.
+ * points: the outline as the midline saw it (smoothed, approximated, rotated), same ranges as tb_outline_rec.res_off / n_res;
+ * segments: {pos.x, pos.y, height, l_length} per midline segment from the tail on, blob k's at [seg_off, seg_off + n_seg);
+ * n_seg = 0 when the reference would return "Too few midline segments calculated." */
+typedef struct tb_posture_params {
+    int32_t outline_smooth_samples;        /* 4     T/core/default_config.cpp:890 */
+    int32_t outline_smooth_step;           /* 1     :889 */
+    int32_t outline_approximate;           /* 3     :888 (0..8) */
+    float   outline_curvature_range_ratio; /* 0.03  :891 */
+    float   midline_walk_offset;           /* 0.025 :892 */
+    int32_t peak_mode;                     /* 0 pointy (:902); broad is not built */
+    int32_t midline_start_with_head;       /* 0     :900 */
+    int32_t midline_invert;                /* 0     :901 */
+} tb_posture_params;
+typedef struct tb_midline_rec { uint32_t seg_off, n_seg; int32_t tail, head; } tb_midline_rec;
+TB_API void tb_posture_default_params(tb_posture_params *p);
+TB_API int tb_seg_midlines(tb_seg *h, const tb_posture_params *p);
+TB_API int tb_seg_midline_result(tb_seg *h, const tb_midline_rec **recs, const float **points, const float **segments, uint32_t *n_blobs);
+
 /* Debug / parity: generate_binary's output image (mask & input) of one device- or host-resident
  * frame, RawProcessing.cpp:597-600.  out is width*height (gray) or width*height*3 (rgb8) host bytes. */
 TB_API int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t *out_host);

@@ -51,6 +51,12 @@ class BlobView(C.Structure):
     _fields_ = [("info", FrameInfo), ("recs", C.POINTER(BlobRec)), ("lines", C.c_void_p), ("pixels", C.c_void_p)]
 
 
+class PostureParams(C.Structure):
+    _fields_ = [("outline_smooth_samples", C.c_int32), ("outline_smooth_step", C.c_int32), ("outline_approximate", C.c_int32),
+                ("outline_curvature_range_ratio", C.c_float), ("midline_walk_offset", C.c_float), ("peak_mode", C.c_int32),
+                ("midline_start_with_head", C.c_int32), ("midline_invert", C.c_int32)]
+
+
 class ViConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
                 ("num_classes", C.c_int32), ("max_images", C.c_int32), ("precision", C.c_int32), ("arch", C.c_int32)]
@@ -64,7 +70,7 @@ SYMBOLS = [
     "tb_seg_debug_binary", "tb_seg_launch_count", "tb_vi_create", "tb_vi_destroy", "tb_vi_set_tensor",
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
     "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_debug_umma_shifted_gemm", "tb_seg_set_stream",
-    "tb_seg_rethreshold", "tb_seg_outlines", "tb_seg_outline_result", "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
+    "tb_seg_rethreshold", "tb_seg_outlines", "tb_seg_outline_result", "tb_posture_default_params", "tb_seg_midlines", "tb_seg_midline_result", "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
 ]
 
 _lib = None
@@ -111,6 +117,9 @@ def lib() -> C.CDLL:
     L.tb_seg_rethreshold.argtypes = [vp, vp, C.c_int]
     L.tb_seg_outlines.argtypes = [vp, C.c_float]
     L.tb_seg_outline_result.argtypes = [vp, vpp, vpp, vpp, C.POINTER(C.c_uint32)]
+    L.tb_posture_default_params.argtypes = [C.POINTER(PostureParams)]; L.tb_posture_default_params.restype = None
+    L.tb_seg_midlines.argtypes = [vp, C.POINTER(PostureParams)]
+    L.tb_seg_midline_result.argtypes = [vp, vpp, vpp, vpp, C.POINTER(C.c_uint32)]
     L.tb_vi_set_top1.argtypes = [vp, vp, vp]
     L.tb_avg_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vpp]
     L.tb_avg_destroy.argtypes = [vp]; L.tb_avg_destroy.restype = None

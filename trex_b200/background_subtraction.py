@@ -209,6 +209,36 @@ class BackgroundSubtraction:
         res = np.ctypeslib.as_array(C.cast(qp, C.POINTER(C.c_float)), (max(n_res, 1), 2))
         return ([raw[o:o + k].copy() for o, k in recs[:, :2]], [res[o:o + k].copy() for o, k in recs[:, 2:]])
 
+    def midlines(self, outline_resample=1.0, **posture_settings):
+        """Outline::calculate_midline for every blob of the last batch (T/tracking/Outline.cpp:768-868; peak_mode pointy): runs
+        outlines(outline_resample) first.  posture_settings: fields of tb_posture_params (outline_smooth_samples, ...).
+        Returns one (segments (n,4) float32, tail index, head index, outline points (m,2)) per blob; segments is empty where
+        the reference reports too few midline segments."""
+        from ._capi import PostureParams
+        check(lib().tb_seg_outlines(self._h, C.c_float(outline_resample)))
+        P = PostureParams()
+        lib().tb_posture_default_params(C.byref(P))
+        for k, v in posture_settings.items():
+            setattr(P, k, v)
+        check(lib().tb_seg_midlines(self._h, C.byref(P)))
+        orp, a, b, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        check(lib().tb_seg_outline_result(self._h, C.byref(orp), C.byref(a), C.byref(b), C.byref(n)))
+        mrp, pp, sp, m = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        check(lib().tb_seg_midline_result(self._h, C.byref(mrp), C.byref(pp), C.byref(sp), C.byref(m)))
+        if m.value == 0:
+            return []
+        orecs = np.ctypeslib.as_array(C.cast(orp, C.POINTER(C.c_uint32)), (n.value, 4))
+        mrecs = np.ctypeslib.as_array(C.cast(mrp, C.POINTER(C.c_int32)), (m.value, 4))
+        top = int((orecs[:, 2] + orecs[:, 3]).max())
+        pts = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), (max(top, 1), 2))
+        segs = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_float)), (max(top, 1), 4))
+        out = []
+        for k in range(m.value):
+            so, ns, tail, head = (int(v) for v in mrecs[k])
+            ro, rn = int(orecs[k, 2]), int(orecs[k, 3])
+            out.append((segs[so:so + ns].copy(), tail, head, pts[ro:ro + rn].copy()))
+        return out
+
     def wait(self):
         check(lib().tb_seg_wait(self._h))
 

@@ -120,6 +120,10 @@ int launch_outlines(const tb_blob_rec *recs, uint32_t nb, const tb_line *lines, 
                     uint8_t *visited, size_t visited_bytes, float rd, uint32_t *row_first, int4 *sel,
                     tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, cudaStream_t s);
 
+// midline.cu: Outline::calculate_midline for nb resampled outlines; 1 launch
+int launch_midlines(const tb_outline_rec *orecs, uint32_t nb, const float *res, uint32_t cap_pts, const tb_posture_params *P,
+                    float *pts_out, float *segs, tb_midline_rec *mrecs, float *scratch, cudaStream_t s);
+
 #ifdef __CUDACC__
 // Exclusive scan of one value per thread across the CTA; `total` = sum over all threads.
 // ws: shared array of >= 33 uint32. All threads must call.

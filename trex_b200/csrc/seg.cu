@@ -1459,7 +1459,10 @@ struct tb_seg {
     // outlines (tb_seg_outlines), allocated on first use
     uint8_t *o_visited = nullptr; uint32_t *o_rowfirst = nullptr; int4 *o_sel = nullptr; tb_outline_rec *o_recs = nullptr; uint32_t *o_totals = nullptr;
     float *o_raw = nullptr, *o_res = nullptr; uint32_t o_cap = 0, o_n = 0;
-    tb_outline_rec *h_o_recs = nullptr; float *h_o_raw = nullptr, *h_o_res = nullptr; uint32_t *h_o_totals = nullptr;    // blur_difference / use_adaptive_threshold: row-sum scratch of box_sub frames
+    tb_outline_rec *h_o_recs = nullptr; float *h_o_raw = nullptr, *h_o_res = nullptr; uint32_t *h_o_totals = nullptr;
+    // midlines (tb_seg_midlines), allocated on first use
+    float *m_pts = nullptr, *m_segs = nullptr, *m_scratch = nullptr; size_t m_scratch_floats = 0; tb_midline_rec *m_recs = nullptr;
+    float *h_m_pts = nullptr, *h_m_segs = nullptr; tb_midline_rec *h_m_recs = nullptr; uint32_t m_n = 0;    // blur_difference / use_adaptive_threshold: row-sum scratch of box_sub frames
     const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
     uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
     double *d_coef = nullptr;                   // `moments` normalisation: inverted warp matrix per crop
@@ -1622,7 +1625,8 @@ extern "C" void tb_seg_destroy(tb_seg *h)
     cudaDeviceSynchronize();
     for (void *p : h->dev_allocs) cudaFree(p);
     void *hp[] = {h->h_infos, h->h_totals, h->h_recs, h->h_lines, h->h_pixels, h->h_crops, h->h_crop_blob,
-                  h->h_o_recs, h->h_o_raw, h->h_o_res, h->h_o_totals};
+                  h->h_o_recs, h->h_o_raw, h->h_o_res, h->h_o_totals, h->h_m_pts, h->h_m_segs, h->h_m_recs};
+    if (h->m_scratch) cudaFree(h->m_scratch);
     for (void *p : hp) if (p) cudaFreeHost(p);
     h->prof.destroy();
     if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -2073,6 +2077,64 @@ extern "C" int tb_seg_outline_result(tb_seg *h, const tb_outline_rec **recs, con
     TB_REQUIRE(h && recs && raw_points && points && n_blobs, TB_ERR_INVALID, "tb_seg_outline_result: null argument");
     TB_REQUIRE(h->h_o_recs, TB_ERR_STATE, "tb_seg_outline_result: call tb_seg_outlines first");
     *recs = h->h_o_recs; *raw_points = h->h_o_raw; *points = h->h_o_res; *n_blobs = h->o_n;
+    return TB_OK;
+}
+
+extern "C" void tb_posture_default_params(tb_posture_params *p)
+{
+    p->outline_smooth_samples = 4; p->outline_smooth_step = 1; p->outline_approximate = 3;
+    p->outline_curvature_range_ratio = 0.03f; p->midline_walk_offset = 0.025f;
+    p->peak_mode = 0; p->midline_start_with_head = 0; p->midline_invert = 0;
+}
+
+extern "C" int tb_seg_midlines(tb_seg *h, const tb_posture_params *p)
+{
+    TB_REQUIRE(h && p, TB_ERR_INVALID, "tb_seg_midlines: null argument");
+    TB_REQUIRE(h->h_o_recs && !h->pending, TB_ERR_STATE, "tb_seg_midlines: call tb_seg_outlines on the batch first");
+    TB_REQUIRE(p->peak_mode == 0, TB_ERR_INVALID, "tb_seg_midlines: peak_mode broad is not built (pointy is the reference's default)");
+    TB_REQUIRE(p->outline_approximate >= 0 && p->outline_approximate <= 8, TB_ERR_INVALID, "tb_seg_midlines: outline_approximate must be 0..8");
+    TB_REQUIRE(p->outline_smooth_samples >= 0 && p->outline_smooth_samples <= 255 && p->outline_smooth_step >= 1 && p->outline_smooth_step <= 255,
+               TB_ERR_INVALID, "tb_seg_midlines: outline_smooth_samples 0..255, outline_smooth_step 1..255 (uint8 settings)");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    const SegDev &d = h->d;
+    if (!h->m_recs) {
+        int r = seg_dev(h, &h->m_pts, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = seg_dev(h, &h->m_segs, (size_t)h->o_cap * 4);
+        if (r == TB_OK) r = seg_dev(h, &h->m_recs, d.blobs_cap);
+        if (r == TB_OK) r = host_alloc(&h->h_m_pts, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = host_alloc(&h->h_m_segs, (size_t)h->o_cap * 4);
+        if (r == TB_OK) r = host_alloc(&h->h_m_recs, d.blobs_cap);
+        if (r != TB_OK) return r;
+    }
+    const uint32_t nb = h->o_n, total = h->h_o_totals[1];
+    h->m_n = 0;
+    const size_t need = 32 * ((size_t)total + 2 * (size_t)nb + 2);
+    if (need > h->m_scratch_floats) {            // work arrays of the walks: 32 floats per outline point, grown on demand
+        if (h->m_scratch) { cudaFree(h->m_scratch); h->m_scratch = nullptr; h->m_scratch_floats = 0; }
+        TB_CUDA(cudaMalloc((void **)&h->m_scratch, need * sizeof(float)));
+        h->m_scratch_floats = need;
+    }
+    cudaStream_t s = h->last_stream ? h->last_stream : h->stream;
+    int r = launch_midlines(h->o_recs, nb, h->o_res, h->o_cap, p, h->m_pts, h->m_segs, h->m_recs, h->m_scratch, s);
+    if (r != TB_OK) return r;
+    h->launches += nb ? 1 : 0;
+    if (nb) {
+        TB_CUDA(cudaMemcpyAsync(h->h_m_recs, h->m_recs, sizeof(tb_midline_rec) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        if (total) {
+            TB_CUDA(cudaMemcpyAsync(h->h_m_pts, h->m_pts, sizeof(float) * 2 * (size_t)total, cudaMemcpyDeviceToHost, s));
+            TB_CUDA(cudaMemcpyAsync(h->h_m_segs, h->m_segs, sizeof(float) * 4 * (size_t)total, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    TB_CUDA(cudaStreamSynchronize(s));
+    h->m_n = nb;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_midline_result(tb_seg *h, const tb_midline_rec **recs, const float **points, const float **segments, uint32_t *n_blobs)
+{
+    TB_REQUIRE(h && recs && points && segments && n_blobs, TB_ERR_INVALID, "tb_seg_midline_result: null argument");
+    TB_REQUIRE(h->h_m_recs, TB_ERR_STATE, "tb_seg_midline_result: call tb_seg_midlines first");
+    *recs = h->h_m_recs; *points = h->h_m_pts; *segments = h->h_m_segs; *n_blobs = h->m_n;
     return TB_OK;
 }
 
