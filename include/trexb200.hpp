@@ -104,6 +104,24 @@ public:
         for (uint32_t k = 0; k < n; ++k) out[k].assign(pts + 2 * (size_t)recs[k].res_off, pts + 2 * ((size_t)recs[k].res_off + recs[k].n_res));
         return out;
     }
+    // Posture's second stage, after outlines(): Outline::calculate_midline per blob (T/tracking/Outline.cpp:768-868; peak_mode
+    // pointy).  One entry per blob of the last apply(): the midline segments {pos.x, pos.y, height, l_length} from the tail on
+    // (empty where the reference reports too few segments) and the tail / head indices into the walked outline.
+    struct Midline { std::vector<float> segments; int tail_index = -1, head_index = -1; };
+    std::vector<Midline> midlines(float outline_resample = 1.f)
+    {
+        check(tb_seg_outlines(_h, outline_resample), "tb_seg_outlines");
+        tb_posture_params pp; tb_posture_default_params(&pp);
+        check(tb_seg_midlines(_h, &pp), "tb_seg_midlines");
+        const tb_midline_rec *recs = nullptr; const float *pts = nullptr, *segs = nullptr; uint32_t n = 0;
+        check(tb_seg_midline_result(_h, &recs, &pts, &segs, &n), "tb_seg_midline_result");
+        std::vector<Midline> out(n);
+        for (uint32_t k = 0; k < n; ++k) {
+            out[k].segments.assign(segs + 4 * (size_t)recs[k].seg_off, segs + 4 * ((size_t)recs[k].seg_off + recs[k].n_seg));
+            out[k].tail_index = recs[k].tail; out[k].head_index = recs[k].head;
+        }
+        return out;
+    }
     tb_seg *handle() { return _h; }
 
 private:

@@ -51,7 +51,7 @@ bs.wait(); torch.cuda.synchronize()
 batch_ms = (time.perf_counter() - t0) / reps * 1e3
 ms, n = bs.kernel_ms()
 tot = bs.totals()
-outline_ms = None
+outline_ms = midline_ms = None
 if len(sys.argv) > 7 and sys.argv[7] == "outlines":      # N4 first stage: find_outer_points + resample of every blob (incl. D2H of the points)
     bs.apply_device(pool[0].data_ptr(), B, stream.cuda_stream, fetch=True); bs.wait()
     lib, h = trex_b200._capi.lib(), bs._h
@@ -61,9 +61,16 @@ if len(sys.argv) > 7 and sys.argv[7] == "outlines":      # N4 first stage: find_
     for i in range(5):
         lib.tb_seg_outlines(h, C.c_float(1.0))
     outline_ms = (time.perf_counter() - t0) / 5 * 1e3
+    from trex_b200._capi import PostureParams
+    P = PostureParams(); lib.tb_posture_default_params(C.byref(P))
+    lib.tb_seg_midlines(h, C.byref(P))
+    t0 = time.perf_counter()
+    for i in range(5):
+        lib.tb_seg_midlines(h, C.byref(P))
+    midline_ms = (time.perf_counter() - t0) / 5 * 1e3
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
 k1 = ms["seg_rle"] / n
 alg = B * W * H * CN + 8 * tot[1]
 print(json.dumps({"B": B, "size": f"{W}x{H}", "channels": CN, "encoding": ENC, "normalization": NORM, "batch_ms_wall": batch_ms, "fpc": os.environ.get("TB_SEG_FPC"), "no_tma": os.environ.get("TB_SEG_NO_TMA"),
                   "seg_rle_ms": k1, "GBps": alg / k1 / 1e6, "frac": alg / k1 / 1e6 / peak,
-                  "ccl_ms": ms["ccl_label"] / n, "emit_ms": ms["blob_emit"] / n, "blobs": tot[0], "outlines_ms_incl_d2h": outline_ms}))
+                  "ccl_ms": ms["ccl_label"] / n, "emit_ms": ms["blob_emit"] / n, "blobs": tot[0], "outlines_ms_incl_d2h": outline_ms, "midlines_ms_incl_d2h": midline_ms}))

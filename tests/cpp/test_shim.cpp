@@ -40,6 +40,9 @@ int main()
         // outline of the 20 x 1 blob: 42 side midpoints, blob on the right hand, no resampling
         auto ol = bs.outlines(0.f);
         if (ol.size() != 1 || ol[0].size() != 2 * 42 || ol[0][0] != 0.0f || ol[0][1] != 0.5f) { std::printf("FAIL outlines %zu\n", ol.empty() ? (size_t)0 : ol[0].size()); return 1; }
+        // its midline: tail at index 0 of the walked outline, head on the far side, more than two segments along the bar
+        auto ml = bs.midlines(1.f);
+        if (ml.size() != 1 || ml[0].tail_index != 0 || ml[0].head_index <= 0 || ml[0].segments.size() < 4 * 3) { std::printf("FAIL midlines\n"); return 1; }
         // colour frames: BGRA input, meta_encoding rgb8 -> B,G,R per blob pixel; gray frames are refused for rgb8
         {
             trexb200::BackgroundSubtraction cs(W, H, 1, 0, 0, 4, trexb200::meta_encoding_t::rgb8);
