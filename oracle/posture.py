@@ -120,5 +120,5 @@ def calculate_midline(points, params: PostureParams | None = None):
     n = _lib().to_calculate_midline(_p(pts), len(pts), C.byref(P), _p(seg), len(seg), C.byref(t), C.byref(h))
     if n < 0:
         raise ValueError({-1: "Empty outline was given, cannot calculate midline.", -2: "Too few midline segments calculated.",
-                          -3: "peak_mode broad is not restated", -4: "capacity"}[int(n)])
+                          -4: "capacity"}[int(n)])
     return seg[:n].copy(), int(t.value), int(h.value), pts

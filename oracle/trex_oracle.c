@@ -1518,14 +1518,67 @@ static void rotate_points(float *p, int64_t N, int64_t k)      /* std::rotate(be
     free(t);
 }
 
-/* Outline::offset_to_middle (T/tracking/Outline.cpp:454-718), peak_mode pointy (the default; the broad branch :621-650 is not
- * restated).  Works in place on the N points (they may be reversed, replaced by their elliptic-Fourier approximation and
+/* is_in_periodic_range (T/tracking/Outline.cpp:442-452) */
+static int in_periodic_range(float period, float r0, float r1, float x, float *cx)
+{
+    if (r0 < 0) {
+        if (x - period >= r0) { *cx = x - period; return 1; }
+        *cx = x; return x <= r1;
+    } else if (r1 >= period) {
+        if (x + period <= r1) { *cx = x + period; return 1; }
+        *cx = x; return x >= r0;
+    }
+    *cx = x; return x >= r0 && x < r1;           /* Range::contains is half open (C/misc/ranges.h:163-168) */
+}
+
+/* The broad-tail index of offset_to_middle (:621-650): the peaks whose integral equals the largest one are merged, and the tail is
+ * the middle of the span of their points that reach 90 % of the highest one.  (The reference collects the points in a std::set
+ * first; only their extent is used, so the order and duplicates do not matter.) */
+static float broad_tail_index(const float *curv, int64_t N, const to_peak_t *mx, int64_t nm)
+{
+    float max_int = -1, minimum = 3.402823466e+38f;
+    for (int64_t i = 0; i < N; ++i) if (curv[i] < minimum) minimum = curv[i];
+    for (int64_t k = 0; k < nm; ++k) if (mx[k].integral > max_int) max_int = mx[k].integral;
+    float m0 = 0, m1 = 0, max_y = 0; int first = 1;
+    for (int64_t k = 0; k < nm; ++k) {
+        if (!((double)fabsf(mx[k].integral - max_int) <= 1e-5)) continue;
+        if (first) { m0 = mx[k].r0; m1 = mx[k].r1; first = 0; }
+        else { if (mx[k].r0 < m0) m0 = mx[k].r0; if (mx[k].r1 > m1) m1 = mx[k].r1; }
+        if (mx[k].max_y > max_y) max_y = mx[k].max_y;
+    }
+    float start = m1, end = m0;
+    for (int64_t k = 0; k < nm; ++k) {
+        if (!((double)fabsf(mx[k].integral - max_int) <= 1e-5)) continue;
+        float chk[3][2]; int nchk = 1;
+        chk[0][0] = mx[k].r0; chk[0][1] = mx[k].r1;
+        float x0 = mx[k].r0, x1 = mx[k].r1;
+        if (x0 < 0) { x0 += (float)N; chk[0][0] = 0; chk[nchk][0] = x0; chk[nchk][1] = (float)(N - 1); ++nchk; }
+        if (x1 >= (float)N) { x1 -= (float)N; chk[0][1] = (float)(N - 1); chk[nchk][0] = 0; chk[nchk][1] = x1; ++nchk; }
+        for (int c = 0; c < nchk; ++c) {
+            if (!(chk[c][1] - chk[c][0] >= 0)) continue;
+            const size_t steps = (size_t)(chk[c][1] - chk[c][0]);
+            for (size_t s2 = 0; s2 < steps; ++s2) {
+                const float i = chk[c][0] + (float)s2;
+                const float y = curv[(size_t)i] - minimum;
+                if (!((double)(y / (mx[k].y - minimum)) >= 0.5)) continue;          /* a point of this peak (:373-389) */
+                float cx;
+                const int in_range = in_periodic_range((float)(size_t)N, m0, m1, i, &cx);
+                if ((double)y >= (double)max_y * 0.9 && in_range) { if (start > cx) start = cx; if (end < cx) end = cx; }
+            }
+        }
+    }
+    float idx = (float)round((double)start + (double)(end - start) * 0.5);
+    if (idx < 0) idx += (float)(size_t)N;
+    if (idx >= (float)(size_t)N) idx -= (float)(size_t)N;
+    return idx;
+}
+
+/* Outline::offset_to_middle (T/tracking/Outline.cpp:454-718), peak_mode pointy (the default) or broad.  Works in place on the N points (they may be reversed, replaced by their elliptic-Fourier approximation and
  * rotated); curv_out (optional, N floats) receives the curvature the peaks were searched in.
- * Returns 0 and tail / head indices, or a negative code: -1 empty, -3 broad mode. */
+ * Returns 0 and tail / head indices, or a negative code: -1 empty. */
 int to_offset_to_middle(float *p, int64_t N, const to_posture_params_t *P, int64_t *tail_out, int64_t *head_out, float *curv_out)
 {
     if (N <= 0) return -1;
-    if (P->peak_mode != 0) return -3;
     if (to_orientation_sum(p, N) < 0)                         /* make it clockwise (:496-498) */
         for (int64_t i = 0, j = N - 1; i < j; ++i, --j) {
             float tx = p[2 * i], ty = p[2 * i + 1];
@@ -1547,11 +1600,12 @@ int to_offset_to_middle(float *p, int64_t N, const to_posture_params_t *P, int64
     to_periodic_curvature(p, N, r, P->outline_approximate > 0, curv);
     if (curv_out) memcpy(curv_out, curv, sizeof(float) * (size_t)N);
     to_peak_t *mx = (to_peak_t *)malloc(sizeof(to_peak_t) * (size_t)(N + 1));
-    const int64_t nm = to_find_peaks(curv, N, 0, mx, N + 1);
+    const int64_t nm = to_find_peaks(curv, N, P->peak_mode != 0, mx, N + 1);
     float max_y = -1, max_y_idx = 0;
     for (int64_t k = 0; k < nm; ++k)
         if (mx[k].y > max_y) { max_y = mx[k].y; max_y_idx = mx[k].x; }
-    const float idx = max_y_idx;                              /* FIND_POINTY (:617-619) */
+    const float idx = P->peak_mode == 0 ? max_y_idx           /* FIND_POINTY (:617-619) */
+                                        : broad_tail_index(curv, N, mx, nm);
     int64_t tail = (int64_t)idx, head = -1;
     float max_d = 0;
     for (int64_t k = 0; k < nm; ++k) {

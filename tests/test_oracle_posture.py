@@ -109,8 +109,11 @@ def test_midline_of_a_fish_shape():
     assert segs[:, 2].max() < 24 and np.allclose(segs[:, 3], segs[:, 2] / 2, atol=1e-3)      # height <= body width, l_length = half
     with pytest.raises(ValueError):
         posture.calculate_midline(np.array([[0, 0], [1, 0], [1, 1]], np.float32))
-    with pytest.raises(ValueError):
-        posture.calculate_midline(ol, posture.default_params(peak_mode=1))
+    # peak_mode broad (:621-650): the tail is the middle of the broadest high-curvature stretch -- for this shape the blunt
+    # head end, whose curvature plateau carries the larger integral; tail and head swap sides, the midline stays on the axis
+    sb, tb, hb, pb = posture.calculate_midline(ol, posture.default_params(peak_mode=1))
+    assert tb == 0 and len(sb) > 40 and np.abs(sb[:, 1] - 11.5).max() < 2.5
+    assert abs(pb[tb][0] - pb[hb][0]) > 60                                      # the two ends of the body
     # midline_invert swaps the two indices (:712-713)
     _, t2, h2, _ = posture.calculate_midline(ol, posture.default_params(midline_invert=1))
     assert (t2, h2) == (head, tail)
