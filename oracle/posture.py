@@ -122,3 +122,45 @@ def calculate_midline(points, params: PostureParams | None = None):
         raise ValueError({-1: "Empty outline was given, cannot calculate midline.", -2: "Too few midline segments calculated.",
                           -4: "capacity"}[int(n)])
     return seg[:n].copy(), int(t.value), int(h.value), pts
+
+
+def calculate_posture(lines, pixels, bg, track_posture_threshold=0, outline_resample=1.0, method=None, params: PostureParams | None = None):
+    """posture::calculate_posture(Frame_t, pv::BlobWeakPtr) (T/tracking/Posture.cpp:305-400) with posture_closing_steps = 0: starting at
+    track_posture_threshold, threshold the blob (pixel::threshold_get_biggest_blob, C/processing/PixelTree.cpp:297-340: the
+    sub-blob with the most pixels, the first one among equals -- here in the oracle's canonical blob order), take its longest
+    outline in the frame of the ORIGINAL blob's bounds (:337), resample it and try calculate_midline; on failure raise the
+    threshold by 2 until the sub-blob has fewer than max(1, pixels / 10) pixels or the threshold reaches the start + 100.
+    Returns dict(outline=(n,2) points, segments=(m,4) or None, tail, head, threshold): like the reference, a posture without a
+    midline still carries the first resampled outline (:386-397); raises ValueError("Cannot find valid posture.") otherwise."""
+    from . import seg
+    method = seg.DIFF_ABSOLUTE if method is None else method
+    lines = np.ascontiguousarray(lines); pixels = np.ascontiguousarray(pixels, np.uint8)
+    npx = int((lines["x1"].astype(np.int64) - lines["x0"] + 1).sum())
+    minimum_pixels = max(1, npx // 10)
+    ox, oy = int(lines["x0"].min()), int(lines["y"].min())
+    one = seg.Blobs(lines, pixels, np.array([0, len(lines)], np.int64), np.array([0, len(pixels)], np.int64))
+    threshold, first_outline = int(track_posture_threshold), None
+    while True:
+        sub = seg.rethreshold(one, bg, threshold, method)
+        sizes = np.diff(sub.px_off)
+        n_sub = 0
+        if len(sub):
+            k = int(np.argmax(sizes))                       # first maximum
+            sl, _ = sub.blob(k)
+            n_sub = int(sizes[k])
+            raw = seg.longest_outline(sl)
+            if len(raw):
+                raw = raw + np.array([int(sl["x0"].min()) - ox, int(sl["y"].min()) - oy], np.float32)
+                pts = seg.outline_resample(raw, outline_resample)
+                try:
+                    segs, tail, head, walked = calculate_midline(pts, params)
+                    return dict(outline=walked, segments=segs, tail=tail, head=head, threshold=threshold)
+                except ValueError:
+                    if first_outline is None and len(pts):
+                        first_outline = pts
+        threshold += 2
+        if n_sub < minimum_pixels or threshold >= track_posture_threshold + 100:
+            break
+    if first_outline is not None:
+        return dict(outline=first_outline, segments=None, tail=-1, head=-1, threshold=None)
+    raise ValueError("Cannot find valid posture.")

@@ -117,3 +117,27 @@ def test_midline_of_a_fish_shape():
     # midline_invert swaps the two indices (:712-713)
     _, t2, h2, _ = posture.calculate_midline(ol, posture.default_params(midline_invert=1))
     assert (t2, h2) == (head, tail)
+
+
+def test_calculate_posture_retry_loop():
+    """Posture.cpp:305-400: the threshold is raised in steps of 2 until a midline is found; a blob with a faint halo needs no
+    retry, a blob that only yields tiny outlines ends with the first outline and no midline."""
+    yy, xx = np.mgrid[0:80, 0:140]
+    bg = np.full((80, 140), 150, np.uint8)
+    fr = bg.copy()
+    body = ((xx - 60) / 35.0) ** 2 + ((yy - 40) / 10.0) ** 2 <= 1
+    fr[body] = 60
+    P = seg.Params(detect_threshold=15, detect_size_filter=[])
+    b = seg.segment_frame(fr, bg, P)
+    lines, px = b.blob(0)
+    r = posture.calculate_posture(lines, px, bg, track_posture_threshold=9, outline_resample=1.0)
+    assert r["threshold"] == 9 and r["segments"] is not None and len(r["segments"]) > 20 and r["tail"] == 0
+    # same result as the stages called by hand (the blob is its own thresholded sub-blob)
+    ol = seg.outline_resample(seg.longest_outline(lines), 1.0)
+    segs, tail, head, _ = posture.calculate_midline(ol)
+    assert np.array_equal(r["segments"], segs) and (r["tail"], r["head"]) == (tail, head)
+    # a 2-pixel blob: outlines too short for a midline at every threshold -> outline only
+    fr2 = bg.copy(); fr2[10, 10:12] = 60
+    l2, p2 = seg.segment_frame(fr2, bg, P).blob(0)
+    r2 = posture.calculate_posture(l2, p2, bg, track_posture_threshold=9)
+    assert r2["segments"] is None and len(r2["outline"]) > 0
