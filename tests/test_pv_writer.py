@@ -59,3 +59,60 @@ def test_frame_payload_bytes_equal_reference_file():
         mine = PVWriter.frame_payload(_recs_from(b), b.lines, b.pixels, timestamp_us=ts, source_index=src)
         body = mine[:-2]                                                             # ours ends with "0 predictions"
         assert pv.data[pos + 1:pos + 1 + len(body)] == body
+
+
+def _lzo_ref():
+    import ctypes as C
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libminilzo.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libminilzo.so not built (needs the reference checkout)")
+    L = C.CDLL(so)
+    L.lzo1x_decompress_safe.argtypes = [C.c_char_p, C.c_ulong, C.c_char_p, C.POINTER(C.c_ulong), C.c_void_p]
+    L.lzo1x_decompress_safe.restype = C.c_int
+
+    def dec(block, n):
+        out = C.create_string_buffer(n + 16); ol = C.c_ulong(n + 16)
+        assert L.lzo1x_decompress_safe(block, len(block), out, C.byref(ol), None) == 0       # LZO_E_OK
+        return out.raw[:ol.value]
+    return dec
+
+
+def test_lzo1x_encoder_round_trips_through_the_reference_decoder():
+    """trex_b200.lzo1x.compress against minilzo's lzo1x_decompress_safe (the reader side of pv.cpp:315-336): every instruction
+    form -- initial / extended literal runs, M2, M3, M4 (distances beyond 16 KiB), trailing literals -- on structured data."""
+    import random
+    from trex_b200.lzo1x import compress
+    dec = _lzo_ref()
+    rng = random.Random(1)
+    blk = bytes(rng.randrange(256) for _ in range(40))
+    cases = [b"", b"a", b"abc", b"abcd", b"a" * 1000, bytes(range(256)) * 4, b"x" * 17 + b"yz" + b"x" * 17,
+             bytes(rng.randrange(256) for _ in range(5000)), bytes(rng.randrange(4) for _ in range(20000)),
+             blk + bytes(rng.randrange(256) for _ in range(20000)) + blk + bytes(rng.randrange(256) for _ in range(30000)) + blk]
+    for t in range(120):
+        cases.append(bytes(rng.randrange(rng.choice([2, 3, 8, 64, 256])) for _ in range(rng.randrange(0, 2500))))
+    for d in cases:
+        assert dec(compress(d), len(d)) == d
+    assert len(compress(b"a" * 1000)) < 20 and len(compress(b"hello world, " * 200)) < 80
+
+
+def test_round_trip_with_lzo(tmp_path):
+    """A file written with compress=True: frames are stored as LZO blocks and the oracle's reader (reference minilzo) returns
+    the same blobs."""
+    _lzo_ref()
+    from oracle.pv15 import PV15
+    g = np.load(os.path.join(GOLDEN, "testpv_golden.npz"))
+    path = str(tmp_path / "lzo.pv")
+    b = seg.segment_frame(g["full0_frame"], g["average"], PV_PARAMS)
+    # a second, highly compressible frame: one blob of constant grey
+    lines = np.array([(100, 400, y, 0) for y in range(50, 120)], seg.LINE_DTYPE)
+    px = np.full(70 * 301, 37, np.uint8)
+    recs2 = np.zeros(1, REC_DTYPE); recs2["n_lines"] = len(lines); recs2["n_pixels"] = len(px)
+    with PVWriter(path, 2304, 2304, g["average"], compress=True) as w:
+        w.add_frame(_recs_from(b), b.lines, b.pixels)
+        w.add_frame(recs2, lines, px, timestamp_us=40000, source_index=1)
+        assert w.compressed_frames >= 1
+    pv = PV15(path)
+    assert pv.num_frames == 2 and pv.data[int(pv.index[1])] == 1                 # stored compressed
+    assert pv.frame(0).as_list() == b.as_list()
+    f1 = pv.frame(1)
+    assert len(f1) == 1 and np.array_equal(f1.lines, lines) and np.array_equal(f1.pixels, px)

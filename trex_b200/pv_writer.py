@@ -3,8 +3,11 @@ reference's `.pv` format so TRex (`-task track`, pvinfo, ...) can open them.  Ho
   Header::write        Application/src/ProcessedVideo/pv.cpp:1053-1165 (layout comment :1060-1100)
   Frame::serialize     pv.cpp:666-775 (uncompressed form; TRex itself stores small frames uncompressed, :713)
   ShortHorizontalLine  Application/src/commons/common/processing/PVBlob.h:296-338, PVBlob.cpp:293-316
-Frames are written uncompressed (compression flag 0), which every reader of the format accepts
-(Frame::read_from, pv.cpp:315-330); LZO blocks are an optional size optimisation of the reference.
+Frames are written uncompressed (compression flag 0) by default, which every reader of the format accepts
+(Frame::read_from, pv.cpp:315-330).  With compress=True a frame payload goes through an LZO1X encoder (trex_b200/lzo1x.py) and is
+stored as {u8 1, u32 compressed size, u32 uncompressed size, block} when that is smaller -- the reference's rule
+(`size < in_len`, pv.cpp:741-763); the encoder is not minilzo's, so the block bytes differ from a TRex-written file while any
+LZO1X decoder reads them.
 """
 from __future__ import annotations
 
@@ -17,7 +20,7 @@ import numpy as np
 
 class PVWriter:
     def __init__(self, path, width, height, average: np.ndarray, *, encoding="gray", source="", name="",
-                 conversion_range=(-1, -1), crop_offsets=(0, 0, 0, 0), metadata: dict | None = None):
+                 conversion_range=(-1, -1), crop_offsets=(0, 0, 0, 0), metadata: dict | None = None, compress=False):
         assert encoding == "gray", "only meta_encoding=gray is built"
         average = np.ascontiguousarray(average, np.uint8)
         assert average.shape == (height, width)
@@ -25,6 +28,8 @@ class PVWriter:
         self.width, self.height = width, height
         self.index = []
         self.metadata = dict(metadata or {})
+        self.compress = bool(compress)
+        self.compressed_frames = 0
         w = self.f.write
         w(b"PV15\0")
         w(encoding.encode() + b"\0")
@@ -69,8 +74,16 @@ class PVWriter:
 
     def add_frame(self, recs, lines, pixels, line_begin=0, px_begin=0, timestamp_us=0, source_index=-1):
         self.index.append(self.f.tell())
+        payload = self.frame_payload(recs, lines, pixels, line_begin, px_begin, timestamp_us, source_index)
+        if self.compress:
+            from .lzo1x import compress
+            block = compress(payload)
+            if len(block) + 8 < len(payload):                        # Frame::serialize keeps the smaller form (pv.cpp:741-763)
+                self.f.write(b"\1" + struct.pack("<II", len(block), len(payload)) + block)
+                self.compressed_frames += 1
+                return
         self.f.write(b"\0")                                          # compression flag
-        self.f.write(self.frame_payload(recs, lines, pixels, line_begin, px_begin, timestamp_us, source_index))
+        self.f.write(payload)
 
     def add_result(self, bs, i, timestamp_us=0, source_index=-1):
         """Append frame i of the last fetched batch of a trex_b200.BackgroundSubtraction."""
