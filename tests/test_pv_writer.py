@@ -116,3 +116,62 @@ def test_round_trip_with_lzo(tmp_path):
     assert pv.frame(0).as_list() == b.as_list()
     f1 = pv.frame(1)
     assert len(f1) == 1 and np.array_equal(f1.lines, lines) and np.array_equal(f1.pixels, px)
+
+
+def test_lzo1x_decoder_reads_minilzo_streams():
+    """trex_b200.lzo1x.decompress on blocks produced by the reference's own compressor (lzo1x_1_compress, what TRex writes)."""
+    import ctypes as C
+    import random
+    from trex_b200.lzo1x import compress, decompress
+    _lzo_ref()
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libminilzo.so")
+    L = C.CDLL(so)
+    L.lzo1x_1_compress.argtypes = [C.c_char_p, C.c_ulong, C.c_char_p, C.POINTER(C.c_ulong), C.c_void_p]
+    L.lzo1x_1_compress.restype = C.c_int
+    wrk = C.create_string_buffer(1 << 17)
+    rng = random.Random(5)
+    blk = bytes(rng.randrange(256) for _ in range(64))
+    cases = [b"", b"a", b"abc", b"a" * 1000, bytes(range(256)) * 8,
+             blk + bytes(rng.randrange(256) for _ in range(30000)) + blk * 3 + bytes(rng.randrange(3) for _ in range(40000)) + blk]
+    for _ in range(150):
+        cases.append(bytes(rng.randrange(rng.choice([2, 3, 5, 16, 64, 256])) for _ in range(rng.randrange(0, 4000))))
+    for d in cases:
+        out = C.create_string_buffer(len(d) + len(d) // 16 + 67); ol = C.c_ulong(0)
+        assert L.lzo1x_1_compress(d, len(d), out, C.byref(ol), wrk) == 0
+        assert decompress(out.raw[:ol.value], len(d)) == d
+        assert decompress(compress(d), len(d)) == d
+    for junk in (b"\x00", b"\x11\x00", b"\xff" * 5, b"\x40\x00\x11\x00\x00"):
+        with pytest.raises(ValueError):
+            decompress(junk, 100)
+
+
+def test_pv_reader_round_trip_and_reference_file(tmp_path):
+    """trex_b200.pv_reader.PVReader: files from PVWriter (plain and LZO frames) and, when the checkout is present, the reference's
+    own videos/test.pv against the oracle's reader."""
+    from trex_b200.pv_reader import PVReader
+    g = np.load(os.path.join(GOLDEN, "testpv_golden.npz"))
+    b = seg.segment_frame(g["full0_frame"], g["average"], PV_PARAMS)
+    lines = np.array([(100, 400, y, 0) for y in range(50, 120)], seg.LINE_DTYPE)
+    px = np.full(70 * 301, 37, np.uint8)
+    recs2 = np.zeros(1, REC_DTYPE); recs2["n_lines"] = len(lines); recs2["n_pixels"] = len(px)
+    for compress_frames in (False, True):
+        path = str(tmp_path / f"r{int(compress_frames)}.pv")
+        with PVWriter(path, 2304, 2304, g["average"], name="rt", source="frames", metadata={"cm_per_pixel": 1}, compress=compress_frames) as w:
+            w.add_frame(_recs_from(b), b.lines, b.pixels, timestamp_us=7, source_index=3)
+            w.add_frame(recs2, lines, px, timestamp_us=40000, source_index=4)
+        pv = PVReader(path)
+        assert (pv.width, pv.height, len(pv), pv.encoding, pv.name, pv.source) == (2304, 2304, 2, "gray", "rt", "frames")
+        assert np.array_equal(pv.average, g["average"]) and pv.mask is None and "cm_per_pixel" in pv.metadata
+        f0, f1 = pv.frame(0), pv.frame(1)
+        assert (f0.timestamp_us, f0.source_index, len(f0)) == (7, 3, len(b))
+        assert np.array_equal(f0.lines, b.lines) and np.array_equal(f0.pixels, b.pixels)
+        assert np.array_equal(f0.line_off, b.line_off) and np.array_equal(f0.px_off, b.px_off)
+        assert np.array_equal(f1.lines, lines) and np.array_equal(f1.pixels, px)
+    ref = "/root/reference/videos/test.pv"
+    if os.path.exists(ref):
+        from oracle.pv15 import PV15
+        mine, theirs = PVReader(ref), PV15(ref)
+        assert len(mine) == theirs.num_frames == 200 and np.array_equal(mine.average, theirs.average)
+        for i in (0, 57, 199):
+            a, c = mine.frame(i), theirs.frame(i)
+            assert np.array_equal(a.lines, c.lines) and np.array_equal(a.pixels, c.pixels) and np.array_equal(a.line_off, c.line_off)

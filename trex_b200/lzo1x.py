@@ -121,3 +121,96 @@ def compress(data: bytes) -> bytes:
         flush_literals(n)
     out += b"\x11\x00\x00"
     return bytes(out)
+
+
+def decompress(block: bytes, max_out: int | None = None) -> bytes:
+    """LZO1X block decoder (what lzo1x_decompress does for pv::Frame::read_from, pv.cpp:315-336).  Raises ValueError on a
+    malformed stream or when the output would exceed max_out."""
+    src = bytes(block)
+    n = len(src)
+    out = bytearray()
+    ip = 0
+
+    def copy_match(dist: int, length: int):
+        if dist <= 0 or dist > len(out):
+            raise ValueError("LZO1X: match distance outside the window")
+        start = len(out) - dist
+        if dist >= length:
+            out.extend(out[start:start + length])
+        else:
+            for k in range(length):
+                out.append(out[start + k])
+        if max_out is not None and len(out) > max_out:
+            raise ValueError("LZO1X: output overrun")
+
+    def literals(k: int):
+        nonlocal ip
+        if ip + k > n:
+            raise ValueError("LZO1X: input overrun")
+        out.extend(src[ip:ip + k]); ip += k
+        if max_out is not None and len(out) > max_out:
+            raise ValueError("LZO1X: output overrun")
+
+    def ext(base: int) -> int:
+        nonlocal ip
+        t = 0
+        while True:
+            if ip >= n:
+                raise ValueError("LZO1X: input overrun")
+            b = src[ip]; ip += 1
+            if b:
+                return t + base + b
+            t += 255
+
+    try:
+        state = "loop"                     # "loop": a literal run may follow; "after_lit": right after a literal run; "match": t holds a match
+        t = 0
+        if n and src[0] > 17:
+            t = src[0] - 17; ip = 1
+            literals(t)
+            state = "match_next0" if t < 4 else "after_lit"
+        while True:
+            if state in ("loop", "after_lit", "match_next0"):
+                t = src[ip]; ip += 1
+                if state == "loop" and t < 16:
+                    k = (t + 3) if t else ext(15) + 3
+                    literals(k)
+                    state = "after_lit"
+                    continue
+                if state == "after_lit" and t < 16:          # 3-byte match just beyond the M2 window
+                    copy_match(1 + 0x800 + (t >> 2) + (src[ip] << 2), 3); ip += 1
+                    trail = src[ip - 2] & 3
+                    if trail:
+                        literals(trail); state = "match_next0"
+                    else:
+                        state = "loop"
+                    continue
+            # t is a match instruction (t >= 16, or an M1 after trailing literals)
+            if t >= 64:
+                copy_match(1 + ((t >> 2) & 7) + (src[ip] << 3), (t >> 5) - 1 + 2); ip += 1
+            elif t >= 32:
+                length = (t & 31) or ext(31)
+                v = src[ip] | (src[ip + 1] << 8); ip += 2
+                copy_match(1 + (v >> 2), length + 2)
+            elif t >= 16:
+                dist = (t & 8) << 11
+                length = (t & 7) or ext(7)
+                v = src[ip] | (src[ip + 1] << 8); ip += 2
+                dist += v >> 2
+                if dist == 0:
+                    if length != 1:
+                        raise ValueError("LZO1X: bad end marker")
+                    break
+                copy_match(dist + 0x4000, length + 2)
+            else:                                               # M1: 2-byte match, only valid after trailing literals
+                copy_match(1 + (t >> 2) + (src[ip] << 2), 2); ip += 1
+            trail = src[ip - 2] & 3
+            if trail:
+                literals(trail); state = "match_next0"
+            else:
+                state = "loop"
+    except IndexError:
+        raise ValueError("LZO1X: input overrun") from None
+    if ip != n:
+        raise ValueError("LZO1X: trailing bytes after the end marker")
+    return bytes(out)
