@@ -10,6 +10,7 @@ Run here (authoring container) only; the GPU box has no reference tree and just 
                      (visual_identification_network_torch.py, imported from the reference tree)
                      for the state_dict oracle.vi.init_state_dict(seed=0) generates.
   vi_nets_golden.npz the same for the other custom networks (V100, V110, V119, V200).
+  posture_golden.npz fish blobs of test.pv with the midline lengths TRex exported for them (compare_data_automatic/*.csv).
   pixels_golden.npz  known-answer vector transcribed from Application/Tests/test_pixels.cpp:1381-1466.
 """
 import os
@@ -144,6 +145,53 @@ def make_vi_nets():
     print("vi_nets_golden.npz", os.path.getsize(os.path.join(HERE, "vi_nets_golden.npz")) // 1024, "KiB")
 
 
+def make_posture():
+    """posture_golden.npz: fish blobs of videos/test.pv (tracker side: re-thresholded with test.settings' track_threshold = 12,
+    sign difference, track_size_filter [70, 420)) next to the `midline_length` / `num_pixels` columns TRex itself exported for
+    them (videos/compare_data_automatic/test_fish*.csv).  The csv files were written from a slightly different .pv (their pixel
+    counts differ by a few pixels from what test.pv yields) and hold the post-processed length rounded to integers, so this is a
+    loose, external corroboration of the outline -> midline chain, not a bit-exact pin."""
+    import csv
+    from oracle import seg
+    from oracle.pv15 import PV15
+    pv = PV15(f"{REF}/videos/test.pv")
+    bg = pv.average
+    fish = [list(csv.DictReader(open(f"{REF}/videos/compare_data_automatic/test_fish{k}.csv"))) for k in range(8)]
+    dec = lambda b: (b >> 19, (b >> 6) & 0x1FFF)
+    out, n = {}, 0
+    for f in (0, 1, 2, 50, 100, 150, 199):
+        trk = seg.rethreshold(pv.frame(f), bg, 12, method=seg.DIFF_SIGN)
+        cand = []
+        for k in range(len(trk)):
+            l, p = trk.blob(k)
+            if 70 <= len(p) < 420:
+                cand.append((k, dec(seg.blob_id(l))))
+        for k8 in range(8):
+            r = fish[k8][f]
+            try:
+                bid, ml, npx = int(float(r["blobid"])), float(r["midline_length"]), int(float(r["num_pixels"]))
+            except (ValueError, OverflowError):      # "inf": the fish was not tracked / had no posture in this frame
+                continue
+            if not np.isfinite(ml) or ml <= 0:
+                continue
+            cx, cy = dec(bid)
+            best = min(cand, key=lambda c: abs(c[1][0] - cx) + abs(c[1][1] - cy), default=None)
+            if best is None or abs(best[1][0] - cx) + abs(best[1][1] - cy) > 6:
+                continue
+            l, p = trk.blob(best[0])
+            if abs(len(p) - npx) > 0.05 * npx:       # the tracker split / merged this blob differently: not the same object
+                continue
+            x0, y0 = max(int(l["x0"].min()) - 4, 0), max(int(l["y"].min()) - 4, 0)
+            x1, y1 = int(l["x1"].max()) + 5, int(l["y"].max()) + 5
+            ls = l.copy(); ls["x0"] -= x0; ls["x1"] -= x0; ls["y"] -= y0
+            out[f"b{n}_lines"] = ls; out[f"b{n}_pixels"] = p.copy(); out[f"b{n}_bg"] = bg[y0:y1, x0:x1].copy()
+            out[f"b{n}_csv"] = np.array([f, k8, ml, npx], np.float64)
+            n += 1
+    out["count"] = np.array(n)
+    np.savez_compressed(os.path.join(HERE, "posture_golden.npz"), **out)
+    print("posture_golden.npz", n, "blobs,", os.path.getsize(os.path.join(HERE, "posture_golden.npz")) // 1024, "KiB")
+
+
 def make_pixels():
     # Application/Tests/test_pixels.cpp:1381-1466 (gray leg): bg gray == the equal-channel BGR values,
     # blob greys = cv::cvtColor of blob_values (only (10,200,10) is not grey: OpenCV fixed point -> 122).
@@ -170,4 +218,4 @@ def make_average():
 
 
 if __name__ == "__main__":
-    make_testpv(); make_vi(); make_vi_nets(); make_pixels(); make_average()
+    make_testpv(); make_vi(); make_vi_nets(); make_pixels(); make_average(); make_posture()

@@ -141,3 +141,31 @@ def test_calculate_posture_retry_loop():
     l2, p2 = seg.segment_frame(fr2, bg, P).blob(0)
     r2 = posture.calculate_posture(l2, p2, bg, track_posture_threshold=9)
     assert r2["segments"] is None and len(r2["outline"]) > 0
+
+
+def test_midline_lengths_against_the_references_own_export():
+    """Loose external corroboration of the whole chain (re-threshold -> outline -> resample 0.5 -> smooth -> Fourier
+    approximation -> curvature peaks -> pairing walk): the length of the raw midline of fish blobs from videos/test.pv next to
+    the `midline_length` TRex itself exported for the same fish and frames (videos/compare_data_automatic/test_fish*.csv,
+    written with videos/test.settings: track_threshold 12, sign difference, track_posture_threshold 9, outline_resample 0.5).
+    The csv was written from a slightly different .pv (pixel counts differ by a few pixels) and holds the post-processed
+    length rounded to an integer, so the agreement is statistical: tests/golden/make_golden.py::make_posture."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "posture_golden.npz"))
+    n = int(g["count"])
+    assert n >= 30
+    ratios, close = [], 0
+    for i in range(n):
+        lines, px, bg = g[f"b{i}_lines"], g[f"b{i}_pixels"], g[f"b{i}_bg"]
+        _, _, ml, npx = g[f"b{i}_csv"]
+        out = posture.calculate_posture(lines, px, bg, track_posture_threshold=9, outline_resample=0.5, method=seg.DIFF_SIGN)
+        assert out["segments"] is not None and out["threshold"] == 9
+        s = out["segments"]
+        length = float(np.linalg.norm(np.diff(s[:, :2], axis=0), axis=1).sum())
+        ratios.append(length / ml)
+        close += abs(length - ml) <= 1.5
+        assert abs(len(px) - npx) <= 0.05 * npx                                  # the same fish (make_posture's filter)
+    ratios = np.array(ratios)
+    assert abs(ratios.mean() - 1) < 0.03 and ratios.std() < 0.05
+    assert close >= 0.8 * n                                                      # within 1.5 px of TRex's integer for most fish
