@@ -66,3 +66,12 @@ def test_transform_results_mirror_matches_oracle():
         b = vi.transform_results(7, idx, rows, 5)
         assert np.array_equal(a, b), idx
     assert (VINetwork.transform_results(4, [2], rows, 5)[:2] == -1).all()
+
+
+def test_blob_properties_mirror():
+    """Blob.num_pixels / Blob.center follow pv::Blob::calculate_properties (PVBlob.cpp:216-243)."""
+    import numpy as np
+    from trex_b200.background_subtraction import LINE_DTYPE, Blob
+    lines = np.array([(10, 14, 7, 0), (8, 20, 8, 0), (9, 9, 9, 0)], LINE_DTYPE)
+    b = Blob(lines, np.zeros(19, np.uint8), 0, (8, 7, 20, 9))
+    assert b.num_pixels == 19 and b.center == (8 + 13 * 0.5, 7 + 3 * 0.5)

@@ -88,6 +88,17 @@ class Blob:
     bid: int
     bounds: tuple          # x0, y0, x1, y1 inclusive
 
+    @property
+    def num_pixels(self) -> int:
+        """pv::Blob::calculate_properties (C/processing/PVBlob.cpp:216-243): the sum of the line lengths."""
+        return int((self.lines["x1"].astype(np.int64) - self.lines["x0"] + 1).sum())
+
+    @property
+    def center(self) -> tuple:
+        """_properties.center = bounds.pos() + bounds.size() * 0.5 (PVBlob.cpp:239), bounds = (x, y, maxx - x + 1, maxy - y + 1)."""
+        x0, y0, x1, y1 = self.bounds
+        return (x0 + (x1 - x0 + 1) * 0.5, y0 + (y1 - y0 + 1) * 0.5)
+
 
 class BackgroundSubtraction:
     def __init__(self, average: np.ndarray | None = None, *, width=None, height=None, settings: DetectSettings | None = None,
