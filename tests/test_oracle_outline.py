@@ -51,3 +51,33 @@ def test_find_outer_points_simple_shapes():
             m[l["y"] + 1, l["x0"] + 1:l["x1"] + 2] = True
         exp = sum(int((m & ~np.roll(m, s, a)).sum()) for s, a in ((1, 0), (-1, 0), (1, 1), (-1, 1)))
         assert n_sides == exp
+
+
+def test_outline_count_equals_one_plus_holes():
+    """Independent structural check (scipy): an 8-connected blob has one outer outline plus one outline per hole, where holes
+    are the 4-connected background regions that do not touch the border of the blob's padded bounding box."""
+    ndimage = __import__("pytest").importorskip("scipy.ndimage")
+    rng = np.random.default_rng(11)
+    checked = 0
+    blobs = []
+    for dens in (0.35, 0.45, 0.55, 0.62):
+        bl = seg.label_image((rng.random((70, 90)) < dens).astype(np.uint8) * 255)
+        blobs += [bl.blob(k)[0] for k in range(len(bl))]
+    for k, lines in enumerate(blobs):
+        if len(lines) < 3:
+            continue
+        x0, y0 = int(lines["x0"].min()), int(lines["y"].min())
+        w, h = int(lines["x1"].max()) - x0 + 1, int(lines["y"].max()) - y0 + 1
+        m = np.zeros((h + 2, w + 2), bool)
+        for l in lines:
+            m[l["y"] - y0 + 1, l["x0"] - x0 + 1:l["x1"] - x0 + 2] = True
+        lab, n = ndimage.label(~m)                          # 4-connectivity by default
+        outside = lab[0, 0]
+        holes = len(set(np.unique(lab)) - {0, outside})
+        ols = seg.find_outer_points(lines)
+        assert len(ols) == 1 + holes, k
+        # the outer outline is the one that reaches the bounding box on all four sides
+        outer = [o for o in ols if o[:, 0].min() == 0 and o[:, 1].min() == 0 and o[:, 0].max() == w and o[:, 1].max() == h]
+        assert len(outer) == 1
+        checked += 1
+    assert checked > 20
