@@ -71,3 +71,36 @@ def test_midline_errors():
     with pytest.raises(trex_b200.TrexB200Error):
         bs.midlines(1.0, peak_mode=1)                       # broad tails are not built
     assert len(bs.midlines(1.0)) == 1
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("TB_RUN_UNVALIDATED"),
+                    reason="written after round 1's GPU budget was spent; enable with TB_RUN_UNVALIDATED=1 (DESIGN.md s8, item 0)")
+def test_midline_lengths_against_the_references_own_export_gpu():
+    """GPU leg of tests/test_oracle_posture.py::test_midline_lengths_against_the_references_own_export: the golden fish blobs of
+    videos/test.pv are pasted into frames over their background windows, segmented with the sign difference at threshold 8
+    (> 8 == >= 9 = track_posture_threshold), and the raw midline length from tb_seg_midlines is compared with TRex's exported
+    midline_length."""
+    import os
+    import trex_b200
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "posture_golden.npz"))
+    n = int(g["count"])
+    H, W = 96, 128
+    ratios = []
+    for i in range(n):
+        lines, px, bgw = g[f"b{i}_lines"], g[f"b{i}_pixels"], g[f"b{i}_bg"]
+        bg = np.full((H, W), 200, np.uint8); bg[:bgw.shape[0], :bgw.shape[1]] = bgw
+        fr = bg.copy()
+        o = 0
+        for l in lines:
+            k = int(l["x1"]) - int(l["x0"]) + 1
+            fr[l["y"], l["x0"]:l["x1"] + 1] = px[o:o + k]; o += k
+        s = trex_b200.DetectSettings(detect_threshold=8, detect_threshold_is_absolute=False, detect_size_filter=[(50, 100000)])
+        bs = trex_b200.BackgroundSubtraction(bg, settings=s, max_batch=1)
+        got = bs.apply([fr])
+        assert len(got[0]) == 1 and got[0][0].num_pixels == len(px)
+        segs, tail, head, _ = bs.midlines(0.5)[0]
+        assert len(segs) > 2
+        ratios.append(float(np.linalg.norm(np.diff(segs[:, :2], axis=0), axis=1).sum()) / float(g[f"b{i}_csv"][2]))
+    ratios = np.array(ratios)
+    assert abs(ratios.mean() - 1) < 0.03 and ratios.std() < 0.05
