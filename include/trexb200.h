@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TB_ABI_VERSION 4
+#define TB_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define TB_API __attribute__((visibility("default")))
@@ -62,6 +62,10 @@ typedef struct tb_seg_params {
     int32_t use_adaptive_threshold;       /* 0; 1: cv::adaptiveThreshold(MEAN_C, BINARY, n, -T) on the difference image instead of the
                                              plain threshold (:487,526), n = int(width * adaptive_threshold_scale) made odd, >= 3 (:427-434) */
     float   adaptive_threshold_scale;     /* 2 (T/core/default_config.cpp:1161)                        */
+    int32_t open_size;                    /* 0; NOT a reference setting (the reference has no opening stage): the optional "2x2 morphological
+                                             open" BASELINE.json's north_star names, applied to the threshold mask before use_closing /
+                                             dilation_size: cv::morphologyEx(mask, MORPH_OPEN, ones(n,n)) = erode then dilate, default anchor
+                                             (n/2, n/2), outside pixels ignored; 0 / 1 = off, 2..15                                      */
 } tb_seg_params;
 
 typedef struct tb_seg_config {
@@ -301,10 +305,70 @@ TB_API int tb_avg_add(tb_avg *h, const uint8_t *frames, int n);
 TB_API int tb_avg_add_device(tb_avg *h, const void *frames_dev, int n, void *stream);
 TB_API int tb_avg_finalize(tb_avg *h, uint8_t *out);
 
-/* Debug / bring-up: one tcgen05 "shifted GEMM" D[128][N] = A[shift+m][:] . B[n][:]^T on bf16 operands in the
- * channel-group-planar layout the convolution kernels use (a: [n_cg][n_pos][8] bf16, b: [n_cg][N][8] bf16,
- * d: [128][N] f32; all host pointers).  Exercised by tests/test_gpu_umma.py. */
-TB_API int tb_debug_umma_shifted_gemm(const void *a, int n_pos, int n_cg, int shift, const void *b, int N, float *d);
+/* ----------------------------------------------------------------------------------------------
+ * Host frame buffers.  The reference hands BackgroundSubtraction::apply frames that live in a pool of reusable
+ * Image::Ptr buffers (buffers::TileBuffers, T/core/TileBuffers.h:13-22: ImageBuffers<Image::Ptr, ImageMaker, 16>, filled by
+ * TileImage's constructor, T/core/TileImage.h:27-45, and returned with TileBuffers::get().move_back,
+ * T/python/BackgroundSubtraction.cpp:336-339).  tb_seg_submit copies from the caller's pointer with cudaMemcpyAsync: from
+ * pageable memory the driver stages through its own bounce buffers (about a third of the PCIe rate, and the call is not
+ * asynchronous), so the pool's buffers should be page-locked -- either allocated here (an ImageMaker that calls
+ * tb_host_alloc) or registered in place once (tb_host_register on the pool's 16 buffers).
+ * ---------------------------------------------------------------------------------------------- */
+TB_API int tb_host_alloc(size_t bytes, void **out);          /* page-locked, mapped for every device; 4096-byte aligned */
+TB_API int tb_host_free(void *p);
+TB_API int tb_host_register(void *p, size_t bytes);          /* page-lock an existing allocation (cudaHostRegisterPortable) */
+TB_API int tb_host_unregister(void *p);
+
+/* ----------------------------------------------------------------------------------------------
+ * Plug-in entry, mirroring the reference's own dlopen convention (SURVEY.md s8b A''): the host resolves ONE C symbol --
+ * the reference's is `extern "C" void trex_python_register()` (T/python/PythonEntryPoint.cpp:142-179), which fills a table
+ * of function pointers (PythonImplInterface) and registers the detection back ends as
+ * detect::BackendHooks{init, deinit, is_initializing, fps, apply, set_background} (T/python/BackendRegistry.h:10-22,
+ * register_yolo_backend, T/python/YOLO.cpp:1738-1747) and the identification service as RecTaskBackend{init, deinit, predict}
+ * (T/python/PythonBackendRegistry.cpp:52-58).  Ours is trex_b200_register(): it fills the pure-C table below (one process-wide
+ * detection handle and one identification handle, like the reference's static BackgroundSubtraction::data()) and, when the
+ * host passes a tb_host_table, hands it to the host's register_backend callback for detect type "background_subtraction".
+ * The C++ shim of INTEGRATION.md s1 wraps the six detection pointers into a detect::BackendHooks.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tb_backend_table {
+    uint32_t abi_version, size;                  /* TB_ABI_VERSION, sizeof(tb_backend_table) */
+    /* detect::BackendHooks */
+    int    (*init)(const tb_seg_config *cfg, const tb_seg_params *params);     /* BackgroundSubtraction::init (.cpp:56-84) */
+    void   (*deinit)(void);                                                    /* ::deinit (:118-120) */
+    int    (*is_initializing)(void);                                           /* hooks.is_initializing: 1 until a background is set */
+    double (*fps)(void);                                                       /* ::fps (:21-35): mean of frames / elapsed per apply */
+    int    (*apply)(const uint8_t *const *frames, int n, int64_t stride, tb_blob_view *views /* n entries */);   /* ::apply (:126-347) */
+    int    (*set_background)(const uint8_t *bg, int width, int height, int channels, int64_t stride);           /* ::set_background (:86-90) */
+    int    (*update_params)(const tb_seg_params *params);                      /* the settings callbacks (RawProcessing.cpp:283-327) */
+    /* RecTaskBackend{init, deinit, predict} + VINetwork::load_weights */
+    int    (*vi_init)(const tb_vi_config *cfg);
+    void   (*vi_deinit)(void);
+    int    (*vi_set_tensor)(const char *name, const float *data, int64_t count);
+    int    (*vi_commit)(void);
+    int    (*vi_predict)(const uint8_t *images, int n, float *probs);
+    const char *(*last_error)(void);
+} tb_backend_table;
+
+typedef struct tb_host_table {                   /* what the host hands in (the reference passes GlobalSettings / the tile-buffer pool
+                                                    through PythonImplInterface::set_settings, T/python/PythonEntryPoint.cpp) */
+    uint32_t abi_version, size;                  /* TB_ABI_VERSION the host was compiled against, sizeof(tb_host_table) */
+    void *user;
+    void (*register_backend)(void *user, const char *detect_type, const tb_backend_table *table);
+    void (*log)(void *user, int level, const char *message);      /* optional (may be NULL) */
+} tb_host_table;
+
+/* Returns TB_OK, or TB_ERR_INVALID when the host's abi_version differs.  host may be NULL (the table is then only reachable
+ * through tb_backend()). */
+TB_API int trex_b200_register(const tb_host_table *host);
+TB_API const tb_backend_table *tb_backend(void);
+
+#ifdef TB_DEBUG_EXPORTS
+/* Debug / bring-up (not part of the product ABI; declared only with -DTB_DEBUG_EXPORTS): one tcgen05 "shifted GEMM"
+ * D[128][N] = A[shift+m][:] . B[n][:]^T on bf16 operands in the channel-group-planar layout the convolution kernels use
+ * (a: [n_cg][n_pos][8] bf16, b: [n_cg][N][8] bf16, d: [128][N] f32; all host pointers).  Exercised by tests/test_gpu_umma.py
+ * through the symbol name tbdbg_umma_shifted_gemm. */
+int tbdbg_umma_shifted_gemm(const void *a, int n_pos, int n_cg, int shift, const void *b, int N, float *d);
+#endif
 
 #ifdef __cplusplus
 }

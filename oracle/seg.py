@@ -32,7 +32,7 @@ class _Params(C.Structure):
         ("image_invert", C.c_int32), ("use_closing", C.c_int32), ("closing_size", C.c_int32),
         ("dilation_size", C.c_int32), ("cm_per_pixel", C.c_float), ("n_size_ranges", C.c_int32),
         ("size_lo", C.c_double * 4), ("size_hi", C.c_double * 4),
-        ("blur_difference", C.c_int32), ("use_adaptive_threshold", C.c_int32), ("adaptive_threshold_scale", C.c_float), ("pad0", C.c_int32),
+        ("blur_difference", C.c_int32), ("use_adaptive_threshold", C.c_int32), ("adaptive_threshold_scale", C.c_float), ("open_size", C.c_int32),
     ]
 
 
@@ -52,6 +52,7 @@ class Params:
     blur_difference: bool = False
     use_adaptive_threshold: bool = False
     adaptive_threshold_scale: float = 2.0
+    open_size: int = 0          # not a reference setting: north_star's optional n x n open of the threshold mask (0 = off)
 
     def c(self) -> _Params:
         p = _Params()
@@ -67,6 +68,7 @@ class Params:
         p.blur_difference = int(self.blur_difference)
         p.use_adaptive_threshold = int(self.use_adaptive_threshold)
         p.adaptive_threshold_scale = self.adaptive_threshold_scale
+        p.open_size = int(self.open_size)
         p.n_size_ranges = len(self.detect_size_filter)
         for i, (lo, hi) in enumerate(self.detect_size_filter):
             p.size_lo[i], p.size_hi[i] = lo, hi

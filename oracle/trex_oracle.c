@@ -49,7 +49,8 @@ typedef struct {
     int32_t blur_difference;          /* grabber default_config.cpp:125 (false) */
     int32_t use_adaptive_threshold;   /* T/core/default_config.cpp:1162 (false) */
     float   adaptive_threshold_scale; /* :1161 (2)                              */
-    int32_t pad0;
+    int32_t open_size;                /* NOT a reference setting: BASELINE north_star's optional "2x2 morphological open" of the
+                                         threshold mask, cv::morphologyEx(MORPH_OPEN, ones(n,n)); 0 / 1 = off (default)  */
 } to_params_t;
 
 /* Blob emission order (SURVEY.md s7 "Blob order"):
@@ -168,7 +169,7 @@ static int gen_mask(const uint8_t *frame, const uint8_t *bg, int w, int h, const
 {
     const size_t n = (size_t)w * h;
     const int T = p->detect_threshold, aT = abs(T);
-    const int need_morph = p->use_closing || p->dilation_size != 0;
+    const int need_morph = p->use_closing || p->dilation_size != 0 || p->open_size > 1;
     uint8_t *diff = NULL, *tmp = NULL;
     if (p->blur_difference) {          /* RawProcessing.cpp:371-387; the difference is taken regardless of enable_difference */
         uint8_t *tz = (uint8_t *)malloc(n), *bl = (uint8_t *)malloc(n);
@@ -209,6 +210,14 @@ static int gen_mask(const uint8_t *frame, const uint8_t *bg, int w, int h, const
             if (T < 0) m = !m;
             mask[i] = m ? 255 : 0;
         }
+    }
+    if (p->open_size > 1) {            /* optional open of the threshold mask: erode, then dilate, ones(n,n), OpenCV's default anchor n/2 */
+        int k = p->open_size;
+        uint8_t *el = (uint8_t *)malloc((size_t)k * k);
+        memset(el, 1, (size_t)k * k);
+        morph(mask, tmp, w, h, el, k, k, k / 2, k / 2, 0);
+        morph(tmp, mask, w, h, el, k, k, k / 2, k / 2, 1);
+        free(el);
     }
     if (p->use_closing) {
         int k = p->closing_size, kn = 2 * k + 1;
@@ -468,7 +477,9 @@ int64_t to_label_runs(const to_line_t *runs, int64_t n, int order, int32_t *labe
 
 /* size filter: T/python/BackgroundSubtraction.cpp:259 -> SizeFilters::in_range_of_one
  * (T/core/SizeFilters.cpp:36-53), Range<double>::contains half-open (C/misc/ranges.h:162-168);
- * num_pixels * SQR(cm_per_pixel) is evaluated in float (Float2_t, C/misc/vec2.h:6). */
+ * num_pixels * SQR(cm_per_pixel) is evaluated in float (Float2_t, C/misc/vec2.h:6).
+ * num_pixels = pixels->size() (:247-251): the BYTES of the blob's pixel payload, i.e. 3 per pixel for
+ * rgb8 blobs (CPULabeling.cpp:302-311 stores `channels` bytes per pixel), 1 for gray / r3g3b2. */
 static int size_ok(const to_params_t *p, uint64_t npx)
 {
     if (p->n_size_ranges <= 0) return 1;
@@ -520,7 +531,7 @@ static int64_t segment_binary(const uint8_t *bin, int w, int h, int c,
     }
     int64_t kept = 0, tl = 0, tp = 0;
     for (int64_t b = 0; b < nb; ++b) {
-        if (size_ok(p, (uint64_t)cnt_p[b]) && cnt_l[b] < 65535) {
+        if (size_ok(p, (uint64_t)cnt_p[b] * (uint64_t)c) && cnt_l[b] < 65535) {
             remap[b] = (int32_t)kept;
             if (kept < cap_blobs) { line_off[kept] = tl; px_off[kept] = tp; }
             cur_l[b] = tl; cur_p[b] = tp;

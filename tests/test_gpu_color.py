@@ -282,3 +282,22 @@ def test_batch_arena_overflow_is_reported_not_corrupting():
     assert all(i.n_blobs == 0 and (i.status & 8) for i in infos[1:])
     ref = seg.segment_frame(frames[0], bg, _params(**kw))
     assert _as_list(bs.result(0)) == ref.as_list()
+
+
+def test_rgb8_size_filter_counts_payload_bytes():
+    """detect_size_filter on rgb8 blobs compares 3 * pixels (pixels->size(), BackgroundSubtraction.cpp:247-259): blobs whose
+    pixel count straddles the bounds are kept / dropped like the oracle does (which pins the rule on a hand-made frame)."""
+    from oracle import seg
+    bg = np.full((48, 64, 3), 128, np.uint8)
+    fr = np.repeat(bg[None], 2, 0).copy()
+    fr[0, 5, 8:12] = (20, 30, 40); fr[0, 20, 10:44] = (20, 30, 40); fr[0, 30, 10:20] = (20, 30, 40)
+    fr[1, 7, 3:6] = (20, 30, 40); fr[1, 9, 3:7] = (200, 30, 40); fr[1, 40, 0:33] = (20, 30, 40); fr[1, 42, 0:34] = (20, 30, 40)
+    kw = dict(detect_threshold=15, detect_size_filter=[(10, 100)])
+    bs = _mk(bg, 3, "rgb8", **kw)
+    got = bs.apply(fr)
+    for f in range(2):
+        ref = seg.segment_frame_color(fr[f], bg, _params(**kw), encoding=seg.ENC_RGB8)
+        assert _as_list(got[f]) == ref.as_list(), f
+    assert sorted(b.num_pixels for b in got[0]) == [4, 10] and sorted(b.num_pixels for b in got[1]) == [4, 33]
+    gs = _mk(seg.bgr2gray(bg), 3, "gray", **kw)
+    assert sorted(b.num_pixels for b in gs.apply(fr)[0]) == [10, 34]

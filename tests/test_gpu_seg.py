@@ -234,6 +234,12 @@ def test_capacity_and_state_errors():
     bs.set_background(bg)
     with pytest.raises(trex_b200.TrexB200Error):
         bs.update_settings(trex_b200.DetectSettings(use_closing=True, closing_size=9))     # element larger than 15x15
+    # a rejected tb_seg_set_params leaves the previous settings fully in place: the handle still segments
+    for bad in (dict(use_adaptive_threshold=True, adaptive_threshold_scale=99.0), dict(blur_difference=True, use_closing=True, closing_size=9)):
+        with pytest.raises(trex_b200.TrexB200Error):
+            bs.update_settings(trex_b200.DetectSettings(**bad))
+    fr0 = bg.copy(); fr0[10:20, 10:30] = 30
+    assert [b.num_pixels for b in bs.apply([fr0])[0]] == [200]
     bs2 = trex_b200.BackgroundSubtraction(bg, max_batch=1, max_runs_per_frame=16,
                                           settings=trex_b200.DetectSettings(detect_size_filter=[]))
     fr = bg.copy(); fr[::2, ::2] = 200       # 1024 runs > capacity
@@ -274,6 +280,9 @@ def test_config4_256_individuals_and_config5_4k():
     dict(use_closing=True, closing_size=1, dilation_size=2),
     dict(dilation_size=-3),
     dict(use_closing=True, closing_size=2, dilation_size=-2),
+    dict(open_size=2),                                           # north_star's "2x2 morphological open" (not a reference stage; default off)
+    dict(open_size=3, use_closing=True, closing_size=2),
+    dict(open_size=2, dilation_size=2),
 ])
 def test_morphology_vs_oracle(kw):
     """Optional closing / dilation of generate_binary (RawProcessing.cpp:438-550); the oracle's closing and

@@ -23,7 +23,7 @@ def test_shifted_gemm(n_cg, N, n_pos, shift):
     a_bits, a = _bf16(rng.standard_normal((n_cg, n_pos, 8)))
     b_bits, b = _bf16(rng.standard_normal((n_cg, N, 8)))
     d = np.zeros((128, N), np.float32)
-    _capi.check(_capi.lib().tb_debug_umma_shifted_gemm(a_bits.ctypes.data_as(C.c_void_p), n_pos, n_cg, shift,
+    _capi.check(_capi.lib().tbdbg_umma_shifted_gemm(a_bits.ctypes.data_as(C.c_void_p), n_pos, n_cg, shift,
                                                        b_bits.ctypes.data_as(C.c_void_p), N, d.ctypes.data_as(C.c_void_p)))
     A = a[:, shift:shift + 128, :].transpose(1, 0, 2).reshape(128, n_cg * 8).astype(np.float64)
     B = b.transpose(1, 0, 2).reshape(N, n_cg * 8).astype(np.float64)

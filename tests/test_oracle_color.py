@@ -156,3 +156,19 @@ def test_generate_binary_r3g3b2_matches_opencv_pipeline():
         lines, px = b.blob(0)
         crop = seg.crop_blob_r3g3b2(lines, px, bg, seg.DIFF_ABSOLUTE)
         assert crop.shape == (80, 80, 3) and crop.any()
+
+
+def test_rgb8_size_filter_counts_payload_bytes():
+    """BackgroundSubtraction.cpp:247-259: num_pixels = pixels->size() -- the blob's payload BYTES (3 per pixel for rgb8,
+    CPULabeling.cpp:302-311) -- so with detect_size_filter [10, 100) a 4-pixel rgb8 blob (12 bytes) is kept and a 34-pixel
+    one (102 bytes) is dropped, while the gray encoding of the same frame does the opposite."""
+    bg = np.full((40, 64, 3), 128, np.uint8)
+    fr = bg.copy()
+    fr[5, 8:12] = (20, 30, 40)            # 4 pixels
+    fr[20, 10:44] = (20, 30, 40)          # 34 pixels
+    fr[30, 10:20] = (20, 30, 40)          # 10 pixels: kept by both
+    P = seg.Params(detect_threshold=15, detect_size_filter=[(10, 100)])
+    rgb = seg.segment_frame_color(fr, bg, P, encoding=seg.ENC_RGB8)
+    assert sorted(len(rgb.blob(k)[1]) // 3 for k in range(len(rgb))) == [4, 10]
+    gray = seg.segment_frame_color(fr, seg.bgr2gray(bg), P, encoding=seg.ENC_GRAY)
+    assert sorted(len(gray.blob(k)[1]) for k in range(len(gray))) == [10, 34]

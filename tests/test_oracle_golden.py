@@ -152,6 +152,28 @@ def test_morphology_matches_opencv():
         assert np.array_equal(got, cv2.bitwise_and(mask, fr)), (closing, k, dil)
 
 
+def test_open_stage_matches_opencv_morphology_ex():
+    """The optional n x n open of the threshold mask (BASELINE north_star's "2x2 morphological open"; no reference counterpart,
+    SURVEY s0.5) is defined against cv2.morphologyEx(MORPH_OPEN, ones(n,n)) with OpenCV's default anchor."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    bg = np.full((90, 121), 120, np.uint8)
+    fr = bg.copy()
+    fr[rng.random(fr.shape) < 0.15] = 30
+    fr[30:50, 40:80] = 20; fr[0:3, 0:3] = 10; fr[87:90, 118:121] = 10; fr[60, 5:100] = 10; fr[62:64, 5:100] = 10
+    for n, closing in ((2, False), (3, False), (4, False), (2, True)):
+        P = seg.Params(detect_threshold=15, open_size=n, use_closing=closing, closing_size=2)
+        d = cv2.absdiff(fr, bg)
+        _, mask = cv2.threshold(d, 15, 255, cv2.THRESH_BINARY)
+        mask = cv2.morphologyEx(mask, cv2.MORPH_OPEN, np.ones((n, n), np.uint8))
+        if closing:
+            el = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5), (2, 2))
+            mask = cv2.erode(cv2.dilate(mask, el), el)
+        assert np.array_equal(seg.generate_binary(fr, bg, P), cv2.bitwise_and(mask, fr)), (n, closing)
+    assert np.array_equal(seg.generate_binary(fr, bg, seg.Params(detect_threshold=15, open_size=1)),
+                          seg.generate_binary(fr, bg, seg.Params(detect_threshold=15)))
+
+
 def test_crop_geometry():
     bg = np.full((200, 300), 100, np.uint8)
     # small blob: centre pad, left/top get the larger half (FilterCache.cpp:187-196)

@@ -24,7 +24,7 @@ class SegParams(C.Structure):
                 ("dilation_size", C.c_int32), ("cm_per_pixel", C.c_float), ("n_size_ranges", C.c_int32),
                 ("size_lo", C.c_double * 4), ("size_hi", C.c_double * 4),
                 ("color_channel", C.c_int32), ("blur_difference", C.c_int32),
-                ("use_adaptive_threshold", C.c_int32), ("adaptive_threshold_scale", C.c_float)]
+                ("use_adaptive_threshold", C.c_int32), ("adaptive_threshold_scale", C.c_float), ("open_size", C.c_int32)]
 
 
 class SegConfig(C.Structure):
@@ -69,8 +69,9 @@ SYMBOLS = [
     "tb_seg_wait", "tb_seg_result", "tb_seg_totals", "tb_seg_device_results", "tb_seg_crops",
     "tb_seg_debug_binary", "tb_seg_launch_count", "tb_vi_create", "tb_vi_destroy", "tb_vi_set_tensor",
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
-    "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_debug_umma_shifted_gemm", "tb_seg_set_stream",
+    "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_seg_set_stream",
     "tb_seg_rethreshold", "tb_seg_outlines", "tb_seg_outline_result", "tb_posture_default_params", "tb_seg_midlines", "tb_seg_midline_result", "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
+    "tb_host_alloc", "tb_host_free", "tb_host_register", "tb_host_unregister", "tb_backend",
 ]
 
 _lib = None
@@ -126,7 +127,13 @@ def lib() -> C.CDLL:
     L.tb_avg_add.argtypes = [vp, vp, C.c_int]
     L.tb_avg_add_device.argtypes = [vp, vp, C.c_int, vp]
     L.tb_avg_finalize.argtypes = [vp, vp]
-    L.tb_debug_umma_shifted_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.tb_host_alloc.argtypes = [C.c_size_t, vpp]
+    L.tb_host_free.argtypes = [vp]
+    L.tb_host_register.argtypes = [vp, C.c_size_t]
+    L.tb_host_unregister.argtypes = [vp]
+    L.trex_b200_register.argtypes = [vp]
+    L.tb_backend.restype = vp
+    L.tbdbg_umma_shifted_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     _lib = L
     return L
 

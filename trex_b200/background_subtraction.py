@@ -55,6 +55,7 @@ class DetectSettings:
     # individual_image_normalization (FilterCache.cpp:318-346): "none" | "moments" (posture / legacy need the tracker's midline)
     individual_image_normalization: str = "none"
     individual_image_scale: float = 1.0        # T/core/default_config.cpp; != 1: resize_image (INTER_NEAREST) before the pad / crop
+    open_size: int = 0                         # NOT a reference key: north_star's optional n x n open of the threshold mask (cv2 MORPH_OPEN, ones(n,n)); 0 = off
 
     def c_params(self) -> SegParams:
         p = SegParams()
@@ -71,6 +72,7 @@ class DetectSettings:
         p.color_channel = -1 if self.color_channel is None else int(self.color_channel)
         p.blur_difference = int(self.blur_difference); p.use_adaptive_threshold = int(self.use_adaptive_threshold)
         p.adaptive_threshold_scale = float(self.adaptive_threshold_scale)
+        p.open_size = int(self.open_size)
         return p
 
     @property

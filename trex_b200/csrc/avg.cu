@@ -60,6 +60,7 @@ struct tb_avg {
     float *fsum = nullptr; uint8_t *ext = nullptr; uint16_t *hist = nullptr;
     uint8_t *stage = nullptr, *out = nullptr; int stage_frames = 0;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_last = nullptr; bool ev_valid = false;    // completion of the last accumulate kernel, whatever stream it ran on
     uint64_t launches = 0;
 };
 
@@ -81,7 +82,8 @@ extern "C" int tb_avg_create(int device, int width, int height, int method, tb_a
     if (r == TB_OK) r = dev_alloc(&h->stage, h->px * h->stage_frames);
     if (r == TB_OK) r = dev_alloc(&h->out, h->px);
     if (r == TB_OK && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); r = TB_ERR_CUDA; }
-    if (r != TB_OK) { delete h; return r; }
+    if (r == TB_OK && cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); r = TB_ERR_CUDA; }
+    if (r != TB_OK) { tb_avg_destroy(h); return r; }
     *out = h;
     return TB_OK;
 }
@@ -92,6 +94,7 @@ extern "C" void tb_avg_destroy(tb_avg *h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->fsum); cudaFree(h->ext); cudaFree(h->hist); cudaFree(h->stage); cudaFree(h->out);
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -102,8 +105,12 @@ extern "C" int tb_avg_add_device(tb_avg *h, const void *frames_dev, int n, void 
     TB_REQUIRE(h->method != AVG_MODE || h->count + n <= 65535, TB_ERR_CAPACITY, "tb_avg_add_device: mode histogram counters hold at most 65535 samples");
     TB_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    // the accumulators are read-modify-written: every add (and the finalize) is ordered behind the previous add, also across streams
+    if (h->ev_valid) TB_CUDA(cudaStreamWaitEvent(s, h->ev_last, 0));
     avg_add_kernel<<<148 * 8, 256, 0, s>>>((const uint8_t *)frames_dev, n, h->px, h->method, h->fsum, h->ext, h->hist);
     TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaEventRecord(h->ev_last, s));
+    h->ev_valid = true;
     h->count += n; h->launches += 1;
     return TB_OK;
 }
@@ -127,6 +134,7 @@ extern "C" int tb_avg_finalize(tb_avg *h, uint8_t *out_host)
     TB_REQUIRE(h && out_host, TB_ERR_INVALID, "tb_avg_finalize: null argument");
     TB_REQUIRE(h->count > 0, TB_ERR_STATE, "tb_avg_finalize: no samples added");
     TB_CUDA(cudaSetDevice(h->device));
+    if (h->ev_valid) TB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_last, 0));
     avg_finalize_kernel<<<148 * 8, 256, 0, h->stream>>>(h->px, h->method, h->count, h->fsum, h->ext, h->hist, h->out);
     TB_CUDA(cudaGetLastError());
     h->launches += 1;

@@ -1027,7 +1027,7 @@ __device__ void ccl_label_body(const SegDev &d, uint32_t *s_par, uint32_t *ws)
         if (k < K) {
             l = nl[k]; px = npx[k];
             keep = d.n_ranges == 0;
-            const double v = (double)((float)px * d.sqcm);
+            const double v = (double)((float)(d.keep_mask ? px : px * (uint32_t)d.opx) * d.sqcm);      // detect side: pixels->size() = payload BYTES (3 per rgb8 pixel), BackgroundSubtraction.cpp:247-259; tracker side: pixel counts
             for (int q = 0; q < d.n_ranges; ++q) keep |= (v >= d.lo[q] && v < d.hi[q]);
             keep = keep && l < 65535u;
         }
@@ -1196,7 +1196,7 @@ ccl_label_kernel(SegDev d)
         if (k < K) {
             l = nl[k]; px = npx[k];
             keep = d.n_ranges == 0;
-            const double v = (double)((float)px * d.sqcm);
+            const double v = (double)((float)(d.keep_mask ? px : px * (uint32_t)d.opx) * d.sqcm);      // detect side: pixels->size() = payload BYTES (3 per rgb8 pixel), BackgroundSubtraction.cpp:247-259; tracker side: pixel counts
             for (int q = 0; q < d.n_ranges; ++q) keep |= (v >= d.lo[q] && v < d.hi[q]);
             keep = keep && l < 65535u;
             if (st_smem) { d.b_xmin[o + k] = xmin[k]; d.b_xmax[o + k] = xmax[k]; d.b_ymax[o + k] = ymax[k]; }
@@ -1466,7 +1466,9 @@ struct tb_seg {
     const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
     uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
     double *d_coef = nullptr;                   // `moments` normalisation: inverted warp matrix per crop
-    MorphEl el_close{}, el_dil{};
+    MorphEl el_close{}, el_dil{}, el_open{};
+    int ws_ctas = 0, col_ctas = 0;              // grid of the persistent K1 (resident CTAs x SMs of THIS handle's device), set on first use
+    unsigned long long *dbg = nullptr;          // TB_SEG_TIMELINE: per-CTA time stamps (debug)
 };
 
 static int seg_make_k(const tb_seg_params &p, SegK &k, std::string &why)
@@ -1645,34 +1647,41 @@ extern "C" int tb_seg_set_stream(tb_seg *h, void *stream)
 extern "C" int tb_seg_set_params(tb_seg *h, const tb_seg_params *p)
 {
     TB_REQUIRE(h && p, TB_ERR_INVALID, "tb_seg_set_params: null argument");
+    // 1. validate everything, 2. allocate what the new settings need, 3. only then touch the handle: a rejected call
+    //    leaves the previous settings fully in place (the caller of update_settings may catch the error and go on)
     SegK k; std::string why;
     if (seg_make_k(*p, k, why) != TB_OK) { set_error("tb_seg_set_params: " + why); return TB_ERR_INVALID; }
     TB_REQUIRE(h->d.CN == 1 || p->color_channel < h->d.CN || p->color_channel >= 4, TB_ERR_INVALID, "tb_seg_set_params: color_channel beyond the frame's channels");
-    h->params = *p; h->k = k;
-    h->d.cc = h->d.r3 ? CC_R3G3B2       // r3g3b2 ignores color_channel (BackgroundSubtraction.cpp:151-158)
-              : ((h->d.CN > 1 && h->d.enc == 0 && p->color_channel >= 0 && p->color_channel < 4) ? p->color_channel : -1);   // >= 4: cvtColor (:161-163)
-    h->morph = p->use_closing || p->dilation_size != 0 || p->blur_difference || p->use_adaptive_threshold;
     TB_REQUIRE(!p->blur_difference || !h->d.enc, TB_ERR_INVALID, "tb_seg_set_params: blur_difference takes a 1-channel background (gray / r3g3b2 encoding)");
     TB_REQUIRE(!p->blur_difference || (h->d.W > 12 && h->d.H > 12), TB_ERR_INVALID, "tb_seg_set_params: blur_difference needs frames larger than its 25x25 window");
     TB_REQUIRE(!p->use_adaptive_threshold || (p->adaptive_threshold_scale >= 0.f && p->adaptive_threshold_scale <= 8.f), TB_ERR_INVALID,
                "tb_seg_set_params: adaptive_threshold_scale must be 0..8");
-    if (h->morph) {
+    TB_REQUIRE(p->open_size >= 0 && p->open_size <= 15, TB_ERR_INVALID, "tb_seg_set_params: open_size must be 0..15");
+    const bool morph = p->use_closing || p->dilation_size != 0 || p->blur_difference || p->use_adaptive_threshold || p->open_size > 1;
+    if (morph) {
         TB_CUDA(cudaSetDevice(h->cfg.device));
         const size_t bytes = (size_t)h->cfg.max_batch * h->d.W * h->d.H;
-        if (!h->m_a) {
-            int r = seg_dev(h, &h->m_a, bytes + 16);
-            if (r == TB_OK) r = seg_dev(h, &h->m_b, bytes + 16);
-            if (r == TB_OK) r = seg_dev(h, &h->m_diff, bytes + 16);
+        if (!h->m_a || !h->m_b || !h->m_diff) {
+            int r = TB_OK;
+            if (!h->m_a) r = seg_dev(h, &h->m_a, bytes + 16);
+            if (r == TB_OK && !h->m_b) r = seg_dev(h, &h->m_b, bytes + 16);
+            if (r == TB_OK && !h->m_diff) r = seg_dev(h, &h->m_diff, bytes + 16);
             if (r != TB_OK) return r;
         }
         if ((p->blur_difference || p->use_adaptive_threshold) && !h->box_hs) {
-            h->box_sub = std::min(h->cfg.max_batch, 8);
-            int r = seg_dev(h, &h->box_hs, (size_t)h->box_sub * h->d.W * h->d.H);
+            const int sub = std::min(h->cfg.max_batch, 8);
+            int r = seg_dev(h, &h->box_hs, (size_t)sub * h->d.W * h->d.H);
             if (r != TB_OK) return r;
+            h->box_sub = sub;
         }
-        if (p->use_closing) h->el_close = ellipse_element(p->closing_size);
-        if (p->dilation_size) h->el_dil = ones_element(std::abs(p->dilation_size));
     }
+    // success path
+    h->params = *p; h->k = k; h->morph = morph;
+    h->d.cc = h->d.r3 ? CC_R3G3B2       // r3g3b2 ignores color_channel (BackgroundSubtraction.cpp:151-158)
+              : ((h->d.CN > 1 && h->d.enc == 0 && p->color_channel >= 0 && p->color_channel < 4) ? p->color_channel : -1);   // >= 4: cvtColor (:161-163)
+    if (p->use_closing) h->el_close = ellipse_element(p->closing_size);
+    if (p->dilation_size) h->el_dil = ones_element(std::abs(p->dilation_size));
+    if (p->open_size > 1) h->el_open = ones_element(p->open_size);
     h->d.sqcm = p->cm_per_pixel * p->cm_per_pixel;        // SQR(cm_per_pixel) in float, BackgroundSubtraction.cpp:139
     h->d.n_ranges = p->n_size_ranges;
     for (int i = 0; i < 4; ++i) { h->d.lo[i] = p->size_lo[i]; h->d.hi[i] = p->size_hi[i]; }
@@ -1750,6 +1759,11 @@ static int seg_morph(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s
         adaptive_mask_kernel<<<grid, nt, 0, s>>>(h->m_diff, tmp, cur, total, p.detect_threshold);
         h->launches += 1 + 2 * (uint64_t)((n + h->box_sub - 1) / h->box_sub);
     }
+    if (p.open_size > 1) {                 // optional n x n open of the threshold mask (north_star; not a reference stage): erode, dilate
+        morph_kernel<<<grid, nt, 0, s>>>(cur, tmp, h->d.W, h->d.H, total, h->el_open, 0);
+        morph_kernel<<<grid, nt, 0, s>>>(tmp, cur, h->d.W, h->d.H, total, h->el_open, 1);
+        h->launches += 2;
+    }
     auto closing = [&]() {
         morph_kernel<<<grid, nt, 0, s>>>(cur, tmp, h->d.W, h->d.H, total, h->el_close, 1);
         morph_kernel<<<grid, nt, 0, s>>>(tmp, cur, h->d.W, h->d.H, total, h->el_close, 0);
@@ -1803,27 +1817,28 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
         if (d.enc) d.nz_plane = h->d_nz;
     }
     if (fused_colour) {
-        static int ctas[2] = {0, 0};
         static DeviceOnce ctas_once[2];
         const int ci = d.CN == 3 ? 0 : 1;
         const int nt = (K1W_MW + 3 + 1) * 32, smem = k1w_smem(3, d.CN);
-        if (ctas_once[ci].need()) {
-            int per_sm = 0, sms = 0;
+        if (ctas_once[ci].need()) {             // function attributes are per device
             if (d.CN == 3) {
                 TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3, 3, true>, nt, smem));
             } else {
                 TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3, 4, true>, nt, smem));
             }
-            TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-            ctas[ci] = std::max(1, per_sm) * std::max(1, sms);
             ctas_once[ci].done();
         }
+        if (!h->col_ctas) {                     // per handle: the grid follows the handle's own device
+            int per_sm = 0, sms = 0;
+            if (d.CN == 3) TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3, 3, true>, nt, smem));
+            else TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3, 4, true>, nt, smem));
+            TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+            h->col_ctas = std::max(1, per_sm) * std::max(1, sms);
+        }
         const unsigned units = (unsigned)d.n_bands * (unsigned)n;
-        const unsigned grid = std::min<unsigned>(units, (unsigned)ctas[ci]);
+        const unsigned grid = std::min<unsigned>(units, (unsigned)h->col_ctas);
         const uint32_t static_units = (uint32_t)((double)(units / grid) * 0.5);
         if (d.CN == 3 && !d.enc) seg_rle_ws_kernel<false, 3, 3, false><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, nullptr);
         else if (d.CN == 3) seg_rle_ws_kernel<false, 3, 3, true><<<grid, nt, smem, s>>>(frames_dev, d, kk, static_units, nullptr);
@@ -1846,26 +1861,28 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     } else if (ws_ok && d.rpt * d.cpr <= K1_CHUNKS) {
         static const int ew = getenv("TB_SEG_EW") ? atoi(getenv("TB_SEG_EW")) : 3;                   // tuning knobs
         static const double static_frac = getenv("TB_SEG_STATIC") ? atof(getenv("TB_SEG_STATIC")) : 0.5;
-        static int ws_ctas = 0;
         static DeviceOnce ws_once;
         const int nt = (K1W_MW + (ew == 4 ? 4 : 3) + 1) * 32, smem = k1w_smem(ew == 4 ? 4 : 3);
-        if (ws_once.need()) {
+        if (ws_once.need()) {                   // function attributes are per device
             TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(3)));
             TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(3)));
             TB_CUDA(cudaFuncSetAttribute(seg_rle_ws_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1w_smem(4)));
+            ws_once.done();
+        }
+        if (!h->ws_ctas) {                      // per handle: the grid follows the handle's own device
             int per_sm = 0, sms = 0;
             if (ew == 4) TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 4>, nt, smem));
             else TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_rle_ws_kernel<false, 3>, nt, smem));
             TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-            ws_ctas = std::max(1, per_sm) * std::max(1, sms);
-            ws_once.done();
+            h->ws_ctas = std::max(1, per_sm) * std::max(1, sms);
         }
+        const int ws_ctas = h->ws_ctas;
         const unsigned units = (unsigned)d.n_bands * (unsigned)n;
         const unsigned grid = std::min<unsigned>(units, (unsigned)ws_ctas);
         const uint32_t static_units = (uint32_t)((double)(units / grid) * static_frac);
         static const bool timeline = getenv("TB_SEG_TIMELINE") != nullptr;                            // debug: per-CTA start / end times
-        static unsigned long long *dbg = nullptr;
-        if (timeline && !dbg) TB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 4 * ws_ctas));
+        if (timeline && !h->dbg) { int r = seg_dev(h, &h->dbg, (size_t)4 * ws_ctas); if (r != TB_OK) return r; }
+        unsigned long long *dbg = h->dbg;
         if (plain && ew == 4) seg_rle_ws_kernel<false, 4><<<grid, nt, smem, s>>>(plane, d, kk, static_units, dbg);
         else if (plain) seg_rle_ws_kernel<false, 3><<<grid, nt, smem, s>>>(plane, d, kk, static_units, dbg);
         else seg_rle_ws_kernel<true, 3><<<grid, (K1W_MW + 3 + 1) * 32, k1w_smem(3), s>>>(plane, d, h->k, static_units, dbg);

@@ -54,14 +54,16 @@ umma_shifted_gemm_kernel(const uint4 *__restrict__ a, int n_pos, int n_cg, int s
 
 }  // namespace tb
 
-extern "C" int tb_debug_umma_shifted_gemm(const void *a_host, int n_pos, int n_cg, int shift, const void *b_host, int N, float *d_host)
+#define TB_DEBUG_EXPORTS 1
+// bring-up entry point: exported for tests/test_gpu_umma.py, declared in the header only under TB_DEBUG_EXPORTS (not product ABI)
+extern "C" __attribute__((visibility("default"))) int tbdbg_umma_shifted_gemm(const void *a_host, int n_pos, int n_cg, int shift, const void *b_host, int N, float *d_host)
 {
     using namespace tb;
-    TB_REQUIRE(a_host && b_host && d_host, TB_ERR_INVALID, "tb_debug_umma_shifted_gemm: null argument");
+    TB_REQUIRE(a_host && b_host && d_host, TB_ERR_INVALID, "tbdbg_umma_shifted_gemm: null argument");
     TB_REQUIRE(n_cg >= 2 && n_cg % 2 == 0 && N >= 16 && N <= 256 && N % 16 == 0 && shift >= 0 && shift + 128 <= n_pos,
-               TB_ERR_INVALID, "tb_debug_umma_shifted_gemm: bad shape");
+               TB_ERR_INVALID, "tbdbg_umma_shifted_gemm: bad shape");
     const size_t abytes = (size_t)n_cg * n_pos * 16, bbytes = (size_t)n_cg * N * 16;
-    TB_REQUIRE(abytes + bbytes <= 200 * 1024, TB_ERR_INVALID, "tb_debug_umma_shifted_gemm: operands exceed shared memory");
+    TB_REQUIRE(abytes + bbytes <= 200 * 1024, TB_ERR_INVALID, "tbdbg_umma_shifted_gemm: operands exceed shared memory");
     void *da = nullptr, *db = nullptr; float *dd = nullptr;
     TB_CUDA(cudaMalloc(&da, abytes)); TB_CUDA(cudaMalloc(&db, bbytes)); TB_CUDA(cudaMalloc((void **)&dd, (size_t)128 * N * 4));
     TB_CUDA(cudaMemcpy(da, a_host, abytes, cudaMemcpyHostToDevice));
