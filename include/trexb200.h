@@ -178,6 +178,23 @@ TB_API int tb_seg_totals(tb_seg *h, uint32_t out[4]);
 TB_API int tb_seg_device_results(tb_seg *h, void **crops, void **n_crops_dev, void **crop_blob_index,
                           void **recs, void **infos);
 
+/* Multi-GPU metadata unit: the per-frame headers, the identification outputs and the blob records of a batch live in
+ * ONE device block laid out for the all-gather -- K2 / K3 write headers and records in place, the identification head writes the
+ * arg-max identity and its probability per crop (pass top_id / top_p to tb_vi_set_top1) -- so the collective sends the first
+ * gather_bytes of `base` without any packing step:
+ *   base + off_infos   tb_frame_info[batch]
+ *   base + off_top_id  uint32[batch * kmax]   identity of crop n (crop n = blob n while no frame exceeds kmax blobs)
+ *   base + off_top_p   float [batch * kmax]
+ *   base + off_recs    tb_blob_rec[...]       the first batch * kmax records are inside the gathered prefix
+ * batch = max_batch, kmax = max_crops_per_frame of the handle (128 at 100 individuals, 256 for BASELINE config 4). */
+typedef struct tb_meta_layout {
+    void *base;
+    uint64_t gather_bytes;
+    uint64_t off_infos, off_top_id, off_top_p, off_recs;
+    uint32_t batch, kmax;
+} tb_meta_layout;
+TB_API int tb_seg_metadata(tb_seg *h, tb_meta_layout *out);
+
 /* Host copy of the crops of the last batch (after tb_seg_wait with fetch=2 and crops enabled). */
 TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_blob_index, uint32_t *n);
 

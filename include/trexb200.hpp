@@ -10,6 +10,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -173,9 +174,45 @@ public:
         return probs;
     }
 
+    // paverages(ids, images) (T/ml/VisualIdentification.h:146-181): the mean probability row of the images of every id -- rows are
+    // added in image order in float and divided by float(samples), like the reference's std::transform chain
+    struct Average { size_t samples = 0; std::vector<float> values; };
+    std::map<uint32_t, Average> paverages(const std::vector<uint32_t> &ids, const std::vector<const uint8_t *> &images)
+    {
+        if (ids.size() != images.size()) throw std::runtime_error("paverages: ids and images differ in length");
+        const std::vector<float> probs = probabilities(images);
+        std::map<uint32_t, Average> averages;
+        for (size_t i = 0; i < ids.size(); ++i) {
+            Average &a = averages[ids[i]];
+            if (a.values.empty()) { a.values.assign((size_t)_m, 0.f); a.samples = 0; }
+            ++a.samples;
+            for (int k = 0; k < _m; ++k) a.values[(size_t)k] = probs[i * (size_t)_m + (size_t)k] + a.values[(size_t)k];
+        }
+        for (auto &kv : averages) {
+            const float N = float(kv.second.samples);
+            for (float &v : kv.second.values) v = v / N;
+        }
+        return averages;
+    }
+
 private:
     tb_vi *_h = nullptr;
     int _m, _c;
+};
+
+// Page-locked frame buffer for the pool BackgroundSubtraction::apply reads from (buffers::TileBuffers / ImageMaker,
+// T/core/TileBuffers.h:9-22): tb_seg_submit copies from it at the full PCIe rate and asynchronously.
+class HostFrame {
+public:
+    explicit HostFrame(size_t bytes) : _n(bytes) { void *p = nullptr; check(tb_host_alloc(bytes, &p), "tb_host_alloc"); _p = (uint8_t *)p; }
+    ~HostFrame() { tb_host_free(_p); }
+    HostFrame(const HostFrame &) = delete;
+    HostFrame &operator=(const HostFrame &) = delete;
+    uint8_t *data() { return _p; }
+    size_t size() const { return _n; }
+private:
+    uint8_t *_p = nullptr;
+    size_t _n = 0;
 };
 
 }  // namespace trexb200

@@ -1,7 +1,9 @@
 // Drives the C++ host layer (include/trexb200.hpp) the way TRex's test_matching.cpp:1556-1602 drives
 // CPULabeling::run: circle + rectangle -> exactly one blob; render -> relabel -> identical lines.
 // Prints "OK <n_lines> <n_pixels>" on success. Built and run by tests/test_gpu_cpp_shim.py.
+#include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "trexb200.hpp"
@@ -57,6 +59,52 @@ int main()
             bool refused = false;
             try { trexb200::BackgroundSubtraction bad(W, H, 1, 0, 0, 1, trexb200::meta_encoding_t::rgb8); } catch (const std::exception &) { refused = true; }
             if (!refused) { std::printf("FAIL rgb8 accepted gray frames\n"); return 1; }
+        }
+        // identification through the C++ wrapper: set_tensor / commit / probabilities / paverages (VisualIdentification.h:92-181)
+        {
+            const int M = 5;
+            trexb200::VINetwork net(M, 16);
+            bool threw = false;
+            std::vector<uint8_t> c0(6400, 0), c1(6400, 0), c2(6400, 0);
+            for (int y = 20; y < 60; ++y) for (int x = 10; x < 70; ++x) { c0[(size_t)y * 80 + x] = (uint8_t)(x + y); c1[(size_t)y * 80 + x] = (uint8_t)(3 * x); }
+            for (int i = 0; i < 6400; ++i) c2[(size_t)i] = (uint8_t)(i * 7);
+            try { net.probabilities({c0.data()}); } catch (const std::exception &) { threw = true; }        // no weights: SoftException in the reference
+            if (!threw) { std::printf("FAIL probabilities without weights\n"); return 1; }
+            uint32_t seed = 12345u;
+            auto fill = [&](size_t n, float scale, float offset) {
+                std::vector<float> v(n);
+                for (auto &x : v) { seed = seed * 1664525u + 1013904223u; x = offset + scale * ((float)(seed >> 8) / 16777216.0f - 0.5f); }
+                return v;
+            };
+            const struct { const char *name; size_t n; float scale, offset; } ts[] = {
+                {"model.conv1.weight", 16 * 25, 0.006f, 0.f}, {"model.conv1.bias", 16, 0.1f, 0.f}, {"model.conv2.weight", 64 * 16 * 25, 0.1f, 0.f}, {"model.conv2.bias", 64, 0.1f, 0.f},
+                {"model.conv3.weight", 128 * 64 * 25, 0.05f, 0.f}, {"model.conv3.bias", 128, 0.1f, 0.f},
+                {"model.bn1.weight", 16, 0.5f, 1.f}, {"model.bn1.bias", 16, 0.2f, 0.f}, {"model.bn1.running_mean", 16, 0.2f, 0.f}, {"model.bn1.running_var", 16, 0.5f, 1.f},
+                {"model.bn2.weight", 64, 0.5f, 1.f}, {"model.bn2.bias", 64, 0.2f, 0.f}, {"model.bn2.running_mean", 64, 0.2f, 0.f}, {"model.bn2.running_var", 64, 0.5f, 1.f},
+                {"model.bn3.weight", 128, 0.5f, 1.f}, {"model.bn3.bias", 128, 0.2f, 0.f}, {"model.bn3.running_mean", 128, 0.2f, 0.f}, {"model.bn3.running_var", 128, 0.5f, 1.f},
+                {"model.fc1.weight", 100 * 12800, 0.02f, 0.f}, {"model.fc1.bias", 100, 0.1f, 0.f}, {"model.bn4.weight", 100, 0.5f, 1.f}, {"model.bn4.bias", 100, 0.2f, 0.f},
+                {"model.fc2.weight", (size_t)M * 100, 0.4f, 0.f}, {"model.fc2.bias", (size_t)M, 0.2f, 0.f}};
+            for (auto &t : ts) net.set_tensor(t.name, fill(t.n, t.scale, t.offset));
+            net.commit();
+            auto pr = net.probabilities({c0.data(), c1.data(), c2.data(), c0.data()});
+            if (pr.size() != 4 * (size_t)M) { std::printf("FAIL probabilities size\n"); return 1; }
+            for (int i = 0; i < 4; ++i) {
+                float sum = 0; for (int k = 0; k < M; ++k) { sum += pr[(size_t)i * M + k]; if (!(pr[(size_t)i * M + k] > 0.f)) { std::printf("FAIL prob <= 0\n"); return 1; } }
+                if (sum < 0.9999f || sum > 1.0001f) { std::printf("FAIL softmax row sums to %f\n", sum); return 1; }
+            }
+            bool differ = false;
+            for (int k = 0; k < M; ++k) { if (pr[(size_t)k] != pr[(size_t)3 * M + k]) { std::printf("FAIL same crop, different row\n"); return 1; } differ |= pr[(size_t)k] != pr[(size_t)M + k]; }
+            if (!differ) { std::printf("FAIL different crops, same row\n"); return 1; }
+            auto av = net.paverages({7u, 9u, 7u, 7u}, {c0.data(), c1.data(), c2.data(), c0.data()});
+            if (av.size() != 2 || av[7u].samples != 3 || av[9u].samples != 1) { std::printf("FAIL paverages groups\n"); return 1; }
+            for (int k = 0; k < M; ++k) {
+                const float e7 = ((pr[(size_t)k] + 0.f) + pr[(size_t)2 * M + k] + pr[(size_t)3 * M + k]) / 3.f;
+                if (av[9u].values[(size_t)k] != pr[(size_t)M + k] || std::fabs(av[7u].values[(size_t)k] - e7) > 1e-6f) { std::printf("FAIL paverages values\n"); return 1; }
+            }
+            trexb200::HostFrame pinned((size_t)W * H);         // page-locked frame buffer of the pool: same results as from pageable memory
+            std::memcpy(pinned.data(), fr.data(), (size_t)W * H);
+            auto again2 = bs.apply({pinned.data()});
+            if (again2[0].size() != 1 || again2[0][0].pixels->size() != 20) { std::printf("FAIL pinned apply\n"); return 1; }
         }
         std::printf("OK %zu %zu\n", blobs[0].lines->size(), blobs[0].pixels->size());
     } catch (const std::exception &e) {

@@ -73,8 +73,6 @@ def test_midline_errors():
     assert len(bs.midlines(1.0)) == 1
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("TB_RUN_UNVALIDATED"),
-                    reason="written after round 1's GPU budget was spent; enable with TB_RUN_UNVALIDATED=1 (DESIGN.md s8, item 0)")
 def test_midline_lengths_against_the_references_own_export_gpu():
     """GPU leg of tests/test_oracle_posture.py::test_midline_lengths_against_the_references_own_export: the golden fish blobs of
     videos/test.pv are pasted into frames over their background windows, segmented with the sign difference at threshold 8

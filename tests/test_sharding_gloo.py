@@ -38,16 +38,21 @@ def _worker(rank, world, port, q):
         ok = True
         for rnd in range(ROUNDS):
             infos, recs = _fake_meta(rank, world, rnd)
-            local = sharding.pack_metadata(torch.from_numpy(infos.view(np.uint8).copy()), torch.from_numpy(recs.view(np.uint8).copy()), B, KMAX)
+            n_all = int(infos["n_blobs"].sum())
+            top_id = np.zeros(B * KMAX, np.uint32); top_p = np.zeros(B * KMAX, np.float32)
+            top_id[:n_all] = recs["bid"][:n_all] % 97; top_p[:n_all] = 1.0 / (1 + recs["n_pixels"][:n_all])
+            local = sharding.pack_metadata(infos, recs, B, KMAX, top_id, top_p)
             assert local.numel() == sharding.meta_bytes(B, KMAX)
             gathered = sharding.all_gather_metadata(local)
-            frames = sharding.unpack_round(gathered, rnd, B, KMAX)
+            frames = sharding.unpack_round(gathered, rnd, B, KMAX, with_identity=True)
             exp_frames = list(range(rnd * world * B, (rnd + 1) * world * B))
             ok &= list(frames) == exp_frames
-            for f, (info, r, trunc) in frames.items():
+            for f, (info, r, trunc, ids, ps) in frames.items():
                 n = (f * 7 + 3) % (KMAX + 1)
                 ok &= int(info["n_blobs"]) == n and not trunc
                 ok &= [int(x) for x in r["bid"]] == [f * 1000 + j for j in range(n)]
+                ok &= [int(x) for x in ids] == [(f * 1000 + j) % 97 for j in range(n)]           # identities travel with their blobs
+                ok &= np.allclose(ps, [1.0 / (11 + j) for j in range(n)])
                 rr, rk, idx = sharding.owner_of(f, world, B)
                 ok &= rr == rnd and sharding.frame_range(rr, rk, world, B)[0] + idx == f
         q.put((rank, bool(ok)))
@@ -78,3 +83,13 @@ def test_frame_partition_covers_everything_once():
             lo, hi = sharding.frame_range(rnd, rank, world, batch)
             seen.extend(range(lo, hi))
     assert seen == list(range(3 * world * batch))
+
+
+def test_meta_layout_mirror():
+    """Host mirror of tb_meta_layout: 32-byte aligned sections, records last (the gathered prefix ends inside the record array)."""
+    lay = sharding.MetaLayout.make(256, 128)
+    assert lay.off_top_id == 256 * 32 and lay.off_top_p == lay.off_top_id + 256 * 128 * 4
+    assert lay.off_recs == lay.off_top_p + 256 * 128 * 4 and lay.gather_bytes == lay.off_recs + 256 * 128 * 32
+    odd = sharding.MetaLayout.make(3, 5)
+    assert odd.off_top_id % 32 == 0 and odd.off_top_p % 32 == 0 and odd.off_recs % 32 == 0
+    assert odd.off_top_p >= odd.off_top_id + 60 and odd.off_recs >= odd.off_top_p + 60

@@ -57,6 +57,11 @@ class PostureParams(C.Structure):
                 ("midline_start_with_head", C.c_int32), ("midline_invert", C.c_int32)]
 
 
+class MetaLayout(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("gather_bytes", C.c_uint64), ("off_infos", C.c_uint64), ("off_top_id", C.c_uint64),
+                ("off_top_p", C.c_uint64), ("off_recs", C.c_uint64), ("batch", C.c_uint32), ("kmax", C.c_uint32)]
+
+
 class ViConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
                 ("num_classes", C.c_int32), ("max_images", C.c_int32), ("precision", C.c_int32), ("arch", C.c_int32)]
@@ -71,7 +76,7 @@ SYMBOLS = [
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
     "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_seg_set_stream",
     "tb_seg_rethreshold", "tb_seg_outlines", "tb_seg_outline_result", "tb_posture_default_params", "tb_seg_midlines", "tb_seg_midline_result", "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
-    "tb_host_alloc", "tb_host_free", "tb_host_register", "tb_host_unregister", "tb_backend",
+    "tb_seg_metadata", "tb_host_alloc", "tb_host_free", "tb_host_register", "tb_host_unregister", "tb_backend",
 ]
 
 _lib = None
@@ -127,6 +132,7 @@ def lib() -> C.CDLL:
     L.tb_avg_add.argtypes = [vp, vp, C.c_int]
     L.tb_avg_add_device.argtypes = [vp, vp, C.c_int, vp]
     L.tb_avg_finalize.argtypes = [vp, vp]
+    L.tb_seg_metadata.argtypes = [vp, C.POINTER(MetaLayout)]
     L.tb_host_alloc.argtypes = [C.c_size_t, vpp]
     L.tb_host_free.argtypes = [vp]
     L.tb_host_register.argtypes = [vp, C.c_size_t]

@@ -315,6 +315,17 @@ class BackgroundSubtraction:
         check(lib().tb_seg_device_results(self._h, *[C.byref(p) for p in ps]))
         return tuple(p.value for p in ps)
 
+    def metadata(self):
+        """tb_meta_layout of the handle: the device block that holds headers | top-1 ids | top-1 probabilities | blob records in
+        the layout of the multi-GPU all-gather (no packing step).  Pass top1_ptrs() to VINetwork.set_top1."""
+        m = _capi.MetaLayout()
+        check(lib().tb_seg_metadata(self._h, C.byref(m)))
+        return m
+
+    def top1_ptrs(self):
+        m = self.metadata()
+        return m.base + m.off_top_id, m.base + m.off_top_p
+
     def debug_binary(self, frame: np.ndarray) -> np.ndarray:
         f = np.ascontiguousarray(frame, np.uint8)
         out = np.empty((self.height, self.width) if self.out_channels == 1 else (self.height, self.width, 3), np.uint8)

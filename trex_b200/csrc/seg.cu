@@ -1467,6 +1467,7 @@ struct tb_seg {
     uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
     double *d_coef = nullptr;                   // `moments` normalisation: inverted warp matrix per crop
     MorphEl el_close{}, el_dil{}, el_open{};
+    uint8_t *d_meta = nullptr; tb_meta_layout meta{};   // headers | top-1 ids | top-1 probabilities | blob records (see tb_seg_metadata)
     int ws_ctas = 0, col_ctas = 0;              // grid of the persistent K1 (resident CTAs x SMs of THIS handle's device), set on first use
     unsigned long long *dbg = nullptr;          // TB_SEG_TIMELINE: per-CTA time stamps (debug)
 };
@@ -1598,7 +1599,25 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     A(d.b_npx, B * d.rcap); A(d.b_nl, B * d.rcap); A(d.b_xmin, B * d.rcap); A(d.b_xmax, B * d.rcap);
     A(d.b_ymax, B * d.rcap); A(d.b_root, B * d.rcap); A(d.b_loff, B * d.rcap); A(d.b_poff, B * d.rcap);
     A(d.kept, B * d.rcap); A(d.frame_tot, B * 4);
-    A(d.infos, B); A(d.recs, d.blobs_cap); A(d.lines, d.lines_cap); A(d.line_px, d.lines_cap);
+    {   // per-frame headers, the identification outputs and the blob records share ONE block laid out as the multi-GPU metadata
+        // unit (tb_meta_layout): K2 / K3 and the identification head write it in place, the all-gather reads its prefix -- no packing
+        const size_t kb = (size_t)B * d.max_crops;
+        h->meta.batch = (uint32_t)B; h->meta.kmax = d.max_crops;
+        h->meta.off_infos = 0;
+        h->meta.off_top_id = (B * sizeof(tb_frame_info) + 31) / 32 * 32;
+        h->meta.off_top_p = (h->meta.off_top_id + kb * 4 + 31) / 32 * 32;
+        h->meta.off_recs = (h->meta.off_top_p + kb * 4 + 31) / 32 * 32;
+        h->meta.gather_bytes = h->meta.off_recs + kb * sizeof(tb_blob_rec);
+        const size_t total = h->meta.off_recs + (size_t)d.blobs_cap * sizeof(tb_blob_rec);
+        A(h->d_meta, total);
+        if (r == TB_OK) {
+            if (cudaMemset(h->d_meta, 0, total) != cudaSuccess) { set_error("cudaMemset failed"); r = TB_ERR_CUDA; }
+            h->meta.base = h->d_meta;
+            d.infos = (tb_frame_info *)(h->d_meta + h->meta.off_infos);
+            d.recs = (tb_blob_rec *)(h->d_meta + h->meta.off_recs);
+        }
+    }
+    A(d.lines, d.lines_cap); A(d.line_px, d.lines_cap);
     A(d.pixels, (size_t)d.px_cap + 16); A(d.crops, (size_t)d.crops_cap * d.crop_w * d.crop_h * d.cpx + 16);
     A(d.crop_blob, d.crops_cap); A(d.totals, 4);
     if (d.crop_norm) A(h->d_coef, (size_t)d.crops_cap * 6);
@@ -2036,6 +2055,13 @@ extern "C" int tb_seg_device_results(tb_seg *h, void **crops, void **n_crops_dev
     if (crop_blob_index) *crop_blob_index = h->d.crop_blob;
     if (recs) *recs = h->d.recs;
     if (infos) *infos = h->d.infos;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_metadata(tb_seg *h, tb_meta_layout *out)
+{
+    TB_REQUIRE(h && out, TB_ERR_INVALID, "tb_seg_metadata: null argument");
+    *out = h->meta;
     return TB_OK;
 }
 

@@ -108,6 +108,19 @@ class VINetwork:
             i += 1
         return probs
 
+    def paverages(self, ids, images):
+        """VINetwork::paverages (T/ml/VisualIdentification.h:146-181): {id: (samples, mean probability row)} over the images of every
+        id; rows are added in image order in float32 and divided by float(samples), like the reference's std::transform chain."""
+        ids = [int(i) for i in ids]
+        probs = self.probabilities(images)
+        if len(ids) != len(probs):
+            raise ValueError("paverages: ids and images differ in length")
+        out = {}
+        for i, k in enumerate(ids):
+            samples, values = out.get(k, (0, np.zeros(self.num_classes, np.float32)))
+            out[k] = (samples + 1, (probs[i] + values).astype(np.float32))
+        return {k: (n, (v / np.float32(n)).astype(np.float32)) for k, (n, v) in sorted(out.items())}
+
     def predict_device(self, images_ptr: int, n_max: int, n_dev_ptr: int, probs_ptr: int, logits_ptr: int = 0, stream: int = 0):
         check(lib().tb_vi_predict_device(self._h, C.c_void_p(images_ptr), n_max, C.c_void_p(n_dev_ptr) if n_dev_ptr else None,
                                          C.c_void_p(probs_ptr), C.c_void_p(logits_ptr) if logits_ptr else None,
