@@ -29,3 +29,31 @@ def test_shifted_gemm(n_cg, N, n_pos, shift):
     B = b.transpose(1, 0, 2).reshape(N, n_cg * 8).astype(np.float64)
     ref = A @ B.T
     assert np.abs(d - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def _e5m2(x):
+    """float32 -> e5m2 bytes (round to nearest even through float16's top byte) and the rounded values."""
+    h = np.ascontiguousarray(x, np.float32).astype(np.float16).view(np.uint16).astype(np.uint32)
+    r = ((h + 0x7F + ((h >> 8) & 1)) >> 8).astype(np.uint8)              # RNE on the low mantissa byte (values stay far from inf here)
+    return r, (r.astype(np.uint16) << 8).view(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("n_cg,n_pl8,N,n_pos,shift", [(2, 2, 64, 160, 0), (2, 2, 64, 200, 37), (8, 8, 128, 180, 5), (8, 8, 224, 200, 47)])
+def test_mixed_f16_plus_e5m2_accumulate(n_cg, n_pl8, N, n_pos, shift):
+    """kind::f16 and kind::f8f6f4 (e5m2, K = 32 over two planes) MMAs into the same fp32 accumulator: the building block of the
+    "fp16c" precision (fp16 main term + 8-bit correction terms).  Products of representable operands are exact in fp32."""
+    from trex_b200 import _capi
+    rng = np.random.default_rng(n_cg * 100 + N + shift)
+    a16 = rng.standard_normal((n_cg, n_pos, 8)).astype(np.float16); b16 = rng.standard_normal((n_cg, N, 8)).astype(np.float16)
+    a8b, a8 = _e5m2(rng.standard_normal((n_pl8, n_pos, 16)) * 4); b8b, b8 = _e5m2(rng.standard_normal((n_pl8, N, 16)) * 0.25)
+    d = np.zeros((128, N), np.float32)
+    L = _capi.lib()
+    L.tbdbg_umma_mixed_gemm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    _capi.check(L.tbdbg_umma_mixed_gemm(a16.ctypes.data_as(C.c_void_p), n_pos, n_cg, shift, b16.ctypes.data_as(C.c_void_p),
+                                        a8b.ctypes.data_as(C.c_void_p), b8b.ctypes.data_as(C.c_void_p), n_pl8, N, d.ctypes.data_as(C.c_void_p)))
+    A = a16[:, shift:shift + 128, :].transpose(1, 0, 2).reshape(128, -1).astype(np.float64)
+    B = b16.transpose(1, 0, 2).reshape(N, -1).astype(np.float64)
+    A8 = a8[:, shift:shift + 128, :].transpose(1, 0, 2).reshape(128, -1).astype(np.float64)
+    B8 = b8.transpose(1, 0, 2).reshape(N, -1).astype(np.float64)
+    ref = A @ B.T + A8 @ B8.T
+    assert np.abs(d - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())

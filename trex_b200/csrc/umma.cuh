@@ -45,6 +45,13 @@ __host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N)
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f8f6f4 with E5M2 A/B (format code 1; K-major both; one MMA covers K = 32 = two 16-byte core matrices), FP32 accumulate.
+// Used for the correction terms of the "fp16c" precision (vi_tc.cuh): twice the K per instruction at the same issue cost.
+__host__ __device__ constexpr uint32_t idesc_e5m2_f32(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -74,6 +81,13 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the same for 8-bit float operands (kind::f8f6f4, K = 32 per instruction); accumulates into the same fp32 TMEM columns
+__device__ __forceinline__ void mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
