@@ -374,10 +374,6 @@ def run_ours(args, cfg):
             sharding.all_gather_metadata(s.block, out=s.meta_all)
             s.ev_gathered.record(side)
 
-    def posture(s):
-        s.bs.wait()
-        s.bs.midlines(1.0)
-
     def step_device(i, precision, logits=False):
         s = slots[i % 2]
         if world_size > 1:
@@ -385,7 +381,7 @@ def run_ours(args, cfg):
         s.bs.apply_device(dev_batches[i % pool].data_ptr(), B, main.cuda_stream, fetch=0)
         net_of(s, precision).predict_device(s.res[0], B * KMAX, s.res[1], s.probs.data_ptr(), s.logits.data_ptr() if logits else 0, main.cuda_stream)
         if cfg["posture"]:
-            posture(s)
+            s.bs.posture_async(1.0, normalize=True, fetch=0)      # outlines -> midlines -> normalised midlines, behind the batch on `main`
         if world_size > 1:
             gather(s, main)
 
@@ -434,6 +430,10 @@ def run_ours(args, cfg):
             for k, v in {**a, **b}.items():
                 per[k] = per.get(k, 0.0) + v
             s.bs.profile(False); net_of(s, precision).profile(False)
+        if cfg["posture"]:
+            for s in slots:
+                for k, v in s.bs.posture_ms()[0].items():
+                    per[k] = per.get(k, 0.0) + v
         per = {k: v / max(n_seg, 1) for k, v in per.items()}          # ms per step (vi events are per chunk, summed over the step)
         ms = max_over_ranks(ms)
         return dict(ms=ms, value=world_size * B * args.steps / (ms * 1e-3), clocks=clocks, launches=int(launches), per=per,
@@ -445,6 +445,8 @@ def run_ours(args, cfg):
         s = slots[i % 2]
         s.bs.submit(batches[i % len(batches)], fetch=1)                     # tb_seg_submit: H2D frames + kernels
         net_of(s, precision).predict_device(s.res[0], B * KMAX, s.res[1], s.probs.data_ptr(), 0, s.stream.cuda_stream)
+        if cfg["posture"]:
+            s.bs.posture_async(1.0, normalize=True, fetch=1)      # results: midline records + normalised midlines to the host
         with torch.cuda.stream(s.stream):
             # identity probabilities back to the host (upper bound of rows: the crop count of this batch is not known yet)
             s.probs_host[:B * cfg["indiv"]].copy_(s.probs[:B * cfg["indiv"]], non_blocking=True)
@@ -458,13 +460,13 @@ def run_ours(args, cfg):
             return 0, 0
         s.bs.wait()                                                          # tb_seg_wait: blob records, lines, pixels on the host
         if cfg["posture"]:
-            s.bs.midlines(1.0)
+            s.bs.posture_wait()                                              # tb_seg_posture_wait: midlines on the host
         s.stream.synchronize()
         if world_size > 1:
             s.ev_gathered.synchronize()
         s.pending = False
         nb, nl, npx, nc = s.bs.totals()
-        return B * H * W, B * 32 + 16 + nb * 32 + nl * 8 + npx + B * cfg["indiv"] * M * 4
+        return B * H * W, B * 32 + 16 + nb * 32 + nl * 8 + npx + B * cfg["indiv"] * M * 4 + (nb * (16 + 32 + 25 * 16) if cfg["posture"] else 0)
 
     def measure_e2e(precision, batches, steps):
         for s in slots:
@@ -534,7 +536,33 @@ def run_ours(args, cfg):
         dl = float(np.abs(s.logits[c0:c0 + n].cpu().numpy() - ovi.forward_logits(sdo, exp[..., None])).max()) if n else 0.0
         dp = float(np.abs(s.probs[c0:c0 + n].cpu().numpy() - ovi.predict(sdo, exp[..., None])).max()) if n else 0.0
         ok = ok and dl < 1e-3 and dp < 1e-3
-        return dict(ok=bool(ok), frame=int(f), blobs=len(ref), max_dlogit=dl, max_dprob=dp)
+        out = dict(ok=bool(ok), frame=int(f), blobs=len(ref), max_dlogit=dl, max_dprob=dp)
+        if cfg["posture"]:                      # the posture chain of that frame's blobs against the oracle: raw midline bit-exact, normalised midline to 1e-4
+            from oracle import posture as opost
+            s.bs.posture_async(1.0, normalize=True, fetch=2)
+            s.bs.posture_wait()
+            pr = s.bs.posture_result()
+            b0 = s.bs.frame_info(f).blob_begin
+            okp, n_mid = True, 0
+            for k in range(len(ref)):
+                so, ns, tail, head = (int(v) for v in pr["midlines"][b0 + k])
+                nr = pr["normalized"][b0 + k]
+                try:
+                    rs, rt, rh, _ = opost.calculate_midline(oseg.outline_resample(oseg.longest_outline(ref.blob(k)[0]), 1.0))
+                except ValueError:
+                    okp = okp and ns == 0
+                    continue
+                okp = okp and (tail, head) == (rt, rh) and np.array_equal(pr["segments"][so:so + ns], rs)
+                pp, _, _, _ = opost.post_process(rs, tail=rt, head=rh)
+                nm = opost.normalize(pp)
+                if nm is None:
+                    okp = okp and int(nr["n_points"]) == 0
+                else:
+                    okp = okp and int(nr["n_points"]) == 25 and float(np.abs(pr["norm_points"][b0 + k] - nm[0]).max()) < 1e-4 and abs(float(nr["len"]) - nm[1]) < 1e-3
+                    n_mid += 1
+            out["posture_ok"] = bool(okp); out["midlines_checked"] = n_mid
+            out["ok"] = bool(ok and okp)
+        return out
 
     def verify_meta():
         """N>1: every rank's gathered block equals what the rank produced (checksums through a second, tiny gather) and unpacks into
@@ -597,7 +625,7 @@ def run_ours(args, cfg):
                 fl = 2 * MACS[k] * r["tot"][3]
                 kern[k] = {"ms": per[k], "share": per[k] / total_k, "bound": "tensor", "achieved": fl / (per[k] * 1e-3) / 1e12,
                            "peak": tensor_peak, "unit": "TFLOP/s"}
-            for k in ("ccl_label", "blob_emit", "head"):
+            for k in ("ccl_label", "blob_emit", "head") + (("outlines", "midlines") if cfg["posture"] else ()):
                 kern[k] = {"ms": per[k], "share": per[k] / total_k}
             for v in kern.values():
                 if "achieved" in v:

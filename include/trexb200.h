@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TB_ABI_VERSION 5
+#define TB_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define TB_API __attribute__((visibility("default")))
@@ -88,7 +88,10 @@ typedef struct tb_seg_config {
                                      B,G,R like imageFromLines does for such blobs, C/processing/Background.cpp:134-139)          */
     int32_t crop_normalize;       /* individual_image_normalization (T/tracking/FilterCache.cpp:318-346): 0 none (centre pad /
                                      crop, :158-235), 1 moments (rotation by the blob's second-moment orientation through
-                                     cv::warpAffine, :329-341 + :21-115; gray encoding); posture / legacy need the tracker's midline */
+                                     cv::warpAffine, :329-341 + :21-115), 2 posture (the reference's default, T/core/default_config.cpp:1089),
+                                     3 legacy: the blob image warped by Midline::transform (:266-276 + :21-115) -- the crops of a batch
+                                     are the `none` crops until tb_seg_posture has run on it with normalize = 1, which re-renders them
+                                     from the normalised midlines.  1..3: gray encoding */
     float   crop_scale;           /* individual_image_scale (T/tracking/FilterCache.cpp:178-180): the masked blob image is resized with
                                      cv::resize(INTER_NEAREST) before the pad / crop; 0 or 1 = no scaling; gray encoding, crop_normalize 0 */
 } tb_seg_config;
@@ -225,8 +228,8 @@ TB_API int tb_seg_outline_result(tb_seg *h, const tb_outline_rec **recs, const f
 /* Midlines ("next" row N4, second stage), after tb_seg_outlines on the same batch: for every blob Outline::calculate_midline
  * (T/tracking/Outline.cpp:768-868) on its resampled outline -- Outline::smooth (:330-452), offset_to_middle (:454-718: clockwise
  * orientation, the elliptic-Fourier approximation periodic::eft / ieft with outline_approximate harmonics, curvature, find_peaks;
- * tail = the highest curvature peak, head = the peak farthest from it; the outline is rotated to start at the tail) and the
- * pairing walk.  peak_mode pointy only (the reference's default); Midline::post_process / normalize are not built.
+ * tail = the highest curvature peak (peak_mode pointy) or the middle of the broadest one (broad, :621-650), head = the peak farthest
+ * from it; the outline is rotated to start at the tail) and the pairing walk.
  * points: the outline as the midline saw it (smoothed, approximated, rotated), same ranges as tb_outline_rec.res_off / n_res;
  * segments: {pos.x, pos.y, height, l_length} per midline segment from the tail on, blob k's at [seg_off, seg_off + n_seg);
  * n_seg = 0 when the reference would return "Too few midline segments calculated." */
@@ -236,14 +239,62 @@ typedef struct tb_posture_params {
     int32_t outline_approximate;           /* 3     :888 (0..8) */
     float   outline_curvature_range_ratio; /* 0.03  :891 */
     float   midline_walk_offset;           /* 0.025 :892 */
-    int32_t peak_mode;                     /* 0 pointy (:902); broad is not built */
+    int32_t peak_mode;                     /* 0 pointy (:902), 1 broad */
     int32_t midline_start_with_head;       /* 0     :900 */
     int32_t midline_invert;                /* 0     :901 */
+    int32_t midline_resolution;            /* 25    :894 (2..256): points of a normalised midline */
+    float   midline_stiff_percentage;      /* 0.15  :893 */
 } tb_posture_params;
 typedef struct tb_midline_rec { uint32_t seg_off, n_seg; int32_t tail, head; } tb_midline_rec;
 TB_API void tb_posture_default_params(tb_posture_params *p);
 TB_API int tb_seg_midlines(tb_seg *h, const tb_posture_params *p);
 TB_API int tb_seg_midline_result(tb_seg *h, const tb_midline_rec **recs, const float **points, const float **segments, uint32_t *n_blobs);
+
+/* The whole posture chain of a batch in one asynchronous call ("next" row N4): outlines -> raw midlines -> (normalize = 1)
+ * Midline::post_process (T/tracking/Outline.cpp:895-1062) and Midline::normalize (:1268-1456) per blob, i.e. what
+ * Individual::calculate_midline_for returns (T/tracking/Individual.cpp:1348-1383) -> (crop_normalize 2 / 3) the crops of the batch
+ * re-rendered through Midline::transform (Outline.cpp:1238-1256) and image::normalize_image (T/tracking/FilterCache.cpp:21-115).
+ * Everything is enqueued behind the batch's kernels on the batch's stream -- tb_seg_posture may be called right after
+ * tb_seg_submit[_device], before tb_seg_wait; the blob count is read on the device -- so the identification network can be
+ * chained behind it.  tb_seg_posture_wait blocks until the requested results are on the host.
+ * A normalised midline has midline_resolution segments {pos.x, pos.y, height, l_length} (blob k's at norm_points + 4 * k *
+ * midline_resolution), pos rotated / translated so that the head end is the origin; len / angle / offset are Midline::len(),
+ * angle(), offset().  n_points = 0 where the reference has no (normalised) midline; flags: bit0 inverted because of the movement
+ * direction, bit1 post_process threw (std::out_of_range), bit2 normalize() returned nullptr. */
+typedef struct tb_midline_norm { float len, angle, offx, offy; uint32_t n_points, flags; int32_t tail, head; } tb_midline_norm;
+typedef struct tb_posture_request {
+    tb_posture_params params;
+    float   outline_resample;              /* 1  T/core/default_config.cpp:898; <= 0: no resampling */
+    int32_t normalize;                     /* 0: raw midlines only; 1: + post_process + normalize (+ crops for crop_normalize 2 / 3) */
+    int32_t fetch;                         /* 0: results stay on the device; 1: midline records + normalised midlines (+ crop validity);
+                                              2: also outline records, outline points and raw midline segments */
+    float   median_midline_length_px;      /* FilterCache::median_midline_length_px of the tracklet (FilterCache.cpp:24,54-58); used when
+                                              median_midline_length_dev is NULL */
+    float   individual_image_scale;        /* 1 (FilterCache.cpp:45); 0 = 1 */
+    const float *move_direction_dev;       /* optional device array, 2 floats per blob: MovementInformation::direction
+                                              (posture_direction_smoothing > 1, Individual.cpp:1365-1368); NULL = (0, 0) */
+    const float *fix_length_dev;           /* optional device array, 1 float per blob: Midline::normalize(fix_length) as
+                                              Individual::fixed_midline calls it (Individual.cpp:507-522); NULL = -1 (none) */
+    const float *median_midline_length_dev;/* optional device array, 1 float per blob */
+} tb_posture_request;
+typedef struct tb_posture_view {
+    uint32_t n_blobs, midline_resolution;
+    const tb_midline_rec *midlines;        /* fetch >= 1 */
+    const tb_midline_norm *normalized;     /* fetch >= 1, normalize = 1 */
+    const float *norm_points;              /* fetch >= 1, normalize = 1 */
+    const uint8_t *crop_valid;             /* fetch >= 1, crop_normalize 2 / 3: 1 per crop that has a posture-normalised image */
+    const tb_outline_rec *outlines;        /* fetch >= 2 */
+    const float *raw_points, *points, *segments;   /* fetch >= 2: find_outer_points' outline, the outline the midline saw, raw segments */
+} tb_posture_view;
+TB_API void tb_posture_default_request(tb_posture_request *r);
+TB_API int tb_seg_posture(tb_seg *h, const tb_posture_request *r);
+TB_API int tb_seg_posture_wait(tb_seg *h);
+TB_API int tb_seg_posture_result(tb_seg *h, tb_posture_view *out);
+/* Device pointers of the last tb_seg_posture call (valid until the next one): records per blob of the batch. */
+TB_API int tb_seg_posture_device(tb_seg *h, void **outline_recs, void **midline_recs, void **normalized, void **norm_points,
+                                 void **points, void **segments);
+/* Measurement hook: summed durations (ms) of {outlines, midlines (+ normalisation), posture crops} and the number of calls. */
+TB_API int tb_seg_posture_ms(tb_seg *h, double out_ms[3], uint64_t *n_calls);
 
 /* Debug / parity: generate_binary's output image (mask & input) of one device- or host-resident
  * frame, RawProcessing.cpp:597-600.  out is width*height (gray) or width*height*3 (rgb8) host bytes. */

@@ -1,7 +1,9 @@
-"""ORACLE ONLY (no CUDA counterpart yet): from a resampled outline to the raw midline -- TEST INFRASTRUCTURE.
+"""From a resampled outline to the raw, post-processed and normalised midline and the posture-normalised crop -- TEST INFRASTRUCTURE.
 
 Python face of the restatement in trex_oracle.c of
   Outline::smooth / offset_to_middle / calculate_midline   Application/src/tracker/tracking/Outline.cpp:330-452,454-718,768-868
+  Midline::post_process / normalize / fix_length / transform  Application/src/tracker/tracking/Outline.cpp:870-1085,1113-1456
+  image::normalize_image (posture / legacy)                Application/src/tracker/tracking/FilterCache.cpp:21-115,133-154,266-276
   periodic::curvature / differentiate / find_peaks / eft / ieft, fast::cos
                                                             Application/src/commons/common/misc/CircularGraph.cpp:12-606
 parity unpinned: the reference has no test vectors for these functions; tests/test_oracle_posture.py checks each piece
@@ -18,7 +20,8 @@ from .seg import _p, lib
 class PostureParams(C.Structure):
     _fields_ = [("outline_smooth_samples", C.c_int32), ("outline_smooth_step", C.c_int32), ("outline_approximate", C.c_int32),
                 ("outline_curvature_range_ratio", C.c_float), ("midline_walk_offset", C.c_float), ("peak_mode", C.c_int32),
-                ("midline_start_with_head", C.c_int32), ("midline_invert", C.c_int32)]
+                ("midline_start_with_head", C.c_int32), ("midline_invert", C.c_int32),
+                ("midline_resolution", C.c_int32), ("midline_stiff_percentage", C.c_float)]
 
 
 PEAK_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("width", "<f4"), ("integral", "<f4"), ("r0", "<f4"), ("r1", "<f4"),
@@ -41,6 +44,13 @@ def _lib():
         L.to_offset_to_middle.restype = C.c_int
         L.to_calculate_midline.argtypes = [vp, C.c_int64, C.POINTER(PostureParams), vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.to_calculate_midline.restype = C.c_int64
+        L.to_midline_post_process.argtypes = [vp, C.c_int64, C.POINTER(PostureParams), vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.to_midline_post_process.restype = C.c_int
+        L.to_midline_normalize.argtypes = [vp, C.c_int64, C.POINTER(PostureParams), C.c_float, vp, vp]; L.to_midline_normalize.restype = C.c_int64
+        L.to_posture_matrix.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, vp]; L.to_posture_matrix.restype = None
+        L.to_crop_blob_posture.argtypes = [vp, C.c_int64, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                           C.c_int, C.c_int, vp]
+        L.to_crop_blob_posture.restype = C.c_int
         L._posture_ready = True
     return L
 
@@ -164,3 +174,45 @@ def calculate_posture(lines, pixels, bg, track_posture_threshold=0, outline_resa
     if first_outline is not None:
         return dict(outline=first_outline, segments=None, tail=-1, head=-1, threshold=None)
     raise ValueError("Cannot find valid posture.")
+
+
+def post_process(segments, params: PostureParams | None = None, move_dir=None, tail=-1, head=-1):
+    """Midline::post_process (Outline.cpp:895-1062) on raw midline segments (n,4).  Returns (segments, tail, head, inverted_because_previous);
+    raises IndexError where the reference's segments().at() throws."""
+    seg = np.ascontiguousarray(segments, np.float32).copy()
+    P = params or default_params()
+    t, h = C.c_int64(tail), C.c_int64(head)
+    md = None if move_dir is None else np.ascontiguousarray(move_dir, np.float32)
+    rc = _lib().to_midline_post_process(_p(seg), len(seg), C.byref(P), _p(md) if md is not None else None, C.byref(t), C.byref(h))
+    if rc < 0:
+        raise IndexError("segments().at(i + 1) out of range in Midline::post_process")
+    return seg, int(t.value), int(h.value), bool(rc)
+
+
+def normalize(segments, params: PostureParams | None = None, fix_length=-1.0):
+    """Midline::normalize (Outline.cpp:1268-1456).  Returns (segments (resolution,4), len, angle, offset (2,)) or None (nullptr)."""
+    seg = np.ascontiguousarray(segments, np.float32)
+    P = params or default_params()
+    out = np.zeros((int(P.midline_resolution) + 2, 4), np.float32)
+    info = np.zeros(4, np.float32)
+    n = _lib().to_midline_normalize(_p(seg), len(seg), C.byref(P), C.c_float(fix_length), _p(out), _p(info))
+    if n <= 0:
+        return None
+    return out[:n].copy(), float(info[0]), float(info[1]), info[2:4].copy()
+
+
+def posture_matrix(angle, offset, midline_length, out_size=(80, 80), image_scale=1.0, legacy=False):
+    M = np.zeros(6, np.float64)
+    _lib().to_posture_matrix(C.c_float(angle), C.c_float(offset[0]), C.c_float(offset[1]), C.c_float(midline_length), C.c_float(image_scale),
+                             int(legacy), int(out_size[0]), int(out_size[1]), _p(M))
+    return M.reshape(2, 3)
+
+
+def crop_blob_posture(lines, pixels, bg, method, angle, offset, midline_length, out_size=(80, 80), image_scale=1.0, legacy=False):
+    """constraints::diff_image(posture | legacy) (FilterCache.cpp:266-276): the blob's (difference) image warped by the midline transform."""
+    lines = np.ascontiguousarray(lines); pixels = np.ascontiguousarray(pixels, np.uint8); bg = np.ascontiguousarray(bg, np.uint8)
+    out = np.zeros((out_size[1], out_size[0]), np.uint8)
+    ok = _lib().to_crop_blob_posture(_p(lines), len(lines), _p(pixels), _p(bg), bg.shape[1], int(method), C.c_float(angle), C.c_float(offset[0]),
+                                     C.c_float(offset[1]), C.c_float(midline_length), C.c_float(image_scale), int(legacy), int(out_size[0]),
+                                     int(out_size[1]), _p(out))
+    return out if ok else None

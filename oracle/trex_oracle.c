@@ -1250,6 +1250,8 @@ typedef struct {
     int32_t peak_mode;                     /* 0 pointy (default, :902), 1 broad */
     int32_t midline_start_with_head;       /* 0   :900 */
     int32_t midline_invert;                /* 0   :901 */
+    int32_t midline_resolution;            /* 25  :894 */
+    float   midline_stiff_percentage;      /* 0.15 :893 */
 } to_posture_params_t;
 
 void to_posture_default_params(to_posture_params_t *p)
@@ -1257,6 +1259,7 @@ void to_posture_default_params(to_posture_params_t *p)
     p->outline_smooth_samples = 4; p->outline_smooth_step = 1; p->outline_approximate = 3;
     p->outline_curvature_range_ratio = 0.03f; p->midline_walk_offset = 0.025f;
     p->peak_mode = 0; p->midline_start_with_head = 0; p->midline_invert = 0;
+    p->midline_resolution = 25; p->midline_stiff_percentage = 0.15f;
 }
 
 /* fast::cos<float> / fast::sin<float>, CircularGraph.cpp:12-30 */
@@ -1691,4 +1694,344 @@ int64_t to_calculate_midline(float *p, int64_t N, const to_posture_params_t *P, 
     }
     if (ns <= 2) return -2;
     return ns;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" row N4, third stage: Midline::post_process / normalize / fix_length / calculate_angle / transform
+ * (T/tracking/Outline.cpp:870-1085, 1113-1456) and the `posture` / `legacy` crop normalisation built on it
+ * (T/tracking/FilterCache.cpp:21-115,133-154,266-276; call site T/tracking/ImageExtractor.cpp:244-270:
+ * Individual::calculate_midline_for = post_process + normalize(), then Midline::transform(type)).
+ * Segments are {pos.x, pos.y, height, l_length}.  Float2_t = float; the double promotions are the reference's.
+ * Third-party libm calls: the reference calls ::atan2f (cmn::atan2, C/misc/math.h:168-170), cos / sin / acos.  They are
+ * restated as the double-precision function rounded to float ((float)atan2((double)y, (double)x)): that is the correctly
+ * rounded float result except for inputs within 2^-29 of a rounding boundary, it is what glibc >= 2.41's atan2f returns,
+ * and it is within 1 ulp of older atan2f versions (tests/test_oracle_posture.py measures the agreement with the local libm).
+ * parity unpinned: the reference holds no vectors for these functions; the normalised length is corroborated against the
+ * midline_length column TRex itself exported (tests/golden/posture_golden.npz).
+ * ------------------------------------------------------------------------------------------ */
+static float atan2_f(float y, float x) { return (float)atan2((double)y, (double)x); }
+
+static void vnormalize(float x, float y, float *ox, float *oy)      /* Vector2D::normalize, C/misc/vec2.h:159-162 */
+{
+    const float L = sqrtf(x * x + y * y);
+    const float s = (float)(L != 0), d = (float)(L == 0) + L;
+    *ox = s * (x / d); *oy = s * (y / d);
+}
+
+/* Midline::midline_direction (:870-887) */
+static void midline_direction(const float *seg, int64_t n, float stiff, float *dx_out, float *dy_out)
+{
+    const int32_t samples = (int32_t)fmaxf(1.f, (float)(size_t)n * stiff);       /* cmn::max(int, float) -> float */
+    float dx = 0, dy = 0;
+    int32_t counted = 0;
+    for (int32_t i = 0; i < samples && i + 1 < (int32_t)n; i++, counted++) {
+        dx += seg[4 * (i + 1)] - seg[4 * i]; dy += seg[4 * (i + 1) + 1] - seg[4 * i + 1];
+    }
+    if (counted > 0) {
+        dx /= (float)counted; dy /= (float)counted;
+        vnormalize(dx, dy, &dx, &dy);
+    }
+    *dx_out = dx; *dy_out = dy;
+}
+
+static void reverse_segments(float *seg, int64_t n)
+{
+    for (int64_t i = 0, j = n - 1; i < j; ++i, --j)
+        for (int k = 0; k < 4; ++k) { const float t = seg[4 * i + k]; seg[4 * i + k] = seg[4 * j + k]; seg[4 * j + k] = t; }
+}
+
+/* Midline::post_process (:895-1062).  seg: n segments, modified in place; move_dir: MovementInformation::direction ((0,0): none,
+ * the default -- posture_direction_smoothing = 0, T/tracking/Individual.cpp:1365-1368); tail / head are swapped when the
+ * movement says so.  Returns 0, 1 when the midline was inverted because of the movement direction, or -5 where the reference
+ * throws (segments().at(i + 1) past the end in the axis loop, :981-984). */
+int to_midline_post_process(float *seg, int64_t n, const to_posture_params_t *P, const float move_dir[2], int64_t *tail, int64_t *head)
+{
+    if (n <= 2) return 0;
+    float dx, dy;
+    midline_direction(seg, n, P->midline_stiff_percentage, &dx, &dy);
+    int needs_invert = !P->midline_invert, inverted_prev = 0;
+    if (!needs_invert) { dx = -dx; dy = -dy; }
+    if (move_dir && (move_dir[0] != 0 || move_dir[1] != 0)) {
+        const float a = (-dx) * move_dir[0] + (-dy) * move_dir[1], b = dx * move_dir[0] + dy * move_dir[1];
+        if (acos((double)a) < acos((double)b)) {
+            needs_invert = !needs_invert; inverted_prev = 1;
+            if (tail && head) { const int64_t t = *tail; *tail = *head; *head = t; }
+        }
+    }
+    if (needs_invert) { if (!P->midline_start_with_head) reverse_segments(seg, n); }
+    else if (P->midline_start_with_head) reverse_segments(seg, n);
+    const float stiff = P->midline_stiff_percentage;
+    if (stiff > 0) {
+        const size_t center = (size_t)fminf((float)(size_t)n - 1, roundf((float)(size_t)n * stiff) + 1);
+        const float cpx = seg[4 * center], cpy = seg[4 * center + 1];
+        float ax = 0, ay = 0;
+        uint32_t count = 0;
+        const size_t extra = (size_t)fmin((double)(int)n, (double)center + fmax(0.0, (double)(size_t)n * 0.1));
+        for (size_t i = center; i < extra; ++i) {
+            if (i + 1 >= (size_t)n) return -5;                      /* segments().at(i + 1) throws std::out_of_range */
+            float nx, ny;
+            vnormalize(seg[4 * i] - seg[4 * (i + 1)], seg[4 * i + 1] - seg[4 * (i + 1) + 1], &nx, &ny);
+            ax += nx; ay += ny; ++count;
+        }
+        if (count > 0) { ax /= (float)count; ay /= (float)count; }
+        float *copy = (float *)malloc(sizeof(float) * 4 * (size_t)n);
+        memcpy(copy, seg, sizeof(float) * 4 * (size_t)n);
+        for (size_t i = center; i > 0; --i) {
+            const float p1x = seg[4 * i], p1y = seg[4 * i + 1];
+            const float lx = copy[4 * i] - copy[4 * (i - 1)], ly = copy[4 * i + 1] - copy[4 * (i - 1) + 1];
+            const float L = sqrtf(lx * lx + ly * ly);
+            float dcx, dcy, tx, ty;
+            vnormalize(seg[4 * (i - 1)] - cpx, seg[4 * (i - 1) + 1] - cpy, &dcx, &dcy);
+            vnormalize((dcx + ax) * 0.5f, (dcy + ay) * 0.5f, &tx, &ty);
+            seg[4 * (i - 1)] = p1x + L * tx; seg[4 * (i - 1) + 1] = p1y + L * ty;
+        }
+        free(copy);
+    }
+    reverse_segments(seg, n);
+    return inverted_prev;
+}
+
+/* Midline::calculate_angle (:1113-1123) */
+static float midline_calculate_angle(const float *seg, int64_t n, float stiff)
+{
+    if (n < 2) return 0;
+    const float center = fmaxf(0.f, (float)((size_t)n - 2) - (float)(size_t)n * stiff);
+    const size_t start = (size_t)center;
+    const float rest = center - (float)start;
+    const float lx = seg[4 * (n - 1)] - (seg[4 * start] * (1 - rest) + seg[4 * (start + 1)] * rest);
+    const float ly = seg[4 * (n - 1) + 1] - (seg[4 * start + 1] * (1 - rest) + seg[4 * (start + 1) + 1] * rest);
+    return atan2_f(ly, lx);
+}
+
+/* t_circle_line (C/misc/math.h:287-310) */
+static void t_circle_line(float x0, float y0, float x1, float y1, float h, float k, float r, float *t0, float *t1)
+{
+    const float a = (x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0);
+    const float b = 2 * (x1 - x0) * (x0 - h) + 2 * (y1 - y0) * (y0 - k);
+    const float c = (x0 - h) * (x0 - h) + (y0 - k) * (y0 - k) - r * r;
+    float disc = b * b - 4 * a * c;
+    if (disc < 0) { *t0 = -1; *t1 = -1; return; }
+    disc = sqrtf(disc);
+    *t0 = (-b + disc) / (2 * a); *t1 = (-b - disc) / (2 * a);
+}
+
+/* Midline::fix_length (:1125-1236) on `resolution` points; pts is replaced by the re-spaced points (count returned). */
+static int64_t midline_fix_length(float len, float *pts, int64_t n_pts, uint32_t resolution)
+{
+    const float step = len / (float)resolution;
+    float *out = (float *)malloc(sizeof(float) * 4 * (size_t)(resolution + 2));
+    int64_t n_out = 0;
+    float seg[4]; memcpy(seg, pts, sizeof seg);
+    memcpy(out + 4 * n_out++, seg, sizeof seg);
+    uint32_t j = 1;
+    float last_t = -1;
+    for (uint32_t i = 1; i < resolution; i++) {
+        int found = 0;
+        float mx = 0, my = 0;
+        for (; j < resolution && j < (uint32_t)n_pts; j++) {
+            const float v0x = pts[4 * (j - 1)], v0y = pts[4 * (j - 1) + 1], v1x = pts[4 * j], v1y = pts[4 * j + 1];
+            const float h0 = pts[4 * (j - 1) + 2], h1 = pts[4 * j + 2];
+            float t0, t1;
+            t_circle_line(v0x, v0y, v1x, v1y, seg[0], seg[1], step, &t0, &t1);
+            if (t0 >= 0 && t0 <= 1 && t0 > last_t) {
+                found = 1; mx = v0x + (v1x - v0x) * t0; my = v0y + (v1y - v0y) * t0;
+                seg[2] = t0 * h1 + (1 - t0) * h0; last_t = t0;
+                break;
+            } else if (t1 >= 0 && t1 <= 1 && t1 > last_t) {
+                found = 1; mx = v0x + (v1x - v0x) * t1; my = v0y + (v1y - v0y) * t1;
+                seg[2] = t1 * h1 + (1 - t1) * h0; last_t = t1;
+                break;
+            }
+            last_t = -1;
+        }
+        if (found) {
+            seg[0] = mx; seg[1] = my;
+            memcpy(out + 4 * n_out++, seg, sizeof seg);
+        } else if (j >= resolution) {
+            if (n_pts >= 3) {
+                const float lx = pts[4 * (n_pts - 1)] - pts[4 * (n_pts - 2)], ly = pts[4 * (n_pts - 1) + 1] - pts[4 * (n_pts - 2) + 1];
+                const float l1x = pts[4 * (n_pts - 2)] - pts[4 * (n_pts - 3)], l1y = pts[4 * (n_pts - 2) + 1] - pts[4 * (n_pts - 3) + 1];
+                const float angle0 = atan2_f(ly, lx), angle1 = atan2_f(l1y, l1x);
+                const float change = angle0 - angle1;
+                float angle = angle0;
+                while ((uint64_t)n_out < resolution) {
+                    seg[0] += (float)cos((double)angle) * step; seg[1] += (float)sin((double)angle) * step;
+                    angle += change;
+                    seg[2] *= 0.5f;
+                    memcpy(out + 4 * n_out++, seg, sizeof seg);
+                    i++;
+                }
+            }
+            break;
+        }
+    }
+    memcpy(pts, out, sizeof(float) * 4 * (size_t)n_out);
+    free(out);
+    return n_out;
+}
+
+/* Midline::normalize (:1268-1456).  seg: n post-processed segments.  out: `resolution` normalised segments (rotated so that the
+ * midline points along -x from the origin); info = {len, angle, offset.x, offset.y}.  fix_length <= 0: none (the default call,
+ * Individual.cpp:1372); > 0: Individual::fixed_midline (:507-522).  Returns resolution, or 0 where the reference returns nullptr. */
+int64_t to_midline_normalize(const float *seg, int64_t n, const to_posture_params_t *P, float fix_length, float *out, float info[4])
+{
+    if (n < 2) return 0;
+    double len = 0.0f;
+    for (int64_t i = 1; i < n; i++) {
+        const float lx = seg[4 * i] - seg[4 * (i - 1)], ly = seg[4 * i + 1] - seg[4 * (i - 1) + 1];
+        len += sqrtf(lx * lx + ly * ly);
+    }
+    if (len == 0.0) return 0;
+    const uint32_t resolution = (uint32_t)P->midline_resolution;
+    const int max_segments = (int)(resolution - 1);
+    const double step = len / (double)max_segments;
+    if (step < 0) return 0;                                          /* the reference throws */
+    size_t index = 0;
+    float *red = (float *)malloc(sizeof(float) * 4 * (size_t)(n + resolution + 4));
+    int64_t nr = 0;
+    memcpy(red + 4 * nr++, seg, sizeof(float) * 4);
+    double last_pt_distance = 0.0, distance;
+    for (distance = 0.0; distance <= len && index < (size_t)n - 1;) {
+        while (distance - last_pt_distance < step && index < (size_t)n - 1) {
+            const float lx = seg[4 * (index + 1)] - seg[4 * index], ly = seg[4 * (index + 1) + 1] - seg[4 * index + 1];
+            distance += sqrtf(lx * lx + ly * ly);
+            index++;
+        }
+        float off = (float)(distance - last_pt_distance);
+        if (off < step) break;
+        while (off >= step) {
+            off = (float)((double)off - step);
+            if (index > 0) {
+                const float *s0 = seg + 4 * (index - 1), *s1 = seg + 4 * index;
+                const float lx = s1[0] - s0[0], ly = s1[1] - s0[1];
+                const float local_d = sqrtf(lx * lx + ly * ly);
+                float percent = off;
+                if (local_d > 0) percent /= local_d;
+                percent = 1.f - percent;
+                float *o = red + 4 * nr++;
+                o[0] = s0[0] + lx * percent; o[1] = s0[1] + ly * percent;
+                o[2] = (float)((double)(s0[2] * percent) + (double)s1[2] * (1.0 - (double)percent));
+                o[3] = s0[3] > s1[3] ? s0[3] : s1[3];                 /* cmn::max -> std::max(a, b): b only when a < b */
+                const float q = (float)(1.0 - (double)percent);       /* line * (1.0 - percent): the double is cast to Scalar first (vec2.h:191-192) */
+                const float qx = lx * q, qy = ly * q;
+                last_pt_distance = distance - (double)sqrtf(qx * qx + qy * qy);
+            } else {
+                float *o = red + 4 * nr++;
+                o[0] = seg[4 * index]; o[1] = seg[4 * index + 1]; o[2] = seg[4 * index + 2]; o[3] = 0;   /* l_length is indeterminate in the reference; unreachable (index > 0 after the walk) */
+                last_pt_distance = distance;
+            }
+            if ((uint64_t)nr > (uint64_t)n + resolution) { free(red); return 0; }   /* cannot be normalised to `resolution` points anyway */
+        }
+    }
+    {
+        const float lx = red[4 * (nr - 1)] - seg[4 * (n - 1)], ly = red[4 * (nr - 1) + 1] - seg[4 * (n - 1) + 1];
+        if ((double)sqrtf(lx * lx + ly * ly) >= 0.01) memcpy(red + 4 * nr++, seg + 4 * (n - 1), sizeof(float) * 4);
+    }
+    if ((uint64_t)nr != resolution) { free(red); return 0; }
+    {
+        const float lx = red[4] - red[0], ly = red[5] - red[1];
+        float percent = sqrtf(lx * lx + ly * ly);
+        if (len > 0) percent = (float)((double)percent / len);
+        red[2] = (float)((double)(red[4 + 2] * percent) + (double)red[2] * (1.0 - (double)percent));
+    }
+    if (fix_length > 0) {
+        reverse_segments(red, nr);
+        nr = midline_fix_length(fix_length, red, nr, resolution);
+        reverse_segments(red, nr);
+    }
+    len = 0.0f;
+    for (int64_t i = 1; i < nr; i++) {
+        const float lx = red[4 * i] - red[4 * (i - 1)], ly = red[4 * i + 1] - red[4 * (i - 1) + 1];
+        len += sqrtf(lx * lx + ly * ly);
+    }
+    const float ang = midline_calculate_angle(red, nr, P->midline_stiff_percentage);
+    const float angle = (float)((double)(-ang) + M_PI);
+    const float offx = red[4 * (nr - 1)], offy = red[4 * (nr - 1) + 1];
+    /* gui::Transform tf; tf.rotate(DEGREE(angle)); tf.translate(-offx, -offy)  (C/gui/Transform.cpp:118-160, doubles) */
+    const float deg = angle * (1.0f / (float)M_PI * 180.0f);
+    const double rad = (double)deg * 3.141592654 / 180.0;
+    const double c = cos(rad), s = sin(rad);
+    const double tx = (double)(-offx), ty = (double)(-offy);
+    const double m0 = 1.0 * c + 0.0 * s + 0.0 * 0.0, m4 = 1.0 * (-s) + 0.0 * c + 0.0 * 0.0, m1 = 0.0 * c + 1.0 * s + 0.0 * 0.0, m5 = 0.0 * (-s) + 1.0 * c + 0.0 * 0.0;
+    const double m12 = m0 * tx + m4 * ty + 0.0 * 1.0, m13 = m1 * tx + m5 * ty + 0.0 * 1.0;
+    for (int64_t i = nr - 1, k = 0; i >= 0; i--, k++) {
+        const double x = red[4 * i], y = red[4 * i + 1];
+        out[4 * k] = (float)(m0 * x + m4 * y + m12); out[4 * k + 1] = (float)(m1 * x + m5 * y + m13);
+        out[4 * k + 2] = red[4 * i + 2]; out[4 * k + 3] = red[4 * i + 3];
+    }
+    const float fx = out[0], fy = out[1];
+    if (fx != 0 || fy != 0)
+        for (int64_t k = 0; k < nr; ++k) { out[4 * k] -= fx; out[4 * k + 1] -= fy; }
+    info[0] = (float)len; info[1] = ang; info[2] = offx; info[3] = offy;
+    free(red);
+    return nr;
+}
+
+/* The affine map of the `posture` (legacy = 0) / `legacy` (1) crop: Midline::transform(type) (:1238-1256: translate(-front())
+ * with front() never set = (0,0), rotate(DEGREE(-angle + pi/4 | pi)), translate(-offset())) combined behind normalize_image's
+ * translate(size / 2) . scale(individual_image_scale) . translate(midline_length * 0.4 | (-midline_length / 2, 0))
+ * (FilterCache.cpp:47-62).  M = {m00, m01, m02, m10, m11, m12}, as toCV() hands it to cv::warpAffine. */
+static void tf_combine(double a[9], const double b[9])               /* row-major 3x3: a = a . b (Transform::combine) */
+{
+    double r[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+    memcpy(a, r, sizeof r);
+}
+void to_posture_matrix(float midline_angle, float offx, float offy, float midline_length, float image_scale, int legacy,
+                       int out_w, int out_h, double M[6])
+{
+    double mt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    {
+        const float angle = legacy ? (float)((double)(-midline_angle) + M_PI) : (float)((double)(-midline_angle) + M_PI * (double)0.25f);
+        const double t0[9] = {1, 0, (double)(-0.f), 0, 1, (double)(-0.f), 0, 0, 1};
+        tf_combine(mt, t0);
+        const float deg = angle * (1.0f / (float)M_PI * 180.0f);
+        const double rad = (double)deg * 3.141592654 / 180.0, c = cos(rad), s = sin(rad);
+        const double rot[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+        tf_combine(mt, rot);
+        const double t1[9] = {1, 0, (double)(-offx), 0, 1, (double)(-offy), 0, 0, 1};
+        tf_combine(mt, t1);
+    }
+    double tr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const double t0[9] = {1, 0, (double)((float)out_w * 0.5f), 0, 1, (double)((float)out_h * 0.5f), 0, 0, 1};
+    tf_combine(tr, t0);
+    const double sc[9] = {(double)image_scale, 0, 0, 0, (double)image_scale, 0, 0, 0, 1};
+    tf_combine(tr, sc);
+    if (legacy) {
+        const double t1[9] = {1, 0, (double)(-midline_length * 0.5f) /* float * double 0.5 is exact either way */, 0, 1, 0.0, 0, 0, 1};
+        tf_combine(tr, t1);
+    } else {
+        const float v = (float)((double)midline_length * 0.4);        /* Vec2(midline_length * 0.4): double product cast to Scalar */
+        const double t1[9] = {1, 0, (double)v, 0, 1, (double)v, 0, 0, 1};
+        tf_combine(tr, t1);
+    }
+    tf_combine(tr, mt);
+    M[0] = tr[0]; M[1] = tr[1]; M[2] = tr[2]; M[3] = tr[3]; M[4] = tr[4]; M[5] = tr[5];
+}
+
+/* The crop: calculate_normalized_diff_image (FilterCache.cpp:133-154) -> normalize_image (:21-115): the blob rendered as for the
+ * `moments` crop, warped (INTER_LINEAR) into the zero-filled out_w x out_h canvas.  midline_length < 0: no image (:32-39) -> returns 0. */
+int to_crop_blob_posture(const to_line_t *lines, int64_t n_lines, const uint8_t *px, const uint8_t *bg, int bg_w, int method,
+                         float midline_angle, float offx, float offy, float midline_length, float image_scale, int legacy,
+                         int out_w, int out_h, uint8_t *out)
+{
+    if (midline_length < 0) return 0;
+    int32_t r[4];
+    int mx = 1 << 30, my = 1 << 30, Mx = -1, My = -1;
+    for (int64_t i = 0; i < n_lines; ++i) {
+        if (lines[i].x0 < mx) mx = lines[i].x0;
+        if (lines[i].y < my) my = lines[i].y;
+        if (lines[i].x1 > Mx) Mx = lines[i].x1;
+        if (lines[i].y > My) My = lines[i].y;
+    }
+    const int bw = Mx - mx + 1, bh = My - my + 1;
+    uint8_t *img = (uint8_t *)malloc((size_t)bw * bh);
+    if (method == 0) to_image_from_lines(lines, n_lines, px, bg, bg_w, 0, 0, r, NULL, img, NULL);
+    else             to_image_from_lines(lines, n_lines, px, bg, bg_w, method, 0, r, NULL, NULL, img);
+    double M[6];
+    to_posture_matrix(midline_angle, offx, offy, midline_length, image_scale, legacy, out_w, out_h, M);
+    to_warp_affine_u8(img, bw, bh, M, out, out_w, out_h);
+    free(img);
+    return 1;
 }

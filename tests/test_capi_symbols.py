@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built):
     for s in declared:
         assert hasattr(L, s), s
     assert hasattr(L, "trex_b200_register")          # the one symbol a host resolves after dlopen (SURVEY s8b A'')
-    assert L.tb_abi_version() == 5
+    assert L.tb_abi_version() == 6
 
 
 def test_struct_sizes_match_header(built):

@@ -1,6 +1,9 @@
-"""GPU parity of the midline stage (N4, second stage): tb_seg_midlines vs the oracle's restatement of Outline::smooth,
-offset_to_middle and calculate_midline (T/tracking/Outline.cpp:330-452,454-718,768-868; C/misc/CircularGraph.cpp:12-606).
-Bit-exact: both sides evaluate the reference's float code without contraction."""
+"""GPU parity of the posture chain (N4): tb_seg_midlines / tb_seg_posture vs the oracle's restatement of Outline::smooth,
+offset_to_middle and calculate_midline (T/tracking/Outline.cpp:330-452,454-718,768-868; C/misc/CircularGraph.cpp:12-606),
+Midline::post_process / normalize (:870-1456) and the posture / legacy crops (T/tracking/FilterCache.cpp:21-115,266-276).
+Raw midlines are bit-exact: both sides evaluate the reference's float code without contraction.  Normalised midlines go through
+atan2 / cos / sin in double on both sides (glibc vs CUDA libm, both within 1-2 double ulp): equal to the last float bit except
+where a double result sits on a float rounding boundary -- asserted to 1e-5 absolute, and the bit-exact share is reported."""
 import numpy as np
 import pytest
 
@@ -34,12 +37,14 @@ def _check(bs, frames, rd, every=1, **kw):
 
 
 def test_midlines_of_the_benchmark_workload():
-    """1080p, 100 elongated individuals per frame: every blob's midline equals the oracle's, bit for bit."""
+    """1080p, 100 elongated individuals per frame: every blob's midline equals the oracle's, bit for bit -- pointy and broad tails."""
     import trex_b200
     from trex_b200.synthetic import BlobWorld
     world = BlobWorld(n_blobs=100, seed=6)
     frames = world.frames(2)
     bs = trex_b200.BackgroundSubtraction(world.bg, settings=trex_b200.DetectSettings(), max_batch=2)
+    n, ok = _check(bs, frames, 1.0, every=3, peak_mode=1)
+    assert n > 150 and ok > 0.25 * n
     n, ok = _check(bs, frames, 1.0)
     assert n > 150 and ok > 0.9 * n
     # an elongated ellipse: tail and head sit at opposite ends of the outline
@@ -48,7 +53,9 @@ def test_midlines_of_the_benchmark_workload():
 
 
 @pytest.mark.parametrize("rd,kw", [(0.5, {}), (1.0, dict(outline_approximate=0)), (1.0, dict(outline_smooth_samples=0, midline_invert=1)),
-                                   (2.0, dict(outline_smooth_samples=2, outline_smooth_step=2, midline_start_with_head=1))])
+                                   (2.0, dict(outline_smooth_samples=2, outline_smooth_step=2, midline_start_with_head=1)),
+                                   (1.0, dict(peak_mode=1)), (0.5, dict(peak_mode=1, outline_approximate=0)),
+                                   (1.0, dict(peak_mode=1, outline_approximate=5, midline_start_with_head=1)), (1.0, dict(outline_approximate=8))])
 def test_midlines_of_noisy_blobs_and_settings(rd, kw):
     """Ragged blobs (holes, single pixels, tiny outlines -> 'too few segments') under non-default settings."""
     import trex_b200
@@ -69,8 +76,12 @@ def test_midline_errors():
     fr = bg.copy(); fr[20:30, 10:50] = 20
     bs.apply([fr])
     with pytest.raises(trex_b200.TrexB200Error):
-        bs.midlines(1.0, peak_mode=1)                       # broad tails are not built
-    assert len(bs.midlines(1.0)) == 1
+        bs.midlines(1.0, peak_mode=2)
+    with pytest.raises(trex_b200.TrexB200Error):
+        bs.midlines(1.0, outline_approximate=9)
+    with pytest.raises(trex_b200.TrexB200Error):
+        bs.posture_async(1.0, midline_resolution=1)
+    assert len(bs.midlines(1.0)) == 1 and len(bs.midlines(1.0, peak_mode=1)) == 1
 
 
 def test_midline_lengths_against_the_references_own_export_gpu():
@@ -102,3 +113,147 @@ def test_midline_lengths_against_the_references_own_export_gpu():
         ratios.append(float(np.linalg.norm(np.diff(segs[:, :2], axis=0), axis=1).sum()) / float(g[f"b{i}_csv"][2]))
     ratios = np.array(ratios)
     assert abs(ratios.mean() - 1) < 0.03 and ratios.std() < 0.05
+
+
+def _posture_reference(blob, rd, P, move=None, fix=-1.0):
+    """The oracle's chain for one blob: raw midline -> post_process -> normalize; None where the reference has no midline."""
+    from oracle import posture, seg
+    ol = seg.outline_resample(seg.longest_outline(blob.lines), rd)
+    try:
+        segs, tail, head, pts = posture.calculate_midline(ol, P)
+    except ValueError:
+        return None
+    try:
+        pp, t2, h2, inv = posture.post_process(segs, P, move_dir=move, tail=tail, head=head)
+    except IndexError:
+        return dict(segs=segs, tail=tail, head=head, threw=True)
+    return dict(segs=segs, tail=tail, head=head, pp=pp, t2=t2, h2=h2, inv=inv, norm=posture.normalize(pp, P, fix))
+
+
+@pytest.mark.parametrize("kw", [{}, dict(midline_resolution=12, midline_stiff_percentage=0.3, midline_start_with_head=1),
+                                dict(peak_mode=1, midline_invert=1, midline_stiff_percentage=0.0)])
+def test_posture_chain_async_normalised_midlines(kw):
+    """tb_seg_posture enqueued BEFORE tb_seg_wait (blob count read on the device), fetch = 2: raw midlines bit-exact, normalised
+    midlines (Individual::calculate_midline_for = post_process + normalize) against the oracle for every blob of the batch."""
+    import torch
+    import trex_b200
+    from oracle import posture
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(n_blobs=100, seed=11)
+    frames = world.frames(3)
+    bs = trex_b200.BackgroundSubtraction(world.bg, settings=trex_b200.DetectSettings(), max_batch=3)
+    bs.submit(np.ascontiguousarray(frames), fetch=1)
+    bs.posture_async(1.0, fetch=2, **kw)               # no wait() in between
+    bs.posture_wait()
+    got = [bs.result(i) for i in range(3)]
+    res = bs.posture_result()
+    P = posture.default_params(**kw)
+    RES = int(P.midline_resolution)
+    n = res["n_blobs"]
+    assert n == sum(len(g) for g in got) > 200 and res["midline_resolution"] == RES
+    k = n_norm = exact = 0
+    worst = 0.0
+    for blobs in got:
+        for b in blobs:
+            ref = _posture_reference(b, 1.0, P)
+            so, ns, tail, head = (int(v) for v in res["midlines"][k])
+            nr = res["normalized"][k]
+            if ref is None:
+                assert ns == 0 and nr["n_points"] == 0
+            else:
+                assert (tail, head) == (ref["tail"], ref["head"]) and np.array_equal(res["segments"][so:so + ns], ref["segs"]), k
+                if ref.get("threw"):
+                    assert nr["n_points"] == 0 and nr["flags"] & 2
+                elif ref["norm"] is None:
+                    assert nr["n_points"] == 0 and nr["flags"] & 4, k
+                else:
+                    pts, length, angle, off = ref["norm"]
+                    assert nr["n_points"] == RES and (nr["tail"], nr["head"]) == (ref["t2"], ref["h2"]) and (nr["flags"] & 1) == int(ref["inv"])
+                    assert np.array_equal([nr["offx"], nr["offy"]], off) and nr["len"] == np.float32(length), k
+                    g = res["norm_points"][k]
+                    assert abs(float(nr["angle"]) - angle) < 1e-6, k
+                    worst = max(worst, float(np.abs(g - pts).max()))
+                    assert np.abs(g - pts).max() < 1e-4, k
+                    exact += int(np.array_equal(g, pts) and nr["angle"] == np.float32(angle))
+                    n_norm += 1
+            k += 1
+    print(f"normalised midlines: {n_norm} of {n} blobs, {exact} bit-exact, worst |d| {worst:.3g}")
+    assert n_norm > 0.8 * n and exact > 0.9 * n_norm
+
+
+def test_posture_movement_direction_and_fixed_length():
+    """Per-blob device inputs: MovementInformation::direction (inverts midlines that point against the movement) and
+    Midline::normalize(fix_length) as Individual::fixed_midline calls it."""
+    import torch
+    import trex_b200
+    from oracle import posture
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(h=540, w=960, n_blobs=30, seed=3)
+    frames = world.frames(2)
+    bs = trex_b200.BackgroundSubtraction(world.bg, settings=trex_b200.DetectSettings(), max_batch=2)
+    got = bs.apply(frames)
+    n = sum(len(g) for g in got)
+    rng = np.random.default_rng(0)
+    move = rng.standard_normal((n, 2)).astype(np.float32); move[::5] = 0
+    fix = (rng.random(n).astype(np.float32) * 60 + 20); fix[::3] = -1
+    dev = torch.device("cuda", 0)
+    move_d, fix_d = torch.from_numpy(move).to(dev), torch.from_numpy(fix).to(dev)
+    bs.posture_async(1.0, fetch=1, move_direction_dev=move_d.data_ptr(), fix_length_dev=fix_d.data_ptr())
+    bs.posture_wait()
+    res = bs.posture_result()
+    P = posture.default_params()
+    k = checked = inverted = 0
+    for blobs in got:
+        for b in blobs:
+            ref = _posture_reference(b, 1.0, P, move=move[k], fix=float(fix[k]))
+            nr = res["normalized"][k]
+            if ref is not None and not ref.get("threw") and ref["norm"] is not None:
+                pts, length, angle, off = ref["norm"]
+                assert nr["n_points"] == 25 and (nr["flags"] & 1) == int(ref["inv"]) and (nr["tail"], nr["head"]) == (ref["t2"], ref["h2"]), k
+                assert abs(float(nr["len"]) - length) < 1e-3 and np.abs(res["norm_points"][k] - pts).max() < 1e-3, k
+                checked += 1; inverted += int(ref["inv"])
+            elif ref is not None and not ref.get("threw"):
+                assert nr["n_points"] == 0
+            k += 1
+    assert checked > 0.7 * n and 0 < inverted < checked
+
+
+@pytest.mark.parametrize("mode", ["posture", "legacy"])
+def test_posture_normalised_crops(mode):
+    """individual_image_normalization = posture (the reference's default) / legacy: the crops of the batch re-rendered through
+    Midline::transform + normalize_image, byte-equal to the oracle's cv::warpAffine restatement fed with the device's own
+    (angle, offset) -- which equal the oracle's to the bit for almost every blob, see above --, and chained into the CNN."""
+    import trex_b200
+    from oracle import posture, seg as oseg
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(h=540, w=960, n_blobs=40, seed=8)
+    frames = world.frames(2)
+    s = trex_b200.DetectSettings(individual_image_normalization=mode)
+    bs = trex_b200.BackgroundSubtraction(world.bg, settings=s, max_batch=2, max_individuals=64)
+    bs.submit(np.ascontiguousarray(frames), fetch=2)
+    bs.posture_async(1.0, fetch=1, median_midline_length_px=42.0)
+    bs.posture_wait()
+    got = [bs.result(i) for i in range(2)]
+    res = bs.posture_result()
+    crops, idx = bs.crops()
+    n = res["n_blobs"]
+    assert len(crops) == n == len(res["crop_valid"]) and n > 50
+    flat = [b for blobs in got for b in blobs]
+    n_valid = 0
+    for c in range(n):
+        b, nr = flat[int(idx[c])], res["normalized"][int(idx[c])]
+        if nr["n_points"] == 0:
+            assert res["crop_valid"][c] == 0 and not crops[c].any()
+            continue
+        assert res["crop_valid"][c] == 1
+        exp = posture.crop_blob_posture(b.lines, b.pixels, world.bg, oseg.DIFF_ABSOLUTE, float(nr["angle"]), (float(nr["offx"]), float(nr["offy"])),
+                                        42.0, legacy=(mode == "legacy"))
+        assert np.array_equal(crops[c], exp), c
+        n_valid += 1
+    assert n_valid > 0.8 * n
+    # the network consumes the normalised crops from the device like any other crops
+    net = trex_b200.VINetwork(16, max_images=2 * 64, precision="bf16x3")
+    from trex_b200.weights import random_v118_3_state_dict
+    net.load_weights(random_v118_3_state_dict(16, seed=0))
+    probs = net.probabilities(crops[..., None])
+    assert probs.shape == (n, 16) and np.allclose(probs.sum(1), 1, atol=1e-4)

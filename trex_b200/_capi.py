@@ -54,7 +54,20 @@ class BlobView(C.Structure):
 class PostureParams(C.Structure):
     _fields_ = [("outline_smooth_samples", C.c_int32), ("outline_smooth_step", C.c_int32), ("outline_approximate", C.c_int32),
                 ("outline_curvature_range_ratio", C.c_float), ("midline_walk_offset", C.c_float), ("peak_mode", C.c_int32),
-                ("midline_start_with_head", C.c_int32), ("midline_invert", C.c_int32)]
+                ("midline_start_with_head", C.c_int32), ("midline_invert", C.c_int32),
+                ("midline_resolution", C.c_int32), ("midline_stiff_percentage", C.c_float)]
+
+
+class PostureRequest(C.Structure):
+    _fields_ = [("params", PostureParams), ("outline_resample", C.c_float), ("normalize", C.c_int32), ("fetch", C.c_int32),
+                ("median_midline_length_px", C.c_float), ("individual_image_scale", C.c_float),
+                ("move_direction_dev", C.c_void_p), ("fix_length_dev", C.c_void_p), ("median_midline_length_dev", C.c_void_p)]
+
+
+class PostureView(C.Structure):
+    _fields_ = [("n_blobs", C.c_uint32), ("midline_resolution", C.c_uint32), ("midlines", C.c_void_p), ("normalized", C.c_void_p),
+                ("norm_points", C.c_void_p), ("crop_valid", C.c_void_p), ("outlines", C.c_void_p), ("raw_points", C.c_void_p),
+                ("points", C.c_void_p), ("segments", C.c_void_p)]
 
 
 class MetaLayout(C.Structure):
@@ -75,7 +88,9 @@ SYMBOLS = [
     "tb_seg_debug_binary", "tb_seg_launch_count", "tb_vi_create", "tb_vi_destroy", "tb_vi_set_tensor",
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
     "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_seg_set_stream",
-    "tb_seg_rethreshold", "tb_seg_outlines", "tb_seg_outline_result", "tb_posture_default_params", "tb_seg_midlines", "tb_seg_midline_result", "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
+    "tb_seg_rethreshold", "tb_seg_outlines", "tb_seg_outline_result", "tb_posture_default_params", "tb_seg_midlines", "tb_seg_midline_result",
+    "tb_posture_default_request", "tb_seg_posture", "tb_seg_posture_wait", "tb_seg_posture_result", "tb_seg_posture_device", "tb_seg_posture_ms",
+    "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
     "tb_seg_metadata", "tb_host_alloc", "tb_host_free", "tb_host_register", "tb_host_unregister", "tb_backend",
 ]
 
@@ -126,6 +141,12 @@ def lib() -> C.CDLL:
     L.tb_posture_default_params.argtypes = [C.POINTER(PostureParams)]; L.tb_posture_default_params.restype = None
     L.tb_seg_midlines.argtypes = [vp, C.POINTER(PostureParams)]
     L.tb_seg_midline_result.argtypes = [vp, vpp, vpp, vpp, C.POINTER(C.c_uint32)]
+    L.tb_posture_default_request.argtypes = [C.POINTER(PostureRequest)]; L.tb_posture_default_request.restype = None
+    L.tb_seg_posture.argtypes = [vp, C.POINTER(PostureRequest)]
+    L.tb_seg_posture_wait.argtypes = [vp]
+    L.tb_seg_posture_result.argtypes = [vp, C.POINTER(PostureView)]
+    L.tb_seg_posture_device.argtypes = [vp, vpp, vpp, vpp, vpp, vpp, vpp]
+    L.tb_seg_posture_ms.argtypes = [vp, C.POINTER(C.c_double * 3), C.POINTER(C.c_uint64)]
     L.tb_vi_set_top1.argtypes = [vp, vp, vp]
     L.tb_avg_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vpp]
     L.tb_avg_destroy.argtypes = [vp]; L.tb_avg_destroy.restype = None

@@ -25,6 +25,8 @@ from ._capi import BlobView, SegConfig, SegParams, check, lib
 LINE_DTYPE = np.dtype([("x0", "<u2"), ("x1", "<u2"), ("y", "<u2"), ("pad", "<u2")])
 REC_DTYPE = np.dtype([("line_off", "<u4"), ("px_off", "<u4"), ("n_lines", "<u4"), ("n_pixels", "<u4"),
                       ("x0", "<u2"), ("y0", "<u2"), ("x1", "<u2"), ("y1", "<u2"), ("bid", "<u4"), ("frame", "<u4")])
+NORM_DTYPE = np.dtype([("len", "<f4"), ("angle", "<f4"), ("offx", "<f4"), ("offy", "<f4"), ("n_points", "<u4"), ("flags", "<u4"),
+                       ("tail", "<i4"), ("head", "<i4")])
 INFO_DTYPE = np.dtype([("blob_begin", "<u4"), ("n_blobs", "<u4"), ("line_begin", "<u4"), ("n_lines", "<u4"),
                        ("px_begin", "<u4"), ("n_pixels", "<u4"), ("n_runs", "<u4"), ("status", "<u4")])
 
@@ -52,7 +54,8 @@ class DetectSettings:
     # colour handling of BackgroundSubtraction::apply (.cpp:151-188): meta_encoding "gray" | "rgb8", color_channel
     meta_encoding: str = "gray"        # "gray" | "rgb8" | "r3g3b2"
     color_channel: int | None = None
-    # individual_image_normalization (FilterCache.cpp:318-346): "none" | "moments" (posture / legacy need the tracker's midline)
+    # individual_image_normalization (FilterCache.cpp:318-346): "none" | "moments" | "posture" | "legacy" (the last two: the crops are
+    # re-rendered by posture(); until then they are the "none" crops)
     individual_image_normalization: str = "none"
     individual_image_scale: float = 1.0        # T/core/default_config.cpp; != 1: resize_image (INTER_NEAREST) before the pad / crop
     open_size: int = 0                         # NOT a reference key: north_star's optional n x n open of the threshold mask (cv2 MORPH_OPEN, ones(n,n)); 0 = off
@@ -124,7 +127,7 @@ class BackgroundSubtraction:
                         crop_height=self.settings.individual_image_size[1],
                         crop_method=self.settings.crop_method, channels=self.channels,
                         encoding={"gray": 0, "rgb8": 1, "r3g3b2": 2}[self.settings.meta_encoding],
-                        crop_normalize={"none": 0, "moments": 1}[self.settings.individual_image_normalization],
+                        crop_normalize={"none": 0, "moments": 1, "posture": 2, "legacy": 3}[self.settings.individual_image_normalization],
                         crop_scale=float(self.settings.individual_image_scale))
         self.max_individuals = int(max_individuals)
         self._h = C.c_void_p()
@@ -223,7 +226,7 @@ class BackgroundSubtraction:
         return ([raw[o:o + k].copy() for o, k in recs[:, :2]], [res[o:o + k].copy() for o, k in recs[:, 2:]])
 
     def midlines(self, outline_resample=1.0, **posture_settings):
-        """Outline::calculate_midline for every blob of the last batch (T/tracking/Outline.cpp:768-868; peak_mode pointy): runs
+        """Outline::calculate_midline for every blob of the last batch (T/tracking/Outline.cpp:768-868): runs
         outlines(outline_resample) first.  posture_settings: fields of tb_posture_params (outline_smooth_samples, ...).
         Returns one (segments (n,4) float32, tail index, head index, outline points (m,2)) per blob; segments is empty where
         the reference reports too few midline segments."""
@@ -251,6 +254,63 @@ class BackgroundSubtraction:
             ro, rn = int(orecs[k, 2]), int(orecs[k, 3])
             out.append((segs[so:so + ns].copy(), tail, head, pts[ro:ro + rn].copy()))
         return out
+
+    def posture_async(self, outline_resample=1.0, normalize=True, fetch=1, median_midline_length_px=0.0, individual_image_scale=1.0,
+                      move_direction_dev=0, fix_length_dev=0, median_midline_length_dev=0, **posture_settings):
+        """tb_seg_posture: enqueue outlines -> midlines -> Midline::post_process / normalize (-> posture crops) behind the last batch's
+        kernels; may be called before wait().  Pair with posture_wait() / posture_result()."""
+        from ._capi import PostureRequest
+        q = PostureRequest()
+        lib().tb_posture_default_request(C.byref(q))
+        for k, v in posture_settings.items():
+            setattr(q.params, k, v)
+        q.outline_resample = float(outline_resample); q.normalize = int(bool(normalize)); q.fetch = int(fetch)
+        q.median_midline_length_px = float(median_midline_length_px); q.individual_image_scale = float(individual_image_scale)
+        q.move_direction_dev = move_direction_dev or None; q.fix_length_dev = fix_length_dev or None
+        q.median_midline_length_dev = median_midline_length_dev or None
+        check(lib().tb_seg_posture(self._h, C.byref(q)))
+
+    def posture_wait(self):
+        check(lib().tb_seg_posture_wait(self._h))
+
+    def posture_result(self):
+        """dict of numpy views of the last posture call (valid until the next one): midlines (n,4) int32 [seg_off, n_seg, tail, head],
+        normalized (structured: len, angle, offx, offy, n_points, flags, tail, head), norm_points (n, resolution, 4), crop_valid,
+        and with fetch=2 outlines (n,4) uint32, raw_points, points, segments arenas."""
+        from ._capi import PostureView
+        v = PostureView()
+        check(lib().tb_seg_posture_result(self._h, C.byref(v)))
+        n, res = int(v.n_blobs), int(v.midline_resolution)
+        out = {"n_blobs": n, "midline_resolution": res}
+        if n == 0:
+            return out
+        if v.midlines:
+            out["midlines"] = np.ctypeslib.as_array(C.cast(v.midlines, C.POINTER(C.c_int32)), (n, 4))
+        if v.normalized:
+            out["normalized"] = np.ctypeslib.as_array(C.cast(v.normalized, C.POINTER(C.c_uint8)), (n * 32,)).view(NORM_DTYPE)
+            out["norm_points"] = np.ctypeslib.as_array(C.cast(v.norm_points, C.POINTER(C.c_float)), (n, res, 4))
+        if v.crop_valid:
+            out["crop_valid"] = np.ctypeslib.as_array(C.cast(v.crop_valid, C.POINTER(C.c_uint8)), (max(self.totals()[3], 1),))
+        if v.outlines:
+            orecs = np.ctypeslib.as_array(C.cast(v.outlines, C.POINTER(C.c_uint32)), (n, 4))
+            out["outlines"] = orecs
+            n_raw, n_res = int((orecs[:, 0] + orecs[:, 1]).max()), int((orecs[:, 2] + orecs[:, 3]).max())
+            out["raw_points"] = np.ctypeslib.as_array(C.cast(v.raw_points, C.POINTER(C.c_float)), (max(n_raw, 1), 2))
+            out["points"] = np.ctypeslib.as_array(C.cast(v.points, C.POINTER(C.c_float)), (max(n_res, 1), 2))
+            out["segments"] = np.ctypeslib.as_array(C.cast(v.segments, C.POINTER(C.c_float)), (max(n_res, 1), 4))
+        return out
+
+    def posture(self, outline_resample=1.0, **kw):
+        """Synchronous form: posture_async(fetch=2) + posture_wait() + posture_result()."""
+        kw.setdefault("fetch", 2)
+        self.posture_async(outline_resample, **kw)
+        self.posture_wait()
+        return self.posture_result()
+
+    def posture_ms(self):
+        ms, n = (C.c_double * 3)(), C.c_uint64()
+        check(lib().tb_seg_posture_ms(self._h, C.byref(ms), C.byref(n)))
+        return dict(zip(("outlines", "midlines", "posture_crops"), ms)), int(n.value)
 
     def wait(self):
         check(lib().tb_seg_wait(self._h))

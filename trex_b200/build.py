@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtrexb200.so")
-SOURCES = ["capi.cu", "seg.cu", "vi.cu", "avg.cu", "umma_test.cu", "crop_norm.cu", "vi_nets.cu", "box.cu", "outline.cu", "midline.cu", "backend.cu"]
-EXTRA_FLAGS = {"crop_norm.cu": ["-fmad=false"], "outline.cu": ["-fmad=false"], "midline.cu": ["-fmad=false"]}      # scalar float / double arithmetic that must round like the reference
+SOURCES = ["capi.cu", "seg.cu", "vi.cu", "avg.cu", "umma_test.cu", "crop_norm.cu", "vi_nets.cu", "box.cu", "outline.cu", "posture.cu", "backend.cu"]
+EXTRA_FLAGS = {"crop_norm.cu": ["-fmad=false"], "outline.cu": ["-fmad=false"], "posture.cu": ["-fmad=false"]}      # scalar float / double arithmetic that must round like the reference
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -115,14 +115,28 @@ int launch_crop_scaled(const tb_blob_rec *recs, const uint32_t *totals, const ui
 // 2 launches per sub-batch of `sub` frames
 int launch_box_mean(const uint8_t *src, uint8_t *dst, uint32_t *hs, int sub, int W, int H, int n, int k, int border, cudaStream_t s);
 
-// outline.cu: longest outline (pixel::find_outer_points) of nb blobs + Outline::resample; 1 memset + 3 launches
-int launch_outlines(const tb_blob_rec *recs, uint32_t nb, const tb_line *lines, const uint32_t *line_px, int opx,
-                    uint8_t *visited, size_t visited_bytes, float rd, uint32_t *row_first, int4 *sel,
-                    tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, cudaStream_t s);
+// crop_norm.cu: cv::warpAffine of every crop's blob image with the inverted map coef[6 * crop]; 1 launch
+int launch_crop_warp(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,
+                     const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
+                     int out_w, int out_h, const double *coef, uint8_t *crops, int max_crops_total, cudaStream_t s);
 
-// midline.cu: Outline::calculate_midline for nb resampled outlines; 1 launch
-int launch_midlines(const tb_outline_rec *orecs, uint32_t nb, const float *res, uint32_t cap_pts, const tb_posture_params *P,
-                    float *pts_out, float *segs, tb_midline_rec *mrecs, float *scratch, cudaStream_t s);
+// outline.cu: longest outline (pixel::find_outer_points) of the batch's blobs + Outline::resample; 1 memset + 3 launches.
+// nb_dev: device word holding the number of blobs (nullptr: nb_max is the count); nb_max bounds the grids.
+int launch_outlines(const tb_blob_rec *recs, const uint32_t *nb_dev, uint32_t nb_max, const tb_line *lines, const uint32_t *line_px, int opx,
+                    uint8_t *visited, size_t visited_bytes, float rd, uint32_t *row_first, int4 *sel,
+                    tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, int sms, cudaStream_t s);
+
+// posture.cu: Outline::calculate_midline (+ Midline::post_process / normalize with do_norm) for the batch's resampled outlines; 1 memset + 1 launch
+int launch_midlines(const tb_outline_rec *orecs, const uint32_t *nb_dev, uint32_t nb_max, const float *res, uint32_t cap_pts,
+                    const tb_posture_params *P, int do_norm, const float *move_dir, const float *fix_len,
+                    float *pts_out, float *segs, tb_midline_rec *mrecs, tb_midline_norm *nrecs, float *norm_pts,
+                    float *arena, unsigned long long arena_floats, unsigned long long *arena_used, uint32_t *status, int sms, cudaStream_t s);
+
+// posture.cu: `posture` / `legacy` crops from the normalised midlines (map per crop, then crop_norm.cu's warp); 2 launches
+int launch_posture_crops(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,
+                         const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
+                         int out_w, int out_h, const tb_midline_norm *nrecs, const float *median_len, float median_len_all,
+                         float image_scale, int legacy, uint8_t *crops, double *coef, uint8_t *valid, int max_crops_total, cudaStream_t s);
 
 #ifdef __CUDACC__
 // Exclusive scan of one value per thread across the CTA; `total` = sum over all threads.

@@ -218,6 +218,16 @@ int launch_crop_scaled(const tb_blob_rec *recs, const uint32_t *totals, const ui
     return TB_OK;
 }
 
+int launch_crop_warp(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,
+                     const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
+                     int out_w, int out_h, const double *coef, uint8_t *crops, int max_crops_total, cudaStream_t s)
+{
+    if (max_crops_total <= 0) return TB_OK;
+    crop_warp_kernel<<<max_crops_total, CW_NT, 0, s>>>(recs, totals, crop_blob, lines, line_px, pixels, bg, W, crop_method, out_w, out_h, coef, crops);
+    TB_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
 int launch_crop_moments(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,
                         const uint32_t *line_px, const uint8_t *pixels, const uint8_t *bg, int W, int crop_method,
                         int out_w, int out_h, uint8_t *crops, double *coef, int max_crops_total, cudaStream_t s)

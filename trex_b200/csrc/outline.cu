@@ -18,6 +18,8 @@
 // Compiled with -fmad=false: the resampling arithmetic must round like the reference's scalar float code.
 #include "common.h"
 
+#include <algorithm>
+
 namespace tb {
 
 __constant__ int c_vx[8] = {0, 1, 1, 1, 0, -1, -1, -1};
@@ -187,19 +189,22 @@ struct LoopPick {
 };
 
 __global__ void __launch_bounds__(OL_NT)
-outline_select_kernel(const tb_blob_rec *__restrict__ recs, uint32_t nb, const tb_line *__restrict__ lines,
+outline_select_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__restrict__ nb_dev, uint32_t nb_max, const tb_line *__restrict__ lines,
                       const uint32_t *__restrict__ line_px, int opx, uint8_t *__restrict__ visited, float rd,
                       uint32_t *__restrict__ row_first, int4 *__restrict__ sel, tb_outline_rec *__restrict__ orecs)
 {
     __shared__ uint32_t s_pool[OL_POOL_WORDS];
     __shared__ uint32_t s_ws[33];
-    const uint32_t q = blockIdx.x * OL_NT + threadIdx.x;
+    const uint32_t nb = min(nb_dev ? *nb_dev : nb_max, nb_max);
+    for (uint32_t base = blockIdx.x * OL_NT; base < nb; base += gridDim.x * OL_NT) {
+    const uint32_t q = base + threadIdx.x;
     const bool valid = q < nb;
     tb_blob_rec r{};
     if (valid) r = recs[q];
     const tb_line *bl = lines + r.line_off;
+    __syncthreads();                                         // the previous group is done with the pool
     Occupancy O = make_occupancy(valid, r, bl, s_pool, s_ws, row_first + r.line_off, true, true);
-    if (!valid) return;
+    if (!valid) continue;
     O.gvis = visited; O.line_px = line_px + r.line_off; O.opx = opx;
     const uint32_t max_n = 4u * r.n_pixels + 4u;            // a loop cannot hold more sides than the blob has
     LoopPick pick; pick.bx = pick.by = pick.bb = 0;
@@ -232,12 +237,14 @@ outline_select_kernel(const tb_blob_rec *__restrict__ recs, uint32_t nb, const t
     // room for the resampled outline: the perimeter is at most n_raw (steps of 1 or sqrt(1/2)), one point per outline_resample walked
     o.n_res = (pick.best_n > 1 && rd > 0.f) ? (uint32_t)fminf((float)pick.best_n / rd + 2.f, 4.0e9f) : pick.best_n;
     orecs[q] = o;
+    }
 }
 
 // arena offsets: exclusive prefix sums of n_raw / the n_res bounds over the blobs (one CTA); totals[0..1] = sums
-__global__ void outline_scan_kernel(tb_outline_rec *__restrict__ orecs, uint32_t nb, uint32_t *__restrict__ totals)
+__global__ void outline_scan_kernel(tb_outline_rec *__restrict__ orecs, const uint32_t *__restrict__ nb_dev, uint32_t nb_max, uint32_t *__restrict__ totals)
 {
     __shared__ uint32_t ws[33];
+    const uint32_t nb = min(nb_dev ? *nb_dev : nb_max, nb_max);
     unsigned long long base_raw = 0, base_res = 0;
     for (uint32_t i0 = 0; i0 < nb; i0 += blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
@@ -255,20 +262,23 @@ __global__ void outline_scan_kernel(tb_outline_rec *__restrict__ orecs, uint32_t
 
 // pass 2, one thread per blob: the raw outline and its resampled version; n_res becomes the number of resampled points
 __global__ void __launch_bounds__(OL_NT)
-outline_emit_kernel(const tb_blob_rec *__restrict__ recs, uint32_t nb, const tb_line *__restrict__ lines,
+outline_emit_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__restrict__ nb_dev, uint32_t nb_max, const tb_line *__restrict__ lines,
                     uint32_t *__restrict__ row_first, const int4 *__restrict__ sel,
                     tb_outline_rec *__restrict__ orecs, float rd, float *__restrict__ raw, float *__restrict__ res, uint32_t cap_pts)
 {
     __shared__ uint32_t s_pool[OL_POOL_WORDS];
     __shared__ uint32_t s_ws[33];
-    const uint32_t q = blockIdx.x * OL_NT + threadIdx.x;
+    const uint32_t nb = min(nb_dev ? *nb_dev : nb_max, nb_max);
+    for (uint32_t base = blockIdx.x * OL_NT; base < nb; base += gridDim.x * OL_NT) {
+    const uint32_t q = base + threadIdx.x;
     tb_outline_rec o{};
     if (q < nb) o = orecs[q];
     const bool valid = q < nb && o.n_raw != 0 && (unsigned long long)o.raw_off + o.n_raw <= cap_pts && (unsigned long long)o.res_off + o.n_res <= cap_pts;
     tb_blob_rec r{};
     if (valid) r = recs[q];
+    __syncthreads();                                         // the previous group is done with the pool
     const Occupancy O = make_occupancy(valid, r, lines + r.line_off, s_pool, s_ws, row_first + r.line_off, false, false);
-    if (!valid) return;
+    if (!valid) { if (q < nb && o.n_raw != 0) orecs[q].n_res = 0; continue; }       // arena overflow: no points (the totals report it)
     const int bx0 = r.x0, by0 = r.y0;
     const int4 s4 = sel[q];
     Side cur{s4.x, s4.y, s4.z};
@@ -285,18 +295,20 @@ outline_emit_kernel(const tb_blob_rec *__restrict__ recs, uint32_t nb, const tb_
         x0 = x1; y0 = y1;
     }
     if (resample) orecs[q].n_res = min(rs.n, o.n_res);
+    }
 }
 
-int launch_outlines(const tb_blob_rec *recs, uint32_t nb, const tb_line *lines, const uint32_t *line_px, int opx,
+int launch_outlines(const tb_blob_rec *recs, const uint32_t *nb_dev, uint32_t nb_max, const tb_line *lines, const uint32_t *line_px, int opx,
                     uint8_t *visited, size_t visited_bytes, float rd, uint32_t *row_first, int4 *sel,
-                    tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, cudaStream_t s)
+                    tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, int sms, cudaStream_t s)
 {
-    if (nb == 0) { TB_CUDA(cudaMemsetAsync(totals, 0, 8, s)); return TB_OK; }
+    if (nb_max == 0) { TB_CUDA(cudaMemsetAsync(totals, 0, 8, s)); return TB_OK; }
     TB_CUDA(cudaMemsetAsync(visited, 0, visited_bytes, s));
-    const unsigned grid = (nb + OL_NT - 1) / OL_NT;
-    outline_select_kernel<<<grid, OL_NT, 0, s>>>(recs, nb, lines, line_px, opx, visited, rd, row_first, sel, orecs);
-    outline_scan_kernel<<<1, 1024, 0, s>>>(orecs, nb, totals);
-    outline_emit_kernel<<<grid, OL_NT, 0, s>>>(recs, nb, lines, row_first, sel, orecs, rd, raw, res, cap_pts);
+    // persistent over groups of OL_NT blobs: 4 CTAs of 47 KB fit an SM
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + OL_NT - 1) / OL_NT, (uint64_t)std::max(1, sms) * 4);
+    outline_select_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, line_px, opx, visited, rd, row_first, sel, orecs);
+    outline_scan_kernel<<<1, 1024, 0, s>>>(orecs, nb_dev, nb_max, totals);
+    outline_emit_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, row_first, sel, orecs, rd, raw, res, cap_pts);
     TB_CUDA(cudaGetLastError());
     return TB_OK;
 }

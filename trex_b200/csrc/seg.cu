@@ -1456,13 +1456,18 @@ struct tb_seg {
     bool morph = false;
     uint8_t *m_a = nullptr, *m_b = nullptr, *m_diff = nullptr;
     uint32_t *box_hs = nullptr; int box_sub = 0;
-    // outlines (tb_seg_outlines), allocated on first use
+    // posture chain (tb_seg_posture / tb_seg_outlines / tb_seg_midlines), allocated on first use
     uint8_t *o_visited = nullptr; uint32_t *o_rowfirst = nullptr; int4 *o_sel = nullptr; tb_outline_rec *o_recs = nullptr; uint32_t *o_totals = nullptr;
     float *o_raw = nullptr, *o_res = nullptr; uint32_t o_cap = 0, o_n = 0;
-    tb_outline_rec *h_o_recs = nullptr; float *h_o_raw = nullptr, *h_o_res = nullptr; uint32_t *h_o_totals = nullptr;
-    // midlines (tb_seg_midlines), allocated on first use
-    float *m_pts = nullptr, *m_segs = nullptr, *m_scratch = nullptr; size_t m_scratch_floats = 0; tb_midline_rec *m_recs = nullptr;
-    float *h_m_pts = nullptr, *h_m_segs = nullptr; tb_midline_rec *h_m_recs = nullptr; uint32_t m_n = 0;    // blur_difference / use_adaptive_threshold: row-sum scratch of box_sub frames
+    tb_outline_rec *h_o_recs = nullptr; float *h_o_raw = nullptr, *h_o_res = nullptr; uint32_t *h_o_totals = nullptr;   // h_o_totals: raw, res, status
+    float *m_pts = nullptr, *m_segs = nullptr; tb_midline_rec *m_recs = nullptr;
+    tb_midline_norm *m_nrecs = nullptr; float *m_norm = nullptr; int m_res = 0;        // normalised midlines: m_res points per blob
+    float *m_arena = nullptr; unsigned long long m_arena_floats = 0, *m_arena_used = nullptr; uint32_t *p_status = nullptr;
+    uint8_t *crop_valid = nullptr, *h_crop_valid = nullptr;
+    float *h_m_pts = nullptr, *h_m_segs = nullptr; tb_midline_rec *h_m_recs = nullptr; uint32_t m_n = 0;
+    tb_midline_norm *h_m_nrecs = nullptr; float *h_m_norm = nullptr;
+    bool p_pending = false, p_has_norm = false, p_has_crops = false; int p_fetch = 0, p_sms = 0; cudaStream_t p_stream = nullptr; uint32_t p_n = 0;
+    EventRing<3> p_prof;
     const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
     uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
     double *d_coef = nullptr;                   // `moments` normalisation: inverted warp matrix per crop
@@ -1539,11 +1544,11 @@ extern "C" int tb_seg_create(const tb_seg_config *cfg, tb_seg **out)
     TB_REQUIRE(cfg->channels == 0 || cfg->channels == 1 || cfg->channels == 3 || cfg->channels == 4, TB_ERR_INVALID,
                "tb_seg_create: channels must be 1 (gray), 3 (BGR) or 4 (BGRA)");
     TB_REQUIRE(cfg->encoding >= 0 && cfg->encoding <= 2, TB_ERR_INVALID, "tb_seg_create: encoding must be 0 (gray), 1 (rgb8) or 2 (r3g3b2)");
-    TB_REQUIRE(cfg->crop_normalize == 0 || (cfg->crop_normalize == 1 && cfg->encoding == 0), TB_ERR_INVALID,
-               "tb_seg_create: crop_normalize must be 0 (none) or 1 (moments, gray encoding); posture / legacy need the tracker's midline");
+    TB_REQUIRE(cfg->crop_normalize == 0 || (cfg->crop_normalize >= 1 && cfg->crop_normalize <= 3 && cfg->encoding == 0), TB_ERR_INVALID,
+               "tb_seg_create: crop_normalize must be 0 (none), 1 (moments), 2 (posture) or 3 (legacy); 1..3 are built for the gray encoding");
     TB_REQUIRE(cfg->encoding == 0 || cfg->channels >= 3, TB_ERR_INVALID,
                "tb_seg_create: rgb8 / r3g3b2 encoding needs colour frames (Invalid number of channels, BackgroundSubtraction.cpp:151-158,177-181)");
-    TB_REQUIRE(cfg->encoding != 2 || cfg->crop_normalize == 0, TB_ERR_INVALID, "tb_seg_create: crop_normalize = moments is built for the gray encoding");
+    TB_REQUIRE(cfg->encoding != 2 || cfg->crop_normalize == 0, TB_ERR_INVALID, "tb_seg_create: crop normalisation is built for the gray encoding");
     TB_REQUIRE(cfg->crop_scale >= 0.f && cfg->crop_scale <= 16.f, TB_ERR_INVALID, "tb_seg_create: crop_scale (individual_image_scale) must be in (0, 16]; 0 = 1");
     TB_REQUIRE(cfg->crop_scale == 0.f || cfg->crop_scale == 1.f || (cfg->encoding == 0 && cfg->crop_normalize == 0), TB_ERR_INVALID,
                "tb_seg_create: crop_scale != 1 is built for the gray encoding without crop normalisation");
@@ -1646,8 +1651,8 @@ extern "C" void tb_seg_destroy(tb_seg *h)
     cudaDeviceSynchronize();
     for (void *p : h->dev_allocs) cudaFree(p);
     void *hp[] = {h->h_infos, h->h_totals, h->h_recs, h->h_lines, h->h_pixels, h->h_crops, h->h_crop_blob,
-                  h->h_o_recs, h->h_o_raw, h->h_o_res, h->h_o_totals, h->h_m_pts, h->h_m_segs, h->h_m_recs};
-    if (h->m_scratch) cudaFree(h->m_scratch);
+                  h->h_o_recs, h->h_o_raw, h->h_o_res, h->h_o_totals, h->h_m_pts, h->h_m_segs, h->h_m_recs, h->h_m_nrecs, h->h_m_norm, h->h_crop_valid};
+    h->p_prof.destroy();
     for (void *p : hp) if (p) cudaFreeHost(p);
     h->prof.destroy();
     if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -1944,7 +1949,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     h->prof.mark(slot, 3);
     h->launches += 3;
     TB_CUDA(cudaGetLastError());
-    if (d.crop_norm && d.max_crops) {          // individual_image_normalization = moments: orientation + cv::warpAffine per crop
+    if (d.crop_norm == 1 && d.max_crops) {     // individual_image_normalization = moments: orientation + cv::warpAffine per crop
         int r = launch_crop_moments(d.recs, d.totals, d.crop_blob, d.lines, d.line_px, d.pixels, h->d_bg, d.W, d.crop_method,
                                     d.crop_w, d.crop_h, d.crops, h->d_coef, n * (int)d.max_crops, s);
         if (r != TB_OK) return r;
@@ -1959,6 +1964,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     TB_CUDA(cudaMemcpyAsync(h->h_totals, d.totals, 16, cudaMemcpyDeviceToHost, s));
     TB_CUDA(cudaMemcpyAsync(h->h_infos, d.infos, sizeof(tb_frame_info) * (size_t)n, cudaMemcpyDeviceToHost, s));
     h->last_n = n; h->last_fetch = fetch; h->pending = true; h->fetched_payload = false; h->fetched_crops = false; h->last_stream = s;
+    h->o_n = 0; h->m_n = 0; h->p_n = 0; h->p_pending = false;      // posture results belong to the previous batch
     return TB_OK;
 }
 
@@ -2075,39 +2081,116 @@ extern "C" int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **c
     return TB_OK;
 }
 
+// ---- posture chain (N4): outlines -> midlines -> normalised midlines -> posture crops, all behind the batch's kernels
+static int posture_alloc(tb_seg *h, int res)
+{
+    const SegDev &d = h->d;
+    int r = TB_OK;
+    if (!h->o_recs) {
+        h->o_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, (uint64_t)h->cfg.max_batch << 15), 1u << 26);
+        static const size_t arena_env = getenv("TB_POSTURE_ARENA_MB") ? (size_t)atol(getenv("TB_POSTURE_ARENA_MB")) : 32;
+        h->m_arena_floats = (unsigned long long)arena_env << 18;       // outlines too long for the shared-memory pool work here
+        r = seg_dev(h, &h->o_visited, (size_t)d.px_cap / d.opx + 16);
+        if (r == TB_OK) r = seg_dev(h, &h->o_rowfirst, d.lines_cap);
+        if (r == TB_OK) r = seg_dev(h, &h->o_sel, d.blobs_cap);
+        if (r == TB_OK) r = seg_dev(h, &h->o_recs, d.blobs_cap);
+        if (r == TB_OK) r = seg_dev(h, &h->o_totals, 4);
+        if (r == TB_OK) r = seg_dev(h, &h->o_raw, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = seg_dev(h, &h->o_res, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = seg_dev(h, &h->m_pts, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = seg_dev(h, &h->m_segs, (size_t)h->o_cap * 4);
+        if (r == TB_OK) r = seg_dev(h, &h->m_recs, d.blobs_cap);
+        if (r == TB_OK) r = seg_dev(h, &h->m_nrecs, d.blobs_cap);
+        if (r == TB_OK) r = seg_dev(h, &h->m_arena, (size_t)h->m_arena_floats);
+        if (r == TB_OK) r = seg_dev(h, &h->m_arena_used, 1);
+        if (r == TB_OK) r = host_alloc(&h->h_o_recs, d.blobs_cap);
+        if (r == TB_OK) r = host_alloc(&h->h_o_raw, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = host_alloc(&h->h_o_res, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = host_alloc(&h->h_o_totals, 4);
+        if (r == TB_OK) r = host_alloc(&h->h_m_pts, (size_t)h->o_cap * 2);
+        if (r == TB_OK) r = host_alloc(&h->h_m_segs, (size_t)h->o_cap * 4);
+        if (r == TB_OK) r = host_alloc(&h->h_m_recs, d.blobs_cap);
+        if (r == TB_OK) r = host_alloc(&h->h_m_nrecs, d.blobs_cap);
+        if (r == TB_OK && d.crops_cap) r = seg_dev(h, &h->crop_valid, d.crops_cap);
+        if (r == TB_OK && d.crops_cap) r = host_alloc(&h->h_crop_valid, d.crops_cap);
+        if (r == TB_OK && d.crops_cap && !h->d_coef) r = seg_dev(h, &h->d_coef, (size_t)d.crops_cap * 6);
+        if (r == TB_OK) { h->p_status = h->o_totals + 2; TB_CUDA(cudaDeviceGetAttribute(&h->p_sms, cudaDevAttrMultiProcessorCount, h->cfg.device)); }
+        if (r != TB_OK) return r;
+    }
+    if (res > h->m_res) {                      // normalised midlines: res float4 per blob (grown when midline_resolution grows)
+        if (h->m_norm) { cudaFree(h->m_norm); h->dev_allocs.erase(std::find(h->dev_allocs.begin(), h->dev_allocs.end(), (void *)h->m_norm)); h->m_norm = nullptr; }
+        if (h->h_m_norm) { cudaFreeHost(h->h_m_norm); h->h_m_norm = nullptr; }
+        h->m_res = 0;
+        r = seg_dev(h, &h->m_norm, (size_t)d.blobs_cap * res * 4);
+        if (r == TB_OK) r = host_alloc(&h->h_m_norm, (size_t)d.blobs_cap * res * 4);
+        if (r != TB_OK) return r;
+        h->m_res = res;
+    }
+    return TB_OK;
+}
+
+static int posture_check_params(const tb_posture_params *p, const char *who)
+{
+    const std::string w(who);
+    TB_REQUIRE(p->peak_mode == 0 || p->peak_mode == 1, TB_ERR_INVALID, w + ": peak_mode must be 0 (pointy) or 1 (broad)");
+    TB_REQUIRE(p->outline_approximate >= 0 && p->outline_approximate <= 8, TB_ERR_INVALID, w + ": outline_approximate must be 0..8");
+    TB_REQUIRE(p->outline_smooth_samples >= 0 && p->outline_smooth_samples <= 255 && p->outline_smooth_step >= 1 && p->outline_smooth_step <= 255,
+               TB_ERR_INVALID, w + ": outline_smooth_samples 0..255, outline_smooth_step 1..255 (uint8 settings)");
+    TB_REQUIRE(p->midline_resolution >= 2 && p->midline_resolution <= 256, TB_ERR_INVALID, w + ": midline_resolution must be 2..256");
+    TB_REQUIRE(p->midline_stiff_percentage >= 0.f && p->midline_stiff_percentage <= 1.f, TB_ERR_INVALID, w + ": midline_stiff_percentage must be 0..1");
+    return TB_OK;
+}
+
+// blob count of the batch: known on the host once tb_seg_wait has run, else read on the device (bounded by the record capacity)
+static inline uint32_t posture_nb_max(const tb_seg *h) { return h->pending ? h->d.blobs_cap : h->h_totals[0]; }
+
+static int posture_enqueue_outlines(tb_seg *h, float rd, cudaStream_t s)
+{
+    const SegDev &d = h->d;
+    const uint32_t nb_max = posture_nb_max(h);
+    TB_CUDA(cudaMemsetAsync(h->o_totals, 0, 16, s));
+    int r = launch_outlines(d.recs, d.totals, nb_max, d.lines, d.line_px, d.opx, h->o_visited, (size_t)d.px_cap / d.opx + 16, rd,
+                            h->o_rowfirst, h->o_sel, h->o_recs, h->o_totals, h->o_raw, h->o_res, h->o_cap, h->p_sms, s);
+    if (r != TB_OK) return r;
+    h->launches += nb_max ? 3 : 0;
+    return TB_OK;
+}
+
+static int posture_enqueue_midlines(tb_seg *h, const tb_posture_params *p, int do_norm, const float *move_dir, const float *fix_len, cudaStream_t s)
+{
+    const uint32_t nb_max = posture_nb_max(h);
+    int r = launch_midlines(h->o_recs, h->d.totals, nb_max, h->o_res, h->o_cap, p, do_norm, move_dir, fix_len, h->m_pts, h->m_segs, h->m_recs,
+                            h->m_nrecs, h->m_norm, h->m_arena, h->m_arena_floats, h->m_arena_used, h->p_status, h->p_sms, s);
+    if (r != TB_OK) return r;
+    h->launches += nb_max ? 1 : 0;
+    return TB_OK;
+}
+
+// after a stream synchronise: the arenas held everything?
+static int posture_check_capacity(tb_seg *h, const char *who)
+{
+    const std::string w(who);
+    TB_REQUIRE(h->h_o_totals[0] <= h->o_cap && h->h_o_totals[1] <= h->o_cap, TB_ERR_CAPACITY, w + ": the outline point arenas are too small for this batch");
+    TB_REQUIRE(!(h->h_o_totals[2] & 1u), TB_ERR_CAPACITY, w + ": the work arena for long outlines is too small for this batch (TB_POSTURE_ARENA_MB)");
+    return TB_OK;
+}
+
 extern "C" int tb_seg_outlines(tb_seg *h, float outline_resample)
 {
     TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_outlines: null handle");
     TB_REQUIRE(!h->pending && h->last_n > 0, TB_ERR_STATE, "tb_seg_outlines: call tb_seg_wait on a submitted batch first");
     TB_REQUIRE(outline_resample < 255.f, TB_ERR_INVALID, "tb_seg_outlines: outline_resample must be < 255 (T/core/default_config.cpp:898)");
     TB_CUDA(cudaSetDevice(h->cfg.device));
-    const SegDev &d = h->d;
-    if (!h->o_recs) {
-        h->o_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, (uint64_t)h->cfg.max_batch << 15), 1u << 26);
-        int r = seg_dev(h, &h->o_visited, (size_t)d.px_cap / d.opx + 16);
-        if (r == TB_OK) r = seg_dev(h, &h->o_rowfirst, d.lines_cap);
-        if (r == TB_OK) r = seg_dev(h, &h->o_sel, d.blobs_cap);
-        if (r == TB_OK) r = seg_dev(h, &h->o_recs, d.blobs_cap);
-        if (r == TB_OK) r = seg_dev(h, &h->o_totals, 2);
-        if (r == TB_OK) r = seg_dev(h, &h->o_raw, (size_t)h->o_cap * 2);
-        if (r == TB_OK) r = seg_dev(h, &h->o_res, (size_t)h->o_cap * 2);
-        if (r == TB_OK) r = host_alloc(&h->h_o_recs, d.blobs_cap);
-        if (r == TB_OK) r = host_alloc(&h->h_o_raw, (size_t)h->o_cap * 2);
-        if (r == TB_OK) r = host_alloc(&h->h_o_res, (size_t)h->o_cap * 2);
-        if (r == TB_OK) r = host_alloc(&h->h_o_totals, 2);
-        if (r != TB_OK) return r;
-    }
+    int r = posture_alloc(h, 0);
+    if (r != TB_OK) return r;
     cudaStream_t s = h->last_stream ? h->last_stream : h->stream;
     const uint32_t nb = h->h_totals[0];
-    h->o_n = 0;
-    int r = launch_outlines(d.recs, nb, d.lines, d.line_px, d.opx, h->o_visited, (size_t)d.px_cap / d.opx + 16, outline_resample,
-                            h->o_rowfirst, h->o_sel, h->o_recs, h->o_totals, h->o_raw, h->o_res, h->o_cap, s);
-    if (r != TB_OK) return r;
-    h->launches += nb ? 3 : 0;
-    TB_CUDA(cudaMemcpyAsync(h->h_o_totals, h->o_totals, 8, cudaMemcpyDeviceToHost, s));
+    h->o_n = 0; h->m_n = 0;
+    if ((r = posture_enqueue_outlines(h, outline_resample, s)) != TB_OK) return r;
+    TB_CUDA(cudaMemcpyAsync(h->h_o_totals, h->o_totals, 16, cudaMemcpyDeviceToHost, s));
     if (nb) TB_CUDA(cudaMemcpyAsync(h->h_o_recs, h->o_recs, sizeof(tb_outline_rec) * (size_t)nb, cudaMemcpyDeviceToHost, s));
     TB_CUDA(cudaStreamSynchronize(s));
-    TB_REQUIRE(h->h_o_totals[0] <= h->o_cap && h->h_o_totals[1] <= h->o_cap, TB_ERR_CAPACITY, "tb_seg_outlines: the outline point arenas are too small for this batch");
+    if ((r = posture_check_capacity(h, "tb_seg_outlines")) != TB_OK) return r;
     if (h->h_o_totals[0]) TB_CUDA(cudaMemcpyAsync(h->h_o_raw, h->o_raw, sizeof(float) * 2 * (size_t)h->h_o_totals[0], cudaMemcpyDeviceToHost, s));
     if (h->h_o_totals[1]) TB_CUDA(cudaMemcpyAsync(h->h_o_res, h->o_res, sizeof(float) * 2 * (size_t)h->h_o_totals[1], cudaMemcpyDeviceToHost, s));
     TB_CUDA(cudaStreamSynchronize(s));
@@ -2128,39 +2211,28 @@ extern "C" void tb_posture_default_params(tb_posture_params *p)
     p->outline_smooth_samples = 4; p->outline_smooth_step = 1; p->outline_approximate = 3;
     p->outline_curvature_range_ratio = 0.03f; p->midline_walk_offset = 0.025f;
     p->peak_mode = 0; p->midline_start_with_head = 0; p->midline_invert = 0;
+    p->midline_resolution = 25; p->midline_stiff_percentage = 0.15f;
+}
+
+extern "C" void tb_posture_default_request(tb_posture_request *r)
+{
+    std::memset(r, 0, sizeof(*r));
+    tb_posture_default_params(&r->params);
+    r->outline_resample = 1.f; r->normalize = 1; r->fetch = 1; r->individual_image_scale = 1.f;
 }
 
 extern "C" int tb_seg_midlines(tb_seg *h, const tb_posture_params *p)
 {
     TB_REQUIRE(h && p, TB_ERR_INVALID, "tb_seg_midlines: null argument");
-    TB_REQUIRE(h->h_o_recs && !h->pending, TB_ERR_STATE, "tb_seg_midlines: call tb_seg_outlines on the batch first");
-    TB_REQUIRE(p->peak_mode == 0, TB_ERR_INVALID, "tb_seg_midlines: peak_mode broad is not built (pointy is the reference's default)");
-    TB_REQUIRE(p->outline_approximate >= 0 && p->outline_approximate <= 8, TB_ERR_INVALID, "tb_seg_midlines: outline_approximate must be 0..8");
-    TB_REQUIRE(p->outline_smooth_samples >= 0 && p->outline_smooth_samples <= 255 && p->outline_smooth_step >= 1 && p->outline_smooth_step <= 255,
-               TB_ERR_INVALID, "tb_seg_midlines: outline_smooth_samples 0..255, outline_smooth_step 1..255 (uint8 settings)");
+    TB_REQUIRE(h->h_o_recs && !h->pending && h->o_n == h->h_totals[0], TB_ERR_STATE, "tb_seg_midlines: call tb_seg_outlines on the batch first");
+    int r = posture_check_params(p, "tb_seg_midlines");
+    if (r != TB_OK) return r;
     TB_CUDA(cudaSetDevice(h->cfg.device));
-    const SegDev &d = h->d;
-    if (!h->m_recs) {
-        int r = seg_dev(h, &h->m_pts, (size_t)h->o_cap * 2);
-        if (r == TB_OK) r = seg_dev(h, &h->m_segs, (size_t)h->o_cap * 4);
-        if (r == TB_OK) r = seg_dev(h, &h->m_recs, d.blobs_cap);
-        if (r == TB_OK) r = host_alloc(&h->h_m_pts, (size_t)h->o_cap * 2);
-        if (r == TB_OK) r = host_alloc(&h->h_m_segs, (size_t)h->o_cap * 4);
-        if (r == TB_OK) r = host_alloc(&h->h_m_recs, d.blobs_cap);
-        if (r != TB_OK) return r;
-    }
     const uint32_t nb = h->o_n, total = h->h_o_totals[1];
     h->m_n = 0;
-    const size_t need = 32 * ((size_t)total + 2 * (size_t)nb + 2);
-    if (need > h->m_scratch_floats) {            // work arrays of the walks: 32 floats per outline point, grown on demand
-        if (h->m_scratch) { cudaFree(h->m_scratch); h->m_scratch = nullptr; h->m_scratch_floats = 0; }
-        TB_CUDA(cudaMalloc((void **)&h->m_scratch, need * sizeof(float)));
-        h->m_scratch_floats = need;
-    }
     cudaStream_t s = h->last_stream ? h->last_stream : h->stream;
-    int r = launch_midlines(h->o_recs, nb, h->o_res, h->o_cap, p, h->m_pts, h->m_segs, h->m_recs, h->m_scratch, s);
-    if (r != TB_OK) return r;
-    h->launches += nb ? 1 : 0;
+    if ((r = posture_enqueue_midlines(h, p, 0, nullptr, nullptr, s)) != TB_OK) return r;
+    TB_CUDA(cudaMemcpyAsync(h->h_o_totals + 2, h->p_status, 4, cudaMemcpyDeviceToHost, s));
     if (nb) {
         TB_CUDA(cudaMemcpyAsync(h->h_m_recs, h->m_recs, sizeof(tb_midline_rec) * (size_t)nb, cudaMemcpyDeviceToHost, s));
         if (total) {
@@ -2169,6 +2241,7 @@ extern "C" int tb_seg_midlines(tb_seg *h, const tb_posture_params *p)
         }
     }
     TB_CUDA(cudaStreamSynchronize(s));
+    if ((r = posture_check_capacity(h, "tb_seg_midlines")) != TB_OK) return r;
     h->m_n = nb;
     return TB_OK;
 }
@@ -2178,6 +2251,119 @@ extern "C" int tb_seg_midline_result(tb_seg *h, const tb_midline_rec **recs, con
     TB_REQUIRE(h && recs && points && segments && n_blobs, TB_ERR_INVALID, "tb_seg_midline_result: null argument");
     TB_REQUIRE(h->h_m_recs, TB_ERR_STATE, "tb_seg_midline_result: call tb_seg_midlines first");
     *recs = h->h_m_recs; *points = h->h_m_pts; *segments = h->h_m_segs; *n_blobs = h->m_n;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_posture(tb_seg *h, const tb_posture_request *q)
+{
+    TB_REQUIRE(h && q, TB_ERR_INVALID, "tb_seg_posture: null argument");
+    TB_REQUIRE(h->last_n > 0, TB_ERR_STATE, "tb_seg_posture: submit a batch first");
+    TB_REQUIRE(q->outline_resample < 255.f, TB_ERR_INVALID, "tb_seg_posture: outline_resample must be < 255 (T/core/default_config.cpp:898)");
+    TB_REQUIRE(q->fetch >= 0 && q->fetch <= 2, TB_ERR_INVALID, "tb_seg_posture: fetch must be 0..2");
+    int r = posture_check_params(&q->params, "tb_seg_posture");
+    if (r != TB_OK) return r;
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    if ((r = posture_alloc(h, q->normalize ? q->params.midline_resolution : 0)) != TB_OK) return r;
+    cudaStream_t s = h->last_stream ? h->last_stream : h->stream;
+    const SegDev &d = h->d;
+    h->o_n = 0; h->m_n = 0; h->p_n = 0;
+    const int slot = h->p_prof.begin(s);
+    h->p_prof.mark(slot, 0);
+    if ((r = posture_enqueue_outlines(h, q->outline_resample, s)) != TB_OK) return r;
+    h->p_prof.mark(slot, 1);
+    if ((r = posture_enqueue_midlines(h, &q->params, q->normalize ? 1 : 0, q->move_direction_dev, q->fix_length_dev, s)) != TB_OK) return r;
+    h->p_prof.mark(slot, 2);
+    h->p_has_crops = false;
+    if (q->normalize && d.crop_norm >= 2 && d.max_crops) {
+        const float scale = q->individual_image_scale > 0.f ? q->individual_image_scale : 1.f;
+        r = launch_posture_crops(d.recs, d.totals, d.crop_blob, d.lines, d.line_px, d.pixels, h->d_bg, d.W, d.crop_method, d.crop_w, d.crop_h,
+                                 h->m_nrecs, q->median_midline_length_dev, q->median_midline_length_px, scale, d.crop_norm == 3,
+                                 d.crops, h->d_coef, h->crop_valid, h->last_n * (int)d.max_crops, s);
+        if (r != TB_OK) return r;
+        h->launches += 2;
+        h->p_has_crops = true;
+    }
+    h->p_prof.mark(slot, 3);
+    TB_CUDA(cudaMemcpyAsync(h->h_o_totals, h->o_totals, 16, cudaMemcpyDeviceToHost, s));
+    h->p_pending = true; h->p_fetch = q->fetch; h->p_has_norm = q->normalize != 0; h->p_stream = s;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_posture_wait(tb_seg *h)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_posture_wait: null handle");
+    TB_REQUIRE(h->p_pending || h->p_n > 0, TB_ERR_STATE, "tb_seg_posture_wait: call tb_seg_posture first");
+    if (!h->p_pending) return TB_OK;
+    int r = tb_seg_wait(h);                            // the blob count, and the batch's own payload as it was asked for
+    if (r != TB_OK && r != TB_ERR_CAPACITY) return r;
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->p_stream;
+    TB_CUDA(cudaStreamSynchronize(s));
+    h->p_pending = false;
+    if ((r = posture_check_capacity(h, "tb_seg_posture_wait")) != TB_OK) return r;
+    const uint32_t nb = h->h_totals[0], nc = h->h_totals[3];
+    const SegDev &d = h->d;
+    if (nb && h->p_fetch >= 1) {
+        TB_CUDA(cudaMemcpyAsync(h->h_m_recs, h->m_recs, sizeof(tb_midline_rec) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        if (h->p_has_norm) {
+            TB_CUDA(cudaMemcpyAsync(h->h_m_nrecs, h->m_nrecs, sizeof(tb_midline_norm) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+            TB_CUDA(cudaMemcpyAsync(h->h_m_norm, h->m_norm, sizeof(float) * 4 * (size_t)nb * h->m_res, cudaMemcpyDeviceToHost, s));
+        }
+        if (h->p_has_crops && nc) {
+            TB_CUDA(cudaMemcpyAsync(h->h_crop_valid, h->crop_valid, nc, cudaMemcpyDeviceToHost, s));
+            if (h->last_fetch >= 2)                    // the crops tb_seg_wait fetched were the un-normalised ones
+                TB_CUDA(cudaMemcpyAsync(h->h_crops, d.crops, (size_t)nc * d.crop_w * d.crop_h * d.cpx, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    if (nb && h->p_fetch >= 2) {
+        TB_CUDA(cudaMemcpyAsync(h->h_o_recs, h->o_recs, sizeof(tb_outline_rec) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        if (h->h_o_totals[0]) TB_CUDA(cudaMemcpyAsync(h->h_o_raw, h->o_raw, sizeof(float) * 2 * (size_t)h->h_o_totals[0], cudaMemcpyDeviceToHost, s));
+        if (h->h_o_totals[1]) {
+            TB_CUDA(cudaMemcpyAsync(h->h_m_pts, h->m_pts, sizeof(float) * 2 * (size_t)h->h_o_totals[1], cudaMemcpyDeviceToHost, s));
+            TB_CUDA(cudaMemcpyAsync(h->h_m_segs, h->m_segs, sizeof(float) * 4 * (size_t)h->h_o_totals[1], cudaMemcpyDeviceToHost, s));
+        }
+    }
+    TB_CUDA(cudaStreamSynchronize(s));
+    h->p_n = nb;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_posture_result(tb_seg *h, tb_posture_view *out)
+{
+    TB_REQUIRE(h && out, TB_ERR_INVALID, "tb_seg_posture_result: null argument");
+    TB_REQUIRE(!h->p_pending && h->h_m_recs, TB_ERR_STATE, "tb_seg_posture_result: call tb_seg_posture and tb_seg_posture_wait first");
+    std::memset(out, 0, sizeof(*out));
+    out->n_blobs = h->p_n; out->midline_resolution = (uint32_t)h->m_res;
+    if (h->p_fetch >= 1) {
+        out->midlines = h->h_m_recs;
+        if (h->p_has_norm) { out->normalized = h->h_m_nrecs; out->norm_points = h->h_m_norm; }
+        if (h->p_has_crops) out->crop_valid = h->h_crop_valid;
+    }
+    if (h->p_fetch >= 2) { out->outlines = h->h_o_recs; out->raw_points = h->h_o_raw; out->points = h->h_m_pts; out->segments = h->h_m_segs; }
+    return TB_OK;
+}
+
+extern "C" int tb_seg_posture_device(tb_seg *h, void **outline_recs, void **midline_recs, void **normalized, void **norm_points,
+                                     void **points, void **segments)
+{
+    TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_posture_device: null handle");
+    TB_REQUIRE(h->o_recs, TB_ERR_STATE, "tb_seg_posture_device: call tb_seg_posture first");
+    if (outline_recs) *outline_recs = h->o_recs;
+    if (midline_recs) *midline_recs = h->m_recs;
+    if (normalized) *normalized = h->m_nrecs;
+    if (norm_points) *norm_points = h->m_norm;
+    if (points) *points = h->m_pts;
+    if (segments) *segments = h->m_segs;
+    return TB_OK;
+}
+
+extern "C" int tb_seg_posture_ms(tb_seg *h, double out_ms[3], uint64_t *n_calls)
+{
+    TB_REQUIRE(h && out_ms && n_calls, TB_ERR_INVALID, "tb_seg_posture_ms: null argument");
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->p_prof.flush() != TB_OK) { set_error("tb_seg_posture_ms: event query failed"); return TB_ERR_CUDA; }
+    for (int k = 0; k < 3; ++k) { out_ms[k] = h->p_prof.acc[k]; h->p_prof.acc[k] = 0; }
+    *n_calls = h->p_prof.n; h->p_prof.n = 0;
     return TB_OK;
 }
 
@@ -2221,7 +2407,7 @@ extern "C" int tb_seg_profile(tb_seg *h, int enable)
 {
     TB_REQUIRE(h, TB_ERR_INVALID, "tb_seg_profile: null handle");
     TB_CUDA(cudaSetDevice(h->cfg.device));
-    if (h->prof.enable(enable != 0) != TB_OK) { set_error("tb_seg_profile: cudaEventCreate failed"); return TB_ERR_CUDA; }
+    if (h->prof.enable(enable != 0) != TB_OK || h->p_prof.enable(enable != 0) != TB_OK) { set_error("tb_seg_profile: cudaEventCreate failed"); return TB_ERR_CUDA; }
     return TB_OK;
 }
 
