@@ -211,6 +211,15 @@ TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_
  * tb_seg_device_results on trk return the tracker-side blobs (and their crops: what the reference feeds the CNN). */
 TB_API int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch);
 
+/* pv::Blob::recount(threshold, background) (C/processing/PVBlob.cpp:934-1027) through Background::count_above_threshold
+ * (C/processing/Background.h:430-489) for every blob of the handle's last batch (after tb_seg_wait): the number of the blob's pixels
+ * whose difference to the background -- the handle's method: enable_difference = 0 none, else absolute / sign -- is >= threshold,
+ * times SQR(cm_per_pixel); threshold 0 = num_pixels (:942-949).  What PrefilterBlobs compares with track_size_filter
+ * (T/tracking/PrefilterBlobs.cpp:227).  out: n >= n_blobs floats on the host, blob order of the batch.  (pv::Blob::threshold, :1040-1116, is
+ * only called by another detector, T/python/PrecomuptedDetection.cpp:729, and is not built; the tracker's own re-threshold is
+ * tb_seg_rethreshold.) */
+TB_API int tb_seg_recount(tb_seg *h, int threshold, float *out, uint32_t n);
+
 /* Outlines ("next" row N4, first stage): pixel::find_outer_points (C/processing/PixelTree.cpp:497-651) for every blob of the
  * handle's last batch (after tb_seg_wait with fetch >= 1), the outline calculate_posture selects (the first of maximal
  * size, T/tracking/Posture.cpp:341-348), and Outline::resample(outline_resample) of it (T/tracking/Outline.cpp:724-766;
@@ -290,6 +299,17 @@ TB_API void tb_posture_default_request(tb_posture_request *r);
 TB_API int tb_seg_posture(tb_seg *h, const tb_posture_request *r);
 TB_API int tb_seg_posture_wait(tb_seg *h);
 TB_API int tb_seg_posture_result(tb_seg *h, tb_posture_view *out);
+/* posture::calculate_posture (T/tracking/Posture.cpp:305-400) for every blob of src's last batch (the tracker-side blobs): starting at
+ * track_posture_threshold the blob is re-thresholded (pixel::threshold_get_biggest_blob, C/processing/PixelTree.cpp:297-340: the
+ * sub-blob with the most pixels, the first among equals in canonical order), the longest outline of that sub-blob is taken in the
+ * frame of the ORIGINAL blob's bounds (:337), resampled, and calculate_midline is tried; blobs without a midline go another round
+ * with the threshold raised by 2 until the sub-blob keeps fewer than max(1, pixels / 10) pixels or the threshold reaches the
+ * start + 100; a blob that never yields a midline keeps its first resampled outline (:381-397).  pst is a second handle of src's
+ * geometry configured like the tracker side of tb_seg_rethreshold (its detect_threshold is driven by this call and restored); the
+ * results live in pst but are indexed by SRC's blobs: tb_seg_posture_wait / _result / _device on pst.  With crop_normalize 2 / 3 on
+ * src, src's crops are re-rendered from these midlines.  One stream synchronisation per round; returns the number of rounds (>= 1)
+ * or a negative tb_status. */
+TB_API int tb_seg_posture_thresholded(tb_seg *src, tb_seg *pst, const tb_posture_request *r, int track_posture_threshold);
 /* Device pointers of the last tb_seg_posture call (valid until the next one): records per blob of the batch. */
 TB_API int tb_seg_posture_device(tb_seg *h, void **outline_recs, void **midline_recs, void **normalized, void **norm_points,
                                  void **points, void **segments);

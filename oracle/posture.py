@@ -120,17 +120,25 @@ def offset_to_middle(points, params: PostureParams | None = None):
     return pts, int(t.value), int(h.value), curv
 
 
+class MidlineError(ValueError):
+    """std::unexpected of Outline::calculate_midline; .points = the outline as the failed call left it (smoothed, approximated, rotated: the
+    reference works on the Outline in place, Outline.cpp:768-777)."""
+    def __init__(self, msg, points):
+        super().__init__(msg)
+        self.points = points
+
+
 def calculate_midline(points, params: PostureParams | None = None):
     """Returns (segments (n,4): pos.x, pos.y, height, l_length; tail index; head index; the outline as the walk saw it),
-    or raises ValueError like the reference returns std::unexpected."""
+    or raises MidlineError (a ValueError) like the reference returns std::unexpected."""
     pts = np.ascontiguousarray(points, np.float32).copy()
     P = params or default_params()
     seg = np.zeros((len(pts) + 4, 4), np.float32)
     t, h = C.c_int64(), C.c_int64()
     n = _lib().to_calculate_midline(_p(pts), len(pts), C.byref(P), _p(seg), len(seg), C.byref(t), C.byref(h))
     if n < 0:
-        raise ValueError({-1: "Empty outline was given, cannot calculate midline.", -2: "Too few midline segments calculated.",
-                          -4: "capacity"}[int(n)])
+        raise MidlineError({-1: "Empty outline was given, cannot calculate midline.", -2: "Too few midline segments calculated.",
+                            -4: "capacity"}[int(n)], pts)
     return seg[:n].copy(), int(t.value), int(h.value), pts
 
 
@@ -165,9 +173,9 @@ def calculate_posture(lines, pixels, bg, track_posture_threshold=0, outline_resa
                 try:
                     segs, tail, head, walked = calculate_midline(pts, params)
                     return dict(outline=walked, segments=segs, tail=tail, head=head, threshold=threshold)
-                except ValueError:
-                    if first_outline is None and len(pts):
-                        first_outline = pts
+                except MidlineError as e:                       # the failed call has already smoothed / rotated the outline in place (:358-366 keeps THOSE points)
+                    if first_outline is None and len(e.points):
+                        first_outline = e.points
         threshold += 2
         if n_sub < minimum_pixels or threshold >= track_posture_threshold + 100:
             break

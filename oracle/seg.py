@@ -480,3 +480,26 @@ def outline_resample(points, distance=1.0):
     if n < 0:
         raise MemoryError
     return out[:n].copy()
+
+
+def blob_recount(lines, pixels, bg, threshold, method, cm_per_pixel=1.0, channels=1):
+    """pv::Blob::recount(threshold, background) (C/processing/PVBlob.cpp:934-1027) = raw_recount * SQR(cm_per_pixel), raw_recount the sum over
+    the blob's lines of Background::count_above_threshold (C/processing/Background.h:430-489): pixels with  none: v >= T | absolute:
+    |bg - v| >= T | sign: bg - v >= T  (int32), v = the pixel's grey value (rgb8 blobs: cmn::bgr2gray, Background.h:76-81) and bg the
+    background's grey image; threshold 0 returns num_pixels (:942-949).  The count is accumulated in a float, the product is float."""
+    lines = np.ascontiguousarray(lines); px = np.ascontiguousarray(pixels, np.uint8)
+    lens = lines["x1"].astype(np.int64) - lines["x0"] + 1
+    if threshold == 0:
+        return np.float32(np.float32(lens.sum()) * np.float32(np.float32(cm_per_pixel) * np.float32(cm_per_pixel)))
+    if channels == 3:
+        v = bgr2gray_tracker(px.reshape(-1, 3)).astype(np.int32).ravel()
+    else:
+        v = px.astype(np.int32)
+    rec, o = np.float32(0), 0
+    for l, n in zip(lines, lens):
+        n = int(n)
+        b = bg[int(l["y"]), int(l["x0"]):int(l["x0"]) + n].astype(np.int32)
+        vv = v[o:o + n]; o += n
+        d = vv if method == DIFF_NONE else (np.abs(b - vv) if method == DIFF_ABSOLUTE else b - vv)
+        rec = np.float32(rec + np.float32(int((d >= int(threshold)).sum())))
+    return np.float32(rec * np.float32(np.float32(cm_per_pixel) * np.float32(cm_per_pixel)))

@@ -301,3 +301,24 @@ def test_rgb8_size_filter_counts_payload_bytes():
     assert sorted(b.num_pixels for b in got[0]) == [4, 10] and sorted(b.num_pixels for b in got[1]) == [4, 33]
     gs = _mk(seg.bgr2gray(bg), 3, "gray", **kw)
     assert sorted(b.num_pixels for b in gs.apply(fr)[0]) == [10, 34]
+
+
+def test_recount_rgb8_blobs():
+    """rgb8 blobs are recounted through cmn::bgr2gray of each pixel against the background's grey image (diffable_pixel_value<rgb8 -> gray>)."""
+    import trex_b200
+    from oracle import seg as oseg
+    rng = np.random.default_rng(12)
+    H, W = 96, 160
+    bg3 = rng.integers(120, 200, (H, W, 3)).astype(np.uint8)
+    fr = bg3.copy()
+    fr[20:50, 30:90] = rng.integers(0, 110, (30, 60, 3)).astype(np.uint8)
+    fr[60:80, 100:140] = rng.integers(0, 255, (20, 40, 3)).astype(np.uint8)
+    s = trex_b200.DetectSettings(meta_encoding="rgb8", detect_size_filter=[])
+    bs = trex_b200.BackgroundSubtraction(bg3, settings=s, max_batch=1, channels=3)
+    got = bs.apply([fr])[0]
+    assert len(got) >= 2
+    bg_gray = oseg.bgr2gray(bg3)
+    for T in (10, 50):
+        rc = bs.recount(T)
+        exp = np.array([oseg.blob_recount(b.lines, b.pixels, bg_gray, T, oseg.DIFF_ABSOLUTE, channels=3) for b in got], np.float32)
+        assert np.array_equal(rc, exp), T

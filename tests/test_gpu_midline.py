@@ -257,3 +257,56 @@ def test_posture_normalised_crops(mode):
     net.load_weights(random_v118_3_state_dict(16, seed=0))
     probs = net.probabilities(crops[..., None])
     assert probs.shape == (n, 16) and np.allclose(probs.sum(1), 1, atol=1e-4)
+
+
+def test_posture_of_thresholded_blobs_with_retries():
+    """posture::calculate_posture (Posture.cpp:305-400) through tb_seg_posture_thresholded: graded blobs whose thresholded sub-blobs
+    shrink round by round (several sub-blobs per parent, ties, parents that end without a midline) against the oracle's loop, blob by
+    blob: the outline the midline saw, the segments, tail / head; the number of rounds equals the longest retry chain."""
+    import trex_b200
+    from oracle import posture, seg as oseg
+    rng = np.random.default_rng(4)
+    H, W = 160, 256
+    bg = np.full((H, W), 200, np.uint8)
+    fr = bg.copy()
+    yy, xx = np.mgrid[0:H, 0:W]
+    for k in range(14):                                   # elongated blobs with a darkness gradient, two of them with two dark cores
+        cx, cy, a, b, th = rng.uniform(30, W - 30), rng.uniform(20, H - 20), rng.uniform(6, 22), rng.uniform(2, 6), rng.uniform(0, np.pi)
+        u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th); v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+        r2 = (u / a) ** 2 + (v / b) ** 2
+        m = r2 < 1
+        depth = rng.uniform(20, 120)
+        core = np.where(k % 5 == 0, np.minimum(((u - a / 2) / (a / 3)) ** 2 + (v / b) ** 2, ((u + a / 2) / (a / 3)) ** 2 + (v / b) ** 2), r2)
+        fr[m] = np.clip(200 - depth * (1 - 0.9 * np.sqrt(core[m]).clip(0, 1)) - rng.integers(0, 4, int(m.sum())), 0, 199).astype(np.uint8)
+    fr[5, 5:8] = 150; fr[150, 200] = 120                  # tiny blobs: no midline at any threshold
+    frames = np.stack([fr, np.roll(fr, 7, axis=1)])
+    det = trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(detect_threshold=10, detect_size_filter=[]), max_batch=2)
+    pst = trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(detect_threshold=0, detect_size_filter=[]), max_batch=2)
+    got = det.apply(frames)
+    T0 = 12
+    rounds, res = det.posture_thresholded(pst, track_posture_threshold=T0, outline_resample=1.0, fetch=2)
+    flat = [b for blobs in got for b in blobs]
+    assert res["n_blobs"] == len(flat) > 20
+    exp_rounds, n_mid, n_outline_only, n_none = 1, 0, 0, 0
+    for k, b in enumerate(flat):
+        so, ns, tail, head = (int(v) for v in res["midlines"][k])
+        ro, rn = int(res["outlines"][k][2]), int(res["outlines"][k][3])
+        try:
+            ref = posture.calculate_posture(b.lines, b.pixels, bg, track_posture_threshold=T0, outline_resample=1.0, method=oseg.DIFF_ABSOLUTE)
+        except ValueError:
+            assert ns == 0 and rn == 0, k
+            n_none += 1
+            continue
+        if ref["segments"] is None:
+            assert ns == 0 and np.array_equal(res["points"][ro:ro + rn], ref["outline"]), k
+            n_outline_only += 1
+        else:
+            assert (tail, head) == (ref["tail"], ref["head"]), k
+            assert np.array_equal(res["points"][ro:ro + rn], ref["outline"]) and np.array_equal(res["segments"][so:so + ns], ref["segments"]), k
+            exp_rounds = max(exp_rounds, (ref["threshold"] - T0) // 2 + 1)
+            nm = posture.normalize(posture.post_process(ref["segments"], tail=ref["tail"], head=ref["head"])[0])
+            nr = res["normalized"][k]
+            assert (nm is None and nr["n_points"] == 0) or (nm is not None and np.abs(res["norm_points"][k] - nm[0]).max() < 1e-4), k
+            n_mid += 1
+    print(f"rounds {rounds}, midlines {n_mid}, outline only {n_outline_only}, nothing {n_none}")
+    assert n_mid > 15 and n_outline_only + n_none >= 2 and rounds >= exp_rounds and rounds > 1

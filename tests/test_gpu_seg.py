@@ -477,3 +477,26 @@ def test_moments_normalised_crops(method):
             assert np.array_equal(crops[n], exp), (f, k, int(np.abs(crops[n].astype(int) - exp).max()))
             n += 1
     assert n == len(crops) and n > 60
+
+
+@pytest.mark.parametrize("diff,absolute", [(True, True), (True, False), (False, True)])
+def test_recount_against_oracle(diff, absolute):
+    """tb_seg_recount = pv::Blob::recount(threshold, background) (PVBlob.cpp:934-1027, Background.h:430-489) for every blob of a batch:
+    the three difference methods, several thresholds incl. 0 (= num_pixels), cm_per_pixel != 1."""
+    import trex_b200
+    from oracle import seg as oseg
+    from trex_b200.synthetic import BlobWorld
+    world = BlobWorld(h=272, w=480, n_blobs=20, seed=9, margin=30)
+    frames = world.frames(2)
+    s = trex_b200.DetectSettings(enable_difference=diff, detect_threshold_is_absolute=absolute, cm_per_pixel=0.25,
+                                 detect_threshold=15 if diff else 40, detect_size_filter=[])
+    bs = trex_b200.BackgroundSubtraction(world.bg, settings=s, max_batch=2)
+    got = bs.apply(frames)
+    flat = [b for blobs in got for b in blobs]
+    assert len(flat) > (10 if diff else 1)              # without the difference the bright background is one frame-wide blob
+    method = oseg.DIFF_NONE if not diff else (oseg.DIFF_ABSOLUTE if absolute else oseg.DIFF_SIGN)
+    for T in (0, 20, 60, 200):
+        rc = bs.recount(T)
+        exp = np.array([oseg.blob_recount(b.lines, b.pixels, world.bg, T, method, cm_per_pixel=0.25) for b in flat], np.float32)
+        assert np.array_equal(rc, exp), T
+    assert np.array_equal(bs.recount(0), np.array([b.num_pixels for b in flat], np.float32) * np.float32(0.0625))

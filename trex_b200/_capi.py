@@ -89,7 +89,7 @@ SYMBOLS = [
     "tb_vi_commit", "tb_vi_predict", "tb_vi_predict_device", "tb_vi_wait", "tb_vi_launch_count",
     "tb_seg_profile", "tb_seg_kernel_ms", "tb_vi_profile", "tb_vi_kernel_ms", "tb_seg_set_stream",
     "tb_seg_rethreshold", "tb_seg_outlines", "tb_seg_outline_result", "tb_posture_default_params", "tb_seg_midlines", "tb_seg_midline_result",
-    "tb_posture_default_request", "tb_seg_posture", "tb_seg_posture_wait", "tb_seg_posture_result", "tb_seg_posture_device", "tb_seg_posture_ms",
+    "tb_posture_default_request", "tb_seg_posture", "tb_seg_posture_wait", "tb_seg_posture_result", "tb_seg_posture_device", "tb_seg_posture_ms", "tb_seg_posture_thresholded", "tb_seg_recount",
     "tb_vi_set_top1", "tb_avg_create", "tb_avg_destroy", "tb_avg_add", "tb_avg_add_device", "tb_avg_finalize",
     "tb_seg_metadata", "tb_host_alloc", "tb_host_free", "tb_host_register", "tb_host_unregister", "tb_backend",
 ]
@@ -143,6 +143,8 @@ def lib() -> C.CDLL:
     L.tb_seg_midline_result.argtypes = [vp, vpp, vpp, vpp, C.POINTER(C.c_uint32)]
     L.tb_posture_default_request.argtypes = [C.POINTER(PostureRequest)]; L.tb_posture_default_request.restype = None
     L.tb_seg_posture.argtypes = [vp, C.POINTER(PostureRequest)]
+    L.tb_seg_posture_thresholded.argtypes = [vp, vp, C.POINTER(PostureRequest), C.c_int]
+    L.tb_seg_recount.argtypes = [vp, C.c_int, vp, C.c_uint32]
     L.tb_seg_posture_wait.argtypes = [vp]
     L.tb_seg_posture_result.argtypes = [vp, C.POINTER(PostureView)]
     L.tb_seg_posture_device.argtypes = [vp, vpp, vpp, vpp, vpp, vpp, vpp]

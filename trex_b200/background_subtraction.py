@@ -210,6 +210,14 @@ class BackgroundSubtraction:
             return [tracker.result(i) for i in range(self._last_n)]
         return None
 
+    def recount(self, threshold: int) -> np.ndarray:
+        """pv::Blob::recount(threshold, background) for every blob of the last batch (PVBlob.cpp:934-1027): pixels whose difference
+        (this handle's method) is >= threshold, times SQR(cm_per_pixel); float32 per blob in batch order."""
+        n = self.totals()[0]
+        out = np.zeros(max(n, 1), np.float32)
+        check(lib().tb_seg_recount(self._h, int(threshold), out.ctypes.data_as(C.c_void_p), len(out)))
+        return out[:n]
+
     def outlines(self, outline_resample=1.0):
         """pixel::find_outer_points + the outline calculate_posture selects + Outline::resample for every blob of the last
         batch (PixelTree.cpp:497-651, Posture.cpp:341-348, Outline.cpp:724-766).  Returns (raw, resampled): two lists with
@@ -270,10 +278,33 @@ class BackgroundSubtraction:
         q.median_midline_length_dev = median_midline_length_dev or None
         check(lib().tb_seg_posture(self._h, C.byref(q)))
 
+    def _posture_request(self, outline_resample, normalize, fetch, median_midline_length_px, individual_image_scale, posture_settings):
+        from ._capi import PostureRequest
+        q = PostureRequest()
+        lib().tb_posture_default_request(C.byref(q))
+        for k, v in posture_settings.items():
+            setattr(q.params, k, v)
+        q.outline_resample = float(outline_resample); q.normalize = int(bool(normalize)); q.fetch = int(fetch)
+        q.median_midline_length_px = float(median_midline_length_px); q.individual_image_scale = float(individual_image_scale)
+        return q
+
+    def posture_thresholded(self, posture_handle: "BackgroundSubtraction", track_posture_threshold=0, outline_resample=1.0, normalize=True, fetch=2,
+                            median_midline_length_px=0.0, individual_image_scale=1.0, **posture_settings):
+        """posture::calculate_posture (Posture.cpp:305-400) for every blob of this handle's last batch: re-threshold at
+        track_posture_threshold (+2 per retry) on `posture_handle` (configured like rethreshold()'s tracker handle), biggest sub-blob,
+        outline in this blob's frame, midline.  Returns (rounds, posture_handle.posture_result())."""
+        q = self._posture_request(outline_resample, normalize, fetch, median_midline_length_px, individual_image_scale, posture_settings)
+        rounds = lib().tb_seg_posture_thresholded(self._h, posture_handle._h, C.byref(q), int(track_posture_threshold))
+        if rounds < 0:
+            check(rounds)
+        check(lib().tb_seg_posture_wait(posture_handle._h))
+        res = posture_handle.posture_result(n_crops=self.totals()[3])
+        return rounds, res
+
     def posture_wait(self):
         check(lib().tb_seg_posture_wait(self._h))
 
-    def posture_result(self):
+    def posture_result(self, n_crops=None):
         """dict of numpy views of the last posture call (valid until the next one): midlines (n,4) int32 [seg_off, n_seg, tail, head],
         normalized (structured: len, angle, offx, offy, n_points, flags, tail, head), norm_points (n, resolution, 4), crop_valid,
         and with fetch=2 outlines (n,4) uint32, raw_points, points, segments arenas."""
@@ -290,7 +321,7 @@ class BackgroundSubtraction:
             out["normalized"] = np.ctypeslib.as_array(C.cast(v.normalized, C.POINTER(C.c_uint8)), (n * 32,)).view(NORM_DTYPE)
             out["norm_points"] = np.ctypeslib.as_array(C.cast(v.norm_points, C.POINTER(C.c_float)), (n, res, 4))
         if v.crop_valid:
-            out["crop_valid"] = np.ctypeslib.as_array(C.cast(v.crop_valid, C.POINTER(C.c_uint8)), (max(self.totals()[3], 1),))
+            out["crop_valid"] = np.ctypeslib.as_array(C.cast(v.crop_valid, C.POINTER(C.c_uint8)), (max(self.totals()[3] if n_crops is None else n_crops, 1),))
         if v.outlines:
             orecs = np.ctypeslib.as_array(C.cast(v.outlines, C.POINTER(C.c_uint32)), (n, 4))
             out["outlines"] = orecs

@@ -122,15 +122,32 @@ int launch_crop_warp(const tb_blob_rec *recs, const uint32_t *totals, const uint
 
 // outline.cu: longest outline (pixel::find_outer_points) of the batch's blobs + Outline::resample; 1 memset + 3 launches.
 // nb_dev: device word holding the number of blobs (nullptr: nb_max is the count); nb_max bounds the grids.
+// map (optional): record q takes its outline from blob index[q] (0xFFFFFFFF: none) with points relative to origin[q]'s bounds; records with
+// skip[q] != 0 are left alone; append: the point arenas continue behind totals[0..1] (posture of thresholded sub-blobs, round by round)
+struct OutlineMap { const uint32_t *index; const tb_blob_rec *origin; const uint8_t *skip; int append; };
 int launch_outlines(const tb_blob_rec *recs, const uint32_t *nb_dev, uint32_t nb_max, const tb_line *lines, const uint32_t *line_px, int opx,
                     uint8_t *visited, size_t visited_bytes, float rd, uint32_t *row_first, int4 *sel,
-                    tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, int sms, cudaStream_t s);
+                    tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, int sms, cudaStream_t s,
+                    const OutlineMap *map = nullptr);
 
 // posture.cu: Outline::calculate_midline (+ Midline::post_process / normalize with do_norm) for the batch's resampled outlines; 1 memset + 1 launch
 int launch_midlines(const tb_outline_rec *orecs, const uint32_t *nb_dev, uint32_t nb_max, const float *res, uint32_t cap_pts,
                     const tb_posture_params *P, int do_norm, const float *move_dir, const float *fix_len,
                     float *pts_out, float *segs, tb_midline_rec *mrecs, tb_midline_norm *nrecs, float *norm_pts,
-                    float *arena, unsigned long long arena_floats, unsigned long long *arena_used, uint32_t *status, int sms, cudaStream_t s);
+                    float *arena, unsigned long long arena_floats, unsigned long long *arena_used, uint32_t *status, int sms, cudaStream_t s,
+                    const uint8_t *skip = nullptr);
+
+// posture.cu: posture::calculate_posture's threshold loop, per round: parents of the re-thresholded sub-blobs + the biggest one per parent,
+// and the per-parent state update after the round's midlines
+struct PostureRound {
+    const tb_blob_rec *parent_recs; const tb_frame_info *parent_infos; const tb_line *parent_lines; const uint32_t *n_parents;   // the blobs whose posture is wanted
+    const tb_blob_rec *sub_recs; const tb_line *sub_lines; const uint32_t *n_subs;                                             // their sub-blobs at this round's threshold
+    unsigned long long *best; uint32_t *index; uint32_t *sub_npx; uint8_t *state; tb_outline_rec *first_outline;               // per parent
+    uint32_t *remaining;
+};
+int launch_posture_parents(const PostureRound &R, uint32_t max_parents, uint32_t max_subs, int sms, cudaStream_t s);
+int launch_posture_round_end(const PostureRound &R, uint32_t max_parents, tb_outline_rec *orecs, tb_midline_rec *mrecs, tb_midline_norm *nrecs,
+                             int do_norm, int last_round, int sms, cudaStream_t s);
 
 // posture.cu: `posture` / `legacy` crops from the normalised midlines (map per crop, then crop_norm.cu's warp); 2 launches
 int launch_posture_crops(const tb_blob_rec *recs, const uint32_t *totals, const uint32_t *crop_blob, const tb_line *lines,

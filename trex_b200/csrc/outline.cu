@@ -191,20 +191,22 @@ struct LoopPick {
 __global__ void __launch_bounds__(OL_NT)
 outline_select_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__restrict__ nb_dev, uint32_t nb_max, const tb_line *__restrict__ lines,
                       const uint32_t *__restrict__ line_px, int opx, uint8_t *__restrict__ visited, float rd,
-                      uint32_t *__restrict__ row_first, int4 *__restrict__ sel, tb_outline_rec *__restrict__ orecs)
+                      uint32_t *__restrict__ row_first, int4 *__restrict__ sel, tb_outline_rec *__restrict__ orecs, OutlineMap map)
 {
     __shared__ uint32_t s_pool[OL_POOL_WORDS];
     __shared__ uint32_t s_ws[33];
     const uint32_t nb = min(nb_dev ? *nb_dev : nb_max, nb_max);
     for (uint32_t base = blockIdx.x * OL_NT; base < nb; base += gridDim.x * OL_NT) {
     const uint32_t q = base + threadIdx.x;
-    const bool valid = q < nb;
+    const bool live = q < nb && !(map.skip && map.skip[q]);
+    const uint32_t qi = live ? (map.index ? map.index[q] : q) : 0xFFFFFFFFu;       // record q's outline comes from blob qi (posture of a sub-blob)
+    const bool valid = qi != 0xFFFFFFFFu;
     tb_blob_rec r{};
-    if (valid) r = recs[q];
+    if (valid) r = recs[qi];
     const tb_line *bl = lines + r.line_off;
     __syncthreads();                                         // the previous group is done with the pool
     Occupancy O = make_occupancy(valid, r, bl, s_pool, s_ws, row_first + r.line_off, true, true);
-    if (!valid) continue;
+    if (!valid) { if (live) orecs[q] = tb_outline_rec{0, 0, 0, 0}; continue; }
     O.gvis = visited; O.line_px = line_px + r.line_off; O.opx = opx;
     const uint32_t max_n = 4u * r.n_pixels + 4u;            // a loop cannot hold more sides than the blob has
     LoopPick pick; pick.bx = pick.by = pick.bb = 0;
@@ -241,18 +243,21 @@ outline_select_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__re
 }
 
 // arena offsets: exclusive prefix sums of n_raw / the n_res bounds over the blobs (one CTA); totals[0..1] = sums
-__global__ void outline_scan_kernel(tb_outline_rec *__restrict__ orecs, const uint32_t *__restrict__ nb_dev, uint32_t nb_max, uint32_t *__restrict__ totals)
+__global__ void outline_scan_kernel(tb_outline_rec *__restrict__ orecs, const uint32_t *__restrict__ nb_dev, uint32_t nb_max, uint32_t *__restrict__ totals,
+                                    const uint8_t *__restrict__ skip, int append)
 {
     __shared__ uint32_t ws[33];
     const uint32_t nb = min(nb_dev ? *nb_dev : nb_max, nb_max);
-    unsigned long long base_raw = 0, base_res = 0;
+    unsigned long long base_raw = append ? totals[0] : 0, base_res = append ? totals[1] : 0;      // append: behind the points of earlier rounds
+    __syncthreads();
     for (uint32_t i0 = 0; i0 < nb; i0 += blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
-        const uint32_t a = i < nb ? orecs[i].n_raw : 0u, b = i < nb ? orecs[i].n_res : 0u;
+        const bool live = i < nb && !(skip && skip[i]);
+        const uint32_t a = live ? orecs[i].n_raw : 0u, b = live ? orecs[i].n_res : 0u;
         uint32_t ta, tb_;
         const uint32_t ea = block_excl_scan(a, ws, ta);
         const uint32_t eb = block_excl_scan(b, ws, tb_);
-        if (i < nb) {
+        if (live) {
             orecs[i].raw_off = (uint32_t)min(base_raw + ea, 0xFFFFFFFFull); orecs[i].res_off = (uint32_t)min(base_res + eb, 0xFFFFFFFFull);
         }
         base_raw += ta; base_res += tb_;
@@ -264,22 +269,24 @@ __global__ void outline_scan_kernel(tb_outline_rec *__restrict__ orecs, const ui
 __global__ void __launch_bounds__(OL_NT)
 outline_emit_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__restrict__ nb_dev, uint32_t nb_max, const tb_line *__restrict__ lines,
                     uint32_t *__restrict__ row_first, const int4 *__restrict__ sel,
-                    tb_outline_rec *__restrict__ orecs, float rd, float *__restrict__ raw, float *__restrict__ res, uint32_t cap_pts)
+                    tb_outline_rec *__restrict__ orecs, float rd, float *__restrict__ raw, float *__restrict__ res, uint32_t cap_pts, OutlineMap map)
 {
     __shared__ uint32_t s_pool[OL_POOL_WORDS];
     __shared__ uint32_t s_ws[33];
     const uint32_t nb = min(nb_dev ? *nb_dev : nb_max, nb_max);
     for (uint32_t base = blockIdx.x * OL_NT; base < nb; base += gridDim.x * OL_NT) {
     const uint32_t q = base + threadIdx.x;
+    const bool live = q < nb && !(map.skip && map.skip[q]);
     tb_outline_rec o{};
-    if (q < nb) o = orecs[q];
-    const bool valid = q < nb && o.n_raw != 0 && (unsigned long long)o.raw_off + o.n_raw <= cap_pts && (unsigned long long)o.res_off + o.n_res <= cap_pts;
+    if (live) o = orecs[q];
+    const bool valid = live && o.n_raw != 0 && (unsigned long long)o.raw_off + o.n_raw <= cap_pts && (unsigned long long)o.res_off + o.n_res <= cap_pts;
     tb_blob_rec r{};
-    if (valid) r = recs[q];
+    if (valid) r = recs[map.index ? map.index[q] : q];
     __syncthreads();                                         // the previous group is done with the pool
     const Occupancy O = make_occupancy(valid, r, lines + r.line_off, s_pool, s_ws, row_first + r.line_off, false, false);
-    if (!valid) { if (q < nb && o.n_raw != 0) orecs[q].n_res = 0; continue; }       // arena overflow: no points (the totals report it)
-    const int bx0 = r.x0, by0 = r.y0;
+    if (!valid) { if (live && o.n_raw != 0) orecs[q].n_res = 0; continue; }       // arena overflow: no points (the totals report it)
+    // points are relative to the blob's own bounds, or -- posture of a sub-blob -- to its parent's (Posture.cpp:337)
+    const int bx0 = map.origin ? (int)map.origin[q].x0 : (int)r.x0, by0 = map.origin ? (int)map.origin[q].y0 : (int)r.y0;
     const int4 s4 = sel[q];
     Side cur{s4.x, s4.y, s4.z};
     float *rp = raw + 2 * (size_t)o.raw_off, *sp = res + 2 * (size_t)o.res_off;
@@ -300,15 +307,16 @@ outline_emit_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__rest
 
 int launch_outlines(const tb_blob_rec *recs, const uint32_t *nb_dev, uint32_t nb_max, const tb_line *lines, const uint32_t *line_px, int opx,
                     uint8_t *visited, size_t visited_bytes, float rd, uint32_t *row_first, int4 *sel,
-                    tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, int sms, cudaStream_t s)
+                    tb_outline_rec *orecs, uint32_t *totals, float *raw, float *res, uint32_t cap_pts, int sms, cudaStream_t s, const OutlineMap *map)
 {
-    if (nb_max == 0) { TB_CUDA(cudaMemsetAsync(totals, 0, 8, s)); return TB_OK; }
+    const OutlineMap m = map ? *map : OutlineMap{nullptr, nullptr, nullptr, 0};
+    if (nb_max == 0) { if (!m.append) TB_CUDA(cudaMemsetAsync(totals, 0, 8, s)); return TB_OK; }
     TB_CUDA(cudaMemsetAsync(visited, 0, visited_bytes, s));
     // persistent over groups of OL_NT blobs: 4 CTAs of 47 KB fit an SM
     const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + OL_NT - 1) / OL_NT, (uint64_t)std::max(1, sms) * 4);
-    outline_select_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, line_px, opx, visited, rd, row_first, sel, orecs);
-    outline_scan_kernel<<<1, 1024, 0, s>>>(orecs, nb_dev, nb_max, totals);
-    outline_emit_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, row_first, sel, orecs, rd, raw, res, cap_pts);
+    outline_select_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, line_px, opx, visited, rd, row_first, sel, orecs, m);
+    outline_scan_kernel<<<1, 1024, 0, s>>>(orecs, nb_dev, nb_max, totals, m.skip, m.append);
+    outline_emit_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, row_first, sel, orecs, rd, raw, res, cap_pts, m);
     TB_CUDA(cudaGetLastError());
     return TB_OK;
 }

@@ -30,6 +30,8 @@
 
 #include <math.h>
 
+#include <algorithm>
+
 namespace tb {
 
 constexpr int ML_WARPS = 8;                      // blobs per CTA pass
@@ -404,7 +406,7 @@ midline_warp_kernel(const tb_outline_rec *__restrict__ orecs, const uint32_t *__
                     float *__restrict__ pts_out, float4 *__restrict__ segs, tb_midline_rec *__restrict__ mrecs,
                     tb_midline_norm *__restrict__ nrecs, float4 *__restrict__ norm_pts,
                     float *__restrict__ arena, unsigned long long arena_floats, unsigned long long *__restrict__ arena_used,
-                    uint32_t *__restrict__ status)
+                    uint32_t *__restrict__ status, const uint8_t *__restrict__ skip)
 {
     extern __shared__ __align__(16) float s_pool[];
     __shared__ uint32_t s_need[ML_WARPS];
@@ -415,7 +417,8 @@ midline_warp_kernel(const tb_outline_rec *__restrict__ orecs, const uint32_t *__
         const uint32_t q = base + warp;
         tb_outline_rec o{};
         int N = 0;
-        if (q < nb) { o = orecs[q]; N = (int)o.n_res; }
+        const bool live = q < nb && !(skip && skip[q]);
+        if (live) { o = orecs[q]; N = (int)o.n_res; }
         if (N <= 0 || (unsigned long long)o.res_off + o.n_res > cap_pts) N = 0;
         const uint32_t need = N > 0 ? (uint32_t)((ml_slice_floats(N, RES) + 3) & ~3) : 0u;
         __syncthreads();                                           // the previous pass is done with the pool
@@ -434,7 +437,7 @@ midline_warp_kernel(const tb_outline_rec *__restrict__ orecs, const uint32_t *__
                 else if (lane == 0) atomicOr(status, 1u);          // the global arena is too small for this batch's long outlines
             }
         }
-        if (q >= nb) continue;
+        if (!live) continue;
         tb_midline_rec mr; mr.seg_off = o.res_off; mr.n_seg = 0; mr.tail = -1; mr.head = -1;
         tb_midline_norm nr{};
         if (!w_) {
@@ -817,10 +820,87 @@ __global__ void posture_coef_kernel(const uint32_t *__restrict__ totals, const u
     if (valid) valid[q] = ok ? 1 : 0;
 }
 
+// ---- posture::calculate_posture's threshold loop (T/tracking/Posture.cpp:305-400), one round.
+// state per parent: 0 active, 1 done (midline found), 2 finished without a midline.
+// (a) every sub-blob finds its parent -- the blob of the same frame that holds the first pixel of its first line -- and competes for
+//     "biggest sub-blob" (pixel::threshold_get_biggest_blob, C/processing/PixelTree.cpp:297-340: most pixels, the first among equals)
+__global__ void posture_parent_kernel(PostureRound R, uint32_t max_subs)
+{
+    const uint32_t ns = min(*R.n_subs, max_subs);
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+        const tb_blob_rec r = R.sub_recs[s];
+        const tb_line first = R.sub_lines[r.line_off];
+        const tb_frame_info fi = R.parent_infos[r.frame];
+        for (uint32_t p = fi.blob_begin; p < fi.blob_begin + fi.n_blobs; ++p) {
+            const tb_blob_rec pr = R.parent_recs[p];
+            if (first.y < pr.y0 || first.y > pr.y1 || first.x0 < pr.x0 || first.x0 > pr.x1) continue;
+            const tb_line *L = R.parent_lines + pr.line_off;
+            uint32_t lo = 0, hi = pr.n_lines;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (L[mid].y < first.y) lo = mid + 1; else hi = mid; }
+            bool inside = false;
+            for (uint32_t j = lo; j < pr.n_lines && L[j].y == first.y && L[j].x0 <= first.x0; ++j) inside |= first.x0 <= L[j].x1;
+            if (inside) {
+                if (R.state[p] == 0) atomicMax(R.best + p, ((unsigned long long)r.n_pixels << 32) | (unsigned long long)(0xFFFFFFFFu - s));
+                break;
+            }
+        }
+    }
+}
+// (b) per parent: the chosen sub-blob of this round
+__global__ void posture_pick_kernel(PostureRound R, uint32_t max_parents)
+{
+    const uint32_t np = min(*R.n_parents, max_parents);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        if (R.state[p]) continue;
+        const unsigned long long b = R.best[p];
+        R.index[p] = b ? 0xFFFFFFFFu - (uint32_t)(b & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+        R.sub_npx[p] = (uint32_t)(b >> 32);
+        R.best[p] = 0;
+    }
+}
+// (c) after the round's outlines and midlines: found -> done; else remember the first resampled outline (:358-366) and go on while the
+//     sub-blob kept at least max(1, pixels / 10) pixels (:373-378; the caller bounds the threshold by start + 100); parents that stop
+//     without a midline get their first outline back (:381-397)
+__global__ void posture_round_end_kernel(PostureRound R, uint32_t max_parents, tb_outline_rec *orecs, tb_midline_rec *mrecs, tb_midline_norm *nrecs,
+                                         int do_norm, int last_round)
+{
+    const uint32_t np = min(*R.n_parents, max_parents);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        if (R.state[p]) continue;
+        if (mrecs[p].n_seg > 2) { R.state[p] = 1; continue; }
+        if (R.first_outline[p].n_res == 0 && orecs[p].n_res != 0) R.first_outline[p] = orecs[p];
+        const uint32_t npx = R.parent_recs[p].n_pixels, minimum = max(1u, npx / 10u);
+        if (R.sub_npx[p] < minimum || last_round) {
+            R.state[p] = 2;
+            orecs[p] = R.first_outline[p];
+            tb_midline_rec mr; mr.seg_off = orecs[p].res_off; mr.n_seg = 0; mr.tail = -1; mr.head = -1;
+            mrecs[p] = mr;
+            if (do_norm) nrecs[p] = tb_midline_norm{};
+        } else atomicAdd(R.remaining, 1u);
+    }
+}
+
+int launch_posture_parents(const PostureRound &R, uint32_t max_parents, uint32_t max_subs, int sms, cudaStream_t s)
+{
+    if (max_subs) posture_parent_kernel<<<std::max(1, sms) * 2, 256, 0, s>>>(R, max_subs);
+    if (max_parents) posture_pick_kernel<<<std::max(1, sms) * 2, 256, 0, s>>>(R, max_parents);
+    TB_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
+int launch_posture_round_end(const PostureRound &R, uint32_t max_parents, tb_outline_rec *orecs, tb_midline_rec *mrecs, tb_midline_norm *nrecs,
+                             int do_norm, int last_round, int sms, cudaStream_t s)
+{
+    if (max_parents) posture_round_end_kernel<<<std::max(1, sms) * 2, 256, 0, s>>>(R, max_parents, orecs, mrecs, nrecs, do_norm, last_round);
+    TB_CUDA(cudaGetLastError());
+    return TB_OK;
+}
+
 int launch_midlines(const tb_outline_rec *orecs, const uint32_t *nb_dev, uint32_t nb_max, const float *res, uint32_t cap_pts,
                     const tb_posture_params *P, int do_norm, const float *move_dir, const float *fix_len,
                     float *pts_out, float *segs, tb_midline_rec *mrecs, tb_midline_norm *nrecs, float *norm_pts,
-                    float *arena, unsigned long long arena_floats, unsigned long long *arena_used, uint32_t *status, int sms, cudaStream_t s)
+                    float *arena, unsigned long long arena_floats, unsigned long long *arena_used, uint32_t *status, int sms, cudaStream_t s,
+                    const uint8_t *skip)
 {
     if (nb_max == 0) return TB_OK;
     static DeviceOnce once;
@@ -832,7 +912,7 @@ int launch_midlines(const tb_outline_rec *orecs, const uint32_t *nb_dev, uint32_
     const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + ML_WARPS - 1) / ML_WARPS, (uint64_t)sms * 2);
     midline_warp_kernel<<<grid, ML_WARPS * 32, ML_POOL * sizeof(float), s>>>(orecs, nb_dev, nb_max, res, cap_pts, *P, do_norm, move_dir, fix_len,
                                                                                  pts_out, (float4 *)segs, mrecs, nrecs, (float4 *)norm_pts,
-                                                                                 arena, arena_floats, arena_used, status);
+                                                                                 arena, arena_floats, arena_used, status, skip);
     TB_CUDA(cudaGetLastError());
     return TB_OK;
 }

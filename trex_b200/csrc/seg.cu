@@ -904,6 +904,38 @@ __global__ void paint_blobs_kernel(const tb_blob_rec *__restrict__ recs, const u
     }
 }
 
+// pv::Blob::recount (C/processing/PVBlob.cpp:934-1027) with Background::count_above_threshold (C/processing/Background.h:430-489) for every
+// blob of a batch: the number of blob pixels whose difference to the background is >= threshold -- method 0 none (the value itself),
+// 1 absolute |bg - v|, 2 sign bg - v (int32, may be negative) -- times SQR(cm_per_pixel).  rgb8 blobs compare cmn::bgr2gray of the pixel
+// with the background's grey image (diffable_pixel_value<rgb8 -> gray>).  One warp per blob, lanes over the blob's lines.
+__global__ void recount_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__restrict__ totals, const tb_line *__restrict__ lines,
+                               const uint32_t *__restrict__ line_px, const uint8_t *__restrict__ pixels, int opx, const uint8_t *__restrict__ bg, int W,
+                               int method, int threshold, float sqcm, float *__restrict__ out)
+{
+    const uint32_t nb = totals[0];
+    const int lane = threadIdx.x & 31;
+    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nb; b += gridDim.x * (blockDim.x >> 5)) {
+        const tb_blob_rec r = recs[b];
+        uint32_t cnt = 0;
+        if (threshold == 0) cnt = lane == 0 ? r.n_pixels : 0u;            // :942-949: num_pixels()
+        else
+            for (uint32_t l = lane; l < r.n_lines; l += 32) {
+                const tb_line ln = lines[r.line_off + l];
+                const uint8_t *px = pixels + line_px[r.line_off + l];
+                const uint8_t *bgr = bg + (size_t)ln.y * W + ln.x0;
+                const int n = (int)ln.x1 - (int)ln.x0 + 1;
+                for (int i = 0; i < n; ++i) {
+                    const int v = opx == 3 ? (int)gray_px_tracker(px + 3 * i) : (int)px[i];
+                    const int d = method == 0 ? v : (method == 1 ? abs((int)bgr[i] - v) : (int)bgr[i] - v);
+                    cnt += d >= threshold;
+                }
+            }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) out[b] = (float)cnt * sqcm;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: one CTA per frame.  Orders the band chunks into raster order, labels runs with a union-find
 // (8-connectivity between vertically adjacent rows, HLine.h:90-92 / CPULabeling.cpp:60-62,91; the
@@ -1468,6 +1500,11 @@ struct tb_seg {
     tb_midline_norm *h_m_nrecs = nullptr; float *h_m_norm = nullptr;
     bool p_pending = false, p_has_norm = false, p_has_crops = false; int p_fetch = 0, p_sms = 0; cudaStream_t p_stream = nullptr; uint32_t p_n = 0;
     EventRing<3> p_prof;
+    // posture of thresholded sub-blobs (tb_seg_posture_thresholded): per-parent round state, allocated on first use
+    unsigned long long *r_best = nullptr; uint32_t *r_index = nullptr, *r_sub_npx = nullptr, *r_remaining = nullptr, *h_r_remaining = nullptr;
+    uint8_t *r_state = nullptr; tb_outline_rec *r_first = nullptr;
+    tb_seg *p_parent = nullptr;
+    float *d_recount = nullptr;                 // tb_seg_recount: one value per blob                 // the handle whose blobs the posture results are indexed by (nullptr: this one)
     const uint8_t *last_frames_dev = nullptr;   // frames of the last batch (device)
     uint8_t *keep_mask = nullptr;               // tracker-side handle: painted detection blobs of the batch
     double *d_coef = nullptr;                   // `moments` normalisation: inverted warp matrix per crop
@@ -1651,7 +1688,8 @@ extern "C" void tb_seg_destroy(tb_seg *h)
     cudaDeviceSynchronize();
     for (void *p : h->dev_allocs) cudaFree(p);
     void *hp[] = {h->h_infos, h->h_totals, h->h_recs, h->h_lines, h->h_pixels, h->h_crops, h->h_crop_blob,
-                  h->h_o_recs, h->h_o_raw, h->h_o_res, h->h_o_totals, h->h_m_pts, h->h_m_segs, h->h_m_recs, h->h_m_nrecs, h->h_m_norm, h->h_crop_valid};
+                  h->h_o_recs, h->h_o_raw, h->h_o_res, h->h_o_totals, h->h_m_pts, h->h_m_segs, h->h_m_recs, h->h_m_nrecs, h->h_m_norm, h->h_crop_valid,
+                  h->h_r_remaining};
     h->p_prof.destroy();
     for (void *p : hp) if (p) cudaFreeHost(p);
     h->prof.destroy();
@@ -2082,6 +2120,18 @@ extern "C" int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **c
 }
 
 // ---- posture chain (N4): outlines -> midlines -> normalised midlines -> posture crops, all behind the batch's kernels
+static int posture_alloc_crops(tb_seg *h)
+{
+    const SegDev &d = h->d;
+    int r = TB_OK;
+    if (d.crops_cap && !h->crop_valid) {
+        r = seg_dev(h, &h->crop_valid, d.crops_cap);
+        if (r == TB_OK) r = host_alloc(&h->h_crop_valid, d.crops_cap);
+        if (r == TB_OK && !h->d_coef) r = seg_dev(h, &h->d_coef, (size_t)d.crops_cap * 6);
+    }
+    return r;
+}
+
 static int posture_alloc(tb_seg *h, int res)
 {
     const SegDev &d = h->d;
@@ -2111,9 +2161,7 @@ static int posture_alloc(tb_seg *h, int res)
         if (r == TB_OK) r = host_alloc(&h->h_m_segs, (size_t)h->o_cap * 4);
         if (r == TB_OK) r = host_alloc(&h->h_m_recs, d.blobs_cap);
         if (r == TB_OK) r = host_alloc(&h->h_m_nrecs, d.blobs_cap);
-        if (r == TB_OK && d.crops_cap) r = seg_dev(h, &h->crop_valid, d.crops_cap);
-        if (r == TB_OK && d.crops_cap) r = host_alloc(&h->h_crop_valid, d.crops_cap);
-        if (r == TB_OK && d.crops_cap && !h->d_coef) r = seg_dev(h, &h->d_coef, (size_t)d.crops_cap * 6);
+        if (r == TB_OK) r = posture_alloc_crops(h);
         if (r == TB_OK) { h->p_status = h->o_totals + 2; TB_CUDA(cudaDeviceGetAttribute(&h->p_sms, cudaDevAttrMultiProcessorCount, h->cfg.device)); }
         if (r != TB_OK) return r;
     }
@@ -2285,7 +2333,7 @@ extern "C" int tb_seg_posture(tb_seg *h, const tb_posture_request *q)
     }
     h->p_prof.mark(slot, 3);
     TB_CUDA(cudaMemcpyAsync(h->h_o_totals, h->o_totals, 16, cudaMemcpyDeviceToHost, s));
-    h->p_pending = true; h->p_fetch = q->fetch; h->p_has_norm = q->normalize != 0; h->p_stream = s;
+    h->p_pending = true; h->p_fetch = q->fetch; h->p_has_norm = q->normalize != 0; h->p_stream = s; h->p_parent = nullptr;
     return TB_OK;
 }
 
@@ -2296,13 +2344,15 @@ extern "C" int tb_seg_posture_wait(tb_seg *h)
     if (!h->p_pending) return TB_OK;
     int r = tb_seg_wait(h);                            // the blob count, and the batch's own payload as it was asked for
     if (r != TB_OK && r != TB_ERR_CAPACITY) return r;
+    tb_seg *ch = h->p_parent ? h->p_parent : h;       // results are indexed by this handle's blobs; its crops were re-rendered
+    if (ch != h && (r = tb_seg_wait(ch)) != TB_OK && r != TB_ERR_CAPACITY) return r;
     TB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = h->p_stream;
     TB_CUDA(cudaStreamSynchronize(s));
     h->p_pending = false;
     if ((r = posture_check_capacity(h, "tb_seg_posture_wait")) != TB_OK) return r;
-    const uint32_t nb = h->h_totals[0], nc = h->h_totals[3];
-    const SegDev &d = h->d;
+    const uint32_t nb = ch->h_totals[0], nc = ch->h_totals[3];
+    const SegDev &d = ch->d;
     if (nb && h->p_fetch >= 1) {
         TB_CUDA(cudaMemcpyAsync(h->h_m_recs, h->m_recs, sizeof(tb_midline_rec) * (size_t)nb, cudaMemcpyDeviceToHost, s));
         if (h->p_has_norm) {
@@ -2310,9 +2360,9 @@ extern "C" int tb_seg_posture_wait(tb_seg *h)
             TB_CUDA(cudaMemcpyAsync(h->h_m_norm, h->m_norm, sizeof(float) * 4 * (size_t)nb * h->m_res, cudaMemcpyDeviceToHost, s));
         }
         if (h->p_has_crops && nc) {
-            TB_CUDA(cudaMemcpyAsync(h->h_crop_valid, h->crop_valid, nc, cudaMemcpyDeviceToHost, s));
-            if (h->last_fetch >= 2)                    // the crops tb_seg_wait fetched were the un-normalised ones
-                TB_CUDA(cudaMemcpyAsync(h->h_crops, d.crops, (size_t)nc * d.crop_w * d.crop_h * d.cpx, cudaMemcpyDeviceToHost, s));
+            TB_CUDA(cudaMemcpyAsync(ch->h_crop_valid, ch->crop_valid, nc, cudaMemcpyDeviceToHost, s));
+            if (ch->last_fetch >= 2)                   // the crops tb_seg_wait fetched were the un-normalised ones
+                TB_CUDA(cudaMemcpyAsync(ch->h_crops, d.crops, (size_t)nc * d.crop_w * d.crop_h * d.cpx, cudaMemcpyDeviceToHost, s));
         }
     }
     if (nb && h->p_fetch >= 2) {
@@ -2337,7 +2387,7 @@ extern "C" int tb_seg_posture_result(tb_seg *h, tb_posture_view *out)
     if (h->p_fetch >= 1) {
         out->midlines = h->h_m_recs;
         if (h->p_has_norm) { out->normalized = h->h_m_nrecs; out->norm_points = h->h_m_norm; }
-        if (h->p_has_crops) out->crop_valid = h->h_crop_valid;
+        if (h->p_has_crops) out->crop_valid = (h->p_parent ? h->p_parent : h)->h_crop_valid;
     }
     if (h->p_fetch >= 2) { out->outlines = h->h_o_recs; out->raw_points = h->h_o_raw; out->points = h->h_m_pts; out->segments = h->h_m_segs; }
     return TB_OK;
@@ -2365,6 +2415,108 @@ extern "C" int tb_seg_posture_ms(tb_seg *h, double out_ms[3], uint64_t *n_calls)
     for (int k = 0; k < 3; ++k) { out_ms[k] = h->p_prof.acc[k]; h->p_prof.acc[k] = 0; }
     *n_calls = h->p_prof.n; h->p_prof.n = 0;
     return TB_OK;
+}
+
+extern "C" int tb_seg_recount(tb_seg *h, int threshold, float *out, uint32_t n)
+{
+    TB_REQUIRE(h && out, TB_ERR_INVALID, "tb_seg_recount: null argument");
+    TB_REQUIRE(!h->pending && h->last_n > 0, TB_ERR_STATE, "tb_seg_recount: call tb_seg_wait on a submitted batch first");
+    TB_REQUIRE(threshold >= 0, TB_ERR_INVALID, "tb_seg_recount: threshold must be >= 0 (the cached forms recount(-1) are host state of pv::Blob)");
+    TB_REQUIRE(!h->d.r3, TB_ERR_INVALID, "tb_seg_recount: built for gray and rgb8 blobs");
+    TB_REQUIRE(h->d.sqcm != 0.f, TB_ERR_INVALID, "tb_seg_recount: cm_per_pixel is 0 (PVBlob.cpp:935-937)");
+    const uint32_t nb = h->h_totals[0];
+    TB_REQUIRE(n >= nb, TB_ERR_INVALID, "tb_seg_recount: the output array is smaller than the batch's blob count");
+    if (nb == 0) return TB_OK;
+    TB_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->d_recount) { int r = seg_dev(h, &h->d_recount, h->d.blobs_cap); if (r != TB_OK) return r; }
+    cudaStream_t s = h->last_stream ? h->last_stream : h->stream;
+    const int method = !h->params.enable_difference ? 0 : (h->params.detect_threshold_is_absolute ? 1 : 2);
+    recount_kernel<<<148 * 4, 256, 0, s>>>(h->d.recs, h->d.totals, h->d.lines, h->d.line_px, h->d.pixels, h->d.opx, h->d_bg, h->d.W, method, threshold,
+                                           h->d.sqcm, h->d_recount);
+    h->launches += 1;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpyAsync(out, h->d_recount, sizeof(float) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    TB_CUDA(cudaStreamSynchronize(s));
+    return TB_OK;
+}
+
+extern "C" int tb_seg_posture_thresholded(tb_seg *src, tb_seg *pst, const tb_posture_request *q, int track_posture_threshold)
+{
+    TB_REQUIRE(src && pst && q && src != pst, TB_ERR_INVALID, "tb_seg_posture_thresholded: need two distinct handles and a request");
+    TB_REQUIRE(src->last_n > 0, TB_ERR_STATE, "tb_seg_posture_thresholded: the source handle has no batch");
+    TB_REQUIRE(q->outline_resample < 255.f, TB_ERR_INVALID, "tb_seg_posture_thresholded: outline_resample must be < 255");
+    TB_REQUIRE(q->fetch >= 0 && q->fetch <= 2, TB_ERR_INVALID, "tb_seg_posture_thresholded: fetch must be 0..2");
+    TB_REQUIRE(pst->d.blobs_cap >= src->d.blobs_cap, TB_ERR_INVALID, "tb_seg_posture_thresholded: the posture handle needs the source handle's max_batch / max_runs_per_frame");
+    int r = posture_check_params(&q->params, "tb_seg_posture_thresholded");
+    if (r != TB_OK) return r;
+    TB_CUDA(cudaSetDevice(pst->cfg.device));
+    if ((r = posture_alloc(pst, q->normalize ? q->params.midline_resolution : 0)) != TB_OK) return r;
+    if (!pst->r_best) {
+        const size_t cap = pst->d.blobs_cap;
+        r = seg_dev(pst, &pst->r_best, cap);
+        if (r == TB_OK) r = seg_dev(pst, &pst->r_index, cap);
+        if (r == TB_OK) r = seg_dev(pst, &pst->r_sub_npx, cap);
+        if (r == TB_OK) r = seg_dev(pst, &pst->r_state, cap);
+        if (r == TB_OK) r = seg_dev(pst, &pst->r_first, cap);
+        if (r == TB_OK) r = seg_dev(pst, &pst->r_remaining, 1);
+        if (r == TB_OK) r = host_alloc(&pst->h_r_remaining, 1);
+        if (r != TB_OK) return r;
+    }
+    cudaStream_t s = src->last_stream ? src->last_stream : src->stream;
+    const uint32_t np_max = posture_nb_max(src);
+    const size_t cap = pst->d.blobs_cap;
+    TB_CUDA(cudaMemsetAsync(pst->r_best, 0, sizeof(unsigned long long) * cap, s));
+    TB_CUDA(cudaMemsetAsync(pst->r_state, 0, cap, s));
+    TB_CUDA(cudaMemsetAsync(pst->r_first, 0, sizeof(tb_outline_rec) * cap, s));
+    TB_CUDA(cudaMemsetAsync(pst->o_recs, 0, sizeof(tb_outline_rec) * cap, s));
+    TB_CUDA(cudaMemsetAsync(pst->m_recs, 0, sizeof(tb_midline_rec) * cap, s));
+    TB_CUDA(cudaMemsetAsync(pst->o_totals, 0, 16, s));
+    pst->o_n = 0; pst->m_n = 0; pst->p_n = 0;
+    const tb_seg_params saved = pst->params;
+    PostureRound R{src->d.recs, src->d.infos, src->d.lines, src->d.totals, pst->d.recs, pst->d.lines, pst->d.totals,
+                   pst->r_best, pst->r_index, pst->r_sub_npx, pst->r_state, pst->r_first, pst->r_remaining};
+    const OutlineMap map{pst->r_index, src->d.recs, pst->r_state, 1};
+    int rounds = 0;
+    for (int thr = track_posture_threshold;; thr += 2) {       // Posture.cpp:326-379
+        tb_seg_params p = saved;
+        p.detect_threshold = thr;
+        if ((r = tb_seg_set_params(pst, &p)) != TB_OK) break;
+        if ((r = tb_seg_rethreshold(src, pst, 0)) != TB_OK) break;      // pixel::threshold_blob of every source blob at this threshold
+        const int last_round = thr + 2 >= track_posture_threshold + 100;
+        if (cudaMemsetAsync(pst->r_remaining, 0, 4, s) != cudaSuccess) { set_error("cudaMemsetAsync failed"); r = TB_ERR_CUDA; break; }
+        if ((r = launch_posture_parents(R, np_max, pst->d.blobs_cap, pst->p_sms, s)) != TB_OK) break;
+        const SegDev &d = pst->d;
+        if ((r = launch_outlines(d.recs, src->d.totals, np_max, d.lines, d.line_px, d.opx, pst->o_visited, (size_t)d.px_cap / d.opx + 16, q->outline_resample,
+                                 pst->o_rowfirst, pst->o_sel, pst->o_recs, pst->o_totals, pst->o_raw, pst->o_res, pst->o_cap, pst->p_sms, s, &map)) != TB_OK) break;
+        if ((r = launch_midlines(pst->o_recs, src->d.totals, np_max, pst->o_res, pst->o_cap, &q->params, q->normalize ? 1 : 0, q->move_direction_dev,
+                                 q->fix_length_dev, pst->m_pts, pst->m_segs, pst->m_recs, pst->m_nrecs, pst->m_norm, pst->m_arena, pst->m_arena_floats,
+                                 pst->m_arena_used, pst->p_status, pst->p_sms, s, pst->r_state)) != TB_OK) break;
+        if ((r = launch_posture_round_end(R, np_max, pst->o_recs, pst->m_recs, pst->m_nrecs, q->normalize ? 1 : 0, last_round, pst->p_sms, s)) != TB_OK) break;
+        pst->launches += 8;
+        if (cudaMemcpyAsync(pst->h_r_remaining, pst->r_remaining, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) { set_error("tb_seg_posture_thresholded: CUDA failure in the threshold loop"); r = TB_ERR_CUDA; break; }
+        ++rounds;
+        pst->pending = false;                          // the round's batch is complete (headers are on the host): the next round may re-submit
+        if (*pst->h_r_remaining == 0 || last_round) break;
+    }
+    const int r2 = tb_seg_set_params(pst, &saved);
+    if (r != TB_OK) return r;
+    if (r2 != TB_OK) return r2;
+    pst->p_has_crops = false;
+    if (q->normalize && src->d.crop_norm >= 2 && src->d.max_crops) {    // the source blobs' crops through the midline transform
+        if ((r = posture_alloc_crops(src)) != TB_OK) return r;
+        const SegDev &sd = src->d;
+        const float scale = q->individual_image_scale > 0.f ? q->individual_image_scale : 1.f;
+        r = launch_posture_crops(sd.recs, sd.totals, sd.crop_blob, sd.lines, sd.line_px, sd.pixels, src->d_bg, sd.W, sd.crop_method, sd.crop_w, sd.crop_h,
+                                 pst->m_nrecs, q->median_midline_length_dev, q->median_midline_length_px, scale, sd.crop_norm == 3,
+                                 sd.crops, src->d_coef, src->crop_valid, src->last_n * (int)sd.max_crops, s);
+        if (r != TB_OK) return r;
+        src->launches += 2;
+        pst->p_has_crops = true;
+    }
+    TB_CUDA(cudaMemcpyAsync(pst->h_o_totals, pst->o_totals, 16, cudaMemcpyDeviceToHost, s));
+    pst->p_pending = true; pst->p_fetch = q->fetch; pst->p_has_norm = q->normalize != 0; pst->p_stream = s; pst->p_parent = src;
+    return rounds;
 }
 
 extern "C" int tb_seg_debug_binary(tb_seg *h, const uint8_t *frame_host, uint8_t *out_host)
