@@ -11,7 +11,8 @@ Weight sets:
   large_logit  benched with fc2 x 16: logits up to +-23, top probabilities up to 0.96 (what a trained classifier produces)
 fp16 (one MMA per k-step in conv2 / conv3) carries a RELATIVE error of ~3e-4 of the logit scale: it meets the absolute tolerance
 for O(1) logits only -- EXPECTED_FAIL lists the combinations that are expected to miss it; they are asserted to stay within
-1e-3 * max|logit| instead, and bf16x3 (the library and bench default) must pass everything.
+1e-3 * max|logit| instead.  bf16x3 (the library default) and fp16c (fp16 + e5m2 correction terms: two MMA slots per k-step instead
+of three) must pass everything.
 """
 import numpy as np
 import pytest
@@ -73,7 +74,7 @@ def test_segmentation_half_every_frame(chain):
 
 
 @pytest.mark.parametrize("weights", ["benched", "survey_cfg3", "large_logit"])
-@pytest.mark.parametrize("precision", ["bf16x3", "fp16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp16", "fp16c"])
 def test_device_chain_every_crop(chain, precision, weights):
     """The chain as bench.py's step_device runs it; logits / probabilities of every crop against the fp32 oracle."""
     import torch

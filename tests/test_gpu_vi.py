@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-PRECISIONS = ["fp32", "bf16x3", "fp16"]
+PRECISIONS = ["fp32", "bf16x3", "fp16", "fp16c"]
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -163,8 +163,9 @@ def test_rgb8_crops_three_input_channels(precision):
 
 
 def test_precision_margins():
-    """Measured max|dlogit| of the two tensor-core precisions against the fp32 oracle on blob-like crops (tolerance 1e-3):
-    bf16x3 (three MMAs per k-step) ~1e-5, fp16 (one MMA per k-step in conv2 / conv3) a few 1e-4."""
+    """Measured max|dlogit| of the tensor-core precisions against the fp32 oracle on blob-like crops (tolerance 1e-3):
+    bf16x3 (three MMAs per k-step) ~1e-5, fp16 (one MMA per k-step in conv2 / conv3) a few 1e-4, fp16c (fp16 + one e5m2
+    correction MMA per k-step) in between."""
     import trex_b200
     from oracle import vi
     M = 100
@@ -181,7 +182,7 @@ def test_precision_margins():
     for seed in (0, 1, 2):
         sd = vi.scale_for_u8_inputs(vi.init_state_dict(M, 1, 80, 80, seed=seed))
         ref = vi.forward_logits(sd, crops)
-        for precision in ("bf16x3", "fp16"):
+        for precision in ("bf16x3", "fp16", "fp16c"):
             net = trex_b200.VINetwork(M, max_images=256, precision=precision)
             net.load_weights(sd)
             _, logits = net.probabilities(crops, return_logits=True)
@@ -190,3 +191,4 @@ def test_precision_margins():
     print("max|dlogit|", worst)
     assert worst["bf16x3"] < 1e-4
     assert worst["fp16"] < TOL
+    assert worst["fp16c"] < 0.25 * worst["fp16"] and worst["fp16c"] < 1.5e-4     # fp16 + e5m2 corrections: ~2^-3 of fp16's rounding error

@@ -373,7 +373,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
                "tb_vi_create: this release builds V118_3 for 80x80 crops with 1 (meta_encoding gray) or 3 (rgb8) channels");
     TB_REQUIRE(cfg->num_classes > 0 && cfg->num_classes <= 1024, TB_ERR_INVALID, "tb_vi_create: num_classes must be 1..1024");
     TB_REQUIRE(cfg->max_images > 0, TB_ERR_INVALID, "tb_vi_create: max_images must be > 0");
-    TB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32), 1 (bf16x3 tensor cores) or 2 (fp16 tensor cores)");
+    TB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 3, TB_ERR_INVALID, "tb_vi_create: precision must be 0 (fp32), 1 (bf16x3), 2 (fp16) or 3 (fp16c: fp16 + e5m2 correction terms) on tensor cores");
     TB_REQUIRE(cfg->arch >= 0 && cfg->arch <= 4, TB_ERR_INVALID, "tb_vi_create: arch must be 0 (v118_3), 1 (v100), 2 (v110), 3 (v119) or 4 (v200)");
     TB_REQUIRE(cfg->arch <= 2 || cfg->precision == 0, TB_ERR_INVALID, "tb_vi_create: v119 / v200 run in fp32 (precision 0); the tensor-core precisions are built for v118_3, v100 and v110");
     int ndev = 0;
@@ -481,15 +481,33 @@ static inline void split_bf16_host(float x, uint16_t &hi, uint16_t &lo)
     uint32_t u = (uint32_t)hi << 16; float fh; std::memcpy(&fh, &u, 4);
     lo = f2bf_host(x - fh);
 }
-// operand encoding of the conv2 / conv3 weights: bf16 hi + lo ("bf16x3"), or one fp16 value in the hi slot ("fp16")
+// operand encoding of the conv2 / conv3 weights: bf16 hi + lo ("bf16x3"), or one fp16 value in the hi slot ("fp16", "fp16c")
 static inline void split_operand_host(float x, bool f16, uint16_t &hi, uint16_t &lo)
 {
     if (f16) { hi = __half_as_ushort(__float2half_rn(x)); lo = 0; }
     else split_bf16_host(x, hi, lo);
 }
+// float -> e5m2 byte (round to nearest even through fp16's top byte; saturates to the largest finite value)
+static inline uint8_t f2e5m2_host(float x)
+{
+    const uint32_t h = __half_as_ushort(__float2half_rn(x));
+    uint32_t r = (h + 0x7Fu + ((h >> 8) & 1u)) >> 8;
+    if ((r & 0x7Fu) >= 0x7Cu) r = (r & 0x80u) | 0x7Bu;
+    return (uint8_t)r;
+}
+// "fp16c": the lo slots of a 16-channel block (two channel-group planes of one row: 16 bytes each) hold the e5m2 correction operands that
+// pair with the activations' [l * 2^8 | h * 2^-8]: plane 0 = fp16(w) * 2^-8, plane 1 = (w - fp16(w)) * 2^8, 16 channels each
+static inline void fp16c_weight_bytes(const float *w16 /* 16 channels */, uint8_t *plane0, uint8_t *plane1)
+{
+    for (int c = 0; c < 16; ++c) {
+        const float h = __half2float(__float2half_rn(w16[c]));
+        plane0[c] = f2e5m2_host(h * (1.f / 256.f));
+        plane1[c] = f2e5m2_host((w16[c] - h) * 256.f);
+    }
+}
 // tensor path: conv weight torch [Cout][Cin][25] -> B operand [tap][hi|lo][cin group][Cout][8] bf16
 // scale: BatchNorm scale per output channel, folded into the weights (y = conv(x, w*s) + t), or nullptr
-static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale, bool f16)
+static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale, bool f16, bool fp16c)
 {
     const int cin = G * 8;
     std::vector<uint16_t> b((size_t)25 * 2 * G * NOUT * 8);
@@ -502,12 +520,22 @@ static int vi_upload_tc_conv(uint8_t *dst, const std::vector<float> &w, int G, i
                     b[((((size_t)tap * 2 + 0) * G + g) * NOUT + co) * 8 + e] = hi;
                     b[((((size_t)tap * 2 + 1) * G + g) * NOUT + co) * 8 + e] = lo;
                 }
+    if (fp16c) {
+        uint8_t *bb = reinterpret_cast<uint8_t *>(b.data());
+        for (int tap = 0; tap < 25; ++tap)
+            for (int j = 0; j < G / 2; ++j)
+                for (int co = 0; co < NOUT; ++co) {
+                    float w16[16];
+                    for (int c = 0; c < 16; ++c) w16[c] = w[((size_t)co * cin + j * 16 + c) * 25 + tap] * (scale ? scale[co] : 1.f);
+                    fp16c_weight_bytes(w16, bb + ((((size_t)tap * 2 + 1) * G + 2 * j) * NOUT + co) * 16, bb + ((((size_t)tap * 2 + 1) * G + 2 * j + 1) * NOUT + co) * 16);
+                }
+    }
     TB_CUDA(cudaMemcpy(dst, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
     return TB_OK;
 }
 
 // conv2 (2-D tile kernel): B operand [tap][cin group][Cout rows of W_hi, then Cout rows of W_lo][8] bf16
-static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale, bool f16)
+static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int G, int NOUT, const float *scale, bool f16, bool fp16c)
 {
     const int cin = G * 8;
     std::vector<uint16_t> b((size_t)25 * G * 2 * NOUT * 8);
@@ -520,6 +548,16 @@ static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int 
                     b[((((size_t)tap * G + g) * 2 + 0) * NOUT + co) * 8 + e] = hi;
                     b[((((size_t)tap * G + g) * 2 + 1) * NOUT + co) * 8 + e] = lo;
                 }
+    if (fp16c) {               // the "lo rows" of groups 2j / 2j + 1 = the two e5m2 planes of channel block j
+        uint8_t *bb = reinterpret_cast<uint8_t *>(b.data());
+        for (int tap = 0; tap < 25; ++tap)
+            for (int j = 0; j < G / 2; ++j)
+                for (int co = 0; co < NOUT; ++co) {
+                    float w16[16];
+                    for (int c = 0; c < 16; ++c) w16[c] = w[((size_t)co * cin + j * 16 + c) * 25 + tap] * (scale ? scale[co] : 1.f);
+                    fp16c_weight_bytes(w16, bb + ((((size_t)tap * G + 2 * j) * 2 + 1) * NOUT + co) * 16, bb + ((((size_t)tap * G + 2 * j + 1) * 2 + 1) * NOUT + co) * 16);
+                }
+    }
     TB_CUDA(cudaMemcpy(dst, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
     return TB_OK;
 }
@@ -656,9 +694,9 @@ extern "C" int tb_vi_commit(tb_vi *h)
         std::vector<float> sc2(64), sc3(128);
         TB_CUDA(cudaMemcpy(sc2.data(), h->s2, 64 * 4, cudaMemcpyDeviceToHost));
         TB_CUDA(cudaMemcpy(sc3.data(), h->s3, 128 * 4, cudaMemcpyDeviceToHost));
-        const bool f16 = h->cfg.precision == 2;
-        if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data(), f16))) return r;
-        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, sc3.data(), f16))) return r;
+        const bool f16 = h->cfg.precision >= 2, fp16c = h->cfg.precision == 3;
+        if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data(), f16, fp16c))) return r;
+        if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, sc3.data(), f16, fp16c))) return r;
         // fc1 B operand [hi|lo][kc = c8*100 + pp][112][8]; torch column = (c8*8+e)*100 + pp
         std::vector<uint16_t> wb((size_t)2 * tc::FC_KC * tc::FC_N * 8, 0);
         for (int kc = 0; kc < tc::FC_KC; ++kc)
@@ -685,15 +723,18 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(1)));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1T::smem(3)));
         TB_CUDA(cudaFuncSetAttribute(conv1_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1P::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<FP16C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<BF16X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<FP16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<FP16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<FP16C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<FP16C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
         attr_done.done();
     }
-    const int f16 = h->cfg.precision == 2;
+    const int prec = h->cfg.precision, f16 = prec == 2 ? 1 : (prec == 3 ? 2 : 0);        // conv1's output encoding: bf16 hi / lo, fp16, fp16 + e5m2 planes
     for (int base = 0; base < n_max; base += h->chunk) {
         const int n = std::min(h->chunk, n_max - base);
         const int slot = h->prof.begin(s);
@@ -703,14 +744,18 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         else if (h->cfg.channels == 1) conv1_tc_kernel<1><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(1), s>>>(img + (size_t)base * 6400, n, n_dev, base, h->w1t, h->t1, h->in2, f16);
         else conv1_tc_kernel<3><<<std::min(n, h->n_sms), Conv1T::THREADS, Conv1T::smem(3), s>>>(img + (size_t)base * 6400 * 3, n, n_dev, base, h->w1t, h->t1, h->in2, f16);
         h->prof.mark(slot, 1);
-        if (f16) conv2_2d_kernel<true><<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
-        else conv2_2d_kernel<false><<<std::min(n * Conv2D::BANDS, h->n_sms), Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
+        {
+            const int g2 = std::min(n * Conv2D::BANDS, h->n_sms);
+            if (prec == 2) conv2_2d_kernel<FP16><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
+            else if (prec == 3) conv2_2d_kernel<FP16C><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
+            else conv2_2d_kernel<BF16X3><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
+        }
         h->prof.mark(slot, 2);
         {
             // full grids run as clusters of two CTAs sharing one multicast weight stream (TB_VI_CONV3_CLUSTER=0: off)
             static const int cl_env = getenv("TB_VI_CONV3_CLUSTER") ? atoi(getenv("TB_VI_CONV3_CLUSTER")) : 1;
             const int grid3 = std::min(n, h->n_sms);
-            const bool cluster = f16 && cl_env != 0 && grid3 == h->n_sms && (grid3 % 2) == 0;     // bf16x3: no gain measured (its taps hide the L2 latency)
+            const bool cluster = prec >= 2 && cl_env != 0 && grid3 == h->n_sms && (grid3 % 2) == 0;     // bf16x3: no gain measured (its taps hide the L2 latency)
             if (cluster) {
                 cudaLaunchConfig_t lc{};
                 lc.gridDim = dim3((unsigned)grid3); lc.blockDim = dim3(Conv3T::THREADS); lc.dynamicSmemBytes = Conv3T::SMEM; lc.stream = s;
@@ -719,9 +764,11 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
                 at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
                 lc.attrs = &at; lc.numAttrs = 1;
                 const uint8_t *a_in = h->in3, *a_w = h->w3t; const float *a_s = h->s3, *a_t = h->t3; uint8_t *a_out = h->fca; int a_g = h->fc_groups;
-                TB_CUDA(cudaLaunchKernelEx(&lc, conv3_t_kernel<true, 2>, a_in, n, n_dev, base, a_w, a_s, a_t, a_out, a_g));
-            } else if (f16) conv3_t_kernel<true, 1><<<grid3, Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
-            else conv3_t_kernel<false, 1><<<grid3, Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+                if (prec == 2) TB_CUDA(cudaLaunchKernelEx(&lc, conv3_t_kernel<FP16, 2>, a_in, n, n_dev, base, a_w, a_s, a_t, a_out, a_g));
+                else TB_CUDA(cudaLaunchKernelEx(&lc, conv3_t_kernel<FP16C, 2>, a_in, n, n_dev, base, a_w, a_s, a_t, a_out, a_g));
+            } else if (prec == 2) conv3_t_kernel<FP16, 1><<<grid3, Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+            else if (prec == 3) conv3_t_kernel<FP16C, 1><<<grid3, Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
+            else conv3_t_kernel<BF16X3, 1><<<grid3, Conv3T::THREADS, Conv3T::SMEM, s>>>(h->in3, n, n_dev, base, h->w3t, h->s3, h->t3, h->fca, h->fc_groups);
         }
         h->prof.mark(slot, 3);
         fc1_tc_kernel<<<dim3((n + 127) / 128, FC_SPLIT), NT, FC_SMEM, s>>>(h->fca, h->fc_groups, n, n_dev, base, h->wfc, h->h1, h->chunk);

@@ -17,7 +17,37 @@
 #pragma once
 #include "umma.cuh"
 
+#include <cuda_fp8.h>
+
 namespace tb { namespace tc {
+
+// Arithmetic of conv2 / conv3 (template parameter MODE):
+//   BF16X3  activations and weights split x = hi + lo (bf16 each), three MMAs per k-step (hi*hi + lo*hi + hi*lo)
+//   FP16    one fp16 x fp16 MMA per k-step (the hi slots of the same buffers hold fp16)
+//   FP16C   "fp16 + corrections": x = h + l with h = fp16(x); the main term h_a * h_w is one kind::f16 MMA (K = 16), the two
+//           first-order correction terms l_a * h_w + h_a * l_w are ONE kind::f8f6f4 MMA (e5m2, K = 32 = [l_a * 2^8 | h_a * 2^-8] .
+//           [h_w * 2^-8 | l_w * 2^8]; the power-of-two scales keep both factors inside e5m2's exponent range and cancel exactly)
+//           into the same fp32 accumulator: two MMA slots per k-step instead of three, the same bytes as BF16X3 (the lo slot of a
+//           channel-group pair holds 16 + 16 e5m2 bytes per position), error ~2^-3 of the fp16 rounding error.
+enum : int { BF16X3 = 0, FP16 = 1, FP16C = 2 };
+constexpr float FC_UP = 256.f, FC_DOWN = 1.f / 256.f;
+
+// 8 fp32 values (one channel group of a position) -> 8 e5m2 bytes of the correction planes: L = (x - fp16(x)) * 2^8, H = fp16(x) * 2^-8
+__device__ __forceinline__ void fp16c_pack(const float (&m)[8], uint32_t (&h16)[4], uint2 &l8, uint2 &h8)
+{
+    uint32_t lw[2] = {0u, 0u}, hw[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const __half a = __float2half_rn(m[j]), b = __float2half_rn(m[j + 1]);
+        h16[j >> 1] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+        const float fa = __half2float(a), fb = __half2float(b);
+        const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((m[j] - fa) * FC_UP, (m[j + 1] - fb) * FC_UP), __NV_SATFINITE, __NV_E5M2);
+        const uint32_t h2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(fa * FC_DOWN, fb * FC_DOWN), __NV_SATFINITE, __NV_E5M2);
+        lw[j >> 2] |= l2 << (16 * ((j >> 1) & 1));
+        hw[j >> 2] |= h2 << (16 * ((j >> 1) & 1));
+    }
+    l8 = make_uint2(lw[0], lw[1]); h8 = make_uint2(hw[0], hw[1]);
+}
 
 constexpr int NT = 192;
 
@@ -77,13 +107,16 @@ struct Conv3T {
 // "full" barrier.  Half the L2 weight reads per SM make the tile-outer order (epilogue of a tile under the MMAs of
 // the other tile) affordable for fp16 as well.  Both CTAs run the same number of image slots; a CTA without an
 // image in the last slot only takes part in the weight hand-shake.
-template <bool F16, int CL>
+template <int MODE, int CL>
 __global__ void __launch_bounds__(Conv3T::THREADS, 1)
 conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
                const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
                uint8_t *__restrict__ out, int out_groups)
 {
     using C = Conv3T;
+    constexpr bool F16 = MODE == FP16;                    // one plane set per operand; FP16C / BF16X3 carry the lo slots too
+    constexpr bool HALF_STAGES = MODE != BF16X3;          // weight ring in half-taps of 16 KB (hi slots | lo slots)
+    constexpr int HALVES = MODE == FP16C ? 2 : 1;         // ring stages consumed per tap
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_in_full[2], bar_in_empty[2], bar_acc_full[Conv3T::TILES], bar_acc_empty[Conv3T::TILES], bar_w_full[4], bar_w_empty[4];
     __shared__ uint32_t s_tmem;
@@ -97,7 +130,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
         for (int i = 0; i < C::TILES; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 1); }
         for (int i = 0; i < 4; ++i) { umma::mbar_init(&bar_w_full[i], 1); umma::mbar_init(&bar_w_empty[i], CL); }
         umma::fence_mbar_init();
-        if (CL == 2) for (int i = 0; i < (F16 ? 4 : 2); ++i) umma::mbar_expect_tx(&bar_w_full[i], F16 ? C::WTAP_BYTES / 2 : C::WTAP_BYTES);   // armed for the first use
+        if (CL == 2) for (int i = 0; i < (HALF_STAGES ? 4 : 2); ++i) umma::mbar_expect_tx(&bar_w_full[i], HALF_STAGES ? C::WTAP_BYTES / 2 : C::WTAP_BYTES);   // armed for the first use
     }
     if (warp == 1) umma::tmem_alloc(&s_tmem, C::TMEM_COLS);
     umma::fence_before_sync();
@@ -116,8 +149,9 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
     // weight ring: a tap is 32 KB (bf16 hi + lo: 2 stages, 1.4 us of MMAs per tap hide the L2 latency) or 16 KB (fp16:
     // 4 stages, because 0.46 us of MMAs per tap do not).  bf16x3 runs tile-outer (the epilogue of a tile under the
     // MMAs of the other one, taps streamed once per tile); fp16 runs tap-outer: twice the L2 weight stream measured slower.
-    constexpr int WB = F16 ? C::WTAP_BYTES / 2 : C::WTAP_BYTES, NWS = F16 ? 4 : 2;
+    constexpr int WB = HALF_STAGES ? C::WTAP_BYTES / 2 : C::WTAP_BYTES, NWS = HALF_STAGES ? 4 : 2;
     constexpr bool TILE_OUTER = !F16 || CL == 2;
+    static_assert(MODE != FP16C || TILE_OUTER, "FP16C runs tile-outer");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -135,21 +169,23 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                     ++it;
                 }
                 if (CL == 2 && crank != 0) continue;                            // the leader streams the weights for both CTAs
-                for (int tt = 0; tt < (TILE_OUTER ? 25 * C::TILES : 25); ++tt, ++tapc) {
-                    const int tap = tt % 25;
+                for (int tt = 0; tt < (TILE_OUTER ? 25 * C::TILES : 25) * HALVES; ++tt, ++tapc) {
+                    const int tap = (tt / HALVES) % 25, half = tt % HALVES;     // FP16C: the hi slots (fp16) of a tap, then its lo slots (e5m2)
                     const uint32_t s = tapc % NWS;
+                    const uint8_t *wsrc = wgt + (size_t)tap * C::WTAP_BYTES + (size_t)half * WB;
                     umma::mbar_wait(&bar_w_empty[s], ((tapc / NWS) & 1) ^ 1);   // CL = 2: both CTAs have released the stage
-                    if (CL == 2) umma::bulk_g2s_multicast(s_w + s * WB, wgt + (size_t)tap * C::WTAP_BYTES, WB, &bar_w_full[s], (uint16_t)3);
+                    if (CL == 2) umma::bulk_g2s_multicast(s_w + s * WB, wsrc, WB, &bar_w_full[s], (uint16_t)3);
                     else {
                         umma::mbar_expect_tx(&bar_w_full[s], WB);
-                        umma::bulk_g2s(s_w + s * WB, wgt + (size_t)tap * C::WTAP_BYTES, WB, &bar_w_full[s]);
+                        umma::bulk_g2s(s_w + s * WB, wsrc, WB, &bar_w_full[s]);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         if (umma::elect_one()) {
-            const uint32_t idesc = F16 ? umma::idesc_f16_f32(128, C::N) : umma::idesc_bf16_f32(128, C::N);
+            const uint32_t idesc = MODE != BF16X3 ? umma::idesc_f16_f32(128, C::N) : umma::idesc_bf16_f32(128, C::N);
+            const uint32_t idesc8 = umma::idesc_e5m2_f32(128, C::N);
             const uint64_t x_base = umma::smem_desc(umma::smem_u32(s_in), C::PIN * 16, 128);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
             uint32_t it = 0, tapc = 0;
@@ -175,10 +211,22 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                         const uint32_t w_hi = wofs + (0 * C::G + 2 * ks) * C::NOUT;
                         const uint32_t w_lo = wofs + (1 * C::G + 2 * ks) * C::NOUT;
                         umma::mma_bf16(d, w_base + w_hi, x_base + x_hi, idesc, (tap | ks) != 0);
-                        if (!F16) {
+                        if (MODE == BF16X3) {
                             umma::mma_bf16(d, w_base + w_hi, x_base + x_lo, idesc, 1);
                             umma::mma_bf16(d, w_base + w_lo, x_base + x_hi, idesc, 1);
                         }
+                    }
+                };
+                // FP16C, second half-stage of a tap: the e5m2 correction MMAs (K = 32 over the lo-slot plane pair of a channel block);
+                // the stage holds the tap's lo slots at its start
+                auto tap_mmas8 = [&](int t, int tap, uint32_t wofs) {
+                    const uint32_t d = tm + (uint32_t)(t * C::N);
+                    const uint32_t shift = (uint32_t)((tap / 5) * C::WP + (tap % 5));
+#pragma unroll
+                    for (int ks = 0; ks < C::G / 2; ++ks) {
+                        const uint32_t x_lo = (1 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
+                        const uint32_t w_lo = wofs + (2 * ks) * C::NOUT;
+                        umma::mma_f8(d, w_base + w_lo, x_base + x_lo, idesc8, 1);
                     }
                 };
                 auto take_stage = [&](uint32_t s) {           // wait for the tap's weights; clusters: re-arm the barrier for its next use
@@ -198,6 +246,13 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                             take_stage(s);
                             if (real) tap_mmas(t, tap, (s * WB) >> 4);
                             umma::commit_a(w_empty_a[s]);
+                            if (MODE == FP16C) {
+                                ++tapc;
+                                const uint32_t s8 = tapc % NWS;
+                                take_stage(s8);
+                                if (real) tap_mmas8(t, tap, (s8 * WB) >> 4);
+                                umma::commit_a(w_empty_a[s8]);
+                            }
                         }
                         if (real) umma::commit(&bar_acc_full[t]);
                     }
@@ -283,7 +338,7 @@ struct Conv2D {
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-template <bool F16>
+template <int MODE>
 __global__ void __launch_bounds__(Conv2D::THREADS, 1)
 conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
                 const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
@@ -291,7 +346,8 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
 {
     using C = Conv2D;
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int NACC = F16 ? 2 * C::NACC : C::NACC, ACC_COLS = F16 ? C::NOUT : C::ACC_COLS;
+    constexpr bool F16 = MODE == FP16, ONE_ACC = MODE != BF16X3;      // FP16 / FP16C: every MMA of a tile lands in the same 64 columns
+    constexpr int NACC = ONE_ACC ? 2 * C::NACC : C::NACC, ACC_COLS = ONE_ACC ? C::NOUT : C::ACC_COLS;
     __shared__ uint64_t bar_in_full[2], bar_in_empty[2], bar_acc_full[2 * C::NACC], bar_acc_empty[2 * C::NACC], bar_w_full;
     __shared__ uint32_t s_tmem;
     uint8_t *s_in = smem;                                            // [2][IN_BYTES]
@@ -337,7 +393,8 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
             // weights per tap: [group][64 rows W_hi + 64 rows W_lo][8]; one N = 128 MMA gives A_hi*(W_hi | W_lo),
             // one N = 64 MMA adds A_lo*W_hi: 14 KB of operand reads per tap instead of 18 KB for three N = 64 MMAs
             const uint32_t idesc128 = umma::idesc_bf16_f32(128, 2 * C::NOUT);
-            const uint32_t idesc64 = F16 ? umma::idesc_f16_f32(128, C::NOUT) : umma::idesc_bf16_f32(128, C::NOUT);
+            const uint32_t idesc64 = MODE != BF16X3 ? umma::idesc_f16_f32(128, C::NOUT) : umma::idesc_bf16_f32(128, C::NOUT);
+            const uint32_t idesc8 = umma::idesc_e5m2_f32(128, C::NOUT);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), 2 * C::NOUT * 16, 128);
             umma::mbar_wait(&bar_w_full, 0);
             uint32_t it = 0, ai = 0;
@@ -359,8 +416,11 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                         const uint32_t pos = (uint32_t)((tap / 5) * C::WP + (tap % 5));
                         const uint32_t a_hi = 0 * C::G * C::BAND_POS + pos, a_lo = 1 * C::G * C::BAND_POS + pos;
                         const uint32_t w = (uint32_t)(tap * C::WTAP_BYTES >> 4);
-                        if (F16) umma::mma_bf16(d, umma::desc_add(a_tile, a_hi), umma::desc_add(w_base, w), idesc64, tap != 0);   // fp16 x fp16, one MMA per tap
-                        else {
+                        if (MODE != BF16X3) {
+                            umma::mma_bf16(d, umma::desc_add(a_tile, a_hi), umma::desc_add(w_base, w), idesc64, tap != 0);   // fp16 x fp16, one MMA per tap
+                            // FP16C: + the e5m2 correction MMA: A = the lo-slot plane pair, B = the "lo rows" (64 ..127) of the two groups
+                            if (MODE == FP16C) umma::mma_f8(d, umma::desc_add(a_tile, a_lo), umma::desc_add(w_base, w + (uint32_t)C::NOUT), idesc8, 1);
+                        } else {
                             umma::mma_bf16(d, umma::desc_add(a_tile, a_hi), umma::desc_add(w_base, w), idesc128, tap != 0);
                             umma::mma_bf16(d, umma::desc_add(a_tile, a_lo), umma::desc_add(w_base, w), idesc64, 1);
                         }
@@ -391,7 +451,7 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                 const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + half * 32;
                 umma::tmem_ld16(ta, *reinterpret_cast<uint32_t (*)[16]>(&v[0]));
                 umma::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t (*)[16]>(&v[16]));
-                if (!F16) {
+                if (!ONE_ACC) {
                     umma::tmem_ld16(ta + C::NOUT, *reinterpret_cast<uint32_t (*)[16]>(&vb[0]));
                     umma::tmem_ld16(ta + C::NOUT + 16, *reinterpret_cast<uint32_t (*)[16]>(&vb[16]));
                 }
@@ -399,7 +459,7 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                 umma::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);     // values are in registers: buffer reusable
-                if (!F16) {
+                if (!ONE_ACC) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vb[j]));
                 }
@@ -438,8 +498,18 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
                             hi[j >> 1] = (uint32_t)__half_as_ushort(__float2half_rn(fmaxf(m2[j] + tt[j], 0.f))) |
                                          ((uint32_t)__half_as_ushort(__float2half_rn(fmaxf(m2[j + 1] + tt[j + 1], 0.f))) << 16);
                     }
+                    if (MODE == FP16C) {        // fp16 in the hi slot; this group's 8 + 8 correction bytes in the lo-slot plane pair of its 16-channel block
+                        float mm[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) mm[j] = fmaxf(m2[j] + tt[j], 0.f);
+                        uint2 l8, h8;
+                        fp16c_pack(mm, hi, l8, h8);
+                        uint8_t *lo_base = out + ((((size_t)img * 2 + 1) * GN + (g & ~1)) * PLN + pos) * 16 + (g & 1) * 8;
+                        *reinterpret_cast<uint2 *>(lo_base) = l8;
+                        *reinterpret_cast<uint2 *>(lo_base + (size_t)PLN * 16) = h8;
+                    }
                     *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 0) * GN + g) * PLN + pos) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    if (!F16) *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 1) * GN + g) * PLN + pos) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    if (MODE == BF16X3) *reinterpret_cast<uint4 *>(out + ((((size_t)img * 2 + 1) * GN + g) * PLN + pos) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
         }
@@ -687,7 +757,16 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
                         for (int u = 0; u < 2; ++u)
                             m[u] = fmaxf(fmaxf(fmaxf(__uint_as_float(v[0][c + u]), __uint_as_float(v[1][c + u])),
                                                fmaxf(__uint_as_float(v[2][c + u]), __uint_as_float(v[3][c + u]))) + s_sh[c + u], 0.f);
-                        if (f16out) {                          // "fp16" precision: conv2 reads one fp16 plane
+                        if (f16out == 2) {                     // "fp16c": fp16 planes + the e5m2 correction planes (L: 16 channels, H: 16 channels)
+                            const __half a = __float2half_rn(m[0]), b = __float2half_rn(m[1]);
+                            hi[c >> 1] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+                            const float fa = __half2float(a), fb = __half2float(b);
+                            const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((m[0] - fa) * FC_UP, (m[1] - fb) * FC_UP), __NV_SATFINITE, __NV_E5M2);
+                            const uint32_t h2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(fa * FC_DOWN, fb * FC_DOWN), __NV_SATFINITE, __NV_E5M2);
+                            // lo[0..3] = the 16 L bytes, lo[4..7] = the 16 H bytes (two channels per step)
+                            if ((c & 2) == 0) { lo[c >> 2] = l2; lo[4 + (c >> 2)] = h2; }
+                            else { lo[c >> 2] |= l2 << 16; lo[4 + (c >> 2)] |= h2 << 16; }
+                        } else if (f16out) {                   // "fp16" precision: conv2 reads one fp16 plane
                             hi[c >> 1] = (uint32_t)__half_as_ushort(__float2half_rn(m[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(m[1])) << 16);
                             lo[c >> 1] = 0u;
                         } else {
@@ -702,7 +781,7 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
                     constexpr size_t PLB = (size_t)Conv2Cfg::PL * 16;
                     *reinterpret_cast<uint4 *>(o + 0 * PLB) = make_uint4(hi[0], hi[1], hi[2], hi[3]);      // hi, channels 0-7
                     *reinterpret_cast<uint4 *>(o + 1 * PLB) = make_uint4(hi[4], hi[5], hi[6], hi[7]);      // hi, channels 8-15
-                    if (!f16out) {
+                    if (f16out != 1) {                         // bf16 lo planes, or (fp16c) the L and H correction planes
                         *reinterpret_cast<uint4 *>(o + 2 * PLB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         *reinterpret_cast<uint4 *>(o + 3 * PLB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     }
@@ -808,7 +887,7 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
             if (pt == 0) umma::mbar_arrive(&bar_plane_full[b]);
         }
     } else if (warp == 1) {                                            // ---- MMA issue ----
-        if (lane == 0) {
+        if (umma::elect_one()) {
             const uint32_t idesc = umma::idesc_bf16_f32(128, C::N);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::N * 16, 128);
             uint32_t a2 = 0;
@@ -866,7 +945,16 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                         for (int u = 0; u < 2; ++u)
                             m[u] = fmaxf(fmaxf(fmaxf(__uint_as_float(v[0][c + u]), __uint_as_float(v[1][c + u])),
                                                fmaxf(__uint_as_float(v[2][c + u]), __uint_as_float(v[3][c + u]))) + s_sh[c + u], 0.f);
-                        if (f16out) {                          // "fp16" precision: conv2 reads one fp16 plane
+                        if (f16out == 2) {                     // "fp16c": fp16 planes + the e5m2 correction planes (L: 16 channels, H: 16 channels)
+                            const __half a = __float2half_rn(m[0]), b = __float2half_rn(m[1]);
+                            hi[c >> 1] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+                            const float fa = __half2float(a), fb = __half2float(b);
+                            const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((m[0] - fa) * FC_UP, (m[1] - fb) * FC_UP), __NV_SATFINITE, __NV_E5M2);
+                            const uint32_t h2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(fa * FC_DOWN, fb * FC_DOWN), __NV_SATFINITE, __NV_E5M2);
+                            // lo[0..3] = the 16 L bytes, lo[4..7] = the 16 H bytes (two channels per step)
+                            if ((c & 2) == 0) { lo[c >> 2] = l2; lo[4 + (c >> 2)] = h2; }
+                            else { lo[c >> 2] |= l2 << 16; lo[4 + (c >> 2)] |= h2 << 16; }
+                        } else if (f16out) {                   // "fp16" precision: conv2 reads one fp16 plane
                             hi[c >> 1] = (uint32_t)__half_as_ushort(__float2half_rn(m[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(m[1])) << 16);
                             lo[c >> 1] = 0u;
                         } else {
@@ -881,7 +969,7 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                     constexpr size_t PLB = (size_t)Conv2Cfg::PL * 16;
                     *reinterpret_cast<uint4 *>(o + 0 * PLB) = make_uint4(hi[0], hi[1], hi[2], hi[3]);      // hi, channels 0-7
                     *reinterpret_cast<uint4 *>(o + 1 * PLB) = make_uint4(hi[4], hi[5], hi[6], hi[7]);      // hi, channels 8-15
-                    if (!f16out) {
+                    if (f16out != 1) {                         // bf16 lo planes, or (fp16c) the L and H correction planes
                         *reinterpret_cast<uint4 *>(o + 2 * PLB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         *reinterpret_cast<uint4 *>(o + 3 * PLB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     }

@@ -64,7 +64,7 @@ class VINetwork:
         if precision is None:
             precision = "bf16x3" if version in ("v118_3", "v100") else "fp32"      # v110's tensor path needs positive BatchNorm scales: opt in
         cfg = ViConfig(device=device, width=width, height=height, channels=channels, num_classes=self.num_classes,
-                       max_images=self.max_images, precision={"fp32": 0, "bf16x3": 1, "fp16": 2}[precision], arch=VERSIONS[version])
+                       max_images=self.max_images, precision={"fp32": 0, "bf16x3": 1, "fp16": 2, "fp16c": 3}[precision], arch=VERSIONS[version])
         self._h = C.c_void_p()
         check(lib().tb_vi_create(C.byref(cfg), C.byref(self._h)))
         self.batch_size = batch_size_for(num_classes)
