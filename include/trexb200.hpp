@@ -123,6 +123,40 @@ public:
         }
         return out;
     }
+    // The whole posture chain of the last apply() in one call: Individual::calculate_midline_for's result per blob
+    // (T/tracking/Individual.cpp:1348-1383 = Outline::calculate_midline + Midline::post_process + Midline::normalize): the normalised
+    // midline (midline_resolution segments {pos.x, pos.y, height, l_length}; empty where the reference has none) with Midline::len(),
+    // angle(), offset() -- what Midline::transform(type) needs (T/tracking/Outline.cpp:1238-1256).
+    struct NormalizedMidline { std::vector<float> segments; float len = 0, angle = 0, offset_x = 0, offset_y = 0; int tail_index = -1, head_index = -1; bool inverted_because_previous = false; };
+    std::vector<NormalizedMidline> posture(float outline_resample = 1.f, const tb_posture_params *params = nullptr, float median_midline_length_px = 0.f)
+    {
+        tb_posture_request q; tb_posture_default_request(&q);
+        if (params) q.params = *params;
+        q.outline_resample = outline_resample; q.normalize = 1; q.fetch = 1; q.median_midline_length_px = median_midline_length_px;
+        check(tb_seg_posture(_h, &q), "tb_seg_posture");
+        check(tb_seg_posture_wait(_h), "tb_seg_posture_wait");
+        tb_posture_view v;
+        check(tb_seg_posture_result(_h, &v), "tb_seg_posture_result");
+        std::vector<NormalizedMidline> out(v.n_blobs);
+        for (uint32_t k = 0; k < v.n_blobs; ++k) {
+            const tb_midline_norm &n = v.normalized[k];
+            NormalizedMidline &m = out[k];
+            m.len = n.len; m.angle = n.angle; m.offset_x = n.offx; m.offset_y = n.offy; m.tail_index = n.tail; m.head_index = n.head;
+            m.inverted_because_previous = (n.flags & 1u) != 0;
+            if (n.n_points) m.segments.assign(v.norm_points + 4 * (size_t)k * v.midline_resolution, v.norm_points + 4 * ((size_t)k + 1) * v.midline_resolution);
+        }
+        return out;
+    }
+    // pv::Blob::recount(threshold, background) for every blob of the last apply() (C/processing/PVBlob.cpp:934-1027)
+    std::vector<float> recount(int threshold)
+    {
+        uint32_t t[4];
+        check(tb_seg_totals(_h, t), "tb_seg_totals");
+        std::vector<float> out(t[0] ? t[0] : 1);
+        check(tb_seg_recount(_h, threshold, out.data(), (uint32_t)out.size()), "tb_seg_recount");
+        out.resize(t[0]);
+        return out;
+    }
     tb_seg *handle() { return _h; }
 
 private:
@@ -152,7 +186,7 @@ public:
         cfg.device = device; cfg.width = 80; cfg.height = 80; cfg.channels = channels;
         cfg.num_classes = num_classes; cfg.max_images = max_images;
         cfg.arch = version;
-        cfg.precision = version <= 1 ? 1 : 0;   // v118_3, v100: bf16x3 on tensor cores (~1e-5 of fp32); the others: fp32
+        cfg.precision = version <= 1 ? 3 : 0;   // v118_3, v100: "fp16c" on tensor cores (fp16 + e5m2 correction terms, ~2e-5 of fp32 on O(1) logits); the others: fp32
         check(tb_vi_create(&cfg, &_h), "tb_vi_create");
     }
     ~VINetwork() { tb_vi_destroy(_h); }

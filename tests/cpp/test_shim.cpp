@@ -45,6 +45,14 @@ int main()
         // its midline: tail at index 0 of the walked outline, head on the far side, more than two segments along the bar
         auto ml = bs.midlines(1.f);
         if (ml.size() != 1 || ml[0].tail_index != 0 || ml[0].head_index <= 0 || ml[0].segments.size() < 4 * 3) { std::printf("FAIL midlines\n"); return 1; }
+        // the whole posture chain (Individual::calculate_midline_for): a normalised midline of midline_resolution = 25 segments whose length
+        // is about the bar's, first point at the origin; and pv::Blob::recount of the 20 px blob (|100 - 20| = 80 >= threshold)
+        auto nm = bs.posture(1.f);
+        if (nm.size() != 1 || nm[0].segments.size() != 4 * 25 || nm[0].segments[0] != 0.f || nm[0].segments[1] != 0.f || nm[0].len < 10.f || nm[0].len > 22.f) {
+            std::printf("FAIL posture %zu %f\n", nm.empty() ? (size_t)0 : nm[0].segments.size(), nm.empty() ? 0.f : nm[0].len); return 1;
+        }
+        auto rc = bs.recount(50), rc2 = bs.recount(90);
+        if (rc.size() != 1 || rc[0] != 20.f || rc2[0] != 0.f) { std::printf("FAIL recount\n"); return 1; }
         // colour frames: BGRA input, meta_encoding rgb8 -> B,G,R per blob pixel; gray frames are refused for rgb8
         {
             trexb200::BackgroundSubtraction cs(W, H, 1, 0, 0, 4, trexb200::meta_encoding_t::rgb8);

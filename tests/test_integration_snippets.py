@@ -1,0 +1,74 @@
+"""N1 as far as this image allows: the C++ snippets of INTEGRATION.md -- the shim a TRex maintainer
+adds around BackgroundSubtraction::apply, the posture call, VINetwork::probabilities and the plug-in registration -- are type-checked
+with g++ against include/trexb200.hpp and a minimal mirror of the TRex declarations they touch (tests/cpp/trex_stubs/trex_stub.h;
+TRex's own headers need OpenCV / glaze, absent here).  When the reference checkout is present the mirrored signatures are pinned to
+the reference headers by text search, so a drifting TRex interface fails here."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+REF = "/root/reference/Application/src"
+
+# (reference header, regular expression that must match in it): the declarations trex_stub.h restates
+PINS = [
+    ("tracker/python/BackgroundSubtraction.h", r"static void apply\(std::vector<TileImage>&& tiled\);"),
+    ("tracker/python/BackgroundSubtraction.h", r"static void set_background\(cmn::Image::Ptr&&\);"),
+    ("tracker/python/BackgroundSubtraction.h", r"static double fps\(\);"),
+    ("tracker/python/BackgroundSubtraction.cpp", r"void BackgroundSubtraction::Data::set\(Image::Ptr&& average\)"),
+    ("tracker/python/BackgroundSubtraction.cpp", r"std::scoped_lock guard\(_background_mutex, _gpu_mutex\);"),
+    ("tracker/python/BackgroundSubtraction.cpp", r"add_time_sample\(double\(tiled\.size\(\)\) / timer\.elapsed\(\)\)"),
+    ("tracker/python/BackgroundSubtraction.cpp", r"buffers::TileBuffers::get\(\)\.move_back\(std::move\(image\)\)"),
+    ("tracker/python/BackgroundSubtraction.cpp", r"tile\.promise->set_exception\("),
+    ("tracker/core/TileImage.h", r"std::vector<Image::Ptr> images;"),
+    ("tracker/core/TileImage.h", r"std::unique_ptr<std::promise<SegmentationData>> promise;"),
+    ("tracker/core/TileImage.h", r"std::function<void\(\)> callback;"),
+    ("tracker/core/TileBuffers.h", r"static Buffers_t& get\(\);"),
+    ("tracker/core/TileBuffers.h", r"max_pool_size = 16"),
+    ("tracker/python/BackendRegistry.h", r"std::function<void\(std::vector<TileImage>&&\)> apply;"),
+    ("tracker/python/BackendRegistry.h", r"std::function<void\(const cmn::Image::Ptr&\)> set_background;"),
+    ("tracker/python/BackendRegistry.h", r"void register_backend\(ObjectDetectionType::Class type, BackendHooks hooks\);"),
+    ("ProcessedVideo/pv.h", r"void add_object\(blob::Pair&& pair\);"),
+    ("commons/common/misc/types.h", r"Pair\(line_ptr_t&& lines, pixel_ptr_t&& pixels, uint8_t extra_flags = 0, Prediction&& pred = \{\}\);"),
+    ("tracker/ml/VisualIdentification.h", r"probabilities\("),
+    ("tracker/core/default_config.cpp", r'CONFIG\("midline_resolution", uint32_t\(25\)'),
+    ("tracker/core/default_config.cpp", r'CONFIG\("midline_stiff_percentage", float\(0\.15\)'),
+    ("tracker/core/default_config.cpp", r'CONFIG\("outline_resample", float\(1\)'),
+]
+
+
+def _snippets():
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    return re.findall(r"```cpp\n(.*?)```", text, re.S)
+
+
+def test_snippets_exist():
+    assert len(_snippets()) >= 4
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_integration_snippet_type_checks(i, tmp_path):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    snip = _snippets()[i]
+    src = tmp_path / f"snippet{i}.cpp"
+    src.write_text('#include "trex_stub.h"\n' + snip)
+    r = subprocess.run([gxx, "-std=c++20", "-fsyntax-only", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Wno-unused-variable",
+                        "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp", "trex_stubs"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_stub_signatures_are_the_references():
+    missing = []
+    for rel, rx in PINS:
+        path = os.path.join(REF, rel)
+        if not os.path.exists(path) or not re.search(rx, open(path, errors="replace").read()):
+            missing.append((rel, rx))
+    assert not missing, missing

@@ -54,15 +54,17 @@ class VINetwork:
     def __init__(self, num_classes: int, width=80, height=80, channels=1, max_images=4096, device=0, precision=None, version="v118_3"):
         """version: visual_identification_version ("v118_3" default; "v100" and "v110" share its tensor-core kernels -- v110 only
         for positive BatchNorm scales, so it defaults to fp32 and the tensor path is an opt-in --; "v119", "v200" run in fp32).
-        precision (default "bf16x3" for v118_3 and v100): "bf16x3" (tensor cores, 3-MMA split, ~1e-5 of fp32; default), "fp16" (tensor cores, one MMA per k-step in
-        conv2/conv3, ~3e-4 on O(1) logits; what bench.py runs) or "fp32" (CUDA cores; an independent implementation for parity tests)."""
+        precision (default "fp16c" for v118_3 and v100): "fp16c" (tensor cores, one fp16 MMA + one e5m2 correction MMA per k-step in conv2 /
+        conv3: ~2e-5 of fp32 on O(1) logits, within 1e-3 for logits of +-23; default and what bench.py's headline runs), "bf16x3" (3-MMA split,
+        ~1e-5: the most accurate), "fp16" (one MMA per k-step, ~3e-4 on O(1) logits: the fastest) or "fp32" (CUDA cores; an independent
+        implementation for parity tests)."""
         self.num_classes, self.width, self.height, self.channels = int(num_classes), width, height, channels
         self.max_images = int(max_images)
         if version not in VERSIONS:
             raise ValueError(f"Model {version} not found. Available models are: {list(VERSIONS)}")      # ModelFetcher.get_model
         self.version = version
         if precision is None:
-            precision = "bf16x3" if version in ("v118_3", "v100") else "fp32"      # v110's tensor path needs positive BatchNorm scales: opt in
+            precision = "fp16c" if version in ("v118_3", "v100") else "fp32"      # v110's tensor path needs positive BatchNorm scales: opt in
         cfg = ViConfig(device=device, width=width, height=height, channels=channels, num_classes=self.num_classes,
                        max_images=self.max_images, precision={"fp32": 0, "bf16x3": 1, "fp16": 2, "fp16c": 3}[precision], arch=VERSIONS[version])
         self._h = C.c_void_p()
