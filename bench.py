@@ -163,6 +163,11 @@ def device_order():
             if 1 < len(groups) < n:
                 order = [g[k] for k in range(max(len(g) for g in groups)) for g in groups if k < len(g)]
                 return order, groups, name
+        if n >= 4 and n % 2 == 0:
+            # no PCIe structure visible (virtualised topology): HGX boards hang GPUs 0 .. n/2-1 and n/2 .. n-1 off different host
+            # bridges -- profiles/r2_h2d_bw_8gpu.jsonl: {0,1,2,3} share 116 GB/s, {0,1,4,5} reach 210 GB/s -- so interleave the halves
+            order = [g for k in range(n // 2) for g in (k, n // 2 + k)]
+            return order, [list(range(n // 2)), list(range(n // 2, n))], "no PCIe structure reported: halves interleaved (h2d_bw table)"
         return list(range(n)), [list(range(n))], "one group (or all separate)"
     except Exception as e:  # noqa: BLE001
         return list(range(n)), [list(range(n))], f"nvml unavailable ({type(e).__name__})"

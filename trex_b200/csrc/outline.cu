@@ -28,7 +28,10 @@ __constant__ int c_vy[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
 // "Is pixel (x, y) of the blob set": either a bit image of the bounding box (+ 1 pixel border) in shared memory, built by
 // the blob's thread from a pool its CTA shares, or -- for blobs whose box does not fit -- a row table into the blob's line
 // list in global memory.
-constexpr int OL_NT = 64, OL_POOL_WORDS = 12032, OL_MAX_WORDS = 2048;    // 47 KB of bit images (blob + visited run ends) per CTA of 64 blobs
+// 47 KB of bit images (blob + visited run ends) per CTA.  A walk is one dependent chain per blob: the chip has far more warp slots than
+// blobs / 32, so only every OL_SPREAD-th lane owns a blob -- 4 x the warps in flight, and at most 8 lanes of a warp hit the shared-memory
+// banks with their (random) bit-image words per step instead of 32
+constexpr int OL_NT = 64, OL_SPREAD = 4, OL_BLOBS = OL_NT / OL_SPREAD, OL_POOL_WORDS = 12032, OL_MAX_WORDS = 2048;
 
 struct Occupancy {
     const uint32_t *bm; int pw;                 // bit image (nullptr: use the lines), words per row
@@ -196,9 +199,9 @@ outline_select_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__re
     __shared__ uint32_t s_pool[OL_POOL_WORDS];
     __shared__ uint32_t s_ws[33];
     const uint32_t nb = min(nb_dev ? *nb_dev : nb_max, nb_max);
-    for (uint32_t base = blockIdx.x * OL_NT; base < nb; base += gridDim.x * OL_NT) {
-    const uint32_t q = base + threadIdx.x;
-    const bool live = q < nb && !(map.skip && map.skip[q]);
+    for (uint32_t base = blockIdx.x * OL_BLOBS; base < nb; base += gridDim.x * OL_BLOBS) {
+    const uint32_t q = base + threadIdx.x / OL_SPREAD;
+    const bool live = (threadIdx.x % OL_SPREAD) == 0 && q < nb && !(map.skip && map.skip[q]);
     const uint32_t qi = live ? (map.index ? map.index[q] : q) : 0xFFFFFFFFu;       // record q's outline comes from blob qi (posture of a sub-blob)
     const bool valid = qi != 0xFFFFFFFFu;
     tb_blob_rec r{};
@@ -274,9 +277,9 @@ outline_emit_kernel(const tb_blob_rec *__restrict__ recs, const uint32_t *__rest
     __shared__ uint32_t s_pool[OL_POOL_WORDS];
     __shared__ uint32_t s_ws[33];
     const uint32_t nb = min(nb_dev ? *nb_dev : nb_max, nb_max);
-    for (uint32_t base = blockIdx.x * OL_NT; base < nb; base += gridDim.x * OL_NT) {
-    const uint32_t q = base + threadIdx.x;
-    const bool live = q < nb && !(map.skip && map.skip[q]);
+    for (uint32_t base = blockIdx.x * OL_BLOBS; base < nb; base += gridDim.x * OL_BLOBS) {
+    const uint32_t q = base + threadIdx.x / OL_SPREAD;
+    const bool live = (threadIdx.x % OL_SPREAD) == 0 && q < nb && !(map.skip && map.skip[q]);
     tb_outline_rec o{};
     if (live) o = orecs[q];
     const bool valid = live && o.n_raw != 0 && (unsigned long long)o.raw_off + o.n_raw <= cap_pts && (unsigned long long)o.res_off + o.n_res <= cap_pts;
@@ -312,8 +315,8 @@ int launch_outlines(const tb_blob_rec *recs, const uint32_t *nb_dev, uint32_t nb
     const OutlineMap m = map ? *map : OutlineMap{nullptr, nullptr, nullptr, 0};
     if (nb_max == 0) { if (!m.append) TB_CUDA(cudaMemsetAsync(totals, 0, 8, s)); return TB_OK; }
     TB_CUDA(cudaMemsetAsync(visited, 0, visited_bytes, s));
-    // persistent over groups of OL_NT blobs: 4 CTAs of 47 KB fit an SM
-    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + OL_NT - 1) / OL_NT, (uint64_t)std::max(1, sms) * 4);
+    // persistent over groups of OL_BLOBS blobs: 4 CTAs of 47 KB fit an SM
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + OL_BLOBS - 1) / OL_BLOBS, (uint64_t)std::max(1, sms) * 4);
     outline_select_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, line_px, opx, visited, rd, row_first, sel, orecs, m);
     outline_scan_kernel<<<1, 1024, 0, s>>>(orecs, nb_dev, nb_max, totals, m.skip, m.append);
     outline_emit_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, row_first, sel, orecs, rd, raw, res, cap_pts, m);

@@ -810,7 +810,7 @@ conv1_tc_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t *__re
 // ------------------------------------------------------------------------------------------------
 struct Conv1P {
     using C = Conv1T;
-    static constexpr int PRODUCERS = 128, THREADS = 64 + 256 + PRODUCERS;
+    static constexpr int PRODUCERS = 128, EPI_SETS = 4, THREADS = 64 + EPI_SETS * 128 + PRODUCERS;     // 16 epilogue warps: four tiles drain concurrently
     static constexpr int SMEM = 2 * C::P_BYTES + C::IMG_BYTES + C::W_BYTES + 64 + 128;
 };
 
@@ -843,8 +843,8 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
     umma::fence_after_sync();
     const uint32_t tm = s_tmem;
 
-    if (warp >= 10) {                                                  // ---- producers ----
-        const int pt = tid - 320;
+    if (warp >= 2 + 4 * Conv1P::EPI_SETS) {                            // ---- producers ----
+        const int pt = tid - (64 + 128 * Conv1P::EPI_SETS);
         int it = 0;
         for (int n = blockIdx.x; n < n_act; n += gridDim.x, ++it) {
             const int b = it & 1;
@@ -866,7 +866,7 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            umma::mbar_wait(&bar_plane_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);       // the MMAs that read this plane have retired
+            umma::mbar_wait_suspend(&bar_plane_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);       // the MMAs that read this plane have retired
             for (int i = pt; i < C::PROWS * (C::PW / 4); i += Conv1P::PRODUCERS) {
                 const int yy = i / (C::PW / 4), p4 = i % (C::PW / 4);
                 const uint2 wa = *reinterpret_cast<const uint2 *>(s_img + yy * C::IMG_PITCH + p4 * 8);
@@ -921,11 +921,11 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
         const int r = quarter * 32 + lane, trow = r >> 3, tx8 = r & 7;
         uint32_t ai = 0;
         for (int n = blockIdx.x; n < n_act; n += gridDim.x, ai += C::TILES) {
-            for (int t = es; t < C::TILES; t += 2) {
+            for (int t = es; t < C::TILES; t += Conv1P::EPI_SETS) {
                 const uint32_t a2 = ai + t, buf = a2 % C::NACC;
                 const int ty = t / C::TILES_X, tx = t % C::TILES_X;
                 const int y0 = ty == 2 ? 24 : ty * 16, ymin = ty == 2 ? 32 : y0;
-                umma::mbar_wait(&bar_acc_full[buf], (a2 / C::NACC) & 1);
+                umma::mbar_wait_suspend(&bar_acc_full[buf], (a2 / C::NACC) & 1);
                 umma::fence_after_sync();
                 uint32_t v[4][16];
                 const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::N;
