@@ -22,16 +22,18 @@
 
 namespace tb {
 
-__constant__ int c_vx[8] = {0, 1, 1, 1, 0, -1, -1, -1};
-__constant__ int c_vy[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+// Direction d = 0 .. 7 (TOP, TOPR, RIGHT, BOTTOMR, BOTTOM, BOTTOML, LEFT, TOPL): offsets {0,1,1,1,0,-1,-1,-1} / {-1,-1,0,1,1,1,0,-1} from 2-bit
+// tables in registers (a walk step is a dependent chain: no constant-memory round trip inside it)
+__device__ __forceinline__ int dir_vx(int d) { return (int)((0x01A9u >> (2 * d)) & 3u) - 1; }        // (vx + 1): 1,2,2,2,1,0,0,0
+__device__ __forceinline__ int dir_vy(int d) { return (int)((0x1A90u >> (2 * d)) & 3u) - 1; }        // (vy + 1): 0,0,1,2,2,2,1,0
 
 // "Is pixel (x, y) of the blob set": either a bit image of the bounding box (+ 1 pixel border) in shared memory, built by
 // the blob's thread from a pool its CTA shares, or -- for blobs whose box does not fit -- a row table into the blob's line
 // list in global memory.
-// 47 KB of bit images (blob + visited run ends) per CTA.  A walk is one dependent chain per blob: the chip has far more warp slots than
-// blobs / 32, so only every OL_SPREAD-th lane owns a blob -- 4 x the warps in flight, and at most 8 lanes of a warp hit the shared-memory
-// banks with their (random) bit-image words per step instead of 32
-constexpr int OL_NT = 64, OL_SPREAD = 4, OL_BLOBS = OL_NT / OL_SPREAD, OL_POOL_WORDS = 12032, OL_MAX_WORDS = 2048;
+// 18 KB of bit images (blob + visited run ends) per CTA of 16 blobs, 12 CTAs per SM.  A walk is one dependent chain per blob: the chip has
+// far more warp slots than blobs / 32, so only every OL_SPREAD-th lane owns a blob -- 4 x the warps in flight for the same number of walks,
+// and at most 8 lanes of a warp hit the shared-memory banks with their (random) bit-image words per step instead of 32
+constexpr int OL_NT = 64, OL_SPREAD = 4, OL_BLOBS = OL_NT / OL_SPREAD, OL_POOL_WORDS = 4608, OL_MAX_WORDS = 2048, OL_CTAS_PER_SM = 12;
 
 struct Occupancy {
     const uint32_t *bm; int pw;                 // bit image (nullptr: use the lines), words per row
@@ -117,22 +119,23 @@ __device__ __forceinline__ Occupancy make_occupancy(bool valid, const tb_blob_re
 
 struct Side { int x, y, b; };                   // pixel, Direction of the missing neighbour (0 TOP, 2 RIGHT, 4 BOTTOM, 6 LEFT)
 
-__device__ __forceinline__ int side_order(int b) { return b == 0 ? 0 : (b == 6 ? 1 : (b == 2 ? 2 : 3)); }     // direction_from_bool
-__device__ __forceinline__ unsigned long long side_key(const Side &s, int bx0, int by0)
+__device__ __forceinline__ int side_order(int b) { return (int)((0x1320u >> (2 * b)) & 3u); }     // direction_from_bool: TOP 0, LEFT 1, RIGHT 2, BOTTOM 3
+// emission order of a sub-node: pixel x-major, then y, then the side; 14 + 16 + 2 bits (frames are at most 16384 x 65534)
+__device__ __forceinline__ uint32_t side_key(const Side &s, int bx0, int by0)
 {
-    return ((((unsigned long long)(s.x - bx0) << 20) | (unsigned long long)(s.y - by0)) << 2) | (unsigned long long)side_order(s.b);
+    return ((((uint32_t)(s.x - bx0) << 16) | (uint32_t)(s.y - by0)) << 2) | (uint32_t)side_order(s.b);
 }
 __device__ __forceinline__ Side side_succ(const Occupancy &O, const Side &s)
 {
     const int l = (s.b + 7) & 7, ll = (s.b + 6) & 7;
-    if (O.set(s.x + c_vx[l], s.y + c_vy[l])) return Side{s.x + c_vx[l], s.y + c_vy[l], (s.b + 2) & 7};
-    if (O.set(s.x + c_vx[ll], s.y + c_vy[ll])) return Side{s.x + c_vx[ll], s.y + c_vy[ll], s.b};
+    if (O.set(s.x + dir_vx(l), s.y + dir_vy(l))) return Side{s.x + dir_vx(l), s.y + dir_vy(l), (s.b + 2) & 7};
+    if (O.set(s.x + dir_vx(ll), s.y + dir_vy(ll))) return Side{s.x + dir_vx(ll), s.y + dir_vy(ll), s.b};
     return Side{s.x, s.y, ll};
 }
 __device__ __forceinline__ void side_pos(const Side &s, int bx0, int by0, float &px, float &py)
 {
-    px = ((float)(s.x - bx0) + 0.5f) + (float)c_vx[s.b] * 0.5f;
-    py = ((float)(s.y - by0) + 0.5f) + (float)c_vy[s.b] * 0.5f;
+    px = ((float)(s.x - bx0) + 0.5f) + (float)dir_vx(s.b) * 0.5f;
+    py = ((float)(s.y - by0) + 0.5f) + (float)dir_vy(s.b) * 0.5f;
 }
 
 // Outline::resample as a state machine over the point stream
@@ -144,8 +147,8 @@ struct Resampler {
         const float lx = x1 - x0, ly = y1 - y0;
         const float len = sqrtf(lx * lx + ly * ly);
         walked += len;
-        const float percent = len / rd;
-        float wp = walked / rd;
+        const float percent = rd == 1.f ? len : len / rd;          // x / 1 is exact: the default outline_resample skips two divisions per step
+        float wp = rd == 1.f ? walked : walked / rd;
         int offset = 0;
         while ((double)wp >= 1.0) {
             const float f = (float)((double)offset * 1.0 / (double)percent);
@@ -163,20 +166,20 @@ struct Resampler {
 // the start candidates; a trace flags the run ends it passes (a second bit image, or a byte per blob pixel on the row-table
 // path), so every loop is walked exactly once, from its first run end in (y, x) order.
 struct LoopPick {
-    uint32_t best_n = 0; unsigned long long best_c = ~0ull, best_cr = ~0ull; int bx, by, bb;
+    uint32_t best_n = 0, best_c = ~0u, best_cr = ~0u; int bx, by, bb;
     __device__ void trace(const Occupancy &O, int x, int y, uint32_t max_n)
     {
         const Side start{x, y, 0};
         Side cur = start;
         uint32_t n = 0;
-        unsigned long long prev_key = 0, first_key = 0, lc = ~0ull, lcr = ~0ull; Side ls = start;
+        uint32_t prev_key = 0, first_key = 0, lc = ~0u, lcr = ~0u; Side ls = start;
         do {
             const Side nx = side_succ(O, cur);
             if (n && cur.b == 0 && !(nx.b == 0 && nx.y == cur.y)) O.visit(cur.x, cur.y);       // a run end of this loop: not a start any more
-            const unsigned long long k = side_key(cur, O.bx0, O.by0);
+            const uint32_t k = side_key(cur, O.bx0, O.by0);
             if (n == 0) first_key = k;
             else {
-                const unsigned long long c = max(k, prev_key), cr = min(k, prev_key);
+                const uint32_t c = max(k, prev_key), cr = min(k, prev_key);
                 if (c < lc || (c == lc && cr < lcr)) { lc = c; lcr = cr; ls = cur; }
             }
             prev_key = k;
@@ -184,7 +187,7 @@ struct LoopPick {
             ++n;
         } while (!(cur.x == start.x && cur.y == start.y && cur.b == start.b) && n < max_n);
         {   // the start's predecessor is the last sub-node of the loop
-            const unsigned long long c = max(first_key, prev_key), cr = min(first_key, prev_key);
+            const uint32_t c = max(first_key, prev_key), cr = min(first_key, prev_key);
             if (c < lc || (c == lc && cr < lcr)) { lc = c; lcr = cr; ls = start; }
         }
         if (n > best_n || (n == best_n && (lc < best_c || (lc == best_c && lcr < best_cr)))) { best_n = n; best_c = lc; best_cr = lcr; bx = ls.x; by = ls.y; bb = ls.b; }
@@ -315,8 +318,8 @@ int launch_outlines(const tb_blob_rec *recs, const uint32_t *nb_dev, uint32_t nb
     const OutlineMap m = map ? *map : OutlineMap{nullptr, nullptr, nullptr, 0};
     if (nb_max == 0) { if (!m.append) TB_CUDA(cudaMemsetAsync(totals, 0, 8, s)); return TB_OK; }
     TB_CUDA(cudaMemsetAsync(visited, 0, visited_bytes, s));
-    // persistent over groups of OL_BLOBS blobs: 4 CTAs of 47 KB fit an SM
-    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + OL_BLOBS - 1) / OL_BLOBS, (uint64_t)std::max(1, sms) * 4);
+    // persistent over groups of OL_BLOBS blobs
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + OL_BLOBS - 1) / OL_BLOBS, (uint64_t)std::max(1, sms) * OL_CTAS_PER_SM);
     outline_select_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, line_px, opx, visited, rd, row_first, sel, orecs, m);
     outline_scan_kernel<<<1, 1024, 0, s>>>(orecs, nb_dev, nb_max, totals, m.skip, m.append);
     outline_emit_kernel<<<grid, OL_NT, 0, s>>>(recs, nb_dev, nb_max, lines, row_first, sel, orecs, rd, raw, res, cap_pts, m);

@@ -35,7 +35,7 @@
 namespace tb {
 
 constexpr int ML_WARPS = 8;                      // blobs per CTA pass
-constexpr int ML_POOL = 24000;                   // floats of shared memory per CTA (96 000 B: two CTAs per SM)
+constexpr int ML_POOL = 18400;                   // floats of shared memory per CTA (73 600 B: three CTAs per SM)
 constexpr float ML_FLT_MAX = 3.402823466e+38f;
 
 __device__ __forceinline__ float ml_fast_cos(float x)
@@ -395,11 +395,365 @@ __device__ int ml_normalize(const float4 *seg, int n, const tb_posture_params &P
     return nr;
 }
 
-// work space of one outline, in floats: [p | t: 4 NP][extra: 4 (RES + 8)][a0..a3: 4 NP][cs: 6 NP][normalize's out + tmp: 8 (RES + 8)]; NP = N + 2 made even
-__device__ __forceinline__ int ml_np(int N) { return (N + 3) & ~1; }
-__device__ __forceinline__ int ml_slice_floats(int N, int res) { return 14 * ml_np(N) + 12 * (res + 8); }
+// work space of one outline, in floats: [p | t: 4 NP][extra: 4 (RES + 8)][a0..a3: 4 NP][xs: 3 NP][normalize's out + tmp: 8 (RES + 8)]; NP >= N + 2, a multiple of 4.
+// The tables of three harmonics (6 N) live in t, a1 and xs while p, the tangents and phi are in use; later xs holds the midline segments.
+__device__ __forceinline__ int ml_np(int N) { return (N + 5) & ~3; }      // >= N + 2, a multiple of 4: every array starts on 16 bytes
+__device__ __forceinline__ int ml_slice_floats(int N, int res) { return 11 * ml_np(N) + 12 * (res + 8); }
 
-__global__ void __launch_bounds__(ML_WARPS * 32, 2)
+// One warp, one outline: everything from the resampled points to the records (see the file header).  w_: the work space.
+__device__ __forceinline__ void ml_process_outline(const tb_outline_rec o, const int N, const uint32_t q, float *w_, const int lane, const int RES,
+                                                   const float *__restrict__ res, const tb_posture_params &P, const int do_norm,
+                                                   const float *__restrict__ move_dir, const float *__restrict__ fix_len,
+                                                   float *__restrict__ pts_out, float4 *__restrict__ segs, tb_midline_rec *__restrict__ mrecs,
+                                                   tb_midline_norm *__restrict__ nrecs, float4 *__restrict__ norm_pts)
+{
+    tb_midline_rec mr; mr.seg_off = o.res_off; mr.n_seg = 0; mr.tail = -1; mr.head = -1;
+    tb_midline_norm nr{};
+    const int NP = ml_np(N), EX = 4 * (RES + 8);
+    float *p = w_, *t = w_ + 2 * NP, *a0 = w_ + 4 * NP + EX, *a1 = a0 + NP, *a2 = a0 + 2 * NP, *a3 = a0 + 3 * NP, *xs = a0 + 4 * NP;
+    float4 *nscr = (float4 *)(xs + 3 * NP);                    // 2 * (RES + 8) float4: normalize's out + tmp
+    {
+        const float2 *src = (const float2 *)res + o.res_off;
+        for (int i = lane; i < N; i += 32) { const float2 v = src[i]; p[2 * i] = v.x; p[2 * i + 1] = v.y; }
+    }
+    __syncwarp();
+    // ---- Outline::smooth (:380-389, smooth_outline :330-378): the normalised tap weights once per outline (a0 .. a3 are free: 4 NP >= 2 N + 1
+    // taps), then one weighted sum per point, taps in the reference's order
+    if (P.outline_smooth_samples > 0 && (float)N > (float)P.outline_smooth_samples) {
+        const float range = (float)P.outline_smooth_samples;
+        const int step = P.outline_smooth_step;
+        const float step_row = range * (float)step;
+        const int k0 = (int)(-step_row);
+        int nw = 0;
+        float wsum = 0;
+        for (int i = k0; (float)i <= step_row; i += step) { wsum += (step_row - (float)abs(i)) / step_row; ++nw; }
+        float *wt = a0;
+        const int nwc = min(nw, 4 * NP);
+        for (int k = lane; k < nwc; k += 32) wt[k] = ((step_row - (float)abs(k0 + k * step)) / step_row) / wsum;
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) {
+            float px = 0, py = 0;
+            int k = 0;
+            for (int j = (int)((float)i - step_row); (float)j <= (float)i + step_row; j += step, ++k) {
+                int idx = j;
+                if (idx < 0) { idx += N; while (idx < 0) idx += N; }
+                else if (idx >= N) { idx -= N; while (idx >= N) idx -= N; }
+                const float wgt = k < nwc ? wt[k] : ((step_row - (float)abs(k0 + k * step)) / step_row) / wsum;
+                px += p[2 * idx] * wgt; py += p[2 * idx + 1] * wgt;
+            }
+            t[2 * i] = px; t[2 * i + 1] = py;
+        }
+        __syncwarp();
+        float *sw = p; p = t; t = sw;
+    }
+    // ---- offset_to_middle (:454-718).  Pass 1: orientation terms and first differences for the sequential chains
+    const int nd = N - 1;
+    const bool approx = P.outline_approximate > 0;
+    for (int i = lane; i < N; i += 32) {
+        const int j = i + 1 < N ? i + 1 : 0;
+        const float x0 = p[2 * i], y0 = p[2 * i + 1], x1 = p[2 * j], y1 = p[2 * j + 1];
+        // _differentiate<true> (CircularGraph.cpp:409-463): the wrap-around term enters with the operands swapped
+        a0[i] = i + 1 < N ? x0 * y1 - x1 * y0 : x1 * y0 - x0 * y1;
+        if (approx && i < nd) { const float dx = x1 - x0, dy = y1 - y0; a1[i] = (float)((double)sqrtf(dx * dx + dy * dy) + 1e-10); }
+    }
+    __syncwarp();
+    // the sequential float sums, one lane each, as TWO code paths (divergent paths of a warp issue one after the other): lanes 0 - 4 sum an
+    // array front to back or back to front (orientation terms; x and y of the centre in both orders), lanes 5 - 6 the arc-length prefix sums
+    float acc = 0;
+    if (lane < 5 && (lane == 0 || approx)) {
+        const float *src = lane == 0 ? a0 : p + ((lane - 1) & 1);
+        const int stride = lane == 0 ? 1 : 2;
+        const bool back = lane >= 3;
+        const float *q0 = back ? src + (N - 1) * stride : src;
+        const int inc = back ? -stride : stride;
+        for (int i = 0; i < N; ++i, q0 += inc) acc += *q0;
+    } else if (approx && lane < 7) {
+        const bool back = lane == 6;
+        float *dst = back ? a3 : a2;
+        const float *q0 = back ? a1 + (nd - 1) : a1;
+        const int inc = back ? -1 : 1;
+        dst[0] = 0;
+        for (int i = 0; i < nd; ++i, q0 += inc) { acc += *q0; dst[i + 1] = acc; }
+    }
+    __syncwarp();
+    const bool reversed = __shfl_sync(0xffffffffu, acc, 0) < 0;
+    if (reversed) {
+        for (int i = lane; i < N / 2; i += 32) {
+            const int j = N - 1 - i;
+            const float tx = p[2 * i], ty = p[2 * i + 1];
+            p[2 * i] = p[2 * j]; p[2 * i + 1] = p[2 * j + 1]; p[2 * j] = tx; p[2 * j + 1] = ty;
+        }
+        __syncwarp();
+    }
+    if (approx) {
+        const float ccx = __shfl_sync(0xffffffffu, acc, reversed ? 3 : 1) / (float)(size_t)N;
+        const float ccy = __shfl_sync(0xffffffffu, acc, reversed ? 4 : 2) / (float)(size_t)N;
+        float *cum = reversed ? a3 : a2, *cyv = reversed ? a2 : a3, *cxv = a0, *dt = a1;
+        const float T = cum[nd];
+        __syncwarp();
+        // eft (:484-561): dt, phi, the unit tangents
+        for (int i = lane; i < N; i += 32) {
+            const float cumi = cum[i];
+            float dti = 0, x = 0, y = 0;
+            if (i < nd) {
+                x = p[2 * (i + 1)] - p[2 * i]; y = p[2 * (i + 1) + 1] - p[2 * i + 1];
+                dti = (float)((double)sqrtf(x * x + y * y) + 1e-10);
+            }
+            cum[i] = i == 0 ? 0.f : (float)(2 * 3.14159265358979323846 * (double)cumi);        // phi, in place
+            if (i < nd) { dt[i] = dti; cxv[i] = x / dti; cyv[i] = y / dti; }
+        }
+        __syncwarp();
+        const float *phi = cum;
+        const float norm_base = (float)((double)T / (2 * (3.14159265358979323846 * 3.14159265358979323846)));
+        const int order_n = min(P.outline_approximate, 8);
+        float coef[8][4];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { coef[g][0] = coef[g][1] = coef[g][2] = coef[g][3] = 0.f; }
+#pragma unroll
+        for (int g0 = 0; g0 < 8; g0 += 3) {
+            if (g0 >= order_n) break;
+            const int ng = min(3, order_n - g0);
+            // cos / sin tables of up to three harmonics in the arrays that are free now: t (2 NP), dt, and the three extra arrays
+            float *const tab[6] = {t, t + NP, dt, xs, xs + NP, xs + 2 * NP};
+            for (int e = lane; e < ng * N; e += 32) {
+                const int h = e / N, i = e - h * N;
+                const float phi_n = phi[i] * (float)(g0 + h + 1) / T;
+                float *tc = h == 0 ? tab[0] : (h == 1 ? tab[2] : tab[4]), *ts = h == 0 ? tab[1] : (h == 1 ? tab[3] : tab[5]);
+                tc[i] = ml_fast_cos(phi_n); ts[i] = ml_fast_sin(phi_n);
+            }
+            __syncwarp();
+            float sum = 0;
+            if (lane < 4 * ng) {                                // chain (h, k): k = 0 cnx, 1 cny, 2 snx, 3 sny
+                const int h = lane >> 2, k = lane & 3;
+                const int ti = 2 * h + (k >> 1);
+                const float *v = (k & 1) ? cyv : cxv;
+                const float *tr = ti == 0 ? tab[0] : ti == 1 ? tab[1] : ti == 2 ? tab[2] : ti == 3 ? tab[3] : ti == 4 ? tab[4] : tab[5];
+                float prev = tr[0];
+                for (int i = 0; i < nd; ++i) { const float nx = tr[i + 1]; sum += v[i] * (nx - prev); prev = nx; }
+                const int n = g0 + h + 1;
+                sum *= norm_base / (float)((size_t)n * (size_t)n);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                if (g0 + h < 8) {
+                    coef[(g0 + h) & 7][0] = __shfl_sync(0xffffffffu, sum, 4 * h + 0);       // a = cnx
+                    coef[(g0 + h) & 7][1] = __shfl_sync(0xffffffffu, sum, 4 * h + 2);       // b = snx
+                    coef[(g0 + h) & 7][2] = __shfl_sync(0xffffffffu, sum, 4 * h + 1);       // c = cny
+                    coef[(g0 + h) & 7][3] = __shfl_sync(0xffffffffu, sum, 4 * h + 3);       // d = sny
+                }
+            }
+        }
+        // ieft (:563-606)
+        for (int j = lane; j < N; j += 32) {
+            float x = ccx, y = ccy;
+            const float tt = (float)((double)j / (double)(N - 1) * 3.14159265358979323846 * 2.0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < order_n) {
+                    const float ct = ml_fast_cos(tt * (float)(i + 1)), st = ml_fast_sin(tt * (float)(i + 1));
+                    x += 1.f * (coef[i][0] * ct + coef[i][1] * st);
+                    y += 1.f * (coef[i][2] * ct + coef[i][3] * st);
+                }
+            }
+            p[2 * j] = x; p[2 * j + 1] = y;
+        }
+        __syncwarp();
+    }
+    // curvature (CircularGraph.cpp:49-113) -> a0, its first difference -> a1
+    float *curv = a0, *diff = a1;
+    {
+        float rf = P.outline_curvature_range_ratio * (float)(size_t)N;
+        if (rf < 1.f) rf = 1.f;
+        const int r = (int)rf;
+        for (int i = lane; i < N; i += 32) {
+            const int i1 = ((i - r) % N + N) % N, i3 = (i + r) % N;
+            const float x1 = p[2 * i1], y1 = p[2 * i1 + 1], x2 = p[2 * i], y2 = p[2 * i + 1], x3 = p[2 * i3], y3 = p[2 * i3 + 1];
+            const bool e12 = x1 == x2 && y1 == y2, e13 = x1 == x3 && y1 == y3, e23 = x2 == x3 && y2 == y3;
+            float v = 0.f;
+            if (!e12 && !e13 && !e23) {
+                const float cross = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
+                const float d12 = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1), d23 = (x3 - x2) * (x3 - x2) + (y3 - y2) * (y3 - y2),
+                            d13 = (x3 - x1) * (x3 - x1) + (y3 - y1) * (y3 - y1);
+                v = 2.f * (approx ? fabsf(cross) : cross) / sqrtf(d12 * d23 * d13);
+            }
+            curv[i] = v;
+        }
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) diff[i] = curv[i + 1 < N ? i + 1 : 0] - curv[i];
+        __syncwarp();
+    }
+    // find_peaks (:115-183): sample i is an extremum iff the sign of diff changes between i - 1 and i (and diff[i] != 0); it is a
+    // maximum iff diff[i - 1] >= 0.  Pointy tail (:617-619): the highest maximum (> -1), the first among equals.
+    float idxf = 0;
+    if (P.peak_mode == 0) {
+        float by = -1.f; int bi = 0x7fffffff;
+        for (int i = lane; i < N; i += 32) {
+            const bool cprev = diff[i == 0 ? N - 1 : i - 1] < 0, c = diff[i] < 0;
+            if (c != cprev && diff[i] != 0 && !cprev) {
+                const float y = curv[i];
+                if (y > by) { by = y; bi = i; }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            const float oy = __shfl_xor_sync(0xffffffffu, by, d); const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            if (oy > by || (oy == by && oi < bi)) { by = oy; bi = oi; }
+        }
+        idxf = bi == 0x7fffffff ? 0.f : (float)bi;
+    } else {
+        // broad tails: compact the extrema / maxima in index order, then lane 0 runs the range bookkeeping.  Free arrays: the extremum
+        // indices -> a2, the is-maximum flags -> a3, order -> t, the peaks (6 floats each; maxima alternate with minima, so there are at
+        // most N / 2) -> the three extra arrays
+        float *ext_i = a2; int *ext_m = (int *)a3; int *order = (int *)t; MlPeak *mx = (MlPeak *)xs;
+        int n_ext = 0, n_max = 0;
+        for (int i0 = 0; i0 < N; i0 += 32) {
+            const int i = i0 + lane;
+            bool is_ext = false, is_max = false;
+            if (i < N) {
+                const bool cprev = diff[i == 0 ? N - 1 : i - 1] < 0, c = diff[i] < 0;
+                is_ext = c != cprev && diff[i] != 0; is_max = is_ext && !cprev;
+            }
+            const unsigned be = __ballot_sync(0xffffffffu, is_ext), bm = __ballot_sync(0xffffffffu, is_max);
+            const unsigned below = (1u << lane) - 1u;
+            if (is_ext) { const int k = n_ext + __popc(be & below); ext_i[k] = (float)i; ext_m[k] = is_max ? 1 : 0; }
+            if (is_max) {
+                const int k = n_max + __popc(bm & below);
+                MlPeak pk; pk.x = (float)i; pk.y = curv[i]; pk.integral = 0; pk.r0 = -1; pk.r1 = -1; pk.max_y = 0; mx[k] = pk;
+            }
+            n_ext += __popc(be); n_max += __popc(bm);
+        }
+        __syncwarp();
+        if (lane == 0) idxf = n_max ? ml_broad_tail(curv, N, ext_i, ext_m, n_ext, mx, n_max, order) : 0.f;
+        idxf = __shfl_sync(0xffffffffu, idxf, 0);
+        __syncwarp();
+    }
+    // head (:652-682): the maximum farthest (periodically) from the tail, the first among equals; d must exceed 0
+    int tail = (int)idxf, head = -1;
+    {
+        float bd = 0.f; int bi = 0x7fffffff;
+        const float sz = (float)(size_t)N;
+        for (int i = lane; i < N; i += 32) {
+            const bool cprev = diff[i == 0 ? N - 1 : i - 1] < 0, c = diff[i] < 0;
+            if (c != cprev && diff[i] != 0 && !cprev) {
+                const float px = (float)i;
+                float d;
+                if (px >= idxf) { const float a = fabsf(px - idxf), b = fabsf(px - idxf - sz); d = a < b ? a : b; }
+                else { const float a = fabsf(idxf - px), b = fabsf(idxf - px - sz); d = a < b ? a : b; }
+                if (d > bd) { bd = d; bi = i; }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, d); const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (bi != 0x7fffffff) head = bi;
+    }
+    int rot;
+    if (P.midline_start_with_head && head != -1) {
+        if (tail != -1) { tail -= head; if (tail < 0) tail += N; }
+        rot = head; head = 0;
+    } else {
+        if (head != -1) { head -= tail; if (head < 0) head += N; }
+        rot = tail; tail = 0;
+    }
+    __syncwarp();
+    if (rot > 0 && rot < N) {                                  // std::rotate(begin, begin + rot, end)
+        for (int i = lane; i < N; i += 32) { const int s = i + rot < N ? i + rot : i + rot - N; t[2 * i] = p[2 * s]; t[2 * i + 1] = p[2 * s + 1]; }
+        __syncwarp();
+        float *sw = p; p = t; t = sw;
+    }
+    if (P.midline_invert) { const int tt = tail; tail = head; head = tt; }
+    mr.tail = tail; mr.head = head;
+    {
+        float2 *dst = (float2 *)pts_out + o.res_off;
+        for (int i = lane; i < N; i += 32) dst[i] = make_float2(p[2 * i], p[2 * i + 1]);
+    }
+    // ---- calculate_midline: the pairing walk (:786-868); segments -> shared (the extra arrays, as float4) and global
+    float4 *sseg = (float4 *)xs;                               // 3 NP floats: room for 0.75 NP segments, the walk makes < N / 2
+    uint32_t ns = 0;
+    if (N > 1) {
+        const int L = N;
+        int idx_r = 1, idx_l = -1;
+        float mo = P.midline_walk_offset * (float)L;
+        if (mo < 3.f) mo = 3.f;
+        const int max_offset = (int)mo;
+        float4 *so = segs + o.res_off;
+        while (idx_r < L + idx_l) {
+            float prx = 0, pry = 0, plx = p[2 * (L + idx_l)], ply = p[2 * (L + idx_l) + 1];
+            float min_d = ML_FLT_MAX; int min_idx = -1;
+            for (int b = 0; b < max_offset && idx_r + b < L; b += 32) {
+                const int i = b + lane;
+                unsigned bits = 0xffffffffu;
+                if (i < max_offset && idx_r + i < L) {
+                    const float dx = p[2 * (idx_r + i)] - plx, dy = p[2 * (idx_r + i) + 1] - ply;
+                    bits = __float_as_uint(sqrtf(dx * dx + dy * dy));
+                }
+                const unsigned m = __reduce_min_sync(0xffffffffu, bits);
+                if (m != 0xffffffffu && __uint_as_float(m) < min_d) {
+                    min_d = __uint_as_float(m);
+                    min_idx = idx_r + b + (__ffs(__ballot_sync(0xffffffffu, bits == m)) - 1);
+                }
+            }
+            if (min_idx != -1) { prx = p[2 * min_idx]; pry = p[2 * min_idx + 1]; idx_r = min_idx; }
+            min_d = ML_FLT_MAX; min_idx = 1;
+            for (int b = 0; b < max_offset && idx_l - b > -L; b += 32) {
+                const int i = b + lane;
+                unsigned bits = 0xffffffffu;
+                if (i < max_offset && idx_l - i > -L) {
+                    const float dx = prx - p[2 * (L + idx_l - i)], dy = pry - p[2 * (L + idx_l - i) + 1];
+                    bits = __float_as_uint(sqrtf(dx * dx + dy * dy));
+                }
+                const unsigned m = __reduce_min_sync(0xffffffffu, bits);
+                if (m != 0xffffffffu && __uint_as_float(m) < min_d) {
+                    min_d = __uint_as_float(m);
+                    min_idx = idx_l - b - (__ffs(__ballot_sync(0xffffffffu, bits == m)) - 1);
+                }
+            }
+            if (min_idx != 1) { plx = p[2 * (L + min_idx)]; ply = p[2 * (L + min_idx) + 1]; idx_l = min_idx; }
+            const float lx = prx - plx, ly = pry - ply;
+            const float mx_ = plx + lx * 0.5f, my_ = ply + ly * 0.5f;
+            if (ns < o.n_res && 4 * ns + 4 <= 3u * (uint32_t)NP && lane == 0) {
+                const float4 sg = make_float4(mx_, my_, sqrtf((prx - plx) * (prx - plx) + (pry - ply) * (pry - ply)),
+                                              sqrtf((plx - mx_) * (plx - mx_) + (ply - my_) * (ply - my_)));
+                so[ns] = sg;
+                sseg[ns] = sg;
+            }
+            ++ns;
+            idx_r++; idx_l--;
+        }
+        mr.n_seg = ns > 2 ? min(ns, o.n_res) : 0;             // "Too few midline segments calculated." (:863-866)
+    }
+    __syncwarp();
+    // ---- Midline::post_process + normalize (lane 0; Individual::calculate_midline_for, T/tracking/Individual.cpp:1348-1383)
+    if (do_norm) {
+        nr.n_points = 0; nr.flags = 0;
+        if (lane == 0 && mr.n_seg > 2) {
+            const int n = (int)mr.n_seg;
+            float4 *red = (float4 *)w_;                        // p | t | extra are free now: NP + RES + 8 entries >= n + RES + 4
+            int tl = mr.tail, hd = mr.head;
+            const float mdx = move_dir ? move_dir[2 * q] : 0.f, mdy = move_dir ? move_dir[2 * q + 1] : 0.f;
+            const int rc = ml_post_process(sseg, n, P, mdx, mdy, tl, hd, red);
+            nr.tail = tl; nr.head = hd;
+            if (rc < 0) nr.flags = 2u;                         // the reference throws std::out_of_range here
+            else {
+                float info[4];
+                float4 *out = nscr, *tmp = nscr + (RES + 8);
+                const int m = ml_normalize(sseg, n, P, fix_len ? fix_len[q] : -1.f, red, tmp, out, info);
+                if (m == RES) {
+                    nr.len = info[0]; nr.angle = info[1]; nr.offx = info[2]; nr.offy = info[3];
+                    nr.n_points = (uint32_t)m; nr.flags = (uint32_t)rc;
+                    for (int k = 0; k < m; ++k) norm_pts[(size_t)q * RES + k] = out[k];
+                } else nr.flags = (uint32_t)rc | 4u;           // normalize() returned nullptr
+            }
+        }
+        if (lane == 0) nrecs[q] = nr;
+    }
+    if (lane == 0) mrecs[q] = mr;
+}
+
+__global__ void __launch_bounds__(ML_WARPS * 32, 3)
 midline_warp_kernel(const tb_outline_rec *__restrict__ orecs, const uint32_t *__restrict__ nb_dev, uint32_t nb_max,
                     const float *__restrict__ res, uint32_t cap_pts, tb_posture_params P, int do_norm,
                     const float *__restrict__ move_dir, const float *__restrict__ fix_len,
@@ -421,352 +775,49 @@ midline_warp_kernel(const tb_outline_rec *__restrict__ orecs, const uint32_t *__
         if (live) { o = orecs[q]; N = (int)o.n_res; }
         if (N <= 0 || (unsigned long long)o.res_off + o.n_res > cap_pts) N = 0;
         const uint32_t need = N > 0 ? (uint32_t)((ml_slice_floats(N, RES) + 3) & ~3) : 0u;
-        __syncthreads();                                           // the previous pass is done with the pool
-        if (lane == 0) s_need[warp] = need <= (uint32_t)ML_POOL ? need : 0u;
-        __syncthreads();
-        uint32_t off = 0;
-        for (int w = 0; w < warp; ++w) off += s_need[w];
-        float *w_ = nullptr;
-        if (need) {
-            if (need <= (uint32_t)ML_POOL && off + need <= (uint32_t)ML_POOL) w_ = s_pool + off;
-            else {
-                unsigned long long a = 0;
-                if (lane == 0) a = atomicAdd(arena_used, (unsigned long long)need);
-                a = __shfl_sync(0xffffffffu, a, 0);
-                if (a + need <= arena_floats) w_ = arena + a;
-                else if (lane == 0) atomicOr(status, 1u);          // the global arena is too small for this batch's long outlines
+        bool todo = need != 0;
+        if (live && !todo && lane == 0) {                          // no outline: empty records
+            tb_midline_rec mr; mr.seg_off = o.res_off; mr.n_seg = 0; mr.tail = -1; mr.head = -1;
+            mrecs[q] = mr;
+            if (do_norm) nrecs[q] = tb_midline_norm{};
+        }
+        // The 8 outlines of a pass share the pool: those that fit (in warp order) run now, the others in a further round of the same
+        // pass -- shared memory is an order of magnitude faster for this kernel than the global arena, which only takes outlines that
+        // exceed the whole pool.
+        for (;;) {
+            __syncthreads();                                       // the previous round is done with the pool
+            if (lane == 0) s_need[warp] = todo ? need : 0u;
+            __syncthreads();
+            uint32_t off = 0, any = 0;
+            for (int w = 0; w < ML_WARPS; ++w) {
+                const uint32_t nw = s_need[w];
+                any |= nw;
+                if (w < warp && nw <= (uint32_t)ML_POOL) off += nw;
             }
-        }
-        if (!live) continue;
-        tb_midline_rec mr; mr.seg_off = o.res_off; mr.n_seg = 0; mr.tail = -1; mr.head = -1;
-        tb_midline_norm nr{};
-        if (!w_) {
-            if (lane == 0) { mrecs[q] = mr; if (do_norm) nrecs[q] = nr; }
-            continue;
-        }
-        const int NP = ml_np(N), EX = 4 * (RES + 8);
-        float *p = w_, *t = w_ + 2 * NP, *a0 = w_ + 4 * NP + EX, *a1 = a0 + NP, *a2 = a0 + 2 * NP, *a3 = a0 + 3 * NP, *cs = a0 + 4 * NP;
-        float4 *nscr = (float4 *)(cs + 6 * NP);                    // 2 * (RES + 8) float4: normalize's out + tmp
-        {
-            const float2 *src = (const float2 *)res + o.res_off;
-            for (int i = lane; i < N; i += 32) { const float2 v = src[i]; p[2 * i] = v.x; p[2 * i + 1] = v.y; }
-        }
-        __syncwarp();
-        // ---- Outline::smooth (:380-389, smooth_outline :330-378)
-        if (P.outline_smooth_samples > 0 && (float)N > (float)P.outline_smooth_samples) {
-            const float range = (float)P.outline_smooth_samples;
-            const int step = P.outline_smooth_step;
-            const float step_row = range * (float)step;
-            float wsum = 0;
-            for (int i = (int)(-step_row); (float)i <= step_row; i += step) wsum += (step_row - (float)abs(i)) / step_row;
-            for (int i = lane; i < N; i += 32) {
-                float px = 0, py = 0;
-                int k = (int)(-step_row);
-                for (int j = (int)((float)i - step_row); (float)j <= (float)i + step_row; j += step, k += step) {
-                    int idx = j;
-                    while (idx < 0) idx += N;
-                    while (idx >= N) idx -= N;
-                    const float wgt = ((step_row - (float)abs(k)) / step_row) / wsum;
-                    px += p[2 * idx] * wgt; py += p[2 * idx + 1] * wgt;
-                }
-                t[2 * i] = px; t[2 * i + 1] = py;
-            }
-            __syncwarp();
-            float *sw = p; p = t; t = sw;
-        }
-        // ---- offset_to_middle (:454-718).  Pass 1: orientation terms and first differences for the sequential chains
-        const int nd = N - 1;
-        const bool approx = P.outline_approximate > 0;
-        for (int i = lane; i < N; i += 32) {
-            const int j = i + 1 < N ? i + 1 : 0;
-            const float x0 = p[2 * i], y0 = p[2 * i + 1], x1 = p[2 * j], y1 = p[2 * j + 1];
-            // _differentiate<true> (CircularGraph.cpp:409-463): the wrap-around term enters with the operands swapped
-            a0[i] = i + 1 < N ? x0 * y1 - x1 * y0 : x1 * y0 - x0 * y1;
-            if (approx && i < nd) { const float dx = x1 - x0, dy = y1 - y0; a1[i] = (float)((double)sqrtf(dx * dx + dy * dy) + 1e-10); }
-        }
-        __syncwarp();
-        float acc = 0;
-        if (lane == 0) { for (int i = 0; i < N; ++i) acc += a0[i]; }
-        else if (approx) {
-            if (lane == 1) { for (int i = 0; i < N; ++i) acc += p[2 * i]; }
-            else if (lane == 2) { for (int i = 0; i < N; ++i) acc += p[2 * i + 1]; }
-            else if (lane == 3) { for (int i = N - 1; i >= 0; --i) acc += p[2 * i]; }
-            else if (lane == 4) { for (int i = N - 1; i >= 0; --i) acc += p[2 * i + 1]; }
-            else if (lane == 5) { a2[0] = 0; for (int i = 0; i < nd; ++i) { acc += a1[i]; a2[i + 1] = acc; } }
-            else if (lane == 6) { a3[0] = 0; for (int i = 0; i < nd; ++i) { acc += a1[nd - 1 - i]; a3[i + 1] = acc; } }
-        }
-        __syncwarp();
-        const bool reversed = __shfl_sync(0xffffffffu, acc, 0) < 0;
-        if (reversed) {
-            for (int i = lane; i < N / 2; i += 32) {
-                const int j = N - 1 - i;
-                const float tx = p[2 * i], ty = p[2 * i + 1];
-                p[2 * i] = p[2 * j]; p[2 * i + 1] = p[2 * j + 1]; p[2 * j] = tx; p[2 * j + 1] = ty;
-            }
-            __syncwarp();
-        }
-        if (approx) {
-            const float ccx = __shfl_sync(0xffffffffu, acc, reversed ? 3 : 1) / (float)(size_t)N;
-            const float ccy = __shfl_sync(0xffffffffu, acc, reversed ? 4 : 2) / (float)(size_t)N;
-            float *cum = reversed ? a3 : a2, *cyv = reversed ? a2 : a3, *cxv = a0, *dt = a1;
-            const float T = cum[nd];
-            __syncwarp();
-            // eft (:484-561): dt, phi, the unit tangents
-            for (int i = lane; i < N; i += 32) {
-                const float cumi = cum[i];
-                float dti = 0, x = 0, y = 0;
-                if (i < nd) {
-                    x = p[2 * (i + 1)] - p[2 * i]; y = p[2 * (i + 1) + 1] - p[2 * i + 1];
-                    dti = (float)((double)sqrtf(x * x + y * y) + 1e-10);
-                }
-                cum[i] = i == 0 ? 0.f : (float)(2 * 3.14159265358979323846 * (double)cumi);        // phi, in place
-                if (i < nd) { dt[i] = dti; cxv[i] = x / dti; cyv[i] = y / dti; }
-            }
-            __syncwarp();
-            const float *phi = cum;
-            const float norm_base = (float)((double)T / (2 * (3.14159265358979323846 * 3.14159265358979323846)));
-            const int order_n = min(P.outline_approximate, 8);
-            float coef[8][4];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) { coef[g][0] = coef[g][1] = coef[g][2] = coef[g][3] = 0.f; }
-#pragma unroll
-            for (int g0 = 0; g0 < 8; g0 += 3) {
-                if (g0 >= order_n) break;
-                const int ng = min(3, order_n - g0);
-                // cos / sin tables of up to three harmonics: cs[(2 * h + {0,1}) * N + i]
-                for (int e = lane; e < ng * N; e += 32) {
-                    const int h = e / N, i = e - h * N;
-                    const float phi_n = phi[i] * (float)(g0 + h + 1) / T;
-                    cs[(2 * h) * N + i] = ml_fast_cos(phi_n); cs[(2 * h + 1) * N + i] = ml_fast_sin(phi_n);
-                }
-                __syncwarp();
-                float sum = 0;
-                if (lane < 4 * ng) {                                // chain (h, k): k = 0 cnx, 1 cny, 2 snx, 3 sny
-                    const int h = lane >> 2, k = lane & 3;
-                    const float *v = (k & 1) ? cyv : cxv, *tr = cs + (2 * h + (k >> 1)) * N;
-                    float prev = tr[0];
-                    for (int i = 0; i < nd; ++i) { const float nx = tr[i + 1]; sum += v[i] * (nx - prev); prev = nx; }
-                    const int n = g0 + h + 1;
-                    sum *= norm_base / (float)((size_t)n * (size_t)n);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int h = 0; h < 3; ++h) {
-                    if (g0 + h < 8) {
-                        coef[(g0 + h) & 7][0] = __shfl_sync(0xffffffffu, sum, 4 * h + 0);       // a = cnx
-                        coef[(g0 + h) & 7][1] = __shfl_sync(0xffffffffu, sum, 4 * h + 2);       // b = snx
-                        coef[(g0 + h) & 7][2] = __shfl_sync(0xffffffffu, sum, 4 * h + 1);       // c = cny
-                        coef[(g0 + h) & 7][3] = __shfl_sync(0xffffffffu, sum, 4 * h + 3);       // d = sny
-                    }
-                }
-            }
-            // ieft (:563-606)
-            for (int j = lane; j < N; j += 32) {
-                float x = ccx, y = ccy;
-                const float tt = (float)((double)j / (double)(N - 1) * 3.14159265358979323846 * 2.0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i < order_n) {
-                        const float ct = ml_fast_cos(tt * (float)(i + 1)), st = ml_fast_sin(tt * (float)(i + 1));
-                        x += 1.f * (coef[i][0] * ct + coef[i][1] * st);
-                        y += 1.f * (coef[i][2] * ct + coef[i][3] * st);
-                    }
-                }
-                p[2 * j] = x; p[2 * j + 1] = y;
-            }
-            __syncwarp();
-        }
-        // curvature (CircularGraph.cpp:49-113) -> a0, its first difference -> a1
-        float *curv = a0, *diff = a1;
-        {
-            float rf = P.outline_curvature_range_ratio * (float)(size_t)N;
-            if (rf < 1.f) rf = 1.f;
-            const int r = (int)rf;
-            for (int i = lane; i < N; i += 32) {
-                const int i1 = ((i - r) % N + N) % N, i3 = (i + r) % N;
-                const float x1 = p[2 * i1], y1 = p[2 * i1 + 1], x2 = p[2 * i], y2 = p[2 * i + 1], x3 = p[2 * i3], y3 = p[2 * i3 + 1];
-                const bool e12 = x1 == x2 && y1 == y2, e13 = x1 == x3 && y1 == y3, e23 = x2 == x3 && y2 == y3;
-                float v = 0.f;
-                if (!e12 && !e13 && !e23) {
-                    const float cross = (x2 - x1) * (y3 - y2) - (y2 - y1) * (x3 - x2);
-                    const float d12 = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1), d23 = (x3 - x2) * (x3 - x2) + (y3 - y2) * (y3 - y2),
-                                d13 = (x3 - x1) * (x3 - x1) + (y3 - y1) * (y3 - y1);
-                    v = 2.f * (approx ? fabsf(cross) : cross) / sqrtf(d12 * d23 * d13);
-                }
-                curv[i] = v;
-            }
-            __syncwarp();
-            for (int i = lane; i < N; i += 32) diff[i] = curv[i + 1 < N ? i + 1 : 0] - curv[i];
-            __syncwarp();
-        }
-        // find_peaks (:115-183): sample i is an extremum iff the sign of diff changes between i - 1 and i (and diff[i] != 0); it is a
-        // maximum iff diff[i - 1] >= 0.  Pointy tail (:617-619): the highest maximum (> -1), the first among equals.
-        float idxf = 0;
-        if (P.peak_mode == 0) {
-            float by = -1.f; int bi = 0x7fffffff;
-            for (int i = lane; i < N; i += 32) {
-                const bool cprev = diff[i == 0 ? N - 1 : i - 1] < 0, c = diff[i] < 0;
-                if (c != cprev && diff[i] != 0 && !cprev) {
-                    const float y = curv[i];
-                    if (y > by) { by = y; bi = i; }
-                }
-            }
-#pragma unroll
-            for (int d = 16; d; d >>= 1) {
-                const float oy = __shfl_xor_sync(0xffffffffu, by, d); const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
-                if (oy > by || (oy == by && oi < bi)) { by = oy; bi = oi; }
-            }
-            idxf = bi == 0x7fffffff ? 0.f : (float)bi;
-        } else {
-            // broad tails: compact the extrema / maxima in index order, then lane 0 runs the range bookkeeping.  cs (6 NP floats):
-            // extremum indices [0, N) | is-maximum flags [N, 2 N) | order [2 N, 2.5 N) | the peaks (6 floats each; maxima alternate
-            // with minima, so there are at most N / 2)
-            float *ext_i = cs; int *ext_m = (int *)(cs + N); int *order = (int *)(cs + 2 * N); MlPeak *mx = (MlPeak *)(cs + 2 * N + (N + 1) / 2);
-            int n_ext = 0, n_max = 0;
-            for (int i0 = 0; i0 < N; i0 += 32) {
-                const int i = i0 + lane;
-                bool is_ext = false, is_max = false;
-                if (i < N) {
-                    const bool cprev = diff[i == 0 ? N - 1 : i - 1] < 0, c = diff[i] < 0;
-                    is_ext = c != cprev && diff[i] != 0; is_max = is_ext && !cprev;
-                }
-                const unsigned be = __ballot_sync(0xffffffffu, is_ext), bm = __ballot_sync(0xffffffffu, is_max);
-                const unsigned below = (1u << lane) - 1u;
-                if (is_ext) { const int k = n_ext + __popc(be & below); ext_i[k] = (float)i; ext_m[k] = is_max ? 1 : 0; }
-                if (is_max) {
-                    const int k = n_max + __popc(bm & below);
-                    MlPeak pk; pk.x = (float)i; pk.y = curv[i]; pk.integral = 0; pk.r0 = -1; pk.r1 = -1; pk.max_y = 0; mx[k] = pk;
-                }
-                n_ext += __popc(be); n_max += __popc(bm);
-            }
-            __syncwarp();
-            if (lane == 0) idxf = n_max ? ml_broad_tail(curv, N, ext_i, ext_m, n_ext, mx, n_max, order) : 0.f;
-            idxf = __shfl_sync(0xffffffffu, idxf, 0);
-            __syncwarp();
-        }
-        // head (:652-682): the maximum farthest (periodically) from the tail, the first among equals; d must exceed 0
-        int tail = (int)idxf, head = -1;
-        {
-            float bd = 0.f; int bi = 0x7fffffff;
-            const float sz = (float)(size_t)N;
-            for (int i = lane; i < N; i += 32) {
-                const bool cprev = diff[i == 0 ? N - 1 : i - 1] < 0, c = diff[i] < 0;
-                if (c != cprev && diff[i] != 0 && !cprev) {
-                    const float px = (float)i;
-                    float d;
-                    if (px >= idxf) { const float a = fabsf(px - idxf), b = fabsf(px - idxf - sz); d = a < b ? a : b; }
-                    else { const float a = fabsf(idxf - px), b = fabsf(idxf - px - sz); d = a < b ? a : b; }
-                    if (d > bd) { bd = d; bi = i; }
-                }
-            }
-#pragma unroll
-            for (int d = 16; d; d >>= 1) {
-                const float od = __shfl_xor_sync(0xffffffffu, bd, d); const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
-                if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-            }
-            if (bi != 0x7fffffff) head = bi;
-        }
-        int rot;
-        if (P.midline_start_with_head && head != -1) {
-            if (tail != -1) { tail -= head; if (tail < 0) tail += N; }
-            rot = head; head = 0;
-        } else {
-            if (head != -1) { head -= tail; if (head < 0) head += N; }
-            rot = tail; tail = 0;
-        }
-        __syncwarp();
-        if (rot > 0 && rot < N) {                                  // std::rotate(begin, begin + rot, end)
-            for (int i = lane; i < N; i += 32) { const int s = i + rot < N ? i + rot : i + rot - N; t[2 * i] = p[2 * s]; t[2 * i + 1] = p[2 * s + 1]; }
-            __syncwarp();
-            float *sw = p; p = t; t = sw;
-        }
-        if (P.midline_invert) { const int tt = tail; tail = head; head = tt; }
-        mr.tail = tail; mr.head = head;
-        {
-            float2 *dst = (float2 *)pts_out + o.res_off;
-            for (int i = lane; i < N; i += 32) dst[i] = make_float2(p[2 * i], p[2 * i + 1]);
-        }
-        // ---- calculate_midline: the pairing walk (:786-868); segments -> shared (cs, as float4) and global
-        float4 *sseg = (float4 *)cs;                               // 6 N floats: room for 1.5 N segments, the walk makes <= N / 2
-        uint32_t ns = 0;
-        if (N > 1) {
-            const int L = N;
-            int idx_r = 1, idx_l = -1;
-            float mo = P.midline_walk_offset * (float)L;
-            if (mo < 3.f) mo = 3.f;
-            const int max_offset = (int)mo;
-            float4 *so = segs + o.res_off;
-            while (idx_r < L + idx_l) {
-                float prx = 0, pry = 0, plx = p[2 * (L + idx_l)], ply = p[2 * (L + idx_l) + 1];
-                float min_d = ML_FLT_MAX; int min_idx = -1;
-                for (int b = 0; b < max_offset && idx_r + b < L; b += 32) {
-                    const int i = b + lane;
-                    unsigned bits = 0xffffffffu;
-                    if (i < max_offset && idx_r + i < L) {
-                        const float dx = p[2 * (idx_r + i)] - plx, dy = p[2 * (idx_r + i) + 1] - ply;
-                        bits = __float_as_uint(sqrtf(dx * dx + dy * dy));
-                    }
-                    const unsigned m = __reduce_min_sync(0xffffffffu, bits);
-                    if (m != 0xffffffffu && __uint_as_float(m) < min_d) {
-                        min_d = __uint_as_float(m);
-                        min_idx = idx_r + b + (__ffs(__ballot_sync(0xffffffffu, bits == m)) - 1);
-                    }
-                }
-                if (min_idx != -1) { prx = p[2 * min_idx]; pry = p[2 * min_idx + 1]; idx_r = min_idx; }
-                min_d = ML_FLT_MAX; min_idx = 1;
-                for (int b = 0; b < max_offset && idx_l - b > -L; b += 32) {
-                    const int i = b + lane;
-                    unsigned bits = 0xffffffffu;
-                    if (i < max_offset && idx_l - i > -L) {
-                        const float dx = prx - p[2 * (L + idx_l - i)], dy = pry - p[2 * (L + idx_l - i) + 1];
-                        bits = __float_as_uint(sqrtf(dx * dx + dy * dy));
-                    }
-                    const unsigned m = __reduce_min_sync(0xffffffffu, bits);
-                    if (m != 0xffffffffu && __uint_as_float(m) < min_d) {
-                        min_d = __uint_as_float(m);
-                        min_idx = idx_l - b - (__ffs(__ballot_sync(0xffffffffu, bits == m)) - 1);
-                    }
-                }
-                if (min_idx != 1) { plx = p[2 * (L + min_idx)]; ply = p[2 * (L + min_idx) + 1]; idx_l = min_idx; }
-                const float lx = prx - plx, ly = pry - ply;
-                const float mx_ = plx + lx * 0.5f, my_ = ply + ly * 0.5f;
-                if (ns < o.n_res && lane == 0) {
-                    const float4 sg = make_float4(mx_, my_, sqrtf((prx - plx) * (prx - plx) + (pry - ply) * (pry - ply)),
-                                                  sqrtf((plx - mx_) * (plx - mx_) + (ply - my_) * (ply - my_)));
-                    so[ns] = sg;
-                    sseg[ns] = sg;
-                }
-                ++ns;
-                idx_r++; idx_l--;
-            }
-            mr.n_seg = ns > 2 ? min(ns, o.n_res) : 0;             // "Too few midline segments calculated." (:863-866)
-        }
-        __syncwarp();
-        // ---- Midline::post_process + normalize (lane 0; Individual::calculate_midline_for, T/tracking/Individual.cpp:1348-1383)
-        if (do_norm) {
-            nr.n_points = 0; nr.flags = 0;
-            if (lane == 0 && mr.n_seg > 2) {
-                const int n = (int)mr.n_seg;
-                float4 *red = (float4 *)w_;                        // p | t | extra are free now: NP + RES + 8 entries >= n + RES + 4
-                int tl = mr.tail, hd = mr.head;
-                const float mdx = move_dir ? move_dir[2 * q] : 0.f, mdy = move_dir ? move_dir[2 * q + 1] : 0.f;
-                const int rc = ml_post_process(sseg, n, P, mdx, mdy, tl, hd, red);
-                nr.tail = tl; nr.head = hd;
-                if (rc < 0) nr.flags = 2u;                         // the reference throws std::out_of_range here
+            if (!any) break;
+            float *w_ = nullptr;
+            bool run = false;
+            if (todo) {
+                if (need <= (uint32_t)ML_POOL) { if (off + need <= (uint32_t)ML_POOL) { w_ = s_pool + off; run = true; } }
                 else {
-                    float info[4];
-                    float4 *out = nscr, *tmp = nscr + (RES + 8);
-                    const int m = ml_normalize(sseg, n, P, fix_len ? fix_len[q] : -1.f, red, tmp, out, info);
-                    if (m == RES) {
-                        nr.len = info[0]; nr.angle = info[1]; nr.offx = info[2]; nr.offy = info[3];
-                        nr.n_points = (uint32_t)m; nr.flags = (uint32_t)rc;
-                        for (int k = 0; k < m; ++k) norm_pts[(size_t)q * RES + k] = out[k];
-                    } else nr.flags = (uint32_t)rc | 4u;           // normalize() returned nullptr
+                    unsigned long long a = 0;
+                    if (lane == 0) a = atomicAdd(arena_used, (unsigned long long)need);
+                    a = __shfl_sync(0xffffffffu, a, 0);
+                    run = true;
+                    if (a + need <= arena_floats) w_ = arena + a;
+                    else if (lane == 0) {                          // the global arena is too small for this batch's long outlines
+                        atomicOr(status, 1u);
+                        tb_midline_rec mr; mr.seg_off = o.res_off; mr.n_seg = 0; mr.tail = -1; mr.head = -1;
+                        mrecs[q] = mr;
+                        if (do_norm) nrecs[q] = tb_midline_norm{};
+                    }
                 }
             }
-            if (lane == 0) nrecs[q] = nr;
+            if (run) {
+                if (w_) ml_process_outline(o, N, q, w_, lane, RES, res, P, do_norm, move_dir, fix_len, pts_out, segs, mrecs, nrecs, norm_pts);
+                todo = false;
+            }
         }
-        if (lane == 0) mrecs[q] = mr;
     }
 }
 
@@ -909,7 +960,7 @@ int launch_midlines(const tb_outline_rec *orecs, const uint32_t *nb_dev, uint32_
         once.done();
     }
     TB_CUDA(cudaMemsetAsync(arena_used, 0, sizeof(unsigned long long), s));
-    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + ML_WARPS - 1) / ML_WARPS, (uint64_t)sms * 2);
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nb_max + ML_WARPS - 1) / ML_WARPS, (uint64_t)sms * 3);
     midline_warp_kernel<<<grid, ML_WARPS * 32, ML_POOL * sizeof(float), s>>>(orecs, nb_dev, nb_max, res, cap_pts, *P, do_norm, move_dir, fix_len,
                                                                                  pts_out, (float4 *)segs, mrecs, nrecs, (float4 *)norm_pts,
                                                                                  arena, arena_floats, arena_used, status, skip);
