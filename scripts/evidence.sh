@@ -1,19 +1,17 @@
 #!/bin/bash
-# Round evidence on a B200 box (run through gpurun from the repo root): GPU parity suite, both bench arms, network micro-benchmark.
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_head.log
-timeout 280 python bench.py > gpurun_out/bench_head.json 2>gpurun_out/bench_head.err; tail -c 300 gpurun_out/bench_head.err
-timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_head.json 2>/dev/null
-timeout 200 python scripts/bench_nets.py 2048 5 2>&1 | grep "^{" > gpurun_out/nets.jsonl
-timeout 150 python scripts/bench_seg.py 128 10 1 gray none 1920x1080 outlines 2>&1 | grep "^{" > gpurun_out/seg_outlines.jsonl
-timeout 150 python scripts/bench_seg.py 32 10 1 gray none 3840x2160 outlines 2>&1 | grep "^{" >> gpurun_out/seg_outlines.jsonl
-timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_posture.csv python scripts/bench_seg.py 128 2 1 gray none 1920x1080 outlines > /dev/null 2>&1
+# Round evidence on ONE B200 (run through gpurun from the repo root): the GPU parity suite, memcheck over the posture / recount tests, the three
+# BASELINE configs at N = 1, the reference arm, and the micro-benchmarks.
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/r2_pytest_gpu_head.txt
+timeout 400 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_midline.py tests/test_gpu_outline.py -x -q -m gpu -k "not benchmark_workload" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|Invalid" | tail -5 | tee gpurun_out/r2_memcheck_posture.txt
+timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_seg.py -x -q -m gpu -k "recount" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|Invalid" | tail -3 | tee -a gpurun_out/r2_memcheck_posture.txt
+for c in 3 4 5; do timeout 400 python bench.py --config $c > gpurun_out/r2_cfg${c}_1gpu.json 2> gpurun_out/r2_cfg${c}_1gpu.err; tail -c 300 gpurun_out/r2_cfg${c}_1gpu.err; done
+timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null
+timeout 100 python scripts/bench_posture.py 128 1920x1080 10 > gpurun_out/r2_posture_micro.jsonl; timeout 100 python scripts/bench_posture.py 64 3840x2160 10 >> gpurun_out/r2_posture_micro.jsonl
 python - <<PY
 import json
-d = json.loads(open("gpurun_out/bench_head.json").read().strip().splitlines()[-1])
-print(round(d["value"]), round(d["e2e"]["value"]), d["roofline"]["frac"], d["kernels"]["seg_rle"]["frac"], d["cpu_baseline"]["value"], d["clocks"])
-r = json.loads(open("gpurun_out/bench_ref_head.json").read().strip().splitlines()[-1]); print(r["value"], r.get("cpu_baseline"))
-for l in open("gpurun_out/seg_outlines.jsonl"):
-    n = json.loads(l); print(n["size"], n["B"], n["blobs"], "outlines ms", n["outlines_ms_incl_d2h"], "midlines ms", n["midlines_ms_incl_d2h"])
-for l in open("gpurun_out/nets.jsonl"):
-    n = json.loads(l); print(n["version"], n["precision"], round(n["crops_per_s"]), round(n["tflops_algorithmic"], 1))
+for c in (3, 4, 5):
+    d = json.loads(open("gpurun_out/r2_cfg%d_1gpu.json" % c).read().strip().splitlines()[-1])
+    print("config", c, round(d["value"]), round(d["e2e"]["value"]), "verified", d["verified"], round(d["roofline"]["frac"], 3), round(d["kernels"]["seg_rle"]["frac"], 3), d["cpu_baseline"]["value"] if d["cpu_baseline"] else None, d["clocks"]["reasons"])
+r = json.loads(open("gpurun_out/r2_bench_reference_arm.json").read().strip().splitlines()[-1]); print("reference arm", r["value"], r.get("cpu_baseline", {}).get("cores"))
 PY
+cat gpurun_out/r2_posture_micro.jsonl | cut -c1-250

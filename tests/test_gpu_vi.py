@@ -12,6 +12,12 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
+def logit_tol(precision, ref):
+    """ABSOLUTE 1e-3 on logits (BASELINE.json north_star) for every precision that is meant to hold it at any logit scale; the single-MMA
+    "fp16" mode carries a relative error of ~3e-4 of the logit scale and is held to 1e-3 * max(1, max|logit|) (tests/test_gpu_chain.py)."""
+    return TOL * max(1.0, float(np.abs(ref).max())) if precision == "fp16" else TOL
+
+
 PRECISIONS = ["fp32", "bf16x3", "fp16", "fp16c"]
 
 
@@ -82,7 +88,7 @@ def test_tensor_path_many_images_persistent_ctas():
     net.load_weights(sd)
     probs, logits = net.probabilities(crops, return_logits=True)
     ref = vi.forward_logits(sd, crops)
-    assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(logits - ref).max() < logit_tol("bf16x3", ref)
     assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
     probs2 = net.probabilities(crops[:100])          # handle reuse, different n
     assert np.abs(probs2 - probs[:100]).max() < 1e-6
@@ -103,7 +109,7 @@ def test_256_classes(precision):
     net.load_weights(sd)
     probs, logits = net.probabilities(crops, return_logits=True)
     ref = vi.forward_logits(sd, crops)
-    assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(logits - ref).max() < logit_tol(precision, ref)
     assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
 
 
@@ -158,7 +164,7 @@ def test_rgb8_crops_three_input_channels(precision):
     crops[0] = 0; crops[1] = 255; crops[2, ..., 0] = 255; crops[3, ..., 2] = 255
     probs, logits = net.probabilities(crops, return_logits=True)
     ref = vi.forward_logits(sd, crops)
-    assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(logits - ref).max() < logit_tol(precision, ref)
     assert np.abs(probs - vi.predict(sd, crops)).max() < TOL
 
 

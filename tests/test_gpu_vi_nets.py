@@ -10,6 +10,12 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+
+
+def logit_tol(precision, ref):
+    """ABSOLUTE 1e-3 on logits (BASELINE.json north_star) for every precision that is meant to hold it at any logit scale; the single-MMA
+    "fp16" mode carries a relative error of ~3e-4 of the logit scale and is held to 1e-3 * max(1, max|logit|) (tests/test_gpu_chain.py)."""
+    return TOL * max(1.0, float(np.abs(ref).max())) if precision == "fp16" else TOL
 ARCHS = ["v100", "v110", "v119", "v200"]
 
 
@@ -109,7 +115,7 @@ def test_tensor_path_batch_vs_oracle(arch):
         net = trex_b200.VINetwork(M, max_images=256, version=arch, precision=precision)
         net.load_weights(sd)
         probs, logits = net.probabilities(crops, return_logits=True)
-        assert np.abs(logits - ref).max() < TOL * max(1.0, float(np.abs(ref).max())), precision
+        assert np.abs(logits - ref).max() < logit_tol(precision, ref), precision
         assert np.abs(probs - vi.predict_arch(arch, sd, crops)).max() < TOL
 
 
