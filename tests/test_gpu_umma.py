@@ -57,3 +57,29 @@ def test_mixed_f16_plus_e5m2_accumulate(n_cg, n_pl8, N, n_pos, shift):
     B8 = b8.transpose(1, 0, 2).reshape(N, -1).astype(np.float64)
     ref = A @ B.T + A8 @ B8.T
     assert np.abs(d - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_tmem_ld_16x256b_layout():
+    """The register layout of tcgen05.ld shape 16x256b.x4 (the mma accumulator fragment: a thread holds TMEM lanes t/4 and t/4 + 8 of two
+    adjacent columns per 8-column group) -- what conv2's tap-pair epilogue relies on to add lane r + 8 without shuffles."""
+    from trex_b200 import _capi
+    rng = np.random.default_rng(5)
+    n_cg, n_pos, N, shift = 2, 160, 128, 3
+    a = rng.standard_normal((n_cg, n_pos, 8)).astype(np.float32); b = rng.standard_normal((n_cg, N, 8)).astype(np.float32)
+    import torch
+    a16 = torch.from_numpy(a).to(torch.bfloat16); b16 = torch.from_numpy(b).to(torch.bfloat16)
+    d = np.zeros((128, N), np.float32); raw = np.zeros((4, N // 32, 2, 32, 16), np.float32)
+    L = _capi.lib()
+    L.tbdbg_tmem_ld_16x256b.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    _capi.check(L.tbdbg_tmem_ld_16x256b(C.c_void_p(a16.data_ptr()), n_pos, n_cg, shift, C.c_void_p(b16.data_ptr()), N,
+                                        d.ctypes.data_as(C.c_void_p), raw.ctypes.data_as(C.c_void_p)))
+    exp = np.zeros_like(raw)
+    for w in range(4):
+        for cb in range(N // 32):
+            for lh in range(2):
+                for t in range(32):
+                    for j in range(4):
+                        for h in range(2):
+                            for e in range(2):
+                                exp[w, cb, lh, t, 4 * j + 2 * h + e] = d[32 * w + 16 * lh + t // 4 + 8 * h, 32 * cb + 8 * j + 2 * (t % 4) + e]
+    assert np.array_equal(raw, exp)

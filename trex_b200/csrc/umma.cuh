@@ -188,6 +188,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
 }
+// TMEM -> registers, shape 16x256b.x4: 16 lanes starting at the address' lane x 32 consecutive columns.  Thread t receives, for column group
+// j = 0 .. 3 (8 columns each), v[4 j + 0 .. 1] = lane (t / 4), columns 8 j + 2 (t % 4) + {0, 1} and v[4 j + 2 .. 3] = lane (t / 4) + 8, same columns
+// (the mma accumulator fragment; checked on hardware by tests/test_gpu_umma.py::test_tmem_ld_16x256b_layout)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // fp32 -> bf16 hi + bf16 lo (x ~= hi + lo, |err| ~ 2^-17 |x|)

@@ -10,7 +10,7 @@ namespace tb {
 
 __global__ void __launch_bounds__(128)
 umma_shifted_gemm_kernel(const uint4 *__restrict__ a, int n_pos, int n_cg, int shift,
-                         const uint4 *__restrict__ b, int N, float *__restrict__ dout)
+                         const uint4 *__restrict__ b, int N, float *__restrict__ dout, float *__restrict__ raw16)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
@@ -46,6 +46,17 @@ umma_shifted_gemm_kernel(const uint4 *__restrict__ a, int n_pos, int n_cg, int s
         umma::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) dout[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    if (raw16) {            // the same accumulator through the 16x256b.x4 shape: raw16[warp][c0 / 32][lane half][thread][16 registers]
+        for (int c0 = 0; c0 + 32 <= N; c0 += 32)
+            for (int lh = 0; lh < 2; ++lh) {
+                uint32_t v[16];
+                umma::tmem_ld_16x256b_x4(tm + ((uint32_t)(warp * 32 + lh * 16) << 16) + (uint32_t)c0, v);
+                umma::tmem_ld_wait();
+                float *o = raw16 + ((((size_t)warp * (N / 32) + c0 / 32) * 2 + lh) * 32 + (tid & 31)) * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]);
+            }
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -112,7 +123,18 @@ umma_mixed_gemm_kernel(const uint4 *__restrict__ a16, int n_pos, int n_cg, int s
 
 #define TB_DEBUG_EXPORTS 1
 // bring-up entry point: exported for tests/test_gpu_umma.py, declared in the header only under TB_DEBUG_EXPORTS (not product ABI)
+static int umma_shifted_gemm_run(const void *a_host, int n_pos, int n_cg, int shift, const void *b_host, int N, float *d_host, float *raw16_host);
 extern "C" __attribute__((visibility("default"))) int tbdbg_umma_shifted_gemm(const void *a_host, int n_pos, int n_cg, int shift, const void *b_host, int N, float *d_host)
+{
+    return umma_shifted_gemm_run(a_host, n_pos, n_cg, shift, b_host, N, d_host, nullptr);
+}
+// the same GEMM; additionally returns the accumulator as the 16x256b.x4 TMEM load shape delivers it: raw16[4 warps][N / 32][2 lane halves][32 threads][16]
+extern "C" __attribute__((visibility("default"))) int tbdbg_tmem_ld_16x256b(const void *a_host, int n_pos, int n_cg, int shift, const void *b_host, int N, float *d_host, float *raw16_host)
+{
+    TB_REQUIRE(raw16_host && N % 32 == 0, TB_ERR_INVALID, "tbdbg_tmem_ld_16x256b: need the raw output and N % 32 == 0");
+    return umma_shifted_gemm_run(a_host, n_pos, n_cg, shift, b_host, N, d_host, raw16_host);
+}
+static int umma_shifted_gemm_run(const void *a_host, int n_pos, int n_cg, int shift, const void *b_host, int N, float *d_host, float *raw16_host)
 {
     using namespace tb;
     TB_REQUIRE(a_host && b_host && d_host, TB_ERR_INVALID, "tbdbg_umma_shifted_gemm: null argument");
@@ -120,16 +142,18 @@ extern "C" __attribute__((visibility("default"))) int tbdbg_umma_shifted_gemm(co
                TB_ERR_INVALID, "tbdbg_umma_shifted_gemm: bad shape");
     const size_t abytes = (size_t)n_cg * n_pos * 16, bbytes = (size_t)n_cg * N * 16;
     TB_REQUIRE(abytes + bbytes <= 200 * 1024, TB_ERR_INVALID, "tbdbg_umma_shifted_gemm: operands exceed shared memory");
-    void *da = nullptr, *db = nullptr; float *dd = nullptr;
+    void *da = nullptr, *db = nullptr; float *dd = nullptr, *dr = nullptr;
     TB_CUDA(cudaMalloc(&da, abytes)); TB_CUDA(cudaMalloc(&db, bbytes)); TB_CUDA(cudaMalloc((void **)&dd, (size_t)128 * N * 4));
+    if (raw16_host) TB_CUDA(cudaMalloc((void **)&dr, (size_t)128 * N * 4));
     TB_CUDA(cudaMemcpy(da, a_host, abytes, cudaMemcpyHostToDevice));
     TB_CUDA(cudaMemcpy(db, b_host, bbytes, cudaMemcpyHostToDevice));
     TB_CUDA(cudaFuncSetAttribute(umma_shifted_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(abytes + bbytes)));
-    umma_shifted_gemm_kernel<<<1, 128, abytes + bbytes>>>((const uint4 *)da, n_pos, n_cg, shift, (const uint4 *)db, N, dd);
+    umma_shifted_gemm_kernel<<<1, 128, abytes + bbytes>>>((const uint4 *)da, n_pos, n_cg, shift, (const uint4 *)db, N, dd, dr);
     TB_CUDA(cudaGetLastError());
     TB_CUDA(cudaDeviceSynchronize());
     TB_CUDA(cudaMemcpy(d_host, dd, (size_t)128 * N * 4, cudaMemcpyDeviceToHost));
-    cudaFree(da); cudaFree(db); cudaFree(dd);
+    if (raw16_host) TB_CUDA(cudaMemcpy(raw16_host, dr, (size_t)128 * N * 4, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dd); if (dr) cudaFree(dr);
     return TB_OK;
 }
 

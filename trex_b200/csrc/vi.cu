@@ -347,7 +347,7 @@ struct tb_vi {
     float *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *h1 = nullptr;
     uint8_t *d_img = nullptr; float *d_probs = nullptr, *d_logits = nullptr;
     // tensor-core path (precision 1)
-    uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w1t = nullptr, *w2t = nullptr, *w3t = nullptr, *wfc = nullptr;
+    uint8_t *in2 = nullptr, *in3 = nullptr, *fca = nullptr, *w1t = nullptr, *w2t = nullptr, *w2p = nullptr, *w3t = nullptr, *wfc = nullptr;
     int fc_groups = 0, n_sms = 148, head_w_smem = 0;
     uint32_t *top_id = nullptr; float *top_p = nullptr;     // optional device outputs: arg-max class and its probability per image
     uint64_t launches = 0;
@@ -408,7 +408,7 @@ extern "C" int tb_vi_create(const tb_vi_config *cfg, tb_vi **out)
         A(h->in2, CH * tc::Conv2Cfg::IMG_BYTES + 256); A(h->in3, CH * tc::Conv3Cfg::IMG_BYTES + 256);
         A(h->fca, (size_t)2 * h->fc_groups * tc::FC_KC * 128);
         A(h->w1t, (size_t)tc::Conv1T::W_BYTES * CI);
-        A(h->w2t, (size_t)tc::Conv2D::W_BYTES); A(h->w3t, (size_t)25 * tc::Conv3Cfg::WTAP_BYTES);
+        A(h->w2t, (size_t)tc::Conv2D::W_BYTES); A(h->w2p, (size_t)tc::Conv2P::W_BYTES); A(h->w3t, (size_t)25 * tc::Conv3Cfg::WTAP_BYTES);
         A(h->wfc, (size_t)2 * tc::FC_KC * tc::FC_N * 16);
         if (r == TB_OK) {   // halo positions are never written by the kernels: zero once
             if (cudaMemset(h->in2, 0, CH * tc::Conv2Cfg::IMG_BYTES + 256) != cudaSuccess || cudaMemset(h->in3, 0, CH * tc::Conv3Cfg::IMG_BYTES + 256) != cudaSuccess ||
@@ -562,6 +562,36 @@ static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int 
     return TB_OK;
 }
 
+// conv2, tap-pair kernel (fp16 / fp16c): 10 pair slots of 8 KB -- [fp16: group 0: 64 rows of tap (dy, dx) then 64 rows of tap (dy + 1, dx) | group 1]
+// [e5m2: plane 0 (fp16(w) * 2^-8): 128 rows | plane 1 ((w - fp16(w)) * 2^8): 128 rows] for dy = 0, 2 -- then 5 single slots of 4 KB (dy = 4, 64-row blocks)
+static int vi_upload_tc_conv2_pair(uint8_t *dst, const std::vector<float> &w, const float *scale, bool fp16c)
+{
+    constexpr int NOUT = 64, CIN = 16;
+    std::vector<uint8_t> b(tc::Conv2P::W_BYTES, 0);
+    auto wt = [&](int co, int ci, int dy, int dx) { return w[((size_t)co * CIN + ci) * 25 + dy * 5 + dx] * (scale ? scale[co] : 1.f); };
+    auto fill = [&](uint8_t *slot, int rows, int row0, int dy, int dx) {      // rows = rows per block (128 pair / 64 single); row0 = 0 or 64
+        uint16_t *h16 = reinterpret_cast<uint16_t *>(slot);
+        uint8_t *f8 = slot + (size_t)2 * rows * 16;
+        for (int co = 0; co < NOUT; ++co) {
+            float w16[16];
+            for (int c = 0; c < 16; ++c) {
+                w16[c] = wt(co, c, dy, dx);
+                h16[(((size_t)(c >> 3) * rows) + row0 + co) * 8 + (c & 7)] = __half_as_ushort(__float2half_rn(w16[c]));
+            }
+            if (fp16c) fp16c_weight_bytes(w16, f8 + ((size_t)0 * rows + row0 + co) * 16, f8 + ((size_t)1 * rows + row0 + co) * 16);
+        }
+    };
+    for (int pr = 0; pr < 2; ++pr)
+        for (int dx = 0; dx < 5; ++dx) {
+            uint8_t *slot = b.data() + (size_t)(pr * 5 + dx) * tc::Conv2P::PAIR_BYTES;
+            fill(slot, 128, 0, 2 * pr, dx);
+            fill(slot, 128, 64, 2 * pr + 1, dx);
+        }
+    for (int dx = 0; dx < 5; ++dx) fill(b.data() + (size_t)10 * tc::Conv2P::PAIR_BYTES + (size_t)dx * tc::Conv2P::SINGLE_BYTES, 64, 0, 4, dx);
+    TB_CUDA(cudaMemcpy(dst, b.data(), b.size(), cudaMemcpyHostToDevice));
+    return TB_OK;
+}
+
 // conv weight torch [Cout][Cin][5][5] -> [tap][Cin][Cout]; BN(eval) folded with the conv bias into
 // y = conv * s + t,  s = gamma / sqrt(var + eps),  t = (bias - mean) * s + beta
 // `cout` is the width the kernels are built for, `creal` the network's (V100 / V110: conv3 has 100 channels, padded with zero
@@ -696,6 +726,7 @@ extern "C" int tb_vi_commit(tb_vi *h)
         TB_CUDA(cudaMemcpy(sc3.data(), h->s3, 128 * 4, cudaMemcpyDeviceToHost));
         const bool f16 = h->cfg.precision >= 2, fp16c = h->cfg.precision == 3;
         if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data(), f16, fp16c))) return r;
+        if (f16 && (r = vi_upload_tc_conv2_pair(h->w2p, *c2, sc2.data(), fp16c))) return r;
         if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, sc3.data(), f16, fp16c))) return r;
         // fc1 B operand [hi|lo][kc = c8*100 + pp][112][8]; torch column = (c8*8+e)*100 + pp
         std::vector<uint16_t> wb((size_t)2 * tc::FC_KC * tc::FC_N * 8, 0);
@@ -726,6 +757,8 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<FP16C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_pair_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2P::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_pair_kernel<FP16C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2P::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<BF16X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<FP16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<FP16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
@@ -746,7 +779,10 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         h->prof.mark(slot, 1);
         {
             const int g2 = std::min(n * Conv2D::BANDS, h->n_sms);
-            if (prec == 2) conv2_2d_kernel<FP16><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
+            static const int pair_env = getenv("TB_VI_CONV2_PAIR") ? atoi(getenv("TB_VI_CONV2_PAIR")) : 1;     // 0: the one-tap-per-MMA kernel
+            if (prec == 2 && pair_env) conv2_pair_kernel<FP16><<<g2, Conv2D::THREADS, Conv2P::SMEM, s>>>(h->in2, n, n_dev, base, h->w2p, h->s2, h->t2, h->in3);
+            else if (prec == 3 && pair_env) conv2_pair_kernel<FP16C><<<g2, Conv2D::THREADS, Conv2P::SMEM, s>>>(h->in2, n, n_dev, base, h->w2p, h->s2, h->t2, h->in3);
+            else if (prec == 2) conv2_2d_kernel<FP16><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
             else if (prec == 3) conv2_2d_kernel<FP16C><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
             else conv2_2d_kernel<BF16X3><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
         }

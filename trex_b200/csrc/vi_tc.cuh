@@ -520,6 +520,218 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv2, "tap-pair" variant for the FP16 / FP16C arithmetic.  conv2_2d_kernel is bound by the tensor core's shared-memory operand
+// feed (position-major: M = 128 positions, N = 64 channels, so every 32-cycle MMA reads 4 KB of A and 2 KB of B: ~97 B / cycle measured,
+// 62 cycles per MMA).  Here two filter rows share one MMA: the B operand holds the weights of tap (dy, dx) in columns 0 .. 63 and of tap
+// (dy + 1, dx) in columns 64 .. 127 (N = 128), the A operand is read once for both.  With the common A start q0 + dy * WP + dx the second
+// block is the contribution of tap (dy + 1, dx) to the output position ONE ROW UP, so
+//     out[ty][tx][c] = D[ty][tx][c] + D[ty + 1][tx][64 + c] :
+// in the 8 x 16 tile TMEM lane r + 8 is the same pixel one row down -- a shuffle by 8 lanes inside a warp, and 8 lanes per warp boundary
+// through a 1 KB shared-memory hand-over.  Row 15 of a tile has no partner: a band yields 14 output rows (bands at y0 = 0, 14, 26 cover the
+// 40 rows like the 16-row bands at 0, 16, 24 did).  Per tile: 10 pair MMAs (filter rows 0+1, 2+3) + 5 single N = 64 MMAs (row 4):
+// 110 KB of operand reads instead of 150 KB per arithmetic term.  Weights: 10 pair slots of 8 KB ([fp16: g0 128 rows | g1 128 rows]
+// [e5m2: plane0 128 rows | plane1 128 rows]) then 5 single slots of 4 KB (64-row blocks), 100 KB like the other variant.
+// ------------------------------------------------------------------------------------------------
+struct Conv2P {
+    using D = Conv2D;
+    static constexpr int ROWS_OUT = 14, NACC = 4, ACC_COLS = 2 * D::NOUT;
+    static constexpr int PAIR_BYTES = 8192, SINGLE_BYTES = 4096, W_BYTES = 10 * PAIR_BYTES + 5 * SINGLE_BYTES;
+    static constexpr int XCH_BYTES = D::EPI_SETS * 2 * 3 * 32 * 8 * 4;        // [set][half][boundary][32 threads][8 values] f32
+    static constexpr int SMEM = 2 * D::IN_BYTES + W_BYTES + D::NOUT * 8 + XCH_BYTES + 128;
+    static_assert(W_BYTES == D::W_BYTES, "same weight buffer size as conv2_2d_kernel");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    __host__ __device__ static constexpr int y0(int band) { return band == 0 ? 0 : (band == 1 ? 14 : 26); }
+    __host__ __device__ static constexpr int ymin(int band) { return band == 0 ? 0 : (band == 1 ? 14 : 28); }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(Conv2D::THREADS, 1)
+conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
+                  const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
+                  uint8_t *__restrict__ out)
+{
+    static_assert(MODE == FP16 || MODE == FP16C, "the tap-pair kernel is built for the fp16 arithmetics");
+    using C = Conv2D;
+    using P = Conv2P;
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr bool F16 = MODE == FP16;
+    constexpr int NACC = P::NACC, ACC_COLS = P::ACC_COLS;
+    __shared__ uint64_t bar_in_full[2], bar_in_empty[2], bar_acc_full[P::NACC], bar_acc_empty[P::NACC], bar_w_full;
+    __shared__ uint32_t s_tmem;
+    uint8_t *s_in = smem;                                            // [2][IN_BYTES]
+    uint8_t *s_w = smem + 2 * C::IN_BYTES;
+    float *s_sc = reinterpret_cast<float *>(s_w + P::W_BYTES), *s_sh = s_sc + C::NOUT;
+    float *s_x = s_sh + C::NOUT;                                     // row hand-over between the warps of a tile
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
+    const int n_items = max(n_act, 0) * C::BANDS;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_in_full[i], 1); umma::mbar_init(&bar_in_empty[i], 1); }
+        for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 8); }
+        umma::mbar_init(&bar_w_full, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(&s_tmem, 512);
+    for (int i = tid; i < C::NOUT; i += C::THREADS) { s_sc[i] = sc[i]; s_sh[i] = sh[i]; }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tm = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            umma::mbar_expect_tx(&bar_w_full, P::W_BYTES);
+            for (int o = 0; o < P::W_BYTES; o += 4096) umma::bulk_g2s(s_w + o, wgt + o, 4096, &bar_w_full);
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int img = item / C::BANDS, band = item % C::BANDS;
+                const int y0 = P::y0(band);
+                const int rows = min(C::IN_ROWS, C::H + 4 - y0);            // the last band ends with the plane (rows 18, 19 only feed discarded outputs)
+                const uint32_t b = it & 1;
+                umma::mbar_wait(&bar_in_empty[b], ((it >> 1) & 1) ^ 1);
+                constexpr int NPL = F16 ? C::G : 2 * C::G;                 // fp16: hi planes only
+                umma::mbar_expect_tx(&bar_in_full[b], (uint32_t)(NPL * rows * C::WP * 16));
+                const uint8_t *src = in + (size_t)img * Conv2Cfg::IMG_BYTES + (size_t)y0 * C::WP * 16;
+                for (int p = 0; p < NPL; ++p)
+                    umma::bulk_g2s(s_in + (size_t)b * C::IN_BYTES + (size_t)p * C::BAND_POS * 16, src + (size_t)p * Conv2Cfg::PL * 16,
+                                   (uint32_t)(rows * C::WP * 16), &bar_in_full[b]);
+            }
+        }
+    } else if (warp == 1) {
+        if (umma::elect_one()) {
+            const uint32_t id128 = umma::idesc_f16_f32(128, 2 * C::NOUT), id64 = umma::idesc_f16_f32(128, C::NOUT);
+            const uint32_t id128_8 = umma::idesc_e5m2_f32(128, 2 * C::NOUT), id64_8 = umma::idesc_e5m2_f32(128, C::NOUT);
+            const uint64_t wp_base = umma::smem_desc(umma::smem_u32(s_w), 2 * C::NOUT * 16, 128);        // pair slots: 128-row blocks
+            const uint64_t ws_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);            // single slots: 64-row blocks
+            umma::mbar_wait(&bar_w_full, 0);
+            uint32_t it = 0, ai = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t b = it & 1;
+                const uint64_t a_base = umma::smem_desc(umma::smem_u32(s_in + (size_t)b * C::IN_BYTES), C::BAND_POS * 16, C::WP * 16);
+                umma::mbar_wait(&bar_in_full[b], (it >> 1) & 1);
+                umma::fence_after_sync();
+#pragma unroll 1
+                for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
+                    const uint32_t buf = ai % NACC;
+                    umma::mbar_wait(&bar_acc_empty[buf], ((ai / NACC) & 1) ^ 1);
+                    umma::fence_after_sync();
+                    const uint32_t d = tm + buf * ACC_COLS;
+                    const uint64_t a_tile = umma::desc_add(a_base, (uint32_t)(tx * 8));
+#pragma unroll
+                    for (int sl = 0; sl < 10; ++sl) {                                   // filter rows (0, 1) and (2, 3), 5 columns each
+                        const uint32_t pos = (uint32_t)((2 * (sl / 5)) * C::WP + (sl % 5));
+                        const uint32_t w = (uint32_t)(sl * P::PAIR_BYTES >> 4);
+                        umma::mma_bf16(d, umma::desc_add(a_tile, pos), umma::desc_add(wp_base, w), id128, sl != 0);
+                        if (MODE == FP16C) umma::mma_f8(d, umma::desc_add(a_tile, (uint32_t)(C::G * C::BAND_POS) + pos), umma::desc_add(wp_base, w + 256u), id128_8, 1);
+                    }
+#pragma unroll
+                    for (int dx = 0; dx < 5; ++dx) {                                    // filter row 4: columns 0 .. 63 only
+                        const uint32_t pos = (uint32_t)(4 * C::WP + dx);
+                        const uint32_t w = (uint32_t)((10 * P::PAIR_BYTES + dx * P::SINGLE_BYTES) >> 4);
+                        umma::mma_bf16(d, umma::desc_add(a_tile, pos), umma::desc_add(ws_base, w), id64, 1);
+                        if (MODE == FP16C) umma::mma_f8(d, umma::desc_add(a_tile, (uint32_t)(C::G * C::BAND_POS) + pos), umma::desc_add(ws_base, w + 128u), id64_8, 1);
+                    }
+                    umma::commit(&bar_acc_full[buf]);
+                }
+                umma::commit(&bar_in_empty[b]);
+            }
+        }
+    } else {
+        // Epilogue with the 16x256b TMEM load shape (the mma accumulator fragment): thread t of a warp holds, for pixel column tx = t / 4 of
+        // the tile, the FOUR tile rows of the warp's lane quarter (lanes t/4, t/4 + 8 of each 16-lane half) and two adjacent channels per
+        // 8-channel group -- so "lane r + 8" (the same pixel one row down) is in the same thread: the tap-pair sum and the vertical half of
+        // the max-pool are thread-local, the horizontal half is one exchange with thread t ^ 4, and only a warp's last row takes its block-B
+        // partner from the next warp (8 values per thread through shared memory).
+        const int ew = (warp - 2) & 7, set = (warp - 2) >> 3, quarter = warp & 3, half = ew >> 2;     // half: which 32 of the 64 output channels
+        const int txq = lane >> 2, cp = lane & 3;                      // pixel column inside the tile, channel pair inside a group
+        float *xw = s_x + (size_t)(((set * 2 + half) * 3 + (quarter - 1)) * 32 + lane) * 8;      // written by quarters 1 .. 3
+        const float *xr = s_x + (size_t)(((set * 2 + half) * 3 + quarter) * 32 + lane) * 8;      // read by quarters 0 .. 2
+        const int prow = 2 * quarter + (txq & 1);                      // pooled row (inside the band) this thread ends up owning
+        float shv[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { shv[2 * j] = s_sh[(half * 4 + j) * 8 + 2 * cp]; shv[2 * j + 1] = s_sh[(half * 4 + j) * 8 + 2 * cp + 1]; }
+        uint32_t ai = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int img = item / C::BANDS, band = item % C::BANDS;
+            const int y0 = P::y0(band), ymin = P::ymin(band);
+            const int y = y0 + 2 * prow;
+            const bool blk_ok = 2 * prow + 1 < P::ROWS_OUT && y >= ymin && y < C::H;      // both rows of the 2x2 block are complete and stored by this band
+#pragma unroll 1
+            for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
+                if ((int)(ai & (C::EPI_SETS - 1)) != set) continue;           // the other set's tile
+                const uint32_t buf = ai % NACC;
+                umma::mbar_wait(&bar_acc_full[buf], (ai / NACC) & 1);
+                umma::fence_after_sync();
+                uint32_t a0[16], a1[16], b0[16], b1[16];                   // rows (0, 1) and (2, 3) of the quarter: block A / block B
+                const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + half * 32;
+                umma::tmem_ld_16x256b_x4(ta + C::NOUT, b0);
+                umma::tmem_ld_16x256b_x4(ta + (16u << 16) + C::NOUT, b1);
+                umma::tmem_ld_16x256b_x4(ta, a0);
+                umma::tmem_ld_16x256b_x4(ta + (16u << 16), a1);
+                umma::tmem_ld_wait();
+                umma::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);     // values are in registers: buffer reusable
+                if (quarter > 0) {                                         // block B of this warp's first row: the partner of the previous warp's last row
+                    *reinterpret_cast<float4 *>(xw) = make_float4(__uint_as_float(b0[0]), __uint_as_float(b0[1]), __uint_as_float(b0[4]), __uint_as_float(b0[5]));
+                    *reinterpret_cast<float4 *>(xw + 4) = make_float4(__uint_as_float(b0[8]), __uint_as_float(b0[9]), __uint_as_float(b0[12]), __uint_as_float(b0[13]));
+                }
+                asm volatile("bar.sync %0, 256;" :: "r"(1 + set) : "memory");
+                float bn[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (quarter < 3) {
+                    const float4 u0 = *reinterpret_cast<const float4 *>(xr), u1 = *reinterpret_cast<const float4 *>(xr + 4);
+                    bn[0] = u0.x; bn[1] = u0.y; bn[2] = u0.z; bn[3] = u0.w; bn[4] = u1.x; bn[5] = u1.y; bn[6] = u1.z; bn[7] = u1.w;
+                }
+                asm volatile("bar.sync %0, 256;" :: "r"(3 + set) : "memory");     // the hand-over buffer may be rewritten
+                // out[k] = A[k] + B[k + 1]; pooled rows: max(out[0], out[1]) and max(out[2], out[3]); registers 4 j + 2 h + e
+                float m[2][8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float o0 = __uint_as_float(a0[4 * j + e]) + __uint_as_float(b0[4 * j + 2 + e]);
+                        const float o1 = __uint_as_float(a0[4 * j + 2 + e]) + __uint_as_float(b1[4 * j + e]);
+                        const float o2 = __uint_as_float(a1[4 * j + e]) + __uint_as_float(b1[4 * j + 2 + e]);
+                        const float o3 = __uint_as_float(a1[4 * j + 2 + e]) + bn[2 * j + e];
+                        m[0][2 * j + e] = fmaxf(o0, o1);
+                        m[1][2 * j + e] = fmaxf(o2, o3);
+                    }
+                // horizontal half of the pool: the even pixel column keeps pooled row 0, the odd one pooled row 1
+                float mm[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float keep = (txq & 1) ? m[1][k] : m[0][k], send = (txq & 1) ? m[0][k] : m[1][k];
+                    mm[k] = fmaxf(fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4)) + shv[k], 0.f);      // BN scale is in the weights; + shift, ReLU
+                }
+                if (blk_ok) {
+                    constexpr int WPN = Conv3Cfg::WP, PLN = Conv3Cfg::PL, GN = Conv3Cfg::G;
+                    const int pos = ((y >> 1) + 2) * WPN + tx * 4 + (txq >> 1) + 2;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int g = half * 4 + j;
+                        const __half h0 = __float2half_rn(mm[2 * j]), h1 = __float2half_rn(mm[2 * j + 1]);
+                        uint8_t *o = out + ((((size_t)img * 2 + 0) * GN + g) * PLN + pos) * 16 + cp * 4;
+                        *reinterpret_cast<uint32_t *>(o) = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        if (MODE == FP16C) {
+                            const float f0 = __half2float(h0), f1 = __half2float(h1);
+                            const uint16_t l2 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2((mm[2 * j] - f0) * FC_UP, (mm[2 * j + 1] - f1) * FC_UP), __NV_SATFINITE, __NV_E5M2);
+                            const uint16_t h2 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(f0 * FC_DOWN, f1 * FC_DOWN), __NV_SATFINITE, __NV_E5M2);
+                            uint8_t *lo_base = out + ((((size_t)img * 2 + 1) * GN + (g & ~1)) * PLN + pos) * 16 + (g & 1) * 8 + cp * 2;
+                            *reinterpret_cast<uint16_t *>(lo_base) = l2;
+                            *reinterpret_cast<uint16_t *>(lo_base + (size_t)PLN * 16) = h2;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tm, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // fc1 on tensor cores: h1[128 images][112] = A[128][12800] * B[112][12800]^T (+ bias), bf16x3.
 // One CTA per 128 images, 3-stage bulk-copy pipeline over K (4 k-steps of 16 per stage).
 // ------------------------------------------------------------------------------------------------
