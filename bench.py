@@ -347,7 +347,7 @@ def run_ours(args, cfg):
         pass
 
     slots = []
-    for k in range(2):
+    for k in range(max(2, args.slots)):
         s = Slot()
         s.bs = trex_b200.BackgroundSubtraction(bg, settings=settings, max_batch=B, max_individuals=KMAX, device=dev_index)
         s.res = s.bs.device_results()
@@ -362,7 +362,7 @@ def run_ours(args, cfg):
         s.stream = torch.cuda.Stream(dev)
         s.meta_all = torch.empty((world_size, s.meta.gather_bytes), dtype=torch.uint8, device=dev) if world_size > 1 else None
         s.ev_done, s.ev_gathered = torch.cuda.Event(), torch.cuda.Event()
-        s.pending = False
+        s.pending = s.used = False
         slots.append(s)
 
     def net_of(s, precision):
@@ -383,6 +383,7 @@ def run_ours(args, cfg):
 
     def step_device(i, precision, logits=False):
         s = slots[i % 2]
+        s.used = True
         if world_size > 1:
             main.wait_event(s.ev_gathered)          # the block of this slot was gathered two steps ago
         s.bs.apply_device(dev_batches[i % pool].data_ptr(), B, main.cuda_stream, fetch=0)
@@ -446,10 +447,14 @@ def run_ours(args, cfg):
         return dict(ms=ms, value=world_size * B * args.steps / (ms * 1e-3), clocks=clocks, launches=int(launches), per=per,
                     tot=tot, runs_per_batch=runs_per_batch)
 
-    # ---- e2e: two slots (seg handle + CNN handle + stream each) so the H2D copy of batch i+1 overlaps the kernels of batch i;
-    # every step still moves its frames host->device and its results device->host ----
+    # ---- e2e: --slots slots (seg handle + CNN handle + stream each) so the H2D copy of batch i+1 overlaps the kernels of batch i; with
+    # three, the copy engine already holds the next batch while the host fetches the results of the previous one.
+    # Every step still moves its frames host->device and its results device->host ----
+    NS = len(slots)
+
     def e2e_submit(i, precision, batches):
-        s = slots[i % 2]
+        s = slots[i % NS]
+        s.used = True
         s.bs.submit(batches[i % len(batches)], fetch=1)                     # tb_seg_submit: H2D frames + kernels
         net_of(s, precision).predict_device(s.res[0], B * KMAX, s.res[1], s.probs.data_ptr(), 0, s.stream.cuda_stream)
         if cfg["posture"]:
@@ -462,7 +467,7 @@ def run_ours(args, cfg):
         s.pending = True
 
     def e2e_wait(i):
-        s = slots[i % 2]
+        s = slots[i % NS]
         if not s.pending:
             return 0, 0
         s.bs.wait()                                                          # tb_seg_wait: blob records, lines, pixels on the host
@@ -477,18 +482,20 @@ def run_ours(args, cfg):
 
     def measure_e2e(precision, batches, steps):
         for s in slots:
-            s.bs.wait()
+            if s.used:
+                s.bs.wait()
             s.bs.set_stream(s.stream.cuda_stream)
-        for i in range(4):
+        for i in range(2 * NS):
             e2e_wait(i); e2e_submit(i, precision, batches)
-        e2e_wait(0); e2e_wait(1)
+        for i in range(NS):
+            e2e_wait(i)
         barrier()
         t0 = time.perf_counter()
         h2d = d2h = 0
         for i in range(steps):
             a, b = e2e_wait(i); h2d += a; d2h += b
             e2e_submit(i, precision, batches)
-        for i in range(2):
+        for i in range(steps, steps + NS):
             a, b = e2e_wait(i); h2d += a; d2h += b
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
@@ -686,7 +693,7 @@ def run_ours(args, cfg):
                     "parallelism": f"frame-batch data parallel x{world_size}" + (", one NCCL all-gather of the in-place metadata block per step on a side stream" if world_size > 1 else ""),
                     "gpu_order": {"cuda_devices": order[:world_size], "groups": groups, "by": order_why}},
             "e2e": {"value": e2e[p0]["value"], "unit": "frames/s", "h2d_bytes_per_step": e2e[p0]["h2d"], "d2h_bytes_per_step": e2e[p0]["d2h"],
-                    "timing": "wall clock bracketed by device syncs, max over ranks; 2 batches in flight (H2D of batch i+1 overlaps kernels of batch i)",
+                    "timing": f"wall clock bracketed by device syncs, max over ranks, pipeline fill and drain inside; {max(2, args.slots)} batches in flight (H2D of batch i+1 overlaps kernels of batch i)",
                     "source": "page-locked host buffers from tb_host_alloc",
                     "pageable": ({"value": pageable["value"], "unit": "frames/s", "source": "ordinary pageable host memory (numpy)"} if pageable else None),
                     "h2d_gbs_per_rank": h2d_gbs, "h2d_gbs_needed_at_value": r0["value"] / world_size * H * W / 1e9,
@@ -716,6 +723,7 @@ def main():
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5], help="3: BASELINE configs[2] (the metric's; default), 4: 256 individuals / classes, "
                     "5: 3840x2160 + posture (outlines and midlines inside the step; headline roofline = the segmentation kernel vs HBM)")
     ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (default: 256 / 128 / 64 for config 3 / 4 / 5)")
+    ap.add_argument("--slots", type=int, default=3, help="batches in flight in the end-to-end loop (handles + streams; the device-timed loop uses two)")
     ap.add_argument("--pool", type=int, default=4, help="distinct resident batches rotated through (defeats L2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU arm / cpu_baseline sample")
