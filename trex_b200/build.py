@@ -42,7 +42,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             continue
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc(), *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), "-c", path, "-o", obj]
+        cmd = [nvcc(), *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), *os.environ.get("TB_NVCC_EXTRA", "").split(), "-c", path, "-o", obj]   # e.g. -DTB_CONV2_STATS
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -96,6 +96,56 @@ __device__ __forceinline__ void commit(uint64_t *mbar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): the MMA of the leader CTA (cluster rank 0) runs on the tensor cores of BOTH SMs of the pair.  M = 256 = 128 rows of A
+// from each CTA's own shared memory (the descriptor offsets are applied in both), N/2 rows of B from each CTA -- so every SM reads only half of the
+// B operand -- and each CTA's TMEM receives its 128 rows x N columns.  Both CTAs' warps of the same index allocate / free together. ----
+__device__ __forceinline__ void tmem_alloc2(uint32_t *smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in every CTA of cta_mask when all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void commit2(uint64_t *mbar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(mbar)), "h"(cta_mask) : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa()); wait with cluster-scope acquire
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// the same without memory ordering: for hand-shakes that publish no generic-proxy data (e.g. "my tcgen05.ld of this accumulator has completed").
+// The .release.cluster form costs a MEMBAR.ALL.GPU, which waits for every earlier global store of the thread.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *mbar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 // the same on a shared::cluster address (e.g. a barrier of the peer CTA of a cluster, see mapa())
 __device__ __forceinline__ void commit_a(uint32_t cluster_addr)
 {

@@ -564,32 +564,63 @@ static int vi_upload_tc_conv_cat(uint8_t *dst, const std::vector<float> &w, int 
 
 // conv2, tap-pair kernel (fp16 / fp16c): 10 pair slots of 8 KB -- [fp16: group 0: 64 rows of tap (dy, dx) then 64 rows of tap (dy + 1, dx) | group 1]
 // [e5m2: plane 0 (fp16(w) * 2^-8): 128 rows | plane 1 ((w - fp16(w)) * 2^8): 128 rows] for dy = 0, 2 -- then 5 single slots of 4 KB (dy = 4, 64-row blocks)
-static int vi_upload_tc_conv2_pair(uint8_t *dst, const std::vector<float> &w, const float *scale, bool fp16c)
+static int vi_upload_tc_conv2_pair(uint8_t *dst, const std::vector<float> &w, const float *scale, bool fp16c, int ncta)
 {
     constexpr int NOUT = 64, CIN = 16;
     std::vector<uint8_t> b(tc::Conv2P::W_BYTES, 0);
     auto wt = [&](int co, int ci, int dy, int dx) { return w[((size_t)co * CIN + ci) * 25 + dy * 5 + dx] * (scale ? scale[co] : 1.f); };
-    auto fill = [&](uint8_t *slot, int rows, int row0, int dy, int dx) {      // rows = rows per block (128 pair / 64 single); row0 = 0 or 64
+    // rows = rows per block of the slot; filter co0 .. co0 + nco - 1 of tap (dy, dx) go to rows row0 ...
+    auto fill = [&](uint8_t *slot, int rows, int row0, int co0, int nco, int dy, int dx) {
         uint16_t *h16 = reinterpret_cast<uint16_t *>(slot);
         uint8_t *f8 = slot + (size_t)2 * rows * 16;
-        for (int co = 0; co < NOUT; ++co) {
+        for (int r = 0; r < nco; ++r) {
             float w16[16];
             for (int c = 0; c < 16; ++c) {
-                w16[c] = wt(co, c, dy, dx);
-                h16[(((size_t)(c >> 3) * rows) + row0 + co) * 8 + (c & 7)] = __half_as_ushort(__float2half_rn(w16[c]));
+                w16[c] = wt(co0 + r, c, dy, dx);
+                h16[(((size_t)(c >> 3) * rows) + row0 + r) * 8 + (c & 7)] = __half_as_ushort(__float2half_rn(w16[c]));
             }
-            if (fp16c) fp16c_weight_bytes(w16, f8 + ((size_t)0 * rows + row0 + co) * 16, f8 + ((size_t)1 * rows + row0 + co) * 16);
+            if (fp16c) fp16c_weight_bytes(w16, f8 + ((size_t)0 * rows + row0 + r) * 16, f8 + ((size_t)1 * rows + row0 + r) * 16);
         }
     };
-    for (int pr = 0; pr < 2; ++pr)
-        for (int dx = 0; dx < 5; ++dx) {
-            uint8_t *slot = b.data() + (size_t)(pr * 5 + dx) * tc::Conv2P::PAIR_BYTES;
-            fill(slot, 128, 0, 2 * pr, dx);
-            fill(slot, 128, 64, 2 * pr + 1, dx);
+    if (ncta == 1) {
+        for (int pr = 0; pr < 2; ++pr)
+            for (int dx = 0; dx < 5; ++dx) {
+                uint8_t *slot = b.data() + (size_t)(pr * 5 + dx) * tc::Conv2P::PAIR_BYTES;
+                fill(slot, 128, 0, 0, NOUT, 2 * pr, dx);
+                fill(slot, 128, 64, 0, NOUT, 2 * pr + 1, dx);
+            }
+        for (int dx = 0; dx < 5; ++dx) fill(b.data() + (size_t)10 * tc::Conv2P::PAIR_BYTES + (size_t)dx * tc::Conv2P::SINGLE_BYTES, 64, 0, 0, NOUT, 4, dx);
+    } else {
+        // CTA pair: rank r of the pair feeds the second half of every B operand's rows: tap (dy + r, dx) of a pair slot, filters 32 r .. 32 r + 31 of a
+        // single slot; the slots shrink to half and each rank's 50 KB are contiguous
+        constexpr int PB = tc::Conv2P::PAIR_BYTES / 2, SB = tc::Conv2P::SINGLE_BYTES / 2, WB = tc::Conv2P::W_BYTES / 2;
+        for (int r = 0; r < 2; ++r) {
+            uint8_t *base = b.data() + (size_t)r * WB;
+            for (int pr = 0; pr < 2; ++pr)
+                for (int dx = 0; dx < 5; ++dx) fill(base + (size_t)(pr * 5 + dx) * PB, 64, 0, 0, NOUT, 2 * pr + r, dx);
+            for (int dx = 0; dx < 5; ++dx) fill(base + (size_t)10 * PB + (size_t)dx * SB, 32, 0, 32 * r, 32, 4, dx);
         }
-    for (int dx = 0; dx < 5; ++dx) fill(b.data() + (size_t)10 * tc::Conv2P::PAIR_BYTES + (size_t)dx * tc::Conv2P::SINGLE_BYTES, 64, 0, 4, dx);
+    }
     TB_CUDA(cudaMemcpy(dst, b.data(), b.size(), cudaMemcpyHostToDevice));
     return TB_OK;
+}
+
+#ifdef TB_CONV2_STATS
+extern "C" __attribute__((visibility("default"))) int tbdbg_conv2_stats(unsigned long long *out16, int reset)
+{
+    cudaDeviceSynchronize();
+    if (out16) cudaMemcpyFromSymbol(out16, tb::tc::g_conv2_stats, 16 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(tb::tc::g_conv2_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
+// TB_VI_CONV2_PAIR: which conv2 kernel the fp16 / fp16c precisions use -- 2 (default): tap pairs on CTA pairs (cta_group::2), 1: tap pairs on single
+// CTAs, 0: the one-tap-per-MMA kernel
+static int vi_conv2_variant()
+{
+    static const int v = getenv("TB_VI_CONV2_PAIR") ? atoi(getenv("TB_VI_CONV2_PAIR")) : 2;
+    return v;
 }
 
 // conv weight torch [Cout][Cin][5][5] -> [tap][Cin][Cout]; BN(eval) folded with the conv bias into
@@ -726,7 +757,7 @@ extern "C" int tb_vi_commit(tb_vi *h)
         TB_CUDA(cudaMemcpy(sc3.data(), h->s3, 128 * 4, cudaMemcpyDeviceToHost));
         const bool f16 = h->cfg.precision >= 2, fp16c = h->cfg.precision == 3;
         if ((r = vi_upload_tc_conv_cat(h->w2t, *c2, 2, 64, sc2.data(), f16, fp16c))) return r;
-        if (f16 && (r = vi_upload_tc_conv2_pair(h->w2p, *c2, sc2.data(), fp16c))) return r;
+        if (f16 && vi_conv2_variant() && (r = vi_upload_tc_conv2_pair(h->w2p, *c2, sc2.data(), fp16c, vi_conv2_variant() == 2 ? 2 : 1))) return r;
         if ((r = vi_upload_tc_conv(h->w3t, *c3, 8, 128, sc3.data(), f16, fp16c))) return r;
         // fc1 B operand [hi|lo][kc = c8*100 + pp][112][8]; torch column = (c8*8+e)*100 + pp
         std::vector<uint16_t> wb((size_t)2 * tc::FC_KC * tc::FC_N * 8, 0);
@@ -757,8 +788,10 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv2_2d_kernel<FP16C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2D::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv2_pair_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2P::SMEM));
-        TB_CUDA(cudaFuncSetAttribute(conv2_pair_kernel<FP16C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2P::SMEM));
+        TB_CUDA(cudaFuncSetAttribute(conv2_pair_kernel<FP16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2P::smem(true, 1)));
+        TB_CUDA(cudaFuncSetAttribute(conv2_pair_kernel<FP16C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2P::smem(false, 1)));
+        TB_CUDA(cudaFuncSetAttribute(conv2_pair_kernel<FP16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2P::smem(true, 2)));
+        TB_CUDA(cudaFuncSetAttribute(conv2_pair_kernel<FP16C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2P::smem(false, 2)));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<BF16X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<FP16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
         TB_CUDA(cudaFuncSetAttribute(conv3_t_kernel<FP16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv3T::SMEM));
@@ -779,9 +812,22 @@ static int vi_forward_tc(tb_vi *h, const uint8_t *img, int n_max, const uint32_t
         h->prof.mark(slot, 1);
         {
             const int g2 = std::min(n * Conv2D::BANDS, h->n_sms);
-            static const int pair_env = getenv("TB_VI_CONV2_PAIR") ? atoi(getenv("TB_VI_CONV2_PAIR")) : 1;     // 0: the one-tap-per-MMA kernel
-            if (prec == 2 && pair_env) conv2_pair_kernel<FP16><<<g2, Conv2D::THREADS, Conv2P::SMEM, s>>>(h->in2, n, n_dev, base, h->w2p, h->s2, h->t2, h->in3);
-            else if (prec == 3 && pair_env) conv2_pair_kernel<FP16C><<<g2, Conv2D::THREADS, Conv2P::SMEM, s>>>(h->in2, n, n_dev, base, h->w2p, h->s2, h->t2, h->in3);
+            const int pair_env = vi_conv2_variant();
+            if (prec >= 2 && pair_env == 2) {
+                // CTA pairs: clusters of two, the leader's MMAs run on both SMs (each reads half of the weights)
+                cudaLaunchConfig_t lc{};
+                lc.gridDim = dim3((unsigned)std::min((n * Conv2D::BANDS + 1) & ~1, h->n_sms & ~1)); lc.blockDim = dim3(Conv2D::THREADS);
+                lc.dynamicSmemBytes = Conv2P::smem(prec == 2, 2); lc.stream = s;
+                cudaLaunchAttribute at{};
+                at.id = cudaLaunchAttributeClusterDimension;
+                at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+                lc.attrs = &at; lc.numAttrs = 1;
+                const uint8_t *a_in = h->in2, *a_w = h->w2p; const float *a_s = h->s2, *a_t = h->t2; uint8_t *a_out = h->in3;
+                if (prec == 2) TB_CUDA(cudaLaunchKernelEx(&lc, conv2_pair_kernel<FP16, 2>, a_in, n, n_dev, base, a_w, a_s, a_t, a_out));
+                else TB_CUDA(cudaLaunchKernelEx(&lc, conv2_pair_kernel<FP16C, 2>, a_in, n, n_dev, base, a_w, a_s, a_t, a_out));
+            }
+            else if (prec == 2 && pair_env) conv2_pair_kernel<FP16, 1><<<g2, Conv2D::THREADS, Conv2P::smem(true, 1), s>>>(h->in2, n, n_dev, base, h->w2p, h->s2, h->t2, h->in3);
+            else if (prec == 3 && pair_env) conv2_pair_kernel<FP16C, 1><<<g2, Conv2D::THREADS, Conv2P::smem(false, 1), s>>>(h->in2, n, n_dev, base, h->w2p, h->s2, h->t2, h->in3);
             else if (prec == 2) conv2_2d_kernel<FP16><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
             else if (prec == 3) conv2_2d_kernel<FP16C><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);
             else conv2_2d_kernel<BF16X3><<<g2, Conv2D::THREADS, Conv2D::SMEM, s>>>(h->in2, n, n_dev, base, h->w2t, h->s2, h->t2, h->in3);

@@ -532,19 +532,44 @@ conv2_2d_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__res
 // 110 KB of operand reads instead of 150 KB per arithmetic term.  Weights: 10 pair slots of 8 KB ([fp16: g0 128 rows | g1 128 rows]
 // [e5m2: plane0 128 rows | plane1 128 rows]) then 5 single slots of 4 KB (64-row blocks), 100 KB like the other variant.
 // ------------------------------------------------------------------------------------------------
+#ifdef TB_CONV2_STATS
+// bring-up counters (cycles, summed over CTAs): [0] MMA thread total, [1] wait own band, [2] wait peer band, [3] wait accumulator free,
+// [4] epilogue warp total, [5] wait accumulator full, [6] hand-over barriers, [7] tiles seen by that warp, [8] producer wait ring slot
+__device__ unsigned long long g_conv2_stats[16];
+#define C2S_DECL long long c2s_t0 = clock64(), c2s_a = 0, c2s_b = 0, c2s_c = 0, c2s_d = 0, c2s_e = 0, c2s_f = 0, c2s_t
+#define C2S_BEGIN c2s_t = clock64()
+#define C2S_END(x) x += clock64() - c2s_t
+#define C2S_FLUSH(i0, i1, i2, i3) do { atomicAdd(&g_conv2_stats[i0], (unsigned long long)(clock64() - c2s_t0)); atomicAdd(&g_conv2_stats[i1], (unsigned long long)c2s_a); \
+    atomicAdd(&g_conv2_stats[i2], (unsigned long long)c2s_b); atomicAdd(&g_conv2_stats[i3], (unsigned long long)c2s_c); } while (0)
+#else
+#define C2S_DECL
+#define C2S_BEGIN
+#define C2S_END(x)
+#define C2S_FLUSH(i0, i1, i2, i3)
+#endif
+
 struct Conv2P {
     using D = Conv2D;
     static constexpr int ROWS_OUT = 14, NACC = 4, ACC_COLS = 2 * D::NOUT;
     static constexpr int PAIR_BYTES = 8192, SINGLE_BYTES = 4096, W_BYTES = 10 * PAIR_BYTES + 5 * SINGLE_BYTES;
     static constexpr int XCH_BYTES = D::EPI_SETS * 2 * 3 * 32 * 8 * 4;        // [set][half][boundary][32 threads][8 values] f32
-    static constexpr int SMEM = 2 * D::IN_BYTES + W_BYTES + D::NOUT * 8 + XCH_BYTES + 128;
+    // NCTA = 2 (CTA pair, cta_group::2): every CTA holds the half of each weight slot that its SM feeds -- rank r the 64 rows of tap (dy + r, dx) of a
+    // pair slot, output channels 32 r .. 32 r + 31 of a single slot.
+    // Input ring: only 18 of a band's 20 input rows feed stored outputs (row 13 = A[13] + B[14] reads rows <= 17), so a plane is loaded as 18 rows and
+    // the planes sit 18 rows apart; the MMAs of the discarded tile rows 14, 15 read on into the next plane / the next region (mapped, never stored).
+    static constexpr int LROWS = 18, PPOS = LROWS * D::WP;
+    static constexpr int planes(bool f16) { return f16 ? D::G : 2 * D::G; }
+    static constexpr int stage_bytes(bool f16) { return planes(f16) * PPOS * 16; }
+    static constexpr int stages(bool f16, int ncta) { return ncta == 2 ? (f16 ? 4 : 3) : 2; }
+    static constexpr int MAX_STAGES = 4;
+    static constexpr int smem(bool f16, int ncta) { return stages(f16, ncta) * stage_bytes(f16) + W_BYTES / ncta + D::NOUT * 8 + XCH_BYTES + 128; }
     static_assert(W_BYTES == D::W_BYTES, "same weight buffer size as conv2_2d_kernel");
-    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     __host__ __device__ static constexpr int y0(int band) { return band == 0 ? 0 : (band == 1 ? 14 : 26); }
     __host__ __device__ static constexpr int ymin(int band) { return band == 0 ? 0 : (band == 1 ? 14 : 28); }
 };
+static_assert(Conv2P::smem(false, 1) <= 227 * 1024 && Conv2P::smem(false, 2) <= 227 * 1024 && Conv2P::smem(true, 2) <= 227 * 1024, "shared memory budget");
 
-template <int MODE>
+template <int MODE, int NCTA>
 __global__ void __launch_bounds__(Conv2D::THREADS, 1)
 conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__restrict__ n_dev, int base,
                   const uint8_t *__restrict__ wgt, const float *__restrict__ sc, const float *__restrict__ sh,
@@ -556,86 +581,122 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr bool F16 = MODE == FP16;
     constexpr int NACC = P::NACC, ACC_COLS = P::ACC_COLS;
-    __shared__ uint64_t bar_in_full[2], bar_in_empty[2], bar_acc_full[P::NACC], bar_acc_empty[P::NACC], bar_w_full;
+    constexpr int WB = P::W_BYTES / NCTA, PAIR_B = P::PAIR_BYTES / NCTA, SINGLE_B = P::SINGLE_BYTES / NCTA;     // this CTA's share of the weights
+    constexpr int STAGES = P::stages(F16, NCTA), STAGE_B = P::stage_bytes(F16), PPOS = P::PPOS;
+    __shared__ uint64_t bar_in_full[P::MAX_STAGES], bar_in_empty[P::MAX_STAGES], bar_acc_full[P::NACC], bar_acc_empty[P::NACC], bar_w_full, bar_peer_full[P::MAX_STAGES];
     __shared__ uint32_t s_tmem;
-    uint8_t *s_in = smem;                                            // [2][IN_BYTES]
-    uint8_t *s_w = smem + 2 * C::IN_BYTES;
-    float *s_sc = reinterpret_cast<float *>(s_w + P::W_BYTES), *s_sh = s_sc + C::NOUT;
+    uint8_t *s_in = smem;                                            // [STAGES][STAGE_B]
+    uint8_t *s_w = smem + STAGES * STAGE_B;
+    float *s_sc = reinterpret_cast<float *>(s_w + WB), *s_sh = s_sc + C::NOUT;
     float *s_x = s_sh + C::NOUT;                                     // row hand-over between the warps of a tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_act = n_dev ? min((int)*n_dev - base, n_max) : n_max;
     const int n_items = max(n_act, 0) * C::BANDS;
+    // NCTA = 2: the two CTAs of a pair walk the item list in lockstep (items 2 q + rank; the odd one out is a dummy: no loads, no stores), because
+    // every MMA the leader issues runs on both SMs, each on its own band
+    const int rank = NCTA == 2 ? (int)umma::cluster_ctarank() : 0;
+    const int first = NCTA == 2 ? (int)(blockIdx.x >> 1) * 2 + rank : (int)blockIdx.x, stride = (int)gridDim.x;
+    const int n_loop = NCTA == 2 ? (n_items + 1) & ~1 : n_items;       // item < n_loop: both CTAs of a pair iterate; item >= n_items: the dummy
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_in_full[i], 1); umma::mbar_init(&bar_in_empty[i], 1); }
-        for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 8); }
+        for (int i = 0; i < STAGES; ++i) { umma::mbar_init(&bar_in_full[i], 1); umma::mbar_init(&bar_in_empty[i], 1); umma::mbar_init(&bar_peer_full[i], 1); }
+        for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bar_acc_full[i], 1); umma::mbar_init(&bar_acc_empty[i], 8 * NCTA); }
         umma::mbar_init(&bar_w_full, 1);
         umma::fence_mbar_init();
     }
-    if (warp == 1) umma::tmem_alloc(&s_tmem, 512);
+    if (warp == 1) { if (NCTA == 2) umma::tmem_alloc2(&s_tmem, 512); else umma::tmem_alloc(&s_tmem, 512); }
     for (int i = tid; i < C::NOUT; i += C::THREADS) { s_sc[i] = sc[i]; s_sh[i] = sh[i]; }
     umma::fence_before_sync();
-    __syncthreads();
+    if (NCTA == 2) umma::cluster_sync(); else __syncthreads();         // barriers of both CTAs initialised before any remote arrive
     umma::fence_after_sync();
     const uint32_t tm = s_tmem;
 
     if (warp == 0) {
         if (lane == 0) {
-            umma::mbar_expect_tx(&bar_w_full, P::W_BYTES);
-            for (int o = 0; o < P::W_BYTES; o += 4096) umma::bulk_g2s(s_w + o, wgt + o, 4096, &bar_w_full);
+            umma::mbar_expect_tx(&bar_w_full, WB);
+            for (int o = 0; o < WB; o += 2048) umma::bulk_g2s(s_w + o, wgt + (size_t)rank * WB + o, 2048, &bar_w_full);
             uint32_t it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            for (int item = first; item < n_loop; item += stride, ++it) {
                 const int img = item / C::BANDS, band = item % C::BANDS;
                 const int y0 = P::y0(band);
-                const int rows = min(C::IN_ROWS, C::H + 4 - y0);            // the last band ends with the plane (rows 18, 19 only feed discarded outputs)
-                const uint32_t b = it & 1;
-                umma::mbar_wait(&bar_in_empty[b], ((it >> 1) & 1) ^ 1);
-                constexpr int NPL = F16 ? C::G : 2 * C::G;                 // fp16: hi planes only
-                umma::mbar_expect_tx(&bar_in_full[b], (uint32_t)(NPL * rows * C::WP * 16));
+                const uint32_t b = it % STAGES;
+                umma::mbar_wait(&bar_in_empty[b], ((it / STAGES) & 1) ^ 1);
+                if (item >= n_items) { umma::mbar_arrive(&bar_in_full[b]); continue; }       // dummy: whatever the buffer holds is multiplied and dropped
+                constexpr int NPL = P::planes(F16);                        // fp16: hi planes only
+                umma::mbar_expect_tx(&bar_in_full[b], (uint32_t)STAGE_B);
                 const uint8_t *src = in + (size_t)img * Conv2Cfg::IMG_BYTES + (size_t)y0 * C::WP * 16;
                 for (int p = 0; p < NPL; ++p)
-                    umma::bulk_g2s(s_in + (size_t)b * C::IN_BYTES + (size_t)p * C::BAND_POS * 16, src + (size_t)p * Conv2Cfg::PL * 16,
-                                   (uint32_t)(rows * C::WP * 16), &bar_in_full[b]);
+                    umma::bulk_g2s(s_in + (size_t)b * STAGE_B + (size_t)p * PPOS * 16, src + (size_t)p * Conv2Cfg::PL * 16, (uint32_t)(PPOS * 16), &bar_in_full[b]);
+            }
+        }
+    } else if (warp == 1 && NCTA == 2 && rank == 1) {
+        // the peer's MMA warp only relays: weights and every input band that landed in THIS CTA's shared memory are announced to the leader
+        if (lane == 0) {
+            umma::mbar_wait(&bar_w_full, 0);
+            uint32_t it = 0;
+            for (int item = first; item < n_loop; item += stride, ++it) {
+                const uint32_t b = it % STAGES;
+                umma::mbar_wait(&bar_in_full[b], (it / STAGES) & 1);
+                umma::mbar_arrive_remote(umma::mapa(umma::smem_u32(&bar_peer_full[b]), 0));
             }
         }
     } else if (warp == 1) {
         if (umma::elect_one()) {
-            const uint32_t id128 = umma::idesc_f16_f32(128, 2 * C::NOUT), id64 = umma::idesc_f16_f32(128, C::NOUT);
-            const uint32_t id128_8 = umma::idesc_e5m2_f32(128, 2 * C::NOUT), id64_8 = umma::idesc_e5m2_f32(128, C::NOUT);
-            const uint64_t wp_base = umma::smem_desc(umma::smem_u32(s_w), 2 * C::NOUT * 16, 128);        // pair slots: 128-row blocks
-            const uint64_t ws_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);            // single slots: 64-row blocks
+            const uint32_t id128 = umma::idesc_f16_f32(128 * NCTA, 2 * C::NOUT), id64 = umma::idesc_f16_f32(128 * NCTA, C::NOUT);
+            const uint32_t id128_8 = umma::idesc_e5m2_f32(128 * NCTA, 2 * C::NOUT), id64_8 = umma::idesc_e5m2_f32(128 * NCTA, C::NOUT);
+            const uint64_t wp_base = umma::smem_desc(umma::smem_u32(s_w), 2 * C::NOUT / NCTA * 16, 128);     // pair slots: 128-row blocks (64 per CTA of a pair)
+            const uint64_t ws_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT / NCTA * 16, 128);         // single slots: 64-row blocks (32 per CTA of a pair)
+            constexpr uint32_t F8P = (uint32_t)(PAIR_B / 2) >> 4, F8S = (uint32_t)(SINGLE_B / 2) >> 4;       // the e5m2 half of a slot, in 16-byte units
             umma::mbar_wait(&bar_w_full, 0);
             uint32_t it = 0, ai = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const uint32_t b = it & 1;
-                const uint64_t a_base = umma::smem_desc(umma::smem_u32(s_in + (size_t)b * C::IN_BYTES), C::BAND_POS * 16, C::WP * 16);
-                umma::mbar_wait(&bar_in_full[b], (it >> 1) & 1);
+            C2S_DECL;
+            for (int item = first; item < n_loop; item += stride, ++it) {
+                const uint32_t b = it % STAGES;
+                const uint64_t a_base = umma::smem_desc(umma::smem_u32(s_in + (size_t)b * STAGE_B), PPOS * 16, C::WP * 16);
+                C2S_BEGIN;
+                umma::mbar_wait(&bar_in_full[b], (it / STAGES) & 1);
+                C2S_END(c2s_a); C2S_BEGIN;
+                if (NCTA == 2) umma::mbar_wait_cluster(&bar_peer_full[b], (it / STAGES) & 1);      // ... and the peer's band (its weights arrived before its first band)
+                C2S_END(c2s_b);
                 umma::fence_after_sync();
 #pragma unroll 1
                 for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
                     const uint32_t buf = ai % NACC;
+                    C2S_BEGIN;
                     umma::mbar_wait(&bar_acc_empty[buf], ((ai / NACC) & 1) ^ 1);
+                    C2S_END(c2s_c);
                     umma::fence_after_sync();
                     const uint32_t d = tm + buf * ACC_COLS;
                     const uint64_t a_tile = umma::desc_add(a_base, (uint32_t)(tx * 8));
 #pragma unroll
                     for (int sl = 0; sl < 10; ++sl) {                                   // filter rows (0, 1) and (2, 3), 5 columns each
                         const uint32_t pos = (uint32_t)((2 * (sl / 5)) * C::WP + (sl % 5));
-                        const uint32_t w = (uint32_t)(sl * P::PAIR_BYTES >> 4);
-                        umma::mma_bf16(d, umma::desc_add(a_tile, pos), umma::desc_add(wp_base, w), id128, sl != 0);
-                        if (MODE == FP16C) umma::mma_f8(d, umma::desc_add(a_tile, (uint32_t)(C::G * C::BAND_POS) + pos), umma::desc_add(wp_base, w + 256u), id128_8, 1);
+                        const uint32_t w = (uint32_t)(sl * PAIR_B >> 4);
+                        if (NCTA == 2) {
+                            umma::mma2_f16(d, umma::desc_add(a_tile, pos), umma::desc_add(wp_base, w), id128, sl != 0);
+                            if (MODE == FP16C) umma::mma2_f8(d, umma::desc_add(a_tile, (uint32_t)(C::G * PPOS) + pos), umma::desc_add(wp_base, w + F8P), id128_8, 1);
+                        } else {
+                            umma::mma_bf16(d, umma::desc_add(a_tile, pos), umma::desc_add(wp_base, w), id128, sl != 0);
+                            if (MODE == FP16C) umma::mma_f8(d, umma::desc_add(a_tile, (uint32_t)(C::G * PPOS) + pos), umma::desc_add(wp_base, w + F8P), id128_8, 1);
+                        }
                     }
 #pragma unroll
                     for (int dx = 0; dx < 5; ++dx) {                                    // filter row 4: columns 0 .. 63 only
                         const uint32_t pos = (uint32_t)(4 * C::WP + dx);
-                        const uint32_t w = (uint32_t)((10 * P::PAIR_BYTES + dx * P::SINGLE_BYTES) >> 4);
-                        umma::mma_bf16(d, umma::desc_add(a_tile, pos), umma::desc_add(ws_base, w), id64, 1);
-                        if (MODE == FP16C) umma::mma_f8(d, umma::desc_add(a_tile, (uint32_t)(C::G * C::BAND_POS) + pos), umma::desc_add(ws_base, w + 128u), id64_8, 1);
+                        const uint32_t w = (uint32_t)((10 * PAIR_B + dx * SINGLE_B) >> 4);
+                        if (NCTA == 2) {
+                            umma::mma2_f16(d, umma::desc_add(a_tile, pos), umma::desc_add(ws_base, w), id64, 1);
+                            if (MODE == FP16C) umma::mma2_f8(d, umma::desc_add(a_tile, (uint32_t)(C::G * PPOS) + pos), umma::desc_add(ws_base, w + F8S), id64_8, 1);
+                        } else {
+                            umma::mma_bf16(d, umma::desc_add(a_tile, pos), umma::desc_add(ws_base, w), id64, 1);
+                            if (MODE == FP16C) umma::mma_f8(d, umma::desc_add(a_tile, (uint32_t)(C::G * PPOS) + pos), umma::desc_add(ws_base, w + F8S), id64_8, 1);
+                        }
                     }
-                    umma::commit(&bar_acc_full[buf]);
+                    if (NCTA == 2) umma::commit2(&bar_acc_full[buf], 3); else umma::commit(&bar_acc_full[buf]);
                 }
-                umma::commit(&bar_in_empty[b]);
+                if (NCTA == 2) umma::commit2(&bar_in_empty[b], 3); else umma::commit(&bar_in_empty[b]);
             }
+            C2S_FLUSH(0, 1, 2, 3);
         }
     } else {
         // Epilogue with the 16x256b TMEM load shape (the mma accumulator fragment): thread t of a warp holds, for pixel column tx = t / 4 of
@@ -652,39 +713,55 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
 #pragma unroll
         for (int j = 0; j < 4; ++j) { shv[2 * j] = s_sh[(half * 4 + j) * 8 + 2 * cp]; shv[2 * j + 1] = s_sh[(half * 4 + j) * 8 + 2 * cp + 1]; }
         uint32_t ai = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        C2S_DECL;
+        for (int item = first; item < n_loop; item += stride) {
             const int img = item / C::BANDS, band = item % C::BANDS;
             const int y0 = P::y0(band), ymin = P::ymin(band);
             const int y = y0 + 2 * prow;
-            const bool blk_ok = 2 * prow + 1 < P::ROWS_OUT && y >= ymin && y < C::H;      // both rows of the 2x2 block are complete and stored by this band
+            const bool blk_ok = 2 * prow + 1 < P::ROWS_OUT && y >= ymin && y < C::H && item < n_items;      // both rows of the 2x2 block are complete and stored by this band
 #pragma unroll 1
             for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
                 if ((int)(ai & (C::EPI_SETS - 1)) != set) continue;           // the other set's tile
                 const uint32_t buf = ai % NACC;
+                C2S_BEGIN;
                 umma::mbar_wait(&bar_acc_full[buf], (ai / NACC) & 1);
+                C2S_END(c2s_a);
                 umma::fence_after_sync();
                 uint32_t a0[16], a1[16], b0[16], b1[16];                   // rows (0, 1) and (2, 3) of the quarter: block A / block B
+                C2S_BEGIN;
                 const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + half * 32;
                 umma::tmem_ld_16x256b_x4(ta + C::NOUT, b0);
                 umma::tmem_ld_16x256b_x4(ta + (16u << 16) + C::NOUT, b1);
                 umma::tmem_ld_16x256b_x4(ta, a0);
                 umma::tmem_ld_16x256b_x4(ta + (16u << 16), a1);
                 umma::tmem_ld_wait();
+                C2S_END(c2s_d);
                 umma::fence_before_sync();
                 __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&bar_acc_empty[buf]);     // values are in registers: buffer reusable
+                if (lane == 0) {                                           // values are in registers: buffer reusable (the leader's barrier counts both CTAs)
+                    if (NCTA == 2 && rank == 1) umma::mbar_arrive_remote_relaxed(umma::mapa(umma::smem_u32(&bar_acc_empty[buf]), 0));
+                    else umma::mbar_arrive(&bar_acc_empty[buf]);
+                }
                 if (quarter > 0) {                                         // block B of this warp's first row: the partner of the previous warp's last row
                     *reinterpret_cast<float4 *>(xw) = make_float4(__uint_as_float(b0[0]), __uint_as_float(b0[1]), __uint_as_float(b0[4]), __uint_as_float(b0[5]));
                     *reinterpret_cast<float4 *>(xw + 4) = make_float4(__uint_as_float(b0[8]), __uint_as_float(b0[9]), __uint_as_float(b0[12]), __uint_as_float(b0[13]));
                 }
+                C2S_BEGIN;
                 asm volatile("bar.sync %0, 256;" :: "r"(1 + set) : "memory");
+                C2S_END(c2s_b);
                 float bn[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (quarter < 3) {
                     const float4 u0 = *reinterpret_cast<const float4 *>(xr), u1 = *reinterpret_cast<const float4 *>(xr + 4);
                     bn[0] = u0.x; bn[1] = u0.y; bn[2] = u0.z; bn[3] = u0.w; bn[4] = u1.x; bn[5] = u1.y; bn[6] = u1.z; bn[7] = u1.w;
                 }
+                C2S_BEGIN;
                 asm volatile("bar.sync %0, 256;" :: "r"(3 + set) : "memory");     // the hand-over buffer may be rewritten
+                C2S_END(c2s_b);
+#ifdef TB_CONV2_STATS
+                ++c2s_c;
+#endif
                 // out[k] = A[k] + B[k + 1]; pooled rows: max(out[0], out[1]) and max(out[2], out[3]); registers 4 j + 2 h + e
+                C2S_BEGIN;
                 float m[2][8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -704,6 +781,7 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
                     const float keep = (txq & 1) ? m[1][k] : m[0][k], send = (txq & 1) ? m[0][k] : m[1][k];
                     mm[k] = fmaxf(fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4)) + shv[k], 0.f);      // BN scale is in the weights; + shift, ReLU
                 }
+                C2S_END(c2s_e); C2S_BEGIN;
                 if (blk_ok) {
                     constexpr int WPN = Conv3Cfg::WP, PLN = Conv3Cfg::PL, GN = Conv3Cfg::G;
                     const int pos = ((y >> 1) + 2) * WPN + tx * 4 + (txq >> 1) + 2;
@@ -723,12 +801,16 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
                         }
                     }
                 }
+                C2S_END(c2s_f);
             }
         }
+#ifdef TB_CONV2_STATS
+        if (warp == 2 && lane == 0) { C2S_FLUSH(4, 5, 6, 7); atomicAdd(&g_conv2_stats[8], (unsigned long long)c2s_d); atomicAdd(&g_conv2_stats[9], (unsigned long long)c2s_e); atomicAdd(&g_conv2_stats[10], (unsigned long long)c2s_f); }
+#endif
     }
     umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tm, 512);
+    if (NCTA == 2) umma::cluster_sync(); else __syncthreads();         // the leader's last MMAs have read the peer's shared memory
+    if (warp == 1) { if (NCTA == 2) umma::tmem_dealloc2(tm, 512); else umma::tmem_dealloc(tm, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------
