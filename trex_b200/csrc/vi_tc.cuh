@@ -552,7 +552,7 @@ struct Conv2P {
     using D = Conv2D;
     static constexpr int ROWS_OUT = 14, NACC = 4, ACC_COLS = 2 * D::NOUT;
     static constexpr int PAIR_BYTES = 8192, SINGLE_BYTES = 4096, W_BYTES = 10 * PAIR_BYTES + 5 * SINGLE_BYTES;
-    static constexpr int XCH_BYTES = D::EPI_SETS * 2 * 3 * 32 * 8 * 4;        // [set][half][boundary][32 threads][8 values] f32
+    static constexpr int XCH_BYTES = 2 * D::EPI_SETS * 2 * 3 * 32 * 8 * 4;    // [parity][set][half][boundary][32 threads][8 values] f32: alternate tiles of a set use alternate buffers
     // NCTA = 2 (CTA pair, cta_group::2): every CTA holds the half of each weight slot that its SM feeds -- rank r the 64 rows of tap (dy + r, dx) of a
     // pair slot, output channels 32 r .. 32 r + 31 of a single slot.
     // Input ring: only 18 of a band's 20 input rows feed stored outputs (row 13 = A[13] + B[14] reads rows <= 17), so a plane is loaded as 18 rows and
@@ -706,19 +706,32 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
         // partner from the next warp (8 values per thread through shared memory).
         const int ew = (warp - 2) & 7, set = (warp - 2) >> 3, quarter = warp & 3, half = ew >> 2;     // half: which 32 of the 64 output channels
         const int txq = lane >> 2, cp = lane & 3;                      // pixel column inside the tile, channel pair inside a group
+        constexpr int XCH_HALF = C::EPI_SETS * 2 * 3 * 32 * 8;        // floats per hand-over buffer; two buffers, so ONE barrier per tile orders
+                                                                       // write -> read AND read -> next write into the same buffer (two tiles later)
         float *xw = s_x + (size_t)(((set * 2 + half) * 3 + (quarter - 1)) * 32 + lane) * 8;      // written by quarters 1 .. 3
         const float *xr = s_x + (size_t)(((set * 2 + half) * 3 + quarter) * 32 + lane) * 8;      // read by quarters 0 .. 2
         const int prow = 2 * quarter + (txq & 1);                      // pooled row (inside the band) this thread ends up owning
-        float shv[8];
+        // this thread's 8 shifts (channels (half * 4 + j) * 8 + 2 cp + e), contiguous in shared memory: two 16-byte loads per tile instead of 8 live registers
+        float *s_shp = s_sc;                                           // the scale slot is free (the BN scale is folded into the weights)
+        if (set == 0 && quarter == 0 && lane < 4) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { shv[2 * j] = s_sh[(half * 4 + j) * 8 + 2 * cp]; shv[2 * j + 1] = s_sh[(half * 4 + j) * 8 + 2 * cp + 1]; }
-        uint32_t ai = 0;
+            for (int j = 0; j < 4; ++j) { s_shp[(half * 4 + cp) * 8 + 2 * j] = sh[(half * 4 + j) * 8 + 2 * cp]; s_shp[(half * 4 + cp) * 8 + 2 * j + 1] = sh[(half * 4 + j) * 8 + 2 * cp + 1]; }
+        }
+        asm volatile("bar.sync 5, %0;" :: "r"(C::EPI_SETS * 256) : "memory");
+        const float4 *shp = reinterpret_cast<const float4 *>(s_shp + (half * 4 + cp) * 8);
+        constexpr int WPN = Conv3Cfg::WP, PLN = Conv3Cfg::PL, GN = Conv3Cfg::G;
+        uint32_t ai = 0, par = 0;                                      // par: hand-over buffer of this set's next tile
         C2S_DECL;
         for (int item = first; item < n_loop; item += stride) {
             const int img = item / C::BANDS, band = item % C::BANDS;
             const int y0 = P::y0(band), ymin = P::ymin(band);
             const int y = y0 + 2 * prow;
             const bool blk_ok = 2 * prow + 1 < P::ROWS_OUT && y >= ymin && y < C::H && item < n_items;      // both rows of the 2x2 block are complete and stored by this band
+            // stores of this item: fp16 plane of group half * 4 + j at o_hi + j * PLN * 16; e5m2 L plane of the group pair at o_lo + (j / 2) * 2 * PLN * 16
+            // + (j & 1) * 8, H plane one plane further; + 64 bytes per tile
+            const int pos0 = ((y >> 1) + 2) * WPN + (txq >> 1) + 2;
+            uint8_t *o_hi = out + ((((size_t)img * 2 + 0) * GN + half * 4) * PLN + pos0) * 16 + cp * 4;
+            uint8_t *o_lo = out + ((((size_t)img * 2 + 1) * GN + half * 4) * PLN + pos0) * 16 + cp * 2;
 #pragma unroll 1
             for (int tx = 0; tx < C::TILES; ++tx, ++ai) {
                 if ((int)(ai & (C::EPI_SETS - 1)) != set) continue;           // the other set's tile
@@ -743,20 +756,18 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
                     else umma::mbar_arrive(&bar_acc_empty[buf]);
                 }
                 if (quarter > 0) {                                         // block B of this warp's first row: the partner of the previous warp's last row
-                    *reinterpret_cast<float4 *>(xw) = make_float4(__uint_as_float(b0[0]), __uint_as_float(b0[1]), __uint_as_float(b0[4]), __uint_as_float(b0[5]));
-                    *reinterpret_cast<float4 *>(xw + 4) = make_float4(__uint_as_float(b0[8]), __uint_as_float(b0[9]), __uint_as_float(b0[12]), __uint_as_float(b0[13]));
+                    *reinterpret_cast<float4 *>(xw + par * XCH_HALF) = make_float4(__uint_as_float(b0[0]), __uint_as_float(b0[1]), __uint_as_float(b0[4]), __uint_as_float(b0[5]));
+                    *reinterpret_cast<float4 *>(xw + par * XCH_HALF + 4) = make_float4(__uint_as_float(b0[8]), __uint_as_float(b0[9]), __uint_as_float(b0[12]), __uint_as_float(b0[13]));
                 }
                 C2S_BEGIN;
                 asm volatile("bar.sync %0, 256;" :: "r"(1 + set) : "memory");
                 C2S_END(c2s_b);
                 float bn[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (quarter < 3) {
-                    const float4 u0 = *reinterpret_cast<const float4 *>(xr), u1 = *reinterpret_cast<const float4 *>(xr + 4);
+                    const float4 u0 = *reinterpret_cast<const float4 *>(xr + par * XCH_HALF), u1 = *reinterpret_cast<const float4 *>(xr + par * XCH_HALF + 4);
                     bn[0] = u0.x; bn[1] = u0.y; bn[2] = u0.z; bn[3] = u0.w; bn[4] = u1.x; bn[5] = u1.y; bn[6] = u1.z; bn[7] = u1.w;
                 }
-                C2S_BEGIN;
-                asm volatile("bar.sync %0, 256;" :: "r"(3 + set) : "memory");     // the hand-over buffer may be rewritten
-                C2S_END(c2s_b);
+                par ^= 1u;
 #ifdef TB_CONV2_STATS
                 ++c2s_c;
 #endif
@@ -775,6 +786,8 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
                         m[1][2 * j + e] = fmaxf(o2, o3);
                     }
                 // horizontal half of the pool: the even pixel column keeps pooled row 0, the odd one pooled row 1
+                const float4 s0 = shp[0], s1 = shp[1];
+                const float shv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 float mm[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -783,19 +796,16 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
                 }
                 C2S_END(c2s_e); C2S_BEGIN;
                 if (blk_ok) {
-                    constexpr int WPN = Conv3Cfg::WP, PLN = Conv3Cfg::PL, GN = Conv3Cfg::G;
-                    const int pos = ((y >> 1) + 2) * WPN + tx * 4 + (txq >> 1) + 2;
+                    uint8_t *oh = o_hi + tx * 64, *ol = o_lo + tx * 64;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int g = half * 4 + j;
                         const __half h0 = __float2half_rn(mm[2 * j]), h1 = __float2half_rn(mm[2 * j + 1]);
-                        uint8_t *o = out + ((((size_t)img * 2 + 0) * GN + g) * PLN + pos) * 16 + cp * 4;
-                        *reinterpret_cast<uint32_t *>(o) = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        *reinterpret_cast<uint32_t *>(oh + (size_t)j * PLN * 16) = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
                         if (MODE == FP16C) {
                             const float f0 = __half2float(h0), f1 = __half2float(h1);
                             const uint16_t l2 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2((mm[2 * j] - f0) * FC_UP, (mm[2 * j + 1] - f1) * FC_UP), __NV_SATFINITE, __NV_E5M2);
                             const uint16_t h2 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(f0 * FC_DOWN, f1 * FC_DOWN), __NV_SATFINITE, __NV_E5M2);
-                            uint8_t *lo_base = out + ((((size_t)img * 2 + 1) * GN + (g & ~1)) * PLN + pos) * 16 + (g & 1) * 8 + cp * 2;
+                            uint8_t *lo_base = ol + (size_t)(j >> 1) * 2 * PLN * 16 + (j & 1) * 8;
                             *reinterpret_cast<uint16_t *>(lo_base) = l2;
                             *reinterpret_cast<uint16_t *>(lo_base + (size_t)PLN * 16) = h2;
                         }
