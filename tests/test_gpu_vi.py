@@ -198,3 +198,47 @@ def test_precision_margins():
     assert worst["bf16x3"] < 1e-4
     assert worst["fp16"] < TOL
     assert worst["fp16c"] < 0.25 * worst["fp16"] and worst["fp16c"] < 1.5e-4     # fp16 + e5m2 corrections: ~2^-3 of fp16's rounding error
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_conv2_fallback_kernels(variant):
+    """TB_VI_CONV2_PAIR selects conv2's kernel for fp16 / fp16c (2, the default everywhere else: tap pairs on CTA pairs; 1: tap pairs on single
+    CTAs; 0: one tap per MMA).  The switch is read once per process, so the two fall-backs run in a child process: same golden logits."""
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import trex_b200
+from oracle import vi
+g = np.load(%r)
+sd = vi.scale_for_u8_inputs(vi.init_state_dict(100, 1, 80, 80, seed=0))
+for precision, tol in (("fp16c", 1e-3), ("fp16", 1e-3)):
+    net = trex_b200.VINetwork(100, max_images=16, precision=precision)
+    net.load_weights(sd)
+    for n in (6, 3):
+        probs, logits = net.probabilities(g["m100_crops"][:n], return_logits=True)
+        d = float(np.abs(logits - g["m100_logits"][:n]).max())
+        assert d < tol, (precision, n, d)
+print("ok")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), os.path.join(GOLDEN, "vi_golden.npz"))
+    env = dict(os.environ, TB_VI_CONV2_PAIR=variant)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp16c"])
+def test_odd_crop_counts_cta_pair_dummy_item(precision):
+    """conv2 on CTA pairs walks 3 bands per crop two at a time: an odd number of crops leaves one CTA of the last pair with a dummy item (it must
+    neither store nor stall its peer).  1, 3 and 5 crops -> 3, 9, 15 items; results equal the same crops inside an even batch."""
+    import trex_b200
+    from oracle import vi
+    g = np.load(os.path.join(GOLDEN, "vi_golden.npz"))
+    sd = vi.scale_for_u8_inputs(vi.init_state_dict(100, 1, 80, 80, seed=0))
+    net = trex_b200.VINetwork(100, max_images=16, precision=precision)
+    net.load_weights(sd)
+    _, full = net.probabilities(g["m100_crops"], return_logits=True)
+    assert np.abs(full - g["m100_logits"]).max() < TOL
+    for n in (1, 3, 5):
+        _, logits = net.probabilities(g["m100_crops"][:n], return_logits=True)
+        assert np.array_equal(logits, full[:n]), n

@@ -607,7 +607,8 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
     if (warp == 1) { if (NCTA == 2) umma::tmem_alloc2(&s_tmem, 512); else umma::tmem_alloc(&s_tmem, 512); }
     for (int i = tid; i < C::NOUT; i += C::THREADS) { s_sc[i] = sc[i]; s_sh[i] = sh[i]; }
     umma::fence_before_sync();
-    if (NCTA == 2) umma::cluster_sync(); else __syncthreads();         // barriers of both CTAs initialised before any remote arrive
+    __syncthreads();                                                   // s_tmem, s_sc / s_sh written (racecheck models this barrier, not the cluster one)
+    if (NCTA == 2) umma::cluster_sync();                               // barriers of both CTAs initialised before any remote arrive
     umma::fence_after_sync();
     const uint32_t tm = s_tmem;
 
@@ -1150,6 +1151,7 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
     if (warp >= 2 + 4 * Conv1P::EPI_SETS) {                            // ---- producers ----
         const int pt = tid - (64 + 128 * Conv1P::EPI_SETS);
         int it = 0;
+        C2S_DECL;
         for (int n = blockIdx.x; n < n_act; n += gridDim.x, ++it) {
             const int b = it & 1;
             uint4 *s_p = reinterpret_cast<uint4 *>(smem + b * C::P_BYTES);
@@ -1170,7 +1172,9 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            C2S_BEGIN;
             umma::mbar_wait_suspend(&bar_plane_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);       // the MMAs that read this plane have retired
+            C2S_END(c2s_a);
             for (int i = pt; i < C::PROWS * (C::PW / 4); i += Conv1P::PRODUCERS) {
                 const int yy = i / (C::PW / 4), p4 = i % (C::PW / 4);
                 const uint2 wa = *reinterpret_cast<const uint2 *>(s_img + yy * C::IMG_PITCH + p4 * 8);
@@ -1190,22 +1194,30 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
             asm volatile("bar.sync 1, 128;" ::: "memory");             // plane complete; s_img free for the next crop
             if (pt == 0) umma::mbar_arrive(&bar_plane_full[b]);
         }
+#ifdef TB_CONV2_STATS
+        if (pt == 0) { C2S_FLUSH(11, 12, 14, 14); }
+#endif
     } else if (warp == 1) {                                            // ---- MMA issue ----
         if (umma::elect_one()) {
             const uint32_t idesc = umma::idesc_bf16_f32(128, C::N);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::N * 16, 128);
             uint32_t a2 = 0;
             int it = 0;
+            C2S_DECL;
             for (int n = blockIdx.x; n < n_act; n += gridDim.x, ++it) {
                 const int b = it & 1;
                 const uint64_t a_base = umma::smem_desc(umma::smem_u32(smem + b * C::P_BYTES), C::PW * 16, 2 * C::PW * 16);
+                C2S_BEGIN;
                 umma::mbar_wait(&bar_plane_full[b], ((uint32_t)it >> 1) & 1u);
+                C2S_END(c2s_a);
                 umma::fence_after_sync();
                 for (int t = 0; t < C::TILES; ++t, ++a2) {
                     const int ty = t / C::TILES_X, tx = t % C::TILES_X;
                     const int y0 = ty == 2 ? 24 : ty * 16;
                     const uint32_t buf = a2 % C::NACC;
+                    C2S_BEGIN;
                     umma::mbar_wait(&bar_acc_empty[buf], ((a2 / C::NACC) & 1) ^ 1);
+                    C2S_END(c2s_c);
                     umma::fence_after_sync();
                     const uint32_t d = tm + buf * C::N;
                     const uint64_t a_tile = umma::desc_add(a_base, (uint32_t)(2 * y0 * C::PW + tx * 8));
@@ -1219,17 +1231,21 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                 }
                 umma::commit(&bar_plane_empty[b]);
             }
+            C2S_FLUSH(0, 1, 2, 3);
         }
     } else if (warp >= 2) {                                            // ---- epilogue ----
         const int es = (warp - 2) >> 2, quarter = warp & 3;
         const int r = quarter * 32 + lane, trow = r >> 3, tx8 = r & 7;
         uint32_t ai = 0;
+        C2S_DECL;
         for (int n = blockIdx.x; n < n_act; n += gridDim.x, ai += C::TILES) {
             for (int t = es; t < C::TILES; t += Conv1P::EPI_SETS) {
                 const uint32_t a2 = ai + t, buf = a2 % C::NACC;
                 const int ty = t / C::TILES_X, tx = t % C::TILES_X;
                 const int y0 = ty == 2 ? 24 : ty * 16, ymin = ty == 2 ? 32 : y0;
+                C2S_BEGIN;
                 umma::mbar_wait_suspend(&bar_acc_full[buf], (a2 / C::NACC) & 1);
+                C2S_END(c2s_a);
                 umma::fence_after_sync();
                 uint32_t v[4][16];
                 const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + buf * C::N;
@@ -1280,6 +1296,9 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                 }
             }
         }
+#ifdef TB_CONV2_STATS
+        if (warp == 2 && lane == 0) { C2S_FLUSH(4, 5, 6, 7); }
+#endif
     }
     umma::fence_before_sync();
     __syncthreads();
