@@ -44,6 +44,9 @@ MACS = {"conv1": 2.56e6, "conv2": 40.96e6, "conv3": 81.92e6, "fc1": 1.28e6}
 # DRAM traffic per unit from `ncu --set full` captures (dram__bytes_read.sum + dram__bytes_write.sum of one launch / units of that
 # launch): NOT measured in this run -- the capture each figure comes from is named next to it
 NCU_TRAFFIC = {
+    "fp16c": {"seg_rle": ((134.86e6 + 5.51e6) / 64, "profiles/r2_step_fp16c_head_ncu_summary.txt (B=64 capture, per frame)"),
+              "conv2": ((507.65e6 + 378.80e6) / 4096, "profiles/r2_step_fp16c_head_ncu_summary.txt (4096-crop launch, per crop)"),
+              "conv3": ((563.21e6 + 183.19e6) / 4096, "profiles/r2_step_fp16c_head_ncu_summary.txt (4096-crop launch, per crop)")},
     "bf16x3": {"seg_rle": ((267.87e6 + 6.47e6) / 128, "profiles/r1_step_bf16x3_ncu_summary.txt (B=128 capture, per frame)"),
                "conv2": ((507.7e6 + 385.1e6) / 4096, "profiles/r1_step_bf16x3_ncu_summary.txt (4096-crop launch, per crop)"),
                "conv3": ((614.06e6 + 184.99e6) / 4096, "profiles/r1_step_bf16x3_ncu_summary.txt (4096-crop launch, per crop)")},

@@ -1152,18 +1152,24 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
         const int pt = tid - (64 + 128 * Conv1P::EPI_SETS);
         int it = 0;
         C2S_DECL;
-        for (int n = blockIdx.x; n < n_act; n += gridDim.x, ++it) {
-            const int b = it & 1;
-            uint4 *s_p = reinterpret_cast<uint4 *>(smem + b * C::P_BYTES);
+        // the crop of the NEXT iteration is already in flight (13 words per thread) while this one is decimated: the global latency is off the
+        // producer's critical path
+        constexpr int NW = (C::H * C::W / 4 + Conv1P::PRODUCERS - 1) / Conv1P::PRODUCERS;
+        uint32_t v[NW];
+        auto fetch = [&](int n) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)n * C::H * C::W);
-            uint32_t v[(C::H * C::W / 4 + Conv1P::PRODUCERS - 1) / Conv1P::PRODUCERS];
 #pragma unroll
-            for (int k = 0; k < (C::H * C::W / 4 + Conv1P::PRODUCERS - 1) / Conv1P::PRODUCERS; ++k) {   // all loads of the crop in flight
+            for (int k = 0; k < NW; ++k) {
                 const int i = pt + k * Conv1P::PRODUCERS;
                 v[k] = i < C::H * C::W / 4 ? src[i] : 0u;
             }
+        };
+        if ((int)blockIdx.x < n_act) fetch(blockIdx.x);
+        for (int n = blockIdx.x; n < n_act; n += gridDim.x, ++it) {
+            const int b = it & 1;
+            uint4 *s_p = reinterpret_cast<uint4 *>(smem + b * C::P_BYTES);
 #pragma unroll
-            for (int k = 0; k < (C::H * C::W / 4 + Conv1P::PRODUCERS - 1) / Conv1P::PRODUCERS; ++k) {
+            for (int k = 0; k < NW; ++k) {
                 const int i = pt + k * Conv1P::PRODUCERS;
                 if (i < C::H * C::W / 4) {
                     const int y = i / (C::W / 4), x4 = i % (C::W / 4);
@@ -1171,6 +1177,7 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                     d16[0] = (uint16_t)v[k]; d16[1] = (uint16_t)(v[k] >> 16);
                 }
             }
+            if (n + (int)gridDim.x < n_act) fetch(n + gridDim.x);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             C2S_BEGIN;
             umma::mbar_wait_suspend(&bar_plane_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);       // the MMAs that read this plane have retired
