@@ -668,6 +668,9 @@ def run_ours(args, cfg):
                 "frac_of_burst_peak": kern[dom]["achieved"] / pk["tensor_burst"] if kern[dom]["bound"] == "tensor" else None,
                 "frac_of_sustained_peak": kern[dom]["achieved"] / pk["tensor_sustained"] if kern[dom]["bound"] == "tensor" else None,
                 "cnn_whole": cnn,
+                # tensor-pipe slots the kernel occupies per algorithmic MAC: 1 (fp16), 2 (fp16c: fp16 K=16 + e5m2 K=32), 3 (bf16x3)
+                "mma_slots_per_mac": {"fp16": 1, "fp16c": 2, "bf16x3": 3}[p0] if kern[dom]["bound"] == "tensor" else None,
+                "frac_of_peak_in_issued_slots": (kern[dom]["frac"] * {"fp16": 1, "fp16c": 2, "bf16x3": 3}[p0]) if kern[dom]["bound"] == "tensor" else None,
                 "note": "algorithmic FLOPs (2*MAC per crop)" + ("; the bf16x3 split issues 3 MMAs per k-step on top of that" if p0 == "bf16x3" else
                                                                  "; fp16c issues 2 MMA slots per k-step (fp16 K=16 + e5m2 K=32) on top of that" if p0 == "fp16c" else "")}
         # cpu baseline on a bounded sample of the same workload (rank 0, N=1 only): all cores, one thread, and an OpenCV cross-check
