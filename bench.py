@@ -647,6 +647,11 @@ def run_ours(args, cfg):
             for v in kern.values():
                 if "achieved" in v:
                     v["frac"] = v["achieved"] / v["peak"]
+            # tensor-pipe slots per algorithmic MAC: conv2 / conv3 follow the precision; conv1 multiplies exact u8 pixels with hi / lo weights (2), fc1 is bf16x3 (3)
+            slots = {"conv1": 2, "conv2": {"fp16": 1, "fp16c": 2, "bf16x3": 3}[p0], "conv3": {"fp16": 1, "fp16c": 2, "bf16x3": 3}[p0], "fc1": 3}
+            for k, n in slots.items():
+                kern[k]["mma_slots_per_mac"] = n
+                kern[k]["frac_in_issued_slots"] = kern[k]["frac"] * n
             cnn_ms = sum(per[k] for k in ("conv1", "conv2", "conv3", "fc1", "head"))
             cnn_fl = r["tot"][3] * (2 * sum(MACS.values()) + 2 * 100 * M)
             return kern, {"tflops_algorithmic": cnn_fl / (cnn_ms * 1e-3) / 1e12, "frac_of_burst_peak": cnn_fl / (cnn_ms * 1e-3) / 1e12 / pk["tensor_burst"],

@@ -90,11 +90,16 @@ struct Conv3T {
     static constexpr int NT_ROWS = 10, TSTEP = NT_ROWS * WP, N = (TSTEP + 15) / 16 * 16, TILES = H / NT_ROWS;   // 2 tiles: 220 positions each, N = 224
     static constexpr int PIN = ((TILES - 1) * TSTEP + N + 4 * WP + 4 + 7) / 8 * 8;  // 536 positions staged
     static constexpr int PL = Conv3Cfg::PL;                                        // plane size in global memory (positions)
-    static constexpr int IN_BYTES = 2 * G * PIN * 16;
+    // bf16x3 / fp16c (2 G planes per image): no room for two images, so the input is staged PER TILE -- tile t reads positions t * TSTEP ... + TPOS
+    // of a plane, the two ranges (rows 0-13 and 10-23) are kept as separate blocks (the 4 shared rows twice) and block t of the next image loads
+    // while the other tile of the current one is multiplied.  fp16 (G planes) double-buffers whole images.
+    static constexpr int TPOS = (N + 4 * WP + 4 + 7) / 8 * 8;                      // 320 positions per tile block
+    static constexpr int IN_BYTES = TILES * 2 * G * TPOS * 16 > 2 * G * PIN * 16 ? TILES * 2 * G * TPOS * 16 : 2 * G * PIN * 16;
     static constexpr int WTAP_BYTES = 2 * G * NOUT * 16;
     static constexpr int SMEM = (IN_BYTES + 127) / 128 * 128 + 2 * WTAP_BYTES + 128;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int THREADS = 64 + 512;               // 16 epilogue warps: (TMEM lane quarter) x (tile) x (row-pair half)
+    static constexpr int THREADS = 64 + 512 + 32;          // weights, MMA issue, 16 epilogue warps: (TMEM lane quarter) x (tile) x (row-pair half), input loader
+    static_assert((TILES - 1) * TSTEP + TPOS <= PL + 8 && TPOS * 16 % 16 == 0, "tile blocks stay inside the plane");
     static_assert(PIN <= PL, "staged positions exceed the plane");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -146,6 +151,8 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
     // fp16: the planes of one image are half the size, so the input is double buffered (stage = G planes) and the next
     // image loads under the MMAs of the current one; bf16x3 keeps one stage of 2 G planes
     constexpr int NBUF = F16 ? 2 : 1, STAGE_POS = C::G * C::PIN;
+    constexpr bool SPLIT = !F16;                          // per-tile input blocks (see Conv3T::TPOS); bar_in_full / bar_in_empty are indexed by tile then
+    constexpr int TBLK = 2 * C::G * C::TPOS;              // positions of one tile block (all planes)
     // weight ring: a tap is 32 KB (bf16 hi + lo: 2 stages, 1.4 us of MMAs per tap hide the L2 latency) or 16 KB (fp16:
     // 4 stages, because 0.46 us of MMAs per tap do not).  bf16x3 runs tile-outer (the epilogue of a tile under the
     // MMAs of the other one, taps streamed once per tile); fp16 runs tap-outer: twice the L2 weight stream measured slower.
@@ -154,21 +161,9 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
     static_assert(MODE != FP16C || TILE_OUTER, "FP16C runs tile-outer");
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0, tapc = 0;
-            int img = blockIdx.x;
-            for (int k = 0; k < slots; ++k, img += gridDim.x) {
-                if (img < n_act) {
-                    const uint32_t ib = it % NBUF, iph = (it / NBUF) & 1;
-                    umma::mbar_wait(&bar_in_empty[ib], iph ^ 1);
-                    constexpr int NPL = F16 ? C::G : 2 * C::G;                  // fp16: hi slots only
-                    umma::mbar_expect_tx(&bar_in_full[ib], NPL * C::PIN * 16);
-                    const uint8_t *src = in + (size_t)img * Conv3Cfg::IMG_BYTES;
-                    for (int p = 0; p < NPL; ++p)
-                        umma::bulk_g2s(s_in + ((size_t)ib * STAGE_POS + (size_t)p * C::PIN) * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full[ib]);
-                    ++it;
-                }
-                if (CL == 2 && crank != 0) continue;                            // the leader streams the weights for both CTAs
+        if (lane == 0 && (CL == 1 || crank == 0)) {                             // the leader streams the weights for both CTAs
+            uint32_t tapc = 0;
+            for (int k = 0; k < slots; ++k) {
                 for (int tt = 0; tt < (TILE_OUTER ? 25 * C::TILES : 25) * HALVES; ++tt, ++tapc) {
                     const int tap = (tt / HALVES) % 25, half = tt % HALVES;     // FP16C: the hi slots (fp16) of a tap, then its lo slots (e5m2)
                     const uint32_t s = tapc % NWS;
@@ -182,11 +177,38 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                 }
             }
         }
+    } else if (warp == 2 + 16) {
+        // input loader (its own warp: waiting for a free block must not hold up the weight stream)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int img = blockIdx.x; img < n_act; img += gridDim.x, ++it) {
+                const uint8_t *src = in + (size_t)img * Conv3Cfg::IMG_BYTES;
+                if (SPLIT) {
+                    for (int t = 0; t < C::TILES; ++t) {
+                        umma::mbar_wait(&bar_in_empty[t], (it & 1) ^ 1);        // the MMAs of tile t of the previous image have retired
+                        constexpr int NPL = 2 * C::G;
+                        // the last block ends with the plane: it is short of TPOS by what the plane lacks (positions no stored output reads)
+                        const int npos = min(C::TPOS, C::PL - t * C::TSTEP);
+                        umma::mbar_expect_tx(&bar_in_full[t], (uint32_t)(NPL * npos * 16));
+                        for (int p = 0; p < NPL; ++p)
+                            umma::bulk_g2s(s_in + ((size_t)t * TBLK + (size_t)p * C::TPOS) * 16, src + ((size_t)p * C::PL + (size_t)t * C::TSTEP) * 16,
+                                           (uint32_t)(npos * 16), &bar_in_full[t]);
+                    }
+                } else {
+                    const uint32_t ib = it % NBUF, iph = (it / NBUF) & 1;
+                    umma::mbar_wait(&bar_in_empty[ib], iph ^ 1);
+                    constexpr int NPL = C::G;                                   // fp16: hi slots only
+                    umma::mbar_expect_tx(&bar_in_full[ib], NPL * C::PIN * 16);
+                    for (int p = 0; p < NPL; ++p)
+                        umma::bulk_g2s(s_in + ((size_t)ib * STAGE_POS + (size_t)p * C::PIN) * 16, src + (size_t)p * C::PL * 16, C::PIN * 16, &bar_in_full[ib]);
+                }
+            }
+        }
     } else if (warp == 1) {
         if (umma::elect_one()) {
             const uint32_t idesc = MODE != BF16X3 ? umma::idesc_f16_f32(128, C::N) : umma::idesc_bf16_f32(128, C::N);
             const uint32_t idesc8 = umma::idesc_e5m2_f32(128, C::N);
-            const uint64_t x_base = umma::smem_desc(umma::smem_u32(s_in), C::PIN * 16, 128);
+            const uint64_t x_base = umma::smem_desc(umma::smem_u32(s_in), (SPLIT ? C::TPOS : C::PIN) * 16, 128);
             const uint64_t w_base = umma::smem_desc(umma::smem_u32(s_w), C::NOUT * 16, 128);
             uint32_t it = 0, tapc = 0;
             // "empty" barrier of a weight stage: this CTA's own, or (clusters) the leader's, through the cluster window
@@ -197,7 +219,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                 const bool real = img < n_act;
                 const uint32_t ib = it % NBUF, iph = (it / NBUF) & 1;
                 const uint32_t xofs = ib * STAGE_POS;
-                if (real) {
+                if (real && !SPLIT) {
                     umma::mbar_wait(&bar_in_full[ib], iph);
                     umma::fence_after_sync();
                 }
@@ -206,8 +228,8 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                     const uint32_t shift = (uint32_t)((tap / 5) * C::WP + (tap % 5));
 #pragma unroll
                     for (int ks = 0; ks < C::G / 2; ++ks) {
-                        const uint32_t x_hi = xofs + (0 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
-                        const uint32_t x_lo = (1 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
+                        const uint32_t x_hi = SPLIT ? t * TBLK + (0 * C::G + 2 * ks) * C::TPOS + shift : xofs + (0 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
+                        const uint32_t x_lo = SPLIT ? t * TBLK + (1 * C::G + 2 * ks) * C::TPOS + shift : (1 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
                         const uint32_t w_hi = wofs + (0 * C::G + 2 * ks) * C::NOUT;
                         const uint32_t w_lo = wofs + (1 * C::G + 2 * ks) * C::NOUT;
                         umma::mma_bf16(d, w_base + w_hi, x_base + x_hi, idesc, (tap | ks) != 0);
@@ -224,7 +246,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                     const uint32_t shift = (uint32_t)((tap / 5) * C::WP + (tap % 5));
 #pragma unroll
                     for (int ks = 0; ks < C::G / 2; ++ks) {
-                        const uint32_t x_lo = (1 * C::G + 2 * ks) * C::PIN + t * C::TSTEP + shift;
+                        const uint32_t x_lo = t * TBLK + (1 * C::G + 2 * ks) * C::TPOS + shift;
                         const uint32_t w_lo = wofs + (2 * ks) * C::NOUT;
                         umma::mma_f8(d, w_base + w_lo, x_base + x_lo, idesc8, 1);
                     }
@@ -238,6 +260,7 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
 #pragma unroll 1
                     for (int t = 0; t < C::TILES; ++t) {
                         if (real) {
+                            if (SPLIT) umma::mbar_wait(&bar_in_full[t], it & 1);
                             umma::mbar_wait(&bar_acc_empty[t], (it & 1) ^ 1);
                             umma::fence_after_sync();
                         }
@@ -254,7 +277,10 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                                 umma::commit_a(w_empty_a[s8]);
                             }
                         }
-                        if (real) umma::commit(&bar_acc_full[t]);
+                        if (real) {
+                            umma::commit(&bar_acc_full[t]);
+                            if (SPLIT) umma::commit(&bar_in_empty[t]);      // block t consumed: the loader may bring in the next image's
+                        }
                     }
                 } else {
                     for (int t = 0; t < C::TILES; ++t) umma::mbar_wait(&bar_acc_empty[t], (it & 1) ^ 1);
@@ -269,12 +295,12 @@ conv3_t_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__rest
                     for (int t = 0; t < C::TILES; ++t) umma::commit(&bar_acc_full[t]);
                 }
                 if (real) {
-                    umma::commit(&bar_in_empty[ib]);          // planes consumed: the producer may refill this stage
+                    if (!SPLIT) umma::commit(&bar_in_empty[ib]);          // planes consumed: the loader may refill this stage
                     ++it;
                 }
             }
         }
-    } else {
+    } else if (warp < 2 + 16) {
         // epilogue: 16 warps; a warp handles TMEM lane quarter (warp & 3) of tile ((ew >> 2) & 1), row pairs 0-2 or 3-4
         const int ew = warp - 2, quarter = warp & 3, t = (ew >> 2) & 1, sub = ew >> 3;
         const int pr0 = sub ? 3 : 0, pr1 = sub ? C::NT_ROWS / 2 : 3;
