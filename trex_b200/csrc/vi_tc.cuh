@@ -735,8 +735,9 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
         const int txq = lane >> 2, cp = lane & 3;                      // pixel column inside the tile, channel pair inside a group
         constexpr int XCH_HALF = C::EPI_SETS * 2 * 3 * 32 * 8;        // floats per hand-over buffer; two buffers, so ONE barrier per tile orders
                                                                        // write -> read AND read -> next write into the same buffer (two tiles later)
-        float *xw = s_x + (size_t)(((set * 2 + half) * 3 + (quarter - 1)) * 32 + lane) * 8;      // written by quarters 1 .. 3
-        const float *xr = s_x + (size_t)(((set * 2 + half) * 3 + quarter) * 32 + lane) * 8;      // read by quarters 0 .. 2
+        // [boundary][2 x 16-byte halves][32 lanes][4 floats]: every 128-bit access of a warp covers 512 contiguous bytes (no bank conflicts)
+        float *xw = s_x + (size_t)((set * 2 + half) * 3 + (quarter - 1)) * 256 + lane * 4;       // written by quarters 1 .. 3
+        const float *xr = s_x + (size_t)((set * 2 + half) * 3 + quarter) * 256 + lane * 4;       // read by quarters 0 .. 2
         const int prow = 2 * quarter + (txq & 1);                      // pooled row (inside the band) this thread ends up owning
         // this thread's 8 shifts (channels (half * 4 + j) * 8 + 2 cp + e), contiguous in shared memory: two 16-byte loads per tile instead of 8 live registers
         float *s_shp = s_sc;                                           // the scale slot is free (the BN scale is folded into the weights)
@@ -784,14 +785,14 @@ conv2_pair_kernel(const uint8_t *__restrict__ in, int n_max, const uint32_t *__r
                 }
                 if (quarter > 0) {                                         // block B of this warp's first row: the partner of the previous warp's last row
                     *reinterpret_cast<float4 *>(xw + par * XCH_HALF) = make_float4(__uint_as_float(b0[0]), __uint_as_float(b0[1]), __uint_as_float(b0[4]), __uint_as_float(b0[5]));
-                    *reinterpret_cast<float4 *>(xw + par * XCH_HALF + 4) = make_float4(__uint_as_float(b0[8]), __uint_as_float(b0[9]), __uint_as_float(b0[12]), __uint_as_float(b0[13]));
+                    *reinterpret_cast<float4 *>(xw + par * XCH_HALF + 128) = make_float4(__uint_as_float(b0[8]), __uint_as_float(b0[9]), __uint_as_float(b0[12]), __uint_as_float(b0[13]));
                 }
                 C2S_BEGIN;
                 asm volatile("bar.sync %0, 256;" :: "r"(1 + set) : "memory");
                 C2S_END(c2s_b);
                 float bn[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (quarter < 3) {
-                    const float4 u0 = *reinterpret_cast<const float4 *>(xr + par * XCH_HALF), u1 = *reinterpret_cast<const float4 *>(xr + par * XCH_HALF + 4);
+                    const float4 u0 = *reinterpret_cast<const float4 *>(xr + par * XCH_HALF), u1 = *reinterpret_cast<const float4 *>(xr + par * XCH_HALF + 128);
                     bn[0] = u0.x; bn[1] = u0.y; bn[2] = u0.z; bn[3] = u0.w; bn[4] = u1.x; bn[5] = u1.y; bn[6] = u1.z; bn[7] = u1.w;
                 }
                 par ^= 1u;
@@ -1176,6 +1177,8 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
 
     if (warp >= 2 + 4 * Conv1P::EPI_SETS) {                            // ---- producers ----
         const int pt = tid - (64 + 128 * Conv1P::EPI_SETS);
+        const uint32_t rot = ((uint32_t)pt >> 1) & 3u;                 // store rotation of the plane build (items of a thread are 128 apart: same rot)
+        static_assert(Conv1P::PRODUCERS % 8 == 0, "the rotation is per thread");
         int it = 0;
         C2S_DECL;
         // the crop of the NEXT iteration is already in flight (13 words per thread) while this one is decimated: the global latency is off the
@@ -1219,9 +1222,17 @@ conv1_tc_pipe_kernel(const uint8_t *__restrict__ img, int n_max, const uint32_t 
                     const uint32_t b0 = (ws4[(2 * k) >> 2] >> (8 * ((2 * k) & 3))) & 0xFFu, b1 = (ws4[(2 * k + 1) >> 2] >> (8 * ((2 * k + 1) & 3))) & 0xFFu;
                     ev[k] = __byte_perm(__float_as_uint((float)b0), __float_as_uint((float)b1), 0x7632);
                 }
+                // item i owns bytes 64 i ... 64 i + 63 of the plane: with every thread storing chunk j in the same instruction, a quarter-warp touches only
+                // two of the eight 16-byte bank groups (4-way conflict: ncu showed 77 % of the store wavefronts as replays).  Thread pairs therefore start
+                // at different chunks: instruction jj stores chunk (jj + rot) & 3, rot = (i / 2) & 3 -- eight distinct groups per quarter-warp
+                uint4 ch[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ch[j] = make_uint4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3]);
+                if (rot & 1u) { const uint4 t0 = ch[0]; ch[0] = ch[1]; ch[1] = ch[2]; ch[2] = ch[3]; ch[3] = t0; }
+                if (rot & 2u) { const uint4 t0 = ch[0], t1 = ch[1]; ch[0] = ch[2]; ch[1] = ch[3]; ch[2] = t0; ch[3] = t1; }
                 uint4 *dst = s_p + yy * C::PW + p4 * 4;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3]);
+                for (int jj = 0; jj < 4; ++jj) dst[(jj + rot) & 3u] = ch[jj];
             }
             umma::fence_async_smem();
             asm volatile("bar.sync 1, 128;" ::: "memory");             // plane complete; s_img free for the next crop
