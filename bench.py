@@ -187,6 +187,16 @@ def bind_near_gpu(cuda_index):
         return None, None
 
 
+def balanced_batches(batch, gbs, tolerance=0.9):
+    """Frames per step of every rank in the end-to-end loop.  Equal shares (`batch`) unless the ranks' CONCURRENT host->device copy rates differ by
+    more than 1 - tolerance: every step ends with one collective, so the rank with the slowest copy path would set the step time of all.  Then a
+    rank's share follows its rate (the fastest keeps `batch`)."""
+    top = max(gbs)
+    if len(gbs) < 2 or top <= 0 or min(gbs) >= tolerance * top:
+        return [batch] * len(gbs)
+    return [max(1, min(batch, int(round(batch * g / top)))) for g in gbs]
+
+
 def make_inputs(cfg, n_frames, seed):
     from trex_b200.synthetic import BlobWorld
     world = BlobWorld(h=cfg["H"], w=cfg["W"], n_blobs=cfg["indiv"], seed=seed)
@@ -458,13 +468,13 @@ def run_ours(args, cfg):
     def e2e_submit(i, precision, batches):
         s = slots[i % NS]
         s.used = True
-        s.bs.submit(batches[i % len(batches)], fetch=1)                     # tb_seg_submit: H2D frames + kernels
+        s.bs.submit(batches[i % len(batches)][:B_e], fetch=1)               # tb_seg_submit: H2D frames + kernels
         net_of(s, precision).predict_device(s.res[0], B * KMAX, s.res[1], s.probs.data_ptr(), 0, s.stream.cuda_stream)
         if cfg["posture"]:
             s.bs.posture_async(1.0, normalize=True, fetch=1)      # results: midline records + normalised midlines to the host
         with torch.cuda.stream(s.stream):
             # identity probabilities back to the host (upper bound of rows: the crop count of this batch is not known yet)
-            s.probs_host[:B * cfg["indiv"]].copy_(s.probs[:B * cfg["indiv"]], non_blocking=True)
+            s.probs_host[:B_e * cfg["indiv"]].copy_(s.probs[:B_e * cfg["indiv"]], non_blocking=True)
         if world_size > 1:
             gather(s, s.stream)
         s.pending = True
@@ -481,7 +491,7 @@ def run_ours(args, cfg):
             s.ev_gathered.synchronize()
         s.pending = False
         nb, nl, npx, nc = s.bs.totals()
-        return B * H * W, B * 32 + 16 + nb * 32 + nl * 8 + npx + B * cfg["indiv"] * M * 4 + (nb * (16 + 32 + 25 * 16) if cfg["posture"] else 0)
+        return B_e * H * W, B_e * 32 + 16 + nb * 32 + nl * 8 + npx + B_e * cfg["indiv"] * M * 4 + (nb * (16 + 32 + 25 * 16) if cfg["posture"] else 0)
 
     def measure_e2e(precision, batches, steps):
         for s in slots:
@@ -504,7 +514,7 @@ def run_ours(args, cfg):
         dt = max_over_ranks(time.perf_counter() - t0)
         for s in slots:
             s.bs.set_stream(0)
-        return dict(value=world_size * B * steps / dt, h2d=h2d // steps, d2h=d2h // steps, s_per_step=dt / steps)
+        return dict(value=sum(B_e_all) * steps / dt, h2d=h2d // steps, d2h=d2h // steps, s_per_step=dt / steps)
 
     def bare_h2d():
         """GB/s of this rank's H2D copies alone (page-locked source), all ranks copying at the same time."""
@@ -614,6 +624,9 @@ def run_ours(args, cfg):
         verified[p] = verify(p)
     meta_ok = verify_meta() if world_size > 1 else None
     h2d_gbs = bare_h2d()
+    # frames per step of every rank in the end-to-end loop (list ordered by rank): equal unless the host's copy paths are not
+    B_e_all = [B] * world_size if args.no_balance else balanced_batches(B, [g for _, g in h2d_gbs])
+    B_e = B_e_all[rank]
     torch.cuda.set_stream(torch.cuda.default_stream(dev))
     e2e = {p: measure_e2e(p, host_batches, args.steps) for p in precisions}
     pageable = None
@@ -707,6 +720,10 @@ def run_ours(args, cfg):
                     "timing": f"wall clock bracketed by device syncs, max over ranks, pipeline fill and drain inside; {max(2, args.slots)} batches in flight (H2D of batch i+1 overlaps kernels of batch i)",
                     "source": "page-locked host buffers from tb_host_alloc",
                     "pageable": ({"value": pageable["value"], "unit": "frames/s", "source": "ordinary pageable host memory (numpy)"} if pageable else None),
+                    "frames_per_step_per_rank": B_e_all,
+                    "sharding": ("frames per rank follow the ranks' concurrent H2D rates (h2d_gbs_per_rank differ by more than 10 %: one collective per step "
+                                 "would make the slowest copy path set every rank's step time); h2d/d2h_bytes_per_step are rank 0's"
+                                 if len(set(B_e_all)) > 1 else "equal frames per rank"),
                     "h2d_gbs_per_rank": h2d_gbs, "h2d_gbs_needed_at_value": r0["value"] / world_size * H * W / 1e9,
                     "host_cpus_near_gpu": len(near_cpus) if near_cpus else None},
             "gpu_launches": r0["launches"], "clocks": r0["clocks"], "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
@@ -740,6 +757,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the CPUs near its GPU")
+    ap.add_argument("--no-balance", action="store_true", help="end-to-end loop: equal frames per rank even when the ranks' H2D copy rates differ")
     ap.add_argument("--no-topo", action="store_true", help="local rank r uses CUDA device r (no PCIe-topology interleaving)")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-source e2e leg")
     ap.add_argument("--single-precision", action="store_true", help="measure only --precision")

@@ -93,3 +93,18 @@ def test_meta_layout_mirror():
     odd = sharding.MetaLayout.make(3, 5)
     assert odd.off_top_id % 32 == 0 and odd.off_top_p % 32 == 0 and odd.off_recs % 32 == 0
     assert odd.off_top_p >= odd.off_top_id + 60 and odd.off_recs >= odd.off_top_p + 60
+
+
+def test_bench_balanced_batches():
+    """bench.py's end-to-end frame shares: equal unless the ranks' concurrent H2D rates differ by more than 10 %, then proportional to the rate."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.balanced_batches(256, [55.0]) == [256]
+    assert bench.balanced_batches(256, [52.4, 55.2, 52.5, 55.1]) == [256] * 4
+    got = bench.balanced_batches(256, [23.24, 35.71, 23.37, 35.62, 23.32, 35.54, 23.3, 35.49])
+    assert got[1] == 256 and got[0] == 167 and all(1 <= g <= 256 for g in got)
+    assert abs(sum(got) * 2.0736e6 / 1e9 / max(g * 2.0736e6 / 1e9 / r for g, r in zip(got, [23.24, 35.71, 23.37, 35.62, 23.32, 35.54, 23.3, 35.49])) - 235.6) < 3   # all ranks finish together
+    assert bench.balanced_batches(64, [0.5, 55.0]) == [1, 64]
