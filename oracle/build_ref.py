@@ -1,35 +1,60 @@
-"""Test infrastructure: builds oracle/_ref/libref_circulargraph.so from the REFERENCE's own source file
-/root/reference/Application/src/commons/common/misc/CircularGraph.cpp (compiled where it lies, unmodified) + the C wrapper oracle/ref_circular_graph.cpp,
-against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled header needs OpenCV / glaze / cnpy, absent here).  The rest of the reference's
-path (Outline.cpp, PixelTree, RawProcessing ...) does not compile without those libraries: see DESIGN.md s6.
+"""Test infrastructure: builds oracle/_ref/libref_posture.so from the REFERENCE's own source files, compiled where they lie and unmodified:
+    tracker/tracking/Outline.cpp                      Outline::resample / smooth / offset_to_middle / calculate_midline, Midline::post_process / normalize / fix_length
+    commons/common/misc/CircularGraph.cpp             periodic::curvature / eft / ieft / differentiate / find_peaks (+ its fast::cos polynomial)
+    commons/common/misc/curve_discussion.cpp, commons/common/gui/Transform.cpp   (linked by Outline.cpp)
+plus the C wrappers oracle/ref_outline.cpp and oracle/ref_circular_graph.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
+header needs OpenCV / glaze / cnpy, absent here; its settings cache, drawing and tracker headers are irrelevant to the functions under test).
+Outline.cpp includes "Posture.h", "DebugDrawing.h" and "Tracker.h" with quotes, which a compiler resolves next to the including file first; it is
+therefore compiled through a symbolic link in oracle/_ref/overlay/tracking/ (the file itself stays in the reference checkout), next to placeholders
+for those three headers.  The rest of the reference's path (PixelTree.cpp, RawProcessing.cpp, CPULabeling.cpp ...) is tied to OpenCV image classes
+and stays restated-only: DESIGN.md s6.
 The .so is git-ignored, not gpurun-ignored.  Only tests/ load it."""
 import os
 import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_COMMON = "/root/reference/Application/src/commons/common"
-OUT = os.path.join(HERE, "_ref", "libref_circulargraph.so")
+REF_SRC = "/root/reference/Application/src"
+REF_COMMON = os.path.join(REF_SRC, "commons", "common")
+OUT = os.path.join(HERE, "_ref", "libref_posture.so")
+OVERLAY = os.path.join(HERE, "_ref", "overlay", "tracking")
+REF_FILES = [os.path.join(REF_SRC, "tracker", "tracking", "Outline.cpp"), os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"),
+             os.path.join(REF_COMMON, "misc", "curve_discussion.cpp"), os.path.join(REF_COMMON, "gui", "Transform.cpp")]
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REF_COMMON, "misc", "CircularGraph.cpp")) and shutil.which("g++") is not None
+    return all(os.path.exists(f) for f in REF_FILES) and shutil.which("g++") is not None
+
+
+def _link(src, dst):
+    if os.path.islink(dst) or os.path.exists(dst):
+        os.remove(dst)
+    os.symlink(src, dst)
 
 
 def build(force: bool = False):
     """Returns the path of the library, or None when neither the reference checkout nor a prebuilt library is present."""
     if not available():
         return OUT if os.path.exists(OUT) else None
-    srcs = [os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"), os.path.join(HERE, "ref_circular_graph.cpp")]
-    deps = srcs + [os.path.join(HERE, "ref_stubs", f) for f in ("commons.pc.h", "misc/ranges.h", "misc/Median.h", "misc/Timer.h")]
+    wrappers = [os.path.join(HERE, "ref_outline.cpp"), os.path.join(HERE, "ref_circular_graph.cpp")]
+    stubs = []
+    for root, _, files in os.walk(os.path.join(HERE, "ref_stubs")):
+        stubs += [os.path.join(root, f) for f in files]
+    deps = REF_FILES + wrappers + stubs + [os.path.join(REF_SRC, "tracker", "tracking", "Outline.h"), os.path.abspath(__file__)]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    # the arithmetic flags of the oracle: no contraction, no fast-math (TRex's own build does not enable fast-math either: CMakeLists.txt)
-    cmd = ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "ref_stubs"), "-I", REF_COMMON, *srcs, "-o", OUT]
+    os.makedirs(OVERLAY, exist_ok=True)
+    _link(REF_FILES[0], os.path.join(OVERLAY, "Outline.cpp"))
+    _link(os.path.join(REF_SRC, "tracker", "tracking", "Outline.h"), os.path.join(OVERLAY, "Outline.h"))
+    for h in ("Posture.h", "DebugDrawing.h", "Tracker.h"):
+        _link(os.path.join(HERE, "ref_stubs", "tracking", h), os.path.join(OVERLAY, h))
+    # the arithmetic flags of the oracle: no contraction, no fast-math (TRex's own CMake files do not enable fast-math either)
+    cmd = ["g++", "-std=c++23", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,--no-undefined",
+           "-I", os.path.join(HERE, "ref_stubs"), "-I", REF_COMMON, "-I", os.path.join(REF_SRC, "tracker"),
+           os.path.join(OVERLAY, "Outline.cpp"), *REF_FILES[1:], *wrappers, "-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("building the reference's CircularGraph.cpp failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("building the reference's posture sources failed:\n" + r.stdout + r.stderr)
     return OUT
 
 

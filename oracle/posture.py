@@ -6,8 +6,10 @@ Python face of the restatement in trex_oracle.c of
   image::normalize_image (posture / legacy)                Application/src/tracker/tracking/FilterCache.cpp:21-115,133-154,266-276
   periodic::curvature / differentiate / find_peaks / eft / ieft, fast::cos
                                                             Application/src/commons/common/misc/CircularGraph.cpp:12-606
-parity unpinned: the reference has no test vectors for these functions; tests/test_oracle_posture.py checks each piece
-against an independent numpy formulation and the whole chain on shapes whose midline is known by construction."""
+Pinned on the reference's own code: tests/test_oracle_ref_circular_graph.py and tests/test_oracle_ref_outline.py compare these functions with
+CircularGraph.cpp / Outline.cpp / gui/Transform.cpp compiled unmodified from the reference checkout (oracle/build_ref.py) bit for bit;
+tests/test_oracle_posture.py additionally checks each piece against an independent numpy formulation and the whole chain on shapes whose midline
+is known by construction.  Not covered by that build: pixel::find_outer_points (PixelTree.cpp) and the threshold loop of Posture.cpp."""
 from __future__ import annotations
 
 import ctypes as C

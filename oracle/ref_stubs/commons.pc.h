@@ -1,20 +1,36 @@
-// Test infrastructure (oracle/): a MINIMAL stand-in for TRex's precompiled header `commons.pc.h`, so that the reference's own
-// commons/common/misc/CircularGraph.cpp (eft, ieft, curvature, differentiate, find_peaks and its fast::cos polynomial) compiles here, unmodified
-// and from where it lies under /root/reference, without OpenCV / glaze / cnpy (oracle/build_ref.py).  Only the declarations that file touches
-// are mirrored; the arithmetic-bearing ones restate the reference 1:1:
-//   Vec2            commons/common/misc/vec2.h:20-215  (Vector2D<float, true>: component-wise float operators, length() = std::sqrt(x*x + y*y))
-//   sqdistance      commons/common/misc/vec2.h:380-383
-//   SQR             commons/common/commons.pc.h:446
-//   cmn::sqrt       commons/common/misc/math.h:23-32   (the float specialisation calls ::sqrtf: EFT::dt's unqualified `sqrt(...)` resolves to it)
-// Everything else (printing, timing, exceptions) is inert.  Nothing under trex_b200/ includes this.
+// Test infrastructure (oracle/): a MINIMAL stand-in for TRex's precompiled header `commons.pc.h`, so that a few of the reference's own source files
+// compile here, unmodified and from where they lie under /root/reference, without OpenCV / glaze / cnpy (oracle/build_ref.py):
+//   commons/common/misc/CircularGraph.cpp   eft, ieft, curvature, differentiate, find_peaks and its fast::cos polynomial
+//   commons/common/misc/curve_discussion.cpp, commons/common/gui/Transform.cpp
+//   tracker/tracking/Outline.cpp            Outline::resample / smooth / offset_to_middle / calculate_midline, Midline::post_process / normalize / fix_length
+// Only the declarations those files touch are provided, written for this purpose; the ones that carry arithmetic follow the reference's
+// definitions operation for operation and cite them:
+//   Vec2 / Size2      commons/common/misc/vec2.h:20-215   (Vector2D<float>: component-wise float operators; length() = std::sqrt(x*x + y*y);
+//                     normalize() = (L != 0) * (v / ((L == 0) + L)); member atan2() = std::atan2(y, x) in float; free atan2(v) = ::atan2 in DOUBLE, :371)
+//   sqdistance, euclidean_distance   vec2.h:380-388
+//   SQR, DEGREE, RADIANS, GETTER*    commons.pc.h:444-457
+//   cmn::min / cmn::max              commons.pc.h:462-528 (mixed arithmetic types: computed in the wider of the two, the second on a tie)
+//   cmn::sqrt / sin / cos / atan2    misc/math.h:4-32,162-170 (float arguments call the f-suffixed C functions), cmn::abs :172-197, cmn::isnan :61-88
+//   narrow_cast, infinity            commons.pc.h (value-preserving static_cast / numeric_limits)
+// Printing, timing, exceptions, drawing and OpenCV types are inert.  Nothing under trex_b200/ includes this.
 #pragma once
 #include <algorithm>
+#include <array>
+#include <atomic>
 #include <cassert>
+#include <cfloat>
 #include <cmath>
 #include <concepts>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <expected>
+#include <functional>
+#include <limits>
+#include <map>
 #include <memory>
+#include <mutex>
+#include <optional>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -27,53 +43,162 @@
 #define M_PI 3.14159265358979323846
 #endif
 #define SQR(X) ((X)*(X))
-#define GETTER(TYPE, VAR) protected: TYPE _##VAR; public: const TYPE& VAR() const { return _##VAR; } protected:
+#define DEGREE(radians) ((radians) * (cmn::ScalarType(1.0) / cmn::ScalarType(M_PI) * cmn::ScalarType(180)))
+#define RADIANS(degree) ((degree) * (cmn::ScalarType(1.0) / cmn::ScalarType(180) * cmn::ScalarType(M_PI)))
+#define GETTER(TYPE, VAR) public: [[nodiscard]] const TYPE& VAR() const { return _##VAR; } protected: TYPE _##VAR
+#define GETTER_NCONST(TYPE, VAR) public: [[nodiscard]] inline const TYPE& VAR() const { return _##VAR; } [[nodiscard]] inline TYPE& VAR() { return _##VAR; } protected: TYPE _##VAR
+#define UNUSED(X) (void)(X)
 
 using long_t = int32_t;
 
 namespace cmn {
 using Float2_t = float;
+typedef float ScalarType;
 constexpr Float2_t operator""_F(long double v) { return Float2_t(v); }
 constexpr Float2_t operator""_F(unsigned long long v) { return Float2_t(v); }
 
+template<typename T> constexpr T infinity() { if constexpr (std::is_floating_point_v<T>) return std::numeric_limits<T>::infinity(); else return std::numeric_limits<T>::max(); }
+template<typename To, typename From> constexpr To narrow_cast(From&& v) { return static_cast<To>(v); }
+template<typename To, typename From> constexpr To sign_cast(From&& v) { return static_cast<To>(v); }
+
+template<typename T = double> inline T cos(const T& s) { return ::cos(s); }
+template<> inline float cos(const float& s) { return ::cosf(s); }
+template<typename T = double> inline T sin(const T& s) { return ::sin(s); }
+template<> inline float sin(const float& s) { return ::sinf(s); }
 template<typename T = double> inline T sqrt(const T& s) { return ::sqrt(s); }
 template<> inline float sqrt(const float& s) { return ::sqrtf(s); }
+template<typename T = double> inline T atan2(const T& y, const T& x) { return ::atan2(y, x); }
+template<> inline float atan2(const float& y, const float& x) { return ::atan2f(y, x); }
 
-struct Vec2 {
+template<typename A, typename B> requires (std::is_arithmetic_v<std::remove_cvref_t<A>> && std::is_arithmetic_v<std::remove_cvref_t<B>>)
+constexpr auto min(A&& a, B&& b) { using A_ = std::remove_cvref_t<A>; using B_ = std::remove_cvref_t<B>; using R = std::conditional_t<(sizeof(A_) > sizeof(B_)), A_, B_>; return std::min(R(a), R(b)); }
+template<typename A, typename B> requires (std::is_arithmetic_v<std::remove_cvref_t<A>> && std::is_arithmetic_v<std::remove_cvref_t<B>>)
+constexpr auto max(A&& a, B&& b) { using A_ = std::remove_cvref_t<A>; using B_ = std::remove_cvref_t<B>; using R = std::conditional_t<(sizeof(A_) > sizeof(B_)), A_, B_>; return std::max(R(a), R(b)); }
+template<typename A, typename B, typename Cc> requires (std::is_arithmetic_v<A> && std::is_arithmetic_v<B> && std::is_arithmetic_v<Cc>)
+constexpr auto min(const A& x, const B& y, const Cc& z) -> decltype(x + y + z) { using R = decltype(x + y + z); return std::min(R(x), std::min(R(y), R(z))); }
+template<typename A, typename B, typename Cc> requires (std::is_arithmetic_v<A> && std::is_arithmetic_v<B> && std::is_arithmetic_v<Cc>)
+constexpr auto max(const A& x, const B& y, const Cc& z) -> decltype(x + y + z) { using R = decltype(x + y + z); return std::max(R(x), std::max(R(y), R(z))); }
+
+template<typename T> requires (std::is_arithmetic_v<T> && !std::unsigned_integral<T>) constexpr auto abs(T x) { return std::abs(x); }
+template<typename T> requires std::unsigned_integral<T> constexpr auto abs(T x) { return x; }
+template<typename T> requires std::is_arithmetic_v<T> constexpr bool isnan(T x) { if constexpr (std::is_floating_point_v<T>) return std::isnan(x); else return false; }
+template<typename T> requires std::is_arithmetic_v<T> constexpr T saturate(T v, T lo, T hi) { return std::clamp(v, lo, hi); }
+
+template<bool IsVec>
+struct Vector2D {
     Float2_t x, y;
-    constexpr Vec2() noexcept : x(0), y(0) {}
+
+    constexpr Vector2D() noexcept : x(0), y(0) {}
+    constexpr Vector2D(const Vector2D& o) noexcept : x(o.x), y(o.y) {}
+    constexpr Vector2D& operator=(const Vector2D& o) noexcept { x = o.x; y = o.y; return *this; }
     template<typename S> requires std::is_arithmetic_v<S>
-    constexpr Vec2(S v) noexcept : x(Float2_t(v)), y(Float2_t(v)) {}
+    constexpr Vector2D(S v) noexcept : x(Float2_t(v)), y(Float2_t(v)) {}
     template<typename S0, typename S1> requires (std::is_arithmetic_v<S0> && std::is_arithmetic_v<S1>)
-    constexpr Vec2(S0 a, S1 b) noexcept : x(Float2_t(a)), y(Float2_t(b)) {}
+    constexpr Vector2D(S0 a, S1 b) noexcept : x(Float2_t(a)), y(Float2_t(b)) {}
+    template<bool K> constexpr Vector2D(const Vector2D<K>& o) noexcept : x(o.x), y(o.y) {}
     constexpr Float2_t A() const { return x; }
     constexpr Float2_t B() const { return y; }
-    constexpr Vec2& operator+=(const Vec2& o) { x += o.x; y += o.y; return *this; }
-    constexpr Vec2& operator-=(const Vec2& o) { x -= o.x; y -= o.y; return *this; }
-    constexpr Vec2& operator+=(Float2_t o) { x += o; y += o; return *this; }
-    constexpr Vec2& operator-=(Float2_t o) { x -= o; y -= o; return *this; }
-    constexpr Vec2& operator*=(Float2_t o) { x *= o; y *= o; return *this; }
-    constexpr Vec2& operator/=(Float2_t o) { x /= o; y /= o; return *this; }
-    template<typename S> requires std::is_arithmetic_v<S> constexpr Vec2 operator/(S o) const { return Vec2{x / Float2_t(o), y / Float2_t(o)}; }
-    template<typename S> requires std::is_arithmetic_v<S> constexpr Vec2 operator*(S o) const { return Vec2{x * Float2_t(o), y * Float2_t(o)}; }
-    template<typename S> requires std::is_arithmetic_v<S> constexpr Vec2 operator-(S o) const { return Vec2{x - Float2_t(o), y - Float2_t(o)}; }
-    template<typename S> requires std::is_arithmetic_v<S> constexpr Vec2 operator+(S o) const { return Vec2{x + Float2_t(o), y + Float2_t(o)}; }
-    constexpr Vec2 operator+(Vec2 o) const { return Vec2{x + o.x, y + o.y}; }
-    constexpr Vec2 operator-(Vec2 o) const { return Vec2{x - o.x, y - o.y}; }
-    constexpr Vec2 operator-() const { return Vec2{-x, -y}; }
+    constexpr Vector2D& operator+=(const Vector2D& o) { x += o.x; y += o.y; return *this; }
+    constexpr Vector2D& operator-=(const Vector2D& o) { x -= o.x; y -= o.y; return *this; }
+    constexpr Vector2D& operator+=(Float2_t o) { x += o; y += o; return *this; }
+    constexpr Vector2D& operator-=(Float2_t o) { x -= o; y -= o; return *this; }
+    constexpr Vector2D& operator*=(Float2_t o) { x *= o; y *= o; return *this; }
+    constexpr Vector2D& operator/=(Float2_t o) { x /= o; y /= o; return *this; }
+    template<typename S> requires std::is_arithmetic_v<S> constexpr Vector2D operator/(S o) const { return Vector2D{x / Float2_t(o), y / Float2_t(o)}; }
+    template<typename S> requires std::is_arithmetic_v<S> constexpr Vector2D operator*(S o) const { return Vector2D{x * Float2_t(o), y * Float2_t(o)}; }
+    template<typename S> requires std::is_arithmetic_v<S> constexpr Vector2D operator-(S o) const { return Vector2D{x - Float2_t(o), y - Float2_t(o)}; }
+    template<typename S> requires std::is_arithmetic_v<S> constexpr Vector2D operator+(S o) const { return Vector2D{x + Float2_t(o), y + Float2_t(o)}; }
+    constexpr Vector2D operator+(Vector2D o) const { return Vector2D{x + o.x, y + o.y}; }
+    constexpr Vector2D operator-(Vector2D o) const { return Vector2D{x - o.x, y - o.y}; }
+    constexpr Vector2D operator-() const { return Vector2D{-x, -y}; }
+    constexpr Vector2D mul(const Vector2D& o) const { return Vector2D{x * o.x, y * o.y}; }
+    constexpr Vector2D div(const Vector2D& o) const { return Vector2D{x / o.x, y / o.y}; }
+    constexpr Vector2D perp() const { return Vector2D{y, -x}; }
+    constexpr Vector2D T() const { return Vector2D{y, x}; }
+    constexpr Float2_t dot(const Vector2D& o) const { return x * o.x + y * o.y; }
     constexpr Float2_t sqlength() const { return x * x + y * y; }
     Float2_t length() const { return std::sqrt(sqlength()); }
-    constexpr bool operator==(const Vec2& o) const { return x == o.x && y == o.y; }
-    constexpr bool operator<(const Vec2& o) const { return o.y < y || (o.y == y && o.x < x); }      // vec2.h:99-102
+    Vector2D normalize() const { auto L = length(); return Float2_t(L != 0) * (*this / (Float2_t(L == 0) + L)); }
+    Float2_t atan2() const { return std::atan2(y, x); }
+    Vector2D abs() const { return Vector2D{std::abs(x), std::abs(y)}; }
+    constexpr Float2_t max() const { return std::max(x, y); }
+    constexpr Float2_t min() const { return std::min(x, y); }
+    constexpr bool empty() const { return x == 0 && y == 0; }
+    constexpr bool operator==(const Vector2D& o) const { return x == o.x && y == o.y; }
+    constexpr bool operator!=(const Vector2D& o) const { return x != o.x || y != o.y; }
+    constexpr bool operator<(const Vector2D& o) const { return o.y < y || (o.y == y && o.x < x); }      // vec2.h:99-102
+    friend constexpr Vector2D operator*(Float2_t s, const Vector2D& v) { return Vector2D{v.x * s, v.y * s}; }
 };
-template<typename S> requires std::is_arithmetic_v<S> constexpr Vec2 operator*(S s, const Vec2& v) { return Vec2{Float2_t(s) * v.x, Float2_t(s) * v.y}; }
+using Vec2 = Vector2D<true>;
+using Size2 = Vector2D<false>;
 inline Float2_t sqdistance(const Vec2& p0, const Vec2& p1) { return SQR(p1.A() - p0.A()) + SQR(p1.B() - p0.B()); }
+inline Float2_t euclidean_distance(const Vec2& p0, const Vec2& p1) { return cmn::sqrt(sqdistance(p0, p1)); }
+inline Float2_t length(const Vec2& v) { return v.length(); }
+inline auto atan2(const Vec2& v) { return ::atan2(v.y, v.x); }           // double: vec2.h:370-373
+inline Vec2 abs(const Vec2& v) { return Vec2(cmn::abs(v.x), cmn::abs(v.y)); }
+template<typename T> inline float crosses_zero(T y0, T y1) { return y1 / (y1 - y0); }      // misc/math.h:354-357 (curve_discussion.cpp; not on the path under test)
+// parameters t0 >= t1 of the intersections of the circle (centre p, radius r) with the line v -> w, (-1, -1) without one: misc/math.h:285-311, all in float,
+// the quadratic's coefficients and the two roots formed in the reference's order
+template<typename P0, typename P1, typename P2>
+inline std::pair<float, float> t_circle_line(const P0& v, const P1& w, const P2& p, float r)
+{
+    const float dx = w.x - v.x, dy = w.y - v.y;
+    const float a = SQR(dx) + SQR(dy);
+    const float b = 2 * dx * (v.x - p.x) + 2 * dy * (v.y - p.y);
+    const float c = SQR(v.x - p.x) + SQR(v.y - p.y) - SQR(r);
+    float disc = SQR(b) - 4 * a * c;
+    if (disc < 0) return {-1, -1};
+    disc = cmn::sqrt(disc);
+    return {(-b + disc) / (2 * a), (-b - disc) / (2 * a)};
+}
+inline bool isnan(const Vec2& v) { return std::isnan(v.x) || std::isnan(v.y); }
+
+struct Bounds {
+    Float2_t x, y, width, height;
+    constexpr Bounds(Float2_t x = 0, Float2_t y = 0, Float2_t w = 0, Float2_t h = 0) : x(x), y(y), width(w), height(h) {}
+    Vec2 pos() const { return Vec2(x, y); }
+    Size2 size() const { return Size2(width, height); }
+};
+
+class Minimizable { public: virtual void minimize_memory() = 0; virtual ~Minimizable() {} };
+
+struct Frame_t {
+    int32_t _frame = -1;
+    constexpr Frame_t() = default;
+    explicit constexpr Frame_t(int32_t f) : _frame(f) {}
+    constexpr bool valid() const { return _frame >= 0; }
+    constexpr int32_t get() const { return _frame; }
+    constexpr bool operator==(const Frame_t&) const = default;
+};
 
 struct Meta {
     template<typename T> static std::string toStr(const T&) { return std::string(); }
 };
 template<typename... A> inline void Print(const A&...) {}
 template<typename... A> inline void FormatWarning(const A&...) {}
+template<typename... A> inline void FormatError(const A&...) {}
+template<typename... A> inline void FormatExcept(const A&...) {}
 template<typename... A> inline std::runtime_error U_EXCEPTION(const char *msg, const A&...) { return std::runtime_error(msg); }
+}
+
+// the handful of OpenCV names the compiled files mention: Transform::toCV (never called here), the debug drawing of offset_to_middle and the
+// outline_use_dft branch of find_tail (both off: they abort if reached)
+#define CV_64F 6
+#define CV_32FC1 5
+#define CV_8UC4 24
+namespace cv {
+struct Scalar { Scalar(double = 0, double = 0, double = 0, double = 0) {} };
+struct Mat {
+    Mat() {}
+    Mat(int, int, int) {}
+    Mat(int, int, int, const Scalar&) {}
+    Mat(int, int, int, void *) {}
+    static Mat zeros(int, int, int) { return Mat(); }
+    template<typename T> T& at(int, int) { static T dummy{}; std::fprintf(stderr, "cv::Mat stand-in used\n"); std::abort(); return dummy; }
+    template<typename T> T* ptr(int = 0, int = 0) { std::abort(); return nullptr; }
+    int cols = 0, rows = 0;
+};
+enum { DFT_INVERSE = 1, DFT_SCALE = 2 };
+inline void dft(const Mat&, Mat&, int = 0) { std::fprintf(stderr, "cv::dft stand-in used\n"); std::abort(); }
 }
 using namespace cmn;

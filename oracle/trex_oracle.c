@@ -1239,7 +1239,8 @@ int64_t to_outline_resample(const float *pts, int64_t L, float rd, float *out, i
  *                                            C/misc/CircularGraph.cpp:12-30,49-113,115-407,409-482,484-606
  *   Outline::calculate_midline               T/tracking/Outline.cpp:768-868
  * Float2_t = scalar_t = float; every double literal / M_PI in the reference promotes exactly as written below.
- * parity unpinned: the reference holds no test vectors for these functions.
+ * Pinned on the reference's own code: CircularGraph.cpp and Outline.cpp are compiled unmodified by oracle/build_ref.py, and
+ * tests/test_oracle_ref_circular_graph.py / tests/test_oracle_ref_outline.py hold these functions to them bit for bit.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     int32_t outline_smooth_samples;        /* 4   T/core/default_config.cpp:890 */
@@ -1706,10 +1707,18 @@ int64_t to_calculate_midline(float *p, int64_t N, const to_posture_params_t *P, 
  * restated as the double-precision function rounded to float ((float)atan2((double)y, (double)x)): that is the correctly
  * rounded float result except for inputs within 2^-29 of a rounding boundary, it is what glibc >= 2.41's atan2f returns,
  * and it is within 1 ulp of older atan2f versions (tests/test_oracle_posture.py measures the agreement with the local libm).
- * parity unpinned: the reference holds no vectors for these functions; the normalised length is corroborated against the
- * midline_length column TRex itself exported (tests/golden/posture_golden.npz).
+ * Pinned on the reference's own code (Outline.cpp and gui/Transform.cpp compiled unmodified, oracle/build_ref.py): post_process is bit-exact,
+ * normalize is bit-exact when this file calls the local libm like the compiled reference does (to_use_local_libm) and within 3e-5 px with
+ * the rounding above, the crop matrix is bit-exact in double (tests/test_oracle_ref_outline.py); the normalised length is also corroborated
+ * against the midline_length column TRex itself exported (tests/golden/posture_golden.npz).
  * ------------------------------------------------------------------------------------------ */
-static float atan2_f(float y, float x) { return (float)atan2((double)y, (double)x); }
+/* to_use_local_libm(1): call the C library's own atan2f / cosf / sinf instead, as the reference binary does on this machine -- only for
+ * tests/test_oracle_ref_outline.py, which compares with the reference's code compiled here (oracle/build_ref.py) bit for bit. */
+static int g_local_libm = 0;
+void to_use_local_libm(int on) { g_local_libm = on; }
+static float atan2_f(float y, float x) { return g_local_libm ? atan2f(y, x) : (float)atan2((double)y, (double)x); }
+static float cos_f(float a) { return g_local_libm ? cosf(a) : (float)cos((double)a); }
+static float sin_f(float a) { return g_local_libm ? sinf(a) : (float)sin((double)a); }
 
 static void vnormalize(float x, float y, float *ox, float *oy)      /* Vector2D::normalize, C/misc/vec2.h:159-162 */
 {
@@ -1855,7 +1864,7 @@ static int64_t midline_fix_length(float len, float *pts, int64_t n_pts, uint32_t
                 const float change = angle0 - angle1;
                 float angle = angle0;
                 while ((uint64_t)n_out < resolution) {
-                    seg[0] += (float)cos((double)angle) * step; seg[1] += (float)sin((double)angle) * step;
+                    seg[0] += cos_f(angle) * step; seg[1] += sin_f(angle) * step;
                     angle += change;
                     seg[2] *= 0.5f;
                     memcpy(out + 4 * n_out++, seg, sizeof seg);

@@ -1,7 +1,8 @@
 """CPU tests of the posture ORACLE (N4: raw midline, Midline::post_process / normalize, posture crops): every piece of oracle/posture.py against an
 independent numpy formulation of the same reference formula, and the whole chain on a shape whose midline is known by
 construction.  Reference: T/tracking/Outline.cpp:330-452,454-718,768-868, C/misc/CircularGraph.cpp:12-606.
-parity unpinned -- the reference has no test vectors for these functions."""
+The reference has no test vectors for these functions; they are pinned on the reference's own compiled code in
+tests/test_oracle_ref_outline.py / tests/test_oracle_ref_circular_graph.py."""
 import numpy as np
 import pytest
 
