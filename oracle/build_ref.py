@@ -2,11 +2,12 @@
     tracker/tracking/Outline.cpp                      Outline::resample / smooth / offset_to_middle / calculate_midline, Midline::post_process / normalize / fix_length
     commons/common/misc/CircularGraph.cpp             periodic::curvature / eft / ieft / differentiate / find_peaks (+ its fast::cos polynomial)
     commons/common/misc/curve_discussion.cpp, commons/common/gui/Transform.cpp   (linked by Outline.cpp)
-plus the C wrappers oracle/ref_outline.cpp and oracle/ref_circular_graph.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
+    commons/common/processing/PixelTree.cpp           pixel::find_outer_points with pixel::Tree (its threshold_blob half only has to compile)
+plus the C wrappers oracle/ref_outline.cpp, oracle/ref_circular_graph.cpp and oracle/ref_pixeltree.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
 header needs OpenCV / glaze / cnpy, absent here; its settings cache, drawing and tracker headers are irrelevant to the functions under test).
 Outline.cpp includes "Posture.h", "DebugDrawing.h" and "Tracker.h" with quotes, which a compiler resolves next to the including file first; it is
 therefore compiled through a symbolic link in oracle/_ref/overlay/tracking/ (the file itself stays in the reference checkout), next to placeholders
-for those three headers.  The rest of the reference's path (PixelTree.cpp, RawProcessing.cpp, CPULabeling.cpp ...) is tied to OpenCV image classes
+for those three headers.  The rest of the reference's path (RawProcessing.cpp, CPULabeling.cpp, Posture.cpp ...) is tied to OpenCV image classes
 and stays restated-only: DESIGN.md s6.
 The .so is git-ignored, not gpurun-ignored.  Only tests/ load it."""
 import os
@@ -19,7 +20,8 @@ REF_COMMON = os.path.join(REF_SRC, "commons", "common")
 OUT = os.path.join(HERE, "_ref", "libref_posture.so")
 OVERLAY = os.path.join(HERE, "_ref", "overlay", "tracking")
 REF_FILES = [os.path.join(REF_SRC, "tracker", "tracking", "Outline.cpp"), os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"),
-             os.path.join(REF_COMMON, "misc", "curve_discussion.cpp"), os.path.join(REF_COMMON, "gui", "Transform.cpp")]
+             os.path.join(REF_COMMON, "misc", "curve_discussion.cpp"), os.path.join(REF_COMMON, "gui", "Transform.cpp"),
+             os.path.join(REF_COMMON, "processing", "PixelTree.cpp")]
 
 
 def available() -> bool:
@@ -36,11 +38,12 @@ def build(force: bool = False):
     """Returns the path of the library, or None when neither the reference checkout nor a prebuilt library is present."""
     if not available():
         return OUT if os.path.exists(OUT) else None
-    wrappers = [os.path.join(HERE, "ref_outline.cpp"), os.path.join(HERE, "ref_circular_graph.cpp")]
+    wrappers = [os.path.join(HERE, "ref_outline.cpp"), os.path.join(HERE, "ref_circular_graph.cpp"), os.path.join(HERE, "ref_pixeltree.cpp")]
     stubs = []
     for root, _, files in os.walk(os.path.join(HERE, "ref_stubs")):
         stubs += [os.path.join(root, f) for f in files]
-    deps = REF_FILES + wrappers + stubs + [os.path.join(REF_SRC, "tracker", "tracking", "Outline.h"), os.path.abspath(__file__)]
+    deps = REF_FILES + wrappers + stubs + [os.path.join(REF_SRC, "tracker", "tracking", "Outline.h"), os.path.join(REF_COMMON, "processing", "PixelTree.h"),
+                                            os.path.abspath(__file__)]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     os.makedirs(OVERLAY, exist_ok=True)

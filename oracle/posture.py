@@ -9,7 +9,8 @@ Python face of the restatement in trex_oracle.c of
 Pinned on the reference's own code: tests/test_oracle_ref_circular_graph.py and tests/test_oracle_ref_outline.py compare these functions with
 CircularGraph.cpp / Outline.cpp / gui/Transform.cpp compiled unmodified from the reference checkout (oracle/build_ref.py) bit for bit;
 tests/test_oracle_posture.py additionally checks each piece against an independent numpy formulation and the whole chain on shapes whose midline
-is known by construction.  Not covered by that build: pixel::find_outer_points (PixelTree.cpp) and the threshold loop of Posture.cpp."""
+is known by construction.  pixel::find_outer_points (oracle/seg.py) is pinned the same way (tests/test_oracle_ref_pixeltree.py); not covered by
+that build: the threshold loop of Posture.cpp."""
 from __future__ import annotations
 
 import ctypes as C

@@ -1,0 +1,3 @@
+// Test infrastructure: placeholder for commons/common/processing/PVBlob.h; the declarations PixelTree.cpp needs are in processing/pixeltree_standins.h.
+#pragma once
+#include <processing/pixeltree_standins.h>

@@ -1085,7 +1085,8 @@ int64_t to_segment_batch(const uint8_t *frames, int n, const uint8_t *bg, int w,
  * vectors with the reference's linear search, and walk() is the reference's deque walk (push_front of edges[0], edges[1]).
  * One deliberate simplification: the node set is "pixels with a missing 4-neighbour" -- what the streaming three-row scan
  * (:543-633) is built to find; a node without missing sides emits no edge, so a superset is harmless.
- * parity unpinned: the reference holds no test vectors for find_outer_points.
+ * Pinned on the reference's own code: PixelTree.cpp is compiled unmodified by oracle/build_ref.py and tests/test_oracle_ref_pixeltree.py holds
+ * every outline of 334 blobs (holes, diagonal contacts, single pixels, a 300-pixel-wide blob) to it point for point, in the reference's order.
  * ------------------------------------------------------------------------------------------ */
 typedef struct { float x, y; int32_t e[2]; int walked; uint64_t index; } subnode_t;
 

@@ -1,6 +1,6 @@
 """CPU tests of the oracle's outline stage (N4, first stage): Outline::resample against the reference's own test vectors
 (Application/Tests/test_outlines.cpp:53-94) and pixel::find_outer_points (C/processing/PixelTree.cpp:497-1130; no reference
-vectors: parity unpinned) on shapes whose outlines are known by construction."""
+vectors; pinned on the compiled PixelTree.cpp in tests/test_oracle_ref_pixeltree.py) on shapes whose outlines are known by construction."""
 import numpy as np
 
 from oracle import seg
