@@ -3,12 +3,14 @@
     commons/common/misc/CircularGraph.cpp             periodic::curvature / eft / ieft / differentiate / find_peaks (+ its fast::cos polynomial)
     commons/common/misc/curve_discussion.cpp, commons/common/gui/Transform.cpp   (linked by Outline.cpp)
     commons/common/processing/PixelTree.cpp           pixel::find_outer_points with pixel::Tree (its threshold_blob half only has to compile)
-plus the C wrappers oracle/ref_outline.cpp, oracle/ref_circular_graph.cpp and oracle/ref_pixeltree.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
+    commons/common/processing/{CPULabeling,Brototype,Source,DLList,ListCache}.cpp + misc/IllegalVector.h
+                                                      CPULabeling::run: extract_lines -> merge_lines (Brototype) -> run_fast
+plus the C wrappers oracle/ref_outline.cpp, ref_circular_graph.cpp, ref_pixeltree.cpp and ref_labeling.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
 header needs OpenCV / glaze / cnpy, absent here; its settings cache, drawing and tracker headers are irrelevant to the functions under test).
 Outline.cpp includes "Posture.h", "DebugDrawing.h" and "Tracker.h" with quotes, which a compiler resolves next to the including file first; it is
 therefore compiled through a symbolic link in oracle/_ref/overlay/tracking/ (the file itself stays in the reference checkout), next to placeholders
-for those three headers.  The rest of the reference's path (RawProcessing.cpp, CPULabeling.cpp, Posture.cpp ...) is tied to OpenCV image classes
-and stays restated-only: DESIGN.md s6.
+for those three headers.  The rest of the reference's path (RawProcessing.cpp, BackgroundSubtraction.cpp, Posture.cpp, FilterCache.cpp ...) is tied to
+OpenCV calls and TRex's image / settings classes and stays restated-only: DESIGN.md s6.
 The .so is git-ignored, not gpurun-ignored.  Only tests/ load it."""
 import os
 import shutil
@@ -21,7 +23,8 @@ OUT = os.path.join(HERE, "_ref", "libref_posture.so")
 OVERLAY = os.path.join(HERE, "_ref", "overlay", "tracking")
 REF_FILES = [os.path.join(REF_SRC, "tracker", "tracking", "Outline.cpp"), os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"),
              os.path.join(REF_COMMON, "misc", "curve_discussion.cpp"), os.path.join(REF_COMMON, "gui", "Transform.cpp"),
-             os.path.join(REF_COMMON, "processing", "PixelTree.cpp")]
+             os.path.join(REF_COMMON, "processing", "PixelTree.cpp")] + \
+            [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp")]
 
 
 def available() -> bool:
@@ -38,7 +41,7 @@ def build(force: bool = False):
     """Returns the path of the library, or None when neither the reference checkout nor a prebuilt library is present."""
     if not available():
         return OUT if os.path.exists(OUT) else None
-    wrappers = [os.path.join(HERE, "ref_outline.cpp"), os.path.join(HERE, "ref_circular_graph.cpp"), os.path.join(HERE, "ref_pixeltree.cpp")]
+    wrappers = [os.path.join(HERE, f) for f in ("ref_outline.cpp", "ref_circular_graph.cpp", "ref_pixeltree.cpp", "ref_labeling.cpp")]
     stubs = []
     for root, _, files in os.walk(os.path.join(HERE, "ref_stubs")):
         stubs += [os.path.join(root, f) for f in files]

@@ -18,6 +18,8 @@
 #include <array>
 #include <atomic>
 #include <cassert>
+#include <climits>
+#include <condition_variable>
 #include <cfloat>
 #include <cmath>
 #include <concepts>
@@ -32,6 +34,7 @@
 #include <mutex>
 #include <optional>
 #include <set>
+#include <shared_mutex>
 #include <stdexcept>
 #include <string>
 #include <string_view>
@@ -181,24 +184,37 @@ template<typename... A> inline void FormatExcept(const A&...) {}
 template<typename... A> inline std::runtime_error U_EXCEPTION(const char *msg, const A&...) { return std::runtime_error(msg); }
 }
 
-// the handful of OpenCV names the compiled files mention: Transform::toCV (never called here), the debug drawing of offset_to_middle and the
-// outline_use_dft branch of find_tail (both off: they abort if reached)
-#define CV_64F 6
+// the handful of OpenCV names the compiled files mention.  cv::Mat is a plain row-major byte image (rows, cols, type = CV_8UC1 / CV_8UC3, step.p =
+// {bytes per row, bytes per pixel}, ptr(row)) -- enough for Source::extract_lines, which only compares bytes with zero; Transform::toCV, the debug drawing of
+// offset_to_middle and the outline_use_dft branch of find_tail are never reached (they abort if they are)
+#define CV_8UC1 0
+#define CV_8UC3 16
 #define CV_32FC1 5
+#define CV_64F 6
 #define CV_8UC4 24
 namespace cv {
 struct Scalar { Scalar(double = 0, double = 0, double = 0, double = 0) {} };
 struct Mat {
+    int rows = 0, cols = 0, _type = CV_8UC1;
+    std::vector<unsigned char> store;
+    unsigned char *data = nullptr;
+    struct Step { size_t p[2] = {0, 0}; } step;
     Mat() {}
-    Mat(int, int, int) {}
-    Mat(int, int, int, const Scalar&) {}
-    Mat(int, int, int, void *) {}
-    static Mat zeros(int, int, int) { return Mat(); }
-    template<typename T> T& at(int, int) { static T dummy{}; std::fprintf(stderr, "cv::Mat stand-in used\n"); std::abort(); return dummy; }
-    template<typename T> T* ptr(int = 0, int = 0) { std::abort(); return nullptr; }
-    int cols = 0, rows = 0;
+    Mat(int r, int c, int t) : rows(r), cols(c), _type(t) { alloc(); }
+    Mat(int r, int c, int t, const Scalar&) : Mat(r, c, t) {}
+    Mat(int r, int c, int t, void *d) : rows(r), cols(c), _type(t), data((unsigned char *)d) { step.p[1] = (size_t)channels(); step.p[0] = (size_t)c * step.p[1]; }
+    static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
+    void alloc() { step.p[1] = (size_t)channels(); step.p[0] = (size_t)cols * step.p[1]; store.assign((size_t)rows * step.p[0] + 64, 0); data = store.data(); }
+    int type() const { return _type; }
+    int channels() const { return _type == CV_8UC3 ? 3 : (_type == CV_8UC4 ? 4 : 1); }
+    bool isContinuous() const { return true; }
+    const unsigned char *ptr(int r = 0) const { return data + (size_t)r * step.p[0]; }
+    unsigned char *ptr(int r = 0) { return data + (size_t)r * step.p[0]; }
+    template<typename T> T *ptr(int r, int = 0) { (void)r; std::fprintf(stderr, "cv::Mat::ptr<T> stand-in used\n"); std::abort(); return nullptr; }
+    template<typename T> T& at(int, int) { static T dummy{}; std::fprintf(stderr, "cv::Mat::at stand-in used\n"); std::abort(); return dummy; }
 };
 enum { DFT_INVERSE = 1, DFT_SCALE = 2 };
 inline void dft(const Mat&, Mat&, int = 0) { std::fprintf(stderr, "cv::dft stand-in used\n"); std::abort(); }
 }
+#include <misc/base_types.h>
 using namespace cmn;

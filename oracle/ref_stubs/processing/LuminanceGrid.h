@@ -1,3 +1,3 @@
-// Test infrastructure: placeholder for commons/common/processing/LuminanceGrid.h; the declarations PixelTree.cpp needs are in processing/pixeltree_standins.h.
+// Test infrastructure: placeholder for commons/common/processing/LuminanceGrid.h (the declarations the compiled files need are in processing/Background.h and processing/PVBlob.h of this directory).
 #pragma once
-#include <processing/pixeltree_standins.h>
+#include <processing/Background.h>

@@ -1,3 +1,52 @@
-// Test infrastructure: placeholder for commons/common/processing/PVBlob.h; the declarations PixelTree.cpp needs are in processing/pixeltree_standins.h.
+// Test infrastructure: pv::Blob (commons/common/processing/PVBlob.h) reduced to what PixelTree.cpp and CPULabeling.cpp touch: the run list, the pixel
+// bytes, the flag byte (Flags / set_flag / get_only_flag / copy_flags restated from PVBlob.h:138-168) and the bounding box of the runs
+// (x = min x0, y = first y, width = max x1 - x + 1, height = last y - y + 1: what pv::Blob::init computes from the lines).
 #pragma once
-#include <processing/pixeltree_standins.h>
+#include <commons.pc.h>
+namespace cmn {
+enum class meta_encoding_t { gray, r3g3b2, rgb8, binary };
+struct InputInfo { uint8_t channels = 1; meta_encoding_t encoding = meta_encoding_t::gray; constexpr bool is_r3g3b2() const { return encoding == meta_encoding_t::r3g3b2; } };
+}
+namespace pv {
+class Blob;
+using BlobPtr = std::unique_ptr<Blob>;
+class Blob {
+    cmn::blob::line_ptr_t _lines;
+    cmn::blob::pixel_ptr_t _pixels;
+    uint8_t _flags = 0;
+    cmn::Bounds _bounds;
+public:
+    enum class Flags { split = 1, is_tag = 2, is_instance_segmentation = 4, is_rgb = 5, is_r3g3b2 = 6, is_binary = 7 };
+    static constexpr void set_flag(uint8_t &flags, Flags flag, bool v) { flags ^= (-uint8_t(v) ^ flags) & (1UL << uint8_t(flag)); }
+    static constexpr uint8_t get_only_flag(Flags flag, bool v) { uint8_t flags = 0; set_flag(flags, flag, v); return flags; }
+    static constexpr bool is_flag(uint8_t flags, Flags flag) { return (flags >> uint8_t(flag)) & 1u; }
+    Blob(cmn::blob::line_ptr_t&& l, cmn::blob::pixel_ptr_t&& p, uint8_t flags = 0, cmn::blob::Prediction&& = {}) : _lines(std::move(l)), _pixels(std::move(p)), _flags(flags)
+    {
+        if (_lines && !_lines->empty()) {
+            int x0 = 1 << 30, x1 = -1;
+            for (auto &h : *_lines) { x0 = std::min<int>(x0, h.x0); x1 = std::max<int>(x1, h.x1); }
+            _bounds = cmn::Bounds((float)x0, (float)_lines->front().y, (float)(x1 - x0 + 1), (float)(_lines->back().y - _lines->front().y + 1));
+        }
+    }
+    Blob(const Blob& o) : Blob(std::make_unique<cmn::blob::lines_t>(*o._lines), o._pixels ? std::make_unique<cmn::PixelArray_t>(*o._pixels) : nullptr, o._flags) {}
+    template<typename... A> static BlobPtr Make(A&&... a) { return std::make_unique<Blob>(std::forward<A>(a)...); }
+    const std::vector<cmn::HorizontalLine>& hor_lines() const { return *_lines; }
+    const cmn::blob::line_ptr_t& lines() const { return _lines; }
+    const cmn::blob::pixel_ptr_t& pixels() const { return _pixels; }
+    cmn::blob::line_ptr_t&& steal_lines() { return std::move(_lines); }
+    const cmn::Bounds& bounds() const { return _bounds; }
+    uint8_t flags() const { return _flags; }
+    uint32_t blob_id() const { return 0; }
+    cmn::blob::Prediction prediction() const { return {}; }
+    bool is_binary() const { return is_flag(_flags, Flags::is_binary); }
+    bool is_rgb() const { return is_flag(_flags, Flags::is_rgb); }
+    bool is_r3g3b2() const { return is_flag(_flags, Flags::is_r3g3b2); }
+    uint8_t channels() const { return is_binary() ? 0 : (is_rgb() ? 3 : 1); }
+    cmn::InputInfo input_info() const { return cmn::InputInfo{channels(), is_rgb() ? cmn::meta_encoding_t::rgb8 : (is_r3g3b2() ? cmn::meta_encoding_t::r3g3b2 : cmn::meta_encoding_t::gray)}; }
+    size_t num_pixels() const { size_t n = 0; for (auto &h : *_lines) n += h.length(); return n; }
+    static constexpr uint8_t copy_flags(const Blob& b)
+    {
+        return get_only_flag(Flags::is_rgb, b.is_rgb()) | get_only_flag(Flags::is_r3g3b2, b.is_r3g3b2()) | get_only_flag(Flags::is_binary, b.is_binary());
+    }
+};
+}
