@@ -207,8 +207,10 @@ TB_API int tb_seg_crops(tb_seg *h, const uint8_t **crops, const uint32_t **crop_
  * enable_difference = track_background_subtraction, detect_threshold_is_absolute = track_threshold_is_absolute,
  * size ranges = track_size_filter (or none).  Gray encoding: trk is a channels = 1 handle (it runs on the grey plane);
  * rgb8: trk has det's channels and encoding, pixels are compared through cmn::bgr2gray (Background.h:76-81) against
- * the background's grey image and keep their B,G,R bytes (test_pixels.cpp:1073-1166).  Afterwards tb_seg_wait / tb_seg_result / tb_seg_crops /
- * tb_seg_device_results on trk return the tracker-side blobs (and their crops: what the reference feeds the CNN). */
+ * the background's grey image and keep their B,G,R bytes (test_pixels.cpp:1073-1166).  Like the entry the tracker calls (:344-356, size_range
+ * (-1, -1)), sub-blobs with a payload of ONE byte are not handed on (`pixels->size() > 1`: a lone grey pixel goes, a lone rgb8 pixel stays).
+ * Afterwards tb_seg_wait / tb_seg_result / tb_seg_crops / tb_seg_device_results on trk return the tracker-side blobs (and their crops: what the
+ * reference feeds the CNN). */
 TB_API int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch);
 
 /* pv::Blob::recount(threshold, background) (C/processing/PVBlob.cpp:934-1027) through Background::count_above_threshold

@@ -162,7 +162,7 @@ def calculate_posture(lines, pixels, bg, track_posture_threshold=0, outline_resa
     one = seg.Blobs(lines, pixels, np.array([0, len(lines)], np.int64), np.array([0, len(pixels)], np.int64))
     threshold, first_outline = int(track_posture_threshold), None
     while True:
-        sub = seg.rethreshold(one, bg, threshold, method)
+        sub = seg.rethreshold(one, bg, threshold, method, keep_single=True)      # threshold_get_biggest_blob sees every sub-blob
         sizes = np.diff(sub.px_off)
         n_sub = 0
         if len(sub):

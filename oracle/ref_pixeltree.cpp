@@ -25,4 +25,39 @@ int64_t ref_find_outer_points(const uint16_t *lines, int64_t n, float *pts, int6
     return k;
 }
 
+
+// pixel::threshold_blob(cache, blob, difference_cache, threshold, Rangel(-1, -1))  (PixelTree.cpp:362-374 over _threshold_blob :90-184): the overload that
+// takes the per-pixel difference values ready-made (tracker/tracking/SplitBlob.cpp:164) -- the same run cutting, relabeling (CPULabeling::run, the
+// reference's own, compiled) and `pixels->size() > 1` rule as the Background overload the tracker calls (:344-356), without needing a Background.
+// lines: n x {x0, x1, y, pad}; pixels: channels bytes per pixel; diff: one byte per pixel.  Output like ref_label_image.
+int64_t ref_threshold_blob_cache(const uint16_t *in_lines, int64_t n, const uint8_t *in_px, int64_t n_px, int channels, const uint8_t *diff, int threshold,
+                                 uint16_t *lines, int64_t cap_lines, uint8_t *pixels, int64_t cap_px, int64_t *line_off, int64_t *px_off, uint8_t *flags, int64_t cap_blobs)
+{
+    auto l = std::make_unique<cmn::blob::lines_t>((size_t)n);
+    for (int64_t i = 0; i < n; ++i) (*l)[(size_t)i] = cmn::HorizontalLine(in_lines[4 * i + 2], in_lines[4 * i], in_lines[4 * i + 1]);
+    auto px = std::make_unique<cmn::PixelArray_t>(in_px, in_px + n_px);
+    pv::Blob blob(std::move(l), std::move(px), pv::Blob::get_only_flag(pv::Blob::Flags::is_rgb, channels == 3));
+    cmn::PixelArray_t cache(diff, diff + n_px / channels);
+    cmn::CPULabeling::ListCache_t lc;
+    auto out = cmn::pixel::threshold_blob(lc, &blob, cache, threshold, cmn::Rangel(-1, -1));
+    int64_t k = 0, nl = 0, np = 0;
+    line_off[0] = 0; px_off[0] = 0;
+    for (auto &b : out) {
+        if (k >= cap_blobs) return -4;
+        for (auto &h : b->hor_lines()) {
+            if (nl >= cap_lines) return -4;
+            lines[4 * nl] = h.x0; lines[4 * nl + 1] = h.x1; lines[4 * nl + 2] = h.y; lines[4 * nl + 3] = 0; ++nl;
+        }
+        if (b->pixels()) {
+            if (np + (int64_t)b->pixels()->size() > cap_px) return -4;
+            std::memcpy(pixels + np, b->pixels()->data(), b->pixels()->size());
+            np += (int64_t)b->pixels()->size();
+        }
+        flags[k] = b->flags();
+        ++k;
+        line_off[k] = nl; px_off[k] = np;
+    }
+    return k;
+}
+
 }

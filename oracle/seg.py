@@ -433,9 +433,11 @@ def average(frames, method="mean"):
     return out
 
 
-def rethreshold(blobs: "Blobs", bg, threshold: int, method=DIFF_ABSOLUTE, rgb=False) -> "Blobs":
+def rethreshold(blobs: "Blobs", bg, threshold: int, method=DIFF_ABSOLUTE, rgb=False, keep_single=False) -> "Blobs":
     """pixel::threshold_blob on every blob of a frame (tracker-side re-threshold, comparison >=).  rgb: the blobs carry
-    B,G,R per pixel and bg is the GREY image of the background (Background's cvtColor, Background.cpp:71-77)."""
+    B,G,R per pixel and bg is the GREY image of the background (Background's cvtColor, Background.cpp:71-77).
+    As the tracker's entry does (PixelTree.cpp:344-356), sub-blobs with a payload of one byte (a single grey pixel) are dropped;
+    keep_single=True gives every sub-blob (what threshold_get_biggest_blob, the posture loop, chooses from)."""
     bg = np.ascontiguousarray(bg, np.uint8)
     lines = np.ascontiguousarray(blobs.lines); px = np.ascontiguousarray(blobs.pixels, np.uint8)
     lo = np.ascontiguousarray(blobs.line_off, np.int64); po = np.ascontiguousarray(blobs.px_off, np.int64)
@@ -443,8 +445,12 @@ def rethreshold(blobs: "Blobs", bg, threshold: int, method=DIFF_ABSOLUTE, rgb=Fa
     ol = np.zeros(capL, LINE_DTYPE); op = np.zeros(capP, np.uint8)
     olo = np.zeros(capB + 1, np.int64); opo = np.zeros(capB + 1, np.int64)
     fn = lib().to_rethreshold_frame_rgb if rgb else lib().to_rethreshold_frame
-    k = fn(_p(lines), _p(lo), _p(px), _p(po), len(blobs), _p(bg), bg.shape[1], method, int(threshold),
-                                   _p(ol), capL, _p(op), capP, _p(olo), _p(opo), capB)
+    lib().to_rethreshold_keep_single(int(bool(keep_single)))
+    try:
+        k = fn(_p(lines), _p(lo), _p(px), _p(po), len(blobs), _p(bg), bg.shape[1], method, int(threshold),
+               _p(ol), capL, _p(op), capP, _p(olo), _p(opo), capB)
+    finally:
+        lib().to_rethreshold_keep_single(0)
     assert k >= 0, k
     return Blobs(ol[:olo[k]].copy(), op[:opo[k]].copy(), olo[:k + 1].copy(), opo[:k + 1].copy())
 

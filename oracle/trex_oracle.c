@@ -889,7 +889,7 @@ void to_crop_blob_moments(const to_line_t *lines, int64_t n_lines, const uint8_t
 
 /* ------------------------------------------------------------------------------------------
  * Tracker-side re-threshold of one frame's blobs ("next" row N3a): pixel::threshold_blob
- * (C/processing/PixelTree.cpp:186-291) applied to every blob: line_without_grid keeps the pixels whose
+ * (C/processing/PixelTree.cpp:186-291 behind the public entry :344-356) applied to every blob: line_without_grid keeps the pixels whose
  * difference to the background is >= threshold (Background::is_value_different, Background.h:415-427;
  * method 0 none: value, 1 absolute: |bg - v|, 2 sign: max(0, bg - v), Background.h:231-294), cutting each
  * line into sub-lines, then CPULabeling::run(lines, pixels) (CPULabeling.cpp:378-414) relabels them.
@@ -922,6 +922,12 @@ int64_t to_rethreshold_frame_rgb(const to_line_t *lines, const int64_t *line_off
     return rethreshold_frame_c(lines, line_off, px, px_off, n_blobs, bg, bg_w, method, threshold,
                                olines, cap_lines, opx, cap_px, oline_off, opx_off, cap_blobs, 3);
 }
+
+/* pixel::threshold_blob as the tracker calls it (PixelTree.cpp:344-356, size_range = Rangel(-1, -1)) hands on only the sub-blobs with
+ * pixels->size() > 1, i.e. more than ONE BYTE of payload: a single grey pixel is dropped, a single rgb8 pixel (3 bytes) is kept.
+ * pixel::threshold_get_biggest_blob (:297-340, the posture loop) has no such rule: to_rethreshold_keep_single(1) switches it off. */
+static int g_rt_keep_single = 0;
+void to_rethreshold_keep_single(int on) { g_rt_keep_single = on; }
 
 static int64_t rethreshold_frame_c(const to_line_t *lines, const int64_t *line_off, const uint8_t *px, const int64_t *px_off,
                              int64_t n_blobs, const uint8_t *bg, int bg_w, int method, int threshold,
@@ -958,6 +964,11 @@ static int64_t rethreshold_frame_c(const to_line_t *lines, const int64_t *line_o
         int64_t nb = to_label_runs(sub, ns, TO_ORDER_CANONICAL, label);
         if (nb < 0) { free(sub); free(src); free(label); return -1; }
         for (int64_t b = 0; b < nb; ++b) {
+            if (!g_rt_keep_single) {                                /* :350-352: pixels->size() > 1 */
+                int64_t bytes = 0;
+                for (int64_t i = 0; i < ns; ++i) if (label[i] == b) bytes += ((int64_t)sub[i].x1 - sub[i].x0 + 1) * c;
+                if (bytes <= 1) continue;
+            }
             if (kept < cap_blobs) { oline_off[kept] = tl; opx_off[kept] = tp; }
             for (int64_t i = 0; i < ns; ++i) {
                 if (label[i] != b) continue;

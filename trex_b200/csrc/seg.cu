@@ -44,6 +44,8 @@ struct SegDev {
     const uint8_t *bg;
     size_t bg_stride;          // 0: one background for all frames; else `bg` holds one mask image per frame (morphology path)
     const uint8_t *keep_mask;  // optional [B][H][W] 0xFF/0 image ANDed with the foreground (tracker-side re-threshold), or null
+    uint32_t min_payload;      // tracker-side re-threshold: blobs whose payload is not MORE than this many bytes are dropped (pixel::threshold_blob,
+                               // C/processing/PixelTree.cpp:350-352: `pixels->size() > 1` -- a lone grey pixel goes, a lone rgb8 pixel stays); 0 elsewhere
     // colour inputs (T/python/BackgroundSubtraction.cpp:151-188): frames are [B][H][W][CN] interleaved B,G,R(,A)
     int CN;                    // bytes per pixel of the submitted frames: 1, 3, 4
     int enc;                   // 0 gray (1 byte per blob pixel), 1 rgb8 (B,G,R per blob pixel)
@@ -1061,7 +1063,7 @@ __device__ void ccl_label_body(const SegDev &d, uint32_t *s_par, uint32_t *ws)
             keep = d.n_ranges == 0;
             const double v = (double)((float)(d.keep_mask ? px : px * (uint32_t)d.opx) * d.sqcm);      // detect side: pixels->size() = payload BYTES (3 per rgb8 pixel), BackgroundSubtraction.cpp:247-259; tracker side: pixel counts
             for (int q = 0; q < d.n_ranges; ++q) keep |= (v >= d.lo[q] && v < d.hi[q]);
-            keep = keep && l < 65535u;
+            keep = keep && l < 65535u && px * (uint32_t)d.opx > d.min_payload;
         }
         uint32_t t0, t1, t2;
         uint32_t e0 = block_excl_scan(keep, ws, t0);
@@ -1230,7 +1232,7 @@ ccl_label_kernel(SegDev d)
             keep = d.n_ranges == 0;
             const double v = (double)((float)(d.keep_mask ? px : px * (uint32_t)d.opx) * d.sqcm);      // detect side: pixels->size() = payload BYTES (3 per rgb8 pixel), BackgroundSubtraction.cpp:247-259; tracker side: pixel counts
             for (int q = 0; q < d.n_ranges; ++q) keep |= (v >= d.lo[q] && v < d.hi[q]);
-            keep = keep && l < 65535u;
+            keep = keep && l < 65535u && px * (uint32_t)d.opx > d.min_payload;
             if (st_smem) { d.b_xmin[o + k] = xmin[k]; d.b_xmax[o + k] = xmax[k]; d.b_ymax[o + k] = ymax[k]; }
         }
         const uint32_t v3[3] = {keep, keep ? l : 0u, keep ? px * (uint32_t)d.opx : 0u};      // pixel arena offsets count bytes
@@ -1847,12 +1849,13 @@ static int seg_morph(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s
     return TB_OK;
 }
 
-static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s, int fetch, const uint8_t *keep_mask = nullptr)
+static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t s, int fetch, const uint8_t *keep_mask = nullptr, uint32_t min_payload = 0)
 {
     SegDev d = h->d;
     d.B = n;
     d.bg_stride = 0;
     d.keep_mask = nullptr;
+    d.min_payload = 0;
     d.nz_plane = nullptr;
     h->last_frames_dev = frames_dev;
     h->gray_valid = false;
@@ -1909,6 +1912,7 @@ static int seg_launch(tb_seg *h, const uint8_t *frames_dev, int n, cudaStream_t 
     } else if (keep_mask) {                 // tracker-side re-threshold: comparison >=, restricted to the painted detection blobs
         TB_REQUIRE(!h->morph, TB_ERR_INVALID, "tb_seg_rethreshold: the tracker-side handle must not enable morphology");
         d.keep_mask = keep_mask;
+        d.min_payload = min_payload;
         kk = h->k; kk.flags |= F_GE;
         seg_rle_kernel<true><<<g1, K1_NT, 0, s>>>(plane, d, kk, fpc);
     } else if (h->morph) {
@@ -2440,6 +2444,7 @@ extern "C" int tb_seg_recount(tb_seg *h, int threshold, float *out, uint32_t n)
     return TB_OK;
 }
 
+static int seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch, uint32_t min_payload);
 extern "C" int tb_seg_posture_thresholded(tb_seg *src, tb_seg *pst, const tb_posture_request *q, int track_posture_threshold)
 {
     TB_REQUIRE(src && pst && q && src != pst, TB_ERR_INVALID, "tb_seg_posture_thresholded: need two distinct handles and a request");
@@ -2481,7 +2486,7 @@ extern "C" int tb_seg_posture_thresholded(tb_seg *src, tb_seg *pst, const tb_pos
         tb_seg_params p = saved;
         p.detect_threshold = thr;
         if ((r = tb_seg_set_params(pst, &p)) != TB_OK) break;
-        if ((r = tb_seg_rethreshold(src, pst, 0)) != TB_OK) break;      // pixel::threshold_blob of every source blob at this threshold
+        if ((r = seg_rethreshold(src, pst, 0, 0u)) != TB_OK) break;      // every sub-blob of every source blob at this threshold (threshold_get_biggest_blob picks)
         const int last_round = thr + 2 >= track_posture_threshold + 100;
         if (cudaMemsetAsync(pst->r_remaining, 0, 4, s) != cudaSuccess) { set_error("cudaMemsetAsync failed"); r = TB_ERR_CUDA; break; }
         if ((r = launch_posture_parents(R, np_max, pst->d.blobs_cap, pst->p_sms, s)) != TB_OK) break;
@@ -2577,7 +2582,11 @@ extern "C" int tb_seg_kernel_ms(tb_seg *h, double out_ms[3], uint64_t *n_batches
 // handle of the same geometry whose params carry the TRACKER settings (detect_threshold = track_threshold,
 // enable_difference = track_background_subtraction, detect_threshold_is_absolute = track_threshold_is_absolute,
 // size ranges = track_size_filter or none).  Results are read from `trk` like after a submit.
-extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch)
+// min_payload: 1 = pixel::threshold_blob as the tracker calls it (sub-blobs of one payload byte are not handed on, PixelTree.cpp:350-352);
+// 0 = every sub-blob (pixel::threshold_get_biggest_blob, :297-340: what the posture loop chooses from)
+static int seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch, uint32_t min_payload);
+extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch) { return seg_rethreshold(det, trk, fetch, 1u); }
+static int seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch, uint32_t min_payload)
 {
     TB_REQUIRE(det && trk && det != trk, TB_ERR_INVALID, "tb_seg_rethreshold: need two distinct handles");
     TB_REQUIRE(det->last_n > 0 && det->last_frames_dev, TB_ERR_STATE, "tb_seg_rethreshold: the detection handle has no batch");
@@ -2603,10 +2612,10 @@ extern "C" int tb_seg_rethreshold(tb_seg *det, tb_seg *trk, int fetch)
     trk->launches += 1;
     TB_CUDA(cudaGetLastError());
     const uint8_t *plane = det->last_frames_dev;
-    if (det->d.enc == 1) return seg_launch(trk, plane, n, s, fetch, trk->keep_mask);     // rgb8: trk converts with the tracker's grey formula
+    if (det->d.enc == 1) return seg_launch(trk, plane, n, s, fetch, trk->keep_mask, min_payload);     // rgb8: trk converts with the tracker's grey formula
     if (det->d.CN > 1) {                       // colour frames, gray encoding: re-threshold the grey plane
         if (!det->gray_valid) { int r = seg_to_gray(det, det->last_frames_dev, n, s); if (r != TB_OK) return r; }
         plane = det->d_gray;
     }
-    return seg_launch(trk, plane, n, s, fetch, trk->keep_mask);
+    return seg_launch(trk, plane, n, s, fetch, trk->keep_mask, min_payload);
 }
