@@ -56,6 +56,7 @@ class PV15:
         self.name = cstr()
         ch = 1 if self.encoding in ("gray", "r3g3b2", "binary") else 3
         self.channels = ch
+        self.storage_channels = 0 if self.encoding == "binary" else ch      # required_storage_channels: `binary` frames carry no pixel bytes
         n = self.width * self.height * ch
         self.average = np.frombuffer(d, np.uint8, n, pos).reshape(self.height, self.width, ch).copy()
         if ch == 1:
@@ -89,7 +90,7 @@ class PV15:
             y = start_y + np.concatenate([[0], np.cumsum(eol)[:-1]])
             ln = np.zeros(nl, LINE_DTYPE)
             ln["x0"], ln["x1"], ln["y"] = x0, x1, y
-            npx = int((x1.astype(np.int64) - x0 + 1).sum()) * self.channels
+            npx = int((x1.astype(np.int64) - x0 + 1).sum()) * self.storage_channels
             pixels.append(np.frombuffer(buf, np.uint8, npx, pos)); pos += npx
             lines.append(ln)
             lo.append(lo[-1] + nl); po.append(po[-1] + npx)

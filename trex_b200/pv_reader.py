@@ -62,7 +62,9 @@ class PVReader:
         (self.index_offset,) = struct.unpack_from("<Q", d, pos); pos += 8
         (self.timestamp,) = struct.unpack_from("<Q", d, pos); pos += 8
         self.name = cstr()
-        self.channels = 3 if self.encoding == "rgb8" else 1          # required_storage_channels(meta_encoding)
+        self.channels = 3 if self.encoding == "rgb8" else 1          # channels of the average image
+        # bytes per blob pixel in the frames: required_storage_channels(meta_encoding) (C/processing/encoding.h:16-27) -- `binary` stores none
+        self.storage_channels = 0 if self.encoding == "binary" else self.channels
         n = self.width * self.height * self.channels
         avg = np.frombuffer(d, np.uint8, n, pos).reshape(self.height, self.width, self.channels).copy(); pos += n
         self.average = avg[..., 0] if self.channels == 1 else avg
@@ -96,7 +98,7 @@ class PVReader:
             ln["x0"] = raw[:, 0]; ln["x1"] = raw[:, 1] & 0x7FFF
             eol = (raw[:, 1] >> 15).astype(np.int64)
             ln["y"] = start_y + np.concatenate([[0], np.cumsum(eol)[:-1]]) if nl else 0
-            npx = int((ln["x1"].astype(np.int64) - ln["x0"] + 1).sum()) * self.channels
+            npx = int((ln["x1"].astype(np.int64) - ln["x0"] + 1).sum()) * self.storage_channels
             pixels.append(np.frombuffer(buf, np.uint8, npx, pos)); pos += npx
             lines.append(ln); flags.append(fl)
             lo.append(lo[-1] + nl); po.append(po[-1] + npx)
