@@ -5,7 +5,10 @@
     commons/common/processing/PixelTree.cpp           pixel::find_outer_points with pixel::Tree (its threshold_blob half only has to compile)
     commons/common/processing/{CPULabeling,Brototype,Source,DLList,ListCache}.cpp + misc/IllegalVector.h
                                                       CPULabeling::run: extract_lines -> merge_lines (Brototype) -> run_fast
-plus the C wrappers oracle/ref_outline.cpp, ref_circular_graph.cpp, ref_pixeltree.cpp and ref_labeling.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
+    commons/common/processing/Background.{h,cpp} + processing/encoding.h, misc/EnumClass.h, misc/matharray.h, misc/FormatColor.h
+                                                      per-pixel difference / is_different / count_above_threshold, cmn::bgr2gray, imageFromLines;
+                                                      with it the Background overload of pixel::threshold_blob is the reference's own code as well
+plus the C wrappers oracle/ref_outline.cpp, ref_circular_graph.cpp, ref_pixeltree.cpp, ref_labeling.cpp and ref_background.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
 header needs OpenCV / glaze / cnpy, absent here; its settings cache, drawing and tracker headers are irrelevant to the functions under test).
 Outline.cpp includes "Posture.h", "DebugDrawing.h" and "Tracker.h" with quotes, which a compiler resolves next to the including file first; it is
 therefore compiled through a symbolic link in oracle/_ref/overlay/tracking/ (the file itself stays in the reference checkout), next to placeholders
@@ -24,7 +27,7 @@ OVERLAY = os.path.join(HERE, "_ref", "overlay", "tracking")
 REF_FILES = [os.path.join(REF_SRC, "tracker", "tracking", "Outline.cpp"), os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"),
              os.path.join(REF_COMMON, "misc", "curve_discussion.cpp"), os.path.join(REF_COMMON, "gui", "Transform.cpp"),
              os.path.join(REF_COMMON, "processing", "PixelTree.cpp")] + \
-            [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp")]
+            [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp")]
 
 
 def available() -> bool:
@@ -41,7 +44,7 @@ def build(force: bool = False):
     """Returns the path of the library, or None when neither the reference checkout nor a prebuilt library is present."""
     if not available():
         return OUT if os.path.exists(OUT) else None
-    wrappers = [os.path.join(HERE, f) for f in ("ref_outline.cpp", "ref_circular_graph.cpp", "ref_pixeltree.cpp", "ref_labeling.cpp")]
+    wrappers = [os.path.join(HERE, f) for f in ("ref_outline.cpp", "ref_circular_graph.cpp", "ref_pixeltree.cpp", "ref_labeling.cpp", "ref_background.cpp")]
     stubs = []
     for root, _, files in os.walk(os.path.join(HERE, "ref_stubs")):
         stubs += [os.path.join(root, f) for f in files]

@@ -85,7 +85,6 @@ constexpr auto max(const A& x, const B& y, const Cc& z) -> decltype(x + y + z) {
 template<typename T> requires (std::is_arithmetic_v<T> && !std::unsigned_integral<T>) constexpr auto abs(T x) { return std::abs(x); }
 template<typename T> requires std::unsigned_integral<T> constexpr auto abs(T x) { return x; }
 template<typename T> requires std::is_arithmetic_v<T> constexpr bool isnan(T x) { if constexpr (std::is_floating_point_v<T>) return std::isnan(x); else return false; }
-template<typename T> requires std::is_arithmetic_v<T> constexpr T saturate(T v, T lo, T hi) { return std::clamp(v, lo, hi); }
 
 template<bool IsVec>
 struct Vector2D {
@@ -159,6 +158,7 @@ inline bool isnan(const Vec2& v) { return std::isnan(v.x) || std::isnan(v.y); }
 struct Bounds {
     Float2_t x, y, width, height;
     constexpr Bounds(Float2_t x = 0, Float2_t y = 0, Float2_t w = 0, Float2_t h = 0) : x(x), y(y), width(w), height(h) {}
+    Bounds(const Vec2& p, const Size2& s) : x(p.x), y(p.y), width(s.x), height(s.y) {}
     Vec2 pos() const { return Vec2(x, y); }
     Size2 size() const { return Size2(width, height); }
 };
@@ -174,9 +174,13 @@ struct Frame_t {
     constexpr bool operator==(const Frame_t&) const = default;
 };
 
+struct glz_json_placeholder {};
 struct Meta {
     template<typename T> static std::string toStr(const T&) { return std::string(); }
+    template<typename T> static std::string name() { return std::string(); }
+    template<typename T, typename S> static T fromStr(S&&) { return T{}; }
 };
+template<typename T> inline auto cvt2json(const T&) { return glz_json_placeholder{}; }
 template<typename... A> inline void Print(const A&...) {}
 template<typename... A> inline void FormatWarning(const A&...) {}
 template<typename... A> inline void FormatError(const A&...) {}
@@ -196,7 +200,7 @@ namespace cv {
 struct Scalar { Scalar(double = 0, double = 0, double = 0, double = 0) {} };
 struct Mat {
     int rows = 0, cols = 0, _type = CV_8UC1;
-    std::vector<unsigned char> store;
+    std::shared_ptr<std::vector<unsigned char>> store;      // copies share the pixels, like cv::Mat
     unsigned char *data = nullptr;
     struct Step { size_t p[2] = {0, 0}; } step;
     Mat() {}
@@ -204,17 +208,34 @@ struct Mat {
     Mat(int r, int c, int t, const Scalar&) : Mat(r, c, t) {}
     Mat(int r, int c, int t, void *d) : rows(r), cols(c), _type(t), data((unsigned char *)d) { step.p[1] = (size_t)channels(); step.p[0] = (size_t)c * step.p[1]; }
     static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
-    void alloc() { step.p[1] = (size_t)channels(); step.p[0] = (size_t)cols * step.p[1]; store.assign((size_t)rows * step.p[0] + 64, 0); data = store.data(); }
+    void alloc() { step.p[1] = (size_t)channels(); step.p[0] = (size_t)cols * step.p[1]; store = std::make_shared<std::vector<unsigned char>>((size_t)rows * step.p[0] + 64, 0); data = store->data(); }
     int type() const { return _type; }
     int channels() const { return _type == CV_8UC3 ? 3 : (_type == CV_8UC4 ? 4 : 1); }
     bool isContinuous() const { return true; }
     const unsigned char *ptr(int r = 0) const { return data + (size_t)r * step.p[0]; }
     unsigned char *ptr(int r = 0) { return data + (size_t)r * step.p[0]; }
     template<typename T> T *ptr(int r, int = 0) { (void)r; std::fprintf(stderr, "cv::Mat::ptr<T> stand-in used\n"); std::abort(); return nullptr; }
-    template<typename T> T& at(int, int) { static T dummy{}; std::fprintf(stderr, "cv::Mat::at stand-in used\n"); std::abort(); return dummy; }
+    template<typename T> T& at(int r, int c) { return *reinterpret_cast<T *>(data + (size_t)r * step.p[0] + (size_t)c * sizeof(T)); }
+    bool empty() const { return data == nullptr; }
+    Mat& operator=(const Scalar&) { if (data) std::memset(data, 0, (size_t)rows * step.p[0]); return *this; }
 };
 enum { DFT_INVERSE = 1, DFT_SCALE = 2 };
 inline void dft(const Mat&, Mat&, int = 0) { std::fprintf(stderr, "cv::dft stand-in used\n"); std::abort(); }
 }
+namespace glz { struct json_t { json_t() = default; template<typename T> json_t(T&&) {} }; }
+namespace cmn::utils {
+inline bool lowercase_equal_to(std::string_view a, std::string_view b)
+{
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i) if (std::tolower((unsigned char)a[i]) != std::tolower((unsigned char)b[i])) return false;
+    return true;
+}
+}
+namespace cmn {
+template<typename Str> concept StringLike = std::is_same_v<std::remove_cvref_t<Str>, std::string> || std::is_same_v<std::remove_cvref_t<Str>, const char*> ||
+                                            std::is_same_v<std::remove_cvref_t<Str>, std::string_view> || std::is_array_v<std::remove_cvref_t<Str>>;
+}
 #include <misc/base_types.h>
+#include <misc/EnumClass.h>
+#include <misc/detail_bits.h>
 using namespace cmn;

@@ -1,3 +1,3 @@
-// Test infrastructure: placeholder for a TRex header that the compiled reference files include but need nothing from here.
+// Test infrastructure: placeholder for commons/common/misc/GlobalSettings.h; the three settings Background.cpp caches and the callback registration are in misc/detail_bits.h.
 #pragma once
 #include <commons.pc.h>

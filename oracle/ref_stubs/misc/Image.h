@@ -1,3 +1,3 @@
-// Test infrastructure: placeholder for commons/common/misc/Image.h (the declarations the compiled files need are in processing/Background.h and processing/PVBlob.h of this directory).
+// Test infrastructure: placeholder for commons/common/misc/Image.h; the cmn::Image stand-in (rows, cols, dims, data(), get() as a cv::Mat view) lives in misc/detail_bits.h.
 #pragma once
-#include <processing/Background.h>
+#include <commons.pc.h>

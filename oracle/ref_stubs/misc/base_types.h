@@ -48,3 +48,4 @@ struct Pair {
 }
 using blobs_t = std::vector<blob::Pair>;
 }
+namespace pv { class Blob; using BlobPtr = std::unique_ptr<Blob>; }

@@ -1,3 +1,3 @@
-// Test infrastructure: placeholder for commons/common/misc/bid.h (the declarations the compiled files need are in processing/Background.h and processing/PVBlob.h of this directory).
+// Test infrastructure: placeholder for commons/common/misc/bid.h (PixelTree.h includes it; blob ids are not used by the functions under test).
 #pragma once
-#include <processing/Background.h>
+#include <commons.pc.h>

@@ -30,4 +30,5 @@ struct Range {
     constexpr arange<T> iterable() const { return arange<T>(start, end); }
     constexpr bool operator==(const Range<T>& o) const { return o.start == start && o.end == end; }
 };
+using Rangel = Range<long_t>;
 }

@@ -1,3 +1,3 @@
-// Test infrastructure: placeholder for commons/common/processing/LuminanceGrid.h (the declarations the compiled files need are in processing/Background.h and processing/PVBlob.h of this directory).
+// Test infrastructure: placeholder for commons/common/processing/LuminanceGrid.h (PixelTree.cpp includes it; the grid variant of its templates is commented out upstream).
 #pragma once
-#include <processing/Background.h>
+#include <commons.pc.h>

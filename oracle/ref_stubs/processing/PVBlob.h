@@ -3,13 +3,8 @@
 // (x = min x0, y = first y, width = max x1 - x + 1, height = last y - y + 1: what pv::Blob::init computes from the lines).
 #pragma once
 #include <commons.pc.h>
-namespace cmn {
-enum class meta_encoding_t { gray, r3g3b2, rgb8, binary };
-struct InputInfo { uint8_t channels = 1; meta_encoding_t encoding = meta_encoding_t::gray; constexpr bool is_r3g3b2() const { return encoding == meta_encoding_t::r3g3b2; } };
-}
+#include <processing/Background.h>
 namespace pv {
-class Blob;
-using BlobPtr = std::unique_ptr<Blob>;
 class Blob {
     cmn::blob::line_ptr_t _lines;
     cmn::blob::pixel_ptr_t _pixels;
@@ -42,7 +37,13 @@ public:
     bool is_rgb() const { return is_flag(_flags, Flags::is_rgb); }
     bool is_r3g3b2() const { return is_flag(_flags, Flags::is_r3g3b2); }
     uint8_t channels() const { return is_binary() ? 0 : (is_rgb() ? 3 : 1); }
-    cmn::InputInfo input_info() const { return cmn::InputInfo{channels(), is_rgb() ? cmn::meta_encoding_t::rgb8 : (is_r3g3b2() ? cmn::meta_encoding_t::r3g3b2 : cmn::meta_encoding_t::gray)}; }
+    cmn::InputInfo input_info() const
+    {
+        cmn::InputInfo i{};
+        i.channels = channels();
+        i.encoding = is_rgb() ? cmn::meta_encoding_t::rgb8 : (is_r3g3b2() ? cmn::meta_encoding_t::r3g3b2 : (is_binary() ? cmn::meta_encoding_t::binary : cmn::meta_encoding_t::gray));
+        return i;
+    }
     size_t num_pixels() const { size_t n = 0; for (auto &h : *_lines) n += h.length(); return n; }
     static constexpr uint8_t copy_flags(const Blob& b)
     {
