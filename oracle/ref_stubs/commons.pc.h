@@ -125,6 +125,7 @@ struct Vector2D {
     Vector2D abs() const { return Vector2D{std::abs(x), std::abs(y)}; }
     constexpr Float2_t max() const { return std::max(x, y); }
     constexpr Float2_t min() const { return std::min(x, y); }
+    constexpr Float2_t mean() const { return (x + y) * 0.5f; }
     constexpr bool empty() const { return x == 0 && y == 0; }
     constexpr bool operator==(const Vector2D& o) const { return x == o.x && y == o.y; }
     constexpr bool operator!=(const Vector2D& o) const { return x != o.x || y != o.y; }
@@ -159,6 +160,10 @@ struct Bounds {
     Float2_t x, y, width, height;
     constexpr Bounds(Float2_t x = 0, Float2_t y = 0, Float2_t w = 0, Float2_t h = 0) : x(x), y(y), width(w), height(h) {}
     Bounds(const Vec2& p, const Size2& s) : x(p.x), y(p.y), width(s.x), height(s.y) {}
+    // only used by Posture.cpp's pose-based outline (never run here): the union of two boxes and shifts by a vector
+    void combine(const Bounds& o) { const Float2_t x1 = std::max(x + width, o.x + o.width), y1 = std::max(y + height, o.y + o.height); x = std::min(x, o.x); y = std::min(y, o.y); width = x1 - x; height = y1 - y; }
+    template<bool K> Bounds operator-(const Vector2D<K>& v) const { return Bounds(x - v.x, y - v.y, width, height); }
+    template<bool K> Bounds operator+(const Vector2D<K>& v) const { return Bounds(x + v.x, y + v.y, width, height); }
     Vec2 pos() const { return Vec2(x, y); }
     Size2 size() const { return Size2(width, height); }
 };

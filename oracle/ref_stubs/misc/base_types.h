@@ -49,3 +49,4 @@ struct Pair {
 using blobs_t = std::vector<blob::Pair>;
 }
 namespace pv { class Blob; using BlobPtr = std::unique_ptr<Blob>; }
+namespace cmn::blob { struct Pose; struct SegmentedOutlines; }      // named by tracker/tracking/Posture.h; look-alikes in tracking/Tracker.h of this directory

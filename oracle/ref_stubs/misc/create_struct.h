@@ -14,6 +14,7 @@ struct Settings {
         float midline_stiff_percentage = 0.15f; uint32_t midline_resolution = 25; uint8_t posture_closing_steps = 0; uint8_t posture_closing_size = 2;
         float outline_resample = 1.f;
         long_t outline_smooth_step = 1; bool midline_invert = false;          // the two FAST_SETTINGs Outline.cpp reads
+        int track_posture_threshold = 0; float outline_compression = 0.f;      // + what Posture.cpp reads (with posture_closing_*, outline_resample above)
     };
     static Values& values() { static Values v; return v; }
     static void init() {}

@@ -30,6 +30,16 @@ public:
     const cmn::blob::pixel_ptr_t& pixels() const { return _pixels; }
     cmn::blob::line_ptr_t&& steal_lines() { return std::move(_lines); }
     const cmn::Bounds& bounds() const { return _bounds; }
+    // pv::Blob::add_offset (processing/PVBlob.cpp:1820-1837): every run moves by the integer part of the vector, clamped so that the box stays at >= 0
+    void add_offset(const cmn::Vec2& off)
+    {
+        if (off == cmn::Vec2(0)) return;
+        int offy = off.y, offx = off.x;
+        if (!_lines->empty() && offy < -float(_bounds.y)) offy = -float(_bounds.y);
+        if (!_lines->empty() && offx < -float(_bounds.x)) offx = -float(_bounds.x);
+        for (auto &h : *_lines) { h.y += offy; h.x0 += offx; h.x1 += offx; }
+        _bounds.x += (float)offx; _bounds.y += (float)offy;
+    }
     uint8_t flags() const { return _flags; }
     uint32_t blob_id() const { return 0; }
     cmn::blob::Prediction prediction() const { return {}; }
