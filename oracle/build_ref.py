@@ -1,6 +1,7 @@
 """Test infrastructure: builds oracle/_ref/libref_posture.so from the REFERENCE's own source files, compiled where they lie and unmodified:
     tracker/tracking/Outline.cpp                      Outline::resample / smooth / offset_to_middle / calculate_midline, Midline::post_process / normalize / fix_length
     tracker/tracking/Posture.cpp                      posture::calculate_posture(Frame_t, pv::BlobWeakPtr): the threshold loop
+    tracker/tracking/FilterCache.cpp                  constraints::diff_image (none / moments / posture / legacy crops), local_midline_length
     commons/common/misc/CircularGraph.cpp             periodic::curvature / eft / ieft / differentiate / find_peaks (+ its fast::cos polynomial)
     commons/common/misc/curve_discussion.cpp, commons/common/gui/Transform.cpp   (linked by Outline.cpp)
     commons/common/processing/PixelTree.cpp           pixel::find_outer_points with pixel::Tree (its threshold_blob half only has to compile)
@@ -9,11 +10,11 @@
     commons/common/processing/Background.{h,cpp} + processing/encoding.h, misc/EnumClass.h, misc/matharray.h, misc/FormatColor.h
                                                       per-pixel difference / is_different / count_above_threshold, cmn::bgr2gray, imageFromLines;
                                                       with it the Background overload of pixel::threshold_blob is the reference's own code as well
-plus the C wrappers oracle/ref_outline.cpp, ref_circular_graph.cpp, ref_pixeltree.cpp, ref_labeling.cpp, ref_background.cpp and ref_posture.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
+plus the C wrappers oracle/ref_outline.cpp, ref_circular_graph.cpp, ref_pixeltree.cpp, ref_labeling.cpp, ref_background.cpp, ref_posture.cpp and ref_filtercache.cpp, against the stand-in headers in oracle/ref_stubs/ (TRex's precompiled
 header needs OpenCV / glaze / cnpy, absent here; its settings cache, drawing and tracker headers are irrelevant to the functions under test).
 Outline.cpp and Posture.cpp include "DebugDrawing.h" and "Tracker.h" with quotes, which a compiler resolves next to the including file first; they are
 therefore compiled through symbolic links in oracle/_ref/overlay/tracking/ (the files themselves stay in the reference checkout), next to placeholders
-for those two headers (Outline.h and Posture.h are linked from the reference).  The rest of the reference's path (RawProcessing.cpp, BackgroundSubtraction.cpp, Posture.cpp, FilterCache.cpp ...) is tied to
+for those two headers (Outline.h and Posture.h are linked from the reference).  The rest of the reference's path (RawProcessing.cpp, BackgroundSubtraction.cpp, PVBlob.cpp ...) is tied to
 OpenCV calls and TRex's image / settings classes and stays restated-only: DESIGN.md s6.
 The .so is git-ignored, not gpurun-ignored.  Only tests/ load it."""
 import os
@@ -26,6 +27,7 @@ REF_COMMON = os.path.join(REF_SRC, "commons", "common")
 OUT = os.path.join(HERE, "_ref", "libref_posture.so")
 OVERLAY = os.path.join(HERE, "_ref", "overlay", "tracking")
 REF_FILES = [os.path.join(REF_SRC, "tracker", "tracking", "Outline.cpp"), os.path.join(REF_SRC, "tracker", "tracking", "Posture.cpp"),
+             os.path.join(REF_SRC, "tracker", "tracking", "FilterCache.cpp"),
              os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"),
              os.path.join(REF_COMMON, "misc", "curve_discussion.cpp"), os.path.join(REF_COMMON, "gui", "Transform.cpp"),
              os.path.join(REF_COMMON, "processing", "PixelTree.cpp")] + \
@@ -46,7 +48,7 @@ def build(force: bool = False):
     """Returns the path of the library, or None when neither the reference checkout nor a prebuilt library is present."""
     if not available():
         return OUT if os.path.exists(OUT) else None
-    wrappers = [os.path.join(HERE, f) for f in ("ref_outline.cpp", "ref_circular_graph.cpp", "ref_pixeltree.cpp", "ref_labeling.cpp", "ref_background.cpp", "ref_posture.cpp")]
+    wrappers = [os.path.join(HERE, f) for f in ("ref_outline.cpp", "ref_circular_graph.cpp", "ref_pixeltree.cpp", "ref_labeling.cpp", "ref_background.cpp", "ref_posture.cpp", "ref_filtercache.cpp")]
     stubs = []
     for root, _, files in os.walk(os.path.join(HERE, "ref_stubs")):
         stubs += [os.path.join(root, f) for f in files]
@@ -57,14 +59,15 @@ def build(force: bool = False):
     os.makedirs(OVERLAY, exist_ok=True)
     _link(REF_FILES[0], os.path.join(OVERLAY, "Outline.cpp"))
     _link(REF_FILES[1], os.path.join(OVERLAY, "Posture.cpp"))
-    for h in ("Outline.h", "Posture.h"):                      # the reference's own headers
+    _link(REF_FILES[2], os.path.join(OVERLAY, "FilterCache.cpp"))
+    for h in ("Outline.h", "Posture.h", "FilterCache.h"):                      # the reference's own headers
         _link(os.path.join(REF_SRC, "tracker", "tracking", h), os.path.join(OVERLAY, h))
     for h in ("DebugDrawing.h", "Tracker.h"):                 # placeholders for the two quote-included headers that pull in the whole tracker
         _link(os.path.join(HERE, "ref_stubs", "tracking", h), os.path.join(OVERLAY, h))
     # the arithmetic flags of the oracle: no contraction, no fast-math (TRex's own CMake files do not enable fast-math either)
     cmd = ["g++", "-std=c++23", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,--no-undefined",
            "-I", os.path.join(HERE, "ref_stubs"), "-I", REF_COMMON, "-I", os.path.join(REF_SRC, "tracker"),
-           os.path.join(OVERLAY, "Outline.cpp"), os.path.join(OVERLAY, "Posture.cpp"), *REF_FILES[2:], *wrappers, "-o", OUT]
+           os.path.join(OVERLAY, "Outline.cpp"), os.path.join(OVERLAY, "Posture.cpp"), os.path.join(OVERLAY, "FilterCache.cpp"), *REF_FILES[3:], *wrappers, "-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building the reference's posture sources failed:\n" + r.stdout + r.stderr)

@@ -32,6 +32,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <numeric>
 #include <optional>
 #include <set>
 #include <shared_mutex>
@@ -86,9 +87,15 @@ template<typename T> requires (std::is_arithmetic_v<T> && !std::unsigned_integra
 template<typename T> requires std::unsigned_integral<T> constexpr auto abs(T x) { return x; }
 template<typename T> requires std::is_arithmetic_v<T> constexpr bool isnan(T x) { if constexpr (std::is_floating_point_v<T>) return std::isnan(x); else return false; }
 
+}
+namespace cv { struct Size { int width = 0, height = 0; Size() = default; template<typename A, typename B> Size(A w, B h) : width(int(w)), height(int(h)) {} }; }
+namespace cmn {
 template<bool IsVec>
 struct Vector2D {
-    Float2_t x, y;
+    union { Float2_t x; Float2_t width; };      // vec2.h: Size2 names its two members width / height (FilterCache.cpp reads them)
+    union { Float2_t y; Float2_t height; };
+    Vector2D(const cv::Size& s) noexcept : x(Float2_t(s.width)), y(Float2_t(s.height)) {}                 // vec2.h:30-33
+    operator cv::Size() const { return cv::Size(x, y); }
 
     constexpr Vector2D() noexcept : x(0), y(0) {}
     constexpr Vector2D(const Vector2D& o) noexcept : x(o.x), y(o.y) {}
@@ -166,6 +173,8 @@ struct Bounds {
     template<bool K> Bounds operator+(const Vector2D<K>& v) const { return Bounds(x + v.x, y + v.y, width, height); }
     Vec2 pos() const { return Vec2(x, y); }
     Size2 size() const { return Size2(width, height); }
+    void operator<<(const Size2& s) { width = s.x; height = s.y; }      // vec2.h:437-444
+    void operator<<(const Vec2& p) { x = p.x; y = p.y; }
 };
 
 class Minimizable { public: virtual void minimize_memory() = 0; virtual ~Minimizable() {} };
@@ -177,7 +186,15 @@ struct Frame_t {
     constexpr bool valid() const { return _frame >= 0; }
     constexpr int32_t get() const { return _frame; }
     constexpr bool operator==(const Frame_t&) const = default;
+    constexpr auto operator<=>(const Frame_t& o) const { return _frame <=> o._frame; }
+    constexpr Frame_t operator-(const Frame_t& o) const { return Frame_t(_frame - o._frame); }
+    constexpr Frame_t operator+(const Frame_t& o) const { return Frame_t(_frame + o._frame); }
 };
+constexpr Frame_t operator""_f(unsigned long long v) { return Frame_t(int32_t(v)); }
+// LOGGED_MUTEX / LOGGED_LOCK without the logging (commons.pc.h:1399-1400)
+struct LoggedMutexStandIn : std::mutex { LoggedMutexStandIn(const char *) {} };
+#define LOGGED_MUTEX(NAME) cmn::LoggedMutexStandIn(NAME)
+#define LOGGED_LOCK(MUTEX) std::unique_lock<std::mutex>{ MUTEX }
 
 struct glz_json_placeholder {};
 struct Meta {
@@ -213,7 +230,8 @@ struct Mat {
     Mat(int r, int c, int t, const Scalar&) : Mat(r, c, t) {}
     Mat(int r, int c, int t, void *d) : rows(r), cols(c), _type(t), data((unsigned char *)d) { step.p[1] = (size_t)channels(); step.p[0] = (size_t)c * step.p[1]; }
     static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
-    void alloc() { step.p[1] = (size_t)channels(); step.p[0] = (size_t)cols * step.p[1]; store = std::make_shared<std::vector<unsigned char>>((size_t)rows * step.p[0] + 64, 0); data = store->data(); }
+    size_t elemSize() const { return (size_t)channels() * (_type == CV_64F ? 8 : (_type == CV_32FC1 ? 4 : 1)); }
+    void alloc() { step.p[1] = elemSize(); step.p[0] = (size_t)cols * step.p[1]; store = std::make_shared<std::vector<unsigned char>>((size_t)rows * step.p[0] + 64, 0); data = store->data(); }
     int type() const { return _type; }
     int channels() const { return _type == CV_8UC3 ? 3 : (_type == CV_8UC4 ? 4 : 1); }
     bool isContinuous() const { return true; }
@@ -223,7 +241,67 @@ struct Mat {
     template<typename T> T& at(int r, int c) { return *reinterpret_cast<T *>(data + (size_t)r * step.p[0] + (size_t)c * sizeof(T)); }
     bool empty() const { return data == nullptr; }
     Mat& operator=(const Scalar&) { if (data) std::memset(data, 0, (size_t)rows * step.p[0]); return *this; }
+    // what tracker/tracking/FilterCache.cpp uses on top: size(), copyTo (plain and masked: a destination of another size / type is re-created, zero-filled
+    // for the masked form), the ROI view padded(Bounds) (the rectangle's members truncated to int: vec2.h:433)
+    Size size() const { return Size(cols, rows); }
+    void create(int r, int c, int t) { if (r != rows || c != cols || t != _type || !data) { rows = r; cols = c; _type = t; alloc(); } }
+    void copyTo(const Mat& dst_) const                 // OpenCV's OutputArray binds to const cv::Mat& as well (FilterCache.cpp:65 copies a const image onto itself)
+    {
+        Mat& dst = const_cast<Mat&>(dst_);
+        if (dst.data == data && dst.rows == rows && dst.cols == cols) return;
+        Mat src = *this;                                   // keeps the pixels alive when dst is the parent of this view
+        dst.create(src.rows, src.cols, src._type);
+        for (int y = 0; y < src.rows; ++y) std::memcpy(dst.ptr(y), src.ptr(y), (size_t)src.cols * src.step.p[1]);
+    }
+    void copyTo(const Mat& dst_, const Mat& mask) const
+    {
+        Mat& dst = const_cast<Mat&>(dst_);
+        if (dst.data == data && dst.rows == rows && dst.cols == cols) return;
+        Mat src = *this;
+        dst.create(src.rows, src.cols, src._type);
+        const size_t es = src.step.p[1];
+        for (int y = 0; y < src.rows; ++y) for (int x = 0; x < src.cols; ++x) if (mask.ptr(y)[x]) std::memcpy(dst.ptr(y) + x * es, src.ptr(y) + x * es, es);
+    }
+    Mat operator()(const cmn::Bounds& b) const
+    {
+        Mat v = *this;
+        v.data = data + (size_t)(int)b.y * step.p[0] + (size_t)(int)b.x * step.p[1]; v.rows = (int)b.height; v.cols = (int)b.width;
+        return v;
+    }
 };
+enum { INTER_NEAREST = 0, INTER_LINEAR = 1, BORDER_CONSTANT = 0 };
+// cv::warpAffine is OpenCV's (third party): the test installs the oracle's bit-exact restatement of its 8-bit INTER_LINEAR / BORDER_CONSTANT path
+// (oracle/trex_oracle.c to_warp_affine_u8, pinned on cv2 4.13 by tests/test_oracle_moments.py) through ref_filtercache_set_warp
+using warp_fn_t = void (*)(const unsigned char *src, int sw, int sh, const double *M, unsigned char *dst, int dw, int dh);
+inline warp_fn_t& warp_hook() { static warp_fn_t f = nullptr; return f; }
+inline void warpAffine(const Mat& src, Mat& dst, const Mat& M, Size dsize, int flags, int)
+{
+    if (!warp_hook() || flags != INTER_LINEAR || src.channels() != 1 || src.step.p[0] != (size_t)src.cols) { std::fprintf(stderr, "cv::warpAffine stand-in: unsupported call\n"); std::abort(); }
+    double m[6];
+    for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) m[r * 3 + c] = const_cast<Mat&>(M).at<double>(r, c);
+    Mat out(dsize.height, dsize.width, src._type);
+    warp_hook()(src.data, src.cols, src.rows, m, out.data, dsize.width, dsize.height);
+    dst = out;
+}
+inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int, int)
+{
+    Mat in = src, out(in.rows + top + bottom, in.cols + left + right, in._type);
+    for (int y = 0; y < in.rows; ++y) std::memcpy(out.ptr(y + top) + (size_t)left * in.step.p[1], in.ptr(y), (size_t)in.cols * in.step.p[1]);
+    dst = out;
+}
+// cv::resize(src, dst, Size(), f, f, INTER_NEAREST) (OpenCV imgproc/resize.cpp): dsize = cvRound(n * f) (round half to even), source index =
+// min(cvFloor(d * (1 / f)), n - 1); the oracle's resize_nearest restates the same and is checked against cv2 in tests/test_oracle_golden.py
+inline void resize(const Mat& src, Mat& dst, Size, double fx, double fy, int flags)
+{
+    if (flags != INTER_NEAREST) { std::fprintf(stderr, "cv::resize stand-in: only INTER_NEAREST\n"); std::abort(); }
+    Mat in = src, out((int)std::lrint(in.rows * fy), (int)std::lrint(in.cols * fx), in._type);
+    const double ifx = 1. / fx, ify = 1. / fy; const size_t es = in.step.p[1];
+    for (int y = 0; y < out.rows; ++y) {
+        const int sy = std::min((int)std::floor(y * ify), in.rows - 1);
+        for (int x = 0; x < out.cols; ++x) { const int sx = std::min((int)std::floor(x * ifx), in.cols - 1); std::memcpy(out.ptr(y) + x * es, in.ptr(sy) + sx * es, es); }
+    }
+    dst = out;
+}
 enum { DFT_INVERSE = 1, DFT_SCALE = 2 };
 inline void dft(const Mat&, Mat&, int = 0) { std::fprintf(stderr, "cv::dft stand-in used\n"); std::abort(); }
 }

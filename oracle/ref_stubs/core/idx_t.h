@@ -8,5 +8,6 @@ struct Idx_t {
     explicit constexpr Idx_t(uint32_t id) : _identity(id) {}
     constexpr uint32_t get() const { return _identity; }
     constexpr bool valid() const { return _identity != cmn::infinity<uint32_t>(); }
+    constexpr auto operator<=>(const Idx_t& o) const = default;
 };
 }

@@ -5,3 +5,6 @@ namespace cmn {
 struct Timing { Timing(const char *, double = 0) {} };
 struct TakeTiming { explicit TakeTiming(Timing&) {} };
 }
+struct Timer { double elapsed() const { return 0; } void reset() {} };      // FilterCache.cpp's message throttle
+namespace cmn {
+}

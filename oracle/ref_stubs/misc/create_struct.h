@@ -15,6 +15,7 @@ struct Settings {
         float outline_resample = 1.f;
         long_t outline_smooth_step = 1; bool midline_invert = false;          // the two FAST_SETTINGs Outline.cpp reads
         int track_posture_threshold = 0; float outline_compression = 0.f;      // + what Posture.cpp reads (with posture_closing_*, outline_resample above)
+        float individual_image_scale = 1.f; bool calculate_posture = true;     // + what FilterCache.cpp reads
     };
     static Values& values() { static Values v; return v; }
     static void init() {}

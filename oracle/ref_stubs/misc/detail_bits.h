@@ -33,6 +33,7 @@ template<uint8_t channels = 3> constexpr auto r3g3b2_to_vec(const uint8_t& c, co
 {
     return RGBArray{static_cast<unsigned char>(((uint8_t(c) >> 6) & 3) * 64), static_cast<unsigned char>(((uint8_t(c) >> 3) & 7) * 32), static_cast<unsigned char>((uint8_t(c) & 7) * 32)};
 }
+template<typename T> inline void resize_image(T& mat, double factor, int flags = cv::INTER_NEAREST) { cv::resize(mat, mat, cv::Size(), factor, factor, flags); }      // misc/detail.h:465-469
 inline void convert_from_r3g3b2(const cv::Mat&, cv::Mat&) { std::fprintf(stderr, "convert_from_r3g3b2 stand-in used\n"); std::abort(); }
 inline cv::Rect2i lines_dimensions(const std::vector<HorizontalLine>& lines)
 {
@@ -52,6 +53,8 @@ public:
     cv::Mat mat;
     Image(uint32_t r, uint32_t c, uint32_t d) : cols(c), rows(r), dims(d), mat((int)r, (int)c, d == 3 ? CV_8UC3 : CV_8UC1) {}
     static Ptr Make(uint32_t r, uint32_t c, uint32_t d) { return std::make_unique<Image>(r, c, d); }
+    explicit Image(const cv::Mat& m) : Image((uint32_t)m.rows, (uint32_t)m.cols, (uint32_t)m.channels()) { m.copyTo(mat); }      // Image::Make(cv::Mat): a copy of the pixels
+    static Ptr Make(const cv::Mat& m) { return std::make_unique<Image>(m); }
     const uchar *data() const { return mat.data; }
     uchar *data() { return mat.data; }
     ptr_safe_t channels() const { return dims; }

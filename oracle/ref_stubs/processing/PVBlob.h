@@ -40,6 +40,11 @@ public:
         for (auto &h : *_lines) { h.y += offy; h.x0 += offx; h.x1 += offx; }
         _bounds.x += (float)offx; _bounds.y += (float)offy;
     }
+    // FilterCache.cpp's `moments` branch: the stand-in does not compute image moments -- the wrapper hands in the orientation (pv::Blob::calculate_moments,
+    // PVBlob.cpp:111-213, stays restated-only in oracle/trex_oracle.c to_blob_orientation)
+    float _orientation = 0;
+    void calculate_moments() {}
+    float orientation() const { return _orientation; }
     uint8_t flags() const { return _flags; }
     uint32_t blob_id() const { return 0; }
     cmn::blob::Prediction prediction() const { return {}; }

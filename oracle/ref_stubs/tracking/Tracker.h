@@ -28,10 +28,13 @@ struct ObjectCache {
 }
 namespace track {
 struct PoseMidlineIndexes { std::vector<uint8_t> indexes; };
-struct BlobBoundsOnly { cmn::Bounds b; cmn::Bounds calculate_bounds() const { return b; } };
+struct BlobBoundsOnly { cmn::Bounds b; bool is_split = false; cmn::Bounds calculate_bounds() const { return b; } bool split() const { return is_split; } };
 struct BasicStuff { BlobBoundsOnly blob; };
 struct Tracker {
     static const cmn::Background *&background_slot() { static const cmn::Background *bg = nullptr; return bg; }
     static const cmn::Background *background() { return background_slot(); }
+    struct Border { bool in_recognition_bounds(const cmn::Vec2&) const { return true; } };
+    Border border() const { return Border{}; }
+    static Tracker *instance() { static Tracker t; return &t; }
 };
 }

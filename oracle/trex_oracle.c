@@ -11,7 +11,8 @@
  * tests/golden/make_golden.py and tests/test_oracle_golden.py) and for
  * imageFromLines (known-answer vector of Application/Tests/test_pixels.cpp:
  * 1381-1466).  The pad/crop-to-80x80 geometry has no golden vector in the
- * reference ("parity unpinned" for that sub-step; restated line by line).
+ * reference; it is pinned on the reference's own FilterCache.cpp, compiled
+ * unmodified (oracle/build_ref.py, tests/test_oracle_ref_filtercache.py).
  *
  * Every function cites the reference file:line it follows.  Paths are relative
  * to the reference checkout:

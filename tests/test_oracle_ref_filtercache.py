@@ -1,0 +1,204 @@
+"""Pins the oracle's crops (constraints::diff_image with its four normalisations) on the REFERENCE'S OWN CODE:
+tracker/tracking/FilterCache.cpp compiled unmodified (oracle/build_ref.py, oracle/ref_filtercache.cpp) over the reference's imageFromLines,
+gui::Transform and Midline::transform:
+  none     image::calculate_diff_image: masked blob image, individual_image_scale, centre pad / centre cut to 80 x 80   <-> seg.crop_blob / crop_blob_scaled / crop_blob_rgb
+  moments  rotate(-orientation + 45 deg) . translate(-size / 2) into normalize_image                                      <-> seg.crop_blob_moments
+  posture / legacy   Midline::transform into normalize_image                                                              <-> posture.crop_blob_posture
+byte for byte, for blobs smaller and larger than the output in either direction (odd and even differences), difference and grey renderings, and
+the position the reference reports with the image.  cv::warpAffine / cv::resize are OpenCV's: the compiled reference calls the oracle's restatement of
+warpAffine (itself pinned on cv2 4.13, tests/test_oracle_moments.py), so what is pinned here is everything AROUND those two calls -- the geometry the
+round-1 review listed as unpinned.  constraints::local_midline_length (the median the posture crops are scaled by; caller side of the C ABI) is run on a
+frame list and compared with its plain description (lower median, population standard deviation of the distinct values).
+Runs wherever oracle/_ref/libref_posture.so exists or can be built; skipped otherwise."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import build_ref, posture, seg
+from test_oracle_ref_labeling import _p
+
+MODE_NONE, MODE_MOMENTS, MODE_POSTURE, MODE_LEGACY = 0, 1, 2, 3
+METHODS = {seg.DIFF_ABSOLUTE: (1, 1), seg.DIFF_SIGN: (0, 1)}      # (track_threshold_is_absolute, track_background_subtraction)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    path = build_ref.build()
+    if path is None:
+        pytest.skip("no reference checkout and no prebuilt oracle/_ref/libref_posture.so")
+    lib = C.CDLL(path)
+    warp = C.cast(seg.lib().to_warp_affine_u8, C.c_void_p)
+    lib.ref_filtercache_set_warp(warp)
+    lib._keep = seg.lib()
+    return lib
+
+
+def frame_of_blobs(seed, H=260, W=340, colour=False):
+    """Ellipses from 3 px to 150 px long (so that both the pad and the cut branches run, with odd and even size differences), textured."""
+    rng = np.random.default_rng(seed)
+    bg = rng.integers(150, 200, (H, W, 3) if colour else (H, W)).astype(np.uint8)
+    fr = bg.copy()
+    yy, xx = np.mgrid[0:H, 0:W]
+    specs = [(60, 60, 70, 9), (200, 70, 50, 46), (90, 190, 8, 60), (250, 200, 44, 4), (160, 150, 3, 2), (300, 40, 12, 7), (30, 230, 20, 11), (310, 130, 1.2, 1.2)]
+    for cx, cy, a, b in specs:
+        th = rng.uniform(0, np.pi)
+        u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th); v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+        m = (u / a) ** 2 + (v / b) ** 2 < 1
+        val = rng.integers(10, 120, (int(m.sum()), 3) if colour else int(m.sum())).astype(np.uint8)
+        fr[m] = val
+    return fr, bg
+
+
+def runs_of(l):
+    raw = np.zeros((len(l), 4), np.uint16)
+    raw[:, 0], raw[:, 1], raw[:, 2] = l["x0"], l["x1"], l["y"]
+    return raw
+
+
+def ref_crop(ref, mode, l, p, ch, bg, with_bg=True, orientation=0.0, angle=0.0, offset=(0.0, 0.0), length=0.0, out=(80, 80)):
+    raw = runs_of(l); p = np.ascontiguousarray(p, np.uint8); bg = np.ascontiguousarray(bg, np.uint8)
+    h, w = bg.shape[:2]
+    buf = np.zeros(out[0] * out[1] * max(ch, 1) + 64, np.uint8); dims = np.zeros(3, np.int32); pos = np.zeros(2, np.float32)
+    k = ref.ref_diff_image(mode, _p(raw), C.c_int64(len(raw)), _p(p), C.c_int64(len(p)), ch, _p(bg), w, h, 3 if bg.ndim == 3 else 1, int(bg.ndim == 3), int(with_bg),
+                           C.c_float(orientation), C.c_float(angle), C.c_float(offset[0]), C.c_float(offset[1]), C.c_float(length), out[0], out[1],
+                           _p(buf), C.c_int64(len(buf)), _p(dims), _p(pos))
+    if k != 1:
+        return k, None, None
+    r, c, d = (int(x) for x in dims)
+    img = buf[:r * c * d].reshape((r, c) if d == 1 else (r, c, d))
+    return 1, img, pos
+
+
+def expected_position(l, scale=1.0, out=(80, 80)):
+    """calculate_diff_image's second result (FilterCache.cpp:183-232): the blob's corner moved by the padding added on the left / top and by the cut."""
+    x0, y0 = int(l["x0"].min()), int(l["y"].min())
+    w, h = int(l["x1"].max()) - x0 + 1, int(l["y"].max()) - y0 + 1
+    if float(np.float32(scale)) != 1.0:
+        w, h = int(np.rint(w * float(np.float32(scale)))), int(np.rint(h * float(np.float32(scale))))
+    def axis(n, m, p):
+        if n < m:
+            d = m - n; return p - (d - d // 2)
+        d = n - m; return p + (d - d // 2)
+    return axis(w, out[0], x0), axis(h, out[1], y0)
+
+
+@pytest.mark.parametrize("method", [seg.DIFF_ABSOLUTE, seg.DIFF_SIGN])
+def test_unnormalised_crops_gray(ref, method):
+    ref.ref_background_settings(*METHODS[method], 0)
+    n = n_cut = 0
+    for scale in (1.0, 0.5, 1.7):
+        ref.ref_filtercache_settings(C.c_float(scale))
+        for seed in (1, 2):
+            fr, bg = frame_of_blobs(seed)
+            blobs = seg.segment_frame(fr, bg, seg.Params(detect_threshold=12, detect_size_filter=[]))
+            for b in range(len(blobs)):
+                l, p = blobs.blob(b)
+                p = np.asarray(p)
+                for with_bg in (True, False):
+                    m = method if with_bg else seg.DIFF_NONE
+                    want = seg.crop_blob(l, p, bg, m) if scale == 1.0 else seg.crop_blob_scaled(l, p, bg, m, scale)
+                    k, img, pos = ref_crop(ref, MODE_NONE, l, p, 1, bg, with_bg)
+                    assert k == 1 and img.shape == (80, 80), (seed, b, k)
+                    assert np.array_equal(img, want), (scale, seed, b, with_bg)
+                    assert (float(pos[0]), float(pos[1])) == tuple(float(v) for v in expected_position(l, scale)), (scale, seed, b)
+                    n += 1
+                n_cut += int(int(l["x1"].max()) - int(l["x0"].min()) + 1 > 80 or int(l["y"].max()) - int(l["y"].min()) + 1 > 80)
+    ref.ref_filtercache_settings(C.c_float(1.0))
+    assert n > 80 and n_cut >= 6
+
+
+def test_unnormalised_crops_rgb8(ref):
+    ref.ref_background_settings(1, 1, 2)
+    n = 0
+    for seed in (3, 4):
+        fr, bg = frame_of_blobs(seed, colour=True)
+        g = np.repeat(seg.bgr2gray(bg)[:, :, None], 3, axis=2)          # B = G = R background: see tests/test_oracle_ref_background.py on colourful ones
+        fr = np.where(fr == bg, g, fr)
+        blobs = seg.segment_frame_color(fr, g, seg.Params(detect_threshold=12, detect_size_filter=[]), seg.ENC_RGB8)
+        for b in range(len(blobs)):
+            l, p = blobs.blob(b)
+            p = np.asarray(p)
+            want = seg.crop_blob_rgb(l, p, g, seg.DIFF_ABSOLUTE)
+            k, img, pos = ref_crop(ref, MODE_NONE, l, p, 3, g, True)
+            assert k == 1, (seed, b, k)
+            if img.ndim == 3:                                            # the difference image of an rgb8 blob: per-channel or grey, as the oracle renders it
+                assert want.shape == img.shape and np.array_equal(img, want), (seed, b)
+            else:
+                assert np.array_equal(img, want), (seed, b)
+            n += 1
+    ref.ref_background_settings(1, 1, 0)
+    assert n > 10
+
+
+@pytest.mark.parametrize("method", [seg.DIFF_ABSOLUTE, seg.DIFF_SIGN])
+def test_moments_crops(ref, method):
+    ref.ref_background_settings(*METHODS[method], 0)
+    ref.ref_filtercache_settings(C.c_float(1.0))
+    n = 0
+    for seed in (5, 6, 7):
+        fr, bg = frame_of_blobs(seed)
+        blobs = seg.segment_frame(fr, bg, seg.Params(detect_threshold=12, detect_size_filter=[]))
+        for b in range(len(blobs)):
+            l, p = blobs.blob(b)
+            p = np.asarray(p)
+            orientation, _ = seg.blob_orientation(l)
+            for with_bg in (True, False):
+                want = seg.crop_blob_moments(l, p, bg, method if with_bg else seg.DIFF_NONE)
+                k, img, _ = ref_crop(ref, MODE_MOMENTS, l, p, 1, bg, with_bg, orientation=orientation)
+                assert k == 1 and np.array_equal(img, want), (seed, b, with_bg)
+                n += 1
+    assert n > 40
+
+
+@pytest.mark.parametrize("legacy", [False, True])
+def test_posture_and_legacy_crops(ref, legacy):
+    ref.ref_background_settings(1, 1, 0)
+    rng = np.random.default_rng(8)
+    n = n_none = 0
+    for scale in (1.0, 0.8):
+        ref.ref_filtercache_settings(C.c_float(scale))
+        for seed in (9, 10):
+            fr, bg = frame_of_blobs(seed)
+            blobs = seg.segment_frame(fr, bg, seg.Params(detect_threshold=12, detect_size_filter=[]))
+            for b in range(len(blobs)):
+                l, p = blobs.blob(b)
+                p = np.asarray(p)
+                w, h = int(l["x1"].max()) - int(l["x0"].min()) + 1, int(l["y"].max()) - int(l["y"].min()) + 1
+                for _ in range(3):
+                    angle = float(np.float32(rng.uniform(-np.pi, np.pi)))
+                    offset = (float(np.float32(rng.uniform(0, w))), float(np.float32(rng.uniform(0, h))))
+                    length = float(np.float32(rng.uniform(5, 90)))
+                    want = posture.crop_blob_posture(l, p, bg, seg.DIFF_ABSOLUTE, angle, offset, length, (80, 80), scale, legacy)
+                    k, img, _ = ref_crop(ref, MODE_LEGACY if legacy else MODE_POSTURE, l, p, 1, bg, True, angle=angle, offset=offset, length=length)
+                    assert k == 1 and np.array_equal(img, want), (scale, seed, b)
+                    n += 1
+                # a negative midline length: no image (FilterCache.cpp:31-38)
+                k, img, _ = ref_crop(ref, MODE_POSTURE, l, p, 1, bg, True, angle=0.3, offset=(1.0, 1.0), length=-1.0)
+                assert k == 0 and posture.crop_blob_posture(l, p, bg, seg.DIFF_ABSOLUTE, 0.3, (1.0, 1.0), -1.0, (80, 80), scale, False) is None
+                n_none += 1
+    ref.ref_filtercache_settings(C.c_float(1.0))
+    assert n > 60 and n_none > 10
+
+
+def test_local_midline_length(ref):
+    rng = np.random.default_rng(11)
+    for n, with_std in ((1, True), (2, True), (37, True), (150, False), (900, True)):
+        length = rng.uniform(20, 60, n).astype(np.float32); angle = rng.uniform(-3, 3, n).astype(np.float32)
+        has = (rng.random(n) < 0.8).astype(np.uint8); has[0] = 1
+        pts = rng.integers(0, 200, n).astype(np.uint32); pts[rng.random(n) < 0.1] = 0
+        split = (rng.random(n) < 0.1).astype(np.uint8); split[0] = 0
+        out = np.zeros(5, np.float32)
+        ref.ref_local_midline_length(3, 100, C.c_int64(n), _p(length), _p(angle), _p(has), _p(pts), _p(split), int(with_std), _p(out))
+        step = 1 if n <= 1 else max(1, int(np.uint32((n - 1) * 0.9)) // 200)          # tracklet.length() = end - start
+        idx = [i for i in range(0, n, step) if not split[i]]
+        L = sorted(float(length[i]) for i in idx if has[i])
+        P = sorted(float(pts[i]) for i in idx if pts[i])
+        lower_median = lambda v: v[(len(v) - 1) // 2]
+        assert out[0] == np.float32(lower_median(L))
+        assert out[1] == (np.float32(lower_median(P)) if P else -1)
+        if with_std:
+            d = np.array(sorted(set(L)), np.float32)
+            assert abs(out[2] - np.sqrt(np.mean((d - d.mean()) ** 2))) < 1e-3 * max(1.0, float(out[2]))
+        else:
+            assert out[2] == -1
