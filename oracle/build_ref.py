@@ -74,5 +74,37 @@ def build(force: bool = False):
     return OUT
 
 
+# ---- the detection build: BackgroundSubtraction::apply / RawProcessing::generate_binary with every cv:: call forwarded to the real OpenCV (Python's cv2) ----
+OUT_DETECT = os.path.join(HERE, "_ref", "libref_detect.so")
+REF_FILES_DETECT = [os.path.join(REF_SRC, "tracker", "python", "BackgroundSubtraction.cpp"), os.path.join(REF_COMMON, "processing", "RawProcessing.cpp"),
+                    os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp")] + \
+                   [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp")]
+
+
+def build_detect(force: bool = False):
+    """oracle/_ref/libref_detect.so: the reference's detection path (tracker/python/BackgroundSubtraction.cpp, commons/common/processing/RawProcessing.cpp,
+    the labeling sources, tracker/core/SizeFilters.cpp), compiled unmodified with -DREF_DETECT against oracle/ref_stubs_detect/ + oracle/ref_stubs/ and the
+    wrapper oracle/ref_detect.cpp.  Returns the path, or None when neither the checkout nor a prebuilt library is present."""
+    if not (all(os.path.exists(f) for f in REF_FILES_DETECT) and shutil.which("g++") is not None):
+        return OUT_DETECT if os.path.exists(OUT_DETECT) else None
+    wrapper = os.path.join(HERE, "ref_detect.cpp")
+    stubs = []
+    for d in ("ref_stubs", "ref_stubs_detect"):
+        for root, _, files in os.walk(os.path.join(HERE, d)):
+            stubs += [os.path.join(root, f) for f in files]
+    deps = REF_FILES_DETECT + [wrapper, os.path.abspath(__file__)] + stubs
+    if not force and os.path.exists(OUT_DETECT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT_DETECT) for d in deps):
+        return OUT_DETECT
+    os.makedirs(os.path.dirname(OUT_DETECT), exist_ok=True)
+    cmd = ["g++", "-std=c++23", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,--no-undefined", "-DREF_DETECT",
+           "-I", os.path.join(HERE, "ref_stubs_detect"), "-I", os.path.join(HERE, "ref_stubs"), "-I", REF_COMMON, "-I", os.path.join(REF_SRC, "tracker"),
+           *REF_FILES_DETECT, wrapper, "-o", OUT_DETECT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building the reference's detection sources failed:\n" + r.stdout + r.stderr)
+    return OUT_DETECT
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_detect(force=True))

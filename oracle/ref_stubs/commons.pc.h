@@ -88,7 +88,7 @@ template<typename T> requires std::unsigned_integral<T> constexpr auto abs(T x) 
 template<typename T> requires std::is_arithmetic_v<T> constexpr bool isnan(T x) { if constexpr (std::is_floating_point_v<T>) return std::isnan(x); else return false; }
 
 }
-namespace cv { struct Size { int width = 0, height = 0; Size() = default; template<typename A, typename B> Size(A w, B h) : width(int(w)), height(int(h)) {} }; }
+namespace cv { struct Mat; struct Size { int width = 0, height = 0; Size() = default; template<typename A, typename B> Size(A w, B h) : width(int(w)), height(int(h)) {} }; }
 namespace cmn {
 template<bool IsVec>
 struct Vector2D {
@@ -96,6 +96,7 @@ struct Vector2D {
     union { Float2_t y; Float2_t height; };
     Vector2D(const cv::Size& s) noexcept : x(Float2_t(s.width)), y(Float2_t(s.height)) {}                 // vec2.h:30-33
     operator cv::Size() const { return cv::Size(x, y); }
+    explicit Vector2D(const cv::Mat& m) noexcept;                                                         // (cols, rows): vec2.h Size2(const cv::Mat&)
 
     constexpr Vector2D() noexcept : x(0), y(0) {}
     constexpr Vector2D(const Vector2D& o) noexcept : x(o.x), y(o.y) {}
@@ -173,6 +174,11 @@ struct Bounds {
     template<bool K> Bounds operator+(const Vector2D<K>& v) const { return Bounds(x + v.x, y + v.y, width, height); }
     Vec2 pos() const { return Vec2(x, y); }
     Size2 size() const { return Size2(width, height); }
+    void restrict_to(const Bounds& b)                                   // only RawProcessing.cpp's tag branch (never run here): clamp to a surrounding box
+    {
+        const Float2_t x1 = std::min(x + width, b.x + b.width), y1 = std::min(y + height, b.y + b.height);
+        x = std::max(x, b.x); y = std::max(y, b.y); width = x1 - x; height = y1 - y;
+    }
     void operator<<(const Size2& s) { width = s.x; height = s.y; }      // vec2.h:437-444
     void operator<<(const Vec2& p) { x = p.x; y = p.y; }
 };
@@ -228,12 +234,25 @@ struct Mat {
     Mat() {}
     Mat(int r, int c, int t) : rows(r), cols(c), _type(t) { alloc(); }
     Mat(int r, int c, int t, const Scalar&) : Mat(r, c, t) {}
-    Mat(int r, int c, int t, void *d) : rows(r), cols(c), _type(t), data((unsigned char *)d) { step.p[1] = (size_t)channels(); step.p[0] = (size_t)c * step.p[1]; }
+    Mat(int r, int c, int t, void *d) : rows(r), cols(c), _type(t), data((unsigned char *)d) { step.p[1] = elemSize(); step.p[0] = (size_t)c * step.p[1]; }
+    template<typename T> explicit Mat(const std::vector<T>&) { std::fprintf(stderr, "cv::Mat(std::vector) stand-in used\n"); std::abort(); }      // RawProcessing.cpp's tag branch only
+    static Mat ones(int r, int c, int t) { Mat m(r, c, t); std::memset(m.data, 1, (size_t)r * m.step.p[0]); return m; }                              // 8-bit only
+    void release() { store.reset(); data = nullptr; rows = cols = 0; }
+    void convertTo(Mat& dst, int t, double alpha = 1.0) const                                  // 8U -> 8U (a copy) and 8U -> 32F (scaled): what the detection path asks for
+    {
+        Mat src = *this;
+        if ((t & 7) == 0 && src.depth() == 0) { src.copyTo(dst); return; }
+        if ((t & 7) != 5 || src.depth() != 0) { std::fprintf(stderr, "cv::Mat::convertTo stand-in: unsupported types\n"); std::abort(); }
+        Mat out(src.rows, src.cols, 5 + ((src.channels() - 1) << 3));
+        for (int y = 0; y < src.rows; ++y) for (int x = 0; x < src.cols * src.channels(); ++x) reinterpret_cast<float *>(out.ptr(y))[x] = float(src.ptr(y)[x] * alpha);
+        dst = out;
+    }
     static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
-    size_t elemSize() const { return (size_t)channels() * (_type == CV_64F ? 8 : (_type == CV_32FC1 ? 4 : 1)); }
+    size_t elemSize() const { return (size_t)channels() * (depth() == 6 ? 8 : (depth() == 5 || depth() == 4 ? 4 : (depth() == 2 || depth() == 3 ? 2 : 1))); }
     void alloc() { step.p[1] = elemSize(); step.p[0] = (size_t)cols * step.p[1]; store = std::make_shared<std::vector<unsigned char>>((size_t)rows * step.p[0] + 64, 0); data = store->data(); }
     int type() const { return _type; }
-    int channels() const { return _type == CV_8UC3 ? 3 : (_type == CV_8UC4 ? 4 : 1); }
+    int channels() const { return (_type >> 3) + 1; }                                      // OpenCV's type code: depth in the low three bits, channels - 1 above
+    int depth() const { return _type & 7; }
     bool isContinuous() const { return true; }
     const unsigned char *ptr(int r = 0) const { return data + (size_t)r * step.p[0]; }
     unsigned char *ptr(int r = 0) { return data + (size_t)r * step.p[0]; }
@@ -269,12 +288,15 @@ struct Mat {
         return v;
     }
 };
+}
+namespace cmn { template<bool K> inline Vector2D<K>::Vector2D(const cv::Mat& m) noexcept : x(Float2_t(m.cols)), y(Float2_t(m.rows)) {} }
+namespace cv {
 enum { INTER_NEAREST = 0, INTER_LINEAR = 1, BORDER_CONSTANT = 0 };
 // cv::warpAffine is OpenCV's (third party): the test installs the oracle's bit-exact restatement of its 8-bit INTER_LINEAR / BORDER_CONSTANT path
 // (oracle/trex_oracle.c to_warp_affine_u8, pinned on cv2 4.13 by tests/test_oracle_moments.py) through ref_filtercache_set_warp
 using warp_fn_t = void (*)(const unsigned char *src, int sw, int sh, const double *M, unsigned char *dst, int dw, int dh);
 inline warp_fn_t& warp_hook() { static warp_fn_t f = nullptr; return f; }
-inline void warpAffine(const Mat& src, Mat& dst, const Mat& M, Size dsize, int flags, int)
+inline void warpAffine(const Mat& src, Mat& dst, const Mat& M, Size dsize, int flags = INTER_LINEAR, int = BORDER_CONSTANT)
 {
     if (!warp_hook() || flags != INTER_LINEAR || src.channels() != 1 || src.step.p[0] != (size_t)src.cols) { std::fprintf(stderr, "cv::warpAffine stand-in: unsupported call\n"); std::abort(); }
     double m[6];
@@ -322,3 +344,6 @@ template<typename Str> concept StringLike = std::is_same_v<std::remove_cvref_t<S
 #include <misc/EnumClass.h>
 #include <misc/detail_bits.h>
 using namespace cmn;
+#ifdef REF_DETECT
+#include <cv_detect.h>
+#endif

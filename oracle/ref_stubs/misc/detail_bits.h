@@ -12,6 +12,7 @@ namespace cv {
 struct Rect2i { int x = 0, y = 0, width = 0, height = 0; Rect2i() = default; template<typename A, typename B, typename C_, typename D> Rect2i(A x, B y, C_ w, D h) : x(int(x)), y(int(y)), width(int(w)), height(int(h)) {} };
 struct Vec3b { unsigned char v[3]; Vec3b() : v{0, 0, 0} {} Vec3b(unsigned char a, unsigned char b, unsigned char c) : v{a, b, c} {} unsigned char& operator[](int i) { return v[i]; } const unsigned char& operator[](int i) const { return v[i]; } };
 enum { COLOR_GRAY2BGR = 8, COLOR_BGR2GRAY = 6 };
+#ifndef REF_DETECT
 inline void cvtColor(const Mat& src, Mat dst, int code)
 {
     for (int y = 0; y < src.rows; ++y) {
@@ -22,6 +23,7 @@ inline void cvtColor(const Mat& src, Mat dst, int code)
         }
     }
 }
+#endif
 }
 #define CV_8UC(n) ((n) == 3 ? CV_8UC3 : ((n) == 4 ? CV_8UC4 : CV_8UC1))
 namespace cmn {
@@ -51,7 +53,7 @@ public:
     using SPtr = std::shared_ptr<Image>;
     uint32_t cols = 0, rows = 0, dims = 1;
     cv::Mat mat;
-    Image(uint32_t r, uint32_t c, uint32_t d) : cols(c), rows(r), dims(d), mat((int)r, (int)c, d == 3 ? CV_8UC3 : CV_8UC1) {}
+    Image(uint32_t r, uint32_t c, uint32_t d) : cols(c), rows(r), dims(d), mat((int)r, (int)c, (int)((d - 1) << 3)) {}      // CV_8UC(d)
     static Ptr Make(uint32_t r, uint32_t c, uint32_t d) { return std::make_unique<Image>(r, c, d); }
     explicit Image(const cv::Mat& m) : Image((uint32_t)m.rows, (uint32_t)m.cols, (uint32_t)m.channels()) { m.copyTo(mat); }      // Image::Make(cv::Mat): a copy of the pixels
     static Ptr Make(const cv::Mat& m) { return std::make_unique<Image>(m); }
@@ -63,20 +65,42 @@ public:
 };
 
 // settings: a three-entry table the test wrapper fills; register_callbacks runs the callback once for every name (as TRex does on registration)
-struct RefSettings { bool track_threshold_is_absolute = true, track_background_subtraction = true; int meta_encoding = 0; std::function<void(std::string_view)> cb; };
+struct RefSettings {
+    bool track_threshold_is_absolute = true, track_background_subtraction = true; int meta_encoding = 0; std::function<void(std::string_view)> cb;
+    std::map<std::string, double> num;                                   // every other (numeric / boolean) setting by name: the detection build (RawProcessing.cpp, BackgroundSubtraction.cpp)
+    std::vector<std::function<void(std::string_view)>> cbs;              // every callback registered so far (cb = the last one)
+};
 inline RefSettings& ref_settings() { static RefSettings s; return s; }
-inline bool bool_setting_config(const char *name) { return std::string_view(name) == "track_threshold_is_absolute" ? ref_settings().track_threshold_is_absolute : ref_settings().track_background_subtraction; }
+inline bool bool_setting_config(const char *name)
+{
+    if (std::string_view(name) == "track_threshold_is_absolute") return ref_settings().track_threshold_is_absolute;
+    if (std::string_view(name) == "track_background_subtraction") return ref_settings().track_background_subtraction;
+    return ref_settings().num[name] != 0;
+}
+struct NoType {};
+struct SettingValueStandIn { double v; template<typename T> T value() const { return T(v); } };
 struct GlobalSettings {
     template<typename Str, typename F> static CallbackFuture register_callbacks(std::initializer_list<Str> names, F&& fn)
     {
         ref_settings().cb = fn;
+        ref_settings().cbs.push_back(fn);
         for (auto &n : names) fn(std::string_view(n));
         return CallbackFuture{true};
     }
     static void unregister_callbacks(CallbackFuture&&) {}
     static bool is_runtime_quiet() { return true; }
+    template<typename> static SettingValueStandIn read_value(std::string_view key) { return SettingValueStandIn{ref_settings().num[std::string(key)]}; }
 };
 }
-namespace cmn { template<typename T> inline T read_setting_config(const char *) { return T{static_cast<std::remove_cvref_t<decltype(T{}.value())>>(ref_settings().meta_encoding)}; } }
+namespace cmn {
+template<typename T> inline T read_setting_config(const char *name)
+{
+    if constexpr (requires { T{}.value(); }) return T{static_cast<std::remove_cvref_t<decltype(T{}.value())>>(ref_settings().meta_encoding)};      // meta_encoding_t
+    else if constexpr (std::is_arithmetic_v<T>) return T(ref_settings().num[name]);
+    else return T{};
+}
+template<typename T> inline T read_setting_config_or(const char *name, T fallback) { auto it = ref_settings().num.find(name); return it == ref_settings().num.end() ? fallback : T(it->second); }
+}
+#define READ_SETTING_WITH_DEFAULT(NAME, DEFAULT) (cmn::read_setting_config_or( #NAME, DEFAULT ))
 #define BOOL_SETTING(NAME) (cmn::bool_setting_config(#NAME))
 #define READ_SETTING(NAME, ...) (cmn::read_setting_config< __VA_ARGS__ >( #NAME ))

@@ -15,6 +15,7 @@ public:
     static constexpr void set_flag(uint8_t &flags, Flags flag, bool v) { flags ^= (-uint8_t(v) ^ flags) & (1UL << uint8_t(flag)); }
     static constexpr uint8_t get_only_flag(Flags flag, bool v) { uint8_t flags = 0; set_flag(flags, flag, v); return flags; }
     static constexpr bool is_flag(uint8_t flags, Flags flag) { return (flags >> uint8_t(flag)) & 1u; }
+    static constexpr uint8_t flag(Flags flag) { return uint8_t(1UL << uint8_t(flag)); }
     Blob(cmn::blob::line_ptr_t&& l, cmn::blob::pixel_ptr_t&& p, uint8_t flags = 0, cmn::blob::Prediction&& = {}) : _lines(std::move(l)), _pixels(std::move(p)), _flags(flags)
     {
         if (_lines && !_lines->empty()) {

@@ -10,7 +10,9 @@
  * the reference's own videos/test.pv fixture bit-exactly, see
  * tests/golden/make_golden.py and tests/test_oracle_golden.py) and for
  * imageFromLines (known-answer vector of Application/Tests/test_pixels.cpp:
- * 1381-1466).  The pad/crop-to-80x80 geometry has no golden vector in the
+ * 1381-1466); generate_binary and BackgroundSubtraction::apply additionally on
+ * the reference's own RawProcessing.cpp / BackgroundSubtraction.cpp compiled
+ * unmodified and run with the real OpenCV (tests/test_oracle_ref_detect.py).  The pad/crop-to-80x80 geometry has no golden vector in the
  * reference; it is pinned on the reference's own FilterCache.cpp, compiled
  * unmodified (oracle/build_ref.py, tests/test_oracle_ref_filtercache.py).
  *
