@@ -60,6 +60,7 @@ public:
     const uchar *data() const { return mat.data; }
     uchar *data() { return mat.data; }
     ptr_safe_t channels() const { return dims; }
+    size_t size() const { return (size_t)rows * cols * dims; }           // bytes (misc/Image.h)
     cv::Mat get() const { return mat; }
     Bounds bounds() const { return Bounds(0, 0, (float)cols, (float)rows); }
 };

@@ -3,7 +3,7 @@
 #include <commons.pc.h>
 namespace buffers {
 struct TileBuffers {
-    struct Buffers_t { size_t returned = 0; void move_back(cmn::Image::Ptr&& p) { p.reset(); ++returned; } };
+    struct Buffers_t { std::vector<cmn::Image::Ptr> pool; void move_back(cmn::Image::Ptr&& p) { pool.emplace_back(std::move(p)); } };      // a pool keeps its buffers alive (the shim page-locks them)
     static Buffers_t& get() { static Buffers_t b; return b; }
 };
 }
