@@ -87,3 +87,56 @@ def test_cuda_path_equals_the_compiled_reference(ref, size, n_blobs, encoding, c
         n += len(mine)
     assert n > 10
     bs.deinit()
+
+
+def test_posture_loop_equals_the_compiled_reference():
+    """posture::calculate_posture (tracker/tracking/Posture.cpp:305-400 with PixelTree / CPULabeling / Outline / CircularGraph, compiled unmodified into
+    oracle/_ref/libref_posture.so) against tb_seg_posture_thresholded, blob by blob: which of the three outcomes, the outline the result carries, the midline
+    segments, tail and head -- bit for bit, including midlines found only after +2 retries.  The workload of tests/test_gpu_midline.py's loop test."""
+    import trex_b200
+    from oracle import build_ref, posture
+    from test_oracle_ref_outline import set_ref_settings
+    from test_oracle_ref_posture import graded_frame
+    path = build_ref.build()
+    if path is None:
+        pytest.skip("no prebuilt oracle/_ref/libref_posture.so and no reference checkout")
+    ref = C.CDLL(path)
+    ref.ref_calculate_posture.restype = C.c_int64
+    T0 = 12
+    set_ref_settings(ref, posture.default_params())
+    ref.ref_posture_settings(int(T0), C.c_float(1.0))
+    ref.ref_background_settings(1, 1, 0)                    # track_threshold_is_absolute, track_background_subtraction, gray
+    fr, bg = graded_frame(4)
+    frames = np.stack([fr, np.roll(fr, 7, axis=1)])
+    det = trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(detect_threshold=10, detect_size_filter=[]), max_batch=2)
+    pst = trex_b200.BackgroundSubtraction(bg, settings=trex_b200.DetectSettings(detect_threshold=0, detect_size_filter=[]), max_batch=2)
+    got = det.apply(frames)
+    rounds, res = det.posture_thresholded(pst, track_posture_threshold=T0, outline_resample=1.0, fetch=2)
+    flat = [b for blobs in got for b in blobs]
+    assert res["n_blobs"] == len(flat) > 20
+    n_mid = n_outline = n_none = 0
+    for k, b in enumerate(flat):
+        so, ns, tail, head = (int(v) for v in res["midlines"][k])
+        ro, rn = int(res["outlines"][k][2]), int(res["outlines"][k][3])
+        raw = np.zeros((len(b.lines), 4), np.uint16); raw[:, 0], raw[:, 1], raw[:, 2] = b.lines["x0"], b.lines["x1"], b.lines["y"]
+        p = np.ascontiguousarray(b.pixels, np.uint8)
+        cap = 4 * len(p) + 64
+        pts = np.zeros((cap, 2), np.float32); segs = np.zeros((cap, 4), np.float32)
+        n_pts, t, h = C.c_int64(), C.c_int64(-1), C.c_int64(-1)
+        r = ref.ref_calculate_posture(_p(raw), C.c_int64(len(raw)), _p(p), C.c_int64(len(p)), 1, _p(bg), bg.shape[1], bg.shape[0], 1, 0,
+                                      _p(pts), C.c_int64(cap), C.byref(n_pts), _p(segs), C.c_int64(cap), C.byref(t), C.byref(h))
+        if r == -2:                                         # "Cannot find valid posture"
+            assert ns == 0 and rn == 0, k
+            n_none += 1
+            continue
+        assert r >= -1, (k, r)
+        mine = np.ascontiguousarray(res["points"][ro:ro + rn], np.float32)
+        assert mine.shape == pts[:n_pts.value].shape and np.array_equal(mine.view(np.uint32), pts[:n_pts.value].view(np.uint32)), k
+        if r == -1:                                         # an outline, no midline
+            assert ns == 0, k
+            n_outline += 1
+        else:
+            assert ns == r and (tail, head) == (t.value, h.value), (k, ns, r)
+            assert np.array_equal(np.ascontiguousarray(res["segments"][so:so + ns], np.float32).view(np.uint32), segs[:r].view(np.uint32)), k
+            n_mid += 1
+    assert n_mid > 15 and n_outline + n_none >= 2 and rounds > 1
