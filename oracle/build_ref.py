@@ -7,6 +7,7 @@
     commons/common/processing/PixelTree.cpp           pixel::find_outer_points with pixel::Tree (its threshold_blob half only has to compile)
     commons/common/processing/{CPULabeling,Brototype,Source,DLList,ListCache}.cpp + misc/IllegalVector.h
                                                       CPULabeling::run: extract_lines -> merge_lines (Brototype) -> run_fast
+    commons/common/processing/BlobIdentity.cpp + misc/bid.h   pv::blob_bid / pv::bid::from_data: the blob id
     commons/common/processing/Background.{h,cpp} + processing/encoding.h, misc/EnumClass.h, misc/matharray.h, misc/FormatColor.h
                                                       per-pixel difference / is_different / count_above_threshold, cmn::bgr2gray, imageFromLines;
                                                       with it the Background overload of pixel::threshold_blob is the reference's own code as well
@@ -31,7 +32,7 @@ REF_FILES = [os.path.join(REF_SRC, "tracker", "tracking", "Outline.cpp"), os.pat
              os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"),
              os.path.join(REF_COMMON, "misc", "curve_discussion.cpp"), os.path.join(REF_COMMON, "gui", "Transform.cpp"),
              os.path.join(REF_COMMON, "processing", "PixelTree.cpp")] + \
-            [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp")]
+            [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp", "BlobIdentity.cpp")]
 
 
 def available() -> bool:
@@ -78,7 +79,7 @@ def build(force: bool = False):
 OUT_DETECT = os.path.join(HERE, "_ref", "libref_detect.so")
 REF_FILES_DETECT = [os.path.join(REF_SRC, "tracker", "python", "BackgroundSubtraction.cpp"), os.path.join(REF_COMMON, "processing", "RawProcessing.cpp"),
                     os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp")] + \
-                   [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp")]
+                   [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp", "BlobIdentity.cpp")]
 
 
 def build_detect(force: bool = False):

@@ -32,6 +32,16 @@ static int64_t store(blobs_t& blobs, uint16_t *lines, int64_t cap_lines, uint8_t
 
 extern "C" {
 
+// pv::blob_bid (processing/BlobIdentity.cpp:7-16 over pv::bid::from_data, misc/bid.h:87-94 -- both the reference's own files): the id pv::Blob::init
+// gives a blob, from its first run and its number of runs (the count passes through from_data's uint8_t parameter)
+uint32_t ref_blob_bid(const uint16_t *in_lines, int64_t n)
+{
+    auto l = std::make_unique<blob::lines_t>((size_t)n);
+    for (int64_t i = 0; i < n; ++i) (*l)[(size_t)i] = HorizontalLine(in_lines[4 * i + 2], in_lines[4 * i], in_lines[4 * i + 1]);
+    pv::Blob blob(std::move(l), nullptr, 0);
+    return (uint32_t)pv::blob_bid(blob);
+}
+
 // CPULabeling::run(image, cache): every non-zero pixel (any channel for 3-channel images) is foreground.  Blobs in the reference's emission order.
 int64_t ref_label_image(const uint8_t *img, int rows, int cols, int channels, uint16_t *lines, int64_t cap_lines, uint8_t *pixels, int64_t cap_px,
                         int64_t *line_off, int64_t *px_off, uint8_t *flags, int64_t cap_blobs)

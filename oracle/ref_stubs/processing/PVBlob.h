@@ -4,7 +4,21 @@
 #pragma once
 #include <commons.pc.h>
 #include <processing/Background.h>
+#include <processing/BlobIdentity.h>
 namespace pv {
+// of CompressedBlob / ShortHorizontalLine (PVBlob.h:246-330) only what processing/BlobIdentity.cpp reads: the packed runs and the first row
+struct ShortHorizontalLine {
+    uint16_t _x0 = 0, _x1 = 0;
+    constexpr ShortHorizontalLine() = default;
+    constexpr ShortHorizontalLine(uint16_t x0, uint16_t x1, bool eol = false) : _x0(x0), _x1((x1 & 0x7FFF) | uint16_t(eol << 15)) {}
+    constexpr uint16_t x0() const { return _x0; }
+    constexpr uint16_t x1() const { return _x1 & 0x7FFF; }
+};
+struct CompressedBlob {
+    uint16_t start_y{0};
+    std::vector<ShortHorizontalLine> _lines;
+    const std::vector<ShortHorizontalLine>& lines() const { return _lines; }
+};
 class Blob {
     cmn::blob::line_ptr_t _lines;
     cmn::blob::pixel_ptr_t _pixels;
@@ -47,7 +61,7 @@ public:
     void calculate_moments() {}
     float orientation() const { return _orientation; }
     uint8_t flags() const { return _flags; }
-    uint32_t blob_id() const { return 0; }
+    pv::bid blob_id() const { return pv::blob_bid(*this); }              // pv::Blob::init (PVBlob.cpp:785): the id is derived from the runs
     cmn::blob::Prediction prediction() const { return {}; }
     bool is_binary() const { return is_flag(_flags, Flags::is_binary); }
     bool is_rgb() const { return is_flag(_flags, Flags::is_rgb); }

@@ -199,3 +199,30 @@ def test_reference_returns_nothing_when_every_run_is_in_row_zero(ref):
     assert len(ref_label_image(ref, img)) == 3
     assert ref_label_lines(ref, np.array([[14, 15, 0]], np.uint16), np.array([1, 2], np.uint8), 1) == []
     assert len(ref_label_lines(ref, np.array([[14, 15, 1]], np.uint16), np.array([1, 2], np.uint8), 1)) == 1
+
+
+def test_blob_id_against_the_references_own_bid(ref):
+    """pv::blob_bid (processing/BlobIdentity.cpp) over pv::bid::from_data (misc/bid.h:87-94), both compiled from the checkout: the id of a blob from its first run
+    and its run count -- which passes through a uint8_t parameter before the % 64 (so 256 runs count as 0, 300 as 44).  Against seg.blob_id (= what K3 writes
+    into tb_blob_rec.bid) for labelled blobs and for constructed run lists with 1 ... 1000 runs and coordinates up to 8191."""
+    ref.ref_blob_bid.restype = C.c_uint32
+    rng = np.random.default_rng(12)
+    n = 0
+    for img in gray_images():
+        for runs, _, _ in ref_label_image(ref, img):
+            if runs[0, 1] >= 8192:                       # from_data asserts 13-bit coordinates (bid.h:88-90); the 9000-pixel run of gray_images() is beyond them
+                continue
+            raw = np.zeros((len(runs), 4), np.uint16); raw[:, :3] = runs
+            l = np.zeros(len(runs), seg.LINE_DTYPE); l["x0"], l["x1"], l["y"] = runs[:, 0], runs[:, 1], runs[:, 2]
+            assert int(ref.ref_blob_bid(_p(raw), C.c_int64(len(raw)))) == seg.blob_id(l)
+            n += 1
+    for count in (1, 2, 63, 64, 65, 255, 256, 257, 300, 511, 512, 1000):
+        for _ in range(4):
+            x0 = int(rng.integers(0, 8100)); x1 = x0 + int(rng.integers(0, 8191 - x0)); y = int(rng.integers(0, 8191 - count))
+            raw = np.zeros((count, 4), np.uint16); raw[:, 0] = x0; raw[:, 1] = x1; raw[:, 2] = y + np.arange(count)
+            l = np.zeros(count, seg.LINE_DTYPE); l["x0"], l["x1"], l["y"] = raw[:, 0], raw[:, 1], raw[:, 2]
+            want = (((x0 + x1 + 1) // 2) << 19) | ((y & 0x1FFF) << 6) | ((count & 0xFF) % 64)
+            got = int(ref.ref_blob_bid(_p(raw), C.c_int64(count)))
+            assert got == seg.blob_id(l) == want, (count, x0, x1, y, got, seg.blob_id(l), want)
+            n += 1
+    assert n > 300
