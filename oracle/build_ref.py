@@ -106,6 +106,36 @@ def build_detect(force: bool = False):
     return OUT_DETECT
 
 
+# ---- the reference's own pv::Blob (PVBlob.{h,cpp}) ----
+OUT_PVBLOB = os.path.join(HERE, "_ref", "libref_pvblob.so")
+REF_FILES_PVBLOB = [os.path.join(REF_COMMON, "processing", f) for f in ("PVBlob.cpp", "BlobIdentity.cpp", "Background.cpp", "PixelTree.cpp", "CPULabeling.cpp", "Brototype.cpp",
+                                                                         "Source.cpp", "DLList.cpp", "ListCache.cpp")]
+
+
+def build_pvblob(force: bool = False):
+    """oracle/_ref/libref_pvblob.so: commons/common/processing/PVBlob.cpp with the REAL PVBlob.h (-DREF_REAL_PVBLOB switches the look-alike of oracle/ref_stubs/ off)
+    and what it links against, plus the wrapper oracle/ref_pvblob.cpp.  Returns the path, or None when neither the checkout nor a prebuilt library is present."""
+    if not (all(os.path.exists(f) for f in REF_FILES_PVBLOB) and shutil.which("g++") is not None):
+        return OUT_PVBLOB if os.path.exists(OUT_PVBLOB) else None
+    wrapper = os.path.join(HERE, "ref_pvblob.cpp")
+    stubs = []
+    for d in ("ref_stubs", "ref_stubs_pvblob"):
+        for root, _, files in os.walk(os.path.join(HERE, d)):
+            stubs += [os.path.join(root, f) for f in files]
+    deps = REF_FILES_PVBLOB + [wrapper, os.path.abspath(__file__)] + stubs
+    if not force and os.path.exists(OUT_PVBLOB) and all(os.path.getmtime(d) <= os.path.getmtime(OUT_PVBLOB) for d in deps):
+        return OUT_PVBLOB
+    os.makedirs(os.path.dirname(OUT_PVBLOB), exist_ok=True)
+    cmd = ["g++", "-std=c++23", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,--no-undefined", "-DREF_REAL_PVBLOB",
+           "-I", os.path.join(HERE, "ref_stubs_pvblob"), "-I", os.path.join(HERE, "ref_stubs"), "-I", REF_COMMON, "-I", os.path.join(REF_SRC, "tracker"),
+           *REF_FILES_PVBLOB, wrapper, "-o", OUT_PVBLOB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building the reference's pv::Blob failed:\n" + r.stdout + r.stderr)
+    return OUT_PVBLOB
+
+
 if __name__ == "__main__":
     print(build(force=True))
     print(build_detect(force=True))
+    print(build_pvblob(force=True))

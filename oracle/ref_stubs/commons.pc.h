@@ -52,6 +52,9 @@
 #define GETTER(TYPE, VAR) public: [[nodiscard]] const TYPE& VAR() const { return _##VAR; } protected: TYPE _##VAR
 #define GETTER_NCONST(TYPE, VAR) public: [[nodiscard]] inline const TYPE& VAR() const { return _##VAR; } [[nodiscard]] inline TYPE& VAR() { return _##VAR; } protected: TYPE _##VAR
 #define UNUSED(X) (void)(X)
+#define GETTER_I(TYPE, VAR, INIT) public: [[nodiscard]] const TYPE& VAR() const { return _##VAR; } protected: TYPE _##VAR = INIT
+#define GETTER_SETTER(TYPE, VAR) public: [[nodiscard]] inline const TYPE& VAR() const { return _##VAR; } inline void set_##VAR(const TYPE& value) { _##VAR = value; } protected: TYPE _##VAR
+#define GETTER_SETTER_I(TYPE, VAR, INIT) public: [[nodiscard]] inline const TYPE& VAR() const { return _##VAR; } inline void set_##VAR(const TYPE& value) { _##VAR = value; } protected: TYPE _##VAR = INIT
 
 using long_t = int32_t;
 
@@ -83,6 +86,19 @@ constexpr auto min(const A& x, const B& y, const Cc& z) -> decltype(x + y + z) {
 template<typename A, typename B, typename Cc> requires (std::is_arithmetic_v<A> && std::is_arithmetic_v<B> && std::is_arithmetic_v<Cc>)
 constexpr auto max(const A& x, const B& y, const Cc& z) -> decltype(x + y + z) { using R = decltype(x + y + z); return std::max(R(x), std::max(R(y), R(z))); }
 
+// misc/math.h:34-59: the 3rd-order fit pv::Blob::calculate_moments takes the orientation from -- restated operation for operation (M_PI_2 / M_PI are doubles there:
+// `M_PI_2 - fast_atan(r)` and `M_PI - angle` are computed in double and rounded to float on assignment)
+inline float fast_atan(float z) { const float n1 = 0.97239411f; const float n2 = -0.19194795f; return (n1 + n2 * z * z) * z; }
+inline float fast_atan2(float y, float x)
+{
+    if (x == 0.0f) return copysignf(M_PI_2, y);
+    float abs_y = fabsf(y), r, angle;
+    if (abs_y < fabsf(x)) { r = abs_y / fabsf(x); angle = fast_atan(r); }
+    else { r = fabsf(x) / abs_y; angle = M_PI_2 - fast_atan(r); }
+    if (x < 0.0f) angle = M_PI - angle;
+    if (y < 0.0f) angle = -angle;
+    return angle;
+}
 template<typename T> requires (std::is_arithmetic_v<T> && !std::unsigned_integral<T>) constexpr auto abs(T x) { return std::abs(x); }
 template<typename T> requires std::unsigned_integral<T> constexpr auto abs(T x) { return x; }
 template<typename T> requires std::is_arithmetic_v<T> constexpr bool isnan(T x) { if constexpr (std::is_floating_point_v<T>) return std::isnan(x); else return false; }
@@ -209,6 +225,7 @@ struct Meta {
     template<typename T, typename S> static T fromStr(S&&) { return T{}; }
 };
 template<typename T> inline auto cvt2json(const T&) { return glz_json_placeholder{}; }
+template<int N> struct dec { template<typename T> dec(T) {} std::string toStr() const { return std::string(); } };
 template<typename... A> inline void Print(const A&...) {}
 template<typename... A> inline void FormatWarning(const A&...) {}
 template<typename... A> inline void FormatError(const A&...) {}
@@ -256,6 +273,8 @@ struct Mat {
     bool isContinuous() const { return true; }
     const unsigned char *ptr(int r = 0) const { return data + (size_t)r * step.p[0]; }
     unsigned char *ptr(int r = 0) { return data + (size_t)r * step.p[0]; }
+    const unsigned char *ptr(int r, int c) const { return data + (size_t)r * step.p[0] + (size_t)c * step.p[1]; }
+    unsigned char *ptr(int r, int c) { return data + (size_t)r * step.p[0] + (size_t)c * step.p[1]; }
     template<typename T> T *ptr(int r, int = 0) { (void)r; std::fprintf(stderr, "cv::Mat::ptr<T> stand-in used\n"); std::abort(); return nullptr; }
     template<typename T> T& at(int r, int c) { return *reinterpret_cast<T *>(data + (size_t)r * step.p[0] + (size_t)c * sizeof(T)); }
     bool empty() const { return data == nullptr; }

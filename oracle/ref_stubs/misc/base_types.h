@@ -14,6 +14,12 @@ using uchar = unsigned char;
 namespace cmn {
 using coord_t = uint16_t;
 using ptr_safe_t = uint64_t;
+template<typename T> class NoInitializeAllocator : public std::allocator<T> {      // misc/types.h:63-95 (skips default construction; std::vector<T> copies from it as a plain allocator)
+public:
+    template<typename U> struct rebind { typedef NoInitializeAllocator<U> other; };
+    NoInitializeAllocator() noexcept : std::allocator<T>() {}
+    NoInitializeAllocator(const NoInitializeAllocator<T>& rhs) noexcept : std::allocator<T>(rhs) {}
+};
 struct HorizontalLine {
     coord_t x0, x1;
     coord_t y, padding;
@@ -23,6 +29,8 @@ struct HorizontalLine {
     constexpr bool operator==(const HorizontalLine& o) const noexcept { return o.x0 == x0 && o.y == y && o.x1 == x1; }
     constexpr bool operator<(const HorizontalLine& o) const noexcept { return y < o.y || (y == o.y && x0 < o.x0); }
     constexpr ptr_safe_t length() const noexcept { return ptr_safe_t(x1) - ptr_safe_t(x0) + 1; }
+    // pv::Blob::init's repair of unordered run lists (misc/detail.cpp): never reached by ordered input
+    template<typename... A> static void repair_lines_array(A&...) { std::fprintf(stderr, "HorizontalLine::repair_lines_array stand-in used\n"); std::abort(); }
 };
 using PixelArray_t = IllegalArray<uchar>;
 template<typename T, typename... A> constexpr bool is_in(const T& v, const A&... a) { return ((v == T(a)) || ...); }

@@ -36,5 +36,15 @@ struct Settings {
     }
 };
 }
+#ifdef REF_REAL_PVBLOB
+namespace pv {            // CREATE_STRUCT(PVSettings, (Float2_t, cm_per_pixel), (bool, correct_illegal_lines)) of processing/PVBlob.cpp:58-61 as a plain table
+struct PVSettings {
+    enum Variables { cm_per_pixel, correct_illegal_lines };
+    static float& cm() { static float v = 1.f; return v; }
+    static void init() {}
+    template<Variables V> static auto get() { if constexpr (V == cm_per_pixel) return cm(); else return false; }
+};
+}
+#endif
 #define CREATE_STRUCT(NAME, ...) static_assert(true, "settings table provided by the stand-in");
 #define FAST_SETTING(NAME) (outline::Settings::values().NAME)

@@ -55,6 +55,12 @@ public:
     cv::Mat mat;
     Image(uint32_t r, uint32_t c, uint32_t d) : cols(c), rows(r), dims(d), mat((int)r, (int)c, (int)((d - 1) << 3)) {}      // CV_8UC(d)
     static Ptr Make(uint32_t r, uint32_t c, uint32_t d) { return std::make_unique<Image>(r, c, d); }
+    Image() {}
+    static Ptr Make() { return std::make_unique<Image>(); }
+    template<typename A, typename B> requires (std::is_arithmetic_v<A> && std::is_arithmetic_v<B>) static Ptr Make(A r, B c) { return std::make_unique<Image>((uint32_t)r, (uint32_t)c, 1u); }
+    void create(uint32_t r, uint32_t c, uint32_t d) { rows = r; cols = c; dims = d; mat = cv::Mat((int)r, (int)c, (int)((d - 1) << 3)); }
+    uchar *ptr(uint32_t y, uint32_t x) { return mat.ptr((int)y, (int)x); }
+    const uchar *ptr(uint32_t y, uint32_t x) const { return mat.ptr((int)y, (int)x); }
     explicit Image(const cv::Mat& m) : Image((uint32_t)m.rows, (uint32_t)m.cols, (uint32_t)m.channels()) { m.copyTo(mat); }      // Image::Make(cv::Mat): a copy of the pixels
     static Ptr Make(const cv::Mat& m) { return std::make_unique<Image>(m); }
     const uchar *data() const { return mat.data; }

@@ -1,6 +1,9 @@
 // Test infrastructure: pv::Blob (commons/common/processing/PVBlob.h) reduced to what PixelTree.cpp and CPULabeling.cpp touch: the run list, the pixel
 // bytes, the flag byte (Flags / set_flag / get_only_flag / copy_flags restated from PVBlob.h:138-168) and the bounding box of the runs
 // (x = min x0, y = first y, width = max x1 - x + 1, height = last y - y + 1: what pv::Blob::init computes from the lines).
+#ifdef REF_REAL_PVBLOB
+#include_next <processing/PVBlob.h>
+#else
 #pragma once
 #include <commons.pc.h>
 #include <processing/Background.h>
@@ -81,3 +84,4 @@ public:
     }
 };
 }
+#endif

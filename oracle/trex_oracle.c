@@ -775,7 +775,7 @@ void to_crop_blob_rgb(const to_line_t *lines, int64_t n_lines, const uint8_t *px
  * individual_image_normalization = moments ("next" row N3b): constraints::diff_image
  * (T/tracking/FilterCache.cpp:329-341) -> calculate_normalized_diff_image (:133-154) -> normalize_image (:21-115).
  *
- * (1) pv::Blob::calculate_moments, C/processing/PVBlob.cpp:111-214, single-thread path (blobs with <= 1000 lines):
+ * (1) pv::Blob::calculate_moments, C/processing/PVBlob.cpp:111-214:
  *     float accumulators, pixels visited line by line; centre = (m10/m00, m01/m00); central moments from INTEGER offsets
  *     vx = int(x0 - centre.x) ..., products in float; angle = 0.5 * fast_atan2(2 mu'11, mu'20 - mu'02)
  *     (C/misc/math.h:34-59: 3rd-order polynomial, no libm).
@@ -791,25 +791,40 @@ static float fast_atan2_f(float y, float x)
     if (y < 0.0f) angle = -angle;
     return angle;
 }
+/* The runs are visited in `packages` consecutive packages with their own float accumulators, merged in package order afterwards: 1 package up to 1000 runs,
+ * min(runs, 4) beyond (PVBlob.cpp:118-122 num_threads; distribute_indexes, C/misc/ThreadPool.h:126-195: runs / packages per package, the last one takes the rest).
+ * The split changes the float rounding of the sums once they pass 2^24, so it is part of the result. */
 float to_blob_orientation(const to_line_t *lines, int64_t n_lines, float centre[2])
 {
+    const int packages = n_lines > 1000 ? (int)(n_lines < 4 ? n_lines : 4) : 1;
+    const int64_t per = n_lines / packages > 1 ? n_lines / packages : 1;
     float m00 = 0, m01 = 0, m10 = 0;
-    for (int64_t i = 0; i < n_lines; ++i) {
-        const unsigned my = lines[i].y;
-        int mx = lines[i].x0;
-        for (int x = lines[i].x0; x <= lines[i].x1; ++x, ++mx) { m00 += 1; m01 += 1 * my; m10 += mx * 1; }
+    for (int p = 0; p < packages; ++p) {
+        const int64_t b = p * per, e = p + 1 == packages ? n_lines : (p + 1) * per;
+        float l00 = 0, l01 = 0, l10 = 0;
+        for (int64_t i = b; i < e; ++i) {
+            const unsigned my = lines[i].y;
+            int mx = lines[i].x0;
+            for (int x = lines[i].x0; x <= lines[i].x1; ++x, ++mx) { l00 += 1; l01 += 1 * my; l10 += mx * 1; }
+        }
+        m00 += l00; m01 += l01; m10 += l10;
     }
     const float cx = m10 / m00, cy = m01 / m00;
     if (centre) { centre[0] = cx; centre[1] = cy; }
     float mu00 = 0, mu02 = 0, mu11 = 0, mu20 = 0;
-    for (int64_t i = 0; i < n_lines; ++i) {
-        const int vy = (int)((lines[i].y) - cy);
-        const int vy2 = vy * vy;
-        int vx = (int)((lines[i].x0) - cx);
-        for (int x = lines[i].x0; x <= lines[i].x1; ++x, ++vx) {
-            const int vx2 = vx * vx;
-            mu00 += 1; mu02 += 1 * vy2; mu11 += (float)vx * (float)vy; mu20 += vx2 * 1;
+    for (int p = 0; p < packages; ++p) {
+        const int64_t b = p * per, e = p + 1 == packages ? n_lines : (p + 1) * per;
+        float l00 = 0, l02 = 0, l11 = 0, l20 = 0;
+        for (int64_t i = b; i < e; ++i) {
+            const int vy = (int)((lines[i].y) - cy);
+            const int vy2 = vy * vy;
+            int vx = (int)((lines[i].x0) - cx);
+            for (int x = lines[i].x0; x <= lines[i].x1; ++x, ++vx) {
+                const int vx2 = vx * vx;
+                l00 += 1; l02 += 1 * vy2; l11 += (float)vx * (float)vy; l20 += vx2 * 1;
+            }
         }
+        mu00 += l00; mu02 += l02; mu11 += l11; mu20 += l20;
     }
     const float inv = 1.0f / mu00;
     const float n11 = mu11 * inv, n20 = mu20 * inv, n02 = mu02 * inv;

@@ -500,3 +500,33 @@ def test_recount_against_oracle(diff, absolute):
         exp = np.array([oseg.blob_recount(b.lines, b.pixels, world.bg, T, method, cm_per_pixel=0.25) for b in flat], np.float32)
         assert np.array_equal(rc, exp), T
     assert np.array_equal(bs.recount(0), np.array([b.num_pixels for b in flat], np.float32) * np.float32(0.0625))
+
+
+def test_moments_crop_of_a_blob_with_more_than_1000_runs():
+    """pv::Blob::calculate_moments sums a blob of more than 1000 runs in four packages with their own float accumulators (PVBlob.cpp:118-204), which changes
+    the rounding of the sums and with it the orientation; the oracle follows that (pinned on the compiled PVBlob.cpp, tests/test_oracle_ref_pvblob.py) and so
+    does blob_moments_kernel.  A porous ellipse of ~1600 runs next to ordinary blobs: crops byte-equal to the oracle's."""
+    import trex_b200
+    from oracle import seg
+    rng = np.random.default_rng(41)
+    H, W = 720, 960
+    bg = np.full((H, W), 180, np.uint8)
+    fr = bg.copy()
+    yy, xx = np.mgrid[0:H, 0:W]
+    u = (xx - 480) * np.cos(0.5) + (yy - 360) * np.sin(0.5); v = -(xx - 480) * np.sin(0.5) + (yy - 360) * np.cos(0.5)
+    m = ((u / 330) ** 2 + (v / 90) ** 2 < 1) & (rng.random((H, W)) < 0.985)
+    fr[m] = rng.integers(20, 120, int(m.sum())).astype(np.uint8)
+    fr[30:50, 40:90] = 60; fr[650:660, 800:930] = 90
+    kw = dict(detect_threshold=15, detect_size_filter=[(1, 10000000)])
+    s = trex_b200.DetectSettings(individual_image_normalization="moments", **kw)
+    bs = trex_b200.BackgroundSubtraction(bg, settings=s, max_batch=1, max_individuals=64, max_runs_per_frame=H * W // 8, max_pixels_per_frame=H * W)
+    (g,) = bs.apply(fr[None])
+    crops, _ = bs.crops()
+    ref = _oracle(fr, bg, **kw)
+    assert _as_list(g) == ref.as_list()
+    assert max(len(ref.blob(k)[0]) for k in range(len(ref))) > 1000
+    n = 0
+    for k in range(min(len(ref), 64)):
+        assert np.array_equal(crops[n], seg.crop_blob_moments(*ref.blob(k), bg, seg.DIFF_ABSOLUTE)), k
+        n += 1
+    assert n == len(crops) and n >= 3

@@ -1,6 +1,6 @@
 // individual_image_normalization = moments ("next" row N3b): the blob is rotated by its second-moment orientation into the
 // 80x80 canvas.  Replaces, for grey blobs,
-//   pv::Blob::calculate_moments              C/processing/PVBlob.cpp:111-214 (single-thread path, <= 1000 lines)
+//   pv::Blob::calculate_moments              C/processing/PVBlob.cpp:111-214 (incl. its four-package float sums beyond 1000 runs)
 //   fast_atan2                               C/misc/math.h:34-59
 //   constraints::diff_image (moments branch) T/tracking/FilterCache.cpp:329-341
 //   image::normalize_image                   T/tracking/FilterCache.cpp:21-115 (gui::Transform in double, C/gui/Transform.cpp)
@@ -36,22 +36,36 @@ __global__ void blob_moments_kernel(const tb_blob_rec *__restrict__ recs, const 
     if (q >= totals[3]) return;
     const tb_blob_rec r = recs[crop_blob[q]];
     const tb_line *L = lines + r.line_off;
+    // the reference sums the runs in `packages` consecutive packages with their own float accumulators and merges them in order: one package up to 1000
+    // runs, min(runs, 4) beyond (PVBlob.cpp:118-122,190-204; distribute_indexes, C/misc/ThreadPool.h:126-195: runs / packages each, the last takes the rest)
+    const uint32_t packages = r.n_lines > 1000u ? 4u : 1u;
+    const uint32_t per = r.n_lines / packages;
     float m00 = 0.f, m01 = 0.f, m10 = 0.f;
-    for (uint32_t i = 0; i < r.n_lines; ++i) {
-        const tb_line l = L[i];
-        const float my = (float)(unsigned)l.y;
-        for (int x = l.x0; x <= (int)l.x1; ++x) { m00 += 1.f; m01 += my; m10 += (float)x; }
+    for (uint32_t p = 0; p < packages; ++p) {
+        const uint32_t b = p * per, e = p + 1 == packages ? r.n_lines : (p + 1) * per;
+        float l00 = 0.f, l01 = 0.f, l10 = 0.f;
+        for (uint32_t i = b; i < e; ++i) {
+            const tb_line l = L[i];
+            const float my = (float)(unsigned)l.y;
+            for (int x = l.x0; x <= (int)l.x1; ++x) { l00 += 1.f; l01 += my; l10 += (float)x; }
+        }
+        m00 += l00; m01 += l01; m10 += l10;
     }
     const float cx = m10 / m00, cy = m01 / m00;
     float mu00 = 0.f, mu02 = 0.f, mu11 = 0.f, mu20 = 0.f;
-    for (uint32_t i = 0; i < r.n_lines; ++i) {
-        const tb_line l = L[i];
-        const int vy = (int)((float)l.y - cy);
-        const int vy2 = vy * vy;
-        int vx = (int)((float)l.x0 - cx);
-        for (int x = l.x0; x <= (int)l.x1; ++x, ++vx) {
-            mu00 += 1.f; mu02 += (float)vy2; mu11 += (float)vx * (float)vy; mu20 += (float)(vx * vx);
+    for (uint32_t p = 0; p < packages; ++p) {
+        const uint32_t b = p * per, e = p + 1 == packages ? r.n_lines : (p + 1) * per;
+        float l00 = 0.f, l02 = 0.f, l11 = 0.f, l20 = 0.f;
+        for (uint32_t i = b; i < e; ++i) {
+            const tb_line l = L[i];
+            const int vy = (int)((float)l.y - cy);
+            const int vy2 = vy * vy;
+            int vx = (int)((float)l.x0 - cx);
+            for (int x = l.x0; x <= (int)l.x1; ++x, ++vx) {
+                l00 += 1.f; l02 += (float)vy2; l11 += (float)vx * (float)vy; l20 += (float)(vx * vx);
+            }
         }
+        mu00 += l00; mu02 += l02; mu11 += l11; mu20 += l20;
     }
     const float inv = 1.0f / mu00;
     const float orientation = (float)(0.5 * (double)fast_atan2_f(2 * (mu11 * inv), mu20 * inv - mu02 * inv));
