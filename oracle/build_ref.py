@@ -78,7 +78,7 @@ def build(force: bool = False):
 # ---- the detection build: BackgroundSubtraction::apply / RawProcessing::generate_binary with every cv:: call forwarded to the real OpenCV (Python's cv2) ----
 OUT_DETECT = os.path.join(HERE, "_ref", "libref_detect.so")
 REF_FILES_DETECT = [os.path.join(REF_SRC, "tracker", "python", "BackgroundSubtraction.cpp"), os.path.join(REF_COMMON, "processing", "RawProcessing.cpp"),
-                    os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp")] + \
+                    os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp"), os.path.join(REF_COMMON, "video", "AveragingAccumulator.cpp")] + \
                    [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp", "BlobIdentity.cpp")]
 
 

@@ -15,17 +15,25 @@ BRIDGE = C.CFUNCTYPE(None, C.c_char_p, C.POINTER(BridgeMat), C.POINTER(BridgeMat
 
 
 def _array(m):
-    """A copy of an 8-bit cv::Mat (possibly a view with a larger row step) as (rows, cols) or (rows, cols, channels)."""
+    """A copy of an 8-bit or float32 cv::Mat (possibly a view with a larger row step) as (rows, cols) or (rows, cols, channels)."""
     m = m.contents
-    if (m.type & 7) != 0:
-        raise TypeError(f"bridge: only 8-bit matrices cross (type {m.type})")
-    row = m.cols * m.channels
+    depth = m.type & 7
+    if depth not in (0, 5):
+        raise TypeError(f"bridge: only 8-bit and float32 matrices cross (type {m.type})")
+    dt, es = (np.uint8, 1) if depth == 0 else (np.float32, 4)
+    row = m.cols * m.channels * es
     if m.rows == 0 or row == 0:
-        return np.zeros((m.rows, m.cols) if m.channels == 1 else (m.rows, m.cols, m.channels), np.uint8)
+        return np.zeros((m.rows, m.cols) if m.channels == 1 else (m.rows, m.cols, m.channels), dt)
     size = (m.rows - 1) * m.step + row
     flat = np.frombuffer((C.c_ubyte * size).from_address(m.data), np.uint8)
-    a = np.lib.stride_tricks.as_strided(flat, (m.rows, row), (m.step, 1)).copy()
+    a = np.lib.stride_tricks.as_strided(flat, (m.rows, row), (m.step, 1)).copy().view(dt)
     return a if m.channels == 1 else a.reshape(m.rows, m.cols, m.channels)
+
+
+def _convert_8u(cv2, a):
+    """cv::Mat::convertTo(dst, CV_8U) of a float32 matrix with OpenCV's own rounding and saturation: cv2.add with a zero matrix and dtype CV_8U runs the same
+    saturate_cast<uchar>(float) (cvRound: round half to even, clamp to 0 ... 255) -- cv2 has no direct convertTo binding."""
+    return cv2.add(a, np.zeros_like(a), dtype=cv2.CV_8U)
 
 
 class Bridge:
@@ -74,15 +82,27 @@ class Bridge:
                 r = cv2.bitwise_and(A, B)
             elif op == "bitwise_or":
                 r = cv2.bitwise_or(A, B)
+            elif op == "add":
+                r = cv2.add(A, B)
+            elif op == "max":
+                r = cv2.max(A, B)
+            elif op == "min":
+                r = cv2.min(A, B)
+            elif op == "divide_mat_scalar":
+                r = cv2.divide(A, (p[0], p[0], p[0], p[0]))                 # cv::divide(src, double): the 1 x 1 scalar divides every channel
+            elif op == "convertTo_8u":
+                r = _convert_8u(cv2, A)
             elif op == "equalizeHist":
                 r = cv2.equalizeHist(A)
             elif op == "getStructuringElement":
                 r = cv2.getStructuringElement(int(p[0]), (int(p[1]), int(p[2])), (int(p[3]), int(p[4])))
             else:
                 raise NotImplementedError(op)
-            r = np.ascontiguousarray(r, np.uint8)
+            if r.dtype not in (np.uint8, np.float32):
+                raise TypeError(f"{op} returned {r.dtype}")
+            r = np.ascontiguousarray(r)
             ch = 1 if r.ndim == 2 else r.shape[2]
-            ptr = self.lib.ref_cv_out(out, r.shape[0], r.shape[1], (ch - 1) << 3)
+            ptr = self.lib.ref_cv_out(out, r.shape[0], r.shape[1], (0 if r.dtype == np.uint8 else 5) + ((ch - 1) << 3))
             C.memmove(ptr, r.ctypes.data, r.nbytes)
         except Exception as e:                                             # noqa: BLE001 -- must not escape a ctypes callback
             self.errors.append(f"{op}: {e!r}")

@@ -12,6 +12,7 @@
 #include <processing/RawProcessing.h>
 #include <processing/Background.h>
 #include <core/TrackingSettings.h>
+#include <video/AveragingAccumulator.h>
 
 using namespace cmn;
 
@@ -64,6 +65,29 @@ void ref_detect_color_channel(int c)
 {
     if (c < 0) detect_settings().color_channel.reset();
     else detect_settings().color_channel = (uint8_t)c;
+}
+
+// AveragingAccumulator(method).add(frame) x n, finalize() (commons/common/video/AveragingAccumulator.cpp, compiled unmodified; cv::add / max / min / divide and the
+// float -> 8-bit convertTo are the real OpenCV's through the bridge).  method: 0 mean, 1 mode, 2 max, 3 min; frames: n x rows x cols x ch; threaded != 0 uses add_threaded
+int ref_average(const uint8_t *frames, int n, int rows, int cols, int ch, int method, int threaded, uint8_t *out)
+{
+    const averaging_method_t::Class m = method == 0 ? averaging_method_t::mean : (method == 1 ? averaging_method_t::mode : (method == 2 ? averaging_method_t::max : averaging_method_t::min));
+    try {
+        AveragingAccumulator acc(m);
+        const size_t bytes = (size_t)rows * cols * ch;
+        for (int i = 0; i < n; ++i) {
+            cv::Mat f(rows, cols, (ch - 1) << 3);
+            std::memcpy(f.data, frames + (size_t)i * bytes, bytes);
+            if (threaded) acc.add_threaded(f); else acc.add(f);
+        }
+        auto img = acc.finalize();
+        if ((size_t)img->rows * img->cols * img->dims != bytes) return -2;
+        std::memcpy(out, img->data(), bytes);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_average: %s\n", e.what());
+        return -1;
+    }
 }
 
 // RawProcessing(average).generate_binary(input, input, output): frame and average have `ch` (1 or 3) channels; out: rows * cols * ch bytes

@@ -231,6 +231,7 @@ template<typename... A> inline void FormatWarning(const A&...) {}
 template<typename... A> inline void FormatError(const A&...) {}
 template<typename... A> inline void FormatExcept(const A&...) {}
 template<typename... A> inline std::runtime_error U_EXCEPTION(const char *msg, const A&...) { return std::runtime_error(msg); }
+template<typename... A> inline std::runtime_error RuntimeError(const char *msg, const A&...) { return std::runtime_error(msg); }
 }
 
 // the handful of OpenCV names the compiled files mention.  cv::Mat is a plain row-major byte image (rows, cols, type = CV_8UC1 / CV_8UC3, step.p =
@@ -255,9 +256,14 @@ struct Mat {
     template<typename T> explicit Mat(const std::vector<T>&) { std::fprintf(stderr, "cv::Mat(std::vector) stand-in used\n"); std::abort(); }      // RawProcessing.cpp's tag branch only
     static Mat ones(int r, int c, int t) { Mat m(r, c, t); std::memset(m.data, 1, (size_t)r * m.step.p[0]); return m; }                              // 8-bit only
     void release() { store.reset(); data = nullptr; rows = cols = 0; }
-    void convertTo(Mat& dst, int t, double alpha = 1.0) const                                  // 8U -> 8U (a copy) and 8U -> 32F (scaled): what the detection path asks for
+    void setTo(int v) { for (int y = 0; y < rows; ++y) std::memset(ptr(y), v, (size_t)cols * step.p[1]); }                   // 8-bit only
+    void convertTo(const Mat& dst_, int t, double alpha = 1.0) const                           // 8U -> 8U (a copy) and 8U -> 32F (scaled) here; 32F -> 8U is OpenCV's rounding: bridged
     {
+        Mat& dst = const_cast<Mat&>(dst_);
         Mat src = *this;
+#ifdef REF_DETECT
+        if ((t & 7) == 0 && src.depth() == 5) { convert_32f_to_8u(src, dst); return; }
+#endif
         if ((t & 7) == 0 && src.depth() == 0) { src.copyTo(dst); return; }
         if ((t & 7) != 5 || src.depth() != 0) { std::fprintf(stderr, "cv::Mat::convertTo stand-in: unsupported types\n"); std::abort(); }
         Mat out(src.rows, src.cols, 5 + ((src.channels() - 1) << 3));
@@ -268,6 +274,7 @@ struct Mat {
     size_t elemSize() const { return (size_t)channels() * (depth() == 6 ? 8 : (depth() == 5 || depth() == 4 ? 4 : (depth() == 2 || depth() == 3 ? 2 : 1))); }
     void alloc() { step.p[1] = elemSize(); step.p[0] = (size_t)cols * step.p[1]; store = std::make_shared<std::vector<unsigned char>>((size_t)rows * step.p[0] + 64, 0); data = store->data(); }
     int type() const { return _type; }
+    static void convert_32f_to_8u(const Mat& src, Mat& dst);          // detection build: forwarded to cv2 (oracle/ref_stubs_detect/cv_detect.h)
     int channels() const { return (_type >> 3) + 1; }                                      // OpenCV's type code: depth in the low three bits, channels - 1 above
     int depth() const { return _type & 7; }
     bool isContinuous() const { return true; }

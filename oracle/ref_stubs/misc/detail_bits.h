@@ -96,6 +96,7 @@ struct GlobalSettings {
     }
     static void unregister_callbacks(CallbackFuture&&) {}
     static bool is_runtime_quiet() { return true; }
+    template<typename T> static T read_value_with_default(const char *, T fallback) { return fallback; }
     template<typename> static SettingValueStandIn read_value(std::string_view key) { return SettingValueStandIn{ref_settings().num[std::string(key)]}; }
 };
 }

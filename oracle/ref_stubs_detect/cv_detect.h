@@ -53,6 +53,11 @@ inline void dilate(const Mat& src, const Mat& dst, const Mat& kernel) { forward(
 inline void erode(const Mat& src, const Mat& dst, const Mat& kernel) { forward("erode", &src, &kernel, dst, {}); }
 inline void bitwise_and(const Mat& a, const Mat& b, const Mat& dst) { forward("bitwise_and", &a, &b, dst, {}); }
 inline void bitwise_or(const Mat& a, const Mat& b, const Mat& dst) { forward("bitwise_or", &a, &b, dst, {}); }
+inline void add(const Mat& a, const Mat& b, const Mat& dst) { forward("add", &a, &b, dst, {}); }
+inline void max(const Mat& a, const Mat& b, const Mat& dst) { forward("max", &a, &b, dst, {}); }
+inline void min(const Mat& a, const Mat& b, const Mat& dst) { forward("min", &a, &b, dst, {}); }
+inline void divide(const Mat& a, double b, const Mat& dst) { forward("divide_mat_scalar", &a, nullptr, dst, {b}); }      // a 1 x 1 double divides every channel
+inline void Mat::convert_32f_to_8u(const Mat& src, Mat& dst) { forward("convertTo_8u", &src, nullptr, dst, {}); }
 inline void equalizeHist(const Mat& src, const Mat& dst) { forward("equalizeHist", &src, nullptr, dst, {}); }
 inline Mat getStructuringElement(int shape, Size k, Point anchor) { Mat m; forward("getStructuringElement", nullptr, nullptr, m, {double(shape), double(k.width), double(k.height), double(anchor.x), double(anchor.y)}); return m; }
 // pure data movement: done here

@@ -228,3 +228,22 @@ def test_apply_rejects_what_the_reference_rejects(ref):
                                                  _p(lines), C.c_int64(n), _p(px), C.c_int64(3 * n), _p(lo), _p(po), _p(fl), C.c_int64(n), C.byref(e), C.byref(called))
         assert k == -1 and called.value == 1
     lib.ref_detect_meta_encoding(0)
+
+
+@pytest.mark.parametrize("method", ["mean", "mode", "max", "min"])
+@pytest.mark.parametrize("threaded", [0, 1])
+def test_averaging_accumulator(ref, method, threaded):
+    """commons/common/video/AveragingAccumulator.cpp compiled unmodified (row N2b): add / add_threaded over n frames, finalize.  cv::add on float matrices,
+    cv::max / cv::min, cv::divide by the count and the float -> 8-bit convertTo are the real OpenCV's.  Against seg.average (= what tb_avg_* reproduces on
+    the GPU): mean with its round-half-to-even, mode with ties (the smallest value wins), max, min; 1, 7 and 40 frames."""
+    lib, br = ref
+    rng = np.random.default_rng(13)
+    for n in (1, 7, 40):
+        frames = rng.integers(0, 256, (n, 60, 88)).astype(np.uint8)
+        frames[:, :20] = rng.integers(100, 104, (n, 20, 88))           # few distinct values: ties for the mode, halves for the mean
+        frames[:, 20:30] = (rng.integers(0, 2, (n, 10, 88)) * 255)      # saturated extremes
+        out = np.zeros((60, 88), np.uint8)
+        rc = lib.ref_average(_p(frames), n, 60, 88, 1, {"mean": 0, "mode": 1, "max": 2, "min": 3}[method], threaded, _p(out))
+        assert rc == 0 and not br.errors, (rc, br.errors)
+        want = seg.average(frames, method)
+        assert np.array_equal(out, want), (method, n, int((out != want).sum()))
