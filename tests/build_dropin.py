@@ -15,7 +15,7 @@ OUT_DIR = os.path.join(HERE, "cpp", "_dropin")
 OUT = os.path.join(OUT_DIR, "libshim_dropin.so")
 OUT_B = os.path.join(OUT_DIR, "libshim_dropin_b.so")
 REF_FILES = [os.path.join(REF_COMMON, "processing", f) for f in ("RawProcessing.cpp", "Background.cpp", "CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "BlobIdentity.cpp")] + \
-            [os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp")]
+            [os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp"), os.path.join(REF_COMMON, "video", "AveragingAccumulator.cpp")]
 
 
 def snippet() -> str:
@@ -40,7 +40,7 @@ def build(force: bool = False):
             deps += [os.path.join(root, f) for f in files]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
-    cmd = ["g++", "-std=c++23", "-O2", "-fPIC", "-shared", "-DREF_DETECT",
+    cmd = ["g++", "-std=c++23", "-O2", "-fPIC", "-shared", "-Wl,--no-undefined", "-DREF_DETECT",
            "-I", os.path.join(ROOT, "oracle", "ref_stubs_detect"), "-I", os.path.join(ROOT, "oracle", "ref_stubs"), "-I", REF_COMMON, "-I", os.path.join(REF_SRC, "tracker"),
            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "cpp"), *srcs, *REF_FILES,
            "-L", os.path.join(ROOT, "trex_b200"), "-ltrexb200", "-Wl,-rpath,$ORIGIN/../../../trex_b200", "-o", OUT]

@@ -72,3 +72,16 @@ def test_stub_signatures_are_the_references():
         if not os.path.exists(path) or not re.search(rx, open(path, errors="replace").read()):
             missing.append((rel, rx))
     assert not missing, missing
+
+
+def test_dropin_shim_library_builds_and_loads():
+    """The drop-in shim of INTEGRATION.md s1 compiled against the reference's own BackgroundSubtraction.h (tests/build_dropin.py) links completely and loads
+    (both copies); what it does on a GPU is tests/test_gpu_dropin_shim.py.  Skipped where neither the reference checkout nor a prebuilt library exists."""
+    import ctypes
+    import build_dropin
+    path = build_dropin.build()
+    if path is None:
+        pytest.skip("no reference checkout and no prebuilt drop-in shim")
+    for p in (path, build_dropin.OUT_B):
+        lib = ctypes.CDLL(p)
+        assert hasattr(lib, "ref_background_subtraction_apply") and hasattr(lib, "ref_cv_set_bridge")
