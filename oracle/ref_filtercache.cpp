@@ -19,6 +19,7 @@ using namespace cmn;
 extern "C" {
 
 void ref_filtercache_set_warp(cv::warp_fn_t f) { cv::warp_hook() = f; }
+void ref_filtercache_set_resize(cv::resize_fn_t f) { cv::resize_hook() = f; }
 void ref_filtercache_settings(float individual_image_scale) { outline::Settings::values().individual_image_scale = individual_image_scale; }
 
 // mode: 0 none, 1 moments, 2 posture, 3 legacy (default_config::individual_image_normalization_t).  The midline of modes 2 / 3 carries what a normalised

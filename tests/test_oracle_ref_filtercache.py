@@ -5,9 +5,10 @@ gui::Transform and Midline::transform:
   moments  rotate(-orientation + 45 deg) . translate(-size / 2) into normalize_image                                      <-> seg.crop_blob_moments
   posture / legacy   Midline::transform into normalize_image                                                              <-> posture.crop_blob_posture
 byte for byte, for blobs smaller and larger than the output in either direction (odd and even differences), difference and grey renderings, and
-the position the reference reports with the image.  cv::warpAffine / cv::resize are OpenCV's: the compiled reference calls the oracle's restatement of
-warpAffine (itself pinned on cv2 4.13, tests/test_oracle_moments.py), so what is pinned here is everything AROUND those two calls -- the geometry the
-round-1 review listed as unpinned.  constraints::local_midline_length (the median the posture crops are scaled by; caller side of the C ABI) is run on a
+the position the reference reports with the image.  cv::warpAffine / cv::resize are OpenCV's: every test runs twice -- once with the REAL cv2.warpAffine /
+cv2.resize called back from inside the compiled reference, once with the oracle's restatement of warpAffine (itself pinned on cv2 4.13,
+tests/test_oracle_moments.py) and the stand-in's nearest resize -- so both the geometry around those calls (what the round-1 review listed as unpinned) and
+the calls themselves are the reference's / OpenCV's own.  constraints::local_midline_length (the median the posture crops are scaled by; caller side of the C ABI) is run on a
 frame list and compared with its plain description (lower median, population standard deviation of the distinct values).
 Runs wherever oracle/_ref/libref_posture.so exists or can be built; skipped otherwise."""
 import ctypes as C
@@ -22,16 +23,60 @@ MODE_NONE, MODE_MOMENTS, MODE_POSTURE, MODE_LEGACY = 0, 1, 2, 3
 METHODS = {seg.DIFF_ABSOLUTE: (1, 1), seg.DIFF_SIGN: (0, 1)}      # (track_threshold_is_absolute, track_background_subtraction)
 
 
-@pytest.fixture(scope="module")
-def ref():
+WARP = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int)
+RESIZE = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int)
+_cv_errors = []
+
+
+def _u8(ptr, n):
+    return np.frombuffer((C.c_ubyte * n).from_address(ptr), np.uint8)
+
+
+@WARP
+def _cv2_warp(src, sw, sh, M, dst, dw, dh):
+    """cv::warpAffine(src, dst, M, dsize, INTER_LINEAR, BORDER_CONSTANT) by the REAL OpenCV."""
+    try:
+        import cv2
+        a = _u8(src, sw * sh).reshape(sh, sw)
+        m = np.array([M[i] for i in range(6)], np.float64).reshape(2, 3)
+        r = cv2.warpAffine(a, m, (dw, dh), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+        _u8(dst, dw * dh)[:] = r.reshape(-1)
+    except Exception as e:  # noqa: BLE001
+        _cv_errors.append(repr(e))
+
+
+@RESIZE
+def _cv2_resize(src, sw, sh, ch, fx, fy, dst, dw, dh):
+    """cv::resize(src, dst, Size(), fx, fy, INTER_NEAREST) by the REAL OpenCV."""
+    try:
+        import cv2
+        a = _u8(src, sw * sh * ch).reshape((sh, sw) if ch == 1 else (sh, sw, ch))
+        r = cv2.resize(a, None, fx=fx, fy=fy, interpolation=cv2.INTER_NEAREST)
+        if r.shape[:2] != (dh, dw):
+            raise ValueError(f"resize: {r.shape} != {(dh, dw)}")
+        _u8(dst, dw * dh * ch)[:] = r.reshape(-1)
+    except Exception as e:  # noqa: BLE001
+        _cv_errors.append(repr(e))
+
+
+@pytest.fixture(scope="module", params=["oracle_warp", "cv2"])
+def ref(request):
+    """OpenCV's two functions inside the compiled FilterCache.cpp are served either by the oracle's restatement of warpAffine + the stand-in's nearest resize, or --
+    where cv2 is importable -- by the real cv2.warpAffine / cv2.resize through callbacks."""
     path = build_ref.build()
     if path is None:
         pytest.skip("no reference checkout and no prebuilt oracle/_ref/libref_posture.so")
     lib = C.CDLL(path)
-    warp = C.cast(seg.lib().to_warp_affine_u8, C.c_void_p)
-    lib.ref_filtercache_set_warp(warp)
+    if request.param == "cv2":
+        pytest.importorskip("cv2")
+        lib.ref_filtercache_set_warp(_cv2_warp)
+        lib.ref_filtercache_set_resize(_cv2_resize)
+    else:
+        lib.ref_filtercache_set_warp(C.cast(seg.lib().to_warp_affine_u8, C.c_void_p))
+        lib.ref_filtercache_set_resize(None)
     lib._keep = seg.lib()
-    return lib
+    yield lib
+    assert not _cv_errors, _cv_errors
 
 
 def frame_of_blobs(seed, H=260, W=340, colour=False):
