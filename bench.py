@@ -309,10 +309,13 @@ def run_reference(args, cfg):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (seg) + f32 (CNN)", "data": "synthetic",
         "config": config_block(cfg),
-        "run": {"frames_per_step": sample, "note": "TRex cannot be built here (needs OpenCV C++/glaze): this arm times the oracle port of its "
-                "CPU algorithm (oracle/trex_oracle.c + torch CPU V118_3) on a bounded sample of the same workload"},
+        "run": {"frames_per_step": sample, "note": "TRex as a whole cannot be built here (needs OpenCV C++ / glaze): this arm times the oracle port of its CPU algorithm (oracle/trex_oracle.c + "
+                "torch CPU V118_3; the CNN is nine tenths of the time) on a bounded sample of the same workload; cpu_baseline.compiled_reference times the segmentation stage "
+                "through the reference's own BackgroundSubtraction.cpp / RawProcessing.cpp / CPULabeling, compiled unmodified, with the real OpenCV"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "cpu": cpu_model(),
-                         "sample": f"{sample} frames x {args.steps} steps, seg over {threads} pthreads + torch CPU CNN ({threads} threads)"},
+                         "sample": f"{sample} frames x {args.steps} steps, seg over {threads} pthreads + torch CPU CNN ({threads} threads)",
+                         # the segmentation stage through the reference's OWN compiled BackgroundSubtraction::apply (oracle/_ref/libref_detect.so), for comparison with the port's
+                         "compiled_reference": compiled_reference_check(cfg, bg, frames[:4])},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
