@@ -85,3 +85,22 @@ def test_dropin_shim_library_builds_and_loads():
     for p in (path, build_dropin.OUT_B):
         lib = ctypes.CDLL(p)
         assert hasattr(lib, "ref_background_subtraction_apply") and hasattr(lib, "ref_cv_set_bridge")
+
+
+@pytest.mark.parametrize("i,prelude", [
+    (3, '#include <python/BackgroundSubtraction.h>\n#include <python/BackendRegistry.h>\nstruct SoftException : std::runtime_error { using std::runtime_error::runtime_error; };\n'),
+])
+def test_snippet_type_checks_against_the_references_real_headers(i, prelude, tmp_path):
+    """Beyond the pinned mirror: the plug-in snippet compiled (-fsyntax-only) against the reference's REAL tracker/python/BackendRegistry.h and
+    BackgroundSubtraction.h from the checkout (TRex's other types from the stand-ins of oracle/ref_stubs*/).  This is the check that showed that a hook cannot
+    name BackgroundSubtraction::apply(std::vector<TileImage>&&) -- it is private.  (The detection shim, snippet 0, is compiled, linked and run the same way by
+    tests/build_dropin.py / tests/test_gpu_dropin_shim.py.)  Skipped without the reference checkout."""
+    gxx = shutil.which("g++")
+    if gxx is None or not os.path.exists(os.path.join(REF, "tracker/python/BackendRegistry.h")):
+        pytest.skip("no g++ or no reference checkout")
+    src = tmp_path / f"real_{i}.cpp"
+    src.write_text(prelude + _snippets()[i])
+    cmd = [gxx, "-std=c++23", "-fsyntax-only", "-DREF_DETECT", "-I", os.path.join(ROOT, "oracle", "ref_stubs_detect"), "-I", os.path.join(ROOT, "oracle", "ref_stubs"),
+           "-I", os.path.join(REF, "commons", "common"), "-I", os.path.join(REF, "tracker"), "-I", os.path.join(ROOT, "include"), str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
