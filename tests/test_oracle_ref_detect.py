@@ -247,3 +247,25 @@ def test_averaging_accumulator(ref, method, threaded):
         assert rc == 0 and not br.errors, (rc, br.errors)
         want = seg.average(frames, method)
         assert np.array_equal(out, want), (method, n, int((out != want).sum()))
+
+
+def test_generate_binary_random_setting_combinations(ref):
+    """300 seeded random combinations of every setting generate_binary reads (thresholds from -200 to 255, threshold_maximum down to 0, difference on / off,
+    signed / absolute, invert, closing 1 ... 6, dilation -4 ... 5, adaptive threshold with seven scales) on frames of random size: the compiled reference
+    with the real OpenCV and the oracle agree on every pixel."""
+    lib, br = ref
+    rng = np.random.default_rng(99)
+    for it in range(300):
+        kw = dict(detect_threshold=int(rng.choice([-200, -60, -15, -1, 0, 1, 5, 15, 40, 120, 254, 255])),
+                  threshold_maximum=int(rng.choice([255, 255, 255, 200, 90, 30, 0])),
+                  enable_difference=int(rng.random() < 0.8), detect_threshold_is_absolute=int(rng.random() < 0.6),
+                  image_invert=int(rng.random() < 0.3), use_closing=int(rng.random() < 0.4), closing_size=int(rng.integers(1, 7)),
+                  dilation_size=int(rng.choice([0, 0, 0, 1, 2, 3, 5, -1, -2, -4])), use_adaptive_threshold=int(rng.random() < 0.25),
+                  adaptive_threshold_scale=float(rng.choice([0.001, 0.02, 0.05, 0.1, 0.3, 1.0, 2.0])))
+        configure(lib, **kw)
+        fr, bg = scene(int(rng.integers(0, 1000)), H=int(rng.integers(72, 110)), W=int(rng.integers(102, 150)))
+        got = ref_binary(lib, fr, bg)
+        assert not br.errors, br.errors
+        want = seg.generate_binary(fr, bg, params(**kw))
+        assert np.array_equal(got, want), (it, kw, int((got != want).sum()))
+    configure(lib)
