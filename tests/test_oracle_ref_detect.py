@@ -269,3 +269,48 @@ def test_generate_binary_random_setting_combinations(ref):
         want = seg.generate_binary(fr, bg, params(**kw))
         assert np.array_equal(got, want), (it, kw, int((got != want).sum()))
     configure(lib)
+
+
+def test_apply_random_configurations(ref):
+    """120 seeded random configurations of BackgroundSubtraction::apply: encoding (gray / rgb8 / r3g3b2), BGR or BGRA frames, color_channel (none, 0 ... 3, out of range),
+    thresholds of both signs, threshold_maximum, signed / absolute, invert, closing, dilation / erosion, cm_per_pixel, zero to two size ranges.  The frame receives the
+    oracle's blob list in the reference's order -- except where EVERY surviving run lies in image row 0: there the reference's labeling returns nothing
+    (Source::RowRef::from_index(0), DESIGN.md s6 deviation (2)), which this sweep meets twice."""
+    lib, br = ref
+    rng = np.random.default_rng(5)
+    n_row0 = 0
+    for it in range(120):
+        enc = [seg.ENC_GRAY, seg.ENC_RGB8, seg.ENC_R3G3B2][int(rng.integers(0, 3))]
+        ch = 4 if enc == seg.ENC_RGB8 else int(rng.choice([3, 4]))
+        cc = -1 if enc != seg.ENC_GRAY else int(rng.choice([-1, -1, 0, 1, 2, 3 if ch == 4 else 2, 9]))
+        kw = dict(detect_threshold=int(rng.choice([-40, -15, 5, 15, 40])), threshold_maximum=int(rng.choice([255, 255, 120])),
+                  detect_threshold_is_absolute=int(rng.random() < 0.6), image_invert=int(rng.random() < 0.2), use_closing=int(rng.random() < 0.3), closing_size=int(rng.integers(1, 4)),
+                  dilation_size=int(rng.choice([0, 0, 1, 2, -2])))
+        cm = float(rng.choice([1.0, 0.5, 0.13]))
+        nf = int(rng.integers(0, 3))
+        filt = sorted([(float(a), float(a + b)) for a, b in zip(rng.uniform(0, 50, nf), rng.uniform(1, 400, nf))])
+        configure(lib, cm_per_pixel=cm, **kw)
+        lib.ref_detect_meta_encoding(ENCODINGS[enc]); lib.ref_detect_color_channel(cc); set_filter(lib, filt)
+        P = params(cm_per_pixel=cm, **kw)
+        P.detect_size_filter = list(filt)
+        fr3, bg3 = scene(int(rng.integers(0, 1000)), colour=True)
+        fr = fr3 if ch == 3 else np.concatenate([fr3, np.full(fr3.shape[:2] + (1,), 255, np.uint8)], axis=2)
+        if enc == seg.ENC_RGB8:
+            bg = bg3
+        elif enc == seg.ENC_R3G3B2:
+            bg = seg.convert_to_r3g3b2(bg3)
+        elif 0 <= cc < 4:
+            bg = np.ascontiguousarray(bg3[:, :, min(cc, 2)])
+        else:
+            bg = seg.bgr2gray(bg3)
+        got, _ = ref_apply(lib, fr, bg)
+        assert not br.errors, br.errors
+        B = seg.segment_frame_color(fr, bg, P, enc, cc, order=seg.ORDER_REF_LAZY)
+        unfiltered = seg.segment_frame_color(fr, bg, params(cm_per_pixel=cm, **kw), enc, cc)
+        if len(unfiltered) and all(int(unfiltered.blob(k)[0]["y"].max()) == 0 for k in range(len(unfiltered))):
+            assert got == [], (it, len(got))
+            n_row0 += 1
+            continue
+        assert same([(g[0], g[1]) for g in got], oracle_blobs(B)), (it, enc, ch, cc, kw, cm, filt, len(got), len(B))
+    configure(lib); lib.ref_detect_meta_encoding(0); lib.ref_detect_color_channel(-1); set_filter(lib, [])
+    assert n_row0 <= 4
