@@ -7,11 +7,12 @@
 // definitions operation for operation and cite them:
 //   Vec2 / Size2      commons/common/misc/vec2.h:20-215   (Vector2D<float>: component-wise float operators; length() = std::sqrt(x*x + y*y);
 //                     normalize() = (L != 0) * (v / ((L == 0) + L)); member atan2() = std::atan2(y, x) in float; free atan2(v) = ::atan2 in DOUBLE, :371)
-//   sqdistance, euclidean_distance   vec2.h:380-388
 //   SQR, DEGREE, RADIANS, GETTER*    commons.pc.h:444-457
 //   cmn::min / cmn::max              commons.pc.h:462-528 (mixed arithmetic types: computed in the wider of the two, the second on a tie)
-//   cmn::sqrt / sin / cos / atan2    misc/math.h:4-32,162-170 (float arguments call the f-suffixed C functions), cmn::abs :172-197, cmn::isnan :61-88
-//   narrow_cast, infinity            commons.pc.h (value-preserving static_cast / numeric_limits)
+//   narrow_cast                      commons.pc.h (value-preserving static_cast)
+// The scalar maths is NOT restated: commons/common/misc/math.h is the reference's own file, included from the checkout (cmn::sqrt / sin / cos / atan2, fast_atan2,
+// abs, isnan, sqdistance, euclidean_distance, t_circle_line, crosses_zero, infinity<T>) -- like misc/IllegalVector.h, misc/EnumClass.h, misc/matharray.h,
+// misc/bid.h, misc/Median.h, processing/encoding.h and every header the compiled .cpp files bring themselves (Outline.h, CircularGraph.h, PixelTree.h, Background.h ...).
 // Printing, timing, exceptions, drawing and OpenCV types are inert.  Nothing under trex_b200/ includes this.
 #pragma once
 #include <algorithm>
@@ -64,19 +65,26 @@ typedef float ScalarType;
 constexpr Float2_t operator""_F(long double v) { return Float2_t(v); }
 constexpr Float2_t operator""_F(unsigned long long v) { return Float2_t(v); }
 
-template<typename T> constexpr T infinity() { if constexpr (std::is_floating_point_v<T>) return std::numeric_limits<T>::infinity(); else return std::numeric_limits<T>::max(); }
 template<typename To, typename From> constexpr To narrow_cast(From&& v) { return static_cast<To>(v); }
 template<typename To, typename From> constexpr To sign_cast(From&& v) { return static_cast<To>(v); }
 
-template<typename T = double> inline T cos(const T& s) { return ::cos(s); }
-template<> inline float cos(const float& s) { return ::cosf(s); }
-template<typename T = double> inline T sin(const T& s) { return ::sin(s); }
-template<> inline float sin(const float& s) { return ::sinf(s); }
-template<typename T = double> inline T sqrt(const T& s) { return ::sqrt(s); }
-template<> inline float sqrt(const float& s) { return ::sqrtf(s); }
-template<typename T = double> inline T atan2(const T& y, const T& x) { return ::atan2(y, x); }
-template<> inline float atan2(const float& y, const float& x) { return ::atan2f(y, x); }
-
+}
+// the REFERENCE'S OWN commons/common/misc/math.h from the checkout: cmn::cos / sin / sqrt / atan2 (float arguments call the f-suffixed C functions), fast_atan /
+// fast_atan2, abs, isnan / isinf, sqdistance / euclidean_distance, t_circle_line, crosses_zero, infinity<T>, next_pow2 ...  It needs only these OpenCV look-alikes
+// (three of its templates mention them; none is instantiated by the compiled files)
+namespace cv {
+struct Point2f { float x = 0, y = 0; Point2f() = default; Point2f(float x, float y) : x(x), y(y) {} float dot(const Point2f& o) const { return x * o.x + y * o.y; } };
+template<typename T, int m, int n> struct Matx { T v[m * n] = {}; T operator()(int i) const { return v[i]; } };
+template<typename T> struct Mat_ {
+    int rows = 0, cols = 0; std::vector<T> v;
+    Mat_() = default;
+    Mat_(int r, int c) : rows(r), cols(c), v((size_t)r * c) {}
+    T& operator()(int r, int c) { return v[(size_t)r * cols + c]; }
+    Mat_ operator*(const Mat_& o) const { Mat_ out(rows, o.cols); for (int i = 0; i < rows; ++i) for (int j = 0; j < o.cols; ++j) { T a{}; for (int k = 0; k < cols; ++k) a += v[(size_t)i * cols + k] * o.v[(size_t)k * o.cols + j]; out(i, j) = a; } return out; }
+};
+}
+namespace cmn {
+// cmn::min / cmn::max (commons.pc.h:462-528) -- math.h calls them
 template<typename A, typename B> requires (std::is_arithmetic_v<std::remove_cvref_t<A>> && std::is_arithmetic_v<std::remove_cvref_t<B>>)
 constexpr auto min(A&& a, B&& b) { using A_ = std::remove_cvref_t<A>; using B_ = std::remove_cvref_t<B>; using R = std::conditional_t<(sizeof(A_) > sizeof(B_)), A_, B_>; return std::min(R(a), R(b)); }
 template<typename A, typename B> requires (std::is_arithmetic_v<std::remove_cvref_t<A>> && std::is_arithmetic_v<std::remove_cvref_t<B>>)
@@ -86,23 +94,13 @@ constexpr auto min(const A& x, const B& y, const Cc& z) -> decltype(x + y + z) {
 template<typename A, typename B, typename Cc> requires (std::is_arithmetic_v<A> && std::is_arithmetic_v<B> && std::is_arithmetic_v<Cc>)
 constexpr auto max(const A& x, const B& y, const Cc& z) -> decltype(x + y + z) { using R = decltype(x + y + z); return std::max(R(x), std::max(R(y), R(z))); }
 
-// misc/math.h:34-59: the 3rd-order fit pv::Blob::calculate_moments takes the orientation from -- restated operation for operation (M_PI_2 / M_PI are doubles there:
-// `M_PI_2 - fast_atan(r)` and `M_PI - angle` are computed in double and rounded to float on assignment)
-inline float fast_atan(float z) { const float n1 = 0.97239411f; const float n2 = -0.19194795f; return (n1 + n2 * z * z) * z; }
-inline float fast_atan2(float y, float x)
-{
-    if (x == 0.0f) return copysignf(M_PI_2, y);
-    float abs_y = fabsf(y), r, angle;
-    if (abs_y < fabsf(x)) { r = abs_y / fabsf(x); angle = fast_atan(r); }
-    else { r = fabsf(x) / abs_y; angle = M_PI_2 - fast_atan(r); }
-    if (x < 0.0f) angle = M_PI - angle;
-    if (y < 0.0f) angle = -angle;
-    return angle;
+namespace check_abs_detail {            // misc/useful_concepts.h:186-196
+template<typename T> concept has_coordinates = requires(T t) { { t.x } -> std::convertible_to<float>; };
+template<typename T> concept has_get = requires(T t) { { t.get() } -> std::convertible_to<float>; };
 }
-template<typename T> requires (std::is_arithmetic_v<T> && !std::unsigned_integral<T>) constexpr auto abs(T x) { return std::abs(x); }
-template<typename T> requires std::unsigned_integral<T> constexpr auto abs(T x) { return x; }
-template<typename T> requires std::is_arithmetic_v<T> constexpr bool isnan(T x) { if constexpr (std::is_floating_point_v<T>) return std::isnan(x); else return false; }
-
+}
+#include <misc/math.h>
+namespace cmn {
 }
 namespace cv { struct Mat; struct Size { int width = 0, height = 0; Size() = default; template<typename A, typename B> Size(A w, B h) : width(int(w)), height(int(h)) {} }; }
 namespace cmn {
@@ -158,28 +156,9 @@ struct Vector2D {
 };
 using Vec2 = Vector2D<true>;
 using Size2 = Vector2D<false>;
-inline Float2_t sqdistance(const Vec2& p0, const Vec2& p1) { return SQR(p1.A() - p0.A()) + SQR(p1.B() - p0.B()); }
-inline Float2_t euclidean_distance(const Vec2& p0, const Vec2& p1) { return cmn::sqrt(sqdistance(p0, p1)); }
-inline Float2_t length(const Vec2& v) { return v.length(); }
+inline Float2_t length(const Vec2& v) { return cmn::sqrt(v.x * v.x + v.y * v.y); }      // = math.h:219-222 (this stand-in's width / height aliases would make math.h's member-detecting overloads ambiguous)
 inline auto atan2(const Vec2& v) { return ::atan2(v.y, v.x); }           // double: vec2.h:370-373
 inline Vec2 abs(const Vec2& v) { return Vec2(cmn::abs(v.x), cmn::abs(v.y)); }
-template<typename T> inline float crosses_zero(T y0, T y1) { return y1 / (y1 - y0); }      // misc/math.h:354-357 (curve_discussion.cpp; not on the path under test)
-// parameters t0 >= t1 of the intersections of the circle (centre p, radius r) with the line v -> w, (-1, -1) without one: misc/math.h:285-311, all in float,
-// the quadratic's coefficients and the two roots formed in the reference's order
-template<typename P0, typename P1, typename P2>
-inline std::pair<float, float> t_circle_line(const P0& v, const P1& w, const P2& p, float r)
-{
-    const float dx = w.x - v.x, dy = w.y - v.y;
-    const float a = SQR(dx) + SQR(dy);
-    const float b = 2 * dx * (v.x - p.x) + 2 * dy * (v.y - p.y);
-    const float c = SQR(v.x - p.x) + SQR(v.y - p.y) - SQR(r);
-    float disc = SQR(b) - 4 * a * c;
-    if (disc < 0) return {-1, -1};
-    disc = cmn::sqrt(disc);
-    return {(-b + disc) / (2 * a), (-b - disc) / (2 * a)};
-}
-inline bool isnan(const Vec2& v) { return std::isnan(v.x) || std::isnan(v.y); }
-
 struct Bounds {
     Float2_t x, y, width, height;
     constexpr Bounds(Float2_t x = 0, Float2_t y = 0, Float2_t w = 0, Float2_t h = 0) : x(x), y(y), width(w), height(h) {}
