@@ -29,7 +29,7 @@ OUT = os.path.join(HERE, "_ref", "libref_posture.so")
 OVERLAY = os.path.join(HERE, "_ref", "overlay", "tracking")
 REF_FILES = [os.path.join(REF_SRC, "tracker", "tracking", "Outline.cpp"), os.path.join(REF_SRC, "tracker", "tracking", "Posture.cpp"),
              os.path.join(REF_SRC, "tracker", "tracking", "FilterCache.cpp"),
-             os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"),
+             os.path.join(REF_COMMON, "misc", "CircularGraph.cpp"), os.path.join(REF_COMMON, "misc", "vec2.cpp"),
              os.path.join(REF_COMMON, "misc", "curve_discussion.cpp"), os.path.join(REF_COMMON, "gui", "Transform.cpp"),
              os.path.join(REF_COMMON, "processing", "PixelTree.cpp")] + \
             [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp", "BlobIdentity.cpp")]
@@ -78,7 +78,7 @@ def build(force: bool = False):
 # ---- the detection build: BackgroundSubtraction::apply / RawProcessing::generate_binary with every cv:: call forwarded to the real OpenCV (Python's cv2) ----
 OUT_DETECT = os.path.join(HERE, "_ref", "libref_detect.so")
 REF_FILES_DETECT = [os.path.join(REF_SRC, "tracker", "python", "BackgroundSubtraction.cpp"), os.path.join(REF_COMMON, "processing", "RawProcessing.cpp"),
-                    os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp"), os.path.join(REF_COMMON, "video", "AveragingAccumulator.cpp")] + \
+                    os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp"), os.path.join(REF_COMMON, "video", "AveragingAccumulator.cpp"), os.path.join(REF_COMMON, "misc", "vec2.cpp")] + \
                    [os.path.join(REF_COMMON, "processing", f) for f in ("CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "Background.cpp", "BlobIdentity.cpp")]
 
 
@@ -109,7 +109,7 @@ def build_detect(force: bool = False):
 # ---- the reference's own pv::Blob (PVBlob.{h,cpp}) ----
 OUT_PVBLOB = os.path.join(HERE, "_ref", "libref_pvblob.so")
 REF_FILES_PVBLOB = [os.path.join(REF_COMMON, "processing", f) for f in ("PVBlob.cpp", "BlobIdentity.cpp", "Background.cpp", "PixelTree.cpp", "CPULabeling.cpp", "Brototype.cpp",
-                                                                         "Source.cpp", "DLList.cpp", "ListCache.cpp")]
+                                                                         "Source.cpp", "DLList.cpp", "ListCache.cpp")] + [os.path.join(REF_COMMON, "misc", "vec2.cpp")]
 
 
 def build_pvblob(force: bool = False):

@@ -3,16 +3,16 @@
 //   commons/common/misc/CircularGraph.cpp   eft, ieft, curvature, differentiate, find_peaks and its fast::cos polynomial
 //   commons/common/misc/curve_discussion.cpp, commons/common/gui/Transform.cpp
 //   tracker/tracking/Outline.cpp            Outline::resample / smooth / offset_to_middle / calculate_midline, Midline::post_process / normalize / fix_length
-// Only the declarations those files touch are provided, written for this purpose; the ones that carry arithmetic follow the reference's
-// definitions operation for operation and cite them:
-//   Vec2 / Size2      commons/common/misc/vec2.h:20-215   (Vector2D<float>: component-wise float operators; length() = std::sqrt(x*x + y*y);
-//                     normalize() = (L != 0) * (v / ((L == 0) + L)); member atan2() = std::atan2(y, x) in float; free atan2(v) = ::atan2 in DOUBLE, :371)
+// Only the declarations those files touch are provided, written for this purpose.  The arithmetic is NOT restated: the vector types and the scalar maths are
+// the reference's own headers, included from the checkout --
+//   commons/common/misc/vec2.h (+ vec2.cpp)   Vec2 / Size2 / Bounds with every operator, length / normalize / atan2, sqdistance, euclidean_distance
+//   commons/common/misc/math.h                cmn::sqrt / sin / cos / atan2 (float arguments call the f-suffixed C functions), fast_atan2, abs, isnan,
+//                                             t_circle_line, crosses_zero, infinity<T>
+// -- like misc/IllegalVector.h, misc/EnumClass.h, misc/matharray.h, misc/bid.h, misc/Median.h, processing/encoding.h and every header the compiled .cpp
+// files bring themselves (Outline.h, CircularGraph.h, PixelTree.h, Background.h, PVBlob.h ...).  Restated here, citing their lines:
 //   SQR, DEGREE, RADIANS, GETTER*    commons.pc.h:444-457
 //   cmn::min / cmn::max              commons.pc.h:462-528 (mixed arithmetic types: computed in the wider of the two, the second on a tie)
-//   narrow_cast                      commons.pc.h (value-preserving static_cast)
-// The scalar maths is NOT restated: commons/common/misc/math.h is the reference's own file, included from the checkout (cmn::sqrt / sin / cos / atan2, fast_atan2,
-// abs, isnan, sqdistance, euclidean_distance, t_circle_line, crosses_zero, infinity<T>) -- like misc/IllegalVector.h, misc/EnumClass.h, misc/matharray.h,
-// misc/bid.h, misc/Median.h, processing/encoding.h and every header the compiled .cpp files bring themselves (Outline.h, CircularGraph.h, PixelTree.h, Background.h ...).
+//   narrow_cast                      commons.pc.h (value-preserving static_cast);  saturate  misc/detail.h:225-229;  Range / arange  misc/ranges.h (misc/ranges.h of this directory)
 // Printing, timing, exceptions, drawing and OpenCV types are inert.  Nothing under trex_b200/ includes this.
 #pragma once
 #include <algorithm>
@@ -62,8 +62,6 @@ using long_t = int32_t;
 namespace cmn {
 using Float2_t = float;
 typedef float ScalarType;
-constexpr Float2_t operator""_F(long double v) { return Float2_t(v); }
-constexpr Float2_t operator""_F(unsigned long long v) { return Float2_t(v); }
 
 template<typename To, typename From> constexpr To narrow_cast(From&& v) { return static_cast<To>(v); }
 template<typename To, typename From> constexpr To sign_cast(From&& v) { return static_cast<To>(v); }
@@ -102,117 +100,19 @@ template<typename T> concept has_get = requires(T t) { { t.get() } -> std::conve
 #include <misc/math.h>
 namespace cmn {
 }
-namespace cv { struct Mat; struct Size { int width = 0, height = 0; Size() = default; template<typename A, typename B> Size(A w, B h) : width(int(w)), height(int(h)) {} }; }
-namespace cmn {
-template<bool IsVec>
-struct Vector2D {
-    union { Float2_t x; Float2_t width; };      // vec2.h: Size2 names its two members width / height (FilterCache.cpp reads them)
-    union { Float2_t y; Float2_t height; };
-    Vector2D(const cv::Size& s) noexcept : x(Float2_t(s.width)), y(Float2_t(s.height)) {}                 // vec2.h:30-33
-    operator cv::Size() const { return cv::Size(x, y); }
-    explicit Vector2D(const cv::Mat& m) noexcept;                                                         // (cols, rows): vec2.h Size2(const cv::Mat&)
-
-    constexpr Vector2D() noexcept : x(0), y(0) {}
-    constexpr Vector2D(const Vector2D& o) noexcept : x(o.x), y(o.y) {}
-    constexpr Vector2D& operator=(const Vector2D& o) noexcept { x = o.x; y = o.y; return *this; }
-    template<typename S> requires std::is_arithmetic_v<S>
-    constexpr Vector2D(S v) noexcept : x(Float2_t(v)), y(Float2_t(v)) {}
-    template<typename S0, typename S1> requires (std::is_arithmetic_v<S0> && std::is_arithmetic_v<S1>)
-    constexpr Vector2D(S0 a, S1 b) noexcept : x(Float2_t(a)), y(Float2_t(b)) {}
-    template<bool K> constexpr Vector2D(const Vector2D<K>& o) noexcept : x(o.x), y(o.y) {}
-    constexpr Float2_t A() const { return x; }
-    constexpr Float2_t B() const { return y; }
-    constexpr Vector2D& operator+=(const Vector2D& o) { x += o.x; y += o.y; return *this; }
-    constexpr Vector2D& operator-=(const Vector2D& o) { x -= o.x; y -= o.y; return *this; }
-    constexpr Vector2D& operator+=(Float2_t o) { x += o; y += o; return *this; }
-    constexpr Vector2D& operator-=(Float2_t o) { x -= o; y -= o; return *this; }
-    constexpr Vector2D& operator*=(Float2_t o) { x *= o; y *= o; return *this; }
-    constexpr Vector2D& operator/=(Float2_t o) { x /= o; y /= o; return *this; }
-    template<typename S> requires std::is_arithmetic_v<S> constexpr Vector2D operator/(S o) const { return Vector2D{x / Float2_t(o), y / Float2_t(o)}; }
-    template<typename S> requires std::is_arithmetic_v<S> constexpr Vector2D operator*(S o) const { return Vector2D{x * Float2_t(o), y * Float2_t(o)}; }
-    template<typename S> requires std::is_arithmetic_v<S> constexpr Vector2D operator-(S o) const { return Vector2D{x - Float2_t(o), y - Float2_t(o)}; }
-    template<typename S> requires std::is_arithmetic_v<S> constexpr Vector2D operator+(S o) const { return Vector2D{x + Float2_t(o), y + Float2_t(o)}; }
-    constexpr Vector2D operator+(Vector2D o) const { return Vector2D{x + o.x, y + o.y}; }
-    constexpr Vector2D operator-(Vector2D o) const { return Vector2D{x - o.x, y - o.y}; }
-    constexpr Vector2D operator-() const { return Vector2D{-x, -y}; }
-    constexpr Vector2D mul(const Vector2D& o) const { return Vector2D{x * o.x, y * o.y}; }
-    constexpr Vector2D div(const Vector2D& o) const { return Vector2D{x / o.x, y / o.y}; }
-    constexpr Vector2D perp() const { return Vector2D{y, -x}; }
-    constexpr Vector2D T() const { return Vector2D{y, x}; }
-    constexpr Float2_t dot(const Vector2D& o) const { return x * o.x + y * o.y; }
-    constexpr Float2_t sqlength() const { return x * x + y * y; }
-    Float2_t length() const { return std::sqrt(sqlength()); }
-    Vector2D normalize() const { auto L = length(); return Float2_t(L != 0) * (*this / (Float2_t(L == 0) + L)); }
-    Float2_t atan2() const { return std::atan2(y, x); }
-    Vector2D abs() const { return Vector2D{std::abs(x), std::abs(y)}; }
-    constexpr Float2_t max() const { return std::max(x, y); }
-    constexpr Float2_t min() const { return std::min(x, y); }
-    constexpr Float2_t mean() const { return (x + y) * 0.5f; }
-    constexpr bool empty() const { return x == 0 && y == 0; }
-    constexpr bool operator==(const Vector2D& o) const { return x == o.x && y == o.y; }
-    constexpr bool operator!=(const Vector2D& o) const { return x != o.x || y != o.y; }
-    constexpr bool operator<(const Vector2D& o) const { return o.y < y || (o.y == y && o.x < x); }      // vec2.h:99-102
-    friend constexpr Vector2D operator*(Float2_t s, const Vector2D& v) { return Vector2D{v.x * s, v.y * s}; }
-};
-using Vec2 = Vector2D<true>;
-using Size2 = Vector2D<false>;
-inline Float2_t length(const Vec2& v) { return cmn::sqrt(v.x * v.x + v.y * v.y); }      // = math.h:219-222 (this stand-in's width / height aliases would make math.h's member-detecting overloads ambiguous)
-inline auto atan2(const Vec2& v) { return ::atan2(v.y, v.x); }           // double: vec2.h:370-373
-inline Vec2 abs(const Vec2& v) { return Vec2(cmn::abs(v.x), cmn::abs(v.y)); }
-struct Bounds {
-    Float2_t x, y, width, height;
-    constexpr Bounds(Float2_t x = 0, Float2_t y = 0, Float2_t w = 0, Float2_t h = 0) : x(x), y(y), width(w), height(h) {}
-    Bounds(const Vec2& p, const Size2& s) : x(p.x), y(p.y), width(s.x), height(s.y) {}
-    // only used by Posture.cpp's pose-based outline (never run here): the union of two boxes and shifts by a vector
-    void combine(const Bounds& o) { const Float2_t x1 = std::max(x + width, o.x + o.width), y1 = std::max(y + height, o.y + o.height); x = std::min(x, o.x); y = std::min(y, o.y); width = x1 - x; height = y1 - y; }
-    template<bool K> Bounds operator-(const Vector2D<K>& v) const { return Bounds(x - v.x, y - v.y, width, height); }
-    template<bool K> Bounds operator+(const Vector2D<K>& v) const { return Bounds(x + v.x, y + v.y, width, height); }
-    Vec2 pos() const { return Vec2(x, y); }
-    Size2 size() const { return Size2(width, height); }
-    void restrict_to(const Bounds& b)                                   // only RawProcessing.cpp's tag branch (never run here): clamp to a surrounding box
-    {
-        const Float2_t x1 = std::min(x + width, b.x + b.width), y1 = std::min(y + height, b.y + b.height);
-        x = std::max(x, b.x); y = std::max(y, b.y); width = x1 - x; height = y1 - y;
-    }
-    void operator<<(const Size2& s) { width = s.x; height = s.y; }      // vec2.h:437-444
-    void operator<<(const Vec2& p) { x = p.x; y = p.y; }
-};
-
-class Minimizable { public: virtual void minimize_memory() = 0; virtual ~Minimizable() {} };
-
-struct Frame_t {
-    int32_t _frame = -1;
-    constexpr Frame_t() = default;
-    explicit constexpr Frame_t(int32_t f) : _frame(f) {}
-    constexpr bool valid() const { return _frame >= 0; }
-    constexpr int32_t get() const { return _frame; }
-    constexpr bool operator==(const Frame_t&) const = default;
-    constexpr auto operator<=>(const Frame_t& o) const { return _frame <=> o._frame; }
-    constexpr Frame_t operator-(const Frame_t& o) const { return Frame_t(_frame - o._frame); }
-    constexpr Frame_t operator+(const Frame_t& o) const { return Frame_t(_frame + o._frame); }
-};
-constexpr Frame_t operator""_f(unsigned long long v) { return Frame_t(int32_t(v)); }
-// LOGGED_MUTEX / LOGGED_LOCK without the logging (commons.pc.h:1399-1400)
-struct LoggedMutexStandIn : std::mutex { LoggedMutexStandIn(const char *) {} };
-#define LOGGED_MUTEX(NAME) cmn::LoggedMutexStandIn(NAME)
-#define LOGGED_LOCK(MUTEX) std::unique_lock<std::mutex>{ MUTEX }
-
-struct glz_json_placeholder {};
-struct Meta {
-    template<typename T> static std::string toStr(const T&) { return std::string(); }
-    template<typename T> static std::string name() { return std::string(); }
-    template<typename T, typename S> static T fromStr(S&&) { return T{}; }
-};
-template<typename T> inline auto cvt2json(const T&) { return glz_json_placeholder{}; }
-template<int N> struct dec { template<typename T> dec(T) {} std::string toStr() const { return std::string(); } };
-template<typename... A> inline void Print(const A&...) {}
-template<typename... A> inline void FormatWarning(const A&...) {}
-template<typename... A> inline void FormatError(const A&...) {}
-template<typename... A> inline void FormatExcept(const A&...) {}
-template<typename... A> inline std::runtime_error U_EXCEPTION(const char *msg, const A&...) { return std::runtime_error(msg); }
-template<typename... A> inline std::runtime_error RuntimeError(const char *msg, const A&...) { return std::runtime_error(msg); }
+// ---- the REFERENCE'S OWN commons/common/misc/vec2.h from the checkout: Vec2, Size2, Bounds with every operator, length / normalize / atan2, sqdistance ... ----
+// (commons/common/misc/vec2.cpp is compiled with it: the explicit instantiations, Bounds::restrict_to / distance.)  What it expects from TRex's precompiled
+// header before it: OpenCV's Point_ / Size_ / Rect_ templates and cv::Mat (below), the is_numeric concept (misc/useful_concepts.h:175), saturate
+// (misc/detail.h:225-229), and glaze / Meta names that only its string and JSON helpers touch (inert here).
+using uint = unsigned int;
+namespace cv {
+template<typename T> struct Point_ { T x{}, y{}; Point_() = default; template<typename A, typename B> Point_(A x_, B y_) : x(T(x_)), y(T(y_)) {} };
+template<typename T> struct Size_ { T width{}, height{}; Size_() = default; template<typename A, typename B> Size_(A w, B h) : width(T(w)), height(T(h)) {} };
+template<typename T> struct Rect_ { T x{}, y{}, width{}, height{}; Rect_() = default; template<typename A, typename B, typename C_, typename D> Rect_(A x_, B y_, C_ w, D h) : x(T(x_)), y(T(y_)), width(T(w)), height(T(h)) {} };
+using Size = Size_<int>;
+using Rect2i = Rect_<int>;
 }
-
+namespace cmn { class Bounds; }
 // the handful of OpenCV names the compiled files mention.  cv::Mat is a plain row-major byte image (rows, cols, type = CV_8UC1 / CV_8UC3, step.p =
 // {bytes per row, bytes per pixel}, ptr(row)) -- enough for Source::extract_lines, which only compares bytes with zero; Transform::toCV, the debug drawing of
 // offset_to_middle and the outline_use_dft branch of find_tail are never reached (they abort if they are)
@@ -286,16 +186,8 @@ struct Mat {
         const size_t es = src.step.p[1];
         for (int y = 0; y < src.rows; ++y) for (int x = 0; x < src.cols; ++x) if (mask.ptr(y)[x]) std::memcpy(dst.ptr(y) + x * es, src.ptr(y) + x * es, es);
     }
-    Mat operator()(const cmn::Bounds& b) const
-    {
-        Mat v = *this;
-        v.data = data + (size_t)(int)b.y * step.p[0] + (size_t)(int)b.x * step.p[1]; v.rows = (int)b.height; v.cols = (int)b.width;
-        return v;
-    }
+    Mat operator()(const cmn::Bounds& b) const;          // defined below, after vec2.h
 };
-}
-namespace cmn { template<bool K> inline Vector2D<K>::Vector2D(const cv::Mat& m) noexcept : x(Float2_t(m.cols)), y(Float2_t(m.rows)) {} }
-namespace cv {
 enum { INTER_NEAREST = 0, INTER_LINEAR = 1, BORDER_CONSTANT = 0 };
 // cv::warpAffine is OpenCV's (third party): the test installs the oracle's bit-exact restatement of its 8-bit INTER_LINEAR / BORDER_CONSTANT path
 // (oracle/trex_oracle.c to_warp_affine_u8, pinned on cv2 4.13 by tests/test_oracle_moments.py) through ref_filtercache_set_warp
@@ -336,7 +228,67 @@ inline void resize(const Mat& src, Mat& dst, Size, double fx, double fy, int fla
 enum { DFT_INVERSE = 1, DFT_SCALE = 2 };
 inline void dft(const Mat&, Mat&, int = 0) { std::fprintf(stderr, "cv::dft stand-in used\n"); std::abort(); }
 }
-namespace glz { struct json_t { json_t() = default; template<typename T> json_t(T&&) {} }; }
+
+namespace glz {
+struct json_t { json_t() = default; template<typename... T> json_t(T&&...) {} bool contains(const char *) const { return false; } json_t operator[](const char *) const { return {}; } double get_number() const { return 0; } };
+enum class error_code { none };
+template<typename... A> inline error_code read_json(A&&...) { return error_code::none; }
+template<typename... A> inline std::string format_error(A&&...) { return std::string(); }
+template<typename T> struct meta;
+template<auto Read, auto Write> inline constexpr int custom = 0;
+template<typename... A> constexpr int array(A...) { return 0; }
+}
+namespace cmn {
+struct Meta {
+    template<typename T> static std::string toStr(const T&) { return std::string(); }
+    template<typename T> static std::string name() { return std::string(); }
+    template<typename T, typename S> static T fromStr(S&&) { return T{}; }
+};
+template<typename Str> concept StringLike = std::is_same_v<std::remove_cvref_t<Str>, std::string> || std::is_same_v<std::remove_cvref_t<Str>, const char*> ||
+                                            std::is_same_v<std::remove_cvref_t<Str>, std::string_view> || std::is_array_v<std::remove_cvref_t<Str>>;
+template<typename T> concept is_numeric = (!std::is_same_v<std::remove_cvref_t<T>, bool>) && (std::floating_point<T> || std::integral<T>);      // misc/useful_concepts.h:175
+template<typename K, typename T = K> constexpr inline T saturate(K val, T min = 0, T max = 255) { return std::clamp(T(val), min, max); }          // misc/detail.h:225-229
+}
+#include <misc/vec2.h>
+namespace cv {
+inline Mat Mat::operator()(const cmn::Bounds& b) const          // the ROI view: the rectangle's members truncated to int (vec2.h:433)
+{
+    Mat v = *this;
+    v.data = data + (size_t)(int)b.y * step.p[0] + (size_t)(int)b.x * step.p[1]; v.rows = (int)b.height; v.cols = (int)b.width;
+    return v;
+}
+}
+namespace cmn {
+class Minimizable { public: virtual void minimize_memory() = 0; virtual ~Minimizable() {} };
+
+struct Frame_t {
+    int32_t _frame = -1;
+    constexpr Frame_t() = default;
+    explicit constexpr Frame_t(int32_t f) : _frame(f) {}
+    constexpr bool valid() const { return _frame >= 0; }
+    constexpr int32_t get() const { return _frame; }
+    constexpr bool operator==(const Frame_t&) const = default;
+    constexpr auto operator<=>(const Frame_t& o) const { return _frame <=> o._frame; }
+    constexpr Frame_t operator-(const Frame_t& o) const { return Frame_t(_frame - o._frame); }
+    constexpr Frame_t operator+(const Frame_t& o) const { return Frame_t(_frame + o._frame); }
+};
+constexpr Frame_t operator""_f(unsigned long long v) { return Frame_t(int32_t(v)); }
+// LOGGED_MUTEX / LOGGED_LOCK without the logging (commons.pc.h:1399-1400)
+struct LoggedMutexStandIn : std::mutex { LoggedMutexStandIn(const char *) {} };
+#define LOGGED_MUTEX(NAME) cmn::LoggedMutexStandIn(NAME)
+#define LOGGED_LOCK(MUTEX) std::unique_lock<std::mutex>{ MUTEX }
+
+struct glz_json_placeholder {};
+template<typename T> inline auto cvt2json(const T&) { return glz_json_placeholder{}; }
+template<int N> struct dec { template<typename T> dec(T) {} std::string toStr() const { return std::string(); } };
+template<typename... A> inline void Print(const A&...) {}
+template<typename... A> inline void FormatWarning(const A&...) {}
+template<typename... A> inline void FormatError(const A&...) {}
+template<typename... A> inline void FormatExcept(const A&...) {}
+template<typename... A> inline std::runtime_error U_EXCEPTION(const char *msg, const A&...) { return std::runtime_error(msg); }
+template<typename... A> inline std::runtime_error RuntimeError(const char *msg, const A&...) { return std::runtime_error(msg); }
+}
+
 namespace cmn::utils {
 inline bool lowercase_equal_to(std::string_view a, std::string_view b)
 {
@@ -344,10 +296,6 @@ inline bool lowercase_equal_to(std::string_view a, std::string_view b)
     for (size_t i = 0; i < a.size(); ++i) if (std::tolower((unsigned char)a[i]) != std::tolower((unsigned char)b[i])) return false;
     return true;
 }
-}
-namespace cmn {
-template<typename Str> concept StringLike = std::is_same_v<std::remove_cvref_t<Str>, std::string> || std::is_same_v<std::remove_cvref_t<Str>, const char*> ||
-                                            std::is_same_v<std::remove_cvref_t<Str>, std::string_view> || std::is_array_v<std::remove_cvref_t<Str>>;
 }
 #include <misc/base_types.h>
 #include <misc/EnumClass.h>

@@ -6,5 +6,4 @@
 #include <compare>
 using ushort = unsigned short;
 namespace cmn { template<typename T> concept unsigned_number = std::unsigned_integral<std::remove_cvref_t<T>>; }
-namespace glz { template<typename T> struct meta; template<auto Read, auto Write> inline constexpr int custom = 0; }
 #include_next <misc/bid.h>

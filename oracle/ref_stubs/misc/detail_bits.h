@@ -9,7 +9,6 @@
 #include <future>
 #include <misc/matharray.h>
 namespace cv {
-struct Rect2i { int x = 0, y = 0, width = 0, height = 0; Rect2i() = default; template<typename A, typename B, typename C_, typename D> Rect2i(A x, B y, C_ w, D h) : x(int(x)), y(int(y)), width(int(w)), height(int(h)) {} };
 struct Vec3b { unsigned char v[3]; Vec3b() : v{0, 0, 0} {} Vec3b(unsigned char a, unsigned char b, unsigned char c) : v{a, b, c} {} unsigned char& operator[](int i) { return v[i]; } const unsigned char& operator[](int i) const { return v[i]; } };
 enum { COLOR_GRAY2BGR = 8, COLOR_BGR2GRAY = 6 };
 #ifndef REF_DETECT
@@ -28,8 +27,6 @@ inline void cvtColor(const Mat& src, Mat dst, int code)
 #define CV_8UC(n) ((n) == 3 ? CV_8UC3 : ((n) == 4 ? CV_8UC4 : CV_8UC1))
 namespace cmn {
 enum class ImageMode { GRAY, RGB, R3G3B2, RGBA };
-template<typename K, typename T = K> requires (!is_rgb_array<K>::value)
-constexpr inline T saturate(K val, T min = 0, T max = 255) { return std::clamp(T(val), min, max); }
 template<typename Vec> constexpr uint8_t vec_to_r3g3b2(const Vec& bgr) { return (uint8_t(bgr[0] / 64) << 6) | (uint8_t(bgr[1] / 32) << 3) | (uint8_t(bgr[2] / 32) << 0); }
 template<uint8_t channels = 3> constexpr auto r3g3b2_to_vec(const uint8_t& c, const uint8_t = 255)
 {

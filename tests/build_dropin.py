@@ -15,7 +15,7 @@ OUT_DIR = os.path.join(HERE, "cpp", "_dropin")
 OUT = os.path.join(OUT_DIR, "libshim_dropin.so")
 OUT_B = os.path.join(OUT_DIR, "libshim_dropin_b.so")
 REF_FILES = [os.path.join(REF_COMMON, "processing", f) for f in ("RawProcessing.cpp", "Background.cpp", "CPULabeling.cpp", "Brototype.cpp", "Source.cpp", "DLList.cpp", "ListCache.cpp", "BlobIdentity.cpp")] + \
-            [os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp"), os.path.join(REF_COMMON, "video", "AveragingAccumulator.cpp")]
+            [os.path.join(REF_SRC, "tracker", "core", "SizeFilters.cpp"), os.path.join(REF_COMMON, "video", "AveragingAccumulator.cpp"), os.path.join(REF_COMMON, "misc", "vec2.cpp")]
 
 
 def snippet() -> str:
